@@ -1,0 +1,339 @@
+"""VMC sampling path restatement: walker state, NN-exchange sweep, XXZ/Heisenberg local energy + holes,
+MC energy/gradient evaluator, SR S-matrix matvec.  Test infrastructure (see oracle/__init__.py).
+
+Reference (relative to include/qlpeps/):
+  * TPSWaveFunctionComponent          vmc_basic/wave_function_component.h:136-379
+  * MCUpdateSquareNNUpdateBaseOBC     vmc_basic/configuration_update_strategies/square_nn_updater.h:29-81
+  * MCUpdateSquareNNExchangeOBC       .../square_nn_updater.h:146-188
+  * SquareNNNModelEnergySolver (NN)   algorithm/vmc_update/model_solvers/base/square_nnn_energy_solver.h:79-315
+  * BondTraversalMixin (vertical)     .../model_solvers/base/bond_traversal_mixin.h:112-143
+  * SquareSpinOneHalfXXZModelMixIn    .../model_solvers/square_spin_onehalf_xxz_obc.h:72-140
+  * MCEnergyGradEvaluator::Evaluate   algorithm/vmc_update/mc_energy_grad_evaluator.h:152-330
+  * MeanAndBinnedErrorSqrtNUniformBin vmc_basic/monte_carlo_tools/statistics.h:146-225
+  * NormalizeStateOrder1              algorithm/vmc_update/monte_carlo_engine.h:206-240
+  * SRSMatrix::operator*              optimizer/stochastic_reconfiguration_smatrix.h:45-91
+"""
+import math
+import numpy as np
+from .bmps import LEFT, DOWN, RIGHT, UP, HORIZONTAL, VERTICAL
+from .contractor import BMPSContractor
+from .mt19937 import MT19937
+
+
+def project(tps, config):
+    """TensorNetwork2D(sitps, config) (tensor_network_2d_basic_impl.h:24-73)."""
+    return [[tps[r][c][int(config[r][c])] for c in range(len(tps[0]))] for r in range(len(tps))]
+
+
+class Walker:
+    """TPSWaveFunctionComponent (wave_function_component.h:136-379)."""
+
+    def __init__(self, tps, config, trunc):
+        self.config = np.array(config, dtype=np.int64)
+        self.rows, self.cols = self.config.shape
+        self.trunc = trunc
+        self.tn = project(tps, self.config)
+        self.contractor = BMPSContractor(self.rows, self.cols)
+        self.contractor.init(self.tn)
+        self.amplitude = 0.0
+        self.evaluate_amplitude()
+
+    def evaluate_amplitude(self):
+        """EvaluateAmplitude (wave_function_component.h:187-212)."""
+        c = self.contractor
+        c.set_truncate_params(*self.trunc)
+        c.grow_bmps_for_row(self.tn, 0)
+        c.grow_full_bten(self.tn, RIGHT, 0, 2, True)
+        c.init_bten(self.tn, LEFT, 0)
+        self.amplitude = c.trace(self.tn, (0, 0), HORIZONTAL)
+        return self.amplitude
+
+    def update_local(self, tps, new_amplitude, *site_configs):
+        """UpdateLocal / UpdateSingleSite_ (wave_function_component.h:345-378)."""
+        for (site, cfg) in site_configs:
+            self.config[site[0], site[1]] = cfg
+            self.tn[site[0]][site[1]] = tps[site[0]][site[1]][cfg]
+            self.contractor.erase_envs_after_update(site)
+        self.amplitude = new_amplitude
+
+
+class NNExchangeUpdater:
+    """MCUpdateSquareNNExchangeOBC with the explicit-seed constructor
+    (monte_carlo_sweep_updater_base.h:37, square_nn_updater.h:29-81, 146-188)."""
+
+    def __init__(self, seed):
+        self.rng = MT19937(seed)
+
+    def two_site_update(self, site1, site2, bond_dir, tps, w):
+        c1 = int(w.config[site1]); c2 = int(w.config[site2])
+        if c1 == c2:
+            return False
+        psi_b = w.contractor.replace_nn_site_trace(w.tn, site1, site2, bond_dir,
+                                                   tps[site1[0]][site1[1]][c2], tps[site2[0]][site2[1]][c1])
+        psi_a = w.amplitude
+        if abs(psi_b) >= abs(psi_a):
+            pass
+        else:
+            div = abs(psi_b) / abs(psi_a)
+            p = div * div
+            if not (self.rng.uniform01() < p):
+                return False
+        w.update_local(tps, psi_b, (site1, c2), (site2, c1))
+        return True
+
+    def sweep(self, tps, w):
+        """operator() (square_nn_updater.h:29-81). Returns accept_rates = [accepted / bond_num]."""
+        tn, c = w.tn, w.contractor
+        rows, cols = w.rows, w.cols
+        accepted = 0
+        c.set_truncate_params(*w.trunc)
+        c.generate_bmps_approach(tn, UP)
+        for row in range(rows):
+            c.init_bten(tn, LEFT, row)
+            c.grow_full_bten(tn, RIGHT, row, 2, True)
+            for col in range(cols - 1):
+                accepted += self.two_site_update((row, col), (row, col + 1), HORIZONTAL, tps, w)
+                if col < cols - 2:
+                    c.shift_bten_window(tn, RIGHT)
+            if row < rows - 1:
+                c.shift_bmps_window(tn, DOWN)
+        c.delete_inner_bmps(LEFT)
+        c.delete_inner_bmps(RIGHT)
+        c.generate_bmps_approach(tn, LEFT)
+        for col in range(cols):
+            c.init_bten(tn, UP, col)
+            c.grow_full_bten(tn, DOWN, col, 2, True)
+            for row in range(rows - 1):
+                accepted += self.two_site_update((row, col), (row + 1, col), VERTICAL, tps, w)
+                if row < rows - 2:
+                    c.shift_bten_window(tn, DOWN)
+            if col < cols - 1:
+                c.shift_bmps_window(tn, RIGHT)
+        c.delete_inner_bmps(UP)
+        bond_num = cols * (rows - 1) + rows * (cols - 1)
+        return [accepted / bond_num]
+
+
+class XXZModel:
+    """SquareSpinOneHalfXXZModelOBC: H = sum_<ij> jz Sz Sz + jxy (Sx Sx + Sy Sy) - h00 Sz(0,0)
+    (square_spin_onehalf_xxz_obc.h:64-159, 174-328). Heisenberg = XXZModel(1, 1, 0)."""
+
+    def __init__(self, jz=1.0, jxy=1.0, pinning00=0.0):
+        self.jz, self.jxy, self.pinning00 = jz, jxy, pinning00
+
+    def bond_energy(self, site1, site2, c1, c2, orient, w, tps, inv_psi):
+        """EvaluateBondEnergy (square_spin_onehalf_xxz_obc.h:72-104)."""
+        if c1 == c2:
+            return 0.25 * self.jz
+        psi_ex = w.contractor.replace_nn_site_trace(w.tn, site1, site2, orient,
+                                                    tps[site1[0]][site1[1]][c2], tps[site2[0]][site2[1]][c1])
+        ratio = np.conj(psi_ex * inv_psi)
+        return -0.25 * self.jz + ratio * 0.5 * self.jxy
+
+    def onsite_energy(self, config):
+        """EvaluateTotalOnsiteEnergy (square_spin_onehalf_xxz_obc.h:131-135)."""
+        return -self.pinning00 * (float(config[0, 0]) - 0.5)
+
+    def energy_and_holes(self, tps, w, calc_holes=True):
+        """CalEnergyAndHolesImpl (square_nnn_energy_solver.h:79-101) for has_nnn=false.
+        Returns (E_loc, holes[rows][cols] or None, psi_list)."""
+        tn, c = w.tn, w.contractor
+        rows, cols = w.rows, w.cols
+        bond_e = []
+        psi_list = []
+        holes = [[None] * cols for _ in range(rows)] if calc_holes else None
+        # horizontal pass (square_nnn_energy_solver.h:104-266)
+        c.set_truncate_params(*w.trunc)
+        c.generate_bmps_approach(tn, UP)
+        for row in range(rows):
+            c.init_bten(tn, LEFT, row)
+            c.grow_full_bten(tn, RIGHT, row, 1, True)
+            psi = c.trace(tn, (row, 0), HORIZONTAL)
+            if psi == 0:
+                raise RuntimeError("Wavefunction amplitude is near zero, causing division by zero.")
+            inv_psi = 1.0 / psi
+            psi_list.append(psi)
+            for col in range(cols):
+                if calc_holes:
+                    holes[row][col] = np.conj(c.punch_hole(tn, (row, col), HORIZONTAL))     # Dag(...)  :163
+                if col < cols - 1:
+                    s1, s2 = (row, col), (row, col + 1)
+                    bond_e.append(self.bond_energy(s1, s2, int(w.config[s1]), int(w.config[s2]),
+                                                   HORIZONTAL, w, tps, inv_psi))
+                    c.shift_bten_window(tn, RIGHT)
+            if row < rows - 1:
+                c.shift_bmps_window(tn, DOWN)
+        # vertical pass (bond_traversal_mixin.h:112-143)
+        c.generate_bmps_approach(tn, LEFT)
+        for col in range(cols):
+            c.init_bten(tn, UP, col)
+            c.grow_full_bten(tn, DOWN, col, 2, True)
+            psi = c.trace(tn, (0, col), VERTICAL)
+            if psi == 0:
+                raise RuntimeError("Wavefunction amplitude is near zero, causing division by zero.")
+            inv_psi = 1.0 / psi
+            psi_list.append(psi)
+            for row in range(rows - 1):
+                s1, s2 = (row, col), (row + 1, col)
+                bond_e.append(self.bond_energy(s1, s2, int(w.config[s1]), int(w.config[s2]),
+                                               VERTICAL, w, tps, inv_psi))
+                if row < rows - 2:
+                    c.shift_bten_window(tn, DOWN)
+            if col < cols - 1:
+                c.shift_bmps_window(tn, RIGHT)
+        e = sum(bond_e[1:], bond_e[0]) if bond_e else 0.0         # std::reduce, in order
+        return e + self.onsite_energy(w.config), holes, psi_list
+
+
+def mean_and_binned_error(samples):
+    """MeanAndBinnedErrorSqrtNUniformBin for one rank (statistics.h:146-225)."""
+    n = len(samples)
+    if n == 0:
+        return 0.0, 0.0
+    bin_size = max(1, int(math.sqrt(n)))
+    num_bins = n // bin_size
+    means = [sum(samples[i * bin_size + 1:(i + 1) * bin_size], samples[i * bin_size]) / bin_size
+             for i in range(num_bins)]
+    return combine_bin_means(means)
+
+
+def combine_bin_means(means):
+    """Master-side part of MeanAndBinnedErrorSqrtNUniformBin (statistics.h:209-223)."""
+    nb = len(means)
+    if nb == 0:
+        return 0.0, 0.0
+    mean = sum(means[1:], means[0]) / nb
+    if nb == 1:
+        return mean, float("inf")
+    var = sum(abs(m - mean) ** 2 for m in means) / (nb - 1)
+    return mean, math.sqrt(var / nb)
+
+
+def tps_like_zeros(tps):
+    return [[[np.zeros_like(t) for t in site] for site in row] for row in tps]
+
+
+class EnergyGradEvaluator:
+    """MCEnergyGradEvaluator::Evaluate for one rank == one walker (mc_energy_grad_evaluator.h:152-330).
+    Multi-rank results are the rank-mean of per-rank gradients (``:296-309``) and the mean over all
+    ranks' bin means for the energy; ``evaluate_ranks`` below does that combination."""
+
+    def __init__(self, tps, model, trunc, sweeps_between_samples=1):
+        self.tps, self.model, self.trunc = tps, model, trunc
+        self.sweeps_between_samples = sweeps_between_samples
+
+    def sample_rank(self, walker, updater, num_samples, collect_sr=False):
+        tps = self.tps
+        ostar_sum = tps_like_zeros(tps)
+        eloc_ostar_sum = tps_like_zeros(tps)
+        energies, ostar_samples, accept = [], [], 0.0
+        for _ in range(num_samples):
+            for _ in range(self.sweeps_between_samples):
+                rates = updater.sweep(tps, walker)
+            accept += rates[0]
+            e_loc, holes, _ = self.model.energy_and_holes(tps, walker, True)
+            e_conj = np.conj(e_loc)
+            inv_amp = np.conj(1.0 / walker.amplitude)
+            energies.append(e_loc)
+            sample = {} if collect_sr else None
+            for r in range(walker.rows):
+                for c in range(walker.cols):
+                    b = int(walker.config[r, c])
+                    ostar = inv_amp * holes[r][c]                       # :259-262
+                    ostar_sum[r][c][b] = ostar_sum[r][c][b] + ostar
+                    eloc_ostar_sum[r][c][b] = eloc_ostar_sum[r][c][b] + e_conj * ostar
+                    if collect_sr:
+                        sample[(r, c)] = (b, ostar)
+            if collect_sr:
+                ostar_samples.append(sample)
+        return dict(energies=energies, ostar_sum=ostar_sum, eloc_ostar_sum=eloc_ostar_sum,
+                    accept=accept / max(1, num_samples), ostar_samples=ostar_samples, n=num_samples)
+
+    @staticmethod
+    def combine(rank_results):
+        """Energy = mean of all ranks' bin means; grad = mean over ranks of
+        (sum E*O*/N - conj(E) sum O*/N)  (mc_energy_grad_evaluator.h:292-309)."""
+        n = rank_results[0]["n"]
+        bin_size = max(1, int(math.sqrt(n)))
+        means = []
+        for rr in rank_results:
+            e = rr["energies"]
+            for i in range(len(e) // bin_size):
+                chunk = e[i * bin_size:(i + 1) * bin_size]
+                means.append(sum(chunk[1:], chunk[0]) / bin_size)
+        energy, err = combine_bin_means(means)
+        nr = len(rank_results)
+        grad = tps_like_zeros(rank_results[0]["ostar_sum"])
+        for rr in rank_results:
+            for r, row in enumerate(grad):
+                for c, site in enumerate(row):
+                    for s in range(len(site)):
+                        g = rr["eloc_ostar_sum"][r][c][s] * (1.0 / n) + np.conj(-energy) * (rr["ostar_sum"][r][c][s] * (1.0 / n))
+                        site[s] = site[s] + g / nr
+        return energy, err, grad
+
+
+def normalize_state_order1(tps, amplitudes):
+    """NormalizeStateOrder1 (monte_carlo_engine.h:206-240): scale = 1/max|psi|, every site tensor
+    multiplied by scale^(1/(Lx*Ly)). Returns the rescaled TPS and the per-site factor."""
+    rows, cols = len(tps), len(tps[0])
+    scale = 1.0 / max(abs(a) for a in amplitudes)
+    f = scale ** (1.0 / (rows * cols))
+    return [[[t * f for t in site] for site in row] for row in tps], f
+
+
+def normalize_all_site(tps):
+    """SplitIndexTPS::NormalizeAllSite (split_index_tps_impl.h:209-255)."""
+    out = []
+    for row in tps:
+        orow = []
+        for site in row:
+            nrm = math.sqrt(sum(float(np.sum(np.abs(t) ** 2)) for t in site))
+            orow.append([t / nrm for t in site])
+        out.append(orow)
+    return out
+
+
+def sr_matvec(ostar_samples_flat, ostar_mean_flat, v, diag_shift=0.0):
+    """SRSMatrix::operator* for one rank group (stochastic_reconfiguration_smatrix.h:45-91):
+    S v = (1/N) sum_i conj(O*_i . v - Obar . v) ... written for flat real/complex vectors:
+    S v = mean_i O*_i (O*_i^dagger v) - Obar (Obar^dagger v) + diag_shift v."""
+    n = len(ostar_samples_flat)
+    acc = np.zeros_like(v)
+    for o in ostar_samples_flat:
+        acc = acc + o * np.vdot(o, v)
+    acc = acc / n - ostar_mean_flat * np.vdot(ostar_mean_flat, v)
+    return acc + diag_shift * v
+
+
+def random_tps(rows, cols, phys, D, seed, signed=False, dtype=np.float64):
+    """Synthetic TPS of SURVEY.md section 8d.1: i.i.d. uniform [0,1) (or [-1,1)) entries, edge legs of
+    dimension 1, NormalizeAllSite applied."""
+    rng = np.random.default_rng(seed)
+    tps = []
+    for r in range(rows):
+        row = []
+        for c in range(cols):
+            shape = (1 if c == 0 else D, 1 if r == rows - 1 else D, 1 if c == cols - 1 else D, 1 if r == 0 else D)
+            site = []
+            for _ in range(phys):
+                t = rng.random(shape)
+                if signed:
+                    t = 2.0 * t - 1.0
+                site.append(t.astype(dtype))
+            row.append(site)
+        tps.append(row)
+    return normalize_all_site(tps)
+
+
+def neel_config(rows, cols):
+    return np.array([[(r + c) % 2 for c in range(cols)] for r in range(rows)], dtype=np.int64)
+
+
+def shuffled_half_filled_config(rows, cols, seed):
+    """Per-walker initial configuration: Fisher-Yates shuffle (oracle.mt19937.shuffle_std) of the
+    half-filled list with mt19937(seed)."""
+    from .mt19937 import shuffle_std
+    n = rows * cols
+    base = [i % 2 for i in range(n)]
+    return np.array(shuffle_std(base, MT19937(seed)), dtype=np.int64).reshape(rows, cols)

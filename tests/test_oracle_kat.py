@@ -1,0 +1,147 @@
+"""Pins the CPU oracle against the reference's own known-answer tests
+before it is trusted as the checker for the CUDA path."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle.bmps import LEFT, RIGHT, UP, DOWN, HORIZONTAL, VERTICAL, truncation_dim
+from oracle.contractor import BMPSContractor
+from oracle.mt19937 import MT19937
+from oracle import vmc
+from helpers import (load_golden_tps, ising_tn, ising_exact_logZ, exact_summation, grad_norm_square,
+                     weighted_probe)
+
+
+def test_mt19937_known_answer():
+    # ISO C++ [rand.predef]: the 10000th consecutive invocation of a default-constructed mt19937 is 4123659995.
+    g = MT19937(5489)
+    for _ in range(9999):
+        g.next_u32()
+    assert g.next_u32() == 4123659995
+    # numpy's legacy RandomState uses the same init_genrand seeding; its 53-bit doubles are a different
+    # construction, but the raw 32-bit stream must agree.
+    g = MT19937(12345)
+    rs = np.random.RandomState(12345)
+    ref = rs.randint(0, 2 ** 32, size=1000, dtype=np.uint64)
+    assert [g.next_u32() for _ in range(1000)] == [int(x) for x in ref]
+
+
+def test_uniform01_is_generate_canonical():
+    g, h = MT19937(7), MT19937(7)
+    for _ in range(100):
+        x0, x1 = h.next_u32(), h.next_u32()
+        assert g.uniform01() == (x0 + x1 * 4294967296.0) / 18446744073709551616.0
+
+
+def test_truncation_rule():
+    s = np.array([1.0, 0.5, 0.1, 1e-9, 0.0])
+    assert truncation_dim(s, 1, 10, 0.0) == 3          # weights below double rounding of the total are dropped down to Dmin
+    assert truncation_dim(s, 5, 10, 0.0) == 5
+    assert truncation_dim(s, 1, 2, 0.0) == 2
+    assert truncation_dim(s, 1, 10, 1e-15) == 3
+    assert truncation_dim(s, 1, 10, 0.009) == 2
+
+
+@pytest.mark.parametrize("L", [6, 12])
+def test_K1_ising_partition_function(L):
+    """reference: tests/test_2d_tn/test_bmps_contractor.cpp:472-493, SVD(10, 30, 1e-15), tol 1e-8 on F/site."""
+    beta = math.log(1 + math.sqrt(2.0)) / 2.0
+    tn = ising_tn(L, beta)
+    lz = ising_exact_logZ(L, beta)
+    c = BMPSContractor(L, L)
+    c.init(tn)
+    c.set_truncate_params(10, 30, 1e-15)
+    zs = []
+    c.grow_bmps_for_row(tn, 2)
+    c.init_bten(tn, LEFT, 2)
+    c.grow_full_bten(tn, RIGHT, 2, 2, True)
+    zs.append(c.trace(tn, (2, 0), HORIZONTAL))
+    c.shift_bten_window(tn, RIGHT)
+    zs.append(c.trace(tn, (2, 1), HORIZONTAL))
+    c.init_bten(tn, LEFT, 2)
+    c.grow_full_bten(tn, RIGHT, 2, 1, True)          # remain=1: the E_loc flow, enables one-site traces
+    zs.append(c.replace_one_site_trace(tn, (2, 0), tn[2][0], HORIZONTAL))
+    c.shift_bten_window(tn, RIGHT)
+    zs.append(c.replace_one_site_trace(tn, (2, 1), tn[2][1], HORIZONTAL))
+    c.grow_bmps_for_col(tn, 1)
+    c.init_bten(tn, UP, 1)
+    c.grow_full_bten(tn, DOWN, 1, 2, True)
+    zs.append(c.trace(tn, (0, 1), VERTICAL))
+    c.shift_bten_window(tn, DOWN)
+    zs.append(c.trace(tn, (1, 1), VERTICAL))
+    c.init_bten(tn, DOWN, 1)
+    c.grow_full_bten(tn, UP, 1, 2, True)
+    zs.append(c.trace(tn, (L - 2, 1), VERTICAL))
+    for z in zs:
+        assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
+
+
+def test_K2_punch_hole_and_invalidation():
+    """reference: tests/test_2d_tn/test_bmps_contractor.cpp:407-470."""
+    L = 8
+    beta = math.log(1 + math.sqrt(2.0)) / 2.0
+    tn = ising_tn(L, beta)
+    c = BMPSContractor(L, L)
+    c.init(tn)
+    c.set_truncate_params(4, 10, 1e-10)
+    c.grow_bmps_for_row(tn, 2)
+    c.grow_full_bten(tn, LEFT, 2, 2, True)
+    c.grow_full_bten(tn, RIGHT, 2, 2, True)
+    val1 = c.trace(tn, (2, 0), HORIZONTAL)
+    hole = c.punch_hole(tn, (2, 1), HORIZONTAL)
+    tr = c.trace(tn, (2, 1), HORIZONTAL)
+    assert abs(np.sum(hole * tn[2][1]) - tr) < 1e-10 * abs(tr)
+    tn[2][1] = tn[2][1] * 0.5
+    c.erase_envs_after_update((2, 1))
+    c.grow_bmps_for_row(tn, 2)
+    c.grow_full_bten(tn, LEFT, 2, 2, True)
+    c.grow_full_bten(tn, RIGHT, 2, 2, True)
+    val2 = c.trace(tn, (2, 0), HORIZONTAL)
+    assert abs(val2 - 0.5 * val1) < 1e-10 * abs(val1)
+
+
+@pytest.mark.parametrize("name,complex_", [("heis2x2_double_lowest", False), ("heis2x2_complex_lowest", True),
+                                            ("heis2x2_double_su", False)])
+def test_K4_K5_exact_summation_goldens(name, complex_):
+    """Energies and gradient signatures asserted by tests/test_algorithm/test_exact_summation_evaluator.cpp:531-606."""
+    tps, z = load_golden_tps(name)
+    energy, grad = exact_summation(tps, vmc.XXZModel(1.0, 1.0, 0.0))
+    assert abs(energy - float(z["exp_energy"])) < float(z["exp_energy_tol"])
+    if "exp_grad_norm" in z:
+        # the reference's tolerance is abs 1e-8; the oracle reproduces the quoted digits to ~1e-18 abs
+        assert abs(grad_norm_square(grad) - float(z["exp_grad_norm"])) < 1e-17
+        p = weighted_probe(grad, complex_)
+        assert abs(np.real(p) - float(z["exp_grad_probe_re"])) < 1e-17
+        assert abs(np.imag(p) - float(z["exp_grad_probe_im"])) < 1e-17
+
+
+def test_hole_is_amplitude_derivative():
+    tps = vmc.random_tps(3, 3, 2, 3, seed=3)
+    cfg = vmc.neel_config(3, 3)
+    w = vmc.Walker(tps, cfg, (1, 1000, 0.0))
+    _, holes, psis = vmc.XXZModel().energy_and_holes(tps, w, True)
+    for r in range(3):
+        for c in range(3):
+            assert abs(np.sum(holes[r][c] * w.tn[r][c]) - psis[r]) < 1e-12 * abs(psis[r])
+    assert max(abs(p - psis[0]) for p in psis) < 1e-12 * abs(psis[0])
+
+
+def test_K6_heisenberg_4x4_D8_mc_energy():
+    """reference: tests/slow_tests/test_boson_mc_peps_measure.cpp:31-76 (e0_state = -9.18912, ED -9.1892).
+    A short chain from the stored configurations must land within a few sigma of the state energy."""
+    tps, z = load_golden_tps("heis4x4_D8_double")
+    cfgs = z["configs"]
+    model = vmc.XXZModel(1.0, 1.0, 0.0)
+    energies = []
+    for k in range(4):
+        w = vmc.Walker(tps, cfgs[k], (8, 16, 1e-15))
+        up = vmc.NNExchangeUpdater(100 + k)
+        for _ in range(8):
+            up.sweep(tps, w)
+            e, _, psis = model.energy_and_holes(tps, w, False)
+            energies.append(e)
+            assert max(abs(p / psis[0] - 1) for p in psis) < 1e-3
+    mean = float(np.mean(energies))
+    err = float(np.std(energies) / math.sqrt(len(energies)))
+    assert abs(mean - float(z["exp_e0_state"])) < max(5 * err, 0.05)
