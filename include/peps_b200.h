@@ -1,0 +1,124 @@
+/*
+ * peps_b200 -- C ABI of the B200-native VMC sampling hot path of QuantumLiquids/PEPS.
+ *
+ * The reference has no FFI; its seams are C++ template contracts. Each entry point
+ * below names the reference interface it replaces (paths relative to /root/reference/include/qlpeps/).
+ * One context owns W walkers (= the reference's MPI ranks, algorithm/vmc_update/monte_carlo_engine.h:563)
+ * on one GPU. All calls are stream-ordered on the context's stream and return 0 on success; on failure
+ * they return non-zero and peps_last_error() describes the fault (no exception crosses the ABI).
+ *
+ * Data conventions: real FP64; site tensor legs (L, D, R, U) row-major (tensor_network_2d.h:38-46);
+ * edge legs have dimension 1; configurations are int32 [W][rows][cols].
+ */
+#ifndef PEPS_B200_H
+#define PEPS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct peps_ctx peps_ctx;
+
+typedef struct {
+  int32_t rows, cols;      /* lattice Ly x Lx */
+  int32_t phys;            /* physical dimension d */
+  int32_t D;               /* PEPS bond dimension (uniform; edge legs are 1) */
+  int32_t walkers;         /* Markov chains batched on this GPU */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t dmin, dmax;      /* BMPSTruncateParams::D_min / D_max (one_dim_tn/boundary_mps/bmps.h:47-98) */
+  double trunc_err;        /* BMPSTruncateParams::trunc_err */
+} peps_config;
+
+/* Library / build identification ("cuda-sm_100a"). */
+const char *peps_backend_name(void);
+
+/* TPSWaveFunctionComponent + MonteCarloEngine construction (vmc_basic/wave_function_component.h:155-162,
+ * algorithm/vmc_update/monte_carlo_engine.h:422-427) for W walkers. */
+int peps_create(peps_ctx **out, const peps_config *cfg);
+void peps_destroy(peps_ctx *ctx);
+const char *peps_last_error(peps_ctx *ctx);
+
+/* Number of doubles of the packed SplitIndexTPS (two_dim_tn/tps/split_index_tps.h:80-607):
+ * sites row-major, per site `phys` tensors (L,D,R,U) row-major. */
+size_t peps_tps_size(peps_ctx *ctx);
+/* Offset (in doubles) of tensor (row, col, phys index 0); phys slices are contiguous after it. */
+size_t peps_tps_site_offset(peps_ctx *ctx, int32_t row, int32_t col);
+/* MonteCarloEngine::AssignState / the evaluator's state broadcast (mc_energy_grad_evaluator.h:152-161). */
+int peps_set_tps(peps_ctx *ctx, const double *host_tps, size_t n);
+int peps_get_tps(peps_ctx *ctx, double *host_tps, size_t n);
+/* BMPSContractor::SetTruncateParams (two_dim_tn/tensor_network_2d/bmps/bmps_contractor.h:216-230). */
+int peps_set_truncation(peps_ctx *ctx, int32_t dmin, int32_t dmax, double trunc_err);
+/* Convergence control of the Jacobi truncation kernel (no reference counterpart: LAPACK gesdd there). */
+int peps_set_jacobi(peps_ctx *ctx, double tol, int32_t inner_sweeps, int32_t max_sweeps);
+/* SquareSpinOneHalfXXZModelOBC(jz, jxy, pinning00) (model_solvers/square_spin_onehalf_xxz_obc.h:174-328). */
+int peps_set_model_xxz(peps_ctx *ctx, double jz, double jxy, double pinning00);
+
+/* Configuration per walker (vmc_basic/configuration.h:57), int32 [W][rows][cols]. */
+int peps_set_configs(peps_ctx *ctx, const int32_t *cfg);
+int peps_get_configs(peps_ctx *ctx, int32_t *cfg);
+/* MonteCarloSweepUpdaterBase(unsigned seed): std::mt19937(seed[w]) per walker
+ * (vmc_basic/configuration_update_strategies/monte_carlo_sweep_updater_base.h:37). */
+int peps_seed_rng(peps_ctx *ctx, const uint32_t *seeds);
+/* Raw std::mt19937 state, [W][624] words + [W] next index, interchangeable with a host engine. */
+int peps_set_rng_state(peps_ctx *ctx, const uint32_t *mt, const int32_t *idx);
+int peps_get_rng_state(peps_ctx *ctx, uint32_t *mt, int32_t *idx);
+
+/* contractor.Init(tn) + EvaluateAmplitude() for every walker (wave_function_component.h:155-212). */
+int peps_init_walkers(peps_ctx *ctx);
+/* TPSWaveFunctionComponent::amplitude per walker. */
+int peps_get_amplitudes(peps_ctx *ctx, double *amp);
+/* MonteCarloEngine::NormalizeStateOrder1 (monte_carlo_engine.h:206-240) over this context's walkers:
+ * returns the per-site factor applied; pass max_abs_override > 0 to use a cross-GPU maximum. */
+int peps_normalize_state_order1(peps_ctx *ctx, double max_abs_override, double *site_factor_out);
+
+/* MonteCarloEngine::StepSweep(n) with MCUpdateSquareNNExchangeOBC
+ * (configuration_update_strategies/square_nn_updater.h:29-81,146-188); accept_rates[W] of the last sweep. */
+int peps_sweep(peps_ctx *ctx, int32_t nsweeps, double *accept_rates);
+/* ModelEnergySolver::CalEnergyAndHoles<calchols> (algorithm/vmc_update/model_energy_solver.h:69-100 ->
+ * model_solvers/base/square_nnn_energy_solver.h:79-315). eloc[W]; psi_list[(rows+cols)][W] may be NULL. */
+int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, double *psi_list);
+/* Hole tensors of the last call: [W][stride], per site (L,D,R,U) at the site's hole offset. */
+size_t peps_holes_stride(peps_ctx *ctx);
+int peps_get_holes(peps_ctx *ctx, double *holes);
+
+/* MCEnergyGradEvaluator accumulation (mc_energy_grad_evaluator.h:245-272): Ostar_sum += O*, ELocConj_Ostar_sum
+ * += E_loc O*, O* = hole / amplitude at the sampled physical index. */
+int peps_zero_accumulators(peps_ctx *ctx);
+int peps_accumulate_ostar(peps_ctx *ctx);
+int peps_get_accumulators(peps_ctx *ctx, double *ostar_sum, double *eloc_ostar_sum, size_t n);
+/* Device pointers of the two accumulators (for NCCL all-reduce by the caller; mc_energy_grad_evaluator.h:296-310). */
+double *peps_ostar_sum_device(peps_ctx *ctx);
+double *peps_eloc_ostar_sum_device(peps_ctx *ctx);
+/* One VMC sample for all walkers = StepSweep(sweeps_between_samples) + CalEnergyAndHoles<true> + accumulation
+ * (the loop body of mc_energy_grad_evaluator.h:205-282). eloc[W], accept_rates[W] may be NULL. */
+int peps_sample(peps_ctx *ctx, int32_t sweeps_between_samples, double *eloc, double *accept_rates);
+
+/* ---- probes for the parity tests ------------------------------------------------------------------ */
+/* BMPSContractor::GrowBMPSForRow + InitBTen/GrowFullBTen + Trace(tn,{row,0},HORIZONTAL) (trace.h:11-28). */
+int peps_probe_trace_row(peps_ctx *ctx, int32_t row, double *psi);
+/* Size of bmps_set_[position]; copy of tensor i of stack entry k, [W][d0][d1][d2]; dims returned. */
+int32_t peps_bmps_stack_size(peps_ctx *ctx, int32_t position);
+int peps_get_bmps_tensor(peps_ctx *ctx, int32_t position, int32_t k, int32_t i, double *out, int32_t dims[3]);
+/* Counters: 0 absorptions, 1 BTen steps, 2 traces, 3 Jacobi sweeps, 4 Jacobi calls, 5 QR calls,
+ * 6 kernel launches, 7 pooled device bytes. */
+int64_t peps_stat(peps_ctx *ctx, int32_t which);
+/* Stream synchronisation and the context's cudaStream_t (for CUDA-event timing by the caller). */
+int peps_sync(peps_ctx *ctx);
+void *peps_stream(peps_ctx *ctx);
+
+/* ---- stand-alone kernels exposed for unit parity tests ---------------------------------------------- */
+/* R factor of W matrices (m x n row-major): out [W][min(m,n)][n]. */
+int peps_test_qr_r(int32_t device, int32_t W, int32_t m, int32_t n, const double *a, double *r_out);
+/* Truncated right singular vectors of W matrices (nr x nc): b_out [W][tcap][nc], kept_out [W], sv2_out [W][nr] (unsorted squared row norms after Jacobi). */
+int peps_test_truncate(int32_t device, int32_t W, int32_t nr, int32_t nc, int32_t dmin, int32_t dmax, double trunc_err,
+                       const double *theta, double *b_out, int32_t *kept_out, int32_t *sweeps_out);
+/* Batched einsum of two tensors per walker (spec like "apb,kea->kepb"), host buffers. */
+int peps_test_einsum(int32_t device, int32_t W, const char *spec, const int32_t *dims_a, int32_t rank_a,
+                     const int32_t *dims_b, int32_t rank_b, const double *a, const double *b, double *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEPS_B200_H */

@@ -1,0 +1,436 @@
+"""Host-side mirror of the reference's plugin / operator interface for the VMC sampling path.
+
+Names, argument meaning and error behaviour follow the reference (paths relative to
+/root/reference/include/qlpeps/):
+
+  BMPSTruncateParams            one_dim_tn/boundary_mps/bmps.h:47-98
+  MonteCarloParams              algorithm/vmc_update/monte_carlo_peps_params.h:37-92
+  Configuration                 vmc_basic/configuration.h:57
+  SplitIndexTPS                 two_dim_tn/tps/split_index_tps.h:80-607 (dense, real FP64)
+  SquareSpinOneHalfXXZModelOBC  algorithm/vmc_update/model_solvers/square_spin_onehalf_xxz_obc.h:174-328
+  MCUpdateSquareNNExchange      vmc_basic/configuration_update_strategies/square_nn_updater.h:146-188
+  MCEnergyGradEvaluator         algorithm/vmc_update/mc_energy_grad_evaluator.h:57-330
+
+The one structural difference: the reference runs ONE Markov chain per MPI rank
+(monte_carlo_engine.h:563); here ``walkers`` chains are batched per GPU, so "rank" in the reference's
+formulas reads "walker" (times the number of GPUs when a torch.distributed group is given).
+
+All arithmetic happens behind the C ABI (include/peps_b200.h); numpy here only packs / unpacks buffers.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+
+
+class PepsError(RuntimeError):
+    """Non-zero status from the C ABI (the reference throws std::runtime_error / std::invalid_argument)."""
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _up(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+
+@dataclass
+class BMPSTruncateParams:
+    D_min: int = 1
+    D_max: int = 2 ** 31 - 1
+    trunc_err: float = 0.0
+
+    @staticmethod
+    def SVD(d_min, d_max, trunc_error):
+        return BMPSTruncateParams(int(d_min), int(d_max), float(trunc_error))
+
+
+class Configuration:
+    """rows x cols grid of physical indices."""
+
+    def __init__(self, rows_or_array, cols=None):
+        if cols is None:
+            self.data = np.array(rows_or_array, dtype=np.int32)
+        else:
+            self.data = np.zeros((rows_or_array, cols), dtype=np.int32)
+
+    def rows(self):
+        return self.data.shape[0]
+
+    def cols(self):
+        return self.data.shape[1]
+
+    def __call__(self, site):
+        return int(self.data[site[0], site[1]])
+
+    def __eq__(self, other):
+        return np.array_equal(self.data, other.data)
+
+
+@dataclass
+class MonteCarloParams:
+    num_samples: int
+    num_warmup_sweeps: int
+    sweeps_between_samples: int
+    initial_config: Optional[Configuration] = None
+    is_warmed_up: bool = False
+
+
+class SplitIndexTPS:
+    """tps(r, c)[s] = dense (L, D, R, U) array; also the gradient / O* vector type (vector-space ops)."""
+
+    def __init__(self, tensors):
+        self.t = tensors
+        self.rows_, self.cols_ = len(tensors), len(tensors[0])
+
+    def rows(self):
+        return self.rows_
+
+    def cols(self):
+        return self.cols_
+
+    def PhysicalDim(self):
+        return len(self.t[0][0])
+
+    def __call__(self, site):
+        return self.t[site[0]][site[1]]
+
+    def bond_dim(self):
+        return max(max(x.shape) for row in self.t for site in row for x in site)
+
+    def pack(self):
+        return np.concatenate([np.ascontiguousarray(x, dtype=np.float64).ravel()
+                               for row in self.t for site in row for x in site])
+
+    @staticmethod
+    def unpack(flat, like):
+        out, pos = [], 0
+        for row in like.t:
+            orow = []
+            for site in row:
+                osite = []
+                for x in site:
+                    osite.append(np.array(flat[pos:pos + x.size]).reshape(x.shape))
+                    pos += x.size
+                orow.append(osite)
+            out.append(orow)
+        return SplitIndexTPS(out)
+
+    def _zip(self, other, fn):
+        return SplitIndexTPS([[[fn(a, b) for a, b in zip(sa, sb)] for sa, sb in zip(ra, rb)]
+                              for ra, rb in zip(self.t, other.t)])
+
+    def __add__(self, o):
+        return self._zip(o, lambda a, b: a + b)
+
+    def __sub__(self, o):
+        return self._zip(o, lambda a, b: a - b)
+
+    def __mul__(self, s):
+        if isinstance(s, SplitIndexTPS):           # operator*(SITPS, SITPS) = sum conj(a) b  (split_index_tps.h:370-377)
+            return sum(np.vdot(a, b) for ra, rb in zip(self.t, s.t) for sa, sb in zip(ra, rb) for a, b in zip(sa, sb))
+        return SplitIndexTPS([[[x * s for x in site] for site in row] for row in self.t])
+
+    __rmul__ = __mul__
+
+    def NormSquare(self):
+        return float(sum(np.sum(np.abs(x) ** 2) for row in self.t for site in row for x in site))
+
+
+@dataclass
+class SquareSpinOneHalfXXZModelOBC:
+    jz: float = 1.0
+    jxy: float = 1.0
+    pinning00: float = 0.0
+
+
+@dataclass
+class MCUpdateSquareNNExchange:
+    """Explicit-seed constructor of the reference updater; walker w draws from std::mt19937(seed + w)."""
+    seed: int = 5489
+
+
+class WalkerBatch:
+    """Thin RAII wrapper over a peps_ctx: W walkers of one lattice on one GPU."""
+
+    def __init__(self, rows, cols, phys, D, walkers, trunc: BMPSTruncateParams, device=0, lib=None):
+        self.lib = lib if lib is not None else _lib.load()
+        self.rows, self.cols, self.phys, self.D, self.W = rows, cols, phys, D, walkers
+        cfg = _lib.PepsConfig(rows, cols, phys, D, walkers, device, trunc.D_min, min(trunc.D_max, 2 ** 31 - 1), trunc.trunc_err)
+        h = C.c_void_p()
+        if self.lib.peps_create(C.byref(h), C.byref(cfg)) != 0:
+            raise PepsError(self.lib.peps_last_error(None).decode())
+        self.h = h
+        self.tps_size = self.lib.peps_tps_size(self.h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.peps_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PepsError(self.lib.peps_last_error(self.h).decode())
+
+    # state
+    def set_tps(self, tps):
+        flat = tps.pack() if isinstance(tps, SplitIndexTPS) else np.ascontiguousarray(tps, dtype=np.float64)
+        if flat.size != self.tps_size:
+            raise PepsError(f"TPS has {flat.size} elements, context expects {self.tps_size}")
+        self._ck(self.lib.peps_set_tps(self.h, _dp(flat), flat.size))
+
+    def get_tps_flat(self):
+        out = np.empty(self.tps_size)
+        self._ck(self.lib.peps_get_tps(self.h, _dp(out), out.size))
+        return out
+
+    def set_truncation(self, trunc):
+        self._ck(self.lib.peps_set_truncation(self.h, trunc.D_min, trunc.D_max, trunc.trunc_err))
+
+    def set_jacobi(self, tol=1e-14, inner_sweeps=1, max_sweeps=40):
+        self._ck(self.lib.peps_set_jacobi(self.h, tol, inner_sweeps, max_sweeps))
+
+    def set_model(self, model):
+        self._ck(self.lib.peps_set_model_xxz(self.h, model.jz, model.jxy, model.pinning00))
+
+    def set_configs(self, cfgs):
+        a = np.ascontiguousarray(cfgs, dtype=np.int32).reshape(self.W, self.rows, self.cols)
+        self._ck(self.lib.peps_set_configs(self.h, _ip(a)))
+
+    def get_configs(self):
+        a = np.empty((self.W, self.rows, self.cols), dtype=np.int32)
+        self._ck(self.lib.peps_get_configs(self.h, _ip(a)))
+        return a
+
+    def seed_rng(self, seeds):
+        a = np.ascontiguousarray(seeds, dtype=np.uint32).reshape(self.W)
+        self._ck(self.lib.peps_seed_rng(self.h, _up(a)))
+
+    def get_rng_state(self):
+        mt = np.empty((self.W, 624), dtype=np.uint32)
+        idx = np.empty(self.W, dtype=np.int32)
+        self._ck(self.lib.peps_get_rng_state(self.h, _up(mt), _ip(idx)))
+        return mt, idx
+
+    def set_rng_state(self, mt, idx):
+        mt = np.ascontiguousarray(mt, dtype=np.uint32)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        self._ck(self.lib.peps_set_rng_state(self.h, _up(mt), _ip(idx)))
+
+    # hot path
+    def init_walkers(self):
+        self._ck(self.lib.peps_init_walkers(self.h))
+
+    def amplitudes(self):
+        a = np.empty(self.W)
+        self._ck(self.lib.peps_get_amplitudes(self.h, _dp(a)))
+        return a
+
+    def normalize_state_order1(self, max_abs_override=0.0):
+        f = C.c_double()
+        self._ck(self.lib.peps_normalize_state_order1(self.h, max_abs_override, C.byref(f)))
+        return f.value
+
+    def sweep(self, n=1):
+        acc = np.empty(self.W)
+        self._ck(self.lib.peps_sweep(self.h, n, _dp(acc)))
+        return acc
+
+    def energy_and_holes(self, calc_holes=True, want_psi=False):
+        e = np.empty(self.W)
+        psi = np.empty((self.rows + self.cols, self.W)) if want_psi else None
+        self._ck(self.lib.peps_energy_and_holes(self.h, int(calc_holes), _dp(e), _dp(psi) if want_psi else None))
+        return (e, psi) if want_psi else e
+
+    def holes(self):
+        n = self.lib.peps_holes_stride(self.h)
+        a = np.empty((self.W, n))
+        self._ck(self.lib.peps_get_holes(self.h, _dp(a)))
+        return a
+
+    def zero_accumulators(self):
+        self._ck(self.lib.peps_zero_accumulators(self.h))
+
+    def accumulate_ostar(self):
+        self._ck(self.lib.peps_accumulate_ostar(self.h))
+
+    def accumulators(self):
+        o, eo = np.empty(self.tps_size), np.empty(self.tps_size)
+        self._ck(self.lib.peps_get_accumulators(self.h, _dp(o), _dp(eo), o.size))
+        return o, eo
+
+    def sample(self, sweeps_between_samples=1):
+        e, acc = np.empty(self.W), np.empty(self.W)
+        self._ck(self.lib.peps_sample(self.h, sweeps_between_samples, _dp(e), _dp(acc)))
+        return e, acc
+
+    # probes
+    def probe_trace_row(self, row):
+        a = np.empty(self.W)
+        self._ck(self.lib.peps_probe_trace_row(self.h, row, _dp(a)))
+        return a
+
+    def bmps_stack_size(self, pos):
+        return self.lib.peps_bmps_stack_size(self.h, pos)
+
+    def bmps_tensor(self, pos, k, i):
+        dims = np.zeros(3, dtype=np.int32)
+        self._ck(self.lib.peps_get_bmps_tensor(self.h, pos, k, i, None, _ip(dims)))
+        out = np.empty((self.W, int(dims[0]), int(dims[1]), int(dims[2])))
+        self._ck(self.lib.peps_get_bmps_tensor(self.h, pos, k, i, _dp(out), _ip(dims)))
+        return out
+
+    def stat(self, which):
+        return int(self.lib.peps_stat(self.h, which))
+
+    def sync(self):
+        self._ck(self.lib.peps_sync(self.h))
+
+    def stream(self):
+        return self.lib.peps_stream(self.h)
+
+    def accumulator_device_ptrs(self):
+        return self.lib.peps_ostar_sum_device(self.h), self.lib.peps_eloc_ostar_sum_device(self.h)
+
+
+@dataclass
+class EvaluateResult:
+    """MCEnergyGradEvaluator::Result (mc_energy_grad_evaluator.h:66-75)."""
+    energy: float
+    energy_error: float
+    gradient: SplitIndexTPS
+    gradient_norm: float
+    accept_rates_avg: List[float]
+    energy_samples: np.ndarray = field(default=None)
+
+
+def combine_energy_bins(energy_samples):
+    """MeanAndBinnedErrorSqrtNUniformBin over all walkers (vmc_basic/monte_carlo_tools/statistics.h:146-225):
+    per walker bins of floor(sqrt(N)) samples, incomplete tail bin discarded, mean / stderr over all bin means.
+    energy_samples: [walkers_total][N]."""
+    es = np.asarray(energy_samples, dtype=np.float64)
+    n = es.shape[1]
+    if n == 0:
+        return 0.0, 0.0
+    bin_size = max(1, int(math.sqrt(n)))
+    nb = n // bin_size
+    means = []
+    for w in range(es.shape[0]):
+        for i in range(nb):
+            s = 0.0
+            for x in es[w, i * bin_size:(i + 1) * bin_size]:
+                s += float(x)
+            means.append(s / bin_size)
+    if not means:
+        return 0.0, 0.0
+    mean = 0.0
+    for m in means:
+        mean += m
+    mean /= len(means)
+    if len(means) == 1:
+        return mean, float("inf")
+    var = sum((m - mean) ** 2 for m in means) / len(means)
+    return mean, math.sqrt(var / (len(means) - 1))
+
+
+class MCEnergyGradEvaluator:
+    """Evaluate(state) -> (energy, gradient, error): the B1 seam of SURVEY.md section 8b.
+
+    ``dist`` is an optional initialised torch.distributed module with world_size > 1: energies are all-gathered
+    and the two accumulators all-reduced (NCCL on the GPU, gloo in CPU tests), replacing the reference's
+    Gather/Gatherv + per-tensor MPI_Send/Recv (mc_energy_grad_evaluator.h:292-310).
+    """
+
+    def __init__(self, mc_params: MonteCarloParams, trunc: BMPSTruncateParams, tps: SplitIndexTPS, model, updater,
+                 walkers, configs=None, device=0, lib=None, dist=None, rank=0, world_size=1):
+        self.mc, self.trunc, self.model, self.updater = mc_params, trunc, model, updater
+        self.state = tps
+        self.dist, self.rank, self.world_size = dist, rank, world_size
+        self.batch = WalkerBatch(tps.rows(), tps.cols(), tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
+        self.batch.set_model(model)
+        self.batch.set_tps(tps)
+        if configs is None:
+            if mc_params.initial_config is None:
+                raise PepsError("MCEnergyGradEvaluator: initial configuration required")
+            configs = np.broadcast_to(mc_params.initial_config.data, (walkers,) + mc_params.initial_config.data.shape)
+        self.batch.set_configs(configs)
+        base = updater.seed + rank * walkers
+        self.batch.seed_rng(np.arange(base, base + walkers, dtype=np.uint64).astype(np.uint32))
+        self.batch.init_walkers()
+        self.warmed_up = mc_params.is_warmed_up
+
+    def WarmUp(self):
+        """MonteCarloEngine::WarmUp (monte_carlo_engine.h:146-173)."""
+        if not self.warmed_up:
+            for _ in range(self.mc.num_warmup_sweeps):
+                self.batch.sweep(1)
+            self.warmed_up = True
+        amps = self.batch.amplitudes()
+        if not np.all(np.isfinite(amps)) or np.any(amps == 0):
+            raise PepsError("Amplitude is still not legal after warm up")
+        mx = float(np.max(np.abs(amps)))
+        if self.dist is not None and self.world_size > 1:
+            mx = self._allreduce_max(mx)
+        self.batch.normalize_state_order1(mx)
+        self.state = SplitIndexTPS.unpack(self.batch.get_tps_flat(), self.state)
+
+    def _allreduce_max(self, x):
+        import torch
+        t = torch.tensor([x], dtype=torch.float64)
+        if self.dist.get_backend() == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.cpu()[0])
+
+    def Evaluate(self, state: Optional[SplitIndexTPS] = None) -> EvaluateResult:
+        b = self.batch
+        if state is not None and state is not self.state:
+            self.state = state
+            b.set_tps(state)
+        b.init_walkers()                       # engine_.RefreshWavefunctionComponent()  (:164)
+        n = self.samples_per_walker()
+        b.zero_accumulators()
+        energies = np.empty((b.W, n))
+        accept = np.zeros(b.W)
+        for s in range(n):                     # the walker loop (:205-282), all walkers in lock step
+            e, acc = b.sample(self.mc.sweeps_between_samples)
+            energies[:, s] = e
+            accept += acc
+        osum, eosum = b.accumulators()
+        all_e = energies
+        if self.dist is not None and self.world_size > 1:
+            import torch
+            nccl = self.dist.get_backend() == "nccl"
+            dev = "cuda" if nccl else "cpu"
+            buf = torch.from_numpy(np.stack([osum, eosum])).to(dev)
+            self.dist.all_reduce(buf)
+            osum, eosum = buf.cpu().numpy()
+            mine = torch.from_numpy(energies).to(dev)
+            gathered = [torch.empty_like(mine) for _ in range(self.world_size)]
+            self.dist.all_gather(gathered, mine)
+            all_e = np.concatenate([g.cpu().numpy() for g in gathered], axis=0)
+        energy, err = combine_energy_bins(all_e)
+        total_walkers = all_e.shape[0]
+        grad_flat = (eosum - energy * osum) / (n * total_walkers)        # (:296-309)
+        grad = SplitIndexTPS.unpack(grad_flat, self.state)
+        return EvaluateResult(energy, err, grad, grad.NormSquare(), [float(np.mean(accept / n))], all_e)
+
+    def samples_per_walker(self):
+        """SamplesPerRank = ceil(total / ranks) (monte_carlo_engine.h:97-98) with ranks = walkers * GPUs."""
+        total = self.batch.W * self.world_size
+        return max(1, -(-self.mc.num_samples // total))

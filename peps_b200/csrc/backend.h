@@ -1,0 +1,129 @@
+// Device-op interface of the B200 VMC sampling library.
+//
+// Every function here is one batched device operation over W walkers. The product implementation is
+// backend_cuda.cu (hand-written sm_100a kernels). tests/hostsim/backend_host.cpp implements the same
+// interface with plain loops for CPU-side tests of the host orchestration (engine.cpp); it is never
+// linked into the product library.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace peps {
+
+// Base address of one batched operand: element base for (walker w, inner batch b) is
+//   p + w*ws + b*bs + (gidx ? gidx[w*gws] * gs : 0)
+// The gather term is the fused "physical-slice gather" of the reference's
+// TensorNetwork2D::UpdateSiteTensor (tensor_network_2d_basic_impl.h:82-108): the site tensor of walker
+// w is read straight out of the shared SplitIndexTPS at slice config[w][site].
+struct Operand {
+  double *p = nullptr;
+  long ws = 0;
+  long bs = 0;
+  const int32_t *gidx = nullptr;
+  int gws = 0;
+  long gs = 0;
+};
+inline Operand mkop(double *p, long ws, long bs = 0) {
+  Operand o; o.p = p; o.ws = ws; o.bs = bs; return o;
+}
+inline Operand mkgather(double *p, const int32_t *gidx, int gws, long gs) {
+  Operand o; o.p = p; o.gidx = gidx; o.gws = gws; o.gs = gs; return o;
+}
+
+// C(m,n) = alpha * sum_k A(m,k) B(k,n) + beta * C(m,n) with separable addressing
+//   A(m,k) = A.base + am[m] + ak[k],  B(k,n) = B.base + bk[k] + bn[n],  C(m,n) = C.base + cm[m] + cn[n]
+// (tables live in device memory; they encode any pairwise tensor contraction without a transpose pass).
+struct GettDesc {
+  int M = 0, N = 0, K = 0;
+  const int32_t *am = nullptr, *ak = nullptr, *bk = nullptr, *bn = nullptr, *cm = nullptr, *cn = nullptr;
+  int a_kfast = 0;   // 1: A's unit-stride index is a contracted one
+  int b_nfast = 1;   // 1: B's unit-stride index is a free one
+};
+
+// ---- memory / stream -------------------------------------------------------------------------------
+void be_init(int device);                 // binds the device, creates the stream
+const char *be_name();                    // "cuda-sm_100a" or "hostsim"
+void *be_malloc(size_t bytes);
+void be_free(void *p);
+void be_memset0(void *p, size_t bytes);
+void be_h2d(void *dst, const void *src, size_t bytes);
+void be_d2h(void *dst, const void *src, size_t bytes);
+void be_d2d(void *dst, const void *src, size_t bytes);
+void be_sync();
+void *be_stream();                        // cudaStream_t of the context (nullptr on hostsim)
+long be_launch_count();                   // number of kernels launched so far (for bench.py gpu_launches)
+
+// ---- tensor contraction ----------------------------------------------------------------------------
+void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, double beta, int W, int NB);
+// out[w] = sum_k A(ak[k]) * B(bk[k])
+void be_dot(int K, const int32_t *ak, const int32_t *bk, Operand A, Operand B, double *out, int W);
+
+// ---- dense helpers ---------------------------------------------------------------------------------
+void be_fill(double *p, double v, long n);
+// dst[w][r][c] = src[w][r][c] for r < rows, c < cols (row strides lds/ldd, walker strides ws/wd)
+void be_copy2d(double *dst, long wd, long ldd, const double *src, long ws, long lds, int rows, int cols, int W);
+// dst[w][t][c] = (t == c) for t < rows, c < cols
+void be_set_identity(double *dst, long wd, int rows, int cols, int W);
+
+// ---- communication-avoiding R-only QR: one panel step -----------------------------------------------
+// For every (walker w, item it): gather the rows rowtab[it*R + s] (s = skip..R-1, skip = (it==0 ? skip0 : 0))
+// of panel columns [col0, col0+pw) of the row-major matrix Abase + w*ws (leading dimension lda) into shared
+// memory, Householder-factorise the (R-skip) x pw panel, write R (upper triangle on the first pw active
+// rows, zeros below) back in place, and emit the explicit reflector block V (unit lower trapezoid) and
+// VT = V * T^T (compact WY: Q^T C = C - VT (V^T C)) into Vw/VTw, laid out [w][it][R][nbw]; skipped slots
+// and columns >= pw are zero.
+struct PanelArgs {
+  double *A; long ws; int lda;
+  const int32_t *rowtab; int R; int skip0; int NI;
+  int col0, pw, nbw;
+  double *Vw, *VTw;
+  int W;
+};
+void be_panel_qr(const PanelArgs &a);
+
+// ---- one-sided block Jacobi on the ROWS of G[w] (nr_pad x nc, leading dimension ld) ----------------------
+// One round of the round-robin block-pair schedule: block pairs (I,J) of `round` are loaded, their
+// (2*bs)x(2*bs) Gram matrix is diagonalised by cyclic two-sided Jacobi (inner_sweeps sweeps) and the
+// rotation is applied to the 2*bs rows, larger norms sorted to the lower row index.
+// offmax[w] is max'ed with the largest |g_pq|/sqrt(g_pp g_qq) seen (before rotation).
+// Walkers with done[w] != 0 are skipped.
+struct JacobiArgs {
+  double *G; long ws; int ld; int nr_pad; int nc; int bs; int nblk; int round;
+  double tol; int inner_sweeps; double *offmax; const int32_t *done; int W;
+};
+void be_jacobi_round(const JacobiArgs &a);
+// done[w] = (offmax[w] <= tol); offmax[w] = 0 for the next sweep. Returns nothing (host reads done[]).
+void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W);
+// norms2[w][r] = |G[w][r][:]|^2
+void be_row_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W);
+// Rank rows by norm (descending, ties by index); kept[w] by the TensorToolkit truncation rule over the
+// nsv = min(nr_true, nc) largest values, capped at tcap; order[w][t] = row index of rank t (t < tcap).
+void be_select_truncate(const double *norms2, int nr, int nsv, int dmin, int dmax, double trunc_err, int tcap,
+                        int32_t *order, int32_t *kept, int W);
+// B[w][t][c] = G[w][order[w][t]][c] / norm  for t < kept[w], else 0   (t < tcap, c < nc)
+void be_gather_rows_normalized(const double *G, long ws, int ld, int nc, const double *norms2, int nr,
+                               const int32_t *order, const int32_t *kept, int tcap, double *B, long wb, int W);
+
+// ---- Monte Carlo state kernels ---------------------------------------------------------------------
+// std::mt19937(seed[w]) for every walker: mt[w][624], idx[w] = 624
+void be_mt_seed(uint32_t *mt, int32_t *idx, const uint32_t *seeds, int W);
+// MCUpdateSquareNNExchangeOBC::TwoSiteNNUpdateLocalImpl decision (square_nn_updater.h:146-188) for all walkers:
+// skip if cfg equal; accept if |psi_b| >= |psi_a| else iff uniform01 < (|psi_b|/|psi_a|)^2 (draw only then);
+// on accept swap cfg[s1], cfg[s2], amplitude = psi_b, accepted[w] += 1.
+void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b, double *amp,
+                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W);
+// EvaluateBondEnergy of SquareSpinOneHalfXXZModelMixIn (square_spin_onehalf_xxz_obc.h:72-104):
+// eloc[w] += (c1==c2) ? 0.25 jz : -0.25 jz + (psi_ex[w] * (1/psi[w])) * 0.5 jxy
+void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const double *psi_ex, const double *psi,
+                        double jz, double jxy, double *eloc, int W);
+// eloc[w] += -h00 * (cfg[w][0] - 0.5)
+void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *eloc, int W);
+// O* accumulation (mc_energy_grad_evaluator.h:245-272) for one sample of all walkers:
+//   o = (1/amp[w]) * hole[w][e];  osum[slot(site,cfg[w][site]) + e] += o;  eosum[...] += eloc[w] * o
+// holes: [W][hole_stride]; per site: offset hole_off[site], size site_size[site]; TPS slot of (site, s) at
+// tps_off[site] + s*site_size[site].
+void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                         const int32_t *tps_off, const int32_t *cfg, int nsites, int phys, const double *amp,
+                         const double *eloc, double *osum, double *eosum, int W);
+
+}  // namespace peps

@@ -1,0 +1,836 @@
+// sm_100a implementation of backend.h: hand-written kernels for the walker-batched VMC sampling path.
+//
+// Kernel inventory (DESIGN.md section 4 gives the roofline of each):
+//   gett_kernel        walker-batched FP64 tensor contraction on the DMMA pipe (mma.sync m8n8k4.f64), operands
+//                      addressed through separable offset tables so no transpose pass ever touches HBM; the
+//                      physical-index slice of the sampled site is gathered straight from the shared TPS.
+//   dot_kernel         rank-3 inner product closing a trace.
+//   panel_qr_kernel    one panel of the communication-avoiding R-only Householder QR, panel resident in smem.
+//   jacobi_round_kernel one round of one-sided block Jacobi (Gram + rotation on DMMA, panel resident in smem).
+//   small kernels      row norms, truncation/selection, RNG + Metropolis decision, energies, O* accumulation.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+#include "backend.h"
+
+namespace peps {
+
+static cudaStream_t g_stream = nullptr;
+static long g_launches = 0;
+static int g_device = -1;
+
+#define CUDA_CHECK(x)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess)                                                                         \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " +     \
+                               __FILE__ + ":" + std::to_string(__LINE__));                         \
+  } while (0)
+
+static inline void post_launch() {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
+
+void be_init(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw std::runtime_error("peps_b200: no CUDA device available; the product has no CPU fallback");
+  CUDA_CHECK(cudaSetDevice(device));
+  g_device = device;
+  if (!g_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+}
+const char *be_name() { return "cuda-sm_100a"; }
+void *be_malloc(size_t bytes) {
+  void *p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 8));
+  return p;
+}
+void be_free(void *p) { if (p) cudaFree(p); }
+void be_memset0(void *p, size_t bytes) { CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, g_stream)); }
+void be_h2d(void *dst, const void *src, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+}
+void be_d2h(void *dst, const void *src, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+}
+void be_d2d(void *dst, const void *src, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream));
+}
+void be_sync() { CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+void *be_stream() { return (void *)g_stream; }
+long be_launch_count() { return g_launches; }
+
+// =====================================================================================================
+// gett: walker-batched FP64 contraction on the tensor (DMMA) pipe
+// =====================================================================================================
+__device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ const double *operand_base(const Operand &o, int w, int b) {
+  const double *p = o.p + (long)w * o.ws + (long)b * o.bs;
+  if (o.gidx) p += (long)o.gidx[(long)w * o.gws] * o.gs;
+  return p;
+}
+
+constexpr int GETT_THREADS = 128;
+constexpr int GETT_BK = 16;
+
+// CTA tile (16*WMT) x (16*WNT), 2x2 warps, each warp (8*WMT) x (8*WNT) made of m8n8k4 DMMA tiles.
+template <int WMT, int WNT>
+__global__ void __launch_bounds__(GETT_THREADS)
+gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double beta) {
+  constexpr int BM = 16 * WMT, BN = 16 * WNT, BK = GETT_BK;
+  constexpr int LDA = BM + 4, LDB = BN + 4;       // +4 doubles: conflict-free DMMA fragment loads
+  constexpr int NA = BM * BK / GETT_THREADS, NBv = BN * BK / GETT_THREADS;
+  __shared__ double As[BK * LDA];
+  __shared__ double Bs[BK * LDB];
+
+  const int tiles_m = (d.M + BM - 1) / BM;
+  const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+  const int m0 = tm * BM, n0 = tn * BN;
+  const int w = blockIdx.z, bb = blockIdx.y;
+  const double *Ab = operand_base(A, w, bb);
+  const double *Bb = operand_base(B, w, bb);
+  double *Cb = const_cast<double *>(operand_base(C, w, bb));
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int wm = warp >> 1, wn = warp & 1;
+
+  // per-thread loader coordinates (fixed part hoisted out of the K loop)
+  int a_ml[NA], a_kl[NA], a_off[NA];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) {
+    int e = t + i * GETT_THREADS;
+    if (d.a_kfast) { a_kl[i] = e % BK; a_ml[i] = e / BK; } else { a_ml[i] = e % BM; a_kl[i] = e / BM; }
+    int m = m0 + a_ml[i];
+    a_off[i] = (m < d.M) ? d.am[m] : -1;
+  }
+  int b_nl[NBv], b_kl[NBv], b_off[NBv];
+#pragma unroll
+  for (int i = 0; i < NBv; ++i) {
+    int e = t + i * GETT_THREADS;
+    if (d.b_nfast) { b_nl[i] = e % BN; b_kl[i] = e / BN; } else { b_kl[i] = e % BK; b_nl[i] = e / BK; }
+    int n = n0 + b_nl[i];
+    b_off[i] = (n < d.N) ? d.bn[n] : -1;
+  }
+
+  double acc[WMT][WNT][2];
+#pragma unroll
+  for (int i = 0; i < WMT; ++i)
+#pragma unroll
+    for (int j = 0; j < WNT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  double ra[NA], rb[NBv];
+  auto load_global = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      int k = k0 + a_kl[i];
+      ra[i] = (a_off[i] >= 0 && k < d.K) ? __ldg(Ab + a_off[i] + d.ak[k]) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < NBv; ++i) {
+      int k = k0 + b_kl[i];
+      rb[i] = (b_off[i] >= 0 && k < d.K) ? __ldg(Bb + b_off[i] + d.bk[k]) : 0.0;
+    }
+  };
+  auto store_smem = [&]() {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) As[a_kl[i] * LDA + a_ml[i]] = ra[i];
+#pragma unroll
+    for (int i = 0; i < NBv; ++i) Bs[b_kl[i] * LDB + b_nl[i]] = rb[i];
+  };
+
+  const int nk = (d.K + BK - 1) / BK;
+  load_global(0);
+  store_smem();
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    if (kt + 1 < nk) load_global((kt + 1) * BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; kk += 4) {
+      double af[WMT], bf[WNT];
+      const int kr = kk + (lane & 3), rr = lane >> 2;
+#pragma unroll
+      for (int i = 0; i < WMT; ++i) af[i] = As[kr * LDA + wm * 8 * WMT + i * 8 + rr];
+#pragma unroll
+      for (int j = 0; j < WNT; ++j) bf[j] = Bs[kr * LDB + wn * 8 * WNT + j * 8 + rr];
+#pragma unroll
+      for (int i = 0; i < WMT; ++i)
+#pragma unroll
+        for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    __syncthreads();
+    if (kt + 1 < nk) {
+      store_smem();
+      __syncthreads();
+    }
+  }
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < WMT; ++i) {
+    int m = m0 + wm * 8 * WMT + i * 8 + (lane >> 2);
+    if (m >= d.M) continue;
+    int cmo = d.cm[m];
+#pragma unroll
+    for (int j = 0; j < WNT; ++j) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int n = n0 + wn * 8 * WNT + j * 8 + 2 * (lane & 3) + h;
+        if (n >= d.N) continue;
+        double *cp = Cb + cmo + d.cn[n];
+        double v = alpha * acc[i][j][h];
+        if (beta != 0.0) v += beta * (*cp);
+        *cp = v;
+      }
+    }
+  }
+}
+
+void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, double beta, int W, int NB) {
+  if (d.M <= 0 || d.N <= 0 || W <= 0 || NB <= 0) return;
+  auto launch = [&](auto kern, int BM, int BN) {
+    int tiles = ((d.M + BM - 1) / BM) * ((d.N + BN - 1) / BN);
+    dim3 grid(tiles, NB, W);
+    kern<<<grid, GETT_THREADS, 0, g_stream>>>(d, A, B, C, alpha, beta);
+    post_launch();
+  };
+  if (d.M > 32 && d.N > 32) launch(gett_kernel<4, 4>, 64, 64);
+  else if (d.M > 32) launch(gett_kernel<4, 1>, 64, 16);
+  else if (d.N > 32) launch(gett_kernel<1, 4>, 16, 64);
+  else launch(gett_kernel<2, 2>, 32, 32);
+}
+
+// =====================================================================================================
+// dot
+// =====================================================================================================
+__global__ void dot_kernel(int K, const int32_t *ak, const int32_t *bk, Operand A, Operand B, double *out) {
+  const int w = blockIdx.x;
+  const double *Ab = operand_base(A, w, 0);
+  const double *Bb = operand_base(B, w, 0);
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s += Ab[ak[k]] * Bb[bk[k]];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int h = blockDim.x / 2; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[w] = red[0];
+}
+void be_dot(int K, const int32_t *ak, const int32_t *bk, Operand A, Operand B, double *out, int W) {
+  dot_kernel<<<W, 256, 0, g_stream>>>(K, ak, bk, A, B, out);
+  post_launch();
+}
+
+// =====================================================================================================
+// dense helpers
+// =====================================================================================================
+__global__ void fill_kernel(double *p, double v, long n) {
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  long stride = (long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+void be_fill(double *p, double v, long n) {
+  if (n <= 0) return;
+  int blocks = (int)((n + 255) / 256 < 148L * 8 ? (n + 255) / 256 : 148L * 8);
+  fill_kernel<<<blocks, 256, 0, g_stream>>>(p, v, n);
+  post_launch();
+}
+__global__ void copy2d_kernel(double *dst, long wd, long ldd, const double *src, long ws, long lds, int rows,
+                              int cols) {
+  const int w = blockIdx.y;
+  long n = (long)rows * cols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols), c = (int)(i % cols);
+    dst[w * wd + r * ldd + c] = src[w * ws + r * lds + c];
+  }
+}
+void be_copy2d(double *dst, long wd, long ldd, const double *src, long ws, long lds, int rows, int cols, int W) {
+  long n = (long)rows * cols;
+  if (n <= 0) return;
+  int bx = (int)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64);
+  copy2d_kernel<<<dim3(bx, W), 256, 0, g_stream>>>(dst, wd, ldd, src, ws, lds, rows, cols);
+  post_launch();
+}
+__global__ void identity_kernel(double *dst, long wd, int rows, int cols) {
+  const int w = blockIdx.y;
+  long n = (long)rows * cols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols), c = (int)(i % cols);
+    dst[w * wd + i] = (r == c) ? 1.0 : 0.0;
+  }
+}
+void be_set_identity(double *dst, long wd, int rows, int cols, int W) {
+  long n = (long)rows * cols;
+  int bx = (int)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64);
+  identity_kernel<<<dim3(bx, W), 256, 0, g_stream>>>(dst, wd, rows, cols);
+  post_launch();
+}
+
+// =====================================================================================================
+// CAQR panel
+// =====================================================================================================
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int PQR_THREADS = 256;
+
+__global__ void __launch_bounds__(PQR_THREADS) panel_qr_kernel(PanelArgs a) {
+  extern __shared__ double sm[];
+  const int it = blockIdx.x, w = blockIdx.y;
+  const int R = a.R, pw = a.pw, nbw = a.nbw;
+  const int skip = (it == 0) ? a.skip0 : 0;
+  const int nact = R - skip;
+  const int LDP = R + 1;
+  double *P = sm;                               // [nbw][LDP] column-major panel
+  double *S = P + (size_t)nbw * LDP;            // [nbw][nbw]
+  double *T = S + nbw * nbw;                    // [nbw][nbw]
+  double *tau = T + nbw * nbw;                  // [nbw]
+  double *scal = tau + nbw;                     // [nbw]
+  double *beta = scal + nbw;                    // [nbw]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = PQR_THREADS / 32;
+  double *Aw = a.A + (long)w * a.ws;
+  const int32_t *rows = a.rowtab + (long)it * R;
+
+  // 1. gather the panel
+  for (int e = t; e < nact * pw; e += PQR_THREADS) {
+    int r = e / pw, c = e % pw;
+    P[c * LDP + r] = Aw[(long)rows[skip + r] * a.lda + a.col0 + c];
+  }
+  __syncthreads();
+
+  // 2. Householder columns (LAPACK dgeqr2 / dlarfg conventions)
+  for (int j = 0; j < pw; ++j) {
+    double tj = 0.0, sj = 0.0, bj = 0.0;
+    if (j < nact) {
+      const double *x = P + j * LDP;
+      double part = 0.0;
+      for (int r = j + 1 + lane; r < nact; r += 32) part += x[r] * x[r];
+      double xn2 = warp_sum(part);
+      double alpha = x[j];
+      bj = alpha;
+      if (xn2 > 0.0) {
+        double nrm = sqrt(alpha * alpha + xn2);
+        bj = (alpha >= 0.0) ? -nrm : nrm;
+        tj = (bj - alpha) / bj;
+        sj = 1.0 / (alpha - bj);
+      }
+      if (tj != 0.0) {
+        for (int c = j + 1 + warp; c < pw; c += nwarp) {
+          double *y = P + c * LDP;
+          double pr = 0.0;
+          for (int r = j + 1 + lane; r < nact; r += 32) pr += x[r] * y[r];
+          double wv = warp_sum(pr) * sj + y[j];
+          double f = tj * wv;
+          for (int r = j + 1 + lane; r < nact; r += 32) y[r] -= f * sj * x[r];
+          if (lane == 0) y[j] -= f;
+        }
+      }
+    }
+    if (t == 0) { tau[j] = tj; scal[j] = sj; beta[j] = bj; }
+    __syncthreads();
+  }
+
+  // 3. S = R-part extraction happens at write-back; build V in place: column c rows > c scaled, keep the
+  //    R entries (rows <= c) in registers? They live in P rows <= c of column c: copy them to S scratch first.
+  //    Rpart[r][c] (r <= c < pw) is stashed in T temporarily (nbw x nbw), then T is rebuilt after S.
+  for (int e = t; e < nbw * nbw; e += PQR_THREADS) {
+    int r = e / nbw, c = e % nbw;
+    double v = 0.0;
+    if (c < pw && r <= c && r < nact) v = (r == c) ? beta[c] : P[c * LDP + r];
+    T[e] = v;                                   // T holds Rpart for now
+  }
+  __syncthreads();
+  // write R part + zeros to A now (panel columns, all active rows)
+  for (int e = t; e < nact * pw; e += PQR_THREADS) {
+    int r = e / pw, c = e % pw;
+    double v = (r < nbw && r <= c) ? T[r * nbw + c] : 0.0;
+    Aw[(long)rows[skip + r] * a.lda + a.col0 + c] = v;
+  }
+  __syncthreads();
+  // V in place
+  for (int e = t; e < nact * pw; e += PQR_THREADS) {
+    int c = e / nact, r = e % nact;
+    double v;
+    if (r < c) v = 0.0;
+    else if (r == c) v = 1.0;
+    else v = P[c * LDP + r] * scal[c];
+    P[c * LDP + r] = v;
+  }
+  __syncthreads();
+  // S = V^T V (strict upper part)
+  for (int pidx = warp; pidx < pw * pw; pidx += nwarp) {
+    int ca = pidx / pw, cb = pidx % pw;
+    if (ca >= cb) continue;
+    const double *x = P + ca * LDP, *y = P + cb * LDP;
+    double pr = 0.0;
+    for (int r = cb + lane; r < nact; r += 32) pr += x[r] * y[r];
+    pr = warp_sum(pr);
+    if (lane == 0) S[ca * nbw + cb] = pr;
+  }
+  __syncthreads();
+  // T (forward, columnwise): T[j][j] = tau_j; T[0:j, j] = -tau_j * T[0:j,0:j] * S[0:j, j]
+  for (int e = t; e < nbw * nbw; e += PQR_THREADS) T[e] = 0.0;
+  __syncthreads();
+  if (warp == 0) {
+    for (int j = 0; j < pw; ++j) {
+      double tj = tau[j];
+      double v = 0.0;
+      if (lane < j) {
+        for (int b2 = lane; b2 < j; ++b2) v += T[lane * nbw + b2] * S[b2 * nbw + j];
+        v *= -tj;
+      }
+      __syncwarp();
+      if (lane < j) T[lane * nbw + j] = v;
+      if (lane == j) T[j * nbw + j] = tj;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // 4. emit V and VT = V * T^T
+  double *Vo = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
+  double *VTo = a.VTw + ((long)w * a.NI + it) * (long)R * nbw;
+  for (int e = t; e < skip * nbw; e += PQR_THREADS) { Vo[e] = 0.0; VTo[e] = 0.0; }
+  for (int e = t; e < nact * nbw; e += PQR_THREADS) {
+    int r = e / nbw, c = e % nbw;
+    double v = (c < pw) ? P[c * LDP + r] : 0.0;
+    Vo[(long)(skip + r) * nbw + c] = v;
+    double acc = 0.0;
+    if (c < pw) {
+      for (int b2 = c; b2 < pw; ++b2) acc += P[b2 * LDP + r] * T[c * nbw + b2];
+    }
+    VTo[(long)(skip + r) * nbw + c] = acc;
+  }
+}
+
+static size_t panel_smem_bytes(int R, int nbw) {
+  return ((size_t)nbw * (R + 1) + 2 * (size_t)nbw * nbw + 3 * nbw) * sizeof(double);
+}
+void be_panel_qr(const PanelArgs &a) {
+  size_t smem = panel_smem_bytes(a.R, a.nbw);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  panel_qr_kernel<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
+  post_launch();
+}
+
+// =====================================================================================================
+// block Jacobi round
+// =====================================================================================================
+constexpr int JAC_THREADS = 256;
+
+__device__ __forceinline__ void rr_pair(int nblk, int round, int q, int &I, int &J) {
+  // round-robin tournament on nblk (even) players: player nblk-1 is fixed
+  const int n1 = nblk - 1;
+  if (q == 0) { I = n1; J = round % n1; }
+  else { I = (round + q) % n1; J = (round - q + n1) % n1; }
+}
+
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a) {
+  extern __shared__ double sm[];
+  const int w = blockIdx.y;
+  if (a.done[w]) return;
+  const int bs = a.bs, n2 = 2 * bs, nc = a.nc;
+  const int ncp = (nc + 7) & ~7;
+  const int LDS = ncp + 4;
+  const int LG = n2 + 1;
+  double *Ps = sm;                         // [n2][LDS]
+  double *Gm = Ps + (size_t)n2 * LDS;      // [n2][LG]
+  double *Wm = Gm + n2 * LG;               // [n2][LG]
+  double *cs = Wm + n2 * LG;               // [n2] : c (first half) s (second half)
+  int *perm = (int *)(cs + n2);            // [n2]
+  int *pairs = perm + n2;                  // [n2]
+  __shared__ double red[JAC_THREADS / 32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = JAC_THREADS / 32;
+
+  int I, J;
+  rr_pair(a.nblk, a.round, blockIdx.x, I, J);
+  const int lo = min(I, J), hi = max(I, J);
+  double *Gw = a.G + (long)w * a.ws;
+
+  // 1. load the two row blocks (zero padded columns)
+  for (int e = t; e < n2 * LDS; e += JAC_THREADS) {
+    int r = e / LDS, c = e % LDS;
+    int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
+    Ps[e] = (c < nc) ? Gw[(long)grow * a.ld + c] : 0.0;
+  }
+  __syncthreads();
+
+  // 2. Gram matrix on the DMMA pipe: tiles of 8x8, K = ncp
+  const int T2 = n2 / 8;
+  for (int tile = warp; tile < T2 * T2; tile += nwarp) {
+    int tp = tile / T2, tq = tile % T2;
+    if (tp > tq) continue;
+    double c0 = 0.0, c1 = 0.0;
+    const double *ap = Ps + (size_t)(tp * 8 + (lane >> 2)) * LDS + (lane & 3);
+    const double *bp = Ps + (size_t)(tq * 8 + (lane >> 2)) * LDS + (lane & 3);
+    for (int k = 0; k < ncp; k += 4) dmma8x8x4(c0, c1, ap[k], bp[k]);
+    int r = tp * 8 + (lane >> 2), c = tq * 8 + 2 * (lane & 3);
+    Gm[r * LG + c] = c0; Gm[r * LG + c + 1] = c1;
+    Gm[c * LG + r] = c0; Gm[(c + 1) * LG + r] = c1;
+  }
+  for (int e = t; e < n2 * n2; e += JAC_THREADS) {
+    int r = e / n2, c = e % n2;
+    Wm[r * LG + c] = (r == c) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+
+  // 3. convergence measure before rotating
+  {
+    double mx = 0.0;
+    for (int e = t; e < n2 * n2; e += JAC_THREADS) {
+      int p = e / n2, q = e % n2;
+      if (p < q) {
+        double gpp = Gm[p * LG + p], gqq = Gm[q * LG + q], gpq = fabs(Gm[p * LG + q]);
+        if (gpp > 0.0 && gqq > 0.0 && gpq > 0.0) mx = fmax(mx, gpq / sqrt(gpp * gqq));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (t == 0) {
+      for (int i = 1; i < nwarp; ++i) mx = fmax(mx, red[i]);
+      if (mx > 0.0) atomicMax((unsigned long long *)(a.offmax + w), (unsigned long long)__double_as_longlong(mx));
+      red[0] = mx;
+    }
+    __syncthreads();
+    if (red[0] <= a.tol) {
+      // nothing to rotate; still sort by norm so the selection sees ordered blocks
+    }
+  }
+
+  // 4. cyclic two-sided Jacobi on Gm, accumulating Wm
+  const int np = n2 / 2;
+  for (int sw = 0; sw < a.inner_sweeps; ++sw) {
+    for (int rd = 0; rd < n2 - 1; ++rd) {
+      if (t < np) {
+        int p, q;
+        rr_pair(n2, rd, t, p, q);
+        if (p > q) { int tmp = p; p = q; q = tmp; }
+        double app = Gm[p * LG + p], aqq = Gm[q * LG + q], apq = Gm[p * LG + q];
+        double c = 1.0, s = 0.0;
+        if (fabs(apq) > a.tol * sqrt(fabs(app * aqq)) && apq != 0.0) {
+          double zeta = (aqq - app) / (2.0 * apq);
+          double tt = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + tt * tt);
+          s = c * tt;
+        }
+        cs[t] = c; cs[np + t] = s;
+        pairs[2 * t] = p; pairs[2 * t + 1] = q;
+      }
+      __syncthreads();
+      // column rotation: G <- G J, W <- W J
+      for (int e = t; e < np * n2; e += JAC_THREADS) {
+        int k = e / n2, i = e % n2;
+        int p = pairs[2 * k], q = pairs[2 * k + 1];
+        double c = cs[k], s = cs[np + k];
+        double gp = Gm[i * LG + p], gq = Gm[i * LG + q];
+        Gm[i * LG + p] = c * gp - s * gq;
+        Gm[i * LG + q] = s * gp + c * gq;
+        double wp = Wm[i * LG + p], wq = Wm[i * LG + q];
+        Wm[i * LG + p] = c * wp - s * wq;
+        Wm[i * LG + q] = s * wp + c * wq;
+      }
+      __syncthreads();
+      // row rotation: G <- J^T G
+      for (int e = t; e < np * n2; e += JAC_THREADS) {
+        int k = e / n2, i = e % n2;
+        int p = pairs[2 * k], q = pairs[2 * k + 1];
+        double c = cs[k], s = cs[np + k];
+        double gp = Gm[p * LG + i], gq = Gm[q * LG + i];
+        Gm[p * LG + i] = c * gp - s * gq;
+        Gm[q * LG + i] = s * gp + c * gq;
+      }
+      __syncthreads();
+    }
+  }
+
+  // 5. permutation: new row r takes rotated direction perm[r], sorted by diagonal descending
+  if (t < n2) {
+    double mine = Gm[t * LG + t];
+    int rank = 0;
+    for (int j = 0; j < n2; ++j) {
+      double o = Gm[j * LG + j];
+      rank += (o > mine) || (o == mine && j < t);
+    }
+    perm[rank] = t;
+  }
+  __syncthreads();
+
+  // 6. apply: Pnew[r][c] = sum_k Wm[k][perm[r]] * Ps[k][c] on the DMMA pipe, in place per 8-column slice
+  const int nslice = ncp / 8;
+  for (int sl = warp; sl < nslice; sl += nwarp) {
+    double acc[4][2];
+    for (int mt = 0; mt < T2; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
+    for (int k = 0; k < n2; k += 4) {
+      double bfrag = Ps[(size_t)(k + (lane & 3)) * LDS + sl * 8 + (lane >> 2)];
+      for (int mt = 0; mt < T2; ++mt) {
+        double afrag = Wm[(k + (lane & 3)) * LG + perm[mt * 8 + (lane >> 2)]];
+        dmma8x8x4(acc[mt][0], acc[mt][1], afrag, bfrag);
+      }
+    }
+    __syncwarp();
+    for (int mt = 0; mt < T2; ++mt) {
+      int r = mt * 8 + (lane >> 2), c = sl * 8 + 2 * (lane & 3);
+      Ps[(size_t)r * LDS + c] = acc[mt][0];
+      Ps[(size_t)r * LDS + c + 1] = acc[mt][1];
+    }
+  }
+  __syncthreads();
+
+  // 7. store
+  for (int e = t; e < n2 * nc; e += JAC_THREADS) {
+    int r = e / nc, c = e % nc;
+    int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
+    Gw[(long)grow * a.ld + c] = Ps[(size_t)r * LDS + c];
+  }
+}
+
+static size_t jacobi_smem_bytes(int bs, int nc) {
+  int n2 = 2 * bs, ncp = (nc + 7) & ~7;
+  return ((size_t)n2 * (ncp + 4) + 2 * (size_t)n2 * (n2 + 1) + n2) * sizeof(double) + 3 * n2 * sizeof(int);
+}
+void be_jacobi_round(const JacobiArgs &a) {
+  size_t smem = jacobi_smem_bytes(a.bs, a.nc);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  jacobi_round_kernel<<<dim3(a.nblk / 2, a.W), JAC_THREADS, smem, g_stream>>>(a);
+  post_launch();
+}
+
+__global__ void jacobi_flags_kernel(double *offmax, int32_t *done, double tol, int W) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < W) {
+    done[w] = (offmax[w] <= tol) ? 1 : 0;
+    offmax[w] = 0.0;
+  }
+}
+void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {
+  jacobi_flags_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(offmax, done, tol, W);
+  post_launch();
+}
+
+__global__ void row_norms2_kernel(const double *G, long ws, int ld, int nr, int nc, double *norms2) {
+  const int w = blockIdx.y;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= nr) return;
+  const double *x = G + (long)w * ws + (long)warp * ld;
+  double s = 0.0;
+  for (int c = lane; c < nc; c += 32) s += x[c] * x[c];
+  s = warp_sum(s);
+  if (lane == 0) norms2[(long)w * nr + warp] = s;
+}
+void be_row_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W) {
+  int wpb = 8;
+  row_norms2_kernel<<<dim3((nr + wpb - 1) / wpb, W), wpb * 32, 0, g_stream>>>(G, ws, ld, nr, nc, norms2);
+  post_launch();
+}
+
+__global__ void select_truncate_kernel(const double *norms2, int nr, int nsv, int dmin, int dmax, double trunc_err,
+                                       int tcap, int32_t *order, int32_t *kept) {
+  extern __shared__ double srt[];   // sorted squared singular values
+  const int w = blockIdx.x;
+  const double *x = norms2 + (long)w * nr;
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    double mine = x[r];
+    int rank = 0;
+    for (int j = 0; j < nr; ++j) {
+      double o = x[j];
+      rank += (o > mine) || (o == mine && j < r);
+    }
+    srt[rank] = mine;
+    if (rank < tcap) order[(long)w * tcap + rank] = r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = nsv;
+    int k = n;
+    if (n > dmin) {
+      double total = 0.0;
+      for (int i = 0; i < n; ++i) total += srt[i];
+      double kept_sum = total;
+      while (k > dmin) {
+        double sv2 = srt[k - 1];
+        if (k <= dmax && total > 0.0 && (1.0 - (kept_sum - sv2) / total) > trunc_err) break;
+        kept_sum -= sv2;
+        --k;
+      }
+    }
+    if (k > tcap) k = tcap;
+    kept[w] = k;
+  }
+}
+void be_select_truncate(const double *norms2, int nr, int nsv, int dmin, int dmax, double trunc_err, int tcap,
+                        int32_t *order, int32_t *kept, int W) {
+  select_truncate_kernel<<<W, 256, nr * sizeof(double), g_stream>>>(norms2, nr, nsv, dmin, dmax, trunc_err, tcap,
+                                                                   order, kept);
+  post_launch();
+}
+
+__global__ void gather_rows_kernel(const double *G, long ws, int ld, int nc, const double *norms2, int nr,
+                                   const int32_t *order, const int32_t *kept, int tcap, double *B, long wb) {
+  const int w = blockIdx.y, tr = blockIdx.x;
+  double *out = B + (long)w * wb + (long)tr * nc;
+  if (tr >= kept[w]) {
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) out[c] = 0.0;
+    return;
+  }
+  int src = order[(long)w * tcap + tr];
+  double n2 = norms2[(long)w * nr + src];
+  double inv = (n2 > 0.0) ? 1.0 / sqrt(n2) : 0.0;
+  const double *x = G + (long)w * ws + (long)src * ld;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) out[c] = x[c] * inv;
+}
+void be_gather_rows_normalized(const double *G, long ws, int ld, int nc, const double *norms2, int nr,
+                               const int32_t *order, const int32_t *kept, int tcap, double *B, long wb, int W) {
+  gather_rows_kernel<<<dim3(tcap, W), 128, 0, g_stream>>>(G, ws, ld, nc, norms2, nr, order, kept, tcap, B, wb);
+  post_launch();
+}
+
+// =====================================================================================================
+// Monte Carlo state kernels
+// =====================================================================================================
+__global__ void mt_seed_kernel(uint32_t *mt, int32_t *idx, const uint32_t *seeds, int W) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  uint32_t *s = mt + (long)w * 624;
+  s[0] = seeds[w];
+  for (int i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i;
+  idx[w] = 624;
+}
+void be_mt_seed(uint32_t *mt, int32_t *idx, const uint32_t *seeds, int W) {
+  mt_seed_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(mt, idx, seeds, W);
+  post_launch();
+}
+
+__device__ uint32_t mt_next(uint32_t *s, int32_t &i) {
+  if (i >= 624) {
+    for (int k = 0; k < 624; ++k) {
+      uint32_t y = (s[k] & 0x80000000u) | (s[(k + 1) % 624] & 0x7fffffffu);
+      s[k] = s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    i = 0;
+  }
+  uint32_t y = s[i++];
+  y ^= y >> 11;
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= y >> 18;
+  return y;
+}
+// libstdc++ generate_canonical<double,53> on mt19937: (x0 + x1 * 2^32) / 2^64 with one rounding of the sum
+__device__ double mt_uniform01(uint32_t *s, int32_t &i) {
+  uint32_t x0 = mt_next(s, i);
+  uint32_t x1 = mt_next(s, i);
+  double sum = (double)x0 + (double)x1 * 4294967296.0;
+  double r = sum / 18446744073709551616.0;
+  if (r >= 1.0) r = 0.99999999999999988897769753748434595763683319091796875;  // nextafter(1, 0)
+  return r;
+}
+
+__global__ void nn_exchange_decide_kernel(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b,
+                                          double *amp, uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  int32_t *c = cfg + (long)w * nsites;
+  int c1 = c[s1], c2 = c[s2];
+  if (c1 == c2) return;
+  double pb = psi_b[w], pa = amp[w];
+  bool ok;
+  if (fabs(pb) >= fabs(pa)) ok = true;
+  else {
+    double div = fabs(pb) / fabs(pa);
+    double P = div * div;
+    int32_t i = idx[w];
+    double u = mt_uniform01(mt + (long)w * 624, i);
+    idx[w] = i;
+    ok = (u < P);
+  }
+  if (ok) {
+    c[s1] = c2; c[s2] = c1;
+    amp[w] = pb;
+    accepted[w] += 1;
+  }
+}
+void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b, double *amp,
+                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+  nn_exchange_decide_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, nsites, s1, s2, psi_b, amp, mt, idx, accepted, W);
+  post_launch();
+}
+
+__global__ void xxz_bond_energy_kernel(const int32_t *cfg, int nsites, int s1, int s2, const double *psi_ex,
+                                       const double *psi, double jz, double jxy, double *eloc, int W) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const int32_t *c = cfg + (long)w * nsites;
+  double e;
+  if (c[s1] == c[s2]) e = 0.25 * jz;
+  else {
+    double inv_psi = 1.0 / psi[w];
+    double ratio = psi_ex[w] * inv_psi;
+    e = -0.25 * jz + ratio * 0.5 * jxy;
+  }
+  eloc[w] += e;
+}
+void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const double *psi_ex, const double *psi,
+                        double jz, double jxy, double *eloc, int W) {
+  xxz_bond_energy_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, s1, s2, psi_ex, psi, jz, jxy, eloc, W);
+  post_launch();
+}
+__global__ void xxz_onsite_kernel(const int32_t *cfg, int nsites, double h00, double *eloc, int W) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < W) eloc[w] += -h00 * ((double)cfg[(long)w * nsites] - 0.5);
+}
+void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *eloc, int W) {
+  xxz_onsite_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, h00, eloc, W);
+  post_launch();
+}
+
+__global__ void accumulate_ostar_kernel(const double *holes, long hole_stride, const int32_t *hole_off,
+                                        const int32_t *site_size, const int32_t *tps_off, const int32_t *cfg,
+                                        int nsites, int phys, const double *amp, const double *eloc, double *osum,
+                                        double *eosum, int W) {
+  const int site = blockIdx.y;
+  const int sz = site_size[site];
+  const long ho = hole_off[site], to = tps_off[site];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < sz; e += gridDim.x * blockDim.x) {
+    for (int w = 0; w < W; ++w) {
+      int s = cfg[(long)w * nsites + site];
+      double inv = 1.0 / amp[w];
+      double o = inv * holes[(long)w * hole_stride + ho + e];
+      long slot = to + (long)s * sz + e;
+      osum[slot] += o;
+      eosum[slot] += eloc[w] * o;
+    }
+  }
+}
+void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                         const int32_t *tps_off, const int32_t *cfg, int nsites, int phys, const double *amp,
+                         const double *eloc, double *osum, double *eosum, int W) {
+  accumulate_ostar_kernel<<<dim3(16, nsites), 256, 0, g_stream>>>(holes, hole_stride, hole_off, site_size, tps_off,
+                                                                  cfg, nsites, phys, amp, eloc, osum, eosum, W);
+  post_launch();
+}
+
+}  // namespace peps

@@ -1,0 +1,194 @@
+// extern "C" surface of libpeps_b200 (include/peps_b200.h). Exceptions never cross the ABI: every entry point
+// catches, stores the message in the context (or a thread-local slot) and returns non-zero.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/peps_b200.h"
+#include "engine.h"
+
+using namespace peps;
+
+struct peps_ctx {
+  std::unique_ptr<Engine> eng;
+  std::string err;
+};
+static thread_local std::string g_err;
+
+#define GUARD(ctx, ...)                                    \
+  try {                                                    \
+    __VA_ARGS__;                                           \
+    return 0;                                              \
+  } catch (const std::exception &e) {                      \
+    if (ctx) (ctx)->err = e.what(); else g_err = e.what(); \
+    return 1;                                              \
+  } catch (...) {                                          \
+    if (ctx) (ctx)->err = "unknown error"; else g_err = "unknown error"; \
+    return 1;                                              \
+  }
+
+extern "C" {
+
+const char *peps_backend_name(void) { return be_name(); }
+
+int peps_create(peps_ctx **out, const peps_config *cfg) {
+  peps_ctx *ctx = nullptr;
+  try {
+    if (!out || !cfg) throw std::invalid_argument("peps_create: null argument");
+    ctx = new peps_ctx();
+    EngineConfig ec;
+    ec.rows = cfg->rows; ec.cols = cfg->cols; ec.phys = cfg->phys; ec.D = cfg->D; ec.walkers = cfg->walkers;
+    ec.device = cfg->device; ec.dmin = cfg->dmin; ec.dmax = cfg->dmax; ec.trunc_err = cfg->trunc_err;
+    ctx->eng.reset(new Engine(ec));
+    *out = ctx;
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    delete ctx;
+    if (out) *out = nullptr;
+    return 1;
+  }
+}
+void peps_destroy(peps_ctx *ctx) { delete ctx; }
+const char *peps_last_error(peps_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+size_t peps_tps_size(peps_ctx *ctx) { return ctx->eng->tps_size(); }
+size_t peps_tps_site_offset(peps_ctx *ctx, int32_t row, int32_t col) { return (size_t)ctx->eng->site_offset(row, col); }
+int peps_set_tps(peps_ctx *ctx, const double *h, size_t n) {
+  GUARD(ctx, { if (n != ctx->eng->tps_size()) throw std::invalid_argument("peps_set_tps: size mismatch"); ctx->eng->set_tps(h); })
+}
+int peps_get_tps(peps_ctx *ctx, double *h, size_t n) {
+  GUARD(ctx, { if (n != ctx->eng->tps_size()) throw std::invalid_argument("peps_get_tps: size mismatch"); ctx->eng->get_tps(h); })
+}
+int peps_set_truncation(peps_ctx *ctx, int32_t dmin, int32_t dmax, double terr) {
+  GUARD(ctx, { if (dmin < 1 || dmax < dmin) throw std::invalid_argument("peps_set_truncation: need 1 <= dmin <= dmax"); ctx->eng->set_truncation(dmin, dmax, terr); })
+}
+int peps_set_jacobi(peps_ctx *ctx, double tol, int32_t inner, int32_t maxs) { GUARD(ctx, ctx->eng->set_jacobi(tol, inner, maxs)) }
+int peps_set_model_xxz(peps_ctx *ctx, double jz, double jxy, double h00) { GUARD(ctx, ctx->eng->set_model_xxz(jz, jxy, h00)) }
+int peps_set_configs(peps_ctx *ctx, const int32_t *c) { GUARD(ctx, ctx->eng->set_configs(c)) }
+int peps_get_configs(peps_ctx *ctx, int32_t *c) { GUARD(ctx, ctx->eng->get_configs(c)) }
+int peps_seed_rng(peps_ctx *ctx, const uint32_t *s) { GUARD(ctx, ctx->eng->seed_rng(s)) }
+int peps_set_rng_state(peps_ctx *ctx, const uint32_t *mt, const int32_t *idx) { GUARD(ctx, ctx->eng->set_rng_state(mt, idx)) }
+int peps_get_rng_state(peps_ctx *ctx, uint32_t *mt, int32_t *idx) { GUARD(ctx, ctx->eng->get_rng_state(mt, idx)) }
+int peps_init_walkers(peps_ctx *ctx) { GUARD(ctx, ctx->eng->init_walkers()) }
+int peps_get_amplitudes(peps_ctx *ctx, double *a) { GUARD(ctx, ctx->eng->get_amplitudes(a)) }
+
+int peps_normalize_state_order1(peps_ctx *ctx, double max_abs_override, double *site_factor_out) {
+  GUARD(ctx, {
+    Engine &e = *ctx->eng;
+    double mx = max_abs_override;
+    if (!(mx > 0.0)) {
+      std::vector<double> a((size_t)e.walkers());
+      e.get_amplitudes(a.data());
+      mx = 0.0;
+      for (double v : a) mx = std::max(mx, std::fabs(v));
+    }
+    if (!(mx > 0.0) || !std::isfinite(mx)) throw std::runtime_error("peps_normalize_state_order1: amplitudes are zero or not finite");
+    double scale = 1.0 / mx;
+    double f = std::pow(scale, 1.0 / double(e.rows() * e.cols()));
+    e.scale_tps(f);
+    e.init_walkers();
+    if (site_factor_out) *site_factor_out = f;
+  })
+}
+
+int peps_sweep(peps_ctx *ctx, int32_t n, double *acc) { GUARD(ctx, ctx->eng->sweep(n, acc)) }
+int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, double *psi_list) {
+  GUARD(ctx, ctx->eng->energy_and_holes(calc_holes != 0, eloc, psi_list))
+}
+size_t peps_holes_stride(peps_ctx *ctx) { return (size_t)ctx->eng->holes_stride(); }
+int peps_get_holes(peps_ctx *ctx, double *h) { GUARD(ctx, ctx->eng->get_holes(h)) }
+int peps_zero_accumulators(peps_ctx *ctx) { GUARD(ctx, ctx->eng->zero_accumulators()) }
+int peps_accumulate_ostar(peps_ctx *ctx) { GUARD(ctx, ctx->eng->accumulate_ostar()) }
+int peps_get_accumulators(peps_ctx *ctx, double *o, double *eo, size_t n) {
+  GUARD(ctx, { if (n != ctx->eng->tps_size()) throw std::invalid_argument("peps_get_accumulators: size mismatch"); ctx->eng->get_accumulators(o, eo); })
+}
+double *peps_ostar_sum_device(peps_ctx *ctx) { return ctx->eng->osum_device(); }
+double *peps_eloc_ostar_sum_device(peps_ctx *ctx) { return ctx->eng->eosum_device(); }
+int peps_sample(peps_ctx *ctx, int32_t sweeps, double *eloc, double *acc) {
+  GUARD(ctx, {
+    ctx->eng->sweep(sweeps, acc);
+    ctx->eng->energy_and_holes(true, eloc, nullptr);
+    ctx->eng->accumulate_ostar();
+  })
+}
+int peps_probe_trace_row(peps_ctx *ctx, int32_t row, double *psi) { GUARD(ctx, ctx->eng->probe_trace_row(row, psi)) }
+int32_t peps_bmps_stack_size(peps_ctx *ctx, int32_t pos) { return ctx->eng->bmps_stack_size(pos); }
+int peps_get_bmps_tensor(peps_ctx *ctx, int32_t pos, int32_t k, int32_t i, double *out, int32_t dims[3]) {
+  GUARD(ctx, { int d[3]; ctx->eng->bmps_tensor(pos, k, i, out, d); for (int a = 0; a < 3; ++a) dims[a] = d[a]; })
+}
+int64_t peps_stat(peps_ctx *ctx, int32_t which) { return ctx->eng->stat(which); }
+int peps_sync(peps_ctx *ctx) { GUARD(ctx, be_sync()) }
+void *peps_stream(peps_ctx *) { return be_stream(); }
+
+// ---- stand-alone kernel tests -----------------------------------------------------------------------
+int peps_test_qr_r(int32_t device, int32_t W, int32_t m, int32_t n, const double *a, double *r_out) {
+  peps_ctx *nullctx = nullptr;
+  GUARD(nullctx, {
+    be_init(device);
+    Pool pool; Planner planner; LinalgCtx cx;
+    cx.W = W; cx.pool = &pool; cx.planner = &planner;
+    QRLayout L = qr_layout(m, n);
+    double *A = (double *)pool.get(sizeof(double) * (size_t)W * L.m_pad * n);
+    be_memset0(A, sizeof(double) * (size_t)W * L.m_pad * n);
+    double *tmp = (double *)pool.get(sizeof(double) * (size_t)W * m * n);
+    be_h2d(tmp, a, sizeof(double) * (size_t)W * m * n);
+    be_copy2d(A, (long)L.m_pad * n, n, tmp, (long)m * n, n, m, n, W);
+    caqr(cx, A, (long)L.m_pad * n, m, n, L);
+    int kk = std::min(m, n);
+    double *R = (double *)pool.get(sizeof(double) * (size_t)W * kk * n);
+    be_copy2d(R, (long)kk * n, n, A, (long)L.m_pad * n, n, kk, n, W);
+    be_d2h(r_out, R, sizeof(double) * (size_t)W * kk * n);
+  })
+}
+
+int peps_test_truncate(int32_t device, int32_t W, int32_t nr, int32_t nc, int32_t dmin, int32_t dmax, double trunc_err,
+                       const double *theta, double *b_out, int32_t *kept_out, int32_t *sweeps_out) {
+  peps_ctx *nullctx = nullptr;
+  GUARD(nullctx, {
+    be_init(device);
+    Pool pool; Planner planner; LinalgCtx cx;
+    cx.W = W; cx.pool = &pool; cx.planner = &planner;
+    cx.offmax = (double *)pool.get(sizeof(double) * W);
+    cx.done = (int32_t *)pool.get(sizeof(int32_t) * W);
+    int brows = truncate_buffer_rows(nr, nc);
+    double *G = (double *)pool.get(sizeof(double) * (size_t)W * brows * nc);
+    be_memset0(G, sizeof(double) * (size_t)W * brows * nc);
+    double *tmp = (double *)pool.get(sizeof(double) * (size_t)W * nr * nc);
+    be_h2d(tmp, theta, sizeof(double) * (size_t)W * nr * nc);
+    be_copy2d(G, (long)brows * nc, nc, tmp, (long)nr * nc, nc, nr, nc, W);
+    int tcap = std::min(dmax, std::min(nr, nc));
+    double *B = (double *)pool.get(sizeof(double) * (size_t)W * tcap * nc);
+    int32_t *kept = (int32_t *)pool.get(sizeof(int32_t) * W);
+    double *norms2 = (double *)pool.get(sizeof(double) * (size_t)W * nr);
+    int32_t *order = (int32_t *)pool.get(sizeof(int32_t) * (size_t)W * tcap);
+    truncate_rows(cx, G, (long)brows * nc, nr, nc, dmin, dmax, trunc_err, tcap, B, (long)tcap * nc, kept, norms2, order);
+    be_d2h(b_out, B, sizeof(double) * (size_t)W * tcap * nc);
+    be_d2h(kept_out, kept, sizeof(int32_t) * W);
+    if (sweeps_out) *sweeps_out = (int32_t)cx.jacobi_sweeps;
+  })
+}
+
+int peps_test_einsum(int32_t device, int32_t W, const char *spec, const int32_t *dims_a, int32_t rank_a,
+                     const int32_t *dims_b, int32_t rank_b, const double *a, const double *b, double *c) {
+  peps_ctx *nullctx = nullptr;
+  GUARD(nullctx, {
+    be_init(device);
+    Pool pool; Planner planner;
+    int da[6], db[6];
+    long na = 1, nb = 1;
+    for (int i = 0; i < rank_a; ++i) { da[i] = dims_a[i]; na *= da[i]; }
+    for (int i = 0; i < rank_b; ++i) { db[i] = dims_b[i]; nb *= db[i]; }
+    const Plan &pl = planner.get(spec, da, rank_a, db, rank_b);
+    double *A = (double *)pool.get(sizeof(double) * (size_t)W * na);
+    double *Bp = (double *)pool.get(sizeof(double) * (size_t)W * nb);
+    double *C = (double *)pool.get(sizeof(double) * (size_t)W * pl.outn);
+    be_h2d(A, a, sizeof(double) * (size_t)W * na);
+    be_h2d(Bp, b, sizeof(double) * (size_t)W * nb);
+    be_gett(pl.d, mkop(A, na), mkop(Bp, nb), mkop(C, pl.outn), 1.0, 0.0, W, 1);
+    be_d2h(c, C, sizeof(double) * (size_t)W * pl.outn);
+  })
+}
+
+}  // extern "C"

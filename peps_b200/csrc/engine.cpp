@@ -1,0 +1,541 @@
+// See engine.h. Backend-agnostic host orchestration of the walker-batched VMC sampling path.
+#include "engine.h"
+#include <cmath>
+#include <cstdio>
+
+namespace peps {
+
+Engine::Engine(const EngineConfig &c)
+    : rows_(c.rows), cols_(c.cols), phys_(c.phys), D_(c.D), W_(c.walkers), nsites_(c.rows * c.cols),
+      dmin_(c.dmin), dmax_(c.dmax), terr_(c.trunc_err) {
+  if (rows_ < 2 || cols_ < 2) throw std::invalid_argument("Engine: lattice must be at least 2x2");
+  if (W_ < 1 || phys_ < 1 || D_ < 1) throw std::invalid_argument("Engine: bad sizes");
+  be_init(c.device);
+  la_.W = W_; la_.pool = &pool_; la_.planner = &planner_;
+  la_.offmax = (double *)be_malloc(sizeof(double) * W_);
+  la_.done = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+  tps_off_h_.resize((size_t)nsites_);
+  site_size_h_.resize((size_t)nsites_);
+  site_dims_h_.resize((size_t)nsites_);
+  hole_off_h_.resize((size_t)nsites_);
+  long off = 0, hoff = 0;
+  for (int r = 0; r < rows_; ++r)
+    for (int cc = 0; cc < cols_; ++cc) {
+      int s = r * cols_ + cc;
+      std::array<int, 4> d = {cc == 0 ? 1 : D_, r == rows_ - 1 ? 1 : D_, cc == cols_ - 1 ? 1 : D_, r == 0 ? 1 : D_};
+      site_dims_h_[(size_t)s] = d;
+      site_size_h_[(size_t)s] = d[0] * d[1] * d[2] * d[3];
+      tps_off_h_[(size_t)s] = off;
+      hole_off_h_[(size_t)s] = hoff;
+      off += (long)phys_ * site_size_h_[(size_t)s];
+      hoff += site_size_h_[(size_t)s];
+    }
+  tps_total_ = off;
+  hole_stride_ = hoff;
+  tps_ = (double *)be_malloc(sizeof(double) * tps_total_);
+  osum_ = (double *)be_malloc(sizeof(double) * tps_total_);
+  eosum_ = (double *)be_malloc(sizeof(double) * tps_total_);
+  be_memset0(osum_, sizeof(double) * tps_total_);
+  be_memset0(eosum_, sizeof(double) * tps_total_);
+  std::vector<int32_t> t32((size_t)nsites_), h32((size_t)nsites_);
+  for (int s = 0; s < nsites_; ++s) { t32[(size_t)s] = (int32_t)tps_off_h_[(size_t)s]; h32[(size_t)s] = (int32_t)hole_off_h_[(size_t)s]; }
+  tps_off_d_ = (int32_t *)be_malloc(sizeof(int32_t) * nsites_);
+  site_size_d_ = (int32_t *)be_malloc(sizeof(int32_t) * nsites_);
+  hole_off_d_ = (int32_t *)be_malloc(sizeof(int32_t) * nsites_);
+  be_h2d(tps_off_d_, t32.data(), sizeof(int32_t) * nsites_);
+  be_h2d(site_size_d_, site_size_h_.data(), sizeof(int32_t) * nsites_);
+  be_h2d(hole_off_d_, h32.data(), sizeof(int32_t) * nsites_);
+  cfg_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)W_ * nsites_);
+  be_memset0(cfg_, sizeof(int32_t) * (size_t)W_ * nsites_);
+  amp_ = (double *)be_malloc(sizeof(double) * W_);
+  mt_ = (uint32_t *)be_malloc(sizeof(uint32_t) * (size_t)W_ * 624);
+  mtidx_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+  accepted_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+  eloc_ = (double *)be_malloc(sizeof(double) * W_);
+  psi_tmp_ = (double *)be_malloc(sizeof(double) * W_);
+  psi_row_ = (double *)be_malloc(sizeof(double) * W_);
+  kept_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+  holes_ = (double *)be_malloc(sizeof(double) * (size_t)W_ * hole_stride_);
+  be_memset0(holes_, sizeof(double) * (size_t)W_ * hole_stride_);
+  be_memset0(amp_, sizeof(double) * W_);
+  be_memset0(eloc_, sizeof(double) * W_);
+  std::vector<uint32_t> seeds((size_t)W_);
+  for (int w = 0; w < W_; ++w) seeds[(size_t)w] = 5489u + (uint32_t)w;
+  seed_rng(seeds.data());
+}
+
+Engine::~Engine() {
+  for (int p = 0; p < 4; ++p) {
+    for (auto &b : bmps_[p]) release(b);
+    for (auto &t : bten_[p]) release(t);
+  }
+  for (void *p : {(void *)tps_, (void *)osum_, (void *)eosum_, (void *)tps_off_d_, (void *)site_size_d_, (void *)hole_off_d_,
+                  (void *)cfg_, (void *)amp_, (void *)mt_, (void *)mtidx_, (void *)accepted_, (void *)eloc_, (void *)psi_tmp_,
+                  (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done})
+    be_free(p);
+}
+
+void Engine::site_dims(int r, int c, int out[4]) const {
+  for (int i = 0; i < 4; ++i) out[i] = site_dims_h_[(size_t)(r * cols_ + c)][(size_t)i];
+}
+void Engine::set_tps(const double *host) { be_h2d(tps_, host, sizeof(double) * tps_total_); }
+void Engine::get_tps(double *host) { be_d2h(host, tps_, sizeof(double) * tps_total_); }
+void Engine::scale_tps(double f) {
+  std::vector<double> h((size_t)tps_total_);
+  get_tps(h.data());
+  for (auto &x : h) x *= f;
+  set_tps(h.data());
+}
+void Engine::set_configs(const int32_t *host) { be_h2d(cfg_, host, sizeof(int32_t) * (size_t)W_ * nsites_); }
+void Engine::get_configs(int32_t *host) { be_d2h(host, cfg_, sizeof(int32_t) * (size_t)W_ * nsites_); }
+void Engine::seed_rng(const uint32_t *seeds) {
+  uint32_t *d = (uint32_t *)pool_.get(sizeof(uint32_t) * W_);
+  be_h2d(d, seeds, sizeof(uint32_t) * W_);
+  be_mt_seed(mt_, mtidx_, d, W_);
+  be_sync();
+  pool_.put(d);
+}
+void Engine::set_rng_state(const uint32_t *mt, const int32_t *idx) {
+  be_h2d(mt_, mt, sizeof(uint32_t) * (size_t)W_ * 624);
+  be_h2d(mtidx_, idx, sizeof(int32_t) * W_);
+}
+void Engine::get_rng_state(uint32_t *mt, int32_t *idx) {
+  be_d2h(mt, mt_, sizeof(uint32_t) * (size_t)W_ * 624);
+  be_d2h(idx, mtidx_, sizeof(int32_t) * W_);
+}
+void Engine::get_amplitudes(double *host) { be_d2h(host, amp_, sizeof(double) * W_); }
+void Engine::get_holes(double *host) { be_d2h(host, holes_, sizeof(double) * (size_t)W_ * hole_stride_); }
+long Engine::stat(int which) const {
+  switch (which) {
+    case 0: return n_absorb_;
+    case 1: return n_bten_;
+    case 2: return n_trace_;
+    case 3: return la_.jacobi_sweeps;
+    case 4: return la_.jacobi_calls;
+    case 5: return la_.qr_calls;
+    case 6: return be_launch_count();
+    case 7: return (long)pool_.total_bytes();
+    default: return -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tensors
+// ---------------------------------------------------------------------------------------------------
+BT Engine::alloc(std::initializer_list<int> dims) {
+  BT t;
+  t.rank = (int)dims.size();
+  long n = 1;
+  int i = 0;
+  for (int d : dims) { t.d[i++] = d; n *= d; }
+  t.n = n;
+  t.p = (double *)pool_.get(sizeof(double) * (size_t)W_ * n);
+  return t;
+}
+BT Engine::ones111() {
+  BT t = alloc({1, 1, 1});
+  be_fill(t.p, 1.0, W_);
+  return t;
+}
+void Engine::release(BT &t) {
+  if (t.p) pool_.put(t.p);
+  t.p = nullptr;
+}
+void Engine::release(BMPSv &v) {
+  for (auto &t : v) release(t);
+  v.clear();
+}
+TRef Engine::ref(const BT &t) const {
+  TRef r;
+  r.op = mkop(t.p, t.n);
+  r.rank = t.rank;
+  for (int i = 0; i < t.rank; ++i) r.d[i] = t.d[i];
+  return r;
+}
+TRef Engine::site_ref(int site, int cfg_site) const {
+  TRef r;
+  r.op = mkgather(tps_ + tps_off_h_[(size_t)site], cfg_ + cfg_site, nsites_, site_size_h_[(size_t)site]);
+  r.rank = 4;
+  for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
+  return r;
+}
+BT Engine::einsum(const std::string &spec, const TRef &a, const TRef &b) {
+  const Plan &pl = planner_.get(spec, a.d, a.rank, b.d, b.rank);
+  BT out;
+  out.rank = (int)pl.outdims.size();
+  for (int i = 0; i < out.rank; ++i) out.d[i] = pl.outdims[(size_t)i];
+  out.n = pl.outn;
+  out.p = (double *)pool_.get(sizeof(double) * (size_t)W_ * out.n);
+  be_gett(pl.d, a.op, b.op, mkop(out.p, out.n), 1.0, 0.0, W_, 1);
+  return out;
+}
+void Engine::einsum_into(const std::string &spec, const TRef &a, const TRef &b, Operand c, const long *sc, double alpha,
+                         double beta) {
+  const Plan &pl = planner_.get(spec, a.d, a.rank, b.d, b.rank, nullptr, nullptr, sc);
+  be_gett(pl.d, a.op, b.op, c, alpha, beta, W_, 1);
+}
+std::string Engine::site_labels(int post, char pre, char toward, char next, char away) {
+  std::string s(4, '?');
+  s[(size_t)((post + 3) % 4)] = pre;
+  s[(size_t)post] = toward;
+  s[(size_t)((post + 1) % 4)] = next;
+  s[(size_t)((post + 2) % 4)] = away;
+  return s;
+}
+std::vector<int> Engine::slice_sites(int num, int orient) const {
+  std::vector<int> v;
+  if (orient == HORIZONTAL) for (int c = 0; c < cols_; ++c) v.push_back(num * cols_ + c);
+  else for (int r = 0; r < rows_; ++r) v.push_back(r * cols_ + num);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BMPS::MultiplyMPOSVDCompress_ (bmps_impl.h:756-862), restated as an R-chain + right-to-left truncation:
+//   forward  : r_{i+1} = R factor of [r_i (x) mps_i (x) mpo_i] as a (k,o) x (f,b) matrix      (:778-850, R only)
+//   backward : Theta_i = r_i . X_i with X_i = mps_i (x) mpo_i (x) E_{i+1}; the kept right singular vectors of
+//              Theta_i are res[i] (= Vt of :235-238); E_i = X_i . res[i]^T carries the truncated right part
+//              (the reference carries the same information as U.S absorbed into res[i-1], :251-254).
+// In exact arithmetic both give the same truncated MPS up to the gauge of each kept subspace.
+// ---------------------------------------------------------------------------------------------------
+Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in, int post) {
+  ++n_absorb_;
+  const int N = (int)mps.size();
+  std::vector<int> sites(sites_in);
+  if (post == RIGHT || post == UP) std::reverse(sites.begin(), sites.end());      // bmps_impl.h:694-699
+  const std::string sl = site_labels(post, 'e', 'p', 'f', 'o');
+  auto sdim = [&](int site, char l) { return site_dims_h_[(size_t)site][sl.find(l)]; };
+  std::vector<BT> r((size_t)N);
+  r[0] = ones111();
+  for (int i = 0; i < N - 1; ++i) {
+    const int site = sites[(size_t)i];
+    TRef sref = site_ref(site, site);
+    BT tmp1 = einsum("apb,kea->kepb", ref(mps[(size_t)i]), ref(r[(size_t)i]));        // bmps_impl.h:806
+    const int k = r[(size_t)i].d[0], o = sdim(site, 'o'), f = sdim(site, 'f'), b = mps[(size_t)i].d[2];
+    const int m = k * o, n = f * b;
+    QRLayout L = qr_layout(m, n);
+    double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * L.m_pad * n);
+    if (L.m_pad > m) be_memset0(A, sizeof(double) * (size_t)W_ * L.m_pad * n);
+    einsum_into("kepb," + sl + "->kofb", ref(tmp1), sref, mkop(A, (long)L.m_pad * n));   // bmps_impl.h:807
+    release(tmp1);
+    caqr(la_, A, (long)L.m_pad * n, m, n, L);                                            // bmps_impl.h:817-821
+    const int kk = std::min(m, n);
+    r[(size_t)i + 1] = alloc({kk, f, b});
+    be_copy2d(r[(size_t)i + 1].p, (long)kk * n, n, A, (long)L.m_pad * n, n, kk, n, W_);
+    pool_.put(A);
+  }
+  BMPSv res((size_t)N);
+  BT E = ones111();                                                                      // E[f,b,j]
+  for (int i = N - 1; i >= 1; --i) {                                                     // bmps_impl.h:853-857
+    const int site = sites[(size_t)i];
+    BT Y = einsum("apb,fbj->apfj", ref(mps[(size_t)i]), ref(E));
+    BT X = einsum("apfj," + sl + "->eaoj", ref(Y), site_ref(site, site));
+    release(Y);
+    const int rows = r[(size_t)i].d[0], o = X.d[2], j = X.d[3], cols = o * j;
+    BT B;
+    if (rows >= cols && cols <= dmin_) {
+      // nothing can be truncated and the row space is the whole space: any orthonormal basis is the same gauge class
+      B = alloc({cols, o, j});
+      be_set_identity(B.p, B.n, cols, cols, W_);
+    } else {
+      const int brows = truncate_buffer_rows(rows, cols);
+      double *G = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows * cols);
+      if (brows > rows) be_memset0(G, sizeof(double) * (size_t)W_ * brows * cols);
+      einsum_into("kea,eaoj->koj", ref(r[(size_t)i]), ref(X), mkop(G, (long)brows * cols));
+      const int tcap = std::min(dmax_, std::min(rows, cols));
+      B = alloc({tcap, o, j});
+      double *norms2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * std::max(rows, 1));
+      int32_t *order = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * tcap);
+      truncate_rows(la_, G, (long)brows * cols, rows, cols, dmin_, dmax_, terr_, tcap, B.p, B.n, kept_, norms2, order);
+      pool_.put(norms2);
+      pool_.put(order);
+      pool_.put(G);
+    }
+    BT En = einsum("eaoj,toj->eat", ref(X), ref(B));
+    release(X);
+    release(E);
+    E = En;
+    res[(size_t)i] = B;
+  }
+  {
+    const int site = sites[0];
+    BT Y = einsum("apb,fbj->apfj", ref(mps[0]), ref(E));
+    BT X = einsum("apfj," + sl + "->eaoj", ref(Y), site_ref(site, site));
+    release(Y);
+    release(E);
+    BT first = X;                   // (e=1, a=1, o, j) viewed as (1, o, j)
+    first.rank = 3;
+    first.d[0] = 1; first.d[1] = X.d[2]; first.d[2] = X.d[3];
+    res[0] = first;
+  }
+  for (auto &t : r) release(t);
+  return res;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// contractor
+// ---------------------------------------------------------------------------------------------------
+void Engine::contractor_init() {                       // impl/bmps_contractor_init.h:25-70
+  for (int p = 0; p < 4; ++p) {
+    for (auto &b : bmps_[p]) release(b);
+    bmps_[p].clear();
+    for (auto &t : bten_[p]) release(t);
+    bten_[p].clear();
+    int n = (p == UP || p == DOWN) ? cols_ : rows_;
+    BMPSv vac;
+    for (int i = 0; i < n; ++i) vac.push_back(ones111());
+    bmps_[p].push_back(vac);
+  }
+}
+const Engine::BMPSv &Engine::bmps_at_slice(int pos, int logical) const {   // bmps_contractor.h:985-999
+  if (pos == DOWN) return bmps_[DOWN].at((size_t)(rows_ - 1 - logical));
+  if (pos == RIGHT) return bmps_[RIGHT].at((size_t)(cols_ - 1 - logical));
+  return bmps_[pos].at((size_t)logical);
+}
+const BT &Engine::bten_at_slice(int pos, int logical) const {              // bmps_contractor.h:1001-1009
+  if (pos == DOWN) return bten_[DOWN].at((size_t)(rows_ - 1 - logical));
+  if (pos == RIGHT) return bten_[RIGHT].at((size_t)(cols_ - 1 - logical));
+  return bten_[pos].at((size_t)logical);
+}
+void Engine::grow_bmps_step(int pos) {                 // grow.h:32-48
+  int existed = (int)bmps_[pos].size();
+  int mpo_num = (pos == UP || pos == LEFT) ? existed - 1 : (pos == DOWN ? rows_ - existed : cols_ - existed);
+  int orient = (pos == UP || pos == DOWN) ? HORIZONTAL : VERTICAL;
+  bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(mpo_num, orient), pos));
+}
+void Engine::grow_full_bmps(int pos) {                 // grow.h:50-86
+  int existed = (int)bmps_[pos].size();
+  if (pos == DOWN) for (int row = rows_ - existed; row > 0; --row) bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(row, HORIZONTAL), pos));
+  else if (pos == UP) for (int row = existed - 1; row < rows_ - 1; ++row) bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(row, HORIZONTAL), pos));
+  else if (pos == LEFT) for (int col = existed - 1; col < cols_ - 1; ++col) bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(col, VERTICAL), pos));
+  else for (int col = cols_ - existed; col > 0; --col) bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(col, VERTICAL), pos));
+}
+void Engine::delete_inner_bmps(int pos) {              // bmps_contractor.h:320-324
+  while (bmps_[pos].size() > 1) { release(bmps_[pos].back()); bmps_[pos].pop_back(); }
+}
+void Engine::grow_bmps_for_row(int row) {              // grow.h:88-104
+  for (int rb = rows_ - (int)bmps_[DOWN].size(); rb > row; --rb) bmps_[DOWN].push_back(absorb(bmps_[DOWN].back(), slice_sites(rb, HORIZONTAL), DOWN));
+  for (int rb = (int)bmps_[UP].size() - 1; rb < row; ++rb) bmps_[UP].push_back(absorb(bmps_[UP].back(), slice_sites(rb, HORIZONTAL), UP));
+}
+void Engine::grow_bmps_for_col(int col) {              // grow.h:106-122
+  for (int cb = cols_ - (int)bmps_[RIGHT].size(); cb > col; --cb) bmps_[RIGHT].push_back(absorb(bmps_[RIGHT].back(), slice_sites(cb, VERTICAL), RIGHT));
+  for (int cb = (int)bmps_[LEFT].size() - 1; cb < col; ++cb) bmps_[LEFT].push_back(absorb(bmps_[LEFT].back(), slice_sites(cb, VERTICAL), LEFT));
+}
+void Engine::shift_bmps_window(int pos) {              // grow.h:143-148
+  release(bmps_[pos].back());
+  bmps_[pos].pop_back();
+  grow_bmps_step(opposite(pos));
+}
+void Engine::init_bten(int pos) {                      // init.h:72-120
+  for (auto &t : bten_[pos]) release(t);
+  bten_[pos].clear();
+  bten_[pos].push_back(ones111());
+}
+BT Engine::bten_step(const BT &bten, const BT &mps1, const TRef &site, const BT &mps2, int post) {   // grow.h:577-579
+  ++n_bten_;
+  const std::string sl = site_labels(post, 'p', 'y', 'f', 'o');
+  BT tmp1 = einsum("apx,xyz->apyz", ref(mps1), ref(bten));
+  BT tmp2 = einsum("apyz," + sl + "->zafo", ref(tmp1), site);
+  release(tmp1);
+  BT out = einsum("zafo,zfb->aob", ref(tmp2), ref(mps2));
+  release(tmp2);
+  return out;
+}
+void Engine::bten_operands(int post, int slice, int bten_size, const BT *&mps1, const BT *&mps2, int &site) const {
+  const int pre_post = (post + 3) % 4, next_post = (post + 1) % 4;
+  const int n = (post == LEFT || post == RIGHT) ? cols_ : rows_;
+  mps1 = &bmps_at_slice(pre_post, slice).at((size_t)(n - bten_size));
+  mps2 = &bmps_at_slice(next_post, slice).at((size_t)(bten_size - 1));
+  if (post == LEFT) site = slice * cols_ + (bten_size - 1);
+  else if (post == RIGHT) site = slice * cols_ + (n - bten_size);
+  else if (post == UP) site = (bten_size - 1) * cols_ + slice;
+  else site = (n - bten_size) * cols_ + slice;
+}
+void Engine::grow_full_bten(int pos, int slice, int remain, bool init) {     // grow.h:243-373
+  if (init) init_bten(pos);
+  const int n = (pos == LEFT || pos == RIGHT) ? cols_ : rows_;
+  for (int i = (int)bten_[pos].size() - 1; i < n - remain; ++i) {
+    const BT *m1, *m2; int site;
+    bten_operands(pos, slice, i + 1, m1, m2, site);
+    bten_[pos].push_back(bten_step(bten_[pos].back(), *m1, site_ref(site, site), *m2, pos));
+  }
+}
+void Engine::grow_bten_step(int post) {                // grow.h:529-582
+  int slice = (post == LEFT || post == RIGHT) ? (int)bmps_[UP].size() - 1 : (int)bmps_[LEFT].size() - 1;
+  const BT *m1, *m2; int site;
+  bten_operands(post, slice, (int)bten_[post].size(), m1, m2, site);
+  bten_[post].push_back(bten_step(bten_[post].back(), *m1, site_ref(site, site), *m2, post));
+}
+void Engine::shift_bten_window(int pos) {              // grow.h:517-521
+  release(bten_[pos].back());
+  bten_[pos].pop_back();
+  grow_bten_step(opposite(pos));
+}
+void Engine::nn_trace(int ra, int ca, int rb, int cb, int orient, int cfg_site_a, int cfg_site_b, double *psi_out) {
+  ++n_trace_;                                          // trace.h:90-205
+  int first, second, slice, ia, ib, n;
+  if (orient == HORIZONTAL) { first = LEFT; second = RIGHT; slice = ra; ia = ca; ib = cb; n = cols_; }
+  else { first = UP; second = DOWN; slice = ca; ia = ra; ib = rb; n = rows_; }
+  const BT *m1, *m2; int site;
+  bten_operands(first, slice, ia + 1, m1, m2, site);
+  BT half_a = bten_step(bten_[first].at((size_t)ia), *m1, site_ref(ra * cols_ + ca, cfg_site_a), *m2, first);
+  bten_operands(second, slice, n - ib, m1, m2, site);
+  BT half_b = bten_step(bten_at_slice(second, ib), *m1, site_ref(rb * cols_ + cb, cfg_site_b), *m2, second);
+  // Contract(tmp2,{0,1,2}, tmp5,{2,1,0})  trace.h:202
+  const int da = half_a.d[0], db = half_a.d[1], dc = half_a.d[2];
+  std::vector<int32_t> ak((size_t)(da * db * dc)), bk(ak.size());
+  for (int a = 0; a < da; ++a)
+    for (int b = 0; b < db; ++b)
+      for (int c = 0; c < dc; ++c) {
+        size_t k = ((size_t)a * db + b) * dc + c;
+        ak[k] = (int32_t)k;
+        bk[k] = (int32_t)(((long)c * db + b) * da + a);
+      }
+  be_dot((int)ak.size(), planner_.upload(ak), planner_.upload(bk), mkop(half_a.p, half_a.n), mkop(half_b.p, half_b.n), psi_out, W_);
+  release(half_a);
+  release(half_b);
+}
+void Engine::punch_hole(int r, int c, int orient) {    // grow.h:150-183
+  const BT *up, *down, *left, *right;
+  if (orient == HORIZONTAL) {
+    up = &bmps_at_slice(UP, r).at((size_t)(cols_ - 1 - c));
+    down = &bmps_at_slice(DOWN, r).at((size_t)c);
+    left = &bten_[LEFT].at((size_t)c);
+    right = &bten_at_slice(RIGHT, c);
+  } else {
+    up = &bten_[UP].at((size_t)r);
+    down = &bten_at_slice(DOWN, r);
+    left = &bmps_at_slice(LEFT, c).at((size_t)r);
+    right = &bmps_at_slice(RIGHT, c).at((size_t)(rows_ - 1 - r));
+  }
+  BT tmp1 = einsum("xlz,zdb->xldb", ref(*left), ref(*down));
+  BT tmp2 = einsum("brz,zux->brux", ref(*right), ref(*up));
+  const int site = r * cols_ + c;
+  einsum_into("xldb,brux->ldru", ref(tmp1), ref(tmp2), mkop(holes_ + hole_off_h_[(size_t)site], hole_stride_));
+  release(tmp1);
+  release(tmp2);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// walker-level operations
+// ---------------------------------------------------------------------------------------------------
+void Engine::evaluate_amplitude() {                    // wave_function_component.h:187-212
+  grow_bmps_for_row(0);
+  grow_full_bten(RIGHT, 0, 2, true);
+  init_bten(LEFT);
+  nn_trace(0, 0, 0, 1, HORIZONTAL, 0, 1, amp_);
+}
+void Engine::init_walkers() {                          // wave_function_component.h:155-162
+  contractor_init();
+  evaluate_amplitude();
+}
+
+void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_updater.h:29-81
+  for (int sw = 0; sw < nsweeps; ++sw) {
+    be_memset0(accepted_, sizeof(int32_t) * W_);
+    generate_bmps_approach(UP);
+    for (int row = 0; row < rows_; ++row) {
+      init_bten(LEFT);
+      grow_full_bten(RIGHT, row, 2, true);
+      for (int col = 0; col < cols_ - 1; ++col) {
+        const int s1 = row * cols_ + col, s2 = s1 + 1;
+        nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);          // :164-166 (masked in the decide kernel)
+        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        if (col < cols_ - 2) shift_bten_window(RIGHT);
+      }
+      if (row < rows_ - 1) shift_bmps_window(DOWN);
+    }
+    delete_inner_bmps(LEFT);
+    delete_inner_bmps(RIGHT);
+    generate_bmps_approach(LEFT);
+    for (int col = 0; col < cols_; ++col) {
+      init_bten(UP);
+      grow_full_bten(DOWN, col, 2, true);
+      for (int row = 0; row < rows_ - 1; ++row) {
+        const int s1 = row * cols_ + col, s2 = s1 + cols_;
+        nn_trace(row, col, row + 1, col, VERTICAL, s2, s1, psi_tmp_);
+        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        if (row < rows_ - 2) shift_bten_window(DOWN);
+      }
+      if (col < cols_ - 1) shift_bmps_window(RIGHT);
+    }
+    delete_inner_bmps(UP);
+  }
+  if (accept_rate_host) {
+    std::vector<int32_t> acc((size_t)W_);
+    be_d2h(acc.data(), accepted_, sizeof(int32_t) * W_);
+    const double bond_num = (double)(cols_ * (rows_ - 1) + rows_ * (cols_ - 1));
+    for (int w = 0; w < W_; ++w) accept_rate_host[w] = (double)acc[(size_t)w] / bond_num;
+  }
+}
+
+void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  // square_nnn_energy_solver.h:79-315 with has_nnn = false, model = SquareSpinOneHalfXXZModelMixIn
+  be_memset0(eloc_, sizeof(double) * W_);
+  int npsi = 0;
+  auto record_psi = [&]() {
+    if (psi_list_host) be_d2h(psi_list_host + (size_t)npsi * W_, psi_row_, sizeof(double) * W_);
+    ++npsi;
+  };
+  generate_bmps_approach(UP);
+  for (int row = 0; row < rows_; ++row) {
+    init_bten(LEFT);
+    grow_full_bten(RIGHT, row, 1, true);
+    nn_trace(row, 0, row, 1, HORIZONTAL, row * cols_, row * cols_ + 1, psi_row_);
+    record_psi();
+    for (int col = 0; col < cols_; ++col) {
+      if (calc_holes) punch_hole(row, col, HORIZONTAL);
+      if (col < cols_ - 1) {
+        const int s1 = row * cols_ + col, s2 = s1 + 1;
+        nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);
+        be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, eloc_, W_);
+        shift_bten_window(RIGHT);
+      }
+    }
+    if (row < rows_ - 1) shift_bmps_window(DOWN);
+  }
+  generate_bmps_approach(LEFT);                        // bond_traversal_mixin.h:112-143
+  for (int col = 0; col < cols_; ++col) {
+    init_bten(UP);
+    grow_full_bten(DOWN, col, 2, true);
+    nn_trace(0, col, 1, col, VERTICAL, col, cols_ + col, psi_row_);
+    record_psi();
+    for (int row = 0; row < rows_ - 1; ++row) {
+      const int s1 = row * cols_ + col, s2 = s1 + cols_;
+      nn_trace(row, col, row + 1, col, VERTICAL, s2, s1, psi_tmp_);
+      be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, eloc_, W_);
+      if (row < rows_ - 2) shift_bten_window(DOWN);
+    }
+    if (col < cols_ - 1) shift_bmps_window(RIGHT);
+  }
+  be_xxz_onsite_energy(cfg_, nsites_, h00_, eloc_, W_);
+  if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
+}
+
+void Engine::zero_accumulators() {
+  be_memset0(osum_, sizeof(double) * tps_total_);
+  be_memset0(eosum_, sizeof(double) * tps_total_);
+}
+void Engine::accumulate_ostar() {                      // mc_energy_grad_evaluator.h:245-272
+  be_accumulate_ostar(holes_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, cfg_, nsites_, phys_, amp_, eloc_,
+                      osum_, eosum_, W_);
+}
+void Engine::get_accumulators(double *osum_host, double *eosum_host) {
+  if (osum_host) be_d2h(osum_host, osum_, sizeof(double) * tps_total_);
+  if (eosum_host) be_d2h(eosum_host, eosum_, sizeof(double) * tps_total_);
+}
+
+long Engine::bmps_tensor(int pos, int k, int i, double *out_host, int dims[3]) {
+  const BT &t = bmps_[pos].at((size_t)k).at((size_t)i);
+  for (int a = 0; a < 3; ++a) dims[a] = t.d[a];
+  if (out_host) be_d2h(out_host, t.p, sizeof(double) * (size_t)W_ * t.n);
+  return t.n;
+}
+void Engine::probe_trace_row(int row, double *psi_host) {
+  grow_bmps_for_row(row);
+  init_bten(LEFT);
+  grow_full_bten(RIGHT, row, 2, true);
+  nn_trace(row, 0, row, 1, HORIZONTAL, row * cols_, row * cols_ + 1, psi_tmp_);
+  be_d2h(psi_host, psi_tmp_, sizeof(double) * W_);
+}
+
+}  // namespace peps

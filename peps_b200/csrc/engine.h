@@ -1,0 +1,160 @@
+// Walker-batched boundary-MPS engine: every walker (Markov chain) runs the reference's contraction
+// sequence in lock step; walkers differ only in which physical slice of the shared SplitIndexTPS each site
+// operand gathers, in the Metropolis decisions and in the RNG stream. Host code drives the (walker-uniform)
+// control flow and launches one batched device op per reference tensor operation.
+//
+// Reference call graph mirrored here (include/qlpeps/...):
+//   BMPS::MultiplyMPOSVDCompress_            one_dim_tn/boundary_mps/bmps_impl.h:756-862      -> absorb()
+//   BMPSContractor grow/shift/delete          two_dim_tn/tensor_network_2d/bmps/impl/bmps_contractor_grow.h
+//   BMPSContractor traces / PunchHole         .../impl/bmps_contractor_trace.h:11-205, grow.h:150-183
+//   TPSWaveFunctionComponent::EvaluateAmplitude  vmc_basic/wave_function_component.h:187-212
+//   MCUpdateSquareNNExchangeOBC sweep         vmc_basic/configuration_update_strategies/square_nn_updater.h:29-188
+//   SquareNNNModelEnergySolver (NN) + XXZ     algorithm/vmc_update/model_solvers/base/square_nnn_energy_solver.h:79-315
+//   MCEnergyGradEvaluator accumulation        algorithm/vmc_update/mc_energy_grad_evaluator.h:205-282
+#pragma once
+#include <array>
+#include <memory>
+#include <string>
+#include <vector>
+#include "linalg.h"
+#include "tensor.h"
+
+namespace peps {
+
+enum Pos { LEFT = 0, DOWN = 1, RIGHT = 2, UP = 3 };
+enum Orient { HORIZONTAL = 0, VERTICAL = 1 };
+inline int opposite(int p) { return (p + 2) % 4; }
+
+struct TRef {           // operand view with dims
+  Operand op;
+  int rank = 0;
+  int d[6] = {1, 1, 1, 1, 1, 1};
+};
+
+struct EngineConfig {
+  int rows = 0, cols = 0, phys = 2, D = 0, walkers = 0, device = 0;
+  int dmin = 1, dmax = 1;
+  double trunc_err = 0.0;
+};
+
+class Engine {
+ public:
+  explicit Engine(const EngineConfig &c);
+  ~Engine();
+
+  // ---- state upload / download
+  size_t tps_size() const { return (size_t)tps_total_; }
+  long site_offset(int r, int c) const { return tps_off_h_[(size_t)(r * cols_ + c)]; }
+  void site_dims(int r, int c, int out[4]) const;
+  void set_tps(const double *host);
+  void get_tps(double *host);
+  void scale_tps(double f);
+  void set_configs(const int32_t *host);
+  void get_configs(int32_t *host);
+  void seed_rng(const uint32_t *seeds);
+  void set_rng_state(const uint32_t *mt, const int32_t *idx);
+  void get_rng_state(uint32_t *mt, int32_t *idx);
+  void get_amplitudes(double *host);
+  void set_truncation(int dmin, int dmax, double terr) { dmin_ = dmin; dmax_ = dmax; terr_ = terr; }
+  void set_jacobi(double tol, int inner, int max_sweeps) {
+    la_.jacobi_tol = tol; la_.jacobi_inner_sweeps = inner; la_.jacobi_max_sweeps = max_sweeps;
+  }
+
+  // ---- the hot path
+  void init_walkers();                                // contractor.Init + EvaluateAmplitude for all walkers
+  void evaluate_amplitude();
+  void sweep(int nsweeps, double *accept_rate_host);  // accept_rate_host[W] (last sweep), may be null
+  void energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host);
+  void zero_accumulators();
+  void accumulate_ostar();                            // uses holes/eloc/amplitude of the last energy_and_holes
+  void get_accumulators(double *osum_host, double *eosum_host);
+  double *osum_device() { return osum_; }
+  double *eosum_device() { return eosum_; }
+  void set_model_xxz(double jz, double jxy, double h00) { jz_ = jz; jxy_ = jxy; h00_ = h00; }
+
+  // ---- probes used by the parity tests (per-walker values of reference contractor calls)
+  int bmps_stack_size(int pos) const { return (int)bmps_[pos].size(); }
+  long bmps_tensor(int pos, int k, int i, double *out_host, int dims[3]);  // copy one BMPS tensor of all walkers
+  void probe_trace_row(int row, double *psi_host);                         // grows what is needed, Trace(tn,{row,0},HORIZONTAL)
+  void get_holes(double *host);
+  long holes_stride() const { return hole_stride_; }
+  int walkers() const { return W_; }
+  int rows() const { return rows_; }
+  int cols() const { return cols_; }
+  long stat(int which) const;
+  const char *backend() const { return be_name(); }
+
+  // ---- contractor API (walker-batched restatement of BMPSContractor)
+  void contractor_init();
+  void grow_bmps_step(int pos);
+  void grow_full_bmps(int pos);
+  void delete_inner_bmps(int pos);
+  void generate_bmps_approach(int post) { delete_inner_bmps(post); grow_full_bmps(opposite(post)); }
+  void grow_bmps_for_row(int row);
+  void grow_bmps_for_col(int col);
+  void shift_bmps_window(int pos);
+  void init_bten(int pos);
+  void grow_full_bten(int pos, int slice, int remain, bool init);
+  void grow_bten_step(int post);
+  void shift_bten_window(int pos);
+  // psi_out[w] = ReplaceNNSiteTrace(site_a, site_b, tensors sitps(site_a)[cfg(cfg_a)], sitps(site_b)[cfg(cfg_b)])
+  void nn_trace(int ra, int ca, int rb, int cb, int orient, int cfg_site_a, int cfg_site_b, double *psi_out);
+  void punch_hole(int r, int c, int orient);          // into the holes buffer
+
+ private:
+  using BMPSv = std::vector<BT>;
+  BT alloc(std::initializer_list<int> dims);
+  BT ones111();
+  void release(BT &t);
+  void release(BMPSv &v);
+  TRef ref(const BT &t) const;
+  TRef site_ref(int site, int cfg_site) const;
+  BT einsum(const std::string &spec, const TRef &a, const TRef &b);
+  void einsum_into(const std::string &spec, const TRef &a, const TRef &b, Operand c, const long *sc = nullptr,
+                   double alpha = 1.0, double beta = 0.0);
+  BMPSv absorb(const BMPSv &mps, const std::vector<int> &sites, int post);
+  BT bten_step(const BT &bten, const BT &mps1, const TRef &site, const BT &mps2, int post);
+  std::vector<int> slice_sites(int num, int orient) const;
+  const BMPSv &bmps_at_slice(int pos, int logical) const;
+  const BT &bten_at_slice(int pos, int logical) const;
+  void bten_operands(int post, int slice, int bten_size, const BT *&mps1, const BT *&mps2, int &site) const;
+  static std::string site_labels(int post, char pre, char toward, char next, char away);
+
+  int rows_, cols_, phys_, D_, W_, nsites_;
+  int dmin_, dmax_;
+  double terr_;
+  double jz_ = 1.0, jxy_ = 1.0, h00_ = 0.0;
+  Pool pool_;
+  Planner planner_;
+  LinalgCtx la_;
+
+  // TPS: per site, phys slices of (dl,dd,dr,du) row-major; site s slice p at tps_ + tps_off[s] + p*site_size[s]
+  double *tps_ = nullptr;
+  long tps_total_ = 0;
+  std::vector<long> tps_off_h_;
+  std::vector<int> site_size_h_;
+  std::vector<std::array<int, 4>> site_dims_h_;
+  int32_t *tps_off_d_ = nullptr, *site_size_d_ = nullptr, *hole_off_d_ = nullptr;
+
+  int32_t *cfg_ = nullptr;        // [W][nsites]
+  double *amp_ = nullptr;         // [W]
+  uint32_t *mt_ = nullptr;        // [W][624]
+  int32_t *mtidx_ = nullptr;      // [W]
+  int32_t *accepted_ = nullptr;   // [W]
+  double *eloc_ = nullptr;        // [W]
+  double *psi_tmp_ = nullptr;     // [W]
+  double *psi_row_ = nullptr;     // [W]
+  double *holes_ = nullptr;       // [W][hole_stride]
+  long hole_stride_ = 0;
+  std::vector<long> hole_off_h_;
+  double *osum_ = nullptr, *eosum_ = nullptr;   // [tps_total]
+  int32_t *kept_ = nullptr, *order_ = nullptr;  // truncation scratch
+  double *norms2_ = nullptr;
+  int scratch_rows_ = 0;
+
+  std::vector<BMPSv> bmps_[4];
+  std::vector<BT> bten_[4];
+  long n_absorb_ = 0, n_bten_ = 0, n_trace_ = 0;
+};
+
+}  // namespace peps

@@ -1,0 +1,202 @@
+// Walker-batched factorisations used by the boundary-MPS absorption:
+//   * caqr()          communication-avoiding R-only Householder QR (flat tree over row blocks, compact-WY
+//                     trailing updates as batched contractions on the DMMA pipe). Replaces the reference's
+//                     QR(tmp2, ldims, ...) in BMPS::MultiplyMPOSVDCompress_ (bmps_impl.h:817-821); Q is never
+//                     formed because the truncation sweep below only needs the R chain.
+//   * truncate_rows() one-sided block Jacobi on the rows of Theta followed by the TensorToolkit truncation
+//                     rule; returns the kept right singular vectors. Replaces SVD(...) in
+//                     BMPS::RightCanonicalizeTruncate (bmps_impl.h:225-263).
+// Backend-agnostic host code.
+#pragma once
+#include <algorithm>
+#include <vector>
+#include "tensor.h"
+
+namespace peps {
+
+struct LinalgCtx {
+  int W = 0;
+  Pool *pool = nullptr;
+  Planner *planner = nullptr;
+  double *offmax = nullptr;      // [W]
+  int32_t *done = nullptr;       // [W]
+  std::vector<int32_t> done_host;
+  // statistics
+  long jacobi_sweeps = 0, jacobi_calls = 0, qr_calls = 0;
+  double jacobi_tol = 1e-14;
+  int jacobi_inner_sweeps = 1;
+  int jacobi_max_sweeps = 40;
+};
+
+constexpr size_t kPanelSmemBudget = 150 * 1024;   // bytes for the panel itself
+constexpr size_t kJacobiSmemBudget = 200 * 1024;
+
+struct QRLayout { int nb = 0, rb = 0, nrb = 0, m_pad = 0; };
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+inline QRLayout qr_layout(int m, int n) {
+  QRLayout L;
+  const int kk = std::min(m, n);
+  for (int nb : {32, 16, 8}) {
+    int rbmax = (int)(kPanelSmemBudget / (sizeof(double) * nb)) / nb * nb;
+    int need = round_up(kk, nb);
+    if (need > rbmax && nb != 8) continue;
+    if (need > rbmax) throw std::runtime_error("qr_layout: matrix too large for the shared-memory panel");
+    int rb0 = std::min(rbmax, round_up(m, nb));
+    int nrb = (m + rb0 - 1) / rb0;
+    int rb = std::max(need, round_up((m + nrb - 1) / nrb, nb));
+    L.nb = nb; L.rb = rb; L.nrb = (m + rb - 1) / rb; L.m_pad = L.nrb * rb;
+    return L;
+  }
+  return L;
+}
+
+inline GettDesc make_desc(Planner &pl, const std::vector<int32_t> &am, const std::vector<int32_t> &ak,
+                          const std::vector<int32_t> &bk, const std::vector<int32_t> &bn,
+                          const std::vector<int32_t> &cm, const std::vector<int32_t> &cn, int a_kfast, int b_nfast) {
+  GettDesc d;
+  d.M = (int)am.size(); d.K = (int)ak.size(); d.N = (int)bn.size();
+  d.am = pl.upload(am); d.ak = pl.upload(ak); d.bk = pl.upload(bk); d.bn = pl.upload(bn);
+  d.cm = pl.upload(cm); d.cn = pl.upload(cn);
+  d.a_kfast = a_kfast; d.b_nfast = b_nfast;
+  return d;
+}
+
+inline std::vector<int32_t> iota_scaled(int n, int scale, int base = 0) {
+  std::vector<int32_t> v((size_t)n);
+  for (int i = 0; i < n; ++i) v[(size_t)i] = base + i * scale;
+  return v;
+}
+
+// In-place R-only QR of A[w] (m x n, row-major, leading dimension n, walker stride ws; the buffer holds
+// L.m_pad rows, rows >= m zero). On return rows [0, min(m,n)) hold R (upper trapezoidal), everything else
+// in the buffer is zero.
+inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout &L) {
+  const int W = cx.W, nb = L.nb, rb = L.rb, nrb = L.nrb, lda = n;
+  const int kk = std::min(m, n);
+  ++cx.qr_calls;
+  if (m <= 1) return;
+  Planner &pl = *cx.planner;
+  double *Vw = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * rb * nb);
+  double *VTw = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * rb * nb);
+  double *Wk = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * nb * n);
+  std::vector<int32_t> rowtab1((size_t)nrb * rb);
+  for (int b = 0; b < nrb; ++b)
+    for (int s = 0; s < rb; ++s) rowtab1[(size_t)b * rb + s] = b * rb + s;
+  const int32_t *rowtab1_d = pl.upload(rowtab1);
+  const int npanel = (kk + nb - 1) / nb;
+  for (int p = 0; p < npanel; ++p) {
+    const int col0 = p * nb, pw = std::min(nb, kk - col0), c1 = col0 + pw, ntrail = n - c1;
+    PanelArgs pa;
+    pa.A = A; pa.ws = ws; pa.lda = lda; pa.rowtab = rowtab1_d; pa.R = rb; pa.skip0 = col0; pa.NI = nrb;
+    pa.col0 = col0; pa.pw = pw; pa.nbw = nb; pa.Vw = Vw; pa.VTw = VTw; pa.W = W;
+    be_panel_qr(pa);
+    if (ntrail > 0) {
+      // Wk[b] = V[b]^T C[b];  C[b] -= VT[b] Wk[b]      (C[b] = rows of block b, columns [c1, n))
+      int dv[2] = {rb, nb}, dc[2] = {rb, ntrail}, dw[2] = {nb, ntrail};
+      long sc[2] = {lda, 1};
+      const Plan &g1 = pl.get("rc,rt->ct", dv, 2, dc, 2, nullptr, sc, nullptr);
+      be_gett(g1.d, mkop(Vw, (long)nrb * rb * nb, (long)rb * nb), mkop(A + c1, ws, (long)rb * lda),
+              mkop(Wk, (long)nrb * nb * ntrail, (long)nb * ntrail), 1.0, 0.0, W, nrb);
+      const Plan &g2 = pl.get("rc,ct->rt", dv, 2, dw, 2, nullptr, nullptr, sc);
+      be_gett(g2.d, mkop(VTw, (long)nrb * rb * nb, (long)rb * nb), mkop(Wk, (long)nrb * nb * ntrail, (long)nb * ntrail),
+              mkop(A + c1, ws, (long)rb * lda), -1.0, 1.0, W, nrb);
+    }
+    if (nrb > 1) {
+      // stage 2: stack the nrb local R blocks and factorise them; update the same rows of the trailing matrix
+      const int R2 = nrb * pw;
+      std::vector<int32_t> rowtab2((size_t)R2);
+      for (int b = 0; b < nrb; ++b)
+        for (int i = 0; i < pw; ++i) rowtab2[(size_t)b * pw + i] = b * rb + (b == 0 ? col0 : 0) + i;
+      PanelArgs p2 = pa;
+      p2.rowtab = pl.upload(rowtab2); p2.R = R2; p2.skip0 = 0; p2.NI = 1;
+      be_panel_qr(p2);
+      if (ntrail > 0) {
+        std::vector<int32_t> rows_lda((size_t)R2);
+        for (int i = 0; i < R2; ++i) rows_lda[(size_t)i] = rowtab2[(size_t)i] * lda;
+        // W2 = V2^T Cg : M = nb (c), K = R2 (r), N = ntrail (t)
+        GettDesc g3 = make_desc(pl, iota_scaled(nb, 1), iota_scaled(R2, nb), rows_lda, iota_scaled(ntrail, 1),
+                                iota_scaled(nb, ntrail), iota_scaled(ntrail, 1), 0, 1);
+        be_gett(g3, mkop(Vw, (long)R2 * nb), mkop(A + c1, ws), mkop(Wk, (long)nb * ntrail), 1.0, 0.0, W, 1);
+        // Cg -= VT2 W2 : M = R2 (r), K = nb (c), N = ntrail (t)
+        GettDesc g4 = make_desc(pl, iota_scaled(R2, nb), iota_scaled(nb, 1), iota_scaled(nb, ntrail),
+                                iota_scaled(ntrail, 1), rows_lda, iota_scaled(ntrail, 1), 1, 1);
+        be_gett(g4, mkop(VTw, (long)R2 * nb), mkop(Wk, (long)nb * ntrail), mkop(A + c1, ws), -1.0, 1.0, W, 1);
+      }
+    }
+  }
+  cx.pool->put(Vw);
+  cx.pool->put(VTw);
+  cx.pool->put(Wk);
+}
+
+struct JacobiLayout { int bs = 0, nblk = 0, nr_pad = 0; };
+
+inline JacobiLayout jacobi_layout(int nr, int nc) {
+  JacobiLayout J;
+  int ncp = round_up(nc, 8);
+  for (int bs : {16, 8, 4}) {
+    size_t bytes = (size_t)2 * bs * (ncp + 4) * sizeof(double);
+    if (bytes > kJacobiSmemBudget && bs != 4) continue;
+    if (bytes > kJacobiSmemBudget) throw std::runtime_error("jacobi_layout: rows too long for the shared-memory panel");
+    if (bs > 4 && nr <= bs) continue;            // prefer one pair covering everything for tiny problems
+    J.bs = bs;
+    break;
+  }
+  int nblk = (nr + J.bs - 1) / J.bs;
+  if (nblk < 2) nblk = 2;
+  if (nblk & 1) ++nblk;
+  J.nblk = nblk; J.nr_pad = nblk * J.bs;
+  return J;
+}
+
+// Rows the Theta buffer must provide for truncate_rows(nr, nc).
+inline int truncate_buffer_rows(int nr, int nc) {
+  int rows = nr;
+  int nr_eff = nr;
+  if (nr > nc) { rows = std::max(rows, qr_layout(nr, nc).m_pad); nr_eff = nc; }
+  rows = std::max(rows, jacobi_layout(nr_eff, nc).nr_pad);
+  return rows;
+}
+
+// Theta[w]: nr x nc (leading dimension nc) inside a zero-padded buffer of truncate_buffer_rows(nr,nc) rows.
+// Writes B[w] (tcap x nc): the kept right singular vectors (rows), zero rows beyond kept[w].
+inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int dmin, int dmax, double trunc_err,
+                          int tcap, double *B, long wb, int32_t *kept, double *norms2_scratch, int32_t *order_scratch) {
+  const int W = cx.W;
+  const int nsv = std::min(nr, nc);
+  int nr_eff = nr;
+  if (nr > nc) {
+    caqr(cx, G, ws, nr, nc, qr_layout(nr, nc));
+    nr_eff = nc;
+  }
+  if (nr_eff > 1) {
+    JacobiLayout J = jacobi_layout(nr_eff, nc);
+    ++cx.jacobi_calls;
+    be_fill(cx.offmax, 0.0, W);
+    be_memset0(cx.done, sizeof(int32_t) * W);
+    JacobiArgs ja;
+    ja.G = G; ja.ws = ws; ja.ld = nc; ja.nr_pad = J.nr_pad; ja.nc = nc; ja.bs = J.bs; ja.nblk = J.nblk;
+    ja.tol = cx.jacobi_tol; ja.inner_sweeps = cx.jacobi_inner_sweeps; ja.offmax = cx.offmax; ja.done = cx.done; ja.W = W;
+    for (int sweep = 0; sweep < cx.jacobi_max_sweeps; ++sweep) {
+      for (int round = 0; round < J.nblk - 1; ++round) {
+        ja.round = round;
+        be_jacobi_round(ja);
+      }
+      ++cx.jacobi_sweeps;
+      be_jacobi_flags(cx.offmax, cx.done, cx.jacobi_tol, W);
+      cx.done_host.resize((size_t)W);
+      be_d2h(cx.done_host.data(), cx.done, sizeof(int32_t) * W);
+      bool all = true;
+      for (int w = 0; w < W; ++w) all = all && cx.done_host[(size_t)w];
+      if (all) break;
+    }
+  }
+  const int nr_sel = std::max(nr_eff, 1);
+  be_row_norms2(G, ws, nc, nr_sel, nc, norms2_scratch, W);
+  be_select_truncate(norms2_scratch, nr_sel, nsv, dmin, dmax, trunc_err, tcap, order_scratch, kept, W);
+  be_gather_rows_normalized(G, ws, nc, nc, norms2_scratch, nr_sel, order_scratch, kept, tcap, B, wb, W);
+}
+
+}  // namespace peps

@@ -1,0 +1,367 @@
+// TEST-ONLY host simulation of peps_b200/csrc/backend.h.
+//
+// This file is never linked into the product library (libpeps_b200.so has no CPU path and throws when no
+// CUDA device is present). It exists so that `-m "not gpu"` tests can exercise the HOST orchestration
+// (engine.cpp: stack discipline, contraction sequences, sweep/energy control flow, the C ABI) in the build
+// container, which has no GPU. Every op is the plain-loop statement of the semantics documented in
+// backend.h; the GPU parity tests compare the CUDA kernels against the oracle, not against this file.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../../peps_b200/csrc/backend.h"
+
+namespace peps {
+
+static long g_launches = 0;
+void be_init(int) {}
+const char *be_name() { return "hostsim"; }
+void *be_malloc(size_t bytes) { return std::malloc(bytes ? bytes : 8); }
+void be_free(void *p) { std::free(p); }
+void be_memset0(void *p, size_t bytes) { std::memset(p, 0, bytes); }
+void be_h2d(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+void be_d2h(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+void be_d2d(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
+void be_sync() {}
+void *be_stream() { return nullptr; }
+long be_launch_count() { return g_launches; }
+
+static const double *obase(const Operand &o, int w, int b) {
+  const double *p = o.p + (long)w * o.ws + (long)b * o.bs;
+  if (o.gidx) p += (long)o.gidx[(long)w * o.gws] * o.gs;
+  return p;
+}
+
+void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, double beta, int W, int NB) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int b = 0; b < NB; ++b) {
+      const double *Ab = obase(A, w, b), *Bb = obase(B, w, b);
+      double *Cb = const_cast<double *>(obase(C, w, b));
+      std::vector<double> out((size_t)d.M * d.N);
+      for (int m = 0; m < d.M; ++m)
+        for (int n = 0; n < d.N; ++n) {
+          double s = 0.0;
+          for (int k = 0; k < d.K; ++k) s += Ab[d.am[m] + d.ak[k]] * Bb[d.bk[k] + d.bn[n]];
+          out[(size_t)m * d.N + n] = s;
+        }
+      for (int m = 0; m < d.M; ++m)
+        for (int n = 0; n < d.N; ++n) {
+          double *cp = Cb + d.cm[m] + d.cn[n];
+          double v = alpha * out[(size_t)m * d.N + n];
+          if (beta != 0.0) v += beta * (*cp);
+          *cp = v;
+        }
+    }
+}
+
+void be_dot(int K, const int32_t *ak, const int32_t *bk, Operand A, Operand B, double *out, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const double *Ab = obase(A, w, 0), *Bb = obase(B, w, 0);
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += Ab[ak[k]] * Bb[bk[k]];
+    out[w] = s;
+  }
+}
+
+void be_fill(double *p, double v, long n) { ++g_launches; for (long i = 0; i < n; ++i) p[i] = v; }
+void be_copy2d(double *dst, long wd, long ldd, const double *src, long ws, long lds, int rows, int cols, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) dst[w * wd + r * ldd + c] = src[w * ws + r * lds + c];
+}
+void be_set_identity(double *dst, long wd, int rows, int cols, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) dst[w * wd + (long)r * cols + c] = (r == c) ? 1.0 : 0.0;
+}
+
+void be_panel_qr(const PanelArgs &a) {
+  ++g_launches;
+  const int R = a.R, pw = a.pw, nbw = a.nbw;
+  for (int w = 0; w < a.W; ++w)
+    for (int it = 0; it < a.NI; ++it) {
+      const int skip = (it == 0) ? a.skip0 : 0, nact = R - skip;
+      double *Aw = a.A + (long)w * a.ws;
+      const int32_t *rows = a.rowtab + (long)it * R;
+      std::vector<double> P((size_t)nact * pw), tau((size_t)pw, 0.0), V((size_t)nact * pw, 0.0), T((size_t)pw * pw, 0.0);
+      auto at = [&](int r, int c) -> double & { return P[(size_t)r * pw + c]; };
+      for (int r = 0; r < nact; ++r)
+        for (int c = 0; c < pw; ++c) at(r, c) = Aw[(long)rows[skip + r] * a.lda + a.col0 + c];
+      for (int j = 0; j < pw; ++j) {
+        if (j >= nact) continue;
+        double xn2 = 0.0;
+        for (int r = j + 1; r < nact; ++r) xn2 += at(r, j) * at(r, j);
+        double alpha = at(j, j), beta = alpha, tj = 0.0, sj = 0.0;
+        if (xn2 > 0.0) {
+          double nrm = std::sqrt(alpha * alpha + xn2);
+          beta = (alpha >= 0.0) ? -nrm : nrm;
+          tj = (beta - alpha) / beta;
+          sj = 1.0 / (alpha - beta);
+        }
+        tau[(size_t)j] = tj;
+        V[(size_t)j * pw + j] = 1.0;
+        for (int r = j + 1; r < nact; ++r) V[(size_t)r * pw + j] = at(r, j) * sj;
+        if (tj != 0.0)
+          for (int c = j + 1; c < pw; ++c) {
+            double wv = at(j, c);
+            for (int r = j + 1; r < nact; ++r) wv += V[(size_t)r * pw + j] * at(r, c);
+            double f = tj * wv;
+            at(j, c) -= f;
+            for (int r = j + 1; r < nact; ++r) at(r, c) -= f * V[(size_t)r * pw + j];
+          }
+        at(j, j) = beta;
+        for (int r = j + 1; r < nact; ++r) at(r, j) = 0.0;
+      }
+      for (int j = 0; j < pw; ++j) {
+        T[(size_t)j * pw + j] = tau[(size_t)j];
+        std::vector<double> s((size_t)j, 0.0);
+        for (int b2 = 0; b2 < j; ++b2)
+          for (int r = 0; r < nact; ++r) s[(size_t)b2] += V[(size_t)r * pw + b2] * V[(size_t)r * pw + j];
+        for (int a2 = 0; a2 < j; ++a2) {
+          double v = 0.0;
+          for (int b2 = a2; b2 < j; ++b2) v += T[(size_t)a2 * pw + b2] * s[(size_t)b2];
+          T[(size_t)a2 * pw + j] = -tau[(size_t)j] * v;
+        }
+      }
+      for (int r = 0; r < nact; ++r)
+        for (int c = 0; c < pw; ++c) Aw[(long)rows[skip + r] * a.lda + a.col0 + c] = (r <= c) ? at(r, c) : 0.0;
+      double *Vo = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
+      double *VTo = a.VTw + ((long)w * a.NI + it) * (long)R * nbw;
+      for (long e = 0; e < (long)R * nbw; ++e) { Vo[e] = 0.0; VTo[e] = 0.0; }
+      for (int r = 0; r < nact; ++r)
+        for (int c = 0; c < pw; ++c) {
+          Vo[(long)(skip + r) * nbw + c] = V[(size_t)r * pw + c];
+          double acc = 0.0;
+          for (int b2 = c; b2 < pw; ++b2) acc += V[(size_t)r * pw + b2] * T[(size_t)c * pw + b2];
+          VTo[(long)(skip + r) * nbw + c] = acc;
+        }
+    }
+}
+
+static void rr_pair(int nblk, int round, int q, int &I, int &J) {
+  const int n1 = nblk - 1;
+  if (q == 0) { I = n1; J = round % n1; }
+  else { I = (round + q) % n1; J = (round - q + n1) % n1; }
+}
+
+void be_jacobi_round(const JacobiArgs &a) {
+  ++g_launches;
+  const int bs = a.bs, n2 = 2 * bs, nc = a.nc;
+  for (int w = 0; w < a.W; ++w) {
+    if (a.done[w]) continue;
+    double *Gw = a.G + (long)w * a.ws;
+    for (int q = 0; q < a.nblk / 2; ++q) {
+      int I, J;
+      rr_pair(a.nblk, a.round, q, I, J);
+      int lo = std::min(I, J), hi = std::max(I, J);
+      auto grow = [&](int r) { return (r < bs) ? lo * bs + r : hi * bs + (r - bs); };
+      std::vector<double> Ps((size_t)n2 * nc), G((size_t)n2 * n2), Wm((size_t)n2 * n2, 0.0);
+      for (int r = 0; r < n2; ++r)
+        for (int c = 0; c < nc; ++c) Ps[(size_t)r * nc + c] = Gw[(long)grow(r) * a.ld + c];
+      for (int p = 0; p < n2; ++p)
+        for (int qq = 0; qq < n2; ++qq) {
+          double s = 0.0;
+          for (int c = 0; c < nc; ++c) s += Ps[(size_t)p * nc + c] * Ps[(size_t)qq * nc + c];
+          G[(size_t)p * n2 + qq] = s;
+        }
+      for (int r = 0; r < n2; ++r) Wm[(size_t)r * n2 + r] = 1.0;
+      double mx = 0.0;
+      for (int p = 0; p < n2; ++p)
+        for (int qq = p + 1; qq < n2; ++qq) {
+          double gpp = G[(size_t)p * n2 + p], gqq = G[(size_t)qq * n2 + qq], gpq = std::fabs(G[(size_t)p * n2 + qq]);
+          if (gpp > 0.0 && gqq > 0.0 && gpq > 0.0) mx = std::max(mx, gpq / std::sqrt(gpp * gqq));
+        }
+      a.offmax[w] = std::max(a.offmax[w], mx);
+      for (int sw = 0; sw < a.inner_sweeps; ++sw)
+        for (int rd = 0; rd < n2 - 1; ++rd) {
+          std::vector<double> cs((size_t)n2);
+          std::vector<int> pr((size_t)n2);
+          for (int t = 0; t < n2 / 2; ++t) {
+            int p, qq;
+            rr_pair(n2, rd, t, p, qq);
+            if (p > qq) std::swap(p, qq);
+            double app = G[(size_t)p * n2 + p], aqq = G[(size_t)qq * n2 + qq], apq = G[(size_t)p * n2 + qq];
+            double c = 1.0, s = 0.0;
+            if (std::fabs(apq) > a.tol * std::sqrt(std::fabs(app * aqq)) && apq != 0.0) {
+              double zeta = (aqq - app) / (2.0 * apq);
+              double tt = ((zeta >= 0.0) ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+              c = 1.0 / std::sqrt(1.0 + tt * tt);
+              s = c * tt;
+            }
+            cs[(size_t)t] = c; cs[(size_t)(n2 / 2 + t)] = s;
+            pr[(size_t)(2 * t)] = p; pr[(size_t)(2 * t + 1)] = qq;
+          }
+          for (int k = 0; k < n2 / 2; ++k) {
+            int p = pr[(size_t)(2 * k)], qq = pr[(size_t)(2 * k + 1)];
+            double c = cs[(size_t)k], s = cs[(size_t)(n2 / 2 + k)];
+            for (int i = 0; i < n2; ++i) {
+              double gp = G[(size_t)i * n2 + p], gq = G[(size_t)i * n2 + qq];
+              G[(size_t)i * n2 + p] = c * gp - s * gq;
+              G[(size_t)i * n2 + qq] = s * gp + c * gq;
+              double wp = Wm[(size_t)i * n2 + p], wq = Wm[(size_t)i * n2 + qq];
+              Wm[(size_t)i * n2 + p] = c * wp - s * wq;
+              Wm[(size_t)i * n2 + qq] = s * wp + c * wq;
+            }
+          }
+          for (int k = 0; k < n2 / 2; ++k) {
+            int p = pr[(size_t)(2 * k)], qq = pr[(size_t)(2 * k + 1)];
+            double c = cs[(size_t)k], s = cs[(size_t)(n2 / 2 + k)];
+            for (int i = 0; i < n2; ++i) {
+              double gp = G[(size_t)p * n2 + i], gq = G[(size_t)qq * n2 + i];
+              G[(size_t)p * n2 + i] = c * gp - s * gq;
+              G[(size_t)qq * n2 + i] = s * gp + c * gq;
+            }
+          }
+        }
+      std::vector<int> perm((size_t)n2);
+      for (int t = 0; t < n2; ++t) {
+        double mine = G[(size_t)t * n2 + t];
+        int rank = 0;
+        for (int j = 0; j < n2; ++j) {
+          double o = G[(size_t)j * n2 + j];
+          rank += (o > mine) || (o == mine && j < t);
+        }
+        perm[(size_t)rank] = t;
+      }
+      for (int r = 0; r < n2; ++r)
+        for (int c = 0; c < nc; ++c) {
+          double s = 0.0;
+          for (int k = 0; k < n2; ++k) s += Wm[(size_t)k * n2 + perm[(size_t)r]] * Ps[(size_t)k * nc + c];
+          Gw[(long)grow(r) * a.ld + c] = s;
+        }
+    }
+  }
+}
+void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) { done[w] = offmax[w] <= tol; offmax[w] = 0.0; }
+}
+void be_row_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int r = 0; r < nr; ++r) {
+      double s = 0.0;
+      for (int c = 0; c < nc; ++c) s += G[w * ws + (long)r * ld + c] * G[w * ws + (long)r * ld + c];
+      norms2[(long)w * nr + r] = s;
+    }
+}
+void be_select_truncate(const double *norms2, int nr, int nsv, int dmin, int dmax, double trunc_err, int tcap,
+                        int32_t *order, int32_t *kept, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const double *x = norms2 + (long)w * nr;
+    std::vector<double> srt((size_t)nr);
+    for (int r = 0; r < nr; ++r) {
+      int rank = 0;
+      for (int j = 0; j < nr; ++j) rank += (x[j] > x[r]) || (x[j] == x[r] && j < r);
+      srt[(size_t)rank] = x[r];
+      if (rank < tcap) order[(long)w * tcap + rank] = r;
+    }
+    int n = nsv, k = n;
+    if (n > dmin) {
+      double total = 0.0;
+      for (int i = 0; i < n; ++i) total += srt[(size_t)i];
+      double kept_sum = total;
+      while (k > dmin) {
+        double sv2 = srt[(size_t)(k - 1)];
+        if (k <= dmax && total > 0.0 && (1.0 - (kept_sum - sv2) / total) > trunc_err) break;
+        kept_sum -= sv2;
+        --k;
+      }
+    }
+    kept[w] = std::min(k, tcap);
+  }
+}
+void be_gather_rows_normalized(const double *G, long ws, int ld, int nc, const double *norms2, int nr,
+                               const int32_t *order, const int32_t *kept, int tcap, double *B, long wb, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int t = 0; t < tcap; ++t) {
+      double *out = B + (long)w * wb + (long)t * nc;
+      if (t >= kept[w]) { for (int c = 0; c < nc; ++c) out[c] = 0.0; continue; }
+      int src = order[(long)w * tcap + t];
+      double n2 = norms2[(long)w * nr + src];
+      double inv = n2 > 0.0 ? 1.0 / std::sqrt(n2) : 0.0;
+      for (int c = 0; c < nc; ++c) out[c] = G[w * ws + (long)src * ld + c] * inv;
+    }
+}
+
+void be_mt_seed(uint32_t *mt, int32_t *idx, const uint32_t *seeds, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    uint32_t *s = mt + (long)w * 624;
+    s[0] = seeds[w];
+    for (int i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i;
+    idx[w] = 624;
+  }
+}
+static uint32_t mt_next(uint32_t *s, int32_t &i) {
+  if (i >= 624) {
+    for (int k = 0; k < 624; ++k) {
+      uint32_t y = (s[k] & 0x80000000u) | (s[(k + 1) % 624] & 0x7fffffffu);
+      s[k] = s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    i = 0;
+  }
+  uint32_t y = s[i++];
+  y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+  return y;
+}
+void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b, double *amp,
+                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    int32_t *c = cfg + (long)w * nsites;
+    int c1 = c[s1], c2 = c[s2];
+    if (c1 == c2) continue;
+    double pb = psi_b[w], pa = amp[w];
+    bool ok;
+    if (std::fabs(pb) >= std::fabs(pa)) ok = true;
+    else {
+      double div = std::fabs(pb) / std::fabs(pa), P = div * div;
+      uint32_t x0 = mt_next(mt + (long)w * 624, idx[w]);
+      uint32_t x1 = mt_next(mt + (long)w * 624, idx[w]);
+      double r = ((double)x0 + (double)x1 * 4294967296.0) / 18446744073709551616.0;
+      if (r >= 1.0) r = std::nextafter(1.0, 0.0);
+      ok = r < P;
+    }
+    if (ok) { c[s1] = c2; c[s2] = c1; amp[w] = pb; accepted[w] += 1; }
+  }
+}
+void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const double *psi_ex, const double *psi,
+                        double jz, double jxy, double *eloc, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const int32_t *c = cfg + (long)w * nsites;
+    double e;
+    if (c[s1] == c[s2]) e = 0.25 * jz;
+    else { double inv = 1.0 / psi[w]; e = -0.25 * jz + (psi_ex[w] * inv) * 0.5 * jxy; }
+    eloc[w] += e;
+  }
+}
+void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *eloc, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) eloc[w] += -h00 * ((double)cfg[(long)w * nsites] - 0.5);
+}
+void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                         const int32_t *tps_off, const int32_t *cfg, int nsites, int phys, const double *amp,
+                         const double *eloc, double *osum, double *eosum, int W) {
+  ++g_launches;
+  (void)phys;
+  for (int site = 0; site < nsites; ++site)
+    for (int e = 0; e < site_size[site]; ++e)
+      for (int w = 0; w < W; ++w) {
+        int s = cfg[(long)w * nsites + site];
+        double o = (1.0 / amp[w]) * holes[(long)w * hole_stride + hole_off[site] + e];
+        long slot = tps_off[site] + (long)s * site_size[site] + e;
+        osum[slot] += o;
+        eosum[slot] += eloc[w] * o;
+      }
+}
+
+}  // namespace peps

@@ -1,0 +1,98 @@
+"""Parity checks shared by the hostsim (CPU, host-logic) tests and the GPU tests: the same scenario is run through
+the C ABI (``lib`` decides which build) and through the oracle, and compared."""
+import numpy as np
+
+from oracle import vmc
+from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+
+
+def make_case(rows, cols, D, W, seed=1, signed=False):
+    tps = vmc.random_tps(rows, cols, 2, D, seed=seed, signed=signed)
+    cfgs = np.stack([vmc.neel_config(rows, cols)] +
+                    [vmc.shuffled_half_filled_config(rows, cols, 10 + w) for w in range(1, W)])
+    return tps, cfgs
+
+
+def flat_holes(holes, rows, cols):
+    return np.concatenate([holes[r][c].ravel() for r in range(rows) for c in range(cols)])
+
+
+def run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=1, signed=False, tol=1e-10, seeds0=100,
+                        check_configs=True):
+    """Sweeps + energy + holes for W walkers through the C ABI vs the oracle, walker by walker."""
+    tps, cfgs = make_case(rows, cols, D, W, seed, signed)
+    tr = BMPSTruncateParams.SVD(*trunc)
+    b = WalkerBatch(rows, cols, 2, D, W, tr, lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.seed_rng(np.arange(seeds0, seeds0 + W))
+    b.init_walkers()
+    ws = [vmc.Walker(tps, cfgs[w], trunc) for w in range(W)]
+    ups = [vmc.NNExchangeUpdater(seeds0 + w) for w in range(W)]
+    model = vmc.XXZModel(1.0, 1.0, 0.0)
+    amp0 = b.amplitudes()
+    ref0 = np.array([w_.amplitude for w_ in ws])
+    report = {"amp0": float(np.max(np.abs(amp0 / ref0 - 1)))}
+    assert report["amp0"] < tol, report
+    worst = dict(amp=0.0, eloc=0.0, hole=0.0, psi=0.0)
+    for it in range(nsweeps):
+        acc = b.sweep(1)
+        racc = np.array([ups[w].sweep(tps, ws[w])[0] for w in range(W)])
+        c = b.get_configs()
+        if check_configs:
+            for w in range(W):
+                assert np.array_equal(c[w], ws[w].config), f"sweep {it}: configuration of walker {w} diverged"
+            assert np.array_equal(acc, racc)
+        amp = b.amplitudes()
+        ramp = np.array([w_.amplitude for w_ in ws])
+        e, psi = b.energy_and_holes(True, True)
+        holes = b.holes()
+        for w in range(W):
+            ee, hh, pp = model.energy_and_holes(tps, ws[w], True)
+            fh = flat_holes(hh, rows, cols)
+            worst["eloc"] = max(worst["eloc"], abs(e[w] - ee) / max(1.0, abs(ee)))
+            worst["hole"] = max(worst["hole"], float(np.max(np.abs(holes[w] - fh)) / np.max(np.abs(fh))))
+            worst["psi"] = max(worst["psi"], float(np.max(np.abs(psi[:, w] / np.array(pp) - 1))))
+        worst["amp"] = max(worst["amp"], float(np.max(np.abs(amp / ramp - 1))))
+    report.update(worst)
+    for k, v in worst.items():
+        assert v < tol, (k, report)
+    b.close()
+    return report
+
+
+def run_gradient_parity(lib, rows, cols, D, W, trunc, nsamples=3, seed=2, tol=1e-10):
+    """peps_sample x nsamples + accumulators vs the oracle's EnergyGradEvaluator (walker == rank)."""
+    tps, cfgs = make_case(rows, cols, D, W, seed)
+    tr = BMPSTruncateParams.SVD(*trunc)
+    b = WalkerBatch(rows, cols, 2, D, W, tr, lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.seed_rng(np.arange(500, 500 + W))
+    b.init_walkers()
+    b.zero_accumulators()
+    energies = np.zeros((W, nsamples))
+    for s in range(nsamples):
+        e, _ = b.sample(1)
+        energies[:, s] = e
+    osum, eosum = b.accumulators()
+    ev = vmc.EnergyGradEvaluator(tps, vmc.XXZModel(), trunc, 1)
+    rr = []
+    for w in range(W):
+        rr.append(ev.sample_rank(vmc.Walker(tps, cfgs[w], trunc), vmc.NNExchangeUpdater(500 + w), nsamples))
+    ref_e = np.array([r["energies"] for r in rr])
+    assert np.max(np.abs(energies - ref_e) / np.maximum(1, np.abs(ref_e))) < tol
+    like = SplitIndexTPS(tps)
+    ref_o = sum((SplitIndexTPS(r["ostar_sum"]) for r in rr[1:]), SplitIndexTPS(rr[0]["ostar_sum"])).pack()
+    ref_eo = sum((SplitIndexTPS(r["eloc_ostar_sum"]) for r in rr[1:]), SplitIndexTPS(rr[0]["eloc_ostar_sum"])).pack()
+    assert np.max(np.abs(osum - ref_o)) < tol * np.max(np.abs(ref_o))
+    assert np.max(np.abs(eosum - ref_eo)) < tol * np.max(np.abs(ref_eo))
+    energy, err, grad = ev.combine(rr)
+    from peps_b200.api import combine_energy_bins
+    e2, err2 = combine_energy_bins(energies)
+    assert abs(e2 - energy) < 1e-12 * max(1, abs(energy))
+    g2 = (eosum - e2 * osum) / (nsamples * W)
+    gref = SplitIndexTPS(grad).pack()
+    assert np.max(np.abs(g2 - gref)) < tol * max(np.max(np.abs(gref)), 1e-300)
+    b.close()
+    return dict(energy=energy, gnorm=float(np.sum(gref ** 2)))

@@ -1,0 +1,106 @@
+"""CPU tests of the HOST logic (engine.cpp orchestration, C ABI, Python mirror) using the test-only host simulation
+of the device ops. The CUDA kernels themselves are checked on the GPU box by tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import hostsim_lib
+from parity_common import run_pipeline_parity, run_gradient_parity
+from peps_b200 import _lib
+from peps_b200.api import (BMPSTruncateParams, SplitIndexTPS, WalkerBatch, MCEnergyGradEvaluator, MonteCarloParams,
+                           Configuration, SquareSpinOneHalfXXZModelOBC, MCUpdateSquareNNExchange, PepsError)
+from oracle import vmc
+from helpers import load_golden_tps, exact_summation
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return hostsim_lib.load()
+
+
+def test_backend_is_hostsim(lib):
+    assert lib.peps_backend_name() == b"hostsim"
+
+
+@pytest.mark.parametrize("rows,cols,D,trunc", [
+    (4, 4, 3, (6, 6, 0.0)),          # fixed-shape truncation (the bench setting Dmin = Dmax = chi)
+    (3, 5, 2, (4, 4, 0.0)),          # ragged lattice
+    (4, 4, 3, (2, 7, 1e-6)),         # walker-dependent kept dimension (Dmin < Dmax, trunc_err > 0)
+    (2, 2, 4, (1, 100, 0.0)),        # smallest lattice, no truncation
+])
+def test_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
+    run_pipeline_parity(lib, rows, cols, D, 3, trunc, nsweeps=2)
+
+
+def test_pipeline_parity_signed_tps(lib):
+    run_pipeline_parity(lib, 4, 4, 3, 2, (9, 9, 0.0), nsweeps=2, signed=True, seed=5)
+
+
+def test_gradient_accumulation_parity_hostsim(lib):
+    run_gradient_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsamples=4)
+
+
+def test_golden_2x2_energy_through_abi(lib):
+    """K4 through the C ABI: exact summation over the six Sz=0 configurations of the 2x2 simple-update fixture."""
+    tps, z = load_golden_tps("heis2x2_double_su")
+    import itertools
+    cfgs = np.array([np.array(b).reshape(2, 2) for b in itertools.product([0, 1], repeat=4) if sum(b) == 2])
+    b = WalkerBatch(2, 2, 2, 4, len(cfgs), BMPSTruncateParams.SVD(1, 100, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    amp = b.amplitudes()
+    e = b.energy_and_holes(True)
+    energy = float(np.sum(amp ** 2 * e) / np.sum(amp ** 2))
+    assert abs(energy - float(z["exp_energy"])) < 1e-10
+    # gradient through the accumulators equals the oracle's exact-summation gradient
+    holes = b.holes()
+    e_ref, g_ref = exact_summation(tps, vmc.XXZModel())
+    wsum = np.sum(amp ** 2)
+    s_o = np.zeros(b.tps_size)
+    s_eo = np.zeros(b.tps_size)
+    site_size = 16
+    for w in range(len(cfgs)):
+        for s in range(4):
+            slot = s * 2 * site_size + int(cfgs[w].ravel()[s]) * site_size
+            inc = amp[w] * holes[w, s * site_size:(s + 1) * site_size]
+            s_o[slot:slot + site_size] += inc
+            s_eo[slot:slot + site_size] += e[w] * inc
+    grad = (s_eo - energy * s_o) / wsum
+    assert np.max(np.abs(grad - SplitIndexTPS(g_ref).pack())) < 1e-12
+
+
+def test_evaluator_mirror_runs(lib):
+    tps = SplitIndexTPS(vmc.random_tps(3, 3, 2, 2, seed=4))
+    mc = MonteCarloParams(num_samples=12, num_warmup_sweeps=2, sweeps_between_samples=1,
+                          initial_config=Configuration(vmc.neel_config(3, 3)))
+    ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(4, 4, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                               MCUpdateSquareNNExchange(7), walkers=4, lib=lib)
+    ev.WarmUp()
+    assert np.isclose(np.max(np.abs(ev.batch.amplitudes())), 1.0, rtol=0.3)
+    res = ev.Evaluate()
+    assert res.energy_samples.shape == (4, 3)
+    assert np.isfinite(res.energy) and np.isfinite(res.gradient_norm)
+    assert res.gradient.pack().shape == tps.pack().shape
+
+
+def test_error_paths(lib):
+    with pytest.raises(PepsError):
+        WalkerBatch(1, 4, 2, 2, 1, BMPSTruncateParams.SVD(2, 2, 0.0), lib=lib)     # lattice too small
+    b = WalkerBatch(2, 2, 2, 2, 1, BMPSTruncateParams.SVD(2, 2, 0.0), lib=lib)
+    with pytest.raises(PepsError):
+        b.set_tps(np.zeros(3))
+    with pytest.raises(PepsError):
+        b.set_truncation(BMPSTruncateParams.SVD(3, 2, 0.0))
+
+
+def test_rng_state_roundtrip_matches_std_mt19937(lib):
+    from oracle.mt19937 import MT19937
+    b = WalkerBatch(2, 2, 2, 2, 2, BMPSTruncateParams.SVD(2, 2, 0.0), lib=lib)
+    b.seed_rng([42, 43])
+    mt, idx = b.get_rng_state()
+    for w, seed in enumerate((42, 43)):
+        ref, ridx = MT19937(seed).state()
+        assert list(mt[w]) == ref and idx[w] == ridx
+    b.set_rng_state(mt, idx)
+    mt2, idx2 = b.get_rng_state()
+    assert np.array_equal(mt, mt2) and np.array_equal(idx, idx2)
