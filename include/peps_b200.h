@@ -104,6 +104,10 @@ int peps_get_bmps_tensor(peps_ctx *ctx, int32_t position, int32_t k, int32_t i, 
 /* Counters: 0 absorptions, 1 BTen steps, 2 traces, 3 Jacobi sweeps, 4 Jacobi calls, 5 QR calls,
  * 6 kernel launches, 7 pooled device bytes. */
 int64_t peps_stat(peps_ctx *ctx, int32_t which);
+/* Per-kernel-class device timing with CUDA events on the launching stream. Classes: 0 contraction (gett),
+ * 1 trace dot, 2 CAQR panel, 3 Jacobi round, 4 small kernels. peps_profile_get syncs and fills arrays of 5. */
+int peps_profile_enable(peps_ctx *ctx, int32_t on);
+int peps_profile_get(peps_ctx *ctx, double *ms, int64_t *launches, double *flops, int32_t reset);
 /* Stream synchronisation and the context's cudaStream_t (for CUDA-event timing by the caller). */
 int peps_sync(peps_ctx *ctx);
 void *peps_stream(peps_ctx *ctx);
@@ -111,7 +115,7 @@ void *peps_stream(peps_ctx *ctx);
 /* ---- stand-alone kernels exposed for unit parity tests ---------------------------------------------- */
 /* R factor of W matrices (m x n row-major): out [W][min(m,n)][n]. */
 int peps_test_qr_r(int32_t device, int32_t W, int32_t m, int32_t n, const double *a, double *r_out);
-/* Truncated right singular vectors of W matrices (nr x nc): b_out [W][tcap][nc], kept_out [W], sv2_out [W][nr] (unsorted squared row norms after Jacobi). */
+/* Truncated right singular vectors of W matrices (nr x nc): b_out [W][tcap][nc], kept_out [W]; total Jacobi sweeps. */
 int peps_test_truncate(int32_t device, int32_t W, int32_t nr, int32_t nc, int32_t dmin, int32_t dmax, double trunc_err,
                        const double *theta, double *b_out, int32_t *kept_out, int32_t *sweeps_out);
 /* Batched einsum of two tensors per walker (spec like "apb,kea->kepb"), host buffers. */

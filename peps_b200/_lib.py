@@ -57,6 +57,8 @@ SIGNATURES = {
     "peps_get_bmps_tensor": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _D, _I]),
     "peps_stat": (C.c_int64, [_P, C.c_int32]),
     "peps_sync": (C.c_int, [_P]),
+    "peps_profile_enable": (C.c_int, [_P, C.c_int32]),
+    "peps_profile_get": (C.c_int, [_P, _D, C.POINTER(C.c_int64), _D, C.c_int32]),
     "peps_stream": (C.c_void_p, [_P]),
     "peps_test_qr_r": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _D, _D]),
     "peps_test_truncate": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double,

@@ -53,6 +53,13 @@ void be_sync();
 void *be_stream();                        // cudaStream_t of the context (nullptr on hostsim)
 long be_launch_count();                   // number of kernels launched so far (for bench.py gpu_launches)
 
+// ---- per-kernel-class device timing (CUDA events on the launching stream) -----------------------------
+enum KernelClass { KC_GETT = 0, KC_DOT, KC_PANEL, KC_JACOBI, KC_SMALL, KC_COUNT };
+void be_profile_enable(int on);           // when on, every launch is bracketed by an event pair
+// Synchronises, folds all pending event pairs into the per-class totals and returns them (arrays of KC_COUNT);
+// `reset` clears the totals afterwards. flops = useful FP64 flops the launches of that class executed.
+void be_profile_collect(double *ms, long *launches, double *flops, int reset);
+
 // ---- tensor contraction ----------------------------------------------------------------------------
 void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, double beta, int W, int NB);
 // out[w] = sum_k A(ak[k]) * B(bk[k])
@@ -90,12 +97,20 @@ void be_panel_qr(const PanelArgs &a);
 struct JacobiArgs {
   double *G; long ws; int ld; int nr_pad; int nc; int bs; int nblk; int round;
   double tol; int inner_sweeps; double *offmax; const int32_t *done; int W;
+  int nactive = 0;   // walkers not yet converged (host-side count, for flop accounting only)
 };
 void be_jacobi_round(const JacobiArgs &a);
 // done[w] = (offmax[w] <= tol); offmax[w] = 0 for the next sweep. Returns nothing (host reads done[]).
 void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W);
 // norms2[w][r] = |G[w][r][:]|^2
 void be_row_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W);
+// order[w][rank] = row index sorted by norm descending (ties by index), for all nr rows;
+// count[w] = number of rows with norms2 > defl2 * max_row(norms2)   (numerical row rank used to shrink the
+// Jacobi problem: the dropped rows perturb Theta by <= sqrt(nr * defl2) * |Theta|, a backward-stable amount).
+void be_rank_rows(const double *norms2, int nr, double defl2, int32_t *order, int32_t *count, int W);
+// dst[w][r][:] = (r < count[w]) ? src[w][order[w][r]][:] : 0     for r < nr_dst
+void be_gather_rows(const double *src, long ws, int ld, int nc, int nr_src, const int32_t *order, const int32_t *count,
+                    double *dst, long wd, int nr_dst, int W);
 // Rank rows by norm (descending, ties by index); kept[w] by the TensorToolkit truncation rule over the
 // nsv = min(nr_true, nc) largest values, capped at tcap; order[w][t] = row index of rank t (t < tcap).
 void be_select_truncate(const double *norms2, int nr, int nsv, int dmin, int dmax, double trunc_err, int tcap,

@@ -14,6 +14,8 @@
 #include <cmath>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <vector>
 #include "backend.h"
 
 namespace peps {
@@ -34,6 +36,51 @@ static inline void post_launch() {
   ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) throw std::runtime_error(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
+
+// ---- per-class event timing --------------------------------------------------------------------------
+struct Profiler {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[KC_COUNT];
+  std::vector<cudaEvent_t> pool;
+  double ms[KC_COUNT] = {0}, flops[KC_COUNT] = {0};
+  long launches[KC_COUNT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreate(&e));
+    return e;
+  }
+};
+static Profiler g_prof;
+struct LaunchScope {          // brackets one kernel launch
+  int c; cudaEvent_t s = nullptr;
+  LaunchScope(int cls, double fl) : c(cls) {
+    g_prof.launches[c] += 1;
+    g_prof.flops[c] += fl;
+    if (g_prof.on) { s = g_prof.get(); cudaEventRecord(s, g_stream); }
+  }
+  ~LaunchScope() {
+    if (s) { cudaEvent_t e = g_prof.get(); cudaEventRecord(e, g_stream); g_prof.pending[c].push_back({s, e}); }
+  }
+};
+void be_profile_enable(int on) { g_prof.on = on != 0; }
+void be_profile_collect(double *ms, long *launches, double *flops, int reset) {
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  for (int c = 0; c < KC_COUNT; ++c) {
+    for (auto &pr : g_prof.pending[c]) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, pr.first, pr.second);
+      g_prof.ms[c] += t;
+      g_prof.pool.push_back(pr.first);
+      g_prof.pool.push_back(pr.second);
+    }
+    g_prof.pending[c].clear();
+    if (ms) ms[c] = g_prof.ms[c];
+    if (launches) launches[c] = g_prof.launches[c];
+    if (flops) flops[c] = g_prof.flops[c];
+    if (reset) { g_prof.ms[c] = 0; g_prof.launches[c] = 0; g_prof.flops[c] = 0; }
+  }
 }
 
 void be_init(int device) {
@@ -198,6 +245,7 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
 
 void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, double beta, int W, int NB) {
   if (d.M <= 0 || d.N <= 0 || W <= 0 || NB <= 0) return;
+  LaunchScope scope(KC_GETT, 2.0 * d.M * d.N * d.K * (double)W * NB);
   auto launch = [&](auto kern, int BM, int BN) {
     int tiles = ((d.M + BM - 1) / BM) * ((d.N + BN - 1) / BN);
     dim3 grid(tiles, NB, W);
@@ -229,6 +277,7 @@ __global__ void dot_kernel(int K, const int32_t *ak, const int32_t *bk, Operand 
   if (threadIdx.x == 0) out[w] = red[0];
 }
 void be_dot(int K, const int32_t *ak, const int32_t *bk, Operand A, Operand B, double *out, int W) {
+  LaunchScope scope(KC_DOT, 2.0 * K * W);
   dot_kernel<<<W, 256, 0, g_stream>>>(K, ak, bk, A, B, out);
   post_launch();
 }
@@ -244,6 +293,7 @@ __global__ void fill_kernel(double *p, double v, long n) {
 void be_fill(double *p, double v, long n) {
   if (n <= 0) return;
   int blocks = (int)((n + 255) / 256 < 148L * 8 ? (n + 255) / 256 : 148L * 8);
+  LaunchScope scope(KC_SMALL, 0.0);
   fill_kernel<<<blocks, 256, 0, g_stream>>>(p, v, n);
   post_launch();
 }
@@ -260,6 +310,7 @@ void be_copy2d(double *dst, long wd, long ldd, const double *src, long ws, long 
   long n = (long)rows * cols;
   if (n <= 0) return;
   int bx = (int)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64);
+  LaunchScope scope(KC_SMALL, 0.0);
   copy2d_kernel<<<dim3(bx, W), 256, 0, g_stream>>>(dst, wd, ldd, src, ws, lds, rows, cols);
   post_launch();
 }
@@ -274,6 +325,7 @@ __global__ void identity_kernel(double *dst, long wd, int rows, int cols) {
 void be_set_identity(double *dst, long wd, int rows, int cols, int W) {
   long n = (long)rows * cols;
   int bx = (int)((n + 255) / 256 < 64 ? (n + 255) / 256 : 64);
+  LaunchScope scope(KC_SMALL, 0.0);
   identity_kernel<<<dim3(bx, W), 256, 0, g_stream>>>(dst, wd, rows, cols);
   post_launch();
 }
@@ -427,6 +479,7 @@ void be_panel_qr(const PanelArgs &a) {
     CUDA_CHECK(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  LaunchScope scope(KC_PANEL, 4.0 * a.R * a.pw * a.pw * (double)a.NI * a.W);
   panel_qr_kernel<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
   post_launch();
 }
@@ -615,6 +668,7 @@ void be_jacobi_round(const JacobiArgs &a) {
     CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
+  LaunchScope scope(KC_JACOBI, 3.0 * (2.0 * a.bs) * (2.0 * a.bs) * a.nc * (a.nblk / 2) * (double)a.nactive);
   jacobi_round_kernel<<<dim3(a.nblk / 2, a.W), JAC_THREADS, smem, g_stream>>>(a);
   post_launch();
 }
@@ -627,6 +681,7 @@ __global__ void jacobi_flags_kernel(double *offmax, int32_t *done, double tol, i
   }
 }
 void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
   jacobi_flags_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(offmax, done, tol, W);
   post_launch();
 }
@@ -643,7 +698,65 @@ __global__ void row_norms2_kernel(const double *G, long ws, int ld, int nr, int 
 }
 void be_row_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W) {
   int wpb = 8;
+  LaunchScope scope(KC_SMALL, 0.0);
   row_norms2_kernel<<<dim3((nr + wpb - 1) / wpb, W), wpb * 32, 0, g_stream>>>(G, ws, ld, nr, nc, norms2);
+  post_launch();
+}
+
+__global__ void rank_rows_kernel(const double *norms2, int nr, double defl2, int32_t *order, int32_t *count) {
+  const int w = blockIdx.x;
+  const double *x = norms2 + (long)w * nr;
+  __shared__ double smax[256];
+  double mx = 0.0;
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) mx = fmax(mx, x[r]);
+  smax[threadIdx.x] = mx;
+  __syncthreads();
+  for (int h = blockDim.x / 2; h > 0; h >>= 1) {
+    if (threadIdx.x < h) smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + h]);
+    __syncthreads();
+  }
+  mx = smax[0];
+  __syncthreads();
+  int cnt = 0;
+  for (int r = threadIdx.x; r < nr; r += blockDim.x) {
+    double mine = x[r];
+    int rank = 0;
+    for (int j = 0; j < nr; ++j) {
+      double o = x[j];
+      rank += (o > mine) || (o == mine && j < r);
+    }
+    order[(long)w * nr + rank] = r;
+    cnt += (mine > defl2 * mx) ? 1 : 0;
+  }
+  __shared__ int scnt[256];
+  scnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int h = blockDim.x / 2; h > 0; h >>= 1) {
+    if (threadIdx.x < h) scnt[threadIdx.x] += scnt[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) count[w] = scnt[0];
+}
+void be_rank_rows(const double *norms2, int nr, double defl2, int32_t *order, int32_t *count, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  rank_rows_kernel<<<W, 256, 0, g_stream>>>(norms2, nr, defl2, order, count);
+  post_launch();
+}
+__global__ void gather_rows_plain_kernel(const double *src, long ws, int ld, int nc, int nr_src, const int32_t *order,
+                                         const int32_t *count, double *dst, long wd) {
+  const int w = blockIdx.y, r = blockIdx.x;
+  double *out = dst + (long)w * wd + (long)r * nc;
+  if (r >= count[w] || r >= nr_src) {
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) out[c] = 0.0;
+    return;
+  }
+  const double *x = src + (long)w * ws + (long)order[(long)w * nr_src + r] * ld;
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) out[c] = x[c];
+}
+void be_gather_rows(const double *src, long ws, int ld, int nc, int nr_src, const int32_t *order, const int32_t *count,
+                    double *dst, long wd, int nr_dst, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  gather_rows_plain_kernel<<<dim3(nr_dst, W), 128, 0, g_stream>>>(src, ws, ld, nc, nr_src, order, count, dst, wd);
   post_launch();
 }
 
@@ -664,14 +777,14 @@ __global__ void select_truncate_kernel(const double *norms2, int nr, int nsv, in
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int n = nsv;
+    int n = nsv;           // singular values beyond the nr rows present are exact zeros
     int k = n;
     if (n > dmin) {
       double total = 0.0;
-      for (int i = 0; i < n; ++i) total += srt[i];
+      for (int i = 0; i < n && i < nr; ++i) total += srt[i];
       double kept_sum = total;
       while (k > dmin) {
-        double sv2 = srt[k - 1];
+        double sv2 = (k - 1 < nr) ? srt[k - 1] : 0.0;
         if (k <= dmax && total > 0.0 && (1.0 - (kept_sum - sv2) / total) > trunc_err) break;
         kept_sum -= sv2;
         --k;
@@ -683,6 +796,7 @@ __global__ void select_truncate_kernel(const double *norms2, int nr, int nsv, in
 }
 void be_select_truncate(const double *norms2, int nr, int nsv, int dmin, int dmax, double trunc_err, int tcap,
                         int32_t *order, int32_t *kept, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
   select_truncate_kernel<<<W, 256, nr * sizeof(double), g_stream>>>(norms2, nr, nsv, dmin, dmax, trunc_err, tcap,
                                                                    order, kept);
   post_launch();
@@ -692,7 +806,7 @@ __global__ void gather_rows_kernel(const double *G, long ws, int ld, int nc, con
                                    const int32_t *order, const int32_t *kept, int tcap, double *B, long wb) {
   const int w = blockIdx.y, tr = blockIdx.x;
   double *out = B + (long)w * wb + (long)tr * nc;
-  if (tr >= kept[w]) {
+  if (tr >= kept[w] || tr >= nr) {
     for (int c = threadIdx.x; c < nc; c += blockDim.x) out[c] = 0.0;
     return;
   }
@@ -704,6 +818,7 @@ __global__ void gather_rows_kernel(const double *G, long ws, int ld, int nc, con
 }
 void be_gather_rows_normalized(const double *G, long ws, int ld, int nc, const double *norms2, int nr,
                                const int32_t *order, const int32_t *kept, int tcap, double *B, long wb, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
   gather_rows_kernel<<<dim3(tcap, W), 128, 0, g_stream>>>(G, ws, ld, nc, norms2, nr, order, kept, tcap, B, wb);
   post_launch();
 }
@@ -720,6 +835,7 @@ __global__ void mt_seed_kernel(uint32_t *mt, int32_t *idx, const uint32_t *seeds
   idx[w] = 624;
 }
 void be_mt_seed(uint32_t *mt, int32_t *idx, const uint32_t *seeds, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
   mt_seed_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(mt, idx, seeds, W);
   post_launch();
 }
@@ -775,6 +891,7 @@ __global__ void nn_exchange_decide_kernel(int32_t *cfg, int nsites, int s1, int 
 }
 void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b, double *amp,
                            uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
   nn_exchange_decide_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, nsites, s1, s2, psi_b, amp, mt, idx, accepted, W);
   post_launch();
 }
@@ -795,6 +912,7 @@ __global__ void xxz_bond_energy_kernel(const int32_t *cfg, int nsites, int s1, i
 }
 void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const double *psi_ex, const double *psi,
                         double jz, double jxy, double *eloc, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
   xxz_bond_energy_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, s1, s2, psi_ex, psi, jz, jxy, eloc, W);
   post_launch();
 }
@@ -803,6 +921,7 @@ __global__ void xxz_onsite_kernel(const int32_t *cfg, int nsites, double h00, do
   if (w < W) eloc[w] += -h00 * ((double)cfg[(long)w * nsites] - 0.5);
 }
 void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *eloc, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
   xxz_onsite_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, h00, eloc, W);
   post_launch();
 }
@@ -828,6 +947,7 @@ __global__ void accumulate_ostar_kernel(const double *holes, long hole_stride, c
 void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
                          const int32_t *tps_off, const int32_t *cfg, int nsites, int phys, const double *amp,
                          const double *eloc, double *osum, double *eosum, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
   accumulate_ostar_kernel<<<dim3(16, nsites), 256, 0, g_stream>>>(holes, hole_stride, hole_off, site_size, tps_off,
                                                                   cfg, nsites, phys, amp, eloc, osum, eosum, W);
   post_launch();

@@ -120,6 +120,14 @@ int peps_get_bmps_tensor(peps_ctx *ctx, int32_t pos, int32_t k, int32_t i, doubl
 }
 int64_t peps_stat(peps_ctx *ctx, int32_t which) { return ctx->eng->stat(which); }
 int peps_sync(peps_ctx *ctx) { GUARD(ctx, be_sync()) }
+int peps_profile_enable(peps_ctx *ctx, int32_t on) { GUARD(ctx, be_profile_enable(on)) }
+int peps_profile_get(peps_ctx *ctx, double *ms, int64_t *launches, double *flops, int32_t reset) {
+  GUARD(ctx, {
+    long l[KC_COUNT];
+    be_profile_collect(ms, l, flops, reset);
+    if (launches) for (int c = 0; c < KC_COUNT; ++c) launches[c] = l[c];
+  })
+}
 void *peps_stream(peps_ctx *) { return be_stream(); }
 
 // ---- stand-alone kernel tests -----------------------------------------------------------------------

@@ -115,6 +115,8 @@ long Engine::stat(int which) const {
     case 5: return la_.qr_calls;
     case 6: return be_launch_count();
     case 7: return (long)pool_.total_bytes();
+    case 8: return la_.rows_in;
+    case 9: return la_.rows_kept;
     default: return -1;
   }
 }

@@ -23,6 +23,8 @@ struct LinalgCtx {
   std::vector<int32_t> done_host;
   // statistics
   long jacobi_sweeps = 0, jacobi_calls = 0, qr_calls = 0;
+  long rows_in = 0, rows_kept = 0;   // Jacobi row counts before / after deflation (summed over calls)
+  double deflation_eps = 1e-15;      // rows of R below eps * (largest row norm) are treated as zero
   double jacobi_tol = 1e-14;
   int jacobi_inner_sweeps = 1;
   int jacobi_max_sweeps = 40;
@@ -153,32 +155,45 @@ inline JacobiLayout jacobi_layout(int nr, int nc) {
 
 // Rows the Theta buffer must provide for truncate_rows(nr, nc).
 inline int truncate_buffer_rows(int nr, int nc) {
-  int rows = nr;
-  int nr_eff = nr;
-  if (nr > nc) { rows = std::max(rows, qr_layout(nr, nc).m_pad); nr_eff = nc; }
-  rows = std::max(rows, jacobi_layout(nr_eff, nc).nr_pad);
-  return rows;
+  return nr > 1 ? std::max(nr, qr_layout(nr, nc).m_pad) : nr;
 }
 
 // Theta[w]: nr x nc (leading dimension nc) inside a zero-padded buffer of truncate_buffer_rows(nr,nc) rows.
 // Writes B[w] (tcap x nc): the kept right singular vectors (rows), zero rows beyond kept[w].
+//   1. R-only QR of Theta (Drmac-Veselic preconditioning: the rows of R are far closer to orthogonal than the
+//      rows of Theta, which roughly halves the Jacobi sweeps; Theta and R share right singular vectors).
+//   2. rows of R below deflation_eps * max row norm are dropped (backward-stable perturbation); the surviving
+//      rows, sorted by norm, form the Jacobi problem (graded spectra shrink it by a large factor).
+//   3. one-sided block Jacobi on those rows, then the TensorToolkit truncation rule on the row norms.
 inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int dmin, int dmax, double trunc_err,
                           int tcap, double *B, long wb, int32_t *kept, double *norms2_scratch, int32_t *order_scratch) {
+  (void)norms2_scratch; (void)order_scratch;
   const int W = cx.W;
   const int nsv = std::min(nr, nc);
-  int nr_eff = nr;
-  if (nr > nc) {
-    caqr(cx, G, ws, nr, nc, qr_layout(nr, nc));
-    nr_eff = nc;
-  }
+  if (nr > 1) caqr(cx, G, ws, nr, nc, qr_layout(nr, nc));
+  const int kk = nsv;
+  double *n2a = (double *)cx.pool->get(sizeof(double) * (size_t)W * kk);
+  int32_t *ord = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * kk);
+  int32_t *cnt = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W);
+  be_row_norms2(G, ws, nc, kk, nc, n2a, W);
+  be_rank_rows(n2a, kk, cx.deflation_eps * cx.deflation_eps, ord, cnt, W);
+  cx.done_host.resize((size_t)W);
+  be_d2h(cx.done_host.data(), cnt, sizeof(int32_t) * W);
+  int nr_eff = 1;
+  for (int w = 0; w < W; ++w) nr_eff = std::max(nr_eff, (int)cx.done_host[(size_t)w]);
+  cx.rows_in += kk; cx.rows_kept += nr_eff;
+  JacobiLayout J = jacobi_layout(nr_eff, nc);
+  double *G2 = (double *)cx.pool->get(sizeof(double) * (size_t)W * J.nr_pad * nc);
+  const long ws2 = (long)J.nr_pad * nc;
+  be_gather_rows(G, ws, nc, nc, kk, ord, cnt, G2, ws2, J.nr_pad, W);
   if (nr_eff > 1) {
-    JacobiLayout J = jacobi_layout(nr_eff, nc);
     ++cx.jacobi_calls;
     be_fill(cx.offmax, 0.0, W);
     be_memset0(cx.done, sizeof(int32_t) * W);
     JacobiArgs ja;
-    ja.G = G; ja.ws = ws; ja.ld = nc; ja.nr_pad = J.nr_pad; ja.nc = nc; ja.bs = J.bs; ja.nblk = J.nblk;
+    ja.G = G2; ja.ws = ws2; ja.ld = nc; ja.nr_pad = J.nr_pad; ja.nc = nc; ja.bs = J.bs; ja.nblk = J.nblk;
     ja.tol = cx.jacobi_tol; ja.inner_sweeps = cx.jacobi_inner_sweeps; ja.offmax = cx.offmax; ja.done = cx.done; ja.W = W;
+    ja.nactive = W;
     for (int sweep = 0; sweep < cx.jacobi_max_sweeps; ++sweep) {
       for (int round = 0; round < J.nblk - 1; ++round) {
         ja.round = round;
@@ -186,17 +201,19 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
       }
       ++cx.jacobi_sweeps;
       be_jacobi_flags(cx.offmax, cx.done, cx.jacobi_tol, W);
-      cx.done_host.resize((size_t)W);
       be_d2h(cx.done_host.data(), cx.done, sizeof(int32_t) * W);
-      bool all = true;
-      for (int w = 0; w < W; ++w) all = all && cx.done_host[(size_t)w];
-      if (all) break;
+      int nact = 0;
+      for (int w = 0; w < W; ++w) nact += cx.done_host[(size_t)w] ? 0 : 1;
+      ja.nactive = nact;
+      if (nact == 0) break;
     }
   }
-  const int nr_sel = std::max(nr_eff, 1);
-  be_row_norms2(G, ws, nc, nr_sel, nc, norms2_scratch, W);
-  be_select_truncate(norms2_scratch, nr_sel, nsv, dmin, dmax, trunc_err, tcap, order_scratch, kept, W);
-  be_gather_rows_normalized(G, ws, nc, nc, norms2_scratch, nr_sel, order_scratch, kept, tcap, B, wb, W);
+  double *n2b = (double *)cx.pool->get(sizeof(double) * (size_t)W * nr_eff);
+  int32_t *ord2 = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * tcap);
+  be_row_norms2(G2, ws2, nc, nr_eff, nc, n2b, W);
+  be_select_truncate(n2b, nr_eff, nsv, dmin, dmax, trunc_err, tcap, ord2, kept, W);
+  be_gather_rows_normalized(G2, ws2, nc, nc, n2b, nr_eff, ord2, kept, tcap, B, wb, W);
+  for (void *p : {(void *)n2a, (void *)ord, (void *)cnt, (void *)G2, (void *)n2b, (void *)ord2}) cx.pool->put(p);
 }
 
 }  // namespace peps

@@ -26,6 +26,10 @@ void be_d2d(void *d, const void *s, size_t b) { std::memcpy(d, s, b); }
 void be_sync() {}
 void *be_stream() { return nullptr; }
 long be_launch_count() { return g_launches; }
+void be_profile_enable(int) {}
+void be_profile_collect(double *ms, long *launches, double *flops, int) {
+  for (int c = 0; c < KC_COUNT; ++c) { if (ms) ms[c] = 0; if (launches) launches[c] = 0; if (flops) flops[c] = 0; }
+}
 
 static const double *obase(const Operand &o, int w, int b) {
   const double *p = o.p + (long)w * o.ws + (long)b * o.bs;
@@ -250,6 +254,33 @@ void be_row_norms2(const double *G, long ws, int ld, int nr, int nc, double *nor
       norms2[(long)w * nr + r] = s;
     }
 }
+void be_rank_rows(const double *norms2, int nr, double defl2, int32_t *order, int32_t *count, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const double *x = norms2 + (long)w * nr;
+    double mx = 0.0;
+    for (int r = 0; r < nr; ++r) mx = std::max(mx, x[r]);
+    int cnt = 0;
+    for (int r = 0; r < nr; ++r) {
+      int rank = 0;
+      for (int j = 0; j < nr; ++j) rank += (x[j] > x[r]) || (x[j] == x[r] && j < r);
+      order[(long)w * nr + rank] = r;
+      cnt += x[r] > defl2 * mx;
+    }
+    count[w] = cnt;
+  }
+}
+void be_gather_rows(const double *src, long ws, int ld, int nc, int nr_src, const int32_t *order, const int32_t *count,
+                    double *dst, long wd, int nr_dst, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int r = 0; r < nr_dst; ++r) {
+      double *out = dst + (long)w * wd + (long)r * nc;
+      if (r >= count[w] || r >= nr_src) { for (int c = 0; c < nc; ++c) out[c] = 0.0; continue; }
+      const double *x = src + (long)w * ws + (long)order[(long)w * nr_src + r] * ld;
+      for (int c = 0; c < nc; ++c) out[c] = x[c];
+    }
+}
 void be_select_truncate(const double *norms2, int nr, int nsv, int dmin, int dmax, double trunc_err, int tcap,
                         int32_t *order, int32_t *kept, int W) {
   ++g_launches;
@@ -265,10 +296,10 @@ void be_select_truncate(const double *norms2, int nr, int nsv, int dmin, int dma
     int n = nsv, k = n;
     if (n > dmin) {
       double total = 0.0;
-      for (int i = 0; i < n; ++i) total += srt[(size_t)i];
+      for (int i = 0; i < n && i < nr; ++i) total += srt[(size_t)i];
       double kept_sum = total;
       while (k > dmin) {
-        double sv2 = srt[(size_t)(k - 1)];
+        double sv2 = (k - 1 < nr) ? srt[(size_t)(k - 1)] : 0.0;
         if (k <= dmax && total > 0.0 && (1.0 - (kept_sum - sv2) / total) > trunc_err) break;
         kept_sum -= sv2;
         --k;
@@ -283,7 +314,7 @@ void be_gather_rows_normalized(const double *G, long ws, int ld, int nc, const d
   for (int w = 0; w < W; ++w)
     for (int t = 0; t < tcap; ++t) {
       double *out = B + (long)w * wb + (long)t * nc;
-      if (t >= kept[w]) { for (int c = 0; c < nc; ++c) out[c] = 0.0; continue; }
+      if (t >= kept[w] || t >= nr) { for (int c = 0; c < nc; ++c) out[c] = 0.0; continue; }
       int src = order[(long)w * tcap + t];
       double n2 = norms2[(long)w * nr + src];
       double inv = n2 > 0.0 ? 1.0 / std::sqrt(n2) : 0.0;

@@ -1,0 +1,196 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle. Run on the GPU box with ``-m gpu``.
+
+Tolerances: FP64, <= 1e-10 relative on amplitudes / local energies / gradients (BASELINE.json north_star);
+sampled configurations and acceptance counts bit-exact for equal RNG streams."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from parity_common import run_pipeline_parity, run_gradient_parity
+from helpers import load_golden_tps, ising_tn, ising_exact_logZ
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from peps_b200 import _lib
+    l = _lib.load()
+    assert l.peps_backend_name() == b"cuda-sm_100a"
+    return l
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+@pytest.mark.parametrize("spec,da,db", [
+    ("apb,kea->kepb", (5, 3, 7), (4, 2, 5)),
+    ("kepb,epfo->kofb", (6, 3, 2, 5), (3, 2, 4, 3)),
+    ("apx,xyz->apyz", (64, 8, 64), (64, 8, 64)),
+    ("apyz,yfop->zafo", (16, 8, 8, 16), (8, 8, 8, 8)),
+    ("zafo,zfb->aob", (64, 64, 8, 8), (64, 8, 64)),
+    ("xldb,brux->ldru", (9, 3, 3, 9), (9, 3, 3, 9)),
+    ("rc,rt->ct", (513, 32), (513, 100)),
+    ("ab,bc->ac", (1, 1), (1, 1)),
+    ("ab,bc->ac", (70, 33), (33, 130)),
+])
+def test_gett_contraction_vs_numpy(lib, spec, da, db):
+    W = 3
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((W,) + da)
+    b = rng.standard_normal((W,) + db)
+    ins, out = spec.split("->")
+    la, lb = ins.split(",")
+    ref = np.einsum(f"w{la},w{lb}->w{out}", a, b)
+    c = np.empty(ref.shape)
+    dda, ddb = np.array(da, dtype=np.int32), np.array(db, dtype=np.int32)
+    rc = lib.peps_test_einsum(0, W, spec.encode(), _ip(dda), len(da), _ip(ddb), len(db), _dp(a), _dp(b), _dp(c))
+    assert rc == 0, lib.peps_last_error(None)
+    assert np.max(np.abs(c - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+
+
+@pytest.mark.parametrize("m,n", [(8, 64), (64, 512), (512, 512), (4096, 512), (1000, 96), (37, 5), (5, 37), (2, 2),
+                                 (1, 9), (600, 600)])
+def test_caqr_r_factor(lib, m, n):
+    W = 2
+    rng = np.random.default_rng(1)
+    a = rng.standard_normal((W, m, n))
+    kk = min(m, n)
+    r = np.empty((W, kk, n))
+    assert lib.peps_test_qr_r(0, W, m, n, _dp(a), _dp(r)) == 0, lib.peps_last_error(None)
+    for w in range(W):
+        rw = r[w]
+        assert np.max(np.abs(np.tril(rw[:, :kk], -1))) == 0.0
+        # R^T R = A^T A  (R is unique up to row signs)
+        ref = a[w].T @ a[w]
+        assert np.max(np.abs(rw.T @ rw - ref)) < 1e-12 * np.max(np.abs(ref))
+        rr = np.linalg.qr(a[w], mode="r")
+        assert np.max(np.abs(np.abs(np.diag(rw)) - np.abs(np.diag(rr)))) < 1e-11 * np.max(np.abs(rr))
+
+
+@pytest.mark.parametrize("nr,nc,dmin,dmax,terr", [(64, 64, 8, 8, 0.0), (512, 512, 64, 64, 0.0), (8, 512, 8, 8, 0.0),
+                                                   (512, 64, 16, 16, 0.0), (40, 72, 4, 30, 1e-6), (3, 3, 2, 2, 0.0),
+                                                   (100, 37, 10, 20, 1e-3)])
+def test_jacobi_truncation_vs_lapack(lib, nr, nc, dmin, dmax, terr):
+    from oracle.bmps import truncation_dim
+    W = 2
+    rng = np.random.default_rng(2)
+    # known SVD with a geometric spectrum: the truth is V, not LAPACK's answer (whose own error is eps*s_1/gap)
+    th = np.empty((W, nr, nc))
+    vs, ss = [], []
+    k = min(nr, nc)
+    for w in range(W):
+        u, _ = np.linalg.qr(rng.standard_normal((nr, k)))
+        v, _ = np.linalg.qr(rng.standard_normal((nc, k)))
+        s = 0.93 ** np.arange(k) * (1 + 0.02 * rng.random(k))
+        s = np.sort(s)[::-1]
+        th[w] = (u * s) @ v.T
+        vs.append(v)
+        ss.append(s)
+    tcap = min(dmax, nr, nc)
+    b = np.empty((W, tcap, nc))
+    kept = np.empty(W, dtype=np.int32)
+    sweeps = C.c_int32()
+    rc = lib.peps_test_truncate(0, W, nr, nc, dmin, dmax, terr, _dp(th), _dp(b), _ip(kept), C.byref(sweeps))
+    assert rc == 0, lib.peps_last_error(None)
+    print("jacobi sweeps", sweeps.value)
+    for w in range(W):
+        t = truncation_dim(ss[w], dmin, dmax, terr)
+        assert kept[w] == t
+        bw = b[w][:t]
+        assert np.max(np.abs(bw @ bw.T - np.eye(t))) < 1e-12
+        # same projector onto the kept right singular subspace; conditioning ~ eps * s_1 / gap at the cut
+        p_ref = vs[w][:, :t] @ vs[w][:, :t].T
+        gap = ss[w][t - 1] - (ss[w][t] if t < k else 0.0)
+        assert np.max(np.abs(bw.T @ bw - p_ref)) < 50 * 2.2e-16 * ss[w][0] / gap + 1e-13
+        assert t == tcap or np.max(np.abs(b[w][t:])) == 0.0
+
+
+@pytest.mark.parametrize("rows,cols,D,trunc,W", [
+    (4, 4, 3, (6, 6, 0.0), 4),
+    (3, 5, 2, (4, 4, 0.0), 3),
+    (4, 4, 3, (2, 7, 1e-6), 3),
+    (2, 2, 4, (1, 100, 0.0), 2),
+    (4, 4, 4, (8, 8, 0.0), 8),       # BASELINE config #1 sizes (TFIM lattice, D=4, chi=8), Heisenberg bonds
+])
+def test_pipeline_parity_gpu(lib, rows, cols, D, trunc, W):
+    rep = run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2)
+    print(rep)
+
+
+def test_pipeline_parity_gpu_signed(lib):
+    run_pipeline_parity(lib, 4, 4, 3, 2, (9, 9, 0.0), nsweeps=2, signed=True, seed=5)
+
+
+def test_gradient_parity_gpu(lib):
+    run_gradient_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsamples=4)
+
+
+def test_golden_4x4_D8_fixture_amplitudes(lib):
+    """K6 fixture: amplitudes / energies of the 32 stored configurations, reference truncation (8, 16, 1e-15)."""
+    from oracle import vmc
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+    tps, z = load_golden_tps("heis4x4_D8_double")
+    cfgs = z["configs"][:8]
+    b = WalkerBatch(4, 4, 2, 8, len(cfgs), BMPSTruncateParams.SVD(8, 16, 1e-15), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    amp = b.amplitudes()
+    e = b.energy_and_holes(False)
+    for w in range(len(cfgs)):
+        wk = vmc.Walker(tps, cfgs[w], (8, 16, 1e-15))
+        assert abs(amp[w] / wk.amplitude - 1) < 1e-9
+        ee, _, _ = vmc.XXZModel().energy_and_holes(tps, wk, False)
+        assert abs(e[w] - ee) < 1e-8 * max(1, abs(ee))
+
+
+def test_K1_ising_partition_function_on_gpu(lib):
+    """The exact-partition-function KAT through the CUDA path: a 'TPS' whose two physical slices are the Ising
+    site tensor (slice 0) and zero (slice 1), configuration all 0."""
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+    L = 8
+    beta = math.log(1 + math.sqrt(2.0)) / 2.0
+    tn = ising_tn(L, beta)
+    tps = [[[tn[r][c], np.zeros_like(tn[r][c])] for c in range(L)] for r in range(L)]
+    b = WalkerBatch(L, L, 2, 2, 1, BMPSTruncateParams.SVD(10, 30, 1e-15), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(np.zeros((1, L, L), dtype=np.int32))
+    b.init_walkers()
+    lz = ising_exact_logZ(L, beta)
+    for row in (0, 2, 5):
+        z = b.probe_trace_row(row)[0]
+        assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
+
+
+def test_full_size_properties(lib):
+    """At a BASELINE-sized bond dimension (D=8, chi=64 on a 4x4 lattice so the oracle is not needed): closure --
+    every row/column trace of the same configuration agrees, and PunchHole . site == amplitude."""
+    from oracle import vmc
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+    rows = cols = 4
+    D, chi, W = 8, 64, 4
+    tps = vmc.random_tps(rows, cols, 2, D, seed=11)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 30 + w) for w in range(W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(chi, chi, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    e, psi = b.energy_and_holes(True, True)
+    assert np.max(np.abs(psi / psi[0] - 1)) < 1e-10          # D^2 = chi: no truncation on 4x4, closures agree
+    holes = b.holes()
+    flat_tn = np.stack([np.concatenate([tps[r][c][cfgs[w, r, c]].ravel() for r in range(rows) for c in range(cols)])
+                        for w in range(W)])
+    sizes = [tps[r][c][0].size for r in range(rows) for c in range(cols)]
+    pos = 0
+    for s, sz in enumerate(sizes):
+        dot = np.sum(holes[:, pos:pos + sz] * flat_tn[:, pos:pos + sz], axis=1)
+        assert np.max(np.abs(dot / psi[s // cols] - 1)) < 1e-10
+        pos += sz
