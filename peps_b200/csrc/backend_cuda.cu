@@ -472,15 +472,207 @@ __global__ void __launch_bounds__(PQR_THREADS) panel_qr_kernel(PanelArgs a) {
 static size_t panel_smem_bytes(int R, int nbw) {
   return ((size_t)nbw * (R + 1) + 2 * (size_t)nbw * nbw + 3 * nbw) * sizeof(double);
 }
-void be_panel_qr(const PanelArgs &a) {
-  size_t smem = panel_smem_bytes(a.R, a.nbw);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+
+// Register-resident variant: warp w owns CPW = NBW/8 panel columns, lane l owns rows l, l+32, ... (RPL of them),
+// so every Householder update is FMA work out of registers; only the current reflector travels through shared
+// memory (double buffered: one barrier per column). S = V^T V falls out of the same dot products, V T^T is formed
+// on the DMMA pipe from a shared-memory copy of V.
+template <int NBW, int RPL>
+__global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs a) {
+  extern __shared__ double sm[];
+  constexpr int CPW = NBW / 8;
+  constexpr int LDV = NBW + 4, LDT = NBW + 4, LDSS = NBW + 1;
+  const int it = blockIdx.x, w = blockIdx.y;
+  const int R = a.R, pw = a.pw, nbw = a.nbw;
+  const int skip = (it == 0) ? a.skip0 : 0;
+  const int nact = R - skip;
+  const int RP = RPL * 32;
+  double *vbuf = sm;                       // [2][RP]
+  double *S = vbuf + 2 * RP;               // [NBW][LDSS]
+  double *Tt = S + NBW * LDSS;             // [NBW][LDT]   T[a][b]
+  double *tau_s = Tt + NBW * LDT;          // [NBW]
+  double *Rd = tau_s + NBW;                // [NBW]
+  double *Vs = Rd + NBW;                   // [round_up(nact,8)][LDV]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  double *Aw = a.A + (long)w * a.ws;
+  const int32_t *rows = a.rowtab + (long)it * R;
+
+  double P[CPW][RPL];
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    const int r = lane + 32 * i;
+    const long off = (r < nact) ? (long)rows[skip + r] * a.lda + a.col0 : 0;
+#pragma unroll
+    for (int cc = 0; cc < CPW; ++cc) {
+      const int c = warp * CPW + cc;
+      P[cc][i] = (r < nact && c < pw) ? Aw[off + c] : 0.0;
+    }
   }
+  for (int e = t; e < NBW * LDSS; e += PQR_THREADS) S[e] = 0.0;
+  for (int e = t; e < NBW * LDT; e += PQR_THREADS) Tt[e] = 0.0;
+  if (t < NBW) { tau_s[t] = 0.0; Rd[t] = 0.0; }
+  __syncthreads();
+
+  for (int j = 0; j < pw; ++j) {
+    double *vb = vbuf + (j & 1) * RP;
+    if (warp == j / CPW) {                 // owner warp builds reflector j
+      const int cj = j % CPW;
+      double x[RPL];
+      double xn2 = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int cc = 0; cc < CPW; ++cc) if (cc == cj) v = P[cc][i];
+        x[i] = v;
+        const int r = lane + 32 * i;
+        if (r == j) vb[r] = v;
+        if (r > j && r < nact) xn2 += v * v;
+      }
+      xn2 = warp_sum(xn2);
+      __syncwarp();
+      const double alpha = (j < nact) ? vb[j] : 0.0;
+      double bj = alpha, tj = 0.0, sj = 0.0;
+      if (xn2 > 0.0) {
+        const double nrm = sqrt(alpha * alpha + xn2);
+        bj = (alpha >= 0.0) ? -nrm : nrm;
+        tj = (bj - alpha) / bj;
+        sj = 1.0 / (alpha - bj);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        const int r = lane + 32 * i;
+        const double v = (r > j) ? x[i] * sj : ((r == j) ? 1.0 : 0.0);
+        if (r < RP) vb[r] = (r < nact) ? v : 0.0;
+        if (r >= j) {
+#pragma unroll
+          for (int cc = 0; cc < CPW; ++cc) if (cc == cj) P[cc][i] = (r < nact) ? v : 0.0;
+        }
+      }
+      if (lane == 0) { tau_s[j] = tj; Rd[j] = bj; }
+    }
+    __syncthreads();
+    {
+      const double tj = tau_s[j];
+      double v[RPL];
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) v[i] = vb[lane + 32 * i];
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = warp * CPW + cc;
+        if (c == j || c >= pw) continue;
+        double dot = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) dot += v[i] * P[cc][i];
+        dot = warp_sum(dot);
+        if (c > j) {
+          const double f = tj * dot;
+          if (f != 0.0) {
+#pragma unroll
+            for (int i = 0; i < RPL; ++i) P[cc][i] -= f * v[i];
+          }
+        } else if (lane == 0) {
+          S[c * LDSS + j] = dot;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // T (forward, columnwise): T[j][j] = tau_j; T[0:j, j] = -tau_j * T[0:j,0:j] * S[0:j, j]
+  if (warp == 0) {
+    for (int j = 0; j < pw; ++j) {
+      const double tj = tau_s[j];
+      double v = 0.0;
+      if (lane < j) {
+        for (int b2 = lane; b2 < j; ++b2) v += Tt[lane * LDT + b2] * S[b2 * LDSS + j];
+        v *= -tj;
+      }
+      __syncwarp();
+      if (lane < j) Tt[lane * LDT + j] = v;
+      if (lane == j) Tt[j * LDT + j] = tj;
+      __syncwarp();
+    }
+  }
+  // emit R (in place) and V; stage V in shared memory
+  double *Vo = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
+  double *VTo = a.VTw + ((long)w * a.NI + it) * (long)R * nbw;
+  for (int e = t; e < skip * nbw; e += PQR_THREADS) { Vo[e] = 0.0; VTo[e] = 0.0; }
+  const int nact8 = (nact + 7) & ~7;
+  for (int e = t; e < (nact8 - nact) * LDV; e += PQR_THREADS) Vs[(size_t)nact * LDV + e] = 0.0;
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    const int r = lane + 32 * i;
+    if (r < nact) {
+      const long off = (long)rows[skip + r] * a.lda + a.col0;
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const int c = warp * CPW + cc;
+        const double pv = P[cc][i];
+        if (c < pw) Aw[off + c] = (r < c) ? pv : ((r == c) ? Rd[c] : 0.0);
+        const double vv = (c < pw && r >= c) ? pv : 0.0;
+        Vo[(long)(skip + r) * nbw + c] = vv;
+        Vs[(size_t)r * LDV + c] = vv;
+      }
+    }
+  }
+  __syncthreads();
+  // VT = V T^T on the DMMA pipe: (nact x NBW) . (NBW x NBW)
+  for (int rt = warp; rt < nact8 / 8; rt += PQR_THREADS / 32) {
+    double acc[NBW / 8][2];
+#pragma unroll
+    for (int nt = 0; nt < NBW / 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+    const double *ap = Vs + (size_t)(rt * 8 + (lane >> 2)) * LDV + (lane & 3);
+#pragma unroll
+    for (int ks = 0; ks < NBW / 4; ++ks) {
+      const double af = ap[ks * 4];
+#pragma unroll
+      for (int nt = 0; nt < NBW / 8; ++nt)
+        dmma8x8x4(acc[nt][0], acc[nt][1], af, Tt[(nt * 8 + (lane >> 2)) * LDT + ks * 4 + (lane & 3)]);
+    }
+    const int r = rt * 8 + (lane >> 2);
+    if (r < nact) {
+#pragma unroll
+      for (int nt = 0; nt < NBW / 8; ++nt) {
+        double2 o; o.x = acc[nt][0]; o.y = acc[nt][1];
+        *reinterpret_cast<double2 *>(VTo + (long)(skip + r) * nbw + nt * 8 + 2 * (lane & 3)) = o;
+      }
+    }
+  }
+}
+
+template <int NBW, int RPL>
+static size_t panel_reg_smem_bytes(int nact_max) {
+  int nact8 = (nact_max + 7) & ~7;
+  return ((size_t)2 * RPL * 32 + (size_t)NBW * (NBW + 1) + (size_t)NBW * (NBW + 4) + 2 * NBW + (size_t)nact8 * (NBW + 4)) *
+         sizeof(double);
+}
+
+void be_panel_qr(const PanelArgs &a) {
   LaunchScope scope(KC_PANEL, 4.0 * a.R * a.pw * a.pw * (double)a.NI * a.W);
-  panel_qr_kernel<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
+  auto launch_reg = [&](auto kern, size_t smem, size_t &configured) {
+    if (smem > configured) {
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    kern<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
+  };
+  static size_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, cg = 0;
+  const int R = a.R;
+  if (a.nbw == 32 && R <= 256) launch_reg(panel_qr_reg_kernel<32, 8>, panel_reg_smem_bytes<32, 8>(R), c0);
+  else if (a.nbw == 32 && R <= 512) launch_reg(panel_qr_reg_kernel<32, 16>, panel_reg_smem_bytes<32, 16>(R), c4);
+  else if (a.nbw == 32 && R <= 576) launch_reg(panel_qr_reg_kernel<32, 18>, panel_reg_smem_bytes<32, 18>(R), c1);
+  else if (a.nbw == 16 && R <= 512) launch_reg(panel_qr_reg_kernel<16, 16>, panel_reg_smem_bytes<16, 16>(R), c2);
+  else if (a.nbw == 16 && R <= 1184) launch_reg(panel_qr_reg_kernel<16, 37>, panel_reg_smem_bytes<16, 37>(R), c3);
+  else {
+    size_t smem = panel_smem_bytes(a.R, a.nbw);
+    if (smem > cg) {
+      CUDA_CHECK(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      cg = smem;
+    }
+    panel_qr_kernel<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
+  }
   post_launch();
 }
 
@@ -488,71 +680,147 @@ void be_panel_qr(const PanelArgs &a) {
 // block Jacobi round
 // =====================================================================================================
 constexpr int JAC_THREADS = 256;
+constexpr int JAC_KGROUPS = 4;          // K (column) split of the Gram matrix across warp pairs
 
-__device__ __forceinline__ void rr_pair(int nblk, int round, int q, int &I, int &J) {
+__host__ __device__ __forceinline__ void rr_pair(int nblk, int round, int q, int &I, int &J) {
   // round-robin tournament on nblk (even) players: player nblk-1 is fixed
   const int n1 = nblk - 1;
   if (q == 0) { I = n1; J = round % n1; }
   else { I = (round + q) % n1; J = (round - q + n1) % n1; }
 }
 
+// Jacobi rotation (c, s) annihilating a_pq of [[app, apq], [apq, aqq]] (p < q), Rutishauser's small-angle choice
+// written with one sqrt, one division and one rsqrt.
+__device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double tol2, double &c, double &s) {
+  c = 1.0; s = 0.0;
+  if (apq * apq > tol2 * fabs(app * aqq) && apq != 0.0) {
+    double d = aqq - app;
+    double r = sqrt(d * d + 4.0 * apq * apq);
+    double t = (d >= 0.0) ? (2.0 * apq) / (d + r) : (-2.0 * apq) / (r - d);
+    c = rsqrt(1.0 + t * t);
+    s = c * t;
+  }
+}
+
+// One round of one-sided block Jacobi for one block pair. N2 = 2*bs rows resident in shared memory.
+//   load -> Gram (DMMA, K split over warp pairs) -> cyclic two-sided Jacobi on the N2 x N2 Gram matrix with one
+//   barrier per rotation set (the angles of set r+1 are computed by 16 threads while the others apply set r)
+//   -> rows <- W^T rows on the DMMA pipe -> store.
+template <int N2>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a) {
   extern __shared__ double sm[];
+  constexpr int T2 = N2 / 8;
+  constexpr int NT = T2 * (T2 + 1) / 2;
+  constexpr int LG = N2 + 1;
+  constexpr int NP = N2 / 2;
+  constexpr int bs = N2 / 2;
   const int w = blockIdx.y;
   if (a.done[w]) return;
-  const int bs = a.bs, n2 = 2 * bs, nc = a.nc;
+  const int nc = a.nc;
   const int ncp = (nc + 7) & ~7;
   const int LDS = ncp + 4;
-  const int LG = n2 + 1;
-  double *Ps = sm;                         // [n2][LDS]
-  double *Gm = Ps + (size_t)n2 * LDS;      // [n2][LG]
-  double *Wm = Gm + n2 * LG;               // [n2][LG]
-  double *cs = Wm + n2 * LG;               // [n2] : c (first half) s (second half)
-  int *perm = (int *)(cs + n2);            // [n2]
-  int *pairs = perm + n2;                  // [n2]
+  double *Ps = sm;                                   // [N2][LDS]
+  double *Gpart = Ps + (size_t)N2 * LDS;             // [JAC_KGROUPS][NT][64]
+  double *Gm = Gpart + JAC_KGROUPS * NT * 64;        // [2][N2][LG]
+  double *Wm = Gm + 2 * N2 * LG;                     // [2][N2][LG]
+  double *coef = Wm + 2 * N2 * LG;                   // [2][2][N2]: (a_i, b_i) double buffered
+  int *perm = (int *)(coef + 4 * N2);                // [N2]
+  unsigned char *part = (unsigned char *)(perm + N2);  // [N2-1][N2] partner of i in rotation set r
   __shared__ double red[JAC_THREADS / 32];
+  __shared__ int tile_p[NT], tile_q[NT];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = JAC_THREADS / 32;
 
   int I, J;
   rr_pair(a.nblk, a.round, blockIdx.x, I, J);
   const int lo = min(I, J), hi = max(I, J);
   double *Gw = a.G + (long)w * a.ws;
+  const double tol2 = a.tol * a.tol;
+
+  // 0. schedule tables
+  if (t < NT) {
+    int idx = 0;
+    for (int p = 0; p < T2; ++p)
+      for (int q = p; q < T2; ++q) { if (idx == t) { tile_p[t] = p; tile_q[t] = q; } ++idx; }
+  }
+  for (int e = t; e < (N2 - 1) * NP; e += JAC_THREADS) {
+    int rd = e / NP, k = e % NP, p, q;
+    rr_pair(N2, rd, k, p, q);
+    part[rd * N2 + p] = (unsigned char)q;
+    part[rd * N2 + q] = (unsigned char)p;
+  }
 
   // 1. load the two row blocks (zero padded columns)
-  for (int e = t; e < n2 * LDS; e += JAC_THREADS) {
-    int r = e / LDS, c = e % LDS;
-    int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
-    Ps[e] = (c < nc) ? Gw[(long)grow * a.ld + c] : 0.0;
+  if ((nc & 1) == 0) {
+    const int nv = nc >> 1;
+    for (int r = warp; r < N2; r += nwarp) {
+      const int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
+      const double2 *src = reinterpret_cast<const double2 *>(Gw + (long)grow * a.ld);
+      double2 *dst = reinterpret_cast<double2 *>(Ps + (size_t)r * LDS);
+      for (int c = lane; c < nv; c += 32) dst[c] = src[c];
+      for (int c = nc + lane; c < LDS; c += 32) Ps[(size_t)r * LDS + c] = 0.0;
+    }
+  } else {
+    for (int r = warp; r < N2; r += nwarp) {
+      const int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
+      for (int c = lane; c < LDS; c += 32) Ps[(size_t)r * LDS + c] = (c < nc) ? Gw[(long)grow * a.ld + c] : 0.0;
+    }
   }
   __syncthreads();
 
-  // 2. Gram matrix on the DMMA pipe: tiles of 8x8, K = ncp
-  const int T2 = n2 / 8;
-  for (int tile = warp; tile < T2 * T2; tile += nwarp) {
-    int tp = tile / T2, tq = tile % T2;
-    if (tp > tq) continue;
-    double c0 = 0.0, c1 = 0.0;
-    const double *ap = Ps + (size_t)(tp * 8 + (lane >> 2)) * LDS + (lane & 3);
-    const double *bp = Ps + (size_t)(tq * 8 + (lane >> 2)) * LDS + (lane & 3);
-    for (int k = 0; k < ncp; k += 4) dmma8x8x4(c0, c1, ap[k], bp[k]);
-    int r = tp * 8 + (lane >> 2), c = tq * 8 + 2 * (lane & 3);
-    Gm[r * LG + c] = c0; Gm[r * LG + c + 1] = c1;
-    Gm[c * LG + r] = c0; Gm[(c + 1) * LG + r] = c1;
+  // 2. Gram matrix on the DMMA pipe: warp (kg, half) accumulates its half of the upper tiles over its K slice
+  {
+    const int kg = warp >> 1, half = warp & 1;
+    const int kq = ((ncp / JAC_KGROUPS) + 3) & ~3;
+    const int k0 = kg * kq, k1 = min(ncp, k0 + kq);
+    constexpr int MAXT = (NT + 1) / 2;
+    double acc[MAXT][2];
+    const double *ap[MAXT], *bp[MAXT];
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) {
+      acc[i][0] = acc[i][1] = 0.0;
+      int ti = 2 * i + half;
+      int tp = (ti < NT) ? tile_p[ti] : 0, tq = (ti < NT) ? tile_q[ti] : 0;
+      ap[i] = Ps + (size_t)(tp * 8 + (lane >> 2)) * LDS + (lane & 3);
+      bp[i] = Ps + (size_t)(tq * 8 + (lane >> 2)) * LDS + (lane & 3);
+    }
+    for (int k = k0; k < k1; k += 4) {
+#pragma unroll
+      for (int i = 0; i < MAXT; ++i)
+        if (2 * i + half < NT) dmma8x8x4(acc[i][0], acc[i][1], ap[i][k], bp[i][k]);
+    }
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) {
+      int ti = 2 * i + half;
+      if (ti < NT) {
+        double *g = Gpart + ((size_t)kg * NT + ti) * 64 + (lane >> 2) * 8 + 2 * (lane & 3);
+        g[0] = acc[i][0]; g[1] = acc[i][1];
+      }
+    }
   }
-  for (int e = t; e < n2 * n2; e += JAC_THREADS) {
-    int r = e / n2, c = e % n2;
+  __syncthreads();
+  for (int e = t; e < NT * 64; e += JAC_THREADS) {
+    int ti = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+    double v = 0.0;
+#pragma unroll
+    for (int kg = 0; kg < JAC_KGROUPS; ++kg) v += Gpart[((size_t)kg * NT + ti) * 64 + (e & 63)];
+    int r = tile_p[ti] * 8 + rr, c = tile_q[ti] * 8 + cc;
+    Gm[r * LG + c] = v;
+    Gm[c * LG + r] = v;
+  }
+  for (int e = t; e < N2 * N2; e += JAC_THREADS) {
+    int r = e / N2, c = e % N2;
     Wm[r * LG + c] = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
 
-  // 3. convergence measure before rotating
+  // 3. convergence measure before rotating: max g_pq^2 / (g_pp g_qq)
   {
     double mx = 0.0;
-    for (int e = t; e < n2 * n2; e += JAC_THREADS) {
-      int p = e / n2, q = e % n2;
+    for (int e = t; e < N2 * N2; e += JAC_THREADS) {
+      int p = e / N2, q = e % N2;
       if (p < q) {
-        double gpp = Gm[p * LG + p], gqq = Gm[q * LG + q], gpq = fabs(Gm[p * LG + q]);
-        if (gpp > 0.0 && gqq > 0.0 && gpq > 0.0) mx = fmax(mx, gpq / sqrt(gpp * gqq));
+        double gpp = Gm[p * LG + p], gqq = Gm[q * LG + q], gpq = Gm[p * LG + q];
+        if (gpp > 0.0 && gqq > 0.0 && gpq != 0.0) mx = fmax(mx, gpq * gpq / (gpp * gqq));
       }
     }
 #pragma unroll
@@ -561,115 +829,139 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     __syncthreads();
     if (t == 0) {
       for (int i = 1; i < nwarp; ++i) mx = fmax(mx, red[i]);
+      mx = sqrt(mx);
       if (mx > 0.0) atomicMax((unsigned long long *)(a.offmax + w), (unsigned long long)__double_as_longlong(mx));
       red[0] = mx;
     }
     __syncthreads();
-    if (red[0] <= a.tol) {
-      // nothing to rotate; still sort by norm so the selection sees ordered blocks
-    }
+    if (red[0] <= a.tol) return;       // the 2*bs rows are already mutually orthogonal: nothing to rotate
   }
 
-  // 4. cyclic two-sided Jacobi on Gm, accumulating Wm
-  const int np = n2 / 2;
-  for (int sw = 0; sw < a.inner_sweeps; ++sw) {
-    for (int rd = 0; rd < n2 - 1; ++rd) {
-      if (t < np) {
-        int p, q;
-        rr_pair(n2, rd, t, p, q);
-        if (p > q) { int tmp = p; p = q; q = tmp; }
-        double app = Gm[p * LG + p], aqq = Gm[q * LG + q], apq = Gm[p * LG + q];
-        double c = 1.0, s = 0.0;
-        if (fabs(apq) > a.tol * sqrt(fabs(app * aqq)) && apq != 0.0) {
-          double zeta = (aqq - app) / (2.0 * apq);
-          double tt = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(1.0 + tt * tt);
-          s = c * tt;
-        }
-        cs[t] = c; cs[np + t] = s;
-        pairs[2 * t] = p; pairs[2 * t + 1] = q;
-      }
-      __syncthreads();
-      // column rotation: G <- G J, W <- W J
-      for (int e = t; e < np * n2; e += JAC_THREADS) {
-        int k = e / n2, i = e % n2;
-        int p = pairs[2 * k], q = pairs[2 * k + 1];
-        double c = cs[k], s = cs[np + k];
-        double gp = Gm[i * LG + p], gq = Gm[i * LG + q];
-        Gm[i * LG + p] = c * gp - s * gq;
-        Gm[i * LG + q] = s * gp + c * gq;
-        double wp = Wm[i * LG + p], wq = Wm[i * LG + q];
-        Wm[i * LG + p] = c * wp - s * wq;
-        Wm[i * LG + q] = s * wp + c * wq;
-      }
-      __syncthreads();
-      // row rotation: G <- J^T G
-      for (int e = t; e < np * n2; e += JAC_THREADS) {
-        int k = e / n2, i = e % n2;
-        int p = pairs[2 * k], q = pairs[2 * k + 1];
-        double c = cs[k], s = cs[np + k];
-        double gp = Gm[p * LG + i], gq = Gm[q * LG + i];
-        Gm[p * LG + i] = c * gp - s * gq;
-        Gm[q * LG + i] = s * gp + c * gq;
-      }
-      __syncthreads();
-    }
+  // 4. cyclic two-sided Jacobi on Gm accumulating Wm, one barrier per rotation set
+  const int nrounds = a.inner_sweeps * (N2 - 1);
+  auto set_coef = [&](double *cf, int p, int q, double c, double s) {
+    cf[p] = c; cf[N2 + p] = -s;      // new_row_p = c row_p - s row_q
+    cf[q] = c; cf[N2 + q] = s;       // new_row_q = s row_p + c row_q
+  };
+  if (t < NP) {
+    int p, q;
+    rr_pair(N2, 0, t, p, q);
+    if (p > q) { int tmp = p; p = q; q = tmp; }
+    double c, s;
+    jacobi_cs(Gm[p * LG + p], Gm[q * LG + q], Gm[p * LG + q], tol2, c, s);
+    set_coef(coef, p, q, c, s);
   }
+  __syncthreads();
+  int cur = 0;
+  for (int g = 0; g < nrounds; ++g) {
+    const int rd = g % (N2 - 1);
+    const double *Gc = Gm + cur * N2 * LG, *Wc = Wm + cur * N2 * LG, *cf = coef + cur * 2 * N2;
+    double *Gn = Gm + (cur ^ 1) * N2 * LG, *Wn = Wm + (cur ^ 1) * N2 * LG, *cfn = coef + (cur ^ 1) * 2 * N2;
+    const unsigned char *pt = part + rd * N2;
+    auto newG = [&](int i, int j) {
+      int pi = pt[i], pj = pt[j];
+      double ai = cf[i], bi = cf[N2 + i], aj = cf[j], bj = cf[N2 + j];
+      return aj * (ai * Gc[i * LG + j] + bi * Gc[pi * LG + j]) + bj * (ai * Gc[i * LG + pj] + bi * Gc[pi * LG + pj]);
+    };
+    if (t < NP && g + 1 < nrounds) {   // angles of the next rotation set from the three updated entries it needs
+      int p, q;
+      rr_pair(N2, (rd + 1) % (N2 - 1), t, p, q);
+      if (p > q) { int tmp = p; p = q; q = tmp; }
+      double c, s;
+      jacobi_cs(newG(p, p), newG(q, q), newG(p, q), tol2, c, s);
+      set_coef(cfn, p, q, c, s);
+    }
+    for (int e = t; e < N2 * N2; e += JAC_THREADS) {
+      int i = e / N2, j = e % N2;
+      Gn[i * LG + j] = newG(i, j);
+      int pj = pt[j];
+      Wn[i * LG + j] = cf[j] * Wc[i * LG + j] + cf[N2 + j] * Wc[i * LG + pj];
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  const double *Gf = Gm + cur * N2 * LG, *Wf = Wm + cur * N2 * LG;
 
   // 5. permutation: new row r takes rotated direction perm[r], sorted by diagonal descending
-  if (t < n2) {
-    double mine = Gm[t * LG + t];
+  if (t < N2) {
+    double mine = Gf[t * LG + t];
     int rank = 0;
-    for (int j = 0; j < n2; ++j) {
-      double o = Gm[j * LG + j];
+    for (int j = 0; j < N2; ++j) {
+      double o = Gf[j * LG + j];
       rank += (o > mine) || (o == mine && j < t);
     }
     perm[rank] = t;
   }
   __syncthreads();
 
-  // 6. apply: Pnew[r][c] = sum_k Wm[k][perm[r]] * Ps[k][c] on the DMMA pipe, in place per 8-column slice
-  const int nslice = ncp / 8;
-  for (int sl = warp; sl < nslice; sl += nwarp) {
-    double acc[4][2];
-    for (int mt = 0; mt < T2; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
-    for (int k = 0; k < n2; k += 4) {
-      double bfrag = Ps[(size_t)(k + (lane & 3)) * LDS + sl * 8 + (lane >> 2)];
-      for (int mt = 0; mt < T2; ++mt) {
-        double afrag = Wm[(k + (lane & 3)) * LG + perm[mt * 8 + (lane >> 2)]];
-        dmma8x8x4(acc[mt][0], acc[mt][1], afrag, bfrag);
-      }
-    }
-    __syncwarp();
+  // 6. apply: Pnew[r][c] = sum_k W[k][perm[r]] * Ps[k][c] on the DMMA pipe, in place per 8-column slice
+  {
+    double af[T2][N2 / 4];
+#pragma unroll
     for (int mt = 0; mt < T2; ++mt) {
-      int r = mt * 8 + (lane >> 2), c = sl * 8 + 2 * (lane & 3);
-      Ps[(size_t)r * LDS + c] = acc[mt][0];
-      Ps[(size_t)r * LDS + c + 1] = acc[mt][1];
+      const int col = perm[mt * 8 + (lane >> 2)];
+#pragma unroll
+      for (int ks = 0; ks < N2 / 4; ++ks) af[mt][ks] = Wf[(ks * 4 + (lane & 3)) * LG + col];
+    }
+    const int nslice = ncp / 8;
+    for (int sl = warp; sl < nslice; sl += nwarp) {
+      double acc[T2][2];
+#pragma unroll
+      for (int mt = 0; mt < T2; ++mt) { acc[mt][0] = 0.0; acc[mt][1] = 0.0; }
+      const double *bcol = Ps + (size_t)(lane & 3) * LDS + sl * 8 + (lane >> 2);
+#pragma unroll
+      for (int ks = 0; ks < N2 / 4; ++ks) {
+        double bfrag = bcol[(size_t)ks * 4 * LDS];
+#pragma unroll
+        for (int mt = 0; mt < T2; ++mt) dmma8x8x4(acc[mt][0], acc[mt][1], af[mt][ks], bfrag);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int mt = 0; mt < T2; ++mt) {
+        double2 v; v.x = acc[mt][0]; v.y = acc[mt][1];
+        *reinterpret_cast<double2 *>(Ps + (size_t)(mt * 8 + (lane >> 2)) * LDS + sl * 8 + 2 * (lane & 3)) = v;
+      }
     }
   }
   __syncthreads();
 
   // 7. store
-  for (int e = t; e < n2 * nc; e += JAC_THREADS) {
-    int r = e / nc, c = e % nc;
-    int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
-    Gw[(long)grow * a.ld + c] = Ps[(size_t)r * LDS + c];
+  if ((nc & 1) == 0) {
+    const int nv = nc >> 1;
+    for (int r = warp; r < N2; r += nwarp) {
+      const int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
+      double2 *dst = reinterpret_cast<double2 *>(Gw + (long)grow * a.ld);
+      const double2 *src = reinterpret_cast<const double2 *>(Ps + (size_t)r * LDS);
+      for (int c = lane; c < nv; c += 32) dst[c] = src[c];
+    }
+  } else {
+    for (int r = warp; r < N2; r += nwarp) {
+      const int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
+      for (int c = lane; c < nc; c += 32) Gw[(long)grow * a.ld + c] = Ps[(size_t)r * LDS + c];
+    }
   }
 }
 
 static size_t jacobi_smem_bytes(int bs, int nc) {
-  int n2 = 2 * bs, ncp = (nc + 7) & ~7;
-  return ((size_t)n2 * (ncp + 4) + 2 * (size_t)n2 * (n2 + 1) + n2) * sizeof(double) + 3 * n2 * sizeof(int);
+  int n2 = 2 * bs, ncp = (nc + 7) & ~7, t2 = n2 / 8, nt = t2 * (t2 + 1) / 2;
+  size_t doubles = (size_t)n2 * (ncp + 4) + (size_t)JAC_KGROUPS * nt * 64 + 4 * (size_t)n2 * (n2 + 1) + 4 * n2;
+  return doubles * sizeof(double) + n2 * sizeof(int) + (size_t)(n2 - 1) * n2 + 16;
 }
 void be_jacobi_round(const JacobiArgs &a) {
   size_t smem = jacobi_smem_bytes(a.bs, a.nc);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(jacobi_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
   LaunchScope scope(KC_JACOBI, 3.0 * (2.0 * a.bs) * (2.0 * a.bs) * a.nc * (a.nblk / 2) * (double)a.nactive);
-  jacobi_round_kernel<<<dim3(a.nblk / 2, a.W), JAC_THREADS, smem, g_stream>>>(a);
+  auto launch = [&](auto kern, size_t &configured) {
+    if (smem > configured) {
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    kern<<<dim3(a.nblk / 2, a.W), JAC_THREADS, smem, g_stream>>>(a);
+  };
+  static size_t c32 = 0, c16 = 0, c8 = 0;
+  if (a.bs == 16) launch(jacobi_round_kernel<32>, c32);
+  else if (a.bs == 8) launch(jacobi_round_kernel<16>, c16);
+  else if (a.bs == 4) launch(jacobi_round_kernel<8>, c8);
+  else throw std::runtime_error("be_jacobi_round: unsupported block size");
   post_launch();
 }
 

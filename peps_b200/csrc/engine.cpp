@@ -117,6 +117,7 @@ long Engine::stat(int which) const {
     case 7: return (long)pool_.total_bytes();
     case 8: return la_.rows_in;
     case 9: return la_.rows_kept;
+    case 10: return la_.jacobi_rounds;
     default: return -1;
   }
 }

@@ -23,6 +23,7 @@ struct LinalgCtx {
   std::vector<int32_t> done_host;
   // statistics
   long jacobi_sweeps = 0, jacobi_calls = 0, qr_calls = 0;
+  long jacobi_rounds = 0;
   long rows_in = 0, rows_kept = 0;   // Jacobi row counts before / after deflation (summed over calls)
   double deflation_eps = 1e-15;      // rows of R below eps * (largest row norm) are treated as zero
   double jacobi_tol = 1e-14;
@@ -31,7 +32,7 @@ struct LinalgCtx {
 };
 
 constexpr size_t kPanelSmemBudget = 150 * 1024;   // bytes for the panel itself
-constexpr size_t kJacobiSmemBudget = 200 * 1024;
+constexpr size_t kJacobiSmemBudget = 168 * 1024;   // panel only; the kernel adds ~56 KB of Gram / rotation state
 
 struct QRLayout { int nb = 0, rb = 0, nrb = 0, m_pad = 0; };
 
@@ -186,33 +187,54 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
   double *G2 = (double *)cx.pool->get(sizeof(double) * (size_t)W * J.nr_pad * nc);
   const long ws2 = (long)J.nr_pad * nc;
   be_gather_rows(G, ws, nc, nc, kk, ord, cnt, G2, ws2, J.nr_pad, W);
+  long ws2cur = ws2;
   if (nr_eff > 1) {
     ++cx.jacobi_calls;
     be_fill(cx.offmax, 0.0, W);
     be_memset0(cx.done, sizeof(int32_t) * W);
     JacobiArgs ja;
-    ja.G = G2; ja.ws = ws2; ja.ld = nc; ja.nr_pad = J.nr_pad; ja.nc = nc; ja.bs = J.bs; ja.nblk = J.nblk;
+    ja.G = G2; ja.ws = ws2cur; ja.ld = nc; ja.nr_pad = J.nr_pad; ja.nc = nc; ja.bs = J.bs; ja.nblk = J.nblk;
     ja.tol = cx.jacobi_tol; ja.inner_sweeps = cx.jacobi_inner_sweeps; ja.offmax = cx.offmax; ja.done = cx.done; ja.W = W;
     ja.nactive = W;
     for (int sweep = 0; sweep < cx.jacobi_max_sweeps; ++sweep) {
-      for (int round = 0; round < J.nblk - 1; ++round) {
+      for (int round = 0; round < ja.nblk - 1; ++round) {
         ja.round = round;
         be_jacobi_round(ja);
       }
       ++cx.jacobi_sweeps;
+      cx.jacobi_rounds += ja.nblk - 1;
       be_jacobi_flags(cx.offmax, cx.done, cx.jacobi_tol, W);
       be_d2h(cx.done_host.data(), cx.done, sizeof(int32_t) * W);
       int nact = 0;
       for (int w = 0; w < W; ++w) nact += cx.done_host[(size_t)w] ? 0 : 1;
       ja.nactive = nact;
       if (nact == 0) break;
+      // dynamic deflation: after a sweep the row norms track the singular values far better than the rows of R
+      // did; rows that fell below deflation_eps * max are dropped and the problem is re-compacted when that
+      // removes at least one block pair worth of work.
+      if (nr_eff > 2 * ja.bs && sweep + 1 < cx.jacobi_max_sweeps) {
+        be_row_norms2(G2, ws2cur, nc, nr_eff, nc, n2a, W);
+        be_rank_rows(n2a, nr_eff, cx.deflation_eps * cx.deflation_eps, ord, cnt, W);
+        std::vector<int32_t> ch((size_t)W);
+        be_d2h(ch.data(), cnt, sizeof(int32_t) * W);
+        int ne = 1;
+        for (int w = 0; w < W; ++w) ne = std::max(ne, (int)ch[(size_t)w]);
+        JacobiLayout Jn = jacobi_layout(ne, nc);
+        if (Jn.bs == ja.bs && Jn.nblk + 2 <= ja.nblk) {
+          double *G3 = (double *)cx.pool->get(sizeof(double) * (size_t)W * Jn.nr_pad * nc);
+          be_gather_rows(G2, ws2cur, nc, nc, nr_eff, ord, cnt, G3, (long)Jn.nr_pad * nc, Jn.nr_pad, W);
+          cx.pool->put(G2);
+          G2 = G3; ws2cur = (long)Jn.nr_pad * nc; nr_eff = ne;
+          ja.G = G2; ja.ws = ws2cur; ja.nr_pad = Jn.nr_pad; ja.nblk = Jn.nblk;
+        }
+      }
     }
   }
   double *n2b = (double *)cx.pool->get(sizeof(double) * (size_t)W * nr_eff);
   int32_t *ord2 = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * tcap);
-  be_row_norms2(G2, ws2, nc, nr_eff, nc, n2b, W);
+  be_row_norms2(G2, ws2cur, nc, nr_eff, nc, n2b, W);
   be_select_truncate(n2b, nr_eff, nsv, dmin, dmax, trunc_err, tcap, ord2, kept, W);
-  be_gather_rows_normalized(G2, ws2, nc, nc, n2b, nr_eff, ord2, kept, tcap, B, wb, W);
+  be_gather_rows_normalized(G2, ws2cur, nc, nc, n2b, nr_eff, ord2, kept, tcap, B, wb, W);
   for (void *p : {(void *)n2a, (void *)ord, (void *)cnt, (void *)G2, (void *)n2b, (void *)ord2}) cx.pool->put(p);
 }
 

@@ -191,9 +191,9 @@ void be_jacobi_round(const JacobiArgs &a) {
             if (p > qq) std::swap(p, qq);
             double app = G[(size_t)p * n2 + p], aqq = G[(size_t)qq * n2 + qq], apq = G[(size_t)p * n2 + qq];
             double c = 1.0, s = 0.0;
-            if (std::fabs(apq) > a.tol * std::sqrt(std::fabs(app * aqq)) && apq != 0.0) {
-              double zeta = (aqq - app) / (2.0 * apq);
-              double tt = ((zeta >= 0.0) ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+            if (apq * apq > a.tol * a.tol * std::fabs(app * aqq) && apq != 0.0) {
+              double d = aqq - app, r = std::sqrt(d * d + 4.0 * apq * apq);
+              double tt = (d >= 0.0) ? (2.0 * apq) / (d + r) : (-2.0 * apq) / (r - d);
               c = 1.0 / std::sqrt(1.0 + tt * tt);
               s = c * tt;
             }
