@@ -88,6 +88,18 @@ struct PanelArgs {
 };
 void be_panel_qr(const PanelArgs &a);
 
+// Trailing update of one CAQR panel step: for every (walker, item) C <- C - VT (V^T C) where C are the rows
+// rowtab[it*R + s] (s < R) and columns [col1, col1 + ntrail) of A, and V / VT are the [R][nbw] blocks emitted by
+// be_panel_qr. One fused kernel (C tile resident in shared memory) instead of two contractions.
+struct ApplyArgs {
+  double *A; long ws; int lda;
+  const int32_t *rowtab; int R; int NI;
+  int col1, ntrail, nbw;
+  const double *Vw, *VTw;
+  int W;
+};
+void be_apply_reflector(const ApplyArgs &a);
+
 // ---- one-sided block Jacobi on the ROWS of G[w] (nr_pad x nc, leading dimension ld) ----------------------
 // One round of the round-robin block-pair schedule: block pairs (I,J) of `round` are loaded, their
 // (2*bs)x(2*bs) Gram matrix is diagonalised by cyclic two-sided Jacobi (inner_sweeps sweeps) and the

@@ -135,7 +135,7 @@ constexpr int GETT_BK = 16;
 
 // CTA tile (16*WMT) x (16*WNT), 2x2 warps, each warp (8*WMT) x (8*WNT) made of m8n8k4 DMMA tiles.
 template <int WMT, int WNT>
-__global__ void __launch_bounds__(GETT_THREADS)
+__global__ void __launch_bounds__(GETT_THREADS, 3)
 gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double beta) {
   constexpr int BM = 16 * WMT, BN = 16 * WNT, BK = GETT_BK;
   constexpr int LDA = BM + 4, LDB = BN + 4;       // +4 doubles: conflict-free DMMA fragment loads
@@ -673,6 +673,163 @@ void be_panel_qr(const PanelArgs &a) {
     }
     panel_qr_kernel<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
   }
+  post_launch();
+}
+
+// Fused trailing update of one CAQR panel step (see backend.h ApplyArgs): the C tile (R rows x NBW columns) stays
+// in shared memory; W = V^T C is accumulated on the DMMA pipe with the row range split over the 8 warps, then
+// C - VT W is formed tile-row by tile-row and written back. V / VT fragments are read straight from L2.
+template <int NBW>
+__global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
+  extern __shared__ double sm[];
+  constexpr int TN = NBW, MT = NBW / 8, NT = NBW / 8, LDC = TN + 4, LDW = TN + 4, NTILE = MT * NT;
+  const int ct = blockIdx.x, it = blockIdx.y, w = blockIdx.z;
+  const int R = a.R, R8 = (R + 7) & ~7, nbw = a.nbw;
+  double *Cs = sm;                               // [R8][LDC]
+  double *part = Cs + (size_t)R8 * LDC;          // [4][NTILE][64]
+  double *Wsm = part + 4 * NTILE * 64;           // [NBW][LDW] = -(V^T C)
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  double *Aw = a.A + (long)w * a.ws;
+  const int32_t *rows = a.rowtab + (long)it * R;
+  const double *V = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
+  const double *VT = a.VTw + ((long)w * a.NI + it) * (long)R * nbw;
+  const int cbase = a.col1 + ct * TN;
+  const int ncols = min(TN, a.ntrail - ct * TN);
+
+  // 0. C tile -> shared memory (row offsets staged first, eight independent row loads in flight per warp)
+  long *roff = reinterpret_cast<long *>(Wsm + NBW * LDW);   // [R8]
+  for (int r = t; r < R8; r += 256) roff[r] = (r < R) ? (long)rows[r] * a.lda + cbase : -1;
+  __syncthreads();
+  for (int r0 = warp * 8; r0 < R8; r0 += 64) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const long o = roff[r0 + u];
+      v[u] = (o >= 0 && lane < ncols) ? Aw[o + lane] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (lane < TN) Cs[(size_t)(r0 + u) * LDC + lane] = v[u];
+      if (lane < LDC - TN) Cs[(size_t)(r0 + u) * LDC + TN + lane] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  // A. partial W = V^T C over this warp's row slice
+  {
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int kslice = ((R8 / 8) + 3) & ~3;
+    const int k0 = warp * kslice, k1 = min(R8, k0 + kslice);
+    for (int k = k0; k < k1; k += 4) {
+      const int kr = k + (lane & 3);
+      double af[MT], bf[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) af[i] = (kr < R) ? __ldg(V + (long)kr * nbw + i * 8 + (lane >> 2)) : 0.0;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bf[j] = Cs[(size_t)kr * LDC + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+    const int eo = (lane >> 2) * 8 + 2 * (lane & 3);
+    if (warp >= 4) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          double *g = part + ((size_t)(warp - 4) * NTILE + i * NT + j) * 64 + eo;
+          g[0] = acc[i][j][0]; g[1] = acc[i][j][1];
+        }
+    }
+    __syncthreads();
+    if (warp < 4) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          double *g = part + ((size_t)warp * NTILE + i * NT + j) * 64 + eo;
+          acc[i][j][0] += g[0]; acc[i][j][1] += g[1];
+        }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          double *g = part + ((size_t)warp * NTILE + i * NT + j) * 64 + eo;
+          g[0] = acc[i][j][0]; g[1] = acc[i][j][1];
+        }
+    }
+    __syncthreads();
+    for (int e = t; e < NTILE * 64; e += 256) {
+      const int tile = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+      double v = 0.0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) v += part[((size_t)g * NTILE + tile) * 64 + (e & 63)];
+      Wsm[((tile / NT) * 8 + rr) * LDW + (tile % NT) * 8 + cc] = -v;
+    }
+    __syncthreads();
+  }
+
+  // C. C <- C + VT (-W), written straight back to global memory
+  {
+    double bw[NBW / 4][NT];
+#pragma unroll
+    for (int ks = 0; ks < NBW / 4; ++ks)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bw[ks][j] = Wsm[(ks * 4 + (lane & 3)) * LDW + j * 8 + (lane >> 2)];
+    for (int rt = warp; rt < R8 / 8; rt += 8) {
+      const int r = rt * 8 + (lane >> 2);
+      double acc[NT][2];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        acc[j][0] = Cs[(size_t)r * LDC + j * 8 + 2 * (lane & 3)];
+        acc[j][1] = Cs[(size_t)r * LDC + j * 8 + 2 * (lane & 3) + 1];
+      }
+      const double *vt = VT + (long)r * nbw + (lane & 3);
+#pragma unroll
+      for (int ks = 0; ks < NBW / 4; ++ks) {
+        const double af = (r < R) ? __ldg(vt + ks * 4) : 0.0;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma8x8x4(acc[j][0], acc[j][1], af, bw[ks][j]);
+      }
+      if (r < R) {
+        double *dst = Aw + roff[r];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int c = j * 8 + 2 * (lane & 3);
+          if (c < ncols) dst[c] = acc[j][0];
+          if (c + 1 < ncols) dst[c + 1] = acc[j][1];
+        }
+      }
+    }
+  }
+}
+
+template <int NBW>
+static size_t apply_smem_bytes(int R) {
+  int R8 = (R + 7) & ~7;
+  return ((size_t)R8 * (NBW + 4) + 4 * (size_t)(NBW / 8) * (NBW / 8) * 64 + (size_t)NBW * (NBW + 4) + (size_t)R8) * sizeof(double);
+}
+void be_apply_reflector(const ApplyArgs &a) {
+  if (a.ntrail <= 0) return;
+  LaunchScope scope(KC_GETT, 4.0 * a.R * a.nbw * (double)a.ntrail * a.NI * a.W);
+  auto launch = [&](auto kern, size_t smem, size_t &configured, int tn) {
+    if (smem > configured) {
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    kern<<<dim3((a.ntrail + tn - 1) / tn, a.NI, a.W), 256, smem, g_stream>>>(a);
+  };
+  static size_t c32 = 0, c16 = 0, c8 = 0;
+  if (a.nbw == 32) launch(apply_reflector_kernel<32>, apply_smem_bytes<32>(a.R), c32, 32);
+  else if (a.nbw == 16) launch(apply_reflector_kernel<16>, apply_smem_bytes<16>(a.R), c16, 16);
+  else if (a.nbw == 8) launch(apply_reflector_kernel<8>, apply_smem_bytes<8>(a.R), c8, 8);
+  else throw std::runtime_error("be_apply_reflector: unsupported panel width");
   post_launch();
 }
 

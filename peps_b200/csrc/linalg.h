@@ -43,6 +43,7 @@ inline QRLayout qr_layout(int m, int n) {
   const int kk = std::min(m, n);
   for (int nb : {32, 16, 8}) {
     int rbmax = (int)(kPanelSmemBudget / (sizeof(double) * nb)) / nb * nb;
+    if (nb == 8) rbmax = 1536;       // keeps the fused trailing-update tile (rows x 12 doubles) inside shared memory
     int need = round_up(kk, nb);
     if (need > rbmax && nb != 8) continue;
     if (need > rbmax) throw std::runtime_error("qr_layout: matrix too large for the shared-memory panel");
@@ -83,7 +84,6 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
   Planner &pl = *cx.planner;
   double *Vw = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * rb * nb);
   double *VTw = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * rb * nb);
-  double *Wk = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * nb * n);
   std::vector<int32_t> rowtab1((size_t)nrb * rb);
   for (int b = 0; b < nrb; ++b)
     for (int s = 0; s < rb; ++s) rowtab1[(size_t)b * rb + s] = b * rb + s;
@@ -96,15 +96,10 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
     pa.col0 = col0; pa.pw = pw; pa.nbw = nb; pa.Vw = Vw; pa.VTw = VTw; pa.W = W;
     be_panel_qr(pa);
     if (ntrail > 0) {
-      // Wk[b] = V[b]^T C[b];  C[b] -= VT[b] Wk[b]      (C[b] = rows of block b, columns [c1, n))
-      int dv[2] = {rb, nb}, dc[2] = {rb, ntrail}, dw[2] = {nb, ntrail};
-      long sc[2] = {lda, 1};
-      const Plan &g1 = pl.get("rc,rt->ct", dv, 2, dc, 2, nullptr, sc, nullptr);
-      be_gett(g1.d, mkop(Vw, (long)nrb * rb * nb, (long)rb * nb), mkop(A + c1, ws, (long)rb * lda),
-              mkop(Wk, (long)nrb * nb * ntrail, (long)nb * ntrail), 1.0, 0.0, W, nrb);
-      const Plan &g2 = pl.get("rc,ct->rt", dv, 2, dw, 2, nullptr, nullptr, sc);
-      be_gett(g2.d, mkop(VTw, (long)nrb * rb * nb, (long)rb * nb), mkop(Wk, (long)nrb * nb * ntrail, (long)nb * ntrail),
-              mkop(A + c1, ws, (long)rb * lda), -1.0, 1.0, W, nrb);
+      ApplyArgs ap;
+      ap.A = A; ap.ws = ws; ap.lda = lda; ap.rowtab = rowtab1_d; ap.R = rb; ap.NI = nrb; ap.col1 = c1; ap.ntrail = ntrail;
+      ap.nbw = nb; ap.Vw = Vw; ap.VTw = VTw; ap.W = W;
+      be_apply_reflector(ap);
     }
     if (nrb > 1) {
       // stage 2: stack the nrb local R blocks and factorise them; update the same rows of the trailing matrix
@@ -116,22 +111,15 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
       p2.rowtab = pl.upload(rowtab2); p2.R = R2; p2.skip0 = 0; p2.NI = 1;
       be_panel_qr(p2);
       if (ntrail > 0) {
-        std::vector<int32_t> rows_lda((size_t)R2);
-        for (int i = 0; i < R2; ++i) rows_lda[(size_t)i] = rowtab2[(size_t)i] * lda;
-        // W2 = V2^T Cg : M = nb (c), K = R2 (r), N = ntrail (t)
-        GettDesc g3 = make_desc(pl, iota_scaled(nb, 1), iota_scaled(R2, nb), rows_lda, iota_scaled(ntrail, 1),
-                                iota_scaled(nb, ntrail), iota_scaled(ntrail, 1), 0, 1);
-        be_gett(g3, mkop(Vw, (long)R2 * nb), mkop(A + c1, ws), mkop(Wk, (long)nb * ntrail), 1.0, 0.0, W, 1);
-        // Cg -= VT2 W2 : M = R2 (r), K = nb (c), N = ntrail (t)
-        GettDesc g4 = make_desc(pl, iota_scaled(R2, nb), iota_scaled(nb, 1), iota_scaled(nb, ntrail),
-                                iota_scaled(ntrail, 1), rows_lda, iota_scaled(ntrail, 1), 1, 1);
-        be_gett(g4, mkop(VTw, (long)R2 * nb), mkop(Wk, (long)nb * ntrail), mkop(A + c1, ws), -1.0, 1.0, W, 1);
+        ApplyArgs ap;
+        ap.A = A; ap.ws = ws; ap.lda = lda; ap.rowtab = p2.rowtab; ap.R = R2; ap.NI = 1; ap.col1 = c1; ap.ntrail = ntrail;
+        ap.nbw = nb; ap.Vw = Vw; ap.VTw = VTw; ap.W = W;
+        be_apply_reflector(ap);
       }
     }
   }
   cx.pool->put(Vw);
   cx.pool->put(VTw);
-  cx.pool->put(Wk);
 }
 
 struct JacobiLayout { int bs = 0, nblk = 0, nr_pad = 0; };

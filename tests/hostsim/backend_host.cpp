@@ -147,6 +147,30 @@ void be_panel_qr(const PanelArgs &a) {
     }
 }
 
+void be_apply_reflector(const ApplyArgs &a) {
+  ++g_launches;
+  for (int w = 0; w < a.W; ++w)
+    for (int it = 0; it < a.NI; ++it) {
+      double *Aw = a.A + (long)w * a.ws;
+      const int32_t *rows = a.rowtab + (long)it * a.R;
+      const double *V = a.Vw + ((long)w * a.NI + it) * (long)a.R * a.nbw;
+      const double *VT = a.VTw + ((long)w * a.NI + it) * (long)a.R * a.nbw;
+      std::vector<double> Wm((size_t)a.nbw * a.ntrail, 0.0);
+      for (int r = 0; r < a.R; ++r)
+        for (int c = 0; c < a.nbw; ++c) {
+          double v = V[(long)r * a.nbw + c];
+          if (v == 0.0) continue;
+          for (int tcol = 0; tcol < a.ntrail; ++tcol) Wm[(size_t)c * a.ntrail + tcol] += v * Aw[(long)rows[r] * a.lda + a.col1 + tcol];
+        }
+      for (int r = 0; r < a.R; ++r)
+        for (int tcol = 0; tcol < a.ntrail; ++tcol) {
+          double s = 0.0;
+          for (int c = 0; c < a.nbw; ++c) s += VT[(long)r * a.nbw + c] * Wm[(size_t)c * a.ntrail + tcol];
+          Aw[(long)rows[r] * a.lda + a.col1 + tcol] -= s;
+        }
+    }
+}
+
 static void rr_pair(int nblk, int round, int q, int &I, int &J) {
   const int n1 = nblk - 1;
   if (q == 0) { I = n1; J = round % n1; }
