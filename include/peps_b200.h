@@ -105,7 +105,8 @@ int peps_get_bmps_tensor(peps_ctx *ctx, int32_t position, int32_t k, int32_t i, 
  * 6 kernel launches, 7 pooled device bytes. */
 int64_t peps_stat(peps_ctx *ctx, int32_t which);
 /* Per-kernel-class device timing with CUDA events on the launching stream. Classes: 0 contraction (gett),
- * 1 trace dot, 2 CAQR panel, 3 Jacobi round, 4 small kernels. peps_profile_get syncs and fills arrays of 5. */
+ * 1 trace dot, 2 CAQR panel, 3 Jacobi round, 4 small kernels, 5 CAQR trailing update. peps_profile_get syncs and
+ * fills arrays of 6. */
 int peps_profile_enable(peps_ctx *ctx, int32_t on);
 int peps_profile_get(peps_ctx *ctx, double *ms, int64_t *launches, double *flops, int32_t reset);
 /* Stream synchronisation and the context's cudaStream_t (for CUDA-event timing by the caller). */

@@ -298,15 +298,15 @@ class WalkerBatch:
     def stat(self, which):
         return int(self.lib.peps_stat(self.h, which))
 
-    KERNEL_CLASSES = ("gett", "dot", "panel_qr", "jacobi_round", "small")
+    KERNEL_CLASSES = ("gett", "dot", "panel_qr", "jacobi_round", "small", "apply_reflector")
 
     def profile_enable(self, on=True):
         self._ck(self.lib.peps_profile_enable(self.h, int(on)))
 
     def profile_get(self, reset=True):
-        ms = np.zeros(5)
-        fl = np.zeros(5)
-        ln = np.zeros(5, dtype=np.int64)
+        ms = np.zeros(6)
+        fl = np.zeros(6)
+        ln = np.zeros(6, dtype=np.int64)
         self._ck(self.lib.peps_profile_get(self.h, _dp(ms), ln.ctypes.data_as(C.POINTER(C.c_int64)), _dp(fl), int(reset)))
         return {k: dict(ms=float(ms[i]), launches=int(ln[i]), flops=float(fl[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
 

@@ -54,7 +54,7 @@ void *be_stream();                        // cudaStream_t of the context (nullpt
 long be_launch_count();                   // number of kernels launched so far (for bench.py gpu_launches)
 
 // ---- per-kernel-class device timing (CUDA events on the launching stream) -----------------------------
-enum KernelClass { KC_GETT = 0, KC_DOT, KC_PANEL, KC_JACOBI, KC_SMALL, KC_COUNT };
+enum KernelClass { KC_GETT = 0, KC_DOT, KC_PANEL, KC_JACOBI, KC_SMALL, KC_APPLY, KC_COUNT };
 void be_profile_enable(int on);           // when on, every launch is bracketed by an event pair
 // Synchronises, folds all pending event pairs into the per-class totals and returns them (arrays of KC_COUNT);
 // `reset` clears the totals afterwards. flops = useful FP64 flops the launches of that class executed.

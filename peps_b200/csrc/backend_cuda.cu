@@ -20,9 +20,11 @@
 
 namespace peps {
 
-static cudaStream_t g_stream = nullptr;
-static long g_launches = 0;
-static int g_device = -1;
+// One stream / launch counter / profiler per HOST THREAD: contexts driven from different host threads run on
+// different streams, so their kernels overlap on the GPU (fills the tails of partially occupied launches).
+static thread_local cudaStream_t g_stream = nullptr;
+static thread_local long g_launches = 0;
+static thread_local int g_device = -1;
 
 #define CUDA_CHECK(x)                                                                              \
   do {                                                                                             \
@@ -52,7 +54,7 @@ struct Profiler {
     return e;
   }
 };
-static Profiler g_prof;
+static thread_local Profiler g_prof;
 struct LaunchScope {          // brackets one kernel launch
   int c; cudaEvent_t s = nullptr;
   LaunchScope(int cls, double fl) : c(cls) {
@@ -89,6 +91,7 @@ void be_init(int device) {
   if (e != cudaSuccess || n == 0)
     throw std::runtime_error("peps_b200: no CUDA device available; the product has no CPU fallback");
   CUDA_CHECK(cudaSetDevice(device));
+  if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
   g_device = device;
   if (!g_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
 }
@@ -492,16 +495,19 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
   double *Tt = S + NBW * LDSS;             // [NBW][LDT]   T[a][b]
   double *tau_s = Tt + NBW * LDT;          // [NBW]
   double *Rd = tau_s + NBW;                // [NBW]
-  double *Vs = Rd + NBW;                   // [round_up(nact,8)][LDV]
+  long *roff = reinterpret_cast<long *>(Rd + NBW);   // [RP] global offset of active row r
+  double *Vs = reinterpret_cast<double *>(roff + RP);   // [round_up(nact,8)][LDV]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   double *Aw = a.A + (long)w * a.ws;
   const int32_t *rows = a.rowtab + (long)it * R;
+  for (int r = t; r < RP; r += PQR_THREADS) roff[r] = (r < nact) ? (long)rows[skip + r] * a.lda + a.col0 : 0;
+  __syncthreads();
 
   double P[CPW][RPL];
 #pragma unroll
   for (int i = 0; i < RPL; ++i) {
     const int r = lane + 32 * i;
-    const long off = (r < nact) ? (long)rows[skip + r] * a.lda + a.col0 : 0;
+    const long off = roff[r];
 #pragma unroll
     for (int cc = 0; cc < CPW; ++cc) {
       const int c = warp * CPW + cc;
@@ -605,7 +611,7 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
   for (int i = 0; i < RPL; ++i) {
     const int r = lane + 32 * i;
     if (r < nact) {
-      const long off = (long)rows[skip + r] * a.lda + a.col0;
+      const long off = roff[r];
 #pragma unroll
       for (int cc = 0; cc < CPW; ++cc) {
         const int c = warp * CPW + cc;
@@ -645,7 +651,7 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
 template <int NBW, int RPL>
 static size_t panel_reg_smem_bytes(int nact_max) {
   int nact8 = (nact_max + 7) & ~7;
-  return ((size_t)2 * RPL * 32 + (size_t)NBW * (NBW + 1) + (size_t)NBW * (NBW + 4) + 2 * NBW + (size_t)nact8 * (NBW + 4)) *
+  return ((size_t)3 * RPL * 32 + (size_t)NBW * (NBW + 1) + (size_t)NBW * (NBW + 4) + 2 * NBW + (size_t)nact8 * (NBW + 4)) *
          sizeof(double);
 }
 
@@ -817,7 +823,7 @@ static size_t apply_smem_bytes(int R) {
 }
 void be_apply_reflector(const ApplyArgs &a) {
   if (a.ntrail <= 0) return;
-  LaunchScope scope(KC_GETT, 4.0 * a.R * a.nbw * (double)a.ntrail * a.NI * a.W);
+  LaunchScope scope(KC_APPLY, 4.0 * a.R * a.nbw * (double)a.ntrail * a.NI * a.W);
   auto launch = [&](auto kern, size_t smem, size_t &configured, int tn) {
     if (smem > configured) {
       CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -846,16 +852,30 @@ __host__ __device__ __forceinline__ void rr_pair(int nblk, int round, int q, int
   else { I = (round + q) % n1; J = (round - q + n1) % n1; }
 }
 
-// Jacobi rotation (c, s) annihilating a_pq of [[app, apq], [apq, aqq]] (p < q), Rutishauser's small-angle choice
-// written with one sqrt, one division and one rsqrt.
+// Jacobi rotation (c, s) annihilating a_pq of [[app, apq], [apq, aqq]] (p < q), Rutishauser's small-angle choice.
+// The tangent only steers the iteration (an error eps in it leaves eps * a_pq behind, which the next visit removes),
+// so it is evaluated in FP32 on exponent-normalised inputs; c = 1/sqrt(1 + t^2) and s = c t are then formed in FP64
+// (float seed + three Newton steps) so the rotation is orthogonal to double rounding. This takes the serial
+// sqrt/div/rsqrt FP64 sequences (~800 cycles) off the per-rotation-set critical path.
 __device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double tol2, double &c, double &s) {
   c = 1.0; s = 0.0;
   if (apq * apq > tol2 * fabs(app * aqq) && apq != 0.0) {
-    double d = aqq - app;
-    double r = sqrt(d * d + 4.0 * apq * apq);
-    double t = (d >= 0.0) ? (2.0 * apq) / (d + r) : (-2.0 * apq) / (r - d);
-    c = rsqrt(1.0 + t * t);
-    s = c * t;
+    const double d = aqq - app, b2 = 2.0 * apq;
+    const double m = fmax(fabs(d), fabs(b2));
+    // scale = 2^-(exponent of m): keeps the FP32 evaluation away from overflow / underflow
+    const int ex = ((__double2hiint(m) >> 20) & 0x7ff) - 1023;
+    const double scale = __hiloint2double((1023 - ex) << 20, 0);
+    const float df = (float)(d * scale), bf = (float)(b2 * scale);
+    const float rf = sqrtf(df * df + bf * bf);
+    const float tf = (df >= 0.0f) ? bf / (df + rf) : -bf / (rf - df);
+    const double t = (double)tf;
+    const double x = 1.0 + t * t;
+    double y = (double)rsqrtf((float)x);
+    y = y * (1.5 - 0.5 * x * y * y);
+    y = y * (1.5 - 0.5 * x * y * y);
+    y = y * (1.5 - 0.5 * x * y * y);
+    c = y;
+    s = y * t;
   }
 }
 
@@ -883,6 +903,9 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
   double *coef = Wm + 2 * N2 * LG;                   // [2][2][N2]: (a_i, b_i) double buffered
   int *perm = (int *)(coef + 4 * N2);                // [N2]
   unsigned char *part = (unsigned char *)(perm + N2);  // [N2-1][N2] partner of i in rotation set r
+  unsigned char *pairidx = part + (N2 - 1) * N2;       // [N2-1][N2] index of the pair containing i in set r
+  unsigned char *pairp = pairidx + (N2 - 1) * N2;      // [N2-1][NP] smaller index of pair k in set r
+  unsigned char *pairq = pairp + (N2 - 1) * NP;        // [N2-1][NP] larger index
   __shared__ double red[JAC_THREADS / 32];
   __shared__ int tile_p[NT], tile_q[NT];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = JAC_THREADS / 32;
@@ -904,6 +927,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     rr_pair(N2, rd, k, p, q);
     part[rd * N2 + p] = (unsigned char)q;
     part[rd * N2 + q] = (unsigned char)p;
+    pairidx[rd * N2 + p] = (unsigned char)k;
+    pairidx[rd * N2 + q] = (unsigned char)k;
+    pairp[rd * NP + k] = (unsigned char)min(p, q);
+    pairq[rd * NP + k] = (unsigned char)max(p, q);
   }
 
   // 1. load the two row blocks (zero padded columns)
@@ -994,19 +1021,16 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     if (red[0] <= a.tol) return;       // the 2*bs rows are already mutually orthogonal: nothing to rotate
   }
 
-  // 4. cyclic two-sided Jacobi on Gm accumulating Wm, one barrier per rotation set
+  // 4. cyclic two-sided Jacobi on Gm accumulating Wm, one barrier per rotation set. Thread (ki, kj) owns the 2x2
+  //    block {p_i, q_i} x {p_j, q_j} of G (and of W): the four outputs need exactly the four inputs it loads.
   const int nrounds = a.inner_sweeps * (N2 - 1);
-  auto set_coef = [&](double *cf, int p, int q, double c, double s) {
-    cf[p] = c; cf[N2 + p] = -s;      // new_row_p = c row_p - s row_q
-    cf[q] = c; cf[N2 + q] = s;       // new_row_q = s row_p + c row_q
-  };
   if (t < NP) {
     int p, q;
     rr_pair(N2, 0, t, p, q);
     if (p > q) { int tmp = p; p = q; q = tmp; }
     double c, s;
     jacobi_cs(Gm[p * LG + p], Gm[q * LG + q], Gm[p * LG + q], tol2, c, s);
-    set_coef(coef, p, q, c, s);
+    coef[t] = c; coef[NP + t] = s;
   }
   __syncthreads();
   int cur = 0;
@@ -1014,25 +1038,46 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     const int rd = g % (N2 - 1);
     const double *Gc = Gm + cur * N2 * LG, *Wc = Wm + cur * N2 * LG, *cf = coef + cur * 2 * N2;
     double *Gn = Gm + (cur ^ 1) * N2 * LG, *Wn = Wm + (cur ^ 1) * N2 * LG, *cfn = coef + (cur ^ 1) * 2 * N2;
-    const unsigned char *pt = part + rd * N2;
-    auto newG = [&](int i, int j) {
-      int pi = pt[i], pj = pt[j];
-      double ai = cf[i], bi = cf[N2 + i], aj = cf[j], bj = cf[N2 + j];
-      return aj * (ai * Gc[i * LG + j] + bi * Gc[pi * LG + j]) + bj * (ai * Gc[i * LG + pj] + bi * Gc[pi * LG + pj]);
+    // rotated 2x2 block of J^T G J for row pair a (pa<qa, ca, sa) and column pair b
+    auto block = [&](int pa, int qa, double ca, double sa, int pb, int qb, double cb, double sb, double &o_pp,
+                     double &o_pq, double &o_qp, double &o_qq) {
+      const double g_pp = Gc[pa * LG + pb], g_pq = Gc[pa * LG + qb], g_qp = Gc[qa * LG + pb], g_qq = Gc[qa * LG + qb];
+      const double r_pp = ca * g_pp - sa * g_qp, r_pq = ca * g_pq - sa * g_qq;     // rows: J^T G
+      const double r_qp = sa * g_pp + ca * g_qp, r_qq = sa * g_pq + ca * g_qq;
+      o_pp = cb * r_pp - sb * r_pq; o_pq = sb * r_pp + cb * r_pq;                  // columns: (.) J
+      o_qp = cb * r_qp - sb * r_qq; o_qq = sb * r_qp + cb * r_qq;
     };
-    if (t < NP && g + 1 < nrounds) {   // angles of the next rotation set from the three updated entries it needs
-      int p, q;
-      rr_pair(N2, (rd + 1) % (N2 - 1), t, p, q);
-      if (p > q) { int tmp = p; p = q; q = tmp; }
+    if (t < NP && g + 1 < nrounds) {   // angles of the next rotation set from the entries it will need
+      const int rn = (rd + 1) % (N2 - 1);
+      const int p = pairp[rn * NP + t], q = pairq[rn * NP + t];
+      // (p, q) belong to two different pairs of the current set: ka (containing p) and kb (containing q)
+      const unsigned char *pt = part + rd * N2;
+      int pa = p, qa = pt[p]; if (pa > qa) { int tmp = pa; pa = qa; qa = tmp; }
+      int pb = q, qb = pt[q]; if (pb > qb) { int tmp = pb; pb = qb; qb = tmp; }
+      const int ka = pairidx[rd * N2 + pa], kb = pairidx[rd * N2 + pb];
+      const double ca = cf[ka], sa = cf[NP + ka], cb = cf[kb], sb = cf[NP + kb];
+      double x0, x1, x2, x3, npp, nqq, npq;
+      block(pa, qa, ca, sa, pa, qa, ca, sa, x0, x1, x2, x3);
+      npp = (p == pa) ? x0 : x3;
+      block(pb, qb, cb, sb, pb, qb, cb, sb, x0, x1, x2, x3);
+      nqq = (q == pb) ? x0 : x3;
+      block(pa, qa, ca, sa, pb, qb, cb, sb, x0, x1, x2, x3);
+      npq = (p == pa) ? ((q == pb) ? x0 : x1) : ((q == pb) ? x2 : x3);
       double c, s;
-      jacobi_cs(newG(p, p), newG(q, q), newG(p, q), tol2, c, s);
-      set_coef(cfn, p, q, c, s);
+      jacobi_cs(npp, nqq, npq, tol2, c, s);
+      cfn[t] = c; cfn[NP + t] = s;
     }
-    for (int e = t; e < N2 * N2; e += JAC_THREADS) {
-      int i = e / N2, j = e % N2;
-      Gn[i * LG + j] = newG(i, j);
-      int pj = pt[j];
-      Wn[i * LG + j] = cf[j] * Wc[i * LG + j] + cf[N2 + j] * Wc[i * LG + pj];
+    for (int e = t; e < NP * NP; e += JAC_THREADS) {
+      const int ka = e / NP, kb = e % NP;
+      const int pa = pairp[rd * NP + ka], qa = pairq[rd * NP + ka], pb = pairp[rd * NP + kb], qb = pairq[rd * NP + kb];
+      const double ca = cf[ka], sa = cf[NP + ka], cb = cf[kb], sb = cf[NP + kb];
+      double o_pp, o_pq, o_qp, o_qq;
+      block(pa, qa, ca, sa, pb, qb, cb, sb, o_pp, o_pq, o_qp, o_qq);
+      Gn[pa * LG + pb] = o_pp; Gn[pa * LG + qb] = o_pq; Gn[qa * LG + pb] = o_qp; Gn[qa * LG + qb] = o_qq;
+      // W <- W J: rows pa, qa of W are just two arbitrary rows here; columns (pb, qb) rotate
+      const double w_pp = Wc[pa * LG + pb], w_pq = Wc[pa * LG + qb], w_qp = Wc[qa * LG + pb], w_qq = Wc[qa * LG + qb];
+      Wn[pa * LG + pb] = cb * w_pp - sb * w_pq; Wn[pa * LG + qb] = sb * w_pp + cb * w_pq;
+      Wn[qa * LG + pb] = cb * w_qp - sb * w_qq; Wn[qa * LG + qb] = sb * w_qp + cb * w_qq;
     }
     __syncthreads();
     cur ^= 1;
@@ -1102,7 +1147,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
 static size_t jacobi_smem_bytes(int bs, int nc) {
   int n2 = 2 * bs, ncp = (nc + 7) & ~7, t2 = n2 / 8, nt = t2 * (t2 + 1) / 2;
   size_t doubles = (size_t)n2 * (ncp + 4) + (size_t)JAC_KGROUPS * nt * 64 + 4 * (size_t)n2 * (n2 + 1) + 4 * n2;
-  return doubles * sizeof(double) + n2 * sizeof(int) + (size_t)(n2 - 1) * n2 + 16;
+  return doubles * sizeof(double) + n2 * sizeof(int) + 3 * (size_t)(n2 - 1) * n2 + 16;
 }
 void be_jacobi_round(const JacobiArgs &a) {
   size_t smem = jacobi_smem_bytes(a.bs, a.nc);

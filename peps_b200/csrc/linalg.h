@@ -9,6 +9,7 @@
 // Backend-agnostic host code.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include "tensor.h"
 
@@ -124,10 +125,21 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
 
 struct JacobiLayout { int bs = 0, nblk = 0, nr_pad = 0; };
 
+inline int jacobi_max_bs() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = std::getenv("PEPS_JACOBI_BS");
+    v = e ? std::atoi(e) : 16;
+    if (v != 4 && v != 8 && v != 16) v = 16;
+  }
+  return v;
+}
+
 inline JacobiLayout jacobi_layout(int nr, int nc) {
   JacobiLayout J;
   int ncp = round_up(nc, 8);
   for (int bs : {16, 8, 4}) {
+    if (bs > jacobi_max_bs()) continue;
     size_t bytes = (size_t)2 * bs * (ncp + 4) * sizeof(double);
     if (bytes > kJacobiSmemBudget && bs != 4) continue;
     if (bytes > kJacobiSmemBudget) throw std::runtime_error("jacobi_layout: rows too long for the shared-memory panel");
