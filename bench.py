@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--walkers", type=int, default=16, help="walkers (Markov chains) per GPU")
+    ap.add_argument("--walkers", type=int, default=64, help="walkers (Markov chains) per GPU")
     ap.add_argument("--workload", default="heisenberg_10x10_D8_chi64", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -268,8 +268,6 @@ def main():
     for _ in range(args.warmup):
         b.sample(1)
     barrier()
-    b.profile_enable(True)
-    b.profile_get(True)
     launches0 = b.stat(6)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -290,9 +288,15 @@ def main():
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
+    launches = b.stat(6) - launches0
+    # one more step of the same loop with every launch bracketed by a CUDA-event pair on the launching stream:
+    # per-kernel-class device time and useful flops for the roofline (kept out of `value`: the 2 x ~100k event
+    # records per step cost about 10 % of a step)
+    b.profile_enable(True)
+    b.profile_get(True)
+    b.sample(1)
     prof = b.profile_get(True)
     b.profile_enable(False)
-    launches = b.stat(6) - launches0
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -332,11 +336,11 @@ def main():
     achieved = dom_p["flops"] / max(dom_p["ms"], 1e-9) / 1e9            # TFLOP/s of useful FP64 work in that kernel class
     step_ms = elapsed_ms / args.steps
     mf = MODEL_FLOPS[args.workload]
-    traffic = {"jacobi_round": 17.3e6}.get(dom_name)                       # ncu --set full, profiles/ (W=8 launch)
+    traffic = {"jacobi_round": 34.9e6, "apply_reflector": 149.4e6}.get(dom_name)   # dram bytes per launch, ncu --set full at W=16 (profiles/)
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 "peak_source": "cuBLAS DGEMM 4096^3 through torch.matmul, measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
-                "traffic": traffic,
+                "traffic": traffic, "measured_on": "one extra step of the timed loop with per-launch CUDA-event pairs (see bench.py)",
                 "launches": dom_p["launches"], "avg_launch_us": 1e3 * dom_p["ms"] / max(dom_p["launches"], 1),
                 "share_of_step": dom_p["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
                 "per_class_ms": {k: round(v["ms"], 1) for k, v in prof.items()},
