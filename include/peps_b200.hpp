@@ -1,0 +1,163 @@
+// C++ host-side wrapper over the C ABI (include/peps_b200.h), mirroring the reference's interface names for the
+// VMC sampling path so existing drivers keep their shape:
+//   qlpeps::BMPSTruncateParams            one_dim_tn/boundary_mps/bmps.h:47-98
+//   qlpeps::MonteCarloParams              algorithm/vmc_update/monte_carlo_peps_params.h:37-92
+//   qlpeps::MCEnergyGradEvaluator         algorithm/vmc_update/mc_energy_grad_evaluator.h:57-330
+//   evaluator callback (seam B1)          algorithm/vmc_update/vmc_peps_optimizer.h:155-157
+// Errors from the ABI become std::runtime_error, like the reference's own failure paths
+// (bmps_impl.h:839-843, square_nnn_energy_solver.h:148-150). Header-only; link against libpeps_b200.so.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+#include "peps_b200.h"
+
+namespace peps_b200 {
+
+struct BMPSTruncateParams {
+  size_t D_min = 1, D_max = 1;
+  double trunc_err = 0.0;
+  static BMPSTruncateParams SVD(size_t dmin, size_t dmax, double err) { return {dmin, dmax, err}; }
+};
+
+struct MonteCarloParams {
+  size_t num_samples = 0, num_warmup_sweeps = 0, sweeps_between_samples = 1;
+  std::vector<int32_t> initial_config;   // rows*cols physical indices (row-major); replicated to every walker
+  bool is_warmed_up = false;
+};
+
+struct XXZModel { double jz = 1.0, jxy = 1.0, pinning00 = 0.0; };   // SquareSpinOneHalfXXZModelOBC(jz, jxy, pinning)
+
+class WalkerBatch {
+ public:
+  WalkerBatch(int rows, int cols, int phys, int D, int walkers, const BMPSTruncateParams &t, int device = 0)
+      : rows_(rows), cols_(cols), walkers_(walkers) {
+    peps_config c{rows, cols, phys, D, walkers, device, (int32_t)t.D_min, (int32_t)t.D_max, t.trunc_err};
+    if (peps_create(&h_, &c) != 0) throw std::runtime_error(peps_last_error(nullptr));
+  }
+  ~WalkerBatch() { if (h_) peps_destroy(h_); }
+  WalkerBatch(const WalkerBatch &) = delete;
+  WalkerBatch &operator=(const WalkerBatch &) = delete;
+  size_t tps_size() const { return peps_tps_size(h_); }
+  int walkers() const { return walkers_; }
+  void SetTPS(const std::vector<double> &flat) { ck(peps_set_tps(h_, flat.data(), flat.size())); }
+  std::vector<double> GetTPS() { std::vector<double> v(tps_size()); ck(peps_get_tps(h_, v.data(), v.size())); return v; }
+  void SetModel(const XXZModel &m) { ck(peps_set_model_xxz(h_, m.jz, m.jxy, m.pinning00)); }
+  void SetConfigs(const std::vector<int32_t> &cfg) { ck(peps_set_configs(h_, cfg.data())); }
+  std::vector<int32_t> GetConfigs() { std::vector<int32_t> v((size_t)walkers_ * rows_ * cols_); ck(peps_get_configs(h_, v.data())); return v; }
+  void SeedRNG(const std::vector<uint32_t> &seeds) { ck(peps_seed_rng(h_, seeds.data())); }
+  void InitWalkers() { ck(peps_init_walkers(h_)); }
+  std::vector<double> Amplitudes() { std::vector<double> v((size_t)walkers_); ck(peps_get_amplitudes(h_, v.data())); return v; }
+  double NormalizeStateOrder1(double max_abs_override = 0.0) { double f = 0; ck(peps_normalize_state_order1(h_, max_abs_override, &f)); return f; }
+  std::vector<double> StepSweep(int n) { std::vector<double> a((size_t)walkers_); ck(peps_sweep(h_, n, a.data())); return a; }
+  void ZeroAccumulators() { ck(peps_zero_accumulators(h_)); }
+  void Sample(int sweeps_between_samples, std::vector<double> &eloc, std::vector<double> &accept) {
+    eloc.resize((size_t)walkers_); accept.resize((size_t)walkers_);
+    ck(peps_sample(h_, sweeps_between_samples, eloc.data(), accept.data()));
+  }
+  void Accumulators(std::vector<double> &osum, std::vector<double> &eosum) {
+    osum.resize(tps_size()); eosum.resize(tps_size());
+    ck(peps_get_accumulators(h_, osum.data(), eosum.data(), osum.size()));
+  }
+  peps_ctx *handle() { return h_; }
+
+ private:
+  void ck(int rc) { if (rc != 0) throw std::runtime_error(peps_last_error(h_)); }
+  peps_ctx *h_ = nullptr;
+  int rows_, cols_, walkers_;
+};
+
+struct EvaluateResult {               // MCEnergyGradEvaluator::Result (mc_energy_grad_evaluator.h:66-75)
+  double energy = 0, energy_error = 0, gradient_norm = 0;
+  std::vector<double> gradient;       // packed like the TPS
+  std::vector<double> accept_rates_avg;
+  std::vector<double> energy_samples; // [walkers][samples_per_walker]
+};
+
+// MeanAndBinnedErrorSqrtNUniformBin with walkers in the role of ranks (monte_carlo_tools/statistics.h:146-225)
+inline std::pair<double, double> BinnedMean(const std::vector<double> &es, size_t walkers, size_t n) {
+  if (n == 0) return {0.0, 0.0};
+  size_t bin = std::max<size_t>(1, (size_t)std::sqrt((double)n)), nb = n / bin;
+  std::vector<double> means;
+  for (size_t w = 0; w < walkers; ++w)
+    for (size_t i = 0; i < nb; ++i) {
+      double s = 0;
+      for (size_t k = 0; k < bin; ++k) s += es[w * n + i * bin + k];
+      means.push_back(s / (double)bin);
+    }
+  if (means.empty()) return {0.0, 0.0};
+  double mean = 0;
+  for (double m : means) mean += m;
+  mean /= (double)means.size();
+  if (means.size() == 1) return {mean, std::numeric_limits<double>::infinity()};
+  double var = 0;
+  for (double m : means) var += (m - mean) * (m - mean);
+  var /= (double)means.size();
+  return {mean, std::sqrt(var / ((double)means.size() - 1.0))};
+}
+
+class MCEnergyGradEvaluator {
+ public:
+  MCEnergyGradEvaluator(const MonteCarloParams &mc, const BMPSTruncateParams &trunc, int rows, int cols, int phys, int D,
+                        int walkers, const XXZModel &model, uint32_t seed, int device = 0)
+      : mc_(mc), batch_(rows, cols, phys, D, walkers, trunc, device) {
+    batch_.SetModel(model);
+    std::vector<int32_t> cfg;
+    for (int w = 0; w < walkers; ++w) cfg.insert(cfg.end(), mc.initial_config.begin(), mc.initial_config.end());
+    batch_.SetConfigs(cfg);
+    std::vector<uint32_t> seeds((size_t)walkers);
+    for (int w = 0; w < walkers; ++w) seeds[(size_t)w] = seed + (uint32_t)w;
+    batch_.SeedRNG(seeds);
+  }
+  // Evaluate(state): state fan-out, RefreshWavefunctionComponent, the walker loop, energy binning, gradient
+  EvaluateResult Evaluate(const std::vector<double> &packed_tps) {
+    batch_.SetTPS(packed_tps);
+    batch_.InitWalkers();
+    const size_t W = (size_t)batch_.walkers();
+    const size_t n = std::max<size_t>(1, (mc_.num_samples + W - 1) / W);
+    batch_.ZeroAccumulators();
+    EvaluateResult r;
+    r.energy_samples.assign(W * n, 0.0);
+    double acc = 0;
+    std::vector<double> e, a;
+    for (size_t s = 0; s < n; ++s) {
+      batch_.Sample((int)mc_.sweeps_between_samples, e, a);
+      for (size_t w = 0; w < W; ++w) { r.energy_samples[w * n + s] = e[w]; acc += a[w]; }
+    }
+    std::vector<double> osum, eosum;
+    batch_.Accumulators(osum, eosum);
+    auto me = BinnedMean(r.energy_samples, W, n);
+    r.energy = me.first; r.energy_error = me.second;
+    r.gradient.resize(osum.size());
+    for (size_t i = 0; i < osum.size(); ++i) {
+      r.gradient[i] = (eosum[i] - r.energy * osum[i]) / (double)(n * W);
+      r.gradient_norm += r.gradient[i] * r.gradient[i];
+    }
+    r.accept_rates_avg = {acc / (double)(n * W)};
+    return r;
+  }
+  WalkerBatch &batch() { return batch_; }
+
+ private:
+  MonteCarloParams mc_;
+  WalkerBatch batch_;
+};
+
+// Seam B1: adapts the evaluator to `std::function<std::tuple<T, SITPS, double>(const SITPS&)>`
+// (VMCPEPSOptimizer::SetEnergyEvaluator). `pack` flattens the caller's SplitIndexTPS, `unpack` builds one back.
+template <class SITPS>
+std::function<std::tuple<double, SITPS, double>(const SITPS &)> MakeEnergyEvaluator(
+    MCEnergyGradEvaluator &ev, std::function<std::vector<double>(const SITPS &)> pack,
+    std::function<SITPS(const std::vector<double> &, const SITPS &like)> unpack) {
+  return [&ev, pack, unpack](const SITPS &state) {
+    EvaluateResult r = ev.Evaluate(pack(state));
+    return std::make_tuple(r.energy, unpack(r.gradient, state), r.energy_error);
+  };
+}
+
+}  // namespace peps_b200

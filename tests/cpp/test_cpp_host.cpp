@@ -1,0 +1,36 @@
+// Compiles the C++ host wrapper (include/peps_b200.hpp) and runs Evaluate through the C ABI.
+// Reads: rows cols phys D walkers chi nsamples seed, then the packed TPS and the initial configuration from stdin;
+// prints energy, energy_error, gradient_norm, accept rate.
+#include <cstdio>
+#include <iostream>
+#include "../../include/peps_b200.hpp"
+
+int main() {
+  int rows, cols, phys, D, walkers, chi, nsamples;
+  unsigned seed;
+  std::cin >> rows >> cols >> phys >> D >> walkers >> chi >> nsamples >> seed;
+  size_t n;
+  std::cin >> n;
+  std::vector<double> tps(n);
+  for (auto &x : tps) std::cin >> x;
+  peps_b200::MonteCarloParams mc;
+  mc.num_samples = (size_t)nsamples; mc.sweeps_between_samples = 1;
+  mc.initial_config.resize((size_t)rows * cols);
+  for (auto &c : mc.initial_config) std::cin >> c;
+  try {
+    peps_b200::MCEnergyGradEvaluator ev(mc, peps_b200::BMPSTruncateParams::SVD(chi, chi, 0.0), rows, cols, phys, D, walkers,
+                                        peps_b200::XXZModel{1.0, 1.0, 0.0}, seed);
+    if (ev.batch().tps_size() != n) throw std::runtime_error("tps size mismatch");
+    auto r = ev.Evaluate(tps);
+    std::printf("%.17g %.17g %.17g %.17g\n", r.energy, r.energy_error, r.gradient_norm, r.accept_rates_avg[0]);
+    auto f = peps_b200::MakeEnergyEvaluator<std::vector<double>>(
+        ev, [](const std::vector<double> &s) { return s; },
+        [](const std::vector<double> &g, const std::vector<double> &) { return g; });
+    auto t = f(tps);
+    std::printf("%.17g\n", std::get<0>(t));
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
