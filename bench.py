@@ -211,6 +211,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--streams", type=int, default=2, help="host threads / CUDA streams sharing the walkers of a GPU")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -230,73 +231,133 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+    import queue
     L, D, chi = WORKLOADS[args.workload]
     W = args.walkers
+    S = max(1, min(args.streams, W))
+    while W % S:
+        S -= 1
+    Ws = W // S
     tps, cfgs, seeds = make_inputs(L, D, W, rank * W)
     sit = SplitIndexTPS(tps)
-    b = WalkerBatch(L, L, 2, D, W, BMPSTruncateParams.SVD(chi, chi, 0.0), device=local_rank)
-    b.set_tps(sit)
-    b.set_configs(cfgs)
-    b.seed_rng(seeds)
-    b.init_walkers()
-    mx = float(np.max(np.abs(b.amplitudes())))
+    dev = torch.device("cuda", local_rank)
+
+    # S host threads, each owning one context (= one CUDA stream) with W/S walkers: kernels of different contexts
+    # overlap on the GPU and fill the tails of partially occupied launches.
+    class Lane(threading.Thread):
+        def __init__(self, i):
+            super().__init__(daemon=True)
+            self.i, self.q, self.r, self.b = i, queue.Queue(), queue.Queue(), None
+            self.start()
+
+        def run(self):
+            while True:
+                fn = self.q.get()
+                if fn is None:
+                    return
+                try:
+                    self.r.put(("ok", fn(self)))
+                except Exception as exc:      # surface worker failures on the main thread
+                    self.r.put(("err", exc))
+
+    lanes = [Lane(i) for i in range(S)]
+
+    def on_all(fn):
+        for ln in lanes:
+            ln.q.put(fn)
+        out = []
+        for ln in lanes:
+            st, v = ln.r.get()
+            if st == "err":
+                raise v
+            out.append(v)
+        return out
+
+    def setup(ln):
+        sl = slice(ln.i * Ws, (ln.i + 1) * Ws)
+        ln.b = WalkerBatch(L, L, 2, D, Ws, BMPSTruncateParams.SVD(chi, chi, 0.0), device=local_rank)
+        ln.b.set_tps(sit)
+        ln.b.set_configs(cfgs[sl])
+        ln.b.seed_rng(seeds[sl])
+        ln.b.init_walkers()
+        return float(np.max(np.abs(ln.b.amplitudes())))
+
+    mx = max(on_all(setup))
     if world > 1:
         t = torch.tensor([mx], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         mx = float(t.item())
-    b.normalize_state_order1(mx)                      # MonteCarloEngine::NormalizeStateOrder1
-    stream = torch.cuda.ExternalStream(b.stream(), device=torch.device("cuda", local_rank))
+    on_all(lambda ln: ln.b.normalize_state_order1(mx))     # MonteCarloEngine::NormalizeStateOrder1
 
     def barrier():
-        b.sync()
+        on_all(lambda ln: ln.b.sync())
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
     # accumulators as torch views for the NCCL all-reduce of [sum O*, sum E_loc O*]
-    n_par = b.tps_size
-    p_o, p_eo = b.accumulator_device_ptrs()
+    n_par = lanes[0].b.tps_size
 
     class _Cai:
         def __init__(self, ptr, n):
             self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
 
-    acc_o = torch.as_tensor(_Cai(p_o, n_par), device=torch.device("cuda", local_rank))
-    acc_eo = torch.as_tensor(_Cai(p_eo, n_par), device=torch.device("cuda", local_rank))
+    views = []
+    for ln in lanes:
+        p_o, p_eo = ln.b.accumulator_device_ptrs()
+        views.append((torch.as_tensor(_Cai(p_o, n_par), device=dev), torch.as_tensor(_Cai(p_eo, n_par), device=dev)))
 
-    b.zero_accumulators()
+    on_all(lambda ln: ln.b.zero_accumulators())
     for _ in range(args.warmup):
-        b.sample(1)
+        on_all(lambda ln: ln.b.sample(1))
     barrier()
-    launches0 = b.stat(6)
+    launches0 = sum(on_all(lambda ln: ln.b.stat(6)))
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    ev0.record(stream)
-    energies = []
-    for _ in range(args.steps):
-        e, _ = b.sample(1)
-        energies.append(e)
+    ev0.record()                                      # device idle on both sides of the timed region
+
+    def timed(ln):
+        last = None
+        for _ in range(args.steps):
+            last, _ = ln.b.sample(1)
+        ln.b.sync()
+        return last
+
+    energies = np.concatenate(on_all(timed))
     if world > 1:                                     # gradient reduction of the iteration (NCCL over NVLink)
-        b.sync()
+        acc_o = torch.stack([v[0] for v in views]).sum(0)
+        acc_eo = torch.stack([v[1] for v in views]).sum(0)
         dist.all_reduce(acc_o)
         dist.all_reduce(acc_eo)
-        torch.cuda.current_stream().synchronize()
-    ev1.record(stream)
+    torch.cuda.synchronize()
+    ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
-    launches = b.stat(6) - launches0
+    launches = sum(on_all(lambda ln: ln.b.stat(6))) - launches0
     # one more step of the same loop with every launch bracketed by a CUDA-event pair on the launching stream:
     # per-kernel-class device time and useful flops for the roofline (kept out of `value`: the 2 x ~100k event
     # records per step cost about 10 % of a step)
-    b.profile_enable(True)
-    b.profile_get(True)
-    b.sample(1)
-    prof = b.profile_get(True)
-    b.profile_enable(False)
+
+    def profiled(ln):
+        ln.b.profile_enable(True)
+        ln.b.profile_get(True)
+        ln.b.sample(1)
+        pr = ln.b.profile_get(True)
+        ln.b.profile_enable(False)
+        return pr
+
+    prs = []
+    for ln in lanes:                                   # one lane at a time: per-launch durations free of overlap
+        ln.q.put(profiled)
+        st, v = ln.r.get()
+        if st == "err":
+            raise v
+        prs.append(v)
+    prof = {k: {f: sum(p[k][f] for p in prs) for f in ("ms", "launches", "flops")} for k in prs[0]}
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,23 +367,28 @@ def main():
 
     # ---- end-to-end through the evaluator-style public call with host buffers
     flat = torch.from_numpy(sit.pack()).pin_memory()
-    h2d = flat.numel() * 8
-    d2h = 2 * n_par * 8 + 2 * W * 8
+    h2d = flat.numel() * 8 * S
+    d2h = (2 * n_par * 8 + 2 * Ws * 8) * S
+
+    def e2e_step(ln):
+        for _ in range(args.e2e_steps):
+            ln.b.set_tps(flat.numpy())                # state fan-out (mc_energy_grad_evaluator.h:161)
+            ln.b.init_walkers()                       # RefreshWavefunctionComponent (:164)
+            ln.b.zero_accumulators()
+            e, acc = ln.b.sample(1)
+            osum, eosum = ln.b.accumulators()
+        return None
+
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        b.set_tps(flat.numpy())                       # state fan-out (mc_energy_grad_evaluator.h:161)
-        b.init_walkers()                              # RefreshWavefunctionComponent (:164)
-        b.zero_accumulators()
-        e, acc = b.sample(1)
-        osum, eosum = b.accumulators()
+    on_all(e2e_step)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = W * world * args.e2e_steps / e2e_s
+    e2e_value = W * world * args.e2e_steps / e2e_s if args.e2e_steps else 0.0
 
     if rank != 0:
         if world > 1:
@@ -360,7 +426,7 @@ def main():
     line = {"metric": "vmc_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "lattice": f"{L}x{L}", "D": D, "chi": chi, "walkers_per_gpu": W,
+            "config": {"workload": args.workload, "lattice": f"{L}x{L}", "D": D, "chi": chi, "walkers_per_gpu": W, "streams_per_gpu": S,
                        "trunc": "Dmin=Dmax=chi, trunc_err=0", "model": "Heisenberg NN (XXZ jz=jxy=1)",
                        "sweeps_between_samples": 1, "tps": f"uniform[0,1) seed {TPS_SEED}, NormalizeAllSite + order-1 rescale",
                        "l2": "per-step working set (walkers x ~60 MB of BMPS stacks + scratch) exceeds the 126 MB L2",
@@ -368,7 +434,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "call": "set_tps + init_walkers + sample + accumulators (Evaluate with 1 sample per walker)"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-            "mean_eloc": float(np.mean(energies[-1]))}
+            "mean_eloc": float(np.mean(energies))}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

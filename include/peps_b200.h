@@ -52,6 +52,9 @@ int peps_get_tps(peps_ctx *ctx, double *host_tps, size_t n);
 int peps_set_truncation(peps_ctx *ctx, int32_t dmin, int32_t dmax, double trunc_err);
 /* Convergence control of the Jacobi truncation kernel (no reference counterpart: LAPACK gesdd there). */
 int peps_set_jacobi(peps_ctx *ctx, double tol, int32_t inner_sweeps, int32_t max_sweeps);
+/* Rows of the QR-preconditioned Theta below eps * (largest row norm) are dropped before / between Jacobi sweeps
+ * (default 1e-13; a backward-stable perturbation of relative size <= sqrt(rows) * eps). 0 disables deflation. */
+int peps_set_deflation(peps_ctx *ctx, double eps);
 /* SquareSpinOneHalfXXZModelOBC(jz, jxy, pinning00) (model_solvers/square_spin_onehalf_xxz_obc.h:174-328). */
 int peps_set_model_xxz(peps_ctx *ctx, double jz, double jxy, double pinning00);
 

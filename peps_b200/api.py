@@ -205,6 +205,9 @@ class WalkerBatch:
     def set_jacobi(self, tol=1e-14, inner_sweeps=1, max_sweeps=40):
         self._ck(self.lib.peps_set_jacobi(self.h, tol, inner_sweeps, max_sweeps))
 
+    def set_deflation(self, eps):
+        self._ck(self.lib.peps_set_deflation(self.h, eps))
+
     def set_model(self, model):
         self._ck(self.lib.peps_set_model_xxz(self.h, model.jz, model.jxy, model.pinning00))
 

@@ -2,6 +2,7 @@
 #include "engine.h"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 namespace peps {
 
@@ -12,6 +13,7 @@ Engine::Engine(const EngineConfig &c)
   if (W_ < 1 || phys_ < 1 || D_ < 1) throw std::invalid_argument("Engine: bad sizes");
   be_init(c.device);
   la_.W = W_; la_.pool = &pool_; la_.planner = &planner_;
+  if (const char *e = std::getenv("PEPS_DEFLATION_EPS")) la_.deflation_eps = std::atof(e);
   la_.offmax = (double *)be_malloc(sizeof(double) * W_);
   la_.done = (int32_t *)be_malloc(sizeof(int32_t) * W_);
   tps_off_h_.resize((size_t)nsites_);

@@ -71,6 +71,7 @@ class Engine {
   double *osum_device() { return osum_; }
   double *eosum_device() { return eosum_; }
   void set_model_xxz(double jz, double jxy, double h00) { jz_ = jz; jxy_ = jxy; h00_ = h00; }
+  void set_deflation(double eps) { la_.deflation_eps = eps; }
 
   // ---- probes used by the parity tests (per-walker values of reference contractor calls)
   int bmps_stack_size(int pos) const { return (int)bmps_[pos].size(); }

@@ -26,7 +26,7 @@ struct LinalgCtx {
   long jacobi_sweeps = 0, jacobi_calls = 0, qr_calls = 0;
   long jacobi_rounds = 0;
   long rows_in = 0, rows_kept = 0;   // Jacobi row counts before / after deflation (summed over calls)
-  double deflation_eps = 1e-15;      // rows of R below eps * (largest row norm) are treated as zero
+  double deflation_eps = 1e-13;      // rows of R below eps * (largest row norm) are treated as zero (perturbs Theta by <= sqrt(rows) * eps * |Theta|)
   double jacobi_tol = 1e-14;
   int jacobi_inner_sweeps = 1;
   int jacobi_max_sweeps = 40;

@@ -194,3 +194,25 @@ def test_full_size_properties(lib):
         dot = np.sum(holes[:, pos:pos + sz] * flat_tn[:, pos:pos + sz], axis=1)
         assert np.max(np.abs(dot / psi[s // cols] - 1)) < 1e-10
         pos += sz
+
+
+def test_full_size_amplitude_parity_10x10_D8_chi64(lib):
+    """BASELINE's headline size against the oracle itself (one CPU amplitude = 9 row absorptions, ~20 s each):
+    amplitudes of two walkers at 10x10, D=8, chi=64 must agree to 1e-10 relative."""
+    import time
+    from oracle import vmc
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+    L, D, chi, W = 10, 8, 64, 2
+    tps = vmc.random_tps(L, L, 2, D, seed=20260101)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, 1000 + w) for w in range(W)])
+    b = WalkerBatch(L, L, 2, D, W, BMPSTruncateParams.SVD(chi, chi, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    amp = b.amplitudes()
+    worst = 0.0
+    for w in range(W):
+        ref = vmc.Walker(tps, cfgs[w], (chi, chi, 0.0)).amplitude
+        worst = max(worst, abs(amp[w] / ref - 1))
+    print("10x10 D8 chi64 amplitude rel err", worst)
+    assert worst < 1e-10
