@@ -74,28 +74,27 @@ void be_set_identity(double *dst, long wd, int rows, int cols, int W);
 
 // ---- communication-avoiding R-only QR: one panel step -----------------------------------------------
 // For every (walker w, item it): gather the rows rowtab[it*R + s] (s = skip..R-1, skip = (it==0 ? skip0 : 0))
-// of panel columns [col0, col0+pw) of the row-major matrix Abase + w*ws (leading dimension lda) into shared
-// memory, Householder-factorise the (R-skip) x pw panel, write R (upper triangle on the first pw active
-// rows, zeros below) back in place, and emit the explicit reflector block V (unit lower trapezoid) and
-// VT = V * T^T (compact WY: Q^T C = C - VT (V^T C)) into Vw/VTw, laid out [w][it][R][nbw]; skipped slots
-// and columns >= pw are zero.
+// of panel columns [col0, col0+pw) of the row-major matrix Abase + w*ws (leading dimension lda), Householder-
+// factorise the (R-skip) x pw panel, write R (upper triangle on the first pw active rows, zeros below) back in
+// place, and emit the explicit reflector block V (unit lower trapezoid, [w][it][R][nbw], skipped slots and columns
+// >= pw zero) and the compact-WY factor T ([w][it][nbw][nbw], upper triangular):  Q^T C = C - V T^T (V^T C).
 struct PanelArgs {
   double *A; long ws; int lda;
   const int32_t *rowtab; int R; int skip0; int NI;
   int col0, pw, nbw;
-  double *Vw, *VTw;
+  double *Vw, *Tw;
   int W;
 };
 void be_panel_qr(const PanelArgs &a);
 
-// Trailing update of one CAQR panel step: for every (walker, item) C <- C - VT (V^T C) where C are the rows
-// rowtab[it*R + s] (s < R) and columns [col1, col1 + ntrail) of A, and V / VT are the [R][nbw] blocks emitted by
+// Trailing update of one CAQR panel step: for every (walker, item) C <- C - V T^T (V^T C) where C are the rows
+// rowtab[it*R + s] (s < R) and columns [col1, col1 + ntrail) of A, and V / T are the blocks emitted by
 // be_panel_qr. One fused kernel (C tile resident in shared memory) instead of two contractions.
 struct ApplyArgs {
   double *A; long ws; int lda;
   const int32_t *rowtab; int R; int NI;
   int col1, ntrail, nbw;
-  const double *Vw, *VTw;
+  const double *Vw, *Tw;
   int W;
 };
 void be_apply_reflector(const ApplyArgs &a);

@@ -456,51 +456,53 @@ __global__ void __launch_bounds__(PQR_THREADS) panel_qr_kernel(PanelArgs a) {
     }
   }
   __syncthreads();
-  // 4. emit V and VT = V * T^T
+  // 4. emit V and T
   double *Vo = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
-  double *VTo = a.VTw + ((long)w * a.NI + it) * (long)R * nbw;
-  for (int e = t; e < skip * nbw; e += PQR_THREADS) { Vo[e] = 0.0; VTo[e] = 0.0; }
+  double *To = a.Tw + ((long)w * a.NI + it) * (long)nbw * nbw;
+  for (int e = t; e < skip * nbw; e += PQR_THREADS) Vo[e] = 0.0;
   for (int e = t; e < nact * nbw; e += PQR_THREADS) {
     int r = e / nbw, c = e % nbw;
-    double v = (c < pw) ? P[c * LDP + r] : 0.0;
-    Vo[(long)(skip + r) * nbw + c] = v;
-    double acc = 0.0;
-    if (c < pw) {
-      for (int b2 = c; b2 < pw; ++b2) acc += P[b2 * LDP + r] * T[c * nbw + b2];
-    }
-    VTo[(long)(skip + r) * nbw + c] = acc;
+    Vo[(long)(skip + r) * nbw + c] = (c < pw) ? P[c * LDP + r] : 0.0;
   }
+  for (int e = t; e < nbw * nbw; e += PQR_THREADS) To[e] = T[e];
 }
 
 static size_t panel_smem_bytes(int R, int nbw) {
   return ((size_t)nbw * (R + 1) + 2 * (size_t)nbw * nbw + 3 * nbw) * sizeof(double);
 }
 
-// Register-resident variant: warp w owns CPW = NBW/8 panel columns, lane l owns rows l, l+32, ... (RPL of them),
-// so every Householder update is FMA work out of registers; only the current reflector travels through shared
-// memory (double buffered: one barrier per column). S = V^T V falls out of the same dot products, V T^T is formed
-// on the DMMA pipe from a shared-memory copy of V.
+// Register-resident variant: warp w owns the CPW = NBW/8 panel columns w, w+8, ... (cyclic, so the work stays
+// balanced as the factorisation advances), lane l owns rows l, l+32, ... (RPL of them): every Householder update is
+// FMA work out of registers. All reflectors live in shared memory (vcols, column-major V) and are published with a
+// per-column ready flag, so there is no block barrier in the column loop: the owner of column j+1 applies
+// reflector j to that column first, builds and publishes reflector j+1, and only then catches up on its other
+// columns, while every other warp runs at its own pace. A warp reduces the dot products of all its columns
+// together (interleaved shuffles). S = V^T V falls out of the same dot products; T is emitted for the trailing
+// update (C - V T^T (V^T C)), so V T^T is never formed.
 template <int NBW, int RPL>
 __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs a) {
   extern __shared__ double sm[];
   constexpr int CPW = NBW / 8;
-  constexpr int LDV = NBW + 4, LDT = NBW + 4, LDSS = NBW + 1;
+  constexpr int LDT = NBW + 1, LDSS = NBW + 1;
+  constexpr int RP = RPL * 32;
   const int it = blockIdx.x, w = blockIdx.y;
   const int R = a.R, pw = a.pw, nbw = a.nbw;
   const int skip = (it == 0) ? a.skip0 : 0;
   const int nact = R - skip;
-  const int RP = RPL * 32;
-  double *vbuf = sm;                       // [2][RP]
-  double *S = vbuf + 2 * RP;               // [NBW][LDSS]
+  double *vcols = sm;                      // [NBW][RP]
+  double *S = vcols + (size_t)NBW * RP;    // [NBW][LDSS]
   double *Tt = S + NBW * LDSS;             // [NBW][LDT]   T[a][b]
-  double *tau_s = Tt + NBW * LDT;          // [NBW]
-  double *Rd = tau_s + NBW;                // [NBW]
-  long *roff = reinterpret_cast<long *>(Rd + NBW);   // [RP] global offset of active row r
-  double *Vs = reinterpret_cast<double *>(roff + RP);   // [round_up(nact,8)][LDV]
+  volatile double *tau_s = Tt + NBW * LDT; // [NBW]
+  double *Rd = const_cast<double *>(tau_s) + NBW;   // [NBW]
+  long *roff = reinterpret_cast<long *>(Rd + NBW);  // [RP] global offset of active row r
+  volatile int *ready = reinterpret_cast<volatile int *>(roff + RP);   // [NBW]
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   double *Aw = a.A + (long)w * a.ws;
   const int32_t *rows = a.rowtab + (long)it * R;
   for (int r = t; r < RP; r += PQR_THREADS) roff[r] = (r < nact) ? (long)rows[skip + r] * a.lda + a.col0 : 0;
+  for (int e = t; e < NBW * LDSS; e += PQR_THREADS) S[e] = 0.0;
+  for (int e = t; e < NBW * LDT; e += PQR_THREADS) Tt[e] = 0.0;
+  if (t < NBW) { tau_s[t] = 0.0; Rd[t] = 0.0; ready[t] = 0; }
   __syncthreads();
 
   double P[CPW][RPL];
@@ -510,103 +512,146 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
     const long off = roff[r];
 #pragma unroll
     for (int cc = 0; cc < CPW; ++cc) {
-      const int c = warp * CPW + cc;
+      const int c = warp + 8 * cc;
       P[cc][i] = (r < nact && c < pw) ? Aw[off + c] : 0.0;
     }
   }
-  for (int e = t; e < NBW * LDSS; e += PQR_THREADS) S[e] = 0.0;
-  for (int e = t; e < NBW * LDT; e += PQR_THREADS) Tt[e] = 0.0;
-  if (t < NBW) { tau_s[t] = 0.0; Rd[t] = 0.0; }
-  __syncthreads();
 
-  for (int j = 0; j < pw; ++j) {
-    double *vb = vbuf + (j & 1) * RP;
-    if (warp == j / CPW) {                 // owner warp builds reflector j
-      const int cj = j % CPW;
-      double x[RPL];
-      double xn2 = 0.0;
+  // builds reflector j from column j (owned by this warp as local column cj), publishes it; P keeps [R | 1 | v]
+  auto build = [&](int j, int cj) {
+    double *vb = vcols + (size_t)j * RP;
+    double x[RPL];
+    double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0, alpha = 0.0;
 #pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-        double v = 0.0;
-#pragma unroll
-        for (int cc = 0; cc < CPW; ++cc) if (cc == cj) v = P[cc][i];
-        x[i] = v;
-        const int r = lane + 32 * i;
-        if (r == j) vb[r] = v;
-        if (r > j && r < nact) xn2 += v * v;
-      }
-      xn2 = warp_sum(xn2);
-      __syncwarp();
-      const double alpha = (j < nact) ? vb[j] : 0.0;
-      double bj = alpha, tj = 0.0, sj = 0.0;
-      if (xn2 > 0.0) {
-        const double nrm = sqrt(alpha * alpha + xn2);
-        bj = (alpha >= 0.0) ? -nrm : nrm;
-        tj = (bj - alpha) / bj;
-        sj = 1.0 / (alpha - bj);
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-        const int r = lane + 32 * i;
-        const double v = (r > j) ? x[i] * sj : ((r == j) ? 1.0 : 0.0);
-        if (r < RP) vb[r] = (r < nact) ? v : 0.0;
-        if (r >= j) {
-#pragma unroll
-          for (int cc = 0; cc < CPW; ++cc) if (cc == cj) P[cc][i] = (r < nact) ? v : 0.0;
-        }
-      }
-      if (lane == 0) { tau_s[j] = tj; Rd[j] = bj; }
-    }
-    __syncthreads();
-    {
-      const double tj = tau_s[j];
-      double v[RPL];
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) v[i] = vb[lane + 32 * i];
-#pragma unroll
-      for (int cc = 0; cc < CPW; ++cc) {
-        const int c = warp * CPW + cc;
-        if (c == j || c >= pw) continue;
-        double dot = 0.0;
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) dot += v[i] * P[cc][i];
-        dot = warp_sum(dot);
-        if (c > j) {
-          const double f = tj * dot;
-          if (f != 0.0) {
-#pragma unroll
-            for (int i = 0; i < RPL; ++i) P[cc][i] -= f * v[i];
-          }
-        } else if (lane == 0) {
-          S[c * LDSS + j] = dot;
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // T (forward, columnwise): T[j][j] = tau_j; T[0:j, j] = -tau_j * T[0:j,0:j] * S[0:j, j]
-  if (warp == 0) {
-    for (int j = 0; j < pw; ++j) {
-      const double tj = tau_s[j];
+    for (int i = 0; i < RPL; ++i) {
       double v = 0.0;
-      if (lane < j) {
-        for (int b2 = lane; b2 < j; ++b2) v += Tt[lane * LDT + b2] * S[b2 * LDSS + j];
-        v *= -tj;
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) if (cc == cj) v = P[cc][i];
+      x[i] = v;
+      const int r = lane + 32 * i;
+      if (r == j) alpha = v;
+      const double q = (r > j && r < nact) ? v * v : 0.0;
+      if ((i & 3) == 0) n0 += q; else if ((i & 3) == 1) n1 += q; else if ((i & 3) == 2) n2 += q; else n3 += q;
+    }
+    double xn2 = (n0 + n1) + (n2 + n3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {     // norm and the diagonal entry travel together
+      xn2 += __shfl_xor_sync(0xffffffffu, xn2, o);
+      alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+    }
+    double bj = alpha, tj = 0.0, sj = 0.0;
+    if (xn2 > 0.0) {
+      const double s2 = alpha * alpha + xn2;
+      const double rs = rsqrt(s2);
+      const double nrm = s2 * rs;
+      bj = (alpha >= 0.0) ? -nrm : nrm;
+      const double inv_b = (alpha >= 0.0) ? -rs : rs;
+      tj = 1.0 - alpha * inv_b;            // (beta - alpha) / beta
+      sj = 1.0 / (alpha - bj);
+    }
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      const int r = lane + 32 * i;
+      const double v = (r < nact) ? ((r > j) ? x[i] * sj : ((r == j) ? 1.0 : 0.0)) : 0.0;
+      vb[r] = v;
+      if (r >= j) {
+#pragma unroll
+        for (int cc = 0; cc < CPW; ++cc) if (cc == cj) P[cc][i] = v;
       }
-      __syncwarp();
-      if (lane < j) Tt[lane * LDT + j] = v;
-      if (lane == j) Tt[j * LDT + j] = tj;
-      __syncwarp();
+    }
+    if (lane == 0) { tau_s[j] = tj; Rd[j] = bj; }
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) ready[j] = 1;
+  };
+
+  if (warp == 0 && pw > 0) build(0, 0);
+  for (int j = 0; j < pw; ++j) {
+    while (ready[j] == 0) __nanosleep(40);
+    __threadfence_block();
+    const double *vb = vcols + (size_t)j * RP;
+    const double tj = tau_s[j];
+    double v[RPL];
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) v[i] = vb[lane + 32 * i];
+    const int jn = j + 1;
+    const bool own_next = (jn < pw) && (warp == (jn & 7));
+    if (own_next) {                         // look-ahead: finish column j+1 and publish its reflector early
+      const int cn = jn >> 3;
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        double pv = 0.0;
+#pragma unroll
+        for (int k = 0; k < CPW; ++k) if (k == cn) pv = P[k][i];
+        const double q = v[i] * pv;
+        if ((i & 3) == 0) d0 += q; else if ((i & 3) == 1) d1 += q; else if ((i & 3) == 2) d2 += q; else d3 += q;
+      }
+      const double f = tj * warp_sum((d0 + d1) + (d2 + d3));
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+#pragma unroll
+        for (int k = 0; k < CPW; ++k) if (k == cn) P[k][i] -= f * v[i];
+      }
+      build(jn, cn);
+    }
+    // all remaining columns of this warp together: dots, one interleaved reduction, updates / S entries
+    double d[CPW][2];
+#pragma unroll
+    for (int cc = 0; cc < CPW; ++cc) d[cc][0] = d[cc][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) d[cc][i & 1] += v[i] * P[cc][i];
+    }
+    double dot[CPW];
+#pragma unroll
+    for (int cc = 0; cc < CPW; ++cc) dot[cc] = d[cc][0] + d[cc][1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) dot[cc] += __shfl_xor_sync(0xffffffffu, dot[cc], o);
+    }
+#pragma unroll
+    for (int cc = 0; cc < CPW; ++cc) {
+      const int c = warp + 8 * cc;
+      if (c >= pw || c == j || (own_next && c == jn)) continue;
+      if (c > j) {
+        const double f = tj * dot[cc];
+        if (f != 0.0) {
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) P[cc][i] -= f * v[i];
+        }
+      } else if (lane == 0) {
+        S[c * LDSS + j] = dot[cc];
+      }
     }
   }
-  // emit R (in place) and V; stage V in shared memory
+  __syncthreads();
+
+  // T (forward, columnwise): T[j][j] = tau_j; T[0:j, j] = -tau_j * T[0:j,0:j] * S[0:j, j]. Row a of T only depends
+  // on row a itself, so lane a of warp 0 runs its own recurrence out of registers (no intra-warp synchronisation).
+  if (warp == 0 && lane < NBW) {
+    double trow[NBW];
+#pragma unroll
+    for (int j = 0; j < NBW; ++j) trow[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NBW; ++j) {
+      const double tj = (j < pw) ? tau_s[j] : 0.0;
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+#pragma unroll
+      for (int b2 = 0; b2 < j; ++b2) {
+        const double q = trow[b2] * S[b2 * LDSS + j];      // trow[b2] is zero for b2 < lane
+        if ((b2 & 3) == 0) v0 += q; else if ((b2 & 3) == 1) v1 += q; else if ((b2 & 3) == 2) v2 += q; else v3 += q;
+      }
+      trow[j] = (j == lane) ? tj : ((j > lane) ? -tj * ((v0 + v1) + (v2 + v3)) : 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < NBW; ++j) Tt[lane * LDT + j] = trow[j];
+  }
+  // emit R (in place) and V
   double *Vo = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
-  double *VTo = a.VTw + ((long)w * a.NI + it) * (long)R * nbw;
-  for (int e = t; e < skip * nbw; e += PQR_THREADS) { Vo[e] = 0.0; VTo[e] = 0.0; }
-  const int nact8 = (nact + 7) & ~7;
-  for (int e = t; e < (nact8 - nact) * LDV; e += PQR_THREADS) Vs[(size_t)nact * LDV + e] = 0.0;
+  for (int e = t; e < skip * nbw; e += PQR_THREADS) Vo[e] = 0.0;
 #pragma unroll
   for (int i = 0; i < RPL; ++i) {
     const int r = lane + 32 * i;
@@ -614,45 +659,22 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
       const long off = roff[r];
 #pragma unroll
       for (int cc = 0; cc < CPW; ++cc) {
-        const int c = warp * CPW + cc;
+        const int c = warp + 8 * cc;
         const double pv = P[cc][i];
         if (c < pw) Aw[off + c] = (r < c) ? pv : ((r == c) ? Rd[c] : 0.0);
-        const double vv = (c < pw && r >= c) ? pv : 0.0;
-        Vo[(long)(skip + r) * nbw + c] = vv;
-        Vs[(size_t)r * LDV + c] = vv;
+        Vo[(long)(skip + r) * nbw + c] = (c < pw && r >= c) ? pv : 0.0;
       }
     }
   }
   __syncthreads();
-  // VT = V T^T on the DMMA pipe: (nact x NBW) . (NBW x NBW)
-  for (int rt = warp; rt < nact8 / 8; rt += PQR_THREADS / 32) {
-    double acc[NBW / 8][2];
-#pragma unroll
-    for (int nt = 0; nt < NBW / 8; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-    const double *ap = Vs + (size_t)(rt * 8 + (lane >> 2)) * LDV + (lane & 3);
-#pragma unroll
-    for (int ks = 0; ks < NBW / 4; ++ks) {
-      const double af = ap[ks * 4];
-#pragma unroll
-      for (int nt = 0; nt < NBW / 8; ++nt)
-        dmma8x8x4(acc[nt][0], acc[nt][1], af, Tt[(nt * 8 + (lane >> 2)) * LDT + ks * 4 + (lane & 3)]);
-    }
-    const int r = rt * 8 + (lane >> 2);
-    if (r < nact) {
-#pragma unroll
-      for (int nt = 0; nt < NBW / 8; ++nt) {
-        double2 o; o.x = acc[nt][0]; o.y = acc[nt][1];
-        *reinterpret_cast<double2 *>(VTo + (long)(skip + r) * nbw + nt * 8 + 2 * (lane & 3)) = o;
-      }
-    }
-  }
+  double *To = a.Tw + ((long)w * a.NI + it) * (long)nbw * nbw;
+  for (int e = t; e < NBW * NBW; e += PQR_THREADS) To[e] = Tt[(e / NBW) * LDT + (e % NBW)];
 }
 
 template <int NBW, int RPL>
 static size_t panel_reg_smem_bytes(int nact_max) {
-  int nact8 = (nact_max + 7) & ~7;
-  return ((size_t)3 * RPL * 32 + (size_t)NBW * (NBW + 1) + (size_t)NBW * (NBW + 4) + 2 * NBW + (size_t)nact8 * (NBW + 4)) *
-         sizeof(double);
+  (void)nact_max;
+  return ((size_t)(NBW + 1) * RPL * 32 + 2 * (size_t)NBW * (NBW + 1) + 2 * NBW) * sizeof(double) + NBW * sizeof(int) + 16;
 }
 
 void be_panel_qr(const PanelArgs &a) {
@@ -698,7 +720,7 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
   double *Aw = a.A + (long)w * a.ws;
   const int32_t *rows = a.rowtab + (long)it * R;
   const double *V = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
-  const double *VT = a.VTw + ((long)w * a.NI + it) * (long)R * nbw;
+  const double *Tg = a.Tw + ((long)w * a.NI + it) * (long)nbw * nbw;
   const int cbase = a.col1 + ct * TN;
   const int ncols = min(TN, a.ntrail - ct * TN);
 
@@ -706,19 +728,22 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
   long *roff = reinterpret_cast<long *>(Wsm + NBW * LDW);   // [R8]
   for (int r = t; r < R8; r += 256) roff[r] = (r < R) ? (long)rows[r] * a.lda + cbase : -1;
   __syncthreads();
-  for (int r0 = warp * 8; r0 < R8; r0 += 64) {
-    double v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const long o = roff[r0 + u];
-      v[u] = (o >= 0 && lane < ncols) ? Aw[o + lane] : 0.0;
+  // asynchronous 8-byte copies straight into shared memory: every row of the tile is in flight at once
+  for (int r = warp; r < R8; r += 8) {
+    const long o = roff[r];
+    double *dstp = Cs + (size_t)r * LDC + lane;
+    if (lane < TN) {
+      if (o >= 0 && lane < ncols) {
+        const unsigned saddr = (unsigned)__cvta_generic_to_shared(dstp);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(Aw + o + lane));
+      } else {
+        *dstp = 0.0;
+      }
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (lane < TN) Cs[(size_t)(r0 + u) * LDC + lane] = v[u];
-      if (lane < LDC - TN) Cs[(size_t)(r0 + u) * LDC + TN + lane] = 0.0;
-    }
+    if (lane < LDC - TN) Cs[(size_t)r * LDC + TN + lane] = 0.0;
   }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
   __syncthreads();
 
   // A. partial W = V^T C over this warp's row slice
@@ -771,17 +796,47 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
         }
     }
     __syncthreads();
-    for (int e = t; e < NTILE * 64; e += 256) {
-      const int tile = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
-      double v = 0.0;
+    double *Wraw = part;                      // reuse: [NBW][LDW] raw W = V^T C after the partial sums are consumed
+    double wv[(NTILE * 64 + 255) / 256];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) v += part[((size_t)g * NTILE + tile) * 64 + (e & 63)];
-      Wsm[((tile / NT) * 8 + rr) * LDW + (tile % NT) * 8 + cc] = -v;
+    for (int u = 0; u < (NTILE * 64 + 255) / 256; ++u) {
+      const int e = t + u * 256;
+      double v = 0.0;
+      if (e < NTILE * 64) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) v += part[((size_t)g * NTILE + (e >> 6)) * 64 + (e & 63)];
+      }
+      wv[u] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < (NTILE * 64 + 255) / 256; ++u) {
+      const int e = t + u * 256;
+      if (e < NTILE * 64) {
+        const int tile = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
+        Wraw[((tile / NT) * 8 + rr) * LDW + (tile % NT) * 8 + cc] = wv[u];
+      }
+    }
+    __syncthreads();
+    // Wsm = -(T^T W):  (T^T W)[a][c] = sum_{b <= a} T[b][a] W[b][c]     (T staged in shared memory)
+    double *Tsm = Wraw + NBW * LDW;            // [NBW][LDW], still inside the partial-sum scratch
+    for (int e = t; e < NBW * NBW; e += 256) Tsm[(e / NBW) * LDW + (e % NBW)] = __ldg(Tg + e);
+    __syncthreads();
+    for (int e = t; e < NBW * TN; e += 256) {
+      const int aa = e / TN, c = e % TN;
+      double v0 = 0.0, v1 = 0.0;
+      int b2 = 0;
+      for (; b2 + 1 <= aa; b2 += 2) {
+        v0 += Tsm[b2 * LDW + aa] * Wraw[b2 * LDW + c];
+        v1 += Tsm[(b2 + 1) * LDW + aa] * Wraw[(b2 + 1) * LDW + c];
+      }
+      if (b2 <= aa) v0 += Tsm[b2 * LDW + aa] * Wraw[b2 * LDW + c];
+      Wsm[aa * LDW + c] = -(v0 + v1);
     }
     __syncthreads();
   }
 
-  // C. C <- C + VT (-W), written straight back to global memory
+  // C. C <- C + V (-(T^T W)), written straight back to global memory
   {
     double bw[NBW / 4][NT];
 #pragma unroll
@@ -796,7 +851,7 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
         acc[j][0] = Cs[(size_t)r * LDC + j * 8 + 2 * (lane & 3)];
         acc[j][1] = Cs[(size_t)r * LDC + j * 8 + 2 * (lane & 3) + 1];
       }
-      const double *vt = VT + (long)r * nbw + (lane & 3);
+      const double *vt = V + (long)r * nbw + (lane & 3);
 #pragma unroll
       for (int ks = 0; ks < NBW / 4; ++ks) {
         const double af = (r < R) ? __ldg(vt + ks * 4) : 0.0;

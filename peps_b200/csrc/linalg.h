@@ -84,7 +84,7 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
   if (m <= 1) return;
   Planner &pl = *cx.planner;
   double *Vw = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * rb * nb);
-  double *VTw = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * rb * nb);
+  double *Tw = (double *)cx.pool->get(sizeof(double) * (size_t)W * nrb * nb * nb);
   std::vector<int32_t> rowtab1((size_t)nrb * rb);
   for (int b = 0; b < nrb; ++b)
     for (int s = 0; s < rb; ++s) rowtab1[(size_t)b * rb + s] = b * rb + s;
@@ -94,12 +94,12 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
     const int col0 = p * nb, pw = std::min(nb, kk - col0), c1 = col0 + pw, ntrail = n - c1;
     PanelArgs pa;
     pa.A = A; pa.ws = ws; pa.lda = lda; pa.rowtab = rowtab1_d; pa.R = rb; pa.skip0 = col0; pa.NI = nrb;
-    pa.col0 = col0; pa.pw = pw; pa.nbw = nb; pa.Vw = Vw; pa.VTw = VTw; pa.W = W;
+    pa.col0 = col0; pa.pw = pw; pa.nbw = nb; pa.Vw = Vw; pa.Tw = Tw; pa.W = W;
     be_panel_qr(pa);
     if (ntrail > 0) {
       ApplyArgs ap;
       ap.A = A; ap.ws = ws; ap.lda = lda; ap.rowtab = rowtab1_d; ap.R = rb; ap.NI = nrb; ap.col1 = c1; ap.ntrail = ntrail;
-      ap.nbw = nb; ap.Vw = Vw; ap.VTw = VTw; ap.W = W;
+      ap.nbw = nb; ap.Vw = Vw; ap.Tw = Tw; ap.W = W;
       be_apply_reflector(ap);
     }
     if (nrb > 1) {
@@ -114,13 +114,13 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
       if (ntrail > 0) {
         ApplyArgs ap;
         ap.A = A; ap.ws = ws; ap.lda = lda; ap.rowtab = p2.rowtab; ap.R = R2; ap.NI = 1; ap.col1 = c1; ap.ntrail = ntrail;
-        ap.nbw = nb; ap.Vw = Vw; ap.VTw = VTw; ap.W = W;
+        ap.nbw = nb; ap.Vw = Vw; ap.Tw = Tw; ap.W = W;
         be_apply_reflector(ap);
       }
     }
   }
   cx.pool->put(Vw);
-  cx.pool->put(VTw);
+  cx.pool->put(Tw);
 }
 
 struct JacobiLayout { int bs = 0, nblk = 0, nr_pad = 0; };

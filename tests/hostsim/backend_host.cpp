@@ -135,15 +135,13 @@ void be_panel_qr(const PanelArgs &a) {
       for (int r = 0; r < nact; ++r)
         for (int c = 0; c < pw; ++c) Aw[(long)rows[skip + r] * a.lda + a.col0 + c] = (r <= c) ? at(r, c) : 0.0;
       double *Vo = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
-      double *VTo = a.VTw + ((long)w * a.NI + it) * (long)R * nbw;
-      for (long e = 0; e < (long)R * nbw; ++e) { Vo[e] = 0.0; VTo[e] = 0.0; }
+      double *To = a.Tw + ((long)w * a.NI + it) * (long)nbw * nbw;
+      for (long e = 0; e < (long)R * nbw; ++e) Vo[e] = 0.0;
+      for (long e = 0; e < (long)nbw * nbw; ++e) To[e] = 0.0;
       for (int r = 0; r < nact; ++r)
-        for (int c = 0; c < pw; ++c) {
-          Vo[(long)(skip + r) * nbw + c] = V[(size_t)r * pw + c];
-          double acc = 0.0;
-          for (int b2 = c; b2 < pw; ++b2) acc += V[(size_t)r * pw + b2] * T[(size_t)c * pw + b2];
-          VTo[(long)(skip + r) * nbw + c] = acc;
-        }
+        for (int c = 0; c < pw; ++c) Vo[(long)(skip + r) * nbw + c] = V[(size_t)r * pw + c];
+      for (int a2 = 0; a2 < pw; ++a2)
+        for (int b2 = a2; b2 < pw; ++b2) To[(long)a2 * nbw + b2] = T[(size_t)a2 * pw + b2];
     }
 }
 
@@ -154,18 +152,24 @@ void be_apply_reflector(const ApplyArgs &a) {
       double *Aw = a.A + (long)w * a.ws;
       const int32_t *rows = a.rowtab + (long)it * a.R;
       const double *V = a.Vw + ((long)w * a.NI + it) * (long)a.R * a.nbw;
-      const double *VT = a.VTw + ((long)w * a.NI + it) * (long)a.R * a.nbw;
-      std::vector<double> Wm((size_t)a.nbw * a.ntrail, 0.0);
+      const double *T = a.Tw + ((long)w * a.NI + it) * (long)a.nbw * a.nbw;
+      std::vector<double> Wm((size_t)a.nbw * a.ntrail, 0.0), W2((size_t)a.nbw * a.ntrail, 0.0);
       for (int r = 0; r < a.R; ++r)
         for (int c = 0; c < a.nbw; ++c) {
           double v = V[(long)r * a.nbw + c];
           if (v == 0.0) continue;
           for (int tcol = 0; tcol < a.ntrail; ++tcol) Wm[(size_t)c * a.ntrail + tcol] += v * Aw[(long)rows[r] * a.lda + a.col1 + tcol];
         }
+      for (int c = 0; c < a.nbw; ++c)          // W2 = T^T W
+        for (int b2 = 0; b2 <= c; ++b2) {
+          double tv = T[(long)b2 * a.nbw + c];
+          if (tv == 0.0) continue;
+          for (int tcol = 0; tcol < a.ntrail; ++tcol) W2[(size_t)c * a.ntrail + tcol] += tv * Wm[(size_t)b2 * a.ntrail + tcol];
+        }
       for (int r = 0; r < a.R; ++r)
         for (int tcol = 0; tcol < a.ntrail; ++tcol) {
           double s = 0.0;
-          for (int c = 0; c < a.nbw; ++c) s += VT[(long)r * a.nbw + c] * Wm[(size_t)c * a.ntrail + tcol];
+          for (int c = 0; c < a.nbw; ++c) s += V[(long)r * a.nbw + c] * W2[(size_t)c * a.ntrail + tcol];
           Aw[(long)rows[r] * a.lda + a.col1 + tcol] -= s;
         }
     }
