@@ -206,12 +206,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--walkers", type=int, default=64, help="walkers (Markov chains) per GPU")
+    ap.add_argument("--walkers", type=int, default=148, help="walkers (Markov chains) per GPU")
+    ap.add_argument("--j2", type=float, default=0.0, help="next-nearest-neighbour coupling (J1-J2 model, BASELINE config #3); 0 = NN Heisenberg headline")
     ap.add_argument("--workload", default="heisenberg_10x10_D8_chi64", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=1)
-    ap.add_argument("--streams", type=int, default=2, help="host threads / CUDA streams sharing the walkers of a GPU")
+    ap.add_argument("--streams", type=int, default=4, help="host threads / CUDA streams sharing the walkers of a GPU")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -277,6 +278,9 @@ def main():
         sl = slice(ln.i * Ws, (ln.i + 1) * Ws)
         ln.b = WalkerBatch(L, L, 2, D, Ws, BMPSTruncateParams.SVD(chi, chi, 0.0), device=local_rank)
         ln.b.set_tps(sit)
+        if args.j2 != 0.0:
+            from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
+            ln.b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, args.j2, args.j2, 0.0))
         ln.b.set_configs(cfgs[sl])
         ln.b.seed_rng(seeds[sl])
         ln.b.init_walkers()
@@ -427,7 +431,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "lattice": f"{L}x{L}", "D": D, "chi": chi, "walkers_per_gpu": W, "streams_per_gpu": S,
-                       "trunc": "Dmin=Dmax=chi, trunc_err=0", "model": "Heisenberg NN (XXZ jz=jxy=1)",
+                       "trunc": "Dmin=Dmax=chi, trunc_err=0",
+                       "model": "Heisenberg NN (XXZ jz=jxy=1)" if args.j2 == 0.0 else f"J1-J2 Heisenberg (j2={args.j2})",
                        "sweeps_between_samples": 1, "tps": f"uniform[0,1) seed {TPS_SEED}, NormalizeAllSite + order-1 rescale",
                        "l2": "per-step working set (walkers x ~60 MB of BMPS stacks + scratch) exceeds the 126 MB L2",
                        "parallelism": f"walkers sharded over {world} GPU(s); NCCL all-reduce of the two accumulators"},

@@ -57,6 +57,10 @@ int peps_set_jacobi(peps_ctx *ctx, double tol, int32_t inner_sweeps, int32_t max
 int peps_set_deflation(peps_ctx *ctx, double eps);
 /* SquareSpinOneHalfXXZModelOBC(jz, jxy, pinning00) (model_solvers/square_spin_onehalf_xxz_obc.h:174-328). */
 int peps_set_model_xxz(peps_ctx *ctx, double jz, double jxy, double pinning00);
+/* SquareSpinOneHalfJ1J2XXZModelOBC(jz, jxy, jz2, jxy2, pinning00) (model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113):
+ * next-nearest-neighbour couplings evaluated through BTen2 + ReplaceNNNSiteTrace in the horizontal pass
+ * (base/square_nnn_energy_solver.h:203-265). jz2 = jxy2 = 0 switches the NNN pass off. */
+int peps_set_model_j1j2_xxz(peps_ctx *ctx, double jz, double jxy, double jz2, double jxy2, double pinning00);
 
 /* Configuration per walker (vmc_basic/configuration.h:57), int32 [W][rows][cols]. */
 int peps_set_configs(peps_ctx *ctx, const int32_t *cfg);

@@ -25,6 +25,7 @@ class BMPSContractor:
         self.rows, self.cols = rows, cols
         self.bmps_set = {p: [] for p in range(4)}
         self.bten_set = {p: [] for p in range(4)}
+        self.bten_set2 = {p: [] for p in range(4)}
         self.trunc = None
         self.n_multiply = 0          # instrumentation: number of MultiplyMPO calls
 
@@ -38,6 +39,7 @@ class BMPSContractor:
             n = self.cols if p in (UP, DOWN) else self.rows
             self.bmps_set[p] = [vacuum_bmps(n)]
             self.bten_set[p] = []
+            self.bten_set2[p] = []
 
     # ---- accessors (bmps_contractor.h:985-1018)
     def bmps_at_slice(self, pos, logical_idx):
@@ -261,3 +263,92 @@ class BMPSContractor:
         del self.bten_set[UP][row + 1:]
         del self.bten_set[RIGHT][self.cols - col:]
         del self.bten_set[DOWN][self.rows - row:]
+        del self.bten_set2[LEFT][col + 1:]
+        del self.bten_set2[UP][row + 1:]
+        del self.bten_set2[RIGHT][self.cols - col:]
+        del self.bten_set2[DOWN][self.rows - row:]
+
+    # ---- two-row environments for next-nearest-neighbour terms
+    #      (impl/bmps_contractor_init.h:130-186, grow.h:375-527, helpers.h:151-180, trace.h:207-324)
+    def init_bten2(self, tn, pos, slice_num1):
+        self.bten_set2[pos] = [np.ones((1, 1, 1, 1))]
+
+    @staticmethod
+    def bten2_step(bten2, mps1, site1, site2, mps2, post):
+        """GrowBTen2StepAfterTransposedMPOTens (helpers.h:151-180) == the loop body of GrowFullBTen2 (grow.h:497-511).
+        site1 is the tensor adjacent to the BMPS at pre_post, site2 the one adjacent to the BMPS at next_post.
+        Result legs (mps1[0], site1[opposite], site2[opposite], mps2[2])."""
+        pre, nxt, opp = (post + 3) % 4, (post + 1) % 4, (post + 2) % 4
+        s1 = np.transpose(site1, (pre, post, opp, nxt))          # GenMpoTen1TransposeAxesForBrowBTen2
+        s2 = np.transpose(site2, (pre, post, nxt, opp))
+        tmp1 = es("apx,xyvz->apyvz", mps1, bten2)
+        tmp2 = es("apyvz,pyon->vzaon", tmp1, s1)
+        tmp3 = es("vzaon,nvfq->zaofq", tmp2, s2)
+        return es("zaofq,zfb->aoqb", tmp3, mps2)
+
+    def _bten2_operands(self, tn, post, slice_num1, bten_size):
+        """(mps1, mps2, site1, site2) of one BTen2 step (SetUpCoordInfoForGrowBTen2 / GrowFullBTen2 grow.h:389-437)."""
+        pre_post, next_post = (post + 3) % 4, (post + 1) % 4
+        n = self.cols if post in (LEFT, RIGHT) else self.rows
+        s1, s2 = slice_num1, slice_num1 + 1
+        if post == LEFT:      # pre = UP (row1), next = DOWN (row2)
+            b1, b2 = self.bmps_at_slice(UP, s1), self.bmps_at_slice(DOWN, s2)
+            site1, site2 = (s1, bten_size - 1), (s2, bten_size - 1)
+        elif post == RIGHT:   # pre = DOWN (row2), next = UP (row1)
+            b1, b2 = self.bmps_at_slice(DOWN, s2), self.bmps_at_slice(UP, s1)
+            site1, site2 = (s2, n - bten_size), (s1, n - bten_size)
+        elif post == UP:      # pre = RIGHT (col2), next = LEFT (col1)
+            b1, b2 = self.bmps_at_slice(RIGHT, s2), self.bmps_at_slice(LEFT, s1)
+            site1, site2 = (bten_size - 1, s2), (bten_size - 1, s1)
+        else:                 # DOWN: pre = LEFT (col1), next = RIGHT (col2)
+            b1, b2 = self.bmps_at_slice(LEFT, s1), self.bmps_at_slice(RIGHT, s2)
+            site1, site2 = (n - bten_size, s1), (n - bten_size, s2)
+        return b1[n - bten_size], b2[bten_size - 1], site1, site2
+
+    def grow_full_bten2(self, tn, post, slice_num1, remain_sites, init):
+        """GrowFullBTen2 (grow.h:375-515)."""
+        if init:
+            self.init_bten2(tn, post, slice_num1)
+        btens = self.bten_set2[post]
+        n = self.cols if post in (LEFT, RIGHT) else self.rows
+        for i in range(len(btens) - 1, n - remain_sites):
+            m1, m2, s1, s2 = self._bten2_operands(tn, post, slice_num1, i + 1)
+            btens.append(self.bten2_step(btens[-1], m1, tn[s1[0]][s1[1]], tn[s2[0]][s2[1]], m2, post))
+
+    def grow_bten2_step(self, tn, post, slice_num1):
+        """GrowBTen2Step (grow.h:447-493)."""
+        btens = self.bten_set2[post]
+        m1, m2, s1, s2 = self._bten2_operands(tn, post, slice_num1, len(btens))
+        btens.append(self.bten2_step(btens[-1], m1, tn[s1[0]][s1[1]], tn[s2[0]][s2[1]], m2, post))
+
+    def shift_bten2_window(self, tn, pos, slice_num1):
+        """ShiftBTen2Window (grow.h:523-527)."""
+        self.bten_set2[pos].pop()
+        self.grow_bten2_step(tn, opposite(pos), slice_num1)
+
+    def bten2_at_slice(self, pos, logical_idx):
+        if pos == DOWN:
+            return self.bten_set2[DOWN][self.rows - 1 - logical_idx]
+        if pos == RIGHT:
+            return self.bten_set2[RIGHT][self.cols - 1 - logical_idx]
+        return self.bten_set2[pos][logical_idx]
+
+    def replace_nnn_site_trace(self, tn, left_up_site, nnn_dir, mps_orient, ten_left, ten_right):
+        """ReplaceNNNSiteTrace, HORIZONTAL MPS orientation (trace.h:207-281). nnn_dir 0 = LEFTUP_TO_RIGHTDOWN
+        (ten_left replaces (row1,col1), ten_right replaces (row2,col2)); 1 = LEFTDOWN_TO_RIGHTUP (ten_left replaces
+        (row2,col1), ten_right replaces (row1,col2))."""
+        assert mps_orient == HORIZONTAL
+        row1, col1 = left_up_site
+        row2, col2 = row1 + 1, col1 + 1
+        t = {(row1, col1): tn[row1][col1], (row2, col1): tn[row2][col1],
+             (row1, col2): tn[row1][col2], (row2, col2): tn[row2][col2]}
+        if nnn_dir == 0:
+            t[(row1, col1)], t[(row2, col2)] = ten_left, ten_right
+        else:
+            t[(row2, col1)], t[(row1, col2)] = ten_left, ten_right
+        n = self.cols
+        m1, m2, _, _ = self._bten2_operands(tn, LEFT, row1, col1 + 1)
+        half_a = self.bten2_step(self.bten_set2[LEFT][col1], m1, t[(row1, col1)], t[(row2, col1)], m2, LEFT)
+        m1, m2, _, _ = self._bten2_operands(tn, RIGHT, row1, n - col2)
+        half_b = self.bten2_step(self.bten2_at_slice(RIGHT, col2), m1, t[(row2, col2)], t[(row1, col2)], m2, RIGHT)
+        return es("aoqb,bqoa->", half_a, half_b).item()      # Contract(tmp[3],{0,1,2,3}, tmp[7],{3,2,1,0})

@@ -118,8 +118,20 @@ class XXZModel:
     """SquareSpinOneHalfXXZModelOBC: H = sum_<ij> jz Sz Sz + jxy (Sx Sx + Sy Sy) - h00 Sz(0,0)
     (square_spin_onehalf_xxz_obc.h:64-159, 174-328). Heisenberg = XXZModel(1, 1, 0)."""
 
-    def __init__(self, jz=1.0, jxy=1.0, pinning00=0.0):
-        self.jz, self.jxy, self.pinning00 = jz, jxy, pinning00
+    def __init__(self, jz=1.0, jxy=1.0, pinning00=0.0, jz2=0.0, jxy2=0.0):
+        """jz2 / jxy2 != 0 gives SquareSpinOneHalfJ1J2XXZModelOBC (square_spin_onehalf_j1j2_xxz_obc.h:34-113)."""
+        self.jz, self.jxy, self.pinning00, self.jz2, self.jxy2 = jz, jxy, pinning00, jz2, jxy2
+        self.has_nnn = (jz2 != 0.0 or jxy2 != 0.0)
+
+    def nnn_energy(self, site1, site2, c1, c2, diagonal_dir, w, tps, inv_psi):
+        """EvaluateNNNEnergy (square_spin_onehalf_xxz_obc.h:106-129)."""
+        if c1 == c2:
+            return 0.25 * self.jz2
+        left_up = site1 if diagonal_dir == 0 else (site2[0], site1[1])
+        psi_ex = w.contractor.replace_nnn_site_trace(w.tn, left_up, diagonal_dir, HORIZONTAL,
+                                                     tps[site1[0]][site1[1]][c2], tps[site2[0]][site2[1]][c1])
+        ratio = np.conj(psi_ex * inv_psi)
+        return -0.25 * self.jz2 + ratio * 0.5 * self.jxy2
 
     def bond_energy(self, site1, site2, c1, c2, orient, w, tps, inv_psi):
         """EvaluateBondEnergy (square_spin_onehalf_xxz_obc.h:72-104)."""
@@ -161,6 +173,16 @@ class XXZModel:
                     bond_e.append(self.bond_energy(s1, s2, int(w.config[s1]), int(w.config[s2]),
                                                    HORIZONTAL, w, tps, inv_psi))
                     c.shift_bten_window(tn, RIGHT)
+            if self.has_nnn and row < rows - 1:               # square_nnn_energy_solver.h:203-265
+                c.init_bten2(tn, LEFT, row)
+                c.grow_full_bten2(tn, RIGHT, row, 2, True)
+                for col in range(cols - 1):
+                    s1, s2 = (row, col), (row + 1, col + 1)
+                    e_nnn = self.nnn_energy(s1, s2, int(w.config[s1]), int(w.config[s2]), 0, w, tps, inv_psi)
+                    s1, s2 = (row + 1, col), (row, col + 1)
+                    e_nnn = e_nnn + self.nnn_energy(s1, s2, int(w.config[s1]), int(w.config[s2]), 1, w, tps, inv_psi)
+                    bond_e.append(e_nnn)
+                    c.shift_bten2_window(tn, RIGHT, row)
             if row < rows - 1:
                 c.shift_bmps_window(tn, DOWN)
         # vertical pass (bond_traversal_mixin.h:112-143)

@@ -154,6 +154,17 @@ class SquareSpinOneHalfXXZModelOBC:
 
 
 @dataclass
+class SquareSpinOneHalfJ1J2XXZModelOBC:
+    """model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113; the one-argument reference ctor (j2) is
+    SquareSpinOneHalfJ1J2XXZModelOBC(1, 1, j2, j2, 0)."""
+    jz: float = 1.0
+    jxy: float = 1.0
+    jz2: float = 0.0
+    jxy2: float = 0.0
+    pinning00: float = 0.0
+
+
+@dataclass
 class MCUpdateSquareNNExchange:
     """Explicit-seed constructor of the reference updater; walker w draws from std::mt19937(seed + w)."""
     seed: int = 5489
@@ -209,7 +220,10 @@ class WalkerBatch:
         self._ck(self.lib.peps_set_deflation(self.h, eps))
 
     def set_model(self, model):
-        self._ck(self.lib.peps_set_model_xxz(self.h, model.jz, model.jxy, model.pinning00))
+        if hasattr(model, "jz2"):
+            self._ck(self.lib.peps_set_model_j1j2_xxz(self.h, model.jz, model.jxy, model.jz2, model.jxy2, model.pinning00))
+        else:
+            self._ck(self.lib.peps_set_model_xxz(self.h, model.jz, model.jxy, model.pinning00))
 
     def set_configs(self, cfgs):
         a = np.ascontiguousarray(cfgs, dtype=np.int32).reshape(self.W, self.rows, self.cols)

@@ -70,6 +70,7 @@ Engine::~Engine() {
   for (int p = 0; p < 4; ++p) {
     for (auto &b : bmps_[p]) release(b);
     for (auto &t : bten_[p]) release(t);
+    for (auto &t : bten2_[p]) release(t);
   }
   for (void *p : {(void *)tps_, (void *)osum_, (void *)eosum_, (void *)tps_off_d_, (void *)site_size_d_, (void *)hole_off_d_,
                   (void *)cfg_, (void *)amp_, (void *)mt_, (void *)mtidx_, (void *)accepted_, (void *)eloc_, (void *)psi_tmp_,
@@ -285,6 +286,8 @@ void Engine::contractor_init() {                       // impl/bmps_contractor_i
     bmps_[p].clear();
     for (auto &t : bten_[p]) release(t);
     bten_[p].clear();
+    for (auto &t : bten2_[p]) release(t);
+    bten2_[p].clear();
     int n = (p == UP || p == DOWN) ? cols_ : rows_;
     BMPSv vac;
     for (int i = 0; i < n; ++i) vac.push_back(ones111());
@@ -385,17 +388,105 @@ void Engine::nn_trace(int ra, int ca, int rb, int cb, int orient, int cfg_site_a
   BT half_a = bten_step(bten_[first].at((size_t)ia), *m1, site_ref(ra * cols_ + ca, cfg_site_a), *m2, first);
   bten_operands(second, slice, n - ib, m1, m2, site);
   BT half_b = bten_step(bten_at_slice(second, ib), *m1, site_ref(rb * cols_ + cb, cfg_site_b), *m2, second);
-  // Contract(tmp2,{0,1,2}, tmp5,{2,1,0})  trace.h:202
-  const int da = half_a.d[0], db = half_a.d[1], dc = half_a.d[2];
-  std::vector<int32_t> ak((size_t)(da * db * dc)), bk(ak.size());
-  for (int a = 0; a < da; ++a)
-    for (int b = 0; b < db; ++b)
-      for (int c = 0; c < dc; ++c) {
-        size_t k = ((size_t)a * db + b) * dc + c;
-        ak[k] = (int32_t)k;
-        bk[k] = (int32_t)(((long)c * db + b) * da + a);
-      }
-  be_dot((int)ak.size(), planner_.upload(ak), planner_.upload(bk), mkop(half_a.p, half_a.n), mkop(half_b.p, half_b.n), psi_out, W_);
+  reverse_dot(half_a, half_b, psi_out);             // Contract(tmp2,{0,1,2}, tmp5,{2,1,0})  trace.h:202
+  release(half_a);
+  release(half_b);
+}
+// out[w] = sum over all indices of a[i0,i1,...] * b[...,i1,i0] (b has the reversed leg order of a)
+void Engine::reverse_dot(const BT &a, const BT &b, double *out) {
+  const long n = a.n;
+  std::vector<int32_t> ak((size_t)n), bk((size_t)n);
+  std::vector<long> bstride((size_t)a.rank);
+  {
+    // b dims are a's reversed: b index order (i_{r-1}, ..., i_0); stride of i_k in b
+    long acc = 1;
+    for (int k = 0; k < a.rank; ++k) { bstride[(size_t)k] = acc; acc *= a.d[k]; }
+  }
+  for (long k = 0; k < n; ++k) {
+    long rem = k, off = 0;
+    for (int ax = a.rank - 1; ax >= 0; --ax) {
+      long idx = rem % a.d[ax];
+      rem /= a.d[ax];
+      off += idx * bstride[(size_t)ax];
+    }
+    ak[(size_t)k] = (int32_t)k;
+    bk[(size_t)k] = (int32_t)off;
+  }
+  be_dot((int)n, planner_.upload(ak), planner_.upload(bk), mkop(a.p, a.n), mkop(b.p, b.n), out, W_);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// two-row environments (BTen2) and next-nearest-neighbour traces
+// ---------------------------------------------------------------------------------------------------
+void Engine::init_bten2(int pos) {                     // init.h:130-186
+  for (auto &t : bten2_[pos]) release(t);
+  bten2_[pos].clear();
+  BT t = alloc({1, 1, 1, 1});
+  be_fill(t.p, 1.0, W_);
+  bten2_[pos].push_back(t);
+}
+const BT &Engine::bten2_at_slice(int pos, int logical) const {
+  if (pos == DOWN) return bten2_[DOWN].at((size_t)(rows_ - 1 - logical));
+  if (pos == RIGHT) return bten2_[RIGHT].at((size_t)(cols_ - 1 - logical));
+  return bten2_[pos].at((size_t)logical);
+}
+BT Engine::bten2_step(const BT &bten2, const BT &mps1, const TRef &site1, const TRef &site2, const BT &mps2, int post) {
+  // helpers.h:151-180 / grow.h:497-511: site1 sits next to the BMPS at pre_post, site2 next to the one at next_post
+  ++n_bten_;
+  const std::string sl1 = site_labels(post, 'p', 'y', 'n', 'o');
+  const std::string sl2 = site_labels(post, 'n', 'v', 'f', 'q');
+  BT tmp1 = einsum("apx,xyvz->apyvz", ref(mps1), ref(bten2));
+  BT tmp2 = einsum("apyvz," + sl1 + "->vzaon", ref(tmp1), site1);
+  release(tmp1);
+  BT tmp3 = einsum("vzaon," + sl2 + "->zaofq", ref(tmp2), site2);
+  release(tmp2);
+  BT out = einsum("zaofq,zfb->aoqb", ref(tmp3), ref(mps2));
+  release(tmp3);
+  return out;
+}
+void Engine::bten2_operands(int post, int slice1, int bten_size, const BT *&mps1, const BT *&mps2, int &site1, int &site2) const {
+  const int n = (post == LEFT || post == RIGHT) ? cols_ : rows_;
+  const int s1 = slice1, s2 = slice1 + 1;
+  const BMPSv *b1, *b2;
+  if (post == LEFT) { b1 = &bmps_at_slice(UP, s1); b2 = &bmps_at_slice(DOWN, s2); site1 = s1 * cols_ + bten_size - 1; site2 = s2 * cols_ + bten_size - 1; }
+  else if (post == RIGHT) { b1 = &bmps_at_slice(DOWN, s2); b2 = &bmps_at_slice(UP, s1); site1 = s2 * cols_ + n - bten_size; site2 = s1 * cols_ + n - bten_size; }
+  else if (post == UP) { b1 = &bmps_at_slice(RIGHT, s2); b2 = &bmps_at_slice(LEFT, s1); site1 = (bten_size - 1) * cols_ + s2; site2 = (bten_size - 1) * cols_ + s1; }
+  else { b1 = &bmps_at_slice(LEFT, s1); b2 = &bmps_at_slice(RIGHT, s2); site1 = (n - bten_size) * cols_ + s1; site2 = (n - bten_size) * cols_ + s2; }
+  mps1 = &b1->at((size_t)(n - bten_size));
+  mps2 = &b2->at((size_t)(bten_size - 1));
+}
+void Engine::grow_full_bten2(int pos, int slice1, int remain, bool init) {       // grow.h:375-515
+  if (init) init_bten2(pos);
+  const int n = (pos == LEFT || pos == RIGHT) ? cols_ : rows_;
+  for (int i = (int)bten2_[pos].size() - 1; i < n - remain; ++i) {
+    const BT *m1, *m2; int s1, s2;
+    bten2_operands(pos, slice1, i + 1, m1, m2, s1, s2);
+    bten2_[pos].push_back(bten2_step(bten2_[pos].back(), *m1, site_ref(s1, s1), site_ref(s2, s2), *m2, pos));
+  }
+}
+void Engine::grow_bten2_step(int post, int slice1) {   // grow.h:447-493
+  const BT *m1, *m2; int s1, s2;
+  bten2_operands(post, slice1, (int)bten2_[post].size(), m1, m2, s1, s2);
+  bten2_[post].push_back(bten2_step(bten2_[post].back(), *m1, site_ref(s1, s1), site_ref(s2, s2), *m2, post));
+}
+void Engine::shift_bten2_window(int pos, int slice1) { // grow.h:523-527
+  release(bten2_[pos].back());
+  bten2_[pos].pop_back();
+  grow_bten2_step(opposite(pos), slice1);
+}
+void Engine::nnn_trace(int row1, int col1, int dir, double *psi_out) {            // trace.h:207-281 (HORIZONTAL)
+  ++n_trace_;
+  const int row2 = row1 + 1, col2 = col1 + 1;
+  const int s11 = row1 * cols_ + col1, s21 = row2 * cols_ + col1, s12 = row1 * cols_ + col2, s22 = row2 * cols_ + col2;
+  // configuration index each of the four plaquette tensors gathers: the two sites on the diagonal exchange theirs
+  int g11 = s11, g21 = s21, g12 = s12, g22 = s22;
+  if (dir == 0) { g11 = s22; g22 = s11; } else { g21 = s12; g12 = s21; }
+  const BT *m1, *m2; int a, b;
+  bten2_operands(LEFT, row1, col1 + 1, m1, m2, a, b);
+  BT half_a = bten2_step(bten2_[LEFT].at((size_t)col1), *m1, site_ref(s11, g11), site_ref(s21, g21), *m2, LEFT);
+  bten2_operands(RIGHT, row1, cols_ - col2, m1, m2, a, b);
+  BT half_b = bten2_step(bten2_at_slice(RIGHT, col2), *m1, site_ref(s22, g22), site_ref(s12, g12), *m2, RIGHT);
+  reverse_dot(half_a, half_b, psi_out);                // Contract(tmp[3],{0,1,2,3}, tmp[7],{3,2,1,0})
   release(half_a);
   release(half_b);
 }
@@ -494,6 +585,17 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
         nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);
         be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, eloc_, W_);
         shift_bten_window(RIGHT);
+      }
+    }
+    if ((jz2_ != 0.0 || jxy2_ != 0.0) && row < rows_ - 1) {     // square_nnn_energy_solver.h:203-265
+      init_bten2(LEFT);
+      grow_full_bten2(RIGHT, row, 2, true);
+      for (int col = 0; col < cols_ - 1; ++col) {
+        nnn_trace(row, col, 0, psi_tmp_);                                            // (row,col) <-> (row+1,col+1)
+        be_xxz_bond_energy(cfg_, nsites_, row * cols_ + col, (row + 1) * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_, eloc_, W_);
+        nnn_trace(row, col, 1, psi_tmp_);                                            // (row+1,col) <-> (row,col+1)
+        be_xxz_bond_energy(cfg_, nsites_, (row + 1) * cols_ + col, row * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_, eloc_, W_);
+        shift_bten2_window(RIGHT, row);
       }
     }
     if (row < rows_ - 1) shift_bmps_window(DOWN);

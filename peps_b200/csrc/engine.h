@@ -72,6 +72,8 @@ class Engine {
   double *eosum_device() { return eosum_; }
   void set_model_xxz(double jz, double jxy, double h00) { jz_ = jz; jxy_ = jxy; h00_ = h00; }
   void set_deflation(double eps) { la_.deflation_eps = eps; }
+  // SquareSpinOneHalfJ1J2XXZModelOBC couplings (model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113); 0 disables NNN
+  void set_model_nnn(double jz2, double jxy2) { jz2_ = jz2; jxy2_ = jxy2; }
 
   // ---- probes used by the parity tests (per-walker values of reference contractor calls)
   int bmps_stack_size(int pos) const { return (int)bmps_[pos].size(); }
@@ -101,6 +103,13 @@ class Engine {
   // psi_out[w] = ReplaceNNSiteTrace(site_a, site_b, tensors sitps(site_a)[cfg(cfg_a)], sitps(site_b)[cfg(cfg_b)])
   void nn_trace(int ra, int ca, int rb, int cb, int orient, int cfg_site_a, int cfg_site_b, double *psi_out);
   void punch_hole(int r, int c, int orient);          // into the holes buffer
+  // two-row environments and next-nearest-neighbour traces (init.h:130-186, grow.h:375-527, trace.h:207-281)
+  void init_bten2(int pos);
+  void grow_full_bten2(int pos, int slice1, int remain, bool init);
+  void grow_bten2_step(int post, int slice1);
+  void shift_bten2_window(int pos, int slice1);
+  // psi_out[w] = ReplaceNNNSiteTrace({row1,col1}, dir, HORIZONTAL, exchanged tensors); dir 0 = LEFTUP_TO_RIGHTDOWN
+  void nnn_trace(int row1, int col1, int dir, double *psi_out);
 
  private:
   using BMPSv = std::vector<BT>;
@@ -115,6 +124,10 @@ class Engine {
                    double alpha = 1.0, double beta = 0.0);
   BMPSv absorb(const BMPSv &mps, const std::vector<int> &sites, int post);
   BT bten_step(const BT &bten, const BT &mps1, const TRef &site, const BT &mps2, int post);
+  BT bten2_step(const BT &bten2, const BT &mps1, const TRef &site1, const TRef &site2, const BT &mps2, int post);
+  void bten2_operands(int post, int slice1, int bten_size, const BT *&mps1, const BT *&mps2, int &site1, int &site2) const;
+  const BT &bten2_at_slice(int pos, int logical) const;
+  void reverse_dot(const BT &a, const BT &b, double *out);
   std::vector<int> slice_sites(int num, int orient) const;
   const BMPSv &bmps_at_slice(int pos, int logical) const;
   const BT &bten_at_slice(int pos, int logical) const;
@@ -124,7 +137,7 @@ class Engine {
   int rows_, cols_, phys_, D_, W_, nsites_;
   int dmin_, dmax_;
   double terr_;
-  double jz_ = 1.0, jxy_ = 1.0, h00_ = 0.0;
+  double jz_ = 1.0, jxy_ = 1.0, h00_ = 0.0, jz2_ = 0.0, jxy2_ = 0.0;
   Pool pool_;
   Planner planner_;
   LinalgCtx la_;
@@ -155,6 +168,7 @@ class Engine {
 
   std::vector<BMPSv> bmps_[4];
   std::vector<BT> bten_[4];
+  std::vector<BT> bten2_[4];
   long n_absorb_ = 0, n_bten_ = 0, n_trace_ = 0;
 };
 

@@ -18,7 +18,7 @@ def flat_holes(holes, rows, cols):
 
 
 def run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=1, signed=False, tol=1e-10, seeds0=100,
-                        check_configs=True):
+                        check_configs=True, j2=0.0):
     """Sweeps + energy + holes for W walkers through the C ABI vs the oracle, walker by walker."""
     tps, cfgs = make_case(rows, cols, D, W, seed, signed)
     tr = BMPSTruncateParams.SVD(*trunc)
@@ -26,10 +26,13 @@ def run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=1, signed=
     b.set_tps(SplitIndexTPS(tps))
     b.set_configs(cfgs)
     b.seed_rng(np.arange(seeds0, seeds0 + W))
+    if j2 != 0.0:
+        from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
+        b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, j2, j2, 0.0))
     b.init_walkers()
     ws = [vmc.Walker(tps, cfgs[w], trunc) for w in range(W)]
     ups = [vmc.NNExchangeUpdater(seeds0 + w) for w in range(W)]
-    model = vmc.XXZModel(1.0, 1.0, 0.0)
+    model = vmc.XXZModel(1.0, 1.0, 0.0, j2, j2)
     amp0 = b.amplitudes()
     ref0 = np.array([w_.amplitude for w_ in ws])
     report = {"amp0": float(np.max(np.abs(amp0 / ref0 - 1)))}

@@ -129,6 +129,12 @@ def test_pipeline_parity_gpu_signed(lib):
     run_pipeline_parity(lib, 4, 4, 3, 2, (9, 9, 0.0), nsweeps=2, signed=True, seed=5)
 
 
+@pytest.mark.parametrize("rows,cols,D,trunc,W", [(4, 4, 3, (6, 6, 0.0), 4), (3, 5, 2, (4, 4, 0.0), 3), (6, 6, 4, (16, 16, 0.0), 2)])
+def test_j1j2_pipeline_parity_gpu(lib, rows, cols, D, trunc, W):
+    """J1-J2 Heisenberg (BASELINE config #3's model): NNN terms through BTen2 + ReplaceNNNSiteTrace on the GPU."""
+    run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=1, j2=0.5)
+
+
 def test_gradient_parity_gpu(lib):
     run_gradient_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsamples=4)
 
@@ -216,3 +222,27 @@ def test_full_size_amplitude_parity_10x10_D8_chi64(lib):
         worst = max(worst, abs(amp[w] / ref - 1))
     print("10x10 D8 chi64 amplitude rel err", worst)
     assert worst < 1e-10
+
+
+def test_config2_8x8_D6_chi36_sample_vs_oracle(lib):
+    """BASELINE config #2 sizes (Heisenberg 8x8, D=6, chi=36): one sweep + E_loc + holes of two walkers vs the oracle."""
+    rep = run_pipeline_parity(lib, 8, 8, 6, 2, (36, 36, 0.0), nsweeps=1, seed=20260101)
+    print(rep)
+
+
+def test_config5_14x14_D10_chi100_smoke(lib):
+    """BASELINE config #5 sizes exercise the 16-wide CAQR panels and the 8-row Jacobi blocks (D*chi = 1000): the
+    amplitude is finite, identical walkers agree bit for bit, and the row closures agree to truncation accuracy."""
+    from oracle import vmc
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+    L, D, chi, W = 14, 10, 100, 2
+    tps = vmc.random_tps(L, L, 2, D, seed=5)
+    cfg = vmc.shuffled_half_filled_config(L, L, 77)
+    b = WalkerBatch(L, L, 2, D, W, BMPSTruncateParams.SVD(chi, chi, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(np.stack([cfg, cfg]))
+    b.init_walkers()
+    amp = b.amplitudes()
+    assert np.all(np.isfinite(amp)) and amp[0] != 0.0 and amp[0] == amp[1]
+    psi_mid = b.probe_trace_row(7)
+    assert abs(psi_mid[0] / amp[0] - 1) < 1e-6

@@ -35,6 +35,12 @@ def test_pipeline_parity_signed_tps(lib):
     run_pipeline_parity(lib, 4, 4, 3, 2, (9, 9, 0.0), nsweeps=2, signed=True, seed=5)
 
 
+@pytest.mark.parametrize("rows,cols,D,trunc", [(4, 4, 3, (6, 6, 0.0)), (3, 5, 2, (4, 4, 0.0))])
+def test_j1j2_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
+    """J1-J2 model (BASELINE config #3): BTen2 growth + NNN traces in the energy pass."""
+    run_pipeline_parity(lib, rows, cols, D, 3, trunc, nsweeps=2, j2=0.5)
+
+
 def test_gradient_accumulation_parity_hostsim(lib):
     run_gradient_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsamples=4)
 

@@ -77,6 +77,55 @@ def test_K1_ising_partition_function(L):
         assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
 
 
+def test_K1_nnn_traces_reproduce_partition_function():
+    """The NNN closures of the reference's K1 list (test_bmps_contractor.cpp:312-335): ReplaceNNNSiteTrace with the
+    original tensors equals Z, before and after ShiftBTen2Window."""
+    L = 8
+    beta = math.log(1 + math.sqrt(2.0)) / 2.0
+    tn = ising_tn(L, beta)
+    lz = ising_exact_logZ(L, beta)
+    c = BMPSContractor(L, L)
+    c.init(tn)
+    c.set_truncate_params(10, 30, 1e-15)
+    c.grow_bmps_for_row(tn, 1)
+    c.init_bten2(tn, LEFT, 1)
+    c.grow_full_bten2(tn, RIGHT, 1, 2, True)
+    zs = [c.replace_nnn_site_trace(tn, (1, 0), 1, HORIZONTAL, tn[2][0], tn[1][1]),
+          c.replace_nnn_site_trace(tn, (1, 0), 0, HORIZONTAL, tn[1][0], tn[2][1])]
+    c.shift_bten2_window(tn, RIGHT, 1)
+    zs += [c.replace_nnn_site_trace(tn, (1, 1), 1, HORIZONTAL, tn[2][1], tn[1][2]),
+           c.replace_nnn_site_trace(tn, (1, 1), 0, HORIZONTAL, tn[1][1], tn[2][2])]
+    for z in zs:
+        assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
+
+
+def test_j1j2_local_energy_equals_brute_force():
+    tps = vmc.random_tps(3, 3, 2, 2, seed=3)
+    cfg = vmc.shuffled_half_filled_config(3, 3, 5)
+    trunc = (1, 1000, 0.0)
+    amp = lambda c: vmc.Walker(tps, c, trunc).amplitude
+    e, _, _ = vmc.XXZModel(1.0, 1.0, 0.0, 0.5, 0.5).energy_and_holes(tps, vmc.Walker(tps, cfg, trunc), True)
+    psi = amp(cfg)
+
+    def bond(s1, s2, jz, jxy):
+        if cfg[s1] == cfg[s2]:
+            return 0.25 * jz
+        c2 = cfg.copy()
+        c2[s1], c2[s2] = cfg[s2], cfg[s1]
+        return -0.25 * jz + 0.5 * jxy * amp(c2) / psi
+
+    ref = 0.0
+    for r in range(3):
+        for c in range(3):
+            if c < 2:
+                ref += bond((r, c), (r, c + 1), 1, 1)
+            if r < 2:
+                ref += bond((r, c), (r + 1, c), 1, 1)
+            if r < 2 and c < 2:
+                ref += bond((r, c), (r + 1, c + 1), 0.5, 0.5) + bond((r + 1, c), (r, c + 1), 0.5, 0.5)
+    assert abs(e - ref) < 1e-12
+
+
 def test_K2_punch_hole_and_invalidation():
     """reference: tests/test_2d_tn/test_bmps_contractor.cpp:407-470."""
     L = 8
