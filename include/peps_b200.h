@@ -102,6 +102,19 @@ double *peps_eloc_ostar_sum_device(peps_ctx *ctx);
  * (the loop body of mc_energy_grad_evaluator.h:205-282). eloc[W], accept_rates[W] may be NULL. */
 int peps_sample(peps_ctx *ctx, int32_t sweeps_between_samples, double *eloc, double *accept_rates);
 
+/* ---- stochastic reconfiguration (optimizer/stochastic_reconfiguration_smatrix.h:45-91) ------------------------
+ * The reference keeps Ostar_samples as vector<SplitIndexTPS> on the host (mc_energy_grad_evaluator.h:273-277); here
+ * they stay in HBM. peps_sr_reserve sizes the store in walker-samples; while peps_sr_collect(1) is set every
+ * peps_accumulate_ostar / peps_sample appends the O* of all walkers. peps_sr_matvec returns the LOCAL, unnormalised
+ * sum_i (O*_i . v - mean_dot_v) O*_i (TPS-shaped vectors); the caller all-reduces it over GPUs, divides by the total
+ * sample count and adds diag_shift * v, exactly the tail of SRSMatrix::operator* (:66,:86-88). */
+int peps_sr_reserve(peps_ctx *ctx, int64_t max_walker_samples);
+int peps_sr_collect(peps_ctx *ctx, int32_t on);
+int peps_sr_clear(peps_ctx *ctx);
+int64_t peps_sr_count(peps_ctx *ctx);
+int peps_sr_matvec(peps_ctx *ctx, const double *v_host, double mean_dot_v, double *out_host, size_t n);
+int peps_sr_matvec_device(peps_ctx *ctx, const double *v_dev, double mean_dot_v, double *out_dev);
+
 /* ---- probes for the parity tests ------------------------------------------------------------------ */
 /* BMPSContractor::GrowBMPSForRow + InitBTen/GrowFullBTen + Trace(tn,{row,0},HORIZONTAL) (trace.h:11-28). */
 int peps_probe_trace_row(peps_ctx *ctx, int32_t row, double *psi);

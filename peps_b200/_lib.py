@@ -54,6 +54,12 @@ SIGNATURES = {
     "peps_ostar_sum_device": (C.c_void_p, [_P]),
     "peps_eloc_ostar_sum_device": (C.c_void_p, [_P]),
     "peps_sample": (C.c_int, [_P, C.c_int32, _D, _D]),
+    "peps_sr_reserve": (C.c_int, [_P, C.c_int64]),
+    "peps_sr_collect": (C.c_int, [_P, C.c_int32]),
+    "peps_sr_clear": (C.c_int, [_P]),
+    "peps_sr_count": (C.c_int64, [_P]),
+    "peps_sr_matvec": (C.c_int, [_P, _D, C.c_double, _D, C.c_size_t]),
+    "peps_sr_matvec_device": (C.c_int, [_P, C.c_void_p, C.c_double, C.c_void_p]),
     "peps_probe_trace_row": (C.c_int, [_P, C.c_int32, _D]),
     "peps_bmps_stack_size": (C.c_int32, [_P, C.c_int32]),
     "peps_get_bmps_tensor": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _D, _I]),

@@ -296,6 +296,25 @@ class WalkerBatch:
         self._ck(self.lib.peps_sample(self.h, sweeps_between_samples, _dp(e), _dp(acc)))
         return e, acc
 
+    # stochastic reconfiguration store
+    def sr_reserve(self, max_walker_samples):
+        self._ck(self.lib.peps_sr_reserve(self.h, int(max_walker_samples)))
+
+    def sr_collect(self, on=True):
+        self._ck(self.lib.peps_sr_collect(self.h, int(on)))
+
+    def sr_clear(self):
+        self._ck(self.lib.peps_sr_clear(self.h))
+
+    def sr_count(self):
+        return int(self.lib.peps_sr_count(self.h))
+
+    def sr_matvec(self, v, mean_dot_v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty(self.tps_size)
+        self._ck(self.lib.peps_sr_matvec(self.h, _dp(v), float(mean_dot_v), _dp(out), out.size))
+        return out
+
     # probes
     def probe_trace_row(self, row):
         a = np.empty(self.W)
@@ -346,6 +365,8 @@ class EvaluateResult:
     gradient_norm: float
     accept_rates_avg: List[float]
     energy_samples: np.ndarray = field(default=None)
+    Ostar_mean: Optional[SplitIndexTPS] = None       # set when SR buffers were collected (O* samples stay in HBM)
+    total_samples: int = 0
 
 
 def combine_energy_bins(energy_samples):
@@ -426,7 +447,7 @@ class MCEnergyGradEvaluator:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.cpu()[0])
 
-    def Evaluate(self, state: Optional[SplitIndexTPS] = None) -> EvaluateResult:
+    def Evaluate(self, state: Optional[SplitIndexTPS] = None, collect_sr_buffers: bool = False) -> EvaluateResult:
         b = self.batch
         if state is not None and state is not self.state:
             self.state = state
@@ -434,6 +455,12 @@ class MCEnergyGradEvaluator:
         b.init_walkers()                       # engine_.RefreshWavefunctionComponent()  (:164)
         n = self.samples_per_walker()
         b.zero_accumulators()
+        if collect_sr_buffers:                 # collect_sr_buffers_ of the reference evaluator (:181-183, :273-277)
+            if b.sr_count() != 0 or getattr(self, "_sr_cap", 0) < n * b.W:
+                b.sr_reserve(n * b.W)
+                self._sr_cap = n * b.W
+            b.sr_clear()
+        b.sr_collect(collect_sr_buffers)
         energies = np.empty((b.W, n))
         accept = np.zeros(b.W)
         for s in range(n):                     # the walker loop (:205-282), all walkers in lock step
@@ -457,7 +484,31 @@ class MCEnergyGradEvaluator:
         total_walkers = all_e.shape[0]
         grad_flat = (eosum - energy * osum) / (n * total_walkers)        # (:296-309)
         grad = SplitIndexTPS.unpack(grad_flat, self.state)
-        return EvaluateResult(energy, err, grad, grad.NormSquare(), [float(np.mean(accept / n))], all_e)
+        b.sr_collect(False)
+        res = EvaluateResult(energy, err, grad, grad.NormSquare(), [float(np.mean(accept / n))], all_e)
+        if collect_sr_buffers:
+            res.Ostar_mean = SplitIndexTPS.unpack(osum / (n * total_walkers), self.state)
+            res.total_samples = n * total_walkers
+        return res
+
+    def CalculateNaturalGradient(self, result: EvaluateResult, diag_shift, cg_params=None, init_guess=None):
+        """Optimizer::CalculateNaturalGradient (optimizer/optimizer_impl.h:1031-1089) against the O* samples kept in
+        HBM by the last Evaluate(collect_sr_buffers=True). Returns (natural_gradient, cg_iterations, residual_norm)."""
+        from . import sr
+        allreduce = None
+        if self.dist is not None and self.world_size > 1:
+            import torch
+
+            def allreduce(x):
+                t = torch.from_numpy(x)
+                if self.dist.get_backend() == "nccl":
+                    t = t.cuda()
+                self.dist.all_reduce(t)
+                return t.cpu().numpy()
+        r = sr.calculate_natural_gradient(self.batch, result.gradient.pack(), result.Ostar_mean.pack(), result.total_samples,
+                                          diag_shift, cg_params or sr.ConjugateGradientParams(),
+                                          None if init_guess is None else init_guess.pack(), allreduce)
+        return SplitIndexTPS.unpack(r.x, self.state), r.iterations, r.residual_norm
 
     def samples_per_walker(self):
         """SamplesPerRank = ceil(total / ranks) (monte_carlo_engine.h:97-98) with ranks = walkers * GPUs."""

@@ -152,4 +152,19 @@ void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *h
                          const int32_t *tps_off, const int32_t *cfg, int nsites, int phys, const double *amp,
                          const double *eloc, double *osum, double *eosum, int W);
 
+// ---- stochastic reconfiguration: device-resident O* sample store and the S-matrix-free matvec ---------------
+// (optimizer/stochastic_reconfiguration_smatrix.h:45-91). A stored sample i keeps O*_i as the [hole_stride] vector
+// of its sampled physical slices plus the configuration that says which TPS slots they occupy.
+// store: ostar[i][e] = holes[w][e] / amp[w], cfgs[i][:] = cfg[w][:] for i = first + w.
+void be_sr_store(const double *holes, long hole_stride, const double *amp, const int32_t *cfg, int nsites,
+                 double *ostar, int32_t *cfgs, long first, int W);
+// delta[i] = (O*_i . v) - mean_dot_v  for i < n   (O*_i . v sums over the sampled slot of every site)
+void be_sr_dots(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
+                const int32_t *site_size, const int32_t *tps_off, int nsites, const double *v, double mean_dot_v,
+                double *delta, long n);
+// out[slot] = sum_i delta[i] O*_i[slot]   over the full TPS-shaped vector (slots a sample does not occupy get 0)
+void be_sr_accumulate(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
+                      const int32_t *site_size, const int32_t *tps_off, int nsites, int phys, const double *delta,
+                      double *out, long n);
+
 }  // namespace peps

@@ -1502,4 +1502,81 @@ void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *h
   post_launch();
 }
 
+
+// =====================================================================================================
+// stochastic reconfiguration (HBM-bound: every O* sample is read once per kernel)
+// =====================================================================================================
+__global__ void sr_store_kernel(const double *holes, long hole_stride, const double *amp, const int32_t *cfg, int nsites,
+                                double *ostar, int32_t *cfgs, long first) {
+  const int w = blockIdx.y;
+  const double inv = 1.0 / amp[w];
+  const double *src = holes + (long)w * hole_stride;
+  double *dst = ostar + (first + w) * hole_stride;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < hole_stride; e += (long)gridDim.x * blockDim.x)
+    dst[e] = inv * src[e];
+  if (blockIdx.x == 0)
+    for (int s = threadIdx.x; s < nsites; s += blockDim.x) cfgs[(first + w) * nsites + s] = cfg[(long)w * nsites + s];
+}
+void be_sr_store(const double *holes, long hole_stride, const double *amp, const int32_t *cfg, int nsites,
+                 double *ostar, int32_t *cfgs, long first, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  sr_store_kernel<<<dim3(32, W), 256, 0, g_stream>>>(holes, hole_stride, amp, cfg, nsites, ostar, cfgs, first);
+  post_launch();
+}
+
+__global__ void sr_dots_kernel(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
+                               const int32_t *site_size, const int32_t *tps_off, int nsites, const double *v,
+                               double mean_dot_v, double *delta) {
+  const long i = blockIdx.x;
+  const double *o = ostar + i * hole_stride;
+  const int32_t *c = cfgs + i * nsites;
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int site = 0; site < nsites; ++site) {
+    const int sz = site_size[site];
+    const double *os = o + hole_off[site];
+    const double *vs = v + tps_off[site] + (long)c[site] * sz;
+    for (int e = threadIdx.x; e < sz; e += blockDim.x) acc += os[e] * vs[e];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int h = blockDim.x / 2; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) delta[i] = red[0] - mean_dot_v;
+}
+void be_sr_dots(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
+                const int32_t *site_size, const int32_t *tps_off, int nsites, const double *v, double mean_dot_v,
+                double *delta, long n) {
+  if (n <= 0) return;
+  LaunchScope scope(KC_SMALL, 2.0 * hole_stride * (double)n);
+  sr_dots_kernel<<<(unsigned)n, 256, 0, g_stream>>>(ostar, cfgs, hole_stride, hole_off, site_size, tps_off, nsites, v,
+                                                    mean_dot_v, delta);
+  post_launch();
+}
+
+__global__ void sr_accumulate_kernel(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
+                                     const int32_t *site_size, const int32_t *tps_off, int nsites, int phys,
+                                     const double *delta, double *out, long n) {
+  const int site = blockIdx.y;
+  const int sz = site_size[site];
+  const long ho = hole_off[site], to = tps_off[site];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < sz; e += gridDim.x * blockDim.x) {
+    for (int s = 0; s < phys; ++s) out[to + (long)s * sz + e] = 0.0;
+    for (long i = 0; i < n; ++i) {
+      const int s = cfgs[i * nsites + site];
+      out[to + (long)s * sz + e] += delta[i] * ostar[i * hole_stride + ho + e];
+    }
+  }
+}
+void be_sr_accumulate(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
+                      const int32_t *site_size, const int32_t *tps_off, int nsites, int phys, const double *delta,
+                      double *out, long n) {
+  LaunchScope scope(KC_SMALL, 2.0 * hole_stride * (double)n);
+  sr_accumulate_kernel<<<dim3(16, nsites), 256, 0, g_stream>>>(ostar, cfgs, hole_stride, hole_off, site_size, tps_off,
+                                                               nsites, phys, delta, out, n);
+  post_launch();
+}
+
 }  // namespace peps

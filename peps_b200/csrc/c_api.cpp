@@ -117,6 +117,14 @@ int peps_sample(peps_ctx *ctx, int32_t sweeps, double *eloc, double *acc) {
     ctx->eng->accumulate_ostar();
   })
 }
+int peps_sr_reserve(peps_ctx *ctx, int64_t n) { GUARD(ctx, ctx->eng->sr_reserve((long)n)) }
+int peps_sr_collect(peps_ctx *ctx, int32_t on) { GUARD(ctx, ctx->eng->sr_collect(on != 0)) }
+int peps_sr_clear(peps_ctx *ctx) { GUARD(ctx, ctx->eng->sr_clear()) }
+int64_t peps_sr_count(peps_ctx *ctx) { return ctx->eng->sr_count(); }
+int peps_sr_matvec(peps_ctx *ctx, const double *v, double mean_dot_v, double *out, size_t n) {
+  GUARD(ctx, { if (n != ctx->eng->tps_size()) throw std::invalid_argument("peps_sr_matvec: size mismatch"); ctx->eng->sr_matvec_host(v, mean_dot_v, out); })
+}
+int peps_sr_matvec_device(peps_ctx *ctx, const double *v, double mean_dot_v, double *out) { GUARD(ctx, ctx->eng->sr_matvec_device(v, mean_dot_v, out)) }
 int peps_probe_trace_row(peps_ctx *ctx, int32_t row, double *psi) { GUARD(ctx, ctx->eng->probe_trace_row(row, psi)) }
 int32_t peps_bmps_stack_size(peps_ctx *ctx, int32_t pos) { return ctx->eng->bmps_stack_size(pos); }
 int peps_get_bmps_tensor(peps_ctx *ctx, int32_t pos, int32_t k, int32_t i, double *out, int32_t dims[3]) {

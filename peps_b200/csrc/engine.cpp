@@ -74,7 +74,8 @@ Engine::~Engine() {
   }
   for (void *p : {(void *)tps_, (void *)osum_, (void *)eosum_, (void *)tps_off_d_, (void *)site_size_d_, (void *)hole_off_d_,
                   (void *)cfg_, (void *)amp_, (void *)mt_, (void *)mtidx_, (void *)accepted_, (void *)eloc_, (void *)psi_tmp_,
-                  (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done})
+                  (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
+                  (void *)sr_cfgs_, (void *)sr_delta_})
     be_free(p);
 }
 
@@ -625,6 +626,40 @@ void Engine::zero_accumulators() {
 void Engine::accumulate_ostar() {                      // mc_energy_grad_evaluator.h:245-272
   be_accumulate_ostar(holes_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, cfg_, nsites_, phys_, amp_, eloc_,
                       osum_, eosum_, W_);
+  if (sr_on_) {                                        // Ostar_samples.emplace_back(...)  (:273-277)
+    if (sr_count_ + W_ > sr_cap_) throw std::runtime_error("SR sample store is full (peps_sr_reserve)");
+    be_sr_store(holes_, hole_stride_, amp_, cfg_, nsites_, sr_ostar_, sr_cfgs_, sr_count_, W_);
+    sr_count_ += W_;
+  }
+}
+void Engine::sr_reserve(long max_samples) {
+  if (max_samples < 0) throw std::invalid_argument("sr_reserve: negative capacity");
+  be_sync();
+  be_free(sr_ostar_); be_free(sr_cfgs_); be_free(sr_delta_);
+  sr_ostar_ = nullptr; sr_cfgs_ = nullptr; sr_delta_ = nullptr;
+  sr_cap_ = max_samples; sr_count_ = 0;
+  if (max_samples > 0) {
+    sr_ostar_ = (double *)be_malloc(sizeof(double) * (size_t)max_samples * hole_stride_);
+    sr_cfgs_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)max_samples * nsites_);
+    sr_delta_ = (double *)be_malloc(sizeof(double) * (size_t)max_samples);
+  }
+}
+void Engine::sr_matvec_device(const double *v_dev, double mean_dot_v, double *out_dev) {
+  // SRSMatrix::operator* without the 1/(N ranks) factor and the diagonal shift (applied by the caller after the
+  // cross-GPU all-reduce): stochastic_reconfiguration_smatrix.h:60-66
+  be_sr_dots(sr_ostar_, sr_cfgs_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, nsites_, v_dev, mean_dot_v,
+             sr_delta_, sr_count_);
+  be_sr_accumulate(sr_ostar_, sr_cfgs_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, nsites_, phys_, sr_delta_,
+                   out_dev, sr_count_);
+}
+void Engine::sr_matvec_host(const double *v, double mean_dot_v, double *out) {
+  double *vd = (double *)pool_.get(sizeof(double) * tps_total_);
+  double *od = (double *)pool_.get(sizeof(double) * tps_total_);
+  be_h2d(vd, v, sizeof(double) * tps_total_);
+  sr_matvec_device(vd, mean_dot_v, od);
+  be_d2h(out, od, sizeof(double) * tps_total_);
+  pool_.put(vd);
+  pool_.put(od);
 }
 void Engine::get_accumulators(double *osum_host, double *eosum_host) {
   if (osum_host) be_d2h(osum_host, osum_, sizeof(double) * tps_total_);

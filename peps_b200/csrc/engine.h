@@ -70,6 +70,15 @@ class Engine {
   void get_accumulators(double *osum_host, double *eosum_host);
   double *osum_device() { return osum_; }
   double *eosum_device() { return eosum_; }
+  // SR: O* sample store (optimizer/stochastic_reconfiguration_smatrix.h). reserve() allocates capacity for
+  // `max_samples` walker-samples; while collecting, accumulate_ostar() also appends O*_w and its configuration.
+  void sr_reserve(long max_samples);
+  void sr_clear() { sr_count_ = 0; }
+  void sr_collect(bool on) { sr_on_ = on; }
+  long sr_count() const { return sr_count_; }
+  // out = sum_i (O*_i . v - mean_dot_v) O*_i over the stored samples (device pointers, TPS-shaped vectors)
+  void sr_matvec_device(const double *v_dev, double mean_dot_v, double *out_dev);
+  void sr_matvec_host(const double *v, double mean_dot_v, double *out);
   void set_model_xxz(double jz, double jxy, double h00) { jz_ = jz; jxy_ = jxy; h00_ = h00; }
   void set_deflation(double eps) { la_.deflation_eps = eps; }
   // SquareSpinOneHalfJ1J2XXZModelOBC couplings (model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113); 0 disables NNN
@@ -165,6 +174,12 @@ class Engine {
   int32_t *kept_ = nullptr, *order_ = nullptr;  // truncation scratch
   double *norms2_ = nullptr;
   int scratch_rows_ = 0;
+
+  double *sr_ostar_ = nullptr;    // [sr_cap_][hole_stride]
+  int32_t *sr_cfgs_ = nullptr;    // [sr_cap_][nsites]
+  double *sr_delta_ = nullptr;    // [sr_cap_]
+  long sr_cap_ = 0, sr_count_ = 0;
+  bool sr_on_ = false;
 
   std::vector<BMPSv> bmps_[4];
   std::vector<BT> bten_[4];

@@ -423,4 +423,37 @@ void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *h
       }
 }
 
+
+void be_sr_store(const double *holes, long hole_stride, const double *amp, const int32_t *cfg, int nsites,
+                 double *ostar, int32_t *cfgs, long first, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    for (long e = 0; e < hole_stride; ++e) ostar[(first + w) * hole_stride + e] = (1.0 / amp[w]) * holes[(long)w * hole_stride + e];
+    for (int s = 0; s < nsites; ++s) cfgs[(first + w) * nsites + s] = cfg[(long)w * nsites + s];
+  }
+}
+void be_sr_dots(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
+                const int32_t *site_size, const int32_t *tps_off, int nsites, const double *v, double mean_dot_v,
+                double *delta, long n) {
+  ++g_launches;
+  for (long i = 0; i < n; ++i) {
+    double acc = 0.0;
+    for (int site = 0; site < nsites; ++site)
+      for (int e = 0; e < site_size[site]; ++e)
+        acc += ostar[i * hole_stride + hole_off[site] + e] * v[tps_off[site] + (long)cfgs[i * nsites + site] * site_size[site] + e];
+    delta[i] = acc - mean_dot_v;
+  }
+}
+void be_sr_accumulate(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
+                      const int32_t *site_size, const int32_t *tps_off, int nsites, int phys, const double *delta,
+                      double *out, long n) {
+  ++g_launches;
+  for (int site = 0; site < nsites; ++site)
+    for (int e = 0; e < site_size[site]; ++e) {
+      for (int s = 0; s < phys; ++s) out[tps_off[site] + (long)s * site_size[site] + e] = 0.0;
+      for (long i = 0; i < n; ++i)
+        out[tps_off[site] + (long)cfgs[i * nsites + site] * site_size[site] + e] += delta[i] * ostar[i * hole_stride + hole_off[site] + e];
+    }
+}
+
 }  // namespace peps

@@ -246,3 +246,9 @@ def test_config5_14x14_D10_chi100_smoke(lib):
     assert np.all(np.isfinite(amp)) and amp[0] != 0.0 and amp[0] == amp[1]
     psi_mid = b.probe_trace_row(7)
     assert abs(psi_mid[0] / amp[0] - 1) < 1e-6
+
+
+def test_sr_matvec_and_natural_gradient_gpu(lib):
+    """O* sample store in HBM + sr_dots / sr_accumulate kernels + CG vs the oracle's dense S matrix."""
+    from test_sr import sr_scenario
+    sr_scenario(lib)
