@@ -44,9 +44,12 @@ MODEL_FLOPS = {"heisenberg_10x10_D8_chi64": dict(gemm=2.96e11, qr=1.18e12, svd=9
                "heisenberg_4x4_D4_chi8": dict(gemm=2.43e6, qr=1.23e6, svd=1.88e6, total=5.5e6)}
 
 
+SIGNED_TPS = False
+
+
 def make_inputs(L, D, n_walkers, first_walker):
     from oracle import vmc
-    tps = vmc.random_tps(L, L, 2, D, seed=TPS_SEED)
+    tps = vmc.random_tps(L, L, 2, D, seed=TPS_SEED, signed=SIGNED_TPS)
     cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, CFG_SEED0 + first_walker + w) for w in range(n_walkers)])
     seeds = np.arange(RNG_SEED0 + first_walker, RNG_SEED0 + first_walker + n_walkers, dtype=np.uint32)
     return tps, cfgs, seeds
@@ -211,10 +214,13 @@ def main():
     ap.add_argument("--workload", default="heisenberg_10x10_D8_chi64", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--signed", action="store_true", help="uniform [-1,1) TPS entries (cancellation stress variant of SURVEY.md 8d.1)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--streams", type=int, default=4, help="host threads / CUDA streams sharing the walkers of a GPU")
     args = ap.parse_args()
 
+    global SIGNED_TPS
+    SIGNED_TPS = args.signed
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -433,7 +439,7 @@ def main():
             "config": {"workload": args.workload, "lattice": f"{L}x{L}", "D": D, "chi": chi, "walkers_per_gpu": W, "streams_per_gpu": S,
                        "trunc": "Dmin=Dmax=chi, trunc_err=0",
                        "model": "Heisenberg NN (XXZ jz=jxy=1)" if args.j2 == 0.0 else f"J1-J2 Heisenberg (j2={args.j2})",
-                       "sweeps_between_samples": 1, "tps": f"uniform[0,1) seed {TPS_SEED}, NormalizeAllSite + order-1 rescale",
+                       "sweeps_between_samples": 1, "tps": ("uniform[-1,1)" if args.signed else "uniform[0,1)") + f" seed {TPS_SEED}, NormalizeAllSite + order-1 rescale",
                        "l2": "per-step working set (walkers x ~60 MB of BMPS stacks + scratch) exceeds the 126 MB L2",
                        "parallelism": f"walkers sharded over {world} GPU(s); NCCL all-reduce of the two accumulators"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

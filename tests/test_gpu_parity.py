@@ -202,14 +202,18 @@ def test_full_size_properties(lib):
         pos += sz
 
 
-def test_full_size_amplitude_parity_10x10_D8_chi64(lib):
+@pytest.mark.parametrize("L,D,chi,signed,tol", [(10, 8, 64, False, 1e-10), (8, 6, 36, True, 1e-9)])
+def test_full_size_amplitude_parity(lib, L, D, chi, signed, tol):
     """BASELINE's headline size against the oracle itself (one CPU amplitude = 9 row absorptions, ~20 s each):
-    amplitudes of two walkers at 10x10, D=8, chi=64 must agree to 1e-10 relative."""
-    import time
+    amplitudes of two walkers at 10x10, D=8, chi=64 must agree to 1e-10 relative (observed 7e-15).
+    The signed [-1,1) TPS is the cancellation stress variant: its boundary spectra are flat, the chi-truncated
+    contraction is not a meaningful approximation of such a state (row closures of ONE configuration differ by
+    factors of ~10 in the oracle too), and the conditioning of the kept subspaces degrades the agreement between any
+    two correct implementations: 1e-12 at 8x8, D=6, chi=36, and no digits at 10x10, D=8, chi=64."""
     from oracle import vmc
     from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
-    L, D, chi, W = 10, 8, 64, 2
-    tps = vmc.random_tps(L, L, 2, D, seed=20260101)
+    W = 2
+    tps = vmc.random_tps(L, L, 2, D, seed=20260101, signed=signed)
     cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, 1000 + w) for w in range(W)])
     b = WalkerBatch(L, L, 2, D, W, BMPSTruncateParams.SVD(chi, chi, 0.0), lib=lib)
     b.set_tps(SplitIndexTPS(tps))
@@ -220,8 +224,8 @@ def test_full_size_amplitude_parity_10x10_D8_chi64(lib):
     for w in range(W):
         ref = vmc.Walker(tps, cfgs[w], (chi, chi, 0.0)).amplitude
         worst = max(worst, abs(amp[w] / ref - 1))
-    print("10x10 D8 chi64 amplitude rel err", worst)
-    assert worst < 1e-10
+    print(f"{L}x{L} D{D} chi{chi} signed={signed} amplitude rel err", worst)
+    assert worst < tol
 
 
 def test_config2_8x8_D6_chi36_sample_vs_oracle(lib):
