@@ -12,8 +12,11 @@ Engine::Engine(const EngineConfig &c)
   if (rows_ < 2 || cols_ < 2) throw std::invalid_argument("Engine: lattice must be at least 2x2");
   if (W_ < 1 || phys_ < 1 || D_ < 1) throw std::invalid_argument("Engine: bad sizes");
   be_init(c.device);
+  row_mod_.assign((size_t)rows_, 1);
+  col_mod_.assign((size_t)cols_, 1);
   la_.W = W_; la_.pool = &pool_; la_.planner = &planner_;
   if (const char *e = std::getenv("PEPS_DEFLATION_EPS")) la_.deflation_eps = std::atof(e);
+  if (const char *e = std::getenv("PEPS_BMPS_MEMO")) memo_on_ = std::atoi(e) != 0;
   la_.offmax = (double *)be_malloc(sizeof(double) * W_);
   la_.done = (int32_t *)be_malloc(sizeof(int32_t) * W_);
   tps_off_h_.resize((size_t)nsites_);
@@ -82,7 +85,7 @@ Engine::~Engine() {
 void Engine::site_dims(int r, int c, int out[4]) const {
   for (int i = 0; i < 4; ++i) out[i] = site_dims_h_[(size_t)(r * cols_ + c)][(size_t)i];
 }
-void Engine::set_tps(const double *host) { be_h2d(tps_, host, sizeof(double) * tps_total_); }
+void Engine::set_tps(const double *host) { be_h2d(tps_, host, sizeof(double) * tps_total_); touch_all(); }
 void Engine::get_tps(double *host) { be_d2h(host, tps_, sizeof(double) * tps_total_); }
 void Engine::scale_tps(double f) {
   std::vector<double> h((size_t)tps_total_);
@@ -90,7 +93,7 @@ void Engine::scale_tps(double f) {
   for (auto &x : h) x *= f;
   set_tps(h.data());
 }
-void Engine::set_configs(const int32_t *host) { be_h2d(cfg_, host, sizeof(int32_t) * (size_t)W_ * nsites_); }
+void Engine::set_configs(const int32_t *host) { be_h2d(cfg_, host, sizeof(int32_t) * (size_t)W_ * nsites_); touch_all(); }
 void Engine::get_configs(int32_t *host) { be_d2h(host, cfg_, sizeof(int32_t) * (size_t)W_ * nsites_); }
 void Engine::seed_rng(const uint32_t *seeds) {
   uint32_t *d = (uint32_t *)pool_.get(sizeof(uint32_t) * W_);
@@ -122,6 +125,7 @@ long Engine::stat(int which) const {
     case 8: return la_.rows_in;
     case 9: return la_.rows_kept;
     case 10: return la_.jacobi_rounds;
+    case 11: return n_memo_hits_;
     default: return -1;
   }
 }
@@ -285,6 +289,9 @@ void Engine::contractor_init() {                       // impl/bmps_contractor_i
   for (int p = 0; p < 4; ++p) {
     for (auto &b : bmps_[p]) release(b);
     bmps_[p].clear();
+    for (auto &m : memo_[p]) release(m.second.v);
+    memo_[p].clear();
+    stamp_[p].assign(1, 1);                            // the vacuum BMPS depends on nothing
     for (auto &t : bten_[p]) release(t);
     bten_[p].clear();
     for (auto &t : bten2_[p]) release(t);
@@ -305,33 +312,93 @@ const BT &Engine::bten_at_slice(int pos, int logical) const {              // bm
   if (pos == RIGHT) return bten_[RIGHT].at((size_t)(cols_ - 1 - logical));
   return bten_[pos].at((size_t)logical);
 }
+bool Engine::slices_unchanged_since(int pos, int k, long stamp) const {
+  // bmps_[pos][k] depends on: UP rows [0,k), DOWN rows [rows-k,rows), LEFT cols [0,k), RIGHT cols [cols-k,cols)
+  if (stamp <= 0) return false;
+  for (int i = 0; i < k; ++i) {
+    long mod = pos == UP ? row_mod_[(size_t)i] : pos == DOWN ? row_mod_[(size_t)(rows_ - 1 - i)]
+             : pos == LEFT ? col_mod_[(size_t)i] : col_mod_[(size_t)(cols_ - 1 - i)];
+    if (mod > stamp) return false;
+  }
+  return true;
+}
+void Engine::touch_site(int site) {
+  ++epoch_;
+  row_mod_[(size_t)(site / cols_)] = epoch_;
+  col_mod_[(size_t)(site % cols_)] = epoch_;
+}
+void Engine::touch_all() {
+  ++epoch_;
+  std::fill(row_mod_.begin(), row_mod_.end(), epoch_);
+  std::fill(col_mod_.begin(), col_mod_.end(), epoch_);
+  purge_memo();
+}
+void Engine::purge_memo() {
+  for (int p = 0; p < 4; ++p)
+    for (auto it = memo_[p].begin(); it != memo_[p].end();) {
+      if (slices_unchanged_since(p, it->first, it->second.stamp)) { ++it; continue; }
+      release(it->second.v);
+      it = memo_[p].erase(it);
+    }
+}
+void Engine::push_grown(int pos, int mpo_num, int orient) {
+  const int k = (int)bmps_[pos].size();
+  auto it = memo_[pos].find(k);
+  if (it != memo_[pos].end()) {
+    const bool ok = slices_unchanged_since(pos, k, it->second.stamp);
+    if (ok) {
+      bmps_[pos].push_back(std::move(it->second.v));
+      stamp_[pos].push_back(it->second.stamp);
+      ++n_memo_hits_;
+    } else {
+      release(it->second.v);
+    }
+    memo_[pos].erase(it);
+    if (ok) return;
+  }
+  const bool pred_ok = k == 1 || slices_unchanged_since(pos, k - 1, stamp_[pos].back());
+  bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(mpo_num, orient), pos));
+  stamp_[pos].push_back(pred_ok ? epoch_ : 0);
+}
 void Engine::grow_bmps_step(int pos) {                 // grow.h:32-48
   int existed = (int)bmps_[pos].size();
   int mpo_num = (pos == UP || pos == LEFT) ? existed - 1 : (pos == DOWN ? rows_ - existed : cols_ - existed);
   int orient = (pos == UP || pos == DOWN) ? HORIZONTAL : VERTICAL;
-  bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(mpo_num, orient), pos));
+  push_grown(pos, mpo_num, orient);
 }
 void Engine::grow_full_bmps(int pos) {                 // grow.h:50-86
   int existed = (int)bmps_[pos].size();
-  if (pos == DOWN) for (int row = rows_ - existed; row > 0; --row) bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(row, HORIZONTAL), pos));
-  else if (pos == UP) for (int row = existed - 1; row < rows_ - 1; ++row) bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(row, HORIZONTAL), pos));
-  else if (pos == LEFT) for (int col = existed - 1; col < cols_ - 1; ++col) bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(col, VERTICAL), pos));
-  else for (int col = cols_ - existed; col > 0; --col) bmps_[pos].push_back(absorb(bmps_[pos].back(), slice_sites(col, VERTICAL), pos));
+  if (pos == DOWN) for (int row = rows_ - existed; row > 0; --row) push_grown(pos, row, HORIZONTAL);
+  else if (pos == UP) for (int row = existed - 1; row < rows_ - 1; ++row) push_grown(pos, row, HORIZONTAL);
+  else if (pos == LEFT) for (int col = existed - 1; col < cols_ - 1; ++col) push_grown(pos, col, VERTICAL);
+  else for (int col = cols_ - existed; col > 0; --col) push_grown(pos, col, VERTICAL);
+}
+void Engine::park_or_release_top(int pos) {
+  const int k = (int)bmps_[pos].size() - 1;
+  if (memo_on_ && slices_unchanged_since(pos, k, stamp_[pos].back())) {
+    auto it = memo_[pos].find(k);
+    if (it != memo_[pos].end()) { release(it->second.v); memo_[pos].erase(it); }
+    memo_[pos].emplace(k, Memo{std::move(bmps_[pos].back()), stamp_[pos].back()});
+  } else {
+    release(bmps_[pos].back());
+  }
+  bmps_[pos].pop_back();
+  stamp_[pos].pop_back();
 }
 void Engine::delete_inner_bmps(int pos) {              // bmps_contractor.h:320-324
-  while (bmps_[pos].size() > 1) { release(bmps_[pos].back()); bmps_[pos].pop_back(); }
+  while (bmps_[pos].size() > 1) park_or_release_top(pos);
+  purge_memo();
 }
 void Engine::grow_bmps_for_row(int row) {              // grow.h:88-104
-  for (int rb = rows_ - (int)bmps_[DOWN].size(); rb > row; --rb) bmps_[DOWN].push_back(absorb(bmps_[DOWN].back(), slice_sites(rb, HORIZONTAL), DOWN));
-  for (int rb = (int)bmps_[UP].size() - 1; rb < row; ++rb) bmps_[UP].push_back(absorb(bmps_[UP].back(), slice_sites(rb, HORIZONTAL), UP));
+  for (int rb = rows_ - (int)bmps_[DOWN].size(); rb > row; --rb) push_grown(DOWN, rb, HORIZONTAL);
+  for (int rb = (int)bmps_[UP].size() - 1; rb < row; ++rb) push_grown(UP, rb, HORIZONTAL);
 }
 void Engine::grow_bmps_for_col(int col) {              // grow.h:106-122
-  for (int cb = cols_ - (int)bmps_[RIGHT].size(); cb > col; --cb) bmps_[RIGHT].push_back(absorb(bmps_[RIGHT].back(), slice_sites(cb, VERTICAL), RIGHT));
-  for (int cb = (int)bmps_[LEFT].size() - 1; cb < col; ++cb) bmps_[LEFT].push_back(absorb(bmps_[LEFT].back(), slice_sites(cb, VERTICAL), LEFT));
+  for (int cb = cols_ - (int)bmps_[RIGHT].size(); cb > col; --cb) push_grown(RIGHT, cb, VERTICAL);
+  for (int cb = (int)bmps_[LEFT].size() - 1; cb < col; ++cb) push_grown(LEFT, cb, VERTICAL);
 }
 void Engine::shift_bmps_window(int pos) {              // grow.h:143-148
-  release(bmps_[pos].back());
-  bmps_[pos].pop_back();
+  park_or_release_top(pos);
   grow_bmps_step(opposite(pos));
 }
 void Engine::init_bten(int pos) {                      // init.h:72-120
@@ -537,6 +604,7 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
         const int s1 = row * cols_ + col, s2 = s1 + 1;
         nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);          // :164-166 (masked in the decide kernel)
         be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        touch_site(s1); touch_site(s2);
         if (col < cols_ - 2) shift_bten_window(RIGHT);
       }
       if (row < rows_ - 1) shift_bmps_window(DOWN);
@@ -551,6 +619,7 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
         const int s1 = row * cols_ + col, s2 = s1 + cols_;
         nn_trace(row, col, row + 1, col, VERTICAL, s2, s1, psi_tmp_);
         be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        touch_site(s1); touch_site(s2);
         if (row < rows_ - 2) shift_bten_window(DOWN);
       }
       if (col < cols_ - 1) shift_bmps_window(RIGHT);

@@ -18,6 +18,7 @@
 #include <vector>
 #include "linalg.h"
 #include "tensor.h"
+#include <map>
 
 namespace peps {
 
@@ -55,9 +56,9 @@ class Engine {
   void set_rng_state(const uint32_t *mt, const int32_t *idx);
   void get_rng_state(uint32_t *mt, int32_t *idx);
   void get_amplitudes(double *host);
-  void set_truncation(int dmin, int dmax, double terr) { dmin_ = dmin; dmax_ = dmax; terr_ = terr; }
+  void set_truncation(int dmin, int dmax, double terr) { dmin_ = dmin; dmax_ = dmax; terr_ = terr; touch_all(); }
   void set_jacobi(double tol, int inner, int max_sweeps) {
-    la_.jacobi_tol = tol; la_.jacobi_inner_sweeps = inner; la_.jacobi_max_sweeps = max_sweeps;
+    la_.jacobi_tol = tol; la_.jacobi_inner_sweeps = inner; la_.jacobi_max_sweeps = max_sweeps; touch_all();
   }
 
   // ---- the hot path
@@ -80,7 +81,7 @@ class Engine {
   void sr_matvec_device(const double *v_dev, double mean_dot_v, double *out_dev);
   void sr_matvec_host(const double *v, double mean_dot_v, double *out);
   void set_model_xxz(double jz, double jxy, double h00) { jz_ = jz; jxy_ = jxy; h00_ = h00; }
-  void set_deflation(double eps) { la_.deflation_eps = eps; }
+  void set_deflation(double eps) { la_.deflation_eps = eps; touch_all(); }
   // SquareSpinOneHalfJ1J2XXZModelOBC couplings (model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113); 0 disables NNN
   void set_model_nnn(double jz2, double jxy2) { jz2_ = jz2; jxy2_ = jxy2; }
 
@@ -182,6 +183,23 @@ class Engine {
   bool sr_on_ = false;
 
   std::vector<BMPSv> bmps_[4];
+  // Boundary-MPS memo. The reference drops stack entries (DeleteInnerBMPS, ShiftBMPSWindow) and later regrows them
+  // from unchanged configurations: the LEFT stack finished by the sweep's vertical pass is rebuilt column by column
+  // by the energy solver's vertical pass, and the DOWN stack consumed by the energy solver's horizontal pass is
+  // rebuilt by the next sweep. Absorption is deterministic, so a dropped entry whose rows/columns have not been
+  // touched since it was computed IS the tensor the regrowth would produce: it is parked here and handed back.
+  struct Memo { BMPSv v; long stamp; };
+  std::vector<long> stamp_[4];                // epoch at which bmps_[pos][k] was computed (0 = built on a stale entry)
+  std::map<int, Memo> memo_[4];               // deleted entries by stack index
+  std::vector<long> row_mod_, col_mod_;       // epoch of the last possible configuration change per row / column
+  long epoch_ = 1, n_memo_hits_ = 0;
+  bool memo_on_ = true;                       // PEPS_BMPS_MEMO=0 disables (A/B tests)
+  bool slices_unchanged_since(int pos, int k, long stamp) const;
+  void touch_site(int site);
+  void touch_all();
+  void purge_memo();
+  void park_or_release_top(int pos);
+  void push_grown(int pos, int mpo_num, int orient);
   std::vector<BT> bten_[4];
   std::vector<BT> bten2_[4];
   long n_absorb_ = 0, n_bten_ = 0, n_trace_ = 0;

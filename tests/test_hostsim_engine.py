@@ -41,6 +41,36 @@ def test_j1j2_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
     run_pipeline_parity(lib, rows, cols, D, 3, trunc, nsweeps=2, j2=0.5)
 
 
+def test_bmps_memo_is_exact_and_saves_one_stack_per_sample(lib, monkeypatch):
+    """The LEFT stack finished by the sweep's vertical pass is handed back to the energy solver's vertical pass, and
+    the DOWN stack consumed by the energy solver's horizontal pass to the next sweep, instead of being re-absorbed
+    (engine.h: Memo). Same chains, energies and holes bit for bit; (cols-1) + (rows-1) fewer absorptions per sample."""
+    rows, cols, D, W = 4, 5, 3, 3
+    tps = vmc.random_tps(rows, cols, 2, D, seed=11)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 50 + w) for w in range(W)])
+    out = {}
+    for memo in ("1", "0"):
+        monkeypatch.setenv("PEPS_BMPS_MEMO", memo)
+        b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(5, 5, 0.0), lib=lib)
+        b.set_tps(SplitIndexTPS(tps))
+        b.set_configs(cfgs)
+        b.seed_rng(np.arange(W, dtype=np.uint32) + 3)
+        b.init_walkers()
+        rec = []
+        a0 = b.stat(0)
+        for _ in range(3):
+            b.sweep(1)
+            e = b.energy_and_holes(True)
+            rec.append((b.get_configs().copy(), e.copy(), b.holes().copy(), b.amplitudes().copy()))
+        out[memo] = (rec, b.stat(0) - a0, b.stat(11))
+    for (c1, e1, h1, a1), (c0, e0, h0, a0) in zip(out["1"][0], out["0"][0]):
+        assert np.array_equal(c1, c0) and np.array_equal(e1, e0) and np.array_equal(h1, h0) and np.array_equal(a1, a0)
+    total = 3 * (4 * (rows - 1) + 4 * (cols - 1)) - (rows - 1)     # the first sweep starts on init_walkers' DOWN stack
+    assert out["0"][1] == total and out["0"][2] == 0
+    hits = 3 * (cols - 1) + 2 * (rows - 1)
+    assert out["1"][2] == hits and out["1"][1] == total - hits
+
+
 def test_gradient_accumulation_parity_hostsim(lib):
     run_gradient_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsamples=4)
 
