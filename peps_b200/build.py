@@ -32,7 +32,8 @@ def build_cuda(force=False, verbose=False):
     srcs = [os.path.join(CSRC, f) for f in ("backend_cuda.cu", "engine.cpp", "c_api.cpp")]
     if not force and not _newer(LIB, srcs + _sources()):
         return LIB
-    cmd = [NVCC] + CUDA_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-lcudart"]
+    extra = os.environ.get("PEPS_NVCC_EXTRA", "").split()       # e.g. -DPEPS_KERNEL_CLOCKS (development builds)
+    cmd = [NVCC] + CUDA_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB, "-lcudart"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 #include "backend.h"
@@ -479,9 +480,19 @@ static size_t panel_smem_bytes(int R, int nbw) {
 // columns, while every other warp runs at its own pace. A warp reduces the dot products of all its columns
 // together (interleaved shuffles). S = V^T V falls out of the same dot products; T is emitted for the trailing
 // update (C - V T^T (V^T C)), so V T^T is never formed.
+// Optional phase clocks of CTA (0,0) (development aid: build with -DPEPS_KERNEL_CLOCKS, run with PEPS_PANEL_CLK=n)
+#ifdef PEPS_KERNEL_CLOCKS
+__device__ long long g_panel_clk[8 + 32 * 8];
+#define PANEL_CLK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_panel_clk[i] = clock64(); } while (0)
+#define COL_CLK(j, k) do { if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) g_panel_clk[8 + (j) * 8 + (k)] = clock64(); } while (0)
+#else
+#define PANEL_CLK(i) do { } while (0)
+#define COL_CLK(j, k) do { } while (0)
+#endif
 template <int NBW, int RPL>
 __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs a) {
   extern __shared__ double sm[];
+  PANEL_CLK(0);
   constexpr int CPW = NBW / 8;
   constexpr int LDT = NBW + 1, LDSS = NBW + 1;
   constexpr int RP = RPL * 32;
@@ -505,33 +516,48 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
   if (t < NBW) { tau_s[t] = 0.0; Rd[t] = 0.0; ready[t] = 0; }
   __syncthreads();
 
+  // The panel travels global <-> registers through a swizzled staging tile (the reflector buffer, idle at both ends
+  // of the kernel): global accesses are whole panel rows (coalesced), the register tile picks its strided elements
+  // out of shared memory without bank conflicts. Element (r, c) sits at r * NBW + (c ^ (r % NBW)).
+  double *stage = vcols;
+  constexpr int RPI = 32 / NBW;             // panel rows per warp-wide access
+  for (int r0 = warp * RPI; r0 < RP; r0 += 8 * RPI) {
+    const int r = r0 + lane / NBW, c = lane % NBW;
+    double *dstp = stage + (size_t)r * NBW + (c ^ (r & (NBW - 1)));
+    if (r < nact && c < pw) {
+      const unsigned saddr = (unsigned)__cvta_generic_to_shared(dstp);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(Aw + roff[r] + c));
+    } else {
+      *dstp = 0.0;
+    }
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncthreads();
   double P[CPW][RPL];
 #pragma unroll
   for (int i = 0; i < RPL; ++i) {
     const int r = lane + 32 * i;
-    const long off = roff[r];
 #pragma unroll
-    for (int cc = 0; cc < CPW; ++cc) {
-      const int c = warp + 8 * cc;
-      P[cc][i] = (r < nact && c < pw) ? Aw[off + c] : 0.0;
-    }
+    for (int cc = 0; cc < CPW; ++cc) P[cc][i] = stage[(size_t)r * NBW + ((warp + 8 * cc) ^ (r & (NBW - 1)))];
   }
+  __syncthreads();                          // the tile is about to be overwritten by reflector 0
 
-  // builds reflector j from column j (owned by this warp as local column cj), publishes it; P keeps [R | 1 | v]
-  auto build = [&](int j, int cj) {
+  // builds reflector j from column j (owned by this warp as LOCAL column CJ, a compile-time index: a run-time index
+  // into the register tile turns every element access into a branch tree on the critical path), publishes it;
+  // P keeps [R | 1 | v]
+  auto build = [&](int j, auto cj_c) {
+    constexpr int CJ = decltype(cj_c)::value;
     double *vb = vcols + (size_t)j * RP;
-    double x[RPL];
     double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0, alpha = 0.0;
 #pragma unroll
-    for (int i = 0; i < RPL; ++i) {
-      double v = 0.0;
-#pragma unroll
-      for (int cc = 0; cc < CPW; ++cc) if (cc == cj) v = P[cc][i];
-      x[i] = v;
+    for (int i = 0; i < RPL; ++i) {        // selects only (rows >= nact hold zeros): a branch per element costs ~60 cycles
+      const double v = P[CJ][i];
       const int r = lane + 32 * i;
-      if (r == j) alpha = v;
-      const double q = (r > j && r < nact) ? v * v : 0.0;
-      if ((i & 3) == 0) n0 += q; else if ((i & 3) == 1) n1 += q; else if ((i & 3) == 2) n2 += q; else n3 += q;
+      alpha = (r == j) ? v : alpha;
+      const double vm = (r > j) ? v : 0.0;
+      if ((i & 3) == 0) n0 = fma(vm, vm, n0); else if ((i & 3) == 1) n1 = fma(vm, vm, n1);
+      else if ((i & 3) == 2) n2 = fma(vm, vm, n2); else n3 = fma(vm, vm, n3);
     }
     double xn2 = (n0 + n1) + (n2 + n3);
 #pragma unroll
@@ -539,6 +565,7 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
       xn2 += __shfl_xor_sync(0xffffffffu, xn2, o);
       alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
     }
+    COL_CLK(j, 3);
     double bj = alpha, tj = 0.0, sj = 0.0;
     if (xn2 > 0.0) {
       const double s2 = alpha * alpha + xn2;
@@ -549,23 +576,41 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
       tj = 1.0 - alpha * inv_b;            // (beta - alpha) / beta
       sj = 1.0 / (alpha - bj);
     }
+    COL_CLK(j, 4);
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       const int r = lane + 32 * i;
-      const double v = (r < nact) ? ((r > j) ? x[i] * sj : ((r == j) ? 1.0 : 0.0)) : 0.0;
+      const double pm = P[CJ][i] * sj;
+      const double v = (r > j) ? pm : ((r == j) ? 1.0 : 0.0);
       vb[r] = v;
-      if (r >= j) {
-#pragma unroll
-        for (int cc = 0; cc < CPW; ++cc) if (cc == cj) P[cc][i] = v;
-      }
+      P[CJ][i] = (r >= j) ? v : P[CJ][i];
     }
     if (lane == 0) { tau_s[j] = tj; Rd[j] = bj; }
+    COL_CLK(j, 5);
     __syncwarp();
     __threadfence_block();
     if (lane == 0) ready[j] = 1;
   };
+  // look-ahead of the owner of column jn: apply reflector j (v, tj) to that column alone, then build reflector jn
+  auto lookahead = [&](int jn, const double (&v)[RPL], double tj, auto cn_c) {
+    constexpr int CN = decltype(cn_c)::value;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      const double q = v[i] * P[CN][i];
+      if ((i & 3) == 0) d0 += q; else if ((i & 3) == 1) d1 += q; else if ((i & 3) == 2) d2 += q; else d3 += q;
+    }
+    const double f = tj * warp_sum((d0 + d1) + (d2 + d3));
+    COL_CLK(jn, 1);
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) P[CN][i] -= f * v[i];
+    COL_CLK(jn, 2);
+    build(jn, cn_c);
+    COL_CLK(jn, 6);
+  };
 
-  if (warp == 0 && pw > 0) build(0, 0);
+  PANEL_CLK(1);
+  if (warp == 0 && pw > 0) build(0, std::integral_constant<int, 0>{});
   for (int j = 0; j < pw; ++j) {
     while (ready[j] == 0) __nanosleep(40);
     __threadfence_block();
@@ -576,24 +621,14 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
     for (int i = 0; i < RPL; ++i) v[i] = vb[lane + 32 * i];
     const int jn = j + 1;
     const bool own_next = (jn < pw) && (warp == (jn & 7));
-    if (own_next) {                         // look-ahead: finish column j+1 and publish its reflector early
-      const int cn = jn >> 3;
-      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-        double pv = 0.0;
-#pragma unroll
-        for (int k = 0; k < CPW; ++k) if (k == cn) pv = P[k][i];
-        const double q = v[i] * pv;
-        if ((i & 3) == 0) d0 += q; else if ((i & 3) == 1) d1 += q; else if ((i & 3) == 2) d2 += q; else d3 += q;
+    if (own_next) {                         // publish reflector j+1 early; the other columns catch up below
+      COL_CLK(jn, 7);
+      switch (jn >> 3) {
+        case 0: lookahead(jn, v, tj, std::integral_constant<int, 0>{}); break;
+        case 1: if constexpr (CPW > 1) lookahead(jn, v, tj, std::integral_constant<int, 1>{}); break;
+        case 2: if constexpr (CPW > 2) lookahead(jn, v, tj, std::integral_constant<int, 2>{}); break;
+        default: if constexpr (CPW > 3) lookahead(jn, v, tj, std::integral_constant<int, 3>{}); break;
       }
-      const double f = tj * warp_sum((d0 + d1) + (d2 + d3));
-#pragma unroll
-      for (int i = 0; i < RPL; ++i) {
-#pragma unroll
-        for (int k = 0; k < CPW; ++k) if (k == cn) P[k][i] -= f * v[i];
-      }
-      build(jn, cn);
     }
     // all remaining columns of this warp together: dots, one interleaved reduction, updates / S entries
     double d[CPW][2];
@@ -627,48 +662,75 @@ __global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs 
       }
     }
   }
+  PANEL_CLK(2);
   __syncthreads();
+  PANEL_CLK(3);
 
-  // T (forward, columnwise): T[j][j] = tau_j; T[0:j, j] = -tau_j * T[0:j,0:j] * S[0:j, j]. Row a of T only depends
-  // on row a itself, so lane a of warp 0 runs its own recurrence out of registers (no intra-warp synchronisation).
-  if (warp == 0 && lane < NBW) {
-    double trow[NBW];
+  // T = (strict_upper(S) + diag(1/tau))^-1, built block-recursively so that the whole CTA works on it:
+  //   8x8 diagonal blocks by the column recurrence T[a][j] = -tau_j sum_{a<=b<j} T[a][b] S[b][j] (one lane per row),
+  //   then T12 = -T11 (S12 T22) for block sizes 8, 16, ... (X = S12 T22 staged in the dead reflector buffer).
+  {
+    if (warp < NBW / 8 && lane < 8) {
+      const int base = warp * 8;
+      double trow[8];
 #pragma unroll
-    for (int j = 0; j < NBW; ++j) trow[j] = 0.0;
+      for (int j = 0; j < 8; ++j) {
+        const double tj = (base + j < pw) ? tau_s[base + j] : 0.0;
+        double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < NBW; ++j) {
-      const double tj = (j < pw) ? tau_s[j] : 0.0;
-      double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-#pragma unroll
-      for (int b2 = 0; b2 < j; ++b2) {
-        const double q = trow[b2] * S[b2 * LDSS + j];      // trow[b2] is zero for b2 < lane
-        if ((b2 & 3) == 0) v0 += q; else if ((b2 & 3) == 1) v1 += q; else if ((b2 & 3) == 2) v2 += q; else v3 += q;
+        for (int b2 = 0; b2 < j; ++b2) acc += trow[b2] * S[(base + b2) * LDSS + base + j];   // trow[b2] = 0 for b2 < lane
+        trow[j] = (j == lane) ? tj : ((j > lane) ? -tj * acc : 0.0);
       }
-      trow[j] = (j == lane) ? tj : ((j > lane) ? -tj * ((v0 + v1) + (v2 + v3)) : 0.0);
-    }
 #pragma unroll
-    for (int j = 0; j < NBW; ++j) Tt[lane * LDT + j] = trow[j];
+      for (int j = 0; j < 8; ++j) Tt[(base + lane) * LDT + base + j] = trow[j];
+    }
+    __syncthreads();
+    double *X = vcols;                     // [NBW][LDT] scratch
+#pragma unroll 1
+    for (int bs = 8; bs < NBW; bs *= 2) {
+      const int nel = (NBW / (2 * bs)) * bs * bs;
+      for (int e = t; e < nel; e += PQR_THREADS) {
+        const int m = e / (bs * bs), aa = (e / bs) % bs, c = e % bs, base = m * 2 * bs;
+        const double *Sr = S + (base + aa) * LDSS + base + bs, *Tc = Tt + (base + bs) * LDT + base + bs + c;
+        double x0 = 0.0, x1 = 0.0;
+        int k = 0;
+        for (; k + 1 <= c; k += 2) { x0 += Sr[k] * Tc[k * LDT]; x1 += Sr[k + 1] * Tc[(k + 1) * LDT]; }
+        if (k <= c) x0 += Sr[k] * Tc[k * LDT];
+        X[(base + aa) * LDT + c] = x0 + x1;
+      }
+      __syncthreads();
+      for (int e = t; e < nel; e += PQR_THREADS) {
+        const int m = e / (bs * bs), aa = (e / bs) % bs, c = e % bs, base = m * 2 * bs;
+        const double *Tr = Tt + (base + aa) * LDT + base, *Xc = X + base * LDT + c;
+        double x0 = 0.0, x1 = 0.0;
+        int k = aa;
+        for (; k + 1 < bs; k += 2) { x0 += Tr[k] * Xc[k * LDT]; x1 += Tr[k + 1] * Xc[(k + 1) * LDT]; }
+        if (k < bs) x0 += Tr[k] * Xc[k * LDT];
+        Tt[(base + aa) * LDT + base + bs + c] = -(x0 + x1);
+      }
+      __syncthreads();
+    }
   }
-  // emit R (in place) and V
-  double *Vo = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
-  for (int e = t; e < skip * nbw; e += PQR_THREADS) Vo[e] = 0.0;
+  PANEL_CLK(4);
+  // emit R (in place, zeros below it) and V through the staging tile
 #pragma unroll
   for (int i = 0; i < RPL; ++i) {
     const int r = lane + 32 * i;
-    if (r < nact) {
-      const long off = roff[r];
 #pragma unroll
-      for (int cc = 0; cc < CPW; ++cc) {
-        const int c = warp + 8 * cc;
-        const double pv = P[cc][i];
-        if (c < pw) Aw[off + c] = (r < c) ? pv : ((r == c) ? Rd[c] : 0.0);
-        Vo[(long)(skip + r) * nbw + c] = (c < pw && r >= c) ? pv : 0.0;
-      }
-    }
+    for (int cc = 0; cc < CPW; ++cc) stage[(size_t)r * NBW + ((warp + 8 * cc) ^ (r & (NBW - 1)))] = P[cc][i];
   }
   __syncthreads();
+  double *Vo = a.Vw + ((long)w * a.NI + it) * (long)R * nbw;
+  for (int e = t; e < skip * nbw; e += PQR_THREADS) Vo[e] = 0.0;
+  for (int e = t; e < nact * NBW; e += PQR_THREADS) {
+    const int r = e / NBW, c = e % NBW;
+    const double pv = stage[(size_t)r * NBW + (c ^ (r & (NBW - 1)))];
+    Vo[(long)(skip + r) * nbw + c] = (c < pw && r >= c) ? pv : 0.0;
+    if (c < pw) Aw[roff[r] + c] = (r < c) ? pv : ((r == c) ? Rd[c] : 0.0);
+  }
   double *To = a.Tw + ((long)w * a.NI + it) * (long)nbw * nbw;
   for (int e = t; e < NBW * NBW; e += PQR_THREADS) To[e] = Tt[(e / NBW) * LDT + (e % NBW)];
+  PANEL_CLK(5);
 }
 
 template <int NBW, int RPL>
@@ -702,6 +764,24 @@ void be_panel_qr(const PanelArgs &a) {
     panel_qr_kernel<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
   }
   post_launch();
+#ifdef PEPS_KERNEL_CLOCKS
+  static const int dbg = std::getenv("PEPS_PANEL_CLK") ? std::atoi(std::getenv("PEPS_PANEL_CLK")) : 0;
+  static int shown = 0;
+  if (dbg && a.nbw == 32 && R > 256 && R <= 512 && shown < dbg) {
+    ++shown;
+    long long h[8 + 32 * 8];
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    CUDA_CHECK(cudaMemcpyFromSymbol(h, g_panel_clk, sizeof(h)));
+    if (shown == 1)
+      for (int j = 2; j < 32; ++j) {
+        const long long *c = h + 8 + j * 8, *pc = h + 8 + (j - 1) * 8;
+        fprintf(stderr, "[col %2d] since prev publish: vload=%lld dot+sum=%lld upd=%lld norm=%lld rsq/div=%lld scale+sts=%lld fence=%lld | period=%lld\n",
+                j, c[7] - pc[6], c[1] - c[7], c[2] - c[1], c[3] - c[2], c[4] - c[3], c[5] - c[4], c[6] - c[5], c[6] - pc[6]);
+      }
+    fprintf(stderr, "[panel clk] R=%d pw=%d NI=%d W=%d load=%lld cols=%lld wait=%lld T=%lld emit=%lld\n", R, a.pw, a.NI, a.W,
+            h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+  }
+#endif
 }
 
 // Fused trailing update of one CAQR panel step (see backend.h ApplyArgs): the C tile (R rows x NBW columns) stays
