@@ -9,10 +9,12 @@
 //   jacobi_round_kernel one round of one-sided block Jacobi (Gram + rotation on DMMA, panel resident in smem).
 //   small kernels      row norms, truncation/selection, RNG + Metropolis decision, energies, O* accumulation.
 #include <cuda_runtime.h>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -786,16 +788,44 @@ void be_panel_qr(const PanelArgs &a) {
 
 // Fused trailing update of one CAQR panel step (see backend.h ApplyArgs): the C tile (R rows x NBW columns) stays
 // in shared memory; W = V^T C is accumulated on the DMMA pipe with the row range split over the 8 warps, then
-// C - VT W is formed tile-row by tile-row and written back. V / VT fragments are read straight from L2.
+// C - V T^T W is formed tile-row by tile-row and written back. V fragments are read straight from L2.
+// Each warp brings in its own 64-row slice with one bulk copy (TMA) per row, completion counted on the warp's own
+// mbarrier: a warp starts its share of V^T C as soon as ITS rows have landed, there is no block-wide wait on the load.
+#ifdef PEPS_KERNEL_CLOCKS
+__device__ long long g_apply_clk[8];
+#define APPLY_CLK(i) do { if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1 && threadIdx.x == 0) g_apply_clk[i] = clock64(); } while (0)   // the LAST CTA: warm caches
+#else
+#define APPLY_CLK(i) do { } while (0)
+#endif
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 template <int NBW>
 __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
+  APPLY_CLK(0);
   constexpr int TN = NBW, MT = NBW / 8, NT = NBW / 8, LDC = TN + 4, LDW = TN + 4, NTILE = MT * NT;
   const int ct = blockIdx.x, it = blockIdx.y, w = blockIdx.z;
   const int R = a.R, R8 = (R + 7) & ~7, nbw = a.nbw;
   double *Cs = sm;                               // [R8][LDC]
   double *part = Cs + (size_t)R8 * LDC;          // [4][NTILE][64]
   double *Wsm = part + 4 * NTILE * 64;           // [NBW][LDW] = -(V^T C)
+  long *roff = reinterpret_cast<long *>(Wsm + NBW * LDW);   // [R8]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(roff + R8); // [8] one per warp
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   double *Aw = a.A + (long)w * a.ws;
   const int32_t *rows = a.rowtab + (long)it * R;
@@ -803,39 +833,68 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
   const double *Tg = a.Tw + ((long)w * a.NI + it) * (long)nbw * nbw;
   const int cbase = a.col1 + ct * TN;
   const int ncols = min(TN, a.ntrail - ct * TN);
+  const int kslice = ((R8 / 8) + 7) & ~7;        // rows per warp (whole 8-row tiles)
+  const int k0 = min(R8, warp * kslice), k1 = min(R8, k0 + kslice);
+  // 16-byte granularity everywhere? (bulk copies and paired stores need it; the 8-byte path below covers the rest)
+  const bool wide = (((a.lda | cbase | ncols) & 1) == 0) && ((a.ws & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0);
 
-  // 0. C tile -> shared memory (row offsets staged first, eight independent row loads in flight per warp)
-  long *roff = reinterpret_cast<long *>(Wsm + NBW * LDW);   // [R8]
-  for (int r = t; r < R8; r += 256) roff[r] = (r < R) ? (long)rows[r] * a.lda + cbase : -1;
-  __syncthreads();
-  // asynchronous 8-byte copies straight into shared memory: every row of the tile is in flight at once
-  for (int r = warp; r < R8; r += 8) {
-    const long o = roff[r];
-    double *dstp = Cs + (size_t)r * LDC + lane;
-    if (lane < TN) {
-      if (o >= 0 && lane < ncols) {
-        const unsigned saddr = (unsigned)__cvta_generic_to_shared(dstp);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(Aw + o + lane));
+  double tpre[(NBW * NBW + 255) / 256];          // T, fetched now, staged in shared memory after V^T C
+#pragma unroll
+  for (int u = 0; u < (NBW * NBW + 255) / 256; ++u) tpre[u] = (t + u * 256 < NBW * NBW) ? __ldg(Tg + t + u * 256) : 0.0;
+
+  // 0. C tile -> shared memory, each warp its own row slice
+  if (lane == 0) mbar_init(&bars[warp], 1);
+  for (int r = k0 + lane; r < k1; r += 32) roff[r] = (r < R) ? (long)rows[r] * a.lda + cbase : -1;
+  APPLY_CLK(6);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncwarp();
+  APPLY_CLK(7);
+  if (wide) {
+    const int nvalid = max(0, min(k1, R) - k0);
+    if (lane == 0) mbar_expect_tx(&bars[warp], (unsigned)(nvalid * ncols * 8));
+    __syncwarp();
+    for (int r = k0 + lane; r < k1; r += 32) {
+      double *dstp = Cs + (size_t)r * LDC;
+      if (r < R) {
+        bulk_g2s(dstp, Aw + roff[r], (unsigned)(ncols * 8), &bars[warp]);
+        for (int c = ncols; c < LDC; ++c) dstp[c] = 0.0;
       } else {
-        *dstp = 0.0;
+        for (int c = 0; c < LDC; ++c) dstp[c] = 0.0;
       }
     }
-    if (lane < LDC - TN) Cs[(size_t)r * LDC + TN + lane] = 0.0;
+    APPLY_CLK(1);
+    mbar_wait(&bars[warp], 0);
+  } else {
+    for (int r = k0; r < k1; ++r) {
+      const long o = roff[r];
+      double *dstp = Cs + (size_t)r * LDC + lane;
+      if (lane < TN) {
+        if (o >= 0 && lane < ncols) {
+          const unsigned saddr = (unsigned)__cvta_generic_to_shared(dstp);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(Aw + o + lane));
+        } else {
+          *dstp = 0.0;
+        }
+      }
+      if (lane < LDC - TN) Cs[(size_t)r * LDC + TN + lane] = 0.0;
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    APPLY_CLK(1);
+    asm volatile("cp.async.wait_group 0;\n" ::);
   }
-  asm volatile("cp.async.commit_group;\n" ::);
-  asm volatile("cp.async.wait_group 0;\n" ::);
-  __syncthreads();
+  __syncwarp();
+  APPLY_CLK(2);
 
-  // A. partial W = V^T C over this warp's row slice
+  double *Wraw = part;                        // [NBW][LDW] raw W = V^T C (inside the partial-sum scratch)
   {
+    // A. partial W = V^T C over this warp's row slice
     double acc[MT][NT][2];
 #pragma unroll
     for (int i = 0; i < MT; ++i)
 #pragma unroll
       for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int kslice = ((R8 / 8) + 3) & ~3;
-    const int k0 = warp * kslice, k1 = min(R8, k0 + kslice);
-    for (int k = k0; k < k1; k += 4) {
+#pragma unroll 4
+    for (int k = k0; k < k1; k += 4) {      // unrolled so that several k-steps of V fragments are in flight from L2
       const int kr = k + (lane & 3);
       double af[MT], bf[NT];
 #pragma unroll
@@ -847,6 +906,7 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
 #pragma unroll
         for (int j = 0; j < NT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
+    APPLY_CLK(3);
     const int eo = (lane >> 2) * 8 + 2 * (lane & 3);
     if (warp >= 4) {
 #pragma unroll
@@ -876,7 +936,6 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
         }
     }
     __syncthreads();
-    double *Wraw = part;                      // reuse: [NBW][LDW] raw W = V^T C after the partial sums are consumed
     double wv[(NTILE * 64 + 255) / 256];
 #pragma unroll
     for (int u = 0; u < (NTILE * 64 + 255) / 256; ++u) {
@@ -897,10 +956,15 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
         Wraw[((tile / NT) * 8 + rr) * LDW + (tile % NT) * 8 + cc] = wv[u];
       }
     }
-    __syncthreads();
+  }
+  {
     // Wsm = -(T^T W):  (T^T W)[a][c] = sum_{b <= a} T[b][a] W[b][c]     (T staged in shared memory)
     double *Tsm = Wraw + NBW * LDW;            // [NBW][LDW], still inside the partial-sum scratch
-    for (int e = t; e < NBW * NBW; e += 256) Tsm[(e / NBW) * LDW + (e % NBW)] = __ldg(Tg + e);
+#pragma unroll
+    for (int u = 0; u < (NBW * NBW + 255) / 256; ++u) {
+      const int e = t + u * 256;
+      if (e < NBW * NBW) Tsm[(e / NBW) * LDW + (e % NBW)] = tpre[u];
+    }
     __syncthreads();
     for (int e = t; e < NBW * TN; e += 256) {
       const int aa = e / TN, c = e % TN;
@@ -916,45 +980,61 @@ __global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
     __syncthreads();
   }
 
-  // C. C <- C + V (-(T^T W)), written straight back to global memory
+  APPLY_CLK(4);
+  // C. C <- C + V (-(T^T W)) over the warp's own row slice, written straight back to global memory; the V fragments
+  // of the next 8-row tile are fetched while the current one is on the DMMA pipe
   {
     double bw[NBW / 4][NT];
 #pragma unroll
     for (int ks = 0; ks < NBW / 4; ++ks)
 #pragma unroll
       for (int j = 0; j < NT; ++j) bw[ks][j] = Wsm[(ks * 4 + (lane & 3)) * LDW + j * 8 + (lane >> 2)];
-    for (int rt = warp; rt < R8 / 8; rt += 8) {
+    double afn[NBW / 4];
+    auto fetch = [&](int rt) {
       const int r = rt * 8 + (lane >> 2);
+      const double *vt = V + (long)r * nbw + (lane & 3);
+#pragma unroll
+      for (int ks = 0; ks < NBW / 4; ++ks) afn[ks] = (r < R) ? __ldg(vt + ks * 4) : 0.0;
+    };
+    if (k0 < k1) fetch(k0 / 8);
+    for (int rt = k0 / 8; rt < k1 / 8; ++rt) {
+      const int r = rt * 8 + (lane >> 2);
+      double af[NBW / 4];
+#pragma unroll
+      for (int ks = 0; ks < NBW / 4; ++ks) af[ks] = afn[ks];
+      if (rt + 1 < k1 / 8) fetch(rt + 1);
       double acc[NT][2];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         acc[j][0] = Cs[(size_t)r * LDC + j * 8 + 2 * (lane & 3)];
         acc[j][1] = Cs[(size_t)r * LDC + j * 8 + 2 * (lane & 3) + 1];
       }
-      const double *vt = V + (long)r * nbw + (lane & 3);
 #pragma unroll
-      for (int ks = 0; ks < NBW / 4; ++ks) {
-        const double af = (r < R) ? __ldg(vt + ks * 4) : 0.0;
+      for (int ks = 0; ks < NBW / 4; ++ks)
 #pragma unroll
-        for (int j = 0; j < NT; ++j) dmma8x8x4(acc[j][0], acc[j][1], af, bw[ks][j]);
-      }
+        for (int j = 0; j < NT; ++j) dmma8x8x4(acc[j][0], acc[j][1], af[ks], bw[ks][j]);
       if (r < R) {
         double *dst = Aw + roff[r];
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const int c = j * 8 + 2 * (lane & 3);
-          if (c < ncols) dst[c] = acc[j][0];
-          if (c + 1 < ncols) dst[c + 1] = acc[j][1];
+          if (wide) {
+            if (c < ncols) *reinterpret_cast<double2 *>(dst + c) = make_double2(acc[j][0], acc[j][1]);
+          } else {
+            if (c < ncols) dst[c] = acc[j][0];
+            if (c + 1 < ncols) dst[c + 1] = acc[j][1];
+          }
         }
       }
     }
   }
+  APPLY_CLK(5);
 }
 
 template <int NBW>
 static size_t apply_smem_bytes(int R) {
   int R8 = (R + 7) & ~7;
-  return ((size_t)R8 * (NBW + 4) + 4 * (size_t)(NBW / 8) * (NBW / 8) * 64 + (size_t)NBW * (NBW + 4) + (size_t)R8) * sizeof(double);
+  return ((size_t)R8 * (NBW + 4) + 4 * (size_t)(NBW / 8) * (NBW / 8) * 64 + (size_t)NBW * (NBW + 4) + (size_t)R8 + 8) * sizeof(double);
 }
 void be_apply_reflector(const ApplyArgs &a) {
   if (a.ntrail <= 0) return;
@@ -972,6 +1052,18 @@ void be_apply_reflector(const ApplyArgs &a) {
   else if (a.nbw == 8) launch(apply_reflector_kernel<8>, apply_smem_bytes<8>(a.R), c8, 8);
   else throw std::runtime_error("be_apply_reflector: unsupported panel width");
   post_launch();
+#ifdef PEPS_KERNEL_CLOCKS
+  static const int dbg = std::getenv("PEPS_APPLY_CLK") ? std::atoi(std::getenv("PEPS_APPLY_CLK")) : 0;
+  static int shown = 0;
+  if (dbg && a.nbw == 32 && a.R == 512 && a.ntrail >= 256 && shown < dbg) {
+    ++shown;
+    long long h[8];
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    CUDA_CHECK(cudaMemcpyFromSymbol(h, g_apply_clk, sizeof(h)));
+    fprintf(stderr, "[apply clk] R=%d ntrail=%d NI=%d W=%d roff=%lld fence=%lld issue=%lld wait=%lld A=%lld reduce+T=%lld C=%lld\n", a.R, a.ntrail, a.NI, a.W,
+            h[6] - h[0], h[7] - h[6], h[1] - h[7], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
+  }
+#endif
 }
 
 // =====================================================================================================
@@ -989,38 +1081,67 @@ __host__ __device__ __forceinline__ void rr_pair(int nblk, int round, int q, int
 
 // Jacobi rotation (c, s) annihilating a_pq of [[app, apq], [apq, aqq]] (p < q), Rutishauser's small-angle choice.
 // The tangent only steers the iteration (an error eps in it leaves eps * a_pq behind, which the next visit removes),
-// so it is evaluated in FP32 on exponent-normalised inputs; c = 1/sqrt(1 + t^2) and s = c t are then formed in FP64
-// (float seed + three Newton steps) so the rotation is orthogonal to double rounding. This takes the serial
-// sqrt/div/rsqrt FP64 sequences (~800 cycles) off the per-rotation-set critical path.
+// so it is evaluated in FP32 with the approximate SFU instructions on exponent-normalised inputs; c = 1/sqrt(1 + t^2)
+// and s = c t are then formed in FP64 (float seed + two Newton steps: 1e-7 -> 2e-14 -> 1e-27) so the rotation is
+// orthogonal to double rounding. Branch-free: this sits on the critical path of every rotation set.
 __device__ __forceinline__ void jacobi_cs(double app, double aqq, double apq, double tol2, double &c, double &s) {
-  c = 1.0; s = 0.0;
-  if (apq * apq > tol2 * fabs(app * aqq) && apq != 0.0) {
-    const double d = aqq - app, b2 = 2.0 * apq;
-    const double m = fmax(fabs(d), fabs(b2));
-    // scale = 2^-(exponent of m): keeps the FP32 evaluation away from overflow / underflow
-    const int ex = ((__double2hiint(m) >> 20) & 0x7ff) - 1023;
-    const double scale = __hiloint2double((1023 - ex) << 20, 0);
-    const float df = (float)(d * scale), bf = (float)(b2 * scale);
-    const float rf = sqrtf(df * df + bf * bf);
-    const float tf = (df >= 0.0f) ? bf / (df + rf) : -bf / (rf - df);
-    const double t = (double)tf;
-    const double x = 1.0 + t * t;
-    double y = (double)rsqrtf((float)x);
-    y = y * (1.5 - 0.5 * x * y * y);
-    y = y * (1.5 - 0.5 * x * y * y);
-    y = y * (1.5 - 0.5 * x * y * y);
-    c = y;
-    s = y * t;
-  }
+  const double d = aqq - app, b2 = 2.0 * apq;
+  const double m = fmax(fabs(d), fabs(b2));
+  // scale = 2^-(exponent of m): keeps the FP32 evaluation away from overflow / underflow
+  const int ex = ((__double2hiint(m) >> 20) & 0x7ff) - 1023;
+  const double scale = __hiloint2double((1023 - ex) << 20, 0);
+  const float df = (float)(d * scale), bf = (float)(b2 * scale);
+  float rf;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(fmaf(df, df, bf * bf)));
+  float tf = __fdividef(bf, fabsf(df) + rf);
+  tf = (df >= 0.0f) ? tf : -tf;
+  float yf;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"(fmaf(tf, tf, 1.0f)));
+  const double t = (double)tf;
+  const double hx = -0.5 * fma(t, t, 1.0);
+  double y = (double)yf;
+  y = y * fma(hx, y * y, 1.5);
+  y = y * fma(hx, y * y, 1.5);
+  const bool rot = (apq * apq > tol2 * fabs(app * aqq)) && (apq != 0.0);     // also discards the 0/0 of an all-zero block
+  c = rot ? y : 1.0;
+  s = rot ? y * t : 0.0;
+}
+
+// Systolic (Brent-Luk) round-robin ordering on 2*NP slots: slots [0, NP) are the "top" row, [NP, 2NP) the "bottom"
+// row, pair k is always (slot k, slot NP + k). After a rotation set the index in slot s moves to slot jac_mu(s):
+// top[0] stays, everything else advances one step along top[1] -> ... -> top[NP-1] -> bot[NP-1] -> ... -> bot[0] ->
+// top[1]. All pairs meet once in 2NP-1 sets, and every shared-memory access of a rotation set is a contiguous run.
+__device__ __forceinline__ int jac_mu(int s, int NP) {
+  if (s == 0) return 0;
+  if (s < NP - 1) return s + 1;
+  if (s == NP - 1) return 2 * NP - 1;
+  if (s == NP) return 1;
+  return s - 1;
+}
+__device__ __forceinline__ int jac_mu_inv(int s, int NP) {
+  if (s == 0) return 0;
+  if (s == 1) return NP;
+  if (s < NP) return s - 1;
+  if (s < 2 * NP - 1) return s + 1;
+  return NP - 1;
 }
 
 // One round of one-sided block Jacobi for one block pair. N2 = 2*bs rows resident in shared memory.
 //   load -> Gram (DMMA, K split over warp pairs) -> cyclic two-sided Jacobi on the N2 x N2 Gram matrix with one
 //   barrier per rotation set (the angles of set r+1 are computed by 16 threads while the others apply set r)
 //   -> rows <- W^T rows on the DMMA pipe -> store.
+#ifdef PEPS_KERNEL_CLOCKS
+__device__ long long g_jac_clk[32];
+#define JAC_CLK(i) do { if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && threadIdx.x == 0) g_jac_clk[i] = clock64(); } while (0)
+#define JAC_CLK_T(tid, i) do { if (blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && threadIdx.x == (tid)) g_jac_clk[i] = clock64(); } while (0)
+#else
+#define JAC_CLK(i) do { } while (0)
+#define JAC_CLK_T(tid, i) do { } while (0)
+#endif
 template <int N2>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a) {
   extern __shared__ double sm[];
+  JAC_CLK(0);
   constexpr int T2 = N2 / 8;
   constexpr int NT = T2 * (T2 + 1) / 2;
   constexpr int LG = N2 + 1;
@@ -1037,10 +1158,6 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
   double *Wm = Gm + 2 * N2 * LG;                     // [2][N2][LG]
   double *coef = Wm + 2 * N2 * LG;                   // [2][2][N2]: (a_i, b_i) double buffered
   int *perm = (int *)(coef + 4 * N2);                // [N2]
-  unsigned char *part = (unsigned char *)(perm + N2);  // [N2-1][N2] partner of i in rotation set r
-  unsigned char *pairidx = part + (N2 - 1) * N2;       // [N2-1][N2] index of the pair containing i in set r
-  unsigned char *pairp = pairidx + (N2 - 1) * N2;      // [N2-1][NP] smaller index of pair k in set r
-  unsigned char *pairq = pairp + (N2 - 1) * NP;        // [N2-1][NP] larger index
   __shared__ double red[JAC_THREADS / 32];
   __shared__ int tile_p[NT], tile_q[NT];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarp = JAC_THREADS / 32;
@@ -1057,17 +1174,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     for (int p = 0; p < T2; ++p)
       for (int q = p; q < T2; ++q) { if (idx == t) { tile_p[t] = p; tile_q[t] = q; } ++idx; }
   }
-  for (int e = t; e < (N2 - 1) * NP; e += JAC_THREADS) {
-    int rd = e / NP, k = e % NP, p, q;
-    rr_pair(N2, rd, k, p, q);
-    part[rd * N2 + p] = (unsigned char)q;
-    part[rd * N2 + q] = (unsigned char)p;
-    pairidx[rd * N2 + p] = (unsigned char)k;
-    pairidx[rd * N2 + q] = (unsigned char)k;
-    pairp[rd * NP + k] = (unsigned char)min(p, q);
-    pairq[rd * NP + k] = (unsigned char)max(p, q);
-  }
-
+  JAC_CLK(1);
   // 1. load the two row blocks (zero padded columns)
   if ((nc & 1) == 0) {
     const int nv = nc >> 1;
@@ -1085,6 +1192,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     }
   }
   __syncthreads();
+  JAC_CLK(2);
 
   // 2. Gram matrix on the DMMA pipe: warp (kg, half) accumulates its half of the upper tiles over its K slice
   {
@@ -1117,6 +1225,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     }
   }
   __syncthreads();
+  JAC_CLK(3);
   for (int e = t; e < NT * 64; e += JAC_THREADS) {
     int ti = e >> 6, rr = (e >> 3) & 7, cc = e & 7;
     double v = 0.0;
@@ -1156,68 +1265,77 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     if (red[0] <= a.tol) return;       // the 2*bs rows are already mutually orthogonal: nothing to rotate
   }
 
+  JAC_CLK(4);
   // 4. cyclic two-sided Jacobi on Gm accumulating Wm, one barrier per rotation set. Thread (ki, kj) owns the 2x2
   //    block {p_i, q_i} x {p_j, q_j} of G (and of W): the four outputs need exactly the four inputs it loads.
+  //    Slots are in the systolic order above, so nothing in the loop depends on the set index.
   const int nrounds = a.inner_sweeps * (N2 - 1);
   if (t < NP) {
-    int p, q;
-    rr_pair(N2, 0, t, p, q);
-    if (p > q) { int tmp = p; p = q; q = tmp; }
     double c, s;
-    jacobi_cs(Gm[p * LG + p], Gm[q * LG + q], Gm[p * LG + q], tol2, c, s);
+    jacobi_cs(Gm[t * LG + t], Gm[(NP + t) * LG + NP + t], Gm[t * LG + NP + t], tol2, c, s);
     coef[t] = c; coef[NP + t] = s;
   }
+  // angle thread k: the indices that will form pair k after the move sit in slots po, qo now
+  const int po = jac_mu_inv(t < NP ? t : 0, NP), qo = jac_mu_inv(NP + (t < NP ? t : 0), NP);
+  const int aka = po % NP, akb = qo % NP;
+  const bool selp = po < NP, selq = qo < NP;
+  // update thread(s): block (ka, kb) -> rows {ka, NP+ka} x columns {kb, NP+kb}, written to the moved slots
   __syncthreads();
   int cur = 0;
   for (int g = 0; g < nrounds; ++g) {
-    const int rd = g % (N2 - 1);
     const double *Gc = Gm + cur * N2 * LG, *Wc = Wm + cur * N2 * LG, *cf = coef + cur * 2 * N2;
     double *Gn = Gm + (cur ^ 1) * N2 * LG, *Wn = Wm + (cur ^ 1) * N2 * LG, *cfn = coef + (cur ^ 1) * 2 * N2;
-    // rotated 2x2 block of J^T G J for row pair a (pa<qa, ca, sa) and column pair b
-    auto block = [&](int pa, int qa, double ca, double sa, int pb, int qb, double cb, double sb, double &o_pp,
-                     double &o_pq, double &o_qp, double &o_qq) {
-      const double g_pp = Gc[pa * LG + pb], g_pq = Gc[pa * LG + qb], g_qp = Gc[qa * LG + pb], g_qq = Gc[qa * LG + qb];
-      const double r_pp = ca * g_pp - sa * g_qp, r_pq = ca * g_pq - sa * g_qq;     // rows: J^T G
-      const double r_qp = sa * g_pp + ca * g_qp, r_qq = sa * g_pq + ca * g_qq;
-      o_pp = cb * r_pp - sb * r_pq; o_pq = sb * r_pp + cb * r_pq;                  // columns: (.) J
-      o_qp = cb * r_qp - sb * r_qq; o_qq = sb * r_qp + cb * r_qq;
-    };
-    if (t < NP && g + 1 < nrounds) {   // angles of the next rotation set from the entries it will need
-      const int rn = (rd + 1) % (N2 - 1);
-      const int p = pairp[rn * NP + t], q = pairq[rn * NP + t];
-      // (p, q) belong to two different pairs of the current set: ka (containing p) and kb (containing q)
-      const unsigned char *pt = part + rd * N2;
-      int pa = p, qa = pt[p]; if (pa > qa) { int tmp = pa; pa = qa; qa = tmp; }
-      int pb = q, qb = pt[q]; if (pb > qb) { int tmp = pb; pb = qb; qb = tmp; }
-      const int ka = pairidx[rd * N2 + pa], kb = pairidx[rd * N2 + pb];
-      const double ca = cf[ka], sa = cf[NP + ka], cb = cf[kb], sb = cf[NP + kb];
-      double x0, x1, x2, x3, npp, nqq, npq;
-      block(pa, qa, ca, sa, pa, qa, ca, sa, x0, x1, x2, x3);
-      npp = (p == pa) ? x0 : x3;
-      block(pb, qb, cb, sb, pb, qb, cb, sb, x0, x1, x2, x3);
-      nqq = (q == pb) ? x0 : x3;
-      block(pa, qa, ca, sa, pb, qb, cb, sb, x0, x1, x2, x3);
-      npq = (p == pa) ? ((q == pb) ? x0 : x1) : ((q == pb) ? x2 : x3);
-      double c, s;
-      jacobi_cs(npp, nqq, npq, tol2, c, s);
-      cfn[t] = c; cfn[NP + t] = s;
+    if (t < NP) {
+      // warp 0: angles of the NEXT rotation set, from the three entries of J^T G J each of its pairs will see
+      if (g + 1 < nrounds) {
+        const int pa = aka, qa = NP + aka, pb = akb, qb = NP + akb;
+        const double ca = cf[aka], sa = cf[NP + aka], cb = cf[akb], sb = cf[NP + akb];
+        const double gaa = Gc[pa * LG + pa], gab = Gc[pa * LG + qa], gba = Gc[qa * LG + pa], gbb = Gc[qa * LG + qa];
+        const double haa = Gc[pb * LG + pb], hab = Gc[pb * LG + qb], hba = Gc[qb * LG + pb], hbb = Gc[qb * LG + qb];
+        const double xpp = Gc[pa * LG + pb], xpq = Gc[pa * LG + qb], xqp = Gc[qa * LG + pb], xqq = Gc[qa * LG + qb];
+        if (g == 3) JAC_CLK(10);
+        // column of the rotation of pair a that lands on p (rows pa, qa); likewise for q in pair b
+        const double ua0 = selp ? ca : sa, ua1 = selp ? -sa : ca;
+        const double ub0 = selq ? cb : sb, ub1 = selq ? -sb : cb;
+        const double npp = ua0 * (gaa * ua0 + gab * ua1) + ua1 * (gba * ua0 + gbb * ua1);
+        const double nqq = ub0 * (haa * ub0 + hab * ub1) + ub1 * (hba * ub0 + hbb * ub1);
+        const double npq = ua0 * (xpp * ub0 + xpq * ub1) + ua1 * (xqp * ub0 + xqq * ub1);
+        double c, s;
+        if (g == 3) JAC_CLK(11);
+        jacobi_cs(npp, nqq, npq, tol2, c, s);
+        cfn[t] = c; cfn[NP + t] = s;
+        if (g == 3) JAC_CLK(12);
+      }
+    } else if (t >= 32) {
+      // warps 1..7: G <- J^T G J and W <- W J by 2x2 blocks (four inputs, four outputs each)
+      if (g == 3) JAC_CLK_T(32, 16);
+      for (int e = t - 32; e < NP * NP; e += JAC_THREADS - 32) {
+        const int ka = e / NP, kb = e % NP;
+        const int pa = ka, qa = NP + ka, pb = kb, qb = NP + kb;
+        const int mpa = jac_mu(pa, NP), mqa = jac_mu(qa, NP), mpb = jac_mu(pb, NP), mqb = jac_mu(qb, NP);
+        const double ca = cf[ka], sa = cf[NP + ka], cb = cf[kb], sb = cf[NP + kb];
+        const double g_pp = Gc[pa * LG + pb], g_pq = Gc[pa * LG + qb], g_qp = Gc[qa * LG + pb], g_qq = Gc[qa * LG + qb];
+        const double w_pp = Wc[pa * LG + pb], w_pq = Wc[pa * LG + qb], w_qp = Wc[qa * LG + pb], w_qq = Wc[qa * LG + qb];
+        if (g == 3 && e < 224) JAC_CLK_T(32, 17);
+        const double r_pp = ca * g_pp - sa * g_qp, r_pq = ca * g_pq - sa * g_qq;     // rows: J^T G
+        const double r_qp = sa * g_pp + ca * g_qp, r_qq = sa * g_pq + ca * g_qq;
+        Gn[mpa * LG + mpb] = cb * r_pp - sb * r_pq; Gn[mpa * LG + mqb] = sb * r_pp + cb * r_pq;   // columns: (.) J
+        Gn[mqa * LG + mpb] = cb * r_qp - sb * r_qq; Gn[mqa * LG + mqb] = sb * r_qp + cb * r_qq;
+        // W <- W J: rows pa, qa of W are just two arbitrary (fixed) rows here; columns (pb, qb) rotate and move
+        Wn[pa * LG + mpb] = cb * w_pp - sb * w_pq; Wn[pa * LG + mqb] = sb * w_pp + cb * w_pq;
+        Wn[qa * LG + mpb] = cb * w_qp - sb * w_qq; Wn[qa * LG + mqb] = sb * w_qp + cb * w_qq;
+        if (g == 3 && e < 224) JAC_CLK_T(32, 18);
+      }
+      if (g == 3) JAC_CLK_T(32, 19);
     }
-    for (int e = t; e < NP * NP; e += JAC_THREADS) {
-      const int ka = e / NP, kb = e % NP;
-      const int pa = pairp[rd * NP + ka], qa = pairq[rd * NP + ka], pb = pairp[rd * NP + kb], qb = pairq[rd * NP + kb];
-      const double ca = cf[ka], sa = cf[NP + ka], cb = cf[kb], sb = cf[NP + kb];
-      double o_pp, o_pq, o_qp, o_qq;
-      block(pa, qa, ca, sa, pb, qb, cb, sb, o_pp, o_pq, o_qp, o_qq);
-      Gn[pa * LG + pb] = o_pp; Gn[pa * LG + qb] = o_pq; Gn[qa * LG + pb] = o_qp; Gn[qa * LG + qb] = o_qq;
-      // W <- W J: rows pa, qa of W are just two arbitrary rows here; columns (pb, qb) rotate
-      const double w_pp = Wc[pa * LG + pb], w_pq = Wc[pa * LG + qb], w_qp = Wc[qa * LG + pb], w_qq = Wc[qa * LG + qb];
-      Wn[pa * LG + pb] = cb * w_pp - sb * w_pq; Wn[pa * LG + qb] = sb * w_pp + cb * w_pq;
-      Wn[qa * LG + pb] = cb * w_qp - sb * w_qq; Wn[qa * LG + qb] = sb * w_qp + cb * w_qq;
-    }
+    if (g == 3) JAC_CLK(13);
     __syncthreads();
+    if (g == 3) JAC_CLK(14);
+    if (g == 2) JAC_CLK(9);
     cur ^= 1;
   }
   const double *Gf = Gm + cur * N2 * LG, *Wf = Wm + cur * N2 * LG;
+  JAC_CLK(5);
 
   // 5. permutation: new row r takes rotated direction perm[r], sorted by diagonal descending
   if (t < N2) {
@@ -1231,6 +1349,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
   }
   __syncthreads();
 
+  JAC_CLK(6);
   // 6. apply: Pnew[r][c] = sum_k W[k][perm[r]] * Ps[k][c] on the DMMA pipe, in place per 8-column slice
   {
     double af[T2][N2 / 4];
@@ -1261,6 +1380,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
     }
   }
   __syncthreads();
+  JAC_CLK(7);
 
   // 7. store
   if ((nc & 1) == 0) {
@@ -1277,12 +1397,13 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
       for (int c = lane; c < nc; c += 32) Gw[(long)grow * a.ld + c] = Ps[(size_t)r * LDS + c];
     }
   }
+  JAC_CLK(8);
 }
 
 static size_t jacobi_smem_bytes(int bs, int nc) {
   int n2 = 2 * bs, ncp = (nc + 7) & ~7, t2 = n2 / 8, nt = t2 * (t2 + 1) / 2;
   size_t doubles = (size_t)n2 * (ncp + 4) + (size_t)JAC_KGROUPS * nt * 64 + 4 * (size_t)n2 * (n2 + 1) + 4 * n2;
-  return doubles * sizeof(double) + n2 * sizeof(int) + 3 * (size_t)(n2 - 1) * n2 + 16;
+  return doubles * sizeof(double) + n2 * sizeof(int) + 16;
 }
 void be_jacobi_round(const JacobiArgs &a) {
   size_t smem = jacobi_smem_bytes(a.bs, a.nc);
@@ -1300,6 +1421,20 @@ void be_jacobi_round(const JacobiArgs &a) {
   else if (a.bs == 4) launch(jacobi_round_kernel<8>, c8);
   else throw std::runtime_error("be_jacobi_round: unsupported block size");
   post_launch();
+#ifdef PEPS_KERNEL_CLOCKS
+  static const int dbg = std::getenv("PEPS_JACOBI_CLK") ? std::atoi(std::getenv("PEPS_JACOBI_CLK")) : 0;
+  static int shown = 0, seen = 0;
+  if (dbg && a.bs == 16 && a.nc == 512 && (++seen % 97) == 0 && shown < dbg) {
+    ++shown;
+    long long h[32];
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    CUDA_CHECK(cudaMemcpyFromSymbol(h, g_jac_clk, sizeof(h)));
+    fprintf(stderr, "[jacobi clk] nblk=%d W=%d tables=%lld load=%lld gram=%lld reduce+conv=%lld rotations=%lld perm=%lld apply=%lld store=%lld\n", a.nblk, a.W,
+            h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4], h[6] - h[5], h[7] - h[6], h[8] - h[7]);
+    fprintf(stderr, "[jacobi upd ] since barrier: start=%lld loads=%lld compute+stores=%lld second_element=%lld\n", h[16] - h[9], h[17] - h[16], h[18] - h[17], h[19] - h[18]);
+    fprintf(stderr, "[jacobi set] loads=%lld entries=%lld cs=%lld to_barrier=%lld barrier=%lld\n", h[10] - h[9], h[11] - h[10], h[12] - h[11], h[13] - h[12], h[14] - h[13]);
+  }
+#endif
 }
 
 __global__ void jacobi_flags_kernel(double *offmax, int32_t *done, double tol, int W) {
