@@ -38,6 +38,11 @@ struct GettDesc {
   const int32_t *am = nullptr, *ak = nullptr, *bk = nullptr, *bn = nullptr, *cm = nullptr, *cn = nullptr;
   int a_kfast = 0;   // 1: A's unit-stride index is a contracted one
   int b_nfast = 1;   // 1: B's unit-stride index is a free one
+  // Optional structural-zero hints (device tables, may be null): A(m,k) == 0 for k < klo_m[m], B(k,n) == 0 for
+  // k < klo_n[n] (the R factors of the forward chain are upper trapezoidal). A backend may start the K loop of a tile
+  // at the largest K step below both bounds; ignoring the hints gives the same result. work = executed / nominal flops.
+  const int32_t *klo_m = nullptr, *klo_n = nullptr;
+  double work = 1.0;
 };
 
 // ---- memory / stream -------------------------------------------------------------------------------

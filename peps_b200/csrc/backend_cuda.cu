@@ -204,10 +204,25 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
   };
 
   const int nk = (d.K + BK - 1) / BK;
-  load_global(0);
-  store_smem();
+  int kt0 = 0;
+  if (d.klo_m != nullptr || d.klo_n != nullptr) {      // structural zeros: skip the K steps below both bounds
+    __shared__ int s_klo[2];
+    if (t < 2) s_klo[t] = 0x7fffffff;
+    __syncthreads();
+    int vm = 0x7fffffff, vn = 0x7fffffff;
+    if (d.klo_m) { for (int i = t; i < BM; i += GETT_THREADS) if (m0 + i < d.M) vm = min(vm, d.klo_m[m0 + i]); } else vm = 0;
+    if (d.klo_n) { for (int i = t; i < BN; i += GETT_THREADS) if (n0 + i < d.N) vn = min(vn, d.klo_n[n0 + i]); } else vn = 0;
+    atomicMin(&s_klo[0], vm);
+    atomicMin(&s_klo[1], vn);
+    __syncthreads();
+    kt0 = min(nk, max(s_klo[0], s_klo[1]) / BK);
+  }
+  if (kt0 < nk) {
+    load_global(kt0 * BK);
+    store_smem();
+  }
   __syncthreads();
-  for (int kt = 0; kt < nk; ++kt) {
+  for (int kt = kt0; kt < nk; ++kt) {
     if (kt + 1 < nk) load_global((kt + 1) * BK);
 #pragma unroll
     for (int kk = 0; kk < BK; kk += 4) {
@@ -251,7 +266,7 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
 
 void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, double beta, int W, int NB) {
   if (d.M <= 0 || d.N <= 0 || W <= 0 || NB <= 0) return;
-  LaunchScope scope(KC_GETT, 2.0 * d.M * d.N * d.K * (double)W * NB);
+  LaunchScope scope(KC_GETT, 2.0 * d.M * d.N * d.K * (double)W * NB * d.work);
   auto launch = [&](auto kern, int BM, int BN) {
     int tiles = ((d.M + BM - 1) / BM) * ((d.N + BN - 1) / BN);
     dim3 grid(tiles, NB, W);

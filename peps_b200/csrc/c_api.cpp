@@ -6,6 +6,9 @@
 #include <string>
 #include <vector>
 #include "../../include/peps_b200.h"
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 #include "engine.h"
 
 using namespace peps;
@@ -207,6 +210,18 @@ int peps_test_einsum(int32_t device, int32_t W, const char *spec, const int32_t 
     be_h2d(A, a, sizeof(double) * (size_t)W * na);
     be_h2d(Bp, b, sizeof(double) * (size_t)W * nb);
     be_gett(pl.d, mkop(A, na), mkop(Bp, nb), mkop(C, pl.outn), 1.0, 0.0, W, 1);
+    if (const char *e = std::getenv("PEPS_EINSUM_TIME")) {      // development aid: device time of `e` repetitions
+      const int reps = std::max(1, std::atoi(e));
+      be_profile_enable(1);
+      double ms[KC_COUNT]; long ln[KC_COUNT]; double fl[KC_COUNT];
+      be_profile_collect(ms, ln, fl, 1);
+      for (int r = 0; r < reps; ++r) be_gett(pl.d, mkop(A, na), mkop(Bp, nb), mkop(C, pl.outn), 1.0, 0.0, W, 1);
+      be_sync();
+      be_profile_collect(ms, ln, fl, 1);
+      be_profile_enable(0);
+      std::fprintf(stderr, "[einsum] %s W=%d M=%d K=%d N=%d: %.1f us per call, %.2f TFLOP/s\n", spec, W, pl.d.M, pl.d.K, pl.d.N,
+                   1e3 * ms[KC_GETT] / reps, fl[KC_GETT] / (ms[KC_GETT] * 1e9));
+    }
     be_d2h(c, C, sizeof(double) * (size_t)W * pl.outn);
   })
 }

@@ -170,20 +170,62 @@ TRef Engine::site_ref(int site, int cfg_site) const {
   for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
   return r;
 }
-BT Engine::einsum(const std::string &spec, const TRef &a, const TRef &b) {
+template <class H>
+static GettDesc with_hints(GettDesc d, const H *h) {
+  if (h) { d.klo_m = h->klo_m; d.klo_n = h->klo_n; d.work = h->work; }
+  return d;
+}
+BT Engine::einsum(const std::string &spec, const TRef &a, const TRef &b, const KHints *h) {
   const Plan &pl = planner_.get(spec, a.d, a.rank, b.d, b.rank);
   BT out;
   out.rank = (int)pl.outdims.size();
   for (int i = 0; i < out.rank; ++i) out.d[i] = pl.outdims[(size_t)i];
   out.n = pl.outn;
   out.p = (double *)pool_.get(sizeof(double) * (size_t)W_ * out.n);
-  be_gett(pl.d, a.op, b.op, mkop(out.p, out.n), 1.0, 0.0, W_, 1);
+  be_gett(with_hints(pl.d, h), a.op, b.op, mkop(out.p, out.n), 1.0, 0.0, W_, 1);
   return out;
 }
 void Engine::einsum_into(const std::string &spec, const TRef &a, const TRef &b, Operand c, const long *sc, double alpha,
-                         double beta) {
+                         double beta, const KHints *h) {
   const Plan &pl = planner_.get(spec, a.d, a.rank, b.d, b.rank, nullptr, nullptr, sc);
-  be_gett(pl.d, a.op, b.op, c, alpha, beta, W_, 1);
+  be_gett(with_hints(pl.d, h), a.op, b.op, c, alpha, beta, W_, 1);
+}
+// r[k][e][a] is an R factor: r[k][col] == 0 for col = e*A + a < k. First possibly non-zero K index per row / column of
+// the three contractions that consume it (K enumerations: a; (e,p) with p = `inner`; (e,a)).
+const Engine::KHints &Engine::r_hints(int which, int k, int e, int a, int p, int b) {
+  std::array<int, 6> key = {which, k, e, a, p, b};
+  auto it = hints_.find(key);
+  if (it != hints_.end()) return it->second;
+  std::vector<int32_t> tab;
+  int K = 0;
+  if (which == 0) {                       // N = (e, k), K = a
+    K = a;
+    tab.resize((size_t)e * k);
+    for (int ee = 0; ee < e; ++ee)
+      for (int kk = 0; kk < k; ++kk) tab[(size_t)ee * k + kk] = std::min(a, std::max(0, kk - ee * a));
+  } else if (which == 1) {                // M = (k, b), K = (e, p): tmp1[e][k][.][.] == 0 for e < floor(k / A)
+    K = e * p;
+    tab.resize((size_t)k * b);
+    for (int kk = 0; kk < k; ++kk)
+      for (int bb = 0; bb < b; ++bb) tab[(size_t)kk * b + bb] = std::min(K, p * (kk / a));
+  } else {                                // M = k, K = (e, a)
+    K = e * a;
+    tab.resize((size_t)k);
+    for (int kk = 0; kk < k; ++kk) tab[(size_t)kk] = std::min(K, kk);
+  }
+  KHints h;
+  const int32_t *dev = planner_.upload(tab);
+  // executed fraction at the kernel's granularity (64-wide tiles, K steps of 16)
+  double done = 0.0, total = 0.0;
+  for (size_t t0 = 0; t0 < tab.size(); t0 += 64) {
+    int lo = K;
+    for (size_t i = t0; i < std::min(tab.size(), t0 + 64); ++i) lo = std::min(lo, (int)tab[i]);
+    done += K - std::min(K, lo / 16 * 16);
+    total += K;
+  }
+  h.work = total > 0 ? done / total : 1.0;
+  if (which == 0) h.klo_n = dev; else h.klo_m = dev;
+  return hints_.emplace(key, h).first->second;
 }
 std::string Engine::site_labels(int post, char pre, char toward, char next, char away) {
   std::string s(4, '?');
@@ -220,13 +262,19 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
   for (int i = 0; i < N - 1; ++i) {
     const int site = sites[(size_t)i];
     TRef sref = site_ref(site, site);
-    BT tmp1 = einsum("apb,kea->kepb", ref(mps[(size_t)i]), ref(r[(size_t)i]));        // bmps_impl.h:806
+    // r_i (i >= 1) is an R factor: upper trapezoidal. The kernels skip the K steps that only meet its zeros.
+    const bool tri = i >= 1;
+    const int rk = r[(size_t)i].d[0], re = r[(size_t)i].d[1], ra = r[(size_t)i].d[2];
+    const int pd = mps[(size_t)i].d[1], bd = mps[(size_t)i].d[2];
+    BT tmp1 = einsum("apb,kea->ekpb", ref(mps[(size_t)i]), ref(r[(size_t)i]),
+                     tri ? &r_hints(0, rk, re, ra, pd, bd) : nullptr);                    // bmps_impl.h:806
     const int k = r[(size_t)i].d[0], o = sdim(site, 'o'), f = sdim(site, 'f'), b = mps[(size_t)i].d[2];
     const int m = k * o, n = f * b;
     QRLayout L = qr_layout(m, n);
     double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * L.m_pad * n);
     if (L.m_pad > m) be_memset0(A, sizeof(double) * (size_t)W_ * L.m_pad * n);
-    einsum_into("kepb," + sl + "->kofb", ref(tmp1), sref, mkop(A, (long)L.m_pad * n));   // bmps_impl.h:807
+    einsum_into("ekpb," + sl + "->kofb", ref(tmp1), sref, mkop(A, (long)L.m_pad * n), nullptr, 1.0, 0.0,
+                tri ? &r_hints(1, rk, re, ra, pd, bd) : nullptr);                         // bmps_impl.h:807
     release(tmp1);
     caqr(la_, A, (long)L.m_pad * n, m, n, L);                                            // bmps_impl.h:817-821
     const int kk = std::min(m, n);
@@ -251,7 +299,8 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
       const int brows = truncate_buffer_rows(rows, cols);
       double *G = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows * cols);
       if (brows > rows) be_memset0(G, sizeof(double) * (size_t)W_ * brows * cols);
-      einsum_into("kea,eaoj->koj", ref(r[(size_t)i]), ref(X), mkop(G, (long)brows * cols));
+      einsum_into("kea,eaoj->koj", ref(r[(size_t)i]), ref(X), mkop(G, (long)brows * cols), nullptr, 1.0, 0.0,
+                  &r_hints(2, r[(size_t)i].d[0], r[(size_t)i].d[1], r[(size_t)i].d[2], 0, 0));
       const int tcap = std::min(dmax_, std::min(rows, cols));
       B = alloc({tcap, o, j});
       double *norms2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * std::max(rows, 1));

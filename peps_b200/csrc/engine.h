@@ -129,9 +129,13 @@ class Engine {
   void release(BMPSv &v);
   TRef ref(const BT &t) const;
   TRef site_ref(int site, int cfg_site) const;
-  BT einsum(const std::string &spec, const TRef &a, const TRef &b);
+  // structural-zero hints for contractions with an upper-trapezoidal R factor of the forward chain (backend.h GettDesc)
+  struct KHints { const int32_t *klo_m = nullptr, *klo_n = nullptr; double work = 1.0; };
+  // which: 0 = "apb,kea->ekpb" (hint on N = (e,k)), 1 = "ekpb,<site>->kofb" (hint on M = (k,b)), 2 = "kea,eaoj->koj" (M = k)
+  const KHints &r_hints(int which, int k, int e, int a, int p, int b);
+  BT einsum(const std::string &spec, const TRef &a, const TRef &b, const KHints *h = nullptr);
   void einsum_into(const std::string &spec, const TRef &a, const TRef &b, Operand c, const long *sc = nullptr,
-                   double alpha = 1.0, double beta = 0.0);
+                   double alpha = 1.0, double beta = 0.0, const KHints *h = nullptr);
   BMPSv absorb(const BMPSv &mps, const std::vector<int> &sites, int post);
   BT bten_step(const BT &bten, const BT &mps1, const TRef &site, const BT &mps2, int post);
   BT bten2_step(const BT &bten2, const BT &mps1, const TRef &site1, const TRef &site2, const BT &mps2, int post);
@@ -182,6 +186,7 @@ class Engine {
   long sr_cap_ = 0, sr_count_ = 0;
   bool sr_on_ = false;
 
+  std::map<std::array<int, 6>, KHints> hints_;
   std::vector<BMPSv> bmps_[4];
   // Boundary-MPS memo. The reference drops stack entries (DeleteInnerBMPS, ShiftBMPSWindow) and later regrows them
   // from unchanged configurations: the LEFT stack finished by the sweep's vertical pass is rebuilt column by column

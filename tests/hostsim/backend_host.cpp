@@ -47,7 +47,12 @@ void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, d
       for (int m = 0; m < d.M; ++m)
         for (int n = 0; n < d.N; ++n) {
           double s = 0.0;
-          for (int k = 0; k < d.K; ++k) s += Ab[d.am[m] + d.ak[k]] * Bb[d.bk[k] + d.bn[n]];
+          // structural-zero hints are honoured PER ELEMENT here (the strictest reading): a wrong hint table shows up
+          // as a parity failure of the host-logic tests
+          int k0 = 0;
+          if (d.klo_m) k0 = std::max(k0, (int)d.klo_m[m]);
+          if (d.klo_n) k0 = std::max(k0, (int)d.klo_n[n]);
+          for (int k = k0; k < d.K; ++k) s += Ab[d.am[m] + d.ak[k]] * Bb[d.bk[k] + d.bn[n]];
           out[(size_t)m * d.N + n] = s;
         }
       for (int m = 0; m < d.M; ++m)
