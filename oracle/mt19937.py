@@ -53,6 +53,20 @@ class MT19937:
             r = math.nextafter(1.0, 0.0)
         return r
 
+    def uniform_long_double(self, a, b):
+        """``std::uniform_real_distribution<long double>(a, b)(engine)`` for libstdc++ on x86 (80-bit long double,
+        ``generate_canonical<long double, 64>`` = two 32-bit draws, exact in the 64-bit significand).
+        ``a``, ``b`` are numpy longdouble."""
+        import numpy as np
+        ld = np.longdouble
+        assert np.finfo(ld).nmant == 63, "oracle needs the x87 80-bit long double of the reference's platform"
+        x0 = self.next_u32()
+        x1 = self.next_u32()
+        u = (ld(x0) + ld(x1) * ld(4294967296.0)) / (ld(4294967296.0) * ld(4294967296.0))
+        if u >= ld(1.0):
+            u = np.nextafter(ld(1.0), ld(0.0))
+        return u * (b - a) + a
+
     def state(self):
         """(624 words, index) -- the layout the C ABI's set/get RNG state uses."""
         return list(self.mt), self.idx

@@ -12,6 +12,9 @@ Reference (relative to include/qlpeps/):
   * MeanAndBinnedErrorSqrtNUniformBin vmc_basic/monte_carlo_tools/statistics.h:146-225
   * NormalizeStateOrder1              algorithm/vmc_update/monte_carlo_engine.h:206-240
   * SRSMatrix::operator*              optimizer/stochastic_reconfiguration_smatrix.h:45-91
+  * SuwaTodoStateUpdate               vmc_basic/monte_carlo_tools/suwa_todo_update.h:53-113
+  * MCUpdateSquareNNFullSpaceUpdateOBC .../square_nn_updater.h:253-293
+  * TransverseFieldIsingSquareOBC     algorithm/vmc_update/model_solvers/transverse_field_ising_square_obc.h:149-247
 """
 import math
 import numpy as np
@@ -112,6 +115,117 @@ class NNExchangeUpdater:
         c.delete_inner_bmps(UP)
         bond_num = cols * (rows - 1) + rows * (cols - 1)
         return [accepted / bond_num]
+
+
+def suwa_todo_state_update(init_state, weights, rng):
+    """SuwaTodoStateUpdate (suwa_todo_update.h:53-113): rejection-free geometric allocation. `weights` are doubles,
+    the prefix sums and the draw are ``long double`` (x87 80-bit) exactly as in the reference."""
+    ld = np.longdouble
+    w = [float(x) for x in weights]
+    n = len(w)
+    max_id = max(range(n), key=lambda i: (w[i], -i))          # std::max_element: first maximum
+    if max_id != 0:
+        w[0], w[max_id] = w[max_id], w[0]
+    if init_state == max_id:
+        init_state = 0
+    elif init_state == 0:
+        init_state = max_id
+    s = [ld(w[0])]
+    for i in range(1, n):
+        s.append(s[i - 1] + ld(w[i]))
+    S = s[-1]
+    s_im1 = ld(0.0) if init_state == 0 else s[init_state - 1]
+    start = s_im1 + ld(w[0])
+    if start >= S:
+        start = start - S
+    hi = np.nextafter(start + ld(w[init_state]), start)
+    x = rng.uniform_long_double(start, hi)
+    if x >= S:
+        x = x - S
+    final_state = n
+    for i in range(n):                                        # std::upper_bound(s, x)
+        if s[i] > x:
+            final_state = i
+            break
+    if max_id != 0:
+        if final_state == 0:
+            final_state = max_id
+        elif final_state == max_id:
+            final_state = 0
+    return final_state
+
+
+class NNFullSpaceUpdater(NNExchangeUpdater):
+    """MCUpdateSquareNNFullSpaceUpdateOBC (square_nn_updater.h:253-293): same bond traversal as the exchange updater,
+    all d^2 local states of a bond weighted by |psi|^2, Suwa-Todo choice (one long double draw per bond)."""
+
+    def two_site_update(self, site1, site2, bond_dir, tps, w):
+        dim = len(tps[0][0])
+        c1 = int(w.config[site1]); c2 = int(w.config[site2])
+        init = c1 * dim + c2
+        alt = [None] * (dim * dim)
+        alt[init] = w.amplitude
+        for a in range(dim):
+            for b in range(dim):
+                cfg = a * dim + b
+                if cfg != init:
+                    alt[cfg] = w.contractor.replace_nn_site_trace(w.tn, site1, site2, bond_dir,
+                                                                  tps[site1[0]][site1[1]][a], tps[site2[0]][site2[1]][b])
+        weights = [abs(x / w.amplitude) ** 2 for x in alt]
+        final = suwa_todo_state_update(init, weights, self.rng)
+        if final == init:
+            return False
+        w.update_local(tps, alt[final], (site1, final // dim), (site2, final % dim))
+        return True
+
+
+class TFIMModel:
+    """TransverseFieldIsingSquareOBC(h): H = -sum_<ij> sigma^z_i sigma^z_j - h sum_i sigma^x_i
+    (transverse_field_ising_square_obc.h:149-247). Only the horizontal pass is needed (one-site terms)."""
+
+    has_nnn = False
+
+    def __init__(self, h):
+        self.h = h
+
+    def diag_energy(self, config):
+        """CalDiagTermEnergy (:160-182)."""
+        rows, cols = config.shape
+        e = 0.0
+        for row in range(rows):
+            for col in range(cols - 1):
+                e += -1 if config[row, col] == config[row, col + 1] else 1
+        for col in range(cols):
+            for row in range(rows - 1):
+                e += -1 if config[row, col] == config[row + 1, col] else 1
+        return e
+
+    def energy_and_holes(self, tps, w, calc_holes=True):
+        """CalEnergyAndHolesImplParsed (:208-247). Returns (E_loc, holes or None, psi_list)."""
+        tn, c = w.tn, w.contractor
+        rows, cols = w.rows, w.cols
+        holes = [[None] * cols for _ in range(rows)] if calc_holes else None
+        psi_list = []
+        energy = 0.0
+        c.set_truncate_params(*w.trunc)
+        c.generate_bmps_approach(tn, UP)
+        for row in range(rows):
+            c.init_bten(tn, LEFT, row)
+            c.grow_full_bten(tn, RIGHT, row, 1, True)
+            psi = c.trace(tn, (row, 0), HORIZONTAL)
+            inv_psi = 1.0 / psi
+            psi_list.append(psi)
+            for col in range(cols):
+                if calc_holes:
+                    holes[row][col] = np.conj(c.punch_hole(tn, (row, col), HORIZONTAL))
+                cfg = int(w.config[row, col])
+                psi_ex = c.replace_one_site_trace(tn, (row, col), tps[row][col][1 - cfg], HORIZONTAL)   # :191-204
+                energy = energy + (-self.h) * np.conj(psi_ex * inv_psi)
+                if col < cols - 1:
+                    c.shift_bten_window(tn, RIGHT)
+            if row < rows - 1:
+                c.shift_bmps_window(tn, DOWN)
+        return energy + self.diag_energy(w.config), holes, psi_list
 
 
 class XXZModel:

@@ -3,7 +3,7 @@
 Run in the build container (needs /root/reference):  python tests/golden/make_golden.py
 The ``.qlten`` payloads are re-packed as ``.npz`` (dense arrays, legs (L, D, R, U)); the expected
 numbers stored beside them are the constants the reference's tests assert
-(tests/test_algorithm/test_exact_summation_evaluator.cpp:578-606,
+(tests/test_algorithm/test_exact_summation_evaluator.cpp:578-606, 700-790,
  tests/slow_tests/test_boson_mc_peps_measure.cpp:31-76).
 """
 import os
@@ -36,6 +36,12 @@ def main():
               grad_probe_im=1.708247848617349e-10)),
         ("heis2x2_double_su", "test_data/heisenberg_tps_double_from_simple_update", False,
          dict(energy=-1.99521278793, energy_tol=1e-10)),
+        # TrivialTransverseIsingTest (test_exact_summation_evaluator.cpp:620-790), J = h = 1, all 16 configurations
+        ("tfim2x2_double_lowest", "test_data/transverse_ising_tps_doublelowest", False,
+         dict(energy=-5.226251859505504, energy_tol=1e-7, grad_norm=1.290630314256308e-10,
+              grad_probe_re=4.081475798300479e-11, grad_probe_im=0.0)),
+        ("tfim2x2_double_su", "test_data/transverse_ising_tps_double_from_simple_update", False,
+         dict(energy=-5.19991995228, energy_tol=1e-10)),
     ]
     for name, rel, cx, exp in two_by_two:
         tps = load_tps_dir(os.path.join(REF, rel), 2, 2, 2, cx)

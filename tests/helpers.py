@@ -60,14 +60,14 @@ def ising_exact_logZ(L, beta):
     return math.log(v @ b) + logscale
 
 
-def exact_summation(tps, model, trunc=(1, 1000, 0.0)):
+def exact_summation(tps, model, trunc=(1, 1000, 0.0), all_configs=False):
     """ExactSumEnergyEvaluatorMPI restated on top of the oracle walker
     (algorithm/vmc_update/exact_summation_energy_evaluator.h:190-295)."""
     from oracle.vmc import Walker, tps_like_zeros
     rows, cols = len(tps), len(tps[0])
     s_o, s_eo, wsum, esum = tps_like_zeros(tps), tps_like_zeros(tps), 0.0, 0.0
     for bits in itertools.product([0, 1], repeat=rows * cols):
-        if sum(bits) != rows * cols // 2:
+        if not all_configs and sum(bits) != rows * cols // 2:
             continue
         cfg = np.array(bits).reshape(rows, cols)
         w = Walker(tps, cfg, trunc)

@@ -165,6 +165,54 @@ def test_K4_K5_exact_summation_goldens(name, complex_):
         assert abs(np.imag(p) - float(z["exp_grad_probe_im"])) < 1e-17
 
 
+@pytest.mark.parametrize("name", ["tfim2x2_double_lowest", "tfim2x2_double_su"])
+def test_K4_K5_transverse_ising_goldens(name):
+    """TrivialTransverseIsingTest (tests/test_algorithm/test_exact_summation_evaluator.cpp:700-790): J = h = 1, all 16
+    configurations, SVD(1, 8, 1e-16); energies -5.19991995228 (quoted) / 2x2 ED, gradient signatures of the lowest
+    state."""
+    tps, z = load_golden_tps(name)
+    energy, grad = exact_summation(tps, vmc.TFIMModel(1.0), (1, 8, 1e-16), all_configs=True)
+    assert abs(energy - float(z["exp_energy"])) < float(z["exp_energy_tol"])
+    if "exp_grad_norm" in z:
+        assert abs(grad_norm_square(grad) - float(z["exp_grad_norm"])) < 1e-19
+        assert abs(np.real(weighted_probe(grad, False)) - float(z["exp_grad_probe_re"])) < 1e-19
+
+
+def test_K9_suwa_todo_is_stationary_and_rejection_free():
+    """SuwaTodoStateUpdate (suwa_todo_update.h:53-113): the update leaves pi ~ weights invariant (balance condition) and
+    the heaviest state never stays put when it holds less than half of the weight."""
+    from oracle.mt19937 import MT19937
+    weights = [0.3, 1.7, 0.9, 0.45]
+    n, trials = len(weights), 4000
+    rng = MT19937(99)
+    flow = np.zeros((n, n))
+    for i in range(n):
+        for _ in range(trials):
+            flow[i, vmc.suwa_todo_state_update(i, weights, rng)] += 1.0 / trials
+    pi = np.array(weights) / sum(weights)
+    assert np.allclose(pi @ flow, pi, atol=0.02)
+    assert flow[1, 1] < 0.05            # w_max = 1.7 < sum of the others = 1.65 + ...: rejection-free up to the surplus
+    assert np.allclose(flow.sum(axis=1), 1.0)
+
+
+def test_full_space_updater_samples_psi_squared():
+    """MCUpdateSquareNNFullSpaceUpdateOBC on a 2x2 lattice: the visit histogram converges to |psi|^2 over all 16
+    configurations (no Sz conservation)."""
+    tps = vmc.random_tps(2, 2, 2, 2, seed=21)
+    w = vmc.Walker(tps, vmc.neel_config(2, 2), (1, 100, 0.0))
+    up = vmc.NNFullSpaceUpdater(5)
+    hist = np.zeros(16)
+    for _ in range(3000):
+        up.sweep(tps, w)
+        hist[int("".join(str(int(x)) for x in w.config.flatten()), 2)] += 1
+    exact = np.zeros(16)
+    for k in range(16):
+        cfg = np.array([int(b) for b in format(k, "04b")]).reshape(2, 2)
+        exact[k] = abs(vmc.Walker(tps, cfg, (1, 100, 0.0)).amplitude) ** 2
+    exact /= exact.sum()
+    assert np.max(np.abs(hist / hist.sum() - exact)) < 0.03
+
+
 def test_hole_is_amplitude_derivative():
     tps = vmc.random_tps(3, 3, 2, 3, seed=3)
     cfg = vmc.neel_config(3, 3)
