@@ -61,6 +61,9 @@ int peps_set_model_xxz(peps_ctx *ctx, double jz, double jxy, double pinning00);
  * next-nearest-neighbour couplings evaluated through BTen2 + ReplaceNNNSiteTrace in the horizontal pass
  * (base/square_nnn_energy_solver.h:203-265). jz2 = jxy2 = 0 switches the NNN pass off. */
 int peps_set_model_j1j2_xxz(peps_ctx *ctx, double jz, double jxy, double jz2, double jxy2, double pinning00);
+/* TransverseFieldIsingSquareOBC(h): H = -sum_<ij> sz_i sz_j - h sum_i sx_i, one ReplaceOneSiteTrace per site in the
+ * horizontal pass (model_solvers/transverse_field_ising_square_obc.h:149-247; BASELINE config #1). phys must be 2. */
+int peps_set_model_tfim(peps_ctx *ctx, double h);
 
 /* Configuration per walker (vmc_basic/configuration.h:57), int32 [W][rows][cols]. */
 int peps_set_configs(peps_ctx *ctx, const int32_t *cfg);
@@ -83,6 +86,12 @@ int peps_normalize_state_order1(peps_ctx *ctx, double max_abs_override, double *
 /* MonteCarloEngine::StepSweep(n) with MCUpdateSquareNNExchangeOBC
  * (configuration_update_strategies/square_nn_updater.h:29-81,146-188); accept_rates[W] of the last sweep. */
 int peps_sweep(peps_ctx *ctx, int32_t nsweeps, double *accept_rates);
+/* MonteCarloEngine::StepSweep(n) with MCUpdateSquareNNFullSpaceUpdateOBC (square_nn_updater.h:253-293): all phys^2
+ * local states of every bond (no Sz conservation), Suwa-Todo choice (monte_carlo_tools/suwa_todo_update.h:53-113) with
+ * the reference's long double prefix sums and draw, taken on the host from the same per-walker mt19937 streams. */
+int peps_sweep_full_space(peps_ctx *ctx, int32_t nsweeps, double *accept_rates);
+/* Selects the updater peps_sample steps with: 0 = MCUpdateSquareNNExchangeOBC (default), 1 = MCUpdateSquareNNFullSpaceUpdateOBC. */
+int peps_set_updater(peps_ctx *ctx, int32_t kind);
 /* ModelEnergySolver::CalEnergyAndHoles<calchols> (algorithm/vmc_update/model_energy_solver.h:69-100 ->
  * model_solvers/base/square_nnn_energy_solver.h:79-315). eloc[W]; psi_list[(rows+cols)][W] may be NULL. */
 int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, double *psi_list);

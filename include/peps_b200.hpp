@@ -32,6 +32,9 @@ struct MonteCarloParams {
 };
 
 struct XXZModel { double jz = 1.0, jxy = 1.0, pinning00 = 0.0; };   // SquareSpinOneHalfXXZModelOBC(jz, jxy, pinning)
+struct J1J2XXZModel { double jz = 1.0, jxy = 1.0, jz2 = 0.0, jxy2 = 0.0, pinning00 = 0.0; };   // SquareSpinOneHalfJ1J2XXZModelOBC
+struct TransverseFieldIsingModel { double h = 1.0; };                 // TransverseFieldIsingSquareOBC(h)
+enum class Updater : int32_t { NNExchange = 0, NNFullSpace = 1 };     // MCUpdateSquareNNExchangeOBC / ...NNFullSpaceUpdateOBC
 
 class WalkerBatch {
  public:
@@ -48,13 +51,20 @@ class WalkerBatch {
   void SetTPS(const std::vector<double> &flat) { ck(peps_set_tps(h_, flat.data(), flat.size())); }
   std::vector<double> GetTPS() { std::vector<double> v(tps_size()); ck(peps_get_tps(h_, v.data(), v.size())); return v; }
   void SetModel(const XXZModel &m) { ck(peps_set_model_xxz(h_, m.jz, m.jxy, m.pinning00)); }
+  void SetModel(const J1J2XXZModel &m) { ck(peps_set_model_j1j2_xxz(h_, m.jz, m.jxy, m.jz2, m.jxy2, m.pinning00)); }
+  void SetModel(const TransverseFieldIsingModel &m) { ck(peps_set_model_tfim(h_, m.h)); }
+  void SetUpdater(Updater u) { updater_ = u; ck(peps_set_updater(h_, (int32_t)u)); }
   void SetConfigs(const std::vector<int32_t> &cfg) { ck(peps_set_configs(h_, cfg.data())); }
   std::vector<int32_t> GetConfigs() { std::vector<int32_t> v((size_t)walkers_ * rows_ * cols_); ck(peps_get_configs(h_, v.data())); return v; }
   void SeedRNG(const std::vector<uint32_t> &seeds) { ck(peps_seed_rng(h_, seeds.data())); }
   void InitWalkers() { ck(peps_init_walkers(h_)); }
   std::vector<double> Amplitudes() { std::vector<double> v((size_t)walkers_); ck(peps_get_amplitudes(h_, v.data())); return v; }
   double NormalizeStateOrder1(double max_abs_override = 0.0) { double f = 0; ck(peps_normalize_state_order1(h_, max_abs_override, &f)); return f; }
-  std::vector<double> StepSweep(int n) { std::vector<double> a((size_t)walkers_); ck(peps_sweep(h_, n, a.data())); return a; }
+  std::vector<double> StepSweep(int n) {
+    std::vector<double> a((size_t)walkers_);
+    ck(updater_ == Updater::NNFullSpace ? peps_sweep_full_space(h_, n, a.data()) : peps_sweep(h_, n, a.data()));
+    return a;
+  }
   void ZeroAccumulators() { ck(peps_zero_accumulators(h_)); }
   void Sample(int sweeps_between_samples, std::vector<double> &eloc, std::vector<double> &accept) {
     eloc.resize((size_t)walkers_); accept.resize((size_t)walkers_);
@@ -70,6 +80,7 @@ class WalkerBatch {
   void ck(int rc) { if (rc != 0) throw std::runtime_error(peps_last_error(h_)); }
   peps_ctx *h_ = nullptr;
   int rows_, cols_, walkers_;
+  Updater updater_ = Updater::NNExchange;
 };
 
 struct EvaluateResult {               // MCEnergyGradEvaluator::Result (mc_energy_grad_evaluator.h:66-75)

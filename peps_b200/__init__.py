@@ -4,8 +4,10 @@ Python here is host-side plumbing over the C ABI (include/peps_b200.h); all arit
 sm_100a kernels of peps_b200/csrc/backend_cuda.cu. See DESIGN.md.
 """
 from .api import (BMPSTruncateParams, MonteCarloParams, SplitIndexTPS, Configuration, SquareSpinOneHalfXXZModelOBC,
-                  SquareSpinOneHalfJ1J2XXZModelOBC, MCUpdateSquareNNExchange, WalkerBatch, MCEnergyGradEvaluator, PepsError)
+                  SquareSpinOneHalfJ1J2XXZModelOBC, TransverseFieldIsingSquareOBC, MCUpdateSquareNNExchange,
+                  MCUpdateSquareNNFullSpaceUpdate, WalkerBatch, MCEnergyGradEvaluator, PepsError)
 
 __all__ = ["BMPSTruncateParams", "MonteCarloParams", "SplitIndexTPS", "Configuration",
-           "SquareSpinOneHalfXXZModelOBC", "SquareSpinOneHalfJ1J2XXZModelOBC", "MCUpdateSquareNNExchange", "WalkerBatch", "MCEnergyGradEvaluator",
+           "SquareSpinOneHalfXXZModelOBC", "SquareSpinOneHalfJ1J2XXZModelOBC", "TransverseFieldIsingSquareOBC", "MCUpdateSquareNNExchange",
+           "MCUpdateSquareNNFullSpaceUpdate", "WalkerBatch", "MCEnergyGradEvaluator",
            "PepsError"]

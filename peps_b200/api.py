@@ -165,9 +165,23 @@ class SquareSpinOneHalfJ1J2XXZModelOBC:
 
 
 @dataclass
+class TransverseFieldIsingSquareOBC:
+    """model_solvers/transverse_field_ising_square_obc.h:28-247: H = -sum_<ij> sz_i sz_j - h sum_i sx_i."""
+    h: float = 1.0
+
+
+@dataclass
 class MCUpdateSquareNNExchange:
     """Explicit-seed constructor of the reference updater; walker w draws from std::mt19937(seed + w)."""
     seed: int = 5489
+    kind = 0
+
+
+@dataclass
+class MCUpdateSquareNNFullSpaceUpdate:
+    """square_nn_updater.h:253-293: all phys^2 local states per bond, Suwa-Todo choice (no Sz conservation)."""
+    seed: int = 5489
+    kind = 1
 
 
 class WalkerBatch:
@@ -219,8 +233,14 @@ class WalkerBatch:
     def set_deflation(self, eps):
         self._ck(self.lib.peps_set_deflation(self.h, eps))
 
+    def set_updater(self, updater):
+        self.updater_kind = int(getattr(updater, "kind", updater))
+        self._ck(self.lib.peps_set_updater(self.h, self.updater_kind))
+
     def set_model(self, model):
-        if hasattr(model, "jz2"):
+        if isinstance(model, TransverseFieldIsingSquareOBC):
+            self._ck(self.lib.peps_set_model_tfim(self.h, model.h))
+        elif hasattr(model, "jz2"):
             self._ck(self.lib.peps_set_model_j1j2_xxz(self.h, model.jz, model.jxy, model.jz2, model.jxy2, model.pinning00))
         else:
             self._ck(self.lib.peps_set_model_xxz(self.h, model.jz, model.jxy, model.pinning00))
@@ -264,8 +284,10 @@ class WalkerBatch:
         return f.value
 
     def sweep(self, n=1):
+        """StepSweep with the updater chosen by set_updater (NN exchange unless told otherwise)."""
         acc = np.empty(self.W)
-        self._ck(self.lib.peps_sweep(self.h, n, _dp(acc)))
+        f = self.lib.peps_sweep_full_space if getattr(self, "updater_kind", 0) == 1 else self.lib.peps_sweep
+        self._ck(f(self.h, n, _dp(acc)))
         return acc
 
     def energy_and_holes(self, calc_holes=True, want_psi=False):
@@ -413,6 +435,7 @@ class MCEnergyGradEvaluator:
         self.dist, self.rank, self.world_size = dist, rank, world_size
         self.batch = WalkerBatch(tps.rows(), tps.cols(), tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
         self.batch.set_model(model)
+        self.batch.set_updater(updater)
         self.batch.set_tps(tps)
         if configs is None:
             if mc_params.initial_config is None:

@@ -147,6 +147,9 @@ void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const doubl
 // eloc[w] += (c1==c2) ? 0.25 jz : -0.25 jz + (psi_ex[w] * (1/psi[w])) * 0.5 jxy
 void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const double *psi_ex, const double *psi,
                         double jz, double jxy, double *eloc, int W);
+// EvaluateOnSiteOffDiagEnergy of TransverseFieldIsingSquareOBC (transverse_field_ising_square_obc.h:191-204):
+// eloc[w] += coef * psi_ex[w] * (1 / psi[w])
+void be_ratio_accumulate(const double *psi_ex, const double *psi, double coef, double *eloc, int W);
 // eloc[w] += -h00 * (cfg[w][0] - 0.5)
 void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *eloc, int W);
 // O* accumulation (mc_energy_grad_evaluator.h:245-272) for one sample of all walkers:

@@ -1695,6 +1695,15 @@ void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const do
   xxz_bond_energy_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, s1, s2, psi_ex, psi, jz, jxy, eloc, W);
   post_launch();
 }
+__global__ void ratio_accumulate_kernel(const double *psi_ex, const double *psi, double coef, double *eloc, int W) {
+  int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < W) eloc[w] += coef * (psi_ex[w] * (1.0 / psi[w]));
+}
+void be_ratio_accumulate(const double *psi_ex, const double *psi, double coef, double *eloc, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  ratio_accumulate_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(psi_ex, psi, coef, eloc, W);
+  post_launch();
+}
 __global__ void xxz_onsite_kernel(const int32_t *cfg, int nsites, double h00, double *eloc, int W) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w < W) eloc[w] += -h00 * ((double)cfg[(long)w * nsites] - 0.5);

@@ -69,10 +69,11 @@ int peps_set_truncation(peps_ctx *ctx, int32_t dmin, int32_t dmax, double terr) 
 }
 int peps_set_jacobi(peps_ctx *ctx, double tol, int32_t inner, int32_t maxs) { GUARD(ctx, ctx->eng->set_jacobi(tol, inner, maxs)) }
 int peps_set_deflation(peps_ctx *ctx, double eps) { GUARD(ctx, { if (eps < 0) throw std::invalid_argument("peps_set_deflation: eps < 0"); ctx->eng->set_deflation(eps); }) }
-int peps_set_model_xxz(peps_ctx *ctx, double jz, double jxy, double h00) { GUARD(ctx, { ctx->eng->set_model_xxz(jz, jxy, h00); ctx->eng->set_model_nnn(0.0, 0.0); }) }
+int peps_set_model_xxz(peps_ctx *ctx, double jz, double jxy, double h00) { GUARD(ctx, { ctx->eng->set_model_kind_xxz(); ctx->eng->set_model_xxz(jz, jxy, h00); ctx->eng->set_model_nnn(0.0, 0.0); }) }
 int peps_set_model_j1j2_xxz(peps_ctx *ctx, double jz, double jxy, double jz2, double jxy2, double h00) {
-  GUARD(ctx, { ctx->eng->set_model_xxz(jz, jxy, h00); ctx->eng->set_model_nnn(jz2, jxy2); })
+  GUARD(ctx, { ctx->eng->set_model_kind_xxz(); ctx->eng->set_model_xxz(jz, jxy, h00); ctx->eng->set_model_nnn(jz2, jxy2); })
 }
+int peps_set_model_tfim(peps_ctx *ctx, double h) { GUARD(ctx, ctx->eng->set_model_tfim(h)) }
 int peps_set_configs(peps_ctx *ctx, const int32_t *c) { GUARD(ctx, ctx->eng->set_configs(c)) }
 int peps_get_configs(peps_ctx *ctx, int32_t *c) { GUARD(ctx, ctx->eng->get_configs(c)) }
 int peps_seed_rng(peps_ctx *ctx, const uint32_t *s) { GUARD(ctx, ctx->eng->seed_rng(s)) }
@@ -101,6 +102,8 @@ int peps_normalize_state_order1(peps_ctx *ctx, double max_abs_override, double *
 }
 
 int peps_sweep(peps_ctx *ctx, int32_t n, double *acc) { GUARD(ctx, ctx->eng->sweep(n, acc)) }
+int peps_set_updater(peps_ctx *ctx, int32_t kind) { GUARD(ctx, ctx->eng->set_updater(kind)) }
+int peps_sweep_full_space(peps_ctx *ctx, int32_t n, double *acc) { GUARD(ctx, ctx->eng->sweep_full_space(n, acc)) }
 int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, double *psi_list) {
   GUARD(ctx, ctx->eng->energy_and_holes(calc_holes != 0, eloc, psi_list))
 }
@@ -115,7 +118,7 @@ double *peps_ostar_sum_device(peps_ctx *ctx) { return ctx->eng->osum_device(); }
 double *peps_eloc_ostar_sum_device(peps_ctx *ctx) { return ctx->eng->eosum_device(); }
 int peps_sample(peps_ctx *ctx, int32_t sweeps, double *eloc, double *acc) {
   GUARD(ctx, {
-    ctx->eng->sweep(sweeps, acc);
+    ctx->eng->step_sweep(sweeps, acc);
     ctx->eng->energy_and_holes(true, eloc, nullptr);
     ctx->eng->accumulate_ostar();
   })

@@ -78,7 +78,7 @@ Engine::~Engine() {
   for (void *p : {(void *)tps_, (void *)osum_, (void *)eosum_, (void *)tps_off_d_, (void *)site_size_d_, (void *)hole_off_d_,
                   (void *)cfg_, (void *)amp_, (void *)mt_, (void *)mtidx_, (void *)accepted_, (void *)eloc_, (void *)psi_tmp_,
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
-                  (void *)sr_cfgs_, (void *)sr_delta_})
+                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_})
     be_free(p);
 }
 
@@ -174,6 +174,13 @@ template <class H>
 static GettDesc with_hints(GettDesc d, const H *h) {
   if (h) { d.klo_m = h->klo_m; d.klo_n = h->klo_n; d.work = h->work; }
   return d;
+}
+TRef Engine::site_ref_idx(int site, const int32_t *idx, int stride) const {
+  TRef r;
+  r.op = mkgather(tps_ + tps_off_h_[(size_t)site], idx, stride, site_size_h_[(size_t)site]);
+  r.rank = 4;
+  for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
+  return r;
 }
 BT Engine::einsum(const std::string &spec, const TRef &a, const TRef &b, const KHints *h) {
   const Plan &pl = planner_.get(spec, a.d, a.rank, b.d, b.rank);
@@ -509,6 +516,29 @@ void Engine::nn_trace(int ra, int ca, int rb, int cb, int orient, int cfg_site_a
   release(half_a);
   release(half_b);
 }
+void Engine::nn_trace_idx(int ra, int ca, int rb, int cb, int orient, const int32_t *idx_a, const int32_t *idx_b, int stride,
+                          double *psi_out) {
+  ++n_trace_;
+  int first, second, slice, ia, ib, n;
+  if (orient == HORIZONTAL) { first = LEFT; second = RIGHT; slice = ra; ia = ca; ib = cb; n = cols_; }
+  else { first = UP; second = DOWN; slice = ca; ia = ra; ib = rb; n = rows_; }
+  const BT *m1, *m2; int site;
+  bten_operands(first, slice, ia + 1, m1, m2, site);
+  BT half_a = bten_step(bten_[first].at((size_t)ia), *m1, site_ref_idx(ra * cols_ + ca, idx_a, stride), *m2, first);
+  bten_operands(second, slice, n - ib, m1, m2, site);
+  BT half_b = bten_step(bten_at_slice(second, ib), *m1, site_ref_idx(rb * cols_ + cb, idx_b, stride), *m2, second);
+  reverse_dot(half_a, half_b, psi_out);
+  release(half_a);
+  release(half_b);
+}
+void Engine::one_site_trace(int r, int c, const int32_t *idx, int stride, double *psi_out) {     // trace.h:30-88
+  ++n_trace_;
+  const BT *m1, *m2; int site;
+  bten_operands(LEFT, r, c + 1, m1, m2, site);
+  BT half = bten_step(bten_[LEFT].at((size_t)c), *m1, site_ref_idx(r * cols_ + c, idx, stride), *m2, LEFT);
+  reverse_dot(half, bten_at_slice(RIGHT, c), psi_out);
+  release(half);
+}
 // out[w] = sum over all indices of a[i0,i1,...] * b[...,i1,i0] (b has the reversed leg order of a)
 void Engine::reverse_dot(const BT &a, const BT &b, double *out) {
   const long n = a.n;
@@ -683,7 +713,186 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
   }
 }
 
+namespace {
+// std::mt19937 on the host, in the state layout of the device streams (624 words + index)
+struct HostMT {
+  uint32_t mt[624];
+  int idx;
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int k = 0; k < 624; ++k) {
+        uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+        mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = mt[idx++];
+    y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+    return y;
+  }
+  // std::uniform_real_distribution<long double>(a, b)(engine) of libstdc++: generate_canonical<long double, 64> takes
+  // two 32-bit draws, exact in the x87 significand
+  long double uniform(long double a, long double b) {
+    const long double x0 = (long double)next(), x1 = (long double)next();
+    long double u = (x0 + x1 * 4294967296.0L) / (4294967296.0L * 4294967296.0L);
+    if (u >= 1.0L) u = std::nextafter(1.0L, 0.0L);
+    return u * (b - a) + a;
+  }
+};
+// SuwaTodoStateUpdate (suwa_todo_update.h:53-113): geometric allocation on the cumulative weights, heaviest state first
+int suwa_todo(int init, std::vector<double> w, HostMT &rng) {
+  const int n = (int)w.size();
+  int imax = 0;
+  for (int i = 1; i < n; ++i) if (w[(size_t)i] > w[(size_t)imax]) imax = i;
+  if (imax != 0) std::swap(w[0], w[(size_t)imax]);
+  if (init == imax) init = 0; else if (init == 0) init = imax;
+  std::vector<long double> cum((size_t)n);
+  cum[0] = (long double)w[0];
+  for (int i = 1; i < n; ++i) cum[(size_t)i] = cum[(size_t)i - 1] + (long double)w[(size_t)i];
+  const long double total = cum.back();
+  long double start = (init == 0 ? 0.0L : cum[(size_t)init - 1]) + (long double)w[0];
+  if (start >= total) start -= total;
+  long double x = rng.uniform(start, std::nextafter(start + (long double)w[(size_t)init], start));
+  if (x >= total) x -= total;
+  int fin = (int)(std::upper_bound(cum.begin(), cum.end(), x) - cum.begin());
+  if (imax != 0) { if (fin == 0) fin = imax; else if (fin == imax) fin = 0; }
+  return fin;
+}
+}  // namespace
+
+void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
+  const int d = phys_, nst = d * d;
+  if (!idx_const_) {
+    idx_const_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)d * W_);
+    std::vector<int32_t> h((size_t)d * W_);
+    for (int s = 0; s < d; ++s) for (int w = 0; w < W_; ++w) h[(size_t)s * W_ + w] = s;
+    be_h2d(idx_const_, h.data(), sizeof(int32_t) * h.size());
+    psi_alt_ = (double *)be_malloc(sizeof(double) * (size_t)nst * W_);
+  }
+  std::vector<int32_t> cfg((size_t)W_ * nsites_), mtidx((size_t)W_);
+  std::vector<uint32_t> mt((size_t)W_ * 624);
+  std::vector<double> amp((size_t)W_), alt((size_t)nst * W_);
+  std::vector<HostMT> rng((size_t)W_);
+  be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
+  be_d2h(amp.data(), amp_, sizeof(double) * amp.size());
+  be_d2h(mt.data(), mt_, sizeof(uint32_t) * mt.size());
+  be_d2h(mtidx.data(), mtidx_, sizeof(int32_t) * mtidx.size());
+  for (int w = 0; w < W_; ++w) {
+    std::copy(mt.begin() + (size_t)w * 624, mt.begin() + (size_t)(w + 1) * 624, rng[(size_t)w].mt);
+    rng[(size_t)w].idx = mtidx[(size_t)w];
+  }
+  std::vector<int> accepted((size_t)W_);
+  auto bond = [&](int ra, int ca, int rb, int cb, int orient) {          // TwoSiteNNUpdateLocalImpl (:257-291)
+    const int s1 = ra * cols_ + ca, s2 = rb * cols_ + cb;
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b)
+        nn_trace_idx(ra, ca, rb, cb, orient, idx_const_ + (size_t)a * W_, idx_const_ + (size_t)b * W_, 1,
+                     psi_alt_ + (size_t)(a * d + b) * W_);
+    be_d2h(alt.data(), psi_alt_, sizeof(double) * alt.size());
+    bool any = false;
+    std::vector<double> wt((size_t)nst);
+    for (int w = 0; w < W_; ++w) {
+      int32_t *c = cfg.data() + (size_t)w * nsites_;
+      const int init = c[s1] * d + c[s2];
+      const double a0 = amp[(size_t)w];
+      for (int i = 0; i < nst; ++i) {
+        const double r = (i == init ? a0 : alt[(size_t)i * W_ + w]) / a0;
+        wt[(size_t)i] = r * r;                                           // std::norm(alternative_psi / amplitude)
+      }
+      const int fin = suwa_todo(init, wt, rng[(size_t)w]);
+      if (fin != init) {
+        c[s1] = fin / d; c[s2] = fin % d;
+        amp[(size_t)w] = alt[(size_t)fin * W_ + w];
+        ++accepted[(size_t)w];
+        any = true;
+      }
+    }
+    if (any) {
+      be_h2d(cfg_, cfg.data(), sizeof(int32_t) * cfg.size());
+      be_h2d(amp_, amp.data(), sizeof(double) * amp.size());
+    }
+    touch_site(s1); touch_site(s2);
+  };
+  for (int sw = 0; sw < nsweeps; ++sw) {                                  // square_nn_updater.h:29-81
+    std::fill(accepted.begin(), accepted.end(), 0);
+    generate_bmps_approach(UP);
+    for (int row = 0; row < rows_; ++row) {
+      init_bten(LEFT);
+      grow_full_bten(RIGHT, row, 2, true);
+      for (int col = 0; col < cols_ - 1; ++col) {
+        bond(row, col, row, col + 1, HORIZONTAL);
+        if (col < cols_ - 2) shift_bten_window(RIGHT);
+      }
+      if (row < rows_ - 1) shift_bmps_window(DOWN);
+    }
+    delete_inner_bmps(LEFT);
+    delete_inner_bmps(RIGHT);
+    generate_bmps_approach(LEFT);
+    for (int col = 0; col < cols_; ++col) {
+      init_bten(UP);
+      grow_full_bten(DOWN, col, 2, true);
+      for (int row = 0; row < rows_ - 1; ++row) {
+        bond(row, col, row + 1, col, VERTICAL);
+        if (row < rows_ - 2) shift_bten_window(DOWN);
+      }
+      if (col < cols_ - 1) shift_bmps_window(RIGHT);
+    }
+    delete_inner_bmps(UP);
+  }
+  for (int w = 0; w < W_; ++w) {
+    std::copy(rng[(size_t)w].mt, rng[(size_t)w].mt + 624, mt.begin() + (size_t)w * 624);
+    mtidx[(size_t)w] = rng[(size_t)w].idx;
+  }
+  be_h2d(mt_, mt.data(), sizeof(uint32_t) * mt.size());
+  be_h2d(mtidx_, mtidx.data(), sizeof(int32_t) * mtidx.size());
+  if (accept_rate_host) {
+    const double bond_num = (double)(cols_ * (rows_ - 1) + rows_ * (cols_ - 1));
+    for (int w = 0; w < W_; ++w) accept_rate_host[w] = accepted[(size_t)w] / bond_num;
+  }
+}
+
+void Engine::energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  // TransverseFieldIsingSquareOBC::CalEnergyAndHolesImplParsed (transverse_field_ising_square_obc.h:208-247)
+  if (phys_ != 2) throw std::invalid_argument("transverse-field Ising model needs phys = 2");
+  std::vector<int32_t> cfg((size_t)W_ * nsites_), flip((size_t)W_ * nsites_);
+  be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
+  std::vector<double> diag((size_t)W_);
+  for (int w = 0; w < W_; ++w) {                                          // CalDiagTermEnergy (:160-182)
+    const int32_t *c = cfg.data() + (size_t)w * nsites_;
+    double e = 0.0;
+    for (int r = 0; r < rows_; ++r) for (int cc = 0; cc < cols_ - 1; ++cc) e += (c[r * cols_ + cc] == c[r * cols_ + cc + 1]) ? -1 : 1;
+    for (int cc = 0; cc < cols_; ++cc) for (int r = 0; r < rows_ - 1; ++r) e += (c[r * cols_ + cc] == c[(r + 1) * cols_ + cc]) ? -1 : 1;
+    diag[(size_t)w] = e;
+  }
+  for (size_t i = 0; i < cfg.size(); ++i) flip[i] = 1 - cfg[i];
+  if (!idx_flip_) idx_flip_ = (int32_t *)be_malloc(sizeof(int32_t) * flip.size());
+  be_h2d(idx_flip_, flip.data(), sizeof(int32_t) * flip.size());
+  be_memset0(eloc_, sizeof(double) * W_);
+  int npsi = 0;
+  generate_bmps_approach(UP);
+  for (int row = 0; row < rows_; ++row) {
+    init_bten(LEFT);
+    grow_full_bten(RIGHT, row, 1, true);
+    nn_trace(row, 0, row, 1, HORIZONTAL, row * cols_, row * cols_ + 1, psi_row_);
+    if (psi_list_host) be_d2h(psi_list_host + (size_t)npsi * W_, psi_row_, sizeof(double) * W_);
+    ++npsi;
+    for (int col = 0; col < cols_; ++col) {
+      if (calc_holes) punch_hole(row, col, HORIZONTAL);
+      one_site_trace(row, col, idx_flip_ + row * cols_ + col, nsites_, psi_tmp_);      // :191-204
+      be_ratio_accumulate(psi_tmp_, psi_row_, -tfim_h_, eloc_, W_);
+      if (col < cols_ - 1) shift_bten_window(RIGHT);
+    }
+    if (row < rows_ - 1) shift_bmps_window(DOWN);
+  }
+  std::vector<double> e((size_t)W_);
+  be_d2h(e.data(), eloc_, sizeof(double) * W_);
+  for (int w = 0; w < W_; ++w) e[(size_t)w] += diag[(size_t)w];
+  be_h2d(eloc_, e.data(), sizeof(double) * W_);
+  if (eloc_host) std::copy(e.begin(), e.end(), eloc_host);
+}
+
 void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  if (tfim_) { energy_and_holes_tfim(calc_holes, eloc_host, psi_list_host); return; }
   // square_nnn_energy_solver.h:79-315 with has_nnn = false, model = SquareSpinOneHalfXXZModelMixIn
   be_memset0(eloc_, sizeof(double) * W_);
   int npsi = 0;

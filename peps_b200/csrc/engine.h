@@ -19,6 +19,7 @@
 #include "linalg.h"
 #include "tensor.h"
 #include <map>
+#include <stdexcept>
 
 namespace peps {
 
@@ -65,6 +66,13 @@ class Engine {
   void init_walkers();                                // contractor.Init + EvaluateAmplitude for all walkers
   void evaluate_amplitude();
   void sweep(int nsweeps, double *accept_rate_host);  // accept_rate_host[W] (last sweep), may be null
+  // MCUpdateSquareNNFullSpaceUpdateOBC (square_nn_updater.h:253-293): all phys^2 local states of a bond by batched
+  // ReplaceNNSiteTrace on the device, Suwa-Todo choice (long double prefix sums + one long double draw per bond,
+  // suwa_todo_update.h:53-113) on the host from the per-walker mt19937 streams
+  void sweep_full_space(int nsweeps, double *accept_rate_host);
+  // MonteCarloEngine::StepSweep with the configured updater (0 = NN exchange, 1 = NN full space)
+  void set_updater(int kind) { if (kind != 0 && kind != 1) throw std::invalid_argument("unknown updater"); updater_ = kind; }
+  void step_sweep(int nsweeps, double *accept_rate_host) { if (updater_ == 1) sweep_full_space(nsweeps, accept_rate_host); else sweep(nsweeps, accept_rate_host); }
   void energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host);
   void zero_accumulators();
   void accumulate_ostar();                            // uses holes/eloc/amplitude of the last energy_and_holes
@@ -84,6 +92,9 @@ class Engine {
   void set_deflation(double eps) { la_.deflation_eps = eps; touch_all(); }
   // SquareSpinOneHalfJ1J2XXZModelOBC couplings (model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113); 0 disables NNN
   void set_model_nnn(double jz2, double jxy2) { jz2_ = jz2; jxy2_ = jxy2; }
+  // TransverseFieldIsingSquareOBC(h) (model_solvers/transverse_field_ising_square_obc.h:28-247); phys must be 2
+  void set_model_tfim(double h) { tfim_ = true; tfim_h_ = h; }
+  void set_model_kind_xxz() { tfim_ = false; }
 
   // ---- probes used by the parity tests (per-walker values of reference contractor calls)
   int bmps_stack_size(int pos) const { return (int)bmps_[pos].size(); }
@@ -113,6 +124,11 @@ class Engine {
   // psi_out[w] = ReplaceNNSiteTrace(site_a, site_b, tensors sitps(site_a)[cfg(cfg_a)], sitps(site_b)[cfg(cfg_b)])
   void nn_trace(int ra, int ca, int rb, int cb, int orient, int cfg_site_a, int cfg_site_b, double *psi_out);
   void punch_hole(int r, int c, int orient);          // into the holes buffer
+  // psi_out[w] = ReplaceOneSiteTrace({r,c}, sitps({r,c})[idx[w*stride]], HORIZONTAL) (trace.h:30-88)
+  void one_site_trace(int r, int c, const int32_t *idx, int stride, double *psi_out);
+  // ReplaceNNSiteTrace with explicit physical indices (device arrays) instead of entries of the configuration
+  void nn_trace_idx(int ra, int ca, int rb, int cb, int orient, const int32_t *idx_a, const int32_t *idx_b, int stride,
+                    double *psi_out);
   // two-row environments and next-nearest-neighbour traces (init.h:130-186, grow.h:375-527, trace.h:207-281)
   void init_bten2(int pos);
   void grow_full_bten2(int pos, int slice1, int remain, bool init);
@@ -129,6 +145,8 @@ class Engine {
   void release(BMPSv &v);
   TRef ref(const BT &t) const;
   TRef site_ref(int site, int cfg_site) const;
+  TRef site_ref_idx(int site, const int32_t *idx, int stride) const;
+  void energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *psi_list_host);
   // structural-zero hints for contractions with an upper-trapezoidal R factor of the forward chain (backend.h GettDesc)
   struct KHints { const int32_t *klo_m = nullptr, *klo_n = nullptr; double work = 1.0; };
   // which: 0 = "apb,kea->ekpb" (hint on N = (e,k)), 1 = "ekpb,<site>->kofb" (hint on M = (k,b)), 2 = "kea,eaoj->koj" (M = k)
@@ -152,6 +170,12 @@ class Engine {
   int dmin_, dmax_;
   double terr_;
   double jz_ = 1.0, jxy_ = 1.0, h00_ = 0.0, jz2_ = 0.0, jxy2_ = 0.0;
+  int updater_ = 0;
+  bool tfim_ = false;
+  double tfim_h_ = 0.0;
+  int32_t *idx_const_ = nullptr;   // [phys][W]: idx_const_[s*W + w] = s
+  int32_t *idx_flip_ = nullptr;    // [W][nsites]: 1 - config
+  double *psi_alt_ = nullptr;      // [phys*phys][W]
   Pool pool_;
   Planner planner_;
   LinalgCtx la_;

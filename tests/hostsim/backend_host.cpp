@@ -397,6 +397,10 @@ void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const doubl
     if (ok) { c[s1] = c2; c[s2] = c1; amp[w] = pb; accepted[w] += 1; }
   }
 }
+void be_ratio_accumulate(const double *psi_ex, const double *psi, double coef, double *eloc, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) eloc[w] += coef * (psi_ex[w] * (1.0 / psi[w]));
+}
 void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const double *psi_ex, const double *psi,
                         double jz, double jxy, double *eloc, int W) {
   ++g_launches;

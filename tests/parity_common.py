@@ -18,8 +18,10 @@ def flat_holes(holes, rows, cols):
 
 
 def run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=1, signed=False, tol=1e-10, seeds0=100,
-                        check_configs=True, j2=0.0):
-    """Sweeps + energy + holes for W walkers through the C ABI vs the oracle, walker by walker."""
+                        check_configs=True, j2=0.0, tfim_h=None):
+    """Sweeps + energy + holes for W walkers through the C ABI vs the oracle, walker by walker.
+    tfim_h: transverse-field Ising model with the full-space (Suwa-Todo) updater instead of XXZ + exchange
+    (BASELINE config #1)."""
     tps, cfgs = make_case(rows, cols, D, W, seed, signed)
     tr = BMPSTruncateParams.SVD(*trunc)
     b = WalkerBatch(rows, cols, 2, D, W, tr, lib=lib)
@@ -29,10 +31,18 @@ def run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=1, signed=
     if j2 != 0.0:
         from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
         b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, j2, j2, 0.0))
+    if tfim_h is not None:
+        from peps_b200.api import TransverseFieldIsingSquareOBC, MCUpdateSquareNNFullSpaceUpdate
+        b.set_model(TransverseFieldIsingSquareOBC(tfim_h))
+        b.set_updater(MCUpdateSquareNNFullSpaceUpdate())
     b.init_walkers()
     ws = [vmc.Walker(tps, cfgs[w], trunc) for w in range(W)]
-    ups = [vmc.NNExchangeUpdater(seeds0 + w) for w in range(W)]
-    model = vmc.XXZModel(1.0, 1.0, 0.0, j2, j2)
+    if tfim_h is not None:
+        ups = [vmc.NNFullSpaceUpdater(seeds0 + w) for w in range(W)]
+        model = vmc.TFIMModel(tfim_h)
+    else:
+        ups = [vmc.NNExchangeUpdater(seeds0 + w) for w in range(W)]
+        model = vmc.XXZModel(1.0, 1.0, 0.0, j2, j2)
     amp0 = b.amplitudes()
     ref0 = np.array([w_.amplitude for w_ in ws])
     report = {"amp0": float(np.max(np.abs(amp0 / ref0 - 1)))}
@@ -55,7 +65,7 @@ def run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=1, signed=
             fh = flat_holes(hh, rows, cols)
             worst["eloc"] = max(worst["eloc"], abs(e[w] - ee) / max(1.0, abs(ee)))
             worst["hole"] = max(worst["hole"], float(np.max(np.abs(holes[w] - fh)) / np.max(np.abs(fh))))
-            worst["psi"] = max(worst["psi"], float(np.max(np.abs(psi[:, w] / np.array(pp) - 1))))
+            worst["psi"] = max(worst["psi"], float(np.max(np.abs(psi[:len(pp), w] / np.array(pp) - 1))))   # TFIM: rows only
         worst["amp"] = max(worst["amp"], float(np.max(np.abs(amp / ramp - 1))))
     report.update(worst)
     for k, v in worst.items():

@@ -135,6 +135,32 @@ def test_j1j2_pipeline_parity_gpu(lib, rows, cols, D, trunc, W):
     run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=1, j2=0.5)
 
 
+@pytest.mark.parametrize("rows,cols,D,trunc,W", [(4, 4, 4, (2, 8, 1e-14), 6), (3, 4, 3, (5, 5, 0.0), 3)])
+def test_tfim_full_space_pipeline_parity_gpu(lib, rows, cols, D, trunc, W):
+    """BASELINE config #1 (4x4, D=4, D_min=2, D_max=8, trunc_err=1e-14, h=0.5, full-space updater;
+    examples/transverse_field_ising_vmc_optimize.cpp:69-90): chains bit-identical to the oracle's (Suwa-Todo with the
+    reference's long double arithmetic), energies / holes / amplitudes to 1e-10."""
+    rep = run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, tfim_h=0.5)
+    print(rep)
+
+
+def test_tfim_golden_2x2_energy_gpu(lib):
+    """K4 (TFIM) on the GPU: exact summation over all 16 configurations of the reference's 2x2 simple-update fixture
+    reproduces the energy its test asserts (test_exact_summation_evaluator.cpp:775)."""
+    from helpers import load_golden_tps
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch, TransverseFieldIsingSquareOBC
+    tps, z = load_golden_tps("tfim2x2_double_su")
+    cfgs = np.array([[int(b) for b in format(k, "04b")] for k in range(16)]).reshape(16, 2, 2)
+    b = WalkerBatch(2, 2, 2, tps[0][0][0].shape[2], 16, BMPSTruncateParams.SVD(1, 8, 1e-16), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.set_model(TransverseFieldIsingSquareOBC(1.0))
+    b.init_walkers()
+    e = b.energy_and_holes(True)
+    wt = b.amplitudes() ** 2
+    assert abs(np.sum(wt * e) / np.sum(wt) - float(z["exp_energy"])) < 1e-10
+
+
 def test_gradient_parity_gpu(lib):
     run_gradient_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsamples=4)
 

@@ -41,6 +41,28 @@ def test_j1j2_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
     run_pipeline_parity(lib, rows, cols, D, 3, trunc, nsweeps=2, j2=0.5)
 
 
+@pytest.mark.parametrize("rows,cols,D,trunc", [(4, 4, 2, (2, 4, 1e-14)), (3, 4, 3, (5, 5, 0.0))])
+def test_tfim_full_space_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
+    """BASELINE config #1 path: transverse-field Ising solver (ReplaceOneSiteTrace per site) + full-space NN updater
+    with the Suwa-Todo choice (long double prefix sums, one long double draw per bond)."""
+    run_pipeline_parity(lib, rows, cols, D, 3, trunc, nsweeps=2, tfim_h=0.5)
+
+
+def test_tfim_golden_2x2_energy_through_abi(lib):
+    """K4 (TFIM) through the C ABI: exact summation over all 16 configurations of the 2x2 simple-update fixture."""
+    from peps_b200.api import TransverseFieldIsingSquareOBC
+    tps, z = load_golden_tps("tfim2x2_double_su")
+    cfgs = np.array([[int(b) for b in format(k, "04b")] for k in range(16)]).reshape(16, 2, 2)
+    b = WalkerBatch(2, 2, 2, tps[0][0][0].shape[2], 16, BMPSTruncateParams.SVD(1, 8, 1e-16), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.set_model(TransverseFieldIsingSquareOBC(1.0))
+    b.init_walkers()
+    e = b.energy_and_holes(True)
+    wt = b.amplitudes() ** 2
+    assert abs(np.sum(wt * e) / np.sum(wt) - float(z["exp_energy"])) < 1e-10
+
+
 def test_bmps_memo_is_exact_and_saves_one_stack_per_sample(lib, monkeypatch):
     """The LEFT stack finished by the sweep's vertical pass is handed back to the energy solver's vertical pass, and
     the DOWN stack consumed by the energy solver's horizontal pass to the next sweep, instead of being re-absorbed
@@ -117,6 +139,20 @@ def test_evaluator_mirror_runs(lib):
     assert res.energy_samples.shape == (4, 3)
     assert np.isfinite(res.energy) and np.isfinite(res.gradient_norm)
     assert res.gradient.pack().shape == tps.pack().shape
+
+
+def test_evaluator_mirror_tfim_full_space(lib):
+    """examples/transverse_field_ising_vmc_optimize.cpp-style evaluator: TFIM h = 0.5, full-space updater."""
+    from peps_b200.api import TransverseFieldIsingSquareOBC, MCUpdateSquareNNFullSpaceUpdate
+    tps = SplitIndexTPS(vmc.random_tps(3, 3, 2, 2, seed=9))
+    mc = MonteCarloParams(num_samples=12, num_warmup_sweeps=2, sweeps_between_samples=2,
+                          initial_config=Configuration(vmc.neel_config(3, 3)))
+    ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(2, 4, 1e-14), tps, TransverseFieldIsingSquareOBC(0.5),
+                               MCUpdateSquareNNFullSpaceUpdate(3), walkers=4, lib=lib)
+    res = ev.Evaluate()
+    assert res.energy_samples.shape == (4, 3)
+    assert np.isfinite(res.energy) and np.isfinite(res.gradient_norm)
+    assert not np.all(ev.batch.get_configs().sum(axis=(1, 2)) == 4)      # Sz is not conserved by this updater
 
 
 def test_error_paths(lib):
