@@ -95,6 +95,12 @@ int peps_set_updater(peps_ctx *ctx, int32_t kind);
 /* ModelEnergySolver::CalEnergyAndHoles<calchols> (algorithm/vmc_update/model_energy_solver.h:69-100 ->
  * model_solvers/base/square_nnn_energy_solver.h:79-315). eloc[W]; psi_list[(rows+cols)][W] may be NULL. */
 int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, double *psi_list);
+/* SquareNNNModelMeasurementSolver::EvaluateObservables for the XXZ / J1-J2 models
+ * (model_solvers/base/square_nnn_model_measurement_solver.h:33-214; registry keys energy, bond_energy_h,
+ * bond_energy_v, bond_energy_dr, bond_energy_ur; spin_z is config - 1/2 and needs no device work): the bond traversal
+ * of the energy solver without holes. Host outputs per walker, any may be NULL: energy[W], e_h[W][rows][cols-1],
+ * e_v[W][rows-1][cols], e_dr / e_ur[W][rows-1][cols-1]. */
+int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur);
 /* Hole tensors of the last call: [W][stride], per site (L,D,R,U) at the site's hole offset. */
 size_t peps_holes_stride(peps_ctx *ctx);
 int peps_get_holes(peps_ctx *ctx, double *holes);

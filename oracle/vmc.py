@@ -260,9 +260,24 @@ class XXZModel:
         """EvaluateTotalOnsiteEnergy (square_spin_onehalf_xxz_obc.h:131-135)."""
         return -self.pinning00 * (float(config[0, 0]) - 0.5)
 
-    def energy_and_holes(self, tps, w, calc_holes=True):
+    def measure(self, tps, w):
+        """SquareNNNModelMeasurementSolver::EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214):
+        the bond traversal of the energy solver without holes, every bond energy kept under its registry key."""
+        rows, cols = w.rows, w.cols
+        rec = {"h": np.zeros((rows, cols - 1)), "v": np.zeros((rows - 1, cols))}
+        if self.has_nnn:
+            rec["dr"] = np.zeros((rows - 1, cols - 1))
+            rec["ur"] = np.zeros((rows - 1, cols - 1))
+        e, _, _ = self.energy_and_holes(tps, w, False, rec=rec)
+        out = {"energy": e, "spin_z": w.config.astype(float) - 0.5,          # CalSpinSzImpl: config - 0.5
+               "bond_energy_h": rec["h"], "bond_energy_v": rec["v"]}
+        if self.has_nnn:
+            out["bond_energy_dr"], out["bond_energy_ur"] = rec["dr"], rec["ur"]
+        return out
+
+    def energy_and_holes(self, tps, w, calc_holes=True, rec=None):
         """CalEnergyAndHolesImpl (square_nnn_energy_solver.h:79-101) for has_nnn=false.
-        Returns (E_loc, holes[rows][cols] or None, psi_list)."""
+        Returns (E_loc, holes[rows][cols] or None, psi_list). rec: optional per-bond record (see measure)."""
         tn, c = w.tn, w.contractor
         rows, cols = w.rows, w.cols
         bond_e = []
@@ -286,6 +301,8 @@ class XXZModel:
                     s1, s2 = (row, col), (row, col + 1)
                     bond_e.append(self.bond_energy(s1, s2, int(w.config[s1]), int(w.config[s2]),
                                                    HORIZONTAL, w, tps, inv_psi))
+                    if rec is not None:
+                        rec["h"][row, col] = bond_e[-1]
                     c.shift_bten_window(tn, RIGHT)
             if self.has_nnn and row < rows - 1:               # square_nnn_energy_solver.h:203-265
                 c.init_bten2(tn, LEFT, row)
@@ -294,7 +311,10 @@ class XXZModel:
                     s1, s2 = (row, col), (row + 1, col + 1)
                     e_nnn = self.nnn_energy(s1, s2, int(w.config[s1]), int(w.config[s2]), 0, w, tps, inv_psi)
                     s1, s2 = (row + 1, col), (row, col + 1)
-                    e_nnn = e_nnn + self.nnn_energy(s1, s2, int(w.config[s1]), int(w.config[s2]), 1, w, tps, inv_psi)
+                    e_ur = self.nnn_energy(s1, s2, int(w.config[s1]), int(w.config[s2]), 1, w, tps, inv_psi)
+                    if rec is not None:
+                        rec["dr"][row, col], rec["ur"][row, col] = e_nnn, e_ur
+                    e_nnn = e_nnn + e_ur
                     bond_e.append(e_nnn)
                     c.shift_bten2_window(tn, RIGHT, row)
             if row < rows - 1:
@@ -313,6 +333,8 @@ class XXZModel:
                 s1, s2 = (row, col), (row + 1, col)
                 bond_e.append(self.bond_energy(s1, s2, int(w.config[s1]), int(w.config[s2]),
                                                VERTICAL, w, tps, inv_psi))
+                if rec is not None:
+                    rec["v"][row, col] = bond_e[-1]
                 if row < rows - 2:
                     c.shift_bten_window(tn, DOWN)
             if col < cols - 1:

@@ -296,6 +296,17 @@ class WalkerBatch:
         self._ck(self.lib.peps_energy_and_holes(self.h, int(calc_holes), _dp(e), _dp(psi) if want_psi else None))
         return (e, psi) if want_psi else e
 
+    def measure(self):
+        """One EvaluateObservables call for every walker (model_solvers/base/square_nnn_model_measurement_solver.h:
+        33-214): dict of per-walker arrays under the reference's registry keys."""
+        W, r, c = self.W, self.rows, self.cols
+        e = np.empty(W)
+        eh, ev = np.empty((W, r, c - 1)), np.empty((W, r - 1, c))
+        edr, eur = np.empty((W, r - 1, c - 1)), np.empty((W, r - 1, c - 1))
+        self._ck(self.lib.peps_measure(self.h, _dp(e), _dp(eh), _dp(ev), _dp(edr), _dp(eur)))
+        return {"energy": e, "spin_z": self.get_configs().astype(float) - 0.5, "bond_energy_h": eh, "bond_energy_v": ev,
+                "bond_energy_dr": edr, "bond_energy_ur": eur}
+
     def holes(self):
         n = self.lib.peps_holes_stride(self.h)
         a = np.empty((self.W, n))
@@ -379,6 +390,51 @@ class WalkerBatch:
 
 
 @dataclass
+class MCPEPSMeasurer:
+    """MCPEPSMeasurer (algorithm/vmc_update/monte_carlo_peps_measurer_impl.h:172-257): warm up, then per sample
+    `sweeps_between_samples` sweeps + EvaluateObservables; a walker plays the role of a rank: per-walker sample means,
+    then mean and standard error across walkers (GatherStatisticListOfData, monte_carlo_tools/statistics.h:288-339).
+    Built keys: energy, spin_z, bond_energy_h / _v / _dr / _ur (the S+S- row correlators are not part of this round)."""
+
+    def __init__(self, mc_params, trunc, tps, model, updater, walkers, device=0, lib=None):
+        rows, cols = tps.rows(), tps.cols()
+        self.mc = mc_params
+        self.batch = WalkerBatch(rows, cols, tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
+        self.batch.set_tps(tps)
+        self.batch.set_model(model)
+        self.batch.set_updater(updater)
+        self.batch.set_configs(np.broadcast_to(np.asarray(mc_params.initial_config.data, dtype=np.int32),
+                                               (walkers, rows, cols)).copy())
+        self.batch.seed_rng(np.arange(walkers, dtype=np.uint32) + np.uint32(updater.seed))
+        self.batch.init_walkers()
+        self.has_nnn = hasattr(model, "jz2") and (model.jz2 != 0.0 or model.jxy2 != 0.0)
+
+    def Execute(self):
+        b, W = self.batch, self.batch.W
+        if not self.mc.is_warmed_up:
+            for _ in range(self.mc.num_warmup_sweeps):
+                b.sweep(1)
+        nper = max(1, -(-self.mc.num_samples // W))
+        sums = None
+        for _ in range(nper):
+            b.sweep(self.mc.sweeps_between_samples)
+            obs = b.measure()
+            if sums is None:
+                sums = {k: np.zeros_like(v, dtype=float) for k, v in obs.items()}
+            for k, v in obs.items():
+                sums[k] += v
+        out = {}
+        for k, v in sums.items():
+            if k in ("bond_energy_dr", "bond_energy_ur") and not self.has_nnn:
+                continue
+            per_walker = v / nper
+            mean = per_walker.mean(axis=0)
+            err = (np.sqrt(((per_walker - mean) ** 2).sum(axis=0) / (W * (W - 1))) if W > 1
+                   else np.full(np.shape(mean), np.inf))
+            out[k] = (mean, err)
+        return out
+
+
 class EvaluateResult:
     """MCEnergyGradEvaluator::Result (mc_energy_grad_evaluator.h:66-75)."""
     energy: float

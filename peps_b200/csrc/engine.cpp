@@ -78,7 +78,7 @@ Engine::~Engine() {
   for (void *p : {(void *)tps_, (void *)osum_, (void *)eosum_, (void *)tps_off_d_, (void *)site_size_d_, (void *)hole_off_d_,
                   (void *)cfg_, (void *)amp_, (void *)mt_, (void *)mtidx_, (void *)accepted_, (void *)eloc_, (void *)psi_tmp_,
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
-                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_})
+                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_})
     be_free(p);
 }
 
@@ -911,7 +911,7 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
       if (col < cols_ - 1) {
         const int s1 = row * cols_ + col, s2 = s1 + 1;
         nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);
-        be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, eloc_, W_);
+        be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, bond_target(0, row, col), W_);
         shift_bten_window(RIGHT);
       }
     }
@@ -920,9 +920,11 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
       grow_full_bten2(RIGHT, row, 2, true);
       for (int col = 0; col < cols_ - 1; ++col) {
         nnn_trace(row, col, 0, psi_tmp_);                                            // (row,col) <-> (row+1,col+1)
-        be_xxz_bond_energy(cfg_, nsites_, row * cols_ + col, (row + 1) * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_, eloc_, W_);
+        be_xxz_bond_energy(cfg_, nsites_, row * cols_ + col, (row + 1) * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_,
+                           bond_target(2, row, col), W_);
         nnn_trace(row, col, 1, psi_tmp_);                                            // (row+1,col) <-> (row,col+1)
-        be_xxz_bond_energy(cfg_, nsites_, (row + 1) * cols_ + col, row * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_, eloc_, W_);
+        be_xxz_bond_energy(cfg_, nsites_, (row + 1) * cols_ + col, row * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_,
+                           bond_target(3, row, col), W_);
         shift_bten2_window(RIGHT, row);
       }
     }
@@ -937,7 +939,7 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
     for (int row = 0; row < rows_ - 1; ++row) {
       const int s1 = row * cols_ + col, s2 = s1 + cols_;
       nn_trace(row, col, row + 1, col, VERTICAL, s2, s1, psi_tmp_);
-      be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, eloc_, W_);
+      be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, bond_target(1, row, col), W_);
       if (row < rows_ - 2) shift_bten_window(DOWN);
     }
     if (col < cols_ - 1) shift_bmps_window(RIGHT);
@@ -946,6 +948,39 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
   if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
 }
 
+double *Engine::bond_target(int kind, int row, int col) {
+  if (!rec_bonds_) return eloc_;
+  const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1);
+  const int idx = kind == 0 ? row * (cols_ - 1) + col : kind == 1 ? nh + row * cols_ + col
+                : kind == 2 ? nh + nv + row * (cols_ - 1) + col : nh + nv + nd + row * (cols_ - 1) + col;
+  return bond_rec_ + (size_t)idx * W_;
+}
+void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur) {
+  if (tfim_) throw std::invalid_argument("measure: bond observables are defined for the XXZ / J1-J2 solvers");
+  const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1), nb = nh + nv + 2 * nd;
+  if (!bond_rec_) bond_rec_ = (double *)be_malloc(sizeof(double) * (size_t)nb * W_);
+  be_memset0(bond_rec_, sizeof(double) * (size_t)nb * W_);
+  rec_bonds_ = true;
+  std::vector<double> onsite((size_t)W_);
+  try {
+    energy_and_holes(false, onsite.data(), nullptr);      // with recording on, eloc_ only receives the on-site term
+  } catch (...) { rec_bonds_ = false; throw; }
+  rec_bonds_ = false;
+  std::vector<double> rec((size_t)nb * W_);
+  be_d2h(rec.data(), bond_rec_, sizeof(double) * rec.size());
+  auto scatter = [&](double *dst, int first, int count) {
+    if (!dst) return;
+    for (int w = 0; w < W_; ++w)
+      for (int i = 0; i < count; ++i) dst[(size_t)w * count + i] = rec[(size_t)(first + i) * W_ + w];
+  };
+  scatter(e_h, 0, nh); scatter(e_v, nh, nv); scatter(e_dr, nh + nv, nd); scatter(e_ur, nh + nv + nd, nd);
+  if (energy)
+    for (int w = 0; w < W_; ++w) {
+      double e = 0.0;
+      for (int i = 0; i < nb; ++i) e += rec[(size_t)i * W_ + w];
+      energy[w] = e + onsite[(size_t)w];
+    }
+}
 void Engine::zero_accumulators() {
   be_memset0(osum_, sizeof(double) * tps_total_);
   be_memset0(eosum_, sizeof(double) * tps_total_);

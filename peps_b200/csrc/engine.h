@@ -74,6 +74,10 @@ class Engine {
   void set_updater(int kind) { if (kind != 0 && kind != 1) throw std::invalid_argument("unknown updater"); updater_ = kind; }
   void step_sweep(int nsweeps, double *accept_rate_host) { if (updater_ == 1) sweep_full_space(nsweeps, accept_rate_host); else sweep(nsweeps, accept_rate_host); }
   void energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host);
+  // SquareNNNModelMeasurementSolver::EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214) for the
+  // XXZ / J1-J2 models: the bond traversal without holes, every bond energy kept. Host outputs (any may be null):
+  // energy[W], e_h[W][rows][cols-1], e_v[W][rows-1][cols], e_dr / e_ur[W][rows-1][cols-1] (zeros without NNN terms).
+  void measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur);
   void zero_accumulators();
   void accumulate_ostar();                            // uses holes/eloc/amplitude of the last energy_and_holes
   void get_accumulators(double *osum_host, double *eosum_host);
@@ -171,6 +175,9 @@ class Engine {
   double terr_;
   double jz_ = 1.0, jxy_ = 1.0, h00_ = 0.0, jz2_ = 0.0, jxy2_ = 0.0;
   int updater_ = 0;
+  double *bond_rec_ = nullptr;     // [n_h + n_v + 2 n_d][W] per-bond energies of the last measure()
+  bool rec_bonds_ = false;
+  double *bond_target(int kind, int row, int col);   // where a bond energy is accumulated (eloc_ unless recording)
   bool tfim_ = false;
   double tfim_h_ = 0.0;
   int32_t *idx_const_ = nullptr;   // [phys][W]: idx_const_[s*W + w] = s

@@ -161,6 +161,28 @@ def test_tfim_golden_2x2_energy_gpu(lib):
     assert abs(np.sum(wt * e) / np.sum(wt) - float(z["exp_energy"])) < 1e-10
 
 
+@pytest.mark.parametrize("j2", [0.0, 0.5])
+def test_measure_bond_energies_parity_gpu(lib, j2):
+    """EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214) on the GPU: every bond energy
+    (horizontal, vertical, both diagonals) against the oracle's measurement restatement."""
+    from oracle import vmc
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch, SquareSpinOneHalfJ1J2XXZModelOBC
+    rows, cols, D, W = 4, 5, 3, 3
+    tps = vmc.random_tps(rows, cols, 2, D, seed=31)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 70 + w) for w in range(W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(6, 6, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 0.8, j2, 0.7 * j2, 0.3))
+    b.init_walkers()
+    obs = b.measure()
+    model = vmc.XXZModel(1.0, 0.8, 0.3, j2, 0.7 * j2)
+    for w in range(W):
+        ref = model.measure(tps, vmc.Walker(tps, cfgs[w], (6, 6, 0.0)))
+        for k, v in ref.items():
+            assert np.allclose(obs[k][w], v, rtol=1e-10, atol=1e-12), (k, w)
+
+
 def test_gradient_parity_gpu(lib):
     run_gradient_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsamples=4)
 

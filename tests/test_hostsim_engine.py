@@ -155,6 +155,48 @@ def test_evaluator_mirror_tfim_full_space(lib):
     assert not np.all(ev.batch.get_configs().sum(axis=(1, 2)) == 4)      # Sz is not conserved by this updater
 
 
+@pytest.mark.parametrize("j2", [0.0, 0.5])
+def test_measure_bond_energies_parity_hostsim(lib, j2):
+    """EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214): every bond energy against the oracle."""
+    from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
+    rows, cols, D, W = 3, 4, 2, 3
+    tps = vmc.random_tps(rows, cols, 2, D, seed=31)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 70 + w) for w in range(W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 0.8, j2, 0.7 * j2, 0.3))
+    b.init_walkers()
+    obs = b.measure()
+    model = vmc.XXZModel(1.0, 0.8, 0.3, j2, 0.7 * j2)
+    for w in range(W):
+        ref = model.measure(tps, vmc.Walker(tps, cfgs[w], (4, 4, 0.0)))
+        for k, v in ref.items():
+            assert np.allclose(obs[k][w], v, rtol=1e-10, atol=1e-12), (k, w)
+    e = b.energy_and_holes(False)
+    assert np.allclose(e, obs["energy"], rtol=1e-12)          # the recording pass leaves the energy path untouched
+
+
+def test_measurer_mirror_on_golden_4x4(lib):
+    """MCPEPSMeasurer on the reference's 4x4 D=8 Heisenberg fixture (slow_tests/test_boson_mc_peps_measure.cpp:31-76):
+    energy near e0 = -9.18912 and nearest-neighbour bond energies near the ED <S_i.S_j> of the reference's
+    ed_reference table (corner bond -0.4618, tests/test_data/ed_reference/square_heisenberg_4x4_obc_ed.json)."""
+    from peps_b200.api import MCPEPSMeasurer
+    tps, z = load_golden_tps("heis4x4_D8_double")
+    mc = MonteCarloParams(num_samples=48, num_warmup_sweeps=3, sweeps_between_samples=1,
+                          initial_config=Configuration(z["configs"][0]))
+    m = MCPEPSMeasurer(mc, BMPSTruncateParams.SVD(8, 8, 0.0), SplitIndexTPS(tps), SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                       MCUpdateSquareNNExchange(11), walkers=8, lib=lib)
+    out = m.Execute()
+    e, err = out["energy"]
+    assert abs(e - float(z["exp_e0_state"])) < max(5 * err, 0.4)
+    eh = out["bond_energy_h"][0]
+    assert eh.shape == (4, 3) and abs(eh[0, 0] - (-0.4618)) < 0.25
+    assert abs(eh.sum() + out["bond_energy_v"][0].sum() - e) < 1e-9
+    assert np.allclose(out["spin_z"][0].sum(), 0.0)
+    assert "bond_energy_dr" not in out
+
+
 def test_error_paths(lib):
     with pytest.raises(PepsError):
         WalkerBatch(1, 4, 2, 2, 1, BMPSTruncateParams.SVD(2, 2, 0.0), lib=lib)     # lattice too small
