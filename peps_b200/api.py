@@ -389,7 +389,6 @@ class WalkerBatch:
         return self.lib.peps_ostar_sum_device(self.h), self.lib.peps_eloc_ostar_sum_device(self.h)
 
 
-@dataclass
 class MCPEPSMeasurer:
     """MCPEPSMeasurer (algorithm/vmc_update/monte_carlo_peps_measurer_impl.h:172-257): warm up, then per sample
     `sweeps_between_samples` sweeps + EvaluateObservables; a walker plays the role of a rank: per-walker sample means,
@@ -435,6 +434,7 @@ class MCPEPSMeasurer:
         return out
 
 
+@dataclass
 class EvaluateResult:
     """MCEnergyGradEvaluator::Result (mc_energy_grad_evaluator.h:66-75)."""
     energy: float
