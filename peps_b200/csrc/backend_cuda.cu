@@ -506,8 +506,8 @@ __device__ long long g_panel_clk[8 + 32 * 8];
 #define PANEL_CLK(i) do { } while (0)
 #define COL_CLK(j, k) do { } while (0)
 #endif
-template <int NBW, int RPL>
-__global__ void __launch_bounds__(PQR_THREADS, 1) panel_qr_reg_kernel(PanelArgs a) {
+template <int NBW, int RPL, int MINB>
+__global__ void __launch_bounds__(PQR_THREADS, MINB) panel_qr_reg_kernel(PanelArgs a) {
   extern __shared__ double sm[];
   PANEL_CLK(0);
   constexpr int CPW = NBW / 8;
@@ -767,11 +767,12 @@ void be_panel_qr(const PanelArgs &a) {
   };
   static size_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, cg = 0;
   const int R = a.R;
-  if (a.nbw == 32 && R <= 256) launch_reg(panel_qr_reg_kernel<32, 8>, panel_reg_smem_bytes<32, 8>(R), c0);
-  else if (a.nbw == 32 && R <= 512) launch_reg(panel_qr_reg_kernel<32, 16>, panel_reg_smem_bytes<32, 16>(R), c4);
-  else if (a.nbw == 32 && R <= 576) launch_reg(panel_qr_reg_kernel<32, 18>, panel_reg_smem_bytes<32, 18>(R), c1);
-  else if (a.nbw == 16 && R <= 512) launch_reg(panel_qr_reg_kernel<16, 16>, panel_reg_smem_bytes<16, 16>(R), c2);
-  else if (a.nbw == 16 && R <= 1184) launch_reg(panel_qr_reg_kernel<16, 37>, panel_reg_smem_bytes<16, 37>(R), c3);
+  // panels of <= 256 rows: 64 KB tile and <= 128 registers, two CTAs share an SM and hide each other's reflector chain
+  if (a.nbw == 32 && R <= 256) launch_reg(panel_qr_reg_kernel<32, 8, 2>, panel_reg_smem_bytes<32, 8>(R), c0);
+  else if (a.nbw == 32 && R <= 512) launch_reg(panel_qr_reg_kernel<32, 16, 1>, panel_reg_smem_bytes<32, 16>(R), c4);
+  else if (a.nbw == 32 && R <= 576) launch_reg(panel_qr_reg_kernel<32, 18, 1>, panel_reg_smem_bytes<32, 18>(R), c1);
+  else if (a.nbw == 16 && R <= 512) launch_reg(panel_qr_reg_kernel<16, 16, 1>, panel_reg_smem_bytes<16, 16>(R), c2);
+  else if (a.nbw == 16 && R <= 1184) launch_reg(panel_qr_reg_kernel<16, 37, 1>, panel_reg_smem_bytes<16, 37>(R), c3);
   else {
     size_t smem = panel_smem_bytes(a.R, a.nbw);
     if (smem > cg) {
@@ -829,8 +830,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                    (unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-template <int NBW>
-__global__ void __launch_bounds__(256, 1) apply_reflector_kernel(ApplyArgs a) {
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"((unsigned)__cvta_generic_to_shared(src)),
+               "r"(bytes) : "memory");
+}
+
+template <int NBW, int MINB>
+__global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a) {
   extern __shared__ __align__(16) double sm[];
   APPLY_CLK(0);
   constexpr int TN = NBW, MT = NBW / 8, NT = NBW / 8, LDC = TN + 4, LDW = TN + 4, NTILE = MT * NT;
@@ -1061,10 +1067,12 @@ void be_apply_reflector(const ApplyArgs &a) {
     }
     kern<<<dim3((a.ntrail + tn - 1) / tn, a.NI, a.W), 256, smem, g_stream>>>(a);
   };
-  static size_t c32 = 0, c16 = 0, c8 = 0;
-  if (a.nbw == 32) launch(apply_reflector_kernel<32>, apply_smem_bytes<32>(a.R), c32, 32);
-  else if (a.nbw == 16) launch(apply_reflector_kernel<16>, apply_smem_bytes<16>(a.R), c16, 16);
-  else if (a.nbw == 8) launch(apply_reflector_kernel<8>, apply_smem_bytes<8>(a.R), c8, 8);
+  static size_t c32 = 0, c32b = 0, c16 = 0, c8 = 0;
+  // row blocks of <= 256 rows: the resident tile is <= 112 KB, two CTAs share an SM and overlap load / DMMA / store
+  if (a.nbw == 32 && apply_smem_bytes<32>(a.R) <= 112 * 1024) launch(apply_reflector_kernel<32, 2>, apply_smem_bytes<32>(a.R), c32b, 32);
+  else if (a.nbw == 32) launch(apply_reflector_kernel<32, 1>, apply_smem_bytes<32>(a.R), c32, 32);
+  else if (a.nbw == 16) launch(apply_reflector_kernel<16, 1>, apply_smem_bytes<16>(a.R), c16, 16);
+  else if (a.nbw == 8) launch(apply_reflector_kernel<8, 1>, apply_smem_bytes<8>(a.R), c8, 8);
   else throw std::runtime_error("be_apply_reflector: unsupported panel width");
   post_launch();
 #ifdef PEPS_KERNEL_CLOCKS
@@ -1155,7 +1163,7 @@ __device__ long long g_jac_clk[32];
 #endif
 template <int N2>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) double sm[];
   JAC_CLK(0);
   constexpr int T2 = N2 / 8;
   constexpr int NT = T2 * (T2 + 1) / 2;
@@ -1190,16 +1198,22 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
       for (int q = p; q < T2; ++q) { if (idx == t) { tile_p[t] = p; tile_q[t] = q; } ++idx; }
   }
   JAC_CLK(1);
-  // 1. load the two row blocks (zero padded columns)
-  if ((nc & 1) == 0) {
-    const int nv = nc >> 1;
-    for (int r = warp; r < N2; r += nwarp) {
-      const int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
-      const double2 *src = reinterpret_cast<const double2 *>(Gw + (long)grow * a.ld);
-      double2 *dst = reinterpret_cast<double2 *>(Ps + (size_t)r * LDS);
-      for (int c = lane; c < nv; c += 32) dst[c] = src[c];
-      for (int c = nc + lane; c < LDS; c += 32) Ps[(size_t)r * LDS + c] = 0.0;
+  // 1. load the two row blocks (zero padded columns): one bulk copy (TMA) per row when the rows are 16-byte granular
+  const bool wide = ((nc & 1) == 0) && ((a.ld & 1) == 0) && ((a.ws & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.G) & 15) == 0);
+  __shared__ uint64_t ld_bar;
+  if (wide) {
+    if (t == 0) {
+      mbar_init(&ld_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      mbar_expect_tx(&ld_bar, (unsigned)(N2 * nc * 8));
     }
+    __syncthreads();
+    if (t < N2) {
+      const int grow = (t < bs) ? lo * bs + t : hi * bs + (t - bs);
+      bulk_g2s(Ps + (size_t)t * LDS, Gw + (long)grow * a.ld, (unsigned)(nc * 8), &ld_bar);
+    }
+    for (int e = t; e < N2 * (LDS - nc); e += JAC_THREADS) Ps[(size_t)(e / (LDS - nc)) * LDS + nc + e % (LDS - nc)] = 0.0;
+    mbar_wait(&ld_bar, 0);
   } else {
     for (int r = warp; r < N2; r += nwarp) {
       const int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
@@ -1397,14 +1411,15 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
   __syncthreads();
   JAC_CLK(7);
 
-  // 7. store
-  if ((nc & 1) == 0) {
-    const int nv = nc >> 1;
-    for (int r = warp; r < N2; r += nwarp) {
-      const int grow = (r < bs) ? lo * bs + r : hi * bs + (r - bs);
-      double2 *dst = reinterpret_cast<double2 *>(Gw + (long)grow * a.ld);
-      const double2 *src = reinterpret_cast<const double2 *>(Ps + (size_t)r * LDS);
-      for (int c = lane; c < nv; c += 32) dst[c] = src[c];
+  // 7. store (bulk copies straight out of shared memory; the CTA waits until its tile has been read)
+  if (wide) {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    __syncthreads();
+    if (t < N2) {
+      const int grow = (t < bs) ? lo * bs + t : hi * bs + (t - bs);
+      bulk_s2g(Gw + (long)grow * a.ld, Ps + (size_t)t * LDS, (unsigned)(nc * 8));
+      asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
     }
   } else {
     for (int r = warp; r < N2; r += nwarp) {

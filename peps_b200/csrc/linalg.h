@@ -39,21 +39,30 @@ struct QRLayout { int nb = 0, rb = 0, nrb = 0, m_pad = 0; };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-inline QRLayout qr_layout(int m, int n) {
-  QRLayout L;
-  const int kk = std::min(m, n);
-  for (int nb : {32, 16, 8}) {
-    int rbmax = (int)(kPanelSmemBudget / (sizeof(double) * nb)) / nb * nb;
-    if (nb == 8) rbmax = 1536;       // keeps the fused trailing-update tile (rows x 12 doubles) inside shared memory
-    int need = round_up(kk, nb);
-    if (need > rbmax && nb != 8) continue;
-    if (need > rbmax) throw std::runtime_error("qr_layout: matrix too large for the shared-memory panel");
-    int rb0 = std::min(rbmax, round_up(m, nb));
-    int nrb = (m + rb0 - 1) / rb0;
-    int rb = std::max(need, round_up((m + nrb - 1) / nrb, nb));
-    L.nb = nb; L.rb = rb; L.nrb = (m + rb - 1) / rb; L.m_pad = L.nrb * rb;
-    return L;
+// Preferred row-block height of the CAQR flat tree (PEPS_QR_RB overrides; multiple of 32). Blocks of 256 rows keep the
+// resident tiles of the panel and trailing-update kernels small enough for two CTAs per SM.
+inline int qr_pref_rb() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = std::getenv("PEPS_QR_RB");
+    v = e ? std::atoi(e) : 512;
+    if (v < 32 || v % 32 != 0) v = 512;
   }
+  return v;
+}
+
+inline QRLayout qr_layout(int m, int n) {
+  (void)n;
+  QRLayout L;
+  const int nb = 32;
+  const int rbmax = (int)(kPanelSmemBudget / (sizeof(double) * nb)) / nb * nb;     // 576 rows: the register panel kernel
+  int rb0 = std::min(std::min(rbmax, round_up(m, nb)), std::max(nb, qr_pref_rb() / nb * nb));
+  int nrb = (m + rb0 - 1) / rb0;
+  const int nrb_max = rbmax / nb;               // the stacked stage-2 panel (nrb * nb rows) must fit the same kernel
+  if (nrb > nrb_max) nrb = nrb_max;
+  int rb = round_up((m + nrb - 1) / nrb, nb);
+  if (rb > rbmax) throw std::runtime_error("qr_layout: matrix too tall for a two-stage CAQR (needs a deeper tree)");
+  L.nb = nb; L.rb = rb; L.nrb = (m + rb - 1) / rb; L.m_pad = L.nrb * rb;
   return L;
 }
 
@@ -92,22 +101,25 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
   const int npanel = (kk + nb - 1) / nb;
   for (int p = 0; p < npanel; ++p) {
     const int col0 = p * nb, pw = std::min(nb, kk - col0), c1 = col0 + pw, ntrail = n - c1;
+    // row blocks above the one holding the diagonal are finished; the diagonal block skips its rows above col0
+    const int b0 = col0 / rb, nact = nrb - b0;
     PanelArgs pa;
-    pa.A = A; pa.ws = ws; pa.lda = lda; pa.rowtab = rowtab1_d; pa.R = rb; pa.skip0 = col0; pa.NI = nrb;
+    pa.A = A; pa.ws = ws; pa.lda = lda; pa.rowtab = rowtab1_d + (size_t)b0 * rb; pa.R = rb; pa.skip0 = col0 - b0 * rb; pa.NI = nact;
     pa.col0 = col0; pa.pw = pw; pa.nbw = nb; pa.Vw = Vw; pa.Tw = Tw; pa.W = W;
     be_panel_qr(pa);
     if (ntrail > 0) {
       ApplyArgs ap;
-      ap.A = A; ap.ws = ws; ap.lda = lda; ap.rowtab = rowtab1_d; ap.R = rb; ap.NI = nrb; ap.col1 = c1; ap.ntrail = ntrail;
+      ap.A = A; ap.ws = ws; ap.lda = lda; ap.rowtab = pa.rowtab; ap.R = rb; ap.NI = nact; ap.col1 = c1; ap.ntrail = ntrail;
       ap.nbw = nb; ap.Vw = Vw; ap.Tw = Tw; ap.W = W;
       be_apply_reflector(ap);
     }
-    if (nrb > 1) {
-      // stage 2: stack the nrb local R blocks and factorise them; update the same rows of the trailing matrix
-      const int R2 = nrb * pw;
+    if (nact > 1) {
+      // stage 2: stack the local R blocks of the active row blocks and factorise them; update the same rows of the
+      // trailing matrix
+      const int R2 = nact * pw;
       std::vector<int32_t> rowtab2((size_t)R2);
-      for (int b = 0; b < nrb; ++b)
-        for (int i = 0; i < pw; ++i) rowtab2[(size_t)b * pw + i] = b * rb + (b == 0 ? col0 : 0) + i;
+      for (int b = 0; b < nact; ++b)
+        for (int i = 0; i < pw; ++i) rowtab2[(size_t)b * pw + i] = (b0 + b) * rb + (b == 0 ? pa.skip0 : 0) + i;
       PanelArgs p2 = pa;
       p2.rowtab = pl.upload(rowtab2); p2.R = R2; p2.skip0 = 0; p2.NI = 1;
       be_panel_qr(p2);

@@ -218,3 +218,34 @@ def test_rng_state_roundtrip_matches_std_mt19937(lib):
     b.set_rng_state(mt, idx)
     mt2, idx2 = b.get_rng_state()
     assert np.array_equal(mt, mt2) and np.array_equal(idx, idx2)
+
+
+@pytest.mark.parametrize("rb", ["32", "64", "512"])
+def test_caqr_host_logic_with_diagonal_crossing_row_blocks(rb):
+    """linalg.h:caqr with row blocks shorter than the matrix is wide (the diagonal walks through several blocks; blocks
+    above it are finished and skipped): R^T R = A^T A and the LAPACK diagonal, through the host simulation.
+    Run in a subprocess because the block height is read once per process (PEPS_QR_RB)."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, ctypes as C, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        import hostsim_lib
+        lib = hostsim_lib.load()
+        dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+        rng = np.random.default_rng(5)
+        for (m, n) in [(200, 96), (96, 96), (70, 130), (300, 40)]:
+            W = 2
+            a = rng.standard_normal((W, m, n)); kk = min(m, n); r = np.empty((W, kk, n))
+            assert lib.peps_test_qr_r(0, W, m, n, dp(a), dp(r)) == 0
+            for w in range(W):
+                assert np.max(np.abs(np.tril(r[w][:, :kk], -1))) == 0.0
+                ref = a[w].T @ a[w]
+                assert np.max(np.abs(r[w].T @ r[w] - ref)) < 1e-12 * np.max(np.abs(ref)), (m, n)
+                rr = np.linalg.qr(a[w], mode="r")
+                assert np.max(np.abs(np.abs(np.diag(r[w])) - np.abs(np.diag(rr)))) < 1e-11 * np.max(np.abs(rr))
+        print("ok")
+    """) % (hostsim_lib.ROOT, hostsim_lib.ROOT + "/tests")
+    import os
+    env = dict(os.environ, PEPS_QR_RB=rb)
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
