@@ -99,8 +99,11 @@ int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, doubl
  * (model_solvers/base/square_nnn_model_measurement_solver.h:33-214; registry keys energy, bond_energy_h,
  * bond_energy_v, bond_energy_dr, bond_energy_ur; spin_z is config - 1/2 and needs no device work): the bond traversal
  * of the energy solver without holes. Host outputs per walker, any may be NULL: energy[W], e_h[W][rows][cols-1],
- * e_v[W][rows-1][cols], e_dr / e_ur[W][rows-1][cols-1]. */
-int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur);
+ * e_v[W][rows-1][cols], e_dr / e_ur[W][rows-1][cols-1], and row_corr[W][cols/2] = the off-diagonal correlator of
+ * MeasureSpinOneHalfOffDiagOrderInRow (model_solvers/square_spin_onehalf_xxz_obc.h:22-60) on row rows/2 from site
+ * (rows/2, cols/4): conj(psi(both spins flipped) / psi), 0 for equal spins (registry keys SmSp_row / SpSm_row by the
+ * spin at the first site, :264-291). */
+int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr);
 /* Hole tensors of the last call: [W][stride], per site (L,D,R,U) at the site's hole offset. */
 size_t peps_holes_stride(peps_ctx *ctx);
 int peps_get_holes(peps_ctx *ctx, double *holes);

@@ -268,12 +268,47 @@ class XXZModel:
         if self.has_nnn:
             rec["dr"] = np.zeros((rows - 1, cols - 1))
             rec["ur"] = np.zeros((rows - 1, cols - 1))
+        rec["row_corr"] = None
         e, _, _ = self.energy_and_holes(tps, w, False, rec=rec)
         out = {"energy": e, "spin_z": w.config.astype(float) - 0.5,          # CalSpinSzImpl: config - 0.5
                "bond_energy_h": rec["h"], "bond_energy_v": rec["v"]}
         if self.has_nnn:
             out["bond_energy_dr"], out["bond_energy_ur"] = rec["dr"], rec["ur"]
+        # EvaluateOffDiagOrderInRow (square_spin_onehalf_xxz_obc.h:264-291): channel split by the spin at (ly/2, lx/4)
+        corr = np.array(rec["row_corr"])
+        zero = np.zeros_like(corr)
+        if int(w.config[rows // 2, cols // 4]) == 0:
+            out["SpSm_row"], out["SmSp_row"] = corr, zero
+        else:
+            out["SmSp_row"], out["SpSm_row"] = corr, zero
+        sz = (w.config.astype(float) - 0.5).ravel()                           # SzSz_all2all, packed i <= j (:226-236)
+        out["SzSz_all2all"] = np.array([sz[i] * sz[j] for i in range(sz.size) for j in range(i, sz.size)])
         return out
+
+    def _row_corr(self, tps, w, row, inv_psi):
+        """MeasureSpinOneHalfOffDiagOrderInRow (square_spin_onehalf_xxz_obc.h:22-60): flip (row, lx/4), walk right,
+        one ReplaceOneSiteTrace per site whose spin differs. Leaves the tensor network as it found it."""
+        tn, c = w.tn, w.contractor
+        lx = w.cols
+        s1 = (row, lx // 4)
+        c1 = int(w.config[s1])
+        tn[s1[0]][s1[1]] = tps[s1[0]][s1[1]][1 - c1]
+        c.erase_envs_after_update(s1)
+        c.grow_bten_step(tn, LEFT)
+        c.grow_full_bten(tn, RIGHT, row, lx // 4 + 2, False)
+        vals = []
+        for i in range(1, lx // 2 + 1):
+            s2 = (row, lx // 4 + i)
+            c2 = int(w.config[s2])
+            if c2 == c1:
+                vals.append(0.0)
+            else:
+                psi_ex = c.replace_one_site_trace(tn, s2, tps[s2[0]][s2[1]][1 - c2], HORIZONTAL)
+                vals.append(np.conj(psi_ex * inv_psi))
+            c.shift_bten_window(tn, RIGHT)
+        tn[s1[0]][s1[1]] = tps[s1[0]][s1[1]][c1]
+        c.erase_envs_after_update(s1)
+        return vals
 
     def energy_and_holes(self, tps, w, calc_holes=True, rec=None):
         """CalEnergyAndHolesImpl (square_nnn_energy_solver.h:79-101) for has_nnn=false.
@@ -317,6 +352,8 @@ class XXZModel:
                     e_nnn = e_nnn + e_ur
                     bond_e.append(e_nnn)
                     c.shift_bten2_window(tn, RIGHT, row)
+            if rec is not None and "row_corr" in rec and row == rows // 2:      # bond_traversal_mixin.h:96-98
+                rec["row_corr"] = self._row_corr(tps, w, row, inv_psi)
             if row < rows - 1:
                 c.shift_bmps_window(tn, DOWN)
         # vertical pass (bond_traversal_mixin.h:112-143)

@@ -303,9 +303,17 @@ class WalkerBatch:
         e = np.empty(W)
         eh, ev = np.empty((W, r, c - 1)), np.empty((W, r - 1, c))
         edr, eur = np.empty((W, r - 1, c - 1)), np.empty((W, r - 1, c - 1))
-        self._ck(self.lib.peps_measure(self.h, _dp(e), _dp(eh), _dp(ev), _dp(edr), _dp(eur)))
-        return {"energy": e, "spin_z": self.get_configs().astype(float) - 0.5, "bond_energy_h": eh, "bond_energy_v": ev,
-                "bond_energy_dr": edr, "bond_energy_ur": eur}
+        corr = np.empty((W, c // 2))
+        self._ck(self.lib.peps_measure(self.h, _dp(e), _dp(eh), _dp(ev), _dp(edr), _dp(eur), _dp(corr)))
+        cfg = self.get_configs()
+        sz = cfg.astype(float) - 0.5
+        first_down = (cfg[:, r // 2, c // 4] == 0)[:, None]          # EvaluateOffDiagOrderInRow channel split (:281-287)
+        flat = sz.reshape(W, -1)
+        iu = np.triu_indices(flat.shape[1])
+        return {"energy": e, "spin_z": sz, "bond_energy_h": eh, "bond_energy_v": ev,
+                "bond_energy_dr": edr, "bond_energy_ur": eur,
+                "SmSp_row": np.where(first_down, 0.0, corr), "SpSm_row": np.where(first_down, corr, 0.0),
+                "SzSz_all2all": flat[:, iu[0]] * flat[:, iu[1]]}
 
     def holes(self):
         n = self.lib.peps_holes_stride(self.h)
@@ -393,7 +401,8 @@ class MCPEPSMeasurer:
     """MCPEPSMeasurer (algorithm/vmc_update/monte_carlo_peps_measurer_impl.h:172-257): warm up, then per sample
     `sweeps_between_samples` sweeps + EvaluateObservables; a walker plays the role of a rank: per-walker sample means,
     then mean and standard error across walkers (GatherStatisticListOfData, monte_carlo_tools/statistics.h:288-339).
-    Built keys: energy, spin_z, bond_energy_h / _v / _dr / _ur (the S+S- row correlators are not part of this round)."""
+    Built keys: energy, spin_z, bond_energy_h / _v / _dr / _ur, SmSp_row / SpSm_row, SzSz_all2all (the structure-factor
+    mixin is not part of this round)."""
 
     def __init__(self, mc_params, trunc, tps, model, updater, walkers, device=0, lib=None):
         rows, cols = tps.rows(), tps.cols()

@@ -107,8 +107,8 @@ int peps_sweep_full_space(peps_ctx *ctx, int32_t n, double *acc) { GUARD(ctx, ct
 int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, double *psi_list) {
   GUARD(ctx, ctx->eng->energy_and_holes(calc_holes != 0, eloc, psi_list))
 }
-int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur) {
-  GUARD(ctx, ctx->eng->measure(energy, e_h, e_v, e_dr, e_ur))
+int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr) {
+  GUARD(ctx, ctx->eng->measure(energy, e_h, e_v, e_dr, e_ur, row_corr))
 }
 size_t peps_holes_stride(peps_ctx *ctx) { return (size_t)ctx->eng->holes_stride(); }
 int peps_get_holes(peps_ctx *ctx, double *h) { GUARD(ctx, ctx->eng->get_holes(h)) }

@@ -488,14 +488,14 @@ void Engine::grow_full_bten(int pos, int slice, int remain, bool init) {     // 
   for (int i = (int)bten_[pos].size() - 1; i < n - remain; ++i) {
     const BT *m1, *m2; int site;
     bten_operands(pos, slice, i + 1, m1, m2, site);
-    bten_[pos].push_back(bten_step(bten_[pos].back(), *m1, site_ref(site, site), *m2, pos));
+    bten_[pos].push_back(bten_step(bten_[pos].back(), *m1, tn_site(site), *m2, pos));
   }
 }
 void Engine::grow_bten_step(int post) {                // grow.h:529-582
   int slice = (post == LEFT || post == RIGHT) ? (int)bmps_[UP].size() - 1 : (int)bmps_[LEFT].size() - 1;
   const BT *m1, *m2; int site;
   bten_operands(post, slice, (int)bten_[post].size(), m1, m2, site);
-  bten_[post].push_back(bten_step(bten_[post].back(), *m1, site_ref(site, site), *m2, post));
+  bten_[post].push_back(bten_step(bten_[post].back(), *m1, tn_site(site), *m2, post));
 }
 void Engine::shift_bten_window(int pos) {              // grow.h:517-521
   release(bten_[pos].back());
@@ -928,6 +928,7 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
         shift_bten2_window(RIGHT, row);
       }
     }
+    if (rec_bonds_ && row == rows_ / 2) row_corr_hook(row);      // bond_traversal_mixin.h:96-98
     if (row < rows_ - 1) shift_bmps_window(DOWN);
   }
   generate_bmps_approach(LEFT);                        // bond_traversal_mixin.h:112-143
@@ -955,18 +956,52 @@ double *Engine::bond_target(int kind, int row, int col) {
                 : kind == 2 ? nh + nv + row * (cols_ - 1) + col : nh + nv + nd + row * (cols_ - 1) + col;
   return bond_rec_ + (size_t)idx * W_;
 }
-void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur) {
+void Engine::upload_flipped_configs() {
+  std::vector<int32_t> cfg((size_t)W_ * nsites_);
+  be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
+  for (auto &c : cfg) c = 1 - c;
+  if (!idx_flip_) idx_flip_ = (int32_t *)be_malloc(sizeof(int32_t) * cfg.size());
+  be_h2d(idx_flip_, cfg.data(), sizeof(int32_t) * cfg.size());
+}
+// MeasureSpinOneHalfOffDiagOrderInRow (square_spin_onehalf_xxz_obc.h:22-60), lock step over the walkers: the tensor at
+// (row, cols/4) is replaced by its flipped slice (tn.UpdateSiteTensor), the LEFT environment regrown across it, then
+// one ReplaceOneSiteTrace with the flipped slice per site to the right. Ratios for equal spins are masked on the host.
+void Engine::row_corr_hook(int row) {
+  const int c1 = cols_ / 4, s1 = row * cols_ + c1, nc = cols_ / 2;
+  const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1);
+  double *corr = bond_rec_ + (size_t)(nh + nv + 2 * nd) * W_;
+  auto truncate_left = [&]() {                                   // EraseEnvsAfterUpdate on the BTen stacks (:556-560)
+    while ((int)bten_[LEFT].size() > c1 + 1) { release(bten_[LEFT].back()); bten_[LEFT].pop_back(); }
+    while ((int)bten_[RIGHT].size() > cols_ - c1) { release(bten_[RIGHT].back()); bten_[RIGHT].pop_back(); }
+  };
+  override_site_ = s1;
+  truncate_left();
+  grow_bten_step(LEFT);
+  grow_full_bten(RIGHT, row, c1 + 2, false);
+  for (int i = 1; i <= nc; ++i) {
+    const int c2 = c1 + i, s2 = row * cols_ + c2;
+    one_site_trace(row, c2, idx_flip_ + s2, nsites_, psi_tmp_);
+    be_ratio_accumulate(psi_tmp_, psi_row_, 1.0, corr + (size_t)(i - 1) * W_, W_);
+    shift_bten_window(RIGHT);
+  }
+  override_site_ = -1;
+  truncate_left();
+}
+void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr) {
   if (tfim_) throw std::invalid_argument("measure: bond observables are defined for the XXZ / J1-J2 solvers");
-  const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1), nb = nh + nv + 2 * nd;
-  if (!bond_rec_) bond_rec_ = (double *)be_malloc(sizeof(double) * (size_t)nb * W_);
-  be_memset0(bond_rec_, sizeof(double) * (size_t)nb * W_);
+  if (phys_ != 2) throw std::invalid_argument("measure: spin-1/2 observables need phys = 2");
+  const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1), ncr = cols_ / 2;
+  const int nb = nh + nv + 2 * nd;
+  if (!bond_rec_) bond_rec_ = (double *)be_malloc(sizeof(double) * (size_t)(nb + ncr) * W_);
+  be_memset0(bond_rec_, sizeof(double) * (size_t)(nb + ncr) * W_);
+  upload_flipped_configs();
   rec_bonds_ = true;
   std::vector<double> onsite((size_t)W_);
   try {
     energy_and_holes(false, onsite.data(), nullptr);      // with recording on, eloc_ only receives the on-site term
-  } catch (...) { rec_bonds_ = false; throw; }
+  } catch (...) { rec_bonds_ = false; override_site_ = -1; throw; }
   rec_bonds_ = false;
-  std::vector<double> rec((size_t)nb * W_);
+  std::vector<double> rec((size_t)(nb + ncr) * W_);
   be_d2h(rec.data(), bond_rec_, sizeof(double) * rec.size());
   auto scatter = [&](double *dst, int first, int count) {
     if (!dst) return;
@@ -974,6 +1009,17 @@ void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, dou
       for (int i = 0; i < count; ++i) dst[(size_t)w * count + i] = rec[(size_t)(first + i) * W_ + w];
   };
   scatter(e_h, 0, nh); scatter(e_v, nh, nv); scatter(e_dr, nh + nv, nd); scatter(e_ur, nh + nv + nd, nd);
+  if (row_corr) {
+    std::vector<int32_t> cfg((size_t)W_ * nsites_);
+    be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
+    const int row = rows_ / 2, c1 = cols_ / 4;
+    for (int w = 0; w < W_; ++w)
+      for (int i = 0; i < ncr; ++i) {
+        const int32_t *c = cfg.data() + (size_t)w * nsites_;
+        const bool equal = c[row * cols_ + c1] == c[row * cols_ + c1 + i + 1];
+        row_corr[(size_t)w * ncr + i] = equal ? 0.0 : rec[(size_t)(nb + i) * W_ + w];
+      }
+  }
   if (energy)
     for (int w = 0; w < W_; ++w) {
       double e = 0.0;

@@ -77,7 +77,9 @@ class Engine {
   // SquareNNNModelMeasurementSolver::EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214) for the
   // XXZ / J1-J2 models: the bond traversal without holes, every bond energy kept. Host outputs (any may be null):
   // energy[W], e_h[W][rows][cols-1], e_v[W][rows-1][cols], e_dr / e_ur[W][rows-1][cols-1] (zeros without NNN terms).
-  void measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur);
+  // row_corr[W][cols/2]: MeasureSpinOneHalfOffDiagOrderInRow (square_spin_onehalf_xxz_obc.h:22-60) on row rows/2 from
+  // site (rows/2, cols/4): conj(psi(both spins flipped) / psi) per distance, 0 where the two spins are equal.
+  void measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr);
   void zero_accumulators();
   void accumulate_ostar();                            // uses holes/eloc/amplitude of the last energy_and_holes
   void get_accumulators(double *osum_host, double *eosum_host);
@@ -175,7 +177,11 @@ class Engine {
   double terr_;
   double jz_ = 1.0, jxy_ = 1.0, h00_ = 0.0, jz2_ = 0.0, jxy2_ = 0.0;
   int updater_ = 0;
-  double *bond_rec_ = nullptr;     // [n_h + n_v + 2 n_d][W] per-bond energies of the last measure()
+  double *bond_rec_ = nullptr;     // [n_h + n_v + 2 n_d + cols/2][W] per-bond energies (+ row correlator) of the last measure()
+  int override_site_ = -1;         // site whose tensor is temporarily replaced by slice idx_flip_ (tn.UpdateSiteTensor)
+  TRef tn_site(int site) const { return site == override_site_ ? site_ref_idx(site, idx_flip_ + site, nsites_) : site_ref(site, site); }
+  void upload_flipped_configs();
+  void row_corr_hook(int row);
   bool rec_bonds_ = false;
   double *bond_target(int kind, int row, int col);   // where a bond energy is accumulated (eloc_ unless recording)
   bool tfim_ = false;
