@@ -95,12 +95,21 @@ void be_panel_qr(const PanelArgs &a);
 // Trailing update of one CAQR panel step: for every (walker, item) C <- C - V T^T (V^T C) where C are the rows
 // rowtab[it*R + s] (s < R) and columns [col1, col1 + ntrail) of A, and V / T are the blocks emitted by
 // be_panel_qr. One fused kernel (C tile resident in shared memory) instead of two contractions.
+// Opaque tile descriptor of a walker-batched row-major matrix (a CUtensorMap on the CUDA backend): lets a kernel
+// fetch a (box_rows x box_cols) tile of walker w with one TMA instruction. be_make_tile_map returns false when the
+// backend or the shape (alignment, box limits) cannot use it; callers then leave ApplyArgs::tmap null.
+struct TileMap { alignas(64) unsigned char blob[128]; };
+bool be_make_tile_map(TileMap *tm, const double *A, long ws, int lda, int rows, int cols, int W, int box_rows, int box_cols);
 struct ApplyArgs {
   double *A; long ws; int lda;
   const int32_t *rowtab; int R; int NI;
   int col1, ntrail, nbw;
   const double *Vw, *Tw;
   int W;
+  // optional fast path: the rows of item `it` are the contiguous range [row0 + it*R, row0 + (it+1)*R) and tmap
+  // describes A with boxes of (R/8 rows x 8 columns)
+  const TileMap *tmap = nullptr;
+  int row0 = 0;
 };
 void be_apply_reflector(const ApplyArgs &a);
 

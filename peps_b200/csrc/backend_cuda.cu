@@ -8,6 +8,7 @@
 //   panel_qr_kernel    one panel of the communication-avoiding R-only Householder QR, panel resident in smem.
 //   jacobi_round_kernel one round of one-sided block Jacobi (Gram + rotation on DMMA, panel resident in smem).
 //   small kernels      row norms, truncation/selection, RNG + Metropolis decision, energies, O* accumulation.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -835,14 +836,26 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned by
                "r"(bytes) : "memory");
 }
 
-template <int NBW, int MINB>
-__global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a) {
+__device__ __forceinline__ void tma_load_3d(void *dst, const void *tmap, int x, int y, int z, uint64_t *bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)), "l"(tmap), "r"(x), "r"(y), "r"(z), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// TM = true: the rows of an item are contiguous and `tm` describes the matrix: each warp fetches its row slice with
+// four TMA tile loads (8 columns x slice rows each) into a chunked tile layout [column chunk][row][8], which the DMMA
+// fragment loads read without bank conflicts and without padding; no row-offset table at all.
+template <int NBW, int MINB, bool TM>
+__global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a, const __grid_constant__ TileMap tm) {
   extern __shared__ __align__(16) double sm[];
   APPLY_CLK(0);
   constexpr int TN = NBW, MT = NBW / 8, NT = NBW / 8, LDC = TN + 4, LDW = TN + 4, NTILE = MT * NT;
   const int ct = blockIdx.x, it = blockIdx.y, w = blockIdx.z;
   const int R = a.R, R8 = (R + 7) & ~7, nbw = a.nbw;
-  double *Cs = sm;                               // [R8][LDC]
+  double *Cs = sm;                               // [R8][LDC], or [NBW/8][R8][8] with tile descriptors
+  auto csi = [&](int r, int c) -> size_t {
+    if constexpr (TM) return ((size_t)(c >> 3) * R8 + r) * 8 + (c & 7);
+    else return (size_t)r * LDC + c;
+  };
   double *part = Cs + (size_t)R8 * LDC;          // [4][NTILE][64]
   double *Wsm = part + 4 * NTILE * 64;           // [NBW][LDW] = -(V^T C)
   long *roff = reinterpret_cast<long *>(Wsm + NBW * LDW);   // [R8]
@@ -865,12 +878,21 @@ __global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a)
 
   // 0. C tile -> shared memory, each warp its own row slice
   if (lane == 0) mbar_init(&bars[warp], 1);
-  for (int r = k0 + lane; r < k1; r += 32) roff[r] = (r < R) ? (long)rows[r] * a.lda + cbase : -1;
+  if constexpr (!TM) { for (int r = k0 + lane; r < k1; r += 32) roff[r] = (r < R) ? (long)rows[r] * a.lda + cbase : -1; }
   APPLY_CLK(6);
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   __syncwarp();
   APPLY_CLK(7);
-  if (wide) {
+  if constexpr (TM) {
+    if (lane == 0 && k1 > k0) {
+      mbar_expect_tx(&bars[warp], (unsigned)((k1 - k0) * NBW * 8));
+#pragma unroll
+      for (int j = 0; j < NBW / 8; ++j)
+        tma_load_3d(Cs + ((size_t)j * R8 + k0) * 8, &tm, cbase + 8 * j, a.row0 + it * R + k0, w, &bars[warp]);
+    }
+    APPLY_CLK(1);
+    if (k1 > k0) mbar_wait(&bars[warp], 0);
+  } else if (wide) {
     const int nvalid = max(0, min(k1, R) - k0);
     if (lane == 0) mbar_expect_tx(&bars[warp], (unsigned)(nvalid * ncols * 8));
     __syncwarp();
@@ -921,7 +943,7 @@ __global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a)
 #pragma unroll
       for (int i = 0; i < MT; ++i) af[i] = (kr < R) ? __ldg(V + (long)kr * nbw + i * 8 + (lane >> 2)) : 0.0;
 #pragma unroll
-      for (int j = 0; j < NT; ++j) bf[j] = Cs[(size_t)kr * LDC + j * 8 + (lane >> 2)];
+      for (int j = 0; j < NT; ++j) bf[j] = Cs[csi(kr, j * 8 + (lane >> 2))];
 #pragma unroll
       for (int i = 0; i < MT; ++i)
 #pragma unroll
@@ -1027,15 +1049,18 @@ __global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a)
       double acc[NT][2];
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
-        acc[j][0] = Cs[(size_t)r * LDC + j * 8 + 2 * (lane & 3)];
-        acc[j][1] = Cs[(size_t)r * LDC + j * 8 + 2 * (lane & 3) + 1];
+        acc[j][0] = Cs[csi(r, j * 8 + 2 * (lane & 3))];
+        acc[j][1] = Cs[csi(r, j * 8 + 2 * (lane & 3) + 1)];
       }
 #pragma unroll
       for (int ks = 0; ks < NBW / 4; ++ks)
 #pragma unroll
         for (int j = 0; j < NT; ++j) dmma8x8x4(acc[j][0], acc[j][1], af[ks], bw[ks][j]);
       if (r < R) {
-        double *dst = Aw + roff[r];
+        // registers -> global directly (a TMA store out of the resident tile was measured slower: 15.0 vs 16.9 TF/s,
+        // the CTA then has to wait for the bulk read of its tile before it can retire)
+        double *dst;
+        if constexpr (TM) dst = Aw + (long)(a.row0 + it * R + r) * a.lda + cbase; else dst = Aw + roff[r];
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
           const int c = j * 8 + 2 * (lane & 3);
@@ -1057,22 +1082,53 @@ static size_t apply_smem_bytes(int R) {
   int R8 = (R + 7) & ~7;
   return ((size_t)R8 * (NBW + 4) + 4 * (size_t)(NBW / 8) * (NBW / 8) * 64 + (size_t)NBW * (NBW + 4) + (size_t)R8 + 8) * sizeof(double);
 }
+bool be_make_tile_map(TileMap *tm, const double *A, long ws, int lda, int rows, int cols, int W, int box_rows, int box_cols) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = []() -> EncodeFn {
+    if (const char *e = std::getenv("PEPS_TILE_MAPS")) if (std::atoi(e) == 0) return nullptr;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (EncodeFn)fn;
+  }();
+  static_assert(sizeof(CUtensorMap) <= sizeof(TileMap), "TileMap too small");
+  if (!encode) return false;
+  if ((lda & 1) || (ws & 1) || (reinterpret_cast<uintptr_t>(A) & 15) || box_rows < 1 || box_rows > 256 || box_cols < 2 ||
+      box_cols > 256 || (box_cols & 1))
+    return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)W};
+  cuuint64_t gstr[2] = {(cuuint64_t)lda * 8, (cuuint64_t)ws * 8};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult rc = encode(reinterpret_cast<CUtensorMap *>(tm), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(A), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS;
+}
+
 void be_apply_reflector(const ApplyArgs &a) {
   if (a.ntrail <= 0) return;
   LaunchScope scope(KC_APPLY, 4.0 * a.R * a.nbw * (double)a.ntrail * a.NI * a.W);
-  auto launch = [&](auto kern, size_t smem, size_t &configured, int tn) {
+  static const TileMap no_map{};
+  auto launch = [&](auto kern, size_t smem, size_t &configured, int tn, const TileMap &tmap) {
     if (smem > configured) {
       CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    kern<<<dim3((a.ntrail + tn - 1) / tn, a.NI, a.W), 256, smem, g_stream>>>(a);
+    kern<<<dim3((a.ntrail + tn - 1) / tn, a.NI, a.W), 256, smem, g_stream>>>(a, tmap);
   };
-  static size_t c32 = 0, c32b = 0, c16 = 0, c8 = 0;
+  static size_t c32 = 0, c32b = 0, c32t = 0, c32bt = 0, c16 = 0, c8 = 0;
+  const bool tile = a.tmap != nullptr && a.nbw == 32 && a.R % 64 == 0;
   // row blocks of <= 256 rows: the resident tile is <= 112 KB, two CTAs share an SM and overlap load / DMMA / store
-  if (a.nbw == 32 && apply_smem_bytes<32>(a.R) <= 112 * 1024) launch(apply_reflector_kernel<32, 2>, apply_smem_bytes<32>(a.R), c32b, 32);
-  else if (a.nbw == 32) launch(apply_reflector_kernel<32, 1>, apply_smem_bytes<32>(a.R), c32, 32);
-  else if (a.nbw == 16) launch(apply_reflector_kernel<16, 1>, apply_smem_bytes<16>(a.R), c16, 16);
-  else if (a.nbw == 8) launch(apply_reflector_kernel<8, 1>, apply_smem_bytes<8>(a.R), c8, 8);
+  const bool small = apply_smem_bytes<32>(a.R) <= 112 * 1024;
+  if (a.nbw == 32 && tile && small) launch(apply_reflector_kernel<32, 2, true>, apply_smem_bytes<32>(a.R), c32bt, 32, *a.tmap);
+  else if (a.nbw == 32 && tile) launch(apply_reflector_kernel<32, 1, true>, apply_smem_bytes<32>(a.R), c32t, 32, *a.tmap);
+  else if (a.nbw == 32 && small) launch(apply_reflector_kernel<32, 2, false>, apply_smem_bytes<32>(a.R), c32b, 32, no_map);
+  else if (a.nbw == 32) launch(apply_reflector_kernel<32, 1, false>, apply_smem_bytes<32>(a.R), c32, 32, no_map);
+  else if (a.nbw == 16) launch(apply_reflector_kernel<16, 1, false>, apply_smem_bytes<16>(a.R), c16, 16, no_map);
+  else if (a.nbw == 8) launch(apply_reflector_kernel<8, 1, false>, apply_smem_bytes<8>(a.R), c8, 8, no_map);
   else throw std::runtime_error("be_apply_reflector: unsupported panel width");
   post_launch();
 #ifdef PEPS_KERNEL_CLOCKS

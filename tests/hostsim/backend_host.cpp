@@ -150,6 +150,7 @@ void be_panel_qr(const PanelArgs &a) {
     }
 }
 
+bool be_make_tile_map(TileMap *, const double *, long, int, int, int, int, int, int) { return false; }
 void be_apply_reflector(const ApplyArgs &a) {
   ++g_launches;
   for (int w = 0; w < a.W; ++w)
