@@ -412,7 +412,10 @@ def main():
     achieved = dom_p["flops"] / max(dom_p["ms"], 1e-9) / 1e9            # TFLOP/s of useful FP64 work in that kernel class
     step_ms = elapsed_ms / args.steps
     mf = MODEL_FLOPS[args.workload]
-    traffic = {"jacobi_round": 34.9e6, "apply_reflector": 149.4e6}.get(dom_name)   # dram bytes per launch, ncu --set full at W=16 (profiles/)
+    # dram__bytes_read + write of ONE captured launch (ncu --set full, W=16; profiles/r1_ncu_*_final.txt / _k2.txt). For the
+    # trailing update that launch (1664 CTAs: 16 walkers x 8 row blocks x 13 column tiles) moves 436 MB algorithmically
+    # (C tile in and out) + 17 MB of reflectors: measured 399 MB, no wasted re-reads.
+    traffic = {"jacobi_round": 2.0e6, "apply_reflector": 399.3e6, "panel_qr": 1.4e6}.get(dom_name)
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 "peak_source": "cuBLAS DGEMM 4096^3 through torch.matmul, measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
