@@ -147,8 +147,8 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
   constexpr int BM = 16 * WMT, BN = 16 * WNT, BK = GETT_BK;
   constexpr int LDA = BM + 4, LDB = BN + 4;       // +4 doubles: conflict-free DMMA fragment loads
   constexpr int NA = BM * BK / GETT_THREADS, NBv = BN * BK / GETT_THREADS;
-  __shared__ double As[BK * LDA];
-  __shared__ double Bs[BK * LDB];
+  __shared__ double As[2][BK * LDA];         // double buffered: one barrier per K step
+  __shared__ double Bs[2][BK * LDB];
 
   const int tiles_m = (d.M + BM - 1) / BM;
   const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
@@ -197,11 +197,11 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
       rb[i] = (b_off[i] >= 0 && k < d.K) ? __ldg(Bb + b_off[i] + d.bk[k]) : 0.0;
     }
   };
-  auto store_smem = [&]() {
+  auto store_smem = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < NA; ++i) As[a_kl[i] * LDA + a_ml[i]] = ra[i];
+    for (int i = 0; i < NA; ++i) As[buf][a_kl[i] * LDA + a_ml[i]] = ra[i];
 #pragma unroll
-    for (int i = 0; i < NBv; ++i) Bs[b_kl[i] * LDB + b_nl[i]] = rb[i];
+    for (int i = 0; i < NBv; ++i) Bs[buf][b_kl[i] * LDB + b_nl[i]] = rb[i];
   };
 
   const int nk = (d.K + BK - 1) / BK;
@@ -220,9 +220,10 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
   }
   if (kt0 < nk) {
     load_global(kt0 * BK);
-    store_smem();
+    store_smem(0);
   }
   __syncthreads();
+  int cur = 0;
   for (int kt = kt0; kt < nk; ++kt) {
     if (kt + 1 < nk) load_global((kt + 1) * BK);
 #pragma unroll
@@ -230,19 +231,17 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
       double af[WMT], bf[WNT];
       const int kr = kk + (lane & 3), rr = lane >> 2;
 #pragma unroll
-      for (int i = 0; i < WMT; ++i) af[i] = As[kr * LDA + wm * 8 * WMT + i * 8 + rr];
+      for (int i = 0; i < WMT; ++i) af[i] = As[cur][kr * LDA + wm * 8 * WMT + i * 8 + rr];
 #pragma unroll
-      for (int j = 0; j < WNT; ++j) bf[j] = Bs[kr * LDB + wn * 8 * WNT + j * 8 + rr];
+      for (int j = 0; j < WNT; ++j) bf[j] = Bs[cur][kr * LDB + wn * 8 * WNT + j * 8 + rr];
 #pragma unroll
       for (int i = 0; i < WMT; ++i)
 #pragma unroll
         for (int j = 0; j < WNT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
+    if (kt + 1 < nk) store_smem(cur ^ 1);      // the other buffer: nobody reads it during this step
     __syncthreads();
-    if (kt + 1 < nk) {
-      store_smem();
-      __syncthreads();
-    }
+    cur ^= 1;
   }
   // epilogue
 #pragma unroll
