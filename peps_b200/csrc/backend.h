@@ -127,6 +127,12 @@ struct JacobiArgs {
 void be_jacobi_round(const JacobiArgs &a);
 // done[w] = (offmax[w] <= tol); offmax[w] = 0 for the next sweep. Returns nothing (host reads done[]).
 void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W);
+// norms2[w][c] = |G[w][:nr][c]|^2   (column norms)
+void be_col_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W);
+// dst[w][r][j] = src[w][r][order[w][j]]  (gather = 1)   or   dst[w][r][order[w][j]] = src[w][r][j]  (gather = 0)
+// for r < nr, j < nc; order[w] is a permutation of [0, nc)
+void be_permute_cols(const double *src, long ws, int lds, int nr, int nc, const int32_t *order, int gather,
+                     double *dst, long wd, int ldd, int W);
 // norms2[w][r] = |G[w][r][:]|^2
 void be_row_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W);
 // order[w][rank] = row index sorted by norm descending (ties by index), for all nr rows;

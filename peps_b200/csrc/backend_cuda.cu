@@ -1535,6 +1535,41 @@ void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {
   post_launch();
 }
 
+// column norms: thread per column (coalesced across a warp), rows split over blockIdx.y-free inner loop
+__global__ void col_norms2_kernel(const double *G, long ws, int ld, int nr, int nc, double *norms2) {
+  const int w = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const double *x = G + (long)w * ws + c;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int r = 0;
+  for (; r + 3 < nr; r += 4) {
+    const double a = x[(long)r * ld], b = x[(long)(r + 1) * ld], e = x[(long)(r + 2) * ld], f = x[(long)(r + 3) * ld];
+    s0 += a * a; s1 += b * b; s2 += e * e; s3 += f * f;
+  }
+  for (; r < nr; ++r) { const double a = x[(long)r * ld]; s0 += a * a; }
+  norms2[(long)w * nc + c] = (s0 + s1) + (s2 + s3);
+}
+void be_col_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  col_norms2_kernel<<<dim3((nc + 63) / 64, W), 64, 0, g_stream>>>(G, ws, ld, nr, nc, norms2);
+  post_launch();
+}
+__global__ void permute_cols_kernel(const double *src, long ws, int lds, int nr, int nc, const int32_t *order, int gather,
+                                    double *dst, long wd, int ldd) {
+  const int w = blockIdx.y, r = blockIdx.x;
+  const double *x = src + (long)w * ws + (long)r * lds;
+  double *y = dst + (long)w * wd + (long)r * ldd;
+  const int32_t *o = order + (long)w * nc;
+  if (gather) { for (int j = threadIdx.x; j < nc; j += blockDim.x) y[j] = x[o[j]]; }
+  else { for (int j = threadIdx.x; j < nc; j += blockDim.x) y[o[j]] = x[j]; }
+}
+void be_permute_cols(const double *src, long ws, int lds, int nr, int nc, const int32_t *order, int gather,
+                     double *dst, long wd, int ldd, int W) {
+  if (nr <= 0) return;
+  LaunchScope scope(KC_SMALL, 0.0);
+  permute_cols_kernel<<<dim3(nr, W), 128, 0, g_stream>>>(src, ws, lds, nr, nc, order, gather, dst, wd, ldd);
+  post_launch();
+}
 __global__ void row_norms2_kernel(const double *G, long ws, int ld, int nr, int nc, double *norms2) {
   const int w = blockIdx.y;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;

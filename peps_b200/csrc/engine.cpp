@@ -17,6 +17,7 @@ Engine::Engine(const EngineConfig &c)
   la_.W = W_; la_.pool = &pool_; la_.planner = &planner_;
   if (const char *e = std::getenv("PEPS_DEFLATION_EPS")) la_.deflation_eps = std::atof(e);
   if (const char *e = std::getenv("PEPS_BMPS_MEMO")) memo_on_ = std::atoi(e) != 0;
+  if (const char *e = std::getenv("PEPS_PRESORT_COLS")) la_.presort_columns = std::atoi(e) != 0;
   la_.offmax = (double *)be_malloc(sizeof(double) * W_);
   la_.done = (int32_t *)be_malloc(sizeof(int32_t) * W_);
   tps_off_h_.resize((size_t)nsites_);

@@ -279,6 +279,26 @@ void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {
   ++g_launches;
   for (int w = 0; w < W; ++w) { done[w] = offmax[w] <= tol; offmax[w] = 0.0; }
 }
+void be_col_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int c = 0; c < nc; ++c) {
+      double s = 0.0;
+      for (int r = 0; r < nr; ++r) s += G[w * ws + (long)r * ld + c] * G[w * ws + (long)r * ld + c];
+      norms2[(long)w * nc + c] = s;
+    }
+}
+void be_permute_cols(const double *src, long ws, int lds, int nr, int nc, const int32_t *order, int gather,
+                     double *dst, long wd, int ldd, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int r = 0; r < nr; ++r)
+      for (int j = 0; j < nc; ++j) {
+        const int o = order[(long)w * nc + j];
+        if (gather) dst[w * wd + (long)r * ldd + j] = src[w * ws + (long)r * lds + o];
+        else dst[w * wd + (long)r * ldd + o] = src[w * ws + (long)r * lds + j];
+      }
+}
 void be_row_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W) {
   ++g_launches;
   for (int w = 0; w < W; ++w)
