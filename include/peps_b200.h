@@ -55,6 +55,11 @@ int peps_set_jacobi(peps_ctx *ctx, double tol, int32_t inner_sweeps, int32_t max
 /* Rows of the QR-preconditioned Theta below eps * (largest row norm) are dropped before / between Jacobi sweeps
  * (default 1e-13; a backward-stable perturbation of relative size <= sqrt(rows) * eps). 0 disables deflation. */
 int peps_set_deflation(peps_ctx *ctx, double eps);
+/* Rank-revealing step of the forward R chain of a row absorption (no reference counterpart: the reference keeps the
+ * full D*chi bond of the exact MPO x MPS product until the SVD sweep): rows of the column-sorted R factor below
+ * eps * (largest row norm) are dropped (default 1e-13; the Gram matrix R^T R changes by <= rows * eps^2 relative).
+ * 0 keeps every row. */
+int peps_set_chain_deflation(peps_ctx *ctx, double eps);
 /* SquareSpinOneHalfXXZModelOBC(jz, jxy, pinning00) (model_solvers/square_spin_onehalf_xxz_obc.h:174-328). */
 int peps_set_model_xxz(peps_ctx *ctx, double jz, double jxy, double pinning00);
 /* SquareSpinOneHalfJ1J2XXZModelOBC(jz, jxy, jz2, jxy2, pinning00) (model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113):

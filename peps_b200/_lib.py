@@ -35,6 +35,7 @@ SIGNATURES = {
     "peps_set_jacobi": (C.c_int, [_P, C.c_double, C.c_int32, C.c_int32]),
     "peps_set_deflation": (C.c_int, [_P, C.c_double]),
     "peps_set_model_xxz": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),
+    "peps_set_chain_deflation": (C.c_int, [_P, C.c_double]),
     "peps_set_model_j1j2_xxz": (C.c_int, [_P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]),
     "peps_set_configs": (C.c_int, [_P, _I]),
     "peps_get_configs": (C.c_int, [_P, _I]),

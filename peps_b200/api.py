@@ -237,6 +237,9 @@ class WalkerBatch:
         self.updater_kind = int(getattr(updater, "kind", updater))
         self._ck(self.lib.peps_set_updater(self.h, self.updater_kind))
 
+    def set_chain_deflation(self, eps):
+        self._ck(self.lib.peps_set_chain_deflation(self.h, eps))
+
     def set_model(self, model):
         if isinstance(model, TransverseFieldIsingSquareOBC):
             self._ck(self.lib.peps_set_model_tfim(self.h, model.h))

@@ -18,6 +18,7 @@ Engine::Engine(const EngineConfig &c)
   if (const char *e = std::getenv("PEPS_DEFLATION_EPS")) la_.deflation_eps = std::atof(e);
   if (const char *e = std::getenv("PEPS_BMPS_MEMO")) memo_on_ = std::atoi(e) != 0;
   if (const char *e = std::getenv("PEPS_PRESORT_COLS")) la_.presort_columns = std::atoi(e) != 0;
+  if (const char *e = std::getenv("PEPS_CHAIN_EPS")) chain_eps_ = std::atof(e);
   la_.offmax = (double *)be_malloc(sizeof(double) * W_);
   la_.done = (int32_t *)be_malloc(sizeof(int32_t) * W_);
   tps_off_h_.resize((size_t)nsites_);
@@ -127,6 +128,8 @@ long Engine::stat(int which) const {
     case 9: return la_.rows_kept;
     case 10: return la_.jacobi_rounds;
     case 11: return n_memo_hits_;
+    case 12: return chain_rows_in_;
+    case 13: return chain_rows_kept_;
     default: return -1;
   }
 }
@@ -266,12 +269,12 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
   const std::string sl = site_labels(post, 'e', 'p', 'f', 'o');
   auto sdim = [&](int site, char l) { return site_dims_h_[(size_t)site][sl.find(l)]; };
   std::vector<BT> r((size_t)N);
+  std::vector<char> r_tri((size_t)N, 0);     // r_i is an upper-trapezoidal R factor (structural-zero hints apply)
   r[0] = ones111();
   for (int i = 0; i < N - 1; ++i) {
     const int site = sites[(size_t)i];
     TRef sref = site_ref(site, site);
-    // r_i (i >= 1) is an R factor: upper trapezoidal. The kernels skip the K steps that only meet its zeros.
-    const bool tri = i >= 1;
+    const bool tri = r_tri[(size_t)i] != 0;
     const int rk = r[(size_t)i].d[0], re = r[(size_t)i].d[1], ra = r[(size_t)i].d[2];
     const int pd = mps[(size_t)i].d[1], bd = mps[(size_t)i].d[2];
     BT tmp1 = einsum("apb,kea->ekpb", ref(mps[(size_t)i]), ref(r[(size_t)i]),
@@ -279,16 +282,50 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
     const int k = r[(size_t)i].d[0], o = sdim(site, 'o'), f = sdim(site, 'f'), b = mps[(size_t)i].d[2];
     const int m = k * o, n = f * b;
     QRLayout L = qr_layout(m, n);
-    double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * L.m_pad * n);
-    if (L.m_pad > m) be_memset0(A, sizeof(double) * (size_t)W_ * L.m_pad * n);
-    einsum_into("ekpb," + sl + "->kofb", ref(tmp1), sref, mkop(A, (long)L.m_pad * n), nullptr, 1.0, 0.0,
+    const long wsA = (long)L.m_pad * n;
+    double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
+    if (L.m_pad > m) be_memset0(A, sizeof(double) * (size_t)W_ * wsA);
+    einsum_into("ekpb," + sl + "->kofb", ref(tmp1), sref, mkop(A, wsA), nullptr, 1.0, 0.0,
                 tri ? &r_hints(1, rk, re, ra, pd, bd) : nullptr);                         // bmps_impl.h:807
     release(tmp1);
-    caqr(la_, A, (long)L.m_pad * n, m, n, L);                                            // bmps_impl.h:817-821
     const int kk = std::min(m, n);
-    r[(size_t)i + 1] = alloc({kk, f, b});
-    be_copy2d(r[(size_t)i + 1].p, (long)kk * n, n, A, (long)L.m_pad * n, n, kk, n, W_);
-    pool_.put(A);
+    if (chain_eps_ > 0.0 && kk >= 16) {
+      // Rank-revealing step of the R chain. Columns sorted by norm (pivoting-lite) grade the rows of R; rows below
+      // chain_eps * (largest row norm) are dropped, a backward-stable perturbation of the left part of relative size
+      // <= sqrt(rows) * chain_eps. The exact MPO x MPS product has bond dimension D*chi, its numerical rank is a
+      // fraction of that, and every later step of the chain (and Theta = r X) shrinks with it.
+      double *cn2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * std::max(n, kk));
+      int32_t *ord = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * std::max(n, kk));
+      int32_t *cord = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * n);
+      int32_t *cnt = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_);
+      be_col_norms2(A, wsA, n, m, n, cn2, W_);
+      be_rank_rows(cn2, n, 0.0, cord, cnt, W_);
+      double *Ap = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
+      if (L.m_pad > m) be_memset0(Ap, sizeof(double) * (size_t)W_ * wsA);
+      be_permute_cols(A, wsA, n, m, n, cord, 1, Ap, wsA, n, W_);
+      pool_.put(A);
+      caqr(la_, Ap, wsA, m, n, L);                                                       // bmps_impl.h:817-821
+      be_row_norms2(Ap, wsA, n, kk, n, cn2, W_);
+      be_rank_rows(cn2, kk, chain_eps_ * chain_eps_, ord, cnt, W_);
+      std::vector<int32_t> ch((size_t)W_);
+      be_d2h(ch.data(), cnt, sizeof(int32_t) * W_);
+      int knew = 1;
+      for (int w = 0; w < W_; ++w) knew = std::max(knew, (int)ch[(size_t)w]);
+      const int gran = kk >= 128 ? 64 : 8;               // few distinct shapes: plans, tables and pool buffers are keyed by size
+      knew = std::min(kk, (knew + gran - 1) / gran * gran);
+      chain_rows_in_ += kk; chain_rows_kept_ += knew;
+      double *Rg = (double *)pool_.get(sizeof(double) * (size_t)W_ * knew * n);
+      be_gather_rows(Ap, wsA, n, n, kk, ord, cnt, Rg, (long)knew * n, knew, W_);
+      r[(size_t)i + 1] = alloc({knew, f, b});
+      be_permute_cols(Rg, (long)knew * n, n, knew, n, cord, 0, r[(size_t)i + 1].p, (long)knew * n, n, W_);
+      for (void *p : {(void *)cn2, (void *)ord, (void *)cord, (void *)cnt, (void *)Ap, (void *)Rg}) pool_.put(p);
+    } else {
+      caqr(la_, A, wsA, m, n, L);                                                        // bmps_impl.h:817-821
+      r[(size_t)i + 1] = alloc({kk, f, b});
+      be_copy2d(r[(size_t)i + 1].p, (long)kk * n, n, A, wsA, n, kk, n, W_);
+      r_tri[(size_t)i + 1] = 1;
+      pool_.put(A);
+    }
   }
   BMPSv res((size_t)N);
   BT E = ones111();                                                                      // E[f,b,j]
@@ -308,7 +345,7 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
       double *G = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows * cols);
       if (brows > rows) be_memset0(G, sizeof(double) * (size_t)W_ * brows * cols);
       einsum_into("kea,eaoj->koj", ref(r[(size_t)i]), ref(X), mkop(G, (long)brows * cols), nullptr, 1.0, 0.0,
-                  &r_hints(2, r[(size_t)i].d[0], r[(size_t)i].d[1], r[(size_t)i].d[2], 0, 0));
+                  r_tri[(size_t)i] ? &r_hints(2, r[(size_t)i].d[0], r[(size_t)i].d[1], r[(size_t)i].d[2], 0, 0) : nullptr);
       const int tcap = std::min(dmax_, std::min(rows, cols));
       B = alloc({tcap, o, j});
       double *norms2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * std::max(rows, 1));

@@ -96,6 +96,8 @@ class Engine {
   void sr_matvec_host(const double *v, double mean_dot_v, double *out);
   void set_model_xxz(double jz, double jxy, double h00) { jz_ = jz; jxy_ = jxy; h00_ = h00; }
   void set_deflation(double eps) { la_.deflation_eps = eps; touch_all(); }
+  // rows of the forward R chain below eps * (largest row norm) are dropped (0 = keep the full D*chi rows)
+  void set_chain_deflation(double eps) { chain_eps_ = eps; touch_all(); }
   // SquareSpinOneHalfJ1J2XXZModelOBC couplings (model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113); 0 disables NNN
   void set_model_nnn(double jz2, double jxy2) { jz2_ = jz2; jxy2_ = jxy2; }
   // TransverseFieldIsingSquareOBC(h) (model_solvers/transverse_field_ising_square_obc.h:28-247); phys must be 2
@@ -245,6 +247,8 @@ class Engine {
   std::vector<BT> bten_[4];
   std::vector<BT> bten2_[4];
   long n_absorb_ = 0, n_bten_ = 0, n_trace_ = 0;
+  double chain_eps_ = 1e-13;       // PEPS_CHAIN_EPS (same threshold as the truncation deflation)
+  long chain_rows_in_ = 0, chain_rows_kept_ = 0;
 };
 
 }  // namespace peps

@@ -26,8 +26,10 @@ class Pool {
   ~Pool() { release_all(); }
   void *get(size_t bytes) {
     bytes = (bytes + 255) & ~size_t(255);
-    auto it = free_.find(bytes);
-    if (it != free_.end() && !it->second.empty()) {
+    // best fit among the cached buffers of up to 25 % more than asked for: the many slightly different shapes of a
+    // rank-adaptive chain reuse each other's buffers instead of growing the pool
+    for (auto it = free_.lower_bound(bytes); it != free_.end() && it->first <= bytes + bytes / 4; ++it) {
+      if (it->second.empty()) continue;
       void *p = it->second.back();
       it->second.pop_back();
       return p;

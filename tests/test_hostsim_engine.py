@@ -249,3 +249,31 @@ def test_caqr_host_logic_with_diagonal_crossing_row_blocks(rb):
     env = dict(os.environ, PEPS_QR_RB=rb)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_chain_deflation_keeps_amplitudes(lib):
+    """Rank-revealing step of the forward R chain (engine.cpp: absorb): dropping the rows of the column-sorted R factor
+    below 1e-14 of the largest one shrinks the chain and leaves amplitudes, energies and holes unchanged to 1e-10."""
+    rows, cols, D, W = 4, 6, 3, 2
+    tps = vmc.random_tps(rows, cols, 2, D, seed=17)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 90 + w) for w in range(W)])
+    out = {}
+    for eps in (0.0, 1e-14, 1e-4):
+        b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(9, 9, 0.0), lib=lib)
+        b.set_chain_deflation(eps)
+        b.set_tps(SplitIndexTPS(tps))
+        b.set_configs(cfgs)
+        b.init_walkers()
+        e = b.energy_and_holes(True)
+        out[eps] = (b.amplitudes().copy(), e.copy(), b.holes().copy(), b.stat(12), b.stat(13))
+    a0, e0, h0, in0, kept0 = out[0.0]
+    a1, e1, h1, in1, kept1 = out[1e-14]
+    assert in0 == 0 and in1 > 0 and kept1 <= in1
+    a2, _, _, in2, kept2 = out[1e-4]
+    assert kept2 < in2 and np.max(np.abs(a2 / a0 - 1)) < 1e-2     # a coarse threshold really shortens the chain
+    assert np.max(np.abs(a1 / a0 - 1)) < 1e-10
+    assert np.max(np.abs(e1 - e0) / np.maximum(1, np.abs(e0))) < 1e-10
+    assert np.max(np.abs(h1 - h0)) < 1e-10 * np.max(np.abs(h0))
+    for w in range(W):
+        ref = vmc.Walker(tps, cfgs[w], (9, 9, 0.0)).amplitude
+        assert abs(a1[w] / ref - 1) < 1e-10

@@ -26,7 +26,7 @@ def tm(f, name):
     if a.profile:
         pr = b.profile_get(True)
         print("   " + "  ".join(f"{k}: {v['ms']:.0f} ms / {v['launches']} launches / {v['flops']/max(v['ms'],1e-9)/1e9:.2f} TF/s" for k, v in pr.items()))
-    print(f"{name}: {dt:.3f} s  stats absorb={b.stat(0)} bten={b.stat(1)} trace={b.stat(2)} jsweeps={b.stat(3)} jcalls={b.stat(4)} qr={b.stat(5)} launches={b.stat(6)} rows_in={b.stat(8)} rows_kept={b.stat(9)} jrounds={b.stat(10)} pool={b.stat(7)/2**30:.2f} GiB", flush=True)
+    print(f"{name}: {dt:.3f} s  stats absorb={b.stat(0)} bten={b.stat(1)} trace={b.stat(2)} jsweeps={b.stat(3)} jcalls={b.stat(4)} qr={b.stat(5)} launches={b.stat(6)} rows_in={b.stat(8)} rows_kept={b.stat(9)} jrounds={b.stat(10)} chain_rows={b.stat(13)}/{b.stat(12)} pool={b.stat(7)/2**30:.2f} GiB", flush=True)
     return r
 tm(b.init_walkers, "init_walkers")
 amp = b.amplitudes(); print("amp", amp[:4])
