@@ -1535,23 +1535,34 @@ void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {
   post_launch();
 }
 
-// column norms: thread per column (coalesced across a warp), rows split over blockIdx.y-free inner loop
+// column norms: a CTA owns 32 columns, its 8 warps stride over the rows (256-byte coalesced reads), partial sums are
+// combined in a fixed order (deterministic)
 __global__ void col_norms2_kernel(const double *G, long ws, int ld, int nr, int nc, double *norms2) {
-  const int w = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
-  const double *x = G + (long)w * ws + c;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int r = 0;
-  for (; r + 3 < nr; r += 4) {
-    const double a = x[(long)r * ld], b = x[(long)(r + 1) * ld], e = x[(long)(r + 2) * ld], f = x[(long)(r + 3) * ld];
-    s0 += a * a; s1 += b * b; s2 += e * e; s3 += f * f;
+  __shared__ double part[8][33];
+  const int w = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  double s0 = 0.0, s1 = 0.0;
+  if (c < nc) {
+    const double *x = G + (long)w * ws + c;
+    int r = warp;
+    for (; r + 8 < nr; r += 16) {
+      const double a = x[(long)r * ld], b = x[(long)(r + 8) * ld];
+      s0 += a * a; s1 += b * b;
+    }
+    if (r < nr) { const double a = x[(long)r * ld]; s0 += a * a; }
   }
-  for (; r < nr; ++r) { const double a = x[(long)r * ld]; s0 += a * a; }
-  norms2[(long)w * nc + c] = (s0 + s1) + (s2 + s3);
+  part[warp][lane] = s0 + s1;
+  __syncthreads();
+  if (warp == 0 && c < nc) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    norms2[(long)w * nc + c] = t;
+  }
 }
 void be_col_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W) {
   LaunchScope scope(KC_SMALL, 0.0);
-  col_norms2_kernel<<<dim3((nc + 63) / 64, W), 64, 0, g_stream>>>(G, ws, ld, nr, nc, norms2);
+  col_norms2_kernel<<<dim3((nc + 31) / 32, W), 256, 0, g_stream>>>(G, ws, ld, nr, nc, norms2);
   post_launch();
 }
 __global__ void permute_cols_kernel(const double *src, long ws, int lds, int nr, int nc, const int32_t *order, int gather,
