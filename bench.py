@@ -444,7 +444,10 @@ def main():
                        "model": "Heisenberg NN (XXZ jz=jxy=1)" if args.j2 == 0.0 else f"J1-J2 Heisenberg (j2={args.j2})",
                        "sweeps_between_samples": 1, "tps": ("uniform[-1,1)" if args.signed else "uniform[0,1)") + f" seed {TPS_SEED}, NormalizeAllSite + order-1 rescale",
                        "l2": "per-step working set (walkers x ~60 MB of BMPS stacks + scratch) exceeds the 126 MB L2",
-                       "parallelism": f"walkers sharded over {world} GPU(s); NCCL all-reduce of the two accumulators"},
+                       "parallelism": f"walkers sharded over {world} GPU(s); NCCL all-reduce of the two accumulators",
+                       "algorithm": "reference call sequence; exact boundary-MPS memo (6(L-1) absorptions per sample instead of "
+                                    "8(L-1), bit-identical); R-only QR chain with rows below 1e-13 of the largest dropped; "
+                                    "column-sorted preconditioning QR + block Jacobi truncation (DESIGN.md section 2)"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "call": "set_tps + init_walkers + sample + accumulators (Evaluate with 1 sample per walker)"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
