@@ -282,24 +282,50 @@ void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, d
 // =====================================================================================================
 // dot
 // =====================================================================================================
-__global__ void dot_kernel(int K, const int32_t *ak, const int32_t *bk, Operand A, Operand B, double *out) {
-  const int w = blockIdx.x;
+// K is split over blockIdx.y (the NNN traces contract 262 k elements per walker); the partial sums are combined in a
+// fixed order by a second tiny kernel, so the result does not depend on scheduling.
+__global__ void dot_kernel(int K, int kchunk, const int32_t *ak, const int32_t *bk, Operand A, Operand B, double *part) {
+  const int w = blockIdx.x, sidx = blockIdx.y;
   const double *Ab = operand_base(A, w, 0);
   const double *Bb = operand_base(B, w, 0);
   __shared__ double red[256];
   double s = 0.0;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) s += Ab[ak[k]] * Bb[bk[k]];
+  const int k1 = min(K, (sidx + 1) * kchunk);
+  for (int k = sidx * kchunk + threadIdx.x; k < k1; k += blockDim.x) s += Ab[ak[k]] * Bb[bk[k]];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int h = blockDim.x / 2; h > 0; h >>= 1) {
     if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[w] = red[0];
+  if (threadIdx.x == 0) part[(long)w * gridDim.y + sidx] = red[0];
+}
+__global__ void dot_finish_kernel(const double *part, int nsplit, double *out, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  double s = 0.0;
+  for (int i = 0; i < nsplit; ++i) s += part[(long)w * nsplit + i];
+  out[w] = s;
 }
 void be_dot(int K, const int32_t *ak, const int32_t *bk, Operand A, Operand B, double *out, int W) {
   LaunchScope scope(KC_DOT, 2.0 * K * W);
-  dot_kernel<<<W, 256, 0, g_stream>>>(K, ak, bk, A, B, out);
+  const int nsplit = std::max(1, std::min(32, K / 4096));
+  if (nsplit == 1) {
+    dot_kernel<<<dim3(W, 1), 256, 0, g_stream>>>(K, K, ak, bk, A, B, out);
+    post_launch();
+    return;
+  }
+  static thread_local double *part = nullptr;
+  static thread_local size_t part_cap = 0;
+  if ((size_t)W * 32 > part_cap) {
+    if (part) cudaFree(part);
+    part_cap = (size_t)W * 32;
+    CUDA_CHECK(cudaMalloc(&part, sizeof(double) * part_cap));
+  }
+  const int kchunk = (K + nsplit - 1) / nsplit;
+  dot_kernel<<<dim3(W, nsplit), 256, 0, g_stream>>>(K, kchunk, ak, bk, A, B, part);
+  ++g_launches;
+  dot_finish_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(part, nsplit, out, W);
   post_launch();
 }
 

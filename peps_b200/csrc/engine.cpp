@@ -580,24 +580,30 @@ void Engine::one_site_trace(int r, int c, const int32_t *idx, int stride, double
 // out[w] = sum over all indices of a[i0,i1,...] * b[...,i1,i0] (b has the reversed leg order of a)
 void Engine::reverse_dot(const BT &a, const BT &b, double *out) {
   const long n = a.n;
-  std::vector<int32_t> ak((size_t)n), bk((size_t)n);
-  std::vector<long> bstride((size_t)a.rank);
-  {
-    // b dims are a's reversed: b index order (i_{r-1}, ..., i_0); stride of i_k in b
-    long acc = 1;
-    for (int k = 0; k < a.rank; ++k) { bstride[(size_t)k] = acc; acc *= a.d[k]; }
-  }
-  for (long k = 0; k < n; ++k) {
-    long rem = k, off = 0;
-    for (int ax = a.rank - 1; ax >= 0; --ax) {
-      long idx = rem % a.d[ax];
-      rem /= a.d[ax];
-      off += idx * bstride[(size_t)ax];
+  // index tables depend on the shape only: built once per shape
+  std::array<int, 7> key = {a.rank, a.d[0], a.d[1], a.d[2], a.d[3], a.d[4], a.d[5]};
+  auto it = rdot_tabs_.find(key);
+  if (it == rdot_tabs_.end()) {
+    std::vector<int32_t> ak((size_t)n), bk((size_t)n);
+    std::vector<long> bstride((size_t)a.rank);
+    {
+      // b dims are a's reversed: b index order (i_{r-1}, ..., i_0); stride of i_k in b
+      long acc = 1;
+      for (int k = 0; k < a.rank; ++k) { bstride[(size_t)k] = acc; acc *= a.d[k]; }
     }
-    ak[(size_t)k] = (int32_t)k;
-    bk[(size_t)k] = (int32_t)off;
+    for (long k = 0; k < n; ++k) {
+      long rem = k, off = 0;
+      for (int ax = a.rank - 1; ax >= 0; --ax) {
+        long idx = rem % a.d[ax];
+        rem /= a.d[ax];
+        off += idx * bstride[(size_t)ax];
+      }
+      ak[(size_t)k] = (int32_t)k;
+      bk[(size_t)k] = (int32_t)off;
+    }
+    it = rdot_tabs_.emplace(key, std::make_pair(planner_.upload(ak), planner_.upload(bk))).first;
   }
-  be_dot((int)n, planner_.upload(ak), planner_.upload(bk), mkop(a.p, a.n), mkop(b.p, b.n), out, W_);
+  be_dot((int)n, it->second.first, it->second.second, mkop(a.p, a.n), mkop(b.p, b.n), out, W_);
 }
 
 // ---------------------------------------------------------------------------------------------------

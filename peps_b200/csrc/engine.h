@@ -226,6 +226,7 @@ class Engine {
   bool sr_on_ = false;
 
   std::map<std::array<int, 6>, KHints> hints_;
+  std::map<std::array<int, 7>, std::pair<const int32_t *, const int32_t *>> rdot_tabs_;
   std::vector<BMPSv> bmps_[4];
   // Boundary-MPS memo. The reference drops stack entries (DeleteInnerBMPS, ShiftBMPSWindow) and later regrows them
   // from unchanged configurations: the LEFT stack finished by the sweep's vertical pass is rebuilt column by column
