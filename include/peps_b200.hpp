@@ -54,6 +54,18 @@ class WalkerBatch {
   void SetModel(const J1J2XXZModel &m) { ck(peps_set_model_j1j2_xxz(h_, m.jz, m.jxy, m.jz2, m.jxy2, m.pinning00)); }
   void SetModel(const TransverseFieldIsingModel &m) { ck(peps_set_model_tfim(h_, m.h)); }
   void SetUpdater(Updater u) { updater_ = u; ck(peps_set_updater(h_, (int32_t)u)); }
+  void SetChainDeflation(double eps) { ck(peps_set_chain_deflation(h_, eps)); }
+  // EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214): per-walker arrays, see peps_measure
+  struct Observables { std::vector<double> energy, bond_energy_h, bond_energy_v, bond_energy_dr, bond_energy_ur, row_corr; };
+  Observables Measure() {
+    Observables o;
+    const size_t W = (size_t)walkers_, r = (size_t)rows_, c = (size_t)cols_;
+    o.energy.resize(W); o.bond_energy_h.resize(W * r * (c - 1)); o.bond_energy_v.resize(W * (r - 1) * c);
+    o.bond_energy_dr.resize(W * (r - 1) * (c - 1)); o.bond_energy_ur.resize(W * (r - 1) * (c - 1)); o.row_corr.resize(W * (c / 2));
+    ck(peps_measure(h_, o.energy.data(), o.bond_energy_h.data(), o.bond_energy_v.data(), o.bond_energy_dr.data(),
+                    o.bond_energy_ur.data(), o.row_corr.data()));
+    return o;
+  }
   void SetConfigs(const std::vector<int32_t> &cfg) { ck(peps_set_configs(h_, cfg.data())); }
   std::vector<int32_t> GetConfigs() { std::vector<int32_t> v((size_t)walkers_ * rows_ * cols_); ck(peps_get_configs(h_, v.data())); return v; }
   void SeedRNG(const std::vector<uint32_t> &seeds) { ck(peps_seed_rng(h_, seeds.data())); }

@@ -28,6 +28,12 @@ int main() {
         [](const std::vector<double> &g, const std::vector<double> &) { return g; });
     auto t = f(tps);
     std::printf("%.17g\n", std::get<0>(t));
+    // measurement through the wrapper: total energy equals the sum of the bond energies (no pinning field here)
+    auto obs = ev.batch().Measure();
+    double e0 = obs.energy[0], sum = 0.0;
+    for (int i = 0; i < rows * (cols - 1); ++i) sum += obs.bond_energy_h[(size_t)i];
+    for (int i = 0; i < (rows - 1) * cols; ++i) sum += obs.bond_energy_v[(size_t)i];
+    std::printf("%.17g %.17g\n", e0, sum);
   } catch (const std::exception &e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -28,7 +28,8 @@ def test_cpp_wrapper_matches_python_mirror():
         inp = f"3 3 2 2 {W} {chi} {ns} {seed}\n{flat.size}\n" + " ".join(repr(float(x)) for x in flat) + "\n" + \
               " ".join(str(int(c)) for c in cfg.ravel()) + "\n"
         out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
-    e_cpp, err_cpp, gn_cpp, acc_cpp, e2 = map(float, out)
+    e_cpp, err_cpp, gn_cpp, acc_cpp, e2, e_meas, e_bonds = map(float, out)
+    assert abs(e_meas - e_bonds) < 1e-10 * max(1.0, abs(e_meas))
     mc = MonteCarloParams(num_samples=ns, num_warmup_sweeps=0, sweeps_between_samples=1, initial_config=Configuration(cfg),
                           is_warmed_up=True)
     ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(chi, chi, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
