@@ -15,17 +15,18 @@ def load_golden_tps(name):
     return tps, z
 
 
-def ising_tn(L, beta):
+def ising_tn(L, beta, cols=None):
     """OBC Ising partition function as a 2D tensor network: one Boltzmann matrix per bond, placed on
     the L and U legs of each site (same network as tests/test_2d_tn/test_bmps_contractor.cpp:153-270
-    of the reference up to the gauge of where the bond matrices sit)."""
+    of the reference up to the gauge of where the bond matrices sit). L rows x cols columns (square by default)."""
     B = np.array([[math.exp(beta), math.exp(-beta)], [math.exp(-beta), math.exp(beta)]])
+    rows, cols = L, (L if cols is None else cols)
     tn = []
-    for r in range(L):
+    for r in range(rows):
         row = []
-        for c in range(L):
-            dl, dd = (1 if c == 0 else 2), (1 if r == L - 1 else 2)
-            dr, du = (1 if c == L - 1 else 2), (1 if r == 0 else 2)
+        for c in range(cols):
+            dl, dd = (1 if c == 0 else 2), (1 if r == rows - 1 else 2)
+            dr, du = (1 if c == cols - 1 else 2), (1 if r == 0 else 2)
             T = np.zeros((dl, dd, dr, du))
             for s in range(2):
                 for l in range(dl):
@@ -38,9 +39,11 @@ def ising_tn(L, beta):
     return tn
 
 
-def ising_exact_logZ(L, beta):
-    """Exact OBC partition function by transfer matrix (reference: test_bmps_contractor.cpp:27-126)."""
+def ising_exact_logZ(L, beta, length=None):
+    """Exact OBC partition function by transfer matrix (reference: test_bmps_contractor.cpp:27-126): strips of width
+    L, `length` of them (square by default)."""
     n = 1 << L
+    length = L if length is None else length
 
     def chain(cfg):
         return sum(1 if ((cfg >> i) & 1) == ((cfg >> (i + 1)) & 1) else -1 for i in range(L - 1))
@@ -52,7 +55,7 @@ def ising_exact_logZ(L, beta):
     Tm = np.exp(beta * (lad + 0.5 * ch[:, None] + 0.5 * ch[None, :]))
     b = np.exp(beta * 0.5 * ch)
     v, logscale = b.copy(), 0.0
-    for _ in range(L - 1):
+    for _ in range(length - 1):
         v = v @ Tm
         s = v.max()
         v /= s

@@ -77,6 +77,30 @@ def test_K1_ising_partition_function(L):
         assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
 
 
+def test_K3_rectangular_ising_partition_function():
+    """reference: OBCIsing2DZ2TenNet (tests/test_2d_tn/test_bmps_contractor.cpp:499-686): 24 rows x 10 columns at the
+    critical point, SVD(1, 10, 1e-15), free energy per site to 1e-8. Dense restatement of the Z2-blocked fixture;
+    closures along rows and along columns of the rectangular lattice."""
+    rows, cols = 24, 10
+    beta = math.log(1 + math.sqrt(2.0)) / 2.0
+    tn = ising_tn(rows, beta, cols)
+    lz = ising_exact_logZ(cols, beta, rows)          # transfer matrix across the short side
+    c = BMPSContractor(rows, cols)
+    c.init(tn)
+    c.set_truncate_params(1, 10, 1e-15)
+    zs = []
+    c.grow_bmps_for_row(tn, 11)
+    c.init_bten(tn, LEFT, 11)
+    c.grow_full_bten(tn, RIGHT, 11, 2, True)
+    zs.append(c.trace(tn, (11, 0), HORIZONTAL))
+    c.grow_bmps_for_col(tn, 4)
+    c.init_bten(tn, UP, 4)
+    c.grow_full_bten(tn, DOWN, 4, 2, True)
+    zs.append(c.trace(tn, (0, 4), VERTICAL))
+    for z in zs:
+        assert abs((math.log(z) - lz) / (rows * cols * beta)) < 1e-8
+
+
 def test_K1_nnn_traces_reproduce_partition_function():
     """The NNN closures of the reference's K1 list (test_bmps_contractor.cpp:312-335): ReplaceNNNSiteTrace with the
     original tensors equals Z, before and after ShiftBTen2Window."""
