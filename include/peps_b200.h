@@ -141,6 +141,10 @@ int peps_sr_matvec_device(peps_ctx *ctx, const double *v_dev, double mean_dot_v,
 /* ---- probes for the parity tests ------------------------------------------------------------------ */
 /* BMPSContractor::GrowBMPSForRow + InitBTen/GrowFullBTen + Trace(tn,{row,0},HORIZONTAL) (trace.h:11-28). */
 int peps_probe_trace_row(peps_ctx *ctx, int32_t row, double *psi);
+/* BMPSContractor::ReplaceTNNSiteTrace (bmps/impl/bmps_contractor_trace.h:326-420): amplitude with the three consecutive
+ * sites starting at (row, col) along `orient` (0 = HORIZONTAL, 1 = VERTICAL) set to the physical indices
+ * cfg3[w][0..2]; grows the environments it needs first. The building block of MCUpdateSquareTNN3SiteExchange. */
+int peps_probe_tnn_trace(peps_ctx *ctx, int32_t row, int32_t col, int32_t orient, const int32_t *cfg3, double *psi);
 /* Size of bmps_set_[position]; copy of tensor i of stack entry k, [W][d0][d1][d2]; dims returned. */
 int32_t peps_bmps_stack_size(peps_ctx *ctx, int32_t position);
 int peps_get_bmps_tensor(peps_ctx *ctx, int32_t position, int32_t k, int32_t i, double *out, int32_t dims[3]);

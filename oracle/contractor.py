@@ -235,6 +235,20 @@ class BMPSContractor:
         half_a = self.bten_step(self.bten_set[first][i], mps1, replace_ten, mps2, first)
         return es("abc,cba->", half_a, self.bten_at_slice(second, i)).item()
 
+    def replace_tnn_site_trace(self, tn, site0, mps_orient, ten0, ten1, ten2):
+        """ReplaceTNNSiteTrace (trace.h:326-420): three consecutive sites of a row (column) replaced; three BTen steps
+        from the LEFT (UP) environment closed with the RIGHT (DOWN) one."""
+        row, col = site0
+        if mps_orient == HORIZONTAL:
+            first, second, slice_num, i = LEFT, RIGHT, row, col
+        else:
+            first, second, slice_num, i = UP, DOWN, col, row
+        cur = self.bten_set[first][i]
+        for step, ten in enumerate((ten0, ten1, ten2)):
+            mps1, mps2, _ = self._bten_operands(tn, first, slice_num, i + step + 1)
+            cur = self.bten_step(cur, mps1, ten, mps2, first)
+        return es("abc,cba->", cur, self.bten_at_slice(second, i + 2)).item()
+
     def punch_hole(self, tn, site, mps_orient):
         """PunchHole (grow.h:150-183), bosonic branch; result legs (L, D, R, U)."""
         row, col = site

@@ -66,6 +66,7 @@ SIGNATURES = {
     "peps_sr_matvec": (C.c_int, [_P, _D, C.c_double, _D, C.c_size_t]),
     "peps_sr_matvec_device": (C.c_int, [_P, C.c_void_p, C.c_double, C.c_void_p]),
     "peps_probe_trace_row": (C.c_int, [_P, C.c_int32, _D]),
+    "peps_probe_tnn_trace": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _I, _D]),
     "peps_bmps_stack_size": (C.c_int32, [_P, C.c_int32]),
     "peps_get_bmps_tensor": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _D, _I]),
     "peps_stat": (C.c_int64, [_P, C.c_int32]),

@@ -365,6 +365,13 @@ class WalkerBatch:
         self._ck(self.lib.peps_probe_trace_row(self.h, row, _dp(a)))
         return a
 
+    def probe_tnn_trace(self, row, col, orient, cfg3):
+        """ReplaceTNNSiteTrace for every walker: cfg3[w] = physical indices of the three consecutive sites."""
+        c3 = np.ascontiguousarray(cfg3, dtype=np.int32).reshape(self.W, 3)
+        a = np.empty(self.W)
+        self._ck(self.lib.peps_probe_tnn_trace(self.h, row, col, orient, _ip(c3), _dp(a)))
+        return a
+
     def bmps_stack_size(self, pos):
         return self.lib.peps_bmps_stack_size(self.h, pos)
 

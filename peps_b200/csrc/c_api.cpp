@@ -136,6 +136,14 @@ int peps_sr_matvec(peps_ctx *ctx, const double *v, double mean_dot_v, double *ou
 }
 int peps_sr_matvec_device(peps_ctx *ctx, const double *v, double mean_dot_v, double *out) { GUARD(ctx, ctx->eng->sr_matvec_device(v, mean_dot_v, out)) }
 int peps_probe_trace_row(peps_ctx *ctx, int32_t row, double *psi) { GUARD(ctx, ctx->eng->probe_trace_row(row, psi)) }
+int peps_probe_tnn_trace(peps_ctx *ctx, int32_t row, int32_t col, int32_t orient, const int32_t *cfg3, double *psi) {
+  GUARD(ctx, {
+    const int n = orient == 0 ? ctx->eng->cols() : ctx->eng->rows(), i0 = orient == 0 ? col : row;
+    if (orient < 0 || orient > 1 || row < 0 || col < 0 || row >= ctx->eng->rows() || col >= ctx->eng->cols() || i0 + 2 >= n)
+      throw std::invalid_argument("peps_probe_tnn_trace: the three sites do not fit the lattice");
+    ctx->eng->probe_tnn_trace(row, col, orient, cfg3, psi);
+  })
+}
 int32_t peps_bmps_stack_size(peps_ctx *ctx, int32_t pos) { return ctx->eng->bmps_stack_size(pos); }
 int peps_get_bmps_tensor(peps_ctx *ctx, int32_t pos, int32_t k, int32_t i, double *out, int32_t dims[3]) {
   GUARD(ctx, { int d[3]; ctx->eng->bmps_tensor(pos, k, i, out, d); for (int a = 0; a < 3; ++a) dims[a] = d[a]; })

@@ -569,6 +569,41 @@ void Engine::nn_trace_idx(int ra, int ca, int rb, int cb, int orient, const int3
   release(half_a);
   release(half_b);
 }
+void Engine::tnn_trace_idx(int r, int c, int orient, const int32_t *idx0, const int32_t *idx1, const int32_t *idx2, int stride,
+                           double *psi_out) {                                                     // trace.h:326-420
+  ++n_trace_;
+  const int first = orient == HORIZONTAL ? LEFT : UP, second = opposite(first);
+  const int slice = orient == HORIZONTAL ? r : c, i0 = orient == HORIZONTAL ? c : r;
+  const int32_t *idx[3] = {idx0, idx1, idx2};
+  BT cur;
+  for (int step = 0; step < 3; ++step) {
+    const BT *m1, *m2; int site;
+    bten_operands(first, slice, i0 + step + 1, m1, m2, site);
+    BT nxt = bten_step(step == 0 ? bten_[first].at((size_t)i0) : cur, *m1, site_ref_idx(site, idx[step], stride), *m2, first);
+    if (step > 0) release(cur);
+    cur = nxt;
+  }
+  reverse_dot(cur, bten_at_slice(second, i0 + 2), psi_out);
+  release(cur);
+}
+void Engine::probe_tnn_trace(int r, int c, int orient, const int32_t *cfg3_host, double *psi_host) {
+  int32_t *d = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * 3);
+  be_h2d(d, cfg3_host, sizeof(int32_t) * (size_t)W_ * 3);
+  if (orient == HORIZONTAL) {
+    grow_bmps_for_row(r);
+    init_bten(LEFT);
+    for (int k = 0; k < c; ++k) grow_bten_step(LEFT);
+    grow_full_bten(RIGHT, r, c + 3, true);
+  } else {
+    grow_bmps_for_col(c);
+    init_bten(UP);
+    for (int k = 0; k < r; ++k) grow_bten_step(UP);
+    grow_full_bten(DOWN, c, r + 3, true);
+  }
+  tnn_trace_idx(r, c, orient, d, d + 1, d + 2, 3, psi_tmp_);
+  be_d2h(psi_host, psi_tmp_, sizeof(double) * W_);
+  pool_.put(d);
+}
 void Engine::one_site_trace(int r, int c, const int32_t *idx, int stride, double *psi_out) {     // trace.h:30-88
   ++n_trace_;
   const BT *m1, *m2; int site;

@@ -134,6 +134,12 @@ class Engine {
   void punch_hole(int r, int c, int orient);          // into the holes buffer
   // psi_out[w] = ReplaceOneSiteTrace({r,c}, sitps({r,c})[idx[w*stride]], HORIZONTAL) (trace.h:30-88)
   void one_site_trace(int r, int c, const int32_t *idx, int stride, double *psi_out);
+  // psi_out[w] = ReplaceTNNSiteTrace({r,c}, orient, slices idx0/1/2[w*stride] of the three consecutive sites) (trace.h:326-420)
+  void tnn_trace_idx(int r, int c, int orient, const int32_t *idx0, const int32_t *idx1, const int32_t *idx2, int stride,
+                     double *psi_out);
+  // test probe: grows the environments of the row (HORIZONTAL) / column (VERTICAL) of `site` and evaluates the three-site
+  // trace starting there with the physical indices cfg3[w][0..2] (host array)
+  void probe_tnn_trace(int r, int c, int orient, const int32_t *cfg3_host, double *psi_host);
   // ReplaceNNSiteTrace with explicit physical indices (device arrays) instead of entries of the configuration
   void nn_trace_idx(int ra, int ca, int rb, int cb, int orient, const int32_t *idx_a, const int32_t *idx_b, int stride,
                     double *psi_out);

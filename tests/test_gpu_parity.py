@@ -183,6 +183,31 @@ def test_measure_bond_energies_parity_gpu(lib, j2):
             assert np.allclose(obs[k][w], v, rtol=1e-10, atol=1e-12), (k, w)
 
 
+@pytest.mark.parametrize("orient", [0, 1])
+def test_three_site_trace_parity_gpu(lib, orient):
+    """ReplaceTNNSiteTrace (bmps/impl/bmps_contractor_trace.h:326-420) on the GPU against amplitudes of the oracle
+    evaluated from scratch on the modified configurations."""
+    from oracle import vmc
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+    rows, cols, D, W = 4, 5, 3, 3
+    tps = vmc.random_tps(rows, cols, 2, D, seed=8)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 20 + w) for w in range(W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(1, 200, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    r0, c0 = (2, 1) if orient == 0 else (1, 3)
+    sites = [(r0, c0 + k) if orient == 0 else (r0 + k, c0) for k in range(3)]
+    new = np.array([[1, 0, 1], [0, 0, 1], [1, 1, 0]], dtype=np.int32)
+    psi = b.probe_tnn_trace(r0, c0, orient, new)
+    for w in range(W):
+        cf = cfgs[w].copy()
+        for k, st in enumerate(sites):
+            cf[st] = new[w, k]
+        ref = vmc.Walker(tps, cf, (1, 200, 0.0)).amplitude
+        assert abs(psi[w] / ref - 1) < 1e-10
+
+
 def test_gradient_parity_gpu(lib):
     run_gradient_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsamples=4)
 

@@ -197,6 +197,28 @@ def test_measurer_mirror_on_golden_4x4(lib):
     assert "bond_energy_dr" not in out
 
 
+@pytest.mark.parametrize("orient", [0, 1])
+def test_three_site_trace_parity_hostsim(lib, orient):
+    """ReplaceTNNSiteTrace (trace.h:326-420) against the oracle and against amplitudes from scratch."""
+    rows, cols, D, W = 4, 5, 2, 3
+    tps = vmc.random_tps(rows, cols, 2, D, seed=8)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 20 + w) for w in range(W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(1, 64, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    r0, c0 = (2, 1) if orient == 0 else (1, 3)
+    sites = [(r0, c0 + k) if orient == 0 else (r0 + k, c0) for k in range(3)]
+    new = np.array([[1, 0, 1], [0, 0, 1], [1, 1, 0]], dtype=np.int32)
+    psi = b.probe_tnn_trace(r0, c0, orient, new)
+    for w in range(W):
+        cf = cfgs[w].copy()
+        for k, st in enumerate(sites):
+            cf[st] = new[w, k]
+        ref = vmc.Walker(tps, cf, (1, 64, 0.0)).amplitude
+        assert abs(psi[w] / ref - 1) < 1e-10
+
+
 def test_error_paths(lib):
     with pytest.raises(PepsError):
         WalkerBatch(1, 4, 2, 2, 1, BMPSTruncateParams.SVD(2, 2, 0.0), lib=lib)     # lattice too small

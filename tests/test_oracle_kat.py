@@ -77,6 +77,31 @@ def test_K1_ising_partition_function(L):
         assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
 
 
+def test_K1_three_site_traces_reproduce_partition_function():
+    """ReplaceTNNSiteTrace closures of the reference's K1 list (tests/test_2d_tn/test_bmps_contractor.cpp:273-405):
+    with the original tensors every closure is the partition function."""
+    L = 8
+    beta = math.log(1 + math.sqrt(2.0)) / 2.0
+    tn = ising_tn(L, beta)
+    lz = ising_exact_logZ(L, beta)
+    c = BMPSContractor(L, L)
+    c.init(tn)
+    c.set_truncate_params(10, 30, 1e-15)
+    zs = []
+    c.grow_bmps_for_row(tn, 3)
+    c.init_bten(tn, LEFT, 3)
+    c.grow_full_bten(tn, RIGHT, 3, 3, True)
+    zs.append(c.replace_tnn_site_trace(tn, (3, 0), HORIZONTAL, tn[3][0], tn[3][1], tn[3][2]))
+    c.shift_bten_window(tn, RIGHT)
+    zs.append(c.replace_tnn_site_trace(tn, (3, 1), HORIZONTAL, tn[3][1], tn[3][2], tn[3][3]))
+    c.grow_bmps_for_col(tn, 2)
+    c.init_bten(tn, UP, 2)
+    c.grow_full_bten(tn, DOWN, 2, 3, True)
+    zs.append(c.replace_tnn_site_trace(tn, (0, 2), VERTICAL, tn[0][2], tn[1][2], tn[2][2]))
+    for z in zs:
+        assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
+
+
 def test_K3_rectangular_ising_partition_function():
     """reference: OBCIsing2DZ2TenNet (tests/test_2d_tn/test_bmps_contractor.cpp:499-686): 24 rows x 10 columns at the
     critical point, SVD(1, 10, 1e-15), free energy per site to 1e-8. Dense restatement of the Z2-blocked fixture;
