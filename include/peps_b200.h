@@ -95,7 +95,12 @@ int peps_sweep(peps_ctx *ctx, int32_t nsweeps, double *accept_rates);
  * local states of every bond (no Sz conservation), Suwa-Todo choice (monte_carlo_tools/suwa_todo_update.h:53-113) with
  * the reference's long double prefix sums and draw, taken on the host from the same per-walker mt19937 streams. */
 int peps_sweep_full_space(peps_ctx *ctx, int32_t nsweeps, double *accept_rates);
-/* Selects the updater peps_sample steps with: 0 = MCUpdateSquareNNExchangeOBC (default), 1 = MCUpdateSquareNNFullSpaceUpdateOBC. */
+/* MonteCarloEngine::StepSweep(n) with MCUpdateSquareTNN3SiteExchange (configuration_update_strategies/
+ * square_3site_updater.h:23-160): permutations of the spins on three consecutive sites through ReplaceTNNSiteTrace,
+ * Suwa-Todo choice; the cached amplitude is refreshed by a three-site trace at every row / column start. */
+int peps_sweep_three_site(peps_ctx *ctx, int32_t nsweeps, double *accept_rates);
+/* Selects the updater peps_sample steps with: 0 = MCUpdateSquareNNExchangeOBC (default), 1 = MCUpdateSquareNNFullSpaceUpdateOBC,
+ * 2 = MCUpdateSquareTNN3SiteExchange. */
 int peps_set_updater(peps_ctx *ctx, int32_t kind);
 /* ModelEnergySolver::CalEnergyAndHoles<calchols> (algorithm/vmc_update/model_energy_solver.h:69-100 ->
  * model_solvers/base/square_nnn_energy_solver.h:79-315). eloc[W]; psi_list[(rows+cols)][W] may be NULL. */

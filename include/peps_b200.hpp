@@ -34,7 +34,7 @@ struct MonteCarloParams {
 struct XXZModel { double jz = 1.0, jxy = 1.0, pinning00 = 0.0; };   // SquareSpinOneHalfXXZModelOBC(jz, jxy, pinning)
 struct J1J2XXZModel { double jz = 1.0, jxy = 1.0, jz2 = 0.0, jxy2 = 0.0, pinning00 = 0.0; };   // SquareSpinOneHalfJ1J2XXZModelOBC
 struct TransverseFieldIsingModel { double h = 1.0; };                 // TransverseFieldIsingSquareOBC(h)
-enum class Updater : int32_t { NNExchange = 0, NNFullSpace = 1 };     // MCUpdateSquareNNExchangeOBC / ...NNFullSpaceUpdateOBC
+enum class Updater : int32_t { NNExchange = 0, NNFullSpace = 1, TNN3SiteExchange = 2 };   // MCUpdateSquareNNExchangeOBC / ...NNFullSpaceUpdateOBC / MCUpdateSquareTNN3SiteExchange
 
 class WalkerBatch {
  public:
@@ -74,7 +74,8 @@ class WalkerBatch {
   double NormalizeStateOrder1(double max_abs_override = 0.0) { double f = 0; ck(peps_normalize_state_order1(h_, max_abs_override, &f)); return f; }
   std::vector<double> StepSweep(int n) {
     std::vector<double> a((size_t)walkers_);
-    ck(updater_ == Updater::NNFullSpace ? peps_sweep_full_space(h_, n, a.data()) : peps_sweep(h_, n, a.data()));
+    ck(updater_ == Updater::NNFullSpace ? peps_sweep_full_space(h_, n, a.data())
+       : updater_ == Updater::TNN3SiteExchange ? peps_sweep_three_site(h_, n, a.data()) : peps_sweep(h_, n, a.data()));
     return a;
   }
   void ZeroAccumulators() { ck(peps_zero_accumulators(h_)); }

@@ -14,6 +14,7 @@ Reference (relative to include/qlpeps/):
   * SRSMatrix::operator*              optimizer/stochastic_reconfiguration_smatrix.h:45-91
   * SuwaTodoStateUpdate               vmc_basic/monte_carlo_tools/suwa_todo_update.h:53-113
   * MCUpdateSquareNNFullSpaceUpdateOBC .../square_nn_updater.h:253-293
+  * MCUpdateSquareTNN3SiteExchange    .../square_3site_updater.h:23-160
   * TransverseFieldIsingSquareOBC     algorithm/vmc_update/model_solvers/transverse_field_ising_square_obc.h:149-247
 """
 import math
@@ -177,6 +178,71 @@ class NNFullSpaceUpdater(NNExchangeUpdater):
             return False
         w.update_local(tps, alt[final], (site1, final // dim), (site2, final % dim))
         return True
+
+
+class TNN3SiteExchangeUpdater:
+    """MCUpdateSquareTNN3SiteExchange (vmc_basic/configuration_update_strategies/square_3site_updater.h:23-160):
+    permutations of the spins on three consecutive sites, Suwa-Todo choice; the cached amplitude is refreshed by a
+    three-site trace at the start of every row / column."""
+
+    def __init__(self, seed):
+        self.rng = MT19937(seed)
+
+    def three_site_update(self, s1, s2, s3, bond_dir, tps, w):
+        spins = [int(w.config[s1]), int(w.config[s2]), int(w.config[s3])]
+        if spins[0] == spins[1] == spins[2]:
+            return False
+        import itertools
+        perms = sorted(set(itertools.permutations(sorted(spins))))          # std::next_permutation order
+        init = perms.index(tuple(spins))
+        psis = []
+        for i, pm in enumerate(perms):
+            if i != init:
+                psis.append(w.contractor.replace_tnn_site_trace(w.tn, s1, bond_dir, tps[s1[0]][s1[1]][pm[0]],
+                                                                tps[s2[0]][s2[1]][pm[1]], tps[s3[0]][s3[1]][pm[2]]))
+            else:
+                psis.append(w.amplitude)
+        mx = max(abs(x) for x in psis)
+        weights = [abs(x / mx) ** 2 for x in psis]
+        final = suwa_todo_state_update(init, weights, self.rng)
+        if final == init:
+            return False
+        pm = perms[final]
+        w.update_local(tps, psis[final], (s1, pm[0]), (s2, pm[1]), (s3, pm[2]))
+        return True
+
+    def sweep(self, tps, w):
+        tn, c = w.tn, w.contractor
+        rows, cols = w.rows, w.cols
+        accepted = 0
+        c.set_truncate_params(*w.trunc)
+        c.generate_bmps_approach(tn, UP)
+        for row in range(rows):
+            c.init_bten(tn, LEFT, row)
+            c.grow_full_bten(tn, RIGHT, row, 3, True)
+            w.amplitude = c.replace_tnn_site_trace(tn, (row, 0), HORIZONTAL, tn[row][0], tn[row][1], tn[row][2])
+            for col in range(cols - 2):
+                accepted += self.three_site_update((row, col), (row, col + 1), (row, col + 2), HORIZONTAL, tps, w)
+                if col < cols - 3:
+                    c.shift_bten_window(tn, RIGHT)
+            if row < rows - 1:
+                c.shift_bmps_window(tn, DOWN)
+        c.delete_inner_bmps(LEFT)
+        c.delete_inner_bmps(RIGHT)
+        c.generate_bmps_approach(tn, LEFT)
+        for col in range(cols):
+            c.init_bten(tn, UP, col)
+            c.grow_full_bten(tn, DOWN, col, 3, True)
+            w.amplitude = c.replace_tnn_site_trace(tn, (0, col), VERTICAL, tn[0][col], tn[1][col], tn[2][col])
+            for row in range(rows - 2):
+                accepted += self.three_site_update((row, col), (row + 1, col), (row + 2, col), VERTICAL, tps, w)
+                if row < rows - 3:
+                    c.shift_bten_window(tn, DOWN)
+            if col < cols - 1:
+                c.shift_bmps_window(tn, RIGHT)
+        c.delete_inner_bmps(UP)
+        total = cols * (rows - 2) + rows * (cols - 2)
+        return [accepted / total]
 
 
 class TFIMModel:

@@ -5,9 +5,9 @@ sm_100a kernels of peps_b200/csrc/backend_cuda.cu. See DESIGN.md.
 """
 from .api import (BMPSTruncateParams, MonteCarloParams, SplitIndexTPS, Configuration, SquareSpinOneHalfXXZModelOBC,
                   SquareSpinOneHalfJ1J2XXZModelOBC, TransverseFieldIsingSquareOBC, MCUpdateSquareNNExchange,
-                  MCUpdateSquareNNFullSpaceUpdate, WalkerBatch, MCEnergyGradEvaluator, MCPEPSMeasurer, PepsError)
+                  MCUpdateSquareNNFullSpaceUpdate, MCUpdateSquareTNN3SiteExchange, WalkerBatch, MCEnergyGradEvaluator, MCPEPSMeasurer, PepsError)
 
 __all__ = ["BMPSTruncateParams", "MonteCarloParams", "SplitIndexTPS", "Configuration",
            "SquareSpinOneHalfXXZModelOBC", "SquareSpinOneHalfJ1J2XXZModelOBC", "TransverseFieldIsingSquareOBC", "MCUpdateSquareNNExchange",
-           "MCUpdateSquareNNFullSpaceUpdate", "WalkerBatch", "MCEnergyGradEvaluator", "MCPEPSMeasurer",
+           "MCUpdateSquareNNFullSpaceUpdate", "MCUpdateSquareTNN3SiteExchange", "WalkerBatch", "MCEnergyGradEvaluator", "MCPEPSMeasurer",
            "PepsError"]

@@ -47,6 +47,7 @@ SIGNATURES = {
     "peps_normalize_state_order1": (C.c_int, [_P, C.c_double, _D]),
     "peps_sweep": (C.c_int, [_P, C.c_int32, _D]),
     "peps_sweep_full_space": (C.c_int, [_P, C.c_int32, _D]),
+    "peps_sweep_three_site": (C.c_int, [_P, C.c_int32, _D]),
     "peps_measure": (C.c_int, [_P, _D, _D, _D, _D, _D, _D]),
     "peps_set_updater": (C.c_int, [_P, C.c_int32]),
     "peps_set_model_tfim": (C.c_int, [_P, C.c_double]),

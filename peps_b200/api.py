@@ -165,6 +165,13 @@ class SquareSpinOneHalfJ1J2XXZModelOBC:
 
 
 @dataclass
+class MCUpdateSquareTNN3SiteExchange:
+    """square_3site_updater.h:23-160: permutations of the spins on three consecutive sites, Suwa-Todo choice."""
+    seed: int = 5489
+    kind = 2
+
+
+@dataclass
 class TransverseFieldIsingSquareOBC:
     """model_solvers/transverse_field_ising_square_obc.h:28-247: H = -sum_<ij> sz_i sz_j - h sum_i sx_i."""
     h: float = 1.0
@@ -289,7 +296,8 @@ class WalkerBatch:
     def sweep(self, n=1):
         """StepSweep with the updater chosen by set_updater (NN exchange unless told otherwise)."""
         acc = np.empty(self.W)
-        f = self.lib.peps_sweep_full_space if getattr(self, "updater_kind", 0) == 1 else self.lib.peps_sweep
+        kind = getattr(self, "updater_kind", 0)
+        f = {0: self.lib.peps_sweep, 1: self.lib.peps_sweep_full_space, 2: self.lib.peps_sweep_three_site}[kind]
         self._ck(f(self.h, n, _dp(acc)))
         return acc
 

@@ -104,6 +104,7 @@ int peps_normalize_state_order1(peps_ctx *ctx, double max_abs_override, double *
 
 int peps_sweep(peps_ctx *ctx, int32_t n, double *acc) { GUARD(ctx, ctx->eng->sweep(n, acc)) }
 int peps_set_updater(peps_ctx *ctx, int32_t kind) { GUARD(ctx, ctx->eng->set_updater(kind)) }
+int peps_sweep_three_site(peps_ctx *ctx, int32_t n, double *acc) { GUARD(ctx, ctx->eng->sweep_three_site(n, acc)) }
 int peps_sweep_full_space(peps_ctx *ctx, int32_t n, double *acc) { GUARD(ctx, ctx->eng->sweep_full_space(n, acc)) }
 int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, double *psi_list) {
   GUARD(ctx, ctx->eng->energy_and_holes(calc_holes != 0, eloc, psi_list))

@@ -1,5 +1,7 @@
 // See engine.h. Backend-agnostic host orchestration of the walker-batched VMC sampling path.
 #include "engine.h"
+#include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -80,7 +82,7 @@ Engine::~Engine() {
   for (void *p : {(void *)tps_, (void *)osum_, (void *)eosum_, (void *)tps_off_d_, (void *)site_size_d_, (void *)hole_off_d_,
                   (void *)cfg_, (void *)amp_, (void *)mt_, (void *)mtidx_, (void *)accepted_, (void *)eloc_, (void *)psi_tmp_,
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
-                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_})
+                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_})
     be_free(p);
 }
 
@@ -846,8 +848,8 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
     std::vector<int32_t> h((size_t)d * W_);
     for (int s = 0; s < d; ++s) for (int w = 0; w < W_; ++w) h[(size_t)s * W_ + w] = s;
     be_h2d(idx_const_, h.data(), sizeof(int32_t) * h.size());
-    psi_alt_ = (double *)be_malloc(sizeof(double) * (size_t)nst * W_);
   }
+  ensure_psi_alt(nst);
   std::vector<int32_t> cfg((size_t)W_ * nsites_), mtidx((size_t)W_);
   std::vector<uint32_t> mt((size_t)W_ * 624);
   std::vector<double> amp((size_t)W_), alt((size_t)nst * W_);
@@ -927,6 +929,123 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
   if (accept_rate_host) {
     const double bond_num = (double)(cols_ * (rows_ - 1) + rows_ * (cols_ - 1));
     for (int w = 0; w < W_; ++w) accept_rate_host[w] = accepted[(size_t)w] / bond_num;
+  }
+}
+
+void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
+  if (rows_ < 3 || cols_ < 3) throw std::invalid_argument("the 3-site updater needs a lattice of at least 3x3");
+  const int maxp = 6;
+  if (!idx_perm_) idx_perm_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)maxp * W_ * 3);
+  ensure_psi_alt(maxp);
+  std::vector<int32_t> cfg((size_t)W_ * nsites_), mtidx((size_t)W_), perm_h((size_t)maxp * W_ * 3);
+  std::vector<uint32_t> mt((size_t)W_ * 624);
+  std::vector<double> amp((size_t)W_), alt((size_t)maxp * W_);
+  std::vector<HostMT> rng((size_t)W_);
+  be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
+  be_d2h(mt.data(), mt_, sizeof(uint32_t) * mt.size());
+  be_d2h(mtidx.data(), mtidx_, sizeof(int32_t) * mtidx.size());
+  for (int w = 0; w < W_; ++w) {
+    std::copy(mt.begin() + (size_t)w * 624, mt.begin() + (size_t)(w + 1) * 624, rng[(size_t)w].mt);
+    rng[(size_t)w].idx = mtidx[(size_t)w];
+  }
+  std::vector<int> accepted((size_t)W_);
+  auto refresh_amplitude = [&](int r, int c, int orient) {            // :39-42, :66-69
+    const int s0 = r * cols_ + c, step = orient == HORIZONTAL ? 1 : cols_;
+    tnn_trace_idx(r, c, orient, cfg_ + s0, cfg_ + s0 + step, cfg_ + s0 + 2 * step, nsites_, amp_);
+    be_d2h(amp.data(), amp_, sizeof(double) * amp.size());
+  };
+  auto triple = [&](int r, int c, int orient) {                       // TNN3SiteUpdateImpl (:108-158)
+    const int s0 = r * cols_ + c, step = orient == HORIZONTAL ? 1 : cols_;
+    const int st[3] = {s0, s0 + step, s0 + 2 * step};
+    std::vector<std::vector<std::array<int, 3>>> perms((size_t)W_);
+    std::vector<int> init((size_t)W_, -1);
+    int nslots = 0;
+    for (int w = 0; w < W_; ++w) {
+      const int32_t *cw = cfg.data() + (size_t)w * nsites_;
+      std::array<int, 3> sp = {cw[st[0]], cw[st[1]], cw[st[2]]};
+      if (sp[0] == sp[1] && sp[1] == sp[2]) continue;                  // no draw for a uniform triple
+      std::array<int, 3> srt = sp;
+      std::sort(srt.begin(), srt.end());
+      do { perms[(size_t)w].push_back(srt); } while (std::next_permutation(srt.begin(), srt.end()));
+      init[(size_t)w] = (int)(std::find(perms[(size_t)w].begin(), perms[(size_t)w].end(), sp) - perms[(size_t)w].begin());
+      nslots = std::max(nslots, (int)perms[(size_t)w].size());
+    }
+    if (nslots == 0) return;
+    for (int s = 0; s < nslots; ++s)
+      for (int w = 0; w < W_; ++w) {
+        const int32_t *cw = cfg.data() + (size_t)w * nsites_;
+        const bool has = s < (int)perms[(size_t)w].size();
+        for (int k = 0; k < 3; ++k)
+          perm_h[((size_t)s * W_ + w) * 3 + k] = has ? perms[(size_t)w][(size_t)s][(size_t)k] : cw[st[k]];
+      }
+    be_h2d(idx_perm_, perm_h.data(), sizeof(int32_t) * (size_t)nslots * W_ * 3);
+    for (int s = 0; s < nslots; ++s) {
+      const int32_t *ix = idx_perm_ + (size_t)s * W_ * 3;
+      tnn_trace_idx(r, c, orient, ix, ix + 1, ix + 2, 3, psi_alt_ + (size_t)s * W_);
+    }
+    be_d2h(alt.data(), psi_alt_, sizeof(double) * (size_t)nslots * W_);
+    bool any = false;
+    for (int w = 0; w < W_; ++w) {
+      const int np = (int)perms[(size_t)w].size();
+      if (np == 0) continue;
+      std::vector<double> psis((size_t)np), wt((size_t)np);
+      double mx = 0.0;
+      for (int i = 0; i < np; ++i) {
+        psis[(size_t)i] = i == init[(size_t)w] ? amp[(size_t)w] : alt[(size_t)i * W_ + w];
+        mx = std::max(mx, std::fabs(psis[(size_t)i]));
+      }
+      for (int i = 0; i < np; ++i) { const double q = psis[(size_t)i] / mx; wt[(size_t)i] = q * q; }
+      const int fin = suwa_todo(init[(size_t)w], wt, rng[(size_t)w]);
+      if (fin == init[(size_t)w]) continue;
+      int32_t *cw = cfg.data() + (size_t)w * nsites_;
+      for (int k = 0; k < 3; ++k) cw[st[k]] = perms[(size_t)w][(size_t)fin][(size_t)k];
+      amp[(size_t)w] = psis[(size_t)fin];
+      ++accepted[(size_t)w];
+      any = true;
+    }
+    if (any) {
+      be_h2d(cfg_, cfg.data(), sizeof(int32_t) * cfg.size());
+      be_h2d(amp_, amp.data(), sizeof(double) * amp.size());
+    }
+    for (int k = 0; k < 3; ++k) touch_site(st[k]);
+  };
+  for (int sw = 0; sw < nsweeps; ++sw) {                                // square_3site_updater.h:29-97
+    std::fill(accepted.begin(), accepted.end(), 0);
+    generate_bmps_approach(UP);
+    for (int row = 0; row < rows_; ++row) {
+      init_bten(LEFT);
+      grow_full_bten(RIGHT, row, 3, true);
+      refresh_amplitude(row, 0, HORIZONTAL);
+      for (int col = 0; col < cols_ - 2; ++col) {
+        triple(row, col, HORIZONTAL);
+        if (col < cols_ - 3) shift_bten_window(RIGHT);
+      }
+      if (row < rows_ - 1) shift_bmps_window(DOWN);
+    }
+    delete_inner_bmps(LEFT);
+    delete_inner_bmps(RIGHT);
+    generate_bmps_approach(LEFT);
+    for (int col = 0; col < cols_; ++col) {
+      init_bten(UP);
+      grow_full_bten(DOWN, col, 3, true);
+      refresh_amplitude(0, col, VERTICAL);
+      for (int row = 0; row < rows_ - 2; ++row) {
+        triple(row, col, VERTICAL);
+        if (row < rows_ - 3) shift_bten_window(DOWN);
+      }
+      if (col < cols_ - 1) shift_bmps_window(RIGHT);
+    }
+    delete_inner_bmps(UP);
+  }
+  for (int w = 0; w < W_; ++w) {
+    std::copy(rng[(size_t)w].mt, rng[(size_t)w].mt + 624, mt.begin() + (size_t)w * 624);
+    mtidx[(size_t)w] = rng[(size_t)w].idx;
+  }
+  be_h2d(mt_, mt.data(), sizeof(uint32_t) * mt.size());
+  be_h2d(mtidx_, mtidx.data(), sizeof(int32_t) * mtidx.size());
+  if (accept_rate_host) {
+    const double total = (double)(cols_ * (rows_ - 2) + rows_ * (cols_ - 2));
+    for (int w = 0; w < W_; ++w) accept_rate_host[w] = accepted[(size_t)w] / total;
   }
 }
 

@@ -70,9 +70,17 @@ class Engine {
   // ReplaceNNSiteTrace on the device, Suwa-Todo choice (long double prefix sums + one long double draw per bond,
   // suwa_todo_update.h:53-113) on the host from the per-walker mt19937 streams
   void sweep_full_space(int nsweeps, double *accept_rate_host);
-  // MonteCarloEngine::StepSweep with the configured updater (0 = NN exchange, 1 = NN full space)
-  void set_updater(int kind) { if (kind != 0 && kind != 1) throw std::invalid_argument("unknown updater"); updater_ = kind; }
-  void step_sweep(int nsweeps, double *accept_rate_host) { if (updater_ == 1) sweep_full_space(nsweeps, accept_rate_host); else sweep(nsweeps, accept_rate_host); }
+  // MCUpdateSquareTNN3SiteExchange (square_3site_updater.h:23-160): permutations of the spins of three consecutive
+  // sites by batched ReplaceTNNSiteTrace (one trace per permutation slot, per-walker physical indices), Suwa-Todo
+  // choice on the host; the cached amplitude is refreshed by a three-site trace at every row / column start
+  void sweep_three_site(int nsweeps, double *accept_rate_host);
+  // MonteCarloEngine::StepSweep with the configured updater (0 = NN exchange, 1 = NN full space, 2 = 3-site exchange)
+  void set_updater(int kind) { if (kind < 0 || kind > 2) throw std::invalid_argument("unknown updater"); updater_ = kind; }
+  void step_sweep(int nsweeps, double *accept_rate_host) {
+    if (updater_ == 1) sweep_full_space(nsweeps, accept_rate_host);
+    else if (updater_ == 2) sweep_three_site(nsweeps, accept_rate_host);
+    else sweep(nsweeps, accept_rate_host);
+  }
   void energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host);
   // SquareNNNModelMeasurementSolver::EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214) for the
   // XXZ / J1-J2 models: the bond traversal without holes, every bond energy kept. Host outputs (any may be null):
@@ -196,7 +204,16 @@ class Engine {
   double tfim_h_ = 0.0;
   int32_t *idx_const_ = nullptr;   // [phys][W]: idx_const_[s*W + w] = s
   int32_t *idx_flip_ = nullptr;    // [W][nsites]: 1 - config
-  double *psi_alt_ = nullptr;      // [phys*phys][W]
+  int32_t *idx_perm_ = nullptr;    // [6][W][3]: physical indices of permutation slot s of walker w (3-site updater)
+  double *psi_alt_ = nullptr;      // [psi_alt_slots_][W] amplitudes of the alternative local states of an update
+  int psi_alt_slots_ = 0;
+  void ensure_psi_alt(int slots) {
+    if (slots <= psi_alt_slots_) return;
+    be_sync();
+    be_free(psi_alt_);
+    psi_alt_ = (double *)be_malloc(sizeof(double) * (size_t)slots * W_);
+    psi_alt_slots_ = slots;
+  }
   Pool pool_;
   Planner planner_;
   LinalgCtx la_;

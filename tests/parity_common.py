@@ -18,7 +18,7 @@ def flat_holes(holes, rows, cols):
 
 
 def run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=1, signed=False, tol=1e-10, seeds0=100,
-                        check_configs=True, j2=0.0, tfim_h=None):
+                        check_configs=True, j2=0.0, tfim_h=None, three_site=False):
     """Sweeps + energy + holes for W walkers through the C ABI vs the oracle, walker by walker.
     tfim_h: transverse-field Ising model with the full-space (Suwa-Todo) updater instead of XXZ + exchange
     (BASELINE config #1)."""
@@ -35,9 +35,15 @@ def run_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=1, signed=
         from peps_b200.api import TransverseFieldIsingSquareOBC, MCUpdateSquareNNFullSpaceUpdate
         b.set_model(TransverseFieldIsingSquareOBC(tfim_h))
         b.set_updater(MCUpdateSquareNNFullSpaceUpdate())
+    if three_site:
+        from peps_b200.api import MCUpdateSquareTNN3SiteExchange
+        b.set_updater(MCUpdateSquareTNN3SiteExchange())
     b.init_walkers()
     ws = [vmc.Walker(tps, cfgs[w], trunc) for w in range(W)]
-    if tfim_h is not None:
+    if three_site:
+        ups = [vmc.TNN3SiteExchangeUpdater(seeds0 + w) for w in range(W)]
+        model = vmc.XXZModel(1.0, 1.0, 0.0, j2, j2)
+    elif tfim_h is not None:
         ups = [vmc.NNFullSpaceUpdater(seeds0 + w) for w in range(W)]
         model = vmc.TFIMModel(tfim_h)
     else:

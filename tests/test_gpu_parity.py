@@ -183,6 +183,12 @@ def test_measure_bond_energies_parity_gpu(lib, j2):
             assert np.allclose(obs[k][w], v, rtol=1e-10, atol=1e-12), (k, w)
 
 
+def test_three_site_updater_pipeline_parity_gpu(lib):
+    """MCUpdateSquareTNN3SiteExchange (square_3site_updater.h:23-160) on the GPU: chains bit-identical to the oracle's."""
+    rep = run_pipeline_parity(lib, 4, 5, 3, 3, (6, 6, 0.0), nsweeps=2, three_site=True)
+    print(rep)
+
+
 @pytest.mark.parametrize("orient", [0, 1])
 def test_three_site_trace_parity_gpu(lib, orient):
     """ReplaceTNNSiteTrace (bmps/impl/bmps_contractor_trace.h:326-420) on the GPU against amplitudes of the oracle

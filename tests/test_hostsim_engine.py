@@ -48,6 +48,13 @@ def test_tfim_full_space_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
     run_pipeline_parity(lib, rows, cols, D, 3, trunc, nsweeps=2, tfim_h=0.5)
 
 
+@pytest.mark.parametrize("rows,cols,D,trunc", [(4, 4, 3, (6, 6, 0.0)), (3, 5, 2, (2, 4, 1e-10))])
+def test_three_site_updater_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
+    """MCUpdateSquareTNN3SiteExchange (square_3site_updater.h:23-160): chains bit-identical to the oracle's, amplitudes
+    (refreshed by the three-site trace at every row / column start), energies and holes to 1e-10."""
+    run_pipeline_parity(lib, rows, cols, D, 3, trunc, nsweeps=2, three_site=True)
+
+
 def test_tfim_golden_2x2_energy_through_abi(lib):
     """K4 (TFIM) through the C ABI: exact summation over all 16 configurations of the 2x2 simple-update fixture."""
     from peps_b200.api import TransverseFieldIsingSquareOBC
