@@ -429,7 +429,7 @@ def main():
                                "contraction_model_tflops": value * mf["gemm"] / world / 1e12}}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU arm is timed at N=1 only (rank 0, all host cores)
         cores = os.cpu_count() or 1
         v, detail = cpu_samples_per_s(L, D, chi, cores)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
