@@ -7,6 +7,12 @@
  * on one GPU. All calls are stream-ordered on the context's stream and return 0 on success; on failure
  * they return non-zero and peps_last_error() describes the fault (no exception crosses the ABI).
  *
+ * Threading: a context owns its CUDA device ordinal and stream. Every entry point binds them to the calling host
+ * thread first (cudaSetDevice + the context's stream), so a context may be created in one thread and used from
+ * another, and contexts on different devices may be interleaved in one thread. A context is NOT re-entrant: at most
+ * one host thread may be inside a call on a given context at any time. Different contexts may be driven concurrently
+ * from different threads (their kernels overlap on the GPU).
+ *
  * Data conventions: real FP64; site tensor legs (L, D, R, U) row-major (tensor_network_2d.h:38-46);
  * edge legs have dimension 1; configurations are int32 [W][rows][cols].
  */
@@ -142,6 +148,28 @@ int peps_sr_clear(peps_ctx *ctx);
 int64_t peps_sr_count(peps_ctx *ctx);
 int peps_sr_matvec(peps_ctx *ctx, const double *v_host, double mean_dot_v, double *out_host, size_t n);
 int peps_sr_matvec_device(peps_ctx *ctx, const double *v_dev, double mean_dot_v, double *out_dev);
+
+/* Optimizer::CalculateNaturalGradient (optimizer/optimizer_impl.h:1031-1089) on the device-resident sample store: solves
+ * (S + diag_shift) x = gradient with the reference's conjugate-gradient loop (utility/conjugate_gradient_solver.h:181-276
+ * and its MPI form :355-611: best-iterate tracking, stagnation / NaN / indefiniteness exits, orthogonality restart,
+ * periodic residual recomputation). Every CG vector stays in HBM; per iteration the only host traffic is a handful of
+ * scalars. `allreduce` (NULL on a single GPU) must sum `n` doubles at DEVICE pointer `device_buf` in place over all
+ * GPUs and return 0 once the result is complete (ncclAllReduce on the pointer + stream synchronisation): it replaces
+ * the reference's master/slave broadcast-and-reduce of the matvec (SRSMatrix::operator* :60-88 under MPI). The vector
+ * algebra is duplicated on every GPU, so no broadcast of the iterate is needed. gradient / ostar_mean / init_guess
+ * (may be NULL = 0) / x_out are host arrays of peps_tps_size() doubles, identical on every rank. reason: 0 converged,
+ * 1 max iterations, 2 stagnated, 3 indefinite matrix, 4 numerical breakdown (the reference's TerminationReason). */
+typedef int (*peps_allreduce_fn)(void *user, double *device_buf, size_t n);
+typedef struct {
+  int32_t max_iter;                     /* ConjugateGradientParams (optimizer/optimizer_params.h:50-57) */
+  double relative_tolerance, absolute_tolerance;
+  int32_t residual_recompute_interval;
+  double orthogonality_threshold;
+} peps_cg_params;
+int peps_sr_natural_gradient(peps_ctx *ctx, const double *gradient, const double *ostar_mean, int64_t total_samples,
+                             double diag_shift, const peps_cg_params *params, const double *init_guess,
+                             peps_allreduce_fn allreduce, void *user, double *x_out, int32_t *iterations,
+                             double *residual_norm, int32_t *reason);
 
 /* ---- probes for the parity tests ------------------------------------------------------------------ */
 /* BMPSContractor::GrowBMPSForRow + InitBTen/GrowFullBTen + Trace(tn,{row,0},HORIZONTAL) (trace.h:11-28). */

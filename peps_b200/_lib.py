@@ -16,6 +16,14 @@ class PepsConfig(C.Structure):
                 ("trunc_err", C.c_double)]
 
 
+class PepsCGParams(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("relative_tolerance", C.c_double), ("absolute_tolerance", C.c_double),
+                ("residual_recompute_interval", C.c_int32), ("orthogonality_threshold", C.c_double)]
+
+
+# int (*peps_allreduce_fn)(void *user, double *device_buf, size_t n)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
 _I = C.POINTER(C.c_int32)
@@ -66,6 +74,8 @@ SIGNATURES = {
     "peps_sr_count": (C.c_int64, [_P]),
     "peps_sr_matvec": (C.c_int, [_P, _D, C.c_double, _D, C.c_size_t]),
     "peps_sr_matvec_device": (C.c_int, [_P, C.c_void_p, C.c_double, C.c_void_p]),
+    "peps_sr_natural_gradient": (C.c_int, [_P, _D, _D, C.c_int64, C.c_double, C.POINTER(PepsCGParams), _D, ALLREDUCE_FN,
+                                           C.c_void_p, _D, C.POINTER(C.c_int32), _D, C.POINTER(C.c_int32)]),
     "peps_probe_trace_row": (C.c_int, [_P, C.c_int32, _D]),
     "peps_probe_tnn_trace": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _I, _D]),
     "peps_bmps_stack_size": (C.c_int32, [_P, C.c_int32]),

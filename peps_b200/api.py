@@ -461,6 +461,13 @@ class MCPEPSMeasurer:
         return out
 
 
+class _CudaView:
+    """__cuda_array_interface__ wrapper of a device pointer owned by the library (zero-copy torch view)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
 @dataclass
 class EvaluateResult:
     """MCEnergyGradEvaluator::Result (mc_energy_grad_evaluator.h:66-75)."""
@@ -514,7 +521,7 @@ class MCEnergyGradEvaluator:
     def __init__(self, mc_params: MonteCarloParams, trunc: BMPSTruncateParams, tps: SplitIndexTPS, model, updater,
                  walkers, configs=None, device=0, lib=None, dist=None, rank=0, world_size=1):
         self.mc, self.trunc, self.model, self.updater = mc_params, trunc, model, updater
-        self.state = tps
+        self.state = tps                       # the device holds its own copy (set_tps below and in every Evaluate(state))
         self.dist, self.rank, self.world_size = dist, rank, world_size
         self.batch = WalkerBatch(tps.rows(), tps.cols(), tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
         self.batch.set_model(model)
@@ -537,11 +544,12 @@ class MCEnergyGradEvaluator:
                 self.batch.sweep(1)
             self.warmed_up = True
         amps = self.batch.amplitudes()
-        if not np.all(np.isfinite(amps)) or np.any(amps == 0):
-            raise PepsError("Amplitude is still not legal after warm up")
-        mx = float(np.max(np.abs(amps)))
+        bad = (not np.all(np.isfinite(amps))) or bool(np.any(amps == 0))
+        mx = float("inf") if bad else float(np.max(np.abs(amps)))
         if self.dist is not None and self.world_size > 1:
-            mx = self._allreduce_max(mx)
+            mx = self._allreduce_max(mx)       # an illegal amplitude on any rank shows up as inf on every rank: all raise together
+        if not math.isfinite(mx):
+            raise PepsError("Amplitude is still not legal after warm up")
         self.batch.normalize_state_order1(mx)
         self.state = SplitIndexTPS.unpack(self.batch.get_tps_flat(), self.state)
 
@@ -555,14 +563,14 @@ class MCEnergyGradEvaluator:
 
     def Evaluate(self, state: Optional[SplitIndexTPS] = None, collect_sr_buffers: bool = False) -> EvaluateResult:
         b = self.batch
-        if state is not None and state is not self.state:
+        if state is not None:                  # always re-upload: the caller may have edited the tensors in place
             self.state = state
             b.set_tps(state)
         b.init_walkers()                       # engine_.RefreshWavefunctionComponent()  (:164)
         n = self.samples_per_walker()
         b.zero_accumulators()
         if collect_sr_buffers:                 # collect_sr_buffers_ of the reference evaluator (:181-183, :273-277)
-            if b.sr_count() != 0 or getattr(self, "_sr_cap", 0) < n * b.W:
+            if getattr(self, "_sr_cap", 0) < n * b.W:   # reallocate only when the store is too small
                 b.sr_reserve(n * b.W)
                 self._sr_cap = n * b.W
             b.sr_clear()
@@ -573,19 +581,30 @@ class MCEnergyGradEvaluator:
             e, acc = b.sample(self.mc.sweeps_between_samples)
             energies[:, s] = e
             accept += acc
-        osum, eosum = b.accumulators()
         all_e = energies
         if self.dist is not None and self.world_size > 1:
             import torch
             nccl = self.dist.get_backend() == "nccl"
             dev = "cuda" if nccl else "cpu"
-            buf = torch.from_numpy(np.stack([osum, eosum])).to(dev)
-            self.dist.all_reduce(buf)
-            osum, eosum = buf.cpu().numpy()
+            if nccl:
+                # NCCL all-reduce straight on the device pointers of the two accumulators (peps_ostar_sum_device /
+                # peps_eloc_ostar_sum_device): the gradient sums never pass through host memory before the reduction
+                b.sync()
+                for ptr in b.accumulator_device_ptrs():
+                    self.dist.all_reduce(torch.as_tensor(_CudaView(ptr, b.tps_size), device="cuda"))
+                torch.cuda.synchronize()
+                osum, eosum = b.accumulators()
+            else:
+                osum, eosum = b.accumulators()
+                buf = torch.from_numpy(np.stack([osum, eosum]))
+                self.dist.all_reduce(buf)
+                osum, eosum = buf.numpy()
             mine = torch.from_numpy(energies).to(dev)
             gathered = [torch.empty_like(mine) for _ in range(self.world_size)]
             self.dist.all_gather(gathered, mine)
             all_e = np.concatenate([g.cpu().numpy() for g in gathered], axis=0)
+        else:
+            osum, eosum = b.accumulators()
         energy, err = combine_energy_bins(all_e)
         total_walkers = all_e.shape[0]
         grad_flat = (eosum - energy * osum) / (n * total_walkers)        # (:296-309)
@@ -601,19 +620,12 @@ class MCEnergyGradEvaluator:
         """Optimizer::CalculateNaturalGradient (optimizer/optimizer_impl.h:1031-1089) against the O* samples kept in
         HBM by the last Evaluate(collect_sr_buffers=True). Returns (natural_gradient, cg_iterations, residual_norm)."""
         from . import sr
-        allreduce = None
+        cb = None
         if self.dist is not None and self.world_size > 1:
-            import torch
-
-            def allreduce(x):
-                t = torch.from_numpy(x)
-                if self.dist.get_backend() == "nccl":
-                    t = t.cuda()
-                self.dist.all_reduce(t)
-                return t.cpu().numpy()
+            cb = sr.device_allreduce_callback(self.dist)      # NCCL on the device pointer of the matvec output
         r = sr.calculate_natural_gradient(self.batch, result.gradient.pack(), result.Ostar_mean.pack(), result.total_samples,
                                           diag_shift, cg_params or sr.ConjugateGradientParams(),
-                                          None if init_guess is None else init_guess.pack(), allreduce)
+                                          None if init_guess is None else init_guess.pack(), cb)
         return SplitIndexTPS.unpack(r.x, self.state), r.iterations, r.residual_norm
 
     def samples_per_walker(self):

@@ -45,8 +45,16 @@ struct GettDesc {
   double work = 1.0;
 };
 
-// ---- memory / stream -------------------------------------------------------------------------------
-void be_init(int device);                 // binds the device, creates the stream
+// ---- backend context / memory / stream -----------------------------------------------------------------
+// A backend context owns the device ordinal, the stream, the launch counter and the profiler of one engine. Every
+// other be_* call acts on the context BOUND to the calling host thread. The C ABI binds the engine's context at every
+// entry point, so a peps_ctx may be created in one thread and used from another (one thread at a time), and several
+// contexts (also on different devices) may be interleaved in one thread.
+struct BeCtx;
+BeCtx *be_ctx_create(int device);         // throws without a CUDA device: the product has no CPU fallback
+void be_ctx_bind(BeCtx *c);               // cudaSetDevice(c->device) when needed + makes c current for this thread
+void be_ctx_destroy(BeCtx *c);
+void be_init(int device);                 // binds a per-thread default context (stand-alone kernel tests)
 const char *be_name();                    // "cuda-sm_100a" or "hostsim"
 void *be_malloc(size_t bytes);
 void be_free(void *p);
@@ -189,5 +197,12 @@ void be_sr_dots(const double *ostar, const int32_t *cfgs, long hole_stride, cons
 void be_sr_accumulate(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
                       const int32_t *site_size, const int32_t *tps_off, int nsites, int phys, const double *delta,
                       double *out, long n);
+
+
+// ---- device-resident vector algebra of the SR conjugate-gradient solver (TPS-shaped vectors of n doubles) ----------
+// out[i] = ca * a[i] + cb * b[i]   (b may be null: out = ca * a; out may alias a or b)
+void be_vec_lincomb(double *out, double ca, const double *a, double cb, const double *b, long n);
+// result[0] = sum_i a[i] * b[i]    (device scalar; fixed-shape two-stage reduction: deterministic)
+void be_vec_dot(const double *a, const double *b, long n, double *result);
 
 }  // namespace peps

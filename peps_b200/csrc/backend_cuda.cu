@@ -18,18 +18,18 @@
 #include <algorithm>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 #include "backend.h"
 
 namespace peps {
 
-// One stream / launch counter / profiler per HOST THREAD: contexts driven from different host threads run on
-// different streams, so their kernels overlap on the GPU (fills the tails of partially occupied launches).
-static thread_local cudaStream_t g_stream = nullptr;
-static thread_local long g_launches = 0;
-static thread_local int g_device = -1;
-
+// Stream, launch counter, profiler and per-device kernel attributes live in a backend context (BeCtx) owned by the
+// engine. Every C-ABI entry binds its context to the calling thread first (be_ctx_bind: cudaSetDevice + current
+// pointer), so a context may be created in one host thread and driven from another, and contexts on different
+// devices can coexist in one thread. Contexts driven from different host threads run on different streams, so
+// their kernels overlap on the GPU.
 #define CUDA_CHECK(x)                                                                              \
   do {                                                                                             \
     cudaError_t e_ = (x);                                                                          \
@@ -37,12 +37,6 @@ static thread_local int g_device = -1;
       throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " +     \
                                __FILE__ + ":" + std::to_string(__LINE__));                         \
   } while (0)
-
-static inline void post_launch() {
-  ++g_launches;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) throw std::runtime_error(std::string("kernel launch failed: ") + cudaGetErrorString(e));
-}
 
 // ---- per-class event timing --------------------------------------------------------------------------
 struct Profiler {
@@ -58,7 +52,79 @@ struct Profiler {
     return e;
   }
 };
-static thread_local Profiler g_prof;
+struct BeCtx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long launches = 0;
+  Profiler prof;
+  std::unordered_map<const void *, size_t> smem_cfg;   // kernel -> configured dynamic shared memory (per device)
+  double *dot_part = nullptr;                          // partial sums of the K-split trace closure
+  double *vdot_part = nullptr;                         // partial sums of be_vec_dot
+  size_t dot_part_cap = 0;
+};
+static thread_local BeCtx *g_cx = nullptr;
+static thread_local int g_cur_device = -1;
+static inline BeCtx &cx() {
+  if (!g_cx) throw std::runtime_error("peps_b200: no backend context bound to this thread");
+  return *g_cx;
+}
+#define g_stream (cx().stream)
+#define g_prof (cx().prof)
+
+BeCtx *be_ctx_create(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    throw std::runtime_error("peps_b200: no CUDA device available; the product has no CPU fallback");
+  if (device < 0 || device >= n) throw std::invalid_argument("peps_b200: CUDA device ordinal out of range");
+  CUDA_CHECK(cudaSetDevice(device));
+  g_cur_device = device;
+  BeCtx *c = new BeCtx();
+  c->device = device;
+  cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (se != cudaSuccess) { delete c; throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(se)); }
+  return c;
+}
+void be_ctx_bind(BeCtx *c) {
+  if (c && g_cur_device != c->device) { CUDA_CHECK(cudaSetDevice(c->device)); g_cur_device = c->device; }
+  g_cx = c;
+}
+void be_ctx_destroy(BeCtx *c) {
+  if (!c) return;
+  if (g_cur_device != c->device) { cudaSetDevice(c->device); g_cur_device = c->device; }
+  cudaStreamSynchronize(c->stream);
+  for (int k = 0; k < KC_COUNT; ++k)
+    for (auto &pr : c->prof.pending[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (cudaEvent_t ev : c->prof.pool) cudaEventDestroy(ev);
+  if (c->dot_part) cudaFree(c->dot_part);
+  if (c->vdot_part) cudaFree(c->vdot_part);
+  cudaStreamDestroy(c->stream);
+  if (g_cx == c) g_cx = nullptr;
+  delete c;
+}
+// stand-alone kernel tests (peps_test_*): one default context per host thread and device
+void be_init(int device) {
+  static thread_local std::unordered_map<int, BeCtx *> defaults;
+  auto it = defaults.find(device);
+  if (it == defaults.end()) it = defaults.emplace(device, be_ctx_create(device)).first;
+  be_ctx_bind(it->second);
+}
+
+static inline void post_launch() {
+  ++cx().launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw std::runtime_error(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
+// dynamic shared memory opt-in, remembered per context (= per device)
+template <class K>
+static inline void ensure_smem(K kern, size_t smem) {
+  size_t &have = cx().smem_cfg[(const void *)kern];
+  if (smem > have) {
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    have = smem;
+  }
+}
+
 struct LaunchScope {          // brackets one kernel launch
   int c; cudaEvent_t s = nullptr;
   LaunchScope(int cls, double fl) : c(cls) {
@@ -89,16 +155,6 @@ void be_profile_collect(double *ms, long *launches, double *flops, int reset) {
   }
 }
 
-void be_init(int device) {
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0)
-    throw std::runtime_error("peps_b200: no CUDA device available; the product has no CPU fallback");
-  CUDA_CHECK(cudaSetDevice(device));
-  if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
-  g_device = device;
-  if (!g_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-}
 const char *be_name() { return "cuda-sm_100a"; }
 void *be_malloc(size_t bytes) {
   void *p = nullptr;
@@ -120,7 +176,7 @@ void be_d2d(void *dst, const void *src, size_t bytes) {
 }
 void be_sync() { CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
 void *be_stream() { return (void *)g_stream; }
-long be_launch_count() { return g_launches; }
+long be_launch_count() { return cx().launches; }
 
 // =====================================================================================================
 // gett: walker-batched FP64 contraction on the tensor (DMMA) pipe
@@ -315,16 +371,16 @@ void be_dot(int K, const int32_t *ak, const int32_t *bk, Operand A, Operand B, d
     post_launch();
     return;
   }
-  static thread_local double *part = nullptr;
-  static thread_local size_t part_cap = 0;
+  double *&part = cx().dot_part;
+  size_t &part_cap = cx().dot_part_cap;
   if ((size_t)W * 32 > part_cap) {
-    if (part) cudaFree(part);
+    if (part) { CUDA_CHECK(cudaStreamSynchronize(g_stream)); cudaFree(part); }
     part_cap = (size_t)W * 32;
     CUDA_CHECK(cudaMalloc(&part, sizeof(double) * part_cap));
   }
   const int kchunk = (K + nsplit - 1) / nsplit;
   dot_kernel<<<dim3(W, nsplit), 256, 0, g_stream>>>(K, kchunk, ak, bk, A, B, part);
-  ++g_launches;
+  ++cx().launches;
   dot_finish_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(part, nsplit, out, W);
   post_launch();
 }
@@ -784,27 +840,20 @@ static size_t panel_reg_smem_bytes(int nact_max) {
 
 void be_panel_qr(const PanelArgs &a) {
   LaunchScope scope(KC_PANEL, 4.0 * a.R * a.pw * a.pw * (double)a.NI * a.W);
-  auto launch_reg = [&](auto kern, size_t smem, size_t &configured) {
-    if (smem > configured) {
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+  auto launch_reg = [&](auto kern, size_t smem) {
+    ensure_smem(kern, smem);
     kern<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
   };
-  static size_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, cg = 0;
   const int R = a.R;
   // panels of <= 256 rows: 64 KB tile and <= 128 registers, two CTAs share an SM and hide each other's reflector chain
-  if (a.nbw == 32 && R <= 256) launch_reg(panel_qr_reg_kernel<32, 8, 2>, panel_reg_smem_bytes<32, 8>(R), c0);
-  else if (a.nbw == 32 && R <= 512) launch_reg(panel_qr_reg_kernel<32, 16, 1>, panel_reg_smem_bytes<32, 16>(R), c4);
-  else if (a.nbw == 32 && R <= 576) launch_reg(panel_qr_reg_kernel<32, 18, 1>, panel_reg_smem_bytes<32, 18>(R), c1);
-  else if (a.nbw == 16 && R <= 512) launch_reg(panel_qr_reg_kernel<16, 16, 1>, panel_reg_smem_bytes<16, 16>(R), c2);
-  else if (a.nbw == 16 && R <= 1184) launch_reg(panel_qr_reg_kernel<16, 37, 1>, panel_reg_smem_bytes<16, 37>(R), c3);
+  if (a.nbw == 32 && R <= 256) launch_reg(panel_qr_reg_kernel<32, 8, 2>, panel_reg_smem_bytes<32, 8>(R));
+  else if (a.nbw == 32 && R <= 512) launch_reg(panel_qr_reg_kernel<32, 16, 1>, panel_reg_smem_bytes<32, 16>(R));
+  else if (a.nbw == 32 && R <= 576) launch_reg(panel_qr_reg_kernel<32, 18, 1>, panel_reg_smem_bytes<32, 18>(R));
+  else if (a.nbw == 16 && R <= 512) launch_reg(panel_qr_reg_kernel<16, 16, 1>, panel_reg_smem_bytes<16, 16>(R));
+  else if (a.nbw == 16 && R <= 1184) launch_reg(panel_qr_reg_kernel<16, 37, 1>, panel_reg_smem_bytes<16, 37>(R));
   else {
     size_t smem = panel_smem_bytes(a.R, a.nbw);
-    if (smem > cg) {
-      CUDA_CHECK(cudaFuncSetAttribute(panel_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      cg = smem;
-    }
+    ensure_smem(panel_qr_kernel, smem);
     panel_qr_kernel<<<dim3(a.NI, a.W), PQR_THREADS, smem, g_stream>>>(a);
   }
   post_launch();
@@ -1137,23 +1186,19 @@ void be_apply_reflector(const ApplyArgs &a) {
   if (a.ntrail <= 0) return;
   LaunchScope scope(KC_APPLY, 4.0 * a.R * a.nbw * (double)a.ntrail * a.NI * a.W);
   static const TileMap no_map{};
-  auto launch = [&](auto kern, size_t smem, size_t &configured, int tn, const TileMap &tmap) {
-    if (smem > configured) {
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+  auto launch = [&](auto kern, size_t smem, int tn, const TileMap &tmap) {
+    ensure_smem(kern, smem);
     kern<<<dim3((a.ntrail + tn - 1) / tn, a.NI, a.W), 256, smem, g_stream>>>(a, tmap);
   };
-  static size_t c32 = 0, c32b = 0, c32t = 0, c32bt = 0, c16 = 0, c8 = 0;
   const bool tile = a.tmap != nullptr && a.nbw == 32 && a.R % 64 == 0;
   // row blocks of <= 256 rows: the resident tile is <= 112 KB, two CTAs share an SM and overlap load / DMMA / store
   const bool small = apply_smem_bytes<32>(a.R) <= 112 * 1024;
-  if (a.nbw == 32 && tile && small) launch(apply_reflector_kernel<32, 2, true>, apply_smem_bytes<32>(a.R), c32bt, 32, *a.tmap);
-  else if (a.nbw == 32 && tile) launch(apply_reflector_kernel<32, 1, true>, apply_smem_bytes<32>(a.R), c32t, 32, *a.tmap);
-  else if (a.nbw == 32 && small) launch(apply_reflector_kernel<32, 2, false>, apply_smem_bytes<32>(a.R), c32b, 32, no_map);
-  else if (a.nbw == 32) launch(apply_reflector_kernel<32, 1, false>, apply_smem_bytes<32>(a.R), c32, 32, no_map);
-  else if (a.nbw == 16) launch(apply_reflector_kernel<16, 1, false>, apply_smem_bytes<16>(a.R), c16, 16, no_map);
-  else if (a.nbw == 8) launch(apply_reflector_kernel<8, 1, false>, apply_smem_bytes<8>(a.R), c8, 8, no_map);
+  if (a.nbw == 32 && tile && small) launch(apply_reflector_kernel<32, 2, true>, apply_smem_bytes<32>(a.R), 32, *a.tmap);
+  else if (a.nbw == 32 && tile) launch(apply_reflector_kernel<32, 1, true>, apply_smem_bytes<32>(a.R), 32, *a.tmap);
+  else if (a.nbw == 32 && small) launch(apply_reflector_kernel<32, 2, false>, apply_smem_bytes<32>(a.R), 32, no_map);
+  else if (a.nbw == 32) launch(apply_reflector_kernel<32, 1, false>, apply_smem_bytes<32>(a.R), 32, no_map);
+  else if (a.nbw == 16) launch(apply_reflector_kernel<16, 1, false>, apply_smem_bytes<16>(a.R), 16, no_map);
+  else if (a.nbw == 8) launch(apply_reflector_kernel<8, 1, false>, apply_smem_bytes<8>(a.R), 8, no_map);
   else throw std::runtime_error("be_apply_reflector: unsupported panel width");
   post_launch();
 #ifdef PEPS_KERNEL_CLOCKS
@@ -1519,17 +1564,13 @@ static size_t jacobi_smem_bytes(int bs, int nc) {
 void be_jacobi_round(const JacobiArgs &a) {
   size_t smem = jacobi_smem_bytes(a.bs, a.nc);
   LaunchScope scope(KC_JACOBI, 3.0 * (2.0 * a.bs) * (2.0 * a.bs) * a.nc * (a.nblk / 2) * (double)a.nactive);
-  auto launch = [&](auto kern, size_t &configured) {
-    if (smem > configured) {
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+  auto launch = [&](auto kern) {
+    ensure_smem(kern, smem);
     kern<<<dim3(a.nblk / 2, a.W), JAC_THREADS, smem, g_stream>>>(a);
   };
-  static size_t c32 = 0, c16 = 0, c8 = 0;
-  if (a.bs == 16) launch(jacobi_round_kernel<32>, c32);
-  else if (a.bs == 8) launch(jacobi_round_kernel<16>, c16);
-  else if (a.bs == 4) launch(jacobi_round_kernel<8>, c8);
+  if (a.bs == 16) launch(jacobi_round_kernel<32>);
+  else if (a.bs == 8) launch(jacobi_round_kernel<16>);
+  else if (a.bs == 4) launch(jacobi_round_kernel<8>);
   else throw std::runtime_error("be_jacobi_round: unsupported block size");
   post_launch();
 #ifdef PEPS_KERNEL_CLOCKS
@@ -1856,6 +1897,7 @@ void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *el
   post_launch();
 }
 
+template <int PHYS>
 __global__ void accumulate_ostar_kernel(const double *holes, long hole_stride, const int32_t *hole_off,
                                         const int32_t *site_size, const int32_t *tps_off, const int32_t *cfg,
                                         int nsites, int phys, const double *amp, const double *eloc, double *osum,
@@ -1864,22 +1906,33 @@ __global__ void accumulate_ostar_kernel(const double *holes, long hole_stride, c
   const int sz = site_size[site];
   const long ho = hole_off[site], to = tps_off[site];
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < sz; e += gridDim.x * blockDim.x) {
-    for (int w = 0; w < W; ++w) {
-      int s = cfg[(long)w * nsites + site];
-      double inv = 1.0 / amp[w];
-      double o = inv * holes[(long)w * hole_stride + ho + e];
-      long slot = to + (long)s * sz + e;
-      osum[slot] += o;
-      eosum[slot] += eloc[w] * o;
+    double ao[PHYS], aeo[PHYS];
+#pragma unroll
+    for (int s = 0; s < PHYS; ++s) { ao[s] = (s < phys) ? osum[to + (long)s * sz + e] : 0.0; aeo[s] = (s < phys) ? eosum[to + (long)s * sz + e] : 0.0; }
+    for (int w = 0; w < W; ++w) {                     // fixed walker order: the sums do not depend on scheduling
+      const int c = cfg[(long)w * nsites + site];
+      const double inv = 1.0 / amp[w];
+      const double o = inv * holes[(long)w * hole_stride + ho + e];
+      const double eo = eloc[w] * o;
+#pragma unroll
+      for (int s = 0; s < PHYS; ++s) { ao[s] += (c == s) ? o : 0.0; aeo[s] += (c == s) ? eo : 0.0; }
     }
+#pragma unroll
+    for (int s = 0; s < PHYS; ++s)
+      if (s < phys) { osum[to + (long)s * sz + e] = ao[s]; eosum[to + (long)s * sz + e] = aeo[s]; }
   }
 }
 void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
                          const int32_t *tps_off, const int32_t *cfg, int nsites, int phys, const double *amp,
                          const double *eloc, double *osum, double *eosum, int W) {
   LaunchScope scope(KC_SMALL, 0.0);
-  accumulate_ostar_kernel<<<dim3(16, nsites), 256, 0, g_stream>>>(holes, hole_stride, hole_off, site_size, tps_off,
-                                                                  cfg, nsites, phys, amp, eloc, osum, eosum, W);
+  if (phys <= 2)
+    accumulate_ostar_kernel<2><<<dim3(16, nsites), 256, 0, g_stream>>>(holes, hole_stride, hole_off, site_size, tps_off,
+                                                                       cfg, nsites, phys, amp, eloc, osum, eosum, W);
+  else if (phys <= 4)
+    accumulate_ostar_kernel<4><<<dim3(16, nsites), 256, 0, g_stream>>>(holes, hole_stride, hole_off, site_size, tps_off,
+                                                                       cfg, nsites, phys, amp, eloc, osum, eosum, W);
+  else throw std::runtime_error("be_accumulate_ostar: physical dimension > 4 is not supported");
   post_launch();
 }
 
@@ -1937,26 +1990,110 @@ void be_sr_dots(const double *ostar, const int32_t *cfgs, long hole_stride, cons
   post_launch();
 }
 
-__global__ void sr_accumulate_kernel(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
-                                     const int32_t *site_size, const int32_t *tps_off, int nsites, int phys,
-                                     const double *delta, double *out, long n) {
+// out[slot(site, s) + e] = sum_i [cfg_i(site) == s] delta[i] O*_i[hole_off(site) + e]: one thread per element of the
+// hole layout, `PHYS` register accumulators, eight samples in flight per thread (the sample loop is the HBM stream:
+// consecutive threads read consecutive elements of the same sample; the configuration entry and delta[i] are uniform
+// per block and come out of L1). Deterministic: a fixed summation order per element.
+template <int PHYS>
+__global__ void __launch_bounds__(256) sr_accumulate_kernel(const double *__restrict__ ostar, const int32_t *__restrict__ cfgs,
+                                                          long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                                                          const int32_t *tps_off, int nsites, int phys,
+                                                          const double *__restrict__ delta, double *out, long n) {
   const int site = blockIdx.y;
   const int sz = site_size[site];
   const long ho = hole_off[site], to = tps_off[site];
+  const int32_t *cs = cfgs + site;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < sz; e += gridDim.x * blockDim.x) {
-    for (int s = 0; s < phys; ++s) out[to + (long)s * sz + e] = 0.0;
-    for (long i = 0; i < n; ++i) {
-      const int s = cfgs[i * nsites + site];
-      out[to + (long)s * sz + e] += delta[i] * ostar[i * hole_stride + ho + e];
+    double acc[PHYS];
+#pragma unroll
+    for (int s = 0; s < PHYS; ++s) acc[s] = 0.0;
+    const double *col = ostar + ho + e;
+    long i = 0;
+    for (; i + 8 <= n; i += 8) {
+      double o[8], d[8];
+      int c[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        o[u] = col[(i + u) * hole_stride];
+        c[u] = cs[(i + u) * nsites];
+        d[u] = delta[i + u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double t = d[u] * o[u];
+#pragma unroll
+        for (int s = 0; s < PHYS; ++s) acc[s] += (c[u] == s) ? t : 0.0;
+      }
     }
+    for (; i < n; ++i) {
+      const double t = delta[i] * col[i * hole_stride];
+      const int c = cs[i * nsites];
+#pragma unroll
+      for (int s = 0; s < PHYS; ++s) acc[s] += (c == s) ? t : 0.0;
+    }
+#pragma unroll
+    for (int s = 0; s < PHYS; ++s)
+      if (s < phys) out[to + (long)s * sz + e] = acc[s];
   }
 }
 void be_sr_accumulate(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
                       const int32_t *site_size, const int32_t *tps_off, int nsites, int phys, const double *delta,
                       double *out, long n) {
   LaunchScope scope(KC_SMALL, 2.0 * hole_stride * (double)n);
-  sr_accumulate_kernel<<<dim3(16, nsites), 256, 0, g_stream>>>(ostar, cfgs, hole_stride, hole_off, site_size, tps_off,
-                                                               nsites, phys, delta, out, n);
+  auto launch = [&](auto kern) {
+    kern<<<dim3(16, nsites), 256, 0, g_stream>>>(ostar, cfgs, hole_stride, hole_off, site_size, tps_off, nsites, phys, delta, out, n);
+  };
+  if (phys <= 2) launch(sr_accumulate_kernel<2>);
+  else if (phys <= 4) launch(sr_accumulate_kernel<4>);
+  else throw std::runtime_error("be_sr_accumulate: physical dimension > 4 is not supported");
+  post_launch();
+}
+
+// ---- vector algebra of the device-resident CG ----------------------------------------------------------
+__global__ void vec_lincomb_kernel(double *out, double ca, const double *a, double cb, const double *b, long n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    out[i] = b ? ca * a[i] + cb * b[i] : ca * a[i];
+}
+void be_vec_lincomb(double *out, double ca, const double *a, double cb, const double *b, long n) {
+  if (n <= 0) return;
+  LaunchScope scope(KC_SMALL, 0.0);
+  const int blocks = (int)std::min<long>((n + 255) / 256, 148L * 8);
+  vec_lincomb_kernel<<<blocks, 256, 0, g_stream>>>(out, ca, a, cb, b, n);
+  post_launch();
+}
+constexpr int VDOT_BLOCKS = 296;
+__global__ void vec_dot_part_kernel(const double *a, const double *b, long n, double *part) {
+  __shared__ double red[256];
+  double s0 = 0.0, s1 = 0.0;
+  long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (; i + stride < n; i += 2 * stride) { s0 += a[i] * b[i]; s1 += a[i + stride] * b[i + stride]; }
+  if (i < n) s0 += a[i] * b[i];
+  red[threadIdx.x] = s0 + s1;
+  __syncthreads();
+  for (int h = blockDim.x / 2; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void vec_dot_finish_kernel(const double *part, int nb, double *result) {
+  __shared__ double red[512];
+  red[threadIdx.x] = (threadIdx.x < nb) ? part[threadIdx.x] : 0.0;
+  __syncthreads();
+  for (int h = blockDim.x / 2; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) result[0] = red[0];
+}
+void be_vec_dot(const double *a, const double *b, long n, double *result) {
+  LaunchScope scope(KC_SMALL, 2.0 * (double)n);
+  double *&part = cx().vdot_part;
+  if (!part) CUDA_CHECK(cudaMalloc(&part, sizeof(double) * VDOT_BLOCKS));
+  vec_dot_part_kernel<<<VDOT_BLOCKS, 256, 0, g_stream>>>(a, b, n, part);
+  ++cx().launches;
+  vec_dot_finish_kernel<<<1, 512, 0, g_stream>>>(part, VDOT_BLOCKS, result);
   post_launch();
 }
 

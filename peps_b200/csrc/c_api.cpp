@@ -19,8 +19,11 @@ struct peps_ctx {
 };
 static thread_local std::string g_err;
 
+// Every entry point first binds the context's device and stream to the calling host thread (Engine::bind), so a
+// context may be driven from any thread (one at a time) and contexts on different devices may be interleaved.
 #define GUARD(ctx, ...)                                    \
   try {                                                    \
+    if (ctx) (ctx)->eng->bind();                           \
     __VA_ARGS__;                                           \
     return 0;                                              \
   } catch (const std::exception &e) {                      \
@@ -136,6 +139,20 @@ int peps_sr_matvec(peps_ctx *ctx, const double *v, double mean_dot_v, double *ou
   GUARD(ctx, { if (n != ctx->eng->tps_size()) throw std::invalid_argument("peps_sr_matvec: size mismatch"); ctx->eng->sr_matvec_host(v, mean_dot_v, out); })
 }
 int peps_sr_matvec_device(peps_ctx *ctx, const double *v, double mean_dot_v, double *out) { GUARD(ctx, ctx->eng->sr_matvec_device(v, mean_dot_v, out)) }
+int peps_sr_natural_gradient(peps_ctx *ctx, const double *gradient, const double *ostar_mean, int64_t total_samples, double diag_shift,
+                             const peps_cg_params *prm, const double *init_guess, peps_allreduce_fn allreduce, void *user, double *x_out,
+                             int32_t *iterations, double *residual_norm, int32_t *reason) {
+  GUARD(ctx, {
+    if (!gradient || !ostar_mean || !x_out) throw std::invalid_argument("peps_sr_natural_gradient: null argument");
+    Engine::CGParams p;
+    if (prm) { p.max_iter = prm->max_iter; p.rel_tol = prm->relative_tolerance; p.abs_tol = prm->absolute_tolerance;
+               p.recompute = prm->residual_recompute_interval; p.ortho = prm->orthogonality_threshold; }
+    Engine::CGOutcome o = ctx->eng->sr_natural_gradient(gradient, ostar_mean, (long)total_samples, diag_shift, p, init_guess, allreduce, user, x_out);
+    if (iterations) *iterations = o.iterations;
+    if (residual_norm) *residual_norm = o.residual_norm;
+    if (reason) *reason = o.reason;
+  })
+}
 int peps_probe_trace_row(peps_ctx *ctx, int32_t row, double *psi) { GUARD(ctx, ctx->eng->probe_trace_row(row, psi)) }
 int peps_probe_tnn_trace(peps_ctx *ctx, int32_t row, int32_t col, int32_t orient, const int32_t *cfg3, double *psi) {
   GUARD(ctx, {
@@ -159,7 +176,9 @@ int peps_profile_get(peps_ctx *ctx, double *ms, int64_t *launches, double *flops
     if (launches) for (int c = 0; c < KC_COUNT; ++c) launches[c] = l[c];
   })
 }
-void *peps_stream(peps_ctx *) { return be_stream(); }
+void *peps_stream(peps_ctx *ctx) {
+  try { ctx->eng->bind(); return be_stream(); } catch (...) { return nullptr; }
+}
 
 // ---- stand-alone kernel tests -----------------------------------------------------------------------
 int peps_test_qr_r(int32_t device, int32_t W, int32_t m, int32_t n, const double *a, double *r_out) {

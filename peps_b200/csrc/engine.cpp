@@ -13,7 +13,8 @@ Engine::Engine(const EngineConfig &c)
       dmin_(c.dmin), dmax_(c.dmax), terr_(c.trunc_err) {
   if (rows_ < 2 || cols_ < 2) throw std::invalid_argument("Engine: lattice must be at least 2x2");
   if (W_ < 1 || phys_ < 1 || D_ < 1) throw std::invalid_argument("Engine: bad sizes");
-  be_init(c.device);
+  bectx_ = be_ctx_create(c.device);
+  be_ctx_bind(bectx_);
   row_mod_.assign((size_t)rows_, 1);
   col_mod_.assign((size_t)cols_, 1);
   la_.W = W_; la_.pool = &pool_; la_.planner = &planner_;
@@ -74,6 +75,8 @@ Engine::Engine(const EngineConfig &c)
 }
 
 Engine::~Engine() {
+  be_ctx_bind(bectx_);
+  be_sync();
   for (int p = 0; p < 4; ++p) {
     for (auto &b : bmps_[p]) release(b);
     for (auto &t : bten_[p]) release(t);
@@ -84,6 +87,9 @@ Engine::~Engine() {
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
                   (void *)sr_cfgs_, (void *)sr_delta_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_})
     be_free(p);
+  pool_.release_all();
+  planner_.release_all();
+  be_ctx_destroy(bectx_);
 }
 
 void Engine::site_dims(int r, int c, int out[4]) const {
@@ -97,7 +103,15 @@ void Engine::scale_tps(double f) {
   for (auto &x : h) x *= f;
   set_tps(h.data());
 }
-void Engine::set_configs(const int32_t *host) { be_h2d(cfg_, host, sizeof(int32_t) * (size_t)W_ * nsites_); touch_all(); }
+void Engine::set_configs(const int32_t *host) {
+  // every entry is used as the physical-slice index of a gather operand: reject anything outside [0, phys)
+  for (size_t i = 0; i < (size_t)W_ * nsites_; ++i)
+    if (host[i] < 0 || host[i] >= phys_)
+      throw std::invalid_argument("set_configs: entry " + std::to_string(host[i]) + " of walker " + std::to_string(i / nsites_) +
+                                  " is outside [0, phys = " + std::to_string(phys_) + ")");
+  be_h2d(cfg_, host, sizeof(int32_t) * (size_t)W_ * nsites_);
+  touch_all();
+}
 void Engine::get_configs(int32_t *host) { be_d2h(host, cfg_, sizeof(int32_t) * (size_t)W_ * nsites_); }
 void Engine::seed_rng(const uint32_t *seeds) {
   uint32_t *d = (uint32_t *)pool_.get(sizeof(uint32_t) * W_);
@@ -1091,6 +1105,7 @@ void Engine::energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *p
 
 void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host) {
   if (tfim_) { energy_and_holes_tfim(calc_holes, eloc_host, psi_list_host); return; }
+  if (phys_ != 2) throw std::invalid_argument("the XXZ / J1-J2 energy solvers need phys = 2");
   // square_nnn_energy_solver.h:79-315 with has_nnn = false, model = SquareSpinOneHalfXXZModelMixIn
   be_memset0(eloc_, sizeof(double) * W_);
   int npsi = 0;
@@ -1266,6 +1281,88 @@ void Engine::sr_matvec_host(const double *v, double mean_dot_v, double *out) {
   be_d2h(out, od, sizeof(double) * tps_total_);
   pool_.put(vd);
   pool_.put(od);
+}
+Engine::CGOutcome Engine::sr_natural_gradient(const double *gradient_host, const double *ostar_mean_host, long total_samples,
+                                              double diag_shift, const CGParams &prm, const double *init_guess_host,
+                                              AllReduceFn allreduce, void *user, double *x_host) {
+  if (total_samples <= 0) throw std::invalid_argument("sr_natural_gradient: total_samples must be positive");
+  const long n = tps_total_;
+  const size_t bytes = sizeof(double) * (size_t)n;
+  enum { B = 0, MEAN, X, R, P, AP, RPREV, BEST, NV };
+  double *v[NV];
+  for (auto &p : v) p = (double *)pool_.get(bytes);
+  double *scal = (double *)pool_.get(sizeof(double) * 2);
+  CGOutcome out;
+  auto dot = [&](const double *a, const double *b2) {
+    double h = 0.0;
+    be_vec_dot(a, b2, n, scal);
+    be_d2h(&h, scal, sizeof(double));
+    return h;
+  };
+  // SRSMatrix::operator* (stochastic_reconfiguration_smatrix.h:45-91): local sum on the device, all-reduce of the
+  // device buffer, 1/N and the diagonal shift
+  auto matvec = [&](const double *x, double *y) {
+    ++out.matvecs;
+    const double mean_dot_v = dot(v[MEAN], x);
+    sr_matvec_device(x, mean_dot_v, y);
+    if (allreduce) {
+      be_sync();
+      if (allreduce(user, y, (size_t)n) != 0) throw std::runtime_error("sr_natural_gradient: the all-reduce callback failed");
+    }
+    be_vec_lincomb(y, 1.0 / (double)total_samples, y, diag_shift, x, n);
+  };
+  auto finish = [&](const double *x, double rsq, int iters, int reason) {
+    be_d2h(x_host, x, bytes);
+    out.iterations = iters; out.residual_norm = std::sqrt(rsq); out.reason = reason;
+    for (auto &p : v) pool_.put(p);
+    pool_.put(scal);
+    return out;
+  };
+  be_h2d(v[B], gradient_host, bytes);
+  be_h2d(v[MEAN], ostar_mean_host, bytes);
+  if (init_guess_host) be_h2d(v[X], init_guess_host, bytes); else be_memset0(v[X], bytes);
+  const double rhs_sq = dot(v[B], v[B]);
+  const double tol_sq = std::max(prm.rel_tol * prm.rel_tol * rhs_sq, prm.abs_tol * prm.abs_tol);
+  matvec(v[X], v[AP]);
+  be_vec_lincomb(v[R], 1.0, v[B], -1.0, v[AP], n);                       // r = b - A x0
+  double r_sq = dot(v[R], v[R]);
+  if (r_sq <= tol_sq) return finish(v[X], r_sq, 0, 0);
+  be_d2d(v[P], v[R], bytes); be_d2d(v[BEST], v[X], bytes); be_d2d(v[RPREV], v[R], bytes);
+  double best_sq = r_sq, rkp1 = r_sq;
+  int stagnation = 0;
+  const double eps = 2.220446049250313e-16;
+  for (int k = 0; k < prm.max_iter; ++k) {
+    const double rk = rkp1;
+    matvec(v[P], v[AP]);
+    const double pap = dot(v[P], v[AP]);
+    if (!(std::isfinite(pap) && pap > 0.0)) return finish(v[BEST], best_sq, k, 3);          // kIndefiniteMatrix
+    const double alpha = rk / pap;
+    be_vec_lincomb(v[X], 1.0, v[X], alpha, v[P], n);
+    if (alpha * alpha * dot(v[P], v[P]) < eps * eps * dot(v[X], v[X])) {
+      if (++stagnation >= 3) return finish(v[BEST], best_sq, k + 1, 2);                    // kStagnated
+    } else {
+      stagnation = 0;
+    }
+    if (prm.recompute > 0 && (k % prm.recompute) == prm.recompute - 1) {
+      matvec(v[X], v[AP]);
+      be_vec_lincomb(v[R], 1.0, v[B], -1.0, v[AP], n);
+    } else {
+      be_vec_lincomb(v[R], 1.0, v[R], -alpha, v[AP], n);
+    }
+    rkp1 = dot(v[R], v[R]);
+    if (!std::isfinite(rkp1)) return finish(v[BEST], best_sq, k + 1, 4);                   // kNumericalBreakdown
+    if (rkp1 < best_sq) { be_d2d(v[BEST], v[X], bytes); best_sq = rkp1; }
+    if (rkp1 <= tol_sq) return finish(v[X], rkp1, k + 1, 0);                               // kConverged
+    if (k > 0 && std::fabs(dot(v[RPREV], v[R])) > prm.ortho * rkp1) {                      // orthogonality restart
+      be_d2d(v[P], v[R], bytes); be_d2d(v[RPREV], v[R], bytes);
+      continue;
+    }
+    be_d2d(v[RPREV], v[R], bytes);
+    const double beta = rkp1 / rk;
+    if (!std::isfinite(beta)) return finish(v[BEST], best_sq, k + 1, 4);
+    be_vec_lincomb(v[P], 1.0, v[R], beta, v[P], n);
+  }
+  return finish(v[BEST], best_sq, prm.max_iter, 1);                                        // kMaxIterations
 }
 void Engine::get_accumulators(double *osum_host, double *eosum_host) {
   if (osum_host) be_d2h(osum_host, osum_, sizeof(double) * tps_total_);

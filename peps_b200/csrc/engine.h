@@ -102,14 +102,31 @@ class Engine {
   // out = sum_i (O*_i . v - mean_dot_v) O*_i over the stored samples (device pointers, TPS-shaped vectors)
   void sr_matvec_device(const double *v_dev, double mean_dot_v, double *out_dev);
   void sr_matvec_host(const double *v, double mean_dot_v, double *out);
-  void set_model_xxz(double jz, double jxy, double h00) { jz_ = jz; jxy_ = jxy; h00_ = h00; }
+  // Optimizer::CalculateNaturalGradient (optimizer/optimizer_impl.h:1031-1089) with every CG vector resident in HBM:
+  // solves (S + diag_shift) x = gradient by the reference's conjugate-gradient loop (utility/conjugate_gradient_solver.h:
+  // 181-276: best-iterate tracking, stagnation / NaN / indefiniteness exits, orthogonality restart, periodic residual
+  // recomputation). S v = (1/total_samples) allreduce(sum_i (O*_i . v - mean . v) O*_i) + diag_shift v; `allreduce`
+  // (may be null on a single GPU) sums a DEVICE buffer in place over all GPUs (NCCL on the device pointer).
+  struct CGParams { int max_iter = 100; double rel_tol = 1e-4, abs_tol = 0.0; int recompute = 20; double ortho = 0.5; };
+  struct CGOutcome { int iterations = 0; double residual_norm = 0.0; int reason = 0; long matvecs = 0; };
+  typedef int (*AllReduceFn)(void *user, double *device_buf, size_t n);
+  CGOutcome sr_natural_gradient(const double *gradient_host, const double *ostar_mean_host, long total_samples,
+                                double diag_shift, const CGParams &prm, const double *init_guess_host, AllReduceFn allreduce,
+                                void *user, double *x_host);
+  void set_model_xxz(double jz, double jxy, double h00) {
+    if (phys_ != 2) throw std::invalid_argument("spin-1/2 XXZ / J1-J2 models need phys = 2");
+    jz_ = jz; jxy_ = jxy; h00_ = h00;
+  }
   void set_deflation(double eps) { la_.deflation_eps = eps; touch_all(); }
   // rows of the forward R chain below eps * (largest row norm) are dropped (0 = keep the full D*chi rows)
   void set_chain_deflation(double eps) { chain_eps_ = eps; touch_all(); }
   // SquareSpinOneHalfJ1J2XXZModelOBC couplings (model_solvers/square_spin_onehalf_j1j2_xxz_obc.h:34-113); 0 disables NNN
   void set_model_nnn(double jz2, double jxy2) { jz2_ = jz2; jxy2_ = jxy2; }
   // TransverseFieldIsingSquareOBC(h) (model_solvers/transverse_field_ising_square_obc.h:28-247); phys must be 2
-  void set_model_tfim(double h) { tfim_ = true; tfim_h_ = h; }
+  void set_model_tfim(double h) {
+    if (phys_ != 2) throw std::invalid_argument("the transverse-field Ising model needs phys = 2");
+    tfim_ = true; tfim_h_ = h;
+  }
   void set_model_kind_xxz() { tfim_ = false; }
 
   // ---- probes used by the parity tests (per-walker values of reference contractor calls)
@@ -123,6 +140,8 @@ class Engine {
   int cols() const { return cols_; }
   long stat(int which) const;
   const char *backend() const { return be_name(); }
+  // makes this engine's backend context (device + stream) current for the calling host thread
+  void bind() const { be_ctx_bind(bectx_); }
 
   // ---- contractor API (walker-batched restatement of BMPSContractor)
   void contractor_init();
@@ -188,6 +207,7 @@ class Engine {
   void bten_operands(int post, int slice, int bten_size, const BT *&mps1, const BT *&mps2, int &site) const;
   static std::string site_labels(int post, char pre, char toward, char next, char away);
 
+  BeCtx *bectx_ = nullptr;
   int rows_, cols_, phys_, D_, W_, nsites_;
   int dmin_, dmax_;
   double terr_;

@@ -68,8 +68,12 @@ struct Plan {
 
 class Planner {
  public:
-  ~Planner() {
+  ~Planner() { release_all(); }
+  void release_all() {
     for (void *p : owned_) be_free(p);
+    owned_.clear();
+    cache_.clear();
+    tabs_.clear();
   }
   // spec "abc,cd->abd"; dims of the two inputs given; a label's stride in its tensor is row-major from dims
   // unless explicit strides are passed. Output is row-major contiguous over the out labels (or out_strides).

@@ -10,10 +10,13 @@ by the reference drop in and vice versa. Dense, TrivialRepQN tensors only (the b
                                   (two_dim_tn/tps/split_index_tps.h:23-29)
   * ``configuration<rank>``       text grid, one row per line (vmc_basic/configuration.h:446-464)
 
-The index hashes TensorToolkit stores are derived from its internal hashing of (qn, degeneracy, direction); files
-written here carry the hash values observed in the reference's own fixtures for TrivialRepQN indices of the same
-direction and dimension layout, which is what its loader recomputes. Leg directions follow the reference's
-convention for projected site tensors: L and U legs IN (-1), D and R legs OUT (+1) (cf. tests/test_data fixtures).
+Hash fields: TensorToolkit stores a hash per sector and per index, derived from its internal hashing of
+(qn, degeneracy, direction); TensorToolkit's source is not available here, so the function is not reproduced. Writers
+copy the hash fields from a ``template`` file of the same index layout (e.g. the state the reference dumped before
+the optimisation step) -- that is the only way files written here are loadable by the reference. WITHOUT a template
+the hash fields are written as 0: such files round-trip through this module and the oracle reader (which ignore the
+hashes) but may be rejected by TensorToolkit's loader. Leg directions follow the reference's convention for projected
+site tensors: L and U legs IN (-1), D and R legs OUT (+1) (cf. tests/test_data fixtures).
 """
 import os
 import struct
@@ -21,9 +24,6 @@ import struct
 import numpy as np
 
 from .api import SplitIndexTPS, Configuration
-
-_SECTOR_HASH = {}      # filled lazily from fixtures when available; see _index_hashes
-
 
 def _tokens(buf):
     pos = 0
@@ -33,8 +33,9 @@ def _tokens(buf):
         pos = e + 1
 
 
-def read_qlten(path, dtype=np.float64):
-    """Returns the dense array (legs in file order). Raises ValueError for multi-sector (symmetric) tensors."""
+def read_qlten(path, dtype=None):
+    """Returns the dense array (legs in file order). ``dtype`` None detects float64 / complex128 from the payload
+    length. Raises ValueError for multi-sector (symmetric) tensors and for truncated or mistyped payloads."""
     buf = open(path, "rb").read()
     it = _tokens(buf)
     rank, pos = next(it)
@@ -53,8 +54,20 @@ def read_qlten(path, dtype=np.float64):
         _, pos = next(it)
     n = int(np.prod(dims)) if dims else 1
     if nblk == 0:
-        return np.zeros(dims, dtype=dtype)
+        return np.zeros(dims, dtype=dtype or np.float64)
+    payload = len(buf) - pos
+    if payload and buf[-1:] == b"\n" and payload % 8 == 1:
+        payload -= 1                            # trailing newline of the stream
+    if dtype is None:
+        if payload == n * 8:
+            dtype = np.float64
+        elif payload == n * 16:
+            dtype = np.complex128
+        else:
+            raise ValueError(f"{path}: payload of {payload} bytes is neither {n} float64 nor {n} complex128 elements")
     item = np.dtype(dtype).itemsize
+    if payload != n * item:
+        raise ValueError(f"{path}: payload of {payload} bytes, expected {n} x {item} (wrong element type or truncated file)")
     return np.frombuffer(buf[pos:pos + n * item], dtype=dtype).reshape(dims).copy()
 
 

@@ -1,6 +1,9 @@
 """Stochastic reconfiguration on top of the device-resident O* sample store.
 
-Host-side restatement (plumbing; O(P) vector algebra once per CG iteration) of
+The product path is ``calculate_natural_gradient`` -> ``peps_sr_natural_gradient`` (C ABI): the whole CG loop runs in the
+engine with every vector resident in HBM and the cross-GPU sum done by NCCL on the device pointer of the matvec
+output. ``conjugate_gradient`` / ``SRSMatrix`` below are the host-side statement of the same loop (numpy vectors,
+matvec through ``peps_sr_matvec``) kept for single-matvec checks and as the readable form of:
   * ConjugateGradientSolver        utility/conjugate_gradient_solver.h:181-276 (serial form; with several GPUs every rank
                                    runs the identical vector updates on the all-reduced matvec, so the reference's
                                    master/slave broadcast of v, :355-611, is not needed)
@@ -107,13 +110,56 @@ class SRSMatrix:
         return out
 
 
+def device_allreduce_callback(dist):
+    """peps_allreduce_fn for an initialised torch.distributed module: wraps the DEVICE pointer handed over by the engine
+    (NCCL: a zero-copy CUDA tensor view, reduced in place over NVLink; gloo in the CPU tests of the host logic, where the
+    'device' buffer of the host simulation is ordinary memory)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+
+    nccl = dist.get_backend() == "nccl"
+
+    def cb(_user, ptr, n):
+        try:
+            if nccl:
+                class _Cai:
+                    __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+                t = torch.as_tensor(_Cai(), device="cuda")
+                dist.all_reduce(t)
+                torch.cuda.synchronize()
+            else:
+                arr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double)), shape=(n,))
+                t = torch.from_numpy(arr)
+                dist.all_reduce(t)
+            return 0
+        except Exception as exc:                      # never let an exception cross the C ABI
+            import sys
+            print("all-reduce callback failed:", exc, file=sys.stderr)
+            return 1
+    return _lib.ALLREDUCE_FN(cb)
+
+
 def calculate_natural_gradient(batch, gradient_flat, ostar_mean_flat, total_samples, diag_shift, cg_params, init_guess=None,
-                               allreduce=None):
-    """Optimizer::CalculateNaturalGradient: solves (S + diag_shift) x = gradient; raises on indefinite / breakdown like
-    the reference, returns the best iterate on non-convergence."""
-    s = SRSMatrix(batch, ostar_mean_flat, total_samples, diag_shift, allreduce)
-    x0 = np.zeros_like(gradient_flat) if init_guess is None else init_guess
-    res = conjugate_gradient(s, gradient_flat, x0, cg_params)
+                               allreduce_cb=None):
+    """Optimizer::CalculateNaturalGradient: solves (S + diag_shift) x = gradient on the device (all CG vectors in HBM);
+    raises on indefinite / breakdown like the reference, returns the best iterate on non-convergence.
+    ``allreduce_cb``: a _lib.ALLREDUCE_FN (see device_allreduce_callback) or None on a single GPU."""
+    import ctypes as C
+    from . import _lib
+    g = np.ascontiguousarray(gradient_flat, dtype=np.float64)
+    m = np.ascontiguousarray(ostar_mean_flat, dtype=np.float64)
+    x0 = None if init_guess is None else np.ascontiguousarray(init_guess, dtype=np.float64)
+    x = np.empty_like(g)
+    prm = _lib.PepsCGParams(cg_params.max_iter, cg_params.relative_tolerance, cg_params.absolute_tolerance,
+                            cg_params.residual_recompute_interval, cg_params.orthogonality_threshold)
+    it, reason, resid = C.c_int32(), C.c_int32(), C.c_double()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    cb = allreduce_cb if allreduce_cb is not None else C.cast(None, _lib.ALLREDUCE_FN)
+    batch._ck(batch.lib.peps_sr_natural_gradient(batch.h, dp(g), dp(m), int(total_samples), float(diag_shift), C.byref(prm),
+                                                 dp(x0) if x0 is not None else None, cb, None, dp(x), C.byref(it),
+                                                 C.byref(resid), C.byref(reason)))
+    res = CGResult(x, resid.value, it.value, reason.value)
     if res.reason in (INDEFINITE_MATRIX, NUMERICAL_BREAKDOWN):
         raise RuntimeError(f"CG solver terminated: {REASONS[res.reason]} iterations={res.iterations} residual_norm={res.residual_norm}")
     return res

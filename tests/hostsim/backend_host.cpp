@@ -15,6 +15,10 @@
 namespace peps {
 
 static long g_launches = 0;
+struct BeCtx { int device; };
+BeCtx *be_ctx_create(int device) { return new BeCtx{device}; }
+void be_ctx_bind(BeCtx *) {}
+void be_ctx_destroy(BeCtx *c) { delete c; }
 void be_init(int) {}
 const char *be_name() { return "hostsim"; }
 void *be_malloc(size_t bytes) { return std::malloc(bytes ? bytes : 8); }
@@ -484,6 +488,17 @@ void be_sr_accumulate(const double *ostar, const int32_t *cfgs, long hole_stride
       for (long i = 0; i < n; ++i)
         out[tps_off[site] + (long)cfgs[i * nsites + site] * site_size[site] + e] += delta[i] * ostar[i * hole_stride + hole_off[site] + e];
     }
+}
+
+void be_vec_lincomb(double *out, double ca, const double *a, double cb, const double *b, long n) {
+  ++g_launches;
+  for (long i = 0; i < n; ++i) out[i] = ca * a[i] + (b ? cb * b[i] : 0.0);
+}
+void be_vec_dot(const double *a, const double *b, long n, double *result) {
+  ++g_launches;
+  double s = 0.0;
+  for (long i = 0; i < n; ++i) s += a[i] * b[i];
+  result[0] = s;
 }
 
 }  // namespace peps

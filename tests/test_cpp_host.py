@@ -14,16 +14,16 @@ from peps_b200.api import (BMPSTruncateParams, SplitIndexTPS, MCEnergyGradEvalua
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_cpp_wrapper_matches_python_mirror():
-    lib = hostsim_lib.load()
-    libdir = os.path.join(ROOT, "tests", "hostsim")
+def run_cpp_wrapper_case(lib, libdir, libfile, extra_link=()):
+    """Builds tests/cpp/test_cpp_host.cpp against `libfile` in `libdir` and compares its Evaluate() with the Python
+    mirror driving `lib` (the ctypes binding of the same shared library)."""
     tps = SplitIndexTPS(vmc.random_tps(3, 3, 2, 2, seed=4))
     cfg = vmc.neel_config(3, 3)
     W, chi, ns, seed = 3, 4, 6, 21
     with tempfile.TemporaryDirectory() as td:
         exe = os.path.join(td, "cpp_host")
         subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "test_cpp_host.cpp"), "-o", exe,
-                               "-L" + libdir, "-lpeps_hostsim", "-Wl,-rpath," + libdir])
+                               "-L" + libdir, "-l:" + libfile, "-Wl,-rpath," + libdir] + list(extra_link))
         flat = tps.pack()
         inp = f"3 3 2 2 {W} {chi} {ns} {seed}\n{flat.size}\n" + " ".join(repr(float(x)) for x in flat) + "\n" + \
               " ".join(str(int(c)) for c in cfg.ravel()) + "\n"
@@ -39,3 +39,7 @@ def test_cpp_wrapper_matches_python_mirror():
     assert np.isfinite(e2)          # second Evaluate through the seam-B1 adapter continues the same chains
     assert abs(gn_cpp - res.gradient_norm) < 1e-12 * max(1.0, res.gradient_norm)
     assert abs(acc_cpp - res.accept_rates_avg[0]) < 1e-12
+
+
+def test_cpp_wrapper_matches_python_mirror():
+    run_cpp_wrapper_case(hostsim_lib.load(), os.path.join(ROOT, "tests", "hostsim"), "libpeps_hostsim.so")

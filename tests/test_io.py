@@ -33,3 +33,26 @@ def test_reads_reference_fixture_and_rewrites_it_byte_for_byte(tmp_path):
     pio.dump_tps(tps, str(tmp_path / "out"), template_dir=d)
     for name in ("tps_ten1_1_0.qlten", "tps_ten0_0_1.qlten", "tps_ten3_3_0.qlten"):
         assert open(os.path.join(d, name), "rb").read() == open(tmp_path / "out" / name, "rb").read()
+
+
+def test_read_qlten_checks_the_payload(tmp_path):
+    a = np.arange(24, dtype=np.float64).reshape(2, 3, 4)
+    p = str(tmp_path / "t.qlten")
+    pio.write_qlten(p, a)
+    assert np.array_equal(pio.read_qlten(p), a)
+    raw = open(p, "rb").read()
+    open(p, "wb").write(raw[:-17])                       # truncated payload
+    with pytest.raises(ValueError):
+        pio.read_qlten(p)
+    with pytest.raises(ValueError):                      # a real file read as complex
+        open(p, "wb").write(raw)
+        pio.read_qlten(p, dtype=np.complex128)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_complex_fixture_is_detected():
+    d = os.path.join(REF, "slow_tests/test_data/tps_square_heisenberg4x4D8Complex")
+    t = pio.read_qlten(os.path.join(d, "tps_ten1_1_0.qlten"))
+    assert t.dtype == np.complex128 and t.shape == (8, 8, 8, 8)
+    with pytest.raises(ValueError):
+        pio.read_qlten(os.path.join(d, "tps_ten1_1_0.qlten"), dtype=np.float64)

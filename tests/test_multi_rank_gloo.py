@@ -28,10 +28,12 @@ mc = MonteCarloParams(num_samples=3 * W * world, num_warmup_sweeps=0, sweeps_bet
 ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(4, 4, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
                            MCUpdateSquareNNExchange(9), walkers=W, configs=cfgs, lib=hostsim_lib.load(), dist=dist,
                            rank=rank, world_size=world)
-res = ev.Evaluate()
+res = ev.Evaluate(collect_sr_buffers=True)
+from peps_b200 import sr
+nat, iters, resid = ev.CalculateNaturalGradient(res, 1e-3, sr.ConjugateGradientParams(max_iter=200, relative_tolerance=1e-10))
 if rank == 0:
-    pickle.dump(dict(energy=res.energy, err=res.energy_error, grad=res.gradient.pack(), es=res.energy_samples),
-                open({out!r}, "wb"))
+    pickle.dump(dict(energy=res.energy, err=res.energy_error, grad=res.gradient.pack(), es=res.energy_samples,
+                     nat=nat.pack(), iters=iters), open({out!r}, "wb"))
 dist.destroy_process_group()
 '''
 
@@ -59,7 +61,13 @@ def test_two_rank_gloo_matches_single_rank():
     mc = MonteCarloParams(num_samples=12, num_warmup_sweeps=0, sweeps_between_samples=1, is_warmed_up=True)
     ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(4, 4, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
                                MCUpdateSquareNNExchange(9), walkers=4, configs=cfgs, lib=hostsim_lib.load())
-    one = ev.Evaluate()
+    one = ev.Evaluate(collect_sr_buffers=True)
+    from peps_b200 import sr
+    nat1, it1, _ = ev.CalculateNaturalGradient(one, 1e-3, sr.ConjugateGradientParams(max_iter=200, relative_tolerance=1e-10))
+    # SR across ranks: every rank holds half of the O* samples, the matvec output is all-reduced through the
+    # peps_allreduce_fn callback on the engine's buffer (NCCL on the device pointer on GPUs)
+    assert np.max(np.abs(two["nat"] - nat1.pack())) < 1e-8 * np.max(np.abs(nat1.pack()))
+    assert abs(two["iters"] - it1) <= 1
     assert two["es"].shape == (4, 3)
     assert np.allclose(two["es"], one.energy_samples, rtol=0, atol=1e-12)
     assert abs(two["energy"] - one.energy) < 1e-12
