@@ -38,6 +38,10 @@ struct GettDesc {
   const int32_t *am = nullptr, *ak = nullptr, *bk = nullptr, *bn = nullptr, *cm = nullptr, *cn = nullptr;
   int a_kfast = 0;   // 1: A's unit-stride index is a contracted one
   int b_nfast = 1;   // 1: B's unit-stride index is a free one
+  // 1: consecutive PAIRS (2i, 2i+1) along the operand's fast index are adjacent in memory and every pair starts at an
+  // even element offset (so a 16-byte copy / store moves a pair when the operand base is 16-byte aligned). For A the
+  // fast index is K when a_kfast else M; for B it is N when b_nfast else K; for C it is N.
+  int a_vec2 = 0, b_vec2 = 0, c_vec2 = 0;
   // Optional structural-zero hints (device tables, may be null): A(m,k) == 0 for k < klo_m[m], B(k,n) == 0 for
   // k < klo_n[n] (the R factors of the forward chain are upper trapezoidal). A backend may start the K loop of a tile
   // at the largest K step below both bounds; ignoring the hints gives the same result. work = executed / nominal flops.
@@ -118,6 +122,8 @@ struct ApplyArgs {
   // describes A with boxes of (R/8 rows x 8 columns)
   const TileMap *tmap = nullptr;
   int row0 = 0;
+  // 0: C <- Q^T C = C - V T^T (V^T C)  (factorisation);  1: C <- Q C = C - V T (V^T C)  (forming / applying Q)
+  int notrans = 0;
 };
 void be_apply_reflector(const ApplyArgs &a);
 
@@ -157,6 +163,31 @@ void be_select_truncate(const double *norms2, int nr, int nsv, int dmin, int dma
 // B[w][t][c] = G[w][order[w][t]][c] / norm  for t < kept[w], else 0   (t < tcap, c < nc)
 void be_gather_rows_normalized(const double *G, long ws, int ld, int nc, const double *norms2, int nr,
                                const int32_t *order, const int32_t *kept, int tcap, double *B, long wb, int W);
+
+// ---- small-matrix SVD path of the truncation (second preconditioning + single-CTA Jacobi) ---------------------------
+// dst[w][c][r] = (r < count[w]) ? src[w][order[w][r]][c] : 0   for c < nc, r < n2 (dst: row-major, leading dimension
+// n2, walker stride wd; rows c >= nc of dst are not touched): the numerically non-zero rows of R, sorted by norm,
+// written TRANSPOSED so that their LQ factorisation is a tall-skinny QR.
+void be_gather_rows_transposed(const double *src, long ws, int ld, int nc, int nr_src, const int32_t *order,
+                               const int32_t *count, double *dst, long wd, int n2, int W);
+// One-sided Jacobi SVD of the n2 x n2 upper-triangular factor Rt[w] (row-major, leading dimension ld; only the
+// leading count[w] columns are non-zero), one CTA per walker with the whole factor resident in shared memory, all
+// sweeps and the convergence test on the device. The COLUMNS of Rt are rotated until mutually orthogonal
+// (|x.y| <= tol |x||y| for every pair during one whole sweep), giving Rt J = Y Sigma; the TensorToolkit truncation rule
+// (dmin, dmax, trunc_err over nsv singular values) picks kept[w]; out[w][i][t] = Y[i][rank t] for i < n2, t < kept[w]
+// and 0 for kept[w] <= t < tcap (row-major, leading dimension tcap, walker stride wo): the kept LEFT singular
+// vectors of Rt, i.e. the kept right singular vectors of the gathered rows in the basis of the QR's Q.
+// sweeps[w] (may be null) receives the number of sweeps walker w needed.
+struct SmallSvdArgs {
+  const double *Rt; long ws; int ld; int n2; const int32_t *count;
+  int nsv, dmin, dmax; double trunc_err; int tcap;
+  double tol; int max_sweeps;
+  double *out; long wo; int32_t *kept; int32_t *sweeps; int W;
+};
+constexpr int kSmallSvdMaxN = 128;        // largest n2 the kernel holds in shared memory
+void be_svd_small(const SmallSvdArgs &a);
+// B[w][t][order ? order[w][j] : j] = C0[w][j][t]   for j < nc, t < tcap  (C0 leading dimension tcap, B leading dim nc)
+void be_transpose_permute(const double *C0, long wc, int nc, int tcap, const int32_t *order, double *B, long wb, int W);
 
 // ---- Monte Carlo state kernels ---------------------------------------------------------------------
 // std::mt19937(seed[w]) for every walker: mt[w][624], idx[w] = 624

@@ -320,9 +320,256 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
   }
 }
 
+// ---- large-tile contraction kernel -----------------------------------------------------------------------
+// CTA tile 128 (M) x 64 (N), 8 warps as 4 x 2, warp tile 32 x 32 (4 x 4 DMMA m8n8k4 tiles, 16 accumulator pairs); or,
+// when the launch would otherwise leave SMs idle, 64 x 64 with 8 warps as 2 x 4 (warp tile 32 x 16).
+// Operand tiles travel global -> shared with cp.async (LDGSTS: no register staging, the copy engine zero-fills the
+// ragged edges) through a 3-stage ring, one barrier per K step of 16; 16-byte copies wherever the planner proved that
+// pairs along the operand's unit-stride index are contiguous and aligned (GettDesc::a_vec2 / b_vec2), 8-byte copies
+// through the offset tables otherwise (true gathers). Each operand tile is laid out in shared memory along ITS OWN
+// unit-stride index -- [k][m] (+4 pad) when the free index is fast, [m][k] (+4 pad) when the contracted index is fast --
+// so both the copy writes and the DMMA fragment reads are bank-conflict free in either case.
+constexpr int GL_BN = 64, GL_BK = 16, GL_THREADS = 256, GL_STAGES = 3;
+constexpr int GL_LDB = GL_BN + 4, GL_LDK = GL_BK + 4;
+constexpr int GL_B_ELEMS = (GL_BK * GL_LDB > GL_BN * GL_LDK) ? GL_BK * GL_LDB : GL_BN * GL_LDK;
+__host__ __device__ constexpr int gl_a_elems(int bm) { return (GL_BK * (bm + 4) > bm * GL_LDK) ? GL_BK * (bm + 4) : bm * GL_LDK; }
+constexpr size_t gl_smem(int bm) { return (size_t)GL_STAGES * (gl_a_elems(bm) + GL_B_ELEMS) * sizeof(double); }
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(saddr), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src, bool valid) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(saddr), "l"(src), "r"(sz));
+}
+
+// AKF: A's unit-stride index is a contracted one (tile stored [m][k]); BKF: likewise for B (tile stored [n][k]).
+// WGM: warps along M (4: 128 x 64 tile, 2: 64 x 64 tile)
+template <bool AKF, bool BKF, int WGM>
+__global__ void __launch_bounds__(GL_THREADS, 2)
+gett_large_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double beta, int avec, int bvec, int cvec) {
+  constexpr int GL_BM = 32 * WGM, GL_LDA = GL_BM + 4, GL_A_ELEMS = gl_a_elems(GL_BM);
+  constexpr int WGN = 8 / WGM, NT = GL_BN / (8 * WGN);        // warps along N, 8-column tiles per warp (4 or 2)
+  constexpr int APT = GL_BM * GL_BK / 2 / GL_THREADS;        // A pairs per thread (4 or 2)
+  extern __shared__ __align__(16) double gl_sm[];
+  double *As = gl_sm;                                        // [STAGES][GL_A_ELEMS]
+  double *Bs = gl_sm + GL_STAGES * GL_A_ELEMS;               // [STAGES][GL_B_ELEMS]
+  const int tiles_m = (d.M + GL_BM - 1) / GL_BM;
+  const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+  const int m0 = tm * GL_BM, n0 = tn * GL_BN;
+  const int w = blockIdx.z, bb = blockIdx.y;
+  const double *Ab = operand_base(A, w, bb);
+  const double *Bb = operand_base(B, w, bb);
+  double *Cb = const_cast<double *>(operand_base(C, w, bb));
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int wm = warp / WGN, wn = warp % WGN;
+
+  // ---- loader coordinates: the free-index part of every offset is fixed for the whole K loop -------------------
+  // A tile = BM * 8 pairs: free-fast -> pair (m2 = q % (BM/2), k = q / (BM/2)); contracted-fast -> pair (k2 = q % 8, m = q / 8)
+  int a_fo[APT][2];      // offsets of the (up to) two elements of pair i along the free index (-1: outside M)
+  int a_kl[APT];         // first K index of pair i inside the K step
+  int a_so[APT];         // shared-memory offset of pair i
+#pragma unroll
+  for (int i = 0; i < APT; ++i) {
+    const int q = t + i * GL_THREADS;
+    if (AKF) {
+      const int kp = q & 7, ml = q >> 3, m = m0 + ml;
+      a_kl[i] = 2 * kp; a_so[i] = ml * GL_LDK + 2 * kp;
+      a_fo[i][0] = (m < d.M) ? d.am[m] : -1; a_fo[i][1] = a_fo[i][0];
+    } else {
+      const int mp = q % (GL_BM / 2), kl = q / (GL_BM / 2), m = m0 + 2 * mp;
+      a_kl[i] = kl; a_so[i] = kl * GL_LDA + 2 * mp;
+      a_fo[i][0] = (m < d.M) ? d.am[m] : -1; a_fo[i][1] = (m + 1 < d.M) ? d.am[m + 1] : -1;
+    }
+  }
+  // B tile = 512 pairs: free-fast -> pair (n2 = q % 32, k = q / 32); contracted-fast -> pair (k2 = q % 8, n = q / 8)
+  int b_fo[2][2], b_kl[2], b_so[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int q = t + i * GL_THREADS;
+    if (BKF) {
+      const int kp = q & 7, nl = q >> 3, n = n0 + nl;
+      b_kl[i] = 2 * kp; b_so[i] = nl * GL_LDK + 2 * kp;
+      b_fo[i][0] = (n < d.N) ? d.bn[n] : -1; b_fo[i][1] = b_fo[i][0];
+    } else {
+      const int np = q & 31, kl = q >> 5, n = n0 + 2 * np;
+      b_kl[i] = kl; b_so[i] = kl * GL_LDB + 2 * np;
+      b_fo[i][0] = (n < d.N) ? d.bn[n] : -1; b_fo[i][1] = (n + 1 < d.N) ? d.bn[n + 1] : -1;
+    }
+  }
+  auto issue = [&](int kt, int stage) {
+    const int k0 = kt * GL_BK;
+    double *as = As + stage * GL_A_ELEMS, *bs = Bs + stage * GL_B_ELEMS;
+#pragma unroll
+    for (int i = 0; i < APT; ++i) {
+      const int k = k0 + a_kl[i];
+      if (AKF) {                                   // the pair runs along K: (k, k+1) of one row m
+        const bool v0 = a_fo[i][0] >= 0 && k < d.K, v1 = a_fo[i][0] >= 0 && k + 1 < d.K;
+        const int o0 = v0 ? a_fo[i][0] + d.ak[k] : 0;
+        if (avec) cp_async16(as + a_so[i], Ab + o0, v0);
+        else {
+          cp_async8(as + a_so[i], Ab + o0, v0);
+          cp_async8(as + a_so[i] + 1, Ab + (v1 ? a_fo[i][0] + d.ak[k + 1] : 0), v1);
+        }
+      } else {                                     // the pair runs along M: (m, m+1) at one k
+        const bool kin = k < d.K;
+        const int ko = kin ? d.ak[k] : 0;
+        const bool v0 = kin && a_fo[i][0] >= 0, v1 = kin && a_fo[i][1] >= 0;
+        if (avec) cp_async16(as + a_so[i], Ab + (v0 ? a_fo[i][0] + ko : 0), v0);
+        else {
+          cp_async8(as + a_so[i], Ab + (v0 ? a_fo[i][0] + ko : 0), v0);
+          cp_async8(as + a_so[i] + 1, Ab + (v1 ? a_fo[i][1] + ko : 0), v1);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = k0 + b_kl[i];
+      if (BKF) {
+        const bool v0 = b_fo[i][0] >= 0 && k < d.K, v1 = b_fo[i][0] >= 0 && k + 1 < d.K;
+        const int o0 = v0 ? b_fo[i][0] + d.bk[k] : 0;
+        if (bvec) cp_async16(bs + b_so[i], Bb + o0, v0);
+        else {
+          cp_async8(bs + b_so[i], Bb + o0, v0);
+          cp_async8(bs + b_so[i] + 1, Bb + (v1 ? b_fo[i][0] + d.bk[k + 1] : 0), v1);
+        }
+      } else {
+        const bool kin = k < d.K;
+        const int ko = kin ? d.bk[k] : 0;
+        const bool v0 = kin && b_fo[i][0] >= 0, v1 = kin && b_fo[i][1] >= 0;
+        if (bvec) cp_async16(bs + b_so[i], Bb + (v0 ? b_fo[i][0] + ko : 0), v0);
+        else {
+          cp_async8(bs + b_so[i], Bb + (v0 ? b_fo[i][0] + ko : 0), v0);
+          cp_async8(bs + b_so[i] + 1, Bb + (v1 ? b_fo[i][1] + ko : 0), v1);
+        }
+      }
+    }
+  };
+
+  const int nk = (d.K + GL_BK - 1) / GL_BK;
+  int kt0 = 0;
+  if (d.klo_m != nullptr || d.klo_n != nullptr) {      // structural zeros: skip the K steps below both bounds
+    __shared__ int s_klo[2];
+    if (t < 2) s_klo[t] = 0x7fffffff;
+    __syncthreads();
+    int vm = 0x7fffffff, vn = 0x7fffffff;
+    if (d.klo_m) { for (int i = t; i < GL_BM; i += GL_THREADS) if (m0 + i < d.M) vm = min(vm, d.klo_m[m0 + i]); } else vm = 0;
+    if (d.klo_n) { for (int i = t; i < GL_BN; i += GL_THREADS) if (n0 + i < d.N) vn = min(vn, d.klo_n[n0 + i]); } else vn = 0;
+    atomicMin(&s_klo[0], vm);
+    atomicMin(&s_klo[1], vn);
+    __syncthreads();
+    kt0 = min(nk, max(s_klo[0], s_klo[1]) / GL_BK);
+  }
+
+  double acc[4][NT][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  // fragment base offsets inside a stage
+  const int fr = lane >> 2, fk = lane & 3;
+  const int a_frag = AKF ? (wm * 32 + fr) * GL_LDK + fk : fk * GL_LDA + wm * 32 + fr;
+  const int b_frag = BKF ? (wn * 8 * NT + fr) * GL_LDK + fk : fk * GL_LDB + wn * 8 * NT + fr;
+  constexpr int A_I = AKF ? 8 * GL_LDK : 8, A_K = AKF ? 1 : GL_LDA;     // strides per 8-row tile / per k
+  constexpr int B_J = BKF ? 8 * GL_LDK : 8, B_K = BKF ? 1 : GL_LDB;
+
+#pragma unroll
+  for (int s = 0; s < GL_STAGES - 1; ++s) {
+    if (kt0 + s < nk) issue(kt0 + s, s);
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  for (int kt = kt0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(GL_STAGES - 2));
+    __syncthreads();                                 // stage kt has landed for everyone; stage kt-1 is free again
+    {
+      const int nxt = kt + GL_STAGES - 1;
+      if (nxt < nk) issue(nxt, (nxt - kt0) % GL_STAGES);
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
+    const int stage = (kt - kt0) % GL_STAGES;
+    const double *as = As + stage * GL_A_ELEMS + a_frag, *bs = Bs + stage * GL_B_ELEMS + b_frag;
+#pragma unroll
+    for (int kk = 0; kk < GL_BK; kk += 4) {
+      double af[4], bf[NT];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = as[kk * A_K + i * A_I];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bf[j] = bs[kk * B_K + j * B_J];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  // epilogue: lane (fr, fk) holds C[row fr][cols 2 fk, 2 fk + 1] of every 8x8 tile
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + wm * 32 + i * 8 + fr;
+    if (m >= d.M) continue;
+    const int cmo = d.cm[m];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int n = n0 + wn * 8 * NT + j * 8 + 2 * fk;
+      if (n >= d.N) continue;
+      double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
+      if (cvec) {                                    // the two columns are adjacent and 16-byte aligned in C
+        double2 *cp = reinterpret_cast<double2 *>(Cb + cmo + d.cn[n]);
+        if (beta != 0.0) { const double2 o = *cp; v0 += beta * o.x; v1 += beta * o.y; }
+        *cp = make_double2(v0, v1);
+      } else {
+        double *cp = Cb + cmo + d.cn[n];
+        if (beta != 0.0) v0 += beta * (*cp);
+        *cp = v0;
+        if (n + 1 < d.N) {
+          double *cq = Cb + cmo + d.cn[n + 1];
+          if (beta != 0.0) v1 += beta * (*cq);
+          *cq = v1;
+        }
+      }
+    }
+  }
+}
+
+static inline bool op_aligned2(const Operand &o) {
+  return ((reinterpret_cast<uintptr_t>(o.p) & 15) == 0) && ((o.ws & 1) == 0) && ((o.bs & 1) == 0) && (o.gidx == nullptr || (o.gs & 1) == 0);
+}
+
 void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, double beta, int W, int NB) {
   if (d.M <= 0 || d.N <= 0 || W <= 0 || NB <= 0) return;
   LaunchScope scope(KC_GETT, 2.0 * d.M * d.N * d.K * (double)W * NB * d.work);
+  static const bool use_large = []() { const char *e = std::getenv("PEPS_GETT_LARGE"); return e ? std::atoi(e) != 0 : true; }();
+  if (use_large && d.M > 32 && d.N > 32 && d.K >= 8) {
+    const int avec = d.a_vec2 && op_aligned2(A), bvec = d.b_vec2 && op_aligned2(B), cvec = d.c_vec2 && op_aligned2(C);
+    const int tn = (d.N + GL_BN - 1) / GL_BN;
+    // 128-row tiles unless that leaves fewer than two CTAs per SM: then 64-row tiles double the CTA count
+    const long ctas128 = (long)((d.M + 127) / 128) * tn * NB * W;
+    const bool half = ctas128 < 2L * 148 || d.M <= 96;
+    const int bm = half ? 64 : 128;
+    dim3 grid(((d.M + bm - 1) / bm) * tn, NB, W);
+    auto go = [&](auto kern) {
+      ensure_smem(kern, gl_smem(bm));
+      kern<<<grid, GL_THREADS, gl_smem(bm), g_stream>>>(d, A, B, C, alpha, beta, avec, bvec, cvec);
+    };
+    const bool akf = d.a_kfast != 0, bkf = d.b_nfast == 0;
+    if (half) {
+      if (akf && bkf) go(gett_large_kernel<true, true, 2>);
+      else if (akf) go(gett_large_kernel<true, false, 2>);
+      else if (bkf) go(gett_large_kernel<false, true, 2>);
+      else go(gett_large_kernel<false, false, 2>);
+    } else {
+      if (akf && bkf) go(gett_large_kernel<true, true, 4>);
+      else if (akf) go(gett_large_kernel<true, false, 4>);
+      else if (bkf) go(gett_large_kernel<false, true, 4>);
+      else go(gett_large_kernel<false, false, 4>);
+    }
+    post_launch();
+    return;
+  }
   auto launch = [&](auto kern, int BM, int BN) {
     int tiles = ((d.M + BM - 1) / BM) * ((d.N + BN - 1) / BN);
     dim3 grid(tiles, NB, W);
@@ -331,7 +578,7 @@ void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, d
   };
   if (d.M > 32 && d.N > 32) launch(gett_kernel<4, 4>, 64, 64);
   else if (d.M > 32) launch(gett_kernel<4, 1>, 64, 16);
-  else if (d.N > 32) launch(gett_kernel<1, 4>, 16, 64);
+  else if (d.N > 32) launch(gett_kernel<1, 4>, 64 / 4, 64);
   else launch(gett_kernel<2, 2>, 32, 32);
 }
 
@@ -1086,12 +1333,16 @@ __global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a,
     for (int e = t; e < NBW * TN; e += 256) {
       const int aa = e / TN, c = e % TN;
       double v0 = 0.0, v1 = 0.0;
-      int b2 = 0;
-      for (; b2 + 1 <= aa; b2 += 2) {
-        v0 += Tsm[b2 * LDW + aa] * Wraw[b2 * LDW + c];
-        v1 += Tsm[(b2 + 1) * LDW + aa] * Wraw[(b2 + 1) * LDW + c];
+      if (a.notrans) {                                 // (T W)[a][c] = sum_{b >= a} T[a][b] W[b][c]: applies Q instead of Q^T
+        for (int b2 = aa; b2 < NBW; ++b2) v0 += Tsm[aa * LDW + b2] * Wraw[b2 * LDW + c];
+      } else {
+        int b2 = 0;
+        for (; b2 + 1 <= aa; b2 += 2) {
+          v0 += Tsm[b2 * LDW + aa] * Wraw[b2 * LDW + c];
+          v1 += Tsm[(b2 + 1) * LDW + aa] * Wraw[(b2 + 1) * LDW + c];
+        }
+        if (b2 <= aa) v0 += Tsm[b2 * LDW + aa] * Wraw[b2 * LDW + c];
       }
-      if (b2 <= aa) v0 += Tsm[b2 * LDW + aa] * Wraw[b2 * LDW + c];
       Wsm[aa * LDW + c] = -(v0 + v1);
     }
     __syncthreads();
@@ -1782,6 +2033,214 @@ void be_gather_rows_normalized(const double *G, long ws, int ld, int nc, const d
                                const int32_t *order, const int32_t *kept, int tcap, double *B, long wb, int W) {
   LaunchScope scope(KC_SMALL, 0.0);
   gather_rows_kernel<<<dim3(tcap, W), 128, 0, g_stream>>>(G, ws, ld, nc, norms2, nr, order, kept, tcap, B, wb);
+  post_launch();
+}
+
+// =====================================================================================================
+// small-matrix SVD path of the truncation
+// =====================================================================================================
+__global__ void gather_rows_transposed_kernel(const double *src, long ws, int ld, int nc, int nr_src, const int32_t *order,
+                                              const int32_t *count, double *dst, long wd, int n2) {
+  __shared__ double tile[32][33];
+  const int w = blockIdx.z, c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  const int cnt = min(count[w], nr_src);
+  for (int rr = ty; rr < 32; rr += 8) {
+    const int r = r0 + rr, c = c0 + tx;
+    double v = 0.0;
+    if (r < cnt && c < nc) v = src[(long)w * ws + (long)order[(long)w * nr_src + r] * ld + c];
+    tile[rr][tx] = v;
+  }
+  __syncthreads();
+  for (int cc = ty; cc < 32; cc += 8) {
+    const int c = c0 + cc, r = r0 + tx;
+    if (c < nc && r < n2) dst[(long)w * wd + (long)c * n2 + r] = tile[tx][cc];
+  }
+}
+void be_gather_rows_transposed(const double *src, long ws, int ld, int nc, int nr_src, const int32_t *order,
+                               const int32_t *count, double *dst, long wd, int n2, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  gather_rows_transposed_kernel<<<dim3((nc + 31) / 32, (n2 + 31) / 32, W), 256, 0, g_stream>>>(src, ws, ld, nc, nr_src, order, count, dst, wd, n2);
+  post_launch();
+}
+
+__global__ void transpose_permute_kernel(const double *C0, long wc, int nc, int tcap, const int32_t *order, double *B, long wb) {
+  __shared__ double tile[32][33];
+  const int w = blockIdx.z, j0 = blockIdx.x * 32, t0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int jj = ty; jj < 32; jj += 8) {
+    const int j = j0 + jj, t = t0 + tx;
+    tile[jj][tx] = (j < nc && t < tcap) ? C0[(long)w * wc + (long)j * tcap + t] : 0.0;
+  }
+  __syncthreads();
+  for (int tt = ty; tt < 32; tt += 8) {
+    const int t = t0 + tt, j = j0 + tx;
+    if (t < tcap && j < nc) {
+      const int col = order ? order[(long)w * nc + j] : j;
+      B[(long)w * wb + (long)t * nc + col] = tile[tx][tt];
+    }
+  }
+}
+void be_transpose_permute(const double *C0, long wc, int nc, int tcap, const int32_t *order, double *B, long wb, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  transpose_permute_kernel<<<dim3((nc + 31) / 32, (tcap + 31) / 32, W), 256, 0, g_stream>>>(C0, wc, nc, tcap, order, B, wb);
+  post_launch();
+}
+
+// One-sided Jacobi SVD of a small square factor, one CTA per walker (see backend.h SmallSvdArgs). The n2 column vectors
+// of Rt live in shared memory as rows X[k][.] (leading dimension NCAP + 8: 16-byte accesses of consecutive vectors hit
+// disjoint bank groups). A rotation set pairs the vectors by the round-robin tournament; four lanes own one pair: each
+// lane keeps NCAP/4 elements of both vectors in registers between the dot products and the rotation, so a set moves
+// every vector through shared memory exactly once in each direction. The pair's Gram entries are summed over the four
+// lanes by two shuffles. After a rotation the vector with the larger norm goes to the lower index (de Rijk), which keeps
+// the singular values nearly sorted and speeds up convergence. A sweep without any rotation ends the iteration.
+constexpr int SVS_THREADS = 256;
+template <int NCAP>
+__global__ void __launch_bounds__(SVS_THREADS, 1) svd_small_kernel(SmallSvdArgs a) {
+  extern __shared__ __align__(16) double svs_sm[];
+  constexpr int LDX = NCAP + 8;
+  constexpr int NCH = NCAP / 8;                      // 8-element chunks per vector; lane j of a group owns elements 8i+2j, 8i+2j+1
+  double *X = svs_sm;                                // [NCAP][LDX]
+  double *nrm = X + (size_t)NCAP * LDX;              // [NCAP] squared norms, then sorted
+  double *srt = nrm + NCAP;                          // [NCAP]
+  int *perm = reinterpret_cast<int *>(srt + NCAP);   // [NCAP]
+  __shared__ int s_kept;
+  const int w = blockIdx.x;
+  const int t = threadIdx.x, lane4 = t & 3, group = t >> 2;
+  const int n2 = a.n2;
+  const int cnt = min(a.count[w], n2);
+  const int nact = (cnt + 1) & ~1;                   // vectors taking part (even); beyond cnt they are zero
+  const int nch = (nact + 7) >> 3;                   // chunks that can hold non-zeros (Rt is upper triangular)
+  const double *Rw = a.Rt + (long)w * a.ws;
+  const double tol2 = a.tol * a.tol;
+
+  // load: X[k][i] = Rt[i][k]
+  for (int e = t; e < NCAP * LDX; e += SVS_THREADS) X[e] = 0.0;
+  __syncthreads();
+  for (int e = t; e < n2 * n2; e += SVS_THREADS) {
+    const int i = e / n2, k = e - i * n2;
+    if (k >= i && k < nact) X[(size_t)k * LDX + i] = Rw[(long)i * a.ld + k];
+  }
+  __syncthreads();
+
+  int sweeps = 0;
+  if (nact >= 2) {
+    const int npair = nact >> 1;
+    for (; sweeps < a.max_sweeps; ++sweeps) {
+      int rotated = 0;
+      for (int step = 0; step < nact - 1; ++step) {
+        for (int pr = group; pr < npair; pr += SVS_THREADS / 4) {
+          int I, J;
+          rr_pair(nact, step, pr, I, J);
+          const int p = min(I, J), q = max(I, J);
+          double2 *xp = reinterpret_cast<double2 *>(X + (size_t)p * LDX) + lane4;
+          double2 *xq = reinterpret_cast<double2 *>(X + (size_t)q * LDX) + lane4;
+          double2 vp[NCH], vq[NCH];
+          double app = 0.0, aqq = 0.0, apq = 0.0;
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            if (i < nch) {
+              vp[i] = xp[4 * i]; vq[i] = xq[4 * i];
+              app = fma(vp[i].x, vp[i].x, app); app = fma(vp[i].y, vp[i].y, app);
+              aqq = fma(vq[i].x, vq[i].x, aqq); aqq = fma(vq[i].y, vq[i].y, aqq);
+              apq = fma(vp[i].x, vq[i].x, apq); apq = fma(vp[i].y, vq[i].y, apq);
+            }
+          }
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {
+            app += __shfl_xor_sync(0xffffffffu, app, o);
+            aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
+            apq += __shfl_xor_sync(0xffffffffu, apq, o);
+          }
+          double c, s;
+          jacobi_cs(app, aqq, apq, tol2, c, s);
+          if (s != 0.0) {                              // uniform over the four lanes of the pair
+            rotated = 1;
+            const double tg = s / c;
+            const bool swap = (app - tg * apq) < (aqq + tg * apq);      // larger norm to the lower index
+            double2 *dp = swap ? xq : xp, *dq = swap ? xp : xq;
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+              if (i < nch) {
+                double2 np, nq;
+                np.x = c * vp[i].x - s * vq[i].x; np.y = c * vp[i].y - s * vq[i].y;
+                nq.x = s * vp[i].x + c * vq[i].x; nq.y = s * vp[i].y + c * vq[i].y;
+                dp[4 * i] = np; dq[4 * i] = nq;
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (!__syncthreads_or(rotated)) { ++sweeps; break; }
+    }
+  }
+  if (a.sweeps && t == 0) a.sweeps[w] = sweeps;
+
+  // squared norms, ranking (descending, ties by index), truncation rule
+  for (int k = group; k < NCAP; k += SVS_THREADS / 4) {
+    double s2 = 0.0;
+    if (k < nact) {
+      const double2 *xk = reinterpret_cast<const double2 *>(X + (size_t)k * LDX) + lane4;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) if (i < nch) { const double2 v = xk[4 * i]; s2 = fma(v.x, v.x, s2); s2 = fma(v.y, v.y, s2); }
+    }
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+    if (lane4 == 0) nrm[k] = s2;
+  }
+  __syncthreads();
+  if (t < NCAP) {
+    const double mine = nrm[t];
+    int rank = 0;
+    for (int j = 0; j < NCAP; ++j) { const double o = nrm[j]; rank += (o > mine) || (o == mine && j < t); }
+    perm[rank] = t; srt[rank] = mine;
+  }
+  __syncthreads();
+  if (t == 0) {
+    const int n = a.nsv;
+    int k = n;
+    if (n > a.dmin) {
+      double total = 0.0;
+      for (int i = 0; i < n && i < NCAP; ++i) total += srt[i];
+      double kept_sum = total;
+      while (k > a.dmin) {
+        const double sv2 = (k - 1 < NCAP) ? srt[k - 1] : 0.0;
+        if (k <= a.dmax && total > 0.0 && (1.0 - (kept_sum - sv2) / total) > a.trunc_err) break;
+        kept_sum -= sv2;
+        --k;
+      }
+    }
+    if (k > a.tcap) k = a.tcap;
+    s_kept = k;
+    a.kept[w] = k;
+  }
+  __syncthreads();
+  const int kept = s_kept;
+  double *out = a.out + (long)w * a.wo;
+  for (int e = t; e < n2 * a.tcap; e += SVS_THREADS) {
+    const int i = e / a.tcap, tt = e - i * a.tcap;
+    double v = 0.0;
+    if (tt < kept && tt < NCAP) {
+      const double s2 = srt[tt];
+      if (s2 > 0.0) v = X[(size_t)perm[tt] * LDX + i] * (1.0 / sqrt(s2));
+    }
+    out[(long)i * a.tcap + tt] = v;
+  }
+}
+template <int NCAP>
+static size_t svd_small_smem() { return ((size_t)NCAP * (NCAP + 8) + 2 * NCAP) * sizeof(double) + NCAP * sizeof(int) + 16; }
+void be_svd_small(const SmallSvdArgs &a) {
+  if (a.n2 > kSmallSvdMaxN || a.n2 < 1 || (a.n2 & 7)) throw std::runtime_error("be_svd_small: n2 must be a multiple of 8 in [8, 128]");
+  // model flops of one sweep: n(n-1)/2 pairs x (3 dots + rotation) x n elements x 2 flops ~ 7 n^3
+  LaunchScope scope(KC_JACOBI, 7.0 * a.n2 * a.n2 * a.n2 * 4.0 * (double)a.W);
+  auto launch = [&](auto kern, size_t smem) {
+    ensure_smem(kern, smem);
+    kern<<<a.W, SVS_THREADS, smem, g_stream>>>(a);
+  };
+  if (a.n2 <= 32) launch(svd_small_kernel<32>, svd_small_smem<32>());
+  else if (a.n2 <= 64) launch(svd_small_kernel<64>, svd_small_smem<64>());
+  else launch(svd_small_kernel<128>, svd_small_smem<128>());
   post_launch();
 }
 

@@ -22,6 +22,7 @@ Engine::Engine(const EngineConfig &c)
   if (const char *e = std::getenv("PEPS_BMPS_MEMO")) memo_on_ = std::atoi(e) != 0;
   if (const char *e = std::getenv("PEPS_PRESORT_COLS")) la_.presort_columns = std::atoi(e) != 0;
   if (const char *e = std::getenv("PEPS_CHAIN_EPS")) chain_eps_ = std::atof(e);
+  if (const char *e = std::getenv("PEPS_SMALL_SVD")) la_.small_svd = std::atoi(e) != 0;
   la_.offmax = (double *)be_malloc(sizeof(double) * W_);
   la_.done = (int32_t *)be_malloc(sizeof(int32_t) * W_);
   tps_off_h_.resize((size_t)nsites_);
@@ -146,6 +147,7 @@ long Engine::stat(int which) const {
     case 11: return n_memo_hits_;
     case 12: return chain_rows_in_;
     case 13: return chain_rows_kept_;
+    case 14: return la_.small_svd_calls;
     default: return -1;
   }
 }

@@ -28,6 +28,8 @@ struct LinalgCtx {
   long rows_in = 0, rows_kept = 0;   // Jacobi row counts before / after deflation (summed over calls)
   double deflation_eps = 1e-13;      // rows of R below eps * (largest row norm) are treated as zero (perturbs Theta by <= sqrt(rows) * eps * |Theta|)
   bool presort_columns = true;       // PEPS_PRESORT_COLS=0 switches the column pre-sorting of truncate_rows off
+  bool small_svd = true;             // PEPS_SMALL_SVD=0 switches the single-CTA SVD path of truncate_rows off
+  long small_svd_calls = 0;
   double jacobi_tol = 1e-14;
   int jacobi_inner_sweeps = 1;
   int jacobi_max_sweeps = 40;
@@ -220,6 +222,60 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
   int nr_eff = 1;
   for (int w = 0; w < W; ++w) nr_eff = std::max(nr_eff, (int)cx.done_host[(size_t)w]);
   cx.rows_in += kk; cx.rows_kept += nr_eff;
+  if (cx.small_svd && nr_eff >= 2 && round_up(nr_eff, 8) <= kSmallSvdMaxN && qr_layout(nc, round_up(nr_eff, 8)).nrb == 1) {
+    // Second preconditioning + single-CTA Jacobi (Drmac-Veselic): the surviving rows G2 (nr_eff x nc) are factorised
+    // G2^T = Q Rt by a tall-skinny QR whose reflectors are KEPT; the one-sided Jacobi runs on the small square factor
+    // Rt (n2 x n2, resident in shared memory, all sweeps and the convergence test on the device: no host round trip
+    // per sweep); the kept left singular vectors Y of Rt are mapped back by B^T = Q [Y; 0] (reflectors applied in
+    // reverse order) and un-permuted. Rows of B: orthonormal to rounding (Q is a product of reflectors, Y comes out
+    // of Jacobi with high relative accuracy).
+    ++cx.jacobi_calls; ++cx.small_svd_calls;
+    const int n2 = round_up(nr_eff, 8), nb = 32;
+    const QRLayout L2 = qr_layout(nc, n2);
+    const int rb = L2.rb, kk2 = std::min(nc, n2), npanel = (kk2 + nb - 1) / nb;
+    const long wsT = (long)rb * n2, wsC = (long)rb * tcap;
+    double *GT = (double *)cx.pool->get(sizeof(double) * (size_t)W * wsT);
+    be_memset0(GT, sizeof(double) * (size_t)W * wsT);
+    be_gather_rows_transposed(G, ws, nc, nc, kk, ord, cnt, GT, wsT, n2, W);
+    double *Vall = (double *)cx.pool->get(sizeof(double) * (size_t)npanel * W * rb * nb);
+    double *Tall = (double *)cx.pool->get(sizeof(double) * (size_t)npanel * W * nb * nb);
+    const int32_t *rowtab = cx.planner->upload(iota_scaled(rb, 1));
+    TileMap tmT, tmC;
+    const bool mapT = (rb % 64 == 0) && be_make_tile_map(&tmT, GT, wsT, n2, rb, n2, W, rb / 8, 8);
+    for (int p = 0; p < npanel; ++p) {
+      const int col0 = p * nb, pw = std::min(nb, kk2 - col0), c1 = col0 + pw, ntrail = n2 - c1;
+      PanelArgs pa;
+      pa.A = GT; pa.ws = wsT; pa.lda = n2; pa.rowtab = rowtab; pa.R = rb; pa.skip0 = col0; pa.NI = 1;
+      pa.col0 = col0; pa.pw = pw; pa.nbw = nb; pa.Vw = Vall + (size_t)p * W * rb * nb; pa.Tw = Tall + (size_t)p * W * nb * nb; pa.W = W;
+      be_panel_qr(pa);
+      if (ntrail > 0) {
+        ApplyArgs ap;
+        ap.A = GT; ap.ws = wsT; ap.lda = n2; ap.rowtab = rowtab; ap.R = rb; ap.NI = 1; ap.col1 = c1; ap.ntrail = ntrail;
+        ap.nbw = nb; ap.Vw = pa.Vw; ap.Tw = pa.Tw; ap.W = W;
+        if (mapT) { ap.tmap = &tmT; ap.row0 = 0; }
+        be_apply_reflector(ap);
+      }
+    }
+    double *C0 = (double *)cx.pool->get(sizeof(double) * (size_t)W * wsC);
+    be_memset0(C0, sizeof(double) * (size_t)W * wsC);
+    SmallSvdArgs sa;
+    sa.Rt = GT; sa.ws = wsT; sa.ld = n2; sa.n2 = n2; sa.count = cnt; sa.nsv = nsv; sa.dmin = dmin; sa.dmax = dmax;
+    sa.trunc_err = trunc_err; sa.tcap = tcap; sa.tol = cx.jacobi_tol; sa.max_sweeps = cx.jacobi_max_sweeps;
+    sa.out = C0; sa.wo = wsC; sa.kept = kept; sa.sweeps = nullptr; sa.W = W;
+    be_svd_small(sa);
+    const bool mapC = (rb % 64 == 0) && be_make_tile_map(&tmC, C0, wsC, tcap, rb, tcap, W, rb / 8, 8);
+    for (int p = npanel - 1; p >= 0; --p) {
+      ApplyArgs ap;
+      ap.A = C0; ap.ws = wsC; ap.lda = tcap; ap.rowtab = rowtab; ap.R = rb; ap.NI = 1; ap.col1 = 0; ap.ntrail = tcap;
+      ap.nbw = nb; ap.Vw = Vall + (size_t)p * W * rb * nb; ap.Tw = Tall + (size_t)p * W * nb * nb; ap.W = W; ap.notrans = 1;
+      if (mapC) { ap.tmap = &tmC; ap.row0 = 0; }
+      be_apply_reflector(ap);
+    }
+    be_transpose_permute(C0, wsC, nc, tcap, presort ? cord : nullptr, B, wb, W);
+    for (void *p : {(void *)GT, (void *)Vall, (void *)Tall, (void *)C0, (void *)n2a, (void *)ord, (void *)cnt}) cx.pool->put(p);
+    if (presort) { cx.pool->put(cord); cx.pool->put(G); }
+    return;
+  }
   JacobiLayout J = jacobi_layout(nr_eff, nc);
   double *G2 = (double *)cx.pool->get(sizeof(double) * (size_t)W * J.nr_pad * nc);
   const long ws2 = (long)J.nr_pad * nc;

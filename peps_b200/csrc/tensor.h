@@ -152,7 +152,19 @@ class Planner {
     char fa = min_label(la, stA), fb = min_label(lb, stB);
     pl.d.a_kfast = (fa && kl.find(fa) != std::string::npos) ? 1 : 0;
     pl.d.b_nfast = (fb && kl.find(fb) != std::string::npos) ? 0 : 1;
+    pl.d.a_vec2 = pairs_ok(pl.d.a_kfast ? ak : am, pl.d.a_kfast ? am : ak);
+    pl.d.b_vec2 = pairs_ok(pl.d.b_nfast ? bn : bk, pl.d.b_nfast ? bk : bn);
+    pl.d.c_vec2 = pairs_ok(cn, cm);
     return cache_.emplace(key, pl).first->second;
+  }
+
+  // 16-byte access along `fast`: even length, pairs (2i, 2i+1) adjacent, every offset that starts a pair even
+  static int pairs_ok(const std::vector<int32_t> &fast, const std::vector<int32_t> &other) {
+    if (fast.size() < 2 || (fast.size() & 1)) return 0;
+    for (size_t i = 0; i < fast.size(); i += 2)
+      if ((fast[i] & 1) || fast[i + 1] != fast[i] + 1) return 0;
+    for (int32_t o : other) if (o & 1) return 0;
+    return 1;
   }
 
   // generic integer table upload, cached by content

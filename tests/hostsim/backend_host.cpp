@@ -170,9 +170,9 @@ void be_apply_reflector(const ApplyArgs &a) {
           if (v == 0.0) continue;
           for (int tcol = 0; tcol < a.ntrail; ++tcol) Wm[(size_t)c * a.ntrail + tcol] += v * Aw[(long)rows[r] * a.lda + a.col1 + tcol];
         }
-      for (int c = 0; c < a.nbw; ++c)          // W2 = T^T W
-        for (int b2 = 0; b2 <= c; ++b2) {
-          double tv = T[(long)b2 * a.nbw + c];
+      for (int c = 0; c < a.nbw; ++c)          // W2 = T^T W   (notrans: T W)
+        for (int b2 = (a.notrans ? c : 0); b2 < (a.notrans ? a.nbw : c + 1); ++b2) {
+          double tv = a.notrans ? T[(long)c * a.nbw + b2] : T[(long)b2 * a.nbw + c];
           if (tv == 0.0) continue;
           for (int tcol = 0; tcol < a.ntrail; ++tcol) W2[(size_t)c * a.ntrail + tcol] += tv * Wm[(size_t)b2 * a.ntrail + tcol];
         }
@@ -490,6 +490,86 @@ void be_sr_accumulate(const double *ostar, const int32_t *cfgs, long hole_stride
     }
 }
 
+void be_gather_rows_transposed(const double *src, long ws, int ld, int nc, int nr_src, const int32_t *order,
+                               const int32_t *count, double *dst, long wd, int n2, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int c = 0; c < nc; ++c)
+      for (int r = 0; r < n2; ++r)
+        dst[w * wd + (long)c * n2 + r] = (r < count[w] && r < nr_src) ? src[w * ws + (long)order[(long)w * nr_src + r] * ld + c] : 0.0;
+}
+static int host_truncation_rule(const std::vector<double> &srt, int nsv, int dmin, int dmax, double trunc_err, int tcap) {
+  const int nr = (int)srt.size();
+  int n = nsv, k = n;
+  if (n > dmin) {
+    double total = 0.0;
+    for (int i = 0; i < n && i < nr; ++i) total += srt[(size_t)i];
+    double kept_sum = total;
+    while (k > dmin) {
+      double sv2 = (k - 1 < nr) ? srt[(size_t)(k - 1)] : 0.0;
+      if (k <= dmax && total > 0.0 && (1.0 - (kept_sum - sv2) / total) > trunc_err) break;
+      kept_sum -= sv2;
+      --k;
+    }
+  }
+  return std::min(k, tcap);
+}
+void be_svd_small(const SmallSvdArgs &a) {
+  ++g_launches;
+  const int n = a.n2;
+  for (int w = 0; w < a.W; ++w) {
+    std::vector<std::vector<double>> X((size_t)n, std::vector<double>((size_t)n));
+    for (int k = 0; k < n; ++k)
+      for (int i = 0; i < n; ++i) X[(size_t)k][(size_t)i] = a.Rt[w * a.ws + (long)i * a.ld + k];
+    int sweeps = 0;
+    for (; sweeps < a.max_sweeps; ++sweeps) {
+      double off = 0.0;
+      for (int p = 0; p < n; ++p)
+        for (int q = p + 1; q < n; ++q) {
+          double app = 0, aqq = 0, apq = 0;
+          for (int i = 0; i < n; ++i) { app += X[p][i] * X[p][i]; aqq += X[q][i] * X[q][i]; apq += X[p][i] * X[q][i]; }
+          if (app <= 0.0 || aqq <= 0.0 || apq == 0.0) continue;
+          off = std::max(off, std::fabs(apq) / std::sqrt(app * aqq));
+          if (apq * apq <= a.tol * a.tol * app * aqq) continue;
+          const double zeta = (aqq - app) / (2.0 * apq);
+          const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+          for (int i = 0; i < n; ++i) {
+            const double x = X[p][i], y = X[q][i];
+            X[p][i] = c * x - sn * y;
+            X[q][i] = sn * x + c * y;
+          }
+        }
+      if (off <= a.tol) { ++sweeps; break; }
+    }
+    if (a.sweeps) a.sweeps[w] = sweeps;
+    std::vector<double> n2v((size_t)n);
+    for (int k = 0; k < n; ++k) { double s2 = 0; for (int i = 0; i < n; ++i) s2 += X[k][i] * X[k][i]; n2v[(size_t)k] = s2; }
+    std::vector<int> perm((size_t)n);
+    for (int k = 0; k < n; ++k) {
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += (n2v[j] > n2v[k]) || (n2v[j] == n2v[k] && j < k);
+      perm[(size_t)rank] = k;
+    }
+    std::vector<double> srt((size_t)n);
+    for (int r = 0; r < n; ++r) srt[(size_t)r] = n2v[(size_t)perm[(size_t)r]];
+    const int kept = host_truncation_rule(srt, a.nsv, a.dmin, a.dmax, a.trunc_err, a.tcap);
+    a.kept[w] = kept;
+    for (int i = 0; i < n; ++i)
+      for (int t = 0; t < a.tcap; ++t) {
+        double v = 0.0;
+        if (t < kept && t < n && srt[(size_t)t] > 0.0) v = X[(size_t)perm[(size_t)t]][(size_t)i] / std::sqrt(srt[(size_t)t]);
+        a.out[w * a.wo + (long)i * a.tcap + t] = v;
+      }
+  }
+}
+void be_transpose_permute(const double *C0, long wc, int nc, int tcap, const int32_t *order, double *B, long wb, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int j = 0; j < nc; ++j)
+      for (int t = 0; t < tcap; ++t)
+        B[w * wb + (long)t * nc + (order ? order[(long)w * nc + j] : j)] = C0[w * wc + (long)j * tcap + t];
+}
 void be_vec_lincomb(double *out, double ca, const double *a, double cb, const double *b, long n) {
   ++g_launches;
   for (long i = 0; i < n; ++i) out[i] = ca * a[i] + (b ? cb * b[i] : 0.0);

@@ -40,6 +40,18 @@ def _ip(a):
     ("rc,rt->ct", (513, 32), (513, 100)),
     ("ab,bc->ac", (1, 1), (1, 1)),
     ("ab,bc->ac", (70, 33), (33, 130)),
+    # large-tile kernel (M > 64, N > 32): the four operand-layout variants, aligned pairs and true 8-byte gathers,
+    # ragged edges in M, N and K
+    ("ba,bc->ac", (34, 200), (34, 130)),
+    ("ba,bc->ac", (33, 71), (33, 67)),
+    ("ab,cb->ac", (200, 34), (130, 34)),
+    ("ab,cb->ac", (71, 35), (67, 35)),
+    ("ba,cb->ac", (40, 130), (66, 40)),
+    ("ab,bc->ac", (129, 64), (64, 65)),
+    ("kea,eaoj->koj", (96, 4, 10), (4, 10, 6, 10)),
+    ("apb,kea->ekpb", (16, 4, 18), (80, 3, 16)),
+    ("ekpb,epfo->kofb", (3, 80, 4, 18), (3, 4, 5, 7)),
+    ("apx,xyz->apyz", (64, 8, 64), (64, 8, 64)),
 ])
 def test_gett_contraction_vs_numpy(lib, spec, da, db):
     W = 3
