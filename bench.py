@@ -58,63 +58,105 @@ def make_inputs(L, D, n_walkers, first_walker):
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm on the host cores
 # ---------------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    """One process == one Markov chain with one BLAS thread (the reference runs one chain per MPI rank with
-    hp_numeric::SetTensorManipulationThreads(1)). Times a bounded slice of one sample and extrapolates by the
-    reference's own operation counts: a sample is 8 full boundary-MPS growths (4 in the sweep, 4 in E_loc) plus
-    2 x 2L row/column passes of BTen / trace / hole work."""
-    L, D, chi, walker, n_rows = args
+# One process == one Markov chain with one BLAS thread (the reference runs one chain per MPI rank with
+# hp_numeric::SetTensorManipulationThreads(1)); `cores` processes run side by side.
+#   * calibration (once): every process runs ONE REAL FULL SAMPLE of its chain (MC sweep + CalEnergyAndHoles<true>) and
+#     times it, then times the bounded slice below -> slice_fraction = t_slice / t_full_sample, both measured.
+#   * step: every process re-runs the bounded slice = one bulk boundary-MPS absorption (BMPS::MultiplyMPO of row L/2
+#     into the UP boundary that already holds rows 0..L/2-1: full D*chi bond, QR chain + truncating SVD sweep), the
+#     unit that carries ~90 % of a sample's flops. The parent times the step by wall clock over all processes.
+#   samples/s = cores * slice_fraction / t_step.
+CAL_FILE = os.path.join(ROOT, "profiles", "cpu_slice_calibration.json")
+_W = {}
+
+
+def _cpu_init(L, D, chi, counter):
     try:
         from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=1)
+        _W["limiter"] = threadpool_limits(limits=1)
     except Exception:
-        limiter = None
+        pass
+    with counter.get_lock():
+        wid = counter.value
+        counter.value += 1
     from oracle import vmc
-    from oracle.bmps import LEFT, RIGHT, UP, HORIZONTAL
-    tps, cfgs, _ = make_inputs(L, D, 1, walker)
-    t0 = time.time()
-    w = vmc.Walker.__new__(vmc.Walker)
-    w.config = np.array(cfgs[0], dtype=np.int64)
-    w.rows = w.cols = L
-    w.trunc = (chi, chi, 0.0)
-    w.tn = vmc.project(tps, w.config)
-    from oracle.contractor import BMPSContractor
-    w.contractor = BMPSContractor(L, L)
-    w.contractor.init(w.tn)
-    w.contractor.set_truncate_params(chi, chi, 0.0)
-    c = w.contractor
-    t0 = time.time()
-    c.generate_bmps_approach(w.tn, UP)             # one full growth of the DOWN stack: (L-1) MultiplyMPO
-    t_grow = time.time() - t0
-    t1 = time.time()
-    rows_done = 0
-    model = vmc.XXZModel()
-    for row in range(min(n_rows, L)):              # E_loc-style row passes (BTen growth, traces, holes)
-        c.init_bten(w.tn, LEFT, row)
-        c.grow_full_bten(w.tn, RIGHT, row, 1, True)
-        psi = c.trace(w.tn, (row, 0), HORIZONTAL)
-        for col in range(L):
-            c.punch_hole(w.tn, (row, col), HORIZONTAL)
-            if col < L - 1:
-                s1, s2 = (row, col), (row, col + 1)
-                model.bond_energy(s1, s2, int(w.config[s1]), int(w.config[s2]), HORIZONTAL, w, tps, 1.0 / psi)
-                c.shift_bten_window(w.tn, RIGHT)
-        rows_done += 1
-        if row < L - 1:
-            break                                  # later rows need shifted BMPS windows; one row is the slice
-    t_row = (time.time() - t1) / max(rows_done, 1)
-    t_sample = 8.0 * t_grow + 4.0 * L * t_row      # 2L passes with holes-class work + 2L lighter passes, bounded above
-    return dict(t_grow=t_grow, t_row=t_row, t_sample=t_sample)
+    from oracle.bmps import multiply_mpo, vacuum_bmps, UP
+    tps, cfgs, _ = make_inputs(L, D, 1, 100000 + wid)
+    tn = vmc.project(tps, cfgs[0])
+    mps = vacuum_bmps(L)
+    for k in range(L // 2):                        # UP boundary with rows 0 .. L/2-1 absorbed
+        mps = multiply_mpo(mps, [tn[k][c] for c in range(L)], UP, chi, chi, 0.0)
+    _W.update(L=L, D=D, chi=chi, wid=wid, tps=tps, cfg=cfgs[0], tn=tn, mps=mps)
 
 
-def cpu_samples_per_s(L, D, chi, cores):
-    import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(L, D, chi, 100000 + i, 1) for i in range(cores)])
-    t_sample = float(np.mean([r["t_sample"] for r in res]))
-    return cores / t_sample, dict(t_grow=float(np.mean([r["t_grow"] for r in res])),
-                                  t_row=float(np.mean([r["t_row"] for r in res])), t_sample=t_sample)
+def _cpu_slice(_):
+    from oracle.bmps import multiply_mpo, UP
+    L, chi, tn = _W["L"], _W["chi"], _W["tn"]
+    t0 = time.perf_counter()
+    multiply_mpo(_W["mps"], [tn[L // 2][c] for c in range(L)], UP, chi, chi, 0.0)
+    return time.perf_counter() - t0
+
+
+def _cpu_full_sample(_):
+    from oracle import vmc
+    chi = _W["chi"]
+    wk = vmc.Walker(_W["tps"], _W["cfg"], (chi, chi, 0.0))
+    up = vmc.NNExchangeUpdater(RNG_SEED0 + 100000 + _W["wid"])
+    t0 = time.perf_counter()
+    up.sweep(_W["tps"], wk)
+    vmc.XXZModel().energy_and_holes(_W["tps"], wk, True)
+    t_full = time.perf_counter() - t0
+    return t_full, _cpu_slice(0)
+
+
+class CpuArm:
+    def __init__(self, L, D, chi, cores):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        self.cores = cores
+        self.pool = ctx.Pool(cores, initializer=_cpu_init, initargs=(L, D, chi, ctx.Value("i", 0)))
+        self.pool.map(_cpu_slice, range(cores), chunksize=1)          # also forces every worker through its setup
+
+    def calibrate(self):
+        res = self.pool.map(_cpu_full_sample, range(self.cores), chunksize=1)
+        t_full = float(np.mean([r[0] for r in res]))
+        t_slice = float(np.mean([r[1] for r in res]))
+        return dict(t_full_sample_s=t_full, t_slice_s=t_slice, slice_fraction=t_slice / t_full, cores=self.cores)
+
+    def step(self):
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_slice, range(self.cores), chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.terminate()
+
+
+SLICE_TEXT = ("one bulk boundary-MPS absorption (BMPS::MultiplyMPO of row L/2, full D*chi bond) per process and step; "
+              "samples/s = cores * slice_fraction / t_step with slice_fraction = t_slice / t_full_sample, both timed "
+              "on this host (one real full sample per process: MC sweep + CalEnergyAndHoles<true>)")
+
+
+def cpu_baseline_quick(L, D, chi, cores, nsteps=3):
+    """cpu_baseline of the main arm: a few slice steps; the slice fraction comes from the calibration the reference arm
+    measured on the GPU box (profiles/cpu_slice_calibration.json) or is measured now if that file is missing."""
+    arm = CpuArm(L, D, chi, cores)
+    try:
+        cal = None
+        if os.path.exists(CAL_FILE):
+            c = json.load(open(CAL_FILE))
+            if c.get("workload") == [L, D, chi]:
+                cal = c
+        src = "profiles/cpu_slice_calibration.json (measured by `bench.py --impl reference` on the B200 box host)"
+        if cal is None:
+            cal = arm.calibrate()
+            src = "measured in this run"
+        ts = [arm.step() for _ in range(nsteps)]
+    finally:
+        arm.close()
+    t = float(np.mean(ts))
+    return cores * cal["slice_fraction"] / t, dict(t_step_s=t, slice_fraction=cal["slice_fraction"], slice_fraction_source=src,
+                                                   t_full_sample_s=cal.get("t_full_sample_s"))
 
 
 def run_reference_arm(args, rank):
@@ -122,21 +164,29 @@ def run_reference_arm(args, rank):
         return
     L, D, chi = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    vals = []
-    detail = None
-    for _ in range(max(1, min(args.steps, 2))):
-        v, detail = cpu_samples_per_s(L, D, chi, cores)
-        vals.append(v)
-    value = float(np.mean(vals))
-    sample = ("per process: one full boundary-MPS growth ((L-1) MultiplyMPO) + one row pass (BTen growth, traces, holes); "
-              "sample time = 8 growths + 4L row passes; one chain and one BLAS thread per core")
+    arm = CpuArm(L, D, chi, cores)
+    try:
+        cal = arm.calibrate()
+        for _ in range(args.warmup):
+            arm.step()
+        ts = [arm.step() for _ in range(args.steps)]
+    finally:
+        arm.close()
+    t = float(np.mean(ts))
+    value = cores * cal["slice_fraction"] / t
+    try:
+        os.makedirs(os.path.dirname(CAL_FILE), exist_ok=True)
+        json.dump(dict(cal, workload=[L, D, chi]), open(os.path.join(ROOT, "gpurun_out", "cpu_slice_calibration.json"), "w"))
+    except Exception:
+        pass
     line = {"impl": "reference", "metric": "vmc_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value if value > 0 else None,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "lattice": f"{L}x{L}", "D": D, "chi": chi,
-                       "trunc": "Dmin=Dmax=chi, trunc_err=0", "model": "Heisenberg NN (XXZ jz=jxy=1)"},
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample,
-                             "detail": detail},
+                       "trunc": "Dmin=Dmax=chi, trunc_err=0", "model": "Heisenberg NN (XXZ jz=jxy=1)",
+                       "sweeps_between_samples": 1, "tps": f"uniform[0,1) seed {TPS_SEED}, NormalizeAllSite"},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": SLICE_TEXT,
+                             "detail": dict(cal, t_step_s=t, whole_sample_check_samples_per_s=cores / cal["t_full_sample_s"])},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -204,6 +254,150 @@ def measure_fp64_peak(torch, n=4096, reps=6):
     return best
 
 
+class LaneSet:
+    """S host threads, each owning one context (= one CUDA stream) with W/S walkers of the same state: kernels of
+    different contexts overlap on the GPU (the per-lane host round trips -- one per chain / truncation step -- are hidden
+    behind the other lanes' kernels)."""
+
+    def __init__(self, L, D, chi, W, S, device, tps, cfgs, seeds, j2=0.0, rank=0, world=1, dist=None, torch=None):
+        import queue
+        from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+        S = max(1, min(S, W))
+        while W % S:
+            S -= 1
+        self.L, self.D, self.chi, self.W, self.S, self.Ws = L, D, chi, W, S, W // S
+        self.sit = tps if isinstance(tps, SplitIndexTPS) else SplitIndexTPS(tps)
+        self.torch, self.dist, self.world = torch, dist, world
+        outer = self
+
+        class Lane(threading.Thread):
+            def __init__(self, i):
+                super().__init__(daemon=True)
+                self.i, self.q, self.r, self.b = i, queue.Queue(), queue.Queue(), None
+                self.start()
+
+            def run(self):
+                while True:
+                    fn = self.q.get()
+                    if fn is None:
+                        return
+                    try:
+                        self.r.put(("ok", fn(self)))
+                    except Exception as exc:      # surface worker failures on the main thread
+                        self.r.put(("err", exc))
+
+        self.lanes = [Lane(i) for i in range(S)]
+
+        def setup(ln):
+            sl = slice(ln.i * outer.Ws, (ln.i + 1) * outer.Ws)
+            ln.b = WalkerBatch(L, L, 2, D, outer.Ws, BMPSTruncateParams.SVD(chi, chi, 0.0), device=device)
+            ln.b.set_tps(outer.sit)
+            if j2 != 0.0:
+                from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
+                ln.b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, j2, j2, 0.0))
+            ln.b.set_configs(cfgs[sl])
+            ln.b.seed_rng(seeds[sl])
+            ln.b.init_walkers()
+            return float(np.max(np.abs(ln.b.amplitudes())))
+
+        mx = max(self.on_all(setup))
+        if world > 1:
+            t = torch.tensor([mx], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            mx = float(t.item())
+        self.on_all(lambda ln: ln.b.normalize_state_order1(mx))     # MonteCarloEngine::NormalizeStateOrder1
+        self.on_all(lambda ln: ln.b.zero_accumulators())
+
+    def on_all(self, fn):
+        for ln in self.lanes:
+            ln.q.put(fn)
+        out = []
+        for ln in self.lanes:
+            st, v = ln.r.get()
+            if st == "err":
+                raise v
+            out.append(v)
+        return out
+
+    def barrier(self):
+        self.on_all(lambda ln: ln.b.sync())
+        if self.torch is not None:
+            self.torch.cuda.synchronize()
+            if self.world > 1:
+                self.dist.barrier()
+
+    def samples(self, n):
+        def run(ln):
+            last = None
+            for _ in range(n):
+                last, _ = ln.b.sample(1)
+            ln.b.sync()
+            return last
+        return np.concatenate(self.on_all(run))
+
+    def timed_samples(self, n):
+        """n samples on every lane between two CUDA events recorded with the device idle; returns (ms, energies)."""
+        torch = self.torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        ev0.record()
+        e = self.samples(n)
+        torch.cuda.synchronize()
+        ev1.record()
+        self.barrier()
+        return ev0.elapsed_time(ev1), e
+
+    def stat_sum(self, which):
+        return sum(self.on_all(lambda ln: ln.b.stat(which)))
+
+    def close(self):
+        def fin(ln):
+            ln.b.close()
+        self.on_all(fin)
+        for ln in self.lanes:
+            ln.q.put(None)
+
+
+def secondary_lines(torch, device, D_chi, walkers, streams):
+    """Non-favourable companions of the headline: the J1-J2 model of BASELINE config #3, the signed
+    [-1,1) TPS (flat boundary spectra: nothing deflates, the Jacobi fallback path runs) and a PHYSICAL state (the
+    reference's converged 4x4 D=8 Heisenberg fixture at chi = 16 and 64). One warm-up + one timed step each, fewer walkers
+    than the headline: indicative samples/s plus the fractions of rows the rank-revealing steps keep."""
+    global SIGNED_TPS
+    from oracle import vmc
+    L, D, chi = D_chi
+    out = []
+
+    def run(name, L, D, chi, W, S, tps, j2=0.0):
+        cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, CFG_SEED0 + w) for w in range(W)])
+        seeds = np.arange(RNG_SEED0, RNG_SEED0 + W, dtype=np.uint32)
+        ls = LaneSet(L, D, chi, W, S, device, tps, cfgs, seeds, j2=j2, torch=torch)
+        try:
+            ls.samples(1)
+            r0 = [ls.stat_sum(k) for k in (8, 9, 12, 13, 4, 14)]
+            ms, e = ls.timed_samples(1)
+            r1 = [ls.stat_sum(k) for k in (8, 9, 12, 13, 4, 14)]
+            d = [b - a for a, b in zip(r0, r1)]
+            out.append({"name": name, "lattice": f"{L}x{L}", "D": D, "chi": chi, "walkers": W, "streams": ls.S,
+                        "samples_per_s": W / (ms * 1e-3), "ms_per_step": ms, "mean_eloc": float(np.mean(e)),
+                        "truncation_rows_kept_frac": d[1] / max(d[0], 1), "chain_rows_kept_frac": d[3] / max(d[2], 1),
+                        "small_svd_path_frac": d[5] / max(d[4], 1)})
+        finally:
+            ls.close()
+
+    SIGNED_TPS = False
+    tps = vmc.random_tps(L, L, 2, D, seed=TPS_SEED)
+    run("j1j2_j2=0.5", L, D, chi, walkers, streams, tps, j2=0.5)
+    run("signed_tps", L, D, chi, walkers, streams, vmc.random_tps(L, L, 2, D, seed=TPS_SEED, signed=True))
+    gold = os.path.join(ROOT, "tests", "golden", "heis4x4_D8_double.npz")
+    if os.path.exists(gold):
+        z = np.load(gold)
+        phys = [[[z[f"t_{r}_{c}_{s}"] for s in range(2)] for c in range(4)] for r in range(4)]
+        for c in (16, 64):
+            run(f"physical_heisenberg_4x4_D8_fixture_chi{c}", 4, 8, c, 296, streams, phys)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,6 +410,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--signed", action="store_true", help="uniform [-1,1) TPS entries (cancellation stress variant of SURVEY.md 8d.1)")
     ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--secondary", type=int, default=1, help="also time the J1-J2 / signed / physical-state companions (N=1 only)")
+    ap.add_argument("--secondary-walkers", type=int, default=74)
     ap.add_argument("--streams", type=int, default=4, help="host threads / CUDA streams sharing the walkers of a GPU")
     args = ap.parse_args()
 
@@ -237,73 +433,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
-    import queue
+    from peps_b200.api import SplitIndexTPS
     L, D, chi = WORKLOADS[args.workload]
     W = args.walkers
-    S = max(1, min(args.streams, W))
-    while W % S:
-        S -= 1
-    Ws = W // S
     tps, cfgs, seeds = make_inputs(L, D, W, rank * W)
     sit = SplitIndexTPS(tps)
     dev = torch.device("cuda", local_rank)
-
-    # S host threads, each owning one context (= one CUDA stream) with W/S walkers: kernels of different contexts
-    # overlap on the GPU and fill the tails of partially occupied launches.
-    class Lane(threading.Thread):
-        def __init__(self, i):
-            super().__init__(daemon=True)
-            self.i, self.q, self.r, self.b = i, queue.Queue(), queue.Queue(), None
-            self.start()
-
-        def run(self):
-            while True:
-                fn = self.q.get()
-                if fn is None:
-                    return
-                try:
-                    self.r.put(("ok", fn(self)))
-                except Exception as exc:      # surface worker failures on the main thread
-                    self.r.put(("err", exc))
-
-    lanes = [Lane(i) for i in range(S)]
-
-    def on_all(fn):
-        for ln in lanes:
-            ln.q.put(fn)
-        out = []
-        for ln in lanes:
-            st, v = ln.r.get()
-            if st == "err":
-                raise v
-            out.append(v)
-        return out
-
-    def setup(ln):
-        sl = slice(ln.i * Ws, (ln.i + 1) * Ws)
-        ln.b = WalkerBatch(L, L, 2, D, Ws, BMPSTruncateParams.SVD(chi, chi, 0.0), device=local_rank)
-        ln.b.set_tps(sit)
-        if args.j2 != 0.0:
-            from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
-            ln.b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, args.j2, args.j2, 0.0))
-        ln.b.set_configs(cfgs[sl])
-        ln.b.seed_rng(seeds[sl])
-        ln.b.init_walkers()
-        return float(np.max(np.abs(ln.b.amplitudes())))
-
-    mx = max(on_all(setup))
-    if world > 1:
-        t = torch.tensor([mx], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        mx = float(t.item())
-    on_all(lambda ln: ln.b.normalize_state_order1(mx))     # MonteCarloEngine::NormalizeStateOrder1
-
-    def barrier():
-        on_all(lambda ln: ln.b.sync())
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+    ls = LaneSet(L, D, chi, W, args.streams, local_rank, sit, cfgs, seeds, j2=args.j2, rank=rank, world=world,
+                 dist=dist if world > 1 else None, torch=torch)
+    lanes, S, Ws, on_all, barrier = ls.lanes, ls.S, ls.Ws, ls.on_all, ls.barrier
 
     # accumulators as torch views for the NCCL all-reduce of [sum O*, sum E_loc O*]
     n_par = lanes[0].b.tps_size
@@ -317,26 +455,18 @@ def main():
         p_o, p_eo = ln.b.accumulator_device_ptrs()
         views.append((torch.as_tensor(_Cai(p_o, n_par), device=dev), torch.as_tensor(_Cai(p_eo, n_par), device=dev)))
 
-    on_all(lambda ln: ln.b.zero_accumulators())
     for _ in range(args.warmup):
         on_all(lambda ln: ln.b.sample(1))
     barrier()
-    launches0 = sum(on_all(lambda ln: ln.b.stat(6)))
+    launches0 = ls.stat_sum(6)
+    stats0 = [ls.stat_sum(k) for k in (8, 9, 12, 13, 4, 14)]
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()                                      # device idle on both sides of the timed region
-
-    def timed(ln):
-        last = None
-        for _ in range(args.steps):
-            last, _ = ln.b.sample(1)
-        ln.b.sync()
-        return last
-
-    energies = np.concatenate(on_all(timed))
+    energies = ls.samples(args.steps)
     if world > 1:                                     # gradient reduction of the iteration (NCCL over NVLink)
         acc_o = torch.stack([v[0] for v in views]).sum(0)
         acc_eo = torch.stack([v[1] for v in views]).sum(0)
@@ -347,7 +477,9 @@ def main():
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else None
-    launches = sum(on_all(lambda ln: ln.b.stat(6))) - launches0
+    launches = ls.stat_sum(6) - launches0
+    stats1 = [ls.stat_sum(k) for k in (8, 9, 12, 13, 4, 14)]
+    dstat = [b_ - a_ for a_, b_ in zip(stats0, stats1)]
     # one more step of the same loop with every launch bracketed by a CUDA-event pair on the launching stream:
     # per-kernel-class device time and useful flops for the roofline (kept out of `value`: the 2 x ~100k event
     # records per step cost about 10 % of a step)
@@ -378,14 +510,17 @@ def main():
     # ---- end-to-end through the evaluator-style public call with host buffers
     flat = torch.from_numpy(sit.pack()).pin_memory()
     h2d = flat.numel() * 8 * S
-    d2h = (2 * n_par * 8 + 2 * Ws * 8) * S
+    d2h = (2 * n_par * 8 + 2 * 2 * Ws * 8) * S
+
+    E2E_SAMPLES = 2                                   # samples per walker and Evaluate call
 
     def e2e_step(ln):
         for _ in range(args.e2e_steps):
             ln.b.set_tps(flat.numpy())                # state fan-out (mc_energy_grad_evaluator.h:161)
             ln.b.init_walkers()                       # RefreshWavefunctionComponent (:164)
             ln.b.zero_accumulators()
-            e, acc = ln.b.sample(1)
+            for _s in range(E2E_SAMPLES):
+                e, acc = ln.b.sample(1)               # per-walker energies come back to the host every sample
             osum, eosum = ln.b.accumulators()
         return None
 
@@ -398,7 +533,7 @@ def main():
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = W * world * args.e2e_steps / e2e_s if args.e2e_steps else 0.0
+    e2e_value = W * world * args.e2e_steps * E2E_SAMPLES / e2e_s if args.e2e_steps else 0.0
 
     if rank != 0:
         if world > 1:
@@ -412,10 +547,7 @@ def main():
     achieved = dom_p["flops"] / max(dom_p["ms"], 1e-9) / 1e9            # TFLOP/s of useful FP64 work in that kernel class
     step_ms = elapsed_ms / args.steps
     mf = MODEL_FLOPS[args.workload]
-    # dram__bytes_read + write of ONE captured launch (ncu --set full, W=16; profiles/r1_ncu_*_final.txt / _k2.txt). For the
-    # trailing update that launch (1664 CTAs: 16 walkers x 8 row blocks x 13 column tiles) moves 436 MB algorithmically
-    # (C tile in and out) + 17 MB of reflectors: measured 399 MB, no wasted re-reads.
-    traffic = {"jacobi_round": 2.0e6, "apply_reflector": 399.3e6, "panel_qr": 1.4e6}.get(dom_name)
+    traffic = None       # dram bytes of the benchmarked launches are not measured in-run; ncu captures: profiles/r2_ncu_*.txt
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 "peak_source": "cuBLAS DGEMM 4096^3 through torch.matmul, measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
@@ -428,13 +560,16 @@ def main():
                                "frac_of_fp64_peak": value * mf["total"] / world / 1e12 / fp64_peak,
                                "contraction_model_tflops": value * mf["gemm"] / world / 1e12}}
 
+    ls.close()
+    secondary = None
+    if args.secondary and world == 1:
+        secondary = secondary_lines(torch, local_rank, (L, D, chi), args.secondary_walkers, 2)
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # the CPU arm is timed at N=1 only (rank 0, all host cores)
         cores = os.cpu_count() or 1
-        v, detail = cpu_samples_per_s(L, D, chi, cores)
+        v, detail = cpu_baseline_quick(L, D, chi, cores)
         cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-               "sample": ("oracle port, one chain + one BLAS thread per core: one full boundary-MPS growth + one row pass timed "
-                          "per process, sample = 8 growths + 4L row passes"), "detail": detail}
+               "sample": "oracle port, one chain + one BLAS thread per core: " + SLICE_TEXT, "detail": detail}
 
     line = {"metric": "vmc_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -447,10 +582,15 @@ def main():
                        "parallelism": f"walkers sharded over {world} GPU(s); NCCL all-reduce of the two accumulators",
                        "algorithm": "reference call sequence; exact boundary-MPS memo (6(L-1) absorptions per sample instead of "
                                     "8(L-1), bit-identical); R-only QR chain with rows below 1e-13 of the largest dropped; "
-                                    "column-sorted preconditioning QR + block Jacobi truncation (DESIGN.md section 2)"},
+                                    "column-sorted preconditioning QR, second (LQ) preconditioning with kept reflectors and a single-CTA "
+                                    "one-sided Jacobi on the small square factor (block Jacobi on the rows when more than 128 "
+                                    "rows survive the deflation) (DESIGN.md section 2)",
+                       "rank_revealing": {"chain_rows_kept_frac": dstat[3] / max(dstat[2], 1), "truncation_rows_kept_frac": dstat[1] / max(dstat[0], 1),
+                                          "small_svd_path_frac": dstat[5] / max(dstat[4], 1),
+                                          "note": "the positive synthetic TPS has low numerical rank; see `secondary` for J1-J2, the signed state and a physical state"}},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "call": "set_tps + init_walkers + sample + accumulators (Evaluate with 1 sample per walker)"},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+                    "steps": args.e2e_steps, "call": "Evaluate-style call with host buffers: set_tps (pinned) + init_walkers + 2 samples per walker (energies to the host each) + download of both accumulators"},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
             "mean_eloc": float(np.mean(energies))}
     print(json.dumps(line))
     if world > 1:

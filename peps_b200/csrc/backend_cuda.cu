@@ -1441,7 +1441,8 @@ void be_apply_reflector(const ApplyArgs &a) {
     ensure_smem(kern, smem);
     kern<<<dim3((a.ntrail + tn - 1) / tn, a.NI, a.W), 256, smem, g_stream>>>(a, tmap);
   };
-  const bool tile = a.tmap != nullptr && a.nbw == 32 && a.R % 64 == 0;
+  // TMA boxes must start on a 16-byte boundary in global memory: an odd first trailing column rules the tile path out
+  const bool tile = a.tmap != nullptr && a.nbw == 32 && a.R % 64 == 0 && (a.col1 & 1) == 0;
   // row blocks of <= 256 rows: the resident tile is <= 112 KB, two CTAs share an SM and overlap load / DMMA / store
   const bool small = apply_smem_bytes<32>(a.R) <= 112 * 1024;
   if (a.nbw == 32 && tile && small) launch(apply_reflector_kernel<32, 2, true>, apply_smem_bytes<32>(a.R), 32, *a.tmap);
@@ -2107,6 +2108,7 @@ __global__ void __launch_bounds__(SVS_THREADS, 1) svd_small_kernel(SmallSvdArgs 
   __shared__ int s_kept;
   const int w = blockIdx.x;
   const int t = threadIdx.x, lane4 = t & 3, group = t >> 2;
+  const unsigned gmask = 0xFu << ((t & 31) & ~3);       // the four lanes of this pair: groups of a warp may diverge
   const int n2 = a.n2;
   const int cnt = min(a.count[w], n2);
   const int nact = (cnt + 1) & ~1;                   // vectors taking part (even); beyond cnt they are zero
@@ -2148,9 +2150,9 @@ __global__ void __launch_bounds__(SVS_THREADS, 1) svd_small_kernel(SmallSvdArgs 
           }
 #pragma unroll
           for (int o = 1; o <= 2; o <<= 1) {
-            app += __shfl_xor_sync(0xffffffffu, app, o);
-            aqq += __shfl_xor_sync(0xffffffffu, aqq, o);
-            apq += __shfl_xor_sync(0xffffffffu, apq, o);
+            app += __shfl_xor_sync(gmask, app, o);
+            aqq += __shfl_xor_sync(gmask, aqq, o);
+            apq += __shfl_xor_sync(gmask, apq, o);
           }
           double c, s;
           jacobi_cs(app, aqq, apq, tol2, c, s);
@@ -2185,8 +2187,8 @@ __global__ void __launch_bounds__(SVS_THREADS, 1) svd_small_kernel(SmallSvdArgs 
 #pragma unroll
       for (int i = 0; i < NCH; ++i) if (i < nch) { const double2 v = xk[4 * i]; s2 = fma(v.x, v.x, s2); s2 = fma(v.y, v.y, s2); }
     }
-    s2 += __shfl_xor_sync(0xffffffffu, s2, 1);
-    s2 += __shfl_xor_sync(0xffffffffu, s2, 2);
+    s2 += __shfl_xor_sync(gmask, s2, 1);
+    s2 += __shfl_xor_sync(gmask, s2, 2);
     if (lane4 == 0) nrm[k] = s2;
   }
   __syncthreads();
