@@ -122,6 +122,9 @@ struct ApplyArgs {
   // describes A with boxes of (R/8 rows x 8 columns)
   const TileMap *tmap = nullptr;
   int row0 = 0;
+  // optional second descriptor of the same matrix with boxes of (R rows x 8 columns): selects the column-streaming
+  // kernel for contiguous row blocks of R <= 256 rows (V resident in shared memory, one 8-column chunk per warp in flight)
+  const TileMap *tmap_cols = nullptr;
   // 0: C <- Q^T C = C - V T^T (V^T C)  (factorisation);  1: C <- Q C = C - V T (V^T C)  (forming / applying Q)
   int notrans = 0;
 };

@@ -1402,6 +1402,116 @@ __global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a,
   APPLY_CLK(5);
 }
 
+// Column-streaming trailing update for contiguous row blocks of R <= 256 rows (R % 16 == 0, 32-wide panels).
+// The round-1 kernel above keeps a (512 x 32) C tile resident and streams V twice from L2 per tile (once per DMMA phase):
+// 524 KB of L2 -> SM traffic per 2.1 MFLOP, one CTA per SM whose load, V^T C, T^T W, C - V W and store phases do not
+// overlap. Here the REFLECTOR block V (R x 32) and T live in shared memory for the whole CTA, and each warp streams
+// 8-column chunks of the trailing matrix through its own (R x 8) buffer: TMA load of the chunk -> W = V^T C (DMMA, no
+// cross-warp reduction: a warp owns all R rows of its 8 columns) -> -(T^T W) (DMMA, warp-private) -> C + V W (DMMA) ->
+// stores straight from registers -> TMA load of the warp's next chunk. No block-wide barrier after the prologue: the
+// eight warps drift apart, so one warp's load latency and serial steps are covered by the others' DMMA work, and V is
+// read from L2 once per CTA instead of twice per tile.
+constexpr int AC_LDV = 36, AC_LDT = 36;
+static size_t apply_cols_smem_bytes(int R) {
+  return ((size_t)R * AC_LDV + 32 * AC_LDT + 8 * ((size_t)R * 8 + 256)) * sizeof(double) + 9 * sizeof(uint64_t);
+}
+__global__ void __launch_bounds__(256, 1) apply_cols_kernel(ApplyArgs a, const __grid_constant__ TileMap tm, int nchunk, int cper) {
+  extern __shared__ __align__(128) double acs[];
+  const int R = a.R;
+  double *Vs = acs;                                   // [R][36]
+  double *Ts = Vs + (size_t)R * AC_LDV;               // [32][36]
+  double *wbase = Ts + 32 * AC_LDT;
+  const int wstride = R * 8 + 256;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, fr = lane >> 2, fk = lane & 3;
+  double *Cw = wbase + (size_t)warp * wstride;        // [R][8] this warp's chunk of the trailing matrix
+  double *Ww = Cw + (size_t)R * 8;                    // [32][8] this warp's W
+  uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + (size_t)8 * wstride);   // [0..7] chunk barriers, [8] V
+  const int cs = blockIdx.x, it = blockIdx.y, w = blockIdx.z;
+  const double *V = a.Vw + ((long)w * a.NI + it) * (long)R * 32;
+  const double *Tg = a.Tw + ((long)w * a.NI + it) * 1024L;
+  double *Aw = a.A + (long)w * a.ws;
+  const int row_base = a.row0 + it * R;
+  const int c_lo = cs * cper, c_hi = min(nchunk, c_lo + cper);
+  if (lane == 0) mbar_init(&bars[warp], 1);
+  if (t == 0) mbar_init(&bars[8], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  __syncthreads();
+  if (t == 0) mbar_expect_tx(&bars[8], (unsigned)(R * 256));
+  int chunk = c_lo + warp;
+  if (chunk < c_hi && lane == 0) {
+    mbar_expect_tx(&bars[warp], (unsigned)(R * 64));
+    tma_load_3d(Cw, &tm, a.col1 + 8 * chunk, row_base, w, &bars[warp]);
+  }
+  __syncthreads();
+  for (int r = t; r < R; r += 256) bulk_g2s(Vs + (size_t)r * AC_LDV, V + (long)r * 32, 256u, &bars[8]);
+  for (int e = t; e < 1024; e += 256) Ts[(e >> 5) * AC_LDT + (e & 31)] = __ldg(Tg + e);
+  __syncthreads();
+  mbar_wait(&bars[8], 0);
+  unsigned ph = 0;
+  for (; chunk < c_hi; chunk += 8) {
+    mbar_wait(&bars[warp], ph);
+    ph ^= 1;
+    // A. W = V^T C over all R rows of the warp's 8 columns
+    double acc[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < R; k += 4) {
+      const int kr = k + fk;
+      const double bf = Cw[kr * 8 + fr];
+      const double *vr = Vs + (size_t)kr * AC_LDV + fr;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dmma8x8x4(acc[i][0], acc[i][1], vr[8 * i], bf);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<double2 *>(Ww + (i * 8 + fr) * 8 + 2 * fk) = make_double2(acc[i][0], acc[i][1]);
+    __syncwarp();
+    // T. Ww <- -(T^T W)   (notrans: -(T W))
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const double bf = Ww[(ks * 4 + fk) * 8 + fr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double af = a.notrans ? Ts[(i * 8 + fr) * AC_LDT + ks * 4 + fk] : Ts[(ks * 4 + fk) * AC_LDT + i * 8 + fr];
+        dmma8x8x4(acc[i][0], acc[i][1], af, bf);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) *reinterpret_cast<double2 *>(Ww + (i * 8 + fr) * 8 + 2 * fk) = make_double2(-acc[i][0], -acc[i][1]);
+    __syncwarp();
+    double bw[8];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) bw[ks] = Ww[(ks * 4 + fk) * 8 + fr];
+    // C. C <- C + V (-(T^T W)), two 8-row tiles in flight, stores straight from registers
+    const int gcol = a.col1 + 8 * chunk + 2 * fk;
+    const bool colok = gcol < a.col1 + a.ntrail;
+    for (int rt = 0; rt < R / 8; rt += 2) {
+      const int r0 = rt * 8 + fr, r1 = r0 + 8;
+      double2 c0 = *reinterpret_cast<const double2 *>(Cw + r0 * 8 + 2 * fk);
+      double2 c1 = *reinterpret_cast<const double2 *>(Cw + r1 * 8 + 2 * fk);
+      const double *v0 = Vs + (size_t)r0 * AC_LDV + fk, *v1 = Vs + (size_t)r1 * AC_LDV + fk;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        dmma8x8x4(c0.x, c0.y, v0[4 * ks], bw[ks]);
+        dmma8x8x4(c1.x, c1.y, v1[4 * ks], bw[ks]);
+      }
+      if (colok) {
+        *reinterpret_cast<double2 *>(Aw + (long)(row_base + r0) * a.lda + gcol) = c0;
+        *reinterpret_cast<double2 *>(Aw + (long)(row_base + r1) * a.lda + gcol) = c1;
+      }
+    }
+    __syncwarp();
+    if (chunk + 8 < c_hi && lane == 0) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      mbar_expect_tx(&bars[warp], (unsigned)(R * 64));
+      tma_load_3d(Cw, &tm, a.col1 + 8 * (chunk + 8), row_base, w, &bars[warp]);
+    }
+  }
+}
+
 template <int NBW>
 static size_t apply_smem_bytes(int R) {
   int R8 = (R + 7) & ~7;
@@ -1437,6 +1547,17 @@ void be_apply_reflector(const ApplyArgs &a) {
   if (a.ntrail <= 0) return;
   LaunchScope scope(KC_APPLY, 4.0 * a.R * a.nbw * (double)a.ntrail * a.NI * a.W);
   static const TileMap no_map{};
+  static const bool use_cols = []() { const char *e = std::getenv("PEPS_APPLY_COLS"); return e ? std::atoi(e) != 0 : true; }();
+  if (use_cols && a.tmap_cols != nullptr && a.nbw == 32 && a.R <= 256 && a.R % 16 == 0 && (a.col1 & 1) == 0 && (a.lda & 1) == 0) {
+    const int nchunk = (a.ntrail + 7) / 8;
+    const int csplit = std::max(1, std::min(8, (nchunk + 12) / 24));
+    const int cper = (nchunk + csplit - 1) / csplit;
+    const size_t smem = apply_cols_smem_bytes(a.R);
+    ensure_smem(apply_cols_kernel, smem);
+    apply_cols_kernel<<<dim3((nchunk + cper - 1) / cper, a.NI, a.W), 256, smem, g_stream>>>(a, *a.tmap_cols, nchunk, cper);
+    post_launch();
+    return;
+  }
   auto launch = [&](auto kern, size_t smem, int tn, const TileMap &tmap) {
     ensure_smem(kern, smem);
     kern<<<dim3((a.ntrail + tn - 1) / tn, a.NI, a.W), 256, smem, g_stream>>>(a, tmap);

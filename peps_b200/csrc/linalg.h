@@ -104,6 +104,9 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
   // stage-1 row blocks are contiguous: the trailing update fetches its tiles through a tile descriptor when it can
   TileMap tmap;
   const bool have_tmap = (rb % 64 == 0) && nb == 32 && be_make_tile_map(&tmap, A, ws, lda, L.m_pad, n, W, rb / 8, 8);
+  // row blocks of <= 256 rows: descriptor with whole-block boxes for the column-streaming trailing update
+  TileMap tmapc;
+  const bool have_tmapc = rb <= 256 && rb % 16 == 0 && nb == 32 && be_make_tile_map(&tmapc, A, ws, lda, L.m_pad, n, W, rb, 8);
   const int npanel = (kk + nb - 1) / nb;
   for (int p = 0; p < npanel; ++p) {
     const int col0 = p * nb, pw = std::min(nb, kk - col0), c1 = col0 + pw, ntrail = n - c1;
@@ -118,6 +121,7 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
       ap.A = A; ap.ws = ws; ap.lda = lda; ap.rowtab = pa.rowtab; ap.R = rb; ap.NI = nact; ap.col1 = c1; ap.ntrail = ntrail;
       ap.nbw = nb; ap.Vw = Vw; ap.Tw = Tw; ap.W = W;
       if (have_tmap) { ap.tmap = &tmap; ap.row0 = b0 * rb; }
+      if (have_tmapc) { ap.tmap_cols = &tmapc; ap.row0 = b0 * rb; }
       be_apply_reflector(ap);
     }
     if (nact > 1) {
