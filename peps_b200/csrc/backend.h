@@ -47,6 +47,11 @@ struct GettDesc {
   // at the largest K step below both bounds; ignoring the hints gives the same result. work = executed / nominal flops.
   const int32_t *klo_m = nullptr, *klo_n = nullptr;
   double work = 1.0;
+  // Optional per-walker zero tails (device arrays, may be null): A(m, .) == 0 for every m >= m_cnt[w] * m_scale, B(., n)
+  // == 0 for every n >= n_cnt[w] * n_scale. Output tiles entirely inside a tail are written as zeros without touching
+  // the operands. Ignoring the hints gives the same result.
+  const int32_t *m_cnt = nullptr, *n_cnt = nullptr;
+  int m_scale = 0, n_scale = 0;
 };
 
 // ---- backend context / memory / stream -----------------------------------------------------------------
@@ -101,6 +106,12 @@ struct PanelArgs {
   int col0, pw, nbw;
   double *Vw, *Tw;
   int W;
+  // Optional per-walker row limit (device array, may be null): rows >= row_cnt[w] * row_scale of A[w] are exactly zero
+  // on entry (the walker's rank-revealing chain kept fewer rows than the batch maximum the buffers are sized for). An
+  // item whose FIRST row (rowtab[it * R]) is at or beyond the limit is skipped: it would produce V = 0, R = 0. The
+  // trailing update must be called with the same limit. Only meaningful for items of ascending contiguous rows.
+  const int32_t *row_cnt = nullptr;
+  int row_scale = 0;
 };
 void be_panel_qr(const PanelArgs &a);
 
@@ -127,6 +138,9 @@ struct ApplyArgs {
   const TileMap *tmap_cols = nullptr;
   // 0: C <- Q^T C = C - V T^T (V^T C)  (factorisation);  1: C <- Q C = C - V T (V^T C)  (forming / applying Q)
   int notrans = 0;
+  // same meaning as PanelArgs::row_cnt / row_scale: items starting at or beyond the walker's limit are skipped
+  const int32_t *row_cnt = nullptr;
+  int row_scale = 0;
 };
 void be_apply_reflector(const ApplyArgs &a);
 

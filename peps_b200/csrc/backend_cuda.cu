@@ -19,6 +19,8 @@
 #include <string>
 #include <type_traits>
 #include <unordered_map>
+#include <map>
+#include <mutex>
 #include <utility>
 #include <vector>
 #include "backend.h"
@@ -57,7 +59,6 @@ struct BeCtx {
   cudaStream_t stream = nullptr;
   long launches = 0;
   Profiler prof;
-  std::unordered_map<const void *, size_t> smem_cfg;   // kernel -> configured dynamic shared memory (per device)
   double *dot_part = nullptr;                          // partial sums of the K-split trace closure
   double *vdot_part = nullptr;                         // partial sums of be_vec_dot
   size_t dot_part_cap = 0;
@@ -116,9 +117,15 @@ static inline void post_launch() {
   if (e != cudaSuccess) throw std::runtime_error(std::string("kernel launch failed: ") + cudaGetErrorString(e));
 }
 // dynamic shared memory opt-in, remembered per context (= per device)
+// The attribute is a property of (device, kernel) shared by every context of the process, and setting it REPLACES the
+// previous value: the largest size ever requested is kept in a process-wide table (contexts on several host threads
+// ask for different sizes of the same kernel concurrently).
 template <class K>
 static inline void ensure_smem(K kern, size_t smem) {
-  size_t &have = cx().smem_cfg[(const void *)kern];
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> table;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &have = table[{cx().device, (const void *)kern}];
   if (smem > have) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     have = smem;
@@ -215,6 +222,13 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
   double *Cb = const_cast<double *>(operand_base(C, w, bb));
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int wm = warp >> 1, wn = warp & 1;
+  if ((d.m_cnt && m0 >= d.m_cnt[w] * d.m_scale) || (d.n_cnt && n0 >= d.n_cnt[w] * d.n_scale)) {
+    for (int e = t; e < BM * BN; e += GETT_THREADS) {
+      const int m = m0 + e / BN, n = n0 + e % BN;
+      if (m < d.M && n < d.N) { double *cp = Cb + d.cm[m] + d.cn[n]; *cp = (beta != 0.0) ? beta * (*cp) : 0.0; }
+    }
+    return;
+  }
 
   // per-thread loader coordinates (fixed part hoisted out of the K loop)
   int a_ml[NA], a_kl[NA], a_off[NA];
@@ -366,6 +380,14 @@ gett_large_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, dou
   double *Cb = const_cast<double *>(operand_base(C, w, bb));
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int wm = warp / WGN, wn = warp % WGN;
+  if ((d.m_cnt && m0 >= d.m_cnt[w] * d.m_scale) || (d.n_cnt && n0 >= d.n_cnt[w] * d.n_scale)) {
+    // the whole tile lies in this walker's zero tail: C = beta * C (+ 0)
+    for (int e = t; e < GL_BM * GL_BN; e += GL_THREADS) {
+      const int m = m0 + e / GL_BN, n = n0 + e % GL_BN;
+      if (m < d.M && n < d.N) { double *cp = Cb + d.cm[m] + d.cn[n]; *cp = (beta != 0.0) ? beta * (*cp) : 0.0; }
+    }
+    return;
+  }
 
   // ---- loader coordinates: the free-index part of every offset is fixed for the whole K loop -------------------
   // A tile = BM * 8 pairs: free-fast -> pair (m2 = q % (BM/2), k = q / (BM/2)); contracted-fast -> pair (k2 = q % 8, m = q / 8)
@@ -694,6 +716,7 @@ constexpr int PQR_THREADS = 256;
 __global__ void __launch_bounds__(PQR_THREADS) panel_qr_kernel(PanelArgs a) {
   extern __shared__ double sm[];
   const int it = blockIdx.x, w = blockIdx.y;
+  if (a.row_cnt && a.rowtab[(long)it * a.R] >= a.row_cnt[w] * a.row_scale) return;     // all-zero item of this walker
   const int R = a.R, pw = a.pw, nbw = a.nbw;
   const int skip = (it == 0) ? a.skip0 : 0;
   const int nact = R - skip;
@@ -843,6 +866,7 @@ __global__ void __launch_bounds__(PQR_THREADS, MINB) panel_qr_reg_kernel(PanelAr
   constexpr int LDT = NBW + 1, LDSS = NBW + 1;
   constexpr int RP = RPL * 32;
   const int it = blockIdx.x, w = blockIdx.y;
+  if (a.row_cnt && a.rowtab[(long)it * a.R] >= a.row_cnt[w] * a.row_scale) return;     // all-zero item of this walker
   const int R = a.R, pw = a.pw, nbw = a.nbw;
   const int skip = (it == 0) ? a.skip0 : 0;
   const int nact = R - skip;
@@ -1171,6 +1195,7 @@ __global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a,
   APPLY_CLK(0);
   constexpr int TN = NBW, MT = NBW / 8, NT = NBW / 8, LDC = TN + 4, LDW = TN + 4, NTILE = MT * NT;
   const int ct = blockIdx.x, it = blockIdx.y, w = blockIdx.z;
+  if (a.row_cnt && a.rowtab[(long)it * a.R] >= a.row_cnt[w] * a.row_scale) return;     // all-zero item of this walker
   const int R = a.R, R8 = (R + 7) & ~7, nbw = a.nbw;
   double *Cs = sm;                               // [R8][LDC], or [NBW/8][R8][8] with tile descriptors
   auto csi = [&](int r, int c) -> size_t {
@@ -1427,6 +1452,7 @@ __global__ void __launch_bounds__(256, 1) apply_cols_kernel(ApplyArgs a, const _
   double *Ww = Cw + (size_t)R * 8;                    // [32][8] this warp's W
   uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + (size_t)8 * wstride);   // [0..7] chunk barriers, [8] V
   const int cs = blockIdx.x, it = blockIdx.y, w = blockIdx.z;
+  if (a.row_cnt && a.row0 + it * R >= a.row_cnt[w] * a.row_scale) return;               // all-zero row block of this walker
   const double *V = a.Vw + ((long)w * a.NI + it) * (long)R * 32;
   const double *Tg = a.Tw + ((long)w * a.NI + it) * 1024L;
   double *Aw = a.A + (long)w * a.ws;

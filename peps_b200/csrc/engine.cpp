@@ -194,7 +194,10 @@ TRef Engine::site_ref(int site, int cfg_site) const {
 }
 template <class H>
 static GettDesc with_hints(GettDesc d, const H *h) {
-  if (h) { d.klo_m = h->klo_m; d.klo_n = h->klo_n; d.work = h->work; }
+  if (h) {
+    d.klo_m = h->klo_m; d.klo_n = h->klo_n; d.work = h->work;
+    d.m_cnt = h->m_cnt; d.m_scale = h->m_scale; d.n_cnt = h->n_cnt; d.n_scale = h->n_scale;
+  }
   return d;
 }
 TRef Engine::site_ref_idx(int site, const int32_t *idx, int stride) const {
@@ -227,11 +230,11 @@ const Engine::KHints &Engine::r_hints(int which, int k, int e, int a, int p, int
   if (it != hints_.end()) return it->second;
   std::vector<int32_t> tab;
   int K = 0;
-  if (which == 0) {                       // N = (e, k), K = a
+  if (which == 0) {                       // N = (k, e), K = a
     K = a;
     tab.resize((size_t)e * k);
     for (int ee = 0; ee < e; ++ee)
-      for (int kk = 0; kk < k; ++kk) tab[(size_t)ee * k + kk] = std::min(a, std::max(0, kk - ee * a));
+      for (int kk = 0; kk < k; ++kk) tab[(size_t)kk * e + ee] = std::min(a, std::max(0, kk - ee * a));
   } else if (which == 1) {                // M = (k, b), K = (e, p): tmp1[e][k][.][.] == 0 for e < floor(k / A)
     K = e * p;
     tab.resize((size_t)k * b);
@@ -288,6 +291,9 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
   auto sdim = [&](int site, char l) { return site_dims_h_[(size_t)site][sl.find(l)]; };
   std::vector<BT> r((size_t)N);
   std::vector<char> r_tri((size_t)N, 0);     // r_i is an upper-trapezoidal R factor (structural-zero hints apply)
+  // per-walker number of non-zero rows of r_i (device, null = all rows): rows beyond it are exact zeros, so the row blocks
+  // / tiles they fill are skipped per walker in the next chain step (the buffers are sized by the batch maximum)
+  std::vector<int32_t *> r_cnt((size_t)N, nullptr);
   r[0] = ones111();
   for (int i = 0; i < N - 1; ++i) {
     const int site = sites[(size_t)i];
@@ -295,16 +301,18 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
     const bool tri = r_tri[(size_t)i] != 0;
     const int rk = r[(size_t)i].d[0], re = r[(size_t)i].d[1], ra = r[(size_t)i].d[2];
     const int pd = mps[(size_t)i].d[1], bd = mps[(size_t)i].d[2];
-    BT tmp1 = einsum("apb,kea->ekpb", ref(mps[(size_t)i]), ref(r[(size_t)i]),
-                     tri ? &r_hints(0, rk, re, ra, pd, bd) : nullptr);                    // bmps_impl.h:806
+    const int32_t *rc = r_cnt[(size_t)i];
+    KHints h1, h2;
+    if (tri) { h1 = r_hints(0, rk, re, ra, pd, bd); h2 = r_hints(1, rk, re, ra, pd, bd); }
+    if (rc) { h1.n_cnt = rc; h1.n_scale = re; h2.m_cnt = rc; h2.m_scale = bd; }
+    BT tmp1 = einsum("apb,kea->kepb", ref(mps[(size_t)i]), ref(r[(size_t)i]), (tri || rc) ? &h1 : nullptr);   // bmps_impl.h:806
     const int k = r[(size_t)i].d[0], o = sdim(site, 'o'), f = sdim(site, 'f'), b = mps[(size_t)i].d[2];
     const int m = k * o, n = f * b;
     QRLayout L = qr_layout(m, n);
     const long wsA = (long)L.m_pad * n;
     double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
     if (L.m_pad > m) be_memset0(A, sizeof(double) * (size_t)W_ * wsA);
-    einsum_into("ekpb," + sl + "->kofb", ref(tmp1), sref, mkop(A, wsA), nullptr, 1.0, 0.0,
-                tri ? &r_hints(1, rk, re, ra, pd, bd) : nullptr);                         // bmps_impl.h:807
+    einsum_into("kepb," + sl + "->kofb", ref(tmp1), sref, mkop(A, wsA), nullptr, 1.0, 0.0, (tri || rc) ? &h2 : nullptr);   // bmps_impl.h:807
     release(tmp1);
     const int kk = std::min(m, n);
     if (chain_eps_ > 0.0 && kk >= 16) {
@@ -322,23 +330,30 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
       if (L.m_pad > m) be_memset0(Ap, sizeof(double) * (size_t)W_ * wsA);
       be_permute_cols(A, wsA, n, m, n, cord, 1, Ap, wsA, n, W_);
       pool_.put(A);
-      caqr(la_, Ap, wsA, m, n, L);                                                       // bmps_impl.h:817-821
+      caqr(la_, Ap, wsA, m, n, L, rc, o);                                                // bmps_impl.h:817-821
       be_row_norms2(Ap, wsA, n, kk, n, cn2, W_);
       be_rank_rows(cn2, kk, chain_eps_ * chain_eps_, ord, cnt, W_);
       std::vector<int32_t> ch((size_t)W_);
       be_d2h(ch.data(), cnt, sizeof(int32_t) * W_);
       int knew = 1;
       for (int w = 0; w < W_; ++w) knew = std::max(knew, (int)ch[(size_t)w]);
-      const int gran = kk >= 128 ? 64 : 8;               // few distinct shapes: plans, tables and pool buffers are keyed by size
+      static const bool dbg_counts = std::getenv("PEPS_DEBUG_COUNTS") != nullptr;
+      if (dbg_counts && kk >= 256) {
+        int mn = kk; double mean = 0.0;
+        for (int w = 0; w < W_; ++w) { mn = std::min(mn, (int)ch[(size_t)w]); mean += ch[(size_t)w]; }
+        std::fprintf(stderr, "[chain] site %d kk=%d count min %d mean %.1f max %d\n", i, kk, mn, mean / W_, knew);
+      }
+      const int gran = kk >= 128 ? 32 : 8;               // few distinct shapes: plans, tables and pool buffers are keyed by size
       knew = std::min(kk, (knew + gran - 1) / gran * gran);
       chain_rows_in_ += kk; chain_rows_kept_ += knew;
       double *Rg = (double *)pool_.get(sizeof(double) * (size_t)W_ * knew * n);
       be_gather_rows(Ap, wsA, n, n, kk, ord, cnt, Rg, (long)knew * n, knew, W_);
       r[(size_t)i + 1] = alloc({knew, f, b});
       be_permute_cols(Rg, (long)knew * n, n, knew, n, cord, 0, r[(size_t)i + 1].p, (long)knew * n, n, W_);
-      for (void *p : {(void *)cn2, (void *)ord, (void *)cord, (void *)cnt, (void *)Ap, (void *)Rg}) pool_.put(p);
+      r_cnt[(size_t)i + 1] = cnt;                        // rows >= cnt[w] of r_{i+1} are zero (be_gather_rows)
+      for (void *p : {(void *)cn2, (void *)ord, (void *)cord, (void *)Ap, (void *)Rg}) pool_.put(p);
     } else {
-      caqr(la_, A, wsA, m, n, L);                                                        // bmps_impl.h:817-821
+      caqr(la_, A, wsA, m, n, L, rc, o);                                                 // bmps_impl.h:817-821
       r[(size_t)i + 1] = alloc({kk, f, b});
       be_copy2d(r[(size_t)i + 1].p, (long)kk * n, n, A, wsA, n, kk, n, W_);
       r_tri[(size_t)i + 1] = 1;
@@ -362,8 +377,11 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
       const int brows = truncate_buffer_rows(rows, cols);
       double *G = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows * cols);
       if (brows > rows) be_memset0(G, sizeof(double) * (size_t)W_ * brows * cols);
+      KHints h3;
+      if (r_tri[(size_t)i]) h3 = r_hints(2, r[(size_t)i].d[0], r[(size_t)i].d[1], r[(size_t)i].d[2], 0, 0);
+      if (r_cnt[(size_t)i]) { h3.m_cnt = r_cnt[(size_t)i]; h3.m_scale = 1; }
       einsum_into("kea,eaoj->koj", ref(r[(size_t)i]), ref(X), mkop(G, (long)brows * cols), nullptr, 1.0, 0.0,
-                  r_tri[(size_t)i] ? &r_hints(2, r[(size_t)i].d[0], r[(size_t)i].d[1], r[(size_t)i].d[2], 0, 0) : nullptr);
+                  (r_tri[(size_t)i] || r_cnt[(size_t)i]) ? &h3 : nullptr);
       const int tcap = std::min(dmax_, std::min(rows, cols));
       B = alloc({tcap, o, j});
       double *norms2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * std::max(rows, 1));
@@ -391,6 +409,7 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
     res[0] = first;
   }
   for (auto &t : r) release(t);
+  for (int32_t *c : r_cnt) if (c) pool_.put(c);
   return res;
 }
 

@@ -189,8 +189,11 @@ class Engine {
   TRef site_ref_idx(int site, const int32_t *idx, int stride) const;
   void energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *psi_list_host);
   // structural-zero hints for contractions with an upper-trapezoidal R factor of the forward chain (backend.h GettDesc)
-  struct KHints { const int32_t *klo_m = nullptr, *klo_n = nullptr; double work = 1.0; };
-  // which: 0 = "apb,kea->ekpb" (hint on N = (e,k)), 1 = "ekpb,<site>->kofb" (hint on M = (k,b)), 2 = "kea,eaoj->koj" (M = k)
+  struct KHints {
+    const int32_t *klo_m = nullptr, *klo_n = nullptr; double work = 1.0;
+    const int32_t *m_cnt = nullptr, *n_cnt = nullptr; int m_scale = 0, n_scale = 0;   // per-walker zero tails (backend.h GettDesc)
+  };
+  // which: 0 = "apb,kea->kepb" (hint on N = (k,e)), 1 = "kepb,<site>->kofb" (hint on M = (k,b)), 2 = "kea,eaoj->koj" (M = k)
   const KHints &r_hints(int which, int k, int e, int a, int p, int b);
   BT einsum(const std::string &spec, const TRef &a, const TRef &b, const KHints *h = nullptr);
   void einsum_into(const std::string &spec, const TRef &a, const TRef &b, Operand c, const long *sc = nullptr,

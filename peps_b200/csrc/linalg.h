@@ -42,14 +42,15 @@ struct QRLayout { int nb = 0, rb = 0, nrb = 0, m_pad = 0; };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// Preferred row-block height of the CAQR flat tree (PEPS_QR_RB overrides; multiple of 32). Blocks of 256 rows keep the
-// resident tiles of the panel and trailing-update kernels small enough for two CTAs per SM.
+// Preferred row-block height of the CAQR flat tree (PEPS_QR_RB overrides; multiple of 32). Blocks of 256 rows: the panel
+// kernel runs two CTAs per SM and the trailing update uses the column-streaming kernel (reflector block resident in
+// shared memory); matrices taller than 18 x 256 rows fall back to taller blocks automatically.
 inline int qr_pref_rb() {
   static int v = -1;
   if (v < 0) {
     const char *e = std::getenv("PEPS_QR_RB");
-    v = e ? std::atoi(e) : 512;
-    if (v < 32 || v % 32 != 0) v = 512;
+    v = e ? std::atoi(e) : 256;
+    if (v < 32 || v % 32 != 0) v = 256;
   }
   return v;
 }
@@ -89,7 +90,8 @@ inline std::vector<int32_t> iota_scaled(int n, int scale, int base = 0) {
 // In-place R-only QR of A[w] (m x n, row-major, leading dimension n, walker stride ws; the buffer holds
 // L.m_pad rows, rows >= m zero). On return rows [0, min(m,n)) hold R (upper trapezoidal), everything else
 // in the buffer is zero.
-inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout &L) {
+inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout &L, const int32_t *row_cnt = nullptr,
+                 int row_scale = 0) {
   const int W = cx.W, nb = L.nb, rb = L.rb, nrb = L.nrb, lda = n;
   const int kk = std::min(m, n);
   ++cx.qr_calls;
@@ -115,6 +117,7 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
     PanelArgs pa;
     pa.A = A; pa.ws = ws; pa.lda = lda; pa.rowtab = rowtab1_d + (size_t)b0 * rb; pa.R = rb; pa.skip0 = col0 - b0 * rb; pa.NI = nact;
     pa.col0 = col0; pa.pw = pw; pa.nbw = nb; pa.Vw = Vw; pa.Tw = Tw; pa.W = W;
+    pa.row_cnt = row_cnt; pa.row_scale = row_scale;        // stage 1 only: all-zero row blocks of a walker are skipped
     be_panel_qr(pa);
     if (ntrail > 0) {
       ApplyArgs ap;
@@ -122,6 +125,7 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
       ap.nbw = nb; ap.Vw = Vw; ap.Tw = Tw; ap.W = W;
       if (have_tmap) { ap.tmap = &tmap; ap.row0 = b0 * rb; }
       if (have_tmapc) { ap.tmap_cols = &tmapc; ap.row0 = b0 * rb; }
+      ap.row_cnt = row_cnt; ap.row_scale = row_scale;
       be_apply_reflector(ap);
     }
     if (nact > 1) {
@@ -132,7 +136,7 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
       for (int b = 0; b < nact; ++b)
         for (int i = 0; i < pw; ++i) rowtab2[(size_t)b * pw + i] = (b0 + b) * rb + (b == 0 ? pa.skip0 : 0) + i;
       PanelArgs p2 = pa;
-      p2.rowtab = pl.upload(rowtab2); p2.R = R2; p2.skip0 = 0; p2.NI = 1;
+      p2.rowtab = pl.upload(rowtab2); p2.R = R2; p2.skip0 = 0; p2.NI = 1; p2.row_cnt = nullptr;
       be_panel_qr(p2);
       if (ntrail > 0) {
         ApplyArgs ap;
@@ -226,7 +230,7 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
   int nr_eff = 1;
   for (int w = 0; w < W; ++w) nr_eff = std::max(nr_eff, (int)cx.done_host[(size_t)w]);
   cx.rows_in += kk; cx.rows_kept += nr_eff;
-  if (cx.small_svd && nr_eff >= 2 && round_up(nr_eff, 8) <= kSmallSvdMaxN && qr_layout(nc, round_up(nr_eff, 8)).nrb == 1) {
+  if (cx.small_svd && nr_eff >= 2 && round_up(nr_eff, 8) <= kSmallSvdMaxN && round_up(nc, 32) <= (int)(kPanelSmemBudget / (sizeof(double) * 32)) / 32 * 32) {
     // Second preconditioning + single-CTA Jacobi (Drmac-Veselic): the surviving rows G2 (nr_eff x nc) are factorised
     // G2^T = Q Rt by a tall-skinny QR whose reflectors are KEPT; the one-sided Jacobi runs on the small square factor
     // Rt (n2 x n2, resident in shared memory, all sweeps and the convergence test on the device: no host round trip
@@ -235,8 +239,7 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
     // of Jacobi with high relative accuracy).
     ++cx.jacobi_calls; ++cx.small_svd_calls;
     const int n2 = round_up(nr_eff, 8), nb = 32;
-    const QRLayout L2 = qr_layout(nc, n2);
-    const int rb = L2.rb, kk2 = std::min(nc, n2), npanel = (kk2 + nb - 1) / nb;
+    const int rb = round_up(nc, 32), kk2 = std::min(nc, n2), npanel = (kk2 + nb - 1) / nb;      // ONE row block (<= 576 rows)
     const long wsT = (long)rb * n2, wsC = (long)rb * tcap;
     double *GT = (double *)cx.pool->get(sizeof(double) * (size_t)W * wsT);
     be_memset0(GT, sizeof(double) * (size_t)W * wsT);

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <stdexcept>
 #include <vector>
 #include "../../peps_b200/csrc/backend.h"
 
@@ -48,9 +49,18 @@ void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, d
       const double *Ab = obase(A, w, b), *Bb = obase(B, w, b);
       double *Cb = const_cast<double *>(obase(C, w, b));
       std::vector<double> out((size_t)d.M * d.N);
+      // per-walker zero tails are honoured per element AND verified: a wrong limit fails the host-logic tests
+      const int mlim = d.m_cnt ? d.m_cnt[w] * d.m_scale : d.M, nlim = d.n_cnt ? d.n_cnt[w] * d.n_scale : d.N;
+      for (int m = 0; m < d.M; ++m)
+        for (int k = 0; k < d.K; ++k)
+          if (m >= mlim && Ab[d.am[m] + d.ak[k]] != 0.0) throw std::logic_error("hostsim gett: m_cnt tail of A is not zero");
+      for (int n = 0; n < d.N; ++n)
+        for (int k = 0; k < d.K; ++k)
+          if (n >= nlim && Bb[d.bk[k] + d.bn[n]] != 0.0) throw std::logic_error("hostsim gett: n_cnt tail of B is not zero");
       for (int m = 0; m < d.M; ++m)
         for (int n = 0; n < d.N; ++n) {
           double s = 0.0;
+          if (m >= mlim || n >= nlim) { out[(size_t)m * d.N + n] = 0.0; continue; }
           // structural-zero hints are honoured PER ELEMENT here (the strictest reading): a wrong hint table shows up
           // as a parity failure of the host-logic tests
           int k0 = 0;
@@ -101,6 +111,12 @@ void be_panel_qr(const PanelArgs &a) {
       const int skip = (it == 0) ? a.skip0 : 0, nact = R - skip;
       double *Aw = a.A + (long)w * a.ws;
       const int32_t *rows = a.rowtab + (long)it * R;
+      if (a.row_cnt && rows[0] >= a.row_cnt[w] * a.row_scale) {       // skipped item: verify that it really is all zero
+        for (int r = 0; r < R; ++r)
+          for (int c = 0; c < a.lda; ++c)
+            if (Aw[(long)rows[r] * a.lda + c] != 0.0) throw std::logic_error("hostsim panel: skipped row block is not zero");
+        continue;
+      }
       std::vector<double> P((size_t)nact * pw), tau((size_t)pw, 0.0), V((size_t)nact * pw, 0.0), T((size_t)pw * pw, 0.0);
       auto at = [&](int r, int c) -> double & { return P[(size_t)r * pw + c]; };
       for (int r = 0; r < nact; ++r)
@@ -161,6 +177,7 @@ void be_apply_reflector(const ApplyArgs &a) {
     for (int it = 0; it < a.NI; ++it) {
       double *Aw = a.A + (long)w * a.ws;
       const int32_t *rows = a.rowtab + (long)it * a.R;
+      if (a.row_cnt && rows[0] >= a.row_cnt[w] * a.row_scale) continue;
       const double *V = a.Vw + ((long)w * a.NI + it) * (long)a.R * a.nbw;
       const double *T = a.Tw + ((long)w * a.NI + it) * (long)a.nbw * a.nbw;
       std::vector<double> Wm((size_t)a.nbw * a.ntrail, 0.0), W2((size_t)a.nbw * a.ntrail, 0.0);
