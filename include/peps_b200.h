@@ -178,6 +178,12 @@ int peps_probe_trace_row(peps_ctx *ctx, int32_t row, double *psi);
  * sites starting at (row, col) along `orient` (0 = HORIZONTAL, 1 = VERTICAL) set to the physical indices
  * cfg3[w][0..2]; grows the environments it needs first. The building block of MCUpdateSquareTNN3SiteExchange. */
 int peps_probe_tnn_trace(peps_ctx *ctx, int32_t row, int32_t col, int32_t orient, const int32_t *cfg3, double *psi);
+/* BMPSContractor::ReplaceNNNSiteTrace (kind 0, bmps/impl/bmps_contractor_trace.h:207-324, both MPS orientations) and
+ * ReplaceSqrt5DistTwoSiteTrace (kind 1, :426-536): amplitude with the two corner sites of the plaquette whose upper-left
+ * site is (row, col) EXCHANGING their physical indices. dir 0 = LEFTUP_TO_RIGHTDOWN, 1 = LEFTDOWN_TO_RIGHTUP; orient
+ * 0 = HORIZONTAL (2 x 2 / 2 x 3 plaquette between two-row environments), 1 = VERTICAL (2 x 2 / 3 x 2 between two-column
+ * environments). Grows InitBTen2 / GrowFullBTen2 (init.h:130-186, grow.h:375-515) first. */
+int peps_probe_plaquette_trace(peps_ctx *ctx, int32_t kind, int32_t row, int32_t col, int32_t dir, int32_t orient, double *psi);
 /* Size of bmps_set_[position]; copy of tensor i of stack entry k, [W][d0][d1][d2]; dims returned. */
 int32_t peps_bmps_stack_size(peps_ctx *ctx, int32_t position);
 int peps_get_bmps_tensor(peps_ctx *ctx, int32_t position, int32_t k, int32_t i, double *out, int32_t dims[3]);

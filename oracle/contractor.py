@@ -348,10 +348,10 @@ class BMPSContractor:
         return self.bten_set2[pos][logical_idx]
 
     def replace_nnn_site_trace(self, tn, left_up_site, nnn_dir, mps_orient, ten_left, ten_right):
-        """ReplaceNNNSiteTrace, HORIZONTAL MPS orientation (trace.h:207-281). nnn_dir 0 = LEFTUP_TO_RIGHTDOWN
-        (ten_left replaces (row1,col1), ten_right replaces (row2,col2)); 1 = LEFTDOWN_TO_RIGHTUP (ten_left replaces
-        (row2,col1), ten_right replaces (row1,col2))."""
-        assert mps_orient == HORIZONTAL
+        """ReplaceNNNSiteTrace (trace.h:207-324), both MPS orientations. nnn_dir 0 = LEFTUP_TO_RIGHTDOWN (ten_left
+        replaces (row1,col1), ten_right replaces (row2,col2)); 1 = LEFTDOWN_TO_RIGHTUP (ten_left replaces (row2,col1),
+        ten_right replaces (row1,col2)). HORIZONTAL closes the two-row environments LEFT | RIGHT of rows row1,row2
+        (:218-281); VERTICAL the two-column environments UP | DOWN of columns col1,col2 (:282-324)."""
         row1, col1 = left_up_site
         row2, col2 = row1 + 1, col1 + 1
         t = {(row1, col1): tn[row1][col1], (row2, col1): tn[row2][col1],
@@ -360,9 +360,53 @@ class BMPSContractor:
             t[(row1, col1)], t[(row2, col2)] = ten_left, ten_right
         else:
             t[(row2, col1)], t[(row1, col2)] = ten_left, ten_right
-        n = self.cols
-        m1, m2, _, _ = self._bten2_operands(tn, LEFT, row1, col1 + 1)
-        half_a = self.bten2_step(self.bten_set2[LEFT][col1], m1, t[(row1, col1)], t[(row2, col1)], m2, LEFT)
-        m1, m2, _, _ = self._bten2_operands(tn, RIGHT, row1, n - col2)
-        half_b = self.bten2_step(self.bten2_at_slice(RIGHT, col2), m1, t[(row2, col2)], t[(row1, col2)], m2, RIGHT)
+        if mps_orient == HORIZONTAL:
+            n = self.cols
+            m1, m2, _, _ = self._bten2_operands(tn, LEFT, row1, col1 + 1)
+            half_a = self.bten2_step(self.bten_set2[LEFT][col1], m1, t[(row1, col1)], t[(row2, col1)], m2, LEFT)
+            m1, m2, _, _ = self._bten2_operands(tn, RIGHT, row1, n - col2)
+            half_b = self.bten2_step(self.bten2_at_slice(RIGHT, col2), m1, t[(row2, col2)], t[(row1, col2)], m2, RIGHT)
+        else:
+            n = self.rows
+            m1, m2, _, _ = self._bten2_operands(tn, UP, col1, row1 + 1)
+            half_a = self.bten2_step(self.bten_set2[UP][row1], m1, t[(row1, col2)], t[(row1, col1)], m2, UP)
+            m1, m2, _, _ = self._bten2_operands(tn, DOWN, col1, n - row2)
+            half_b = self.bten2_step(self.bten2_at_slice(DOWN, row2), m1, t[(row2, col1)], t[(row2, col2)], m2, DOWN)
         return es("aoqb,bqoa->", half_a, half_b).item()      # Contract(tmp[3],{0,1,2,3}, tmp[7],{3,2,1,0})
+
+    def replace_sqrt5_dist_two_site_trace(self, tn, left_up_site, link_dir, mps_orient, ten_left, ten_right):
+        """ReplaceSqrt5DistTwoSiteTrace (trace.h:426-536): the two sites at the far corners of a 2 x 3 (HORIZONTAL) or
+        3 x 2 (VERTICAL) plaquette replaced. link_dir 0 = LEFTUP_TO_RIGHTDOWN: ten_left at (row1,col1), ten_right at the
+        opposite lower-right corner; 1 = LEFTDOWN_TO_RIGHTUP: ten_left at the lower-left corner, ten_right at the upper
+        right one. Two environment steps from the first side (:463-466 + :473-476), one from the other (:468-471),
+        closed by Contract(tmp[11],{0,1,2,3}, tmp[7],{3,2,1,0}) (:534)."""
+        row1, col1 = left_up_site
+        if mps_orient == HORIZONTAL:
+            row2, col2, col3 = row1 + 1, col1 + 1, col1 + 2
+            t = {(r, c): tn[r][c] for r in (row1, row2) for c in (col1, col2, col3)}
+            if link_dir == 0:
+                t[(row1, col1)], t[(row2, col3)] = ten_left, ten_right
+            else:
+                t[(row2, col1)], t[(row1, col3)] = ten_left, ten_right
+            n = self.cols
+            m1, m2, _, _ = self._bten2_operands(tn, LEFT, row1, col1 + 1)
+            a = self.bten2_step(self.bten_set2[LEFT][col1], m1, t[(row1, col1)], t[(row2, col1)], m2, LEFT)
+            m1, m2, _, _ = self._bten2_operands(tn, LEFT, row1, col2 + 1)
+            a = self.bten2_step(a, m1, t[(row1, col2)], t[(row2, col2)], m2, LEFT)
+            m1, m2, _, _ = self._bten2_operands(tn, RIGHT, row1, n - col3)
+            b = self.bten2_step(self.bten2_at_slice(RIGHT, col3), m1, t[(row2, col3)], t[(row1, col3)], m2, RIGHT)
+        else:
+            row2, row3, col2 = row1 + 1, row1 + 2, col1 + 1
+            t = {(r, c): tn[r][c] for r in (row1, row2, row3) for c in (col1, col2)}
+            if link_dir == 0:
+                t[(row1, col1)], t[(row3, col2)] = ten_left, ten_right
+            else:
+                t[(row3, col1)], t[(row1, col2)] = ten_left, ten_right
+            n = self.rows
+            m1, m2, _, _ = self._bten2_operands(tn, UP, col1, row1 + 1)
+            a = self.bten2_step(self.bten_set2[UP][row1], m1, t[(row1, col2)], t[(row1, col1)], m2, UP)
+            m1, m2, _, _ = self._bten2_operands(tn, UP, col1, row2 + 1)
+            a = self.bten2_step(a, m1, t[(row2, col2)], t[(row2, col1)], m2, UP)
+            m1, m2, _, _ = self._bten2_operands(tn, DOWN, col1, n - row3)
+            b = self.bten2_step(self.bten2_at_slice(DOWN, row3), m1, t[(row3, col1)], t[(row3, col2)], m2, DOWN)
+        return es("aoqb,bqoa->", a, b).item()

@@ -78,6 +78,7 @@ SIGNATURES = {
                                            C.c_void_p, _D, C.POINTER(C.c_int32), _D, C.POINTER(C.c_int32)]),
     "peps_probe_trace_row": (C.c_int, [_P, C.c_int32, _D]),
     "peps_probe_tnn_trace": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _I, _D]),
+    "peps_probe_plaquette_trace": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _D]),
     "peps_bmps_stack_size": (C.c_int32, [_P, C.c_int32]),
     "peps_get_bmps_tensor": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _D, _I]),
     "peps_stat": (C.c_int64, [_P, C.c_int32]),

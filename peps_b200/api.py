@@ -380,6 +380,12 @@ class WalkerBatch:
         self._ck(self.lib.peps_probe_tnn_trace(self.h, row, col, orient, _ip(c3), _dp(a)))
         return a
 
+    def probe_plaquette_trace(self, kind, row, col, direction, orient):
+        """kind 0: ReplaceNNNSiteTrace, 1: ReplaceSqrt5DistTwoSiteTrace, the two corner sites exchanging their spins."""
+        a = np.empty(self.W)
+        self._ck(self.lib.peps_probe_plaquette_trace(self.h, kind, row, col, direction, orient, _dp(a)))
+        return a
+
     def bmps_stack_size(self, pos):
         return self.lib.peps_bmps_stack_size(self.h, pos)
 

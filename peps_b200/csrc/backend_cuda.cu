@@ -343,11 +343,18 @@ gett_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double be
 // through the offset tables otherwise (true gathers). Each operand tile is laid out in shared memory along ITS OWN
 // unit-stride index -- [k][m] (+4 pad) when the free index is fast, [m][k] (+4 pad) when the contracted index is fast --
 // so both the copy writes and the DMMA fragment reads are bank-conflict free in either case.
-constexpr int GL_BN = 64, GL_BK = 16, GL_THREADS = 256, GL_STAGES = 3;
+constexpr int GL_BN = 64, GL_BK = 16, GL_THREADS = 256;
 constexpr int GL_LDB = GL_BN + 4, GL_LDK = GL_BK + 4;
-constexpr int GL_B_ELEMS = (GL_BK * GL_LDB > GL_BN * GL_LDK) ? GL_BK * GL_LDB : GL_BN * GL_LDK;
-__host__ __device__ constexpr int gl_a_elems(int bm) { return (GL_BK * (bm + 4) > bm * GL_LDK) ? GL_BK * (bm + 4) : bm * GL_LDK; }
-constexpr size_t gl_smem(int bm) { return (size_t)GL_STAGES * (gl_a_elems(bm) + GL_B_ELEMS) * sizeof(double); }
+__host__ __device__ constexpr int gl_a_elems(int bm, bool akf) { return akf ? bm * GL_LDK : GL_BK * (bm + 4); }
+__host__ __device__ constexpr int gl_b_elems(bool bkf) { return bkf ? GL_BN * GL_LDK : GL_BK * GL_LDB; }
+// ring depth: four stages when two CTAs of that size still share an SM (the K = 64 contractions then have every K step in
+// flight from the start), three otherwise
+__host__ __device__ constexpr int gl_stages(int bm, bool akf, bool bkf) {
+  return (size_t)4 * (gl_a_elems(bm, akf) + gl_b_elems(bkf)) * sizeof(double) <= 113 * 1024 ? 4 : 3;
+}
+__host__ __device__ constexpr size_t gl_smem(int bm, bool akf, bool bkf) {
+  return (size_t)gl_stages(bm, akf, bkf) * (gl_a_elems(bm, akf) + gl_b_elems(bkf)) * sizeof(double);
+}
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
   const unsigned saddr = (unsigned)__cvta_generic_to_shared(dst);
@@ -365,7 +372,8 @@ __device__ __forceinline__ void cp_async8(void *dst, const void *src, bool valid
 template <bool AKF, bool BKF, int WGM>
 __global__ void __launch_bounds__(GL_THREADS, 2)
 gett_large_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, double beta, int avec, int bvec, int cvec) {
-  constexpr int GL_BM = 32 * WGM, GL_LDA = GL_BM + 4, GL_A_ELEMS = gl_a_elems(GL_BM);
+  constexpr int GL_BM = 32 * WGM, GL_LDA = GL_BM + 4, GL_A_ELEMS = gl_a_elems(GL_BM, AKF), GL_B_ELEMS = gl_b_elems(BKF);
+  constexpr int GL_STAGES = gl_stages(GL_BM, AKF, BKF);
   constexpr int WGN = 8 / WGM, NT = GL_BN / (8 * WGN);        // warps along N, 8-column tiles per warp (4 or 2)
   constexpr int APT = GL_BM * GL_BK / 2 / GL_THREADS;        // A pairs per thread (4 or 2)
   extern __shared__ __align__(16) double gl_sm[];
@@ -528,27 +536,34 @@ gett_large_kernel(GettDesc d, Operand A, Operand B, Operand C, double alpha, dou
     }
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
-  // epilogue: lane (fr, fk) holds C[row fr][cols 2 fk, 2 fk + 1] of every 8x8 tile
+  // epilogue: lane (fr, fk) holds C[row fr][cols 2 fk, 2 fk + 1] of every 8x8 tile; the offset-table entries of the
+  // lane's rows and columns are fetched together up front (one latency instead of one per tile)
+  int cmo[4], cno[NT][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const int m = m0 + wm * 32 + i * 8 + fr; cmo[i] = (m < d.M) ? d.cm[m] : -1; }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int n = n0 + wn * 8 * NT + j * 8 + 2 * fk;
+    cno[j][0] = (n < d.N) ? d.cn[n] : -1;
+    cno[j][1] = (n + 1 < d.N) ? d.cn[n + 1] : -1;
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int m = m0 + wm * 32 + i * 8 + fr;
-    if (m >= d.M) continue;
-    const int cmo = d.cm[m];
+    if (cmo[i] < 0) continue;
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      const int n = n0 + wn * 8 * NT + j * 8 + 2 * fk;
-      if (n >= d.N) continue;
+      if (cno[j][0] < 0) continue;
       double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
       if (cvec) {                                    // the two columns are adjacent and 16-byte aligned in C
-        double2 *cp = reinterpret_cast<double2 *>(Cb + cmo + d.cn[n]);
+        double2 *cp = reinterpret_cast<double2 *>(Cb + cmo[i] + cno[j][0]);
         if (beta != 0.0) { const double2 o = *cp; v0 += beta * o.x; v1 += beta * o.y; }
         *cp = make_double2(v0, v1);
       } else {
-        double *cp = Cb + cmo + d.cn[n];
+        double *cp = Cb + cmo[i] + cno[j][0];
         if (beta != 0.0) v0 += beta * (*cp);
         *cp = v0;
-        if (n + 1 < d.N) {
-          double *cq = Cb + cmo + d.cn[n + 1];
+        if (cno[j][1] >= 0) {
+          double *cq = Cb + cmo[i] + cno[j][1];
           if (beta != 0.0) v1 += beta * (*cq);
           *cq = v1;
         }
@@ -573,11 +588,12 @@ void be_gett(const GettDesc &d, Operand A, Operand B, Operand C, double alpha, d
     const bool half = ctas128 < 2L * 148 || d.M <= 96;
     const int bm = half ? 64 : 128;
     dim3 grid(((d.M + bm - 1) / bm) * tn, NB, W);
-    auto go = [&](auto kern) {
-      ensure_smem(kern, gl_smem(bm));
-      kern<<<grid, GL_THREADS, gl_smem(bm), g_stream>>>(d, A, B, C, alpha, beta, avec, bvec, cvec);
-    };
     const bool akf = d.a_kfast != 0, bkf = d.b_nfast == 0;
+    const size_t smem = gl_smem(bm, akf, bkf);
+    auto go = [&](auto kern) {
+      ensure_smem(kern, smem);
+      kern<<<grid, GL_THREADS, smem, g_stream>>>(d, A, B, C, alpha, beta, avec, bvec, cvec);
+    };
     if (half) {
       if (akf && bkf) go(gett_large_kernel<true, true, 2>);
       else if (akf) go(gett_large_kernel<true, false, 2>);

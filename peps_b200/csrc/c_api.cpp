@@ -162,6 +162,16 @@ int peps_probe_tnn_trace(peps_ctx *ctx, int32_t row, int32_t col, int32_t orient
     ctx->eng->probe_tnn_trace(row, col, orient, cfg3, psi);
   })
 }
+int peps_probe_plaquette_trace(peps_ctx *ctx, int32_t kind, int32_t row, int32_t col, int32_t dir, int32_t orient, double *psi) {
+  GUARD(ctx, {
+    Engine &e = *ctx->eng;
+    const int span = kind == 0 ? 2 : 3;
+    const int h = orient == 0 ? 2 : span, wd = orient == 0 ? span : 2;
+    if (kind < 0 || kind > 1 || dir < 0 || dir > 1 || orient < 0 || orient > 1 || row < 0 || col < 0 || row + h > e.rows() || col + wd > e.cols())
+      throw std::invalid_argument("peps_probe_plaquette_trace: the plaquette does not fit the lattice");
+    e.probe_plaquette_trace(kind, row, col, dir, orient, psi);
+  })
+}
 int32_t peps_bmps_stack_size(peps_ctx *ctx, int32_t pos) { return ctx->eng->bmps_stack_size(pos); }
 int peps_get_bmps_tensor(peps_ctx *ctx, int32_t pos, int32_t k, int32_t i, double *out, int32_t dims[3]) {
   GUARD(ctx, { int d[3]; ctx->eng->bmps_tensor(pos, k, i, out, d); for (int a = 0; a < 3; ++a) dims[a] = d[a]; })

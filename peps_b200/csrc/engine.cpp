@@ -737,7 +737,7 @@ void Engine::shift_bten2_window(int pos, int slice1) { // grow.h:523-527
   bten2_[pos].pop_back();
   grow_bten2_step(opposite(pos), slice1);
 }
-void Engine::nnn_trace(int row1, int col1, int dir, double *psi_out) {            // trace.h:207-281 (HORIZONTAL)
+void Engine::nnn_trace(int row1, int col1, int dir, double *psi_out, int orient) {   // trace.h:207-324
   ++n_trace_;
   const int row2 = row1 + 1, col2 = col1 + 1;
   const int s11 = row1 * cols_ + col1, s21 = row2 * cols_ + col1, s12 = row1 * cols_ + col2, s22 = row2 * cols_ + col2;
@@ -745,13 +745,69 @@ void Engine::nnn_trace(int row1, int col1, int dir, double *psi_out) {          
   int g11 = s11, g21 = s21, g12 = s12, g22 = s22;
   if (dir == 0) { g11 = s22; g22 = s11; } else { g21 = s12; g12 = s21; }
   const BT *m1, *m2; int a, b;
-  bten2_operands(LEFT, row1, col1 + 1, m1, m2, a, b);
-  BT half_a = bten2_step(bten2_[LEFT].at((size_t)col1), *m1, site_ref(s11, g11), site_ref(s21, g21), *m2, LEFT);
-  bten2_operands(RIGHT, row1, cols_ - col2, m1, m2, a, b);
-  BT half_b = bten2_step(bten2_at_slice(RIGHT, col2), *m1, site_ref(s22, g22), site_ref(s12, g12), *m2, RIGHT);
+  BT half_a, half_b;
+  if (orient == HORIZONTAL) {                          // two-row environments LEFT | RIGHT (:218-281)
+    bten2_operands(LEFT, row1, col1 + 1, m1, m2, a, b);
+    half_a = bten2_step(bten2_[LEFT].at((size_t)col1), *m1, site_ref(s11, g11), site_ref(s21, g21), *m2, LEFT);
+    bten2_operands(RIGHT, row1, cols_ - col2, m1, m2, a, b);
+    half_b = bten2_step(bten2_at_slice(RIGHT, col2), *m1, site_ref(s22, g22), site_ref(s12, g12), *m2, RIGHT);
+  } else {                                             // two-column environments UP | DOWN (:282-324)
+    bten2_operands(UP, col1, row1 + 1, m1, m2, a, b);
+    half_a = bten2_step(bten2_[UP].at((size_t)row1), *m1, site_ref(s12, g12), site_ref(s11, g11), *m2, UP);
+    bten2_operands(DOWN, col1, rows_ - row2, m1, m2, a, b);
+    half_b = bten2_step(bten2_at_slice(DOWN, row2), *m1, site_ref(s21, g21), site_ref(s22, g22), *m2, DOWN);
+  }
   reverse_dot(half_a, half_b, psi_out);                // Contract(tmp[3],{0,1,2,3}, tmp[7],{3,2,1,0})
   release(half_a);
   release(half_b);
+}
+// ReplaceSqrt5DistTwoSiteTrace (trace.h:426-536) with the two corner sites EXCHANGING their physical indices: a 2 x 3
+// (HORIZONTAL) or 3 x 2 (VERTICAL) plaquette, two environment steps from the first side, one from the other.
+void Engine::sqrt5_trace(int row1, int col1, int dir, int orient, double *psi_out) {
+  ++n_trace_;
+  const BT *m1, *m2; int a, b;
+  auto S = [&](int r, int c) { return r * cols_ + c; };
+  BT h1, h2, hb;
+  if (orient == HORIZONTAL) {
+    const int row2 = row1 + 1, col2 = col1 + 1, col3 = col1 + 2;
+    int g[2][3];
+    for (int r = 0; r < 2; ++r) for (int c = 0; c < 3; ++c) g[r][c] = S(row1 + r, col1 + c);
+    if (dir == 0) std::swap(g[0][0], g[1][2]); else std::swap(g[1][0], g[0][2]);
+    bten2_operands(LEFT, row1, col1 + 1, m1, m2, a, b);
+    h1 = bten2_step(bten2_[LEFT].at((size_t)col1), *m1, site_ref(S(row1, col1), g[0][0]), site_ref(S(row2, col1), g[1][0]), *m2, LEFT);
+    bten2_operands(LEFT, row1, col2 + 1, m1, m2, a, b);
+    h2 = bten2_step(h1, *m1, site_ref(S(row1, col2), g[0][1]), site_ref(S(row2, col2), g[1][1]), *m2, LEFT);
+    bten2_operands(RIGHT, row1, cols_ - col3, m1, m2, a, b);
+    hb = bten2_step(bten2_at_slice(RIGHT, col3), *m1, site_ref(S(row2, col3), g[1][2]), site_ref(S(row1, col3), g[0][2]), *m2, RIGHT);
+  } else {
+    const int row2 = row1 + 1, row3 = row1 + 2, col2 = col1 + 1;
+    int g[3][2];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 2; ++c) g[r][c] = S(row1 + r, col1 + c);
+    if (dir == 0) std::swap(g[0][0], g[2][1]); else std::swap(g[2][0], g[0][1]);
+    bten2_operands(UP, col1, row1 + 1, m1, m2, a, b);
+    h1 = bten2_step(bten2_[UP].at((size_t)row1), *m1, site_ref(S(row1, col2), g[0][1]), site_ref(S(row1, col1), g[0][0]), *m2, UP);
+    bten2_operands(UP, col1, row2 + 1, m1, m2, a, b);
+    h2 = bten2_step(h1, *m1, site_ref(S(row2, col2), g[1][1]), site_ref(S(row2, col1), g[1][0]), *m2, UP);
+    bten2_operands(DOWN, col1, rows_ - row3, m1, m2, a, b);
+    hb = bten2_step(bten2_at_slice(DOWN, row3), *m1, site_ref(S(row3, col1), g[2][0]), site_ref(S(row3, col2), g[2][1]), *m2, DOWN);
+  }
+  reverse_dot(h2, hb, psi_out);                        // Contract(tmp[11],{0,1,2,3}, tmp[7],{3,2,1,0})  (:534)
+  release(h1); release(h2); release(hb);
+}
+// test probes: grow the two-slice environments around the plaquette, then evaluate the exchange trace
+void Engine::probe_plaquette_trace(int kind, int row1, int col1, int dir, int orient, double *psi_host) {
+  const int span = kind == 0 ? 2 : 3;                  // plaquette extent along the MPS orientation
+  if (orient == HORIZONTAL) {
+    grow_bmps_for_row(row1);                           // UP stack to row1, DOWN stack to rows below row1
+    grow_full_bten2(LEFT, row1, cols_ - col1, true);
+    grow_full_bten2(RIGHT, row1, col1 + span, true);
+  } else {
+    grow_bmps_for_col(col1);
+    grow_full_bten2(UP, col1, rows_ - row1, true);
+    grow_full_bten2(DOWN, col1, row1 + span, true);
+  }
+  if (kind == 0) nnn_trace(row1, col1, dir, psi_tmp_, orient); else sqrt5_trace(row1, col1, dir, orient, psi_tmp_);
+  be_d2h(psi_host, psi_tmp_, sizeof(double) * W_);
 }
 void Engine::punch_hole(int r, int c, int orient) {    // grow.h:150-183
   const BT *up, *down, *left, *right;

@@ -175,8 +175,12 @@ class Engine {
   void grow_full_bten2(int pos, int slice1, int remain, bool init);
   void grow_bten2_step(int post, int slice1);
   void shift_bten2_window(int pos, int slice1);
-  // psi_out[w] = ReplaceNNNSiteTrace({row1,col1}, dir, HORIZONTAL, exchanged tensors); dir 0 = LEFTUP_TO_RIGHTDOWN
-  void nnn_trace(int row1, int col1, int dir, double *psi_out);
+  // psi_out[w] = ReplaceNNNSiteTrace({row1,col1}, dir, orient, exchanged tensors); dir 0 = LEFTUP_TO_RIGHTDOWN
+  void nnn_trace(int row1, int col1, int dir, double *psi_out, int orient = HORIZONTAL);
+  // psi_out[w] = ReplaceSqrt5DistTwoSiteTrace({row1,col1}, dir, orient, exchanged tensors) (trace.h:426-536)
+  void sqrt5_trace(int row1, int col1, int dir, int orient, double *psi_out);
+  // kind 0: NNN plaquette (2 x 2), 1: sqrt(5)-distance plaquette (2 x 3 / 3 x 2); grows the environments first
+  void probe_plaquette_trace(int kind, int row1, int col1, int dir, int orient, double *psi_host);
 
  private:
   using BMPSv = std::vector<BT>;

@@ -115,3 +115,31 @@ def run_gradient_parity(lib, rows, cols, D, W, trunc, nsamples=3, seed=2, tol=1e
     assert np.max(np.abs(g2 - gref)) < tol * max(np.max(np.abs(gref)), 1e-300)
     b.close()
     return dict(energy=energy, gnorm=float(np.sum(gref ** 2)))
+
+
+def run_plaquette_trace_parity(lib, rows=4, cols=5, D=2, W=3, tol=1e-10):
+    """peps_probe_plaquette_trace (ReplaceNNNSiteTrace / ReplaceSqrt5DistTwoSiteTrace, both link directions and both MPS
+    orientations) vs the oracle amplitude of the configuration with the two corner spins exchanged."""
+    tps = vmc.random_tps(rows, cols, 2, D, seed=12)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 3 + w) for w in range(W)])
+    trunc = (1, 1000, 0.0)
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    worst = 0.0
+    for kind in (0, 1):
+        for d in (0, 1):
+            for o in (0, 1):
+                r1, c1 = 1, 1
+                h, wd = (2, 2) if kind == 0 else ((2, 3) if o == 0 else (3, 2))
+                a_, b_ = ((r1, c1), (r1 + h - 1, c1 + wd - 1)) if d == 0 else ((r1 + h - 1, c1), (r1, c1 + wd - 1))
+                psi = b.probe_plaquette_trace(kind, r1, c1, d, o)
+                for w in range(W):
+                    c2 = cfgs[w].copy()
+                    c2[a_], c2[b_] = cfgs[w][b_], cfgs[w][a_]
+                    ref = vmc.Walker(tps, c2, trunc).amplitude
+                    worst = max(worst, abs(psi[w] / ref - 1))
+                    assert abs(psi[w] / ref - 1) < tol, (kind, d, o, w, psi[w], ref)
+    b.close()
+    return worst

@@ -592,3 +592,10 @@ def test_two_rank_nccl_evaluator_and_sr(lib):
     g1 = one.gradient.pack()
     assert np.max(np.abs(two["grad"] - g1)) < 1e-10 * np.max(np.abs(g1))
     assert np.max(np.abs(two["nat"] - nat1.pack())) < 1e-7 * np.max(np.abs(nat1.pack()))
+
+
+def test_plaquette_traces_gpu(lib):
+    """ReplaceNNNSiteTrace with VERTICAL MPS orientation and ReplaceSqrt5DistTwoSiteTrace (trace.h:282-324, 426-536) on
+    the GPU: equal to the oracle amplitude of the exchanged configuration."""
+    from parity_common import run_plaquette_trace_parity
+    print("plaquette traces worst rel err", run_plaquette_trace_parity(lib))

@@ -306,3 +306,10 @@ def test_chain_deflation_keeps_amplitudes(lib):
     for w in range(W):
         ref = vmc.Walker(tps, cfgs[w], (9, 9, 0.0)).amplitude
         assert abs(a1[w] / ref - 1) < 1e-10
+
+
+def test_plaquette_traces_hostsim():
+    """ReplaceNNNSiteTrace (both MPS orientations) and ReplaceSqrt5DistTwoSiteTrace through the C ABI (host-simulated
+    device ops) against amplitudes of the exchanged configurations evaluated from scratch by the oracle."""
+    from parity_common import run_plaquette_trace_parity
+    run_plaquette_trace_parity(hostsim_lib.load())

@@ -291,3 +291,67 @@ def test_K6_heisenberg_4x4_D8_mc_energy():
     mean = float(np.mean(energies))
     err = float(np.std(energies) / math.sqrt(len(energies)))
     assert abs(mean - float(z["exp_e0_state"])) < max(5 * err, 0.05)
+
+
+def test_K1_vertical_nnn_and_sqrt5_traces_reproduce_partition_function():
+    """The remaining closures of the reference's K1 list (test_bmps_contractor.cpp:342-405): ReplaceSqrt5DistTwoSiteTrace
+    in both link directions and both MPS orientations, and ReplaceNNNSiteTrace with VERTICAL MPS orientation, all with the
+    original tensors, equal Z."""
+    L = 8
+    beta = math.log(1 + math.sqrt(2.0)) / 2.0
+    tn = ising_tn(L, beta)
+    lz = ising_exact_logZ(L, beta)
+    c = BMPSContractor(L, L)
+    c.init(tn)
+    c.set_truncate_params(10, 30, 1e-15)
+    c.grow_bmps_for_row(tn, 1)
+    c.init_bten2(tn, LEFT, 1)
+    c.grow_full_bten2(tn, LEFT, 1, L - 1, False)
+    c.grow_full_bten2(tn, RIGHT, 1, 3, True)
+    zs = [c.replace_sqrt5_dist_two_site_trace(tn, (1, 0), 1, HORIZONTAL, tn[2][0], tn[1][2]),
+          c.replace_sqrt5_dist_two_site_trace(tn, (1, 1), 1, HORIZONTAL, tn[2][1], tn[1][3]),
+          c.replace_sqrt5_dist_two_site_trace(tn, (1, 0), 0, HORIZONTAL, tn[1][0], tn[2][2]),
+          c.replace_sqrt5_dist_two_site_trace(tn, (1, 1), 0, HORIZONTAL, tn[1][1], tn[2][3])]
+    c.grow_bmps_for_col(tn, 1)
+    c.grow_full_bten2(tn, DOWN, 1, 3, True)
+    c.grow_full_bten2(tn, UP, 1, L - 2, True)
+    zs += [c.replace_nnn_site_trace(tn, (2, 1), 1, VERTICAL, tn[3][1], tn[2][2]),
+           c.replace_nnn_site_trace(tn, (2, 1), 0, VERTICAL, tn[2][1], tn[3][2]),
+           c.replace_nnn_site_trace(tn, (1, 1), 1, VERTICAL, tn[2][1], tn[1][2]),
+           c.replace_nnn_site_trace(tn, (1, 1), 0, VERTICAL, tn[1][1], tn[2][2]),
+           c.replace_sqrt5_dist_two_site_trace(tn, (1, 1), 1, VERTICAL, tn[3][1], tn[1][2]),
+           c.replace_sqrt5_dist_two_site_trace(tn, (1, 1), 0, VERTICAL, tn[1][1], tn[3][2])]
+    for z in zs:
+        assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
+
+
+def test_plaquette_traces_equal_amplitudes_of_exchanged_configurations():
+    """On a random (asymmetric) TPS every plaquette trace must equal the amplitude evaluated from scratch on the
+    configuration with the two corner spins exchanged: pins WHICH sites the replacement tensors land on."""
+    rows, cols = 4, 5
+    tps = vmc.random_tps(rows, cols, 2, 2, seed=12)
+    cfg = vmc.shuffled_half_filled_config(rows, cols, 3)
+    trunc = (1, 1000, 0.0)
+    w = vmc.Walker(tps, cfg, trunc)
+    c, tn = w.contractor, w.tn
+    cases = [(0, 1, 1, d, o) for d in (0, 1) for o in (HORIZONTAL, VERTICAL)] + \
+            [(1, 1, 1, d, o) for d in (0, 1) for o in (HORIZONTAL, VERTICAL)]
+    for kind, r1, c1, d, o in cases:
+        h, wd = (2, 2) if kind == 0 else ((2, 3) if o == HORIZONTAL else (3, 2))
+        a, b = ((r1, c1), (r1 + h - 1, c1 + wd - 1)) if d == 0 else ((r1 + h - 1, c1), (r1, c1 + wd - 1))
+        span = 2 if kind == 0 else 3
+        if o == HORIZONTAL:
+            c.grow_bmps_for_row(tn, r1)
+            c.grow_full_bten2(tn, LEFT, r1, cols - c1, True)
+            c.grow_full_bten2(tn, RIGHT, r1, c1 + span, True)
+        else:
+            c.grow_bmps_for_col(tn, c1)
+            c.grow_full_bten2(tn, UP, c1, rows - r1, True)
+            c.grow_full_bten2(tn, DOWN, c1, r1 + span, True)
+        ta, tb = tps[a[0]][a[1]][int(cfg[b])], tps[b[0]][b[1]][int(cfg[a])]
+        f = c.replace_nnn_site_trace if kind == 0 else c.replace_sqrt5_dist_two_site_trace
+        psi = f(tn, (r1, c1), d, o, ta, tb)
+        c2 = cfg.copy()
+        c2[a], c2[b] = cfg[b], cfg[a]
+        ref = vmc.Walker(tps, c2, trunc).amplitude
+        assert abs(psi / ref - 1) < 1e-11, (kind, d, o, psi, ref)
