@@ -76,6 +76,22 @@ int peps_set_model_j1j2_xxz(peps_ctx *ctx, double jz, double jxy, double jz2, do
  * horizontal pass (model_solvers/transverse_field_ising_square_obc.h:149-247; BASELINE config #1). phys must be 2. */
 int peps_set_model_tfim(peps_ctx *ctx, double h);
 
+/* Seam B2 as data -- a user model without an engine patch. The reference's model mix-ins implement
+ * EvaluateBondEnergy(site1, site2, cfg1, cfg2, orient, tn, contractor, ..., inv_psi), EvaluateNNNEnergy(...) and
+ * EvaluateTotalOnsiteEnergy(config) (model_solvers/base/square_nnn_energy_solver.h:31-36, 171-198): pure arithmetic on the
+ * local configuration, the couplings and amplitude ratios psi(S')/psi(S) of locally modified configurations. Here the same
+ * information is uploaded as tables and the engine runs the reference's traversal (:79-315, base/bond_traversal_mixin.h:
+ * 112-143) with one batched replacement trace per target slot. kind: 0 = nearest-neighbour bonds (both orientations),
+ * 1 = next-nearest-neighbour links (both diagonals), 2 = on-site. Local state p = c1 (* phys + c2), site1 = the left /
+ * upper site of the bond (diagonals: the left site of the link). diag[p] = <p|H|p>; for slot t < T: target[p*T + t] = a
+ * local state p' != p with <p|H|p'> != 0 (or -1 when the slot is unused), coef[p*T + t] = <p|H|p'>.
+ *   E_loc += diag[p] + sum_t coef[p][t] * psi(S with p -> p'_t) / psi(S)
+ * Setting any term switches the table-driven solver on (it replaces the built-in XXZ / J1-J2 / TFIM branches, which are
+ * reproduced exactly by their tables: include/peps_b200.hpp XXZBondTerm, TFIMTerms); peps_clear_model_terms switches
+ * back. Works for any phys (spin-1, t-J-like bosonic parts, ...). */
+int peps_set_model_term(peps_ctx *ctx, int32_t kind, int32_t T, const double *diag, const int32_t *target, const double *coef);
+int peps_clear_model_terms(peps_ctx *ctx);
+
 /* Configuration per walker (vmc_basic/configuration.h:57), int32 [W][rows][cols]. */
 int peps_set_configs(peps_ctx *ctx, const int32_t *cfg);
 int peps_get_configs(peps_ctx *ctx, int32_t *cfg);

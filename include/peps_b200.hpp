@@ -34,6 +34,98 @@ struct MonteCarloParams {
 struct XXZModel { double jz = 1.0, jxy = 1.0, pinning00 = 0.0; };   // SquareSpinOneHalfXXZModelOBC(jz, jxy, pinning)
 struct J1J2XXZModel { double jz = 1.0, jxy = 1.0, jz2 = 0.0, jxy2 = 0.0, pinning00 = 0.0; };   // SquareSpinOneHalfJ1J2XXZModelOBC
 struct TransverseFieldIsingModel { double h = 1.0; };                 // TransverseFieldIsingSquareOBC(h)
+// ---- seam B2 as data ------------------------------------------------------------------------------------------------
+// A model term as tables (peps_set_model_term). ProbeTwoSiteTerm / ProbeOneSiteTerm build them from a reference-style
+// bond-energy functor: the reference's mix-in hook
+//   EvaluateBondEnergy(site1, site2, cfg1, cfg2, orient, tn, contractor, sitps1, sitps2, inv_psi)
+// (model_solvers/base/square_nnn_energy_solver.h:171-198) is pure arithmetic on (cfg1, cfg2), the couplings and the
+// amplitude ratios psi(S')/psi(S) it obtains through contractor.ReplaceNNSiteTrace(...) * inv_psi. The probe calls the
+// functor with a recording `ratio(c1', c2')` callback: once returning 0 (-> the diagonal element), then once per recorded
+// target with an indicator ratio (-> the matrix element). Any model whose bond energy is linear in the ratios -- every
+// model of the reference -- becomes a table, and the engine needs no patch.
+struct ModelTerm {
+  int32_t kind = 0;                    // 0 NN bonds, 1 NNN links, 2 on-site
+  int32_t T = 0;                       // target slots per local state
+  std::vector<double> diag, coef;      // [np], [np * T]
+  std::vector<int32_t> target;         // [np * T], -1 = unused
+};
+// f(c1, c2, ratio) -> bond energy, ratio(c1', c2') = psi(S with (c1,c2) -> (c1',c2')) / psi(S)
+inline ModelTerm ProbeTwoSiteTerm(int32_t kind, int phys,
+                                  const std::function<double(int, int, const std::function<double(int, int)> &)> &f) {
+  const int np = phys * phys;
+  std::vector<std::vector<int>> tg((size_t)np);
+  std::vector<std::vector<double>> cf((size_t)np);
+  ModelTerm m;
+  m.kind = kind; m.diag.assign((size_t)np, 0.0);
+  for (int p = 0; p < np; ++p) {
+    std::vector<int> seen;
+    m.diag[(size_t)p] = f(p / phys, p % phys, [&](int a, int b) { int q = a * phys + b; if (q != p) { bool k = false; for (int s : seen) k |= (s == q); if (!k) seen.push_back(q); } return 0.0; });
+    for (int q : seen) {
+      const double v = f(p / phys, p % phys, [&](int a, int b) { return (a * phys + b == q) ? 1.0 : 0.0; }) - m.diag[(size_t)p];
+      if (v != 0.0) { tg[(size_t)p].push_back(q); cf[(size_t)p].push_back(v); }
+    }
+    m.T = std::max<int32_t>(m.T, (int32_t)tg[(size_t)p].size());
+  }
+  m.target.assign((size_t)np * std::max(m.T, 1), -1); m.coef.assign((size_t)np * std::max(m.T, 1), 0.0);
+  for (int p = 0; p < np; ++p)
+    for (size_t t = 0; t < tg[(size_t)p].size(); ++t) { m.target[(size_t)p * m.T + t] = tg[(size_t)p][t]; m.coef[(size_t)p * m.T + t] = cf[(size_t)p][t]; }
+  return m;
+}
+// f(c, ratio) -> on-site energy, ratio(c') = psi(S with c -> c') / psi(S)
+inline ModelTerm ProbeOneSiteTerm(int phys, const std::function<double(int, const std::function<double(int)> &)> &f) {
+  ModelTerm m;
+  m.kind = 2; m.diag.assign((size_t)phys, 0.0);
+  std::vector<std::vector<int>> tg((size_t)phys);
+  std::vector<std::vector<double>> cf((size_t)phys);
+  for (int p = 0; p < phys; ++p) {
+    std::vector<int> seen;
+    m.diag[(size_t)p] = f(p, [&](int q) { if (q != p) { bool k = false; for (int s : seen) k |= (s == q); if (!k) seen.push_back(q); } return 0.0; });
+    for (int q : seen) {
+      const double v = f(p, [&](int a) { return a == q ? 1.0 : 0.0; }) - m.diag[(size_t)p];
+      if (v != 0.0) { tg[(size_t)p].push_back(q); cf[(size_t)p].push_back(v); }
+    }
+    m.T = std::max<int32_t>(m.T, (int32_t)tg[(size_t)p].size());
+  }
+  m.target.assign((size_t)phys * std::max(m.T, 1), -1); m.coef.assign((size_t)phys * std::max(m.T, 1), 0.0);
+  for (int p = 0; p < phys; ++p)
+    for (size_t t = 0; t < tg[(size_t)p].size(); ++t) { m.target[(size_t)p * m.T + t] = tg[(size_t)p][t]; m.coef[(size_t)p * m.T + t] = cf[(size_t)p][t]; }
+  return m;
+}
+// SquareSpinOneHalfXXZModelMixIn::EvaluateBondEnergy (square_spin_onehalf_xxz_obc.h:72-104) written against the probe
+inline ModelTerm XXZBondTerm(int32_t kind, double jz, double jxy) {
+  return ProbeTwoSiteTerm(kind, 2, [=](int c1, int c2, const std::function<double(int, int)> &ratio) {
+    if (c1 == c2) return 0.25 * jz;
+    return -0.25 * jz + ratio(c2, c1) * 0.5 * jxy;
+  });
+}
+
+// ---- runtime parameter packs (algorithm/vmc_update/monte_carlo_peps_params.h) and their free functions -----------------
+struct ConfigurationRescueParams {
+  bool enabled = true;
+  double amplitude_min_threshold = std::numeric_limits<double>::min();
+  double amplitude_max_threshold = std::numeric_limits<double>::max();
+};
+// CheckWaveFunctionAmplitudeValidity (vmc_basic/wave_function_component.h:393-401)
+inline bool CheckWaveFunctionAmplitudeValidity(double amplitude, double min_threshold, double max_threshold) {
+  const double a = std::fabs(amplitude);
+  return !std::isnan(a) && !std::isinf(a) && a > min_threshold && a < max_threshold;
+}
+// ComputePsiConsistencySummaryAligned (algorithm/vmc_update/psi_consistency.h:76-130): {psi_mean, psi_rel_err}
+inline std::pair<double, double> ComputePsiConsistencySummaryAligned(const std::vector<double> &psi) {
+  if (psi.empty()) return {0.0, 0.0};
+  size_t ri = 0;
+  for (size_t i = 0; i < psi.size(); ++i) if (std::fabs(psi[i]) > std::fabs(psi[ri])) ri = i;
+  const bool ref_valid = std::fabs(psi[ri]) > 1e-14;
+  std::vector<double> al(psi);
+  double mean = 0.0;
+  for (auto &v : al) { if (ref_valid && v * psi[ri] < 0.0) v = -v; mean += v; }
+  mean /= (double)psi.size();
+  const double denom = std::max(std::fabs(mean), std::numeric_limits<double>::epsilon());
+  double dev = 0.0;
+  for (double v : al) dev = std::max(dev, std::fabs(v - mean));
+  return {mean, dev / denom};
+}
+
 enum class Updater : int32_t { NNExchange = 0, NNFullSpace = 1, TNN3SiteExchange = 2 };   // MCUpdateSquareNNExchangeOBC / ...NNFullSpaceUpdateOBC / MCUpdateSquareTNN3SiteExchange
 
 class WalkerBatch {
@@ -53,6 +145,37 @@ class WalkerBatch {
   void SetModel(const XXZModel &m) { ck(peps_set_model_xxz(h_, m.jz, m.jxy, m.pinning00)); }
   void SetModel(const J1J2XXZModel &m) { ck(peps_set_model_j1j2_xxz(h_, m.jz, m.jxy, m.jz2, m.jxy2, m.pinning00)); }
   void SetModel(const TransverseFieldIsingModel &m) { ck(peps_set_model_tfim(h_, m.h)); }
+  // table-driven model (seam B2 as data): one call per term; ClearModelTerms returns to the built-in solvers
+  void SetModelTerm(const ModelTerm &m) { ck(peps_set_model_term(h_, m.kind, m.T, m.diag.data(), m.target.data(), m.coef.data())); }
+  void ClearModelTerms() { ck(peps_clear_model_terms(h_)); }
+  std::vector<double> EnergyAndHoles(bool calc_holes) {
+    std::vector<double> e((size_t)walkers_);
+    ck(peps_energy_and_holes(h_, calc_holes ? 1 : 0, e.data(), nullptr));
+    return e;
+  }
+  // MonteCarloEngine::EnsureConfigurationValidity (monte_carlo_engine.h:340-414) with walkers as ranks: invalid walkers
+  // take the first valid walker's configuration; returns the rescued walkers, throws when disabled / nobody is valid.
+  std::vector<int> EnsureConfigurationValidity(const ConfigurationRescueParams &rp = ConfigurationRescueParams()) {
+    std::vector<double> amp = Amplitudes();
+    std::vector<int> bad;
+    int src = -1;
+    for (int w = 0; w < walkers_; ++w) {
+      if (CheckWaveFunctionAmplitudeValidity(amp[(size_t)w], rp.amplitude_min_threshold, rp.amplitude_max_threshold)) { if (src < 0) src = w; }
+      else bad.push_back(w);
+    }
+    if (bad.empty()) return bad;
+    if (!rp.enabled) throw std::runtime_error("invalid configurations and configuration rescue is disabled");
+    if (src < 0) throw std::runtime_error("all walkers have invalid configurations: check bond dimension, truncation cutoff, initial configuration");
+    std::vector<int32_t> cfg = GetConfigs();
+    const size_t ns = (size_t)rows_ * cols_;
+    for (int w : bad) std::copy(cfg.begin() + (size_t)src * ns, cfg.begin() + (size_t)(src + 1) * ns, cfg.begin() + (size_t)w * ns);
+    SetConfigs(cfg);
+    InitWalkers();
+    for (double a : Amplitudes())
+      if (!CheckWaveFunctionAmplitudeValidity(a, rp.amplitude_min_threshold, rp.amplitude_max_threshold))
+        throw std::runtime_error("rescue FAILED: the valid configuration of another walker is not valid here");
+    return bad;
+  }
   void SetUpdater(Updater u) { updater_ = u; ck(peps_set_updater(h_, (int32_t)u)); }
   void SetChainDeflation(double eps) { ck(peps_set_chain_deflation(h_, eps)); }
   // EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214): per-walker arrays, see peps_measure

@@ -446,6 +446,82 @@ class XXZModel:
         return e + self.onsite_energy(w.config), holes, psi_list
 
 
+class TableModel:
+    """Generic square-lattice model given by local Hamiltonian matrices, evaluated with the reference's bond traversal
+    (square_nnn_energy_solver.h:79-315 + bond_traversal_mixin.h:112-143): what a user-defined `EvaluateBondEnergy /
+    EvaluateNNNEnergy / EvaluateTotalOnsiteEnergy` mix-in (square_nnn_energy_solver.h:171-198) computes, with the
+    matrix elements as data.  h2 / h2_nnn: (d*d, d*d) matrices in the basis p = c1*d + c2 (site1 = left / upper site of
+    the bond; for the diagonals site1 = the LEFT site of the link); h1: (d, d).  E_loc = sum_terms sum_p' H[p, p'] psi(p')/psi."""
+
+    def __init__(self, phys, h2=None, h2_nnn=None, h1=None):
+        self.d, self.h2, self.h2n, self.h1 = phys, h2, h2_nnn, h1
+
+    def _two(self, H, p, amp_of, inv_psi):
+        e = H[p, p]
+        for q in range(self.d * self.d):
+            if q != p and H[p, q] != 0.0:
+                e = e + H[p, q] * (amp_of(q // self.d, q % self.d) * inv_psi)
+        return e
+
+    def energy_and_holes(self, tps, w, calc_holes=True):
+        tn, c = w.tn, w.contractor
+        rows, cols, d = w.rows, w.cols, self.d
+        e_tot, psi_list = 0.0, []
+        holes = [[None] * cols for _ in range(rows)] if calc_holes else None
+        c.set_truncate_params(*w.trunc)
+        c.generate_bmps_approach(tn, UP)
+        for row in range(rows):
+            c.init_bten(tn, LEFT, row)
+            c.grow_full_bten(tn, RIGHT, row, 1, True)
+            psi = c.trace(tn, (row, 0), HORIZONTAL)
+            inv_psi = 1.0 / psi
+            psi_list.append(psi)
+            for col in range(cols):
+                if calc_holes:
+                    holes[row][col] = np.conj(c.punch_hole(tn, (row, col), HORIZONTAL))
+                s = (row, col)
+                if self.h1 is not None:
+                    p = int(w.config[s])
+                    e_tot = e_tot + self.h1[p, p]
+                    for q in range(d):
+                        if q != p and self.h1[p, q] != 0.0:
+                            e_tot = e_tot + self.h1[p, q] * (c.replace_one_site_trace(tn, s, tps[row][col][q], HORIZONTAL) * inv_psi)
+                if col < cols - 1:
+                    s2 = (row, col + 1)
+                    if self.h2 is not None:
+                        amp = lambda a, b: c.replace_nn_site_trace(tn, s, s2, HORIZONTAL, tps[row][col][a], tps[row][col + 1][b])
+                        e_tot = e_tot + self._two(self.h2, int(w.config[s]) * d + int(w.config[s2]), amp, inv_psi)
+                    c.shift_bten_window(tn, RIGHT)
+            if self.h2n is not None and row < rows - 1:
+                c.init_bten2(tn, LEFT, row)
+                c.grow_full_bten2(tn, RIGHT, row, 2, True)
+                for col in range(cols - 1):
+                    for nnn_dir, (s1, s2) in enumerate((((row, col), (row + 1, col + 1)), ((row + 1, col), (row, col + 1)))):
+                        amp = lambda a, b: c.replace_nnn_site_trace(tn, (row, col), nnn_dir, HORIZONTAL,
+                                                                    tps[s1[0]][s1[1]][a], tps[s2[0]][s2[1]][b])
+                        e_tot = e_tot + self._two(self.h2n, int(w.config[s1]) * d + int(w.config[s2]), amp, inv_psi)
+                    c.shift_bten2_window(tn, RIGHT, row)
+            if row < rows - 1:
+                c.shift_bmps_window(tn, DOWN)
+        c.generate_bmps_approach(tn, LEFT)
+        for col in range(cols):
+            c.init_bten(tn, UP, col)
+            c.grow_full_bten(tn, DOWN, col, 2, True)
+            psi = c.trace(tn, (0, col), VERTICAL)
+            inv_psi = 1.0 / psi
+            psi_list.append(psi)
+            for row in range(rows - 1):
+                s1, s2 = (row, col), (row + 1, col)
+                if self.h2 is not None:
+                    amp = lambda a, b: c.replace_nn_site_trace(tn, s1, s2, VERTICAL, tps[row][col][a], tps[row + 1][col][b])
+                    e_tot = e_tot + self._two(self.h2, int(w.config[s1]) * d + int(w.config[s2]), amp, inv_psi)
+                if row < rows - 2:
+                    c.shift_bten_window(tn, DOWN)
+            if col < cols - 1:
+                c.shift_bmps_window(tn, RIGHT)
+        return e_tot, holes, psi_list
+
+
 def mean_and_binned_error(samples):
     """MeanAndBinnedErrorSqrtNUniformBin for one rank (statistics.h:146-225)."""
     n = len(samples)

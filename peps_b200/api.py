@@ -77,6 +77,46 @@ class Configuration:
 
 
 @dataclass
+class PsiConsistencyWarningParams:
+    """algorithm/vmc_update/monte_carlo_peps_params.h (RuntimeParams::psi_consistency)."""
+    enabled: bool = True
+    master_only: bool = False
+    threshold: float = 1e-3
+    max_warnings: int = 50
+    max_print_elems: int = 8
+
+
+@dataclass
+class ConfigurationRescueParams:
+    """RuntimeParams::config_rescue: amplitudes with |psi| <= min or >= max (or NaN / inf) are invalid."""
+    enabled: bool = True
+    amplitude_min_threshold: float = np.finfo(np.float64).tiny
+    amplitude_max_threshold: float = np.finfo(np.float64).max
+
+
+def check_wavefunction_amplitude_validity(amplitudes, min_threshold, max_threshold):
+    """CheckWaveFunctionAmplitudeValidity (vmc_basic/wave_function_component.h:393-401), element-wise over walkers."""
+    a = np.abs(np.asarray(amplitudes))
+    with np.errstate(invalid="ignore"):
+        return np.isfinite(a) & (a > min_threshold) & (a < max_threshold)
+
+
+def compute_psi_consistency_summary_aligned(psi_list):
+    """ComputePsiConsistencySummaryAligned (algorithm/vmc_update/psi_consistency.h:76-130): (psi_mean, psi_rel_err) of
+    one configuration's list of contraction results, signs aligned to the element of largest magnitude."""
+    psi = np.asarray(psi_list)
+    if psi.size == 0:
+        return 0.0, 0.0
+    ref = psi[int(np.argmax(np.abs(psi)))]
+    aligned = psi.copy()
+    if abs(ref) > 1e-14:
+        aligned = np.where(np.real(psi * np.conj(ref)) < 0.0, -psi, psi)
+    mean = np.sum(aligned) / psi.size
+    denom = max(abs(mean), np.finfo(np.float64).eps)
+    return mean, float(np.max(np.abs(aligned - mean)) / denom)
+
+
+@dataclass
 class MonteCarloParams:
     num_samples: int
     num_warmup_sweeps: int
@@ -164,6 +204,43 @@ class SquareSpinOneHalfJ1J2XXZModelOBC:
     pinning00: float = 0.0
 
 
+class TableModel:
+    """A model given by local Hamiltonian matrices (seam B2 as data, include/peps_b200.h peps_set_model_term): h2 /
+    h2_nnn are (d*d, d*d) matrices in the basis p = c1*d + c2 (site1 = left / upper site; diagonals: left site of the
+    link), h1 is (d, d). What a reference-style EvaluateBondEnergy / EvaluateNNNEnergy / EvaluateTotalOnsiteEnergy mix-in
+    (square_nnn_energy_solver.h:171-198) computes, with its matrix elements as data."""
+
+    def __init__(self, phys, h2=None, h2_nnn=None, h1=None):
+        self.phys, self.h2, self.h2_nnn, self.h1 = phys, h2, h2_nnn, h1
+
+    @staticmethod
+    def tables(H):
+        H = np.asarray(H, dtype=np.float64)
+        n = H.shape[0]
+        off = [[q for q in range(n) if q != p and H[p, q] != 0.0] for p in range(n)]
+        T = max((len(o) for o in off), default=0)
+        target = -np.ones((n, max(T, 1)), dtype=np.int32)
+        coef = np.zeros((n, max(T, 1)))
+        for p, o in enumerate(off):
+            for t, q in enumerate(o):
+                target[p, t], coef[p, t] = q, H[p, q]
+        return T, np.ascontiguousarray(np.diag(H)), target, coef
+
+    @staticmethod
+    def xxz(jz=1.0, jxy=1.0, jz2=0.0, jxy2=0.0, pinning00=None):
+        """SquareSpinOneHalfXXZModelMixIn (square_spin_onehalf_xxz_obc.h:72-140) as tables; cfg 0/1, Sz = cfg - 1/2."""
+        def bond(a, b):
+            H = np.diag([0.25 * a, -0.25 * a, -0.25 * a, 0.25 * a])
+            H[1, 2] = H[2, 1] = 0.5 * b
+            return H
+        return TableModel(2, bond(jz, jxy), bond(jz2, jxy2) if (jz2 or jxy2) else None)
+
+    @staticmethod
+    def tfim(h):
+        """TransverseFieldIsingSquareOBC (transverse_field_ising_square_obc.h:149-247): -sz sz bonds, -h sx on-site."""
+        return TableModel(2, np.diag([-1.0, 1.0, 1.0, -1.0]), None, np.array([[0.0, -h], [-h, 0.0]]))
+
+
 @dataclass
 class MCUpdateSquareTNN3SiteExchange:
     """square_3site_updater.h:23-160: permutations of the spins on three consecutive sites, Suwa-Todo choice."""
@@ -248,6 +325,15 @@ class WalkerBatch:
         self._ck(self.lib.peps_set_chain_deflation(self.h, eps))
 
     def set_model(self, model):
+        if isinstance(model, TableModel):
+            self._ck(self.lib.peps_clear_model_terms(self.h))
+            for kind, H in ((0, model.h2), (1, model.h2_nnn), (2, model.h1)):
+                if H is None:
+                    continue
+                T, diag, target, coef = TableModel.tables(H)
+                self._ck(self.lib.peps_set_model_term(self.h, kind, T, _dp(diag), _ip(target), _dp(coef)))
+            return
+        self._ck(self.lib.peps_clear_model_terms(self.h))
         if isinstance(model, TransverseFieldIsingSquareOBC):
             self._ck(self.lib.peps_set_model_tfim(self.h, model.h))
         elif hasattr(model, "jz2"):
@@ -525,8 +611,13 @@ class MCEnergyGradEvaluator:
     """
 
     def __init__(self, mc_params: MonteCarloParams, trunc: BMPSTruncateParams, tps: SplitIndexTPS, model, updater,
-                 walkers, configs=None, device=0, lib=None, dist=None, rank=0, world_size=1):
+                 walkers, configs=None, device=0, lib=None, dist=None, rank=0, world_size=1, config_rescue=None,
+                 psi_consistency=None):
         self.mc, self.trunc, self.model, self.updater = mc_params, trunc, model, updater
+        self.config_rescue = config_rescue or ConfigurationRescueParams()
+        self.psi_consistency = psi_consistency or PsiConsistencyWarningParams()
+        self.psi_warnings = []                 # (sample index, walker, psi_rel_err) above the threshold, up to max_warnings
+        self.rescued = []                      # walkers whose configuration was replaced by EnsureConfigurationValidity
         self.state = tps                       # the device holds its own copy (set_tps below and in every Evaluate(state))
         self.dist, self.rank, self.world_size = dist, rank, world_size
         self.batch = WalkerBatch(tps.rows(), tps.cols(), tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
@@ -542,6 +633,52 @@ class MCEnergyGradEvaluator:
         self.batch.seed_rng(np.arange(base, base + walkers, dtype=np.uint64).astype(np.uint32))
         self.batch.init_walkers()
         self.warmed_up = mc_params.is_warmed_up
+
+    def EnsureConfigurationValidity(self):
+        """MonteCarloEngine::EnsureConfigurationValidity (monte_carlo_engine.h:340-414), walkers playing the ranks: a
+        walker whose amplitude is NaN / inf / outside (min, max) takes the configuration of the FIRST valid walker (in
+        global walker order over all GPUs) and is re-evaluated; the batch is then marked as not warmed up (walkers run in
+        lock step, so the warm-up sweeps are repeated for all of them). Raises when rescue is disabled or no walker on any
+        GPU is valid. Returns the list of rescued local walkers."""
+        b = self.batch
+        rp = self.config_rescue
+        valid = check_wavefunction_amplitude_validity(b.amplitudes(), rp.amplitude_min_threshold, rp.amplitude_max_threshold)
+        src_cfg, n_valid_global, n_total = None, int(valid.sum()), b.W * self.world_size
+        cfgs = b.get_configs()
+        if self.dist is not None and self.world_size > 1:
+            import torch
+            dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
+            first = int(np.argmax(valid)) if valid.any() else -1
+            mine = torch.tensor([int(valid.sum()), first], dtype=torch.int64, device=dev)
+            allv = [torch.empty_like(mine) for _ in range(self.world_size)]
+            self.dist.all_gather(allv, mine)
+            allv = [t.cpu().numpy() for t in allv]
+            n_valid_global = int(sum(t[0] for t in allv))
+            src_rank = next((r for r, t in enumerate(allv) if t[1] >= 0), -1)
+            if n_valid_global < n_total and src_rank >= 0:
+                buf = torch.from_numpy(cfgs[int(allv[src_rank][1])].astype(np.int32) if self.rank == src_rank
+                                       else np.zeros((b.rows, b.cols), dtype=np.int32)).to(dev)
+                self.dist.broadcast(buf, src=src_rank)
+                src_cfg = buf.cpu().numpy()
+        elif valid.any():
+            src_cfg = cfgs[int(np.argmax(valid))]
+        if n_valid_global == n_total:
+            return []
+        if not rp.enabled:
+            raise PepsError(f"{n_total - n_valid_global}/{n_total} walkers have invalid configurations and configuration rescue is disabled")
+        if n_valid_global == 0 or src_cfg is None:
+            raise PepsError(f"all {n_total} walkers have invalid configurations: check bond dimension, truncation cutoff, initial configuration")
+        bad = np.flatnonzero(~valid)
+        if bad.size:
+            cfgs[bad] = src_cfg
+            b.set_configs(cfgs)
+            b.init_walkers()                   # TryConstructWavefunction_ for the rescued walkers (monte_carlo_engine.h:396)
+            again = check_wavefunction_amplitude_validity(b.amplitudes(), rp.amplitude_min_threshold, rp.amplitude_max_threshold)
+            if not again.all():
+                raise PepsError("rescue FAILED: the valid configuration of another walker is not valid here (TPS or truncation parameter issue)")
+            self.warmed_up = False
+        self.rescued = [int(w) for w in bad]
+        return self.rescued
 
     def WarmUp(self):
         """MonteCarloEngine::WarmUp (monte_carlo_engine.h:146-173)."""
@@ -583,8 +720,20 @@ class MCEnergyGradEvaluator:
         b.sr_collect(collect_sr_buffers)
         energies = np.empty((b.W, n))
         accept = np.zeros(b.W)
+        pc = self.psi_consistency
         for s in range(n):                     # the walker loop (:205-282), all walkers in lock step
-            e, acc = b.sample(self.mc.sweeps_between_samples)
+            if pc.enabled:                     # psi list of the energy solver -> consistency summary (psi_consistency.h)
+                acc = b.sweep(self.mc.sweeps_between_samples)
+                e, psi = b.energy_and_holes(True, True)
+                b.accumulate_ostar()
+                for w in range(b.W):
+                    _, rel = compute_psi_consistency_summary_aligned(psi[:, w])
+                    if rel > pc.threshold and len(self.psi_warnings) < pc.max_warnings:
+                        self.psi_warnings.append((s, w, rel))
+            else:
+                e, acc = b.sample(self.mc.sweeps_between_samples)
+            if not np.all(np.isfinite(e)):     # zero amplitude: std::runtime_error in the reference solver (square_nnn_energy_solver.h:148-150)
+                raise PepsError("local energy is not finite (zero or illegal amplitude): run EnsureConfigurationValidity / WarmUp first")
             energies[:, s] = e
             accept += acc
         all_e = energies

@@ -223,6 +223,17 @@ void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const do
 void be_ratio_accumulate(const double *psi_ex, const double *psi, double coef, double *eloc, int W);
 // eloc[w] += -h00 * (cfg[w][0] - 0.5)
 void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *eloc, int W);
+// ---- table-driven model terms (seam B2 as data: square_nnn_energy_solver.h:171-198 EvaluateBondEnergy) -----------------
+// A term acts on `nsite` (1 or 2) sites with local state index p = c1 (* phys + c2). Tables (device): diag[p] = <p|H|p>;
+// for slot t < T: target[p*T + t] = local state p' with <p'|H|p> != 0 (or -1), coef[p*T + t] = <p'|H|p>.
+// be_term_targets: idx_a[w], idx_b[w] = physical indices of target slot t of walker w's local state (its own state when the
+// slot is empty), coefw[w] = the matrix element (0 when empty). s2 < 0: one-site term.
+void be_term_targets(const int32_t *cfg, int nsites, int s1, int s2, int phys, const int32_t *target, const double *coef, int T,
+                     int t, int32_t *idx_a, int32_t *idx_b, double *coefw, int W);
+// eloc[w] += (diag ? diag[p_w] : 0) + (coefw ? coefw[w] * (psi_ex[w] * (1 / psi[w])) : 0)
+void be_term_accumulate(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag, const double *coefw,
+                        const double *psi_ex, const double *psi, double *eloc, int W);
+
 // O* accumulation (mc_energy_grad_evaluator.h:245-272) for one sample of all walkers:
 //   o = (1/amp[w]) * hole[w][e];  osum[slot(site,cfg[w][site]) + e] += o;  eosum[...] += eloc[w] * o
 // holes: [W][hole_stride]; per site: offset hole_off[site], size site_size[site]; TPS slot of (site, s) at

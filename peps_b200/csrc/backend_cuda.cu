@@ -2511,6 +2511,40 @@ void be_ratio_accumulate(const double *psi_ex, const double *psi, double coef, d
   ratio_accumulate_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(psi_ex, psi, coef, eloc, W);
   post_launch();
 }
+__global__ void term_targets_kernel(const int32_t *cfg, int nsites, int s1, int s2, int phys, const int32_t *target, const double *coef,
+                                    int T, int t, int32_t *idx_a, int32_t *idx_b, double *coefw, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const int32_t *c = cfg + (long)w * nsites;
+  const int c1 = c[s1], c2 = s2 >= 0 ? c[s2] : 0;
+  const int p = s2 >= 0 ? c1 * phys + c2 : c1;
+  const int tg = target[p * T + t];
+  idx_a[w] = tg < 0 ? c1 : (s2 >= 0 ? tg / phys : tg);
+  if (idx_b) idx_b[w] = tg < 0 ? c2 : tg % phys;
+  coefw[w] = tg < 0 ? 0.0 : coef[p * T + t];
+}
+void be_term_targets(const int32_t *cfg, int nsites, int s1, int s2, int phys, const int32_t *target, const double *coef, int T,
+                     int t, int32_t *idx_a, int32_t *idx_b, double *coefw, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  term_targets_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, s1, s2, phys, target, coef, T, t, idx_a, idx_b, coefw, W);
+  post_launch();
+}
+__global__ void term_accumulate_kernel(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag,
+                                       const double *coefw, const double *psi_ex, const double *psi, double *eloc, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const int32_t *c = cfg + (long)w * nsites;
+  const int p = s2 >= 0 ? c[s1] * phys + c[s2] : c[s1];
+  double e = diag ? diag[p] : 0.0;
+  if (coefw && coefw[w] != 0.0) e += coefw[w] * (psi_ex[w] * (1.0 / psi[w]));
+  eloc[w] += e;
+}
+void be_term_accumulate(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag, const double *coefw,
+                        const double *psi_ex, const double *psi, double *eloc, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  term_accumulate_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, s1, s2, phys, diag, coefw, psi_ex, psi, eloc, W);
+  post_launch();
+}
 __global__ void xxz_onsite_kernel(const int32_t *cfg, int nsites, double h00, double *eloc, int W) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w < W) eloc[w] += -h00 * ((double)cfg[(long)w * nsites] - 0.5);

@@ -86,8 +86,9 @@ Engine::~Engine() {
   for (void *p : {(void *)tps_, (void *)osum_, (void *)eosum_, (void *)tps_off_d_, (void *)site_size_d_, (void *)hole_off_d_,
                   (void *)cfg_, (void *)amp_, (void *)mt_, (void *)mtidx_, (void *)accepted_, (void *)eloc_, (void *)psi_tmp_,
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
-                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_})
+                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)psi_list_d_, (void *)term_ia_, (void *)term_ib_, (void *)term_cw_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_})
     be_free(p);
+  for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); }
   pool_.release_all();
   planner_.release_all();
   be_ctx_destroy(bectx_);
@@ -738,24 +739,29 @@ void Engine::shift_bten2_window(int pos, int slice1) { // grow.h:523-527
   grow_bten2_step(opposite(pos), slice1);
 }
 void Engine::nnn_trace(int row1, int col1, int dir, double *psi_out, int orient) {   // trace.h:207-324
-  ++n_trace_;
   const int row2 = row1 + 1, col2 = col1 + 1;
   const int s11 = row1 * cols_ + col1, s21 = row2 * cols_ + col1, s12 = row1 * cols_ + col2, s22 = row2 * cols_ + col2;
   // configuration index each of the four plaquette tensors gathers: the two sites on the diagonal exchange theirs
   int g11 = s11, g21 = s21, g12 = s12, g22 = s22;
   if (dir == 0) { g11 = s22; g22 = s11; } else { g21 = s12; g12 = s21; }
+  nnn_trace_refs(row1, col1, orient, site_ref(s11, g11), site_ref(s21, g21), site_ref(s12, g12), site_ref(s22, g22), psi_out);
+}
+void Engine::nnn_trace_refs(int row1, int col1, int orient, const TRef &t11, const TRef &t21, const TRef &t12, const TRef &t22,
+                            double *psi_out) {
+  ++n_trace_;
+  const int row2 = row1 + 1, col2 = col1 + 1;
   const BT *m1, *m2; int a, b;
   BT half_a, half_b;
   if (orient == HORIZONTAL) {                          // two-row environments LEFT | RIGHT (:218-281)
     bten2_operands(LEFT, row1, col1 + 1, m1, m2, a, b);
-    half_a = bten2_step(bten2_[LEFT].at((size_t)col1), *m1, site_ref(s11, g11), site_ref(s21, g21), *m2, LEFT);
+    half_a = bten2_step(bten2_[LEFT].at((size_t)col1), *m1, t11, t21, *m2, LEFT);
     bten2_operands(RIGHT, row1, cols_ - col2, m1, m2, a, b);
-    half_b = bten2_step(bten2_at_slice(RIGHT, col2), *m1, site_ref(s22, g22), site_ref(s12, g12), *m2, RIGHT);
+    half_b = bten2_step(bten2_at_slice(RIGHT, col2), *m1, t22, t12, *m2, RIGHT);
   } else {                                             // two-column environments UP | DOWN (:282-324)
     bten2_operands(UP, col1, row1 + 1, m1, m2, a, b);
-    half_a = bten2_step(bten2_[UP].at((size_t)row1), *m1, site_ref(s12, g12), site_ref(s11, g11), *m2, UP);
+    half_a = bten2_step(bten2_[UP].at((size_t)row1), *m1, t12, t11, *m2, UP);
     bten2_operands(DOWN, col1, rows_ - row2, m1, m2, a, b);
-    half_b = bten2_step(bten2_at_slice(DOWN, row2), *m1, site_ref(s21, g21), site_ref(s22, g22), *m2, DOWN);
+    half_b = bten2_step(bten2_at_slice(DOWN, row2), *m1, t21, t22, *m2, DOWN);
   }
   reverse_dot(half_a, half_b, psi_out);                // Contract(tmp[3],{0,1,2,3}, tmp[7],{3,2,1,0})
   release(half_a);
@@ -1181,13 +1187,15 @@ void Engine::energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *p
 }
 
 void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  if (tables_on_) { energy_and_holes_tables(calc_holes, eloc_host, psi_list_host); return; }
   if (tfim_) { energy_and_holes_tfim(calc_holes, eloc_host, psi_list_host); return; }
   if (phys_ != 2) throw std::invalid_argument("the XXZ / J1-J2 energy solvers need phys = 2");
   // square_nnn_energy_solver.h:79-315 with has_nnn = false, model = SquareSpinOneHalfXXZModelMixIn
   be_memset0(eloc_, sizeof(double) * W_);
   int npsi = 0;
-  auto record_psi = [&]() {
-    if (psi_list_host) be_d2h(psi_list_host + (size_t)npsi * W_, psi_row_, sizeof(double) * W_);
+  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * W_);
+  auto record_psi = [&]() {                            // kept on the device: ONE download at the end, no sync per row
+    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * W_, psi_row_, sizeof(double) * W_);
     ++npsi;
   };
   generate_bmps_approach(UP);
@@ -1236,6 +1244,112 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
     if (col < cols_ - 1) shift_bmps_window(RIGHT);
   }
   be_xxz_onsite_energy(cfg_, nsites_, h00_, eloc_, W_);
+  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * W_);
+  if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
+}
+
+void Engine::set_model_term(int kind, int T, const double *diag, const int32_t *target, const double *coef) {
+  if (kind < 0 || kind > 2) throw std::invalid_argument("set_model_term: kind must be 0 (NN), 1 (NNN) or 2 (on-site)");
+  if (T < 0 || !diag || (T > 0 && (!target || !coef))) throw std::invalid_argument("set_model_term: null table");
+  const int np = kind == 2 ? phys_ : phys_ * phys_;
+  for (int i = 0; i < np * T; ++i)
+    if (target[i] >= np) throw std::invalid_argument("set_model_term: target state out of range");
+  TermTable &t = term_[kind];
+  be_sync();
+  be_free(t.diag); be_free(t.target); be_free(t.coef);
+  t = TermTable();
+  t.T = T; t.set = true;
+  t.diag = (double *)be_malloc(sizeof(double) * np);
+  be_h2d(t.diag, diag, sizeof(double) * np);
+  if (T > 0) {
+    t.target = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)np * T);
+    t.coef = (double *)be_malloc(sizeof(double) * (size_t)np * T);
+    be_h2d(t.target, target, sizeof(int32_t) * (size_t)np * T);
+    be_h2d(t.coef, coef, sizeof(double) * (size_t)np * T);
+  }
+  if (!term_ia_) {
+    term_ia_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+    term_ib_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+    term_cw_ = (double *)be_malloc(sizeof(double) * W_);
+  }
+  tables_on_ = true;
+}
+void Engine::clear_model_terms() {
+  be_sync();
+  for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); t = TermTable(); }
+  tables_on_ = false;
+}
+// The traversal of SquareNNNModelEnergySolver (square_nnn_energy_solver.h:79-315, bond_traversal_mixin.h:112-143) with every
+// term evaluated from its table: diagonal element + one replacement trace per target slot, masked per walker.
+void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  be_memset0(eloc_, sizeof(double) * W_);
+  int npsi = 0;
+  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * W_);
+  auto record_psi = [&]() {
+    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * W_, psi_row_, sizeof(double) * W_);
+    ++npsi;
+  };
+  const TermTable &nn = term_[0], &nnn = term_[1], &on = term_[2];
+  // one term on (s1, s2): trace(idx_a, idx_b, out) evaluates the amplitude with the replacement physical indices
+  auto term = [&](const TermTable &tt, int s1, int s2, auto &&trace) {
+    if (tt.T == 0) { be_term_accumulate(cfg_, nsites_, s1, s2, phys_, tt.diag, nullptr, nullptr, psi_row_, eloc_, W_); return; }
+    for (int t = 0; t < tt.T; ++t) {
+      be_term_targets(cfg_, nsites_, s1, s2, phys_, tt.target, tt.coef, tt.T, t, term_ia_, s2 >= 0 ? term_ib_ : nullptr, term_cw_, W_);
+      trace(term_ia_, term_ib_, psi_tmp_);
+      be_term_accumulate(cfg_, nsites_, s1, s2, phys_, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_row_, eloc_, W_);
+    }
+  };
+  generate_bmps_approach(UP);
+  for (int row = 0; row < rows_; ++row) {
+    init_bten(LEFT);
+    grow_full_bten(RIGHT, row, 1, true);
+    nn_trace(row, 0, row, 1, HORIZONTAL, row * cols_, row * cols_ + 1, psi_row_);
+    record_psi();
+    for (int col = 0; col < cols_; ++col) {
+      if (calc_holes) punch_hole(row, col, HORIZONTAL);
+      const int s1 = row * cols_ + col;
+      if (on.set) term(on, s1, -1, [&](const int32_t *ia, const int32_t *, double *out) { one_site_trace(row, col, ia, 1, out); });
+      if (col < cols_ - 1) {
+        if (nn.set)
+          term(nn, s1, s1 + 1, [&](const int32_t *ia, const int32_t *ib, double *out) {
+            nn_trace_idx(row, col, row, col + 1, HORIZONTAL, ia, ib, 1, out);
+          });
+        shift_bten_window(RIGHT);
+      }
+    }
+    if (nnn.set && row < rows_ - 1) {                    // square_nnn_energy_solver.h:203-265
+      init_bten2(LEFT);
+      grow_full_bten2(RIGHT, row, 2, true);
+      for (int col = 0; col < cols_ - 1; ++col) {
+        const int s11 = row * cols_ + col, s21 = s11 + cols_, s12 = s11 + 1, s22 = s21 + 1;
+        term(nnn, s11, s22, [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row,col) - (row+1,col+1)
+          nnn_trace_refs(row, col, HORIZONTAL, site_ref_idx(s11, ia, 1), site_ref(s21, s21), site_ref(s12, s12), site_ref_idx(s22, ib, 1), out);
+        });
+        term(nnn, s21, s12, [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row+1,col) - (row,col+1)
+          nnn_trace_refs(row, col, HORIZONTAL, site_ref(s11, s11), site_ref_idx(s21, ia, 1), site_ref_idx(s12, ib, 1), site_ref(s22, s22), out);
+        });
+        shift_bten2_window(RIGHT, row);
+      }
+    }
+    if (row < rows_ - 1) shift_bmps_window(DOWN);
+  }
+  generate_bmps_approach(LEFT);
+  for (int col = 0; col < cols_; ++col) {
+    init_bten(UP);
+    grow_full_bten(DOWN, col, 2, true);
+    nn_trace(0, col, 1, col, VERTICAL, col, cols_ + col, psi_row_);
+    record_psi();
+    for (int row = 0; row < rows_ - 1; ++row) {
+      const int s1 = row * cols_ + col, s2 = s1 + cols_;
+      if (nn.set)
+        term(nn, s1, s2, [&](const int32_t *ia, const int32_t *ib, double *out) {
+          nn_trace_idx(row, col, row + 1, col, VERTICAL, ia, ib, 1, out);
+        });
+      if (row < rows_ - 2) shift_bten_window(DOWN);
+    }
+    if (col < cols_ - 1) shift_bmps_window(RIGHT);
+  }
+  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * W_);
   if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
 }
 

@@ -128,6 +128,13 @@ class Engine {
     tfim_ = true; tfim_h_ = h;
   }
   void set_model_kind_xxz() { tfim_ = false; }
+  // Seam B2 as data: a model given by the matrix elements of its local terms instead of an engine branch (the data a
+  // user's EvaluateBondEnergy / EvaluateNNNEnergy / EvaluateTotalOnsiteEnergy mix-in encodes, square_nnn_energy_solver.h:
+  // 171-198). kind: 0 = NN bonds (both orientations), 1 = NNN (both diagonals), 2 = on-site. Local state p = c1 (* phys +
+  // c2) with site1 the left / upper site (diagonals: the left site of the link). diag[p] = <p|H|p>; slot t < T:
+  // target[p*T+t] = p' (or -1), coef[p*T+t] = <p|H|p'>. Setting any term switches the table-driven solver on.
+  void set_model_term(int kind, int T, const double *diag, const int32_t *target, const double *coef);
+  void clear_model_terms();
 
   // ---- probes used by the parity tests (per-walker values of reference contractor calls)
   int bmps_stack_size(int pos) const { return (int)bmps_[pos].size(); }
@@ -192,6 +199,14 @@ class Engine {
   TRef site_ref(int site, int cfg_site) const;
   TRef site_ref_idx(int site, const int32_t *idx, int stride) const;
   void energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *psi_list_host);
+  void energy_and_holes_tables(bool calc_holes, double *eloc_host, double *psi_list_host);
+  struct TermTable { bool set = false; int T = 0; double *diag = nullptr; int32_t *target = nullptr; double *coef = nullptr; };
+  TermTable term_[3];
+  bool tables_on_ = false;
+  int32_t *term_ia_ = nullptr, *term_ib_ = nullptr;   // [W] replacement physical indices of the current target slot
+  double *term_cw_ = nullptr;                          // [W] matrix element of the current target slot
+  void nnn_trace_refs(int row1, int col1, int orient, const TRef &t11, const TRef &t21, const TRef &t12, const TRef &t22,
+                      double *psi_out);
   // structural-zero hints for contractions with an upper-trapezoidal R factor of the forward chain (backend.h GettDesc)
   struct KHints {
     const int32_t *klo_m = nullptr, *klo_n = nullptr; double work = 1.0;
@@ -261,6 +276,7 @@ class Engine {
   double *eloc_ = nullptr;        // [W]
   double *psi_tmp_ = nullptr;     // [W]
   double *psi_row_ = nullptr;     // [W]
+  double *psi_list_d_ = nullptr;  // [(rows + cols)][W] psi list of the last energy_and_holes (downloaded once)
   double *holes_ = nullptr;       // [W][hole_stride]
   long hole_stride_ = 0;
   std::vector<long> hole_off_h_;

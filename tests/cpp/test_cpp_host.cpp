@@ -34,6 +34,15 @@ int main() {
     for (int i = 0; i < rows * (cols - 1); ++i) sum += obs.bond_energy_h[(size_t)i];
     for (int i = 0; i < (rows - 1) * cols; ++i) sum += obs.bond_energy_v[(size_t)i];
     std::printf("%.17g %.17g\n", e0, sum);
+    // seam B2 as data: the XXZ bond term probed from a reference-style EvaluateBondEnergy functor reproduces the built-in
+    // solver; rescue of an illegal walker is a no-op on legal configurations
+    auto e_builtin = ev.batch().EnergyAndHoles(false);
+    ev.batch().SetModelTerm(peps_b200::XXZBondTerm(0, 1.0, 1.0));
+    auto e_table = ev.batch().EnergyAndHoles(false);
+    ev.batch().ClearModelTerms();
+    double dmax = 0.0;
+    for (size_t w = 0; w < e_builtin.size(); ++w) dmax = std::max(dmax, std::fabs(e_builtin[w] - e_table[w]));
+    std::printf("%.17g %d\n", dmax, (int)ev.batch().EnsureConfigurationValidity().size());
   } catch (const std::exception &e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -143,3 +143,59 @@ def run_plaquette_trace_parity(lib, rows=4, cols=5, D=2, W=3, tol=1e-10):
                     assert abs(psi[w] / ref - 1) < tol, (kind, d, o, w, psi[w], ref)
     b.close()
     return worst
+
+
+def spin_one_matrices(j1=1.0, j2=0.3, dz=0.4, hx=0.2):
+    """Spin-1 test model: J1/J2 Heisenberg bonds, single-ion anisotropy dz (Sz)^2 and a transverse field hx Sx (d = 3)."""
+    sz = np.diag([1.0, 0.0, -1.0])
+    sp = np.zeros((3, 3)); sp[0, 1] = sp[1, 2] = np.sqrt(2.0)
+    sm = sp.T
+    hb = np.kron(sz, sz) + 0.5 * (np.kron(sp, sm) + np.kron(sm, sp))
+    h1 = dz * sz @ sz + hx * 0.5 * (sp + sm)
+    return j1 * hb, j2 * hb, h1
+
+
+def run_table_model_parity(lib, tol=1e-10):
+    """Seam B2 as data: (i) the XXZ / J1-J2 tables reproduce the built-in solver exactly, (ii) the TFIM tables reproduce
+    the built-in TFIM solver, (iii) a spin-1 (phys = 3) J1-J2 model with single-ion anisotropy and a transverse field --
+    a model the engine has no branch for -- matches the oracle's generic restatement of the reference traversal."""
+    from peps_b200.api import TableModel, SquareSpinOneHalfJ1J2XXZModelOBC, TransverseFieldIsingSquareOBC
+    rows, cols, D, W = 3, 4, 2, 3
+    tps = vmc.random_tps(rows, cols, 2, D, seed=21)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 30 + w) for w in range(W)])
+    trunc = (1, 64, 0.0)
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
+    b.set_tps(SplitIndexTPS(tps)); b.set_configs(cfgs); b.init_walkers()
+    b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 0.8, 0.5, 0.35, 0.0))
+    e_builtin, psi_b = b.energy_and_holes(True, True)
+    h_builtin = b.holes()
+    b.set_model(TableModel.xxz(1.0, 0.8, 0.5, 0.35))
+    e_tab, psi_t = b.energy_and_holes(True, True)
+    assert np.array_equal(psi_b, psi_t) and np.array_equal(h_builtin, b.holes())
+    assert np.max(np.abs(e_tab - e_builtin)) < 1e-13 * np.max(np.abs(e_builtin))
+    b.set_model(TransverseFieldIsingSquareOBC(0.7))
+    e_builtin = b.energy_and_holes(False)
+    b.set_model(TableModel.tfim(0.7))
+    e_tab = b.energy_and_holes(False)
+    assert np.max(np.abs(e_tab - e_builtin)) < 1e-12 * np.max(np.abs(e_builtin))
+    b.close()
+    # spin-1
+    h2, h2n, h1 = spin_one_matrices()
+    tps3 = vmc.random_tps(rows, cols, 3, D, seed=22)
+    rng = np.random.default_rng(5)
+    cfg3 = rng.integers(0, 3, size=(W, rows, cols))
+    b3 = WalkerBatch(rows, cols, 3, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
+    b3.set_tps(SplitIndexTPS(tps3)); b3.set_configs(cfg3); b3.init_walkers()
+    b3.set_model(TableModel(3, h2, h2n, h1))
+    e3, psi3 = b3.energy_and_holes(True, True)
+    holes3 = b3.holes()
+    om = vmc.TableModel(3, h2, h2n, h1)
+    worst = 0.0
+    for w in range(W):
+        wk = vmc.Walker(tps3, cfg3[w], trunc)
+        ee, hh, pp = om.energy_and_holes(tps3, wk, True)
+        worst = max(worst, abs(e3[w] - ee) / max(1.0, abs(ee)))
+        assert np.max(np.abs(holes3[w] - flat_holes(hh, rows, cols))) < tol * np.max(np.abs(holes3[w]))
+    assert worst < tol, worst
+    b3.close()
+    return worst

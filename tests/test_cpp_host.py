@@ -28,7 +28,8 @@ def run_cpp_wrapper_case(lib, libdir, libfile, extra_link=()):
         inp = f"3 3 2 2 {W} {chi} {ns} {seed}\n{flat.size}\n" + " ".join(repr(float(x)) for x in flat) + "\n" + \
               " ".join(str(int(c)) for c in cfg.ravel()) + "\n"
         out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
-    e_cpp, err_cpp, gn_cpp, acc_cpp, e2, e_meas, e_bonds = map(float, out)
+    e_cpp, err_cpp, gn_cpp, acc_cpp, e2, e_meas, e_bonds, d_table, n_rescued = map(float, out)
+    assert d_table < 1e-13 and n_rescued == 0
     assert abs(e_meas - e_bonds) < 1e-10 * max(1.0, abs(e_meas))
     mc = MonteCarloParams(num_samples=ns, num_warmup_sweeps=0, sweeps_between_samples=1, initial_config=Configuration(cfg),
                           is_warmed_up=True)

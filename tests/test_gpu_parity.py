@@ -599,3 +599,10 @@ def test_plaquette_traces_gpu(lib):
     the GPU: equal to the oracle amplitude of the exchanged configuration."""
     from parity_common import run_plaquette_trace_parity
     print("plaquette traces worst rel err", run_plaquette_trace_parity(lib))
+
+
+def test_table_model_gpu(lib):
+    """Seam B2 as data on the GPU: XXZ / J1-J2 and TFIM tables reproduce the built-in solvers; a spin-1 model with no
+    engine branch matches the oracle's generic restatement."""
+    from parity_common import run_table_model_parity
+    print("table model worst rel err", run_table_model_parity(lib))

@@ -313,3 +313,94 @@ def test_plaquette_traces_hostsim():
     device ops) against amplitudes of the exchanged configurations evaluated from scratch by the oracle."""
     from parity_common import run_plaquette_trace_parity
     run_plaquette_trace_parity(hostsim_lib.load())
+
+
+def test_configuration_rescue_and_psi_consistency_hostsim():
+    """EnsureConfigurationValidity (monte_carlo_engine.h:340-414) with walkers as ranks: a TPS whose spin-1 slice at
+    site (0,0) is zero makes every configuration with that spin up illegal (amplitude exactly 0); such walkers take the
+    first valid walker's configuration. Psi-consistency summaries (psi_consistency.h:76-130) stay below the threshold
+    for an exact contraction and fire for a strongly truncated one."""
+    from peps_b200.api import (MCEnergyGradEvaluator, MonteCarloParams, SquareSpinOneHalfXXZModelOBC, MCUpdateSquareNNExchange,
+                               ConfigurationRescueParams, PsiConsistencyWarningParams, PepsError, BMPSTruncateParams, SplitIndexTPS,
+                               compute_psi_consistency_summary_aligned, check_wavefunction_amplitude_validity)
+    lib = hostsim_lib.load()
+    tl = vmc.random_tps(3, 3, 2, 2, seed=4)
+    tl[0][0][1] = np.zeros_like(tl[0][0][1])
+    tps = SplitIndexTPS(tl)
+    good = np.array([[0, 1, 0], [1, 0, 1], [0, 1, 1]])       # spin 0 at (0,0): legal
+    bad = np.array([[1, 0, 1], [0, 1, 0], [1, 0, 0]])        # spin 1 at (0,0): amplitude 0
+    cfgs = np.stack([bad, good, bad, good])
+    mc = MonteCarloParams(num_samples=8, num_warmup_sweeps=1, sweeps_between_samples=1, is_warmed_up=True)
+    ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(4, 4, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                               MCUpdateSquareNNExchange(3), walkers=4, configs=cfgs, lib=lib)
+    amp = ev.batch.amplitudes()
+    assert amp[0] == 0.0 and amp[2] == 0.0 and amp[1] != 0.0
+    assert list(check_wavefunction_amplitude_validity(amp, 2.3e-308, 1.7e308)) == [False, True, False, True]
+    assert ev.EnsureConfigurationValidity() == [0, 2]
+    c = ev.batch.get_configs()
+    assert np.array_equal(c[0], good) and np.array_equal(c[2], good) and not ev.warmed_up
+    assert np.all(ev.batch.amplitudes() != 0.0)
+    assert ev.EnsureConfigurationValidity() == []
+    # disabled rescue / nobody valid -> error like the reference's abort
+    ev2 = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(4, 4, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                                MCUpdateSquareNNExchange(3), walkers=2, configs=np.stack([bad, good]), lib=lib,
+                                config_rescue=ConfigurationRescueParams(enabled=False))
+    with pytest.raises(PepsError):
+        ev2.EnsureConfigurationValidity()
+    ev3 = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(4, 4, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                                MCUpdateSquareNNExchange(3), walkers=2, configs=np.stack([bad, bad]), lib=lib)
+    with pytest.raises(PepsError):
+        ev3.EnsureConfigurationValidity()
+    # psi consistency: exact contraction -> no warnings; chi = 1 on a D = 3 state -> closures disagree -> warnings
+    assert compute_psi_consistency_summary_aligned([1.0, -1.0 - 1e-9, 1.0])[1] < 1e-8
+    t2 = SplitIndexTPS(vmc.random_tps(4, 4, 2, 3, seed=9, signed=True))
+    cf = np.stack([vmc.shuffled_half_filled_config(4, 4, 40 + w) for w in range(2)])
+    for chi, expect in ((200, False), (1, True)):
+        e4 = MCEnergyGradEvaluator(MonteCarloParams(4, 0, 1, is_warmed_up=True), BMPSTruncateParams.SVD(1, chi, 0.0), t2,
+                                   SquareSpinOneHalfXXZModelOBC(1, 1, 0), MCUpdateSquareNNExchange(3), walkers=2, configs=cf,
+                                   lib=lib, psi_consistency=PsiConsistencyWarningParams(threshold=1e-6))
+        e4.Evaluate()
+        assert (len(e4.psi_warnings) > 0) == expect
+
+
+def test_table_model_hostsim():
+    from parity_common import run_table_model_parity
+    run_table_model_parity(hostsim_lib.load())
+
+
+def test_oracle_table_model_equals_brute_force():
+    """The oracle's generic TableModel (reference traversal with matrix elements as data) equals
+    E_loc = sum_S' <S|H|S'> psi(S') / psi(S) evaluated term by term from scratch amplitudes (spin-1, d = 3)."""
+    from parity_common import spin_one_matrices
+    rows, cols, d = 2, 3, 3
+    h2, h2n, h1 = spin_one_matrices()
+    tps = vmc.random_tps(rows, cols, d, 2, seed=7)
+    cfg = np.array([[0, 2, 1], [1, 1, 0]])
+    trunc = (1, 1000, 0.0)
+    amp = lambda c: vmc.Walker(tps, c, trunc).amplitude
+    psi = amp(cfg)
+    e, _, _ = vmc.TableModel(d, h2, h2n, h1).energy_and_holes(tps, vmc.Walker(tps, cfg, trunc), False)
+
+    def two(H, s1, s2):
+        p = cfg[s1] * d + cfg[s2]
+        tot = 0.0
+        for q in range(d * d):
+            if H[p, q] != 0.0:
+                c2 = cfg.copy(); c2[s1], c2[s2] = q // d, q % d
+                tot += H[p, q] * amp(c2) / psi
+        return tot
+    ref = 0.0
+    for r in range(rows):
+        for c in range(cols):
+            p = cfg[r, c]
+            for q in range(d):
+                if h1[p, q] != 0.0:
+                    c2 = cfg.copy(); c2[r, c] = q
+                    ref += h1[p, q] * amp(c2) / psi
+            if c < cols - 1:
+                ref += two(h2, (r, c), (r, c + 1))
+            if r < rows - 1:
+                ref += two(h2, (r, c), (r + 1, c))
+            if r < rows - 1 and c < cols - 1:
+                ref += two(h2n, (r, c), (r + 1, c + 1)) + two(h2n, (r + 1, c), (r, c + 1))
+    assert abs(e - ref) < 1e-11 * max(1.0, abs(ref))
