@@ -136,6 +136,14 @@ int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, doubl
  * (rows/2, cols/4): conj(psi(both spins flipped) / psi), 0 for equal spins (registry keys SmSp_row / SpSm_row by the
  * spin at the first site, :264-291). */
 int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr);
+/* StructureFactorMeasurementMixin::MeasureStructureFactor (model_solvers/base/structure_factor_measurement_mixin.h:89-228,
+ * registry key SpSm_cross): all-pairs S+(y1,x1) S-(y2,x2) overlaps with y2 > y1 by "excited state propagation" -- the UP
+ * boundary is forked at row y1 (BMPSContractor::BMPSWalker, bmps/impl/bmps_walker.h), absorbs the row with S+ applied and
+ * is propagated through the rows below; every target is closed against the DOWN stack through LEFT / RIGHT environments.
+ * out[W][pairs], pairs = cols^2 * rows (rows - 1) / 2 in the order (y1, x1, y2, x2), x2 fastest; RAW overlaps like the
+ * reference (divide by the amplitude), 0 where S+ or S- annihilates the walker's configuration. phys must be 2. */
+int64_t peps_structure_factor_pairs(peps_ctx *ctx);
+int peps_measure_structure_factor(peps_ctx *ctx, double *out);
 /* Hole tensors of the last call: [W][stride], per site (L,D,R,U) at the site's hole offset. */
 size_t peps_holes_stride(peps_ctx *ctx);
 int peps_get_holes(peps_ctx *ctx, double *holes);

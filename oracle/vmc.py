@@ -446,6 +446,53 @@ class XXZModel:
         return e + self.onsite_energy(w.config), holes, psi_list
 
 
+def measure_structure_factor(tps, w):
+    """StructureFactorMeasurementMixin::MeasureStructureFactor (model_solvers/base/structure_factor_measurement_mixin.h:
+    89-228), "excited state propagation": for every source (y1, x1) the UP boundary that has absorbed rows 0..y1-1 is
+    forked, absorbs row y1 with S+ applied at x1 (spin-1 slice when the source spin is down), and is propagated through the
+    rows y2 > y1; at each target (y2, x2) with spin up the amplitude with S- applied there is closed against the DOWN
+    stack through LEFT / RIGHT environments (BMPSWalker::InitBTenLeft / TraceWithBTen / GrowBTenRightStep, bmps_walker.h).
+    Returns the list of (y1, x1, y2, x2, value) in the reference's order; values are RAW overlaps (the caller divides by
+    the amplitude), zero where S+ or S- annihilates the configuration."""
+    from .bmps import multiply_mpo, vacuum_bmps, es
+    tn, c = w.tn, w.contractor
+    rows, cols = w.rows, w.cols
+    dmin, dmax, terr = w.trunc
+    c.set_truncate_params(*w.trunc)
+    c.generate_bmps_approach(tn, UP)                 # full DOWN stack
+    down = c.bmps_set[DOWN]
+    main = vacuum_bmps(cols)
+    out = []
+    for y1 in range(rows - 1):
+        for x1 in range(cols):
+            src_down = int(w.config[y1, x1]) == 0
+            row = [tn[y1][x] for x in range(cols)]
+            if src_down:
+                row[x1] = tps[y1][x1][1]
+            exc = multiply_mpo(main, row, UP, dmin, dmax, terr)
+            for y2 in range(y1 + 1, rows):
+                bottom = down[rows - 1 - y2]
+                std = [tn[y2][x] for x in range(cols)]
+                # LEFT environments over the whole row (UP storage is column-reversed: AtLogicalCol)
+                left = [np.ones((1, 1, 1))]
+                for x in range(cols):
+                    left.append(c.bten_step(left[-1], exc[cols - 1 - x], std[x], bottom[x], LEFT))
+                right = np.ones((1, 1, 1))
+                vals = [0.0] * cols
+                for x2 in range(cols - 1, -1, -1):
+                    if src_down and int(w.config[y2, x2]) == 1:
+                        half = c.bten_step(left[x2], exc[cols - 1 - x2], tps[y2][x2][0], bottom[x2], LEFT)
+                        vals[x2] = es("abc,cba->", half, right).item()
+                    if x2 > 0:
+                        right = c.bten_step(right, bottom[x2], std[x2], exc[cols - 1 - x2], RIGHT)
+                for x2 in range(cols):
+                    out.append((y1, x1, y2, x2, vals[x2]))
+                if y2 < rows - 1:
+                    exc = multiply_mpo(exc, std, UP, dmin, dmax, terr)
+        main = multiply_mpo(main, [tn[y1][x] for x in range(cols)], UP, dmin, dmax, terr)
+    return out
+
+
 class TableModel:
     """Generic square-lattice model given by local Hamiltonian matrices, evaluated with the reference's bond traversal
     (square_nnn_energy_solver.h:79-315 + bond_traversal_mixin.h:112-143): what a user-defined `EvaluateBondEnergy /

@@ -62,6 +62,8 @@ SIGNATURES = {
     "peps_set_updater": (C.c_int, [_P, C.c_int32]),
     "peps_set_model_tfim": (C.c_int, [_P, C.c_double]),
     "peps_energy_and_holes": (C.c_int, [_P, C.c_int32, _D, _D]),
+    "peps_structure_factor_pairs": (C.c_int64, [_P]),
+    "peps_measure_structure_factor": (C.c_int, [_P, _D]),
     "peps_holes_stride": (C.c_size_t, [_P]),
     "peps_get_holes": (C.c_int, [_P, _D]),
     "peps_zero_accumulators": (C.c_int, [_P]),

@@ -412,6 +412,16 @@ class WalkerBatch:
                 "SmSp_row": np.where(first_down, 0.0, corr), "SpSm_row": np.where(first_down, corr, 0.0),
                 "SzSz_all2all": flat[:, iu[0]] * flat[:, iu[1]]}
 
+    def measure_structure_factor(self):
+        """MeasureStructureFactor (structure_factor_measurement_mixin.h:89-228): (pairs [n][4] = (y1, x1, y2, x2),
+        values [W][n]) -- raw S+S- overlaps; the registry key SpSm_cross holds value / amplitude."""
+        n = int(self.lib.peps_structure_factor_pairs(self.h))
+        out = np.empty((self.W, n))
+        self._ck(self.lib.peps_measure_structure_factor(self.h, _dp(out)))
+        pairs = np.array([(y1, x1, y2, x2) for y1 in range(self.rows - 1) for x1 in range(self.cols)
+                          for y2 in range(y1 + 1, self.rows) for x2 in range(self.cols)], dtype=np.int32)
+        return pairs, out
+
     def holes(self):
         n = self.lib.peps_holes_stride(self.h)
         a = np.empty((self.W, n))
@@ -511,12 +521,13 @@ class MCPEPSMeasurer:
     """MCPEPSMeasurer (algorithm/vmc_update/monte_carlo_peps_measurer_impl.h:172-257): warm up, then per sample
     `sweeps_between_samples` sweeps + EvaluateObservables; a walker plays the role of a rank: per-walker sample means,
     then mean and standard error across walkers (GatherStatisticListOfData, monte_carlo_tools/statistics.h:288-339).
-    Built keys: energy, spin_z, bond_energy_h / _v / _dr / _ur, SmSp_row / SpSm_row, SzSz_all2all (the structure-factor
-    mixin is not part of this round)."""
+    Built keys: energy, spin_z, bond_energy_h / _v / _dr / _ur, SmSp_row / SpSm_row, SzSz_all2all and, with
+    enable_structure_factor, SpSm_cross (all pairs with y2 > y1; self.sf_pairs lists (y1, x1, y2, x2))."""
 
-    def __init__(self, mc_params, trunc, tps, model, updater, walkers, device=0, lib=None):
+    def __init__(self, mc_params, trunc, tps, model, updater, walkers, device=0, lib=None, enable_structure_factor=False):
         rows, cols = tps.rows(), tps.cols()
         self.mc = mc_params
+        self.enable_structure_factor = enable_structure_factor      # StructureFactorMeasurementMixin::SetEnableStructureFactor
         self.batch = WalkerBatch(rows, cols, tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
         self.batch.set_tps(tps)
         self.batch.set_model(model)
@@ -537,6 +548,9 @@ class MCPEPSMeasurer:
         for _ in range(nper):
             b.sweep(self.mc.sweeps_between_samples)
             obs = b.measure()
+            if self.enable_structure_factor:                         # registry key SpSm_cross: overlap / amplitude
+                self.sf_pairs, raw = b.measure_structure_factor()
+                obs["SpSm_cross"] = raw / b.amplitudes()[:, None]
             if sums is None:
                 sums = {k: np.zeros_like(v, dtype=float) for k, v in obs.items()}
             for k, v in obs.items():

@@ -119,6 +119,8 @@ int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, doubl
 int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr) {
   GUARD(ctx, ctx->eng->measure(energy, e_h, e_v, e_dr, e_ur, row_corr))
 }
+int64_t peps_structure_factor_pairs(peps_ctx *ctx) { return ctx->eng->structure_factor_pairs(); }
+int peps_measure_structure_factor(peps_ctx *ctx, double *out) { GUARD(ctx, ctx->eng->measure_structure_factor(out)) }
 size_t peps_holes_stride(peps_ctx *ctx) { return (size_t)ctx->eng->holes_stride(); }
 int peps_get_holes(peps_ctx *ctx, double *h) { GUARD(ctx, ctx->eng->get_holes(h)) }
 int peps_zero_accumulators(peps_ctx *ctx) { GUARD(ctx, ctx->eng->zero_accumulators()) }

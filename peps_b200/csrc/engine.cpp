@@ -298,7 +298,7 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
   r[0] = ones111();
   for (int i = 0; i < N - 1; ++i) {
     const int site = sites[(size_t)i];
-    TRef sref = site_ref(site, site);
+    TRef sref = tn_site(site);
     const bool tri = r_tri[(size_t)i] != 0;
     const int rk = r[(size_t)i].d[0], re = r[(size_t)i].d[1], ra = r[(size_t)i].d[2];
     const int pd = mps[(size_t)i].d[1], bd = mps[(size_t)i].d[2];
@@ -366,7 +366,7 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
   for (int i = N - 1; i >= 1; --i) {                                                     // bmps_impl.h:853-857
     const int site = sites[(size_t)i];
     BT Y = einsum("apb,fbj->apfj", ref(mps[(size_t)i]), ref(E));
-    BT X = einsum("apfj," + sl + "->eaoj", ref(Y), site_ref(site, site));
+    BT X = einsum("apfj," + sl + "->eaoj", ref(Y), tn_site(site));
     release(Y);
     const int rows = r[(size_t)i].d[0], o = X.d[2], j = X.d[3], cols = o * j;
     BT B;
@@ -401,7 +401,7 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
   {
     const int site = sites[0];
     BT Y = einsum("apb,fbj->apfj", ref(mps[0]), ref(E));
-    BT X = einsum("apfj," + sl + "->eaoj", ref(Y), site_ref(site, site));
+    BT X = einsum("apfj," + sl + "->eaoj", ref(Y), tn_site(site));
     release(Y);
     release(E);
     BT first = X;                   // (e=1, a=1, o, j) viewed as (1, o, j)
@@ -938,14 +938,17 @@ int suwa_todo(int init, std::vector<double> w, HostMT &rng) {
 }
 }  // namespace
 
+void Engine::ensure_idx_const() {
+  if (idx_const_) return;
+  const int d = phys_;
+  idx_const_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)d * W_);
+  std::vector<int32_t> h((size_t)d * W_);
+  for (int s = 0; s < d; ++s) for (int w = 0; w < W_; ++w) h[(size_t)s * W_ + w] = s;
+  be_h2d(idx_const_, h.data(), sizeof(int32_t) * h.size());
+}
 void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
   const int d = phys_, nst = d * d;
-  if (!idx_const_) {
-    idx_const_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)d * W_);
-    std::vector<int32_t> h((size_t)d * W_);
-    for (int s = 0; s < d; ++s) for (int w = 0; w < W_; ++w) h[(size_t)s * W_ + w] = s;
-    be_h2d(idx_const_, h.data(), sizeof(int32_t) * h.size());
-  }
+  ensure_idx_const();
   ensure_psi_alt(nst);
   std::vector<int32_t> cfg((size_t)W_ * nsites_), mtidx((size_t)W_);
   std::vector<uint32_t> mt((size_t)W_ * 624);
@@ -1378,7 +1381,7 @@ void Engine::row_corr_hook(int row) {
     while ((int)bten_[LEFT].size() > c1 + 1) { release(bten_[LEFT].back()); bten_[LEFT].pop_back(); }
     while ((int)bten_[RIGHT].size() > cols_ - c1) { release(bten_[RIGHT].back()); bten_[RIGHT].pop_back(); }
   };
-  override_site_ = s1;
+  override_site_ = s1; override_idx_ = idx_flip_ + s1; override_stride_ = nsites_;
   truncate_left();
   grow_bten_step(LEFT);
   grow_full_bten(RIGHT, row, c1 + 2, false);
@@ -1430,6 +1433,72 @@ void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, dou
       for (int i = 0; i < nb; ++i) e += rec[(size_t)i * W_ + w];
       energy[w] = e + onsite[(size_t)w];
     }
+}
+void Engine::measure_structure_factor(double *out_host) {
+  if (phys_ != 2) throw std::invalid_argument("measure_structure_factor: S+ S- correlators are defined for spin-1/2 (phys = 2)");
+  ensure_idx_const();
+  const int32_t *up_idx = idx_const_ + (size_t)1 * W_, *dn_idx = idx_const_;     // spin-up / spin-down slices for every walker
+  const long npairs = structure_factor_pairs();
+  double *vals = (double *)pool_.get(sizeof(double) * (size_t)npairs * W_);       // [pair][W]
+  be_memset0(vals, sizeof(double) * (size_t)npairs * W_);
+  generate_bmps_approach(UP);                                  // the full DOWN stack (structure_factor...h:118)
+  long pair = 0;
+  for (int y1 = 0; y1 < rows_ - 1; ++y1) {
+    while ((int)bmps_[UP].size() <= y1) grow_bmps_step(UP);    // main_walker.Evolve(row y1 - 1): the UP stack itself
+    const BMPSv &main = bmps_[UP].at((size_t)y1);
+    for (int x1 = 0; x1 < cols_; ++x1) {
+      // excited row: S+ at (y1, x1) = the spin-up slice for every walker (a no-op where the spin is already up; those
+      // walkers' values are masked below like the reference's zeros)
+      override_site_ = y1 * cols_ + x1; override_idx_ = up_idx; override_stride_ = 1;
+      BMPSv exc;
+      try { exc = absorb(main, slice_sites(y1, HORIZONTAL), UP); } catch (...) { override_site_ = -1; pool_.put(vals); throw; }
+      override_site_ = -1;
+      for (int y2 = y1 + 1; y2 < rows_; ++y2) {
+        const BMPSv &bottom = bmps_at_slice(DOWN, y2);
+        std::vector<BT> left;                                  // InitBTenLeft over the whole row (bmps_walker.h)
+        left.push_back(ones111());
+        for (int x = 0; x < cols_; ++x)
+          left.push_back(bten_step(left.back(), exc.at((size_t)(cols_ - 1 - x)), site_ref(y2 * cols_ + x, y2 * cols_ + x), bottom.at((size_t)x), LEFT));
+        BT right = ones111();
+        for (int x2 = cols_ - 1; x2 >= 0; --x2) {
+          const int s2 = y2 * cols_ + x2;
+          BT half = bten_step(left.at((size_t)x2), exc.at((size_t)(cols_ - 1 - x2)), site_ref_idx(s2, dn_idx, 1), bottom.at((size_t)x2), LEFT);
+          reverse_dot(half, right, vals + (size_t)(pair + x2) * W_);             // TraceWithBTen
+          release(half);
+          if (x2 > 0) {                                                           // GrowBTenRightStep
+            BT nr = bten_step(right, bottom.at((size_t)x2), site_ref(s2, s2), exc.at((size_t)(cols_ - 1 - x2)), RIGHT);
+            release(right);
+            right = nr;
+          }
+        }
+        release(right);
+        for (auto &t : left) release(t);
+        pair += cols_;
+        if (y2 < rows_ - 1) {
+          BMPSv nxt = absorb(exc, slice_sites(y2, HORIZONTAL), UP);
+          release(exc);
+          exc = std::move(nxt);
+        }
+      }
+      release(exc);
+    }
+  }
+  // mask on the host: S+ needs a down spin at the source, S- an up spin at the target; transpose to [W][pair]
+  std::vector<double> h((size_t)npairs * W_);
+  std::vector<int32_t> cfg((size_t)W_ * nsites_);
+  be_d2h(h.data(), vals, sizeof(double) * h.size());
+  be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
+  pool_.put(vals);
+  long p = 0;
+  for (int y1 = 0; y1 < rows_ - 1; ++y1)
+    for (int x1 = 0; x1 < cols_; ++x1)
+      for (int y2 = y1 + 1; y2 < rows_; ++y2)
+        for (int x2 = 0; x2 < cols_; ++x2, ++p)
+          for (int w = 0; w < W_; ++w) {
+            const int32_t *c = cfg.data() + (size_t)w * nsites_;
+            const bool ok = c[y1 * cols_ + x1] == 0 && c[y2 * cols_ + x2] == 1;
+            out_host[(size_t)w * npairs + p] = ok ? h[(size_t)p * W_ + w] : 0.0;
+          }
 }
 void Engine::zero_accumulators() {
   be_memset0(osum_, sizeof(double) * tps_total_);

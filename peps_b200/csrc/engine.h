@@ -88,6 +88,11 @@ class Engine {
   // row_corr[W][cols/2]: MeasureSpinOneHalfOffDiagOrderInRow (square_spin_onehalf_xxz_obc.h:22-60) on row rows/2 from
   // site (rows/2, cols/4): conj(psi(both spins flipped) / psi) per distance, 0 where the two spins are equal.
   void measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr);
+  // StructureFactorMeasurementMixin::MeasureStructureFactor (model_solvers/base/structure_factor_measurement_mixin.h:
+  // 89-228): S+(y1,x1) S-(y2,x2) overlaps for all pairs with y2 > y1 by excited-state propagation of the UP boundary.
+  // out[W][npairs], pair order (y1, x1, y2, x2) with x2 fastest; RAW overlaps, 0 where S+ / S- annihilate (spin-1/2 only).
+  long structure_factor_pairs() const { return (long)cols_ * cols_ * (rows_ * (rows_ - 1) / 2); }
+  void measure_structure_factor(double *out_host);
   void zero_accumulators();
   void accumulate_ostar();                            // uses holes/eloc/amplitude of the last energy_and_holes
   void get_accumulators(double *osum_host, double *eosum_host);
@@ -236,8 +241,13 @@ class Engine {
   double jz_ = 1.0, jxy_ = 1.0, h00_ = 0.0, jz2_ = 0.0, jxy2_ = 0.0;
   int updater_ = 0;
   double *bond_rec_ = nullptr;     // [n_h + n_v + 2 n_d + cols/2][W] per-bond energies (+ row correlator) of the last measure()
-  int override_site_ = -1;         // site whose tensor is temporarily replaced by slice idx_flip_ (tn.UpdateSiteTensor)
-  TRef tn_site(int site) const { return site == override_site_ ? site_ref_idx(site, idx_flip_ + site, nsites_) : site_ref(site, site); }
+  int override_site_ = -1;         // site whose tensor is temporarily replaced (tn.UpdateSiteTensor): slice override_idx_[w * override_stride_]
+  const int32_t *override_idx_ = nullptr;
+  int override_stride_ = 0;
+  TRef tn_site(int site) const {
+    return site == override_site_ ? site_ref_idx(site, override_idx_, override_stride_) : site_ref(site, site);
+  }
+  void ensure_idx_const();
   void upload_flipped_configs();
   void row_corr_hook(int row);
   bool rec_bonds_ = false;

@@ -199,3 +199,25 @@ def run_table_model_parity(lib, tol=1e-10):
     assert worst < tol, worst
     b3.close()
     return worst
+
+
+def run_structure_factor_parity(lib, rows=3, cols=4, D=2, W=3, chi=64, tol=1e-10):
+    """peps_measure_structure_factor vs the oracle's restatement of MeasureStructureFactor, pair by pair."""
+    tps = vmc.random_tps(rows, cols, 2, D, seed=17)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 5 + w) for w in range(W)])
+    trunc = (1, chi, 0.0)
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
+    b.set_tps(SplitIndexTPS(tps)); b.set_configs(cfgs); b.init_walkers()
+    pairs, vals = b.measure_structure_factor()
+    worst = 0.0
+    for w in range(W):
+        ref = vmc.measure_structure_factor(tps, vmc.Walker(tps, cfgs[w], trunc))
+        assert len(ref) == len(pairs)
+        scale = max(abs(r[4]) for r in ref)
+        for k, r in enumerate(ref):
+            assert tuple(pairs[k]) == r[:4]
+            assert (r[4] == 0.0) == (vals[w, k] == 0.0)
+            worst = max(worst, abs(vals[w, k] - r[4]) / scale)
+    assert worst < tol, worst
+    b.close()
+    return worst

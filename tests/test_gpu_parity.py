@@ -606,3 +606,10 @@ def test_table_model_gpu(lib):
     engine branch matches the oracle's generic restatement."""
     from parity_common import run_table_model_parity
     print("table model worst rel err", run_table_model_parity(lib))
+
+
+def test_structure_factor_gpu(lib):
+    """MeasureStructureFactor (all-pairs S+S- by excited-state propagation, structure_factor_measurement_mixin.h:89-228)
+    on the GPU against the oracle, with and without truncation of the propagated boundary."""
+    from parity_common import run_structure_factor_parity
+    print("structure factor worst rel err", run_structure_factor_parity(lib), run_structure_factor_parity(lib, 4, 4, 3, 2, chi=5))

@@ -404,3 +404,21 @@ def test_oracle_table_model_equals_brute_force():
             if r < rows - 1 and c < cols - 1:
                 ref += two(h2n, (r, c), (r + 1, c + 1)) + two(h2n, (r + 1, c), (r, c + 1))
     assert abs(e - ref) < 1e-11 * max(1.0, abs(ref))
+
+
+def test_structure_factor_hostsim_and_brute_force():
+    """All-pairs S+S- overlaps: engine (host-simulated device ops) == oracle restatement of MeasureStructureFactor, and
+    the oracle == amplitudes of the doubly flipped configurations evaluated from scratch (exact contraction)."""
+    from parity_common import run_structure_factor_parity
+    run_structure_factor_parity(hostsim_lib.load())
+    rows, cols = 3, 3
+    tps = vmc.random_tps(rows, cols, 2, 2, seed=3)
+    cfg = vmc.shuffled_half_filled_config(rows, cols, 2)
+    trunc = (1, 1000, 0.0)
+    for (y1, x1, y2, x2, v) in vmc.measure_structure_factor(tps, vmc.Walker(tps, cfg, trunc)):
+        if cfg[y1, x1] == 0 and cfg[y2, x2] == 1:
+            c2 = cfg.copy(); c2[y1, x1] = 1; c2[y2, x2] = 0
+            ref = vmc.Walker(tps, c2, trunc).amplitude
+            assert abs(v / ref - 1) < 1e-11
+        else:
+            assert v == 0.0
