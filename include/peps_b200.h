@@ -56,6 +56,12 @@ int peps_set_tps(peps_ctx *ctx, const double *host_tps, size_t n);
 int peps_get_tps(peps_ctx *ctx, double *host_tps, size_t n);
 /* BMPSContractor::SetTruncateParams (two_dim_tn/tensor_network_2d/bmps/bmps_contractor.h:216-230). */
 int peps_set_truncation(peps_ctx *ctx, int32_t dmin, int32_t dmax, double trunc_err);
+/* BMPSTruncateParams::compress_scheme (one_dim_tn/boundary_mps/bmps.h:31-35, 54-97): 0 = SVD_COMPRESS (default),
+ * 1 = VARIATION2Site, 2 = VARIATION1Site (bmps_impl.h:864-1172) with convergence_tol and iter_max; boundaries of two sites
+ * always take the SVD path (:416). The batch sweeps until EVERY walker meets convergence_tol (lock step), and the
+ * orthonormal factors are the kept singular vectors instead of LAPACK's U / Householder Q: the same boundary MPS up to the
+ * gauge of each bond. */
+int peps_set_compress_scheme(peps_ctx *ctx, int32_t scheme, double convergence_tol, int32_t iter_max);
 /* Convergence control of the Jacobi truncation kernel (no reference counterpart: LAPACK gesdd there). */
 int peps_set_jacobi(peps_ctx *ctx, double tol, int32_t inner_sweeps, int32_t max_sweeps);
 /* Rows of the QR-preconditioned Theta below eps * (largest row norm) are dropped before / between Jacobi sweeps

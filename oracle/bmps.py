@@ -110,3 +110,123 @@ def right_canonicalize_truncate(res, site, dmin, dmax, trunc_err):
     us = u[:, :t] * s[:t]
     res[site - 1] = es("aok,kt->aot", res[site - 1], us)
     return t, err
+
+
+# ---- variational compression (bmps_impl.h:864-1260) -------------------------------------------------------------------
+def compress_mps(mps, dmin, dmax, trunc_err):
+    """The bond-dimension reduction inside MakeVariationalInitGuess_ (bmps_impl.h:1197-1201): Centralize(N-1)
+    (LeftCanonicalize by QR, :119-170), then RightCanonicalizeTruncate(i, dmin, dmax, trunc_err) for i = N-1 .. 1."""
+    res = [np.array(t) for t in mps]
+    n = len(res)
+    for i in range(n - 1):
+        a, p, b = res[i].shape
+        q, r = np.linalg.qr(res[i].reshape(a * p, b), mode="reduced")
+        res[i] = q.reshape(a, p, q.shape[1])
+        res[i + 1] = es("kb,bqc->kqc", r, res[i + 1])
+    for i in range(n - 1, 0, -1):
+        right_canonicalize_truncate(res, i, dmin, dmax, trunc_err)
+    return res
+
+
+def _two_site_theta(lenv, renv, mps_i, mps_j, m_i, m_j):
+    """tmp[1], tmp[3], tmp[4] of the two-site update (bmps_impl.h:893-898): L2[k,o,f,b], R2[f,b,u,j], theta[k,o,u,j]."""
+    l2 = es("kepb,epfo->kofb", es("kea,apb->kepb", lenv, mps_i), m_i)
+    r2 = es("bqgj,fqgu->fbuj", es("bqc,cgj->bqgj", mps_j, renv), m_j)
+    return l2, r2, es("kofb,fbuj->kouj", l2, r2)
+
+
+def _svd_trunc(theta, dmin, dmax, trunc_err):
+    k, o, u, j = theta.shape
+    uu, sv, vt = np.linalg.svd(theta.reshape(k * o, u * j), full_matrices=False)
+    t = truncation_dim(sv, dmin, dmax, trunc_err)
+    return uu[:, :t].reshape(k, o, t), sv[:t], vt[:t].reshape(t, u, j)
+
+
+def multiply_mpo_variational(mps, mpo_sites, post, dmin, dmax, trunc_err, tol, max_iter, one_site=False):
+    """BMPS::MultiplyMPO with VARIATION2Site / VARIATION1Site (bmps_impl.h:404-437 -> 864-995 / 997-1172).
+    Init guess (:1176-1212): the MPS reduced to bond dimension <= 2, multiplied by the MPO with SVD compression.
+    lenv[k, e, a] / renv[c, g, j]: (result bond, MPO bond, MPS bond) / (MPS bond, MPO bond, result bond) (:703-729)."""
+    n = len(mps)
+    if n == 2:
+        return multiply_mpo(mps, mpo_sites, post, dmin, dmax, trunc_err)
+    mpo = list(mpo_sites)
+    if post in (RIGHT, UP):
+        mpo = mpo[::-1]
+    perm = mpo_perm(post)
+    m = [np.transpose(t, perm) for t in mpo]                # m[e, p, f, o]
+    small = compress_mps(mps, 1, 2, 0.0)
+    if one_site:
+        res = multiply_mpo(small, mpo_sites, post, dmax, dmax, 0.0)
+    else:
+        res = multiply_mpo(small, mpo_sites, post, dmin, dmax, trunc_err)
+    lenvs = [np.ones((1, 1, 1))]
+    renvs = [np.ones((1, 1, 1))]
+    for i in range(n - 1, 1, -1):                            # GrowRightEnvironments_ (:731-743)
+        r1 = es("bqc,cgj->bqgj", mps[i], renvs[-1])
+        renvs.append(es("fbuj,tuj->bft", es("bqgj,fqgu->fbuj", r1, m[i]), res[i]))
+
+    def sweep_two_site(d0, d1):
+        s_last = None
+        for i in range(n - 2):                               # towards larger i: res[i] = U (:891-918)
+            l2, r2, th = _two_site_theta(lenvs[-1], renvs[-1], mps[i], mps[i + 1], m[i], m[i + 1])
+            u, s_last, vt = _svd_trunc(th, d0, d1, trunc_err)
+            res[i] = u
+            lenvs.append(es("kofb,kot->tfb", l2, u))
+            renvs.pop()
+        for i in range(n - 2, 0, -1):                        # back: res[i+1] = Vt (:920-947)
+            l2, r2, th = _two_site_theta(lenvs[-1], renvs[-1], mps[i], mps[i + 1], m[i], m[i + 1])
+            u, s_last, vt = _svd_trunc(th, d0, d1, trunc_err)
+            res[i + 1] = vt
+            renvs.append(es("fbuj,tuj->bft", r2, vt))
+            lenvs.pop()
+        return s_last
+
+    if not one_site:
+        s_prev = None
+        for it in range(max_iter):
+            s = sweep_two_site(dmin, dmax)
+            if it == 0 or s_prev is None or len(s) != len(s_prev):
+                s_prev = s
+                continue
+            if float(np.sum(np.abs(s - s_prev))) / s[0] < tol:
+                break
+            s_prev = s
+        l2, r2, th = _two_site_theta(lenvs[-1], renvs[-1], mps[0], mps[1], m[0], m[1])
+        u, s, vt = _svd_trunc(th, dmin, dmax, trunc_err)
+        res[0] = u * s
+        res[1] = vt
+        return res
+    # one-site scheme: one two-site sweep at D_min = D_max to fix the bond dimensions (:1021-1085), then QR sweeps
+    sweep_two_site(dmax, dmax)
+    l2, r2, th = _two_site_theta(lenvs[-1], renvs[-1], mps[0], mps[1], m[0], m[1])
+    u, s, vt = _svd_trunc(th, dmin, dmax, trunc_err)
+    res[0] = u * s
+    res[1] = vt
+    renvs.append(es("fbuj,tuj->bft", r2, vt))                # :1108-1110
+    last = 0.0
+    for it in range(max_iter):
+        for i in range(n - 1):                               # :1116-1131
+            l2 = es("kepb,epfo->kofb", es("kea,apb->kepb", lenvs[-1], mps[i]), m[i])
+            a = es("kofb,bft->kot", l2, renvs[-1])
+            k, o, t = a.shape
+            q, _ = np.linalg.qr(a.reshape(k * o, t), mode="reduced")
+            res[i] = q.reshape(k, o, q.shape[1])
+            lenvs.append(es("kofb,kot->tfb", l2, res[i]))
+            renvs.pop()
+        r_norm = 0.0
+        for i in range(n - 1, 0, -1):                        # :1133-1151
+            r2 = es("bqgj,fqgu->fbuj", es("bqc,cgj->bqgj", mps[i], renvs[-1]), m[i])
+            a = es("fbuj,kfb->ujk", r2, lenvs[-1])           # Contract(tmp+1,{3,1}, lenv,{1,2}) -> (u, j, k)
+            u_, j_, k_ = a.shape
+            q, r = np.linalg.qr(a.reshape(u_ * j_, k_), mode="reduced")
+            res[i] = np.transpose(q.reshape(u_, j_, q.shape[1]), (2, 0, 1))
+            renvs.append(es("fbuj,tuj->bft", r2, res[i]))
+            lenvs.pop()
+            r_norm = float(np.linalg.norm(r))
+        if it == 0 or abs(r_norm - last) / abs(r_norm) > tol:
+            last = r_norm
+            continue
+        break
+    l2 = es("kepb,epfo->kofb", es("kea,apb->kepb", lenvs[-1], mps[0]), m[0])
+    res[0] = es("kofb,bft->kot", l2, renvs[-1])               # :1161-1166
+    return res

@@ -30,6 +30,10 @@ class BMPSContractor:
         self.n_multiply = 0          # instrumentation: number of MultiplyMPO calls
 
     # ---- parameters (bmps_contractor.h:216-230)
+    def set_compress_scheme(self, scheme, tol=1e-12, max_iter=10):
+        """BMPSTruncateParams::Variational2Site / Variational1Site (bmps.h:81-97): 0 SVD, 1 two-site, 2 one-site."""
+        self.scheme, self.var_tol, self.var_iter = scheme, tol, max_iter
+
     def set_truncate_params(self, dmin, dmax, trunc_err):
         self.trunc = (int(dmin), int(dmax), float(trunc_err))
 
@@ -71,7 +75,12 @@ class BMPSContractor:
     def _grow_with_mpo(self, pos, mpo):
         dmin, dmax, terr = self.trunc
         stack = self.bmps_set[pos]
-        stack.append(multiply_mpo(stack[-1], mpo, pos, dmin, dmax, terr))
+        if getattr(self, "scheme", 0) == 0:
+            stack.append(multiply_mpo(stack[-1], mpo, pos, dmin, dmax, terr))
+        else:                                                # CompressMPSScheme::VARIATION2Site (1) / VARIATION1Site (2)
+            from .bmps import multiply_mpo_variational
+            stack.append(multiply_mpo_variational(stack[-1], mpo, pos, dmin, dmax, terr, self.var_tol, self.var_iter,
+                                                  one_site=self.scheme == 2))
         self.n_multiply += 1
         return len(stack)
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     "peps_set_tps": (C.c_int, [_P, _D, C.c_size_t]),
     "peps_get_tps": (C.c_int, [_P, _D, C.c_size_t]),
     "peps_set_truncation": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_double]),
+    "peps_set_compress_scheme": (C.c_int, [_P, C.c_int32, C.c_double, C.c_int32]),
     "peps_set_jacobi": (C.c_int, [_P, C.c_double, C.c_int32, C.c_int32]),
     "peps_set_deflation": (C.c_int, [_P, C.c_double]),
     "peps_set_model_xxz": (C.c_int, [_P, C.c_double, C.c_double, C.c_double]),

@@ -48,10 +48,21 @@ class BMPSTruncateParams:
     D_min: int = 1
     D_max: int = 2 ** 31 - 1
     trunc_err: float = 0.0
+    compress_scheme: int = 0            # CompressMPSScheme: 0 SVD_COMPRESS, 1 VARIATION2Site, 2 VARIATION1Site
+    convergence_tol: float = 0.0
+    iter_max: int = 1
 
     @staticmethod
     def SVD(d_min, d_max, trunc_error):
         return BMPSTruncateParams(int(d_min), int(d_max), float(trunc_error))
+
+    @staticmethod
+    def Variational2Site(d_min, d_max, trunc_error, convergence_tol, iter_max):
+        return BMPSTruncateParams(int(d_min), int(d_max), float(trunc_error), 1, float(convergence_tol), int(iter_max))
+
+    @staticmethod
+    def Variational1Site(d_min, d_max, trunc_error, convergence_tol, iter_max):
+        return BMPSTruncateParams(int(d_min), int(d_max), float(trunc_error), 2, float(convergence_tol), int(iter_max))
 
 
 class Configuration:
@@ -280,6 +291,8 @@ class WalkerBatch:
             raise PepsError(self.lib.peps_last_error(None).decode())
         self.h = h
         self.tps_size = self.lib.peps_tps_size(self.h)
+        if trunc.compress_scheme != 0:
+            self._ck(self.lib.peps_set_compress_scheme(self.h, trunc.compress_scheme, trunc.convergence_tol, trunc.iter_max))
 
     def close(self):
         if getattr(self, "h", None):
@@ -310,6 +323,7 @@ class WalkerBatch:
 
     def set_truncation(self, trunc):
         self._ck(self.lib.peps_set_truncation(self.h, trunc.D_min, trunc.D_max, trunc.trunc_err))
+        self._ck(self.lib.peps_set_compress_scheme(self.h, trunc.compress_scheme, trunc.convergence_tol, max(1, trunc.iter_max)))
 
     def set_jacobi(self, tol=1e-14, inner_sweeps=1, max_sweeps=40):
         self._ck(self.lib.peps_set_jacobi(self.h, tol, inner_sweeps, max_sweeps))

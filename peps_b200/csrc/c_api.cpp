@@ -70,6 +70,7 @@ int peps_get_tps(peps_ctx *ctx, double *h, size_t n) {
 int peps_set_truncation(peps_ctx *ctx, int32_t dmin, int32_t dmax, double terr) {
   GUARD(ctx, { if (dmin < 1 || dmax < dmin) throw std::invalid_argument("peps_set_truncation: need 1 <= dmin <= dmax"); ctx->eng->set_truncation(dmin, dmax, terr); })
 }
+int peps_set_compress_scheme(peps_ctx *ctx, int32_t scheme, double tol, int32_t max_iter) { GUARD(ctx, ctx->eng->set_compress_scheme(scheme, tol, max_iter)) }
 int peps_set_jacobi(peps_ctx *ctx, double tol, int32_t inner, int32_t maxs) { GUARD(ctx, ctx->eng->set_jacobi(tol, inner, maxs)) }
 int peps_set_deflation(peps_ctx *ctx, double eps) { GUARD(ctx, { if (eps < 0) throw std::invalid_argument("peps_set_deflation: eps < 0"); ctx->eng->set_deflation(eps); }) }
 int peps_set_chain_deflation(peps_ctx *ctx, double eps) { GUARD(ctx, { if (eps < 0) throw std::invalid_argument("peps_set_chain_deflation: eps < 0"); ctx->eng->set_chain_deflation(eps); }) }

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 
 namespace peps {
 
@@ -284,6 +285,11 @@ std::vector<int> Engine::slice_sites(int num, int orient) const {
 // In exact arithmetic both give the same truncated MPS up to the gauge of each kept subspace.
 // ---------------------------------------------------------------------------------------------------
 Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in, int post) {
+  // BMPS::MultiplyMPO (bmps_impl.h:404-437): N == 2 always takes the SVD path
+  if (scheme_ != 0 && mps.size() > 2) return absorb_variational(mps, sites_in, post, scheme_ == 2);
+  return absorb_svd(mps, sites_in, post);
+}
+Engine::BMPSv Engine::absorb_svd(const BMPSv &mps, const std::vector<int> &sites_in, int post) {
   ++n_absorb_;
   const int N = (int)mps.size();
   std::vector<int> sites(sites_in);
@@ -411,6 +417,206 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
   }
   for (auto &t : r) release(t);
   for (int32_t *c : r_cnt) if (c) pool_.put(c);
+  return res;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// variational compression: BMPS::MultiplyMPO2SiteVariationalCompress_ / 1Site (bmps_impl.h:864-995 / 997-1172)
+// ---------------------------------------------------------------------------------------------------
+// kept right singular vectors of theta[w] (rows x cols matrix view of a batched tensor): B (tcap, cols)
+BT Engine::truncated_right_vectors(const BT &theta, int rows, int cols, int dmin, int dmax, double terr) {
+  const int tcap = std::min(dmax, std::min(rows, cols));
+  BT B = alloc({tcap, cols});
+  if (rows >= cols && cols <= dmin) { be_set_identity(B.p, B.n, cols, cols, W_); return B; }
+  const int brows = truncate_buffer_rows(rows, cols);
+  double *G = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows * cols);
+  if (brows > rows) be_memset0(G, sizeof(double) * (size_t)W_ * brows * cols);
+  be_copy2d(G, (long)brows * cols, cols, theta.p, theta.n, cols, rows, cols, W_);
+  truncate_rows(la_, G, (long)brows * cols, rows, cols, dmin, dmax, terr, tcap, B.p, B.n, kept_, nullptr, nullptr);
+  pool_.put(G);
+  return B;
+}
+// The bond-dimension reduction of MakeVariationalInitGuess_ (bmps_impl.h:1197-1201: Centralize(N-1) + RightCanonicalize-
+// Truncate(i, dmin, dmax, terr) for i = N-1..1), restated like absorb_svd: forward R chain, backward truncation.
+Engine::BMPSv Engine::compress_mps(const BMPSv &mps, int dmin, int dmax, double terr) {
+  const int N = (int)mps.size();
+  std::vector<BT> r((size_t)N);
+  r[0] = alloc({1, 1});
+  be_fill(r[0].p, 1.0, W_);
+  for (int i = 0; i < N - 1; ++i) {
+    const int k = r[(size_t)i].d[0], p = mps[(size_t)i].d[1], b = mps[(size_t)i].d[2], m = k * p, kk = std::min(m, b);
+    QRLayout L = qr_layout(m, b);
+    const long wsA = (long)L.m_pad * b;
+    double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
+    if (L.m_pad > m) be_memset0(A, sizeof(double) * (size_t)W_ * wsA);
+    einsum_into("ka,apb->kpb", ref(r[(size_t)i]), ref(mps[(size_t)i]), mkop(A, wsA));
+    caqr(la_, A, wsA, m, b, L);
+    r[(size_t)i + 1] = alloc({kk, b});
+    be_copy2d(r[(size_t)i + 1].p, (long)kk * b, b, A, wsA, b, kk, b, W_);
+    pool_.put(A);
+  }
+  BMPSv res((size_t)N);
+  BT E = alloc({1, 1});
+  be_fill(E.p, 1.0, W_);
+  for (int i = N - 1; i >= 1; --i) {
+    BT X = einsum("apb,bj->apj", ref(mps[(size_t)i]), ref(E));
+    BT Th = einsum("ka,apj->kpj", ref(r[(size_t)i]), ref(X));
+    BT B2 = truncated_right_vectors(Th, Th.d[0], Th.d[1] * Th.d[2], dmin, dmax, terr);
+    release(Th);
+    BT B = B2; B.rank = 3; B.d[0] = B2.d[0]; B.d[1] = X.d[1]; B.d[2] = X.d[2];
+    BT En = einsum("apj,tpj->at", ref(X), ref(B));
+    release(X); release(E);
+    E = En;
+    res[(size_t)i] = B;
+  }
+  res[0] = einsum("apb,bj->apj", ref(mps[0]), ref(E));
+  release(E);
+  for (auto &t : r) release(t);
+  return res;
+}
+Engine::BMPSv Engine::absorb_variational(const BMPSv &mps, const std::vector<int> &sites_in, int post, bool one_site) {
+  const int N = (int)mps.size();
+  std::vector<int> sites(sites_in);
+  if (post == RIGHT || post == UP) std::reverse(sites.begin(), sites.end());
+  const std::string sli = site_labels(post, 'e', 'p', 'f', 'o'), slj = site_labels(post, 'f', 'q', 'g', 'u');
+  // initial guess (:1176-1212): the boundary reduced to bond dimension <= 2, multiplied with SVD compression
+  BMPSv small = compress_mps(mps, 1, 2, 0.0);
+  const int dmin0 = dmin_, dmax0 = dmax_; const double terr0 = terr_;
+  if (one_site) { dmin_ = dmax_; terr_ = 0.0; }
+  BMPSv res = absorb_svd(small, sites_in, post);
+  dmin_ = dmin0; dmax_ = dmax0; terr_ = terr0;
+  release(small);
+  std::vector<BT> lenvs, renvs;
+  lenvs.push_back(ones111());
+  renvs.push_back(ones111());
+  auto right2 = [&](int j, const BT &renv) {              // R2[f,b,u,j] = mps_j . renv . site_j   (:896-897)
+    BT r1 = einsum("bqc,cgj->bqgj", ref(mps[(size_t)j]), ref(renv));
+    BT r2 = einsum("bqgj," + slj + "->fbuj", ref(r1), tn_site(sites[(size_t)j]));
+    release(r1);
+    return r2;
+  };
+  auto left2 = [&](int i2, const BT &lenv) {              // L2[k,o,f,b] = lenv . mps_i . site_i    (:893-894)
+    BT l1 = einsum("kea,apb->kepb", ref(lenv), ref(mps[(size_t)i2]));
+    BT l2 = einsum("kepb," + sli + "->kofb", ref(l1), tn_site(sites[(size_t)i2]));
+    release(l1);
+    return l2;
+  };
+  for (int i = N - 1; i > 1; --i) {                       // GrowRightEnvironments_ (:731-743)
+    BT r2 = right2(i, renvs.back());
+    renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(res[(size_t)i])));
+    release(r2);
+  }
+  // one two-site sweep; returns the batch maximum of sum |s - s_last| / s_0 over the last bond when `track`
+  std::vector<double> s_last;                             // [W][t] singular values of the last bond of the previous sweep
+  int s_last_t = -1;
+  auto sweep_two_site = [&](int d0, int d1, bool track) -> double {
+    for (int i = 0; i < N - 2; ++i) {                     // res[i] = U (:891-918)
+      BT l2 = left2(i, lenvs.back()), r2 = right2(i + 1, renvs.back());
+      BT thT = einsum("kofb,fbuj->ujko", ref(l2), ref(r2));
+      BT U = truncated_right_vectors(thT, thT.d[0] * thT.d[1], thT.d[2] * thT.d[3], d0, d1, terr_);
+      BT Ut = U; Ut.rank = 3; Ut.d[0] = U.d[0]; Ut.d[1] = l2.d[0]; Ut.d[2] = l2.d[1];     // (t, k, o)
+      lenvs.push_back(einsum("kofb,tko->tfb", ref(l2), ref(Ut)));
+      release(thT); release(l2); release(r2); release(U);
+      release(renvs.back()); renvs.pop_back();
+    }
+    double diff = 0.0;
+    for (int i = N - 2; i > 0; --i) {                     // res[i+1] = Vt (:920-947)
+      BT l2 = left2(i, lenvs.back()), r2 = right2(i + 1, renvs.back());
+      BT th = einsum("kofb,fbuj->kouj", ref(l2), ref(r2));
+      BT V = truncated_right_vectors(th, th.d[0] * th.d[1], th.d[2] * th.d[3], d0, d1, terr_);
+      BT Vt = V; Vt.rank = 3; Vt.d[0] = V.d[0]; Vt.d[1] = r2.d[2]; Vt.d[2] = r2.d[3];      // (t, u, j)
+      if (track && i == 1) {                              // singular values of this bond: column norms of theta V^T
+        BT us = einsum("kouj,tuj->tko", ref(th), ref(Vt));
+        const int t = us.d[0], nc = us.d[1] * us.d[2];
+        double *n2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * t);
+        be_row_norms2(us.p, us.n, nc, t, nc, n2, W_);
+        std::vector<double> h((size_t)W_ * t);
+        be_d2h(h.data(), n2, sizeof(double) * h.size());
+        pool_.put(n2); release(us);
+        for (auto &x : h) x = std::sqrt(x);
+        if (s_last_t == t) {
+          for (int w = 0; w < W_; ++w) {
+            double d = 0.0;
+            for (int q = 0; q < t; ++q) d += std::fabs(h[(size_t)w * t + q] - s_last[(size_t)w * t + q]);
+            diff = std::max(diff, d / h[(size_t)w * t]);
+          }
+        } else {
+          diff = std::numeric_limits<double>::infinity();
+        }
+        s_last = h; s_last_t = t;
+      }
+      release(res[(size_t)i + 1]);
+      res[(size_t)i + 1] = Vt;
+      renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Vt)));
+      release(th); release(l2); release(r2);
+      release(lenvs.back()); lenvs.pop_back();
+    }
+    return diff;
+  };
+  auto finish_two_site = [&](bool keep_renv) {            // sites 0, 1: res[0] = U S, res[1] = Vt (:963-988)
+    BT l2 = left2(0, lenvs.back()), r2 = right2(1, renvs.back());
+    BT th = einsum("kofb,fbuj->kouj", ref(l2), ref(r2));
+    BT V = truncated_right_vectors(th, th.d[0] * th.d[1], th.d[2] * th.d[3], dmin_, dmax_, terr_);
+    BT Vt = V; Vt.rank = 3; Vt.d[0] = V.d[0]; Vt.d[1] = r2.d[2]; Vt.d[2] = r2.d[3];
+    release(res[0]); release(res[1]);
+    res[0] = einsum("kouj,tuj->kot", ref(th), ref(Vt));
+    res[1] = Vt;
+    if (keep_renv) renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Vt)));       // :1108-1110
+    release(th); release(l2); release(r2);
+  };
+  if (!one_site) {
+    for (int it = 0; it < var_iter_; ++it) {
+      const double diff = sweep_two_site(dmin_, dmax_, true);
+      if (it > 0 && diff < var_tol_) break;              // every walker converged (:949-960)
+    }
+    finish_two_site(false);
+  } else {
+    sweep_two_site(dmax_, dmax_, false);                  // fixes the bond dimensions at D_max (:1021-1085)
+    finish_two_site(true);
+    double last = 0.0;
+    for (int it = 0; it < var_iter_; ++it) {
+      for (int i = 0; i < N - 1; ++i) {                   // res[i] = Q of (L2 . renv) (:1116-1131); any orthonormal basis of
+        BT l2 = left2(i, lenvs.back());                   // the same column space is the same MPS up to the bond gauge
+        BT aT = einsum("kofb,bft->tko", ref(l2), ref(renvs.back()));
+        const int t = aT.d[0], nc = aT.d[1] * aT.d[2];
+        BT Q = truncated_right_vectors(aT, t, nc, std::min(t, nc), std::min(t, nc), 0.0);
+        BT Qt = Q; Qt.rank = 3; Qt.d[0] = Q.d[0]; Qt.d[1] = l2.d[0]; Qt.d[2] = l2.d[1];  // (t', k, o)
+        lenvs.push_back(einsum("kofb,tko->tfb", ref(l2), ref(Qt)));
+        release(aT); release(l2); release(Q);
+        release(renvs.back()); renvs.pop_back();
+      }
+      double r_norm = 0.0;
+      for (int i = N - 1; i > 0; --i) {                   // :1133-1151
+        BT r2 = right2(i, renvs.back());
+        BT a = einsum("fbuj,kfb->kuj", ref(r2), ref(lenvs.back()));
+        const int k = a.d[0], nc = a.d[1] * a.d[2];
+        if (i == 1) {                                     // r.Get2Norm() of the last QR = |a|_F, batch maximum of the change
+          double *n2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * k);
+          be_row_norms2(a.p, a.n, nc, k, nc, n2, W_);
+          std::vector<double> h((size_t)W_ * k);
+          be_d2h(h.data(), n2, sizeof(double) * h.size());
+          pool_.put(n2);
+          for (int w = 0; w < W_; ++w) { double s2 = 0; for (int q = 0; q < k; ++q) s2 += h[(size_t)w * k + q]; r_norm = std::max(r_norm, std::sqrt(s2)); }
+        }
+        BT Q = truncated_right_vectors(a, k, nc, std::min(k, nc), std::min(k, nc), 0.0);
+        BT Qt = Q; Qt.rank = 3; Qt.d[0] = Q.d[0]; Qt.d[1] = r2.d[2]; Qt.d[2] = r2.d[3];     // (t, u, j)
+        release(res[(size_t)i]);
+        res[(size_t)i] = Qt;
+        renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Qt)));
+        release(a); release(r2);
+        release(lenvs.back()); lenvs.pop_back();
+      }
+      if (it > 0 && std::fabs(r_norm - last) / std::fabs(r_norm) <= var_tol_) break;
+      last = r_norm;
+    }
+    BT l2 = left2(0, lenvs.back());                       // :1161-1166
+    release(res[0]);
+    res[0] = einsum("kofb,bft->kot", ref(l2), ref(renvs.back()));
+    release(l2);
+  }
+  for (auto &t : lenvs) release(t);
+  for (auto &t : renvs) release(t);
+  ++n_absorb_;
   return res;
 }
 

@@ -58,6 +58,12 @@ class Engine {
   void get_rng_state(uint32_t *mt, int32_t *idx);
   void get_amplitudes(double *host);
   void set_truncation(int dmin, int dmax, double terr) { dmin_ = dmin; dmax_ = dmax; terr_ = terr; touch_all(); }
+  // BMPSTruncateParams::Variational2Site / Variational1Site (one_dim_tn/boundary_mps/bmps.h:81-97): scheme 0 = SVD
+  // compression, 1 = two-site, 2 = one-site variational; the batch iterates until EVERY walker meets convergence_tol
+  void set_compress_scheme(int scheme, double tol, int max_iter) {
+    if (scheme < 0 || scheme > 2 || max_iter < 1) throw std::invalid_argument("set_compress_scheme: scheme in {0,1,2}, max_iter >= 1");
+    scheme_ = scheme; var_tol_ = tol; var_iter_ = max_iter; touch_all();
+  }
   void set_jacobi(double tol, int inner, int max_sweeps) {
     la_.jacobi_tol = tol; la_.jacobi_inner_sweeps = inner; la_.jacobi_max_sweeps = max_sweeps; touch_all();
   }
@@ -223,6 +229,14 @@ class Engine {
   void einsum_into(const std::string &spec, const TRef &a, const TRef &b, Operand c, const long *sc = nullptr,
                    double alpha = 1.0, double beta = 0.0, const KHints *h = nullptr);
   BMPSv absorb(const BMPSv &mps, const std::vector<int> &sites, int post);
+  // variational compression (bmps_impl.h:864-1260)
+  BMPSv absorb_svd(const BMPSv &mps, const std::vector<int> &sites, int post);
+  BMPSv absorb_variational(const BMPSv &mps, const std::vector<int> &sites, int post, bool one_site);
+  BMPSv compress_mps(const BMPSv &mps, int dmin, int dmax, double terr);
+  BT truncated_right_vectors(const BT &theta, int rows, int cols, int dmin, int dmax, double terr);
+  int scheme_ = 0;                 // CompressMPSScheme: 0 SVD_COMPRESS, 1 VARIATION2Site, 2 VARIATION1Site
+  double var_tol_ = 1e-12;
+  int var_iter_ = 10;
   BT bten_step(const BT &bten, const BT &mps1, const TRef &site, const BT &mps2, int post);
   BT bten2_step(const BT &bten2, const BT &mps1, const TRef &site1, const TRef &site2, const BT &mps2, int post);
   void bten2_operands(int post, int slice1, int bten_size, const BT *&mps1, const BT *&mps2, int &site1, int &site2) const;

@@ -613,3 +613,10 @@ def test_structure_factor_gpu(lib):
     on the GPU against the oracle, with and without truncation of the propagated boundary."""
     from parity_common import run_structure_factor_parity
     print("structure factor worst rel err", run_structure_factor_parity(lib), run_structure_factor_parity(lib, 4, 4, 3, 2, chi=5))
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_variational_compression_gpu(lib, scheme):
+    """VARIATION2Site / VARIATION1Site boundary compression (bmps_impl.h:864-1172) on the GPU vs the oracle."""
+    from parity_common import run_variational_parity
+    print("variational scheme", scheme, "worst rel err", run_variational_parity(lib, scheme))

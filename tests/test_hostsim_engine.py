@@ -422,3 +422,9 @@ def test_structure_factor_hostsim_and_brute_force():
             assert abs(v / ref - 1) < 1e-11
         else:
             assert v == 0.0
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_variational_compression_hostsim(scheme):
+    from parity_common import run_variational_parity
+    print(run_variational_parity(hostsim_lib.load(), scheme))

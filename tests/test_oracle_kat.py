@@ -355,3 +355,27 @@ def test_plaquette_traces_equal_amplitudes_of_exchanged_configurations():
         c2[a], c2[b] = cfg[b], cfg[a]
         ref = vmc.Walker(tps, c2, trunc).amplitude
         assert abs(psi / ref - 1) < 1e-11, (kind, d, o, psi, ref)
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_K1_variational_compression_reproduces_partition_function(scheme):
+    """The reference runs K1 with the variational schemes too (test_bmps_contractor.cpp:474-485: Variational2Site /
+    Variational1Site, free energy per site to 1e-8)."""
+    L = 8
+    beta = math.log(1 + math.sqrt(2.0)) / 2.0
+    tn = ising_tn(L, beta)
+    lz = ising_exact_logZ(L, beta)
+    c = BMPSContractor(L, L)
+    c.init(tn)
+    c.set_truncate_params(10, 30, 1e-15)
+    c.set_compress_scheme(scheme, 1e-13, 20)
+    c.grow_bmps_for_row(tn, 3)
+    c.init_bten(tn, LEFT, 3)
+    c.grow_full_bten(tn, RIGHT, 3, 2, True)
+    z = c.trace(tn, (3, 0), HORIZONTAL)
+    assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
+    c.grow_bmps_for_col(tn, 2)
+    c.init_bten(tn, UP, 2)
+    c.grow_full_bten(tn, DOWN, 2, 2, True)
+    z = c.trace(tn, (0, 2), VERTICAL)
+    assert abs((math.log(z) - lz) / (L * L * beta)) < 1e-8
