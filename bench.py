@@ -398,6 +398,68 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
     return out
 
 
+def run_sr_bench(args, torch, device):
+    """--sr: the stochastic-reconfiguration matvec on the device-resident O* store (SRSMatrix::operator*,
+    optimizer/stochastic_reconfiguration_smatrix.h:45-91), the HBM-bound piece next to the sampling path: every stored O*
+    sample is streamed twice per matvec (sr_dots, sr_accumulate). Reports GB/s against the measured HBM bandwidth and the
+    device-resident CG (peps_sr_natural_gradient) iterations/s."""
+    import ctypes as C
+    from oracle import vmc
+    from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+    from peps_b200 import sr
+    L, D, chi = WORKLOADS[args.workload]
+    W = 148
+    tps, cfgs, seeds = make_inputs(L, D, W, 0)
+    b = WalkerBatch(L, L, 2, D, W, BMPSTruncateParams.SVD(chi, chi, 0.0), device=device)
+    b.set_tps(SplitIndexTPS(tps)); b.set_configs(cfgs); b.seed_rng(seeds); b.init_walkers()
+    b.normalize_state_order1()
+    reps = max(1, -(-args.sr_samples // W))
+    b.sr_reserve(reps * W)
+    b.sr_collect(True)
+    b.zero_accumulators()
+    b.sample(1)                                   # one real sample of every walker ...
+    for _ in range(reps - 1):
+        b.accumulate_ostar()                      # ... replicated into the store (the kernels only see bytes)
+    b.sr_collect(False)
+    ns = b.sr_count()
+    stride = int(b.lib.peps_holes_stride(b.h))
+    P = b.tps_size
+    v = torch.randn(P, dtype=torch.float64, device="cuda")
+    out = torch.empty(P, dtype=torch.float64, device="cuda")
+    call = lambda: b._ck(b.lib.peps_sr_matvec_device(b.h, C.c_void_p(v.data_ptr()), 0.1, C.c_void_p(out.data_ptr())))
+    for _ in range(3):
+        call()
+    b.sync()
+    # L2 flush between timed matvecs is unnecessary: the store (ns * stride * 8 bytes) is far larger than the 126 MB L2
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    b.sync(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_it = 20
+    for _ in range(n_it):
+        call()
+    b.sync()
+    dt = (time.perf_counter() - t0) / n_it
+    bytes_per = 2.0 * ns * stride * 8 + 2.0 * P * 8 + ns * L * L * 4 * 2
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    peak = float(peaks.get("hbm_gbs", 6548.8))
+    # device-resident CG on the same store
+    osum, _ = b.accumulators()
+    g = np.random.default_rng(0).standard_normal(P)
+    t1 = time.perf_counter()
+    res = sr.calculate_natural_gradient(b, g, osum / ns, ns, 1e-3, sr.ConjugateGradientParams(max_iter=30, relative_tolerance=1e-14))
+    cg_dt = time.perf_counter() - t1
+    line = {"metric": "sr_matvec_GBps", "value": bytes_per / dt / 1e9, "unit": "GB/s", "n_gpus": 1, "higher_is_better": True,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": args.workload, "stored_samples": ns, "ostar_doubles_per_sample": stride,
+                                                              "store_GB": ns * stride * 8 / 1e9, "l2": "store >> 126 MB L2"},
+            "ms_per_matvec": dt * 1e3,
+            "roofline": {"bound": "hbm", "achieved": bytes_per / dt / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_per / dt / 1e9 / peak,
+                         "bytes_per_matvec": bytes_per, "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
+            "cg": {"iterations": res.iterations, "seconds": cg_dt, "iterations_per_s": res.iterations / cg_dt, "reason": sr.REASONS[res.reason],
+                   "note": "every CG vector resident in HBM; two matvec-class passes over the store per iteration"}}
+    print(json.dumps(line))
+    b.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -412,6 +474,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--secondary", type=int, default=1, help="also time the J1-J2 / signed / physical-state companions (N=1 only)")
     ap.add_argument("--secondary-walkers", type=int, default=74)
+    ap.add_argument("--sr", action="store_true", help="time the SR matvec / CG on the device-resident O* store instead of the sampling path")
+    ap.add_argument("--sr-samples", type=int, default=2048)
     ap.add_argument("--streams", type=int, default=4, help="host threads / CUDA streams sharing the walkers of a GPU")
     args = ap.parse_args()
 
@@ -433,6 +497,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if args.sr:
+        run_sr_bench(args, torch, local_rank)
+        return
     from peps_b200.api import SplitIndexTPS
     L, D, chi = WORKLOADS[args.workload]
     W = args.walkers

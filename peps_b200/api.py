@@ -578,7 +578,19 @@ class MCPEPSMeasurer:
             err = (np.sqrt(((per_walker - mean) ** 2).sum(axis=0) / (W * (W - 1))) if W > 1
                    else np.full(np.shape(mean), np.inf))
             out[k] = (mean, err)
+        self.results = out
+        self.samples_per_walker = nper
         return out
+
+    def DumpData(self, path=""):
+        """MCPEPSMeasurer::DumpData: stats CSVs + metadata.txt of the last Execute() (see dump_measurement_stats)."""
+        b = self.batch
+        meta = {"total_samples_requested": self.mc.num_samples, "samples_per_rank": self.samples_per_walker,
+                "samples_scheduled_total": self.samples_per_walker * b.W, "samples_collected_total": self.samples_per_walker * b.W,
+                "mpi_size": b.W, "warmup_sweeps": self.mc.num_warmup_sweeps, "sweeps_between_samples": self.mc.sweeps_between_samples,
+                "initial_config_warmed_up": "true" if self.mc.is_warmed_up else "false", "lx": b.cols, "ly": b.rows,
+                "boundary_condition": "Open", "peps_bond_dimension": b.D}
+        dump_measurement_stats(self.results, path, meta)
 
 
 class _CudaView:
@@ -586,6 +598,40 @@ class _CudaView:
 
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+def _csv(x):
+    """ToCsvString (monte_carlo_peps_measurer_impl.h:24-29): scientific, max_digits10 = 17 significant digits."""
+    return "%.16e" % float(x)
+
+
+def dump_measurement_stats(results, path, meta=None):
+    """MCPEPSMeasurer::DumpData (monte_carlo_peps_measurer_impl.h:266-330, 396-440, 544-620): ``<path>/stats/<key>_mean.csv``
+    + ``_stderr.csv`` for observables registered with a 2-D shape (one lattice row per line), ``<path>/stats/<key>.csv``
+    with the header ``index,mean,stderr`` for everything else, and ``<path>/metadata.txt``. ``results``: {key: (mean,
+    stderr)} as returned by MCPEPSMeasurer.Execute()."""
+    import os
+    base = (path.rstrip("/") + "/") if path else "./"
+    stats = base + "stats/"
+    os.makedirs(stats, exist_ok=True)
+    for key, (mean, err) in results.items():
+        mean, err = np.asarray(mean, dtype=float), np.asarray(err, dtype=float)
+        if mean.ndim == 2:
+            for suffix, arr in (("_mean.csv", mean), ("_stderr.csv", err)):
+                with open(stats + key + suffix, "w") as f:
+                    for row in arr:
+                        f.write(",".join(_csv(v) for v in row) + "\n")
+        else:
+            with open(stats + key + ".csv", "w") as f:
+                f.write("index,mean,stderr\n")
+                for i, (m, e) in enumerate(zip(mean.ravel(), err.ravel())):
+                    f.write(f"{i},{_csv(m)},{_csv(e)}\n")
+    with open(base + "metadata.txt", "w") as f:
+        f.write("format_version 1\n")
+        for k, v in (meta or {}).items():
+            f.write(f"{k} {v}\n")
+        f.write(f"registered_observables {len(results)}\n")
+        f.write(f"stats_path {base}stats\n")
 
 
 @dataclass

@@ -56,3 +56,18 @@ def test_complex_fixture_is_detected():
     assert t.dtype == np.complex128 and t.shape == (8, 8, 8, 8)
     with pytest.raises(ValueError):
         pio.read_qlten(os.path.join(d, "tps_ten1_1_0.qlten"), dtype=np.float64)
+
+
+def test_measurement_stats_dump_layout(tmp_path):
+    """MCPEPSMeasurer::DumpData layout (monte_carlo_peps_measurer_impl.h:266-330, 544-620): 2-D observables as
+    <key>_mean.csv / <key>_stderr.csv (17 significant digits, scientific), flat ones as index,mean,stderr."""
+    from peps_b200.api import dump_measurement_stats
+    res = {"spin_z": (np.array([[0.5, -0.25], [0.125, 1 / 3]]), np.array([[0.1, 0.2], [0.3, 0.4]])),
+           "energy": (np.array(-1.9952127879312345), np.array(1e-3))}
+    dump_measurement_stats(res, str(tmp_path / "out"), {"lx": 2, "ly": 2})
+    rows = open(tmp_path / "out" / "stats" / "spin_z_mean.csv").read().splitlines()
+    assert rows[0] == "5.0000000000000000e-01,-2.5000000000000000e-01" and float(rows[1].split(",")[1]) == 1 / 3
+    flat = open(tmp_path / "out" / "stats" / "energy.csv").read().splitlines()
+    assert flat[0] == "index,mean,stderr" and flat[1].startswith("0,-1.9952127879312345e+00,")
+    meta = open(tmp_path / "out" / "metadata.txt").read()
+    assert meta.startswith("format_version 1\n") and "lx 2" in meta
