@@ -112,8 +112,17 @@ struct PanelArgs {
   // trailing update must be called with the same limit. Only meaningful for items of ascending contiguous rows.
   const int32_t *row_cnt = nullptr;
   int row_scale = 0;
+  // Optional early-termination flags (device, may be null): walkers with stopped[w] != 0 are skipped entirely -- their
+  // trailing matrix is already numerically zero (be_trailing_check), the R rows not computed would be dropped anyway.
+  const int32_t *stopped = nullptr;
 };
 void be_panel_qr(const PanelArgs &a);
+// Early termination of a rank-revealing QR: acc[w] += |A[w][row0:nrows, col0:ncols]|_F^2 (rows / columns of the trailing
+// block), then stopped[w] = (acc[w] <= thresh2 * colnorm2[w][colorder[w][0]]) and acc[w] = 0. Walkers already stopped
+// are not read again. colnorm2 / colorder: squared column norms of the matrix before the factorisation and their
+// descending order (the largest one bounds the largest row norm of R from below).
+void be_trailing_check(const double *A, long ws, int lda, int row0, int nrows, int col0, int ncols, const double *colnorm2,
+                       const int32_t *colorder, int n, double thresh2, double *acc, int32_t *stopped, int W);
 
 // Trailing update of one CAQR panel step: for every (walker, item) C <- C - V T^T (V^T C) where C are the rows
 // rowtab[it*R + s] (s < R) and columns [col1, col1 + ntrail) of A, and V / T are the blocks emitted by
@@ -141,6 +150,7 @@ struct ApplyArgs {
   // same meaning as PanelArgs::row_cnt / row_scale: items starting at or beyond the walker's limit are skipped
   const int32_t *row_cnt = nullptr;
   int row_scale = 0;
+  const int32_t *stopped = nullptr;     // PanelArgs::stopped
 };
 void be_apply_reflector(const ApplyArgs &a);
 

@@ -733,6 +733,7 @@ __global__ void __launch_bounds__(PQR_THREADS) panel_qr_kernel(PanelArgs a) {
   extern __shared__ double sm[];
   const int it = blockIdx.x, w = blockIdx.y;
   if (a.row_cnt && a.rowtab[(long)it * a.R] >= a.row_cnt[w] * a.row_scale) return;     // all-zero item of this walker
+  if (a.stopped && a.stopped[w]) return;                                                // factorisation of this walker already terminated
   const int R = a.R, pw = a.pw, nbw = a.nbw;
   const int skip = (it == 0) ? a.skip0 : 0;
   const int nact = R - skip;
@@ -883,6 +884,7 @@ __global__ void __launch_bounds__(PQR_THREADS, MINB) panel_qr_reg_kernel(PanelAr
   constexpr int RP = RPL * 32;
   const int it = blockIdx.x, w = blockIdx.y;
   if (a.row_cnt && a.rowtab[(long)it * a.R] >= a.row_cnt[w] * a.row_scale) return;     // all-zero item of this walker
+  if (a.stopped && a.stopped[w]) return;                                                // factorisation of this walker already terminated
   const int R = a.R, pw = a.pw, nbw = a.nbw;
   const int skip = (it == 0) ? a.skip0 : 0;
   const int nact = R - skip;
@@ -1212,6 +1214,7 @@ __global__ void __launch_bounds__(256, MINB) apply_reflector_kernel(ApplyArgs a,
   constexpr int TN = NBW, MT = NBW / 8, NT = NBW / 8, LDC = TN + 4, LDW = TN + 4, NTILE = MT * NT;
   const int ct = blockIdx.x, it = blockIdx.y, w = blockIdx.z;
   if (a.row_cnt && a.rowtab[(long)it * a.R] >= a.row_cnt[w] * a.row_scale) return;     // all-zero item of this walker
+  if (a.stopped && a.stopped[w]) return;
   const int R = a.R, R8 = (R + 7) & ~7, nbw = a.nbw;
   double *Cs = sm;                               // [R8][LDC], or [NBW/8][R8][8] with tile descriptors
   auto csi = [&](int r, int c) -> size_t {
@@ -1469,6 +1472,7 @@ __global__ void __launch_bounds__(256, 1) apply_cols_kernel(ApplyArgs a, const _
   uint64_t *bars = reinterpret_cast<uint64_t *>(wbase + (size_t)8 * wstride);   // [0..7] chunk barriers, [8] V
   const int cs = blockIdx.x, it = blockIdx.y, w = blockIdx.z;
   if (a.row_cnt && a.row0 + it * R >= a.row_cnt[w] * a.row_scale) return;               // all-zero row block of this walker
+  if (a.stopped && a.stopped[w]) return;
   const double *V = a.Vw + ((long)w * a.NI + it) * (long)R * 32;
   const double *Tg = a.Tw + ((long)w * a.NI + it) * 1024L;
   double *Aw = a.A + (long)w * a.ws;
@@ -1628,6 +1632,48 @@ void be_apply_reflector(const ApplyArgs &a) {
             h[6] - h[0], h[7] - h[6], h[1] - h[7], h[2] - h[1], h[3] - h[2], h[4] - h[3], h[5] - h[4]);
   }
 #endif
+}
+
+// Early termination of the rank-revealing factorisations (backend.h be_trailing_check)
+__global__ void trailing_norm_kernel(const double *A, long ws, int lda, int row0, int nrows, int col0, int ncols, double *acc,
+                                     const int32_t *stopped) {
+  const int w = blockIdx.y;
+  if (stopped[w]) return;
+  const double *Aw = A + (long)w * ws;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  double s0 = 0.0, s1 = 0.0;
+  for (int r = row0 + blockIdx.x * nwarp + warp; r < nrows; r += gridDim.x * nwarp) {
+    const double *x = Aw + (long)r * lda;
+    int c = col0 + lane;
+    for (; c + 32 < ncols; c += 64) { const double a = x[c], b = x[c + 32]; s0 = fma(a, a, s0); s1 = fma(b, b, s1); }
+    if (c < ncols) { const double a = x[c]; s0 = fma(a, a, s0); }
+  }
+  double s = warp_sum(s0 + s1);
+  __shared__ double red[8];
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < nwarp; ++i) t += red[i];
+    if (t != 0.0) atomicAdd(acc + w, t);
+  }
+}
+__global__ void trailing_decide_kernel(const double *colnorm2, const int32_t *colorder, int n, double thresh2, double *acc,
+                                       int32_t *stopped, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W || stopped[w]) return;
+  stopped[w] = (acc[w] <= thresh2 * colnorm2[(long)w * n + colorder[(long)w * n]]) ? 1 : 0;
+  acc[w] = 0.0;
+}
+void be_trailing_check(const double *A, long ws, int lda, int row0, int nrows, int col0, int ncols, const double *colnorm2,
+                       const int32_t *colorder, int n, double thresh2, double *acc, int32_t *stopped, int W) {
+  if (nrows <= row0 || ncols <= col0) return;
+  LaunchScope scope(KC_SMALL, 0.0);
+  const int bx = std::max(1, std::min(16, (nrows - row0 + 63) / 64));
+  trailing_norm_kernel<<<dim3(bx, W), 256, 0, g_stream>>>(A, ws, lda, row0, nrows, col0, ncols, acc, stopped);
+  ++cx().launches;
+  trailing_decide_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(colnorm2, colorder, n, thresh2, acc, stopped, W);
+  post_launch();
 }
 
 // =====================================================================================================

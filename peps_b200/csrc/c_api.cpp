@@ -227,6 +227,7 @@ int peps_test_truncate(int32_t device, int32_t W, int32_t nr, int32_t nc, int32_
     cx.W = W; cx.pool = &pool; cx.planner = &planner;
     if (const char *e = std::getenv("PEPS_PRESORT_COLS")) cx.presort_columns = std::atoi(e) != 0;
     if (const char *e = std::getenv("PEPS_SMALL_SVD")) cx.small_svd = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PEPS_QR_EARLY_STOP")) cx.qr_early_stop = std::atoi(e) != 0;
     cx.offmax = (double *)pool.get(sizeof(double) * W);
     cx.done = (int32_t *)pool.get(sizeof(int32_t) * W);
     int brows = truncate_buffer_rows(nr, nc);

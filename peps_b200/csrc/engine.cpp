@@ -24,6 +24,7 @@ Engine::Engine(const EngineConfig &c)
   if (const char *e = std::getenv("PEPS_PRESORT_COLS")) la_.presort_columns = std::atoi(e) != 0;
   if (const char *e = std::getenv("PEPS_CHAIN_EPS")) chain_eps_ = std::atof(e);
   if (const char *e = std::getenv("PEPS_SMALL_SVD")) la_.small_svd = std::atoi(e) != 0;
+  if (const char *e = std::getenv("PEPS_QR_EARLY_STOP")) la_.qr_early_stop = std::atoi(e) != 0;
   la_.offmax = (double *)be_malloc(sizeof(double) * W_);
   la_.done = (int32_t *)be_malloc(sizeof(int32_t) * W_);
   tps_off_h_.resize((size_t)nsites_);
@@ -337,7 +338,9 @@ Engine::BMPSv Engine::absorb_svd(const BMPSv &mps, const std::vector<int> &sites
       if (L.m_pad > m) be_memset0(Ap, sizeof(double) * (size_t)W_ * wsA);
       be_permute_cols(A, wsA, n, m, n, cord, 1, Ap, wsA, n, W_);
       pool_.put(A);
-      caqr(la_, Ap, wsA, m, n, L, rc, o);                                                // bmps_impl.h:817-821
+      QRStop st;                                         // early termination: the rank of r_{i+1} is close to that of r_i
+      st.colnorm2 = cn2; st.colorder = cord; st.eps = chain_eps_; st.first_col = std::max(0, std::min(rk, kk) - 96);
+      caqr(la_, Ap, wsA, m, n, L, rc, o, &st);                                           // bmps_impl.h:817-821
       be_row_norms2(Ap, wsA, n, kk, n, cn2, W_);
       be_rank_rows(cn2, kk, chain_eps_ * chain_eps_, ord, cnt, W_);
       std::vector<int32_t> ch((size_t)W_);

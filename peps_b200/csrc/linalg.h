@@ -28,6 +28,7 @@ struct LinalgCtx {
   long rows_in = 0, rows_kept = 0;   // Jacobi row counts before / after deflation (summed over calls)
   double deflation_eps = 1e-13;      // rows of R below eps * (largest row norm) are treated as zero (perturbs Theta by <= sqrt(rows) * eps * |Theta|)
   bool presort_columns = true;       // PEPS_PRESORT_COLS=0 switches the column pre-sorting of truncate_rows off
+  bool qr_early_stop = true;         // PEPS_QR_EARLY_STOP=0 switches the early termination of the rank-revealing QRs off
   bool small_svd = true;             // PEPS_SMALL_SVD=0 switches the single-CTA SVD path of truncate_rows off
   long small_svd_calls = 0;
   double jacobi_tol = 1e-14;
@@ -90,8 +91,20 @@ inline std::vector<int32_t> iota_scaled(int n, int scale, int base = 0) {
 // In-place R-only QR of A[w] (m x n, row-major, leading dimension n, walker stride ws; the buffer holds
 // L.m_pad rows, rows >= m zero). On return rows [0, min(m,n)) hold R (upper trapezoidal), everything else
 // in the buffer is zero.
+// Early termination of a rank-revealing factorisation (columns pre-sorted by norm, rows of R below eps * max dropped by
+// the caller afterwards): once the trailing block of a walker is below 0.1 * eps * (largest column norm) in Frobenius
+// norm, every R row still to come would be dropped anyway -- the walker's remaining panels are skipped (device-side
+// flags, no host round trip). Rows >= the stopping column then hold the negligible unfactored block instead of R rows /
+// zeros; the caller's deflation discards them (their norms are below its threshold by construction).
+struct QRStop {
+  const double *colnorm2 = nullptr;      // [W][n] squared column norms before the factorisation
+  const int32_t *colorder = nullptr;     // [W][n] columns by descending norm
+  double eps = 0.0;                      // the caller's deflation threshold (0 disables)
+  int first_col = 0;                     // start checking once this many columns are factorised (a rank hint)
+};
+
 inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout &L, const int32_t *row_cnt = nullptr,
-                 int row_scale = 0) {
+                 int row_scale = 0, const QRStop *stop = nullptr) {
   const int W = cx.W, nb = L.nb, rb = L.rb, nrb = L.nrb, lda = n;
   const int kk = std::min(m, n);
   ++cx.qr_calls;
@@ -110,6 +123,15 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
   TileMap tmapc;
   const bool have_tmapc = rb <= 256 && rb % 16 == 0 && nb == 32 && be_make_tile_map(&tmapc, A, ws, lda, L.m_pad, n, W, rb, 8);
   const int npanel = (kk + nb - 1) / nb;
+  const bool stopping = stop && stop->eps > 0.0 && cx.qr_early_stop && npanel > 2;
+  int32_t *stopped = nullptr;
+  double *stop_acc = nullptr;
+  if (stopping) {
+    stopped = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W);
+    stop_acc = (double *)cx.pool->get(sizeof(double) * (size_t)W);
+    be_memset0(stopped, sizeof(int32_t) * (size_t)W);
+    be_memset0(stop_acc, sizeof(double) * (size_t)W);
+  }
   for (int p = 0; p < npanel; ++p) {
     const int col0 = p * nb, pw = std::min(nb, kk - col0), c1 = col0 + pw, ntrail = n - c1;
     // row blocks above the one holding the diagonal are finished; the diagonal block skips its rows above col0
@@ -118,6 +140,7 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
     pa.A = A; pa.ws = ws; pa.lda = lda; pa.rowtab = rowtab1_d + (size_t)b0 * rb; pa.R = rb; pa.skip0 = col0 - b0 * rb; pa.NI = nact;
     pa.col0 = col0; pa.pw = pw; pa.nbw = nb; pa.Vw = Vw; pa.Tw = Tw; pa.W = W;
     pa.row_cnt = row_cnt; pa.row_scale = row_scale;        // stage 1 only: all-zero row blocks of a walker are skipped
+    pa.stopped = stopped;
     be_panel_qr(pa);
     if (ntrail > 0) {
       ApplyArgs ap;
@@ -125,7 +148,7 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
       ap.nbw = nb; ap.Vw = Vw; ap.Tw = Tw; ap.W = W;
       if (have_tmap) { ap.tmap = &tmap; ap.row0 = b0 * rb; }
       if (have_tmapc) { ap.tmap_cols = &tmapc; ap.row0 = b0 * rb; }
-      ap.row_cnt = row_cnt; ap.row_scale = row_scale;
+      ap.row_cnt = row_cnt; ap.row_scale = row_scale; ap.stopped = stopped;
       be_apply_reflector(ap);
     }
     if (nact > 1) {
@@ -141,11 +164,14 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
       if (ntrail > 0) {
         ApplyArgs ap;
         ap.A = A; ap.ws = ws; ap.lda = lda; ap.rowtab = p2.rowtab; ap.R = R2; ap.NI = 1; ap.col1 = c1; ap.ntrail = ntrail;
-        ap.nbw = nb; ap.Vw = Vw; ap.Tw = Tw; ap.W = W;
+        ap.nbw = nb; ap.Vw = Vw; ap.Tw = Tw; ap.W = W; ap.stopped = stopped;
         be_apply_reflector(ap);
       }
     }
+    if (stopping && ntrail > 0 && c1 < m && c1 >= stop->first_col && p + 1 < npanel)
+      be_trailing_check(A, ws, lda, c1, m, c1, n, stop->colnorm2, stop->colorder, n, 0.01 * stop->eps * stop->eps, stop_acc, stopped, W);
   }
+  if (stopping) { cx.pool->put(stopped); cx.pool->put(stop_acc); }
   cx.pool->put(Vw);
   cx.pool->put(Tw);
 }
@@ -215,10 +241,14 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
     if (brows > nr) be_memset0(G, sizeof(double) * (size_t)W * brows * nc);
     be_permute_cols(Gin, ws, nc, nr, nc, cord, 1, G, (long)brows * nc, nc, W);
     ws = (long)brows * nc;
-    cx.pool->put(cn2);
     cx.pool->put(ccnt);
+    QRStop st;
+    st.colnorm2 = cn2; st.colorder = cord; st.eps = cx.deflation_eps; st.first_col = std::max(0, std::min(dmax, nsv) - 32);
+    if (nr > 1) caqr(cx, G, ws, nr, nc, qr_layout(nr, nc), nullptr, 0, &st);
+    cx.pool->put(cn2);
+  } else if (nr > 1) {
+    caqr(cx, G, ws, nr, nc, qr_layout(nr, nc));
   }
-  if (nr > 1) caqr(cx, G, ws, nr, nc, qr_layout(nr, nc));
   const int kk = nsv;
   double *n2a = (double *)cx.pool->get(sizeof(double) * (size_t)W * kk);
   int32_t *ord = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * kk);

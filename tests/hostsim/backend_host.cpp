@@ -103,11 +103,24 @@ void be_set_identity(double *dst, long wd, int rows, int cols, int W) {
       for (int c = 0; c < cols; ++c) dst[w * wd + (long)r * cols + c] = (r == c) ? 1.0 : 0.0;
 }
 
+void be_trailing_check(const double *A, long ws, int lda, int row0, int nrows, int col0, int ncols, const double *colnorm2,
+                       const int32_t *colorder, int n, double thresh2, double *acc, int32_t *stopped, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    if (stopped[w]) continue;
+    double s2 = 0.0;
+    for (int r = row0; r < nrows; ++r)
+      for (int c = col0; c < ncols; ++c) { const double v = A[w * ws + (long)r * lda + c]; s2 += v * v; }
+    stopped[w] = (s2 <= thresh2 * colnorm2[(long)w * n + colorder[(long)w * n]]) ? 1 : 0;
+    acc[w] = 0.0;
+  }
+}
 void be_panel_qr(const PanelArgs &a) {
   ++g_launches;
   const int R = a.R, pw = a.pw, nbw = a.nbw;
   for (int w = 0; w < a.W; ++w)
     for (int it = 0; it < a.NI; ++it) {
+      if (a.stopped && a.stopped[w]) continue;
       const int skip = (it == 0) ? a.skip0 : 0, nact = R - skip;
       double *Aw = a.A + (long)w * a.ws;
       const int32_t *rows = a.rowtab + (long)it * R;
@@ -178,6 +191,7 @@ void be_apply_reflector(const ApplyArgs &a) {
       double *Aw = a.A + (long)w * a.ws;
       const int32_t *rows = a.rowtab + (long)it * a.R;
       if (a.row_cnt && rows[0] >= a.row_cnt[w] * a.row_scale) continue;
+      if (a.stopped && a.stopped[w]) continue;
       const double *V = a.Vw + ((long)w * a.NI + it) * (long)a.R * a.nbw;
       const double *T = a.Tw + ((long)w * a.NI + it) * (long)a.nbw * a.nbw;
       std::vector<double> Wm((size_t)a.nbw * a.ntrail, 0.0), W2((size_t)a.nbw * a.ntrail, 0.0);
