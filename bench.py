@@ -259,9 +259,9 @@ class LaneSet:
     different contexts overlap on the GPU (the per-lane host round trips -- one per chain / truncation step -- are hidden
     behind the other lanes' kernels)."""
 
-    def __init__(self, L, D, chi, W, S, device, tps, cfgs, seeds, j2=0.0, rank=0, world=1, dist=None, torch=None):
+    def __init__(self, L, D, chi, W, S, device, tps, cfgs, seeds, j2=0.0, rank=0, world=1, dist=None, torch=None, model=None):
         import queue
-        from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, WalkerBatch
+        from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, FermionSplitIndexTPS, WalkerBatch
         S = max(1, min(S, W))
         while W % S:
             S -= 1
@@ -291,7 +291,11 @@ class LaneSet:
         def setup(ln):
             sl = slice(ln.i * outer.Ws, (ln.i + 1) * outer.Ws)
             ln.b = WalkerBatch(L, L, 2, D, outer.Ws, BMPSTruncateParams.SVD(chi, chi, 0.0), device=device)
+            if isinstance(outer.sit, FermionSplitIndexTPS):
+                ln.b.set_fermion(outer.sit)           # fZ2-graded tensors (BASELINE config #4)
             ln.b.set_tps(outer.sit)
+            if model is not None:
+                ln.b.set_model(model)
             if j2 != 0.0:
                 from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
                 ln.b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, j2, j2, 0.0))
@@ -368,10 +372,10 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
     L, D, chi = D_chi
     out = []
 
-    def run(name, L, D, chi, W, S, tps, j2=0.0):
+    def run(name, L, D, chi, W, S, tps, j2=0.0, model=None):
         cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, CFG_SEED0 + w) for w in range(W)])
         seeds = np.arange(RNG_SEED0, RNG_SEED0 + W, dtype=np.uint32)
-        ls = LaneSet(L, D, chi, W, S, device, tps, cfgs, seeds, j2=j2, torch=torch)
+        ls = LaneSet(L, D, chi, W, S, device, tps, cfgs, seeds, j2=j2, torch=torch, model=model)
         try:
             ls.samples(1)
             r0 = [ls.stat_sum(k) for k in (8, 9, 12, 13, 4, 14)]
@@ -389,6 +393,10 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
     tps = vmc.random_tps(L, L, 2, D, seed=TPS_SEED)
     run("j1j2_j2=0.5", L, D, chi, walkers, streams, tps, j2=0.5)
     run("signed_tps", L, D, chi, walkers, streams, vmc.random_tps(L, L, 2, D, seed=TPS_SEED, signed=True))
+    # BASELINE config #4: 8x8 spinless fermions, fZ2 tensors with even / odd blocks of D/2, chi = 64
+    from peps_b200.api import FermionSplitIndexTPS, TableModel
+    run("fermion_spinless_8x8_D8_chi64_fZ2", 8, 8, 64, walkers, streams, FermionSplitIndexTPS.random(8, 8, 8, TPS_SEED),
+        model=TableModel.spinless_fermion(1.0, 0.0, 0.0))
     gold = os.path.join(ROOT, "tests", "golden", "heis4x4_D8_double.npz")
     if os.path.exists(gold):
         z = np.load(gold)

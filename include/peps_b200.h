@@ -98,6 +98,21 @@ int peps_set_model_tfim(peps_ctx *ctx, double h);
 int peps_set_model_term(peps_ctx *ctx, int32_t kind, int32_t T, const double *diag, const int32_t *target, const double *coef);
 int peps_clear_model_terms(peps_ctx *ctx);
 
+/* Fermionic (fZ2-graded) tensors -- QLTensor<T, fZ2QN> states of the reference (BASELINE config #4: SquareSpinlessFermion,
+ * model_solvers/square_spinless_fermion.h:51-213; SquaretJNNModel / SquaretJVModel, model_solvers/square_tJ_model.h:85-420).
+ * phys_par[phys]: fermion parity of every physical state (spinless fermion {1, 0}: 0 = occupied, 1 = empty; t-J {1, 1, 0}).
+ * leg_par: for every site in row-major order the parity of every index value of its L, D, R, U legs, concatenated
+ * (n_leg_par = sum over sites of dL + dD + dR + dU; the `qnval` of the sector an index value belongs to in the .qlten
+ * header). The TPS is uploaded by peps_set_tps as dense (L, D, R, U) blocks with the dim-1 parity leg dropped, exactly as
+ * for bosons. Call once, before peps_set_tps and peps_set_model_term. The engine then evaluates the graded network of the
+ * reference (fermionic branches of bmps_impl.h:21-96, 756-862, bmps_contractor_trace.h:90-205, grow.h:150-183) as an
+ * ordinary network of sign-dressed site tensors ("Fermions"): same |psi|, same Markov chain, psi_ex / psi per
+ * bond along one contraction path (square_nnn_energy_solver.h:143-310), O* = Pi(R*) of utility/helpers.h:57-67 and
+ * mc_energy_grad_evaluator.h:259-266 as the Euclidean gradient of log psi* in the uploaded tensor entries. Models are
+ * tables (peps_set_model_term); an off-diagonal target must either move one fermion between the two sites of the term or
+ * keep both site parities (hopping, spin exchange). Updater: NN exchange (peps_sweep). */
+int peps_set_fermion(peps_ctx *ctx, const int32_t *phys_par, const int32_t *leg_par, size_t n_leg_par);
+
 /* Configuration per walker (vmc_basic/configuration.h:57), int32 [W][rows][cols]. */
 int peps_set_configs(peps_ctx *ctx, const int32_t *cfg);
 int peps_get_configs(peps_ctx *ctx, int32_t *cfg);

@@ -197,6 +197,45 @@ class SplitIndexTPS:
         return float(sum(np.sum(np.abs(x) ** 2) for row in self.t for site in row for x in site))
 
 
+class FermionSplitIndexTPS(SplitIndexTPS):
+    """SplitIndexTPS<T, fZ2QN>: dense (L, D, R, U) blocks (the dim-1 parity leg dropped) plus the fermion parity of
+    every index value (par[r][c] = [pL, pD, pR, pU]) and of every physical state (phys_par). The vector-space operations
+    are those of the dense container; gradients / O* come back in the same entries."""
+
+    def __init__(self, tensors, par, phys_par):
+        super().__init__(tensors)
+        self.par = par
+        self.phys_par = tuple(int(x) for x in phys_par)
+
+    def leg_par_flat(self):
+        return np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32).ravel()
+                                                    for row in self.par for site in row for p in site]), dtype=np.int32)
+
+    @staticmethod
+    def unpack(flat, like):
+        d = SplitIndexTPS.unpack(flat, like)
+        return FermionSplitIndexTPS(d.t, like.par, like.phys_par)
+
+    @staticmethod
+    def random(rows, cols, D, seed, phys_par=(1, 0), n_odd=None):
+        """Parity-conserving uniform [-1, 1) tensors; every bond has D//2 (or n_odd) odd index values, placed last
+        (SURVEY.md 8d.1, config #4: 'even/odd blocks D/2 each')."""
+        rng = np.random.default_rng(seed)
+        n_odd = D // 2 if n_odd is None else n_odd
+        bp = np.array([0] * (D - n_odd) + [1] * n_odd, dtype=np.int32)
+        one = np.zeros(1, dtype=np.int32)
+        T = [[None] * cols for _ in range(rows)]
+        par = [[None] * cols for _ in range(rows)]
+        for r in range(rows):
+            for c in range(cols):
+                ps = [bp if c > 0 else one, bp if r < rows - 1 else one, bp if c < cols - 1 else one, bp if r > 0 else one]
+                tot = (ps[0][:, None, None, None] + ps[1][None, :, None, None] + ps[2][None, None, :, None]
+                       + ps[3][None, None, None, :]) % 2
+                par[r][c] = ps
+                T[r][c] = [rng.uniform(-1.0, 1.0, tot.shape) * (tot == pp) for pp in phys_par]
+        return FermionSplitIndexTPS(T, par, phys_par)
+
+
 @dataclass
 class SquareSpinOneHalfXXZModelOBC:
     jz: float = 1.0
@@ -245,6 +284,33 @@ class TableModel:
             H[1, 2] = H[2, 1] = 0.5 * b
             return H
         return TableModel(2, bond(jz, jxy), bond(jz2, jxy2) if (jz2 or jxy2) else None)
+
+    @staticmethod
+    def spinless_fermion(t, t2=0.0, V=0.0):
+        """SquareSpinlessFermion(t, t2, V) (model_solvers/square_spinless_fermion.h:51-213) as tables; 0 = occupied,
+        1 = empty. The hop amplitude is the matrix element in the engine's fermion mode: the Jordan-Wigner sign of the
+        move is supplied by the contraction (psi_ex / psi along one path), as in the reference."""
+        h2 = np.zeros((4, 4))
+        h2[0, 0] = V
+        h2[1, 2] = h2[2, 1] = -t
+        h2n = None
+        if t2 != 0.0:
+            h2n = np.zeros((4, 4))
+            h2n[1, 2] = h2n[2, 1] = -t2
+        return TableModel(2, h2, h2n)
+
+    @staticmethod
+    def tj(t, J, V=0.0, mu=0.0):
+        """SquaretJNNModel(t, J, mu) / SquaretJVModel(t, 0, J, V, mu) (model_solvers/square_tJ_model.h:300-345);
+        0 = up, 1 = down, 2 = empty."""
+        h2 = np.zeros((9, 9))
+        for a in (0, 1):
+            h2[a * 3 + a, a * 3 + a] = V
+            h2[a * 3 + 2, 2 * 3 + a] = h2[2 * 3 + a, a * 3 + 2] = -t
+        h2[1, 1] = h2[3, 3] = -0.5 * J + V
+        h2[1, 3] = h2[3, 1] = 0.5 * J
+        h1 = np.diag([-mu, -mu, 0.0]) if mu != 0.0 else None
+        return TableModel(3, h2, None, h1)
 
     @staticmethod
     def tfim(h):
@@ -310,6 +376,12 @@ class WalkerBatch:
             raise PepsError(self.lib.peps_last_error(self.h).decode())
 
     # state
+    def set_fermion(self, ftps):
+        """Switch the context to fZ2-graded tensors (peps_set_fermion); before set_tps / set_model."""
+        pp = np.ascontiguousarray(ftps.phys_par, dtype=np.int32)
+        lp = ftps.leg_par_flat()
+        self._ck(self.lib.peps_set_fermion(self.h, _ip(pp), _ip(lp), lp.size))
+
     def set_tps(self, tps):
         flat = tps.pack() if isinstance(tps, SplitIndexTPS) else np.ascontiguousarray(tps, dtype=np.float64)
         if flat.size != self.tps_size:
@@ -695,6 +767,8 @@ class MCEnergyGradEvaluator:
         self.state = tps                       # the device holds its own copy (set_tps below and in every Evaluate(state))
         self.dist, self.rank, self.world_size = dist, rank, world_size
         self.batch = WalkerBatch(tps.rows(), tps.cols(), tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
+        if isinstance(tps, FermionSplitIndexTPS):
+            self.batch.set_fermion(tps)
         self.batch.set_model(model)
         self.batch.set_updater(updater)
         self.batch.set_tps(tps)
@@ -768,7 +842,7 @@ class MCEnergyGradEvaluator:
         if not math.isfinite(mx):
             raise PepsError("Amplitude is still not legal after warm up")
         self.batch.normalize_state_order1(mx)
-        self.state = SplitIndexTPS.unpack(self.batch.get_tps_flat(), self.state)
+        self.state = type(self.state).unpack(self.batch.get_tps_flat(), self.state)
 
     def _allreduce_max(self, x):
         import torch
@@ -837,11 +911,11 @@ class MCEnergyGradEvaluator:
         energy, err = combine_energy_bins(all_e)
         total_walkers = all_e.shape[0]
         grad_flat = (eosum - energy * osum) / (n * total_walkers)        # (:296-309)
-        grad = SplitIndexTPS.unpack(grad_flat, self.state)
+        grad = type(self.state).unpack(grad_flat, self.state)
         b.sr_collect(False)
         res = EvaluateResult(energy, err, grad, grad.NormSquare(), [float(np.mean(accept / n))], all_e)
         if collect_sr_buffers:
-            res.Ostar_mean = SplitIndexTPS.unpack(osum / (n * total_walkers), self.state)
+            res.Ostar_mean = type(self.state).unpack(osum / (n * total_walkers), self.state)
             res.total_samples = n * total_walkers
         return res
 
@@ -855,7 +929,7 @@ class MCEnergyGradEvaluator:
         r = sr.calculate_natural_gradient(self.batch, result.gradient.pack(), result.Ostar_mean.pack(), result.total_samples,
                                           diag_shift, cg_params or sr.ConjugateGradientParams(),
                                           None if init_guess is None else init_guess.pack(), cb)
-        return SplitIndexTPS.unpack(r.x, self.state), r.iterations, r.residual_norm
+        return type(self.state).unpack(r.x, self.state), r.iterations, r.residual_norm
 
     def samples_per_walker(self):
         """SamplesPerRank = ceil(total / ranks) (monte_carlo_engine.h:97-98) with ranks = walkers * GPUs."""

@@ -244,6 +244,58 @@ void be_term_targets(const int32_t *cfg, int nsites, int s1, int s2, int phys, c
 void be_term_accumulate(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag, const double *coefw,
                         const double *psi_ex, const double *psi, double *eloc, int W);
 
+// ---- fermionic (fZ2-graded) tensors as sign-dressed dense tensors ---------------------------------------------------
+// A graded network of parity-conserving site tensors equals a bosonic network of dressed tensors (engine.h, "fermion
+// mode"). Per site the device TPS holds FERMION_VARIANTS * phys slices: variant v, state s at slice v * phys + s.
+//   v = 0..5: horizontal machinery, leg-sign masks {0, U, R, R|U, R|D, R|D|U};  v = 6, 7: vertical machinery, {0, L}.
+constexpr int FERMION_VARIANTS = 8;
+// Jordan-Wigner bits and gather indices of the current configurations (one thread per walker):
+//   jw_h[w][site] = parity of the sites left of `site` in its row, jw_v = above it in its column;
+//   gidx_h = jw_h * phys + cfg,  gidx_v = (6 + jw_v) * phys + cfg.
+void be_fermion_gather(const int32_t *cfg, int rows, int cols, int phys, const int32_t *phys_par, int32_t *gidx_h,
+                       int32_t *gidx_v, int32_t *jw_h, int32_t *jw_v, int W);
+// Replacement slices and signed matrix element of target slot t of a two-site term on (s1, s2) (square_spinless_fermion.h:
+// 118-211, square_tJ_model.h:300-345: psi_ex / psi along one contraction path). kind 0: horizontal NN bond, 1: vertical
+// NN bond, 2: diagonal s1 = left-up, s2 = right-down, 3: diagonal s1 = left-down, s2 = right-up (kinds 0, 2, 3 in the
+// horizontal machinery, 1 in the vertical). target == nullptr: the exchange of the two states with element 1 (updater).
+// A target that moves a fermion (both site parities flip) gets the leg-sign masks and the Jordan-Wigner sign of the hop;
+// parity-preserving targets keep the canonical masks; empty slots give the walker's own slices and coefw = 0.
+#if defined(__CUDACC__)
+#define PEPS_HD __host__ __device__
+#else
+#define PEPS_HD
+#endif
+// one walker of be_fermion_targets (shared by the CUDA kernel and the test-only host simulation)
+PEPS_HD inline void fermion_target_one(const int32_t *c, const int32_t *jh, const int32_t *jv, int s1, int s2, int phys,
+                                       const int32_t *par, int kind, const int32_t *target, const double *coef, int T, int t,
+                                       int32_t &idx_a, int32_t &idx_b, double &coefw) {
+  const int c1 = c[s1], c2 = c[s2], p = c1 * phys + c2;
+  int tg;
+  double cf;
+  if (target) { tg = target[p * T + t]; cf = tg < 0 ? 0.0 : coef[p * T + t]; }
+  else { tg = c1 != c2 ? c2 * phys + c1 : -1; cf = tg < 0 ? 0.0 : 1.0; }
+  const int n1 = tg < 0 ? c1 : tg / phys, n2 = tg < 0 ? c2 : tg % phys;
+  const int moved = (par[c1] ^ par[n1]) & (par[c2] ^ par[n2]);
+  int va, vb, neg = 0;
+  if (kind == 1) { va = 6 + jv[s1]; vb = 6 + (jv[s2] ^ moved); }
+  else if (kind == 0 || !moved) { va = jh[s1]; vb = jh[s2] ^ moved; }
+  else if (kind == 2) { va = 2 + jh[s1]; vb = jh[s2] ^ 1; neg = jh[s2]; }
+  else { va = jh[s1]; vb = 4 + jh[s2]; neg = jh[s1]; }
+  idx_a = va * phys + n1;
+  idx_b = vb * phys + n2;
+  coefw = neg ? -cf : cf;
+}
+void be_fermion_targets(const int32_t *cfg, int nsites, int s1, int s2, int phys, const int32_t *phys_par,
+                        const int32_t *jw_h, const int32_t *jw_v, int kind, const int32_t *target, const double *coef,
+                        int T, int t, int32_t *idx_a, int32_t *idx_b, double *coefw, int W);
+// CalGTenForFermionicTensors + ActFermionPOps (utility/helpers.h:57-67, mc_energy_grad_evaluator.h:259-266) on the holes
+// of the horizontal machinery: psi_site = <hole, dressed site tensor>; hole <- hole * sign[jw_h] * amp[w] / psi_site, so
+// that hole / amp is O* = conj(d psi / d T) / conj(psi_site) in the user's (undressed) tensor entries.
+// sign: [2][hole_stride] (+1 / -1 per element for jw_h = 0 / 1); gtps_off[site]: offset of the site's dressed slices.
+void be_fermion_finish_holes(double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                             const double *gtps, const int64_t *gtps_off, const int32_t *gidx_h, const int32_t *jw_h,
+                             int nsites, const double *sign, const double *amp, int W);
+
 // O* accumulation (mc_energy_grad_evaluator.h:245-272) for one sample of all walkers:
 //   o = (1/amp[w]) * hole[w][e];  osum[slot(site,cfg[w][site]) + e] += o;  eosum[...] += eloc[w] * o
 // holes: [W][hole_stride]; per site: offset hole_off[site], size site_size[site]; TPS slot of (site, s) at

@@ -2601,6 +2601,85 @@ void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *el
   post_launch();
 }
 
+// =====================================================================================================
+// fermion mode (sign-dressed dense tensors; backend.h)
+// =====================================================================================================
+__global__ void fermion_gather_kernel(const int32_t *cfg, int rows, int cols, int phys, const int32_t *par, int32_t *gh,
+                                      int32_t *gv, int32_t *jh, int32_t *jv, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const long base = (long)w * rows * cols;
+  for (int r = 0; r < rows; ++r) {
+    int acc = 0;
+    for (int c = 0; c < cols; ++c) {
+      const long i = base + r * cols + c;
+      jh[i] = acc;
+      gh[i] = acc * phys + cfg[i];
+      acc ^= par[cfg[i]];
+    }
+  }
+  for (int c = 0; c < cols; ++c) {
+    int acc = 0;
+    for (int r = 0; r < rows; ++r) {
+      const long i = base + r * cols + c;
+      jv[i] = acc;
+      gv[i] = (6 + acc) * phys + cfg[i];
+      acc ^= par[cfg[i]];
+    }
+  }
+}
+void be_fermion_gather(const int32_t *cfg, int rows, int cols, int phys, const int32_t *phys_par, int32_t *gidx_h,
+                       int32_t *gidx_v, int32_t *jw_h, int32_t *jw_v, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  fermion_gather_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, rows, cols, phys, phys_par, gidx_h, gidx_v, jw_h, jw_v, W);
+  post_launch();
+}
+__global__ void fermion_targets_kernel(const int32_t *cfg, int nsites, int s1, int s2, int phys, const int32_t *par,
+                                       const int32_t *jh, const int32_t *jv, int kind, const int32_t *target,
+                                       const double *coef, int T, int t, int32_t *idx_a, int32_t *idx_b, double *coefw, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const long o = (long)w * nsites;
+  fermion_target_one(cfg + o, jh + o, jv + o, s1, s2, phys, par, kind, target, coef, T, t, idx_a[w], idx_b[w], coefw[w]);
+}
+void be_fermion_targets(const int32_t *cfg, int nsites, int s1, int s2, int phys, const int32_t *phys_par,
+                        const int32_t *jw_h, const int32_t *jw_v, int kind, const int32_t *target, const double *coef,
+                        int T, int t, int32_t *idx_a, int32_t *idx_b, double *coefw, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  fermion_targets_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, s1, s2, phys, phys_par, jw_h, jw_v, kind, target,
+                                                                coef, T, t, idx_a, idx_b, coefw, W);
+  post_launch();
+}
+// one CTA per (site, walker): fixed-order tree reduction of <hole, dressed tensor>, then the rescale of the hole
+__global__ void fermion_finish_holes_kernel(double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                                            const double *gtps, const int64_t *gtps_off, const int32_t *gidx_h,
+                                            const int32_t *jw_h, int nsites, const double *sign, const double *amp) {
+  __shared__ double red[256];
+  const int site = blockIdx.x, w = blockIdx.y;
+  const int sz = site_size[site];
+  double *h = holes + (long)w * hole_stride + hole_off[site];
+  const double *t = gtps + gtps_off[site] + (long)gidx_h[(long)w * nsites + site] * sz;
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < sz; e += blockDim.x) acc += h[e] * t[e];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double f = amp[w] / red[0];
+  const double *sg = sign + (long)jw_h[(long)w * nsites + site] * hole_stride + hole_off[site];
+  for (int e = threadIdx.x; e < sz; e += blockDim.x) h[e] = h[e] * sg[e] * f;
+}
+void be_fermion_finish_holes(double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                             const double *gtps, const int64_t *gtps_off, const int32_t *gidx_h, const int32_t *jw_h,
+                             int nsites, const double *sign, const double *amp, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  fermion_finish_holes_kernel<<<dim3(nsites, W), 256, 0, g_stream>>>(holes, hole_stride, hole_off, site_size, gtps, gtps_off,
+                                                                     gidx_h, jw_h, nsites, sign, amp);
+  post_launch();
+}
+
 template <int PHYS>
 __global__ void accumulate_ostar_kernel(const double *holes, long hole_stride, const int32_t *hole_off,
                                         const int32_t *site_size, const int32_t *tps_off, const int32_t *cfg,

@@ -83,6 +83,16 @@ int peps_set_model_term(peps_ctx *ctx, int32_t kind, int32_t T, const double *di
   GUARD(ctx, ctx->eng->set_model_term(kind, T, diag, target, coef))
 }
 int peps_clear_model_terms(peps_ctx *ctx) { GUARD(ctx, ctx->eng->clear_model_terms()) }
+int peps_set_fermion(peps_ctx *ctx, const int32_t *phys_par, const int32_t *leg_par, size_t n_leg_par) {
+  GUARD(ctx, {
+    Engine &e = *ctx->eng;
+    size_t need = 0;
+    for (int r = 0; r < e.rows(); ++r)
+      for (int c = 0; c < e.cols(); ++c) { int d[4]; e.site_dims(r, c, d); need += (size_t)(d[0] + d[1] + d[2] + d[3]); }
+    if (n_leg_par != need) throw std::invalid_argument("peps_set_fermion: leg_par must hold " + std::to_string(need) + " entries");
+    e.set_fermion(phys_par, leg_par);
+  })
+}
 int peps_set_configs(peps_ctx *ctx, const int32_t *c) { GUARD(ctx, ctx->eng->set_configs(c)) }
 int peps_get_configs(peps_ctx *ctx, int32_t *c) { GUARD(ctx, ctx->eng->get_configs(c)) }
 int peps_seed_rng(peps_ctx *ctx, const uint32_t *s) { GUARD(ctx, ctx->eng->seed_rng(s)) }

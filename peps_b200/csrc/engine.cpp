@@ -46,6 +46,8 @@ Engine::Engine(const EngineConfig &c)
   tps_total_ = off;
   hole_stride_ = hoff;
   tps_ = (double *)be_malloc(sizeof(double) * tps_total_);
+  gtps_ = tps_;
+  gtps_off_h_ = tps_off_h_;
   osum_ = (double *)be_malloc(sizeof(double) * tps_total_);
   eosum_ = (double *)be_malloc(sizeof(double) * tps_total_);
   be_memset0(osum_, sizeof(double) * tps_total_);
@@ -88,7 +90,9 @@ Engine::~Engine() {
   for (void *p : {(void *)tps_, (void *)osum_, (void *)eosum_, (void *)tps_off_d_, (void *)site_size_d_, (void *)hole_off_d_,
                   (void *)cfg_, (void *)amp_, (void *)mt_, (void *)mtidx_, (void *)accepted_, (void *)eloc_, (void *)psi_tmp_,
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
-                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)psi_list_d_, (void *)term_ia_, (void *)term_ib_, (void *)term_cw_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_})
+                  (void *)sr_cfgs_, (void *)sr_delta_, (void *)psi_list_d_, (void *)term_ia_, (void *)term_ib_, (void *)term_cw_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_,
+                  (void *)(fermion_ ? gtps_ : nullptr), (void *)gtps_off_d_, (void *)gidx_[0], (void *)gidx_[1], (void *)jw_[0],
+                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_})
     be_free(p);
   for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); }
   pool_.release_all();
@@ -99,7 +103,39 @@ Engine::~Engine() {
 void Engine::site_dims(int r, int c, int out[4]) const {
   for (int i = 0; i < 4; ++i) out[i] = site_dims_h_[(size_t)(r * cols_ + c)][(size_t)i];
 }
-void Engine::set_tps(const double *host) { be_h2d(tps_, host, sizeof(double) * tps_total_); touch_all(); }
+void Engine::set_tps(const double *host) {
+  be_h2d(tps_, host, sizeof(double) * tps_total_);
+  if (fermion_) {                                       // dress: FERMION_VARIANTS sign patterns per site (backend.h)
+    std::vector<double> g((size_t)(tps_total_ * FERMION_VARIANTS));
+    static const int vmask[FERMION_VARIANTS] = {0, 8, 4, 12, 6, 14, 0, 1};     // bits: L = 1, D = 2, R = 4, U = 8
+    for (int site = 0; site < nsites_; ++site) {
+      const auto &d = site_dims_h_[(size_t)site];
+      const int sz = site_size_h_[(size_t)site];
+      const std::vector<int32_t> *par = &leg_par_h_[(size_t)site * 4];
+      for (int v = 0; v < FERMION_VARIANTS; ++v) {
+        const bool vert = v >= 6;
+        int e = 0;
+        for (int l = 0; l < d[0]; ++l)
+          for (int dd = 0; dd < d[1]; ++dd)
+            for (int r = 0; r < d[2]; ++r)
+              for (int u = 0; u < d[3]; ++u, ++e) {
+                const int pl = par[0][(size_t)l], pd = par[1][(size_t)dd], pr = par[2][(size_t)r], pu = par[3][(size_t)u];
+                int q = vert ? (pl & pd) ^ (pl & pr) ^ (pl & pu) ^ pl ^ pd : (pl & pd) ^ (pl & pr) ^ (pd & pr) ^ pl ^ pd;
+                if (vmask[v] & 1) q ^= pl;
+                if (vmask[v] & 2) q ^= pd;
+                if (vmask[v] & 4) q ^= pr;
+                if (vmask[v] & 8) q ^= pu;
+                const double sg = q ? -1.0 : 1.0;
+                for (int p = 0; p < phys_; ++p)
+                  g[(size_t)(gtps_off_h_[(size_t)site] + ((long)v * phys_ + p) * sz + e)] =
+                      sg * host[tps_off_h_[(size_t)site] + (long)p * sz + e];
+              }
+      }
+    }
+    be_h2d(gtps_, g.data(), sizeof(double) * g.size());
+  }
+  touch_all();
+}
 void Engine::get_tps(double *host) { be_d2h(host, tps_, sizeof(double) * tps_total_); }
 void Engine::scale_tps(double f) {
   std::vector<double> h((size_t)tps_total_);
@@ -114,6 +150,7 @@ void Engine::set_configs(const int32_t *host) {
       throw std::invalid_argument("set_configs: entry " + std::to_string(host[i]) + " of walker " + std::to_string(i / nsites_) +
                                   " is outside [0, phys = " + std::to_string(phys_) + ")");
   be_h2d(cfg_, host, sizeof(int32_t) * (size_t)W_ * nsites_);
+  refresh_gather();
   touch_all();
 }
 void Engine::get_configs(int32_t *host) { be_d2h(host, cfg_, sizeof(int32_t) * (size_t)W_ * nsites_); }
@@ -190,7 +227,8 @@ TRef Engine::ref(const BT &t) const {
 }
 TRef Engine::site_ref(int site, int cfg_site) const {
   TRef r;
-  r.op = mkgather(tps_ + tps_off_h_[(size_t)site], cfg_ + cfg_site, nsites_, site_size_h_[(size_t)site]);
+  if (fermion_ && cfg_site != site) throw std::logic_error("fermion mode: exchanged tensors need explicit dressed slices");
+  r.op = mkgather(gtps_ + gtps_off_h_[(size_t)site], (fermion_ ? gidx_[gmode_] : cfg_) + cfg_site, nsites_, site_size_h_[(size_t)site]);
   r.rank = 4;
   for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
   return r;
@@ -205,7 +243,7 @@ static GettDesc with_hints(GettDesc d, const H *h) {
 }
 TRef Engine::site_ref_idx(int site, const int32_t *idx, int stride) const {
   TRef r;
-  r.op = mkgather(tps_ + tps_off_h_[(size_t)site], idx, stride, site_size_h_[(size_t)site]);
+  r.op = mkgather(gtps_ + gtps_off_h_[(size_t)site], idx, stride, site_size_h_[(size_t)site]);
   r.rank = 4;
   for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
   return r;
@@ -683,6 +721,7 @@ void Engine::purge_memo() {
     }
 }
 void Engine::push_grown(int pos, int mpo_num, int orient) {
+  mode_for_bmps(pos);
   const int k = (int)bmps_[pos].size();
   auto it = memo_[pos].find(k);
   if (it != memo_[pos].end()) {
@@ -769,6 +808,7 @@ void Engine::bten_operands(int post, int slice, int bten_size, const BT *&mps1, 
 }
 void Engine::grow_full_bten(int pos, int slice, int remain, bool init) {     // grow.h:243-373
   if (init) init_bten(pos);
+  mode_for_bten(pos);
   const int n = (pos == LEFT || pos == RIGHT) ? cols_ : rows_;
   for (int i = (int)bten_[pos].size() - 1; i < n - remain; ++i) {
     const BT *m1, *m2; int site;
@@ -777,6 +817,7 @@ void Engine::grow_full_bten(int pos, int slice, int remain, bool init) {     // 
   }
 }
 void Engine::grow_bten_step(int post) {                // grow.h:529-582
+  mode_for_bten(post);
   int slice = (post == LEFT || post == RIGHT) ? (int)bmps_[UP].size() - 1 : (int)bmps_[LEFT].size() - 1;
   const BT *m1, *m2; int site;
   bten_operands(post, slice, (int)bten_[post].size(), m1, m2, site);
@@ -789,6 +830,7 @@ void Engine::shift_bten_window(int pos) {              // grow.h:517-521
 }
 void Engine::nn_trace(int ra, int ca, int rb, int cb, int orient, int cfg_site_a, int cfg_site_b, double *psi_out) {
   ++n_trace_;                                          // trace.h:90-205
+  gmode_ = orient;
   int first, second, slice, ia, ib, n;
   if (orient == HORIZONTAL) { first = LEFT; second = RIGHT; slice = ra; ia = ca; ib = cb; n = cols_; }
   else { first = UP; second = DOWN; slice = ca; ia = ra; ib = rb; n = rows_; }
@@ -930,6 +972,7 @@ void Engine::bten2_operands(int post, int slice1, int bten_size, const BT *&mps1
 }
 void Engine::grow_full_bten2(int pos, int slice1, int remain, bool init) {       // grow.h:375-515
   if (init) init_bten2(pos);
+  mode_for_bten(pos);
   const int n = (pos == LEFT || pos == RIGHT) ? cols_ : rows_;
   for (int i = (int)bten2_[pos].size() - 1; i < n - remain; ++i) {
     const BT *m1, *m2; int s1, s2;
@@ -938,6 +981,7 @@ void Engine::grow_full_bten2(int pos, int slice1, int remain, bool init) {      
   }
 }
 void Engine::grow_bten2_step(int post, int slice1) {   // grow.h:447-493
+  mode_for_bten(post);
   const BT *m1, *m2; int s1, s2;
   bten2_operands(post, slice1, (int)bten2_[post].size(), m1, m2, s1, s2);
   bten2_[post].push_back(bten2_step(bten2_[post].back(), *m1, site_ref(s1, s1), site_ref(s2, s2), *m2, post));
@@ -1060,7 +1104,8 @@ void Engine::init_walkers() {                          // wave_function_componen
 }
 
 void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_updater.h:29-81
-  for (int sw = 0; sw < nsweeps; ++sw) {
+  if (fermion_) sweep_fermion(nsweeps);
+  else for (int sw = 0; sw < nsweeps; ++sw) {
     be_memset0(accepted_, sizeof(int32_t) * W_);
     generate_bmps_approach(UP);
     for (int row = 0; row < rows_; ++row) {
@@ -1156,6 +1201,7 @@ void Engine::ensure_idx_const() {
   be_h2d(idx_const_, h.data(), sizeof(int32_t) * h.size());
 }
 void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
+  require_boson("the full-space updater");
   const int d = phys_, nst = d * d;
   ensure_idx_const();
   ensure_psi_alt(nst);
@@ -1242,6 +1288,7 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
 }
 
 void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
+  require_boson("the three-site updater");
   if (rows_ < 3 || cols_ < 3) throw std::invalid_argument("the 3-site updater needs a lattice of at least 3x3");
   const int maxp = 6;
   if (!idx_perm_) idx_perm_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)maxp * W_ * 3);
@@ -1359,6 +1406,7 @@ void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
 }
 
 void Engine::energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  require_boson("the transverse-field Ising solver");
   // TransverseFieldIsingSquareOBC::CalEnergyAndHolesImplParsed (transverse_field_ising_square_obc.h:208-247)
   if (phys_ != 2) throw std::invalid_argument("transverse-field Ising model needs phys = 2");
   std::vector<int32_t> cfg((size_t)W_ * nsites_), flip((size_t)W_ * nsites_);
@@ -1399,6 +1447,7 @@ void Engine::energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *p
 }
 
 void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  if (fermion_) { energy_and_holes_fermion(calc_holes, eloc_host, psi_list_host); return; }
   if (tables_on_) { energy_and_holes_tables(calc_holes, eloc_host, psi_list_host); return; }
   if (tfim_) { energy_and_holes_tfim(calc_holes, eloc_host, psi_list_host); return; }
   if (phys_ != 2) throw std::invalid_argument("the XXZ / J1-J2 energy solvers need phys = 2");
@@ -1466,6 +1515,17 @@ void Engine::set_model_term(int kind, int T, const double *diag, const int32_t *
   const int np = kind == 2 ? phys_ : phys_ * phys_;
   for (int i = 0; i < np * T; ++i)
     if (target[i] >= np) throw std::invalid_argument("set_model_term: target state out of range");
+  if (fermion_) {
+    if (kind == 2 && T > 0) throw std::invalid_argument("set_model_term: fermion mode supports diagonal on-site terms only");
+    for (int p = 0; kind != 2 && p < np; ++p)
+      for (int t = 0; t < T; ++t) {
+        const int tg = target[p * T + t];
+        if (tg < 0) continue;
+        const int d1 = phys_par_h_[(size_t)(p / phys_)] ^ phys_par_h_[(size_t)(tg / phys_)];
+        const int d2 = phys_par_h_[(size_t)(p % phys_)] ^ phys_par_h_[(size_t)(tg % phys_)];
+        if (d1 != d2) throw std::invalid_argument("set_model_term: fermion mode needs targets that move one fermion between the two sites or keep both parities");
+      }
+  }
   TermTable &t = term_[kind];
   be_sync();
   be_free(t.diag); be_free(t.target); be_free(t.coef);
@@ -1565,6 +1625,206 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
   if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// fermion mode (engine.h: set_fermion)
+// ---------------------------------------------------------------------------------------------------
+void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
+  if (!phys_par || !leg_par) throw std::invalid_argument("set_fermion: null table");
+  if (fermion_) throw std::logic_error("set_fermion: already in fermion mode");
+  if (tables_on_) throw std::logic_error("set_fermion: call it before set_model_term");
+  for (int p = 0; p < phys_; ++p)
+    if (phys_par[p] != 0 && phys_par[p] != 1) throw std::invalid_argument("set_fermion: parities must be 0 or 1");
+  be_sync();
+  phys_par_h_.assign(phys_par, phys_par + phys_);
+  leg_par_h_.assign((size_t)nsites_ * 4, {});
+  long pos = 0;
+  for (int site = 0; site < nsites_; ++site)
+    for (int k = 0; k < 4; ++k) {
+      const int d = site_dims_h_[(size_t)site][(size_t)k];
+      auto &v = leg_par_h_[(size_t)site * 4 + (size_t)k];
+      v.assign(leg_par + pos, leg_par + pos + d);
+      for (int x : v) if (x != 0 && x != 1) throw std::invalid_argument("set_fermion: parities must be 0 or 1");
+      pos += d;
+    }
+  // the two ends of a bond must carry the same parities; boundary legs are even
+  for (int r = 0; r < rows_; ++r)
+    for (int c = 0; c < cols_; ++c) {
+      const int s = r * cols_ + c;
+      if (c + 1 < cols_ && leg_par_h_[(size_t)s * 4 + 2] != leg_par_h_[(size_t)(s + 1) * 4 + 0])
+        throw std::invalid_argument("set_fermion: R / L parities of a horizontal bond differ");
+      if (r + 1 < rows_ && leg_par_h_[(size_t)s * 4 + 1] != leg_par_h_[(size_t)(s + cols_) * 4 + 3])
+        throw std::invalid_argument("set_fermion: D / U parities of a vertical bond differ");
+      if ((c == 0 && leg_par_h_[(size_t)s * 4 + 0][0]) || (r == rows_ - 1 && leg_par_h_[(size_t)s * 4 + 1][0]) ||
+          (c == cols_ - 1 && leg_par_h_[(size_t)s * 4 + 2][0]) || (r == 0 && leg_par_h_[(size_t)s * 4 + 3][0]))
+        throw std::invalid_argument("set_fermion: boundary legs must be even");
+    }
+  fermion_ = true;
+  gtps_off_h_.resize((size_t)nsites_);
+  for (int s = 0; s < nsites_; ++s) gtps_off_h_[(size_t)s] = tps_off_h_[(size_t)s] * FERMION_VARIANTS;
+  gtps_ = (double *)be_malloc(sizeof(double) * (size_t)tps_total_ * FERMION_VARIANTS);
+  be_memset0(gtps_, sizeof(double) * (size_t)tps_total_ * FERMION_VARIANTS);
+  std::vector<int64_t> o64(gtps_off_h_.begin(), gtps_off_h_.end());
+  gtps_off_d_ = (int64_t *)be_malloc(sizeof(int64_t) * nsites_);
+  be_h2d(gtps_off_d_, o64.data(), sizeof(int64_t) * nsites_);
+  for (int m = 0; m < 2; ++m) {
+    gidx_[m] = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)W_ * nsites_);
+    jw_[m] = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)W_ * nsites_);
+  }
+  phys_par_d_ = (int32_t *)be_malloc(sizeof(int32_t) * phys_);
+  be_h2d(phys_par_d_, phys_par_h_.data(), sizeof(int32_t) * phys_);
+  psi_loc_ = (double *)be_malloc(sizeof(double) * W_);
+  if (!term_ia_) {
+    term_ia_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+    term_ib_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+    term_cw_ = (double *)be_malloc(sizeof(double) * W_);
+  }
+  // sign of d psi_H / d T per element: (-1)^(l d + l r + d r + l + d + u J_H)
+  std::vector<double> sg((size_t)hole_stride_ * 2);
+  for (int site = 0; site < nsites_; ++site) {
+    const auto &d = site_dims_h_[(size_t)site];
+    const std::vector<int32_t> *par = &leg_par_h_[(size_t)site * 4];
+    long e = hole_off_h_[(size_t)site];
+    for (int l = 0; l < d[0]; ++l)
+      for (int dd = 0; dd < d[1]; ++dd)
+        for (int r = 0; r < d[2]; ++r)
+          for (int u = 0; u < d[3]; ++u, ++e) {
+            const int pl = par[0][(size_t)l], pd = par[1][(size_t)dd], pr = par[2][(size_t)r], pu = par[3][(size_t)u];
+            const int q = (pl & pd) ^ (pl & pr) ^ (pd & pr) ^ pl ^ pd;
+            sg[(size_t)e] = q ? -1.0 : 1.0;
+            sg[(size_t)(hole_stride_ + e)] = (q ^ pu) ? -1.0 : 1.0;
+          }
+  }
+  fsign_ = (double *)be_malloc(sizeof(double) * sg.size());
+  be_h2d(fsign_, sg.data(), sizeof(double) * sg.size());
+  refresh_gather();
+  touch_all();
+}
+void Engine::refresh_gather() {
+  if (fermion_) be_fermion_gather(cfg_, rows_, cols_, phys_, phys_par_d_, gidx_[HORIZONTAL], gidx_[VERTICAL], jw_[HORIZONTAL], jw_[VERTICAL], W_);
+}
+// MCUpdateSquareNNExchangeOBC on fZ2 tensors (square_nn_updater.h:29-81, 146-188): same visit order, decisions and draws;
+// the exchanged tensors are the dressed slices of be_fermion_targets, the gather indices follow every decision.
+void Engine::sweep_fermion(int nsweeps) {
+  for (int sw = 0; sw < nsweeps; ++sw) {
+    be_memset0(accepted_, sizeof(int32_t) * W_);
+    generate_bmps_approach(UP);
+    for (int row = 0; row < rows_; ++row) {
+      init_bten(LEFT);
+      grow_full_bten(RIGHT, row, 2, true);
+      for (int col = 0; col < cols_ - 1; ++col) {
+        const int s1 = row * cols_ + col, s2 = s1 + 1;
+        be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], 0, nullptr, nullptr, 0, 0, term_ia_, term_ib_, term_cw_, W_);
+        nn_trace_idx(row, col, row, col + 1, HORIZONTAL, term_ia_, term_ib_, 1, psi_tmp_);
+        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        refresh_gather();
+        touch_site(s1); touch_site(s2);
+        if (col < cols_ - 2) shift_bten_window(RIGHT);
+      }
+      if (row < rows_ - 1) shift_bmps_window(DOWN);
+    }
+    delete_inner_bmps(LEFT);
+    delete_inner_bmps(RIGHT);
+    generate_bmps_approach(LEFT);
+    for (int col = 0; col < cols_; ++col) {
+      init_bten(UP);
+      grow_full_bten(DOWN, col, 2, true);
+      for (int row = 0; row < rows_ - 1; ++row) {
+        const int s1 = row * cols_ + col, s2 = s1 + cols_;
+        be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], 1, nullptr, nullptr, 0, 0, term_ia_, term_ib_, term_cw_, W_);
+        nn_trace_idx(row, col, row + 1, col, VERTICAL, term_ia_, term_ib_, 1, psi_tmp_);
+        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        refresh_gather();
+        touch_site(s1); touch_site(s2);
+        if (row < rows_ - 2) shift_bten_window(DOWN);
+      }
+      if (col < cols_ - 1) shift_bmps_window(RIGHT);
+    }
+    delete_inner_bmps(UP);
+  }
+}
+// SquareNNNModelEnergySolver traversal for fermionic tensors (square_nnn_energy_solver.h:143-310): psi is recomputed per
+// bond by Trace (NN) and once per plaquette by ReplaceNNNSiteTrace with the original tensors (NNN), so that psi_ex / psi
+// runs along one contraction path; the terms come from the model tables (SquareSpinlessFermion, SquaretJ*Model as data).
+void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  be_memset0(eloc_, sizeof(double) * W_);
+  int npsi = 0;
+  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * W_);
+  auto record_psi = [&](const double *psi) {
+    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * W_, psi, sizeof(double) * W_);
+    ++npsi;
+  };
+  const TermTable &nn = term_[0], &nnn = term_[1], &on = term_[2];
+  auto term = [&](const TermTable &tt, int s1, int s2, int kind, auto &&trace) {
+    if (tt.T == 0) { be_term_accumulate(cfg_, nsites_, s1, s2, phys_, tt.diag, nullptr, nullptr, psi_loc_, eloc_, W_); return; }
+    for (int t = 0; t < tt.T; ++t) {
+      be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], kind, tt.target, tt.coef, tt.T, t, term_ia_, term_ib_, term_cw_, W_);
+      trace(term_ia_, term_ib_, psi_tmp_);
+      be_term_accumulate(cfg_, nsites_, s1, s2, phys_, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_loc_, eloc_, W_);
+    }
+  };
+  generate_bmps_approach(UP);
+  for (int row = 0; row < rows_; ++row) {
+    init_bten(LEFT);
+    grow_full_bten(RIGHT, row, 1, true);
+    for (int col = 0; col < cols_; ++col) {
+      if (calc_holes) punch_hole(row, col, HORIZONTAL);
+      const int s1 = row * cols_ + col;
+      if (on.set) be_term_accumulate(cfg_, nsites_, s1, -1, phys_, on.diag, nullptr, nullptr, psi_loc_, eloc_, W_);
+      if (col < cols_ - 1) {
+        if (nn.set) {
+          nn_trace(row, col, row, col + 1, HORIZONTAL, s1, s1 + 1, psi_loc_);       // Trace(tn, site1, site2, orient)
+          if (col == 0) record_psi(psi_loc_);
+          term(nn, s1, s1 + 1, 0, [&](const int32_t *ia, const int32_t *ib, double *out) {
+            nn_trace_idx(row, col, row, col + 1, HORIZONTAL, ia, ib, 1, out);
+          });
+        }
+        shift_bten_window(RIGHT);
+      }
+    }
+    if (nnn.set && row < rows_ - 1) {
+      init_bten2(LEFT);
+      grow_full_bten2(RIGHT, row, 2, true);
+      for (int col = 0; col < cols_ - 1; ++col) {
+        const int s11 = row * cols_ + col, s21 = s11 + cols_, s12 = s11 + 1, s22 = s21 + 1;
+        gmode_ = HORIZONTAL;
+        nnn_trace_refs(row, col, HORIZONTAL, site_ref(s11, s11), site_ref(s21, s21), site_ref(s12, s12), site_ref(s22, s22), psi_loc_);
+        term(nnn, s11, s22, 2, [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row,col) - (row+1,col+1)
+          gmode_ = HORIZONTAL;
+          nnn_trace_refs(row, col, HORIZONTAL, site_ref_idx(s11, ia, 1), site_ref(s21, s21), site_ref(s12, s12), site_ref_idx(s22, ib, 1), out);
+        });
+        term(nnn, s21, s12, 3, [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row+1,col) - (row,col+1)
+          gmode_ = HORIZONTAL;
+          nnn_trace_refs(row, col, HORIZONTAL, site_ref(s11, s11), site_ref_idx(s21, ia, 1), site_ref_idx(s12, ib, 1), site_ref(s22, s22), out);
+        });
+        shift_bten2_window(RIGHT, row);
+      }
+    }
+    if (row < rows_ - 1) shift_bmps_window(DOWN);
+  }
+  if (calc_holes)
+    be_fermion_finish_holes(holes_, hole_stride_, hole_off_d_, site_size_d_, gtps_, gtps_off_d_, gidx_[HORIZONTAL], jw_[HORIZONTAL],
+                            nsites_, fsign_, amp_, W_);
+  generate_bmps_approach(LEFT);
+  for (int col = 0; col < cols_; ++col) {
+    init_bten(UP);
+    grow_full_bten(DOWN, col, 2, true);
+    for (int row = 0; row < rows_ - 1; ++row) {
+      const int s1 = row * cols_ + col, s2 = s1 + cols_;
+      if (nn.set) {
+        nn_trace(row, col, row + 1, col, VERTICAL, s1, s2, psi_loc_);
+        if (row == 0) record_psi(psi_loc_);
+        term(nn, s1, s2, 1, [&](const int32_t *ia, const int32_t *ib, double *out) {
+          nn_trace_idx(row, col, row + 1, col, VERTICAL, ia, ib, 1, out);
+        });
+      }
+      if (row < rows_ - 2) shift_bten_window(DOWN);
+    }
+    if (col < cols_ - 1) shift_bmps_window(RIGHT);
+  }
+  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * W_);
+  if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
+}
+
 double *Engine::bond_target(int kind, int row, int col) {
   if (!rec_bonds_) return eloc_;
   const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1);
@@ -1604,6 +1864,7 @@ void Engine::row_corr_hook(int row) {
   truncate_left();
 }
 void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr) {
+  require_boson("the spin measurement solver");
   if (tfim_) throw std::invalid_argument("measure: bond observables are defined for the XXZ / J1-J2 solvers");
   if (phys_ != 2) throw std::invalid_argument("measure: spin-1/2 observables need phys = 2");
   const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1), ncr = cols_ / 2;
@@ -1644,6 +1905,7 @@ void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, dou
     }
 }
 void Engine::measure_structure_factor(double *out_host) {
+  require_boson("the structure-factor measurement");
   if (phys_ != 2) throw std::invalid_argument("measure_structure_factor: S+ S- correlators are defined for spin-1/2 (phys = 2)");
   ensure_idx_const();
   const int32_t *up_idx = idx_const_ + (size_t)1 * W_, *dn_idx = idx_const_;     // spin-up / spin-down slices for every walker

@@ -146,6 +146,17 @@ class Engine {
   // target[p*T+t] = p' (or -1), coef[p*T+t] = <p|H|p'>. Setting any term switches the table-driven solver on.
   void set_model_term(int kind, int T, const double *diag, const int32_t *target, const double *coef);
   void clear_model_terms();
+  // Fermion mode (fZ2-graded tensors, BASELINE config #4): the graded network is evaluated as a bosonic network of
+  // sign-dressed site tensors, B = T * (-1)^q with q_H = l d + l r + d r + l + d + u J_H for the row machinery (UP / DOWN
+  // boundary MPS, LEFT / RIGHT BTen, BTen2) and q_V = l d + l r + l u + l + d + l J_V for the column machinery; J_H / J_V =
+  // parity of the sites left of / above the site (a Jordan-Wigner bit per walker and site, part of the gather index). The
+  // boundary MPS differ from the reference's graded ones (bmps_impl.h:21-96, 756-862 fermionic branches) by diagonal sign
+  // gauges only. phys_par[phys] = fermion parity of each physical state; leg_par = for every site (row-major) the parities
+  // of the index values of its L, D, R, U legs, concatenated (site_dims entries each). Call before set_tps; models are
+  // given by set_model_term tables (kinds 0 / 1 / 2) whose off-diagonal targets either move one fermion between the two
+  // sites or keep both site parities. Derivation and checks: oracle/fermion.py, tests/test_fermion_oracle.py.
+  void set_fermion(const int32_t *phys_par, const int32_t *leg_par);
+  bool fermion() const { return fermion_; }
 
   // ---- probes used by the parity tests (per-walker values of reference contractor calls)
   int bmps_stack_size(int pos) const { return (int)bmps_[pos].size(); }
@@ -211,6 +222,26 @@ class Engine {
   TRef site_ref_idx(int site, const int32_t *idx, int stride) const;
   void energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *psi_list_host);
   void energy_and_holes_tables(bool calc_holes, double *eloc_host, double *psi_list_host);
+  void energy_and_holes_fermion(bool calc_holes, double *eloc_host, double *psi_list_host);
+  void sweep_fermion(int nsweeps);
+  void refresh_gather();
+  void require_boson(const char *what) const {
+    if (fermion_) throw std::logic_error(std::string(what) + " is not available in fermion mode");
+  }
+  bool fermion_ = false;
+  mutable int gmode_ = HORIZONTAL;        // machinery whose dressing tn_site() / site_ref() gather (fermion mode)
+  void mode_for_bmps(int pos) const { gmode_ = (pos == UP || pos == DOWN) ? HORIZONTAL : VERTICAL; }
+  void mode_for_bten(int pos) const { gmode_ = (pos == LEFT || pos == RIGHT) ? HORIZONTAL : VERTICAL; }
+  double *gtps_ = nullptr;                // gathered TPS: == tps_ for bosons; FERMION_VARIANTS * phys dressed slices per site
+  std::vector<long> gtps_off_h_;
+  int64_t *gtps_off_d_ = nullptr;
+  int32_t *gidx_[2] = {nullptr, nullptr}; // [W][nsites] gather index per machinery (fermion mode)
+  int32_t *jw_[2] = {nullptr, nullptr};   // [W][nsites] Jordan-Wigner bits
+  int32_t *phys_par_d_ = nullptr;
+  std::vector<int32_t> phys_par_h_;
+  std::vector<std::vector<int32_t>> leg_par_h_;   // [site * 4 + leg]
+  double *fsign_ = nullptr;               // [2][hole_stride] sign of d psi / d T per element for J_H = 0 / 1
+  double *psi_loc_ = nullptr;             // [W] psi of the current bond / plaquette along the same contraction path
   struct TermTable { bool set = false; int T = 0; double *diag = nullptr; int32_t *target = nullptr; double *coef = nullptr; };
   TermTable term_[3];
   bool tables_on_ = false;

@@ -492,6 +492,48 @@ void be_term_accumulate(const int32_t *cfg, int nsites, int s1, int s2, int phys
     eloc[w] += e;
   }
 }
+void be_fermion_gather(const int32_t *cfg, int rows, int cols, int phys, const int32_t *par, int32_t *gh, int32_t *gv,
+                       int32_t *jh, int32_t *jv, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const long base = (long)w * rows * cols;
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) {
+        const long i = base + r * cols + c;
+        int left = 0, above = 0;
+        for (int k = 0; k < c; ++k) left ^= par[cfg[base + r * cols + k]];
+        for (int k = 0; k < r; ++k) above ^= par[cfg[base + k * cols + c]];
+        jh[i] = left; jv[i] = above;
+        gh[i] = left * phys + cfg[i];
+        gv[i] = (6 + above) * phys + cfg[i];
+      }
+  }
+}
+void be_fermion_targets(const int32_t *cfg, int nsites, int s1, int s2, int phys, const int32_t *phys_par,
+                        const int32_t *jw_h, const int32_t *jw_v, int kind, const int32_t *target, const double *coef,
+                        int T, int t, int32_t *idx_a, int32_t *idx_b, double *coefw, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const long o = (long)w * nsites;
+    fermion_target_one(cfg + o, jw_h + o, jw_v + o, s1, s2, phys, phys_par, kind, target, coef, T, t, idx_a[w], idx_b[w], coefw[w]);
+  }
+}
+void be_fermion_finish_holes(double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                             const double *gtps, const int64_t *gtps_off, const int32_t *gidx_h, const int32_t *jw_h,
+                             int nsites, const double *sign, const double *amp, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int site = 0; site < nsites; ++site) {
+      const int sz = site_size[site];
+      double *h = holes + (long)w * hole_stride + hole_off[site];
+      const double *t = gtps + gtps_off[site] + (long)gidx_h[(long)w * nsites + site] * sz;
+      double psi = 0.0;
+      for (int e = 0; e < sz; ++e) psi += h[e] * t[e];
+      const double f = amp[w] / psi;
+      const double *sg = sign + (long)jw_h[(long)w * nsites + site] * hole_stride + hole_off[site];
+      for (int e = 0; e < sz; ++e) h[e] = h[e] * sg[e] * f;
+    }
+}
 void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *eloc, int W) {
   ++g_launches;
   for (int w = 0; w < W; ++w) eloc[w] += -h00 * ((double)cfg[(long)w * nsites] - 0.5);

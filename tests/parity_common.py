@@ -253,3 +253,75 @@ def run_variational_parity(lib, scheme, rows=5, cols=5, D=3, chi=5, W=2, iters=3
     assert np.max(np.abs(b.amplitudes() / exact - 1)) < 0.2
     b.close()
     return worst
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fermion mode (fZ2-graded tensors as sign-dressed dense tensors)
+# ---------------------------------------------------------------------------------------------------------------------
+def fermion_configs(rows, cols, W, phys, seed=10):
+    """Half-filled (spinless) / two-holes-per-... configurations with an even fermion number, one per walker."""
+    out = []
+    n = rows * cols
+    for w in range(W):
+        rng = np.random.default_rng(seed + w)
+        if phys == 2:
+            base = np.array([0] * (n // 2 - (n // 2) % 2) + [1] * (n - n // 2 + (n // 2) % 2))
+        else:                                   # t-J: up / down / empty, even number of electrons
+            ne = (2 * n // 3) - ((2 * n // 3) % 2)
+            base = np.array([0] * (ne // 2) + [1] * (ne - ne // 2) + [2] * (n - ne))
+        out.append(rng.permutation(base).reshape(rows, cols))
+    return np.stack(out)
+
+
+def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", nsweeps=2, seed=3, tol=1e-10, seeds0=200,
+                                t2=0.6, check_holes=True):
+    """Sweeps + E_loc + O* of W walkers through the C ABI in fermion mode vs oracle/fermion.py, walker by walker:
+    configurations and acceptance counts bit-identical, |amplitudes|, E_loc, O* to `tol` (relative)."""
+    from oracle import fermion as F
+    from peps_b200.api import FermionSplitIndexTPS, TableModel
+    phys_par = (1, 0) if model == "spinless" else (1, 1, 0)
+    f = F.FermionTPS.random(rows, cols, D, seed, phys_par=phys_par)
+    ftps = FermionSplitIndexTPS(f.T, f.par, phys_par)
+    if model == "spinless":
+        omodel = F.SpinlessFermionModel(1.0, t2, 0.3)
+        tmodel = TableModel.spinless_fermion(1.0, t2, 0.3)
+    else:
+        omodel = F.tJModel(1.0, 0.3, mu=0.2, V=0.075)
+        tmodel = TableModel.tj(1.0, 0.3, V=0.075, mu=0.2)
+    cfgs = fermion_configs(rows, cols, W, len(phys_par))
+    tr = BMPSTruncateParams.SVD(*trunc)
+    b = WalkerBatch(rows, cols, len(phys_par), D, W, tr, lib=lib)
+    b.set_fermion(ftps)
+    b.set_tps(ftps)
+    b.set_model(tmodel)
+    b.set_configs(cfgs)
+    b.seed_rng(np.arange(seeds0, seeds0 + W))
+    b.init_walkers()
+    ws = [F.FermionWalker(f, cfgs[w], trunc) for w in range(W)]
+    ups = [F.FermionNNExchangeUpdater(seeds0 + w) for w in range(W)]
+    a0 = np.abs(b.amplitudes())
+    r0 = np.abs(np.array([w_.amplitude for w_ in ws]))
+    assert np.max(np.abs(a0 / r0 - 1)) < tol
+    worst = dict(amp=0.0, eloc=0.0, ostar=0.0)
+    for it in range(nsweeps):
+        acc = b.sweep(1)
+        racc = np.array([ups[w].sweep(ws[w])[0] for w in range(W)])
+        c = b.get_configs()
+        for w in range(W):
+            assert np.array_equal(c[w], ws[w].config), (it, w)
+        assert np.array_equal(acc, racc), (acc, racc)
+        amp = b.amplitudes()
+        ramp = np.array([w_.amplitude for w_ in ws])
+        worst["amp"] = max(worst["amp"], float(np.max(np.abs(np.abs(amp) / np.abs(ramp) - 1))))
+        e = b.energy_and_holes(check_holes)
+        holes = b.holes() if check_holes else None
+        for w in range(W):
+            re, rost, _ = omodel.energy_and_holes(ws[w], check_holes)
+            worst["eloc"] = max(worst["eloc"], abs(e[w] - re) / max(1.0, abs(re)))
+            if check_holes:
+                ref = np.concatenate([rost[r][c_].ravel() for r in range(rows) for c_ in range(cols)])
+                got = holes[w] / amp[w]                       # O* = finished hole / cached amplitude
+                worst["ostar"] = max(worst["ostar"], float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
+    assert worst["amp"] < tol and worst["eloc"] < tol and worst["ostar"] < tol, worst
+    b.close()
+    return worst

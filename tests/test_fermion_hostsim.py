@@ -1,0 +1,101 @@
+"""Fermion mode of the engine (fZ2-graded tensors as sign-dressed dense tensors) through the C ABI on the test-only host
+simulation of the device ops, against oracle/fermion.py (which is pinned by the reference's K8 energies)."""
+import itertools
+import os
+import numpy as np
+import pytest
+
+import hostsim_lib
+from parity_common import run_fermion_pipeline_parity
+from peps_b200.api import (BMPSTruncateParams, FermionSplitIndexTPS, TableModel, WalkerBatch, MCEnergyGradEvaluator,
+                           MonteCarloParams, Configuration, MCUpdateSquareNNExchange, PepsError)
+from test_fermion_oracle import load_golden, perms
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return hostsim_lib.load()
+
+
+@pytest.mark.parametrize("rows,cols,D,trunc", [
+    (4, 4, 4, (8, 8, 0.0)),
+    (3, 5, 2, (4, 4, 0.0)),
+    (4, 4, 2, (2, 6, 1e-8)),
+    (2, 2, 4, (1, 100, 0.0)),
+])
+def test_spinless_fermion_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
+    run_fermion_pipeline_parity(lib, rows, cols, D, 3, trunc, model="spinless", nsweeps=2)
+
+
+def test_tj_pipeline_parity_hostsim(lib):
+    run_fermion_pipeline_parity(lib, 4, 4, 4, 3, (8, 8, 0.0), model="tj", nsweeps=2)
+
+
+@pytest.mark.parametrize("t2", [2.1, -2.5])
+def test_k8_energy_through_abi(lib, t2):
+    """K8 through the C ABI: exact summation over the 6 half-filled configurations of the 2x2 simple-update fixture."""
+    f, z = load_golden(f"sf2x2_t2_{t2:+.1f}_double_su")
+    cfgs = np.stack(perms([0, 0, 1, 1], 2, 2))
+    ftps = FermionSplitIndexTPS(f.T, f.par, f.phys_par)
+    b = WalkerBatch(2, 2, 2, ftps.bond_dim(), len(cfgs), BMPSTruncateParams.SVD(8, 8, 1e-16), lib=lib)
+    b.set_fermion(ftps)
+    b.set_tps(ftps)
+    b.set_model(TableModel.spinless_fermion(1.0, t2, 0.0))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    e = b.energy_and_holes(False)
+    w = b.amplitudes() ** 2
+    assert abs(float(np.sum(w * e) / np.sum(w)) - float(z["exp_energy"])) < 1e-9
+
+
+def test_fermion_mode_rejects_unsupported(lib):
+    ftps = FermionSplitIndexTPS.random(3, 3, 2, 1)
+    b = WalkerBatch(3, 3, 2, 2, 2, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+    b.set_fermion(ftps)
+    with pytest.raises(PepsError):
+        b.set_fermion(ftps)                                       # once only
+    pair = np.zeros((4, 4)); pair[0, 3] = pair[3, 0] = 1.0        # pair creation: parities of both sites flip, no hop
+    b.set_model(TableModel(2, pair))                              # both flip -> allowed structure (moves counted as hop)
+    bad = np.zeros((4, 4)); bad[0, 1] = bad[1, 0] = 1.0           # one site parity flips
+    with pytest.raises(PepsError):
+        b.set_model(TableModel(2, bad))
+    b.close()
+
+
+def test_evaluator_gradient_fermion(lib):
+    """MCEnergyGradEvaluator on a FermionSplitIndexTPS: energy and gradient equal the oracle chain's accumulation."""
+    from oracle import fermion as F
+    rows, cols, D, W, n = 3, 4, 2, 2, 3
+    trunc = (4, 4, 0.0)
+    f = F.FermionTPS.random(rows, cols, D, 21)
+    ftps = FermionSplitIndexTPS(f.T, f.par, f.phys_par)
+    from parity_common import fermion_configs
+    cfgs = fermion_configs(rows, cols, W, 2)
+    ev = MCEnergyGradEvaluator(MonteCarloParams(n * W, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(*trunc), ftps,
+                               TableModel.spinless_fermion(1.0, 0.5, 0.2), MCUpdateSquareNNExchange(seed=77), W, configs=cfgs, lib=lib)
+    res = ev.Evaluate(ftps)
+    omodel = F.SpinlessFermionModel(1.0, 0.5, 0.2)
+    es = []
+    osum = [[[np.zeros_like(x) for x in site] for site in row] for row in f.T]
+    eosum = [[[np.zeros_like(x) for x in site] for site in row] for row in f.T]
+    for w in range(W):
+        wk = F.FermionWalker(f, cfgs[w], trunc)
+        up = F.FermionNNExchangeUpdater(77 + w)
+        for _ in range(n):
+            up.sweep(wk)
+            e, ost, _ = omodel.energy_and_holes(wk, True)
+            es.append((w, e))
+            for r in range(rows):
+                for c in range(cols):
+                    s = int(wk.config[r, c])
+                    osum[r][c][s] += ost[r][c]
+                    eosum[r][c][s] += e * ost[r][c]
+    N = n * W
+    from peps_b200.api import combine_energy_bins
+    emean, _ = combine_energy_bins(np.array([e for _, e in es]).reshape(W, n))
+    assert abs(res.energy - emean) < 1e-10
+    grad = np.concatenate([(eosum[r][c][s] / N - emean * osum[r][c][s] / N).ravel()
+                           for r in range(rows) for c in range(cols) for s in range(2)])
+    got = res.gradient.pack()
+    assert np.max(np.abs(got - grad)) <= 1e-9 * max(1.0, np.max(np.abs(grad)))
+    assert isinstance(res.gradient, FermionSplitIndexTPS)
