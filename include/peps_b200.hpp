@@ -99,6 +99,37 @@ inline ModelTerm XXZBondTerm(int32_t kind, double jz, double jxy) {
   });
 }
 
+// SquareSpinlessFermion::EvaluateBondEnergy / EvaluateNNNEnergy (square_spinless_fermion.h:118-211) against the probe:
+// states 0 = occupied, 1 = empty; the ratio is psi_ex / psi along one contraction path (fermion mode of the engine).
+inline ModelTerm SpinlessFermionBondTerm(double t, double V) {
+  return ProbeTwoSiteTerm(0, 2, [=](int c1, int c2, const std::function<double(int, int)> &ratio) {
+    const double e = V * double(1 - c1) * double(1 - c2);
+    return c1 == c2 ? e : -t * ratio(c2, c1) + e;
+  });
+}
+inline ModelTerm SpinlessFermionNNNTerm(double t2) {
+  return ProbeTwoSiteTerm(1, 2, [=](int c1, int c2, const std::function<double(int, int)> &ratio) {
+    return c1 == c2 ? 0.0 : -t2 * ratio(c2, c1);
+  });
+}
+// SquaretJModelMixIn::EvaluateBondEnergy (square_tJ_model.h:300-345): 0 = up, 1 = down, 2 = empty
+inline ModelTerm tJBondTerm(double t, double J, double V) {
+  return ProbeTwoSiteTerm(0, 3, [=](int c1, int c2, const std::function<double(int, int)> &ratio) {
+    if (c1 == c2) return c1 == 2 ? 0.0 : V;
+    if (c1 == 2 || c2 == 2) return -t * ratio(c2, c1);
+    return (-0.5 + ratio(c2, c1) * 0.5) * J + V;
+  });
+}
+// EvaluateTotalOnsiteEnergy of the t-J models (square_tJ_model.h:248-262): -mu per electron
+inline ModelTerm tJOnsiteTerm(double mu) {
+  return ProbeOneSiteTerm(3, [=](int c, const std::function<double(int)> &) { return c == 2 ? 0.0 : -mu; });
+}
+// Parities of a QLTensor<T, fZ2QN> SplitIndexTPS for WalkerBatch::SetFermion: phys_par[s] = parity of physical state s,
+// leg_par = per site (row-major) the parity of every index value of the L, D, R, U legs, concatenated.
+struct FermionParities {
+  std::vector<int32_t> phys_par, leg_par;
+};
+
 // ---- runtime parameter packs (algorithm/vmc_update/monte_carlo_peps_params.h) and their free functions -----------------
 struct ConfigurationRescueParams {
   bool enabled = true;
@@ -148,6 +179,8 @@ class WalkerBatch {
   // table-driven model (seam B2 as data): one call per term; ClearModelTerms returns to the built-in solvers
   void SetModelTerm(const ModelTerm &m) { ck(peps_set_model_term(h_, m.kind, m.T, m.diag.data(), m.target.data(), m.coef.data())); }
   void ClearModelTerms() { ck(peps_clear_model_terms(h_)); }
+  // fZ2-graded tensors (peps_set_fermion): once, before SetTPS and SetModelTerm
+  void SetFermion(const FermionParities &p) { ck(peps_set_fermion(h_, p.phys_par.data(), p.leg_par.data(), p.leg_par.size())); }
   std::vector<double> EnergyAndHoles(bool calc_holes) {
     std::vector<double> e((size_t)walkers_);
     ck(peps_energy_and_holes(h_, calc_holes ? 1 : 0, e.data(), nullptr));

@@ -99,3 +99,30 @@ def test_evaluator_gradient_fermion(lib):
     got = res.gradient.pack()
     assert np.max(np.abs(got - grad)) <= 1e-9 * max(1.0, np.max(np.abs(grad)))
     assert isinstance(res.gradient, FermionSplitIndexTPS)
+
+
+def run_cpp_fermion_case(libdir, libfile, extra_link=()):
+    """tests/cpp/test_cpp_fermion.cpp (the C++ wrapper: SetFermion + probe-built SpinlessFermion terms) on the 2x2
+    simple-update fixture must print the reference's golden energy -4.98966397657 (t2 = -2.5)."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    f, z = load_golden("sf2x2_t2_-2.5_double_su")
+    cfgs = np.stack(perms([0, 0, 1, 1], 2, 2))
+    ftps = FermionSplitIndexTPS(f.T, f.par, f.phys_par)
+    flat, lp = ftps.pack(), ftps.leg_par_flat()
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "cpp_fermion")
+        subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "cpp", "test_cpp_fermion.cpp"), "-o", exe,
+                               "-L" + libdir, "-l:" + libfile, "-Wl,-rpath," + libdir] + list(extra_link))
+        inp = (f"2 2 2 {ftps.bond_dim()} {len(cfgs)} 8 1.0 -2.5 0.0\n" + " ".join(map(str, ftps.phys_par)) + f"\n{lp.size} "
+               + " ".join(map(str, lp)) + f"\n{flat.size} " + " ".join(repr(float(x)) for x in flat) + "\n"
+               + " ".join(str(int(c)) for c in cfgs.ravel()) + "\n")
+        out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout
+    assert abs(float(out) - float(z["exp_energy"])) < 1e-9
+
+
+def test_cpp_wrapper_fermion_golden():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hostsim_lib.load()
+    run_cpp_fermion_case(os.path.join(root, "tests", "hostsim"), "libpeps_hostsim.so")

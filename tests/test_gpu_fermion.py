@@ -112,3 +112,13 @@ def test_config4_8x8_D8_chi64_fermion_properties(lib):
             off += 2 * sz
             hoff += sz
     b.close()
+
+
+def test_cpp_wrapper_fermion_on_cuda_library(lib):
+    """The C++ wrapper (SetFermion + probe-built SquareSpinlessFermion terms) linked against libpeps_b200.so reproduces
+    the reference's golden energy of the 2x2 simple-update fixture (t2 = -2.5)."""
+    import os
+    from test_fermion_hostsim import run_cpp_fermion_case
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run_cpp_fermion_case(os.path.join(root, "peps_b200"), "libpeps_b200.so",
+                         extra_link=["-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
