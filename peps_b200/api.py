@@ -381,6 +381,7 @@ class WalkerBatch:
         pp = np.ascontiguousarray(ftps.phys_par, dtype=np.int32)
         lp = ftps.leg_par_flat()
         self._ck(self.lib.peps_set_fermion(self.h, _ip(pp), _ip(lp), lp.size))
+        self.phys_par = tuple(int(x) for x in ftps.phys_par)
 
     def set_tps(self, tps):
         flat = tps.pack() if isinstance(tps, SplitIndexTPS) else np.ascontiguousarray(tps, dtype=np.float64)
@@ -489,6 +490,9 @@ class WalkerBatch:
         corr = np.empty((W, c // 2))
         self._ck(self.lib.peps_measure(self.h, _dp(e), _dp(eh), _dp(ev), _dp(edr), _dp(eur), _dp(corr)))
         cfg = self.get_configs()
+        if getattr(self, "phys_par", None) is not None:        # fermion models: requires_density_measurement (charge)
+            return {"energy": e, "charge": np.asarray(self.phys_par, dtype=float)[cfg], "bond_energy_h": eh,
+                    "bond_energy_v": ev, "bond_energy_dr": edr, "bond_energy_ur": eur}
         sz = cfg.astype(float) - 0.5
         first_down = (cfg[:, r // 2, c // 4] == 0)[:, None]          # EvaluateOffDiagOrderInRow channel split (:281-287)
         flat = sz.reshape(W, -1)

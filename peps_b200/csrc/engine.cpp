@@ -1754,12 +1754,12 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
     ++npsi;
   };
   const TermTable &nn = term_[0], &nnn = term_[1], &on = term_[2];
-  auto term = [&](const TermTable &tt, int s1, int s2, int kind, auto &&trace) {
-    if (tt.T == 0) { be_term_accumulate(cfg_, nsites_, s1, s2, phys_, tt.diag, nullptr, nullptr, psi_loc_, eloc_, W_); return; }
+  auto term = [&](const TermTable &tt, int s1, int s2, int kind, double *dst, auto &&trace) {
+    if (tt.T == 0) { be_term_accumulate(cfg_, nsites_, s1, s2, phys_, tt.diag, nullptr, nullptr, psi_loc_, dst, W_); return; }
     for (int t = 0; t < tt.T; ++t) {
       be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], kind, tt.target, tt.coef, tt.T, t, term_ia_, term_ib_, term_cw_, W_);
       trace(term_ia_, term_ib_, psi_tmp_);
-      be_term_accumulate(cfg_, nsites_, s1, s2, phys_, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_loc_, eloc_, W_);
+      be_term_accumulate(cfg_, nsites_, s1, s2, phys_, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_loc_, dst, W_);
     }
   };
   generate_bmps_approach(UP);
@@ -1774,7 +1774,7 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
         if (nn.set) {
           nn_trace(row, col, row, col + 1, HORIZONTAL, s1, s1 + 1, psi_loc_);       // Trace(tn, site1, site2, orient)
           if (col == 0) record_psi(psi_loc_);
-          term(nn, s1, s1 + 1, 0, [&](const int32_t *ia, const int32_t *ib, double *out) {
+          term(nn, s1, s1 + 1, 0, bond_target(0, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {
             nn_trace_idx(row, col, row, col + 1, HORIZONTAL, ia, ib, 1, out);
           });
         }
@@ -1788,11 +1788,11 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
         const int s11 = row * cols_ + col, s21 = s11 + cols_, s12 = s11 + 1, s22 = s21 + 1;
         gmode_ = HORIZONTAL;
         nnn_trace_refs(row, col, HORIZONTAL, site_ref(s11, s11), site_ref(s21, s21), site_ref(s12, s12), site_ref(s22, s22), psi_loc_);
-        term(nnn, s11, s22, 2, [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row,col) - (row+1,col+1)
+        term(nnn, s11, s22, 2, bond_target(2, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row,col) - (row+1,col+1)
           gmode_ = HORIZONTAL;
           nnn_trace_refs(row, col, HORIZONTAL, site_ref_idx(s11, ia, 1), site_ref(s21, s21), site_ref(s12, s12), site_ref_idx(s22, ib, 1), out);
         });
-        term(nnn, s21, s12, 3, [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row+1,col) - (row,col+1)
+        term(nnn, s21, s12, 3, bond_target(3, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row+1,col) - (row,col+1)
           gmode_ = HORIZONTAL;
           nnn_trace_refs(row, col, HORIZONTAL, site_ref(s11, s11), site_ref_idx(s21, ia, 1), site_ref_idx(s12, ib, 1), site_ref(s22, s22), out);
         });
@@ -1813,7 +1813,7 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
       if (nn.set) {
         nn_trace(row, col, row + 1, col, VERTICAL, s1, s2, psi_loc_);
         if (row == 0) record_psi(psi_loc_);
-        term(nn, s1, s2, 1, [&](const int32_t *ia, const int32_t *ib, double *out) {
+        term(nn, s1, s2, 1, bond_target(1, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {
           nn_trace_idx(row, col, row + 1, col, VERTICAL, ia, ib, 1, out);
         });
       }
@@ -1864,14 +1864,14 @@ void Engine::row_corr_hook(int row) {
   truncate_left();
 }
 void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr) {
-  require_boson("the spin measurement solver");
-  if (tfim_) throw std::invalid_argument("measure: bond observables are defined for the XXZ / J1-J2 solvers");
-  if (phys_ != 2) throw std::invalid_argument("measure: spin-1/2 observables need phys = 2");
+  // fermion mode: the same registry (energy, bond energies of the table model); the spin-1/2 row correlator is zero
+  if (!fermion_ && tfim_) throw std::invalid_argument("measure: bond observables are defined for the XXZ / J1-J2 solvers");
+  if (!fermion_ && phys_ != 2) throw std::invalid_argument("measure: spin-1/2 observables need phys = 2");
   const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1), ncr = cols_ / 2;
   const int nb = nh + nv + 2 * nd;
   if (!bond_rec_) bond_rec_ = (double *)be_malloc(sizeof(double) * (size_t)(nb + ncr) * W_);
   be_memset0(bond_rec_, sizeof(double) * (size_t)(nb + ncr) * W_);
-  upload_flipped_configs();
+  if (!fermion_) upload_flipped_configs();
   rec_bonds_ = true;
   std::vector<double> onsite((size_t)W_);
   try {
@@ -1894,7 +1894,7 @@ void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, dou
       for (int i = 0; i < ncr; ++i) {
         const int32_t *c = cfg.data() + (size_t)w * nsites_;
         const bool equal = c[row * cols_ + c1] == c[row * cols_ + c1 + i + 1];
-        row_corr[(size_t)w * ncr + i] = equal ? 0.0 : rec[(size_t)(nb + i) * W_ + w];
+        row_corr[(size_t)w * ncr + i] = (equal || fermion_) ? 0.0 : rec[(size_t)(nb + i) * W_ + w];
       }
   }
   if (energy)

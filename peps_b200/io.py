@@ -1,5 +1,7 @@
 """On-disk formats either side of the path, so states and warmed-up configurations written
-by the reference drop in and vice versa. Dense, TrivialRepQN tensors only (the bosonic models of this path).
+by the reference drop in and vice versa: dense TrivialRepQN tensors (the bosonic models) and multi-block fZ2 tensors
+(fermionic states: read_qlten_fz2 / load_fermion_tps return the dense blocks plus the parity of every index value, which
+is all the engine's fermion mode needs).
 
   * ``.qlten`` tensor stream      TensorToolkit QLTensor stream I/O as used by SplitIndexTPS::Dump / Load
                                   (two_dim_tn/tps/split_index_tps_impl.h:300-400); decoded in SURVEY.md section 8c:
@@ -23,7 +25,7 @@ import struct
 
 import numpy as np
 
-from .api import SplitIndexTPS, Configuration
+from .api import SplitIndexTPS, FermionSplitIndexTPS, Configuration
 
 def _tokens(buf):
     pos = 0
@@ -69,6 +71,76 @@ def read_qlten(path, dtype=None):
     if payload != n * item:
         raise ValueError(f"{path}: payload of {payload} bytes, expected {n} x {item} (wrong element type or truncated file)")
     return np.frombuffer(buf[pos:pos + n * item], dtype=dtype).reshape(dims).copy()
+
+
+def read_qlten_fz2(path, dtype=np.float64):
+    """fZ2-graded (block-sparse) QLTensor stream. Per index: ``nsct``, per sector ``qnval qnhash dgnc hash``, then
+    ``dir dim hash``; ``nblocks`` and the sector coordinates of every block; payload = the blocks in listed order, each
+    row-major. Returns (dense array, [parity of every index value per leg], [direction per leg])."""
+    buf = open(path, "rb").read()
+    it = _tokens(buf)
+    rank, pos = next(it)
+    legs = []
+    for _ in range(rank):
+        nsct, pos = next(it)
+        scts = []
+        for _ in range(nsct):
+            qn, _ = next(it); next(it)
+            dg, _ = next(it); next(it)
+            scts.append((qn, dg))
+        di, _ = next(it)
+        dm, _ = next(it)
+        _, pos = next(it)
+        if sum(dg for _, dg in scts) != dm:
+            raise ValueError(f"{path}: sector degeneracies do not add up to the index dimension (not an fZ2 tensor?)")
+        legs.append((scts, di, dm))
+    nblk, pos = next(it)
+    coords = []
+    for _ in range(nblk):
+        c = []
+        for _ in range(rank):
+            v, pos = next(it)
+            c.append(v)
+        coords.append(c)
+    out = np.zeros([l[2] for l in legs], dtype=dtype)
+    offs = [np.concatenate([[0], np.cumsum([dg for _, dg in l[0]])]) for l in legs]
+    item = np.dtype(dtype).itemsize
+    for c in coords:
+        shp = [legs[k][0][c[k]][1] for k in range(rank)]
+        n = int(np.prod(shp))
+        if pos + n * item > len(buf):
+            raise ValueError(f"{path}: truncated payload (wrong element type?)")
+        out[tuple(slice(offs[k][c[k]], offs[k][c[k] + 1]) for k in range(rank))] = \
+            np.frombuffer(buf[pos:pos + n * item], dtype=dtype).reshape(shp)
+        pos += n * item
+    if len(buf) - pos > 1:
+        raise ValueError(f"{path}: {len(buf) - pos} trailing bytes (wrong element type?)")
+    par = [np.concatenate([np.full(dg, qn % 2, dtype=np.int32) for qn, dg in l[0]]) for l in legs]
+    return out, par, [l[1] for l in legs]
+
+
+def load_fermion_tps(directory):
+    """SplitIndexTPS<T, fZ2QN>::Load: tensors (L, D, R, U, parity leg of dim 1) -> FermionSplitIndexTPS."""
+    rows, cols, phys = map(int, open(os.path.join(directory, "tps_meta.txt")).read().split()[:3])
+    T = [[[None] * phys for _ in range(cols)] for _ in range(rows)]
+    par = [[None] * cols for _ in range(rows)]
+    phys_par = [None] * phys
+    for r in range(rows):
+        for c in range(cols):
+            for s in range(phys):
+                d, p, dirs = read_qlten_fz2(os.path.join(directory, f"tps_ten{r}_{c}_{s}.qlten"))
+                if d.ndim != 5 or d.shape[4] != 1 or dirs != [-1, 1, 1, -1, -1]:
+                    raise ValueError("expected (L in, D out, R out, U in, parity in) site tensors")
+                T[r][c][s] = np.ascontiguousarray(d[..., 0])
+                if par[r][c] is None:
+                    par[r][c] = p[:4]
+                elif any((a != b).any() for a, b in zip(par[r][c], p[:4])):
+                    raise ValueError("virtual index sectors differ between the physical components of a site")
+                if phys_par[s] is None:
+                    phys_par[s] = int(p[4][0])
+                elif phys_par[s] != int(p[4][0]):
+                    raise ValueError("parity of a physical state differs between sites")
+    return FermionSplitIndexTPS(T, par, phys_par)
 
 
 def _header_template(path):

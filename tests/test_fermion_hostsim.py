@@ -126,3 +126,25 @@ def test_cpp_wrapper_fermion_golden():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     hostsim_lib.load()
     run_cpp_fermion_case(os.path.join(root, "tests", "hostsim"), "libpeps_hostsim.so")
+
+
+def test_fermion_measure_bond_energies(lib):
+    """peps_measure in fermion mode: the recorded bond energies add up to E_loc and 'charge' is the density."""
+    from parity_common import fermion_configs
+    rows, cols, D, W = 3, 4, 2, 3
+    ftps = FermionSplitIndexTPS.random(rows, cols, D, 8)
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+    b.set_fermion(ftps)
+    b.set_tps(ftps)
+    b.set_model(TableModel.spinless_fermion(1.0, 0.4, 0.7))
+    cfgs = fermion_configs(rows, cols, W, 2)
+    b.set_configs(cfgs)
+    b.init_walkers()
+    e = b.energy_and_holes(False)
+    m = b.measure()
+    tot = m["bond_energy_h"].reshape(W, -1).sum(1) + m["bond_energy_v"].reshape(W, -1).sum(1) \
+        + m["bond_energy_dr"].reshape(W, -1).sum(1) + m["bond_energy_ur"].reshape(W, -1).sum(1)
+    assert np.allclose(tot, e, rtol=1e-12, atol=1e-12) and np.allclose(m["energy"], e, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(m["charge"], 1.0 - cfgs)
+    assert np.any(m["bond_energy_dr"] != 0) and np.any(m["bond_energy_ur"] != 0)
+    b.close()

@@ -71,3 +71,24 @@ def test_measurement_stats_dump_layout(tmp_path):
     assert flat[0] == "index,mean,stderr" and flat[1].startswith("0,-1.9952127879312345e+00,")
     meta = open(tmp_path / "out" / "metadata.txt").read()
     assert meta.startswith("format_version 1\n") and "lx 2" in meta
+
+
+def test_fermion_tps_loader_matches_repacked_fixture():
+    """peps_b200.io.load_fermion_tps on the reference's fZ2 fixture == the committed re-packed golden (needs the
+    reference tree: skipped on the GPU box)."""
+    import os
+    import pytest
+    d = "/root/reference/tests/test_data/spinless_fermion_tps_t2_2.100000_double_from_simple_update"
+    if not os.path.isdir(d):
+        pytest.skip("reference fixtures not present")
+    from peps_b200.io import load_fermion_tps
+    from test_fermion_oracle import load_golden
+    f = load_fermion_tps(d)
+    g, _ = load_golden("sf2x2_t2_+2.1_double_su")
+    assert f.phys_par == g.phys_par == (1, 0)
+    for r in range(2):
+        for c in range(2):
+            for s in range(2):
+                assert np.array_equal(f.t[r][c][s], g.T[r][c][s])
+            for k in range(4):
+                assert np.array_equal(f.par[r][c][k], g.par[r][c][k])
