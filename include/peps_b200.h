@@ -113,6 +113,16 @@ int peps_clear_model_terms(peps_ctx *ctx);
  * keep both site parities (hopping, spin exchange). Updater: NN exchange (peps_sweep). */
 int peps_set_fermion(peps_ctx *ctx, const int32_t *phys_par, const int32_t *leg_par, size_t n_leg_par);
 
+/* Jastrow-dressed wave function psi(S) = psi_PEPS(S) * exp(sum_{i<j} v_ij n_i n_j): TPSWaveFunctionComponent<..., JastrowDress>
+ * (vmc_basic/wave_function_component.h:107-135) with JastrowFactor (vmc_basic/jastrow_factor.h:34-121). v: [nsites][nsites]
+ * symmetric, row-major site index, diagonal ignored; density[phys]: particle number of each physical state (t-J: {1, 1, 0}).
+ * peps_sweep then is MCUpdateSquareNNExchangeJastrowDressedTJ (square_nn_updater.h:380-438: the Jastrow ratio enters the
+ * acceptance, the cached amplitude stays the PEPS part) and the table-driven / fermionic energy solvers multiply every
+ * exchange matrix element by the Jastrow ratio (square_tJ_model.h:352-410). Needs a model given by peps_set_model_term whose
+ * off-diagonal targets are exchanges of the two local states. */
+int peps_set_jastrow(peps_ctx *ctx, const double *v, const int32_t *density);
+int peps_clear_jastrow(peps_ctx *ctx);
+
 /* Configuration per walker (vmc_basic/configuration.h:57), int32 [W][rows][cols]. */
 int peps_set_configs(peps_ctx *ctx, const int32_t *cfg);
 int peps_get_configs(peps_ctx *ctx, int32_t *cfg);

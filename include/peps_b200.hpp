@@ -180,6 +180,8 @@ class WalkerBatch {
   void SetModelTerm(const ModelTerm &m) { ck(peps_set_model_term(h_, m.kind, m.T, m.diag.data(), m.target.data(), m.coef.data())); }
   void ClearModelTerms() { ck(peps_clear_model_terms(h_)); }
   // fZ2-graded tensors (peps_set_fermion): once, before SetTPS and SetModelTerm
+  // JastrowDress: v[nsites * nsites] symmetric, density[phys] (peps_set_jastrow)
+  void SetJastrow(const std::vector<double> &v, const std::vector<int32_t> &density) { ck(peps_set_jastrow(h_, v.data(), density.data())); }
   void SetFermion(const FermionParities &p) { ck(peps_set_fermion(h_, p.phys_par.data(), p.leg_par.data(), p.leg_par.size())); }
   std::vector<double> EnergyAndHoles(bool calc_holes) {
     std::vector<double> e((size_t)walkers_);

@@ -294,6 +294,23 @@ def hop_variants(ftps, config, jw_h, jw_v, kind, a, b):
     return ftps.variant(*a, cb, HORIZONTAL, ma), ftps.variant(*b, ca, HORIZONTAL, mb), sign
 
 
+def jastrow_ratio(v, density, config, a, b):
+    """Jastrow-factor ratio (new / old) of exchanging the states of a and b: JastrowFieldAtSite
+    (vmc_basic/jastrow_factor.h:99-111) and the exp(field difference) of square_nn_updater.h:402-419."""
+    n = np.asarray(density)[np.asarray(config)]
+    if n[a] == n[b]:
+        return 1.0
+    cols = n.shape[1]
+    ia, ib = a[0] * cols + a[1], b[0] * cols + b[1]
+    fa = fb = 0.0
+    for j, nj in enumerate(n.reshape(-1)):
+        if j != ia:
+            fa += v[ia, j] * float(nj)
+        if j != ib:
+            fb += v[ib, j] * float(nj)
+    return float(np.exp(fa - fb)) if n[a] < n[b] else float(np.exp(fb - fa))
+
+
 class FermionWalker:
     """TPSWaveFunctionComponent for fZ2 tensors (wave_function_component.h:136-379): two dressed projections of the
     same configuration, tn_h for the row machinery and tn_v for the column machinery."""
@@ -337,8 +354,11 @@ class FermionWalker:
 class FermionNNExchangeUpdater:
     """MCUpdateSquareNNExchangeOBC on fZ2 tensors (square_nn_updater.h:29-81, 146-188): same decisions, same draws."""
 
-    def __init__(self, seed):
+    def __init__(self, seed, jastrow=None):
+        """jastrow = (v[nsites][nsites], density[phys]): MCUpdateSquareNNExchangeJastrowDressedTJ
+        (square_nn_updater.h:380-438)."""
         self.rng = MT19937(seed)
+        self.jastrow = jastrow
 
     def two_site_update(self, a, b, bond_dir, w):
         c1, c2 = int(w.config[a]), int(w.config[b])
@@ -349,7 +369,11 @@ class FermionNNExchangeUpdater:
         tn = w.tn_h if bond_dir == HORIZONTAL else w.tn_v
         psi_b = w.contractor.replace_nn_site_trace(tn, a, b, bond_dir, ta, tb)
         psi_a = w.amplitude
-        if not abs(psi_b) >= abs(psi_a):
+        if self.jastrow is not None:
+            ratio = abs(psi_b * jastrow_ratio(self.jastrow[0], self.jastrow[1], w.config, a, b)) / abs(psi_a)
+            if not (ratio >= 1.0 or self.rng.uniform01() < ratio * ratio):
+                return False
+        elif not abs(psi_b) >= abs(psi_a):
             div = abs(psi_b) / abs(psi_a)
             if not (self.rng.uniform01() < div * div):
                 return False
@@ -391,6 +415,10 @@ class FermionModel:
     """SquareNNNModelEnergySolver traversal for fermionic tensors (square_nnn_energy_solver.h:104-310): psi is
     recomputed per bond by Trace (NN) / ReplaceNNNSiteTrace with the original tensors (NNN, once per plaquette)."""
     has_nnn = False
+    jastrow = None          # (v, density): Jastrow-dressed solver (square_tJ_model.h:352-410)
+
+    def _jr(self, w, a, b):
+        return 1.0 if self.jastrow is None else jastrow_ratio(self.jastrow[0], self.jastrow[1], w.config, a, b)
 
     def diag_nn(self, c1, c2):
         return 0.0
@@ -414,7 +442,7 @@ class FermionModel:
         psi = w.contractor.trace(tn, a, orient)
         ta, tb, sg = hop_variants(w.ftps, w.config, w.jw_h, w.jw_v, 'h' if orient == HORIZONTAL else 'v', a, b)
         psi_ex = sg * w.contractor.replace_nn_site_trace(tn, a, b, orient, ta, tb)
-        return e + self.offdiag_nn(c1, c2) * np.conj(psi_ex / psi), psi
+        return e + self.offdiag_nn(c1, c2) * self._jr(w, a, b) * np.conj(psi_ex / psi), psi
 
     def nnn_energy(self, a, b, diagonal_dir, w, psi):
         c1, c2 = int(w.config[a]), int(w.config[b])
@@ -426,7 +454,7 @@ class FermionModel:
                                                       w.tn_h[a[0]][a[1]], w.tn_h[b[0]][b[1]])
         ta, tb, sg = hop_variants(w.ftps, w.config, w.jw_h, w.jw_v, 'dr' if diagonal_dir == 0 else 'ur', a, b)
         psi_ex = sg * w.contractor.replace_nnn_site_trace(w.tn_h, left_up, diagonal_dir, HORIZONTAL, ta, tb)
-        return self.offdiag_nnn(c1, c2) * np.conj(psi_ex / psi), psi
+        return self.offdiag_nnn(c1, c2) * self._jr(w, a, b) * np.conj(psi_ex / psi), psi
 
     def energy_and_holes(self, w, calc_holes=True):
         """Returns (E_loc, O*[rows][cols] or None, psi_list).  O*(site) = conj(d psi / d T_site[cfg]) / conj(psi_site)

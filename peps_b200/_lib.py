@@ -49,6 +49,8 @@ SIGNATURES = {
     "peps_set_model_term": (C.c_int, [_P, C.c_int32, C.c_int32, _D, _I, _D]),
     "peps_clear_model_terms": (C.c_int, [_P]),
     "peps_set_fermion": (C.c_int, [_P, _I, _I, C.c_size_t]),
+    "peps_set_jastrow": (C.c_int, [_P, _D, _I]),
+    "peps_clear_jastrow": (C.c_int, [_P]),
     "peps_set_configs": (C.c_int, [_P, _I]),
     "peps_get_configs": (C.c_int, [_P, _I]),
     "peps_seed_rng": (C.c_int, [_P, _U]),

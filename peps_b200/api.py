@@ -383,6 +383,13 @@ class WalkerBatch:
         self._ck(self.lib.peps_set_fermion(self.h, _ip(pp), _ip(lp), lp.size))
         self.phys_par = tuple(int(x) for x in ftps.phys_par)
 
+    def set_jastrow(self, v, density):
+        """JastrowDress (wave_function_component.h:107-135): v[nsites][nsites] symmetric, density[phys]."""
+        n = self.rows * self.cols
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(n, n)
+        d = np.ascontiguousarray(density, dtype=np.int32).reshape(self.phys)
+        self._ck(self.lib.peps_set_jastrow(self.h, _dp(v), _ip(d)))
+
     def set_tps(self, tps):
         flat = tps.pack() if isinstance(tps, SplitIndexTPS) else np.ascontiguousarray(tps, dtype=np.float64)
         if flat.size != self.tps_size:

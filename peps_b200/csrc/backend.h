@@ -222,8 +222,16 @@ void be_mt_seed(uint32_t *mt, int32_t *idx, const uint32_t *seeds, int W);
 // MCUpdateSquareNNExchangeOBC::TwoSiteNNUpdateLocalImpl decision (square_nn_updater.h:146-188) for all walkers:
 // skip if cfg equal; accept if |psi_b| >= |psi_a| else iff uniform01 < (|psi_b|/|psi_a|)^2 (draw only then);
 // on accept swap cfg[s1], cfg[s2], amplitude = psi_b, accepted[w] += 1.
+// jastrow != nullptr: MCUpdateSquareNNExchangeJastrowDressedTJ (square_nn_updater.h:380-438): abs_ratio = |psi_b * jastrow[w]| /
+// |psi_a|, accept iff abs_ratio >= 1 or uniform01 < abs_ratio^2 (the draw happens only then); the cached amplitude stays the PEPS part.
 void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b, double *amp,
-                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W);
+                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W, const double *jastrow = nullptr);
+// Jastrow factor exp(sum_{i<j} v_ij n_i n_j) (vmc_basic/jastrow_factor.h:34-121): ratio[w] of exchanging the states of s1 and s2,
+// 1 when the two densities are equal, else exp(field(empty site) - field(filled site)) with field(i) = sum_{j != i} v[i][j] n_j
+// over the sites in row-major order (JastrowFieldAtSite). dens[phys] = density of a physical state, v = [nsites][nsites].
+void be_jastrow_ratio(const int32_t *cfg, int nsites, int s1, int s2, const int32_t *dens, const double *v, double *ratio, int W);
+// x[w] *= s[w]
+void be_scale(double *x, const double *s, int W);
 // EvaluateBondEnergy of SquareSpinOneHalfXXZModelMixIn (square_spin_onehalf_xxz_obc.h:72-104):
 // eloc[w] += (c1==c2) ? 0.25 jz : -0.25 jz + (psi_ex[w] * (1/psi[w])) * 0.5 jxy
 void be_xxz_bond_energy(const int32_t *cfg, int nsites, int s1, int s2, const double *psi_ex, const double *psi,

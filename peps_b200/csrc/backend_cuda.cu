@@ -2498,7 +2498,7 @@ __device__ double mt_uniform01(uint32_t *s, int32_t &i) {
 }
 
 __global__ void nn_exchange_decide_kernel(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b,
-                                          double *amp, uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+                                          double *amp, uint32_t *mt, int32_t *idx, int32_t *accepted, int W, const double *jastrow) {
   int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   int32_t *c = cfg + (long)w * nsites;
@@ -2506,9 +2506,11 @@ __global__ void nn_exchange_decide_kernel(int32_t *cfg, int nsites, int s1, int 
   if (c1 == c2) return;
   double pb = psi_b[w], pa = amp[w];
   bool ok;
-  if (fabs(pb) >= fabs(pa)) ok = true;
-  else {
-    double div = fabs(pb) / fabs(pa);
+  double div = 0.0;
+  if (jastrow) { div = fabs(pb * jastrow[w]) / fabs(pa); ok = div >= 1.0; }
+  else ok = fabs(pb) >= fabs(pa);
+  if (!ok) {
+    if (!jastrow) div = fabs(pb) / fabs(pa);
     double P = div * div;
     int32_t i = idx[w];
     double u = mt_uniform01(mt + (long)w * 624, i);
@@ -2522,9 +2524,38 @@ __global__ void nn_exchange_decide_kernel(int32_t *cfg, int nsites, int s1, int 
   }
 }
 void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b, double *amp,
-                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W, const double *jastrow) {
   LaunchScope scope(KC_SMALL, 0.0);
-  nn_exchange_decide_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, nsites, s1, s2, psi_b, amp, mt, idx, accepted, W);
+  nn_exchange_decide_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, nsites, s1, s2, psi_b, amp, mt, idx, accepted, W, jastrow);
+  post_launch();
+}
+__global__ void jastrow_ratio_kernel(const int32_t *cfg, int nsites, int s1, int s2, const int32_t *dens, const double *v,
+                                     double *ratio, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const int32_t *c = cfg + (long)w * nsites;
+  const int n1 = dens[c[s1]], n2 = dens[c[s2]];
+  if (n1 == n2) { ratio[w] = 1.0; return; }
+  double f1 = 0.0, f2 = 0.0;
+  for (int j = 0; j < nsites; ++j) {
+    const double nj = (double)dens[c[j]];
+    if (j != s1) f1 += v[(long)s1 * nsites + j] * nj;
+    if (j != s2) f2 += v[(long)s2 * nsites + j] * nj;
+  }
+  ratio[w] = n1 < n2 ? exp(f1 - f2) : exp(f2 - f1);
+}
+void be_jastrow_ratio(const int32_t *cfg, int nsites, int s1, int s2, const int32_t *dens, const double *v, double *ratio, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  jastrow_ratio_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, nsites, s1, s2, dens, v, ratio, W);
+  post_launch();
+}
+__global__ void scale_kernel(double *x, const double *s, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < W) x[w] *= s[w];
+}
+void be_scale(double *x, const double *s, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  scale_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(x, s, W);
   post_launch();
 }
 

@@ -83,6 +83,8 @@ int peps_set_model_term(peps_ctx *ctx, int32_t kind, int32_t T, const double *di
   GUARD(ctx, ctx->eng->set_model_term(kind, T, diag, target, coef))
 }
 int peps_clear_model_terms(peps_ctx *ctx) { GUARD(ctx, ctx->eng->clear_model_terms()) }
+int peps_set_jastrow(peps_ctx *ctx, const double *v, const int32_t *density) { GUARD(ctx, ctx->eng->set_jastrow(v, density)) }
+int peps_clear_jastrow(peps_ctx *ctx) { GUARD(ctx, ctx->eng->clear_jastrow()) }
 int peps_set_fermion(peps_ctx *ctx, const int32_t *phys_par, const int32_t *leg_par, size_t n_leg_par) {
   GUARD(ctx, {
     Engine &e = *ctx->eng;

@@ -92,7 +92,7 @@ Engine::~Engine() {
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
                   (void *)sr_cfgs_, (void *)sr_delta_, (void *)psi_list_d_, (void *)term_ia_, (void *)term_ib_, (void *)term_cw_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_,
                   (void *)(fermion_ ? gtps_ : nullptr), (void *)gtps_off_d_, (void *)gidx_[0], (void *)gidx_[1], (void *)jw_[0],
-                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_})
+                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_, (void *)jastrow_v_, (void *)jr_, (void *)dens_d_})
     be_free(p);
   for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); }
   pool_.release_all();
@@ -1114,7 +1114,7 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
       for (int col = 0; col < cols_ - 1; ++col) {
         const int s1 = row * cols_ + col, s2 = s1 + 1;
         nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);          // :164-166 (masked in the decide kernel)
-        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
         touch_site(s1); touch_site(s2);
         if (col < cols_ - 2) shift_bten_window(RIGHT);
       }
@@ -1129,7 +1129,7 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
       for (int row = 0; row < rows_ - 1; ++row) {
         const int s1 = row * cols_ + col, s2 = s1 + cols_;
         nn_trace(row, col, row + 1, col, VERTICAL, s2, s1, psi_tmp_);
-        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
         touch_site(s1); touch_site(s2);
         if (row < rows_ - 2) shift_bten_window(DOWN);
       }
@@ -1447,6 +1447,8 @@ void Engine::energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *p
 }
 
 void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_list_host) {
+  if (jastrow_on_ && !(fermion_ || tables_on_)) throw std::logic_error("Jastrow dressing needs a table-driven model (peps_set_model_term)");
+  if (jastrow_on_ && !tables_exchange_only_) throw std::logic_error("Jastrow dressing supports exchange terms only");
   if (fermion_) { energy_and_holes_fermion(calc_holes, eloc_host, psi_list_host); return; }
   if (tables_on_) { energy_and_holes_tables(calc_holes, eloc_host, psi_list_host); return; }
   if (tfim_) { energy_and_holes_tfim(calc_holes, eloc_host, psi_list_host); return; }
@@ -1526,6 +1528,12 @@ void Engine::set_model_term(int kind, int T, const double *diag, const int32_t *
         if (d1 != d2) throw std::invalid_argument("set_model_term: fermion mode needs targets that move one fermion between the two sites or keep both parities");
       }
   }
+  for (int p = 0; kind != 2 && p < np; ++p)
+    for (int tt = 0; tt < T; ++tt) {
+      const int tg = target[p * T + tt];
+      if (tg >= 0 && tg != (p % phys_) * phys_ + p / phys_) tables_exchange_only_ = false;
+    }
+  if (kind == 2 && T > 0) tables_exchange_only_ = false;
   TermTable &t = term_[kind];
   be_sync();
   be_free(t.diag); be_free(t.target); be_free(t.coef);
@@ -1550,6 +1558,7 @@ void Engine::clear_model_terms() {
   be_sync();
   for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); t = TermTable(); }
   tables_on_ = false;
+  tables_exchange_only_ = true;
 }
 // The traversal of SquareNNNModelEnergySolver (square_nnn_energy_solver.h:79-315, bond_traversal_mixin.h:112-143) with every
 // term evaluated from its table: diagonal element + one replacement trace per target slot, masked per walker.
@@ -1567,6 +1576,7 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
     if (tt.T == 0) { be_term_accumulate(cfg_, nsites_, s1, s2, phys_, tt.diag, nullptr, nullptr, psi_row_, eloc_, W_); return; }
     for (int t = 0; t < tt.T; ++t) {
       be_term_targets(cfg_, nsites_, s1, s2, phys_, tt.target, tt.coef, tt.T, t, term_ia_, s2 >= 0 ? term_ib_ : nullptr, term_cw_, W_);
+      if (s2 >= 0) if (const double *jr = jastrow_for(s1, s2)) be_scale(term_cw_, jr, W_);
       trace(term_ia_, term_ib_, psi_tmp_);
       be_term_accumulate(cfg_, nsites_, s1, s2, phys_, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_row_, eloc_, W_);
     }
@@ -1699,6 +1709,21 @@ void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
   refresh_gather();
   touch_all();
 }
+void Engine::set_jastrow(const double *v, const int32_t *density) {
+  if (!v || !density) throw std::invalid_argument("set_jastrow: null table");
+  for (int i = 0; i < nsites_; ++i)
+    for (int j = 0; j < i; ++j)
+      if (v[(size_t)i * nsites_ + j] != v[(size_t)j * nsites_ + i]) throw std::invalid_argument("set_jastrow: v must be symmetric");
+  be_sync();
+  if (!jastrow_v_) {
+    jastrow_v_ = (double *)be_malloc(sizeof(double) * (size_t)nsites_ * nsites_);
+    jr_ = (double *)be_malloc(sizeof(double) * W_);
+    dens_d_ = (int32_t *)be_malloc(sizeof(int32_t) * phys_);
+  }
+  be_h2d(jastrow_v_, v, sizeof(double) * (size_t)nsites_ * nsites_);
+  be_h2d(dens_d_, density, sizeof(int32_t) * phys_);
+  jastrow_on_ = true;
+}
 void Engine::refresh_gather() {
   if (fermion_) be_fermion_gather(cfg_, rows_, cols_, phys_, phys_par_d_, gidx_[HORIZONTAL], gidx_[VERTICAL], jw_[HORIZONTAL], jw_[VERTICAL], W_);
 }
@@ -1715,7 +1740,7 @@ void Engine::sweep_fermion(int nsweeps) {
         const int s1 = row * cols_ + col, s2 = s1 + 1;
         be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], 0, nullptr, nullptr, 0, 0, term_ia_, term_ib_, term_cw_, W_);
         nn_trace_idx(row, col, row, col + 1, HORIZONTAL, term_ia_, term_ib_, 1, psi_tmp_);
-        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
         refresh_gather();
         touch_site(s1); touch_site(s2);
         if (col < cols_ - 2) shift_bten_window(RIGHT);
@@ -1732,7 +1757,7 @@ void Engine::sweep_fermion(int nsweeps) {
         const int s1 = row * cols_ + col, s2 = s1 + cols_;
         be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], 1, nullptr, nullptr, 0, 0, term_ia_, term_ib_, term_cw_, W_);
         nn_trace_idx(row, col, row + 1, col, VERTICAL, term_ia_, term_ib_, 1, psi_tmp_);
-        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_);
+        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
         refresh_gather();
         touch_site(s1); touch_site(s2);
         if (row < rows_ - 2) shift_bten_window(DOWN);
@@ -1758,6 +1783,7 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
     if (tt.T == 0) { be_term_accumulate(cfg_, nsites_, s1, s2, phys_, tt.diag, nullptr, nullptr, psi_loc_, dst, W_); return; }
     for (int t = 0; t < tt.T; ++t) {
       be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], kind, tt.target, tt.coef, tt.T, t, term_ia_, term_ib_, term_cw_, W_);
+      if (const double *jr = jastrow_for(s1, s2)) be_scale(term_cw_, jr, W_);
       trace(term_ia_, term_ib_, psi_tmp_);
       be_term_accumulate(cfg_, nsites_, s1, s2, phys_, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_loc_, dst, W_);
     }

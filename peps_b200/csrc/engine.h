@@ -156,6 +156,13 @@ class Engine {
   // given by set_model_term tables (kinds 0 / 1 / 2) whose off-diagonal targets either move one fermion between the two
   // sites or keep both site parities. Derivation and checks: oracle/fermion.py, tests/test_fermion_oracle.py.
   void set_fermion(const int32_t *phys_par, const int32_t *leg_par);
+  // Jastrow-dressed wave function psi(S) = psi_PEPS(S) exp(sum_{i<j} v_ij n_i n_j) (TPSWaveFunctionComponent<..., JastrowDress>,
+  // vmc_basic/wave_function_component.h:107-135, vmc_basic/jastrow_factor.h): v = [nsites][nsites] symmetric (diagonal ignored),
+  // density[phys] = particle number of a physical state. The NN exchange sweep takes the Jastrow ratio into the acceptance
+  // (MCUpdateSquareNNExchangeJastrowDressedTJ, square_nn_updater.h:380-438; the cached amplitude stays the PEPS part) and the
+  // table-driven / fermionic energy solvers multiply every exchange matrix element by it (square_tJ_model.h:352-410, 480-520).
+  void set_jastrow(const double *v, const int32_t *density);
+  void clear_jastrow() { jastrow_on_ = false; }
   bool fermion() const { return fermion_; }
 
   // ---- probes used by the parity tests (per-walker values of reference contractor calls)
@@ -229,6 +236,14 @@ class Engine {
     if (fermion_) throw std::logic_error(std::string(what) + " is not available in fermion mode");
   }
   bool fermion_ = false;
+  bool jastrow_on_ = false, tables_exchange_only_ = true;
+  double *jastrow_v_ = nullptr, *jr_ = nullptr;   // [nsites][nsites], [W]
+  int32_t *dens_d_ = nullptr;                      // [phys]
+  const double *jastrow_for(int s1, int s2) {      // Jastrow ratio of exchanging s1 and s2 for every walker (null when off)
+    if (!jastrow_on_) return nullptr;
+    be_jastrow_ratio(cfg_, nsites_, s1, s2, dens_d_, jastrow_v_, jr_, W_);
+    return jr_;
+  }
   mutable int gmode_ = HORIZONTAL;        // machinery whose dressing tn_site() / site_ref() gather (fermion mode)
   void mode_for_bmps(int pos) const { gmode_ = (pos == UP || pos == DOWN) ? HORIZONTAL : VERTICAL; }
   void mode_for_bten(int pos) const { gmode_ = (pos == LEFT || pos == RIGHT) ? HORIZONTAL : VERTICAL; }

@@ -433,7 +433,7 @@ static uint32_t mt_next(uint32_t *s, int32_t &i) {
   return y;
 }
 void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const double *psi_b, double *amp,
-                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+                           uint32_t *mt, int32_t *idx, int32_t *accepted, int W, const double *jastrow) {
   ++g_launches;
   for (int w = 0; w < W; ++w) {
     int32_t *c = cfg + (long)w * nsites;
@@ -441,9 +441,12 @@ void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const doubl
     if (c1 == c2) continue;
     double pb = psi_b[w], pa = amp[w];
     bool ok;
-    if (std::fabs(pb) >= std::fabs(pa)) ok = true;
-    else {
-      double div = std::fabs(pb) / std::fabs(pa), P = div * div;
+    double div = 0.0;
+    if (jastrow) { div = std::fabs(pb * jastrow[w]) / std::fabs(pa); ok = div >= 1.0; }
+    else ok = std::fabs(pb) >= std::fabs(pa);
+    if (!ok) {
+      if (!jastrow) div = std::fabs(pb) / std::fabs(pa);
+      double P = div * div;
       uint32_t x0 = mt_next(mt + (long)w * 624, idx[w]);
       uint32_t x1 = mt_next(mt + (long)w * 624, idx[w]);
       double r = ((double)x0 + (double)x1 * 4294967296.0) / 18446744073709551616.0;
@@ -452,6 +455,24 @@ void be_nn_exchange_decide(int32_t *cfg, int nsites, int s1, int s2, const doubl
     }
     if (ok) { c[s1] = c2; c[s2] = c1; amp[w] = pb; accepted[w] += 1; }
   }
+}
+void be_jastrow_ratio(const int32_t *cfg, int nsites, int s1, int s2, const int32_t *dens, const double *v, double *ratio, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const int32_t *c = cfg + (long)w * nsites;
+    const int n1 = dens[c[s1]], n2 = dens[c[s2]];
+    if (n1 == n2) { ratio[w] = 1.0; continue; }
+    double f1 = 0.0, f2 = 0.0;
+    for (int j = 0; j < nsites; ++j) {
+      if (j != s1) f1 += v[(long)s1 * nsites + j] * (double)dens[c[j]];
+      if (j != s2) f2 += v[(long)s2 * nsites + j] * (double)dens[c[j]];
+    }
+    ratio[w] = n1 < n2 ? std::exp(f1 - f2) : std::exp(f2 - f1);
+  }
+}
+void be_scale(double *x, const double *s, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) x[w] *= s[w];
 }
 void be_ratio_accumulate(const double *psi_ex, const double *psi, double coef, double *eloc, int W) {
   ++g_launches;

@@ -274,7 +274,7 @@ def fermion_configs(rows, cols, W, phys, seed=10):
 
 
 def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", nsweeps=2, seed=3, tol=1e-10, seeds0=200,
-                                t2=0.6, check_holes=True):
+                                t2=0.6, check_holes=True, jastrow=False):
     """Sweeps + E_loc + O* of W walkers through the C ABI in fermion mode vs oracle/fermion.py, walker by walker:
     configurations and acceptance counts bit-identical, |amplitudes|, E_loc, O* to `tol` (relative)."""
     from oracle import fermion as F
@@ -294,11 +294,20 @@ def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", 
     b.set_fermion(ftps)
     b.set_tps(ftps)
     b.set_model(tmodel)
+    jas = None
+    if jastrow:                                 # JastrowDress: v_ij = 0.3 / (1 + distance^2), density = fermion number
+        n = rows * cols
+        yy, xx = np.divmod(np.arange(n), cols)
+        v = 0.3 / (1.0 + (yy[:, None] - yy[None, :]) ** 2 + (xx[:, None] - xx[None, :]) ** 2)
+        np.fill_diagonal(v, 0.0)
+        jas = (v, np.array(phys_par, dtype=np.int32))
+        b.set_jastrow(*jas)
+        omodel.jastrow = jas
     b.set_configs(cfgs)
     b.seed_rng(np.arange(seeds0, seeds0 + W))
     b.init_walkers()
     ws = [F.FermionWalker(f, cfgs[w], trunc) for w in range(W)]
-    ups = [F.FermionNNExchangeUpdater(seeds0 + w) for w in range(W)]
+    ups = [F.FermionNNExchangeUpdater(seeds0 + w, jastrow=jas) for w in range(W)]
     a0 = np.abs(b.amplitudes())
     r0 = np.abs(np.array([w_.amplitude for w_ in ws]))
     assert np.max(np.abs(a0 / r0 - 1)) < tol

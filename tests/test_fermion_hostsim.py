@@ -148,3 +148,10 @@ def test_fermion_measure_bond_energies(lib):
     assert np.array_equal(m["charge"], 1.0 - cfgs)
     assert np.any(m["bond_energy_dr"] != 0) and np.any(m["bond_energy_ur"] != 0)
     b.close()
+
+
+def test_tj_jastrow_dressed_pipeline_parity_hostsim(lib):
+    """MCUpdateSquareNNExchangeJastrowDressedTJ + the Jastrow-dressed t-J solver (square_nn_updater.h:380-438,
+    square_tJ_model.h:352-410): chains bit-identical to the oracle, E_loc and O* to 1e-10."""
+    run_fermion_pipeline_parity(lib, 4, 4, 2, 3, (4, 4, 0.0), model="tj", nsweeps=2, jastrow=True)
+    run_fermion_pipeline_parity(lib, 3, 4, 2, 2, (4, 4, 0.0), model="spinless", nsweeps=2, jastrow=True)

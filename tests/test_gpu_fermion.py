@@ -122,3 +122,8 @@ def test_cpp_wrapper_fermion_on_cuda_library(lib):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     run_cpp_fermion_case(os.path.join(root, "peps_b200"), "libpeps_b200.so",
                          extra_link=["-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
+
+
+def test_tj_jastrow_dressed_pipeline_parity_gpu(lib):
+    """Jastrow-dressed t-J sampling (MCUpdateSquareNNExchangeJastrowDressedTJ + dressed solver) on the CUDA path."""
+    run_fermion_pipeline_parity(lib, 4, 4, 4, 4, (8, 8, 0.0), model="tj", nsweeps=2, jastrow=True)
