@@ -120,6 +120,13 @@ inline ModelTerm tJBondTerm(double t, double J, double V) {
     return (-0.5 + ratio(c2, c1) * 0.5) * J + V;
   });
 }
+// SquaretJModelMixIn::EvaluateNNNEnergy (square_tJ_model.h:424-460): t2 hopping when exactly one site is empty
+inline ModelTerm tJNNNTerm(double t2) {
+  return ProbeTwoSiteTerm(1, 3, [=](int c1, int c2, const std::function<double(int, int)> &ratio) {
+    if (c1 == c2 || (c1 != 2 && c2 != 2)) return 0.0;
+    return -t2 * ratio(c2, c1);
+  });
+}
 // EvaluateTotalOnsiteEnergy of the t-J models (square_tJ_model.h:248-262): -mu per electron
 inline ModelTerm tJOnsiteTerm(double mu) {
   return ProbeOneSiteTerm(3, [=](int c, const std::function<double(int)> &) { return c == 2 ? 0.0 : -mu; });

@@ -534,8 +534,13 @@ class tJModel(FermionModel):
     """SquaretJNNModel(t, J, mu) / SquaretJVModel: states 0 = up, 1 = down, 2 = empty (square_tJ_model.h:85-345)."""
     phys_par = (1, 1, 0)
 
-    def __init__(self, t, J, mu=0.0, V=0.0):
-        self.t, self.J, self.mu, self.V = t, J, mu, V
+    def __init__(self, t, J, mu=0.0, V=0.0, t2=0.0):
+        self.t, self.J, self.mu, self.V, self.t2 = t, J, mu, V, t2
+        self.has_nnn = t2 != 0.0
+
+    def offdiag_nnn(self, c1, c2):
+        """EvaluateNNNEnergy (square_tJ_model.h:424-460): t2 hopping only (one site empty)."""
+        return -self.t2 if (c1 == 2 or c2 == 2) else 0.0
 
     def diag_nn(self, c1, c2):
         if c1 == c2:

@@ -300,9 +300,9 @@ class TableModel:
         return TableModel(2, h2, h2n)
 
     @staticmethod
-    def tj(t, J, V=0.0, mu=0.0):
-        """SquaretJNNModel(t, J, mu) / SquaretJVModel(t, 0, J, V, mu) (model_solvers/square_tJ_model.h:300-345);
-        0 = up, 1 = down, 2 = empty."""
+    def tj(t, J, V=0.0, mu=0.0, t2=0.0):
+        """SquaretJNNModel(t, J, mu) / SquaretJVModel(t, t2, J, V, mu) / SquaretJNNNModel (model_solvers/square_tJ_model.h:
+        300-345, NNN hopping :424-460); 0 = up, 1 = down, 2 = empty."""
         h2 = np.zeros((9, 9))
         for a in (0, 1):
             h2[a * 3 + a, a * 3 + a] = V
@@ -310,7 +310,12 @@ class TableModel:
         h2[1, 1] = h2[3, 3] = -0.5 * J + V
         h2[1, 3] = h2[3, 1] = 0.5 * J
         h1 = np.diag([-mu, -mu, 0.0]) if mu != 0.0 else None
-        return TableModel(3, h2, None, h1)
+        h2n = None
+        if t2 != 0.0:
+            h2n = np.zeros((9, 9))
+            for a in (0, 1):
+                h2n[a * 3 + 2, 2 * 3 + a] = h2n[2 * 3 + a, a * 3 + 2] = -t2
+        return TableModel(3, h2, h2n, h1)
 
     @staticmethod
     def tfim(h):

@@ -286,8 +286,8 @@ def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", 
         omodel = F.SpinlessFermionModel(1.0, t2, 0.3)
         tmodel = TableModel.spinless_fermion(1.0, t2, 0.3)
     else:
-        omodel = F.tJModel(1.0, 0.3, mu=0.2, V=0.075)
-        tmodel = TableModel.tj(1.0, 0.3, V=0.075, mu=0.2)
+        omodel = F.tJModel(1.0, 0.3, mu=0.2, V=0.075, t2=t2 if model == "tj_nnn" else 0.0)
+        tmodel = TableModel.tj(1.0, 0.3, V=0.075, mu=0.2, t2=t2 if model == "tj_nnn" else 0.0)
     cfgs = fermion_configs(rows, cols, W, len(phys_par))
     tr = BMPSTruncateParams.SVD(*trunc)
     b = WalkerBatch(rows, cols, len(phys_par), D, W, tr, lib=lib)

@@ -31,6 +31,11 @@ def test_tj_pipeline_parity_hostsim(lib):
     run_fermion_pipeline_parity(lib, 4, 4, 4, 3, (8, 8, 0.0), model="tj", nsweeps=2)
 
 
+def test_tj_nnn_hopping_pipeline_parity_hostsim(lib):
+    """SquaretJNNNModel: t2 hopping on both diagonals through the BTen2 plaquette traces with the fermionic hop rules."""
+    run_fermion_pipeline_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), model="tj_nnn", nsweeps=2, t2=0.45)
+
+
 @pytest.mark.parametrize("t2", [2.1, -2.5])
 def test_k8_energy_through_abi(lib, t2):
     """K8 through the C ABI: exact summation over the 6 half-filled configurations of the 2x2 simple-update fixture."""

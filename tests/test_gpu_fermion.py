@@ -32,6 +32,7 @@ def test_spinless_fermion_pipeline_parity_gpu(lib, rows, cols, D, trunc, W):
 
 def test_tj_pipeline_parity_gpu(lib):
     run_fermion_pipeline_parity(lib, 4, 4, 4, 4, (8, 8, 0.0), model="tj", nsweeps=2)
+    run_fermion_pipeline_parity(lib, 4, 4, 2, 3, (4, 4, 0.0), model="tj_nnn", nsweeps=2, t2=0.45)
 
 
 @pytest.mark.parametrize("t2", [2.1, 0.0, -2.5])
