@@ -1135,7 +1135,9 @@ void be_panel_qr(const PanelArgs &a) {
   };
   const int R = a.R;
   // panels of <= 256 rows: 64 KB tile and <= 128 registers, two CTAs share an SM and hide each other's reflector chain
-  if (a.nbw == 32 && R <= 256) launch_reg(panel_qr_reg_kernel<32, 8, 2>, panel_reg_smem_bytes<32, 8>(R));
+  // panels of <= 128 rows (PEPS_QR_RB=128): 16 panel values per thread, up to four CTAs per SM
+  if (a.nbw == 32 && R <= 128) launch_reg(panel_qr_reg_kernel<32, 4, 4>, panel_reg_smem_bytes<32, 4>(R));
+  else if (a.nbw == 32 && R <= 256) launch_reg(panel_qr_reg_kernel<32, 8, 2>, panel_reg_smem_bytes<32, 8>(R));
   else if (a.nbw == 32 && R <= 512) launch_reg(panel_qr_reg_kernel<32, 16, 1>, panel_reg_smem_bytes<32, 16>(R));
   else if (a.nbw == 32 && R <= 576) launch_reg(panel_qr_reg_kernel<32, 18, 1>, panel_reg_smem_bytes<32, 18>(R));
   else if (a.nbw == 16 && R <= 512) launch_reg(panel_qr_reg_kernel<16, 16, 1>, panel_reg_smem_bytes<16, 16>(R));
