@@ -585,9 +585,8 @@ def main():
     # ---- end-to-end through the evaluator-style public call with host buffers
     flat = torch.from_numpy(sit.pack()).pin_memory()
     h2d = flat.numel() * 8 * S
-    d2h = (2 * n_par * 8 + 2 * 2 * Ws * 8) * S
-
-    E2E_SAMPLES = 2                                   # samples per walker and Evaluate call
+    E2E_SAMPLES = 4                                   # samples per walker and Evaluate call (the reference's examples take tens per rank)
+    d2h = (2 * n_par * 8 + 2 * E2E_SAMPLES * Ws * 8) * S
 
     def e2e_step(ln):
         for _ in range(args.e2e_steps):
@@ -664,7 +663,7 @@ def main():
                                           "small_svd_path_frac": dstat[5] / max(dstat[4], 1),
                                           "note": "the positive synthetic TPS has low numerical rank; see `secondary` for J1-J2, the signed state and a physical state"}},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "call": "Evaluate-style call with host buffers: set_tps (pinned) + init_walkers + 2 samples per walker (energies to the host each) + download of both accumulators"},
+                    "steps": args.e2e_steps, "call": "Evaluate-style call with host buffers: set_tps (pinned) + init_walkers + 4 samples per walker (energies to the host each) + download of both accumulators"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
             "mean_eloc": float(np.mean(energies))}
     print(json.dumps(line))

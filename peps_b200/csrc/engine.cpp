@@ -25,6 +25,7 @@ Engine::Engine(const EngineConfig &c)
   if (const char *e = std::getenv("PEPS_CHAIN_EPS")) chain_eps_ = std::atof(e);
   if (const char *e = std::getenv("PEPS_SMALL_SVD")) la_.small_svd = std::atoi(e) != 0;
   if (const char *e = std::getenv("PEPS_QR_EARLY_STOP")) la_.qr_early_stop = std::atoi(e) != 0;
+  if (const char *e = std::getenv("PEPS_QR_STOP_STRIDE")) la_.qr_stop_stride = std::max(1, std::atoi(e));
   la_.offmax = (double *)be_malloc(sizeof(double) * W_);
   la_.done = (int32_t *)be_malloc(sizeof(int32_t) * W_);
   tps_off_h_.resize((size_t)nsites_);

@@ -29,6 +29,7 @@ struct LinalgCtx {
   double deflation_eps = 1e-13;      // rows of R below eps * (largest row norm) are treated as zero (perturbs Theta by <= sqrt(rows) * eps * |Theta|)
   bool presort_columns = true;       // PEPS_PRESORT_COLS=0 switches the column pre-sorting of truncate_rows off
   bool qr_early_stop = true;         // PEPS_QR_EARLY_STOP=0 switches the early termination of the rank-revealing QRs off
+  int qr_stop_stride = 1;            // trailing-norm check every n-th panel (PEPS_QR_STOP_STRIDE)
   bool small_svd = true;             // PEPS_SMALL_SVD=0 switches the single-CTA SVD path of truncate_rows off
   long small_svd_calls = 0;
   double jacobi_tol = 1e-14;
@@ -168,7 +169,8 @@ inline void caqr(LinalgCtx &cx, double *A, long ws, int m, int n, const QRLayout
         be_apply_reflector(ap);
       }
     }
-    if (stopping && ntrail > 0 && c1 < m && c1 >= stop->first_col && p + 1 < npanel)
+    // the exact trailing norm is a full pass over the trailing block: every `stop_stride`-th panel only (PEPS_QR_STOP_STRIDE)
+    if (stopping && ntrail > 0 && c1 < m && c1 >= stop->first_col && p + 1 < npanel && (p % cx.qr_stop_stride) == cx.qr_stop_stride - 1)
       be_trailing_check(A, ws, lda, c1, m, c1, n, stop->colnorm2, stop->colorder, n, 0.01 * stop->eps * stop->eps, stop_acc, stopped, W);
   }
   if (stopping) { cx.pool->put(stopped); cx.pool->put(stop_acc); }
