@@ -29,7 +29,7 @@ struct LinalgCtx {
   double deflation_eps = 1e-13;      // rows of R below eps * (largest row norm) are treated as zero (perturbs Theta by <= sqrt(rows) * eps * |Theta|)
   bool presort_columns = true;       // PEPS_PRESORT_COLS=0 switches the column pre-sorting of truncate_rows off
   bool qr_early_stop = true;         // PEPS_QR_EARLY_STOP=0 switches the early termination of the rank-revealing QRs off
-  int qr_stop_stride = 1;            // trailing-norm check every n-th panel (PEPS_QR_STOP_STRIDE)
+  int qr_stop_stride = 3;            // trailing-norm check every n-th panel (PEPS_QR_STOP_STRIDE): 1 -> 29.2, 2 -> 29.2, 3 -> 29.4 samples/s, off -> 28.8
   bool small_svd = true;             // PEPS_SMALL_SVD=0 switches the single-CTA SVD path of truncate_rows off
   long small_svd_calls = 0;
   double jacobi_tol = 1e-14;
