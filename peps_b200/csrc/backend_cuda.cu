@@ -2307,7 +2307,7 @@ void be_transpose_permute(const double *C0, long wc, int nc, int tcap, const int
 // lanes by two shuffles. After a rotation the vector with the larger norm goes to the lower index (de Rijk), which keeps
 // the singular values nearly sorted and speeds up convergence. A sweep without any rotation ends the iteration.
 constexpr int SVS_THREADS = 256;
-template <int NCAP, bool BLOCKED>
+template <int NCAP>
 __global__ void __launch_bounds__(SVS_THREADS, 1) svd_small_kernel(SmallSvdArgs a) {
   extern __shared__ __align__(16) double svs_sm[];
   constexpr int LDX = NCAP + 8;
@@ -2337,79 +2337,6 @@ __global__ void __launch_bounds__(SVS_THREADS, 1) svd_small_kernel(SmallSvdArgs 
   __syncthreads();
 
   int sweeps = 0;
-  if constexpr (BLOCKED) {
-    // Blocked ordering: the vectors are grouped in blocks of two, a round pairs the BLOCKS by the round-robin tournament
-    // and eight lanes own one block pair: four vectors stay in registers for the four cross rotations of the pair (and,
-    // in the first round of a sweep, the two rotations inside the blocks), so a sweep moves every vector through shared
-    // memory (NB - 1) times instead of (n - 1) times -- the kernel is bound by exactly that traffic.
-    constexpr int NV2 = NCAP / 16;                     // double2 per vector and lane (8 lanes per vector)
-    const int lane8 = t & 7, grp = t >> 3;
-    const unsigned m8 = 0xFFu << ((t & 31) & ~7);
-    const int nact4 = (cnt + 3) & ~3;                  // vectors padded to a multiple of four (zero vectors beyond cnt)
-    const int NB = nact4 >> 1;                         // blocks (even)
-    const int nv2 = (nact4 + 15) >> 4;                 // double2 chunks per lane that can hold non-zeros
-    if (cnt >= 2) {
-      for (; sweeps < a.max_sweeps; ++sweeps) {
-        int rotated = 0;
-        for (int round = 0; round < NB - 1; ++round) {
-          for (int pr = grp; pr < (NB >> 1); pr += SVS_THREADS / 8) {
-            int I, J;
-            rr_pair(NB, round, pr, I, J);
-            const int bi = min(I, J), bj = max(I, J);
-            double2 *x0 = reinterpret_cast<double2 *>(X + (size_t)(2 * bi) * LDX) + lane8;
-            double2 *x1 = reinterpret_cast<double2 *>(X + (size_t)(2 * bi + 1) * LDX) + lane8;
-            double2 *y0 = reinterpret_cast<double2 *>(X + (size_t)(2 * bj) * LDX) + lane8;
-            double2 *y1 = reinterpret_cast<double2 *>(X + (size_t)(2 * bj + 1) * LDX) + lane8;
-            double2 a0[NV2], a1[NV2], b0[NV2], b1[NV2];
-#pragma unroll
-            for (int i = 0; i < NV2; ++i) {
-              if (i < nv2) { a0[i] = x0[8 * i]; a1[i] = x1[8 * i]; b0[i] = y0[8 * i]; b1[i] = y1[8 * i]; }
-              else { a0[i] = a1[i] = b0[i] = b1[i] = make_double2(0.0, 0.0); }
-            }
-            // one rotation of the pair (p, q), p the lower index: larger norm to p (de Rijk)
-            auto rot = [&](double2 (&vp)[NV2], double2 (&vq)[NV2]) {
-              double app = 0.0, aqq = 0.0, apq = 0.0;
-#pragma unroll
-              for (int i = 0; i < NV2; ++i) {
-                app = fma(vp[i].x, vp[i].x, app); app = fma(vp[i].y, vp[i].y, app);
-                aqq = fma(vq[i].x, vq[i].x, aqq); aqq = fma(vq[i].y, vq[i].y, aqq);
-                apq = fma(vp[i].x, vq[i].x, apq); apq = fma(vp[i].y, vq[i].y, apq);
-              }
-#pragma unroll
-              for (int o = 1; o <= 4; o <<= 1) {
-                app += __shfl_xor_sync(m8, app, o);
-                aqq += __shfl_xor_sync(m8, aqq, o);
-                apq += __shfl_xor_sync(m8, apq, o);
-              }
-              double c, sn;
-              jacobi_cs(app, aqq, apq, tol2, c, sn);
-              if (sn != 0.0) {                           // uniform over the eight lanes of the block pair
-                rotated = 1;
-                const double tg = sn / c;
-                const bool swap = (app - tg * apq) < (aqq + tg * apq);
-#pragma unroll
-                for (int i = 0; i < NV2; ++i) {
-                  double2 np, nq;
-                  np.x = c * vp[i].x - sn * vq[i].x; np.y = c * vp[i].y - sn * vq[i].y;
-                  nq.x = sn * vp[i].x + c * vq[i].x; nq.y = sn * vp[i].y + c * vq[i].y;
-                  vp[i] = swap ? nq : np;
-                  vq[i] = swap ? np : nq;
-                }
-              }
-            };
-            if (round == 0) { rot(a0, a1); rot(b0, b1); }
-            rot(a0, b0); rot(a1, b1);
-            rot(a0, b1); rot(a1, b0);
-#pragma unroll
-            for (int i = 0; i < NV2; ++i)
-              if (i < nv2) { x0[8 * i] = a0[i]; x1[8 * i] = a1[i]; y0[8 * i] = b0[i]; y1[8 * i] = b1[i]; }
-          }
-          __syncthreads();
-        }
-        if (!__syncthreads_or(rotated)) { ++sweeps; break; }
-      }
-    }
-  } else
   if (nact >= 2) {
     const int npair = nact >> 1;
     for (; sweeps < a.max_sweeps; ++sweeps) {
@@ -2422,16 +2349,17 @@ __global__ void __launch_bounds__(SVS_THREADS, 1) svd_small_kernel(SmallSvdArgs 
           double2 *xp = reinterpret_cast<double2 *>(X + (size_t)p * LDX) + lane4;
           double2 *xq = reinterpret_cast<double2 *>(X + (size_t)q * LDX) + lane4;
           double2 vp[NCH], vq[NCH];
-          double app = 0.0, aqq = 0.0, apq = 0.0;
-#pragma unroll
+          double app = 0.0, aqq = 0.0, apq = 0.0, app1 = 0.0, aqq1 = 0.0, apq1 = 0.0;   // two partial sums each: the
+#pragma unroll                                                                            // FMA chains are on the critical path
           for (int i = 0; i < NCH; ++i) {
             if (i < nch) {
               vp[i] = xp[4 * i]; vq[i] = xq[4 * i];
-              app = fma(vp[i].x, vp[i].x, app); app = fma(vp[i].y, vp[i].y, app);
-              aqq = fma(vq[i].x, vq[i].x, aqq); aqq = fma(vq[i].y, vq[i].y, aqq);
-              apq = fma(vp[i].x, vq[i].x, apq); apq = fma(vp[i].y, vq[i].y, apq);
+              app = fma(vp[i].x, vp[i].x, app); app1 = fma(vp[i].y, vp[i].y, app1);
+              aqq = fma(vq[i].x, vq[i].x, aqq); aqq1 = fma(vq[i].y, vq[i].y, aqq1);
+              apq = fma(vp[i].x, vq[i].x, apq); apq1 = fma(vp[i].y, vq[i].y, apq1);
             }
           }
+          app += app1; aqq += aqq1; apq += apq1;
 #pragma unroll
           for (int o = 1; o <= 2; o <<= 1) {
             app += __shfl_xor_sync(gmask, app, o);
@@ -2524,16 +2452,9 @@ void be_svd_small(const SmallSvdArgs &a) {
     ensure_smem(kern, smem);
     kern<<<a.W, SVS_THREADS, smem, g_stream>>>(a);
   };
-  static const bool blocked = []() { const char *e = std::getenv("PEPS_SVD_BLOCKED"); return e ? std::atoi(e) != 0 : true; }();
-  if (blocked) {
-    if (a.n2 <= 32) launch(svd_small_kernel<32, true>, svd_small_smem<32>());
-    else if (a.n2 <= 64) launch(svd_small_kernel<64, true>, svd_small_smem<64>());
-    else launch(svd_small_kernel<128, true>, svd_small_smem<128>());
-  } else {
-    if (a.n2 <= 32) launch(svd_small_kernel<32, false>, svd_small_smem<32>());
-    else if (a.n2 <= 64) launch(svd_small_kernel<64, false>, svd_small_smem<64>());
-    else launch(svd_small_kernel<128, false>, svd_small_smem<128>());
-  }
+  if (a.n2 <= 32) launch(svd_small_kernel<32>, svd_small_smem<32>());
+  else if (a.n2 <= 64) launch(svd_small_kernel<64>, svd_small_smem<64>());
+  else launch(svd_small_kernel<128>, svd_small_smem<128>());
   post_launch();
 }
 
