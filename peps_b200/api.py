@@ -631,6 +631,8 @@ class MCPEPSMeasurer:
         self.mc = mc_params
         self.enable_structure_factor = enable_structure_factor      # StructureFactorMeasurementMixin::SetEnableStructureFactor
         self.batch = WalkerBatch(rows, cols, tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
+        if isinstance(tps, FermionSplitIndexTPS):              # config #4: fZ2 states, keys energy / charge / bond energies
+            self.batch.set_fermion(tps)
         self.batch.set_tps(tps)
         self.batch.set_model(model)
         self.batch.set_updater(updater)
@@ -638,7 +640,8 @@ class MCPEPSMeasurer:
                                                (walkers, rows, cols)).copy())
         self.batch.seed_rng(np.arange(walkers, dtype=np.uint32) + np.uint32(updater.seed))
         self.batch.init_walkers()
-        self.has_nnn = hasattr(model, "jz2") and (model.jz2 != 0.0 or model.jxy2 != 0.0)
+        self.has_nnn = (hasattr(model, "jz2") and (model.jz2 != 0.0 or model.jxy2 != 0.0)) or \
+                       (isinstance(model, TableModel) and model.h2_nnn is not None)
 
     def Execute(self):
         b, W = self.batch, self.batch.W

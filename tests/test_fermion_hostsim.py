@@ -160,3 +160,20 @@ def test_tj_jastrow_dressed_pipeline_parity_hostsim(lib):
     square_tJ_model.h:352-410): chains bit-identical to the oracle, E_loc and O* to 1e-10."""
     run_fermion_pipeline_parity(lib, 4, 4, 2, 3, (4, 4, 0.0), model="tj", nsweeps=2, jastrow=True)
     run_fermion_pipeline_parity(lib, 3, 4, 2, 2, (4, 4, 0.0), model="spinless", nsweeps=2, jastrow=True)
+
+
+def test_mcpeps_measurer_on_fermion_state(lib):
+    """MCPEPSMeasurer (config #4: sampling + measurement) on an fZ2 state: energy / charge / bond-energy statistics."""
+    from peps_b200.api import MCPEPSMeasurer
+    from parity_common import fermion_configs
+    rows, cols, D, W = 3, 4, 2, 4
+    ftps = FermionSplitIndexTPS.random(rows, cols, D, 31)
+    cfg = fermion_configs(rows, cols, 1, 2)[0]
+    mc = MonteCarloParams(8, 1, 1, Configuration(cfg), False)
+    m = MCPEPSMeasurer(mc, BMPSTruncateParams.SVD(4, 4, 0.0), ftps, TableModel.spinless_fermion(1.0, 0.3, 0.5),
+                       MCUpdateSquareNNExchange(seed=5), W, lib=lib)
+    out = m.Execute()
+    assert set(out) == {"energy", "charge", "bond_energy_h", "bond_energy_v", "bond_energy_dr", "bond_energy_ur"}
+    assert abs(out["charge"][0].sum() - 6.0) < 1e-12              # the exchange updater conserves the fermion number
+    tot = out["bond_energy_h"][0].sum() + out["bond_energy_v"][0].sum() + out["bond_energy_dr"][0].sum() + out["bond_energy_ur"][0].sum()
+    assert abs(tot - out["energy"][0]) < 1e-10
