@@ -164,10 +164,21 @@ struct JacobiArgs {
   double *G; long ws; int ld; int nr_pad; int nc; int bs; int nblk; int round;
   double tol; int inner_sweeps; double *offmax; const int32_t *done; int W;
   int nactive = 0;   // walkers not yet converged (host-side count, for flop accounting only)
+  // Z2 sectors (fermion mode): bsec[w][b] = sector (0 / 1, 2 = empty) of row block b; block pairs of different sectors are
+  // orthogonal to rounding (disjoint column supports) and are skipped -- which also keeps every block sector-pure; the
+  // driver finishes with unrestricted sweeps, so a wrong label costs time, never accuracy
+  const int32_t *bsec = nullptr;
 };
 void be_jacobi_round(const JacobiArgs &a);
 // done[w] = (offmax[w] <= tol); offmax[w] = 0 for the next sweep. Returns nothing (host reads done[]).
 void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W);
+// Fermion mode: the rows of src[w] (count[w] valid rows of nc columns, leading dimension ld) fall into two parity sectors with
+// disjoint column supports -- up to rounding noise, so labels compare weights: a row is in sector 0 when it carries more
+// weight on the sector-0 columns (the support of row 0, re-estimated once by column majority) than off them; dst[w] (zero-initialised by the caller, nblk * bs rows) receives the rows of
+// sector 0 from row 0 on and the rows of sector 1 from the next multiple of bs on, each in their original order;
+// bsec[w][b] = 0 / 1 / 2 (empty) per block of bs rows.
+void be_sector_arrange(const double *src, long ws, int ld, int nc, const int32_t *count, int bs, int nblk, double *dst, long wd,
+                       int32_t *bsec, int W);
 // norms2[w][c] = |G[w][:nr][c]|^2   (column norms)
 void be_col_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W);
 // dst[w][r][j] = src[w][r][order[w][j]]  (gather = 1)   or   dst[w][r][order[w][j]] = src[w][r][j]  (gather = 0)

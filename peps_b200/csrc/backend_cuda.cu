@@ -1776,6 +1776,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
 
   int I, J;
   rr_pair(a.nblk, a.round, blockIdx.x, I, J);
+  if (a.bsec) {                                      // Z2 sectors: cross-sector and empty block pairs are no-ops
+    const int sI = a.bsec[(long)w * a.nblk + I], sJ = a.bsec[(long)w * a.nblk + J];
+    if (sI != sJ || sI == 2) return;
+  }
   const int lo = min(I, J), hi = max(I, J);
   double *Gw = a.G + (long)w * a.ws;
   const double tol2 = a.tol * a.tol;
@@ -2058,6 +2062,74 @@ __global__ void jacobi_flags_kernel(double *offmax, int32_t *done, double tol, i
     done[w] = (offmax[w] <= tol) ? 1 : 0;
     offmax[w] = 0.0;
   }
+}
+// one CTA per walker; labels / column marks in shared memory (rows <= 2048, columns <= 4096). In floating point the
+// sector structure holds up to rounding noise only (a Householder QR puts R rows at pivot POSITIONS, which mixes in noise),
+// so the labels compare weights: a row belongs to sector 0 when it carries more weight on the sector-0 columns than off
+// them; the sector-0 columns start as the support of row 0 (largest norm) and are re-estimated once by column majority.
+__global__ void __launch_bounds__(256) sector_arrange_kernel(const double *src, long ws, int ld, int nc, const int32_t *count, int bs,
+                                                             int nblk, double *dst, long wd, int32_t *bsec) {
+  extern __shared__ int sa_sm[];
+  int *colA = sa_sm;              // [nc] column belongs to the sector of row 0
+  int *lab = colA + nc;           // [nrows] 0 = sector of row 0, 1 = other
+  int *pos = lab + nblk * bs;     // [nrows] destination row
+  __shared__ double s_red[8];
+  const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int n = min(count[w], nblk * bs);
+  const double *S = src + (long)w * ws;
+  double mx = 0.0;
+  for (int c = t; c < nc; c += 256) mx = fmax(mx, n > 0 ? fabs(S[c]) : 0.0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  mx = 0.0;
+  for (int i = 0; i < 8; ++i) mx = fmax(mx, s_red[i]);
+  for (int c = t; c < nc; c += 256) colA[c] = (n > 0 && fabs(S[c]) > 1e-8 * mx) ? 1 : 0;
+  __syncthreads();
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int r = warp; r < n; r += 8) {
+      double in = 0.0, out = 0.0;
+      for (int c = lane; c < nc; c += 32) { const double v = fabs(S[(long)r * ld + c]); if (colA[c]) in += v; else out += v; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { in += __shfl_xor_sync(0xffffffffu, in, o); out += __shfl_xor_sync(0xffffffffu, out, o); }
+      if (lane == 0) lab[r] = in >= out ? 0 : 1;
+    }
+    __syncthreads();
+    if (pass == 0) {
+      for (int c = t; c < nc; c += 256) {
+        double wa = 0.0, wb = 0.0;
+        for (int r = 0; r < n; ++r) { const double v = fabs(S[(long)r * ld + c]); if (lab[r] == 0) wa += v; else wb += v; }
+        colA[c] = wa >= wb ? 1 : 0;
+      }
+      __syncthreads();
+    }
+  }
+  if (t == 0) {
+    int nA = 0, nB = 0;
+    for (int r = 0; r < n; ++r) nA += (lab[r] == 0);
+    const int baseB = (nA + bs - 1) / bs * bs;
+    int ia = 0;
+    for (int r = 0; r < n; ++r) { if (lab[r] == 0) pos[r] = ia++; else pos[r] = baseB + nB++; }
+    const int blkA = (nA + bs - 1) / bs, blkB = (nB + bs - 1) / bs;
+    for (int b = 0; b < nblk; ++b) bsec[(long)w * nblk + b] = b < blkA ? 0 : (b < blkA + blkB ? 1 : 2);
+  }
+  __syncthreads();
+  double *D = dst + (long)w * wd;
+  for (int r = warp; r < n; r += 8) {
+    const int p = pos[r];
+    if (p < nblk * bs)
+      for (int c = lane; c < nc; c += 32) D[(long)p * ld + c] = S[(long)r * ld + c];
+  }
+}
+void be_sector_arrange(const double *src, long ws, int ld, int nc, const int32_t *count, int bs, int nblk, double *dst, long wd,
+                       int32_t *bsec, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  const size_t smem = sizeof(int) * ((size_t)nc + 2 * (size_t)nblk * bs);
+  if (smem > 96 * 1024) throw std::runtime_error("be_sector_arrange: matrix too large for the label tables");
+  ensure_smem(sector_arrange_kernel, smem);
+  sector_arrange_kernel<<<W, 256, smem, g_stream>>>(src, ws, ld, nc, count, bs, nblk, dst, wd, bsec);
+  post_launch();
 }
 void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {
   LaunchScope scope(KC_SMALL, 0.0);

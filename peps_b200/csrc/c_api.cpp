@@ -240,6 +240,7 @@ int peps_test_truncate(int32_t device, int32_t W, int32_t nr, int32_t nc, int32_
     if (const char *e = std::getenv("PEPS_PRESORT_COLS")) cx.presort_columns = std::atoi(e) != 0;
     if (const char *e = std::getenv("PEPS_SMALL_SVD")) cx.small_svd = std::atoi(e) != 0;
     if (const char *e = std::getenv("PEPS_QR_EARLY_STOP")) cx.qr_early_stop = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PEPS_Z2_SECTORS")) cx.z2_sectors = std::atoi(e) != 0;     // test hook: block-diagonal Theta
     cx.offmax = (double *)pool.get(sizeof(double) * W);
     cx.done = (int32_t *)pool.get(sizeof(int32_t) * W);
     int brows = truncate_buffer_rows(nr, nc);

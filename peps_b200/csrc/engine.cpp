@@ -1670,6 +1670,8 @@ void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
         throw std::invalid_argument("set_fermion: boundary legs must be even");
     }
   fermion_ = true;
+  la_.z2_sectors = true;
+  if (const char *e = std::getenv("PEPS_Z2_SECTORS")) la_.z2_sectors = std::atoi(e) != 0;
   gtps_off_h_.resize((size_t)nsites_);
   for (int s = 0; s < nsites_; ++s) gtps_off_h_[(size_t)s] = tps_off_h_[(size_t)s] * FERMION_VARIANTS;
   gtps_ = (double *)be_malloc(sizeof(double) * (size_t)tps_total_ * FERMION_VARIANTS);

@@ -8,6 +8,7 @@
 //                     BMPS::RightCanonicalizeTruncate (bmps_impl.h:225-263).
 // Backend-agnostic host code.
 #pragma once
+#include <cstdio>
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -29,6 +30,7 @@ struct LinalgCtx {
   double deflation_eps = 1e-13;      // rows of R below eps * (largest row norm) are treated as zero (perturbs Theta by <= sqrt(rows) * eps * |Theta|)
   bool presort_columns = true;       // PEPS_PRESORT_COLS=0 switches the column pre-sorting of truncate_rows off
   bool qr_early_stop = true;         // PEPS_QR_EARLY_STOP=0 switches the early termination of the rank-revealing QRs off
+  bool z2_sectors = false;           // fermion mode: rows of Theta fall into two parity sectors with disjoint column supports
   int qr_stop_stride = 3;            // trailing-norm check every n-th panel (PEPS_QR_STOP_STRIDE): 1 -> 29.2, 2 -> 29.2, 3 -> 29.4 samples/s, off -> 28.8
   bool small_svd = true;             // PEPS_SMALL_SVD=0 switches the single-CTA SVD path of truncate_rows off
   long small_svd_calls = 0;
@@ -320,6 +322,22 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
   const long ws2 = (long)J.nr_pad * nc;
   be_gather_rows(G, ws, nc, nc, kk, ord, cnt, G2, ws2, J.nr_pad, W);
   long ws2cur = ws2;
+  // Z2 sectors (fermion mode): regroup the rows so that every block of the Jacobi schedule is sector-pure and skip the block
+  // pairs of different sectors (exactly orthogonal: disjoint column supports); half of the block pairs remain.
+  int32_t *bsec = nullptr;
+  const bool sectors = cx.z2_sectors && nr_eff > 2 * J.bs;
+  if (sectors) {
+    JacobiLayout Jz = J;
+    Jz.nblk = (nr_eff + J.bs - 1) / J.bs + 1;                       // one extra block: each sector is padded to whole blocks
+    if (Jz.nblk & 1) ++Jz.nblk;
+    Jz.nr_pad = Jz.nblk * J.bs;
+    double *Gz = (double *)cx.pool->get(sizeof(double) * (size_t)W * Jz.nr_pad * nc);
+    be_memset0(Gz, sizeof(double) * (size_t)W * Jz.nr_pad * nc);
+    bsec = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * Jz.nblk);
+    be_sector_arrange(G2, ws2, nc, nc, cnt, J.bs, Jz.nblk, Gz, (long)Jz.nr_pad * nc, bsec, W);
+    cx.pool->put(G2);
+    G2 = Gz; J = Jz; ws2cur = (long)Jz.nr_pad * nc; nr_eff = Jz.nr_pad;
+  }
   if (nr_eff > 1) {
     ++cx.jacobi_calls;
     be_fill(cx.offmax, 0.0, W);
@@ -328,6 +346,7 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
     ja.G = G2; ja.ws = ws2cur; ja.ld = nc; ja.nr_pad = J.nr_pad; ja.nc = nc; ja.bs = J.bs; ja.nblk = J.nblk;
     ja.tol = cx.jacobi_tol; ja.inner_sweeps = cx.jacobi_inner_sweeps; ja.offmax = cx.offmax; ja.done = cx.done; ja.W = W;
     ja.nactive = W;
+    ja.bsec = bsec;
     for (int sweep = 0; sweep < cx.jacobi_max_sweeps; ++sweep) {
       for (int round = 0; round < ja.nblk - 1; ++round) {
         ja.round = round;
@@ -335,16 +354,27 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
       }
       ++cx.jacobi_sweeps;
       cx.jacobi_rounds += ja.nblk - 1;
-      be_jacobi_flags(cx.offmax, cx.done, cx.jacobi_tol, W);
+      be_jacobi_flags(cx.offmax, cx.done, ja.tol, W);
       be_d2h(cx.done_host.data(), cx.done, sizeof(int32_t) * W);
       int nact = 0;
       for (int w = 0; w < W; ++w) nact += cx.done_host[(size_t)w] ? 0 : 1;
       ja.nactive = nact;
+      if (nact == 0 && ja.bsec) {
+        // sector phase converged: finish with unrestricted sweeps over ALL pairs at a looser threshold. Cross-sector pairs
+        // are orthogonal to rounding noise (1e-16 .. 1e-14 relative), a mislabelled row would show O(1e-3 .. 1) overlaps:
+        // pairs below 1e-11 leave after their Gram matrix (no rotation), anything above is rotated -- a wrong label costs
+        // time, never accuracy (an unrotated 1e-11 overlap perturbs a kept vector by <= 1e-11, below the 1e-10 parity bar).
+        ja.bsec = nullptr;
+        ja.tol = std::max(cx.jacobi_tol, 1e-11);
+        be_memset0(cx.done, sizeof(int32_t) * W);
+        ja.nactive = W;
+        continue;
+      }
       if (nact == 0) break;
       // dynamic deflation: after a sweep the row norms track the singular values far better than the rows of R
       // did; rows that fell below deflation_eps * max are dropped and the problem is re-compacted when that
       // removes at least one block pair worth of work.
-      if (nr_eff > 2 * ja.bs && sweep + 1 < cx.jacobi_max_sweeps) {
+      if (!sectors && nr_eff > 2 * ja.bs && sweep + 1 < cx.jacobi_max_sweeps) {
         be_row_norms2(G2, ws2cur, nc, nr_eff, nc, n2a, W);
         be_rank_rows(n2a, nr_eff, cx.deflation_eps * cx.deflation_eps, ord, cnt, W);
         std::vector<int32_t> ch((size_t)W);
@@ -377,6 +407,7 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
     be_gather_rows_normalized(G2, ws2cur, nc, nc, n2b, nr_eff, ord2, kept, tcap, B, wb, W);
   }
   for (void *p : {(void *)n2a, (void *)ord, (void *)cnt, (void *)G2, (void *)n2b, (void *)ord2}) cx.pool->put(p);
+  if (bsec) cx.pool->put(bsec);
 }
 
 }  // namespace peps

@@ -7,6 +7,7 @@
 // backend.h; the GPU parity tests compare the CUDA kernels against the oracle, not against this file.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -222,6 +223,43 @@ static void rr_pair(int nblk, int round, int q, int &I, int &J) {
   else { I = (round + q) % n1; J = (round - q + n1) % n1; }
 }
 
+void be_sector_arrange(const double *src, long ws, int ld, int nc, const int32_t *count, int bs, int nblk, double *dst, long wd,
+                       int32_t *bsec, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const int n = std::min((int)count[w], nblk * bs);
+    const double *S = src + (long)w * ws;
+    std::vector<int> colA((size_t)nc, 0), lab((size_t)std::max(n, 1), 1);
+    double mx = 0.0;
+    for (int c = 0; c < nc && n > 0; ++c) mx = std::max(mx, std::fabs(S[c]));
+    for (int c = 0; c < nc; ++c) colA[(size_t)c] = (n > 0 && std::fabs(S[c]) > 1e-8 * mx);
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int r = 0; r < n; ++r) {
+        double in = 0.0, out = 0.0;
+        for (int c = 0; c < nc; ++c) { const double v = std::fabs(S[(long)r * ld + c]); if (colA[(size_t)c]) in += v; else out += v; }
+        lab[(size_t)r] = in >= out ? 0 : 1;
+      }
+      if (pass == 0)
+        for (int c = 0; c < nc; ++c) {
+          double wa = 0.0, wb = 0.0;
+          for (int r = 0; r < n; ++r) { const double v = std::fabs(S[(long)r * ld + c]); if (lab[(size_t)r] == 0) wa += v; else wb += v; }
+          colA[(size_t)c] = wa >= wb;
+        }
+    }
+    int nA = 0, nB = 0;
+    for (int r = 0; r < n; ++r) nA += (lab[(size_t)r] == 0);
+    const int baseB = (nA + bs - 1) / bs * bs;
+    int ia = 0;
+    double *D = dst + (long)w * wd;
+    for (int r = 0; r < n; ++r) {
+      const int p = lab[(size_t)r] == 0 ? ia++ : baseB + nB++;
+      if (p < nblk * bs) for (int c = 0; c < nc; ++c) D[(long)p * ld + c] = S[(long)r * ld + c];
+    }
+    const int blkA = (nA + bs - 1) / bs, blkB = (nB + bs - 1) / bs;
+    for (int b = 0; b < nblk; ++b) bsec[(long)w * nblk + b] = b < blkA ? 0 : (b < blkA + blkB ? 1 : 2);
+    if (std::getenv("PEPS_DEBUG_SECTORS")) std::fprintf(stderr, "[sectors] w=%d n=%d nc=%d nA=%d nB=%d\n", w, n, nc, nA, nB);
+  }
+}
 void be_jacobi_round(const JacobiArgs &a) {
   ++g_launches;
   const int bs = a.bs, n2 = 2 * bs, nc = a.nc;
@@ -231,6 +269,10 @@ void be_jacobi_round(const JacobiArgs &a) {
     for (int q = 0; q < a.nblk / 2; ++q) {
       int I, J;
       rr_pair(a.nblk, a.round, q, I, J);
+      if (a.bsec) {
+        const int sI = a.bsec[(long)w * a.nblk + I], sJ = a.bsec[(long)w * a.nblk + J];
+        if (sI != sJ || sI == 2) continue;
+      }
       int lo = std::min(I, J), hi = std::max(I, J);
       auto grow = [&](int r) { return (r < bs) ? lo * bs + r : hi * bs + (r - bs); };
       std::vector<double> Ps((size_t)n2 * nc), G((size_t)n2 * n2), Wm((size_t)n2 * n2, 0.0);

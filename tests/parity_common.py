@@ -334,3 +334,43 @@ def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", 
     assert worst["amp"] < tol and worst["eloc"] < tol and worst["ostar"] < tol, worst
     b.close()
     return worst
+
+
+def run_sector_truncation_case(lib, nr=160, nc=192, t=24, W=3, seed=4):
+    """Standalone truncation (peps_test_truncate) of Theta matrices with the Z2 structure of fermion mode: rows and columns
+    fall into two parity sectors (interleaved at random), entries outside the two diagonal blocks are exact zeros. With
+    PEPS_Z2_SECTORS=1 the block-Jacobi schedule regroups the rows and skips cross-sector pairs; the kept right singular
+    subspace must equal the exact one (projector to 1e-11) and the kept rows must be orthonormal."""
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    th = np.zeros((W, nr, nc))
+    projs = []
+    for w in range(W):
+        rsec = rng.integers(0, 2, nr)
+        csec = rng.integers(0, 2, nc)
+        pi = int(rng.integers(0, 2))
+        idx = [(np.flatnonzero(rsec == (s ^ pi)), np.flatnonzero(csec == s)) for s in (0, 1)]
+        ks = [min(len(ri), len(ci)) for ri, ci in idx]
+        # flat spectrum (full rank, nothing deflates) with a clear gap at the cut, dealt to the two sectors at random
+        allsv = np.sort(0.5 + rng.random(ks[0] + ks[1]))[::-1]
+        allsv[:t] += 0.05
+        owner = rng.permutation(np.array([0] * ks[0] + [1] * ks[1]))
+        for s, (ri, ci) in enumerate(idx):
+            k = ks[s]
+            u, _ = np.linalg.qr(rng.standard_normal((len(ri), k)))
+            v, _ = np.linalg.qr(rng.standard_normal((len(ci), k)))
+            th[w][np.ix_(ri, ci)] = (u * allsv[owner == s]) @ v.T
+        _, s_all, vt = np.linalg.svd(th[w])
+        assert s_all[t - 1] - s_all[t] > 0.04
+        projs.append(vt[:t].T @ vt[:t])
+    b = np.empty((W, t, nc))
+    kept = np.empty(W, dtype=np.int32)
+    sweeps = C.c_int32()
+    dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    rc = lib.peps_test_truncate(0, W, nr, nc, t, t, 0.0, dp(th), dp(b), kept.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(sweeps))
+    assert rc == 0, lib.peps_last_error(None)
+    for w in range(W):
+        assert kept[w] == t
+        assert np.max(np.abs(b[w] @ b[w].T - np.eye(t))) < 1e-12
+        assert np.max(np.abs(b[w].T @ b[w] - projs[w])) < 1e-11
+    return sweeps.value

@@ -177,3 +177,20 @@ def test_mcpeps_measurer_on_fermion_state(lib):
     assert abs(out["charge"][0].sum() - 6.0) < 1e-12              # the exchange updater conserves the fermion number
     tot = out["bond_energy_h"][0].sum() + out["bond_energy_v"][0].sum() + out["bond_energy_dr"][0].sum() + out["bond_energy_ur"][0].sum()
     assert abs(tot - out["energy"][0]) < 1e-10
+
+
+@pytest.mark.parametrize("sectors", ["1", "0"])
+def test_block_jacobi_path_with_z2_sectors(lib, monkeypatch, sectors):
+    """The full-rank truncation path (block Jacobi instead of the small SVD) in fermion mode: rows regrouped by parity
+    sector, cross-sector block pairs skipped (PEPS_Z2_SECTORS=1, default) vs. the plain schedule; both match the oracle."""
+    monkeypatch.setenv("PEPS_SMALL_SVD", "0")
+    monkeypatch.setenv("PEPS_Z2_SECTORS", sectors)
+    run_fermion_pipeline_parity(lib, 4, 4, 4, 2, (16, 16, 0.0), model="spinless", nsweeps=1)
+
+
+@pytest.mark.parametrize("sectors", ["1", "0"])
+def test_sector_truncation_hostsim(lib, monkeypatch, sectors):
+    from parity_common import run_sector_truncation_case
+    monkeypatch.setenv("PEPS_SMALL_SVD", "0")
+    monkeypatch.setenv("PEPS_Z2_SECTORS", sectors)
+    run_sector_truncation_case(lib, nr=96, nc=112, t=16, W=2)

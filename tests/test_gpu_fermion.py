@@ -128,3 +128,14 @@ def test_cpp_wrapper_fermion_on_cuda_library(lib):
 def test_tj_jastrow_dressed_pipeline_parity_gpu(lib):
     """Jastrow-dressed t-J sampling (MCUpdateSquareNNExchangeJastrowDressedTJ + dressed solver) on the CUDA path."""
     run_fermion_pipeline_parity(lib, 4, 4, 4, 4, (8, 8, 0.0), model="tj", nsweeps=2, jastrow=True)
+
+
+@pytest.mark.parametrize("sectors", ["1", "0"])
+def test_sector_truncation_gpu(lib, monkeypatch, sectors):
+    """Block-Jacobi truncation of two-sector (block-diagonal up to permutations) Theta matrices at config #4's shape
+    (512 x 512, chi = 64), with and without the sector regrouping / cross-sector pair skipping."""
+    from parity_common import run_sector_truncation_case
+    monkeypatch.setenv("PEPS_SMALL_SVD", "0")
+    monkeypatch.setenv("PEPS_Z2_SECTORS", sectors)
+    run_sector_truncation_case(lib, nr=160, nc=192, t=24, W=3)
+    run_sector_truncation_case(lib, nr=512, nc=512, t=64, W=2, seed=9)
