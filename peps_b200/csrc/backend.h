@@ -168,6 +168,9 @@ struct JacobiArgs {
   // orthogonal to rounding (disjoint column supports) and are skipped -- which also keeps every block sector-pure; the
   // driver finishes with unrestricted sweeps, so a wrong label costs time, never accuracy
   const int32_t *bsec = nullptr;
+  // cwin[w] = {c0, width} of sector 0, {c0, width} of sector 1: the column window a same-sector block pair works on
+  // (the columns are sorted by sector; outside its window a row holds rounding noise). Ignored without bsec.
+  const int32_t *cwin = nullptr;
 };
 void be_jacobi_round(const JacobiArgs &a);
 // done[w] = (offmax[w] <= tol); offmax[w] = 0 for the next sweep. Returns nothing (host reads done[]).
@@ -176,9 +179,11 @@ void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W);
 // disjoint column supports -- up to rounding noise, so labels compare weights: a row is in sector 0 when it carries more
 // weight on the sector-0 columns (the support of row 0, re-estimated once by column majority) than off them; dst[w] (zero-initialised by the caller, nblk * bs rows) receives the rows of
 // sector 0 from row 0 on and the rows of sector 1 from the next multiple of bs on, each in their original order;
-// bsec[w][b] = 0 / 1 / 2 (empty) per block of bs rows.
+// bsec[w][b] = 0 / 1 / 2 (empty) per block of bs rows. The COLUMNS are regrouped too (sector-0 columns first, original
+// order kept inside a sector): cord_out[w][new column] = cord_in[w][old column] (cord_in null = identity) composes the
+// caller's column permutation with it, cwin[w] = the two column windows (JacobiArgs::cwin).
 void be_sector_arrange(const double *src, long ws, int ld, int nc, const int32_t *count, int bs, int nblk, double *dst, long wd,
-                       int32_t *bsec, int W);
+                       int32_t *bsec, const int32_t *cord_in, int32_t *cord_out, int32_t *cwin, int W);
 // norms2[w][c] = |G[w][:nr][c]|^2   (column norms)
 void be_col_norms2(const double *G, long ws, int ld, int nr, int nc, double *norms2, int W);
 // dst[w][r][j] = src[w][r][order[w][j]]  (gather = 1)   or   dst[w][r][order[w][j]] = src[w][r][j]  (gather = 0)

@@ -1761,9 +1761,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
   constexpr int bs = N2 / 2;
   const int w = blockIdx.y;
   if (a.done[w]) return;
-  const int nc = a.nc;
-  const int ncp = (nc + 7) & ~7;
-  const int LDS = ncp + 4;
+  const int LDS = ((a.nc + 7) & ~7) + 4;             // shared-memory row stride: sized by the full width
   double *Ps = sm;                                   // [N2][LDS]
   double *Gpart = Ps + (size_t)N2 * LDS;             // [JAC_KGROUPS][NT][64]
   double *Gm = Gpart + JAC_KGROUPS * NT * 64;        // [2][N2][LG]
@@ -1776,12 +1774,18 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
 
   int I, J;
   rr_pair(a.nblk, a.round, blockIdx.x, I, J);
+  int c0 = 0, nc = a.nc;                             // column window of this block pair
   if (a.bsec) {                                      // Z2 sectors: cross-sector and empty block pairs are no-ops
     const int sI = a.bsec[(long)w * a.nblk + I], sJ = a.bsec[(long)w * a.nblk + J];
     if (sI != sJ || sI == 2) return;
+    if (a.cwin) {                                    // the rows of a sector live on that sector's columns (sorted first / last)
+      c0 = a.cwin[(long)w * 4 + 2 * sI]; nc = a.cwin[(long)w * 4 + 2 * sI + 1];
+      if (nc <= 0) return;
+    }
   }
+  const int ncp = (nc + 7) & ~7;
   const int lo = min(I, J), hi = max(I, J);
-  double *Gw = a.G + (long)w * a.ws;
+  double *Gw = a.G + (long)w * a.ws + c0;
   const double tol2 = a.tol * a.tol;
 
   // 0. schedule tables
@@ -1792,7 +1796,7 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(JacobiArgs a)
   }
   JAC_CLK(1);
   // 1. load the two row blocks (zero padded columns): one bulk copy (TMA) per row when the rows are 16-byte granular
-  const bool wide = ((nc & 1) == 0) && ((a.ld & 1) == 0) && ((a.ws & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.G) & 15) == 0);
+  const bool wide = ((nc & 1) == 0) && ((c0 & 1) == 0) && ((a.ld & 1) == 0) && ((a.ws & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.G) & 15) == 0);
   __shared__ uint64_t ld_bar;
   if (wide) {
     if (t == 0) {
@@ -2068,11 +2072,13 @@ __global__ void jacobi_flags_kernel(double *offmax, int32_t *done, double tol, i
 // so the labels compare weights: a row belongs to sector 0 when it carries more weight on the sector-0 columns than off
 // them; the sector-0 columns start as the support of row 0 (largest norm) and are re-estimated once by column majority.
 __global__ void __launch_bounds__(256) sector_arrange_kernel(const double *src, long ws, int ld, int nc, const int32_t *count, int bs,
-                                                             int nblk, double *dst, long wd, int32_t *bsec) {
+                                                             int nblk, double *dst, long wd, int32_t *bsec, const int32_t *cord_in,
+                                                             int32_t *cord_out, int32_t *cwin) {
   extern __shared__ int sa_sm[];
   int *colA = sa_sm;              // [nc] column belongs to the sector of row 0
   int *lab = colA + nc;           // [nrows] 0 = sector of row 0, 1 = other
   int *pos = lab + nblk * bs;     // [nrows] destination row
+  int *cpos = pos + nblk * bs;    // [nc] destination column: sector-0 columns first
   __shared__ double s_red[8];
   const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int n = min(count[w], nblk * bs);
@@ -2113,22 +2119,33 @@ __global__ void __launch_bounds__(256) sector_arrange_kernel(const double *src, 
     for (int r = 0; r < n; ++r) { if (lab[r] == 0) pos[r] = ia++; else pos[r] = baseB + nB++; }
     const int blkA = (nA + bs - 1) / bs, blkB = (nB + bs - 1) / bs;
     for (int b = 0; b < nblk; ++b) bsec[(long)w * nblk + b] = b < blkA ? 0 : (b < blkA + blkB ? 1 : 2);
+    int cA = 0;
+    for (int c = 0; c < nc; ++c) cA += colA[c];
+    int ja = 0, jb = cA;
+    for (int c = 0; c < nc; ++c) cpos[c] = colA[c] ? ja++ : jb++;
+    // windows with even starts and widths (16-byte row copies): a window may take in one column of the other sector,
+    // where the rows of this sector hold rounding noise only
+    int32_t *cw = cwin + (long)w * 4;
+    cw[0] = 0; cw[1] = min(nc, (cA + 1) & ~1);
+    cw[2] = cA & ~1; cw[3] = nc - cw[2];
+    if ((nc & 1) && (cw[3] & 1)) { /* odd full width: the kernel's scalar path handles odd windows */ }
   }
   __syncthreads();
+  for (int c = t; c < nc; c += 256) cord_out[(long)w * nc + cpos[c]] = cord_in ? cord_in[(long)w * nc + c] : c;
   double *D = dst + (long)w * wd;
   for (int r = warp; r < n; r += 8) {
     const int p = pos[r];
     if (p < nblk * bs)
-      for (int c = lane; c < nc; c += 32) D[(long)p * ld + c] = S[(long)r * ld + c];
+      for (int c = lane; c < nc; c += 32) D[(long)p * ld + cpos[c]] = S[(long)r * ld + c];
   }
 }
 void be_sector_arrange(const double *src, long ws, int ld, int nc, const int32_t *count, int bs, int nblk, double *dst, long wd,
-                       int32_t *bsec, int W) {
+                       int32_t *bsec, const int32_t *cord_in, int32_t *cord_out, int32_t *cwin, int W) {
   LaunchScope scope(KC_SMALL, 0.0);
-  const size_t smem = sizeof(int) * ((size_t)nc + 2 * (size_t)nblk * bs);
+  const size_t smem = sizeof(int) * (2 * (size_t)nc + 2 * (size_t)nblk * bs);
   if (smem > 96 * 1024) throw std::runtime_error("be_sector_arrange: matrix too large for the label tables");
   ensure_smem(sector_arrange_kernel, smem);
-  sector_arrange_kernel<<<W, 256, smem, g_stream>>>(src, ws, ld, nc, count, bs, nblk, dst, wd, bsec);
+  sector_arrange_kernel<<<W, 256, smem, g_stream>>>(src, ws, ld, nc, count, bs, nblk, dst, wd, bsec, cord_in, cord_out, cwin);
   post_launch();
 }
 void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {

@@ -324,7 +324,7 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
   long ws2cur = ws2;
   // Z2 sectors (fermion mode): regroup the rows so that every block of the Jacobi schedule is sector-pure and skip the block
   // pairs of different sectors (exactly orthogonal: disjoint column supports); half of the block pairs remain.
-  int32_t *bsec = nullptr;
+  int32_t *bsec = nullptr, *cwin = nullptr, *cord2 = nullptr;
   const bool sectors = cx.z2_sectors && nr_eff > 2 * J.bs;
   if (sectors) {
     JacobiLayout Jz = J;
@@ -334,7 +334,9 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
     double *Gz = (double *)cx.pool->get(sizeof(double) * (size_t)W * Jz.nr_pad * nc);
     be_memset0(Gz, sizeof(double) * (size_t)W * Jz.nr_pad * nc);
     bsec = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * Jz.nblk);
-    be_sector_arrange(G2, ws2, nc, nc, cnt, J.bs, Jz.nblk, Gz, (long)Jz.nr_pad * nc, bsec, W);
+    cwin = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * 4);
+    cord2 = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * nc);       // column order: presort composed with the sector grouping
+    be_sector_arrange(G2, ws2, nc, nc, cnt, J.bs, Jz.nblk, Gz, (long)Jz.nr_pad * nc, bsec, presort ? cord : nullptr, cord2, cwin, W);
     cx.pool->put(G2);
     G2 = Gz; J = Jz; ws2cur = (long)Jz.nr_pad * nc; nr_eff = Jz.nr_pad;
   }
@@ -346,7 +348,7 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
     ja.G = G2; ja.ws = ws2cur; ja.ld = nc; ja.nr_pad = J.nr_pad; ja.nc = nc; ja.bs = J.bs; ja.nblk = J.nblk;
     ja.tol = cx.jacobi_tol; ja.inner_sweeps = cx.jacobi_inner_sweeps; ja.offmax = cx.offmax; ja.done = cx.done; ja.W = W;
     ja.nactive = W;
-    ja.bsec = bsec;
+    ja.bsec = bsec; ja.cwin = cwin;
     for (int sweep = 0; sweep < cx.jacobi_max_sweeps; ++sweep) {
       for (int round = 0; round < ja.nblk - 1; ++round) {
         ja.round = round;
@@ -396,18 +398,17 @@ inline void truncate_rows(LinalgCtx &cx, double *G, long ws, int nr, int nc, int
   int32_t *ord2 = (int32_t *)cx.pool->get(sizeof(int32_t) * (size_t)W * tcap);
   be_row_norms2(G2, ws2cur, nc, nr_eff, nc, n2b, W);
   be_select_truncate(n2b, nr_eff, nsv, dmin, dmax, trunc_err, tcap, ord2, kept, W);
-  if (presort) {
+  if (presort || cord2) {
     double *Bp = (double *)cx.pool->get(sizeof(double) * (size_t)W * tcap * nc);
     be_gather_rows_normalized(G2, ws2cur, nc, nc, n2b, nr_eff, ord2, kept, tcap, Bp, (long)tcap * nc, W);
-    be_permute_cols(Bp, (long)tcap * nc, nc, tcap, nc, cord, 0, B, wb, nc, W);
+    be_permute_cols(Bp, (long)tcap * nc, nc, tcap, nc, cord2 ? cord2 : cord, 0, B, wb, nc, W);
     cx.pool->put(Bp);
-    cx.pool->put(cord);
-    cx.pool->put(G);
+    if (presort) { cx.pool->put(cord); cx.pool->put(G); }
   } else {
     be_gather_rows_normalized(G2, ws2cur, nc, nc, n2b, nr_eff, ord2, kept, tcap, B, wb, W);
   }
   for (void *p : {(void *)n2a, (void *)ord, (void *)cnt, (void *)G2, (void *)n2b, (void *)ord2}) cx.pool->put(p);
-  if (bsec) cx.pool->put(bsec);
+  if (bsec) { cx.pool->put(bsec); cx.pool->put(cwin); cx.pool->put(cord2); }
 }
 
 }  // namespace peps

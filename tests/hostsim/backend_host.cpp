@@ -224,7 +224,7 @@ static void rr_pair(int nblk, int round, int q, int &I, int &J) {
 }
 
 void be_sector_arrange(const double *src, long ws, int ld, int nc, const int32_t *count, int bs, int nblk, double *dst, long wd,
-                       int32_t *bsec, int W) {
+                       int32_t *bsec, const int32_t *cord_in, int32_t *cord_out, int32_t *cwin, int W) {
   ++g_launches;
   for (int w = 0; w < W; ++w) {
     const int n = std::min((int)count[w], nblk * bs);
@@ -251,9 +251,17 @@ void be_sector_arrange(const double *src, long ws, int ld, int nc, const int32_t
     const int baseB = (nA + bs - 1) / bs * bs;
     int ia = 0;
     double *D = dst + (long)w * wd;
+    int cA = 0;
+    for (int c = 0; c < nc; ++c) cA += colA[(size_t)c];
+    std::vector<int> cpos((size_t)nc);
+    int ja = 0, jb = cA;
+    for (int c = 0; c < nc; ++c) cpos[(size_t)c] = colA[(size_t)c] ? ja++ : jb++;
+    for (int c = 0; c < nc; ++c) cord_out[(long)w * nc + cpos[(size_t)c]] = cord_in ? cord_in[(long)w * nc + c] : c;
+    cwin[(long)w * 4 + 0] = 0; cwin[(long)w * 4 + 1] = std::min(nc, (cA + 1) & ~1);
+    cwin[(long)w * 4 + 2] = cA & ~1; cwin[(long)w * 4 + 3] = nc - (cA & ~1);
     for (int r = 0; r < n; ++r) {
       const int p = lab[(size_t)r] == 0 ? ia++ : baseB + nB++;
-      if (p < nblk * bs) for (int c = 0; c < nc; ++c) D[(long)p * ld + c] = S[(long)r * ld + c];
+      if (p < nblk * bs) for (int c = 0; c < nc; ++c) D[(long)p * ld + cpos[(size_t)c]] = S[(long)r * ld + c];
     }
     const int blkA = (nA + bs - 1) / bs, blkB = (nB + bs - 1) / bs;
     for (int b = 0; b < nblk; ++b) bsec[(long)w * nblk + b] = b < blkA ? 0 : (b < blkA + blkB ? 1 : 2);
@@ -274,6 +282,9 @@ void be_jacobi_round(const JacobiArgs &a) {
         if (sI != sJ || sI == 2) continue;
       }
       int lo = std::min(I, J), hi = std::max(I, J);
+      int c0 = 0, nc = a.nc;
+      if (a.bsec && a.cwin) { const int sI = a.bsec[(long)w * a.nblk + I]; c0 = a.cwin[(long)w * 4 + 2 * sI]; nc = a.cwin[(long)w * 4 + 2 * sI + 1]; if (nc <= 0) continue; }
+      double *Gw = a.G + (long)w * a.ws + c0;
       auto grow = [&](int r) { return (r < bs) ? lo * bs + r : hi * bs + (r - bs); };
       std::vector<double> Ps((size_t)n2 * nc), G((size_t)n2 * n2), Wm((size_t)n2 * n2, 0.0);
       for (int r = 0; r < n2; ++r)
