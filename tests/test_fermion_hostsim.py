@@ -194,3 +194,9 @@ def test_sector_truncation_hostsim(lib, monkeypatch, sectors):
     monkeypatch.setenv("PEPS_SMALL_SVD", "0")
     monkeypatch.setenv("PEPS_Z2_SECTORS", sectors)
     run_sector_truncation_case(lib, nr=96, nc=112, t=16, W=2)
+
+
+def test_fermion_pipeline_block_jacobi_path_hostsim(lib, monkeypatch):
+    """Same scenario as the GPU test of that name, smaller: the sector path inside the full pipeline vs the oracle."""
+    monkeypatch.setenv("PEPS_SMALL_SVD", "0")
+    run_fermion_pipeline_parity(lib, 5, 5, 4, 1, (16, 16, 0.0), model="spinless", nsweeps=1, check_holes=False)

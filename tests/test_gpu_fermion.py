@@ -139,3 +139,12 @@ def test_sector_truncation_gpu(lib, monkeypatch, sectors):
     monkeypatch.setenv("PEPS_Z2_SECTORS", sectors)
     run_sector_truncation_case(lib, nr=160, nc=192, t=24, W=3)
     run_sector_truncation_case(lib, nr=512, nc=512, t=64, W=2, seed=9)
+
+
+@pytest.mark.parametrize("sectors", ["1", "0"])
+def test_fermion_pipeline_block_jacobi_path_gpu(lib, monkeypatch, sectors):
+    """Full pipeline vs the oracle with the truncations forced onto the block-Jacobi path (PEPS_SMALL_SVD=0), with and
+    without the sector regrouping / column windows: configurations bit-identical, E_loc and O* to 1e-10."""
+    monkeypatch.setenv("PEPS_SMALL_SVD", "0")
+    monkeypatch.setenv("PEPS_Z2_SECTORS", sectors)
+    run_fermion_pipeline_parity(lib, 6, 6, 4, 2, (16, 16, 0.0), model="spinless", nsweeps=1)
