@@ -372,7 +372,7 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
     L, D, chi = D_chi
     out = []
 
-    def run(name, L, D, chi, W, S, tps, j2=0.0, model=None):
+    def run(name, L, D, chi, W, S, tps, j2=0.0, model=None, note=None):
         cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, CFG_SEED0 + w) for w in range(W)])
         seeds = np.arange(RNG_SEED0, RNG_SEED0 + W, dtype=np.uint32)
         ls = LaneSet(L, D, chi, W, S, device, tps, cfgs, seeds, j2=j2, torch=torch, model=model)
@@ -385,18 +385,23 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
             out.append({"name": name, "lattice": f"{L}x{L}", "D": D, "chi": chi, "walkers": W, "streams": ls.S,
                         "samples_per_s": W / (ms * 1e-3), "ms_per_step": ms, "mean_eloc": float(np.mean(e)),
                         "truncation_rows_kept_frac": d[1] / max(d[0], 1), "chain_rows_kept_frac": d[3] / max(d[2], 1),
-                        "small_svd_path_frac": d[5] / max(d[4], 1)})
+                        "small_svd_path_frac": d[5] / max(d[4], 1), **({"note": note} if note else {})})
         finally:
             ls.close()
 
     SIGNED_TPS = False
     tps = vmc.random_tps(L, L, 2, D, seed=TPS_SEED)
     run("j1j2_j2=0.5", L, D, chi, walkers, streams, tps, j2=0.5)
-    run("signed_tps", L, D, chi, walkers, streams, vmc.random_tps(L, L, 2, D, seed=TPS_SEED, signed=True))
+    run("signed_tps", L, D, chi, walkers, streams, vmc.random_tps(L, L, 2, D, seed=TPS_SEED, signed=True),
+        note="throughput stress line only: a chi-truncated contraction of a uniform[-1,1) state is ill-conditioned at this size (row "
+             "closures of ONE configuration differ by ~10x in the oracle too, CUDA vs oracle share no digits); parity of this code "
+             "path is asserted where it is well-posed (8x8 D=6 chi=36 signed: 1e-9, tests/test_gpu_parity.py)")
     # BASELINE config #4: 8x8 spinless fermions, fZ2 tensors with even / odd blocks of D/2, chi = 64
     from peps_b200.api import FermionSplitIndexTPS, TableModel
     run("fermion_spinless_8x8_D8_chi64_fZ2", 8, 8, 64, walkers, streams, FermionSplitIndexTPS.random(8, 8, 8, TPS_SEED),
-        model=TableModel.spinless_fermion(1.0, 0.0, 0.0))
+        model=TableModel.spinless_fermion(1.0, 0.0, 0.0),
+        note="BASELINE config #4: fZ2-graded state evaluated as a sign-dressed dense network (DESIGN.md section 9); random "
+             "parity-conserving tensors are full rank, so the sector-aware block-Jacobi truncation path runs")
     gold = os.path.join(ROOT, "tests", "golden", "heis4x4_D8_double.npz")
     if os.path.exists(gold):
         z = np.load(gold)
