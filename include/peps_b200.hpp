@@ -303,6 +303,22 @@ class MCEnergyGradEvaluator {
     for (int w = 0; w < walkers; ++w) seeds[(size_t)w] = seed + (uint32_t)w;
     batch_.SeedRNG(seeds);
   }
+  // Models given as data (seam B2) and, with `fermion`, fZ2-graded states: e.g. {SpinlessFermionBondTerm(t, V),
+  // SpinlessFermionNNNTerm(t2)} or {tJBondTerm(t, J, V), tJOnsiteTerm(mu)} with the parities of the SplitIndexTPS
+  // (SquareSpinlessFermion / SquaretJ*Model runs of the reference, BASELINE config #4)
+  MCEnergyGradEvaluator(const MonteCarloParams &mc, const BMPSTruncateParams &trunc, int rows, int cols, int phys, int D,
+                        int walkers, const std::vector<ModelTerm> &terms, uint32_t seed, const FermionParities *fermion = nullptr,
+                        int device = 0)
+      : mc_(mc), batch_(rows, cols, phys, D, walkers, trunc, device) {
+    if (fermion) batch_.SetFermion(*fermion);
+    for (const auto &t : terms) batch_.SetModelTerm(t);
+    std::vector<int32_t> cfg;
+    for (int w = 0; w < walkers; ++w) cfg.insert(cfg.end(), mc.initial_config.begin(), mc.initial_config.end());
+    batch_.SetConfigs(cfg);
+    std::vector<uint32_t> seeds((size_t)walkers);
+    for (int w = 0; w < walkers; ++w) seeds[(size_t)w] = seed + (uint32_t)w;
+    batch_.SeedRNG(seeds);
+  }
   // Evaluate(state): state fan-out, RefreshWavefunctionComponent, the walker loop, energy binning, gradient
   EvaluateResult Evaluate(const std::vector<double> &packed_tps) {
     batch_.SetTPS(packed_tps);

@@ -34,6 +34,16 @@ int main() {
     double num = 0.0, den = 0.0;
     for (int w = 0; w < W; ++w) { num += a[(size_t)w] * a[(size_t)w] * e[(size_t)w]; den += a[(size_t)w] * a[(size_t)w]; }
     std::printf("%.15e\n", num / den);
+    // the evaluator built from model terms + parities: 2 samples per walker from the first configuration, seed 77
+    peps_b200::MonteCarloParams mc;
+    mc.num_samples = (size_t)(2 * W); mc.num_warmup_sweeps = 0; mc.sweeps_between_samples = 1;
+    mc.initial_config.assign(cfg.begin(), cfg.begin() + rows * cols);
+    std::vector<peps_b200::ModelTerm> terms = {peps_b200::SpinlessFermionBondTerm(t, V)};
+    if (t2 != 0.0) terms.push_back(peps_b200::SpinlessFermionNNNTerm(t2));
+    peps_b200::MCEnergyGradEvaluator ev(mc, peps_b200::BMPSTruncateParams::SVD((size_t)chi, (size_t)chi, 1e-16), rows, cols, phys, D, W,
+                                        terms, 77u, &par);
+    peps_b200::EvaluateResult r = ev.Evaluate(tps);
+    std::printf("%.15e %.15e\n", r.energy, r.gradient_norm);
   } catch (const std::exception &ex) {
     std::fprintf(stderr, "error: %s\n", ex.what());
     return 1;

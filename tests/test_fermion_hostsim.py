@@ -123,14 +123,26 @@ def run_cpp_fermion_case(libdir, libfile, extra_link=()):
         inp = (f"2 2 2 {ftps.bond_dim()} {len(cfgs)} 8 1.0 -2.5 0.0\n" + " ".join(map(str, ftps.phys_par)) + f"\n{lp.size} "
                + " ".join(map(str, lp)) + f"\n{flat.size} " + " ".join(repr(float(x)) for x in flat) + "\n"
                + " ".join(str(int(c)) for c in cfgs.ravel()) + "\n")
-        out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout
-    assert abs(float(out) - float(z["exp_energy"])) < 1e-9
+        out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
+    assert abs(float(out[0]) - float(z["exp_energy"])) < 1e-9
+    return float(out[1]), float(out[2]), ftps, cfgs
+
+
+def check_cpp_fermion_evaluator(lib, e_cpp, gn_cpp, ftps, cfgs):
+    """The C++ MCEnergyGradEvaluator built from model terms + parities equals the Python mirror on the same library."""
+    W = len(cfgs)
+    ev = MCEnergyGradEvaluator(MonteCarloParams(2 * W, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(8, 8, 1e-16), ftps,
+                               TableModel.spinless_fermion(1.0, -2.5, 0.0), MCUpdateSquareNNExchange(seed=77), W, lib=lib)
+    res = ev.Evaluate(ftps)
+    assert abs(res.energy - e_cpp) < 1e-11 * max(1.0, abs(e_cpp))
+    assert abs(res.gradient_norm - gn_cpp) < 1e-10 * max(1.0, gn_cpp)
 
 
 def test_cpp_wrapper_fermion_golden():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    hostsim_lib.load()
-    run_cpp_fermion_case(os.path.join(root, "tests", "hostsim"), "libpeps_hostsim.so")
+    lib = hostsim_lib.load()
+    e, gn, ftps, cfgs = run_cpp_fermion_case(os.path.join(root, "tests", "hostsim"), "libpeps_hostsim.so")
+    check_cpp_fermion_evaluator(lib, e, gn, ftps, cfgs)
 
 
 def test_fermion_measure_bond_energies(lib):

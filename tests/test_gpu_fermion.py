@@ -119,10 +119,11 @@ def test_cpp_wrapper_fermion_on_cuda_library(lib):
     """The C++ wrapper (SetFermion + probe-built SquareSpinlessFermion terms) linked against libpeps_b200.so reproduces
     the reference's golden energy of the 2x2 simple-update fixture (t2 = -2.5)."""
     import os
-    from test_fermion_hostsim import run_cpp_fermion_case
+    from test_fermion_hostsim import run_cpp_fermion_case, check_cpp_fermion_evaluator
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    run_cpp_fermion_case(os.path.join(root, "peps_b200"), "libpeps_b200.so",
-                         extra_link=["-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
+    e, gn, ftps, cfgs = run_cpp_fermion_case(os.path.join(root, "peps_b200"), "libpeps_b200.so",
+                                             extra_link=["-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
+    check_cpp_fermion_evaluator(lib, e, gn, ftps, cfgs)
 
 
 def test_tj_jastrow_dressed_pipeline_parity_gpu(lib):
