@@ -2071,7 +2071,7 @@ __global__ void jacobi_flags_kernel(double *offmax, int32_t *done, double tol, i
 // sector structure holds up to rounding noise only (a Householder QR puts R rows at pivot POSITIONS, which mixes in noise),
 // so the labels compare weights: a row belongs to sector 0 when it carries more weight on the sector-0 columns than off
 // them; the sector-0 columns start as the support of row 0 (largest norm) and are re-estimated once by column majority.
-__global__ void __launch_bounds__(256) sector_arrange_kernel(const double *src, long ws, int ld, int nc, const int32_t *count, int bs,
+__global__ void __launch_bounds__(1024) sector_arrange_kernel(const double *src, long ws, int ld, int nc, const int32_t *count, int bs,
                                                              int nblk, double *dst, long wd, int32_t *bsec, const int32_t *cord_in,
                                                              int32_t *cord_out, int32_t *cwin) {
   extern __shared__ int sa_sm[];
@@ -2079,22 +2079,22 @@ __global__ void __launch_bounds__(256) sector_arrange_kernel(const double *src, 
   int *lab = colA + nc;           // [nrows] 0 = sector of row 0, 1 = other
   int *pos = lab + nblk * bs;     // [nrows] destination row
   int *cpos = pos + nblk * bs;    // [nc] destination column: sector-0 columns first
-  __shared__ double s_red[8];
-  const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ double s_red[32];
+  const int w = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, NT = blockDim.x, NW = blockDim.x >> 5;
   const int n = min(count[w], nblk * bs);
   const double *S = src + (long)w * ws;
   double mx = 0.0;
-  for (int c = t; c < nc; c += 256) mx = fmax(mx, n > 0 ? fabs(S[c]) : 0.0);
+  for (int c = t; c < nc; c += NT) mx = fmax(mx, n > 0 ? fabs(S[c]) : 0.0);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if (lane == 0) s_red[warp] = mx;
   __syncthreads();
   mx = 0.0;
-  for (int i = 0; i < 8; ++i) mx = fmax(mx, s_red[i]);
-  for (int c = t; c < nc; c += 256) colA[c] = (n > 0 && fabs(S[c]) > 1e-8 * mx) ? 1 : 0;
+  for (int i = 0; i < NW; ++i) mx = fmax(mx, s_red[i]);
+  for (int c = t; c < nc; c += NT) colA[c] = (n > 0 && fabs(S[c]) > 1e-8 * mx) ? 1 : 0;
   __syncthreads();
   for (int pass = 0; pass < 2; ++pass) {
-    for (int r = warp; r < n; r += 8) {
+    for (int r = warp; r < n; r += NW) {
       double in = 0.0, out = 0.0;
       for (int c = lane; c < nc; c += 32) { const double v = fabs(S[(long)r * ld + c]); if (colA[c]) in += v; else out += v; }
 #pragma unroll
@@ -2103,7 +2103,7 @@ __global__ void __launch_bounds__(256) sector_arrange_kernel(const double *src, 
     }
     __syncthreads();
     if (pass == 0) {
-      for (int c = t; c < nc; c += 256) {
+      for (int c = t; c < nc; c += NT) {
         double wa = 0.0, wb = 0.0;
         for (int r = 0; r < n; ++r) { const double v = fabs(S[(long)r * ld + c]); if (lab[r] == 0) wa += v; else wb += v; }
         colA[c] = wa >= wb ? 1 : 0;
@@ -2131,9 +2131,9 @@ __global__ void __launch_bounds__(256) sector_arrange_kernel(const double *src, 
     if ((nc & 1) && (cw[3] & 1)) { /* odd full width: the kernel's scalar path handles odd windows */ }
   }
   __syncthreads();
-  for (int c = t; c < nc; c += 256) cord_out[(long)w * nc + cpos[c]] = cord_in ? cord_in[(long)w * nc + c] : c;
+  for (int c = t; c < nc; c += NT) cord_out[(long)w * nc + cpos[c]] = cord_in ? cord_in[(long)w * nc + c] : c;
   double *D = dst + (long)w * wd;
-  for (int r = warp; r < n; r += 8) {
+  for (int r = warp; r < n; r += NW) {
     const int p = pos[r];
     if (p < nblk * bs)
       for (int c = lane; c < nc; c += 32) D[(long)p * ld + cpos[c]] = S[(long)r * ld + c];
@@ -2145,7 +2145,7 @@ void be_sector_arrange(const double *src, long ws, int ld, int nc, const int32_t
   const size_t smem = sizeof(int) * (2 * (size_t)nc + 2 * (size_t)nblk * bs);
   if (smem > 96 * 1024) throw std::runtime_error("be_sector_arrange: matrix too large for the label tables");
   ensure_smem(sector_arrange_kernel, smem);
-  sector_arrange_kernel<<<W, 256, smem, g_stream>>>(src, ws, ld, nc, count, bs, nblk, dst, wd, bsec, cord_in, cord_out, cwin);
+  sector_arrange_kernel<<<W, 1024, smem, g_stream>>>(src, ws, ld, nc, count, bs, nblk, dst, wd, bsec, cord_in, cord_out, cwin);
   post_launch();
 }
 void be_jacobi_flags(double *offmax, int32_t *done, double tol, int W) {

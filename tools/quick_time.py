@@ -14,6 +14,7 @@ ap.add_argument("--walkers", type=int, default=8)
 ap.add_argument("--reps", type=int, default=1)
 ap.add_argument("--inner", type=int, default=1)
 ap.add_argument("--profile", type=int, default=1)
+ap.add_argument("--j2", type=float, default=0.0)
 a = ap.parse_args()
 L, D, chi, W = a.L, a.D, a.chi, a.walkers
 tps = vmc.random_tps(L, L, 2, D, seed=20260101)
@@ -21,6 +22,9 @@ cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, 1000 + w) for w in range(
 b = WalkerBatch(L, L, 2, D, W, BMPSTruncateParams.SVD(chi, chi, 0.0))
 b.set_jacobi(1e-14, a.inner, 60); b.profile_enable(bool(a.profile))
 b.set_tps(SplitIndexTPS(tps)); b.set_configs(cfgs); b.seed_rng(np.arange(W) + 7)
+if a.j2 != 0.0:
+    from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
+    b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, a.j2, a.j2, 0.0))
 def tm(f, name):
     b.sync(); t = time.time(); r = f(); b.sync(); dt = time.time() - t
     if a.profile:
