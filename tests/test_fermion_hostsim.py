@@ -212,3 +212,41 @@ def test_fermion_pipeline_block_jacobi_path_hostsim(lib, monkeypatch):
     """Same scenario as the GPU test of that name, smaller: the sector path inside the full pipeline vs the oracle."""
     monkeypatch.setenv("PEPS_SMALL_SVD", "0")
     run_fermion_pipeline_parity(lib, 5, 5, 4, 1, (16, 16, 0.0), model="spinless", nsweeps=1, check_holes=False)
+
+
+def test_fermion_sr_natural_gradient(lib):
+    """SR on an fZ2 state (the O* store holds the physical O* = Pi(R*) in the uploaded tensor entries, so the S matrix and
+    the CG need no parity wrapping: docs/dev/design/math/fermion-vmc-implementation.md section 3): the device matvec /
+    natural gradient against the dense S built from the oracle chain's O* samples."""
+    from oracle import fermion as F
+    from peps_b200 import sr
+    from parity_common import fermion_configs
+    rows, cols, D, W, n, trunc, shift = 3, 3, 2, 3, 4, (4, 4, 0.0), 1e-3
+    f = F.FermionTPS.random(rows, cols, D, 13)
+    ftps = FermionSplitIndexTPS(f.T, f.par, f.phys_par)
+    cfgs = fermion_configs(rows, cols, W, 2)
+    ev = MCEnergyGradEvaluator(MonteCarloParams(n * W, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(*trunc), ftps,
+                               TableModel.spinless_fermion(1.0, 0.5, 0.2), MCUpdateSquareNNExchange(seed=41), W, configs=cfgs, lib=lib)
+    res = ev.Evaluate(collect_sr_buffers=True)
+    assert ev.batch.sr_count() == n * W
+    omodel = F.SpinlessFermionModel(1.0, 0.5, 0.2)
+    ostars = []
+    for w in range(W):
+        wk = F.FermionWalker(f, cfgs[w], trunc)
+        up = F.FermionNNExchangeUpdater(41 + w)
+        for _ in range(n):
+            up.sweep(wk)
+            _, ost, _ = omodel.energy_and_holes(wk, True)
+            dense = [[[np.zeros_like(x) for x in site] for site in row] for row in f.T]
+            for r in range(rows):
+                for c in range(cols):
+                    dense[r][c][int(wk.config[r, c])] = ost[r][c]
+            ostars.append(np.concatenate([x.ravel() for row in dense for site in row for x in site]))
+    o = np.stack(ostars)
+    obar = o.mean(0)
+    assert np.max(np.abs(res.Ostar_mean.pack() - obar)) < 1e-10 * np.max(np.abs(obar))
+    g = res.gradient.pack()
+    nat, iters, _ = ev.CalculateNaturalGradient(res, shift, sr.ConjugateGradientParams(max_iter=300, relative_tolerance=1e-11))
+    s_dense = (o - obar).T @ (o - obar) / len(ostars) + shift * np.eye(obar.size)
+    x_dense = np.linalg.solve(s_dense, g)
+    assert np.max(np.abs(nat.pack() - x_dense)) < 1e-6 * np.max(np.abs(x_dense))
