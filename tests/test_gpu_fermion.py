@@ -140,6 +140,8 @@ def test_sector_truncation_gpu(lib, monkeypatch, sectors):
     monkeypatch.setenv("PEPS_Z2_SECTORS", sectors)
     run_sector_truncation_case(lib, nr=160, nc=192, t=24, W=3)
     run_sector_truncation_case(lib, nr=512, nc=512, t=64, W=2, seed=9)
+    run_sector_truncation_case(lib, nr=70, nc=81, t=10, W=2, seed=3)        # odd width: scalar (non-TMA) tile path, odd windows
+    run_sector_truncation_case(lib, nr=41, nc=130, t=12, W=2, seed=5)       # wide matrix
 
 
 @pytest.mark.parametrize("sectors", ["1", "0"])
