@@ -375,7 +375,11 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
     def run(name, L, D, chi, W, S, tps, j2=0.0, model=None, note=None):
         cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, CFG_SEED0 + w) for w in range(W)])
         seeds = np.arange(RNG_SEED0, RNG_SEED0 + W, dtype=np.uint32)
-        ls = LaneSet(L, D, chi, W, S, device, tps, cfgs, seeds, j2=j2, torch=torch, model=model)
+        try:
+            ls = LaneSet(L, D, chi, W, S, device, tps, cfgs, seeds, j2=j2, torch=torch, model=model)
+        except Exception as exc:                     # noqa: BLE001  (a companion line must not take the others down)
+            out.append({"name": name, "error": repr(exc)[:300]})
+            return
         try:
             ls.samples(1)
             r0 = [ls.stat_sum(k) for k in (8, 9, 12, 13, 4, 14)]
@@ -386,6 +390,8 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
                         "samples_per_s": W / (ms * 1e-3), "ms_per_step": ms, "mean_eloc": float(np.mean(e)),
                         "truncation_rows_kept_frac": d[1] / max(d[0], 1), "chain_rows_kept_frac": d[3] / max(d[2], 1),
                         "small_svd_path_frac": d[5] / max(d[4], 1), **({"note": note} if note else {})})
+        except Exception as exc:                     # noqa: BLE001
+            out.append({"name": name, "error": repr(exc)[:300]})
         finally:
             ls.close()
 
@@ -642,7 +648,10 @@ def main():
     ls.close()
     secondary = None
     if args.secondary and world == 1:
-        secondary = secondary_lines(torch, local_rank, (L, D, chi), args.secondary_walkers, 2)
+        try:                                         # companions must never take the headline line down with them
+            secondary = secondary_lines(torch, local_rank, (L, D, chi), args.secondary_walkers, 2)
+        except Exception as exc:                     # noqa: BLE001
+            secondary = [{"name": "secondary lines failed", "error": repr(exc)[:300]}]
     cpu = None
     if not args.no_cpu_baseline and world == 1:      # the CPU arm is timed at N=1 only (rank 0, all host cores)
         cores = os.cpu_count() or 1
