@@ -106,6 +106,7 @@ void Engine::site_dims(int r, int c, int out[4]) const {
 }
 void Engine::set_tps(const double *host) {
   be_h2d(tps_, host, sizeof(double) * tps_total_);
+  tps_loaded_ = true;
   if (fermion_) {                                       // dress: FERMION_VARIANTS sign patterns per site (backend.h)
     std::vector<double> g((size_t)(tps_total_ * FERMION_VARIANTS));
     static const int vmask[FERMION_VARIANTS] = {0, 8, 4, 12, 6, 14, 0, 1};     // bits: L = 1, D = 2, R = 4, U = 8
@@ -1711,6 +1712,11 @@ void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
   be_h2d(fsign_, sg.data(), sizeof(double) * sg.size());
   refresh_gather();
   touch_all();
+  if (tps_loaded_) {                                    // a state uploaded before the switch: dress it now
+    std::vector<double> h((size_t)tps_total_);
+    get_tps(h.data());
+    set_tps(h.data());
+  }
 }
 void Engine::set_jastrow(const double *v, const int32_t *density) {
   if (!v || !density) throw std::invalid_argument("set_jastrow: null table");

@@ -235,7 +235,7 @@ class Engine {
   void require_boson(const char *what) const {
     if (fermion_) throw std::logic_error(std::string(what) + " is not available in fermion mode");
   }
-  bool fermion_ = false;
+  bool fermion_ = false, tps_loaded_ = false;
   bool jastrow_on_ = false, tables_exchange_only_ = true;
   double *jastrow_v_ = nullptr, *jr_ = nullptr;   // [nsites][nsites], [W]
   int32_t *dens_d_ = nullptr;                      // [phys]

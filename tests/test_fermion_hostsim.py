@@ -250,3 +250,22 @@ def test_fermion_sr_natural_gradient(lib):
     s_dense = (o - obar).T @ (o - obar) / len(ostars) + shift * np.eye(obar.size)
     x_dense = np.linalg.solve(s_dense, g)
     assert np.max(np.abs(nat.pack() - x_dense)) < 1e-6 * np.max(np.abs(x_dense))
+
+
+def test_set_fermion_after_set_tps(lib):
+    """Order independence: a state uploaded before peps_set_fermion is dressed when the mode is switched on."""
+    from parity_common import fermion_configs
+    ftps = FermionSplitIndexTPS.random(3, 3, 2, 3)
+    cfgs = fermion_configs(3, 3, 2, 2)
+    amps = []
+    for order in (0, 1):
+        b = WalkerBatch(3, 3, 2, 2, 2, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+        if order == 0:
+            b.set_fermion(ftps); b.set_tps(ftps)
+        else:
+            b.set_tps(ftps); b.set_fermion(ftps)
+        b.set_configs(cfgs)
+        b.init_walkers()
+        amps.append(b.amplitudes())
+        b.close()
+    assert np.array_equal(amps[0], amps[1]) and np.all(amps[0] != 0)
