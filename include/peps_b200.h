@@ -113,6 +113,20 @@ int peps_clear_model_terms(peps_ctx *ctx);
  * keep both site parities (hopping, spin exchange). Updater: NN exchange (peps_sweep). */
 int peps_set_fermion(peps_ctx *ctx, const int32_t *phys_par, const int32_t *leg_par, size_t n_leg_par);
 
+/* Complex states (QLTEN_Complex instantiations of the reference: SplitIndexTPS<QLTEN_Complex, QNT>, every test of
+ * tests/CMakeLists.txt:57-83 is compiled for both element types). peps_set_complex switches a fresh context (before the
+ * first peps_set_tps*) to complex arithmetic: tensors live as two real planes, a contraction is four launches of the real
+ * contraction kernel, the boundary-MPS factorisations run on the real embedding [[Ar, -Ai], [Ai, Ar]] of their matrices
+ * (DESIGN.md). Built for the headline path -- amplitude, NN-exchange sweep (|psi| = hypot), XXZ / J1-J2 local energy with
+ * conj(psi_ex / psi) (square_spin_onehalf_xxz_obc.h:72-104), holes and O* = conj(hole / psi), sum O*, sum conj(E_loc) O*
+ * (mc_energy_grad_evaluator.h:245-272). peps_set_tps_c uploads the two planes of the packed state; peps_get_planar reads
+ * per-walker / state-shaped results as planes: what = 0 amplitudes [W], 1 local energies [W] (after
+ * peps_energy_and_holes), 2 holes [W][holes_stride] (the raw environment; O* = conj(hole / amplitude)), 3 sum O*,
+ * 4 sum conj(E_loc) O* [tps_size]. The real getters return the real planes. */
+int peps_set_complex(peps_ctx *ctx);
+int peps_set_tps_c(peps_ctx *ctx, const double *re, const double *im, size_t n);
+int peps_get_planar(peps_ctx *ctx, int32_t what, double *re, double *im);
+
 /* Jastrow-dressed wave function psi(S) = psi_PEPS(S) * exp(sum_{i<j} v_ij n_i n_j): TPSWaveFunctionComponent<..., JastrowDress>
  * (vmc_basic/wave_function_component.h:107-135) with JastrowFactor (vmc_basic/jastrow_factor.h:34-121). v: [nsites][nsites]
  * symmetric, row-major site index, diagonal ignored; density[phys]: particle number of each physical state (t-J: {1, 1, 0}).

@@ -50,6 +50,9 @@ SIGNATURES = {
     "peps_clear_model_terms": (C.c_int, [_P]),
     "peps_set_fermion": (C.c_int, [_P, _I, _I, C.c_size_t]),
     "peps_set_jastrow": (C.c_int, [_P, _D, _I]),
+    "peps_set_complex": (C.c_int, [_P]),
+    "peps_set_tps_c": (C.c_int, [_P, _D, _D, C.c_size_t]),
+    "peps_get_planar": (C.c_int, [_P, C.c_int32, _D, _D]),
     "peps_clear_jastrow": (C.c_int, [_P]),
     "peps_set_configs": (C.c_int, [_P, _I]),
     "peps_get_configs": (C.c_int, [_P, _I]),

@@ -388,6 +388,30 @@ class WalkerBatch:
         self._ck(self.lib.peps_set_fermion(self.h, _ip(pp), _ip(lp), lp.size))
         self.phys_par = tuple(int(x) for x in ftps.phys_par)
 
+    # complex (QLTEN_Complex) states: planar arrays across the ABI, numpy complex here
+    def set_complex(self):
+        """Switch a fresh context to complex arithmetic (peps_set_complex): before the first set_tps."""
+        self._ck(self.lib.peps_set_complex(self.h))
+        self.is_complex = True
+
+    def _planar(self, what, shape):
+        re, im = np.empty(shape), np.empty(shape)
+        self._ck(self.lib.peps_get_planar(self.h, what, _dp(re), _dp(im)))
+        return re + 1j * im
+
+    def amplitudes_c(self):
+        return self._planar(0, self.W)
+
+    def eloc_c(self):
+        return self._planar(1, self.W)
+
+    def holes_c(self):
+        """Raw environments PunchHole(site) per walker; the reference's hole_res is their conjugate (Dag)."""
+        return self._planar(2, (self.W, self.lib.peps_holes_stride(self.h)))
+
+    def accumulators_c(self):
+        return self._planar(3, self.tps_size), self._planar(4, self.tps_size)
+
     def set_jastrow(self, v, density):
         """JastrowDress (wave_function_component.h:107-135): v[nsites][nsites] symmetric, density[phys]."""
         n = self.rows * self.cols
@@ -396,6 +420,14 @@ class WalkerBatch:
         self._ck(self.lib.peps_set_jastrow(self.h, _dp(v), _ip(d)))
 
     def set_tps(self, tps):
+        if getattr(self, "is_complex", False):
+            flat = (np.concatenate([np.asarray(x, dtype=np.complex128).ravel() for row in tps.t for site in row for x in site])
+                    if isinstance(tps, SplitIndexTPS) else np.asarray(tps, dtype=np.complex128).ravel())
+            if flat.size != self.tps_size:
+                raise PepsError(f"TPS has {flat.size} elements, context expects {self.tps_size}")
+            re, im = np.ascontiguousarray(flat.real), np.ascontiguousarray(flat.imag)
+            self._ck(self.lib.peps_set_tps_c(self.h, _dp(re), _dp(im), re.size))
+            return
         flat = tps.pack() if isinstance(tps, SplitIndexTPS) else np.ascontiguousarray(tps, dtype=np.float64)
         if flat.size != self.tps_size:
             raise PepsError(f"TPS has {flat.size} elements, context expects {self.tps_size}")

@@ -268,6 +268,36 @@ void be_term_targets(const int32_t *cfg, int nsites, int s1, int s2, int phys, c
 void be_term_accumulate(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag, const double *coefw,
                         const double *psi_ex, const double *psi, double *eloc, int W);
 
+// ---- complex (c128) tensors as split planes ----------------------------------------------------------------------------
+// A complex walker-batched tensor is two real planes (re, im). Contractions are four real be_gett launches; the
+// factorisations run on the REAL EMBEDDING M = [[Ar, -Ai], [Ai, Ar]] (2m x 2n) of a complex m x n matrix A:
+//   * any real R with R^T R = M^T M gives the complex factor r = (R1 - i R2) / sqrt(2) with r^H r = A^H A, where R1 | R2 are
+//     the two column halves of R (be_split_r);
+//   * the singular values of M are those of A twice over, and its kept right singular subspace is invariant under
+//     J (multiplication by i): be_complex_basis turns 2 t real orthonormal vectors b into t complex orthonormal ones by
+//     pivoted Gram-Schmidt of z = b[:n] + i b[n:] (the Gram matrix of the z has eigenvalues 2 and 0 only).
+// M[w] (2m x 2n, leading dimension 2n, walker stride wm) <- planes Ar / Ai [w] (m x n, leading dimension n, stride wa)
+void be_embed_complex(const double *Ar, const double *Ai, long wa, int m, int n, double *M, long wm, int W);
+// planes (rows x n, stride wo) <- R[w] (rows x 2n, leading dimension 2n, stride wr): re = R[:, :n] / sqrt2, im = -R[:, n:] / sqrt2
+void be_split_r(const double *R, long wr, int rows, int n, double *outr, double *outi, long wo, int W);
+// Bm[w]: tcap2 x 2n real (leading dimension 2n, stride wb), kept2[w] orthonormal rows (the rest zero). Writes planes
+// Br / Bi [w] (tcap x n, stride wo): keptc[w] = (kept2[w] + 1) / 2 orthonormal complex rows = rows of Vt = V^H (the
+// CONJUGATES of the right singular vectors z, Theta = U S V^H), zero rows beyond; keptc is written back. One CTA per walker, modified Gram-Schmidt with pivoting, twice.
+void be_complex_basis(double *Bm, long wb, int tcap2, int n, const int32_t *kept2, double *Br, double *Bi, long wo, int tcap,
+                      int32_t *keptc, int W);
+// out[w] (planes outr / outi) = (d0 - d1) + i (d2 + d3) for the four real dots of a bilinear complex dot product
+void be_complex_combine(const double *d0, const double *d1, const double *d2, const double *d3, double *outr, double *outi, int W);
+// complex twins of the Monte Carlo kernels: amplitudes / energies as planes [2][W]; |psi| = hypot(re, im)
+void be_nn_exchange_decide_c(int32_t *cfg, int nsites, int s1, int s2, const double *pbr, const double *pbi, double *ampr,
+                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W);
+// eloc += (c1 == c2) ? 0.25 jz : -0.25 jz + conj(psi_ex / psi) * 0.5 jxy     (square_spin_onehalf_xxz_obc.h:72-104)
+void be_xxz_bond_energy_c(const int32_t *cfg, int nsites, int s1, int s2, const double *exr, const double *exi, const double *pr,
+                          const double *pi, double jz, double jxy, double *er, double *ei, int W);
+// O* = conj(hole / psi) (mc_energy_grad_evaluator.h:245-272): osum += O*, eosum += conj(E_loc) O*; all arrays as planes
+void be_accumulate_ostar_c(const double *hr, const double *hi, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                           const int32_t *tps_off, const int32_t *cfg, int nsites, const double *ampr, const double *ampi,
+                           const double *er, const double *ei, double *osr, double *osi, double *eor, double *eoi, int W);
+
 // ---- fermionic (fZ2-graded) tensors as sign-dressed dense tensors ---------------------------------------------------
 // A graded network of parity-conserving site tensors equals a bosonic network of dressed tensors (engine.h, "fermion
 // mode"). Per site the device TPS holds FERMION_VARIANTS * phys slices: variant v, state s at slice v * phys + s.

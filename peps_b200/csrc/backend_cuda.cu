@@ -2725,6 +2725,219 @@ void be_xxz_onsite_energy(const int32_t *cfg, int nsites, double h00, double *el
 }
 
 // =====================================================================================================
+// complex (c128) tensors as split planes (backend.h)
+// =====================================================================================================
+__global__ void embed_complex_kernel(const double *Ar, const double *Ai, long wa, int m, int n, double *M, long wm) {
+  const int w = blockIdx.y;
+  const double *ar = Ar + (long)w * wa, *ai = Ai + (long)w * wa;
+  double *Mw = M + (long)w * wm;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < (long)m * n; e += (long)gridDim.x * blockDim.x) {
+    const long r = e / n, c = e - r * n;
+    const double a = ar[e], b = ai[e];
+    Mw[r * 2 * n + c] = a;  Mw[r * 2 * n + n + c] = -b;
+    Mw[(r + m) * 2 * n + c] = b;  Mw[(r + m) * 2 * n + n + c] = a;
+  }
+}
+void be_embed_complex(const double *Ar, const double *Ai, long wa, int m, int n, double *M, long wm, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  embed_complex_kernel<<<dim3(64, W), 256, 0, g_stream>>>(Ar, Ai, wa, m, n, M, wm);
+  post_launch();
+}
+__global__ void split_r_kernel(const double *R, long wr, int rows, int n, double *outr, double *outi, long wo) {
+  const int w = blockIdx.y;
+  const double *Rw = R + (long)w * wr;
+  const double s = 0.70710678118654752440;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < (long)rows * n; e += (long)gridDim.x * blockDim.x) {
+    const long r = e / n, c = e - r * n;
+    outr[(long)w * wo + e] = s * Rw[r * 2 * n + c];
+    outi[(long)w * wo + e] = -s * Rw[r * 2 * n + n + c];
+  }
+}
+void be_split_r(const double *R, long wr, int rows, int n, double *outr, double *outi, long wo, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  split_r_kernel<<<dim3(32, W), 256, 0, g_stream>>>(R, wr, rows, n, outr, outi, wo);
+  post_launch();
+}
+// one CTA per walker; the 2t candidate vectors stay in Bm (global / L2), z_j = Bm[j][:n] + i Bm[j][n:]
+__global__ void __launch_bounds__(256) complex_basis_kernel(double *Bm, long wb, int tcap2, int n, const int32_t *kept2, double *Br,
+                                                            double *Bi, long wo, int tcap, int32_t *keptc) {
+  __shared__ double red[256], red2[256];
+  __shared__ int s_piv;
+  __shared__ double s_cr, s_ci;
+  const int w = blockIdx.x, t = threadIdx.x;
+  double *B = Bm + (long)w * wb;
+  double *outr = Br + (long)w * wo, *outi = Bi + (long)w * wo;
+  const int k2 = min(kept2[w], tcap2);
+  const int kc = min((k2 + 1) / 2, tcap);
+  int kc_done = kc;
+  for (long e = t; e < (long)tcap * n; e += 256) { outr[e] = 0.0; outi[e] = 0.0; }
+  __syncthreads();
+  for (int q = 0; q < kc; ++q) {
+    // pivot: the remaining candidate of largest norm
+    double best = -1.0; int bi = -1;
+    for (int j = t; j < k2; j += 256) {
+      double s = 0.0;
+      for (int c = 0; c < 2 * n; ++c) { const double v = B[(long)j * 2 * n + c]; s = fma(v, v, s); }
+      if (s > best) { best = s; bi = j; }
+    }
+    red[t] = best; red2[t] = (double)bi;
+    __syncthreads();
+    if (t == 0) {
+      double b = -1.0; int p = -1;
+      for (int i = 0; i < 256; ++i) if (red[i] > b || (red[i] == b && (int)red2[i] >= 0 && (int)red2[i] < p)) { b = red[i]; p = (int)red2[i]; }
+      s_piv = p; s_cr = b;
+    }
+    __syncthreads();
+    const int p = s_piv;
+    // candidates are unit rows (or zero rows beyond the numerical rank); once the best residual is rounding noise the
+    // subspace is exhausted: the remaining rows stay ZERO, exactly like the zero-padded rows of the real path (a normalised
+    // noise vector would be a spurious direction)
+    if (p < 0 || s_cr < 1e-10) { kc_done = q; break; }
+    const double inv = 1.0 / sqrt(s_cr);
+    // q-th basis vector = normalised pivot; re-orthogonalised against the previous ones (second Gram-Schmidt pass)
+    for (int c = t; c < n; c += 256) { outr[(long)q * n + c] = inv * B[(long)p * 2 * n + c]; outi[(long)q * n + c] = inv * B[(long)p * 2 * n + n + c]; }
+    __syncthreads();
+    for (int prev = 0; prev < q; ++prev) {
+      double cr = 0.0, ci = 0.0;                 // <u_prev, u_q> = sum conj(u_prev) u_q
+      for (int c = t; c < n; c += 256) {
+        const double ar = outr[(long)prev * n + c], ai = outi[(long)prev * n + c], br = outr[(long)q * n + c], bi2 = outi[(long)q * n + c];
+        cr += ar * br + ai * bi2; ci += ar * bi2 - ai * br;
+      }
+      red[t] = cr; red2[t] = ci;
+      __syncthreads();
+      for (int s = 128; s > 0; s >>= 1) { if (t < s) { red[t] += red[t + s]; red2[t] += red2[t + s]; } __syncthreads(); }
+      cr = red[0]; ci = red2[0];
+      __syncthreads();
+      for (int c = t; c < n; c += 256) {
+        const double ar = outr[(long)prev * n + c], ai = outi[(long)prev * n + c];
+        outr[(long)q * n + c] -= cr * ar - ci * ai;
+        outi[(long)q * n + c] -= cr * ai + ci * ar;
+      }
+      __syncthreads();
+    }
+    {
+      double s = 0.0;
+      for (int c = t; c < n; c += 256) { const double a = outr[(long)q * n + c], b = outi[(long)q * n + c]; s += a * a + b * b; }
+      red[t] = s;
+      __syncthreads();
+      for (int st = 128; st > 0; st >>= 1) { if (t < st) red[t] += red[t + st]; __syncthreads(); }
+      const double nv = red[0] > 0.0 ? 1.0 / sqrt(red[0]) : 0.0;
+      __syncthreads();
+      for (int c = t; c < n; c += 256) { outr[(long)q * n + c] *= nv; outi[(long)q * n + c] *= nv; }
+      __syncthreads();
+    }
+    // project u_q out of every candidate: z_j -= <u_q, z_j> u_q   (complex; the pivot itself becomes ~0)
+    for (int j = 0; j < k2; ++j) {
+      double cr = 0.0, ci = 0.0;
+      for (int c = t; c < n; c += 256) {
+        const double ar = outr[(long)q * n + c], ai = outi[(long)q * n + c], br = B[(long)j * 2 * n + c], bi2 = B[(long)j * 2 * n + n + c];
+        cr += ar * br + ai * bi2; ci += ar * bi2 - ai * br;
+      }
+      red[t] = cr; red2[t] = ci;
+      __syncthreads();
+      for (int s = 128; s > 0; s >>= 1) { if (t < s) { red[t] += red[t + s]; red2[t] += red2[t + s]; } __syncthreads(); }
+      cr = red[0]; ci = red2[0];
+      __syncthreads();
+      for (int c = t; c < n; c += 256) {
+        const double ar = outr[(long)q * n + c], ai = outi[(long)q * n + c];
+        B[(long)j * 2 * n + c] -= cr * ar - ci * ai;
+        B[(long)j * 2 * n + n + c] -= cr * ai + ci * ar;
+      }
+      __syncthreads();
+    }
+  }
+  // the MPS tensor is Vt = V^H: its rows are the CONJUGATES of the right singular vectors z (Theta = U S V^H)
+  __syncthreads();
+  for (long e = t; e < (long)kc_done * n; e += 256) outi[e] = -outi[e];
+  if (t == 0) keptc[w] = kc;                       // the kept count follows the truncation rule; rows beyond kc_done are zero
+}
+void be_complex_basis(double *Bm, long wb, int tcap2, int n, const int32_t *kept2, double *Br, double *Bi, long wo, int tcap,
+                      int32_t *keptc, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  complex_basis_kernel<<<W, 256, 0, g_stream>>>(Bm, wb, tcap2, n, kept2, Br, Bi, wo, tcap, keptc);
+  post_launch();
+}
+__global__ void complex_combine_kernel(const double *d0, const double *d1, const double *d2, const double *d3, double *outr,
+                                       double *outi, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < W) { outr[w] = d0[w] - d1[w]; outi[w] = d2[w] + d3[w]; }
+}
+void be_complex_combine(const double *d0, const double *d1, const double *d2, const double *d3, double *outr, double *outi, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  complex_combine_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(d0, d1, d2, d3, outr, outi, W);
+  post_launch();
+}
+__global__ void nn_exchange_decide_c_kernel(int32_t *cfg, int nsites, int s1, int s2, const double *pbr, const double *pbi,
+                                            double *ampr, double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  int32_t *c = cfg + (long)w * nsites;
+  const int c1 = c[s1], c2 = c[s2];
+  if (c1 == c2) return;
+  const double ab = hypot(pbr[w], pbi[w]), aa = hypot(ampr[w], ampi[w]);
+  bool ok = ab >= aa;
+  if (!ok) {
+    const double div = ab / aa, P = div * div;
+    int32_t i = idx[w];
+    const double u = mt_uniform01(mt + (long)w * 624, i);
+    idx[w] = i;
+    ok = u < P;
+  }
+  if (ok) { c[s1] = c2; c[s2] = c1; ampr[w] = pbr[w]; ampi[w] = pbi[w]; accepted[w] += 1; }
+}
+void be_nn_exchange_decide_c(int32_t *cfg, int nsites, int s1, int s2, const double *pbr, const double *pbi, double *ampr,
+                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  nn_exchange_decide_c_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, nsites, s1, s2, pbr, pbi, ampr, ampi, mt, idx, accepted, W);
+  post_launch();
+}
+__global__ void xxz_bond_energy_c_kernel(const int32_t *cfg, int nsites, int s1, int s2, const double *exr, const double *exi,
+                                         const double *pr, const double *pi, double jz, double jxy, double *er, double *ei, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const int32_t *c = cfg + (long)w * nsites;
+  if (c[s1] == c[s2]) { er[w] += 0.25 * jz; return; }
+  const double d = pr[w] * pr[w] + pi[w] * pi[w];
+  const double rr = (exr[w] * pr[w] + exi[w] * pi[w]) / d, ri = (exi[w] * pr[w] - exr[w] * pi[w]) / d;   // psi_ex / psi
+  er[w] += -0.25 * jz + rr * 0.5 * jxy;
+  ei[w] += -ri * 0.5 * jxy;                                                                              // conj
+}
+void be_xxz_bond_energy_c(const int32_t *cfg, int nsites, int s1, int s2, const double *exr, const double *exi, const double *pr,
+                          const double *pi, double jz, double jxy, double *er, double *ei, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  xxz_bond_energy_c_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, s1, s2, exr, exi, pr, pi, jz, jxy, er, ei, W);
+  post_launch();
+}
+__global__ void accumulate_ostar_c_kernel(const double *hr, const double *hi, long hole_stride, const int32_t *hole_off,
+                                          const int32_t *site_size, const int32_t *tps_off, const int32_t *cfg, int nsites,
+                                          const double *ampr, const double *ampi, const double *er, const double *ei, double *osr,
+                                          double *osi, double *eor, double *eoi, int W) {
+  const int site = blockIdx.y;
+  const int sz = site_size[site];
+  const long ho = hole_off[site], to = tps_off[site];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < sz; e += gridDim.x * blockDim.x)
+    for (int w = 0; w < W; ++w) {                       // fixed walker order
+      const int c = cfg[(long)w * nsites + site];
+      const double d = ampr[w] * ampr[w] + ampi[w] * ampi[w];
+      const double a = hr[(long)w * hole_stride + ho + e], b = hi[(long)w * hole_stride + ho + e];
+      const double qr = (a * ampr[w] + b * ampi[w]) / d, qi = (b * ampr[w] - a * ampi[w]) / d;          // hole / psi
+      const double orr = qr, oi = -qi;                                                                  // O* = conj
+      const long slot = to + (long)c * sz + e;
+      osr[slot] += orr; osi[slot] += oi;
+      eor[slot] += er[w] * orr + ei[w] * oi;            // conj(E) O* = (er - i ei)(or + i oi)
+      eoi[slot] += er[w] * oi - ei[w] * orr;
+    }
+}
+void be_accumulate_ostar_c(const double *hr, const double *hi, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                           const int32_t *tps_off, const int32_t *cfg, int nsites, const double *ampr, const double *ampi,
+                           const double *er, const double *ei, double *osr, double *osi, double *eor, double *eoi, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  accumulate_ostar_c_kernel<<<dim3(16, nsites), 256, 0, g_stream>>>(hr, hi, hole_stride, hole_off, site_size, tps_off, cfg, nsites,
+                                                                  ampr, ampi, er, ei, osr, osi, eor, eoi, W);
+  post_launch();
+}
+
+// =====================================================================================================
 // fermion mode (sign-dressed dense tensors; backend.h)
 // =====================================================================================================
 __global__ void fermion_gather_kernel(const int32_t *cfg, int rows, int cols, int phys, const int32_t *par, int32_t *gh,

@@ -83,6 +83,11 @@ int peps_set_model_term(peps_ctx *ctx, int32_t kind, int32_t T, const double *di
   GUARD(ctx, ctx->eng->set_model_term(kind, T, diag, target, coef))
 }
 int peps_clear_model_terms(peps_ctx *ctx) { GUARD(ctx, ctx->eng->clear_model_terms()) }
+int peps_set_complex(peps_ctx *ctx) { GUARD(ctx, ctx->eng->set_complex()) }
+int peps_set_tps_c(peps_ctx *ctx, const double *re, const double *im, size_t n) {
+  GUARD(ctx, { if (n != ctx->eng->tps_size()) throw std::invalid_argument("peps_set_tps_c: wrong element count"); ctx->eng->set_tps_c(re, im); })
+}
+int peps_get_planar(peps_ctx *ctx, int32_t what, double *re, double *im) { GUARD(ctx, ctx->eng->get_planar(what, re, im)) }
 int peps_set_jastrow(peps_ctx *ctx, const double *v, const int32_t *density) { GUARD(ctx, ctx->eng->set_jastrow(v, density)) }
 int peps_clear_jastrow(peps_ctx *ctx) { GUARD(ctx, ctx->eng->clear_jastrow()) }
 int peps_set_fermion(peps_ctx *ctx, const int32_t *phys_par, const int32_t *leg_par, size_t n_leg_par) {

@@ -106,6 +106,7 @@ void Engine::site_dims(int r, int c, int out[4]) const {
 }
 void Engine::set_tps(const double *host) {
   be_h2d(tps_, host, sizeof(double) * tps_total_);
+  if (complex_) be_memset0(tps_ + tps_total_, sizeof(double) * tps_total_);     // a real state in a complex context
   tps_loaded_ = true;
   if (fermion_) {                                       // dress: FERMION_VARIANTS sign patterns per site (backend.h)
     std::vector<double> g((size_t)(tps_total_ * FERMION_VARIANTS));
@@ -140,10 +141,11 @@ void Engine::set_tps(const double *host) {
 }
 void Engine::get_tps(double *host) { be_d2h(host, tps_, sizeof(double) * tps_total_); }
 void Engine::scale_tps(double f) {
-  std::vector<double> h((size_t)tps_total_);
-  get_tps(h.data());
+  std::vector<double> h((size_t)tps_total_ * (complex_ ? 2 : 1));
+  be_d2h(h.data(), tps_, sizeof(double) * h.size());
   for (auto &x : h) x *= f;
-  set_tps(h.data());
+  if (complex_) set_tps_c(h.data(), h.data() + tps_total_);
+  else set_tps(h.data());
 }
 void Engine::set_configs(const int32_t *host) {
   // every entry is used as the physical-slice index of a gather operand: reject anything outside [0, phys)
@@ -204,12 +206,13 @@ BT Engine::alloc(std::initializer_list<int> dims) {
   int i = 0;
   for (int d : dims) { t.d[i++] = d; n *= d; }
   t.n = n;
-  t.p = (double *)pool_.get(sizeof(double) * (size_t)W_ * n);
+  t.p = (double *)pool_.get(sizeof(double) * (size_t)W_ * n * (complex_ ? 2 : 1));
   return t;
 }
 BT Engine::ones111() {
   BT t = alloc({1, 1, 1});
   be_fill(t.p, 1.0, W_);
+  if (complex_) be_memset0(imag(t), sizeof(double) * W_);
   return t;
 }
 void Engine::release(BT &t) {
@@ -223,6 +226,7 @@ void Engine::release(BMPSv &v) {
 TRef Engine::ref(const BT &t) const {
   TRef r;
   r.op = mkop(t.p, t.n);
+  if (complex_) r.opi = mkop(imag(t), t.n);
   r.rank = t.rank;
   for (int i = 0; i < t.rank; ++i) r.d[i] = t.d[i];
   return r;
@@ -231,6 +235,7 @@ TRef Engine::site_ref(int site, int cfg_site) const {
   TRef r;
   if (fermion_ && cfg_site != site) throw std::logic_error("fermion mode: exchanged tensors need explicit dressed slices");
   r.op = mkgather(gtps_ + gtps_off_h_[(size_t)site], (fermion_ ? gidx_[gmode_] : cfg_) + cfg_site, nsites_, site_size_h_[(size_t)site]);
+  if (complex_) r.opi = mkgather(tps_ + tps_total_ + tps_off_h_[(size_t)site], cfg_ + cfg_site, nsites_, site_size_h_[(size_t)site]);
   r.rank = 4;
   for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
   return r;
@@ -246,24 +251,40 @@ static GettDesc with_hints(GettDesc d, const H *h) {
 TRef Engine::site_ref_idx(int site, const int32_t *idx, int stride) const {
   TRef r;
   r.op = mkgather(gtps_ + gtps_off_h_[(size_t)site], idx, stride, site_size_h_[(size_t)site]);
+  if (complex_) r.opi = mkgather(tps_ + tps_total_ + tps_off_h_[(size_t)site], idx, stride, site_size_h_[(size_t)site]);
   r.rank = 4;
   for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
   return r;
 }
-BT Engine::einsum(const std::string &spec, const TRef &a, const TRef &b, const KHints *h) {
+BT Engine::einsum(const std::string &spec, const TRef &a, const TRef &b, const KHints *h, bool conj_b) {
   const Plan &pl = planner_.get(spec, a.d, a.rank, b.d, b.rank);
   BT out;
   out.rank = (int)pl.outdims.size();
   for (int i = 0; i < out.rank; ++i) out.d[i] = pl.outdims[(size_t)i];
   out.n = pl.outn;
-  out.p = (double *)pool_.get(sizeof(double) * (size_t)W_ * out.n);
-  be_gett(with_hints(pl.d, h), a.op, b.op, mkop(out.p, out.n), 1.0, 0.0, W_, 1);
+  out.p = (double *)pool_.get(sizeof(double) * (size_t)W_ * out.n * (complex_ ? 2 : 1));
+  if (!complex_) {
+    be_gett(with_hints(pl.d, h), a.op, b.op, mkop(out.p, out.n), 1.0, 0.0, W_, 1);
+    return out;
+  }
+  // (ar + i ai)(br + i s bi), s = -1 for conj(b): four real products on the split planes (no structural-zero hints)
+  const double sb = conj_b ? -1.0 : 1.0;
+  const Operand cr = mkop(out.p, out.n), ci = mkop(imag(out), out.n);
+  be_gett(pl.d, a.op, b.op, cr, 1.0, 0.0, W_, 1);
+  be_gett(pl.d, a.opi, b.opi, cr, -sb, 1.0, W_, 1);
+  be_gett(pl.d, a.op, b.opi, ci, sb, 0.0, W_, 1);
+  be_gett(pl.d, a.opi, b.op, ci, 1.0, 1.0, W_, 1);
   return out;
 }
 void Engine::einsum_into(const std::string &spec, const TRef &a, const TRef &b, Operand c, const long *sc, double alpha,
-                         double beta, const KHints *h) {
+                         double beta, const KHints *h, const Operand *c_im) {
   const Plan &pl = planner_.get(spec, a.d, a.rank, b.d, b.rank, nullptr, nullptr, sc);
-  be_gett(with_hints(pl.d, h), a.op, b.op, c, alpha, beta, W_, 1);
+  if (!complex_) { be_gett(with_hints(pl.d, h), a.op, b.op, c, alpha, beta, W_, 1); return; }
+  if (!c_im || alpha != 1.0 || beta != 0.0) throw std::logic_error("einsum_into: this contraction is not available for complex states");
+  be_gett(pl.d, a.op, b.op, c, 1.0, 0.0, W_, 1);
+  be_gett(pl.d, a.opi, b.opi, c, -1.0, 1.0, W_, 1);
+  be_gett(pl.d, a.op, b.opi, *c_im, 1.0, 0.0, W_, 1);
+  be_gett(pl.d, a.opi, b.op, *c_im, 1.0, 1.0, W_, 1);
 }
 // r[k][e][a] is an R factor: r[k][col] == 0 for col = e*A + a < k. First possibly non-zero K index per row / column of
 // the three contractions that consume it (K enumerations: a; (e,p) with p = `inner`; (e,a)).
@@ -330,6 +351,64 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
   if (scheme_ != 0 && mps.size() > 2) return absorb_variational(mps, sites_in, post, scheme_ == 2);
   return absorb_svd(mps, sites_in, post);
 }
+// One step of the forward R chain on a real matrix A[w] (m x n inside a zero-padded buffer of L.m_pad rows, consumed):
+// returns a real factor R (rows x n, column order of A) with R^T R = A^T A up to the rows dropped by the rank-revealing
+// deflation. rc / o: per-walker zero-tail hint of the rows (null = none); rk: rank of the previous factor (early-stop hint).
+Engine::ChainR Engine::chain_factor(double *A, long wsA, int m, int n, const QRLayout &L, const int32_t *rc, int o, int rk,
+                                    int site_idx) {
+  ChainR out;
+  const int kk = std::min(m, n);
+  if (chain_eps_ > 0.0 && kk >= 16) {
+    // Rank-revealing step of the R chain. Columns sorted by norm (pivoting-lite) grade the rows of R; rows below
+    // chain_eps * (largest row norm) are dropped, a backward-stable perturbation of the left part of relative size
+    // <= sqrt(rows) * chain_eps. The exact MPO x MPS product has bond dimension D*chi, its numerical rank is a
+    // fraction of that, and every later step of the chain (and Theta = r X) shrinks with it.
+    double *cn2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * std::max(n, kk));
+    int32_t *ord = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * std::max(n, kk));
+    int32_t *cord = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * n);
+    int32_t *cnt = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_);
+    be_col_norms2(A, wsA, n, m, n, cn2, W_);
+    be_rank_rows(cn2, n, 0.0, cord, cnt, W_);
+    double *Ap = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
+    if (L.m_pad > m) be_memset0(Ap, sizeof(double) * (size_t)W_ * wsA);
+    be_permute_cols(A, wsA, n, m, n, cord, 1, Ap, wsA, n, W_);
+    pool_.put(A);
+    QRStop st;                                         // early termination: the rank of r_{i+1} is close to that of r_i
+    st.colnorm2 = cn2; st.colorder = cord; st.eps = chain_eps_; st.first_col = std::max(0, std::min(rk, kk) - 96);
+    caqr(la_, Ap, wsA, m, n, L, rc, o, &st);
+    be_row_norms2(Ap, wsA, n, kk, n, cn2, W_);
+    be_rank_rows(cn2, kk, chain_eps_ * chain_eps_, ord, cnt, W_);
+    std::vector<int32_t> ch((size_t)W_);
+    be_d2h(ch.data(), cnt, sizeof(int32_t) * W_);
+    int knew = 1;
+    for (int w = 0; w < W_; ++w) knew = std::max(knew, (int)ch[(size_t)w]);
+    static const bool dbg_counts = std::getenv("PEPS_DEBUG_COUNTS") != nullptr;
+    if (dbg_counts && kk >= 256) {
+      int mn = kk; double mean = 0.0;
+      for (int w = 0; w < W_; ++w) { mn = std::min(mn, (int)ch[(size_t)w]); mean += ch[(size_t)w]; }
+      std::fprintf(stderr, "[chain] site %d kk=%d count min %d mean %.1f max %d\n", site_idx, kk, mn, mean / W_, knew);
+    }
+    const int gran = kk >= 128 ? 32 : 8;               // few distinct shapes: plans, tables and pool buffers are keyed by size
+    knew = std::min(kk, (knew + gran - 1) / gran * gran);
+    chain_rows_in_ += kk; chain_rows_kept_ += knew;
+    double *Rg = (double *)pool_.get(sizeof(double) * (size_t)W_ * knew * n);
+    be_gather_rows(Ap, wsA, n, n, kk, ord, cnt, Rg, (long)knew * n, knew, W_);
+    out.R = (double *)pool_.get(sizeof(double) * (size_t)W_ * knew * n);
+    be_permute_cols(Rg, (long)knew * n, n, knew, n, cord, 0, out.R, (long)knew * n, n, W_);
+    out.rows = knew;
+    out.cnt = cnt;                                     // rows >= cnt[w] of the factor are zero (be_gather_rows)
+    for (void *p : {(void *)cn2, (void *)ord, (void *)cord, (void *)Ap, (void *)Rg}) pool_.put(p);
+  } else {
+    caqr(la_, A, wsA, m, n, L, rc, o);
+    out.R = (double *)pool_.get(sizeof(double) * (size_t)W_ * kk * n);
+    be_copy2d(out.R, (long)kk * n, n, A, wsA, n, kk, n, W_);
+    out.rows = kk;
+    out.tri = true;
+    pool_.put(A);
+  }
+  return out;
+}
+
 Engine::BMPSv Engine::absorb_svd(const BMPSv &mps, const std::vector<int> &sites_in, int post) {
   ++n_absorb_;
   const int N = (int)mps.size();
@@ -356,58 +435,39 @@ Engine::BMPSv Engine::absorb_svd(const BMPSv &mps, const std::vector<int> &sites
     BT tmp1 = einsum("apb,kea->kepb", ref(mps[(size_t)i]), ref(r[(size_t)i]), (tri || rc) ? &h1 : nullptr);   // bmps_impl.h:806
     const int k = r[(size_t)i].d[0], o = sdim(site, 'o'), f = sdim(site, 'f'), b = mps[(size_t)i].d[2];
     const int m = k * o, n = f * b;
-    QRLayout L = qr_layout(m, n);
-    const long wsA = (long)L.m_pad * n;
-    double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
-    if (L.m_pad > m) be_memset0(A, sizeof(double) * (size_t)W_ * wsA);
-    einsum_into("kepb," + sl + "->kofb", ref(tmp1), sref, mkop(A, wsA), nullptr, 1.0, 0.0, (tri || rc) ? &h2 : nullptr);   // bmps_impl.h:807
-    release(tmp1);
-    const int kk = std::min(m, n);
-    if (chain_eps_ > 0.0 && kk >= 16) {
-      // Rank-revealing step of the R chain. Columns sorted by norm (pivoting-lite) grade the rows of R; rows below
-      // chain_eps * (largest row norm) are dropped, a backward-stable perturbation of the left part of relative size
-      // <= sqrt(rows) * chain_eps. The exact MPO x MPS product has bond dimension D*chi, its numerical rank is a
-      // fraction of that, and every later step of the chain (and Theta = r X) shrinks with it.
-      double *cn2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * std::max(n, kk));
-      int32_t *ord = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * std::max(n, kk));
-      int32_t *cord = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * n);
-      int32_t *cnt = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_);
-      be_col_norms2(A, wsA, n, m, n, cn2, W_);
-      be_rank_rows(cn2, n, 0.0, cord, cnt, W_);
-      double *Ap = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
-      if (L.m_pad > m) be_memset0(Ap, sizeof(double) * (size_t)W_ * wsA);
-      be_permute_cols(A, wsA, n, m, n, cord, 1, Ap, wsA, n, W_);
-      pool_.put(A);
-      QRStop st;                                         // early termination: the rank of r_{i+1} is close to that of r_i
-      st.colnorm2 = cn2; st.colorder = cord; st.eps = chain_eps_; st.first_col = std::max(0, std::min(rk, kk) - 96);
-      caqr(la_, Ap, wsA, m, n, L, rc, o, &st);                                           // bmps_impl.h:817-821
-      be_row_norms2(Ap, wsA, n, kk, n, cn2, W_);
-      be_rank_rows(cn2, kk, chain_eps_ * chain_eps_, ord, cnt, W_);
-      std::vector<int32_t> ch((size_t)W_);
-      be_d2h(ch.data(), cnt, sizeof(int32_t) * W_);
-      int knew = 1;
-      for (int w = 0; w < W_; ++w) knew = std::max(knew, (int)ch[(size_t)w]);
-      static const bool dbg_counts = std::getenv("PEPS_DEBUG_COUNTS") != nullptr;
-      if (dbg_counts && kk >= 256) {
-        int mn = kk; double mean = 0.0;
-        for (int w = 0; w < W_; ++w) { mn = std::min(mn, (int)ch[(size_t)w]); mean += ch[(size_t)w]; }
-        std::fprintf(stderr, "[chain] site %d kk=%d count min %d mean %.1f max %d\n", i, kk, mn, mean / W_, knew);
-      }
-      const int gran = kk >= 128 ? 32 : 8;               // few distinct shapes: plans, tables and pool buffers are keyed by size
-      knew = std::min(kk, (knew + gran - 1) / gran * gran);
-      chain_rows_in_ += kk; chain_rows_kept_ += knew;
-      double *Rg = (double *)pool_.get(sizeof(double) * (size_t)W_ * knew * n);
-      be_gather_rows(Ap, wsA, n, n, kk, ord, cnt, Rg, (long)knew * n, knew, W_);
-      r[(size_t)i + 1] = alloc({knew, f, b});
-      be_permute_cols(Rg, (long)knew * n, n, knew, n, cord, 0, r[(size_t)i + 1].p, (long)knew * n, n, W_);
-      r_cnt[(size_t)i + 1] = cnt;                        // rows >= cnt[w] of r_{i+1} are zero (be_gather_rows)
-      for (void *p : {(void *)cn2, (void *)ord, (void *)cord, (void *)Ap, (void *)Rg}) pool_.put(p);
+    if (!complex_) {
+      QRLayout L = qr_layout(m, n);
+      const long wsA = (long)L.m_pad * n;
+      double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
+      if (L.m_pad > m) be_memset0(A, sizeof(double) * (size_t)W_ * wsA);
+      einsum_into("kepb," + sl + "->kofb", ref(tmp1), sref, mkop(A, wsA), nullptr, 1.0, 0.0, (tri || rc) ? &h2 : nullptr);   // bmps_impl.h:807
+      release(tmp1);
+      ChainR cr = chain_factor(A, wsA, m, n, L, rc, o, rk, i);                              // bmps_impl.h:817-821
+      BT rn;
+      rn.p = cr.R; rn.rank = 3; rn.d[0] = cr.rows; rn.d[1] = f; rn.d[2] = b; rn.n = (long)cr.rows * n;
+      r[(size_t)i + 1] = rn;
+      r_cnt[(size_t)i + 1] = cr.cnt;
+      r_tri[(size_t)i + 1] = cr.tri ? 1 : 0;
     } else {
-      caqr(la_, A, wsA, m, n, L, rc, o);                                                 // bmps_impl.h:817-821
-      r[(size_t)i + 1] = alloc({kk, f, b});
-      be_copy2d(r[(size_t)i + 1].p, (long)kk * n, n, A, wsA, n, kk, n, W_);
-      r_tri[(size_t)i + 1] = 1;
-      pool_.put(A);
+      // complex: the planes of A are embedded as M = [[Ar, -Ai], [Ai, Ar]]; any real R with R^T R = M^T M gives the
+      // complex factor (R1 - i R2) / sqrt(2) (backend.h)
+      const long wa = (long)m * n;
+      double *Ar = (double *)pool_.get(sizeof(double) * (size_t)W_ * wa), *Ai = (double *)pool_.get(sizeof(double) * (size_t)W_ * wa);
+      const Operand ci = mkop(Ai, wa);
+      einsum_into("kepb," + sl + "->kofb", ref(tmp1), sref, mkop(Ar, wa), nullptr, 1.0, 0.0, nullptr, &ci);
+      release(tmp1);
+      const int m2 = 2 * m, n2 = 2 * n;
+      QRLayout L2 = qr_layout(m2, n2);
+      const long wsM = (long)L2.m_pad * n2;
+      double *M = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsM);
+      if (L2.m_pad > m2) be_memset0(M, sizeof(double) * (size_t)W_ * wsM);
+      be_embed_complex(Ar, Ai, wa, m, n, M, wsM, W_);
+      pool_.put(Ar); pool_.put(Ai);
+      ChainR cr = chain_factor(M, wsM, m2, n2, L2, nullptr, 0, 2 * rk, i);
+      r[(size_t)i + 1] = alloc({cr.rows, f, b});
+      be_split_r(cr.R, (long)cr.rows * n2, cr.rows, n, r[(size_t)i + 1].p, imag(r[(size_t)i + 1]), (long)cr.rows * n, W_);
+      pool_.put(cr.R);
+      if (cr.cnt) pool_.put(cr.cnt);
     }
   }
   BMPSv res((size_t)N);
@@ -423,6 +483,30 @@ Engine::BMPSv Engine::absorb_svd(const BMPSv &mps, const std::vector<int> &sites
       // nothing can be truncated and the row space is the whole space: any orthonormal basis is the same gauge class
       B = alloc({cols, o, j});
       be_set_identity(B.p, B.n, cols, cols, W_);
+      if (complex_) be_memset0(imag(B), sizeof(double) * (size_t)W_ * B.n);
+    } else if (complex_) {
+      // complex truncation through the real embedding of Theta: singular values come in exact pairs (keep 2 chi), the kept
+      // right singular subspace is J-invariant and be_complex_basis turns its 2t real vectors into t complex ones
+      const long wg = (long)rows * cols;
+      double *Gr = (double *)pool_.get(sizeof(double) * (size_t)W_ * wg), *Gi = (double *)pool_.get(sizeof(double) * (size_t)W_ * wg);
+      const Operand gi = mkop(Gi, wg);
+      einsum_into("kea,eaoj->koj", ref(r[(size_t)i]), ref(X), mkop(Gr, wg), nullptr, 1.0, 0.0, nullptr, &gi);
+      const int rows2 = 2 * rows, cols2 = 2 * cols;
+      const int brows2 = truncate_buffer_rows(rows2, cols2);
+      double *GM = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows2 * cols2);
+      if (brows2 > rows2) be_memset0(GM, sizeof(double) * (size_t)W_ * brows2 * cols2);
+      be_embed_complex(Gr, Gi, wg, rows, cols, GM, (long)brows2 * cols2, W_);
+      pool_.put(Gr); pool_.put(Gi);
+      const int dmax2 = (int)std::min<long>(2L * dmax_, std::numeric_limits<int>::max()), dmin2 = (int)std::min<long>(2L * dmin_, dmax2);
+      const int tcap2 = std::min(dmax2, std::min(rows2, cols2)), tcap = std::min(dmax_, std::min(rows, cols));
+      double *Bm = (double *)pool_.get(sizeof(double) * (size_t)W_ * tcap2 * cols2);
+      double *norms2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * rows2);
+      int32_t *order = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * tcap2);
+      truncate_rows(la_, GM, (long)brows2 * cols2, rows2, cols2, dmin2, dmax2, terr_, tcap2, Bm, (long)tcap2 * cols2, kept_, norms2, order);
+      B = alloc({tcap, o, j});
+      if (std::getenv("PEPS_DEBUG_CPLX")) { std::vector<int32_t> kk2((size_t)W_); be_d2h(kk2.data(), kept_, sizeof(int32_t) * W_); std::fprintf(stderr, "[cplx trunc] site %d rows=%d cols=%d tcap2=%d tcap=%d kept2=%d\n", i, rows, cols, tcap2, tcap, kk2[0]); }
+      be_complex_basis(Bm, (long)tcap2 * cols2, tcap2, cols, kept_, B.p, imag(B), (long)tcap * cols, tcap, kept_, W_);
+      for (void *q : {(void *)GM, (void *)Bm, (void *)norms2, (void *)order}) pool_.put(q);
     } else {
       const int brows = truncate_buffer_rows(rows, cols);
       double *G = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows * cols);
@@ -441,7 +525,7 @@ Engine::BMPSv Engine::absorb_svd(const BMPSv &mps, const std::vector<int> &sites
       pool_.put(order);
       pool_.put(G);
     }
-    BT En = einsum("eaoj,toj->eat", ref(X), ref(B));
+    BT En = einsum("eaoj,toj->eat", ref(X), ref(B), nullptr, /*conj_b=*/true);     // U S = Theta Vt^H (bmps_impl.h:251-254)
     release(X);
     release(E);
     E = En;
@@ -929,7 +1013,16 @@ void Engine::reverse_dot(const BT &a, const BT &b, double *out) {
     }
     it = rdot_tabs_.emplace(key, std::make_pair(planner_.upload(ak), planner_.upload(bk))).first;
   }
-  be_dot((int)n, it->second.first, it->second.second, mkop(a.p, a.n), mkop(b.p, b.n), out, W_);
+  if (!complex_) { be_dot((int)n, it->second.first, it->second.second, mkop(a.p, a.n), mkop(b.p, b.n), out, W_); return; }
+  // bilinear complex dot: (ar.br - ai.bi) + i (ar.bi + ai.br); out is planar [2][W]
+  double *d = (double *)pool_.get(sizeof(double) * 4 * (size_t)W_);
+  const Operand ar = mkop(a.p, a.n), ai = mkop(imag(a), a.n), br = mkop(b.p, b.n), bi = mkop(imag(b), b.n);
+  be_dot((int)n, it->second.first, it->second.second, ar, br, d, W_);
+  be_dot((int)n, it->second.first, it->second.second, ai, bi, d + W_, W_);
+  be_dot((int)n, it->second.first, it->second.second, ar, bi, d + 2 * W_, W_);
+  be_dot((int)n, it->second.first, it->second.second, ai, br, d + 3 * W_, W_);
+  be_complex_combine(d, d + W_, d + 2 * W_, d + 3 * W_, out, out + W_, W_);
+  pool_.put(d);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -940,6 +1033,7 @@ void Engine::init_bten2(int pos) {                     // init.h:130-186
   bten2_[pos].clear();
   BT t = alloc({1, 1, 1, 1});
   be_fill(t.p, 1.0, W_);
+  if (complex_) be_memset0(imag(t), sizeof(double) * W_);
   bten2_[pos].push_back(t);
 }
 const BT &Engine::bten2_at_slice(int pos, int logical) const {
@@ -1086,7 +1180,9 @@ void Engine::punch_hole(int r, int c, int orient) {    // grow.h:150-183
   BT tmp1 = einsum("xlz,zdb->xldb", ref(*left), ref(*down));
   BT tmp2 = einsum("brz,zux->brux", ref(*right), ref(*up));
   const int site = r * cols_ + c;
-  einsum_into("xldb,brux->ldru", ref(tmp1), ref(tmp2), mkop(holes_ + hole_off_h_[(size_t)site], hole_stride_));
+  const Operand hi = mkop(holes_ + (long)W_ * hole_stride_ + hole_off_h_[(size_t)site], hole_stride_);
+  einsum_into("xldb,brux->ldru", ref(tmp1), ref(tmp2), mkop(holes_ + hole_off_h_[(size_t)site], hole_stride_), nullptr, 1.0, 0.0,
+              nullptr, complex_ ? &hi : nullptr);
   release(tmp1);
   release(tmp2);
 }
@@ -1116,7 +1212,8 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
       for (int col = 0; col < cols_ - 1; ++col) {
         const int s1 = row * cols_ + col, s2 = s1 + 1;
         nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);          // :164-166 (masked in the decide kernel)
-        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
+        if (complex_) be_nn_exchange_decide_c(cfg_, nsites_, s1, s2, psi_tmp_, psi_tmp_ + W_, amp_, amp_ + W_, mt_, mtidx_, accepted_, W_);
+        else be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
         touch_site(s1); touch_site(s2);
         if (col < cols_ - 2) shift_bten_window(RIGHT);
       }
@@ -1131,7 +1228,8 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
       for (int row = 0; row < rows_ - 1; ++row) {
         const int s1 = row * cols_ + col, s2 = s1 + cols_;
         nn_trace(row, col, row + 1, col, VERTICAL, s2, s1, psi_tmp_);
-        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
+        if (complex_) be_nn_exchange_decide_c(cfg_, nsites_, s1, s2, psi_tmp_, psi_tmp_ + W_, amp_, amp_ + W_, mt_, mtidx_, accepted_, W_);
+        else be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
         touch_site(s1); touch_site(s2);
         if (row < rows_ - 2) shift_bten_window(DOWN);
       }
@@ -1456,7 +1554,8 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
   if (tfim_) { energy_and_holes_tfim(calc_holes, eloc_host, psi_list_host); return; }
   if (phys_ != 2) throw std::invalid_argument("the XXZ / J1-J2 energy solvers need phys = 2");
   // square_nnn_energy_solver.h:79-315 with has_nnn = false, model = SquareSpinOneHalfXXZModelMixIn
-  be_memset0(eloc_, sizeof(double) * W_);
+  if (complex_ && (psi_list_host || rec_bonds_)) throw std::logic_error("psi lists / bond records are not available for complex states");
+  be_memset0(eloc_, sizeof(double) * W_ * (complex_ ? 2 : 1));
   int npsi = 0;
   if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * W_);
   auto record_psi = [&]() {                            // kept on the device: ONE download at the end, no sync per row
@@ -1474,7 +1573,7 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
       if (col < cols_ - 1) {
         const int s1 = row * cols_ + col, s2 = s1 + 1;
         nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);
-        be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, bond_target(0, row, col), W_);
+        bond_energy(s1, s2, psi_tmp_, psi_row_, jz_, jxy_, bond_target(0, row, col));
         shift_bten_window(RIGHT);
       }
     }
@@ -1483,11 +1582,9 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
       grow_full_bten2(RIGHT, row, 2, true);
       for (int col = 0; col < cols_ - 1; ++col) {
         nnn_trace(row, col, 0, psi_tmp_);                                            // (row,col) <-> (row+1,col+1)
-        be_xxz_bond_energy(cfg_, nsites_, row * cols_ + col, (row + 1) * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_,
-                           bond_target(2, row, col), W_);
+        bond_energy(row * cols_ + col, (row + 1) * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_, bond_target(2, row, col));
         nnn_trace(row, col, 1, psi_tmp_);                                            // (row+1,col) <-> (row,col+1)
-        be_xxz_bond_energy(cfg_, nsites_, (row + 1) * cols_ + col, row * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_,
-                           bond_target(3, row, col), W_);
+        bond_energy((row + 1) * cols_ + col, row * cols_ + col + 1, psi_tmp_, psi_row_, jz2_, jxy2_, bond_target(3, row, col));
         shift_bten2_window(RIGHT, row);
       }
     }
@@ -1503,7 +1600,7 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
     for (int row = 0; row < rows_ - 1; ++row) {
       const int s1 = row * cols_ + col, s2 = s1 + cols_;
       nn_trace(row, col, row + 1, col, VERTICAL, s2, s1, psi_tmp_);
-      be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_tmp_, psi_row_, jz_, jxy_, bond_target(1, row, col), W_);
+      bond_energy(s1, s2, psi_tmp_, psi_row_, jz_, jxy_, bond_target(1, row, col));
       if (row < rows_ - 2) shift_bten_window(DOWN);
     }
     if (col < cols_ - 1) shift_bmps_window(RIGHT);
@@ -1640,9 +1737,60 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
 // ---------------------------------------------------------------------------------------------------
 // fermion mode (engine.h: set_fermion)
 // ---------------------------------------------------------------------------------------------------
+void Engine::bond_energy(int s1, int s2, const double *psi_ex, const double *psi, double jz, double jxy, double *target) {
+  if (complex_) be_xxz_bond_energy_c(cfg_, nsites_, s1, s2, psi_ex, psi_ex + W_, psi, psi + W_, jz, jxy, target, target + W_, W_);
+  else be_xxz_bond_energy(cfg_, nsites_, s1, s2, psi_ex, psi, jz, jxy, target, W_);
+}
+void Engine::set_complex() {
+  if (complex_) return;
+  if (fermion_ || tables_on_ || tfim_ || jastrow_on_ || updater_ != 0 || scheme_ != 0 || tps_loaded_)
+    throw std::logic_error("set_complex: call right after construction (XXZ / J1-J2 models, NN exchange updater, SVD compression)");
+  be_sync();
+  auto grow = [&](double *&p, size_t n) { be_free(p); p = (double *)be_malloc(sizeof(double) * 2 * n); be_memset0(p, sizeof(double) * 2 * n); };
+  grow(tps_, (size_t)tps_total_); gtps_ = tps_;
+  grow(osum_, (size_t)tps_total_); grow(eosum_, (size_t)tps_total_);
+  grow(amp_, (size_t)W_); grow(eloc_, (size_t)W_); grow(psi_tmp_, (size_t)W_); grow(psi_row_, (size_t)W_);
+  grow(holes_, (size_t)W_ * hole_stride_);
+  for (int p = 0; p < 4; ++p) {                     // tensors allocated so far are real-sized: drop them
+    for (auto &b : bmps_[p]) release(b);
+    bmps_[p].clear(); stamp_[p].clear();
+    for (auto &m : memo_[p]) release(m.second.v);
+    memo_[p].clear();
+    for (auto &t : bten_[p]) release(t);
+    bten_[p].clear();
+    for (auto &t : bten2_[p]) release(t);
+    bten2_[p].clear();
+  }
+  complex_ = true;
+  touch_all();
+}
+void Engine::set_tps_c(const double *re, const double *im) {
+  if (!complex_) throw std::logic_error("set_tps_c: the context is real (peps_set_complex)");
+  be_h2d(tps_, re, sizeof(double) * tps_total_);
+  be_h2d(tps_ + tps_total_, im, sizeof(double) * tps_total_);
+  tps_loaded_ = true;
+  touch_all();
+}
+void Engine::get_planar(int what, double *re, double *im) {
+  const double *p; size_t n;
+  switch (what) {
+    case 0: p = amp_; n = (size_t)W_; break;
+    case 1: p = eloc_; n = (size_t)W_; break;
+    case 2: p = holes_; n = (size_t)W_ * hole_stride_; break;
+    case 3: p = osum_; n = (size_t)tps_total_; break;
+    case 4: p = eosum_; n = (size_t)tps_total_; break;
+    default: throw std::invalid_argument("get_planar: unknown array");
+  }
+  if (re) be_d2h(re, p, sizeof(double) * n);
+  if (im) {
+    if (complex_) be_d2h(im, p + n, sizeof(double) * n);
+    else std::fill(im, im + n, 0.0);
+  }
+}
 void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
   if (!phys_par || !leg_par) throw std::invalid_argument("set_fermion: null table");
   if (fermion_) throw std::logic_error("set_fermion: already in fermion mode");
+  require_real("the fermion mode");
   if (tables_on_) throw std::logic_error("set_fermion: call it before set_model_term");
   for (int p = 0; p < phys_; ++p)
     if (phys_par[p] != 0 && phys_par[p] != 1) throw std::invalid_argument("set_fermion: parities must be 0 or 1");
@@ -2007,10 +2155,16 @@ void Engine::measure_structure_factor(double *out_host) {
           }
 }
 void Engine::zero_accumulators() {
-  be_memset0(osum_, sizeof(double) * tps_total_);
-  be_memset0(eosum_, sizeof(double) * tps_total_);
+  be_memset0(osum_, sizeof(double) * tps_total_ * (complex_ ? 2 : 1));
+  be_memset0(eosum_, sizeof(double) * tps_total_ * (complex_ ? 2 : 1));
 }
 void Engine::accumulate_ostar() {                      // mc_energy_grad_evaluator.h:245-272
+  if (complex_) {
+    if (sr_on_) throw std::logic_error("the SR sample store is not available for complex states");
+    be_accumulate_ostar_c(holes_, holes_ + (long)W_ * hole_stride_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, cfg_, nsites_, amp_,
+                          amp_ + W_, eloc_, eloc_ + W_, osum_, osum_ + tps_total_, eosum_, eosum_ + tps_total_, W_);
+    return;
+  }
   be_accumulate_ostar(holes_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, cfg_, nsites_, phys_, amp_, eloc_,
                       osum_, eosum_, W_);
   if (sr_on_) {                                        // Ostar_samples.emplace_back(...)  (:273-277)

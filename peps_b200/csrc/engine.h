@@ -29,6 +29,7 @@ inline int opposite(int p) { return (p + 2) % 4; }
 
 struct TRef {           // operand view with dims
   Operand op;
+  Operand opi;          // imaginary plane (complex mode)
   int rank = 0;
   int d[6] = {1, 1, 1, 1, 1, 1};
 };
@@ -156,6 +157,15 @@ class Engine {
   // given by set_model_term tables (kinds 0 / 1 / 2) whose off-diagonal targets either move one fermion between the two
   // sites or keep both site parities. Derivation and checks: oracle/fermion.py, tests/test_fermion_oracle.py.
   void set_fermion(const int32_t *phys_par, const int32_t *leg_par);
+  // Complex (QLTEN_Complex) states: tensors become two real planes (re, im), a contraction four real launches of the
+  // contraction kernel, the factorisations run on the real embedding [[Ar, -Ai], [Ai, Ar]] (backend.h "complex tensors as
+  // split planes"). Call right after construction. Built for the headline path: amplitude, NN-exchange sweep, XXZ /
+  // J1-J2 local energy, holes / O* and the two accumulators; per-walker scalars and the accumulators are planar
+  // ([2][..], imaginary plane second). The other updaters / solvers, SR and the fermion mode stay real-only.
+  void set_complex();
+  bool is_complex() const { return complex_; }
+  void set_tps_c(const double *re, const double *im);
+  void get_planar(int what, double *re, double *im);   // 0 amplitudes, 1 eloc, 2 holes, 3 osum, 4 eosum
   // Jastrow-dressed wave function psi(S) = psi_PEPS(S) exp(sum_{i<j} v_ij n_i n_j) (TPSWaveFunctionComponent<..., JastrowDress>,
   // vmc_basic/wave_function_component.h:107-135, vmc_basic/jastrow_factor.h): v = [nsites][nsites] symmetric (diagonal ignored),
   // density[phys] = particle number of a physical state. The NN exchange sweep takes the Jastrow ratio into the acceptance
@@ -236,6 +246,15 @@ class Engine {
     if (fermion_) throw std::logic_error(std::string(what) + " is not available in fermion mode");
   }
   bool fermion_ = false, tps_loaded_ = false;
+  bool complex_ = false;
+  double *imag(const BT &t) const { return t.p + (long)W_ * t.n; }
+  void require_real(const char *what) const {
+    if (complex_) throw std::logic_error(std::string(what) + " is not available for complex states");
+  }
+  // R-only factor of the forward chain (the rank-revealing step): consumes A, returns a real (rows x n) matrix
+  struct ChainR { double *R = nullptr; int rows = 0; int32_t *cnt = nullptr; bool tri = false; };
+  ChainR chain_factor(double *A, long wsA, int m, int n, const QRLayout &L, const int32_t *rc, int o, int rk, int site_idx);
+  void bond_energy(int s1, int s2, const double *psi_ex, const double *psi, double jz, double jxy, double *target);
   bool jastrow_on_ = false, tables_exchange_only_ = true;
   double *jastrow_v_ = nullptr, *jr_ = nullptr;   // [nsites][nsites], [W]
   int32_t *dens_d_ = nullptr;                      // [phys]
@@ -271,9 +290,9 @@ class Engine {
   };
   // which: 0 = "apb,kea->kepb" (hint on N = (k,e)), 1 = "kepb,<site>->kofb" (hint on M = (k,b)), 2 = "kea,eaoj->koj" (M = k)
   const KHints &r_hints(int which, int k, int e, int a, int p, int b);
-  BT einsum(const std::string &spec, const TRef &a, const TRef &b, const KHints *h = nullptr);
+  BT einsum(const std::string &spec, const TRef &a, const TRef &b, const KHints *h = nullptr, bool conj_b = false);
   void einsum_into(const std::string &spec, const TRef &a, const TRef &b, Operand c, const long *sc = nullptr,
-                   double alpha = 1.0, double beta = 0.0, const KHints *h = nullptr);
+                   double alpha = 1.0, double beta = 0.0, const KHints *h = nullptr, const Operand *c_im = nullptr);
   BMPSv absorb(const BMPSv &mps, const std::vector<int> &sites, int post);
   // variational compression (bmps_impl.h:864-1260)
   BMPSv absorb_svd(const BMPSv &mps, const std::vector<int> &sites, int post);

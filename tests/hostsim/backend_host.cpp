@@ -566,6 +566,132 @@ void be_term_accumulate(const int32_t *cfg, int nsites, int s1, int s2, int phys
     eloc[w] += e;
   }
 }
+// ---- complex (c128) tensors as split planes (backend.h) -----------------------------------------------------------------
+void be_embed_complex(const double *Ar, const double *Ai, long wa, int m, int n, double *M, long wm, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (long r = 0; r < m; ++r)
+      for (long c = 0; c < n; ++c) {
+        const double a = Ar[(long)w * wa + r * n + c], b = Ai[(long)w * wa + r * n + c];
+        double *Mw = M + (long)w * wm;
+        Mw[r * 2 * n + c] = a; Mw[r * 2 * n + n + c] = -b;
+        Mw[(r + m) * 2 * n + c] = b; Mw[(r + m) * 2 * n + n + c] = a;
+      }
+}
+void be_split_r(const double *R, long wr, int rows, int n, double *outr, double *outi, long wo, int W) {
+  ++g_launches;
+  const double s = 0.70710678118654752440;
+  for (int w = 0; w < W; ++w)
+    for (long r = 0; r < rows; ++r)
+      for (long c = 0; c < n; ++c) {
+        outr[(long)w * wo + r * n + c] = s * R[(long)w * wr + r * 2 * n + c];
+        outi[(long)w * wo + r * n + c] = -s * R[(long)w * wr + r * 2 * n + n + c];
+      }
+}
+void be_complex_basis(double *Bm, long wb, int tcap2, int n, const int32_t *kept2, double *Br, double *Bi, long wo, int tcap,
+                      int32_t *keptc, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    double *B = Bm + (long)w * wb, *outr = Br + (long)w * wo, *outi = Bi + (long)w * wo;
+    const int k2 = std::min((int)kept2[w], tcap2), kc = std::min((k2 + 1) / 2, tcap);
+    for (long e = 0; e < (long)tcap * n; ++e) { outr[e] = 0.0; outi[e] = 0.0; }
+    for (int q = 0; q < kc; ++q) {
+      double best = -1.0; int p = -1;
+      for (int j = 0; j < k2; ++j) {
+        double sq = 0.0;
+        for (int c = 0; c < 2 * n; ++c) sq += B[(long)j * 2 * n + c] * B[(long)j * 2 * n + c];
+        if (sq > best) { best = sq; p = j; }
+      }
+      if (p < 0 || best < 1e-10) break;                      // subspace exhausted: the remaining rows stay zero
+      const double inv = 1.0 / std::sqrt(best);
+      for (int c = 0; c < n; ++c) { outr[(long)q * n + c] = inv * B[(long)p * 2 * n + c]; outi[(long)q * n + c] = inv * B[(long)p * 2 * n + n + c]; }
+      for (int prev = 0; prev < q; ++prev) {
+        double cr = 0.0, ci = 0.0;
+        for (int c = 0; c < n; ++c) {
+          const double ar = outr[(long)prev * n + c], ai = outi[(long)prev * n + c], br = outr[(long)q * n + c], bi = outi[(long)q * n + c];
+          cr += ar * br + ai * bi; ci += ar * bi - ai * br;
+        }
+        for (int c = 0; c < n; ++c) {
+          const double ar = outr[(long)prev * n + c], ai = outi[(long)prev * n + c];
+          outr[(long)q * n + c] -= cr * ar - ci * ai;
+          outi[(long)q * n + c] -= cr * ai + ci * ar;
+        }
+      }
+      double nn = 0.0;
+      for (int c = 0; c < n; ++c) nn += outr[(long)q * n + c] * outr[(long)q * n + c] + outi[(long)q * n + c] * outi[(long)q * n + c];
+      const double nv = nn > 0.0 ? 1.0 / std::sqrt(nn) : 0.0;
+      for (int c = 0; c < n; ++c) { outr[(long)q * n + c] *= nv; outi[(long)q * n + c] *= nv; }
+      for (int j = 0; j < k2; ++j) {
+        double cr = 0.0, ci = 0.0;
+        for (int c = 0; c < n; ++c) {
+          const double ar = outr[(long)q * n + c], ai = outi[(long)q * n + c], br = B[(long)j * 2 * n + c], bi = B[(long)j * 2 * n + n + c];
+          cr += ar * br + ai * bi; ci += ar * bi - ai * br;
+        }
+        for (int c = 0; c < n; ++c) {
+          const double ar = outr[(long)q * n + c], ai = outi[(long)q * n + c];
+          B[(long)j * 2 * n + c] -= cr * ar - ci * ai;
+          B[(long)j * 2 * n + n + c] -= cr * ai + ci * ar;
+        }
+      }
+    }
+    for (long e = 0; e < (long)tcap * n; ++e) outi[e] = -outi[e];     // rows of Vt = V^H: conjugates of the right singular vectors
+    keptc[w] = kc;
+  }
+}
+void be_complex_combine(const double *d0, const double *d1, const double *d2, const double *d3, double *outr, double *outi, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) { outr[w] = d0[w] - d1[w]; outi[w] = d2[w] + d3[w]; }
+}
+void be_nn_exchange_decide_c(int32_t *cfg, int nsites, int s1, int s2, const double *pbr, const double *pbi, double *ampr,
+                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    int32_t *c = cfg + (long)w * nsites;
+    const int c1 = c[s1], c2 = c[s2];
+    if (c1 == c2) continue;
+    const double ab = std::hypot(pbr[w], pbi[w]), aa = std::hypot(ampr[w], ampi[w]);
+    bool ok = ab >= aa;
+    if (!ok) {
+      const double div = ab / aa, P = div * div;
+      uint32_t x0 = mt_next(mt + (long)w * 624, idx[w]);
+      uint32_t x1 = mt_next(mt + (long)w * 624, idx[w]);
+      double r = ((double)x0 + (double)x1 * 4294967296.0) / 18446744073709551616.0;
+      if (r >= 1.0) r = std::nextafter(1.0, 0.0);
+      ok = r < P;
+    }
+    if (ok) { c[s1] = c2; c[s2] = c1; ampr[w] = pbr[w]; ampi[w] = pbi[w]; accepted[w] += 1; }
+  }
+}
+void be_xxz_bond_energy_c(const int32_t *cfg, int nsites, int s1, int s2, const double *exr, const double *exi, const double *pr,
+                          const double *pi, double jz, double jxy, double *er, double *ei, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const int32_t *c = cfg + (long)w * nsites;
+    if (c[s1] == c[s2]) { er[w] += 0.25 * jz; continue; }
+    const double d = pr[w] * pr[w] + pi[w] * pi[w];
+    const double rr = (exr[w] * pr[w] + exi[w] * pi[w]) / d, ri = (exi[w] * pr[w] - exr[w] * pi[w]) / d;
+    er[w] += -0.25 * jz + rr * 0.5 * jxy;
+    ei[w] += -ri * 0.5 * jxy;
+  }
+}
+void be_accumulate_ostar_c(const double *hr, const double *hi, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                           const int32_t *tps_off, const int32_t *cfg, int nsites, const double *ampr, const double *ampi,
+                           const double *er, const double *ei, double *osr, double *osi, double *eor, double *eoi, int W) {
+  ++g_launches;
+  for (int site = 0; site < nsites; ++site)
+    for (int e = 0; e < site_size[site]; ++e)
+      for (int w = 0; w < W; ++w) {
+        const int c = cfg[(long)w * nsites + site];
+        const double d = ampr[w] * ampr[w] + ampi[w] * ampi[w];
+        const double a = hr[(long)w * hole_stride + hole_off[site] + e], b = hi[(long)w * hole_stride + hole_off[site] + e];
+        const double qr = (a * ampr[w] + b * ampi[w]) / d, qi = (b * ampr[w] - a * ampi[w]) / d;
+        const double orr = qr, oi = -qi;
+        const long slot = tps_off[site] + (long)c * site_size[site] + e;
+        osr[slot] += orr; osi[slot] += oi;
+        eor[slot] += er[w] * orr + ei[w] * oi;
+        eoi[slot] += er[w] * oi - ei[w] * orr;
+      }
+}
 void be_fermion_gather(const int32_t *cfg, int rows, int cols, int phys, const int32_t *par, int32_t *gh, int32_t *gv,
                        int32_t *jh, int32_t *jv, int W) {
   ++g_launches;

@@ -374,3 +374,79 @@ def run_sector_truncation_case(lib, nr=160, nc=192, t=24, W=3, seed=4):
         assert np.max(np.abs(b[w] @ b[w].T - np.eye(t))) < 1e-12
         assert np.max(np.abs(b[w].T @ b[w] - projs[w])) < 1e-11
     return sweeps.value
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# complex (QLTEN_Complex) states
+# ---------------------------------------------------------------------------------------------------------------------
+def complex_tps(rows, cols, D, seed):
+    """uniform [0,1) real parts and uniform [-0.5, 0.5) imaginary parts, NormalizeAllSite."""
+    rng = np.random.default_rng(seed)
+    tps = vmc.random_tps(rows, cols, 2, D, seed=seed, dtype=np.complex128)
+    for row in tps:
+        for site in row:
+            for s in range(len(site)):
+                site[s] = site[s] + 1j * (rng.random(site[s].shape) - 0.5) * np.max(np.abs(site[s]))
+    return vmc.normalize_all_site(tps)
+
+
+def run_complex_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=6, tol=1e-10, seeds0=300, j2=0.0):
+    """Sweeps + E_loc + holes + accumulators of W walkers on a COMPLEX state through the C ABI vs the oracle (which is
+    pinned on the reference's complex goldens, K5): configurations and acceptance counts bit-identical, amplitudes,
+    E_loc = sum ... conj(psi_ex / psi), O* = conj(hole / psi), sum O* and sum conj(E_loc) O* to `tol` (relative)."""
+    tps = complex_tps(rows, cols, D, seed)
+    cfgs = np.stack([vmc.neel_config(rows, cols)] + [vmc.shuffled_half_filled_config(rows, cols, 20 + w) for w in range(1, W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
+    b.set_complex()
+    b.set_tps(SplitIndexTPS(tps))
+    if j2 != 0.0:
+        from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
+        b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, j2, j2, 0.0))
+    b.set_configs(cfgs)
+    b.seed_rng(np.arange(seeds0, seeds0 + W))
+    b.init_walkers()
+    ws = [vmc.Walker(tps, cfgs[w], trunc) for w in range(W)]
+    ups = [vmc.NNExchangeUpdater(seeds0 + w) for w in range(W)]
+    model = vmc.XXZModel(1.0, 1.0, 0.0, j2, j2)
+    a0 = b.amplitudes_c()
+    r0 = np.array([w_.amplitude for w_ in ws])
+    assert np.max(np.abs(a0 / r0 - 1)) < tol, np.max(np.abs(a0 / r0 - 1))
+    worst = dict(amp=0.0, eloc=0.0, ostar=0.0, acc=0.0)
+    b.zero_accumulators()
+    osum = np.zeros(b.tps_size, dtype=complex)
+    eosum = np.zeros(b.tps_size, dtype=complex)
+    like = SplitIndexTPS(tps)
+    for it in range(nsweeps):
+        acc = b.sweep(1)
+        racc = np.array([ups[w].sweep(tps, ws[w])[0] for w in range(W)])
+        c = b.get_configs()
+        for w in range(W):
+            assert np.array_equal(c[w], ws[w].config), (it, w)
+        assert np.array_equal(acc, racc)
+        amp = b.amplitudes_c()
+        ramp = np.array([w_.amplitude for w_ in ws])
+        worst["amp"] = max(worst["amp"], float(np.max(np.abs(amp / ramp - 1))))
+        b.energy_and_holes(True)
+        e = b.eloc_c()
+        holes = b.holes_c()
+        b.accumulate_ostar()
+        for w in range(W):
+            re, rh, _ = model.energy_and_holes(tps, ws[w], True)
+            worst["eloc"] = max(worst["eloc"], abs(e[w] - re) / max(1.0, abs(re)))
+            ost_ref = flat_holes(rh, rows, cols) * np.conj(1.0 / ws[w].amplitude)          # inverse_amplitude * holes (:245-272)
+            ost = np.conj(holes[w] / amp[w])
+            worst["ostar"] = max(worst["ostar"], float(np.max(np.abs(ost - ost_ref)) / np.max(np.abs(ost_ref))))
+            off = hoff = 0
+            for r in range(rows):
+                for cc in range(cols):
+                    sz = tps[r][cc][0].size
+                    s_ = int(ws[w].config[r, cc])
+                    osum[off + s_ * sz: off + (s_ + 1) * sz] += ost_ref[hoff:hoff + sz]
+                    eosum[off + s_ * sz: off + (s_ + 1) * sz] += np.conj(re) * ost_ref[hoff:hoff + sz]
+                    off += 2 * sz
+                    hoff += sz
+    go, geo = b.accumulators_c()
+    worst["acc"] = max(float(np.max(np.abs(go - osum)) / np.max(np.abs(osum))), float(np.max(np.abs(geo - eosum)) / np.max(np.abs(eosum))))
+    assert all(v < tol for v in worst.values()), worst
+    b.close()
+    return worst
