@@ -450,3 +450,54 @@ def run_complex_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=6,
     assert all(v < tol for v in worst.values()), worst
     b.close()
     return worst
+
+
+def run_complex_k5_golden(lib):
+    """K5 (complex) through the C ABI: exact summation over the six S_z = 0 configurations of the reference's 2x2 complex
+    Heisenberg fixture with device amplitudes / E_loc / holes: energy -2 and the reference's gradient signatures
+    kGradNorm = 2.277663798157925e-08, kGradProbe = (7.37963070602707e-09, 1.708247848617349e-10)
+    (tests/test_algorithm/test_exact_summation_evaluator.cpp:578-597; their tolerance is 1e-8 absolute, here relative)."""
+    import itertools
+    from helpers import load_golden_tps
+    tps, z = load_golden_tps("heis2x2_complex_lowest")
+    cfgs = np.stack([np.array(p).reshape(2, 2) for p in sorted(set(itertools.permutations([0, 0, 1, 1])))])
+    W = len(cfgs)
+    D = max(max(x.shape) for row in tps for site in row for x in site)
+    b = WalkerBatch(2, 2, 2, D, W, BMPSTruncateParams.SVD(1, 1000, 0.0), lib=lib)
+    b.set_complex()
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.init_walkers()
+    b.energy_and_holes(True)
+    amp, e, holes = b.amplitudes_c(), b.eloc_c(), b.holes_c()
+    wt = np.abs(amp) ** 2
+    energy = np.sum(wt * e) / np.sum(wt)
+    assert abs(energy - float(z["exp_energy"])) < float(z["exp_energy_tol"])
+    s_o = np.zeros(b.tps_size, dtype=complex)
+    s_eo = np.zeros(b.tps_size, dtype=complex)
+    for w in range(W):
+        off = hoff = 0
+        for r in range(2):
+            for c in range(2):
+                sz = tps[r][c][0].size
+                s_ = int(cfgs[w, r, c])
+                inc = amp[w] * np.conj(holes[w, hoff:hoff + sz])
+                s_o[off + s_ * sz: off + (s_ + 1) * sz] += inc
+                s_eo[off + s_ * sz: off + (s_ + 1) * sz] += np.conj(e[w]) * inc
+                off += 2 * sz
+                hoff += sz
+    grad = (s_eo - np.conj(energy) * s_o) / np.sum(wt)
+    gn = float(np.sum(np.abs(grad) ** 2))
+    assert abs(gn / float(z["exp_grad_norm"]) - 1) < 1e-5, (gn, float(z["exp_grad_norm"]))
+    probe = 0.0
+    off = 0
+    for r in range(2):
+        for c in range(2):
+            for i in range(2):
+                sz = tps[r][c][i].size
+                base = complex(0.012 * ((r + 1) * 11 + (c + 1) * 5 + (i + 1) * 2), 0.0025 * ((r + 1) + (i + 1)))
+                t = grad[off:off + sz]
+                probe = probe + np.sum(np.conj(t) * (t * base))
+                off += sz
+    assert abs(probe.real / float(z["exp_grad_probe_re"]) - 1) < 1e-5 and abs(probe.imag / float(z["exp_grad_probe_im"]) - 1) < 1e-5
+    b.close()

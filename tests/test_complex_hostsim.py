@@ -20,3 +20,22 @@ def lib():
 ])
 def test_complex_pipeline_parity_hostsim(lib, rows, cols, D, trunc):
     run_complex_pipeline_parity(lib, rows, cols, D, 2, trunc, nsweeps=2)
+
+
+def test_complex_j1j2_pipeline_parity_hostsim(lib):
+    """J1-J2 (BTen2 / NNN traces) on a complex state."""
+    run_complex_pipeline_parity(lib, 3, 4, 2, 2, (4, 4, 0.0), nsweeps=1, j2=0.5)
+
+
+def test_k5_complex_golden_through_abi(lib):
+    from parity_common import run_complex_k5_golden
+    run_complex_k5_golden(lib)
+
+
+def test_complex_mode_guards(lib):
+    from peps_b200.api import BMPSTruncateParams, WalkerBatch, PepsError, TableModel, FermionSplitIndexTPS
+    b = WalkerBatch(3, 3, 2, 2, 1, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+    b.set_complex()
+    with pytest.raises(PepsError):
+        b.set_fermion(FermionSplitIndexTPS.random(3, 3, 2, 1))
+    b.close()

@@ -1,0 +1,35 @@
+"""Complex (QLTEN_Complex) states on the CUDA path through the C ABI against the oracle (pinned on the reference's complex
+goldens). Run on the GPU box with ``-m gpu``. Tolerance 1e-10 relative; configurations / acceptance counts bit-exact."""
+import numpy as np
+import pytest
+
+from parity_common import run_complex_pipeline_parity, run_complex_k5_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from peps_b200 import _lib
+    l = _lib.load()
+    assert l.peps_backend_name() == b"cuda-sm_100a"
+    return l
+
+
+@pytest.mark.parametrize("rows,cols,D,trunc,W", [
+    (2, 2, 3, (1, 100, 0.0), 2),
+    (4, 4, 3, (6, 6, 0.0), 4),
+    (3, 5, 2, (4, 4, 0.0), 3),
+    (4, 4, 4, (2, 8, 1e-8), 3),
+    (6, 6, 4, (16, 16, 0.0), 2),
+])
+def test_complex_pipeline_parity_gpu(lib, rows, cols, D, trunc, W):
+    run_complex_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2)
+
+
+def test_complex_j1j2_pipeline_parity_gpu(lib):
+    run_complex_pipeline_parity(lib, 4, 4, 3, 3, (6, 6, 0.0), nsweeps=1, j2=0.5)
+
+
+def test_k5_complex_golden_gpu(lib):
+    run_complex_k5_golden(lib)
