@@ -354,9 +354,41 @@ Engine::BMPSv Engine::absorb(const BMPSv &mps, const std::vector<int> &sites_in,
 // One step of the forward R chain on a real matrix A[w] (m x n inside a zero-padded buffer of L.m_pad rows, consumed):
 // returns a real factor R (rows x n, column order of A) with R^T R = A^T A up to the rows dropped by the rank-revealing
 // deflation. rc / o: per-walker zero-tail hint of the rows (null = none); rk: rank of the previous factor (early-stop hint).
-Engine::ChainR Engine::chain_factor(double *A, long wsA, int m, int n, const QRLayout &L, const int32_t *rc, int o, int rk,
+Engine::ChainR Engine::chain_factor(double *A, long wsA, int m, int n, const QRLayout &L_in, const int32_t *rc, int o, int rk,
                                     int site_idx) {
   ChainR out;
+  QRLayout L = L_in;
+  // Matrices taller than the two-stage CAQR takes (the real embeddings of the complex path at the headline size) are
+  // reduced first: R factors of row chunks, stacked (one more tree level, R^T R unchanged).
+  auto reduce_tall = [&](double *&Ap) {
+    while (m > qr_max_rows()) {
+      const int nchunk = (m + qr_max_rows() - 1) / qr_max_rows();
+      const int chunk = ((m + nchunk - 1) / nchunk + 31) / 32 * 32;
+      int stacked = 0;
+      for (int c = 0; c * chunk < m; ++c) stacked += std::min(std::min(chunk, m - c * chunk), n);
+      QRLayout Ls;
+      if (stacked <= qr_max_rows()) Ls = qr_layout(stacked, n);
+      else { Ls.m_pad = stacked; Ls.nb = 32; }
+      const long wsS = (long)Ls.m_pad * n;
+      double *S = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsS);
+      be_memset0(S, sizeof(double) * (size_t)W_ * wsS);
+      int off = 0;
+      for (int c = 0; c * chunk < m; ++c) {
+        const int rows_c = std::min(chunk, m - c * chunk), kkc = std::min(rows_c, n);
+        QRLayout Lc = qr_layout(rows_c, n);
+        const long wsC = (long)Lc.m_pad * n;
+        double *buf = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsC);
+        if (Lc.m_pad > rows_c) be_memset0(buf, sizeof(double) * (size_t)W_ * wsC);
+        be_copy2d(buf, wsC, n, Ap + (long)c * chunk * n, wsA, n, rows_c, n, W_);
+        caqr(la_, buf, wsC, rows_c, n, Lc);
+        be_copy2d(S + (long)off * n, wsS, n, buf, wsC, n, kkc, n, W_);
+        off += kkc;
+        pool_.put(buf);
+      }
+      pool_.put(Ap);
+      Ap = S; wsA = wsS; m = stacked; L = Ls; rc = nullptr; o = 0;
+    }
+  };
   const int kk = std::min(m, n);
   if (chain_eps_ > 0.0 && kk >= 16) {
     // Rank-revealing step of the R chain. Columns sorted by norm (pivoting-lite) grade the rows of R; rows below
@@ -373,6 +405,7 @@ Engine::ChainR Engine::chain_factor(double *A, long wsA, int m, int n, const QRL
     if (L.m_pad > m) be_memset0(Ap, sizeof(double) * (size_t)W_ * wsA);
     be_permute_cols(A, wsA, n, m, n, cord, 1, Ap, wsA, n, W_);
     pool_.put(A);
+    reduce_tall(Ap);
     QRStop st;                                         // early termination: the rank of r_{i+1} is close to that of r_i
     st.colnorm2 = cn2; st.colorder = cord; st.eps = chain_eps_; st.first_col = std::max(0, std::min(rk, kk) - 96);
     caqr(la_, Ap, wsA, m, n, L, rc, o, &st);
@@ -399,6 +432,7 @@ Engine::ChainR Engine::chain_factor(double *A, long wsA, int m, int n, const QRL
     out.cnt = cnt;                                     // rows >= cnt[w] of the factor are zero (be_gather_rows)
     for (void *p : {(void *)cn2, (void *)ord, (void *)cord, (void *)Ap, (void *)Rg}) pool_.put(p);
   } else {
+    reduce_tall(A);
     caqr(la_, A, wsA, m, n, L, rc, o);
     out.R = (double *)pool_.get(sizeof(double) * (size_t)W_ * kk * n);
     be_copy2d(out.R, (long)kk * n, n, A, wsA, n, kk, n, W_);
@@ -457,7 +491,9 @@ Engine::BMPSv Engine::absorb_svd(const BMPSv &mps, const std::vector<int> &sites
       einsum_into("kepb," + sl + "->kofb", ref(tmp1), sref, mkop(Ar, wa), nullptr, 1.0, 0.0, nullptr, &ci);
       release(tmp1);
       const int m2 = 2 * m, n2 = 2 * n;
-      QRLayout L2 = qr_layout(m2, n2);
+      QRLayout L2;
+      if (m2 <= qr_max_rows()) L2 = qr_layout(m2, n2);
+      else { L2.m_pad = m2; L2.nb = 32; }            // reduced by row chunks inside chain_factor
       const long wsM = (long)L2.m_pad * n2;
       double *M = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsM);
       if (L2.m_pad > m2) be_memset0(M, sizeof(double) * (size_t)W_ * wsM);

@@ -43,6 +43,12 @@ constexpr size_t kPanelSmemBudget = 150 * 1024;   // bytes for the panel itself
 constexpr size_t kJacobiSmemBudget = 168 * 1024;   // panel only; the kernel adds ~56 KB of Gram / rotation state
 
 struct QRLayout { int nb = 0, rb = 0, nrb = 0, m_pad = 0; };
+// tallest matrix handed to one two-stage CAQR (the flat tree takes 18 x 576 rows); PEPS_QR_MAX_ROWS lowers it (tests)
+inline int qr_max_rows() {
+  const char *e = std::getenv("PEPS_QR_MAX_ROWS");      // read per call: cheap next to a factorisation, and tests toggle it
+  const int v = e ? std::atoi(e) : 8192;
+  return (v < 64 || v > 8192) ? 8192 : v;
+}
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 

@@ -39,3 +39,10 @@ def test_complex_mode_guards(lib):
     with pytest.raises(PepsError):
         b.set_fermion(FermionSplitIndexTPS.random(3, 3, 2, 1))
     b.close()
+
+
+def test_complex_tall_chain_matrices_are_reduced_by_chunks(lib, monkeypatch):
+    """The real embeddings of the complex chain matrices exceed the two-stage CAQR height at the headline size; they are
+    reduced by row chunks first. Forced here at a small size (PEPS_QR_MAX_ROWS=64): results unchanged."""
+    monkeypatch.setenv("PEPS_QR_MAX_ROWS", "64")
+    run_complex_pipeline_parity(lib, 4, 4, 3, 2, (6, 6, 0.0), nsweeps=1)
