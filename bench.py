@@ -259,7 +259,8 @@ class LaneSet:
     different contexts overlap on the GPU (the per-lane host round trips -- one per chain / truncation step -- are hidden
     behind the other lanes' kernels)."""
 
-    def __init__(self, L, D, chi, W, S, device, tps, cfgs, seeds, j2=0.0, rank=0, world=1, dist=None, torch=None, model=None):
+    def __init__(self, L, D, chi, W, S, device, tps, cfgs, seeds, j2=0.0, rank=0, world=1, dist=None, torch=None, model=None,
+                 complex_=False):
         import queue
         from peps_b200.api import BMPSTruncateParams, SplitIndexTPS, FermionSplitIndexTPS, WalkerBatch
         S = max(1, min(S, W))
@@ -291,6 +292,8 @@ class LaneSet:
         def setup(ln):
             sl = slice(ln.i * outer.Ws, (ln.i + 1) * outer.Ws)
             ln.b = WalkerBatch(L, L, 2, D, outer.Ws, BMPSTruncateParams.SVD(chi, chi, 0.0), device=device)
+            if complex_:
+                ln.b.set_complex()                    # QLTEN_Complex states: split planes
             if isinstance(outer.sit, FermionSplitIndexTPS):
                 ln.b.set_fermion(outer.sit)           # fZ2-graded tensors (BASELINE config #4)
             ln.b.set_tps(outer.sit)
@@ -302,7 +305,7 @@ class LaneSet:
             ln.b.set_configs(cfgs[sl])
             ln.b.seed_rng(seeds[sl])
             ln.b.init_walkers()
-            return float(np.max(np.abs(ln.b.amplitudes())))
+            return float(np.max(np.abs(ln.b.amplitudes_c() if complex_ else ln.b.amplitudes())))
 
         mx = max(self.on_all(setup))
         if world > 1:
@@ -372,11 +375,11 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
     L, D, chi = D_chi
     out = []
 
-    def run(name, L, D, chi, W, S, tps, j2=0.0, model=None, note=None):
+    def run(name, L, D, chi, W, S, tps, j2=0.0, model=None, note=None, complex_=False):
         cfgs = np.stack([vmc.shuffled_half_filled_config(L, L, CFG_SEED0 + w) for w in range(W)])
         seeds = np.arange(RNG_SEED0, RNG_SEED0 + W, dtype=np.uint32)
         try:
-            ls = LaneSet(L, D, chi, W, S, device, tps, cfgs, seeds, j2=j2, torch=torch, model=model)
+            ls = LaneSet(L, D, chi, W, S, device, tps, cfgs, seeds, j2=j2, torch=torch, model=model, complex_=complex_)
         except Exception as exc:                     # noqa: BLE001  (a companion line must not take the others down)
             out.append({"name": name, "error": repr(exc)[:300]})
             return
@@ -408,6 +411,16 @@ def secondary_lines(torch, device, D_chi, walkers, streams):
         model=TableModel.spinless_fermion(1.0, 0.0, 0.0),
         note="BASELINE config #4: fZ2-graded state evaluated as a sign-dressed dense network (DESIGN.md section 9); random "
              "parity-conserving tensors are full rank, so the sector-aware block-Jacobi truncation path runs")
+    # complex (QLTEN_Complex) state at BASELINE config #2's size: uniform [0,1) real parts + uniform [-0.5,0.5) imaginary parts
+    rng = np.random.default_rng(TPS_SEED)
+    ctps = vmc.random_tps(8, 8, 2, 6, seed=TPS_SEED, dtype=np.complex128)
+    for row in ctps:
+        for site in row:
+            for k in range(len(site)):
+                site[k] = site[k] + 1j * (rng.random(site[k].shape) - 0.5) * np.max(np.abs(site[k]))
+    run("complex_heisenberg_8x8_D6_chi36", 8, 6, 36, walkers, streams, vmc.normalize_all_site(ctps), complex_=True,
+        note="QLTEN_Complex state on split planes: four real contraction launches per complex contraction, factorisations on "
+             "the real embedding (DESIGN.md section 11)")
     gold = os.path.join(ROOT, "tests", "golden", "heis4x4_D8_double.npz")
     if os.path.exists(gold):
         z = np.load(gold)

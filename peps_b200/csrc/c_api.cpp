@@ -113,10 +113,10 @@ int peps_normalize_state_order1(peps_ctx *ctx, double max_abs_override, double *
     Engine &e = *ctx->eng;
     double mx = max_abs_override;
     if (!(mx > 0.0)) {
-      std::vector<double> a((size_t)e.walkers());
-      e.get_amplitudes(a.data());
+      std::vector<double> a((size_t)e.walkers()), ai((size_t)e.walkers());
+      e.get_planar(0, a.data(), ai.data());            // |psi| = hypot(re, im) (imaginary plane zero for real states)
       mx = 0.0;
-      for (double v : a) mx = std::max(mx, std::fabs(v));
+      for (size_t k = 0; k < a.size(); ++k) mx = std::max(mx, std::hypot(a[k], ai[k]));
     }
     if (!(mx > 0.0) || !std::isfinite(mx)) throw std::runtime_error("peps_normalize_state_order1: amplitudes are zero or not finite");
     double scale = 1.0 / mx;
