@@ -818,6 +818,12 @@ class MCEnergyGradEvaluator:
         self.state = tps                       # the device holds its own copy (set_tps below and in every Evaluate(state))
         self.dist, self.rank, self.world_size = dist, rank, world_size
         self.batch = WalkerBatch(tps.rows(), tps.cols(), tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
+        self.is_complex = bool(np.iscomplexobj(tps.t[0][0][0]))    # QLTEN_Complex state: complex arithmetic on the device
+        if self.is_complex:
+            if dist is not None and world_size > 1:
+                raise PepsError("complex states: the multi-GPU reduction of the evaluator is not wired yet")
+            self.batch.set_complex()
+            self.psi_consistency.enabled = False                   # the psi list is real-only
         if isinstance(tps, FermionSplitIndexTPS):
             self.batch.set_fermion(tps)
         self.batch.set_model(model)
@@ -917,7 +923,7 @@ class MCEnergyGradEvaluator:
                 self._sr_cap = n * b.W
             b.sr_clear()
         b.sr_collect(collect_sr_buffers)
-        energies = np.empty((b.W, n))
+        energies = np.empty((b.W, n), dtype=complex if self.is_complex else float)
         accept = np.zeros(b.W)
         pc = self.psi_consistency
         for s in range(n):                     # the walker loop (:205-282), all walkers in lock step
@@ -931,6 +937,8 @@ class MCEnergyGradEvaluator:
                         self.psi_warnings.append((s, w, rel))
             else:
                 e, acc = b.sample(self.mc.sweeps_between_samples)
+                if self.is_complex:
+                    e = b.eloc_c()
             if not np.all(np.isfinite(e)):     # zero amplitude: std::runtime_error in the reference solver (square_nnn_energy_solver.h:148-150)
                 raise PepsError("local energy is not finite (zero or illegal amplitude): run EnsureConfigurationValidity / WarmUp first")
             energies[:, s] = e
@@ -957,11 +965,18 @@ class MCEnergyGradEvaluator:
             gathered = [torch.empty_like(mine) for _ in range(self.world_size)]
             self.dist.all_gather(gathered, mine)
             all_e = np.concatenate([g.cpu().numpy() for g in gathered], axis=0)
+        elif self.is_complex:
+            osum, eosum = b.accumulators_c()
         else:
             osum, eosum = b.accumulators()
-        energy, err = combine_energy_bins(all_e)
+        if self.is_complex:                    # complex mean of the bin means, error bar from the real parts
+            er, err = combine_energy_bins(all_e.real)
+            ei, _ = combine_energy_bins(all_e.imag)
+            energy = complex(er, ei)
+        else:
+            energy, err = combine_energy_bins(all_e)
         total_walkers = all_e.shape[0]
-        grad_flat = (eosum - energy * osum) / (n * total_walkers)        # (:296-309)
+        grad_flat = (eosum - np.conj(energy) * osum) / (n * total_walkers)        # (:296-309)
         grad = type(self.state).unpack(grad_flat, self.state)
         b.sr_collect(False)
         res = EvaluateResult(energy, err, grad, grad.NormSquare(), [float(np.mean(accept / n))], all_e)

@@ -46,3 +46,45 @@ def test_complex_tall_chain_matrices_are_reduced_by_chunks(lib, monkeypatch):
     reduced by row chunks first. Forced here at a small size (PEPS_QR_MAX_ROWS=64): results unchanged."""
     monkeypatch.setenv("PEPS_QR_MAX_ROWS", "64")
     run_complex_pipeline_parity(lib, 4, 4, 3, 2, (6, 6, 0.0), nsweeps=1)
+
+
+def test_complex_evaluator_matches_oracle_chain(lib):
+    """MCEnergyGradEvaluator on a complex state (seam B1): energy and gradient = sum conj(E_loc) O* / N - conj(E) sum O* / N
+    from the oracle chain's samples."""
+    from parity_common import complex_tps, flat_holes
+    from oracle import vmc
+    from peps_b200.api import (BMPSTruncateParams, SplitIndexTPS, MCEnergyGradEvaluator, MonteCarloParams, Configuration,
+                               SquareSpinOneHalfXXZModelOBC, MCUpdateSquareNNExchange, combine_energy_bins)
+    rows, cols, D, W, n, trunc = 3, 3, 2, 2, 3, (4, 4, 0.0)
+    tps = complex_tps(rows, cols, D, 9)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 70 + w) for w in range(W)])
+    ev = MCEnergyGradEvaluator(MonteCarloParams(n * W, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(*trunc),
+                               SplitIndexTPS(tps), SquareSpinOneHalfXXZModelOBC(1, 1, 0), MCUpdateSquareNNExchange(seed=55), W,
+                               configs=cfgs, lib=lib)
+    res = ev.Evaluate()
+    model = vmc.XXZModel()
+    es = np.zeros((W, n), dtype=complex)
+    osum = np.zeros(ev.batch.tps_size, dtype=complex)
+    eosum = np.zeros(ev.batch.tps_size, dtype=complex)
+    for w in range(W):
+        wk = vmc.Walker(tps, cfgs[w], trunc)
+        up = vmc.NNExchangeUpdater(55 + w)
+        for k in range(n):
+            up.sweep(tps, wk)
+            e, holes, _ = model.energy_and_holes(tps, wk, True)
+            es[w, k] = e
+            ost = flat_holes(holes, rows, cols) * np.conj(1.0 / wk.amplitude)
+            off = hoff = 0
+            for r in range(rows):
+                for c in range(cols):
+                    sz = tps[r][c][0].size
+                    s_ = int(wk.config[r, c])
+                    osum[off + s_ * sz: off + (s_ + 1) * sz] += ost[hoff:hoff + sz]
+                    eosum[off + s_ * sz: off + (s_ + 1) * sz] += np.conj(e) * ost[hoff:hoff + sz]
+                    off += 2 * sz
+                    hoff += sz
+    energy = complex(combine_energy_bins(es.real)[0], combine_energy_bins(es.imag)[0])
+    grad = (eosum - np.conj(energy) * osum) / (n * W)
+    assert abs(res.energy - energy) < 1e-10
+    got = np.concatenate([x.ravel() for row in res.gradient.t for site in row for x in site])
+    assert np.max(np.abs(got - grad)) <= 1e-9 * max(1.0, np.max(np.abs(grad)))
