@@ -156,6 +156,13 @@ def suwa_todo_state_update(init_state, weights, rng):
     return final_state
 
 
+def _std_norm(z):
+    """std::norm: re^2 + im^2 (not |z|^2 through a hypot), so that complex weights round like the reference's."""
+    if np.iscomplexobj(z):
+        return float(z.real) ** 2 + float(z.imag) ** 2
+    return abs(z) ** 2
+
+
 class NNFullSpaceUpdater(NNExchangeUpdater):
     """MCUpdateSquareNNFullSpaceUpdateOBC (square_nn_updater.h:253-293): same bond traversal as the exchange updater,
     all d^2 local states of a bond weighted by |psi|^2, Suwa-Todo choice (one long double draw per bond)."""
@@ -172,7 +179,7 @@ class NNFullSpaceUpdater(NNExchangeUpdater):
                 if cfg != init:
                     alt[cfg] = w.contractor.replace_nn_site_trace(w.tn, site1, site2, bond_dir,
                                                                   tps[site1[0]][site1[1]][a], tps[site2[0]][site2[1]][b])
-        weights = [abs(x / w.amplitude) ** 2 for x in alt]
+        weights = [_std_norm(x / w.amplitude) for x in alt]
         final = suwa_todo_state_update(init, weights, self.rng)
         if final == init:
             return False
@@ -203,7 +210,8 @@ class TNN3SiteExchangeUpdater:
             else:
                 psis.append(w.amplitude)
         mx = max(abs(x) for x in psis)
-        weights = [abs(x / mx) ** 2 for x in psis]
+        # complex / double divides the two components (std::complex operator/ with a real divisor)
+        weights = [_std_norm(complex(x.real / mx, x.imag / mx) if np.iscomplexobj(x) else x / mx) for x in psis]
         final = suwa_todo_state_update(init, weights, self.rng)
         if final == init:
             return False
@@ -330,10 +338,11 @@ class XXZModel:
         """SquareNNNModelMeasurementSolver::EvaluateObservables (base/square_nnn_model_measurement_solver.h:33-214):
         the bond traversal of the energy solver without holes, every bond energy kept under its registry key."""
         rows, cols = w.rows, w.cols
-        rec = {"h": np.zeros((rows, cols - 1)), "v": np.zeros((rows - 1, cols))}
+        dt = np.result_type(tps[0][0][0].dtype, np.float64)                  # complex states: complex bond energies
+        rec = {"h": np.zeros((rows, cols - 1), dt), "v": np.zeros((rows - 1, cols), dt)}
         if self.has_nnn:
-            rec["dr"] = np.zeros((rows - 1, cols - 1))
-            rec["ur"] = np.zeros((rows - 1, cols - 1))
+            rec["dr"] = np.zeros((rows - 1, cols - 1), dt)
+            rec["ur"] = np.zeros((rows - 1, cols - 1), dt)
         rec["row_corr"] = None
         e, _, _ = self.energy_and_holes(tps, w, False, rec=rec)
         out = {"energy": e, "spin_z": w.config.astype(float) - 0.5,          # CalSpinSzImpl: config - 0.5
@@ -507,7 +516,8 @@ class TableModel:
         e = H[p, p]
         for q in range(self.d * self.d):
             if q != p and H[p, q] != 0.0:
-                e = e + H[p, q] * (amp_of(q // self.d, q % self.d) * inv_psi)
+                # complex states: the reference's mix-ins conjugate every ratio (square_spin_onehalf_xxz_obc.h:72-104)
+                e = e + H[p, q] * np.conj(amp_of(q // self.d, q % self.d) * inv_psi)
         return e
 
     def energy_and_holes(self, tps, w, calc_holes=True):
@@ -532,7 +542,7 @@ class TableModel:
                     e_tot = e_tot + self.h1[p, p]
                     for q in range(d):
                         if q != p and self.h1[p, q] != 0.0:
-                            e_tot = e_tot + self.h1[p, q] * (c.replace_one_site_trace(tn, s, tps[row][col][q], HORIZONTAL) * inv_psi)
+                            e_tot = e_tot + self.h1[p, q] * np.conj(c.replace_one_site_trace(tn, s, tps[row][col][q], HORIZONTAL) * inv_psi)
                 if col < cols - 1:
                     s2 = (row, col + 1)
                     if self.h2 is not None:

@@ -519,20 +519,30 @@ class WalkerBatch:
         return acc
 
     def energy_and_holes(self, calc_holes=True, want_psi=False):
+        """CalEnergyAndHoles for every walker. Complex context: returns complex E_loc (and psi list) -- the psi list crosses
+        the ABI as [entry][re W | im W], E_loc is read back through peps_get_planar."""
+        cx = getattr(self, "is_complex", False)
         e = np.empty(self.W)
-        psi = np.empty((self.rows + self.cols, self.W)) if want_psi else None
+        psi = np.empty((self.rows + self.cols, 2 if cx else 1, self.W)) if want_psi else None
         self._ck(self.lib.peps_energy_and_holes(self.h, int(calc_holes), _dp(e), _dp(psi) if want_psi else None))
+        if cx:
+            e = self.eloc_c()
+            psi = psi[:, 0] + 1j * psi[:, 1] if want_psi else None
+        elif want_psi:
+            psi = psi[:, 0]
         return (e, psi) if want_psi else e
 
     def measure(self):
         """One EvaluateObservables call for every walker (model_solvers/base/square_nnn_model_measurement_solver.h:
         33-214): dict of per-walker arrays under the reference's registry keys."""
         W, r, c = self.W, self.rows, self.cols
-        e = np.empty(W)
-        eh, ev = np.empty((W, r, c - 1)), np.empty((W, r - 1, c))
-        edr, eur = np.empty((W, r - 1, c - 1)), np.empty((W, r - 1, c - 1))
-        corr = np.empty((W, c // 2))
+        npl = 2 if getattr(self, "is_complex", False) else 1         # complex context: planar arrays (re block, im block)
+        e = np.empty((npl, W))
+        eh, ev = np.empty((npl, W, r, c - 1)), np.empty((npl, W, r - 1, c))
+        edr, eur = np.empty((npl, W, r - 1, c - 1)), np.empty((npl, W, r - 1, c - 1))
+        corr = np.empty((npl, W, c // 2))
         self._ck(self.lib.peps_measure(self.h, _dp(e), _dp(eh), _dp(ev), _dp(edr), _dp(eur), _dp(corr)))
+        e, eh, ev, edr, eur, corr = [(a[0] + 1j * a[1]) if npl == 2 else a[0] for a in (e, eh, ev, edr, eur, corr)]
         cfg = self.get_configs()
         if getattr(self, "phys_par", None) is not None:        # fermion models: requires_density_measurement (charge)
             return {"energy": e, "charge": np.asarray(self.phys_par, dtype=float)[cfg], "bond_energy_h": eh,

@@ -288,11 +288,19 @@ void be_complex_basis(double *Bm, long wb, int tcap2, int n, const int32_t *kept
 // out[w] (planes outr / outi) = (d0 - d1) + i (d2 + d3) for the four real dots of a bilinear complex dot product
 void be_complex_combine(const double *d0, const double *d1, const double *d2, const double *d3, double *outr, double *outi, int W);
 // complex twins of the Monte Carlo kernels: amplitudes / energies as planes [2][W]; |psi| = hypot(re, im)
+// jastrow != nullptr: the Jastrow-dressed acceptance of be_nn_exchange_decide with |psi_b * jastrow| = hypot of the scaled planes
 void be_nn_exchange_decide_c(int32_t *cfg, int nsites, int s1, int s2, const double *pbr, const double *pbi, double *ampr,
-                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W);
+                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W, const double *jastrow = nullptr);
 // eloc += (c1 == c2) ? 0.25 jz : -0.25 jz + conj(psi_ex / psi) * 0.5 jxy     (square_spin_onehalf_xxz_obc.h:72-104)
 void be_xxz_bond_energy_c(const int32_t *cfg, int nsites, int s1, int s2, const double *exr, const double *exi, const double *pr,
                           const double *pi, double jz, double jxy, double *er, double *ei, int W);
+// complex twins of be_ratio_accumulate / be_term_accumulate: the reference conjugates every amplitude ratio that enters E_loc
+// (transverse_field_ising_square_obc.h:191-204, square_nnn_energy_solver.h:171-198): e += coef * conj(psi_ex / psi)
+void be_ratio_accumulate_c(const double *exr, const double *exi, const double *pr, const double *pi, double coef, double *er,
+                           double *ei, int W);
+// e += (diag ? diag[p_w] : 0) + (coefw ? coefw[w] * conj(psi_ex[w] / psi[w]) : 0)   (tables are real)
+void be_term_accumulate_c(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag, const double *coefw,
+                          const double *exr, const double *exi, const double *pr, const double *pi, double *er, double *ei, int W);
 // O* = conj(hole / psi) (mc_energy_grad_evaluator.h:245-272): osum += O*, eosum += conj(E_loc) O*; all arrays as planes
 void be_accumulate_ostar_c(const double *hr, const double *hi, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
                            const int32_t *tps_off, const int32_t *cfg, int nsites, const double *ampr, const double *ampi,
@@ -349,6 +357,13 @@ void be_fermion_targets(const int32_t *cfg, int nsites, int s1, int s2, int phys
 void be_fermion_finish_holes(double *holes, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
                              const double *gtps, const int64_t *gtps_off, const int32_t *gidx_h, const int32_t *jw_h,
                              int nsites, const double *sign, const double *amp, int W);
+
+// complex twin: holes / dressed tensors / amplitudes as planes (the im plane of gtps starts gtps_im_off doubles after the
+// re plane); psi_site = bilinear <hole, tensor>, hole <- hole * sign * amp / psi_site in complex arithmetic, so that
+// conj(hole / amp) = conj(d psi / d T) / conj(psi_site) (be_accumulate_ostar_c).
+void be_fermion_finish_holes_c(double *hr, double *hi, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                               const double *gtps, long gtps_im_off, const int64_t *gtps_off, const int32_t *gidx_h,
+                               const int32_t *jw_h, int nsites, const double *sign, const double *ampr, const double *ampi, int W);
 
 // O* accumulation (mc_energy_grad_evaluator.h:245-272) for one sample of all walkers:
 //   o = (1/amp[w]) * hole[w][e];  osum[slot(site,cfg[w][site]) + e] += o;  eosum[...] += eloc[w] * o

@@ -2868,14 +2868,16 @@ void be_complex_combine(const double *d0, const double *d1, const double *d2, co
   post_launch();
 }
 __global__ void nn_exchange_decide_c_kernel(int32_t *cfg, int nsites, int s1, int s2, const double *pbr, const double *pbi,
-                                            double *ampr, double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+                                            double *ampr, double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W,
+                                            const double *jastrow) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   int32_t *c = cfg + (long)w * nsites;
   const int c1 = c[s1], c2 = c[s2];
   if (c1 == c2) return;
-  const double ab = hypot(pbr[w], pbi[w]), aa = hypot(ampr[w], ampi[w]);
-  bool ok = ab >= aa;
+  const double j = jastrow ? jastrow[w] : 1.0;
+  const double ab = jastrow ? hypot(pbr[w] * j, pbi[w] * j) : hypot(pbr[w], pbi[w]), aa = hypot(ampr[w], ampi[w]);
+  bool ok = jastrow ? ab / aa >= 1.0 : ab >= aa;
   if (!ok) {
     const double div = ab / aa, P = div * div;
     int32_t i = idx[w];
@@ -2886,9 +2888,47 @@ __global__ void nn_exchange_decide_c_kernel(int32_t *cfg, int nsites, int s1, in
   if (ok) { c[s1] = c2; c[s2] = c1; ampr[w] = pbr[w]; ampi[w] = pbi[w]; accepted[w] += 1; }
 }
 void be_nn_exchange_decide_c(int32_t *cfg, int nsites, int s1, int s2, const double *pbr, const double *pbi, double *ampr,
-                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W, const double *jastrow) {
   LaunchScope scope(KC_SMALL, 0.0);
-  nn_exchange_decide_c_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, nsites, s1, s2, pbr, pbi, ampr, ampi, mt, idx, accepted, W);
+  nn_exchange_decide_c_kernel<<<(W + 63) / 64, 64, 0, g_stream>>>(cfg, nsites, s1, s2, pbr, pbi, ampr, ampi, mt, idx, accepted, W, jastrow);
+  post_launch();
+}
+__global__ void ratio_accumulate_c_kernel(const double *exr, const double *exi, const double *pr, const double *pi, double coef,
+                                          double *er, double *ei, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const double d = pr[w] * pr[w] + pi[w] * pi[w];
+  const double rr = (exr[w] * pr[w] + exi[w] * pi[w]) / d, ri = (exi[w] * pr[w] - exr[w] * pi[w]) / d;   // psi_ex / psi
+  er[w] += coef * rr;
+  ei[w] += -coef * ri;                                                                                   // conj
+}
+void be_ratio_accumulate_c(const double *exr, const double *exi, const double *pr, const double *pi, double coef, double *er,
+                           double *ei, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  ratio_accumulate_c_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(exr, exi, pr, pi, coef, er, ei, W);
+  post_launch();
+}
+__global__ void term_accumulate_c_kernel(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag,
+                                         const double *coefw, const double *exr, const double *exi, const double *pr,
+                                         const double *pi, double *er, double *ei, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  const int32_t *c = cfg + (long)w * nsites;
+  const int p = s2 >= 0 ? c[s1] * phys + c[s2] : c[s1];
+  double e_r = diag ? diag[p] : 0.0, e_i = 0.0;
+  if (coefw && coefw[w] != 0.0) {
+    const double d = pr[w] * pr[w] + pi[w] * pi[w];
+    const double rr = (exr[w] * pr[w] + exi[w] * pi[w]) / d, ri = (exi[w] * pr[w] - exr[w] * pi[w]) / d;
+    e_r += coefw[w] * rr;
+    e_i -= coefw[w] * ri;
+  }
+  er[w] += e_r;
+  ei[w] += e_i;
+}
+void be_term_accumulate_c(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag, const double *coefw,
+                          const double *exr, const double *exi, const double *pr, const double *pi, double *er, double *ei, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  term_accumulate_c_kernel<<<(W + 127) / 128, 128, 0, g_stream>>>(cfg, nsites, s1, s2, phys, diag, coefw, exr, exi, pr, pi, er, ei, W);
   post_launch();
 }
 __global__ void xxz_bond_energy_c_kernel(const int32_t *cfg, int nsites, int s1, int s2, const double *exr, const double *exi,
@@ -3013,6 +3053,45 @@ void be_fermion_finish_holes(double *holes, long hole_stride, const int32_t *hol
   LaunchScope scope(KC_SMALL, 0.0);
   fermion_finish_holes_kernel<<<dim3(nsites, W), 256, 0, g_stream>>>(holes, hole_stride, hole_off, site_size, gtps, gtps_off,
                                                                      gidx_h, jw_h, nsites, sign, amp);
+  post_launch();
+}
+
+// complex twin: two fixed-order tree reductions (re, im of the bilinear <hole, tensor>), complex rescale
+__global__ void fermion_finish_holes_c_kernel(double *hr, double *hi, long hole_stride, const int32_t *hole_off,
+                                              const int32_t *site_size, const double *gtps, long gtps_im_off,
+                                              const int64_t *gtps_off, const int32_t *gidx_h, const int32_t *jw_h, int nsites,
+                                              const double *sign, const double *ampr, const double *ampi) {
+  __shared__ double redr[256], redi[256];
+  const int site = blockIdx.x, w = blockIdx.y;
+  const int sz = site_size[site];
+  double *a = hr + (long)w * hole_stride + hole_off[site], *b = hi + (long)w * hole_stride + hole_off[site];
+  const double *tr = gtps + gtps_off[site] + (long)gidx_h[(long)w * nsites + site] * sz, *ti = tr + gtps_im_off;
+  double accr = 0.0, acci = 0.0;
+  for (int e = threadIdx.x; e < sz; e += blockDim.x) {
+    accr += a[e] * tr[e] - b[e] * ti[e];
+    acci += a[e] * ti[e] + b[e] * tr[e];
+  }
+  redr[threadIdx.x] = accr; redi[threadIdx.x] = acci;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) { redr[threadIdx.x] += redr[threadIdx.x + s]; redi[threadIdx.x] += redi[threadIdx.x + s]; }
+    __syncthreads();
+  }
+  const double pr = redr[0], pi = redi[0], d = pr * pr + pi * pi;
+  const double fr = (ampr[w] * pr + ampi[w] * pi) / d, fi = (ampi[w] * pr - ampr[w] * pi) / d;          // amp / psi_site
+  const double *sg = sign + (long)jw_h[(long)w * nsites + site] * hole_stride + hole_off[site];
+  for (int e = threadIdx.x; e < sz; e += blockDim.x) {
+    const double x = a[e] * sg[e], y = b[e] * sg[e];
+    a[e] = x * fr - y * fi;
+    b[e] = x * fi + y * fr;
+  }
+}
+void be_fermion_finish_holes_c(double *hr, double *hi, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                               const double *gtps, long gtps_im_off, const int64_t *gtps_off, const int32_t *gidx_h,
+                               const int32_t *jw_h, int nsites, const double *sign, const double *ampr, const double *ampi, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  fermion_finish_holes_c_kernel<<<dim3(nsites, W), 256, 0, g_stream>>>(hr, hi, hole_stride, hole_off, site_size, gtps, gtps_im_off,
+                                                                       gtps_off, gidx_h, jw_h, nsites, sign, ampr, ampi);
   post_launch();
 }
 

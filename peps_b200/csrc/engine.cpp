@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <complex>
 #include <cstdio>
 #include <cstdlib>
 #include <limits>
@@ -48,6 +49,7 @@ Engine::Engine(const EngineConfig &c)
   hole_stride_ = hoff;
   tps_ = (double *)be_malloc(sizeof(double) * tps_total_);
   gtps_ = tps_;
+  gtps_total_ = tps_total_;
   gtps_off_h_ = tps_off_h_;
   osum_ = (double *)be_malloc(sizeof(double) * tps_total_);
   eosum_ = (double *)be_malloc(sizeof(double) * tps_total_);
@@ -108,7 +110,15 @@ void Engine::set_tps(const double *host) {
   be_h2d(tps_, host, sizeof(double) * tps_total_);
   if (complex_) be_memset0(tps_ + tps_total_, sizeof(double) * tps_total_);     // a real state in a complex context
   tps_loaded_ = true;
-  if (fermion_) {                                       // dress: FERMION_VARIANTS sign patterns per site (backend.h)
+  if (fermion_) {
+    dress_plane(host, gtps_);
+    if (complex_) be_memset0(gtps_ + gtps_total_, sizeof(double) * gtps_total_);
+  }
+  touch_all();
+}
+// fermion mode: FERMION_VARIANTS sign patterns per site (backend.h) of one plane of the user's tensors
+void Engine::dress_plane(const double *host, double *dst) {
+  {
     std::vector<double> g((size_t)(tps_total_ * FERMION_VARIANTS));
     static const int vmask[FERMION_VARIANTS] = {0, 8, 4, 12, 6, 14, 0, 1};     // bits: L = 1, D = 2, R = 4, U = 8
     for (int site = 0; site < nsites_; ++site) {
@@ -135,9 +145,8 @@ void Engine::set_tps(const double *host) {
               }
       }
     }
-    be_h2d(gtps_, g.data(), sizeof(double) * g.size());
+    be_h2d(dst, g.data(), sizeof(double) * g.size());
   }
-  touch_all();
 }
 void Engine::get_tps(double *host) { be_d2h(host, tps_, sizeof(double) * tps_total_); }
 void Engine::scale_tps(double f) {
@@ -235,7 +244,7 @@ TRef Engine::site_ref(int site, int cfg_site) const {
   TRef r;
   if (fermion_ && cfg_site != site) throw std::logic_error("fermion mode: exchanged tensors need explicit dressed slices");
   r.op = mkgather(gtps_ + gtps_off_h_[(size_t)site], (fermion_ ? gidx_[gmode_] : cfg_) + cfg_site, nsites_, site_size_h_[(size_t)site]);
-  if (complex_) r.opi = mkgather(tps_ + tps_total_ + tps_off_h_[(size_t)site], cfg_ + cfg_site, nsites_, site_size_h_[(size_t)site]);
+  if (complex_) r.opi = mkgather(gtps_ + gtps_total_ + gtps_off_h_[(size_t)site], (fermion_ ? gidx_[gmode_] : cfg_) + cfg_site, nsites_, site_size_h_[(size_t)site]);
   r.rank = 4;
   for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
   return r;
@@ -251,7 +260,7 @@ static GettDesc with_hints(GettDesc d, const H *h) {
 TRef Engine::site_ref_idx(int site, const int32_t *idx, int stride) const {
   TRef r;
   r.op = mkgather(gtps_ + gtps_off_h_[(size_t)site], idx, stride, site_size_h_[(size_t)site]);
-  if (complex_) r.opi = mkgather(tps_ + tps_total_ + tps_off_h_[(size_t)site], idx, stride, site_size_h_[(size_t)site]);
+  if (complex_) r.opi = mkgather(gtps_ + gtps_total_ + gtps_off_h_[(size_t)site], idx, stride, site_size_h_[(size_t)site]);
   r.rank = 4;
   for (int i = 0; i < 4; ++i) r.d[i] = site_dims_h_[(size_t)site][(size_t)i];
   return r;
@@ -1248,8 +1257,7 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
       for (int col = 0; col < cols_ - 1; ++col) {
         const int s1 = row * cols_ + col, s2 = s1 + 1;
         nn_trace(row, col, row, col + 1, HORIZONTAL, s2, s1, psi_tmp_);          // :164-166 (masked in the decide kernel)
-        if (complex_) be_nn_exchange_decide_c(cfg_, nsites_, s1, s2, psi_tmp_, psi_tmp_ + W_, amp_, amp_ + W_, mt_, mtidx_, accepted_, W_);
-        else be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
+        exchange_decide(s1, s2, psi_tmp_, jastrow_for(s1, s2));
         touch_site(s1); touch_site(s2);
         if (col < cols_ - 2) shift_bten_window(RIGHT);
       }
@@ -1264,8 +1272,7 @@ void Engine::sweep(int nsweeps, double *accept_rate_host) {      // square_nn_up
       for (int row = 0; row < rows_ - 1; ++row) {
         const int s1 = row * cols_ + col, s2 = s1 + cols_;
         nn_trace(row, col, row + 1, col, VERTICAL, s2, s1, psi_tmp_);
-        if (complex_) be_nn_exchange_decide_c(cfg_, nsites_, s1, s2, psi_tmp_, psi_tmp_ + W_, amp_, amp_ + W_, mt_, mtidx_, accepted_, W_);
-        else be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
+        exchange_decide(s1, s2, psi_tmp_, jastrow_for(s1, s2));
         touch_site(s1); touch_site(s2);
         if (row < rows_ - 2) shift_bten_window(DOWN);
       }
@@ -1343,7 +1350,8 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
   ensure_psi_alt(nst);
   std::vector<int32_t> cfg((size_t)W_ * nsites_), mtidx((size_t)W_);
   std::vector<uint32_t> mt((size_t)W_ * 624);
-  std::vector<double> amp((size_t)W_), alt((size_t)nst * W_);
+  const size_t S = sw();                                                 // complex: every amplitude array is [re W][im W]
+  std::vector<double> amp(S), alt((size_t)nst * S);
   std::vector<HostMT> rng((size_t)W_);
   be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
   be_d2h(amp.data(), amp_, sizeof(double) * amp.size());
@@ -1359,22 +1367,31 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
     for (int a = 0; a < d; ++a)
       for (int b = 0; b < d; ++b)
         nn_trace_idx(ra, ca, rb, cb, orient, idx_const_ + (size_t)a * W_, idx_const_ + (size_t)b * W_, 1,
-                     psi_alt_ + (size_t)(a * d + b) * W_);
+                     psi_alt_ + (size_t)(a * d + b) * S);
     be_d2h(alt.data(), psi_alt_, sizeof(double) * alt.size());
     bool any = false;
     std::vector<double> wt((size_t)nst);
     for (int w = 0; w < W_; ++w) {
       int32_t *c = cfg.data() + (size_t)w * nsites_;
       const int init = c[s1] * d + c[s2];
-      const double a0 = amp[(size_t)w];
-      for (int i = 0; i < nst; ++i) {
-        const double r = (i == init ? a0 : alt[(size_t)i * W_ + w]) / a0;
-        wt[(size_t)i] = r * r;                                           // std::norm(alternative_psi / amplitude)
+      if (!complex_) {
+        const double a0 = amp[(size_t)w];
+        for (int i = 0; i < nst; ++i) {
+          const double r = (i == init ? a0 : alt[(size_t)i * W_ + w]) / a0;
+          wt[(size_t)i] = r * r;                                         // std::norm(alternative_psi / amplitude)
+        }
+      } else {
+        const std::complex<double> a0(amp[(size_t)w], amp[(size_t)W_ + w]);
+        for (int i = 0; i < nst; ++i) {
+          const std::complex<double> x(alt[(size_t)i * S + w], alt[(size_t)i * S + W_ + w]);
+          wt[(size_t)i] = std::norm((i == init ? a0 : x) / a0);
+        }
       }
       const int fin = suwa_todo(init, wt, rng[(size_t)w]);
       if (fin != init) {
         c[s1] = fin / d; c[s2] = fin % d;
-        amp[(size_t)w] = alt[(size_t)fin * W_ + w];
+        amp[(size_t)w] = alt[(size_t)fin * S + w];
+        if (complex_) amp[(size_t)W_ + w] = alt[(size_t)fin * S + W_ + w];
         ++accepted[(size_t)w];
         any = true;
       }
@@ -1431,7 +1448,8 @@ void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
   ensure_psi_alt(maxp);
   std::vector<int32_t> cfg((size_t)W_ * nsites_), mtidx((size_t)W_), perm_h((size_t)maxp * W_ * 3);
   std::vector<uint32_t> mt((size_t)W_ * 624);
-  std::vector<double> amp((size_t)W_), alt((size_t)maxp * W_);
+  const size_t S = sw();                                               // complex: every amplitude array is [re W][im W]
+  std::vector<double> amp(S), alt((size_t)maxp * S);
   std::vector<HostMT> rng((size_t)W_);
   be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
   be_d2h(mt.data(), mt_, sizeof(uint32_t) * mt.size());
@@ -1473,25 +1491,31 @@ void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
     be_h2d(idx_perm_, perm_h.data(), sizeof(int32_t) * (size_t)nslots * W_ * 3);
     for (int s = 0; s < nslots; ++s) {
       const int32_t *ix = idx_perm_ + (size_t)s * W_ * 3;
-      tnn_trace_idx(r, c, orient, ix, ix + 1, ix + 2, 3, psi_alt_ + (size_t)s * W_);
+      tnn_trace_idx(r, c, orient, ix, ix + 1, ix + 2, 3, psi_alt_ + (size_t)s * S);
     }
-    be_d2h(alt.data(), psi_alt_, sizeof(double) * (size_t)nslots * W_);
+    be_d2h(alt.data(), psi_alt_, sizeof(double) * (size_t)nslots * S);
     bool any = false;
     for (int w = 0; w < W_; ++w) {
       const int np = (int)perms[(size_t)w].size();
       if (np == 0) continue;
-      std::vector<double> psis((size_t)np), wt((size_t)np);
+      std::vector<double> psis((size_t)np), psii((size_t)np, 0.0), wt((size_t)np);
       double mx = 0.0;
       for (int i = 0; i < np; ++i) {
-        psis[(size_t)i] = i == init[(size_t)w] ? amp[(size_t)w] : alt[(size_t)i * W_ + w];
-        mx = std::max(mx, std::fabs(psis[(size_t)i]));
+        const bool own = i == init[(size_t)w];
+        psis[(size_t)i] = own ? amp[(size_t)w] : alt[(size_t)i * S + w];
+        if (complex_) psii[(size_t)i] = own ? amp[(size_t)W_ + w] : alt[(size_t)i * S + W_ + w];
+        mx = std::max(mx, complex_ ? std::hypot(psis[(size_t)i], psii[(size_t)i]) : std::fabs(psis[(size_t)i]));
       }
-      for (int i = 0; i < np; ++i) { const double q = psis[(size_t)i] / mx; wt[(size_t)i] = q * q; }
+      for (int i = 0; i < np; ++i) {                                   // std::norm(psis[i] / psi_abs_max)
+        const double q = psis[(size_t)i] / mx, qi = psii[(size_t)i] / mx;
+        wt[(size_t)i] = complex_ ? q * q + qi * qi : q * q;
+      }
       const int fin = suwa_todo(init[(size_t)w], wt, rng[(size_t)w]);
       if (fin == init[(size_t)w]) continue;
       int32_t *cw = cfg.data() + (size_t)w * nsites_;
       for (int k = 0; k < 3; ++k) cw[st[k]] = perms[(size_t)w][(size_t)fin][(size_t)k];
       amp[(size_t)w] = psis[(size_t)fin];
+      if (complex_) amp[(size_t)W_ + w] = psii[(size_t)fin];
       ++accepted[(size_t)w];
       any = true;
     }
@@ -1558,19 +1582,19 @@ void Engine::energy_and_holes_tfim(bool calc_holes, double *eloc_host, double *p
   for (size_t i = 0; i < cfg.size(); ++i) flip[i] = 1 - cfg[i];
   if (!idx_flip_) idx_flip_ = (int32_t *)be_malloc(sizeof(int32_t) * flip.size());
   be_h2d(idx_flip_, flip.data(), sizeof(int32_t) * flip.size());
-  be_memset0(eloc_, sizeof(double) * W_);
+  be_memset0(eloc_, sizeof(double) * sw());
   int npsi = 0;
   generate_bmps_approach(UP);
   for (int row = 0; row < rows_; ++row) {
     init_bten(LEFT);
     grow_full_bten(RIGHT, row, 1, true);
     nn_trace(row, 0, row, 1, HORIZONTAL, row * cols_, row * cols_ + 1, psi_row_);
-    if (psi_list_host) be_d2h(psi_list_host + (size_t)npsi * W_, psi_row_, sizeof(double) * W_);
+    if (psi_list_host) be_d2h(psi_list_host + (size_t)npsi * sw(), psi_row_, sizeof(double) * sw());
     ++npsi;
     for (int col = 0; col < cols_; ++col) {
       if (calc_holes) punch_hole(row, col, HORIZONTAL);
       one_site_trace(row, col, idx_flip_ + row * cols_ + col, nsites_, psi_tmp_);      // :191-204
-      be_ratio_accumulate(psi_tmp_, psi_row_, -tfim_h_, eloc_, W_);
+      ratio_acc(psi_tmp_, psi_row_, -tfim_h_, eloc_);
       if (col < cols_ - 1) shift_bten_window(RIGHT);
     }
     if (row < rows_ - 1) shift_bmps_window(DOWN);
@@ -1590,12 +1614,11 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
   if (tfim_) { energy_and_holes_tfim(calc_holes, eloc_host, psi_list_host); return; }
   if (phys_ != 2) throw std::invalid_argument("the XXZ / J1-J2 energy solvers need phys = 2");
   // square_nnn_energy_solver.h:79-315 with has_nnn = false, model = SquareSpinOneHalfXXZModelMixIn
-  if (complex_ && (psi_list_host || rec_bonds_)) throw std::logic_error("psi lists / bond records are not available for complex states");
-  be_memset0(eloc_, sizeof(double) * W_ * (complex_ ? 2 : 1));
+  be_memset0(eloc_, sizeof(double) * sw());
   int npsi = 0;
-  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * W_);
+  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * sw());
   auto record_psi = [&]() {                            // kept on the device: ONE download at the end, no sync per row
-    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * W_, psi_row_, sizeof(double) * W_);
+    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * sw(), psi_row_, sizeof(double) * sw());
     ++npsi;
   };
   generate_bmps_approach(UP);
@@ -1642,7 +1665,7 @@ void Engine::energy_and_holes(bool calc_holes, double *eloc_host, double *psi_li
     if (col < cols_ - 1) shift_bmps_window(RIGHT);
   }
   be_xxz_onsite_energy(cfg_, nsites_, h00_, eloc_, W_);
-  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * W_);
+  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * sw());
   if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
 }
 
@@ -1698,22 +1721,22 @@ void Engine::clear_model_terms() {
 // The traversal of SquareNNNModelEnergySolver (square_nnn_energy_solver.h:79-315, bond_traversal_mixin.h:112-143) with every
 // term evaluated from its table: diagonal element + one replacement trace per target slot, masked per walker.
 void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double *psi_list_host) {
-  be_memset0(eloc_, sizeof(double) * W_);
+  be_memset0(eloc_, sizeof(double) * sw());
   int npsi = 0;
-  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * W_);
+  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * sw());
   auto record_psi = [&]() {
-    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * W_, psi_row_, sizeof(double) * W_);
+    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * sw(), psi_row_, sizeof(double) * sw());
     ++npsi;
   };
   const TermTable &nn = term_[0], &nnn = term_[1], &on = term_[2];
   // one term on (s1, s2): trace(idx_a, idx_b, out) evaluates the amplitude with the replacement physical indices
   auto term = [&](const TermTable &tt, int s1, int s2, auto &&trace) {
-    if (tt.T == 0) { be_term_accumulate(cfg_, nsites_, s1, s2, phys_, tt.diag, nullptr, nullptr, psi_row_, eloc_, W_); return; }
+    if (tt.T == 0) { term_acc(s1, s2, tt.diag, nullptr, nullptr, psi_row_, eloc_); return; }
     for (int t = 0; t < tt.T; ++t) {
       be_term_targets(cfg_, nsites_, s1, s2, phys_, tt.target, tt.coef, tt.T, t, term_ia_, s2 >= 0 ? term_ib_ : nullptr, term_cw_, W_);
       if (s2 >= 0) if (const double *jr = jastrow_for(s1, s2)) be_scale(term_cw_, jr, W_);
       trace(term_ia_, term_ib_, psi_tmp_);
-      be_term_accumulate(cfg_, nsites_, s1, s2, phys_, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_row_, eloc_, W_);
+      term_acc(s1, s2, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_row_, eloc_);
     }
   };
   generate_bmps_approach(UP);
@@ -1766,7 +1789,7 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
     }
     if (col < cols_ - 1) shift_bmps_window(RIGHT);
   }
-  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * W_);
+  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * sw());
   if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
 }
 
@@ -1779,9 +1802,13 @@ void Engine::bond_energy(int s1, int s2, const double *psi_ex, const double *psi
 }
 void Engine::set_complex() {
   if (complex_) return;
-  if (fermion_ || tables_on_ || tfim_ || jastrow_on_ || updater_ != 0 || scheme_ != 0 || tps_loaded_)
-    throw std::logic_error("set_complex: call right after construction (XXZ / J1-J2 models, NN exchange updater, SVD compression)");
+  if (fermion_ || scheme_ != 0 || tps_loaded_ || sr_on_)
+    throw std::logic_error("set_complex: call right after construction, before set_fermion / set_tps (SVD compression only)");
   be_sync();
+  // per-walker scalar buffers allocated lazily so far are real-sized: drop them, they come back as planes
+  be_free(psi_alt_); psi_alt_ = nullptr; psi_alt_slots_ = 0;
+  be_free(psi_list_d_); psi_list_d_ = nullptr;
+  be_free(bond_rec_); bond_rec_ = nullptr;
   auto grow = [&](double *&p, size_t n) { be_free(p); p = (double *)be_malloc(sizeof(double) * 2 * n); be_memset0(p, sizeof(double) * 2 * n); };
   grow(tps_, (size_t)tps_total_); gtps_ = tps_;
   grow(osum_, (size_t)tps_total_); grow(eosum_, (size_t)tps_total_);
@@ -1805,6 +1832,7 @@ void Engine::set_tps_c(const double *re, const double *im) {
   be_h2d(tps_, re, sizeof(double) * tps_total_);
   be_h2d(tps_ + tps_total_, im, sizeof(double) * tps_total_);
   tps_loaded_ = true;
+  if (fermion_) { dress_plane(re, gtps_); dress_plane(im, gtps_ + gtps_total_); }
   touch_all();
 }
 void Engine::get_planar(int what, double *re, double *im) {
@@ -1826,7 +1854,6 @@ void Engine::get_planar(int what, double *re, double *im) {
 void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
   if (!phys_par || !leg_par) throw std::invalid_argument("set_fermion: null table");
   if (fermion_) throw std::logic_error("set_fermion: already in fermion mode");
-  require_real("the fermion mode");
   if (tables_on_) throw std::logic_error("set_fermion: call it before set_model_term");
   for (int p = 0; p < phys_; ++p)
     if (phys_par[p] != 0 && phys_par[p] != 1) throw std::invalid_argument("set_fermion: parities must be 0 or 1");
@@ -1859,8 +1886,10 @@ void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
   if (const char *e = std::getenv("PEPS_Z2_SECTORS")) la_.z2_sectors = std::atoi(e) != 0;
   gtps_off_h_.resize((size_t)nsites_);
   for (int s = 0; s < nsites_; ++s) gtps_off_h_[(size_t)s] = tps_off_h_[(size_t)s] * FERMION_VARIANTS;
-  gtps_ = (double *)be_malloc(sizeof(double) * (size_t)tps_total_ * FERMION_VARIANTS);
-  be_memset0(gtps_, sizeof(double) * (size_t)tps_total_ * FERMION_VARIANTS);
+  gtps_total_ = tps_total_ * FERMION_VARIANTS;
+  gtps_ = (double *)be_malloc(sizeof(double) * (size_t)gtps_total_ * (complex_ ? 2 : 1));
+  be_memset0(gtps_, sizeof(double) * (size_t)gtps_total_ * (complex_ ? 2 : 1));
+  if (complex_) la_.z2_sectors = false;               // the sector labels are those of Theta, not of its real embedding
   std::vector<int64_t> o64(gtps_off_h_.begin(), gtps_off_h_.end());
   gtps_off_d_ = (int64_t *)be_malloc(sizeof(int64_t) * nsites_);
   be_h2d(gtps_off_d_, o64.data(), sizeof(int64_t) * nsites_);
@@ -1870,7 +1899,7 @@ void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
   }
   phys_par_d_ = (int32_t *)be_malloc(sizeof(int32_t) * phys_);
   be_h2d(phys_par_d_, phys_par_h_.data(), sizeof(int32_t) * phys_);
-  psi_loc_ = (double *)be_malloc(sizeof(double) * W_);
+  psi_loc_ = (double *)be_malloc(sizeof(double) * sw());
   if (!term_ia_) {
     term_ia_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
     term_ib_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
@@ -1897,9 +1926,10 @@ void Engine::set_fermion(const int32_t *phys_par, const int32_t *leg_par) {
   refresh_gather();
   touch_all();
   if (tps_loaded_) {                                    // a state uploaded before the switch: dress it now
-    std::vector<double> h((size_t)tps_total_);
-    get_tps(h.data());
-    set_tps(h.data());
+    std::vector<double> h((size_t)tps_total_ * (complex_ ? 2 : 1));
+    be_d2h(h.data(), tps_, sizeof(double) * h.size());
+    if (complex_) set_tps_c(h.data(), h.data() + tps_total_);
+    else set_tps(h.data());
   }
 }
 void Engine::set_jastrow(const double *v, const int32_t *density) {
@@ -1933,7 +1963,7 @@ void Engine::sweep_fermion(int nsweeps) {
         const int s1 = row * cols_ + col, s2 = s1 + 1;
         be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], 0, nullptr, nullptr, 0, 0, term_ia_, term_ib_, term_cw_, W_);
         nn_trace_idx(row, col, row, col + 1, HORIZONTAL, term_ia_, term_ib_, 1, psi_tmp_);
-        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
+        exchange_decide(s1, s2, psi_tmp_, jastrow_for(s1, s2));
         refresh_gather();
         touch_site(s1); touch_site(s2);
         if (col < cols_ - 2) shift_bten_window(RIGHT);
@@ -1950,7 +1980,7 @@ void Engine::sweep_fermion(int nsweeps) {
         const int s1 = row * cols_ + col, s2 = s1 + cols_;
         be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], 1, nullptr, nullptr, 0, 0, term_ia_, term_ib_, term_cw_, W_);
         nn_trace_idx(row, col, row + 1, col, VERTICAL, term_ia_, term_ib_, 1, psi_tmp_);
-        be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_tmp_, amp_, mt_, mtidx_, accepted_, W_, jastrow_for(s1, s2));
+        exchange_decide(s1, s2, psi_tmp_, jastrow_for(s1, s2));
         refresh_gather();
         touch_site(s1); touch_site(s2);
         if (row < rows_ - 2) shift_bten_window(DOWN);
@@ -1964,21 +1994,21 @@ void Engine::sweep_fermion(int nsweeps) {
 // bond by Trace (NN) and once per plaquette by ReplaceNNNSiteTrace with the original tensors (NNN), so that psi_ex / psi
 // runs along one contraction path; the terms come from the model tables (SquareSpinlessFermion, SquaretJ*Model as data).
 void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double *psi_list_host) {
-  be_memset0(eloc_, sizeof(double) * W_);
+  be_memset0(eloc_, sizeof(double) * sw());
   int npsi = 0;
-  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * W_);
+  if (psi_list_host && !psi_list_d_) psi_list_d_ = (double *)be_malloc(sizeof(double) * (size_t)(rows_ + cols_) * sw());
   auto record_psi = [&](const double *psi) {
-    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * W_, psi, sizeof(double) * W_);
+    if (psi_list_host) be_d2d(psi_list_d_ + (size_t)npsi * sw(), psi, sizeof(double) * sw());
     ++npsi;
   };
   const TermTable &nn = term_[0], &nnn = term_[1], &on = term_[2];
   auto term = [&](const TermTable &tt, int s1, int s2, int kind, double *dst, auto &&trace) {
-    if (tt.T == 0) { be_term_accumulate(cfg_, nsites_, s1, s2, phys_, tt.diag, nullptr, nullptr, psi_loc_, dst, W_); return; }
+    if (tt.T == 0) { term_acc(s1, s2, tt.diag, nullptr, nullptr, psi_loc_, dst); return; }
     for (int t = 0; t < tt.T; ++t) {
       be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], kind, tt.target, tt.coef, tt.T, t, term_ia_, term_ib_, term_cw_, W_);
       if (const double *jr = jastrow_for(s1, s2)) be_scale(term_cw_, jr, W_);
       trace(term_ia_, term_ib_, psi_tmp_);
-      be_term_accumulate(cfg_, nsites_, s1, s2, phys_, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_loc_, dst, W_);
+      term_acc(s1, s2, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_loc_, dst);
     }
   };
   generate_bmps_approach(UP);
@@ -1988,7 +2018,7 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
     for (int col = 0; col < cols_; ++col) {
       if (calc_holes) punch_hole(row, col, HORIZONTAL);
       const int s1 = row * cols_ + col;
-      if (on.set) be_term_accumulate(cfg_, nsites_, s1, -1, phys_, on.diag, nullptr, nullptr, psi_loc_, eloc_, W_);
+      if (on.set) term_acc(s1, -1, on.diag, nullptr, nullptr, psi_loc_, eloc_);
       if (col < cols_ - 1) {
         if (nn.set) {
           nn_trace(row, col, row, col + 1, HORIZONTAL, s1, s1 + 1, psi_loc_);       // Trace(tn, site1, site2, orient)
@@ -2020,9 +2050,14 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
     }
     if (row < rows_ - 1) shift_bmps_window(DOWN);
   }
-  if (calc_holes)
-    be_fermion_finish_holes(holes_, hole_stride_, hole_off_d_, site_size_d_, gtps_, gtps_off_d_, gidx_[HORIZONTAL], jw_[HORIZONTAL],
-                            nsites_, fsign_, amp_, W_);
+  if (calc_holes) {
+    if (complex_)
+      be_fermion_finish_holes_c(holes_, holes_ + (long)W_ * hole_stride_, hole_stride_, hole_off_d_, site_size_d_, gtps_, gtps_total_,
+                                gtps_off_d_, gidx_[HORIZONTAL], jw_[HORIZONTAL], nsites_, fsign_, amp_, amp_ + W_, W_);
+    else
+      be_fermion_finish_holes(holes_, hole_stride_, hole_off_d_, site_size_d_, gtps_, gtps_off_d_, gidx_[HORIZONTAL], jw_[HORIZONTAL],
+                              nsites_, fsign_, amp_, W_);
+  }
   generate_bmps_approach(LEFT);
   for (int col = 0; col < cols_; ++col) {
     init_bten(UP);
@@ -2040,7 +2075,7 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
     }
     if (col < cols_ - 1) shift_bmps_window(RIGHT);
   }
-  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * W_);
+  if (psi_list_host) be_d2h(psi_list_host, psi_list_d_, sizeof(double) * (size_t)npsi * sw());
   if (eloc_host) be_d2h(eloc_host, eloc_, sizeof(double) * W_);
 }
 
@@ -2049,7 +2084,7 @@ double *Engine::bond_target(int kind, int row, int col) {
   const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1);
   const int idx = kind == 0 ? row * (cols_ - 1) + col : kind == 1 ? nh + row * cols_ + col
                 : kind == 2 ? nh + nv + row * (cols_ - 1) + col : nh + nv + nd + row * (cols_ - 1) + col;
-  return bond_rec_ + (size_t)idx * W_;
+  return bond_rec_ + (size_t)idx * sw();
 }
 void Engine::upload_flipped_configs() {
   std::vector<int32_t> cfg((size_t)W_ * nsites_);
@@ -2064,7 +2099,7 @@ void Engine::upload_flipped_configs() {
 void Engine::row_corr_hook(int row) {
   const int c1 = cols_ / 4, s1 = row * cols_ + c1, nc = cols_ / 2;
   const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1);
-  double *corr = bond_rec_ + (size_t)(nh + nv + 2 * nd) * W_;
+  double *corr = bond_rec_ + (size_t)(nh + nv + 2 * nd) * sw();
   auto truncate_left = [&]() {                                   // EraseEnvsAfterUpdate on the BTen stacks (:556-560)
     while ((int)bten_[LEFT].size() > c1 + 1) { release(bten_[LEFT].back()); bten_[LEFT].pop_back(); }
     while ((int)bten_[RIGHT].size() > cols_ - c1) { release(bten_[RIGHT].back()); bten_[RIGHT].pop_back(); }
@@ -2076,7 +2111,7 @@ void Engine::row_corr_hook(int row) {
   for (int i = 1; i <= nc; ++i) {
     const int c2 = c1 + i, s2 = row * cols_ + c2;
     one_site_trace(row, c2, idx_flip_ + s2, nsites_, psi_tmp_);
-    be_ratio_accumulate(psi_tmp_, psi_row_, 1.0, corr + (size_t)(i - 1) * W_, W_);
+    ratio_acc(psi_tmp_, psi_row_, 1.0, corr + (size_t)(i - 1) * sw());
     shift_bten_window(RIGHT);
   }
   override_site_ = -1;
@@ -2088,43 +2123,51 @@ void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, dou
   if (!fermion_ && phys_ != 2) throw std::invalid_argument("measure: spin-1/2 observables need phys = 2");
   const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1), ncr = cols_ / 2;
   const int nb = nh + nv + 2 * nd;
-  if (!bond_rec_) bond_rec_ = (double *)be_malloc(sizeof(double) * (size_t)(nb + ncr) * W_);
-  be_memset0(bond_rec_, sizeof(double) * (size_t)(nb + ncr) * W_);
+  const size_t S = sw();
+  const int np = complex_ ? 2 : 1;        // complex context: every output array is planar, its real block then its imaginary block
+  if (!bond_rec_) bond_rec_ = (double *)be_malloc(sizeof(double) * (size_t)(nb + ncr) * S);
+  be_memset0(bond_rec_, sizeof(double) * (size_t)(nb + ncr) * S);
   if (!fermion_) upload_flipped_configs();
   rec_bonds_ = true;
-  std::vector<double> onsite((size_t)W_);
   try {
-    energy_and_holes(false, onsite.data(), nullptr);      // with recording on, eloc_ only receives the on-site term
+    energy_and_holes(false, nullptr, nullptr);            // with recording on, eloc_ only receives the on-site term
   } catch (...) { rec_bonds_ = false; override_site_ = -1; throw; }
   rec_bonds_ = false;
-  std::vector<double> rec((size_t)(nb + ncr) * W_);
+  std::vector<double> onsite(S);
+  be_d2h(onsite.data(), eloc_, sizeof(double) * S);
+  std::vector<double> rec((size_t)(nb + ncr) * S);
   be_d2h(rec.data(), bond_rec_, sizeof(double) * rec.size());
   auto scatter = [&](double *dst, int first, int count) {
     if (!dst) return;
-    for (int w = 0; w < W_; ++w)
-      for (int i = 0; i < count; ++i) dst[(size_t)w * count + i] = rec[(size_t)(first + i) * W_ + w];
+    for (int pl = 0; pl < np; ++pl)
+      for (int w = 0; w < W_; ++w)
+        for (int i = 0; i < count; ++i)
+          dst[(size_t)pl * W_ * count + (size_t)w * count + i] = rec[(size_t)(first + i) * S + (size_t)pl * W_ + w];
   };
   scatter(e_h, 0, nh); scatter(e_v, nh, nv); scatter(e_dr, nh + nv, nd); scatter(e_ur, nh + nv + nd, nd);
   if (row_corr) {
     std::vector<int32_t> cfg((size_t)W_ * nsites_);
     be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
     const int row = rows_ / 2, c1 = cols_ / 4;
-    for (int w = 0; w < W_; ++w)
-      for (int i = 0; i < ncr; ++i) {
-        const int32_t *c = cfg.data() + (size_t)w * nsites_;
-        const bool equal = c[row * cols_ + c1] == c[row * cols_ + c1 + i + 1];
-        row_corr[(size_t)w * ncr + i] = (equal || fermion_) ? 0.0 : rec[(size_t)(nb + i) * W_ + w];
-      }
+    for (int pl = 0; pl < np; ++pl)
+      for (int w = 0; w < W_; ++w)
+        for (int i = 0; i < ncr; ++i) {
+          const int32_t *c = cfg.data() + (size_t)w * nsites_;
+          const bool equal = c[row * cols_ + c1] == c[row * cols_ + c1 + i + 1];
+          row_corr[(size_t)pl * W_ * ncr + (size_t)w * ncr + i] = (equal || fermion_) ? 0.0 : rec[(size_t)(nb + i) * S + (size_t)pl * W_ + w];
+        }
   }
   if (energy)
-    for (int w = 0; w < W_; ++w) {
-      double e = 0.0;
-      for (int i = 0; i < nb; ++i) e += rec[(size_t)i * W_ + w];
-      energy[w] = e + onsite[(size_t)w];
-    }
+    for (int pl = 0; pl < np; ++pl)
+      for (int w = 0; w < W_; ++w) {
+        double e = 0.0;
+        for (int i = 0; i < nb; ++i) e += rec[(size_t)i * S + (size_t)pl * W_ + w];
+        energy[(size_t)pl * W_ + w] = e + onsite[(size_t)pl * W_ + w];
+      }
 }
 void Engine::measure_structure_factor(double *out_host) {
   require_boson("the structure-factor measurement");
+  require_real("the structure-factor measurement");
   if (phys_ != 2) throw std::invalid_argument("measure_structure_factor: S+ S- correlators are defined for spin-1/2 (phys = 2)");
   ensure_idx_const();
   const int32_t *up_idx = idx_const_ + (size_t)1 * W_, *dn_idx = idx_const_;     // spin-up / spin-down slices for every walker

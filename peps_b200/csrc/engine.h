@@ -63,6 +63,7 @@ class Engine {
   // compression, 1 = two-site, 2 = one-site variational; the batch iterates until EVERY walker meets convergence_tol
   void set_compress_scheme(int scheme, double tol, int max_iter) {
     if (scheme < 0 || scheme > 2 || max_iter < 1) throw std::invalid_argument("set_compress_scheme: scheme in {0,1,2}, max_iter >= 1");
+    if (scheme != 0) require_real("variational compression");
     scheme_ = scheme; var_tol_ = tol; var_iter_ = max_iter; touch_all();
   }
   void set_jacobi(double tol, int inner, int max_sweeps) {
@@ -165,6 +166,7 @@ class Engine {
   void set_complex();
   bool is_complex() const { return complex_; }
   void set_tps_c(const double *re, const double *im);
+  void dress_plane(const double *host, double *dst);
   void get_planar(int what, double *re, double *im);   // 0 amplitudes, 1 eloc, 2 holes, 3 osum, 4 eosum
   // Jastrow-dressed wave function psi(S) = psi_PEPS(S) exp(sum_{i<j} v_ij n_i n_j) (TPSWaveFunctionComponent<..., JastrowDress>,
   // vmc_basic/wave_function_component.h:107-135, vmc_basic/jastrow_factor.h): v = [nsites][nsites] symmetric (diagonal ignored),
@@ -248,6 +250,22 @@ class Engine {
   bool fermion_ = false, tps_loaded_ = false;
   bool complex_ = false;
   double *imag(const BT &t) const { return t.p + (long)W_ * t.n; }
+  // doubles of one per-walker scalar array ([W], or the two planes [2][W] of a complex context)
+  size_t sw() const { return (size_t)W_ * (complex_ ? 2 : 1); }
+  // eloc-style accumulations on real arrays or planes: dst += coef * conj(psi_ex / psi)  /  the table term of be_term_accumulate
+  void ratio_acc(const double *psi_ex, const double *psi, double coef, double *dst) {
+    if (complex_) be_ratio_accumulate_c(psi_ex, psi_ex + W_, psi, psi + W_, coef, dst, dst + W_, W_);
+    else be_ratio_accumulate(psi_ex, psi, coef, dst, W_);
+  }
+  void term_acc(int s1, int s2, const double *diag, const double *coefw, const double *psi_ex, const double *psi, double *dst) {
+    if (complex_)
+      be_term_accumulate_c(cfg_, nsites_, s1, s2, phys_, diag, coefw, psi_ex, psi_ex ? psi_ex + W_ : nullptr, psi, psi + W_, dst, dst + W_, W_);
+    else be_term_accumulate(cfg_, nsites_, s1, s2, phys_, diag, coefw, psi_ex, psi, dst, W_);
+  }
+  void exchange_decide(int s1, int s2, const double *psi_b, const double *jastrow) {
+    if (complex_) be_nn_exchange_decide_c(cfg_, nsites_, s1, s2, psi_b, psi_b + W_, amp_, amp_ + W_, mt_, mtidx_, accepted_, W_, jastrow);
+    else be_nn_exchange_decide(cfg_, nsites_, s1, s2, psi_b, amp_, mt_, mtidx_, accepted_, W_, jastrow);
+  }
   void require_real(const char *what) const {
     if (complex_) throw std::logic_error(std::string(what) + " is not available for complex states");
   }
@@ -267,6 +285,7 @@ class Engine {
   void mode_for_bmps(int pos) const { gmode_ = (pos == UP || pos == DOWN) ? HORIZONTAL : VERTICAL; }
   void mode_for_bten(int pos) const { gmode_ = (pos == LEFT || pos == RIGHT) ? HORIZONTAL : VERTICAL; }
   double *gtps_ = nullptr;                // gathered TPS: == tps_ for bosons; FERMION_VARIANTS * phys dressed slices per site
+  long gtps_total_ = 0;                   // doubles of one plane of gtps_ (complex: the im plane follows the re plane)
   std::vector<long> gtps_off_h_;
   int64_t *gtps_off_d_ = nullptr;
   int32_t *gidx_[2] = {nullptr, nullptr}; // [W][nsites] gather index per machinery (fermion mode)
@@ -342,7 +361,7 @@ class Engine {
     if (slots <= psi_alt_slots_) return;
     be_sync();
     be_free(psi_alt_);
-    psi_alt_ = (double *)be_malloc(sizeof(double) * (size_t)slots * W_);
+    psi_alt_ = (double *)be_malloc(sizeof(double) * (size_t)slots * sw());
     psi_alt_slots_ = slots;
   }
   Pool pool_;

@@ -643,14 +643,15 @@ void be_complex_combine(const double *d0, const double *d1, const double *d2, co
   for (int w = 0; w < W; ++w) { outr[w] = d0[w] - d1[w]; outi[w] = d2[w] + d3[w]; }
 }
 void be_nn_exchange_decide_c(int32_t *cfg, int nsites, int s1, int s2, const double *pbr, const double *pbi, double *ampr,
-                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W) {
+                             double *ampi, uint32_t *mt, int32_t *idx, int32_t *accepted, int W, const double *jastrow) {
   ++g_launches;
   for (int w = 0; w < W; ++w) {
     int32_t *c = cfg + (long)w * nsites;
     const int c1 = c[s1], c2 = c[s2];
     if (c1 == c2) continue;
-    const double ab = std::hypot(pbr[w], pbi[w]), aa = std::hypot(ampr[w], ampi[w]);
-    bool ok = ab >= aa;
+    const double j = jastrow ? jastrow[w] : 1.0;
+    const double ab = jastrow ? std::hypot(pbr[w] * j, pbi[w] * j) : std::hypot(pbr[w], pbi[w]), aa = std::hypot(ampr[w], ampi[w]);
+    bool ok = jastrow ? ab / aa >= 1.0 : ab >= aa;
     if (!ok) {
       const double div = ab / aa, P = div * div;
       uint32_t x0 = mt_next(mt + (long)w * 624, idx[w]);
@@ -673,6 +674,54 @@ void be_xxz_bond_energy_c(const int32_t *cfg, int nsites, int s1, int s2, const 
     er[w] += -0.25 * jz + rr * 0.5 * jxy;
     ei[w] += -ri * 0.5 * jxy;
   }
+}
+void be_ratio_accumulate_c(const double *exr, const double *exi, const double *pr, const double *pi, double coef, double *er,
+                           double *ei, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const double d = pr[w] * pr[w] + pi[w] * pi[w];
+    const double rr = (exr[w] * pr[w] + exi[w] * pi[w]) / d, ri = (exi[w] * pr[w] - exr[w] * pi[w]) / d;
+    er[w] += coef * rr;
+    ei[w] += -coef * ri;
+  }
+}
+void be_term_accumulate_c(const int32_t *cfg, int nsites, int s1, int s2, int phys, const double *diag, const double *coefw,
+                          const double *exr, const double *exi, const double *pr, const double *pi, double *er, double *ei, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const int32_t *c = cfg + (long)w * nsites;
+    const int p = s2 >= 0 ? c[s1] * phys + c[s2] : c[s1];
+    double e_r = diag ? diag[p] : 0.0, e_i = 0.0;
+    if (coefw && coefw[w] != 0.0) {
+      const double d = pr[w] * pr[w] + pi[w] * pi[w];
+      const double rr = (exr[w] * pr[w] + exi[w] * pi[w]) / d, ri = (exi[w] * pr[w] - exr[w] * pi[w]) / d;
+      e_r += coefw[w] * rr;
+      e_i -= coefw[w] * ri;
+    }
+    er[w] += e_r;
+    ei[w] += e_i;
+  }
+}
+void be_fermion_finish_holes_c(double *hr, double *hi, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
+                               const double *gtps, long gtps_im_off, const int64_t *gtps_off, const int32_t *gidx_h,
+                               const int32_t *jw_h, int nsites, const double *sign, const double *ampr, const double *ampi, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w)
+    for (int site = 0; site < nsites; ++site) {
+      const int sz = site_size[site];
+      double *a = hr + (long)w * hole_stride + hole_off[site], *b = hi + (long)w * hole_stride + hole_off[site];
+      const double *tr = gtps + gtps_off[site] + (long)gidx_h[(long)w * nsites + site] * sz, *ti = tr + gtps_im_off;
+      double pr = 0.0, pi = 0.0;
+      for (int e = 0; e < sz; ++e) { pr += a[e] * tr[e] - b[e] * ti[e]; pi += a[e] * ti[e] + b[e] * tr[e]; }
+      const double d = pr * pr + pi * pi;
+      const double fr = (ampr[w] * pr + ampi[w] * pi) / d, fi = (ampi[w] * pr - ampr[w] * pi) / d;
+      const double *sg = sign + (long)jw_h[(long)w * nsites + site] * hole_stride + hole_off[site];
+      for (int e = 0; e < sz; ++e) {
+        const double x = a[e] * sg[e], y = b[e] * sg[e];
+        a[e] = x * fr - y * fi;
+        b[e] = x * fi + y * fr;
+      }
+    }
 }
 void be_accumulate_ostar_c(const double *hr, const double *hi, long hole_stride, const int32_t *hole_off, const int32_t *site_size,
                            const int32_t *tps_off, const int32_t *cfg, int nsites, const double *ampr, const double *ampi,

@@ -274,13 +274,13 @@ def fermion_configs(rows, cols, W, phys, seed=10):
 
 
 def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", nsweeps=2, seed=3, tol=1e-10, seeds0=200,
-                                t2=0.6, check_holes=True, jastrow=False):
+                                t2=0.6, check_holes=True, jastrow=False, complex_=False):
     """Sweeps + E_loc + O* of W walkers through the C ABI in fermion mode vs oracle/fermion.py, walker by walker:
     configurations and acceptance counts bit-identical, |amplitudes|, E_loc, O* to `tol` (relative)."""
     from oracle import fermion as F
     from peps_b200.api import FermionSplitIndexTPS, TableModel
     phys_par = (1, 0) if model == "spinless" else (1, 1, 0)
-    f = F.FermionTPS.random(rows, cols, D, seed, phys_par=phys_par)
+    f = F.FermionTPS.random(rows, cols, D, seed, phys_par=phys_par, complex_=complex_)
     ftps = FermionSplitIndexTPS(f.T, f.par, phys_par)
     if model == "spinless":
         omodel = F.SpinlessFermionModel(1.0, t2, 0.3)
@@ -291,6 +291,8 @@ def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", 
     cfgs = fermion_configs(rows, cols, W, len(phys_par))
     tr = BMPSTruncateParams.SVD(*trunc)
     b = WalkerBatch(rows, cols, len(phys_par), D, W, tr, lib=lib)
+    if complex_:
+        b.set_complex()
     b.set_fermion(ftps)
     b.set_tps(ftps)
     b.set_model(tmodel)
@@ -308,7 +310,8 @@ def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", 
     b.init_walkers()
     ws = [F.FermionWalker(f, cfgs[w], trunc) for w in range(W)]
     ups = [F.FermionNNExchangeUpdater(seeds0 + w, jastrow=jas) for w in range(W)]
-    a0 = np.abs(b.amplitudes())
+    amps = b.amplitudes_c if complex_ else b.amplitudes
+    a0 = np.abs(amps())
     r0 = np.abs(np.array([w_.amplitude for w_ in ws]))
     assert np.max(np.abs(a0 / r0 - 1)) < tol
     worst = dict(amp=0.0, eloc=0.0, ostar=0.0)
@@ -319,17 +322,17 @@ def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", 
         for w in range(W):
             assert np.array_equal(c[w], ws[w].config), (it, w)
         assert np.array_equal(acc, racc), (acc, racc)
-        amp = b.amplitudes()
+        amp = amps()
         ramp = np.array([w_.amplitude for w_ in ws])
         worst["amp"] = max(worst["amp"], float(np.max(np.abs(np.abs(amp) / np.abs(ramp) - 1))))
         e = b.energy_and_holes(check_holes)
-        holes = b.holes() if check_holes else None
+        holes = (b.holes_c() if complex_ else b.holes()) if check_holes else None
         for w in range(W):
             re, rost, _ = omodel.energy_and_holes(ws[w], check_holes)
             worst["eloc"] = max(worst["eloc"], abs(e[w] - re) / max(1.0, abs(re)))
             if check_holes:
                 ref = np.concatenate([rost[r][c_].ravel() for r in range(rows) for c_ in range(cols)])
-                got = holes[w] / amp[w]                       # O* = finished hole / cached amplitude
+                got = np.conj(holes[w] / amp[w])              # O* = conj(finished hole / cached amplitude)
                 worst["ostar"] = max(worst["ostar"], float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
     assert worst["amp"] < tol and worst["eloc"] < tol and worst["ostar"] < tol, worst
     b.close()
@@ -379,10 +382,10 @@ def run_sector_truncation_case(lib, nr=160, nc=192, t=24, W=3, seed=4):
 # ---------------------------------------------------------------------------------------------------------------------
 # complex (QLTEN_Complex) states
 # ---------------------------------------------------------------------------------------------------------------------
-def complex_tps(rows, cols, D, seed):
+def complex_tps(rows, cols, D, seed, phys=2):
     """uniform [0,1) real parts and uniform [-0.5, 0.5) imaginary parts, NormalizeAllSite."""
     rng = np.random.default_rng(seed)
-    tps = vmc.random_tps(rows, cols, 2, D, seed=seed, dtype=np.complex128)
+    tps = vmc.random_tps(rows, cols, phys, D, seed=seed, dtype=np.complex128)
     for row in tps:
         for site in row:
             for s in range(len(site)):
@@ -390,24 +393,47 @@ def complex_tps(rows, cols, D, seed):
     return vmc.normalize_all_site(tps)
 
 
-def run_complex_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=6, tol=1e-10, seeds0=300, j2=0.0):
+def run_complex_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=6, tol=1e-10, seeds0=300, j2=0.0,
+                                tfim_h=None, three_site=False, table=None):
     """Sweeps + E_loc + holes + accumulators of W walkers on a COMPLEX state through the C ABI vs the oracle (which is
     pinned on the reference's complex goldens, K5): configurations and acceptance counts bit-identical, amplitudes,
-    E_loc = sum ... conj(psi_ex / psi), O* = conj(hole / psi), sum O* and sum conj(E_loc) O* to `tol` (relative)."""
-    tps = complex_tps(rows, cols, D, seed)
-    cfgs = np.stack([vmc.neel_config(rows, cols)] + [vmc.shuffled_half_filled_config(rows, cols, 20 + w) for w in range(1, W)])
-    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
+    E_loc = sum ... conj(psi_ex / psi), O* = conj(hole / psi), sum O* and sum conj(E_loc) O* to `tol` (relative).
+    tfim_h: transverse-field Ising + full-space (Suwa-Todo) updater; three_site: the 3-site exchange updater;
+    table = "xxz": the XXZ / J1-J2 model as tables (seam B2), "spin1": the phys = 3 table model of run_table_model_parity."""
+    phys = 3 if table == "spin1" else 2
+    tps = complex_tps(rows, cols, D, seed, phys)
+    if phys == 2:
+        cfgs = np.stack([vmc.neel_config(rows, cols)] + [vmc.shuffled_half_filled_config(rows, cols, 20 + w) for w in range(1, W)])
+    else:
+        cfgs = np.random.default_rng(seed).integers(0, 3, size=(W, rows, cols))
+    b = WalkerBatch(rows, cols, phys, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
     b.set_complex()
     b.set_tps(SplitIndexTPS(tps))
-    if j2 != 0.0:
-        from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
+    from peps_b200.api import (SquareSpinOneHalfJ1J2XXZModelOBC, TransverseFieldIsingSquareOBC, TableModel,
+                               MCUpdateSquareNNFullSpaceUpdate, MCUpdateSquareTNN3SiteExchange)
+    model = vmc.XXZModel(1.0, 1.0, 0.0, j2, j2)
+    ups = [vmc.NNExchangeUpdater(seeds0 + w) for w in range(W)]
+    if table == "xxz":
+        b.set_model(TableModel.xxz(1.0, 1.0, j2, j2))
+    elif table == "spin1":
+        h2, h2n, h1 = spin_one_matrices()
+        b.set_model(TableModel(3, h2, h2n, h1))
+        model = vmc.TableModel(3, h2, h2n, h1)
+    elif j2 != 0.0:
         b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 1.0, j2, j2, 0.0))
+    if tfim_h is not None:
+        b.set_model(TransverseFieldIsingSquareOBC(tfim_h))
+        model = vmc.TFIMModel(tfim_h)
+    if tfim_h is not None or table == "spin1":
+        b.set_updater(MCUpdateSquareNNFullSpaceUpdate())
+        ups = [vmc.NNFullSpaceUpdater(seeds0 + w) for w in range(W)]
+    if three_site:
+        b.set_updater(MCUpdateSquareTNN3SiteExchange())
+        ups = [vmc.TNN3SiteExchangeUpdater(seeds0 + w) for w in range(W)]
     b.set_configs(cfgs)
     b.seed_rng(np.arange(seeds0, seeds0 + W))
     b.init_walkers()
     ws = [vmc.Walker(tps, cfgs[w], trunc) for w in range(W)]
-    ups = [vmc.NNExchangeUpdater(seeds0 + w) for w in range(W)]
-    model = vmc.XXZModel(1.0, 1.0, 0.0, j2, j2)
     a0 = b.amplitudes_c()
     r0 = np.array([w_.amplitude for w_ in ws])
     assert np.max(np.abs(a0 / r0 - 1)) < tol, np.max(np.abs(a0 / r0 - 1))
@@ -426,13 +452,13 @@ def run_complex_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=6,
         amp = b.amplitudes_c()
         ramp = np.array([w_.amplitude for w_ in ws])
         worst["amp"] = max(worst["amp"], float(np.max(np.abs(amp / ramp - 1))))
-        b.energy_and_holes(True)
-        e = b.eloc_c()
+        e, psi = b.energy_and_holes(True, True)
         holes = b.holes_c()
         b.accumulate_ostar()
         for w in range(W):
-            re, rh, _ = model.energy_and_holes(tps, ws[w], True)
+            re, rh, pp = model.energy_and_holes(tps, ws[w], True)
             worst["eloc"] = max(worst["eloc"], abs(e[w] - re) / max(1.0, abs(re)))
+            worst["psi"] = max(worst.get("psi", 0.0), float(np.max(np.abs(psi[:len(pp), w] / np.array(pp) - 1))))
             ost_ref = flat_holes(rh, rows, cols) * np.conj(1.0 / ws[w].amplitude)          # inverse_amplitude * holes (:245-272)
             ost = np.conj(holes[w] / amp[w])
             worst["ostar"] = max(worst["ostar"], float(np.max(np.abs(ost - ost_ref)) / np.max(np.abs(ost_ref))))
@@ -443,7 +469,7 @@ def run_complex_pipeline_parity(lib, rows, cols, D, W, trunc, nsweeps=2, seed=6,
                     s_ = int(ws[w].config[r, cc])
                     osum[off + s_ * sz: off + (s_ + 1) * sz] += ost_ref[hoff:hoff + sz]
                     eosum[off + s_ * sz: off + (s_ + 1) * sz] += np.conj(re) * ost_ref[hoff:hoff + sz]
-                    off += 2 * sz
+                    off += phys * sz
                     hoff += sz
     go, geo = b.accumulators_c()
     worst["acc"] = max(float(np.max(np.abs(go - osum)) / np.max(np.abs(osum))), float(np.max(np.abs(geo - eosum)) / np.max(np.abs(eosum))))
@@ -500,4 +526,61 @@ def run_complex_k5_golden(lib):
                 probe = probe + np.sum(np.conj(t) * (t * base))
                 off += sz
     assert abs(probe.real / float(z["exp_grad_probe_re"]) - 1) < 1e-5 and abs(probe.imag / float(z["exp_grad_probe_im"]) - 1) < 1e-5
+    b.close()
+
+
+def run_complex_k8_goldens(lib):
+    """K8 in QLTEN_Complex through the C ABI: exact summation with device amplitudes / E_loc over the reference's complex fZ2
+    fixtures (tests/test_algorithm/test_exact_summation_evaluator.cpp:137-151, 353-425, 807): the spinless-fermion energies
+    for t2 = 2.1 / 0 / -2.5 (simple-update and lowest states) and the t-J energy."""
+    from test_fermion_oracle import load_golden, perms
+    from peps_b200.api import FermionSplitIndexTPS, TableModel
+    out = {}
+    cases = [(f"sf2x2_t2_{t2:+.1f}_complex_{kind}", TableModel.spinless_fermion(1.0, t2, 0.0), [0, 0, 1, 1], (8, 8, 1e-16))
+             for t2 in (2.1, 0.0, -2.5) for kind in ("su", "lowest")]
+    cases += [(f"tj2x2_complex_{kind}", TableModel.tj(1.0, 0.3, V=0.3 / 4, mu=0.0), [0, 1, 2, 2], (4, 4, 0.0)) for kind in ("su", "lowest")]
+    for name, model, occ, trunc in cases:
+        f, z = load_golden(name)
+        cfgs = np.stack(perms(occ, 2, 2))
+        ftps = FermionSplitIndexTPS(f.T, f.par, f.phys_par)
+        assert np.iscomplexobj(ftps.t[0][0][0])
+        b = WalkerBatch(2, 2, len(f.phys_par), ftps.bond_dim(), len(cfgs), BMPSTruncateParams.SVD(*trunc), lib=lib)
+        b.set_complex()
+        b.set_fermion(ftps)
+        b.set_tps(ftps)
+        b.set_model(model)
+        b.set_configs(cfgs)
+        b.init_walkers()
+        e = b.energy_and_holes(False)
+        w = np.abs(b.amplitudes_c()) ** 2
+        energy = np.sum(w * e) / np.sum(w)
+        out[name] = energy
+        tol = float(z["exp_energy_tol"])                      # the reference test's own tolerance for this fixture
+        assert abs(energy.real - float(z["exp_energy"])) < tol and abs(energy.imag) < tol, (name, energy, float(z["exp_energy"]))
+        b.close()
+    return out
+
+
+def run_complex_measure_parity(lib, j2=0.5, fermion=False):
+    """EvaluateObservables on a complex state: every (complex) bond energy, the row correlator channels and the energy
+    against the oracle; the arrays cross the ABI as planes."""
+    rows, cols, D, W = 3, 4, 2, 3
+    from peps_b200.api import SquareSpinOneHalfJ1J2XXZModelOBC
+    tps = complex_tps(rows, cols, D, 31)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 70 + w) for w in range(W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+    b.set_complex()
+    b.set_tps(SplitIndexTPS(tps))
+    b.set_configs(cfgs)
+    b.set_model(SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 0.8, j2, 0.7 * j2, 0.3))
+    b.init_walkers()
+    obs = b.measure()
+    model = vmc.XXZModel(1.0, 0.8, 0.3, j2, 0.7 * j2)
+    for w in range(W):
+        ref = model.measure(tps, vmc.Walker(tps, cfgs[w], (4, 4, 0.0)))
+        for k, v in ref.items():
+            assert np.allclose(obs[k][w], v, rtol=1e-10, atol=1e-12), (k, w)
+    assert np.max(np.abs(obs["bond_energy_h"].imag)) > 1e-3                # genuinely complex records
+    e = b.energy_and_holes(False)
+    assert np.allclose(e, obs["energy"], rtol=1e-12)
     b.close()

@@ -36,8 +36,15 @@ def test_complex_mode_guards(lib):
     from peps_b200.api import BMPSTruncateParams, WalkerBatch, PepsError, TableModel, FermionSplitIndexTPS
     b = WalkerBatch(3, 3, 2, 2, 1, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
     b.set_complex()
+    with pytest.raises(PepsError):                       # still real-only: variational compression, structure factor, SR store
+        b.set_truncation(BMPSTruncateParams.Variational2Site(4, 4, 0.0, 1e-9, 5))
     with pytest.raises(PepsError):
-        b.set_fermion(FermionSplitIndexTPS.random(3, 3, 2, 1))
+        b.measure_structure_factor()
+    b.close()
+    b = WalkerBatch(3, 3, 2, 2, 1, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+    b.set_tps(np.zeros(b.tps_size))
+    with pytest.raises(PepsError):                       # the switch comes before the first state
+        b.set_complex()
     b.close()
 
 
@@ -88,3 +95,25 @@ def test_complex_evaluator_matches_oracle_chain(lib):
     assert abs(res.energy - energy) < 1e-10
     got = np.concatenate([x.ravel() for row in res.gradient.t for site in row for x in site])
     assert np.max(np.abs(got - grad)) <= 1e-9 * max(1.0, np.max(np.abs(grad)))
+
+
+def test_complex_tfim_full_space_pipeline_parity_hostsim(lib):
+    """Transverse-field Ising + full-space (Suwa-Todo) updater on a complex state (BASELINE config #1's flow in QLTEN_Complex)."""
+    run_complex_pipeline_parity(lib, 3, 3, 2, 2, (4, 4, 0.0), nsweeps=2, tfim_h=0.7)
+
+
+def test_complex_three_site_updater_pipeline_parity_hostsim(lib):
+    run_complex_pipeline_parity(lib, 3, 4, 2, 2, (4, 4, 0.0), nsweeps=2, three_site=True)
+
+
+@pytest.mark.parametrize("table,j2", [("xxz", 0.0), ("xxz", 0.4), ("spin1", 0.0)])
+def test_complex_table_model_pipeline_parity_hostsim(lib, table, j2):
+    """Seam B2 as data on complex states: XXZ / J1-J2 as tables against the oracle's XXZ solver, and the phys = 3 spin-1
+    model (NN + NNN + on-site off-diagonal terms) with the full-space updater against the oracle's generic traversal."""
+    run_complex_pipeline_parity(lib, 3, 3, 2, 2, (4, 4, 0.0), nsweeps=1, j2=j2, table=table)
+
+
+@pytest.mark.parametrize("j2", [0.0, 0.5])
+def test_complex_measure_parity_hostsim(lib, j2):
+    from parity_common import run_complex_measure_parity
+    run_complex_measure_parity(lib, j2)

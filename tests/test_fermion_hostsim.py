@@ -269,3 +269,25 @@ def test_set_fermion_after_set_tps(lib):
         amps.append(b.amplitudes())
         b.close()
     assert np.array_equal(amps[0], amps[1]) and np.all(amps[0] != 0)
+
+
+@pytest.mark.parametrize("model,rows,cols,D,trunc", [
+    ("spinless", 3, 3, 2, (4, 4, 0.0)),
+    ("spinless", 3, 4, 3, (2, 6, 1e-9)),
+    ("tj", 3, 3, 2, (4, 4, 0.0)),
+    ("tj_nnn", 3, 3, 2, (4, 4, 0.0)),
+])
+def test_complex_fermion_pipeline_parity_hostsim(lib, model, rows, cols, D, trunc):
+    """fZ2 tensors with complex entries (QLTEN_Complex + fZ2QN, the reference's *_complex fermion fixtures): the dressed
+    planes, complex E_loc = ... conj(psi_ex / psi) and O* = conj(d psi / d T) / conj(psi_site) against oracle/fermion.py,
+    which is pinned on the complex K8 goldens."""
+    run_fermion_pipeline_parity(lib, rows, cols, D, 2, trunc, model=model, nsweeps=2, complex_=True)
+
+
+def test_complex_tj_jastrow_dressed_pipeline_parity_hostsim(lib):
+    run_fermion_pipeline_parity(lib, 3, 3, 2, 2, (4, 4, 0.0), model="tj", nsweeps=2, jastrow=True, complex_=True)
+
+
+def test_k8_complex_goldens_through_abi(lib):
+    from parity_common import run_complex_k8_goldens
+    run_complex_k8_goldens(lib)

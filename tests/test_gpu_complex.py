@@ -33,3 +33,22 @@ def test_complex_j1j2_pipeline_parity_gpu(lib):
 
 def test_k5_complex_golden_gpu(lib):
     run_complex_k5_golden(lib)
+
+
+def test_complex_tfim_full_space_pipeline_parity_gpu(lib):
+    """BASELINE config #1's flow (TFIM + full-space Suwa-Todo updater) on a complex state."""
+    run_complex_pipeline_parity(lib, 4, 4, 3, 3, (6, 6, 0.0), nsweeps=2, tfim_h=0.7)
+
+
+def test_complex_three_site_updater_pipeline_parity_gpu(lib):
+    run_complex_pipeline_parity(lib, 4, 4, 3, 3, (6, 6, 0.0), nsweeps=2, three_site=True)
+
+
+@pytest.mark.parametrize("table,j2", [("xxz", 0.4), ("spin1", 0.0)])
+def test_complex_table_model_pipeline_parity_gpu(lib, table, j2):
+    run_complex_pipeline_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), nsweeps=1, j2=j2, table=table)
+
+
+def test_complex_measure_parity_gpu(lib):
+    from parity_common import run_complex_measure_parity
+    run_complex_measure_parity(lib, 0.5)

@@ -151,3 +151,24 @@ def test_fermion_pipeline_block_jacobi_path_gpu(lib, monkeypatch, sectors):
     monkeypatch.setenv("PEPS_SMALL_SVD", "0")
     monkeypatch.setenv("PEPS_Z2_SECTORS", sectors)
     run_fermion_pipeline_parity(lib, 6, 6, 4, 2, (16, 16, 0.0), model="spinless", nsweeps=1)
+
+
+@pytest.mark.parametrize("model,rows,cols,D,trunc,W", [
+    ("spinless", 4, 4, 4, (8, 8, 0.0), 3),
+    ("spinless", 4, 4, 2, (2, 6, 1e-8), 3),
+    ("tj_nnn", 3, 4, 2, (4, 4, 0.0), 3),
+])
+def test_complex_fermion_pipeline_parity_gpu(lib, model, rows, cols, D, trunc, W):
+    """fZ2 tensors with complex entries: dressed planes, complex E_loc and O* on the CUDA path against the oracle."""
+    run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model=model, nsweeps=2, complex_=True)
+
+
+def test_complex_tj_jastrow_dressed_pipeline_parity_gpu(lib):
+    run_fermion_pipeline_parity(lib, 4, 4, 2, 3, (4, 4, 0.0), model="tj", nsweeps=2, jastrow=True, complex_=True)
+
+
+def test_k8_complex_goldens_gpu(lib):
+    """The reference's complex fZ2 known answers (spinless fermions t2 = 2.1 / 0 / -2.5, t-J; su and lowest states) through
+    the CUDA path."""
+    from parity_common import run_complex_k8_goldens
+    run_complex_k8_goldens(lib)
