@@ -117,12 +117,18 @@ int peps_set_fermion(peps_ctx *ctx, const int32_t *phys_par, const int32_t *leg_
  * tests/CMakeLists.txt:57-83 is compiled for both element types). peps_set_complex switches a fresh context (before the
  * first peps_set_tps*) to complex arithmetic: tensors live as two real planes, a contraction is four launches of the real
  * contraction kernel, the boundary-MPS factorisations run on the real embedding [[Ar, -Ai], [Ai, Ar]] of their matrices
- * (DESIGN.md). Built for the headline path -- amplitude, NN-exchange sweep (|psi| = hypot), XXZ / J1-J2 local energy with
+ * (DESIGN.md section 11). Covered: amplitude, the three updaters (|psi| = hypot; Suwa-Todo weights std::norm), every energy
+ * solver (XXZ / J1-J2, transverse-field Ising, table models, fermion mode: call peps_set_complex BEFORE peps_set_fermion) with
  * conj(psi_ex / psi) (square_spin_onehalf_xxz_obc.h:72-104), holes and O* = conj(hole / psi), sum O*, sum conj(E_loc) O*
- * (mc_energy_grad_evaluator.h:245-272). peps_set_tps_c uploads the two planes of the packed state; peps_get_planar reads
- * per-walker / state-shaped results as planes: what = 0 amplitudes [W], 1 local energies [W] (after
- * peps_energy_and_holes), 2 holes [W][holes_stride] (the raw environment; O* = conj(hole / amplitude)), 3 sum O*,
- * 4 sum conj(E_loc) O* [tps_size]. The real getters return the real planes. */
+ * (mc_energy_grad_evaluator.h:245-272), measurement, the SR store / matvec / natural gradient. Real-only: variational
+ * compression and the structure-factor measurement. Conventions of a complex context:
+ *   - peps_set_tps_c uploads the two planes of the packed state; peps_get_planar reads per-walker / state-shaped results as
+ *     planes: what = 0 amplitudes [W], 1 local energies [W] (after peps_energy_and_holes), 2 holes [W][holes_stride] (the
+ *     raw environment; O* = conj(hole / amplitude); fermion mode: the finished hole), 3 sum O*, 4 sum conj(E_loc) O*
+ *     [tps_size], 5 the state [tps_size]. The real getters return the real planes.
+ *   - the psi list of peps_energy_and_holes holds (rows+cols) entries of 2 W doubles (re[W] then im[W]);
+ *   - every output array of peps_measure is planar: its real block followed by its imaginary block (twice the real size);
+ *   - the accumulator device pointers address 2 * tps_size doubles (re plane, im plane). */
 int peps_set_complex(peps_ctx *ctx);
 int peps_set_tps_c(peps_ctx *ctx, const double *re, const double *im, size_t n);
 int peps_get_planar(peps_ctx *ctx, int32_t what, double *re, double *im);
@@ -217,6 +223,11 @@ int peps_sr_clear(peps_ctx *ctx);
 int64_t peps_sr_count(peps_ctx *ctx);
 int peps_sr_matvec(peps_ctx *ctx, const double *v_host, double mean_dot_v, double *out_host, size_t n);
 int peps_sr_matvec_device(peps_ctx *ctx, const double *v_dev, double mean_dot_v, double *out_dev);
+/* Complex context (peps_set_complex): TPS-shaped vectors are planar, peps_tps_size() real parts followed by peps_tps_size()
+ * imaginary parts; <O*_i, v> is the conjugating inner product of SplitIndexTPS::operator* and mean_dot_v = <Obar, v> is
+ * complex. The store keeps the real embedding of the samples, so the same HBM-streaming kernels serve both cases. In a
+ * complex context peps_sr_natural_gradient takes / returns planar arrays of 2 * peps_tps_size() doubles. */
+int peps_sr_matvec_c(peps_ctx *ctx, const double *v_host, double mean_dot_v_re, double mean_dot_v_im, double *out_host, size_t n);
 
 /* Optimizer::CalculateNaturalGradient (optimizer/optimizer_impl.h:1031-1089) on the device-resident sample store: solves
  * (S + diag_shift) x = gradient with the reference's conjugate-gradient loop (utility/conjugate_gradient_solver.h:181-276

@@ -8,6 +8,7 @@
 // (bmps_impl.h:839-843, square_nnn_energy_solver.h:148-150). Header-only; link against libpeps_b200.so.
 #pragma once
 #include <cmath>
+#include <complex>
 #include <cstdint>
 #include <functional>
 #include <limits>
@@ -179,6 +180,27 @@ class WalkerBatch {
   size_t tps_size() const { return peps_tps_size(h_); }
   int walkers() const { return walkers_; }
   void SetTPS(const std::vector<double> &flat) { ck(peps_set_tps(h_, flat.data(), flat.size())); }
+  // QLTEN_Complex states (SplitIndexTPS<QLTEN_Complex, QNT>): SetComplex on the fresh batch (before SetFermion / SetTPS); the
+  // ABI moves planes, this wrapper std::complex<double>
+  using cplx = std::complex<double>;
+  void SetComplex() { ck(peps_set_complex(h_)); complex_ = true; }
+  bool is_complex() const { return complex_; }
+  void SetTPS(const std::vector<cplx> &flat) {
+    std::vector<double> re(flat.size()), im(flat.size());
+    for (size_t i = 0; i < flat.size(); ++i) { re[i] = flat[i].real(); im[i] = flat[i].imag(); }
+    ck(peps_set_tps_c(h_, re.data(), im.data(), re.size()));
+  }
+  // what: 0 amplitudes, 1 local energies, 2 holes, 3 sum O*, 4 sum conj(E_loc) O*, 5 the state (peps_get_planar)
+  std::vector<cplx> Planar(int what, size_t n) {
+    std::vector<double> re(n), im(n);
+    ck(peps_get_planar(h_, what, re.data(), im.data()));
+    std::vector<cplx> out(n);
+    for (size_t i = 0; i < n; ++i) out[i] = cplx(re[i], im[i]);
+    return out;
+  }
+  std::vector<cplx> AmplitudesComplex() { return Planar(0, (size_t)walkers_); }
+  std::vector<cplx> LocalEnergiesComplex() { return Planar(1, (size_t)walkers_); }
+  void Accumulators(std::vector<cplx> &osum, std::vector<cplx> &eosum) { osum = Planar(3, tps_size()); eosum = Planar(4, tps_size()); }
   std::vector<double> GetTPS() { std::vector<double> v(tps_size()); ck(peps_get_tps(h_, v.data(), v.size())); return v; }
   void SetModel(const XXZModel &m) { ck(peps_set_model_xxz(h_, m.jz, m.jxy, m.pinning00)); }
   void SetModel(const J1J2XXZModel &m) { ck(peps_set_model_j1j2_xxz(h_, m.jz, m.jxy, m.jz2, m.jxy2, m.pinning00)); }
@@ -258,6 +280,7 @@ class WalkerBatch {
   void ck(int rc) { if (rc != 0) throw std::runtime_error(peps_last_error(h_)); }
   peps_ctx *h_ = nullptr;
   int rows_, cols_, walkers_;
+  bool complex_ = false;
   Updater updater_ = Updater::NNExchange;
 };
 
@@ -266,6 +289,14 @@ struct EvaluateResult {               // MCEnergyGradEvaluator::Result (mc_energ
   std::vector<double> gradient;       // packed like the TPS
   std::vector<double> accept_rates_avg;
   std::vector<double> energy_samples; // [walkers][samples_per_walker]
+};
+
+struct EvaluateResultComplex {        // the same for TenElemT = QLTEN_Complex
+  std::complex<double> energy = 0;
+  double energy_error = 0, gradient_norm = 0;
+  std::vector<std::complex<double>> gradient;
+  std::vector<double> accept_rates_avg;
+  std::vector<std::complex<double>> energy_samples;
 };
 
 // MeanAndBinnedErrorSqrtNUniformBin with walkers in the role of ranks (monte_carlo_tools/statistics.h:146-225)
@@ -342,6 +373,37 @@ class MCEnergyGradEvaluator {
     for (size_t i = 0; i < osum.size(); ++i) {
       r.gradient[i] = (eosum[i] - r.energy * osum[i]) / (double)(n * W);
       r.gradient_norm += r.gradient[i] * r.gradient[i];
+    }
+    r.accept_rates_avg = {acc / (double)(n * W)};
+    return r;
+  }
+  // Evaluate for a QLTEN_Complex state (batch().SetComplex() first): E_loc = ... conj(psi_ex / psi), gradient =
+  // sum conj(E_loc) O* / N - conj(E) sum O* / N (mc_energy_grad_evaluator.h:245-309); error bar from the real parts
+  EvaluateResultComplex Evaluate(const std::vector<std::complex<double>> &packed_tps) {
+    if (!batch_.is_complex()) throw std::runtime_error("Evaluate(complex state): call batch().SetComplex() right after construction");
+    using cplx = std::complex<double>;
+    batch_.SetTPS(packed_tps);
+    batch_.InitWalkers();
+    const size_t W = (size_t)batch_.walkers();
+    const size_t n = std::max<size_t>(1, (mc_.num_samples + W - 1) / W);
+    batch_.ZeroAccumulators();
+    EvaluateResultComplex r;
+    r.energy_samples.assign(W * n, cplx(0));
+    std::vector<double> re(W * n), im(W * n), e, a;
+    double acc = 0;
+    for (size_t s = 0; s < n; ++s) {
+      batch_.Sample((int)mc_.sweeps_between_samples, e, a);
+      const std::vector<cplx> ec = batch_.LocalEnergiesComplex();
+      for (size_t w = 0; w < W; ++w) { r.energy_samples[w * n + s] = ec[w]; re[w * n + s] = ec[w].real(); im[w * n + s] = ec[w].imag(); acc += a[w]; }
+    }
+    std::vector<cplx> osum, eosum;
+    batch_.Accumulators(osum, eosum);
+    auto mr = BinnedMean(re, W, n), mi = BinnedMean(im, W, n);
+    r.energy = cplx(mr.first, mi.first); r.energy_error = mr.second;
+    r.gradient.resize(osum.size());
+    for (size_t i = 0; i < osum.size(); ++i) {
+      r.gradient[i] = (eosum[i] - std::conj(r.energy) * osum[i]) / (double)(n * W);
+      r.gradient_norm += std::norm(r.gradient[i]);
     }
     r.accept_rates_avg = {acc / (double)(n * W)};
     return r;

@@ -85,6 +85,7 @@ SIGNATURES = {
     "peps_sr_count": (C.c_int64, [_P]),
     "peps_sr_matvec": (C.c_int, [_P, _D, C.c_double, _D, C.c_size_t]),
     "peps_sr_matvec_device": (C.c_int, [_P, C.c_void_p, C.c_double, C.c_void_p]),
+    "peps_sr_matvec_c": (C.c_int, [_P, _D, C.c_double, C.c_double, _D, C.c_size_t]),
     "peps_sr_natural_gradient": (C.c_int, [_P, _D, _D, C.c_int64, C.c_double, C.POINTER(PepsCGParams), _D, ALLREDUCE_FN,
                                            C.c_void_p, _D, C.POINTER(C.c_int32), _D, C.POINTER(C.c_int32)]),
     "peps_probe_trace_row": (C.c_int, [_P, C.c_int32, _D]),

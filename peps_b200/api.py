@@ -159,8 +159,8 @@ class SplitIndexTPS:
         return max(max(x.shape) for row in self.t for site in row for x in site)
 
     def pack(self):
-        return np.concatenate([np.ascontiguousarray(x, dtype=np.float64).ravel()
-                               for row in self.t for site in row for x in site])
+        dt = np.complex128 if np.iscomplexobj(self.t[0][0][0]) else np.float64
+        return np.concatenate([np.ascontiguousarray(x, dtype=dt).ravel() for row in self.t for site in row for x in site])
 
     @staticmethod
     def unpack(flat, like):
@@ -434,6 +434,8 @@ class WalkerBatch:
         self._ck(self.lib.peps_set_tps(self.h, _dp(flat), flat.size))
 
     def get_tps_flat(self):
+        if getattr(self, "is_complex", False):
+            return self._planar(5, self.tps_size)
         out = np.empty(self.tps_size)
         self._ck(self.lib.peps_get_tps(self.h, _dp(out), out.size))
         return out
@@ -602,6 +604,13 @@ class WalkerBatch:
         return int(self.lib.peps_sr_count(self.h))
 
     def sr_matvec(self, v, mean_dot_v):
+        if getattr(self, "is_complex", False):             # planar across the ABI, numpy complex here
+            v = np.asarray(v, dtype=np.complex128)
+            pv = np.ascontiguousarray(np.concatenate([v.real, v.imag]))
+            out = np.empty(2 * self.tps_size)
+            m = complex(mean_dot_v)
+            self._ck(self.lib.peps_sr_matvec_c(self.h, _dp(pv), m.real, m.imag, _dp(out), out.size))
+            return out[:self.tps_size] + 1j * out[self.tps_size:]
         v = np.ascontiguousarray(v, dtype=np.float64)
         out = np.empty(self.tps_size)
         self._ck(self.lib.peps_sr_matvec(self.h, _dp(v), float(mean_dot_v), _dp(out), out.size))
@@ -830,10 +839,7 @@ class MCEnergyGradEvaluator:
         self.batch = WalkerBatch(tps.rows(), tps.cols(), tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
         self.is_complex = bool(np.iscomplexobj(tps.t[0][0][0]))    # QLTEN_Complex state: complex arithmetic on the device
         if self.is_complex:
-            if dist is not None and world_size > 1:
-                raise PepsError("complex states: the multi-GPU reduction of the evaluator is not wired yet")
             self.batch.set_complex()
-            self.psi_consistency.enabled = False                   # the psi list is real-only
         if isinstance(tps, FermionSplitIndexTPS):
             self.batch.set_fermion(tps)
         self.batch.set_model(model)
@@ -857,7 +863,7 @@ class MCEnergyGradEvaluator:
         GPU is valid. Returns the list of rescued local walkers."""
         b = self.batch
         rp = self.config_rescue
-        valid = check_wavefunction_amplitude_validity(b.amplitudes(), rp.amplitude_min_threshold, rp.amplitude_max_threshold)
+        valid = check_wavefunction_amplitude_validity(self._amps(), rp.amplitude_min_threshold, rp.amplitude_max_threshold)
         src_cfg, n_valid_global, n_total = None, int(valid.sum()), b.W * self.world_size
         cfgs = b.get_configs()
         if self.dist is not None and self.world_size > 1:
@@ -888,7 +894,7 @@ class MCEnergyGradEvaluator:
             cfgs[bad] = src_cfg
             b.set_configs(cfgs)
             b.init_walkers()                   # TryConstructWavefunction_ for the rescued walkers (monte_carlo_engine.h:396)
-            again = check_wavefunction_amplitude_validity(b.amplitudes(), rp.amplitude_min_threshold, rp.amplitude_max_threshold)
+            again = check_wavefunction_amplitude_validity(self._amps(), rp.amplitude_min_threshold, rp.amplitude_max_threshold)
             if not again.all():
                 raise PepsError("rescue FAILED: the valid configuration of another walker is not valid here (TPS or truncation parameter issue)")
             self.warmed_up = False
@@ -901,7 +907,7 @@ class MCEnergyGradEvaluator:
             for _ in range(self.mc.num_warmup_sweeps):
                 self.batch.sweep(1)
             self.warmed_up = True
-        amps = self.batch.amplitudes()
+        amps = self._amps()
         bad = (not np.all(np.isfinite(amps))) or bool(np.any(amps == 0))
         mx = float("inf") if bad else float(np.max(np.abs(amps)))
         if self.dist is not None and self.world_size > 1:
@@ -910,6 +916,9 @@ class MCEnergyGradEvaluator:
             raise PepsError("Amplitude is still not legal after warm up")
         self.batch.normalize_state_order1(mx)
         self.state = type(self.state).unpack(self.batch.get_tps_flat(), self.state)
+
+    def _amps(self):
+        return self.batch.amplitudes_c() if self.is_complex else self.batch.amplitudes()
 
     def _allreduce_max(self, x):
         import torch
@@ -962,19 +971,22 @@ class MCEnergyGradEvaluator:
                 # NCCL all-reduce straight on the device pointers of the two accumulators (peps_ostar_sum_device /
                 # peps_eloc_ostar_sum_device): the gradient sums never pass through host memory before the reduction
                 b.sync()
-                for ptr in b.accumulator_device_ptrs():
-                    self.dist.all_reduce(torch.as_tensor(_CudaView(ptr, b.tps_size), device="cuda"))
+                for ptr in b.accumulator_device_ptrs():        # complex: both planes of an accumulator are contiguous
+                    self.dist.all_reduce(torch.as_tensor(_CudaView(ptr, b.tps_size * (2 if self.is_complex else 1)), device="cuda"))
                 torch.cuda.synchronize()
-                osum, eosum = b.accumulators()
+                osum, eosum = b.accumulators_c() if self.is_complex else b.accumulators()
             else:
-                osum, eosum = b.accumulators()
-                buf = torch.from_numpy(np.stack([osum, eosum]))
+                osum, eosum = b.accumulators_c() if self.is_complex else b.accumulators()
+                host = np.ascontiguousarray(np.stack([osum, eosum]))
+                buf = torch.from_numpy(host.view(np.float64))          # complex sums reduce as (re, im) pairs
                 self.dist.all_reduce(buf)
-                osum, eosum = buf.numpy()
-            mine = torch.from_numpy(energies).to(dev)
+                osum, eosum = host
+            mine = torch.from_numpy(np.ascontiguousarray(energies).view(np.float64)).to(dev)
             gathered = [torch.empty_like(mine) for _ in range(self.world_size)]
             self.dist.all_gather(gathered, mine)
             all_e = np.concatenate([g.cpu().numpy() for g in gathered], axis=0)
+            if self.is_complex:
+                all_e = np.ascontiguousarray(all_e).view(np.complex128)
         elif self.is_complex:
             osum, eosum = b.accumulators_c()
         else:

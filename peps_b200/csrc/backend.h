@@ -379,6 +379,12 @@ void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *h
 // store: ostar[i][e] = holes[w][e] / amp[w], cfgs[i][:] = cfg[w][:] for i = first + w.
 void be_sr_store(const double *holes, long hole_stride, const double *amp, const int32_t *cfg, int nsites,
                  double *ostar, int32_t *cfgs, long first, int W);
+// Complex states through the real embedding: with O*_i = conj(hole / amp) = o_r + i o_i, the real-linear map v -> sum_i
+// <O*_i, v> O*_i on planar vectors [v_r ; v_i] is sum_i (x_i x_i^T + y_i y_i^T) with x_i = [o_r ; o_i] and y_i = J x_i =
+// [-o_i ; o_r]: the REAL kernels below run on 2 N samples of a lattice with 2 nsites "sites" (re plane, im plane).
+// ostar: [2 cap][2 hole_stride], row first + w = x, row cap + first + w = y; cfgs: [2 cap][2 nsites] = the configuration twice.
+void be_sr_store_c(const double *hr, const double *hi, long hole_stride, const double *ampr, const double *ampi, const int32_t *cfg,
+                   int nsites, double *ostar, int32_t *cfgs, long first, long cap, int W);
 // delta[i] = (O*_i . v) - mean_dot_v  for i < n   (O*_i . v sums over the sampled slot of every site)
 void be_sr_dots(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
                 const int32_t *site_size, const int32_t *tps_off, int nsites, const double *v, double mean_dot_v,

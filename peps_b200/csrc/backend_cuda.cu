@@ -3156,6 +3156,32 @@ void be_sr_store(const double *holes, long hole_stride, const double *amp, const
   post_launch();
 }
 
+__global__ void sr_store_c_kernel(const double *hr, const double *hi, long hole_stride, const double *ampr, const double *ampi,
+                                  const int32_t *cfg, int nsites, double *ostar, int32_t *cfgs, long first, long cap) {
+  const int w = blockIdx.y;
+  const double d = ampr[w] * ampr[w] + ampi[w] * ampi[w];
+  const double *a = hr + (long)w * hole_stride, *b = hi + (long)w * hole_stride;
+  double *x = ostar + (first + w) * 2 * hole_stride, *y = ostar + (cap + first + w) * 2 * hole_stride;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < hole_stride; e += (long)gridDim.x * blockDim.x) {
+    const double qr = (a[e] * ampr[w] + b[e] * ampi[w]) / d, qi = (b[e] * ampr[w] - a[e] * ampi[w]) / d;   // hole / amp
+    const double o_r = qr, o_i = -qi;                                                                      // O* = conj
+    x[e] = o_r; x[hole_stride + e] = o_i;
+    y[e] = -o_i; y[hole_stride + e] = o_r;
+  }
+  if (blockIdx.x == 0)
+    for (int s = threadIdx.x; s < 2 * nsites; s += blockDim.x) {
+      const int32_t c = cfg[(long)w * nsites + (s % nsites)];
+      cfgs[(first + w) * 2 * nsites + s] = c;
+      cfgs[(cap + first + w) * 2 * nsites + s] = c;
+    }
+}
+void be_sr_store_c(const double *hr, const double *hi, long hole_stride, const double *ampr, const double *ampi, const int32_t *cfg,
+                   int nsites, double *ostar, int32_t *cfgs, long first, long cap, int W) {
+  LaunchScope scope(KC_SMALL, 0.0);
+  sr_store_c_kernel<<<dim3(32, W), 256, 0, g_stream>>>(hr, hi, hole_stride, ampr, ampi, cfg, nsites, ostar, cfgs, first, cap);
+  post_launch();
+}
+
 __global__ void sr_dots_kernel(const double *ostar, const int32_t *cfgs, long hole_stride, const int32_t *hole_off,
                                const int32_t *site_size, const int32_t *tps_off, int nsites, const double *v,
                                double mean_dot_v, double *delta) {

@@ -162,6 +162,9 @@ int64_t peps_sr_count(peps_ctx *ctx) { return ctx->eng->sr_count(); }
 int peps_sr_matvec(peps_ctx *ctx, const double *v, double mean_dot_v, double *out, size_t n) {
   GUARD(ctx, { if (n != ctx->eng->tps_size()) throw std::invalid_argument("peps_sr_matvec: size mismatch"); ctx->eng->sr_matvec_host(v, mean_dot_v, out); })
 }
+int peps_sr_matvec_c(peps_ctx *ctx, const double *v, double mean_re, double mean_im, double *out, size_t n) {
+  GUARD(ctx, { if (n != 2 * ctx->eng->tps_size()) throw std::invalid_argument("peps_sr_matvec_c: size mismatch (planar vectors of 2 * peps_tps_size() doubles)"); ctx->eng->sr_matvec_host_c(v, mean_re, mean_im, out); })
+}
 int peps_sr_matvec_device(peps_ctx *ctx, const double *v, double mean_dot_v, double *out) { GUARD(ctx, ctx->eng->sr_matvec_device(v, mean_dot_v, out)) }
 int peps_sr_natural_gradient(peps_ctx *ctx, const double *gradient, const double *ostar_mean, int64_t total_samples, double diag_shift,
                              const peps_cg_params *prm, const double *init_guess, peps_allreduce_fn allreduce, void *user, double *x_out,

@@ -95,7 +95,7 @@ Engine::~Engine() {
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
                   (void *)sr_cfgs_, (void *)sr_delta_, (void *)psi_list_d_, (void *)term_ia_, (void *)term_ib_, (void *)term_cw_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_,
                   (void *)(fermion_ ? gtps_ : nullptr), (void *)gtps_off_d_, (void *)gidx_[0], (void *)gidx_[1], (void *)jw_[0],
-                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_, (void *)jastrow_v_, (void *)jr_, (void *)dens_d_})
+                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_, (void *)jastrow_v_, (void *)jr_, (void *)dens_d_, (void *)sr_desc2_})
     be_free(p);
   for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); }
   pool_.release_all();
@@ -1802,13 +1802,14 @@ void Engine::bond_energy(int s1, int s2, const double *psi_ex, const double *psi
 }
 void Engine::set_complex() {
   if (complex_) return;
-  if (fermion_ || scheme_ != 0 || tps_loaded_ || sr_on_)
+  if (fermion_ || scheme_ != 0 || tps_loaded_)
     throw std::logic_error("set_complex: call right after construction, before set_fermion / set_tps (SVD compression only)");
   be_sync();
   // per-walker scalar buffers allocated lazily so far are real-sized: drop them, they come back as planes
   be_free(psi_alt_); psi_alt_ = nullptr; psi_alt_slots_ = 0;
   be_free(psi_list_d_); psi_list_d_ = nullptr;
   be_free(bond_rec_); bond_rec_ = nullptr;
+  if (sr_cap_ > 0) sr_reserve(0);
   auto grow = [&](double *&p, size_t n) { be_free(p); p = (double *)be_malloc(sizeof(double) * 2 * n); be_memset0(p, sizeof(double) * 2 * n); };
   grow(tps_, (size_t)tps_total_); gtps_ = tps_;
   grow(osum_, (size_t)tps_total_); grow(eosum_, (size_t)tps_total_);
@@ -1843,6 +1844,7 @@ void Engine::get_planar(int what, double *re, double *im) {
     case 2: p = holes_; n = (size_t)W_ * hole_stride_; break;
     case 3: p = osum_; n = (size_t)tps_total_; break;
     case 4: p = eosum_; n = (size_t)tps_total_; break;
+    case 5: p = tps_; n = (size_t)tps_total_; break;
     default: throw std::invalid_argument("get_planar: unknown array");
   }
   if (re) be_d2h(re, p, sizeof(double) * n);
@@ -2239,9 +2241,14 @@ void Engine::zero_accumulators() {
 }
 void Engine::accumulate_ostar() {                      // mc_energy_grad_evaluator.h:245-272
   if (complex_) {
-    if (sr_on_) throw std::logic_error("the SR sample store is not available for complex states");
     be_accumulate_ostar_c(holes_, holes_ + (long)W_ * hole_stride_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, cfg_, nsites_, amp_,
                           amp_ + W_, eloc_, eloc_ + W_, osum_, osum_ + tps_total_, eosum_, eosum_ + tps_total_, W_);
+    if (sr_on_) {
+      if (sr_count_ + W_ > sr_cap_) throw std::runtime_error("SR sample store is full (peps_sr_reserve)");
+      be_sr_store_c(holes_, holes_ + (long)W_ * hole_stride_, hole_stride_, amp_, amp_ + W_, cfg_, nsites_, sr_ostar_, sr_cfgs_, sr_count_,
+                    sr_cap_, W_);
+      sr_count_ += W_;
+    }
     return;
   }
   be_accumulate_ostar(holes_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, cfg_, nsites_, phys_, amp_, eloc_,
@@ -2258,19 +2265,59 @@ void Engine::sr_reserve(long max_samples) {
   be_free(sr_ostar_); be_free(sr_cfgs_); be_free(sr_delta_);
   sr_ostar_ = nullptr; sr_cfgs_ = nullptr; sr_delta_ = nullptr;
   sr_cap_ = max_samples; sr_count_ = 0;
+  const size_t k = complex_ ? 4 : 1;                   // complex: x and y samples of doubled length (real embedding)
   if (max_samples > 0) {
-    sr_ostar_ = (double *)be_malloc(sizeof(double) * (size_t)max_samples * hole_stride_);
-    sr_cfgs_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)max_samples * nsites_);
-    sr_delta_ = (double *)be_malloc(sizeof(double) * (size_t)max_samples);
+    sr_ostar_ = (double *)be_malloc(sizeof(double) * (size_t)max_samples * hole_stride_ * k);
+    sr_cfgs_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)max_samples * nsites_ * k);
+    sr_delta_ = (double *)be_malloc(sizeof(double) * (size_t)max_samples * (complex_ ? 2 : 1));
+  }
+  if (complex_ && !sr_desc2_) {
+    std::vector<int32_t> d((size_t)6 * nsites_);
+    for (int s = 0; s < nsites_; ++s) {
+      d[(size_t)s] = (int32_t)hole_off_h_[(size_t)s];
+      d[(size_t)(nsites_ + s)] = (int32_t)(hole_stride_ + hole_off_h_[(size_t)s]);
+      d[(size_t)(2 * nsites_ + s)] = d[(size_t)(3 * nsites_ + s)] = site_size_h_[(size_t)s];
+      d[(size_t)(4 * nsites_ + s)] = (int32_t)tps_off_h_[(size_t)s];
+      d[(size_t)(5 * nsites_ + s)] = (int32_t)(tps_total_ + tps_off_h_[(size_t)s]);
+    }
+    sr_desc2_ = (int32_t *)be_malloc(sizeof(int32_t) * d.size());
+    be_h2d(sr_desc2_, d.data(), sizeof(int32_t) * d.size());
   }
 }
+// complex states: v, out planar [2][tps_total]; the x samples are centred with Re(mean . v), the y samples with Im
+void Engine::sr_matvec_device_c(const double *v_dev, double mean_re, double mean_im, double *out_dev) {
+  if (!complex_) throw std::logic_error("sr_matvec_device_c: the context is real");
+  const int32_t *ho2 = sr_desc2_, *ss2 = sr_desc2_ + 2 * nsites_, *to2 = sr_desc2_ + 4 * nsites_;
+  const long hs2 = 2 * hole_stride_;
+  const int ns2 = 2 * nsites_;
+  const double *oy = sr_ostar_ + (size_t)sr_cap_ * hs2;
+  const int32_t *cy = sr_cfgs_ + (size_t)sr_cap_ * ns2;
+  double *tmp = (double *)pool_.get(sizeof(double) * 2 * (size_t)tps_total_);
+  be_sr_dots(sr_ostar_, sr_cfgs_, hs2, ho2, ss2, to2, ns2, v_dev, mean_re, sr_delta_, sr_count_);
+  be_sr_dots(oy, cy, hs2, ho2, ss2, to2, ns2, v_dev, mean_im, sr_delta_ + sr_cap_, sr_count_);
+  be_sr_accumulate(sr_ostar_, sr_cfgs_, hs2, ho2, ss2, to2, ns2, phys_, sr_delta_, out_dev, sr_count_);
+  be_sr_accumulate(oy, cy, hs2, ho2, ss2, to2, ns2, phys_, sr_delta_ + sr_cap_, tmp, sr_count_);
+  be_vec_lincomb(out_dev, 1.0, out_dev, 1.0, tmp, 2 * (long)tps_total_);
+  pool_.put(tmp);
+}
 void Engine::sr_matvec_device(const double *v_dev, double mean_dot_v, double *out_dev) {
+  require_real("sr_matvec with a real mean (peps_sr_matvec_c takes the planar vectors of a complex context)");
   // SRSMatrix::operator* without the 1/(N ranks) factor and the diagonal shift (applied by the caller after the
   // cross-GPU all-reduce): stochastic_reconfiguration_smatrix.h:60-66
   be_sr_dots(sr_ostar_, sr_cfgs_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, nsites_, v_dev, mean_dot_v,
              sr_delta_, sr_count_);
   be_sr_accumulate(sr_ostar_, sr_cfgs_, hole_stride_, hole_off_d_, site_size_d_, tps_off_d_, nsites_, phys_, sr_delta_,
                    out_dev, sr_count_);
+}
+void Engine::sr_matvec_host_c(const double *v, double mean_re, double mean_im, double *out) {
+  const size_t bytes = sizeof(double) * 2 * (size_t)tps_total_;
+  double *vd = (double *)pool_.get(bytes);
+  double *od = (double *)pool_.get(bytes);
+  be_h2d(vd, v, bytes);
+  sr_matvec_device_c(vd, mean_re, mean_im, od);
+  be_d2h(out, od, bytes);
+  pool_.put(vd);
+  pool_.put(od);
 }
 void Engine::sr_matvec_host(const double *v, double mean_dot_v, double *out) {
   double *vd = (double *)pool_.get(sizeof(double) * tps_total_);
@@ -2285,9 +2332,11 @@ Engine::CGOutcome Engine::sr_natural_gradient(const double *gradient_host, const
                                               double diag_shift, const CGParams &prm, const double *init_guess_host,
                                               AllReduceFn allreduce, void *user, double *x_host) {
   if (total_samples <= 0) throw std::invalid_argument("sr_natural_gradient: total_samples must be positive");
-  const long n = tps_total_;
+  // complex context: planar vectors of 2 tps_total doubles; the real dot of two planar vectors is Re <a, b>, which is all
+  // the Hermitian CG needs (alpha, beta real); <mean, x> = dot(MEAN, x) + i dot(MEANJ, x) with MEANJ = J mean = [-m_i ; m_r]
+  const long n = tps_total_ * (complex_ ? 2 : 1);
   const size_t bytes = sizeof(double) * (size_t)n;
-  enum { B = 0, MEAN, X, R, P, AP, RPREV, BEST, NV };
+  enum { B = 0, MEAN, X, R, P, AP, RPREV, BEST, MEANJ, NV };
   double *v[NV];
   for (auto &p : v) p = (double *)pool_.get(bytes);
   double *scal = (double *)pool_.get(sizeof(double) * 2);
@@ -2303,7 +2352,8 @@ Engine::CGOutcome Engine::sr_natural_gradient(const double *gradient_host, const
   auto matvec = [&](const double *x, double *y) {
     ++out.matvecs;
     const double mean_dot_v = dot(v[MEAN], x);
-    sr_matvec_device(x, mean_dot_v, y);
+    if (complex_) sr_matvec_device_c(x, mean_dot_v, dot(v[MEANJ], x), y);
+    else sr_matvec_device(x, mean_dot_v, y);
     if (allreduce) {
       be_sync();
       if (allreduce(user, y, (size_t)n) != 0) throw std::runtime_error("sr_natural_gradient: the all-reduce callback failed");
@@ -2319,6 +2369,10 @@ Engine::CGOutcome Engine::sr_natural_gradient(const double *gradient_host, const
   };
   be_h2d(v[B], gradient_host, bytes);
   be_h2d(v[MEAN], ostar_mean_host, bytes);
+  if (complex_) {
+    be_d2d(v[MEANJ] + tps_total_, v[MEAN], bytes / 2);                   // im plane <- m_r
+    be_vec_lincomb(v[MEANJ], -1.0, v[MEAN] + tps_total_, 0.0, nullptr, tps_total_);      // re plane <- -m_i
+  }
   if (init_guess_host) be_h2d(v[X], init_guess_host, bytes); else be_memset0(v[X], bytes);
   const double rhs_sq = dot(v[B], v[B]);
   const double tol_sq = std::max(prm.rel_tol * prm.rel_tol * rhs_sq, prm.abs_tol * prm.abs_tol);

@@ -115,6 +115,7 @@ class Engine {
   // out = sum_i (O*_i . v - mean_dot_v) O*_i over the stored samples (device pointers, TPS-shaped vectors)
   void sr_matvec_device(const double *v_dev, double mean_dot_v, double *out_dev);
   void sr_matvec_host(const double *v, double mean_dot_v, double *out);
+  void sr_matvec_host_c(const double *v, double mean_re, double mean_im, double *out);   // complex context, planar vectors
   // Optimizer::CalculateNaturalGradient (optimizer/optimizer_impl.h:1031-1089) with every CG vector resident in HBM:
   // solves (S + diag_shift) x = gradient by the reference's conjugate-gradient loop (utility/conjugate_gradient_solver.h:
   // 181-276: best-iterate tracking, stagnation / NaN / indefiniteness exits, orthogonality restart, periodic residual
@@ -396,6 +397,10 @@ class Engine {
   double *sr_ostar_ = nullptr;    // [sr_cap_][hole_stride]
   int32_t *sr_cfgs_ = nullptr;    // [sr_cap_][nsites]
   double *sr_delta_ = nullptr;    // [sr_cap_]
+  // complex context: the store holds the real embedding (backend.h be_sr_store_c): [2 sr_cap_] rows of 2 hole_stride doubles,
+  // configurations twice, and the doubled site descriptors (re plane sites, then im plane sites) of the planar TPS layout
+  int32_t *sr_desc2_ = nullptr;   // [3][2 nsites]: hole_off2, site_size2, tps_off2
+  void sr_matvec_device_c(const double *v_dev, double mean_re, double mean_im, double *out_dev);
   long sr_cap_ = 0, sr_count_ = 0;
   bool sr_on_ = false;
 

@@ -100,7 +100,7 @@ class SRSMatrix:
         self.batch, self.mean, self.n, self.diag_shift, self.allreduce = batch, ostar_mean_flat, total_samples, diag_shift, allreduce
 
     def __call__(self, v):
-        mean_dot_v = float(np.dot(self.mean, v))
+        mean_dot_v = np.vdot(self.mean, v) if np.iscomplexobj(self.mean) else float(np.dot(self.mean, v))   # conj(mean) . v
         out = self.batch.sr_matvec(v, mean_dot_v)
         if self.allreduce is not None:
             out = self.allreduce(out)
@@ -147,9 +147,11 @@ def calculate_natural_gradient(batch, gradient_flat, ostar_mean_flat, total_samp
     ``allreduce_cb``: a _lib.ALLREDUCE_FN (see device_allreduce_callback) or None on a single GPU."""
     import ctypes as C
     from . import _lib
-    g = np.ascontiguousarray(gradient_flat, dtype=np.float64)
-    m = np.ascontiguousarray(ostar_mean_flat, dtype=np.float64)
-    x0 = None if init_guess is None else np.ascontiguousarray(init_guess, dtype=np.float64)
+    cx = bool(getattr(batch, "is_complex", False))          # complex context: planar arrays (re block, im block) across the ABI
+    pk = (lambda a: np.ascontiguousarray(np.concatenate([np.asarray(a).real, np.asarray(a).imag]), dtype=np.float64)) if cx \
+        else (lambda a: np.ascontiguousarray(a, dtype=np.float64))
+    g, m = pk(gradient_flat), pk(ostar_mean_flat)
+    x0 = None if init_guess is None else pk(init_guess)
     x = np.empty_like(g)
     prm = _lib.PepsCGParams(cg_params.max_iter, cg_params.relative_tolerance, cg_params.absolute_tolerance,
                             cg_params.residual_recompute_interval, cg_params.orthogonality_threshold)
@@ -159,6 +161,8 @@ def calculate_natural_gradient(batch, gradient_flat, ostar_mean_flat, total_samp
     batch._ck(batch.lib.peps_sr_natural_gradient(batch.h, dp(g), dp(m), int(total_samples), float(diag_shift), C.byref(prm),
                                                  dp(x0) if x0 is not None else None, cb, None, dp(x), C.byref(it),
                                                  C.byref(resid), C.byref(reason)))
+    if cx:
+        x = x[:x.size // 2] + 1j * x[x.size // 2:]
     res = CGResult(x, resid.value, it.value, reason.value)
     if res.reason in (INDEFINITE_MATRIX, NUMERICAL_BREAKDOWN):
         raise RuntimeError(f"CG solver terminated: {REASONS[res.reason]} iterations={res.iterations} residual_norm={res.residual_norm}")

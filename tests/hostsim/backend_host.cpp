@@ -804,6 +804,26 @@ void be_accumulate_ostar(const double *holes, long hole_stride, const int32_t *h
 }
 
 
+void be_sr_store_c(const double *hr, const double *hi, long hole_stride, const double *ampr, const double *ampi, const int32_t *cfg,
+                   int nsites, double *ostar, int32_t *cfgs, long first, long cap, int W) {
+  ++g_launches;
+  for (int w = 0; w < W; ++w) {
+    const double d = ampr[w] * ampr[w] + ampi[w] * ampi[w];
+    const double *a = hr + (long)w * hole_stride, *b = hi + (long)w * hole_stride;
+    double *x = ostar + (first + w) * 2 * hole_stride, *y = ostar + (cap + first + w) * 2 * hole_stride;
+    for (long e = 0; e < hole_stride; ++e) {
+      const double qr = (a[e] * ampr[w] + b[e] * ampi[w]) / d, qi = (b[e] * ampr[w] - a[e] * ampi[w]) / d;
+      const double o_r = qr, o_i = -qi;
+      x[e] = o_r; x[hole_stride + e] = o_i;
+      y[e] = -o_i; y[hole_stride + e] = o_r;
+    }
+    for (int s = 0; s < 2 * nsites; ++s) {
+      const int32_t c = cfg[(long)w * nsites + (s % nsites)];
+      cfgs[(first + w) * 2 * nsites + s] = c;
+      cfgs[(cap + first + w) * 2 * nsites + s] = c;
+    }
+  }
+}
 void be_sr_store(const double *holes, long hole_stride, const double *amp, const int32_t *cfg, int nsites,
                  double *ostar, int32_t *cfgs, long first, int W) {
   ++g_launches;

@@ -584,3 +584,48 @@ def run_complex_measure_parity(lib, j2=0.5, fermion=False):
     e = b.energy_and_holes(False)
     assert np.allclose(e, obs["energy"], rtol=1e-12)
     b.close()
+
+
+def run_complex_sr(lib, rows=3, cols=3, D=2, W=3, n=4, chi=4, diag_shift=1e-3):
+    """SR on a complex state: the store keeps the real embedding of the O* samples (x = [o_r; o_i], y = J x), the matvec and the
+    CG run with the real kernels on planar vectors. Checked against the dense Hermitian S = <(O - Obar)(O - Obar)^H> of the
+    oracle chain (SRSMatrix::operator* with the conjugating SplitIndexTPS inner product) and its dense solve."""
+    from oracle import sr as osr
+    from peps_b200 import sr
+    from peps_b200.api import (MCEnergyGradEvaluator, MonteCarloParams, SquareSpinOneHalfXXZModelOBC, MCUpdateSquareNNExchange)
+    tps_l = complex_tps(rows, cols, D, 8)
+    tps = SplitIndexTPS(tps_l)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 60 + w) for w in range(W)])
+    mc = MonteCarloParams(num_samples=n * W, num_warmup_sweeps=0, sweeps_between_samples=1, is_warmed_up=True)
+    ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(chi, chi, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                               MCUpdateSquareNNExchange(31), walkers=W, configs=cfgs, lib=lib)
+    res = ev.Evaluate(collect_sr_buffers=True)
+    assert ev.batch.sr_count() == n * W and res.total_samples == n * W
+    model = vmc.XXZModel()
+    ostars = []
+    for w in range(W):
+        wk = vmc.Walker(tps_l, cfgs[w], (chi, chi, 0.0))
+        up = vmc.NNExchangeUpdater(31 + w)
+        for _ in range(n):
+            up.sweep(tps_l, wk)
+            _, holes, _ = model.energy_and_holes(tps_l, wk, True)
+            inv = np.conj(1.0 / wk.amplitude)
+            sample = {(r, c): (int(wk.config[r, c]), holes[r][c] * inv) for r in range(rows) for c in range(cols)}
+            ostars.append(osr.dense_ostar(sample, tps_l))
+    o = np.stack(ostars)
+    obar = o.mean(axis=0)
+    assert np.max(np.abs(res.Ostar_mean.pack() - obar)) < 1e-12 * np.max(np.abs(obar))
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(obar.size) + 1j * rng.standard_normal(obar.size)
+    # S v = (1/N) sum_i (<O_i, v> - <Obar, v>) O_i + shift v,  <a, b> = sum conj(a) b   (stochastic_reconfiguration_smatrix.h:45-91)
+    ref = sum((np.vdot(oi, v) - np.vdot(obar, v)) * oi for oi in o) / len(o) + diag_shift * v
+    smat = sr.SRSMatrix(ev.batch, res.Ostar_mean.pack(), res.total_samples, diag_shift)
+    assert np.max(np.abs(smat(v) - ref)) < 1e-11 * np.max(np.abs(ref))
+    g = res.gradient.pack()
+    params = sr.ConjugateGradientParams(max_iter=300, relative_tolerance=1e-10)
+    nat, iters, resid = ev.CalculateNaturalGradient(res, diag_shift, params)
+    oc = o - obar
+    s_dense = oc.T @ oc.conj() / len(o) + diag_shift * np.eye(obar.size)      # S_ab = <(O - Obar)_a conj((O - Obar)_b)>
+    x_dense = np.linalg.solve(s_dense, g)
+    assert np.max(np.abs(nat.pack() - x_dense)) < 1e-6 * np.max(np.abs(x_dense)), np.max(np.abs(nat.pack() - x_dense)) / np.max(np.abs(x_dense))
+    return iters

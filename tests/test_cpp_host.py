@@ -44,3 +44,32 @@ def run_cpp_wrapper_case(lib, libdir, libfile, extra_link=()):
 
 def test_cpp_wrapper_matches_python_mirror():
     run_cpp_wrapper_case(hostsim_lib.load(), os.path.join(ROOT, "tests", "hostsim"), "libpeps_hostsim.so")
+
+
+def run_cpp_complex_case(lib, libdir, libfile, extra_link=()):
+    """tests/cpp/test_cpp_complex.cpp: the C++ wrapper's complex Evaluate against the Python mirror on the same library."""
+    from parity_common import complex_tps
+    tps = SplitIndexTPS(complex_tps(3, 3, 2, 4))
+    cfg = vmc.neel_config(3, 3)
+    W, chi, ns, seed = 3, 4, 6, 21
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "cpp_complex")
+        subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "test_cpp_complex.cpp"), "-o", exe,
+                               "-L" + libdir, "-l:" + libfile, "-Wl,-rpath," + libdir] + list(extra_link))
+        flat = tps.pack()
+        inp = f"3 3 2 2 {W} {chi} {ns} {seed}\n{flat.size}\n" + " ".join(f"{float(x.real)!r} {float(x.imag)!r}" for x in flat) + "\n" + \
+              " ".join(str(int(c)) for c in cfg.ravel()) + "\n"
+        out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
+    er, ei, err, gn, acc = map(float, out)
+    mc = MonteCarloParams(num_samples=ns, num_warmup_sweeps=0, sweeps_between_samples=1, initial_config=Configuration(cfg),
+                          is_warmed_up=True)
+    ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(chi, chi, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                               MCUpdateSquareNNExchange(seed), walkers=W, lib=lib)
+    res = ev.Evaluate()
+    assert abs(complex(er, ei) - res.energy) < 1e-12 and abs(ei) > 1e-6
+    assert abs(gn - res.gradient_norm) < 1e-12 * max(1.0, res.gradient_norm)
+    assert abs(acc - res.accept_rates_avg[0]) < 1e-12
+
+
+def test_cpp_wrapper_complex_matches_python_mirror():
+    run_cpp_complex_case(hostsim_lib.load(), os.path.join(ROOT, "tests", "hostsim"), "libpeps_hostsim.so")

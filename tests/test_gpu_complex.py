@@ -52,3 +52,17 @@ def test_complex_table_model_pipeline_parity_gpu(lib, table, j2):
 def test_complex_measure_parity_gpu(lib):
     from parity_common import run_complex_measure_parity
     run_complex_measure_parity(lib, 0.5)
+
+
+def test_complex_sr_matvec_and_natural_gradient_gpu(lib):
+    """The O* store as the real embedding of complex samples: matvec vs the dense Hermitian S of the oracle chain, CG vs the
+    dense solve, on the CUDA kernels."""
+    from parity_common import run_complex_sr
+    run_complex_sr(lib)
+
+
+def test_cpp_wrapper_complex_on_cuda_library(lib):
+    import os
+    from test_cpp_host import run_cpp_complex_case, ROOT
+    run_cpp_complex_case(lib, os.path.join(ROOT, "peps_b200"), "libpeps_b200.so",
+                         extra_link=["-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])

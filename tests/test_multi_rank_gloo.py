@@ -21,7 +21,8 @@ from peps_b200.api import (BMPSTruncateParams, SplitIndexTPS, MCEnergyGradEvalua
                            SquareSpinOneHalfXXZModelOBC, MCUpdateSquareNNExchange)
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
-tps = SplitIndexTPS(vmc.random_tps(3, 3, 2, 2, seed=4))
+from parity_common import complex_tps
+tps = SplitIndexTPS(complex_tps(3, 3, 2, 4) if {cx!r} else vmc.random_tps(3, 3, 2, 2, seed=4))
 W = 2
 cfgs = np.stack([vmc.shuffled_half_filled_config(3, 3, 50 + rank * W + w) for w in range(W)])
 mc = MonteCarloParams(num_samples=3 * W * world, num_warmup_sweeps=0, sweeps_between_samples=1, is_warmed_up=True)
@@ -38,7 +39,12 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_rank_gloo_matches_single_rank():
+import pytest
+
+
+@pytest.mark.parametrize("cx", [False, True])
+def test_two_rank_gloo_matches_single_rank(cx):
+    """cx: a complex state -- planar accumulators / CG vectors through the same all-reduces."""
     import pickle
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -49,14 +55,15 @@ def test_two_rank_gloo_matches_single_rank():
     with tempfile.TemporaryDirectory() as td:
         out = os.path.join(td, "res.pkl")
         script = os.path.join(td, "worker.py")
-        open(script, "w").write(WORKER.format(root=ROOT, out=out))
-        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", WORLD_SIZE="2")
+        open(script, "w").write(WORKER.format(root=ROOT, out=out, cx=cx))
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29612" if cx else "29611", WORLD_SIZE="2")
         procs = [subprocess.Popen([sys.executable, script], env=dict(env, RANK=str(r))) for r in range(2)]
         for p in procs:
             assert p.wait(timeout=300) == 0
         two = pickle.load(open(out, "rb"))
     # single rank with the same four walkers (seeds 9..12, configurations 50..53)
-    tps = SplitIndexTPS(vmc.random_tps(3, 3, 2, 2, seed=4))
+    from parity_common import complex_tps
+    tps = SplitIndexTPS(complex_tps(3, 3, 2, 4) if cx else vmc.random_tps(3, 3, 2, 2, seed=4))
     cfgs = np.stack([vmc.shuffled_half_filled_config(3, 3, 50 + w) for w in range(4)])
     mc = MonteCarloParams(num_samples=12, num_warmup_sweeps=0, sweeps_between_samples=1, is_warmed_up=True)
     ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(4, 4, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),

@@ -59,3 +59,8 @@ def test_cg_reference_exits():
     assert r.reason == sr.INDEFINITE_MATRIX
     r = sr.conjugate_gradient(lambda v: a @ v, b, np.linalg.solve(a, b), sr.ConjugateGradientParams())
     assert r.iterations == 0 and r.reason == sr.CONVERGED
+
+
+def test_complex_sr_matvec_and_natural_gradient_hostsim():
+    from parity_common import run_complex_sr
+    assert run_complex_sr(hostsim_lib.load()) > 0
