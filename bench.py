@@ -159,6 +159,24 @@ def cpu_baseline_quick(L, D, chi, cores, nsteps=3):
                                                    t_full_sample_s=cal.get("t_full_sample_s"))
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line: the same for the product arm and the reference arm (the driver compares them)."""
+    L, D, chi = WORKLOADS[args.workload]
+    return {"workload": args.workload, "lattice": f"{L}x{L}", "D": D, "chi": chi, "walkers_per_gpu": args.walkers,
+            "streams_per_gpu": args.streams, "trunc": "Dmin=Dmax=chi, trunc_err=0",
+            "model": "Heisenberg NN (XXZ jz=jxy=1)" if args.j2 == 0.0 else f"J1-J2 Heisenberg (j2={args.j2})",
+            "sweeps_between_samples": 1,
+            "tps": ("uniform[-1,1)" if args.signed else "uniform[0,1)") + f" seed {TPS_SEED}, NormalizeAllSite + order-1 rescale",
+            "l2": "per-step working set (walkers x ~60 MB of BMPS stacks + scratch) exceeds the 126 MB L2",
+            "parallelism": f"walkers sharded over {world} GPU(s); NCCL all-reduce of the two accumulators",
+            "algorithm": "reference call sequence; exact boundary-MPS memo (6(L-1) absorptions per sample instead of "
+                         "8(L-1), bit-identical); R-only QR chain with rows below 1e-13 of the largest dropped; "
+                         "column-sorted preconditioning QR, second (LQ) preconditioning with kept reflectors and a single-CTA "
+                         "one-sided Jacobi on the small square factor (block Jacobi on the rows when more than 128 "
+                         "rows survive the deflation) (DESIGN.md section 2); the CPU arm runs the reference's own algorithm "
+                         "(full SVD-compression absorptions) on the same workload"}
+
+
 def run_reference_arm(args, rank):
     if rank != 0:
         return
@@ -182,9 +200,7 @@ def run_reference_arm(args, rank):
     line = {"impl": "reference", "metric": "vmc_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "lattice": f"{L}x{L}", "D": D, "chi": chi,
-                       "trunc": "Dmin=Dmax=chi, trunc_err=0", "model": "Heisenberg NN (XXZ jz=jxy=1)",
-                       "sweeps_between_samples": 1, "tps": f"uniform[0,1) seed {TPS_SEED}, NormalizeAllSite"},
+            "config": workload_config(args, args.gpus),
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": SLICE_TEXT,
                              "detail": dict(cal, t_step_s=t, whole_sample_check_samples_per_s=cores / cal["t_full_sample_s"])},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -675,20 +691,10 @@ def main():
     line = {"metric": "vmc_samples_per_s", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "lattice": f"{L}x{L}", "D": D, "chi": chi, "walkers_per_gpu": W, "streams_per_gpu": S,
-                       "trunc": "Dmin=Dmax=chi, trunc_err=0",
-                       "model": "Heisenberg NN (XXZ jz=jxy=1)" if args.j2 == 0.0 else f"J1-J2 Heisenberg (j2={args.j2})",
-                       "sweeps_between_samples": 1, "tps": ("uniform[-1,1)" if args.signed else "uniform[0,1)") + f" seed {TPS_SEED}, NormalizeAllSite + order-1 rescale",
-                       "l2": "per-step working set (walkers x ~60 MB of BMPS stacks + scratch) exceeds the 126 MB L2",
-                       "parallelism": f"walkers sharded over {world} GPU(s); NCCL all-reduce of the two accumulators",
-                       "algorithm": "reference call sequence; exact boundary-MPS memo (6(L-1) absorptions per sample instead of "
-                                    "8(L-1), bit-identical); R-only QR chain with rows below 1e-13 of the largest dropped; "
-                                    "column-sorted preconditioning QR, second (LQ) preconditioning with kept reflectors and a single-CTA "
-                                    "one-sided Jacobi on the small square factor (block Jacobi on the rows when more than 128 "
-                                    "rows survive the deflation) (DESIGN.md section 2)",
-                       "rank_revealing": {"chain_rows_kept_frac": dstat[3] / max(dstat[2], 1), "truncation_rows_kept_frac": dstat[1] / max(dstat[0], 1),
-                                          "small_svd_path_frac": dstat[5] / max(dstat[4], 1),
-                                          "note": "the positive synthetic TPS has low numerical rank; see `secondary` for J1-J2, the signed state and a physical state"}},
+            "config": workload_config(args, world),
+            "rank_revealing": {"chain_rows_kept_frac": dstat[3] / max(dstat[2], 1), "truncation_rows_kept_frac": dstat[1] / max(dstat[0], 1),
+                               "small_svd_path_frac": dstat[5] / max(dstat[4], 1),
+                               "note": "the positive synthetic TPS has low numerical rank; see `secondary` for J1-J2, the signed state and a physical state"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": args.e2e_steps, "call": "Evaluate-style call with host buffers: set_tps (pinned) + init_walkers + 4 samples per walker (energies to the host each) + download of both accumulators"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,

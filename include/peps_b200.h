@@ -97,6 +97,14 @@ int peps_set_model_tfim(peps_ctx *ctx, double h);
  * back. Works for any phys (spin-1, t-J-like bosonic parts, ...). */
 int peps_set_model_term(peps_ctx *ctx, int32_t kind, int32_t T, const double *diag, const int32_t *target, const double *coef);
 int peps_clear_model_terms(peps_ctx *ctx);
+/* An extra table term on ONE nearest-neighbour bond, added to the local energy by the table-driven / fermionic solvers: the
+ * singlet-pair pinning field of the t-J models, SquaretJModelMixIn::SetSingletPairPinningField + EvaluateSingletPairPinningEnergy_
+ * (model_solvers/square_tJ_model.h:86-137, 256-289), as data: delta * (delta_dag + delta) of EvaluateBondSingletPairFortJModel
+ * (:546-602) is the table {(E,E) -> (up,dn): +delta/sqrt2, (E,E) -> (dn,up): -delta/sqrt2, (up,dn) -> (E,E): +delta/sqrt2,
+ * (dn,up) -> (E,E): -delta/sqrt2}. site1 = row-major index of the left / upper site, site2 = site1 + 1 or site1 + cols; a bond
+ * outside the lattice is an error (ValidateSingletPairPinningBondInLattice_, :240-250). Same table layout as kind 0 of
+ * peps_set_model_term; T = 0 clears the pin; peps_clear_model_terms clears it too. Call after the model terms. */
+int peps_set_bond_pin(peps_ctx *ctx, int32_t site1, int32_t site2, int32_t T, const double *diag, const int32_t *target, const double *coef);
 
 /* Fermionic (fZ2-graded) tensors -- QLTensor<T, fZ2QN> states of the reference (BASELINE config #4: SquareSpinlessFermion,
  * model_solvers/square_spinless_fermion.h:51-213; SquaretJNNModel / SquaretJVModel, model_solvers/square_tJ_model.h:85-420).
@@ -187,6 +195,14 @@ int peps_energy_and_holes(peps_ctx *ctx, int32_t calc_holes, double *eloc, doubl
  * (rows/2, cols/4): conj(psi(both spins flipped) / psi), 0 for equal spins (registry keys SmSp_row / SpSm_row by the
  * spin at the first site, :264-291). */
 int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr);
+/* A two-site operator given as a table (layout of kind 0 of peps_set_model_term), evaluated on every nearest-neighbour bond of
+ * the current configurations: out_h[W][rows][cols-1], out_v[W][rows-1][cols] = sum_p' <p|O|p'> conj(psi(p') / psi). The data
+ * form of a model's EvaluateBondSC hook (base/square_nnn_model_measurement_solver.h:116-131): for the t-J models the pair
+ * (delta_dag, delta) of EvaluateBondSingletPairFortJModel (square_tJ_model.h:546-602) is two tables and
+ * SC_bond_singlet_h / _v = (conj(delta_dag) + delta) / 2. Works for bosonic contexts and in fermion mode (hops, pair
+ * creation / annihilation, parity-preserving targets); complex contexts return planar arrays. The model and its state are
+ * untouched. */
+int peps_measure_bond_term(peps_ctx *ctx, int32_t T, const double *diag, const int32_t *target, const double *coef, double *out_h, double *out_v);
 /* StructureFactorMeasurementMixin::MeasureStructureFactor (model_solvers/base/structure_factor_measurement_mixin.h:89-228,
  * registry key SpSm_cross): all-pairs S+(y1,x1) S-(y2,x2) overlaps with y2 > y1 by "excited state propagation" -- the UP
  * boundary is forked at row y1 (BMPSContractor::BMPSWalker, bmps/impl/bmps_walker.h), absorbs the row with S+ applied and

@@ -128,6 +128,18 @@ inline ModelTerm tJNNNTerm(double t2) {
     return -t2 * ratio(c2, c1);
   });
 }
+// EvaluateBondSingletPairFortJModel (square_tJ_model.h:546-602) against the probe: delta_dag (which = 0), delta (which = 1)
+// or the pinning source delta_pin * (delta_dag + delta) (which = 2; SetSingletPairPinningField, :86-137, 256-289)
+inline ModelTerm tJSingletPairTerm(int which, double delta_pin = 1.0) {
+  const double s = 1.0 / std::sqrt(2.0);
+  return ProbeTwoSiteTerm(0, 3, [=](int c1, int c2, const std::function<double(int, int)> &ratio) {
+    double dd = 0.0, d = 0.0;
+    if (c1 == 2 && c2 == 2) dd = (ratio(0, 1) - ratio(1, 0)) * s;
+    else if (c1 == 0 && c2 == 1) d = ratio(2, 2) * s;
+    else if (c1 == 1 && c2 == 0) d = -ratio(2, 2) * s;
+    return which == 0 ? dd : which == 1 ? d : delta_pin * (dd + d);
+  });
+}
 // EvaluateTotalOnsiteEnergy of the t-J models (square_tJ_model.h:248-262): -mu per electron
 inline ModelTerm tJOnsiteTerm(double mu) {
   return ProbeOneSiteTerm(3, [=](int c, const std::function<double(int)> &) { return c == 2 ? 0.0 : -mu; });
@@ -208,6 +220,17 @@ class WalkerBatch {
   // table-driven model (seam B2 as data): one call per term; ClearModelTerms returns to the built-in solvers
   void SetModelTerm(const ModelTerm &m) { ck(peps_set_model_term(h_, m.kind, m.T, m.diag.data(), m.target.data(), m.coef.data())); }
   void ClearModelTerms() { ck(peps_clear_model_terms(h_)); }
+  // SquaretJModelMixIn::SetSingletPairPinningField as data (peps_set_bond_pin): `m` (a kind-0 ModelTerm, e.g.
+  // tJSingletPairPinningTerm(delta)) acts on the one NN bond (site1, site2), row-major site indices, site1 the left / upper site
+  void SetBondPin(int site1, int site2, const ModelTerm &m) { ck(peps_set_bond_pin(h_, site1, site2, m.T, m.diag.data(), m.target.data(), m.coef.data())); }
+  void ClearBondPin() { ck(peps_set_bond_pin(h_, 0, 1, 0, nullptr, nullptr, nullptr)); }
+  // EvaluateBondSC-style observable as data (peps_measure_bond_term): values on the horizontal [W][rows][cols-1] and the
+  // vertical [W][rows-1][cols] bonds (real contexts)
+  std::pair<std::vector<double>, std::vector<double>> MeasureBondTerm(const ModelTerm &m) {
+    std::vector<double> h((size_t)walkers_ * rows_ * (cols_ - 1)), v((size_t)walkers_ * (rows_ - 1) * cols_);
+    ck(peps_measure_bond_term(h_, m.T, m.diag.data(), m.target.data(), m.coef.data(), h.data(), v.data()));
+    return {h, v};
+  }
   // fZ2-graded tensors (peps_set_fermion): once, before SetTPS and SetModelTerm
   // JastrowDress: v[nsites * nsites] symmetric, density[phys] (peps_set_jastrow)
   void SetJastrow(const std::vector<double> &v, const std::vector<int32_t> &density) { ck(peps_set_jastrow(h_, v.data(), density.data())); }

@@ -294,6 +294,19 @@ def hop_variants(ftps, config, jw_h, jw_v, kind, a, b):
     return ftps.variant(*a, cb, HORIZONTAL, ma), ftps.variant(*b, ca, HORIZONTAL, mb), sign
 
 
+def bond_variants(ftps, config, jw_h, jw_v, kind, a, b, na, nb):
+    """Replacement tensors of an NN bond (kind 'h' / 'v') for ANY parity-consistent pair of new states (na, nb): a hop, a
+    pair creation / annihilation (both site parities change) or a parity-preserving change. The same masks as
+    hop_variants; psi(S') / psi(S) along one contraction path equals between_sign * the ratio of the graded amplitudes
+    (checked in tests/test_fermion_oracle.py)."""
+    ca, cb = int(config[a]), int(config[b])
+    da, db = ftps.phys_par[ca] ^ ftps.phys_par[na], ftps.phys_par[cb] ^ ftps.phys_par[nb]
+    assert da == db, "one site parity alone cannot change"
+    if kind == 'v':
+        return ftps.variant(*a, na, VERTICAL, ML * int(jw_v[a])), ftps.variant(*b, nb, VERTICAL, ML * (int(jw_v[b]) ^ da))
+    return ftps.variant(*a, na, HORIZONTAL, MU * int(jw_h[a])), ftps.variant(*b, nb, HORIZONTAL, MU * (int(jw_h[b]) ^ da))
+
+
 def jastrow_ratio(v, density, config, a, b):
     """Jastrow-factor ratio (new / old) of exchanging the states of a and b: JastrowFieldAtSite
     (vmc_basic/jastrow_factor.h:99-111) and the exp(field difference) of square_nn_updater.h:402-419."""
@@ -433,7 +446,53 @@ class FermionModel:
     def onsite_energy(self, config):
         return 0.0
 
+    pin = None              # (a, b, H): extra two-site table term on one NN bond (singlet-pair pinning, square_tJ_model.h:256-289)
+
+    def table_value(self, H, a, b, orient, w, psi=None):
+        """sum_p' H[p, p'] conj(psi(p') / psi) on the NN bond (a, b): a two-site operator given by its matrix in the basis
+        p = c1 * d + c2 (EvaluateBondSC-style hooks, square_tJ_model.h:546-602)."""
+        d = w.ftps.phys
+        p = int(w.config[a]) * d + int(w.config[b])
+        tn = w.tn_h if orient == HORIZONTAL else w.tn_v
+        val = H[p, p]
+        for q in range(d * d):
+            if q == p or H[p, q] == 0.0:
+                continue
+            if psi is None:
+                psi = w.contractor.trace(tn, a, orient)
+            ta, tb = bond_variants(w.ftps, w.config, w.jw_h, w.jw_v, 'h' if orient == HORIZONTAL else 'v', a, b, q // d, q % d)
+            val = val + H[p, q] * np.conj(w.contractor.replace_nn_site_trace(tn, a, b, orient, ta, tb) / psi)
+        return val, psi
+
     def bond_energy(self, a, b, orient, w):
+        e, psi = self._bond_energy(a, b, orient, w)
+        if self.pin is not None and (a, b) == (tuple(self.pin[0]), tuple(self.pin[1])):
+            pe, psi = self.table_value(self.pin[2], a, b, orient, w, psi)
+            e = e + pe
+        return e, psi
+
+    def measure_bond_table(self, H, w):
+        """(horizontal [rows][cols-1], vertical [rows-1][cols]) values of table_value on every NN bond."""
+        saved = self._bond_energy, self.pin
+        rec = {}
+        self.pin = None
+        self._bond_energy = lambda a, b, orient, ww: (rec.__setitem__((a, b), self.table_value(H, a, b, orient, ww)[0]) or 0.0,
+                                                     ww.contractor.trace(ww.tn_h if orient == HORIZONTAL else ww.tn_v, a, orient))
+        try:
+            FermionModel.energy_and_holes(self, w, False)
+        finally:
+            del self._bond_energy
+            self.pin = saved[1]
+        dt = np.result_type(w.ftps.T[0][0][0].dtype, np.float64)
+        h, v = np.zeros((w.rows, w.cols - 1), dt), np.zeros((w.rows - 1, w.cols), dt)
+        for (a, b), val in rec.items():
+            if a[0] == b[0]:
+                h[a] = val
+            else:
+                v[a] = val
+        return h, v
+
+    def _bond_energy(self, a, b, orient, w):
         c1, c2 = int(w.config[a]), int(w.config[b])
         e = self.diag_nn(c1, c2)
         if c1 == c2:

@@ -260,6 +260,37 @@ class TableModel:
     link), h1 is (d, d). What a reference-style EvaluateBondEnergy / EvaluateNNNEnergy / EvaluateTotalOnsiteEnergy mix-in
     (square_nnn_energy_solver.h:171-198) computes, with its matrix elements as data."""
 
+    bond_pin = None         # (site1, site2, H): an extra two-site term on ONE NN bond (peps_set_bond_pin)
+    enable_sc_measurement = False   # t-J measurement solvers: also record SC_bond_singlet_h / _v (MCPEPSMeasurer)
+
+    def SetSingletPairPinningField(self, site1, site2, delta):
+        """SquaretJModelMixIn::SetSingletPairPinningField (square_tJ_model.h:109-133): delta * (delta_dag + delta) on one NN
+        bond of a t-J model (states 0 = up, 1 = down, 2 = empty); the two sites in either order."""
+        if not np.isfinite(delta):
+            raise ValueError("Singlet pair pinning delta must be finite.")
+        (r1, c1), (r2, c2) = site1, site2
+        if abs(r1 - r2) + abs(c1 - c2) != 1:
+            raise ValueError("Singlet pair pinning field requires a nearest-neighbor bond.")
+        if (r2, c2) < (r1, c1):
+            (r1, c1), (r2, c2) = (r2, c2), (r1, c1)
+        dd, d = TableModel.tj_singlet_pair_tables()
+        self.bond_pin = ((r1, c1), (r2, c2), delta * (dd + d))
+        return self
+
+    def ClearSingletPairPinningField(self):
+        self.bond_pin = None
+        return self
+
+    @staticmethod
+    def tj_singlet_pair_tables():
+        """(delta_dag, delta) of EvaluateBondSingletPairFortJModel (square_tJ_model.h:546-602) as 9x9 tables in the basis
+        p = c1*3 + c2: value = sum_p' H[p, p'] conj(psi(p') / psi)."""
+        s = 1.0 / np.sqrt(2.0)
+        dd, d = np.zeros((9, 9)), np.zeros((9, 9))
+        dd[8, 1], dd[8, 3] = s, -s             # (E, E) -> (up, dn) - (dn, up)
+        d[1, 8], d[3, 8] = s, -s               # (up, dn) -> (E, E);  (dn, up) -> -(E, E)
+        return dd, d
+
     def __init__(self, phys, h2=None, h2_nnn=None, h1=None):
         self.phys, self.h2, self.h2_nnn, self.h1 = phys, h2, h2_nnn, h1
 
@@ -465,6 +496,10 @@ class WalkerBatch:
                     continue
                 T, diag, target, coef = TableModel.tables(H)
                 self._ck(self.lib.peps_set_model_term(self.h, kind, T, _dp(diag), _ip(target), _dp(coef)))
+            if model.bond_pin is not None:
+                (r1, c1), (r2, c2), H = model.bond_pin
+                T, diag, target, coef = TableModel.tables(H)
+                self._ck(self.lib.peps_set_bond_pin(self.h, r1 * self.cols + c1, r2 * self.cols + c2, T, _dp(diag), _ip(target), _dp(coef)))
             return
         self._ck(self.lib.peps_clear_model_terms(self.h))
         if isinstance(model, TransverseFieldIsingSquareOBC):
@@ -557,6 +592,24 @@ class WalkerBatch:
                 "bond_energy_dr": edr, "bond_energy_ur": eur,
                 "SmSp_row": np.where(first_down, 0.0, corr), "SpSm_row": np.where(first_down, corr, 0.0),
                 "SzSz_all2all": flat[:, iu[0]] * flat[:, iu[1]]}
+
+    def measure_bond_observable(self, H):
+        """A two-site operator as a (d*d, d*d) table on every NN bond (peps_measure_bond_term): (horizontal [W][rows][cols-1],
+        vertical [W][rows-1][cols]) of sum_p' H[p, p'] conj(psi(p') / psi)."""
+        W, r, c = self.W, self.rows, self.cols
+        npl = 2 if getattr(self, "is_complex", False) else 1
+        T, diag, target, coef = TableModel.tables(H)
+        oh, ov = np.empty((npl, W, r, c - 1)), np.empty((npl, W, r - 1, c))
+        self._ck(self.lib.peps_measure_bond_term(self.h, T, _dp(diag), _ip(target), _dp(coef), _dp(oh), _dp(ov)))
+        return (oh[0] + 1j * oh[1], ov[0] + 1j * ov[1]) if npl == 2 else (oh[0], ov[0])
+
+    def measure_sc_bond_singlet(self):
+        """SC_bond_singlet_h / _v of the t-J measurement solvers (base/square_nnn_model_measurement_solver.h:116-131):
+        (conj(delta_dag) + delta) / 2 per bond."""
+        dd, d = TableModel.tj_singlet_pair_tables()
+        ddh, ddv = self.measure_bond_observable(dd)
+        dh, dv = self.measure_bond_observable(d)
+        return (np.conj(ddh) + dh) / 2.0, (np.conj(ddv) + dv) / 2.0
 
     def measure_structure_factor(self):
         """MeasureStructureFactor (structure_factor_measurement_mixin.h:89-228): (pairs [n][4] = (y1, x1, y2, x2),
@@ -680,8 +733,12 @@ class MCPEPSMeasurer:
     def __init__(self, mc_params, trunc, tps, model, updater, walkers, device=0, lib=None, enable_structure_factor=False):
         rows, cols = tps.rows(), tps.cols()
         self.mc = mc_params
+        self.model = model
+        self.is_complex = bool(np.iscomplexobj(tps.t[0][0][0]))
         self.enable_structure_factor = enable_structure_factor      # StructureFactorMeasurementMixin::SetEnableStructureFactor
         self.batch = WalkerBatch(rows, cols, tps.PhysicalDim(), tps.bond_dim(), walkers, trunc, device, lib)
+        if self.is_complex:
+            self.batch.set_complex()
         if isinstance(tps, FermionSplitIndexTPS):              # config #4: fZ2 states, keys energy / charge / bond energies
             self.batch.set_fermion(tps)
         self.batch.set_tps(tps)
@@ -704,11 +761,13 @@ class MCPEPSMeasurer:
         for _ in range(nper):
             b.sweep(self.mc.sweeps_between_samples)
             obs = b.measure()
+            if getattr(self.model, "enable_sc_measurement", False):  # t-J solvers: ModelType::enable_sc_measurement
+                obs["SC_bond_singlet_h"], obs["SC_bond_singlet_v"] = b.measure_sc_bond_singlet()
             if self.enable_structure_factor:                         # registry key SpSm_cross: overlap / amplitude
                 self.sf_pairs, raw = b.measure_structure_factor()
-                obs["SpSm_cross"] = raw / b.amplitudes()[:, None]
+                obs["SpSm_cross"] = raw / b.amplitudes()[:, None]        # (real states only: peps_measure_structure_factor)
             if sums is None:
-                sums = {k: np.zeros_like(v, dtype=float) for k, v in obs.items()}
+                sums = {k: np.zeros_like(v, dtype=complex if np.iscomplexobj(v) else float) for k, v in obs.items()}
             for k, v in obs.items():
                 sums[k] += v
         out = {}
@@ -717,7 +776,7 @@ class MCPEPSMeasurer:
                 continue
             per_walker = v / nper
             mean = per_walker.mean(axis=0)
-            err = (np.sqrt(((per_walker - mean) ** 2).sum(axis=0) / (W * (W - 1))) if W > 1
+            err = (np.sqrt((np.abs(per_walker - mean) ** 2).sum(axis=0) / (W * (W - 1))) if W > 1
                    else np.full(np.shape(mean), np.inf))
             out[k] = (mean, err)
         self.results = out

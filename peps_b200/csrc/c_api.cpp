@@ -138,6 +138,12 @@ int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double
   GUARD(ctx, ctx->eng->measure(energy, e_h, e_v, e_dr, e_ur, row_corr))
 }
 int64_t peps_structure_factor_pairs(peps_ctx *ctx) { return ctx->eng->structure_factor_pairs(); }
+int peps_measure_bond_term(peps_ctx *ctx, int32_t T, const double *diag, const int32_t *target, const double *coef, double *out_h, double *out_v) {
+  GUARD(ctx, ctx->eng->measure_bond_term(T, diag, target, coef, out_h, out_v))
+}
+int peps_set_bond_pin(peps_ctx *ctx, int32_t site1, int32_t site2, int32_t T, const double *diag, const int32_t *target, const double *coef) {
+  GUARD(ctx, ctx->eng->set_bond_pin(site1, site2, T, diag, target, coef))
+}
 int peps_measure_structure_factor(peps_ctx *ctx, double *out) { GUARD(ctx, ctx->eng->measure_structure_factor(out)) }
 size_t peps_holes_stride(peps_ctx *ctx) { return (size_t)ctx->eng->holes_stride(); }
 int peps_get_holes(peps_ctx *ctx, double *h) { GUARD(ctx, ctx->eng->get_holes(h)) }

@@ -1677,14 +1677,7 @@ void Engine::set_model_term(int kind, int T, const double *diag, const int32_t *
     if (target[i] >= np) throw std::invalid_argument("set_model_term: target state out of range");
   if (fermion_) {
     if (kind == 2 && T > 0) throw std::invalid_argument("set_model_term: fermion mode supports diagonal on-site terms only");
-    for (int p = 0; kind != 2 && p < np; ++p)
-      for (int t = 0; t < T; ++t) {
-        const int tg = target[p * T + t];
-        if (tg < 0) continue;
-        const int d1 = phys_par_h_[(size_t)(p / phys_)] ^ phys_par_h_[(size_t)(tg / phys_)];
-        const int d2 = phys_par_h_[(size_t)(p % phys_)] ^ phys_par_h_[(size_t)(tg % phys_)];
-        if (d1 != d2) throw std::invalid_argument("set_model_term: fermion mode needs targets that move one fermion between the two sites or keep both parities");
-      }
+    if (kind != 2) check_two_site_table(T, target);
   }
   for (int p = 0; kind != 2 && p < np; ++p)
     for (int tt = 0; tt < T; ++tt) {
@@ -1692,10 +1685,32 @@ void Engine::set_model_term(int kind, int T, const double *diag, const int32_t *
       if (tg >= 0 && tg != (p % phys_) * phys_ + p / phys_) tables_exchange_only_ = false;
     }
   if (kind == 2 && T > 0) tables_exchange_only_ = false;
-  TermTable &t = term_[kind];
   be_sync();
+  upload_table(term_[kind], np, T, diag, target, coef);
+  if (!term_ia_) {
+    term_ia_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+    term_ib_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
+    term_cw_ = (double *)be_malloc(sizeof(double) * W_);
+  }
+  tables_on_ = true;
+}
+// fermion mode: both site parities of a two-site target change together (a hop or a pair) or not at all
+void Engine::check_two_site_table(int T, const int32_t *target) const {
+  for (int p = 0; p < phys_ * phys_; ++p)
+    for (int t = 0; t < T; ++t) {
+      const int tg = target[p * T + t];
+      if (tg < 0) continue;
+      const int d1 = phys_par_h_[(size_t)(p / phys_)] ^ phys_par_h_[(size_t)(tg / phys_)];
+      const int d2 = phys_par_h_[(size_t)(p % phys_)] ^ phys_par_h_[(size_t)(tg % phys_)];
+      if (d1 != d2) throw std::invalid_argument("fermion mode needs two-site targets that move one fermion between the two sites, create / annihilate a pair, or keep both parities");
+    }
+}
+void Engine::free_table(TermTable &t) {
   be_free(t.diag); be_free(t.target); be_free(t.coef);
   t = TermTable();
+}
+void Engine::upload_table(TermTable &t, int np, int T, const double *diag, const int32_t *target, const double *coef) {
+  free_table(t);
   t.T = T; t.set = true;
   t.diag = (double *)be_malloc(sizeof(double) * np);
   be_h2d(t.diag, diag, sizeof(double) * np);
@@ -1705,16 +1720,49 @@ void Engine::set_model_term(int kind, int T, const double *diag, const int32_t *
     be_h2d(t.target, target, sizeof(int32_t) * (size_t)np * T);
     be_h2d(t.coef, coef, sizeof(double) * (size_t)np * T);
   }
-  if (!term_ia_) {
-    term_ia_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
-    term_ib_ = (int32_t *)be_malloc(sizeof(int32_t) * W_);
-    term_cw_ = (double *)be_malloc(sizeof(double) * W_);
-  }
-  tables_on_ = true;
+}
+void Engine::set_bond_pin(int s1, int s2, int T, const double *diag, const int32_t *target, const double *coef) {
+  be_sync();
+  if (T <= 0) { free_table(pin_); pin_s1_ = pin_s2_ = -1; return; }
+  if (!diag || !target || !coef) throw std::invalid_argument("set_bond_pin: null table");
+  const bool horizontal = s2 == s1 + 1 && s1 >= 0 && (s1 % cols_) < cols_ - 1 && s2 < nsites_;
+  const bool vertical = s2 == s1 + cols_ && s1 >= 0 && s2 < nsites_;
+  if (!horizontal && !vertical)                       // ValidateSingletPairPinningBondInLattice_ (square_tJ_model.h:240-250)
+    throw std::invalid_argument("set_bond_pin: (site1, site2) must be a nearest-neighbour bond inside the lattice, site1 the left / upper site");
+  const int np = phys_ * phys_;
+  for (int i = 0; i < np * T; ++i)
+    if (target[i] >= np) throw std::invalid_argument("set_bond_pin: target state out of range");
+  if (fermion_) check_two_site_table(T, target);
+  if (!tables_on_) throw std::logic_error("set_bond_pin: needs a table-driven model (peps_set_model_term) first");
+  upload_table(pin_, np, T, diag, target, coef);
+  pin_s1_ = s1; pin_s2_ = s2;
+  tables_exchange_only_ = false;
+}
+void Engine::measure_bond_term(int T, const double *diag, const int32_t *target, const double *coef, double *out_h, double *out_v) {
+  if (T < 0 || !diag || (T > 0 && (!target || !coef))) throw std::invalid_argument("measure_bond_term: null table");
+  be_sync();
+  TermTable saved[3] = {term_[0], term_[1], term_[2]}, saved_pin = pin_;
+  const bool s_on = tables_on_, s_ex = tables_exchange_only_, s_j = jastrow_on_;
+  for (auto &t : term_) t = TermTable();
+  pin_ = TermTable();
+  auto restore = [&]() {
+    be_sync();
+    free_table(term_[0]);
+    for (int k = 0; k < 3; ++k) term_[k] = saved[k];
+    pin_ = saved_pin;
+    tables_on_ = s_on; tables_exchange_only_ = s_ex; jastrow_on_ = s_j;
+  };
+  try {
+    set_model_term(0, T, diag, target, coef);
+    jastrow_on_ = false;
+    measure(nullptr, out_h, out_v, nullptr, nullptr, nullptr);
+  } catch (...) { restore(); throw; }
+  restore();
 }
 void Engine::clear_model_terms() {
   be_sync();
-  for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); t = TermTable(); }
+  for (auto &t : term_) free_table(t);
+  free_table(pin_); pin_s1_ = pin_s2_ = -1;
   tables_on_ = false;
   tables_exchange_only_ = true;
 }
@@ -1730,14 +1778,19 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
   };
   const TermTable &nn = term_[0], &nnn = term_[1], &on = term_[2];
   // one term on (s1, s2): trace(idx_a, idx_b, out) evaluates the amplitude with the replacement physical indices
-  auto term = [&](const TermTable &tt, int s1, int s2, auto &&trace) {
-    if (tt.T == 0) { term_acc(s1, s2, tt.diag, nullptr, nullptr, psi_row_, eloc_); return; }
+  // dst: eloc_, or the bond's record while measure() runs (bond_target)
+  auto term = [&](const TermTable &tt, int s1, int s2, double *dst, auto &&trace) {
+    if (tt.T == 0) { term_acc(s1, s2, tt.diag, nullptr, nullptr, psi_row_, dst); return; }
     for (int t = 0; t < tt.T; ++t) {
       be_term_targets(cfg_, nsites_, s1, s2, phys_, tt.target, tt.coef, tt.T, t, term_ia_, s2 >= 0 ? term_ib_ : nullptr, term_cw_, W_);
       if (s2 >= 0) if (const double *jr = jastrow_for(s1, s2)) be_scale(term_cw_, jr, W_);
       trace(term_ia_, term_ib_, psi_tmp_);
-      term_acc(s1, s2, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_row_, eloc_);
+      term_acc(s1, s2, t == 0 ? tt.diag : nullptr, term_cw_, psi_tmp_, psi_row_, dst);
     }
+  };
+  auto nn_terms = [&](int s1, int s2, double *dst, auto &&trace) {
+    if (nn.set) term(nn, s1, s2, dst, trace);
+    if (pin_.set && s1 == pin_s1_ && s2 == pin_s2_) term(pin_, s1, s2, dst, trace);
   };
   generate_bmps_approach(UP);
   for (int row = 0; row < rows_; ++row) {
@@ -1748,12 +1801,11 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
     for (int col = 0; col < cols_; ++col) {
       if (calc_holes) punch_hole(row, col, HORIZONTAL);
       const int s1 = row * cols_ + col;
-      if (on.set) term(on, s1, -1, [&](const int32_t *ia, const int32_t *, double *out) { one_site_trace(row, col, ia, 1, out); });
+      if (on.set) term(on, s1, -1, eloc_, [&](const int32_t *ia, const int32_t *, double *out) { one_site_trace(row, col, ia, 1, out); });
       if (col < cols_ - 1) {
-        if (nn.set)
-          term(nn, s1, s1 + 1, [&](const int32_t *ia, const int32_t *ib, double *out) {
-            nn_trace_idx(row, col, row, col + 1, HORIZONTAL, ia, ib, 1, out);
-          });
+        nn_terms(s1, s1 + 1, bond_target(0, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {
+          nn_trace_idx(row, col, row, col + 1, HORIZONTAL, ia, ib, 1, out);
+        });
         shift_bten_window(RIGHT);
       }
     }
@@ -1762,10 +1814,10 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
       grow_full_bten2(RIGHT, row, 2, true);
       for (int col = 0; col < cols_ - 1; ++col) {
         const int s11 = row * cols_ + col, s21 = s11 + cols_, s12 = s11 + 1, s22 = s21 + 1;
-        term(nnn, s11, s22, [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row,col) - (row+1,col+1)
+        term(nnn, s11, s22, bond_target(2, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row,col) - (row+1,col+1)
           nnn_trace_refs(row, col, HORIZONTAL, site_ref_idx(s11, ia, 1), site_ref(s21, s21), site_ref(s12, s12), site_ref_idx(s22, ib, 1), out);
         });
-        term(nnn, s21, s12, [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row+1,col) - (row,col+1)
+        term(nnn, s21, s12, bond_target(3, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {     // (row+1,col) - (row,col+1)
           nnn_trace_refs(row, col, HORIZONTAL, site_ref(s11, s11), site_ref_idx(s21, ia, 1), site_ref_idx(s12, ib, 1), site_ref(s22, s22), out);
         });
         shift_bten2_window(RIGHT, row);
@@ -1781,10 +1833,9 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
     record_psi();
     for (int row = 0; row < rows_ - 1; ++row) {
       const int s1 = row * cols_ + col, s2 = s1 + cols_;
-      if (nn.set)
-        term(nn, s1, s2, [&](const int32_t *ia, const int32_t *ib, double *out) {
-          nn_trace_idx(row, col, row + 1, col, VERTICAL, ia, ib, 1, out);
-        });
+      nn_terms(s1, s2, bond_target(1, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {
+        nn_trace_idx(row, col, row + 1, col, VERTICAL, ia, ib, 1, out);
+      });
       if (row < rows_ - 2) shift_bten_window(DOWN);
     }
     if (col < cols_ - 1) shift_bmps_window(RIGHT);
@@ -2025,9 +2076,9 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
         if (nn.set) {
           nn_trace(row, col, row, col + 1, HORIZONTAL, s1, s1 + 1, psi_loc_);       // Trace(tn, site1, site2, orient)
           if (col == 0) record_psi(psi_loc_);
-          term(nn, s1, s1 + 1, 0, bond_target(0, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {
-            nn_trace_idx(row, col, row, col + 1, HORIZONTAL, ia, ib, 1, out);
-          });
+          auto tr = [&](const int32_t *ia, const int32_t *ib, double *out) { nn_trace_idx(row, col, row, col + 1, HORIZONTAL, ia, ib, 1, out); };
+          term(nn, s1, s1 + 1, 0, bond_target(0, row, col), tr);
+          if (pin_.set && s1 == pin_s1_ && s1 + 1 == pin_s2_) term(pin_, s1, s1 + 1, 0, bond_target(0, row, col), tr);
         }
         shift_bten_window(RIGHT);
       }
@@ -2069,9 +2120,9 @@ void Engine::energy_and_holes_fermion(bool calc_holes, double *eloc_host, double
       if (nn.set) {
         nn_trace(row, col, row + 1, col, VERTICAL, s1, s2, psi_loc_);
         if (row == 0) record_psi(psi_loc_);
-        term(nn, s1, s2, 1, bond_target(1, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {
-          nn_trace_idx(row, col, row + 1, col, VERTICAL, ia, ib, 1, out);
-        });
+        auto tr = [&](const int32_t *ia, const int32_t *ib, double *out) { nn_trace_idx(row, col, row + 1, col, VERTICAL, ia, ib, 1, out); };
+        term(nn, s1, s2, 1, bond_target(1, row, col), tr);
+        if (pin_.set && s1 == pin_s1_ && s2 == pin_s2_) term(pin_, s1, s2, 1, bond_target(1, row, col), tr);
       }
       if (row < rows_ - 2) shift_bten_window(DOWN);
     }
@@ -2121,15 +2172,16 @@ void Engine::row_corr_hook(int row) {
 }
 void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, double *e_ur, double *row_corr) {
   // fermion mode: the same registry (energy, bond energies of the table model); the spin-1/2 row correlator is zero
-  if (!fermion_ && tfim_) throw std::invalid_argument("measure: bond observables are defined for the XXZ / J1-J2 solvers");
-  if (!fermion_ && phys_ != 2) throw std::invalid_argument("measure: spin-1/2 observables need phys = 2");
+  const bool builtin_xxz = !fermion_ && !tables_on_;   // table models (bosons and fermions) record their bond energies only
+  if (builtin_xxz && tfim_) throw std::invalid_argument("measure: bond observables are defined for the XXZ / J1-J2 solvers and for table models");
+  if (builtin_xxz && phys_ != 2) throw std::invalid_argument("measure: spin-1/2 observables need phys = 2");
   const int nh = rows_ * (cols_ - 1), nv = (rows_ - 1) * cols_, nd = (rows_ - 1) * (cols_ - 1), ncr = cols_ / 2;
   const int nb = nh + nv + 2 * nd;
   const size_t S = sw();
   const int np = complex_ ? 2 : 1;        // complex context: every output array is planar, its real block then its imaginary block
   if (!bond_rec_) bond_rec_ = (double *)be_malloc(sizeof(double) * (size_t)(nb + ncr) * S);
   be_memset0(bond_rec_, sizeof(double) * (size_t)(nb + ncr) * S);
-  if (!fermion_) upload_flipped_configs();
+  if (builtin_xxz) upload_flipped_configs();
   rec_bonds_ = true;
   try {
     energy_and_holes(false, nullptr, nullptr);            // with recording on, eloc_ only receives the on-site term
@@ -2156,7 +2208,7 @@ void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, dou
         for (int i = 0; i < ncr; ++i) {
           const int32_t *c = cfg.data() + (size_t)w * nsites_;
           const bool equal = c[row * cols_ + c1] == c[row * cols_ + c1 + i + 1];
-          row_corr[(size_t)pl * W_ * ncr + (size_t)w * ncr + i] = (equal || fermion_) ? 0.0 : rec[(size_t)(nb + i) * S + (size_t)pl * W_ + w];
+          row_corr[(size_t)pl * W_ * ncr + (size_t)w * ncr + i] = (equal || !builtin_xxz) ? 0.0 : rec[(size_t)(nb + i) * S + (size_t)pl * W_ + w];
         }
   }
   if (energy)

@@ -149,6 +149,14 @@ class Engine {
   // target[p*T+t] = p' (or -1), coef[p*T+t] = <p|H|p'>. Setting any term switches the table-driven solver on.
   void set_model_term(int kind, int T, const double *diag, const int32_t *target, const double *coef);
   void clear_model_terms();
+  // A two-site operator given by its table, measured on every NN bond of the current configurations: out_h[W][rows][cols-1],
+  // out_v[W][rows-1][cols] = sum_p' <p|O|p'> conj(psi(p') / psi) -- the data form of a model's EvaluateBondSC hook
+  // (base/square_nnn_model_measurement_solver.h:116-131; t-J: delta_dag / delta of square_tJ_model.h:546-602 as two
+  // tables). Runs the measurement traversal with the operator in place of the model (Jastrow dressing off).
+  void measure_bond_term(int T, const double *diag, const int32_t *target, const double *coef, double *out_h, double *out_v);
+  // An extra table term on ONE NN bond (s1 = left / upper site, s2 = s1 + 1 or s1 + cols), added to the energy: the
+  // singlet-pair pinning field of the t-J models (square_tJ_model.h:86-137, 256-289) as data. T = 0 clears it.
+  void set_bond_pin(int s1, int s2, int T, const double *diag, const int32_t *target, const double *coef);
   // Fermion mode (fZ2-graded tensors, BASELINE config #4): the graded network is evaluated as a bosonic network of
   // sign-dressed site tensors, B = T * (-1)^q with q_H = l d + l r + d r + l + d + u J_H for the row machinery (UP / DOWN
   // boundary MPS, LEFT / RIGHT BTen, BTen2) and q_V = l d + l r + l u + l + d + l J_V for the column machinery; J_H / J_V =
@@ -298,6 +306,11 @@ class Engine {
   double *psi_loc_ = nullptr;             // [W] psi of the current bond / plaquette along the same contraction path
   struct TermTable { bool set = false; int T = 0; double *diag = nullptr; int32_t *target = nullptr; double *coef = nullptr; };
   TermTable term_[3];
+  TermTable pin_;                         // extra term on the NN bond (pin_s1_, pin_s2_)
+  int pin_s1_ = -1, pin_s2_ = -1;
+  void upload_table(TermTable &t, int np, int T, const double *diag, const int32_t *target, const double *coef);
+  void check_two_site_table(int T, const int32_t *target) const;
+  static void free_table(TermTable &t);
   bool tables_on_ = false;
   int32_t *term_ia_ = nullptr, *term_ib_ = nullptr;   // [W] replacement physical indices of the current target slot
   double *term_cw_ = nullptr;                          // [W] matrix element of the current target slot

@@ -629,3 +629,95 @@ def run_complex_sr(lib, rows=3, cols=3, D=2, W=3, n=4, chi=4, diag_shift=1e-3):
     x_dense = np.linalg.solve(s_dense, g)
     assert np.max(np.abs(nat.pack() - x_dense)) < 1e-6 * np.max(np.abs(x_dense)), np.max(np.abs(nat.pack() - x_dense)) / np.max(np.abs(x_dense))
     return iters
+
+
+def run_tj_pairing_parity(lib, rows=3, cols=4, D=2, W=4, trunc=(4, 4, 0.0), complex_=False, tol=1e-10):
+    """t-J model with a singlet-pair pinning field (SetSingletPairPinningField, square_tJ_model.h:86-137, 256-289) and the
+    bond-singlet SC observable (EvaluateBondSC -> SC_bond_singlet_h / _v, base/square_nnn_model_measurement_solver.h:116-131)
+    through the C ABI in fermion mode against oracle/fermion.py (pair rule checked against the graded contraction):
+    pinned E_loc, the difference to the unpinned model = delta * (delta_dag + delta) on that bond, and (conj(delta_dag) +
+    delta) / 2 on every bond."""
+    from oracle import fermion as F
+    from peps_b200.api import FermionSplitIndexTPS, TableModel
+    phys_par = (1, 1, 0)
+    f = F.FermionTPS.random(rows, cols, D, 23, phys_par=phys_par, complex_=complex_)
+    ftps = FermionSplitIndexTPS(f.T, f.par, phys_par)
+    rng = np.random.default_rng(8)
+    cfgs = []
+    while len(cfgs) < W:                                   # any even-parity configuration: empty pairs and up/down pairs occur
+        c = rng.integers(0, 3, size=(rows, cols))
+        if f.parities(c).sum() % 2 == 0:
+            cfgs.append(c)
+    cfgs = np.stack(cfgs)
+    delta = 0.07
+    worst = 0.0
+    dd, d = TableModel.tj_singlet_pair_tables()
+    for pin in (((0, 1), (0, 0)), ((1, 2), (2, 2))):       # a horizontal bond (sites given in reverse order) and a vertical one
+        b = WalkerBatch(rows, cols, 3, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
+        if complex_:
+            b.set_complex()
+        b.set_fermion(ftps)
+        b.set_tps(ftps)
+        b.set_configs(cfgs)
+        b.init_walkers()
+        base = TableModel.tj(1.0, 0.3, mu=0.2)
+        b.set_model(base)
+        e0 = b.energy_and_holes(False)
+        pinned = TableModel.tj(1.0, 0.3, mu=0.2).SetSingletPairPinningField(pin[0], pin[1], delta)
+        b.set_model(pinned)
+        e1 = b.energy_and_holes(False)
+        sc_h, sc_v = b.measure_sc_bond_singlet()
+        assert np.array_equal(b.energy_and_holes(False), e1)                 # the observable leaves the model untouched
+        b.set_model(pinned.ClearSingletPairPinningField())
+        assert np.array_equal(b.energy_and_holes(False), e0)
+        a_, b_ = sorted(pin)
+        omodel = F.tJModel(1.0, 0.3, mu=0.2)
+        opinned = F.tJModel(1.0, 0.3, mu=0.2)
+        opinned.pin = (a_, b_, delta * (dd + d))
+        for w in range(W):
+            wk = F.FermionWalker(f, cfgs[w], trunc)
+            r0 = omodel.energy_and_holes(wk, False)[0]
+            r1 = opinned.energy_and_holes(wk, False)[0]
+            worst = max(worst, abs(e0[w] - r0) / max(1.0, abs(r0)), abs(e1[w] - r1) / max(1.0, abs(r1)))
+            hdd, vdd = omodel.measure_bond_table(dd, wk)
+            hd, vd = omodel.measure_bond_table(d, wk)
+            rh, rv = (np.conj(hdd) + hd) / 2, (np.conj(vdd) + vd) / 2
+            worst = max(worst, float(np.max(np.abs(sc_h[w] - rh))), float(np.max(np.abs(sc_v[w] - rv))))
+            src = (hdd + hd)[a_] if a_[0] == b_[0] else (vdd + vd)[a_]   # the pinned energy adds delta * (delta_dag + delta) on the bond
+            assert abs((e1[w] - e0[w]) - delta * src) < 1e-10
+        assert np.max(np.abs(sc_h)) + np.max(np.abs(sc_v)) > 1e-3
+        b.close()
+    assert worst < tol, worst
+    # a bond outside the lattice is an error (ValidateSingletPairPinningBondInLattice_)
+    from peps_b200.api import PepsError
+    b = WalkerBatch(rows, cols, 3, D, 1, BMPSTruncateParams.SVD(*trunc), lib=lib)
+    b.set_fermion(ftps)
+    try:
+        b.set_model(TableModel.tj(1.0, 0.3).SetSingletPairPinningField((rows, 0), (rows, 1), delta))
+        raise AssertionError("out-of-lattice pin accepted")
+    except PepsError:
+        pass
+    b.close()
+    return worst
+
+
+def run_boson_bond_observable_parity(lib):
+    """peps_measure_bond_term on a bosonic context: the XXZ bond operator as a table reproduces the per-bond energies of the
+    built-in measurement, for a table model too (whose measure() now records its bond energies)."""
+    from peps_b200.api import SquareSpinOneHalfXXZModelOBC, TableModel
+    rows, cols, D, W = 3, 4, 2, 3
+    tps = vmc.random_tps(rows, cols, 2, D, seed=31)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 70 + w) for w in range(W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+    b.set_tps(SplitIndexTPS(tps)); b.set_configs(cfgs); b.init_walkers()
+    b.set_model(SquareSpinOneHalfXXZModelOBC(1.0, 0.8, 0.0))
+    obs = b.measure()
+    oh, ov = b.measure_bond_observable(TableModel.xxz(1.0, 0.8).h2)
+    assert np.allclose(oh, obs["bond_energy_h"], rtol=1e-12, atol=1e-13) and np.allclose(ov, obs["bond_energy_v"], rtol=1e-12, atol=1e-13)
+    b.set_model(TableModel.xxz(1.0, 0.8, 0.5, 0.35))
+    obs_t = b.measure()
+    b.set_model(__import__("peps_b200.api", fromlist=["x"]).SquareSpinOneHalfJ1J2XXZModelOBC(1.0, 0.8, 0.5, 0.35, 0.0))
+    obs_b = b.measure()
+    for k in ("energy", "bond_energy_h", "bond_energy_v", "bond_energy_dr", "bond_energy_ur"):
+        assert np.allclose(obs_t[k], obs_b[k], rtol=1e-12, atol=1e-13), k
+    b.close()

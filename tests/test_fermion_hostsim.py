@@ -291,3 +291,14 @@ def test_complex_tj_jastrow_dressed_pipeline_parity_hostsim(lib):
 def test_k8_complex_goldens_through_abi(lib):
     from parity_common import run_complex_k8_goldens
     run_complex_k8_goldens(lib)
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+def test_tj_singlet_pair_pinning_and_sc_bond_singlet_hostsim(lib, complex_):
+    from parity_common import run_tj_pairing_parity
+    run_tj_pairing_parity(lib, complex_=complex_)
+
+
+def test_boson_bond_observable_hostsim(lib):
+    from parity_common import run_boson_bond_observable_parity
+    run_boson_bond_observable_parity(lib)

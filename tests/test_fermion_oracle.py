@@ -148,3 +148,36 @@ def test_sweep_keeps_amplitude_consistent():
     fresh = F.FermionWalker(f, w.config, (16, 16, 0.0))
     assert abs(abs(w.amplitude) - abs(fresh.amplitude)) <= 1e-9 * abs(fresh.amplitude)
     assert abs(abs(fresh.amplitude) - abs(F.graded_amplitude(f, w.config))) <= 1e-9 * abs(fresh.amplitude)
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 2, 11), (3, 4, 2, 5), (4, 3, 2, 7)])
+def test_pair_terms_equal_graded_matrix_elements(shape):
+    """Pair creation / annihilation on an NN bond (the t-J singlet-pair source, square_tJ_model.h:546-602): the ratio
+    psi(S') / psi(S) of the dressed traversal with F.bond_variants equals between_sign * the ratio of the graded amplitudes
+    (row-major mode order), the same rule the K8-pinned hops obey."""
+    rows, cols, D, seed = shape
+    f = F.FermionTPS.random(rows, cols, D, seed=seed, phys_par=(1, 1, 0))
+    dd = np.zeros((9, 9)); dd[8, 1] = 1.0; dd[8, 3] = 1.0; dd[1, 8] = 1.0; dd[3, 8] = 1.0     # every pair process, weight 1
+    model = F.FermionModel()
+    rng = np.random.default_rng(3)
+    n = checked = 0
+    while n < 5:
+        cfg = rng.integers(0, 3, size=(rows, cols))
+        if f.parities(cfg).sum() % 2:
+            continue
+        n += 1
+        w = F.FermionWalker(f, cfg, (64, 64, 0.0))
+        psi = F.graded_amplitude(f, cfg)
+        h, v = model.measure_bond_table(dd, w)
+        for (arr, step) in ((h, (0, 1)), (v, (1, 0))):
+            for a in np.ndindex(arr.shape):
+                b = (a[0] + step[0], a[1] + step[1])
+                pair = (int(cfg[a]), int(cfg[b]))
+                new = {(2, 2): [(0, 1), (1, 0)], (0, 1): [(2, 2)], (1, 0): [(2, 2)]}.get(pair, [])
+                ref = 0.0
+                for na, nb in new:
+                    c2 = cfg.copy(); c2[a], c2[b] = na, nb
+                    ref += F.between_sign(f, cfg, a, b) * np.conj(F.graded_amplitude(f, c2) / psi)
+                    checked += 1
+                assert abs(arr[a] - ref) <= 1e-10 * max(1.0, abs(ref)), (a, b, pair)
+    assert checked > 10

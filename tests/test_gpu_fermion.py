@@ -172,3 +172,16 @@ def test_k8_complex_goldens_gpu(lib):
     the CUDA path."""
     from parity_common import run_complex_k8_goldens
     run_complex_k8_goldens(lib)
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+def test_tj_singlet_pair_pinning_and_sc_bond_singlet_gpu(lib, complex_):
+    """Singlet-pair pinning field in E_loc and the SC_bond_singlet observable (pair creation / annihilation targets) on the
+    CUDA path against the oracle."""
+    from parity_common import run_tj_pairing_parity
+    run_tj_pairing_parity(lib, complex_=complex_)
+
+
+def test_boson_bond_observable_gpu(lib):
+    from parity_common import run_boson_bond_observable_parity
+    run_boson_bond_observable_parity(lib)
