@@ -424,6 +424,113 @@ class FermionNNExchangeUpdater:
         return [accepted / (cols * (rows - 1) + rows * (cols - 1))]
 
 
+def line_variants(ftps, jw_h, jw_v, orient, sites, states):
+    """Dressed tensors of consecutive sites along a row (orient HORIZONTAL, row machinery) or a column (VERTICAL, column
+    machinery) carrying NEW states: the Jordan-Wigner bit of each site follows the new states of the sites before it in
+    the line (the bit of the first site is that of the current configuration); sites after the line are unaffected as
+    long as the total parity of the line is conserved."""
+    bit = int((jw_h if orient == HORIZONTAL else jw_v)[sites[0]])
+    out = []
+    for site, st in zip(sites, states):
+        out.append(ftps.variant(site[0], site[1], st, orient, (MU if orient == HORIZONTAL else ML) * bit))
+        bit ^= int(ftps.phys_par[st])
+    return out
+
+
+class FermionNNFullSpaceUpdater(FermionNNExchangeUpdater):
+    """MCUpdateSquareNNFullSpaceUpdateOBC on fZ2 tensors (square_nn_updater.h:253-293; "work for both fermion and boson",
+    :251): all d^2 local states of the bond, Suwa-Todo choice. Targets that change the parity of one site alone have zero
+    amplitude (the parity-conserving tensors contract to zero), hence zero weight."""
+
+    def two_site_update(self, a, b, bond_dir, w):
+        from .vmc import suwa_todo_state_update, _std_norm
+        d = w.ftps.phys
+        par = w.ftps.phys_par
+        c1, c2 = int(w.config[a]), int(w.config[b])
+        init = c1 * d + c2
+        tn = w.tn_h if bond_dir == HORIZONTAL else w.tn_v
+        alt = [0.0] * (d * d)
+        alt[init] = w.amplitude
+        for q in range(d * d):
+            na, nb = q // d, q % d
+            if q == init or (par[c1] ^ par[na]) != (par[c2] ^ par[nb]):
+                continue
+            ta, tb = line_variants(w.ftps, w.jw_h, w.jw_v, bond_dir, [a, b], [na, nb])
+            alt[q] = w.contractor.replace_nn_site_trace(tn, a, b, bond_dir, ta, tb)
+        weights = [_std_norm(x / w.amplitude) for x in alt]
+        final = suwa_todo_state_update(init, weights, self.rng)
+        if final == init:
+            return False
+        w.update_local(alt[final], (a, final // d), (b, final % d))
+        return True
+
+
+class FermionTNN3SiteExchangeUpdater:
+    """MCUpdateSquareTNN3SiteExchange on fZ2 tensors (square_3site_updater.h:23-160): permutations of the states of three
+    consecutive sites (how holes move two sites in the t-J runs), Suwa-Todo choice; the cached amplitude is refreshed by a
+    three-site trace at the start of every row / column."""
+
+    def __init__(self, seed):
+        self.rng = MT19937(seed)
+
+    def three_site_update(self, sites, bond_dir, w):
+        import itertools
+        from .vmc import suwa_todo_state_update, _std_norm
+        spins = [int(w.config[s]) for s in sites]
+        if spins[0] == spins[1] == spins[2]:
+            return False
+        perms = sorted(set(itertools.permutations(sorted(spins))))
+        init = perms.index(tuple(spins))
+        tn = w.tn_h if bond_dir == HORIZONTAL else w.tn_v
+        psis = []
+        for i, pm in enumerate(perms):
+            if i == init:
+                psis.append(w.amplitude)
+            else:
+                t = line_variants(w.ftps, w.jw_h, w.jw_v, bond_dir, sites, pm)
+                psis.append(w.contractor.replace_tnn_site_trace(tn, sites[0], bond_dir, t[0], t[1], t[2]))
+        mx = max(abs(x) for x in psis)
+        weights = [_std_norm(complex(x.real / mx, x.imag / mx) if np.iscomplexobj(x) else x / mx) for x in psis]
+        final = suwa_todo_state_update(init, weights, self.rng)
+        if final == init:
+            return False
+        pm = perms[final]
+        w.update_local(psis[final], *[(s, st) for s, st in zip(sites, pm)])
+        return True
+
+    def sweep(self, w):
+        c = w.contractor
+        rows, cols = w.rows, w.cols
+        accepted = 0
+        c.set_truncate_params(*w.trunc)
+        c.generate_bmps_approach(w.tn_h, UP)
+        for row in range(rows):
+            c.init_bten(w.tn_h, LEFT, row)
+            c.grow_full_bten(w.tn_h, RIGHT, row, 3, True)
+            w.amplitude = c.replace_tnn_site_trace(w.tn_h, (row, 0), HORIZONTAL, w.tn_h[row][0], w.tn_h[row][1], w.tn_h[row][2])
+            for col in range(cols - 2):
+                accepted += self.three_site_update([(row, col), (row, col + 1), (row, col + 2)], HORIZONTAL, w)
+                if col < cols - 3:
+                    c.shift_bten_window(w.tn_h, RIGHT)
+            if row < rows - 1:
+                c.shift_bmps_window(w.tn_h, DOWN)
+        c.delete_inner_bmps(LEFT)
+        c.delete_inner_bmps(RIGHT)
+        c.generate_bmps_approach(w.tn_v, LEFT)
+        for col in range(cols):
+            c.init_bten(w.tn_v, UP, col)
+            c.grow_full_bten(w.tn_v, DOWN, col, 3, True)
+            w.amplitude = c.replace_tnn_site_trace(w.tn_v, (0, col), VERTICAL, w.tn_v[0][col], w.tn_v[1][col], w.tn_v[2][col])
+            for row in range(rows - 2):
+                accepted += self.three_site_update([(row, col), (row + 1, col), (row + 2, col)], VERTICAL, w)
+                if row < rows - 3:
+                    c.shift_bten_window(w.tn_v, DOWN)
+            if col < cols - 1:
+                c.shift_bmps_window(w.tn_v, RIGHT)
+        c.delete_inner_bmps(UP)
+        return [accepted / (cols * (rows - 2) + rows * (cols - 2))]
+
+
 class FermionModel:
     """SquareNNNModelEnergySolver traversal for fermionic tensors (square_nnn_energy_solver.h:104-310): psi is
     recomputed per bond by Trace (NN) / ReplaceNNNSiteTrace with the original tensors (NNN, once per plaquette)."""

@@ -615,8 +615,10 @@ class WalkerBatch:
         """MeasureStructureFactor (structure_factor_measurement_mixin.h:89-228): (pairs [n][4] = (y1, x1, y2, x2),
         values [W][n]) -- raw S+S- overlaps; the registry key SpSm_cross holds value / amplitude."""
         n = int(self.lib.peps_structure_factor_pairs(self.h))
-        out = np.empty((self.W, n))
+        cx = getattr(self, "is_complex", False)
+        out = np.empty((2 if cx else 1, self.W, n))
         self._ck(self.lib.peps_measure_structure_factor(self.h, _dp(out)))
+        out = out[0] + 1j * out[1] if cx else out[0]
         pairs = np.array([(y1, x1, y2, x2) for y1 in range(self.rows - 1) for x1 in range(self.cols)
                           for y2 in range(y1 + 1, self.rows) for x2 in range(self.cols)], dtype=np.int32)
         return pairs, out
@@ -765,7 +767,7 @@ class MCPEPSMeasurer:
                 obs["SC_bond_singlet_h"], obs["SC_bond_singlet_v"] = b.measure_sc_bond_singlet()
             if self.enable_structure_factor:                         # registry key SpSm_cross: overlap / amplitude
                 self.sf_pairs, raw = b.measure_structure_factor()
-                obs["SpSm_cross"] = raw / b.amplitudes()[:, None]        # (real states only: peps_measure_structure_factor)
+                obs["SpSm_cross"] = raw / (b.amplitudes_c() if self.is_complex else b.amplitudes())[:, None]
             if sums is None:
                 sums = {k: np.zeros_like(v, dtype=complex if np.iscomplexobj(v) else float) for k, v in obs.items()}
             for k, v in obs.items():

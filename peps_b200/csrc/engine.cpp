@@ -95,7 +95,7 @@ Engine::~Engine() {
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
                   (void *)sr_cfgs_, (void *)sr_delta_, (void *)psi_list_d_, (void *)term_ia_, (void *)term_ib_, (void *)term_cw_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_,
                   (void *)(fermion_ ? gtps_ : nullptr), (void *)gtps_off_d_, (void *)gidx_[0], (void *)gidx_[1], (void *)jw_[0],
-                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_, (void *)jastrow_v_, (void *)jr_, (void *)dens_d_, (void *)sr_desc2_})
+                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_, (void *)jastrow_v_, (void *)jr_, (void *)dens_d_, (void *)sr_desc2_, (void *)fs_target_d_, (void *)fs_coef_d_})
     be_free(p);
   for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); }
   pool_.release_all();
@@ -1344,10 +1344,25 @@ void Engine::ensure_idx_const() {
   be_h2d(idx_const_, h.data(), sizeof(int32_t) * h.size());
 }
 void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
-  require_boson("the full-space updater");
   const int d = phys_, nst = d * d;
   ensure_idx_const();
   ensure_psi_alt(nst);
+  // fermion mode ("work for both fermion and boson", square_nn_updater.h:251): every target state through the dressed
+  // replacement rule of be_fermion_targets (a full table: slot t = local state t where both site parities change together,
+  // empty otherwise -- those amplitudes vanish for parity-conserving tensors and get weight 0)
+  if (fermion_ && !fs_target_d_) {
+    std::vector<int32_t> tg((size_t)nst * nst);
+    std::vector<double> cf((size_t)nst * nst, 1.0);
+    for (int p = 0; p < nst; ++p)
+      for (int q = 0; q < nst; ++q) {
+        const bool ok = (phys_par_h_[(size_t)(p / d)] ^ phys_par_h_[(size_t)(q / d)]) == (phys_par_h_[(size_t)(p % d)] ^ phys_par_h_[(size_t)(q % d)]);
+        tg[(size_t)p * nst + q] = ok ? q : -1;
+      }
+    fs_target_d_ = (int32_t *)be_malloc(sizeof(int32_t) * tg.size());
+    fs_coef_d_ = (double *)be_malloc(sizeof(double) * cf.size());
+    be_h2d(fs_target_d_, tg.data(), sizeof(int32_t) * tg.size());
+    be_h2d(fs_coef_d_, cf.data(), sizeof(double) * cf.size());
+  }
   std::vector<int32_t> cfg((size_t)W_ * nsites_), mtidx((size_t)W_);
   std::vector<uint32_t> mt((size_t)W_ * 624);
   const size_t S = sw();                                                 // complex: every amplitude array is [re W][im W]
@@ -1365,9 +1380,16 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
   auto bond = [&](int ra, int ca, int rb, int cb, int orient) {          // TwoSiteNNUpdateLocalImpl (:257-291)
     const int s1 = ra * cols_ + ca, s2 = rb * cols_ + cb;
     for (int a = 0; a < d; ++a)
-      for (int b = 0; b < d; ++b)
-        nn_trace_idx(ra, ca, rb, cb, orient, idx_const_ + (size_t)a * W_, idx_const_ + (size_t)b * W_, 1,
-                     psi_alt_ + (size_t)(a * d + b) * S);
+      for (int b = 0; b < d; ++b) {
+        if (fermion_) {
+          be_fermion_targets(cfg_, nsites_, s1, s2, phys_, phys_par_d_, jw_[0], jw_[1], orient == HORIZONTAL ? 0 : 1, fs_target_d_, fs_coef_d_,
+                             nst, a * d + b, term_ia_, term_ib_, term_cw_, W_);
+          nn_trace_idx(ra, ca, rb, cb, orient, term_ia_, term_ib_, 1, psi_alt_ + (size_t)(a * d + b) * S);
+        } else {
+          nn_trace_idx(ra, ca, rb, cb, orient, idx_const_ + (size_t)a * W_, idx_const_ + (size_t)b * W_, 1,
+                       psi_alt_ + (size_t)(a * d + b) * S);
+        }
+      }
     be_d2h(alt.data(), psi_alt_, sizeof(double) * alt.size());
     bool any = false;
     std::vector<double> wt((size_t)nst);
@@ -1387,6 +1409,10 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
           wt[(size_t)i] = std::norm((i == init ? a0 : x) / a0);
         }
       }
+      if (fermion_)
+        for (int i = 0; i < nst; ++i)
+          if ((phys_par_h_[(size_t)(init / d)] ^ phys_par_h_[(size_t)(i / d)]) != (phys_par_h_[(size_t)(init % d)] ^ phys_par_h_[(size_t)(i % d)]))
+            wt[(size_t)i] = 0.0;
       const int fin = suwa_todo(init, wt, rng[(size_t)w]);
       if (fin != init) {
         c[s1] = fin / d; c[s2] = fin % d;
@@ -1399,6 +1425,7 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
     if (any) {
       be_h2d(cfg_, cfg.data(), sizeof(int32_t) * cfg.size());
       be_h2d(amp_, amp.data(), sizeof(double) * amp.size());
+      refresh_gather();
     }
     touch_site(s1); touch_site(s2);
   };
@@ -1441,7 +1468,6 @@ void Engine::sweep_full_space(int nsweeps, double *accept_rate_host) {
 }
 
 void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
-  require_boson("the three-site updater");
   if (rows_ < 3 || cols_ < 3) throw std::invalid_argument("the 3-site updater needs a lattice of at least 3x3");
   const int maxp = 6;
   if (!idx_perm_) idx_perm_ = (int32_t *)be_malloc(sizeof(int32_t) * (size_t)maxp * W_ * 3);
@@ -1461,8 +1487,19 @@ void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
   std::vector<int> accepted((size_t)W_);
   auto refresh_amplitude = [&](int r, int c, int orient) {            // :39-42, :66-69
     const int s0 = r * cols_ + c, step = orient == HORIZONTAL ? 1 : cols_;
-    tnn_trace_idx(r, c, orient, cfg_ + s0, cfg_ + s0 + step, cfg_ + s0 + 2 * step, nsites_, amp_);
+    const int32_t *own = fermion_ ? gidx_[orient] : cfg_;            // fermion mode: the dressed slices of the machinery
+    tnn_trace_idx(r, c, orient, own + s0, own + s0 + step, own + s0 + 2 * step, nsites_, amp_);
     be_d2h(amp.data(), amp_, sizeof(double) * amp.size());
+  };
+  // fermion mode: gather index of `state` at the k-th site of the triple when the sites before it carry `st[0..k-1]`: the
+  // Jordan-Wigner bit follows the new states (the triple's parity is conserved, later sites are unaffected)
+  auto dressed = [&](const int32_t *cw, int r, int c, int orient, const std::array<int, 3> &st, int k) -> int32_t {
+    if (!fermion_) return st[(size_t)k];
+    int bit = 0;
+    if (orient == HORIZONTAL) for (int x = 0; x < c; ++x) bit ^= phys_par_h_[(size_t)cw[r * cols_ + x]];
+    else for (int y = 0; y < r; ++y) bit ^= phys_par_h_[(size_t)cw[y * cols_ + c]];
+    for (int q = 0; q < k; ++q) bit ^= phys_par_h_[(size_t)st[(size_t)q]];
+    return (int32_t)(((orient == HORIZONTAL ? 0 : 6) + bit) * phys_ + st[(size_t)k]);
   };
   auto triple = [&](int r, int c, int orient) {                       // TNN3SiteUpdateImpl (:108-158)
     const int s0 = r * cols_ + c, step = orient == HORIZONTAL ? 1 : cols_;
@@ -1485,8 +1522,9 @@ void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
       for (int w = 0; w < W_; ++w) {
         const int32_t *cw = cfg.data() + (size_t)w * nsites_;
         const bool has = s < (int)perms[(size_t)w].size();
-        for (int k = 0; k < 3; ++k)
-          perm_h[((size_t)s * W_ + w) * 3 + k] = has ? perms[(size_t)w][(size_t)s][(size_t)k] : cw[st[k]];
+        const std::array<int, 3> own = {cw[st[0]], cw[st[1]], cw[st[2]]};
+        const std::array<int, 3> &use = has ? perms[(size_t)w][(size_t)s] : own;
+        for (int k = 0; k < 3; ++k) perm_h[((size_t)s * W_ + w) * 3 + k] = dressed(cw, r, c, orient, use, k);
       }
     be_h2d(idx_perm_, perm_h.data(), sizeof(int32_t) * (size_t)nslots * W_ * 3);
     for (int s = 0; s < nslots; ++s) {
@@ -1522,6 +1560,7 @@ void Engine::sweep_three_site(int nsweeps, double *accept_rate_host) {
     if (any) {
       be_h2d(cfg_, cfg.data(), sizeof(int32_t) * cfg.size());
       be_h2d(amp_, amp.data(), sizeof(double) * amp.size());
+      refresh_gather();
     }
     for (int k = 0; k < 3; ++k) touch_site(st[k]);
   };
@@ -2221,13 +2260,13 @@ void Engine::measure(double *energy, double *e_h, double *e_v, double *e_dr, dou
 }
 void Engine::measure_structure_factor(double *out_host) {
   require_boson("the structure-factor measurement");
-  require_real("the structure-factor measurement");
   if (phys_ != 2) throw std::invalid_argument("measure_structure_factor: S+ S- correlators are defined for spin-1/2 (phys = 2)");
   ensure_idx_const();
   const int32_t *up_idx = idx_const_ + (size_t)1 * W_, *dn_idx = idx_const_;     // spin-up / spin-down slices for every walker
   const long npairs = structure_factor_pairs();
-  double *vals = (double *)pool_.get(sizeof(double) * (size_t)npairs * W_);       // [pair][W]
-  be_memset0(vals, sizeof(double) * (size_t)npairs * W_);
+  const size_t S = sw();                                                           // complex: [pair][re W | im W]
+  double *vals = (double *)pool_.get(sizeof(double) * (size_t)npairs * S);         // [pair][W]
+  be_memset0(vals, sizeof(double) * (size_t)npairs * S);
   generate_bmps_approach(UP);                                  // the full DOWN stack (structure_factor...h:118)
   long pair = 0;
   for (int y1 = 0; y1 < rows_ - 1; ++y1) {
@@ -2250,7 +2289,7 @@ void Engine::measure_structure_factor(double *out_host) {
         for (int x2 = cols_ - 1; x2 >= 0; --x2) {
           const int s2 = y2 * cols_ + x2;
           BT half = bten_step(left.at((size_t)x2), exc.at((size_t)(cols_ - 1 - x2)), site_ref_idx(s2, dn_idx, 1), bottom.at((size_t)x2), LEFT);
-          reverse_dot(half, right, vals + (size_t)(pair + x2) * W_);             // TraceWithBTen
+          reverse_dot(half, right, vals + (size_t)(pair + x2) * S);              // TraceWithBTen
           release(half);
           if (x2 > 0) {                                                           // GrowBTenRightStep
             BT nr = bten_step(right, bottom.at((size_t)x2), site_ref(s2, s2), exc.at((size_t)(cols_ - 1 - x2)), RIGHT);
@@ -2271,7 +2310,8 @@ void Engine::measure_structure_factor(double *out_host) {
     }
   }
   // mask on the host: S+ needs a down spin at the source, S- an up spin at the target; transpose to [W][pair]
-  std::vector<double> h((size_t)npairs * W_);
+  // (complex context: out_host is planar, the [W][pair] real block followed by the imaginary block)
+  std::vector<double> h((size_t)npairs * S);
   std::vector<int32_t> cfg((size_t)W_ * nsites_);
   be_d2h(h.data(), vals, sizeof(double) * h.size());
   be_d2h(cfg.data(), cfg_, sizeof(int32_t) * cfg.size());
@@ -2284,7 +2324,8 @@ void Engine::measure_structure_factor(double *out_host) {
           for (int w = 0; w < W_; ++w) {
             const int32_t *c = cfg.data() + (size_t)w * nsites_;
             const bool ok = c[y1 * cols_ + x1] == 0 && c[y2 * cols_ + x2] == 1;
-            out_host[(size_t)w * npairs + p] = ok ? h[(size_t)p * W_ + w] : 0.0;
+            out_host[(size_t)w * npairs + p] = ok ? h[(size_t)p * S + w] : 0.0;
+            if (complex_) out_host[(size_t)W_ * npairs + (size_t)w * npairs + p] = ok ? h[(size_t)p * S + W_ + w] : 0.0;
           }
 }
 void Engine::zero_accumulators() {

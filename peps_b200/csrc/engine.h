@@ -368,6 +368,8 @@ class Engine {
   double tfim_h_ = 0.0;
   int32_t *idx_const_ = nullptr;   // [phys][W]: idx_const_[s*W + w] = s
   int32_t *idx_flip_ = nullptr;    // [W][nsites]: 1 - config
+  int32_t *fs_target_d_ = nullptr;   // fermion mode, full-space updater: [phys^2][phys^2] target table (parity-consistent states)
+  double *fs_coef_d_ = nullptr;
   int32_t *idx_perm_ = nullptr;    // [6][W][3]: physical indices of permutation slot s of walker w (3-site updater)
   double *psi_alt_ = nullptr;      // [psi_alt_slots_][W] amplitudes of the alternative local states of an update
   int psi_alt_slots_ = 0;

@@ -201,12 +201,14 @@ def run_table_model_parity(lib, tol=1e-10):
     return worst
 
 
-def run_structure_factor_parity(lib, rows=3, cols=4, D=2, W=3, chi=64, tol=1e-10):
+def run_structure_factor_parity(lib, rows=3, cols=4, D=2, W=3, chi=64, tol=1e-10, complex_=False):
     """peps_measure_structure_factor vs the oracle's restatement of MeasureStructureFactor, pair by pair."""
-    tps = vmc.random_tps(rows, cols, 2, D, seed=17)
+    tps = complex_tps(rows, cols, D, 17) if complex_ else vmc.random_tps(rows, cols, 2, D, seed=17)
     cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 5 + w) for w in range(W)])
     trunc = (1, chi, 0.0)
     b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(*trunc), lib=lib)
+    if complex_:
+        b.set_complex()
     b.set_tps(SplitIndexTPS(tps)); b.set_configs(cfgs); b.init_walkers()
     pairs, vals = b.measure_structure_factor()
     worst = 0.0
@@ -274,7 +276,7 @@ def fermion_configs(rows, cols, W, phys, seed=10):
 
 
 def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", nsweeps=2, seed=3, tol=1e-10, seeds0=200,
-                                t2=0.6, check_holes=True, jastrow=False, complex_=False):
+                                t2=0.6, check_holes=True, jastrow=False, complex_=False, updater="exchange"):
     """Sweeps + E_loc + O* of W walkers through the C ABI in fermion mode vs oracle/fermion.py, walker by walker:
     configurations and acceptance counts bit-identical, |amplitudes|, E_loc, O* to `tol` (relative)."""
     from oracle import fermion as F
@@ -310,6 +312,14 @@ def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", 
     b.init_walkers()
     ws = [F.FermionWalker(f, cfgs[w], trunc) for w in range(W)]
     ups = [F.FermionNNExchangeUpdater(seeds0 + w, jastrow=jas) for w in range(W)]
+    if updater == "full_space":                 # MCUpdateSquareNNFullSpaceUpdateOBC on fZ2 tensors (fermion number not conserved)
+        from peps_b200.api import MCUpdateSquareNNFullSpaceUpdate
+        b.set_updater(MCUpdateSquareNNFullSpaceUpdate())
+        ups = [F.FermionNNFullSpaceUpdater(seeds0 + w) for w in range(W)]
+    elif updater == "three_site":               # MCUpdateSquareTNN3SiteExchange on fZ2 tensors
+        from peps_b200.api import MCUpdateSquareTNN3SiteExchange
+        b.set_updater(MCUpdateSquareTNN3SiteExchange())
+        ups = [F.FermionTNN3SiteExchangeUpdater(seeds0 + w) for w in range(W)]
     amps = b.amplitudes_c if complex_ else b.amplitudes
     a0 = np.abs(amps())
     r0 = np.abs(np.array([w_.amplitude for w_ in ws]))

@@ -36,10 +36,8 @@ def test_complex_mode_guards(lib):
     from peps_b200.api import BMPSTruncateParams, WalkerBatch, PepsError, TableModel, FermionSplitIndexTPS
     b = WalkerBatch(3, 3, 2, 2, 1, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
     b.set_complex()
-    with pytest.raises(PepsError):                       # still real-only: variational compression, structure factor, SR store
+    with pytest.raises(PepsError):                       # still real-only: variational compression
         b.set_truncation(BMPSTruncateParams.Variational2Site(4, 4, 0.0, 1e-9, 5))
-    with pytest.raises(PepsError):
-        b.measure_structure_factor()
     b.close()
     b = WalkerBatch(3, 3, 2, 2, 1, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
     b.set_tps(np.zeros(b.tps_size))
@@ -117,3 +115,8 @@ def test_complex_table_model_pipeline_parity_hostsim(lib, table, j2):
 def test_complex_measure_parity_hostsim(lib, j2):
     from parity_common import run_complex_measure_parity
     run_complex_measure_parity(lib, j2)
+
+
+def test_complex_structure_factor_hostsim(lib):
+    from parity_common import run_structure_factor_parity
+    run_structure_factor_parity(lib, complex_=True)

@@ -302,3 +302,11 @@ def test_tj_singlet_pair_pinning_and_sc_bond_singlet_hostsim(lib, complex_):
 def test_boson_bond_observable_hostsim(lib):
     from parity_common import run_boson_bond_observable_parity
     run_boson_bond_observable_parity(lib)
+
+
+@pytest.mark.parametrize("updater,model,complex_", [("full_space", "tj", False), ("three_site", "tj", False),
+                                                    ("full_space", "spinless", True), ("three_site", "tj_nnn", True)])
+def test_fermion_full_space_and_three_site_updaters_hostsim(lib, updater, model, complex_):
+    """The multi-state updaters on fZ2 tensors ("work for both fermion and boson", square_nn_updater.h:251): chains
+    bit-identical to the oracle's restatement, E_loc / O* after every sweep."""
+    run_fermion_pipeline_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), model=model, nsweeps=2, updater=updater, complex_=complex_)

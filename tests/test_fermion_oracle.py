@@ -181,3 +181,23 @@ def test_pair_terms_equal_graded_matrix_elements(shape):
                     checked += 1
                 assert abs(arr[a] - ref) <= 1e-10 * max(1.0, abs(ref)), (a, b, pair)
     assert checked > 10
+
+
+@pytest.mark.parametrize("updater", ["full_space", "three_site"])
+def test_fermion_full_space_and_three_site_updaters_keep_amplitude_consistent(updater):
+    """The dressed replacement rule of the multi-state updaters (line_variants: Jordan-Wigner bits follow the new states):
+    after sweeps the cached amplitude equals |psi| of the configuration from the graded contraction, moves are accepted,
+    and the fermion parity is conserved."""
+    f = F.FermionTPS.random(3, 4, 2, seed=9, phys_par=(1, 1, 0))
+    cfg = np.array([[0, 2, 1, 2], [2, 0, 2, 1], [1, 2, 0, 2]])
+    w = F.FermionWalker(f, cfg, (64, 64, 0.0))
+    up = F.FermionNNFullSpaceUpdater(7) if updater == "full_space" else F.FermionTNN3SiteExchangeUpdater(7)
+    acc = 0.0
+    for _ in range(3):
+        acc += up.sweep(w)[0]
+        g = F.graded_amplitude(f, w.config)
+        assert abs(abs(w.amplitude) - abs(g)) <= 1e-9 * abs(g)
+    assert acc > 0
+    assert f.parities(w.config).sum() % 2 == 0
+    if updater == "three_site":
+        assert sorted(w.config.ravel()) == sorted(cfg.ravel())              # permutations only

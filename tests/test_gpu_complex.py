@@ -66,3 +66,8 @@ def test_cpp_wrapper_complex_on_cuda_library(lib):
     from test_cpp_host import run_cpp_complex_case, ROOT
     run_cpp_complex_case(lib, os.path.join(ROOT, "peps_b200"), "libpeps_b200.so",
                          extra_link=["-Wl,-rpath,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
+
+
+def test_complex_structure_factor_gpu(lib):
+    from parity_common import run_structure_factor_parity
+    run_structure_factor_parity(lib, complex_=True)

@@ -185,3 +185,9 @@ def test_tj_singlet_pair_pinning_and_sc_bond_singlet_gpu(lib, complex_):
 def test_boson_bond_observable_gpu(lib):
     from parity_common import run_boson_bond_observable_parity
     run_boson_bond_observable_parity(lib)
+
+
+@pytest.mark.parametrize("updater,model,complex_", [("full_space", "tj", False), ("three_site", "tj", False),
+                                                    ("three_site", "tj_nnn", True)])
+def test_fermion_full_space_and_three_site_updaters_gpu(lib, updater, model, complex_):
+    run_fermion_pipeline_parity(lib, 4, 4, 2, 3, (4, 4, 0.0), model=model, nsweeps=2, updater=updater, complex_=complex_)
