@@ -655,26 +655,47 @@ def main():
         return
 
     # ---- roofline of the dominant kernel
+    # The lanes of the timed loop hold W/S walkers each, so a launch profiled with its lane running ALONE covers a fraction of
+    # the SMs (the other lanes fill the rest in the timed loop): those per-lane figures stay in `per_lane`. The kernel's own
+    # roofline position is measured on launches of the full batch: the same W walkers in ONE lane (one warm-up sample, then
+    # one sample with every launch bracketed by a CUDA-event pair on its stream, the kernel alone on the GPU).
+    ls.close()
+    lane_prof = prof
+    full = LaneSet(L, D, chi, W, 1, local_rank, sit, cfgs, seeds, j2=args.j2, torch=torch)
+    full.samples(1)
+    full.lanes[0].q.put(profiled)
+    st, prof = full.lanes[0].r.get()
+    if st == "err":
+        raise prof
+    full.close()
     dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
     dom_name, dom_p = dom
     fp64_peak = measure_fp64_peak(torch)
     achieved = dom_p["flops"] / max(dom_p["ms"], 1e-9) / 1e9            # TFLOP/s of useful FP64 work in that kernel class
     step_ms = elapsed_ms / args.steps
     mf = MODEL_FLOPS[args.workload]
+    lane_dom = lane_prof[dom_name]
     traffic = None       # dram bytes of the benchmarked launches are not measured in-run; ncu captures: profiles/r2_ncu_*.txt
     roofline = {"kernel": dom_name, "bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak,
                 "peak_source": "cuBLAS DGEMM 4096^3 through torch.matmul, measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
-                "traffic": traffic, "measured_on": "one extra step of the timed loop with per-launch CUDA-event pairs (see bench.py)",
+                "traffic": traffic,
+                "measured_on": f"one extra sample of the same workload with all {W} walkers in one lane (full-batch launches, the kernel alone "
+                               "on the GPU), every launch bracketed by a CUDA-event pair on its stream; `per_lane` holds the same "
+                               f"measurement on the timed loop's own lanes ({Ws} walkers each, one lane at a time)",
                 "launches": dom_p["launches"], "avg_launch_us": 1e3 * dom_p["ms"] / max(dom_p["launches"], 1),
                 "share_of_step": dom_p["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
                 "per_class_ms": {k: round(v["ms"], 1) for k, v in prof.items()},
                 "per_class_tflops": {k: (v["flops"] / max(v["ms"], 1e-9) / 1e9) for k, v in prof.items()},
+                "per_class_frac": {k: (v["flops"] / max(v["ms"], 1e-9) / 1e9) / fp64_peak for k, v in prof.items() if v["flops"] > 0},
+                "per_lane": {"walkers_per_launch": Ws, "achieved": lane_dom["flops"] / max(lane_dom["ms"], 1e-9) / 1e9,
+                             "frac": lane_dom["flops"] / max(lane_dom["ms"], 1e-9) / 1e9 / fp64_peak,
+                             "per_class_ms": {k: round(v["ms"], 1) for k, v in lane_prof.items()},
+                             "per_class_tflops": {k: (v["flops"] / max(v["ms"], 1e-9) / 1e9) for k, v in lane_prof.items()}},
                 "whole_path": {"model_flops_per_sample": mf["total"], "model_tflops": value * mf["total"] / world / 1e12,
                                "frac_of_fp64_peak": value * mf["total"] / world / 1e12 / fp64_peak,
                                "contraction_model_tflops": value * mf["gemm"] / world / 1e12}}
 
-    ls.close()
     secondary = None
     if args.secondary and world == 1:
         try:                                         # companions must never take the headline line down with them
