@@ -400,6 +400,23 @@ class MCEnergyGradEvaluator {
     r.accept_rates_avg = {acc / (double)(n * W)};
     return r;
   }
+  // EvaluateEnergyOnly (mc_energy_grad_evaluator.h:331-392): the step-selector trial -- StepSweep + CalEnergy per sample, no
+  // holes / O* / gradient. Returns {energy, energy_error, mean acceptance rate}.
+  std::tuple<double, double, double> EvaluateEnergyOnly(const std::vector<double> &packed_tps) {
+    batch_.SetTPS(packed_tps);
+    batch_.InitWalkers();
+    const size_t W = (size_t)batch_.walkers();
+    const size_t n = std::max<size_t>(1, (mc_.num_samples + W - 1) / W);
+    std::vector<double> es(W * n);
+    double acc = 0;
+    for (size_t s = 0; s < n; ++s) {
+      for (double a : batch_.StepSweep((int)mc_.sweeps_between_samples)) acc += a;
+      const std::vector<double> e = batch_.EnergyAndHoles(false);
+      for (size_t w = 0; w < W; ++w) es[w * n + s] = e[w];
+    }
+    auto me = BinnedMean(es, W, n);
+    return std::make_tuple(me.first, me.second, acc / (double)(n * W));
+  }
   // Evaluate for a QLTEN_Complex state (batch().SetComplex() first): E_loc = ... conj(psi_ex / psi), gradient =
   // sum conj(E_loc) O* / N - conj(E) sum O* / N (mc_energy_grad_evaluator.h:245-309); error bar from the real parts
   EvaluateResultComplex Evaluate(const std::vector<std::complex<double>> &packed_tps) {

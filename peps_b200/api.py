@@ -1068,6 +1068,40 @@ class MCEnergyGradEvaluator:
             res.total_samples = n * total_walkers
         return res
 
+    def EvaluateEnergyOnly(self, state: Optional[SplitIndexTPS] = None):
+        """MCEnergyGradEvaluator::EvaluateEnergyOnly (mc_energy_grad_evaluator.h:331-392), the step-selector trial: the same
+        chains with CalEnergy (no holes, no O*, no gradient reduction). Returns (energy, energy_error, accept_rates_avg)."""
+        b = self.batch
+        if state is not None:
+            self.state = state
+            b.set_tps(state)
+        b.init_walkers()
+        n = self.samples_per_walker()
+        energies = np.empty((b.W, n), dtype=complex if self.is_complex else float)
+        accept = np.zeros(b.W)
+        for s in range(n):
+            accept += b.sweep(self.mc.sweeps_between_samples)
+            e = b.energy_and_holes(False)
+            if not np.all(np.isfinite(e)):
+                raise PepsError("local energy is not finite (zero or illegal amplitude): run EnsureConfigurationValidity / WarmUp first")
+            energies[:, s] = e
+        all_e = energies
+        if self.dist is not None and self.world_size > 1:
+            import torch
+            dev = "cuda" if self.dist.get_backend() == "nccl" else "cpu"
+            mine = torch.from_numpy(np.ascontiguousarray(energies).view(np.float64)).to(dev)
+            gathered = [torch.empty_like(mine) for _ in range(self.world_size)]
+            self.dist.all_gather(gathered, mine)
+            all_e = np.concatenate([g.cpu().numpy() for g in gathered], axis=0)
+            if self.is_complex:
+                all_e = np.ascontiguousarray(all_e).view(np.complex128)
+        if self.is_complex:
+            er, err = combine_energy_bins(all_e.real)
+            energy = complex(er, combine_energy_bins(all_e.imag)[0])
+        else:
+            energy, err = combine_energy_bins(all_e)
+        return energy, err, [float(np.mean(accept / n))]
+
     def CalculateNaturalGradient(self, result: EvaluateResult, diag_shift, cg_params=None, init_guess=None):
         """Optimizer::CalculateNaturalGradient (optimizer/optimizer_impl.h:1031-1089) against the O* samples kept in
         HBM by the last Evaluate(collect_sr_buffers=True). Returns (natural_gradient, cg_iterations, residual_norm)."""

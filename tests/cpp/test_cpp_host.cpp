@@ -43,6 +43,11 @@ int main() {
     double dmax = 0.0;
     for (size_t w = 0; w < e_builtin.size(); ++w) dmax = std::max(dmax, std::fabs(e_builtin[w] - e_table[w]));
     std::printf("%.17g %d\n", dmax, (int)ev.batch().EnsureConfigurationValidity().size());
+    // EvaluateEnergyOnly on a fresh evaluator: the same chains as Evaluate (same seeds), so the same energy
+    peps_b200::MCEnergyGradEvaluator ev2(mc, peps_b200::BMPSTruncateParams::SVD(chi, chi, 0.0), rows, cols, phys, D, walkers,
+                                         peps_b200::XXZModel{1.0, 1.0, 0.0}, seed);
+    auto eo = ev2.EvaluateEnergyOnly(tps);
+    std::printf("%.17g %.17g\n", std::get<0>(eo), std::get<2>(eo));
   } catch (const std::exception &e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -28,7 +28,8 @@ def run_cpp_wrapper_case(lib, libdir, libfile, extra_link=()):
         inp = f"3 3 2 2 {W} {chi} {ns} {seed}\n{flat.size}\n" + " ".join(repr(float(x)) for x in flat) + "\n" + \
               " ".join(str(int(c)) for c in cfg.ravel()) + "\n"
         out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
-    e_cpp, err_cpp, gn_cpp, acc_cpp, e2, e_meas, e_bonds, d_table, n_rescued = map(float, out)
+    e_cpp, err_cpp, gn_cpp, acc_cpp, e2, e_meas, e_bonds, d_table, n_rescued, e_only, acc_only = map(float, out)
+    assert abs(e_only - e_cpp) < 1e-12 and abs(acc_only - acc_cpp) < 1e-12     # EvaluateEnergyOnly: same chains, no holes
     assert d_table < 1e-13 and n_rescued == 0
     assert abs(e_meas - e_bonds) < 1e-10 * max(1.0, abs(e_meas))
     mc = MonteCarloParams(num_samples=ns, num_warmup_sweeps=0, sweeps_between_samples=1, initial_config=Configuration(cfg),
@@ -40,6 +41,10 @@ def run_cpp_wrapper_case(lib, libdir, libfile, extra_link=()):
     assert np.isfinite(e2)          # second Evaluate through the seam-B1 adapter continues the same chains
     assert abs(gn_cpp - res.gradient_norm) < 1e-12 * max(1.0, res.gradient_norm)
     assert abs(acc_cpp - res.accept_rates_avg[0]) < 1e-12
+    ev2 = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(chi, chi, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                                MCUpdateSquareNNExchange(seed), walkers=W, lib=lib)
+    e_py, err_py, acc_py = ev2.EvaluateEnergyOnly()
+    assert abs(e_py - res.energy) < 1e-12 and abs(err_py - res.energy_error) < 1e-12 and abs(acc_py[0] - res.accept_rates_avg[0]) < 1e-12
 
 
 def test_cpp_wrapper_matches_python_mirror():

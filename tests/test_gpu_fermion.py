@@ -157,6 +157,8 @@ def test_fermion_pipeline_block_jacobi_path_gpu(lib, monkeypatch, sectors):
     ("spinless", 4, 4, 4, (8, 8, 0.0), 3),
     ("spinless", 4, 4, 2, (2, 6, 1e-8), 3),
     ("tj_nnn", 3, 4, 2, (4, 4, 0.0), 3),
+    ("spinless", 6, 6, 4, (16, 16, 0.0), 2),
+    ("tj", 6, 6, 4, (8, 16, 1e-9), 2),
 ])
 def test_complex_fermion_pipeline_parity_gpu(lib, model, rows, cols, D, trunc, W):
     """fZ2 tensors with complex entries: dressed planes, complex E_loc and O* on the CUDA path against the oracle."""
