@@ -73,11 +73,8 @@ def read_qlten(path, dtype=None):
     return np.frombuffer(buf[pos:pos + n * item], dtype=dtype).reshape(dims).copy()
 
 
-def read_qlten_fz2(path, dtype=np.float64):
-    """fZ2-graded (block-sparse) QLTensor stream. Per index: ``nsct``, per sector ``qnval qnhash dgnc hash``, then
-    ``dir dim hash``; ``nblocks`` and the sector coordinates of every block; payload = the blocks in listed order, each
-    row-major. Returns (dense array, [parity of every index value per leg], [direction per leg])."""
-    buf = open(path, "rb").read()
+def _fz2_header(path, buf):
+    """Parses the header of an fZ2 stream: (legs = [(sectors [(qn, dgnc)], dir, dim)], block coordinates, payload offset)."""
     it = _tokens(buf)
     rank, pos = next(it)
     legs = []
@@ -102,6 +99,21 @@ def read_qlten_fz2(path, dtype=np.float64):
             v, pos = next(it)
             c.append(v)
         coords.append(c)
+    return legs, coords, pos
+
+
+def read_qlten_fz2(path, dtype=None):
+    """fZ2-graded (block-sparse) QLTensor stream. Per index: ``nsct``, per sector ``qnval qnhash dgnc hash``, then
+    ``dir dim hash``; ``nblocks`` and the sector coordinates of every block; payload = the blocks in listed order, each
+    row-major. ``dtype`` None detects float64 / complex128 from the payload length. Returns (dense array, [parity of every
+    index value per leg], [direction per leg])."""
+    buf = open(path, "rb").read()
+    legs, coords, pos = _fz2_header(path, buf)
+    rank = len(legs)
+    if dtype is None:
+        nel = sum(int(np.prod([legs[k][0][c[k]][1] for k in range(rank)])) for c in coords)
+        payload = len(buf) - pos - (1 if buf[-1:] == b"\n" and (len(buf) - pos) % 8 == 1 else 0)
+        dtype = np.complex128 if nel and payload == 16 * nel else np.float64
     out = np.zeros([l[2] for l in legs], dtype=dtype)
     offs = [np.concatenate([[0], np.cumsum([dg for _, dg in l[0]])]) for l in legs]
     item = np.dtype(dtype).itemsize
@@ -117,6 +129,44 @@ def read_qlten_fz2(path, dtype=np.float64):
         raise ValueError(f"{path}: {len(buf) - pos} trailing bytes (wrong element type?)")
     par = [np.concatenate([np.full(dg, qn % 2, dtype=np.int32) for qn, dg in l[0]]) for l in legs]
     return out, par, [l[1] for l in legs]
+
+
+def write_qlten_fz2(path, array, template):
+    """Rewrites an fZ2 tensor with new elements: header (sectors, hashes, block list) copied verbatim from the ``template``
+    file -- the state the reference dumped before the optimisation has the same index structure as the optimised one --
+    followed by the blocks of ``array`` (dense, legs in file order) in the template's block order. Elements of ``array``
+    outside the template's blocks must be zero (they would be lost)."""
+    buf = open(template, "rb").read()
+    legs, coords, pos = _fz2_header(template, buf)
+    rank = len(legs)
+    a = np.asarray(array)
+    if list(a.shape) != [l[2] for l in legs]:
+        raise ValueError(f"{path}: array shape {a.shape} does not match the template's index dimensions")
+    dt = np.complex128 if np.iscomplexobj(a) else np.float64
+    offs = [np.concatenate([[0], np.cumsum([dg for _, dg in l[0]])]) for l in legs]
+    mask = np.zeros(a.shape, dtype=bool)
+    parts = []
+    for c in coords:
+        sl = tuple(slice(offs[k][c[k]], offs[k][c[k] + 1]) for k in range(rank))
+        parts.append(np.ascontiguousarray(a[sl], dtype=dt).tobytes())
+        mask[sl] = True
+    if np.any(a[~mask] != 0):
+        raise ValueError(f"{path}: non-zero elements outside the template's blocks (parity-violating entries)")
+    with open(path, "wb") as f:
+        f.write(buf[:pos] + b"".join(parts) + b"\n")
+
+
+def dump_fermion_tps(ftps, directory, template_dir):
+    """SplitIndexTPS<T, fZ2QN>::Dump with the headers of ``template_dir`` (a TPS directory of the same index structure, e.g.
+    the initial state): the files load back into the reference."""
+    os.makedirs(directory, exist_ok=True)
+    with open(os.path.join(directory, "tps_meta.txt"), "w") as f:
+        f.write(f"{ftps.rows()} {ftps.cols()} {ftps.PhysicalDim()}")
+    for r in range(ftps.rows()):
+        for c in range(ftps.cols()):
+            for s in range(ftps.PhysicalDim()):
+                name = f"tps_ten{r}_{c}_{s}.qlten"
+                write_qlten_fz2(os.path.join(directory, name), np.asarray(ftps((r, c))[s])[..., None], os.path.join(template_dir, name))
 
 
 def load_fermion_tps(directory):
