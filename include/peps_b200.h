@@ -128,15 +128,16 @@ int peps_set_fermion(peps_ctx *ctx, const int32_t *phys_par, const int32_t *leg_
  * (DESIGN.md section 11). Covered: amplitude, the three updaters (|psi| = hypot; Suwa-Todo weights std::norm), every energy
  * solver (XXZ / J1-J2, transverse-field Ising, table models, fermion mode: call peps_set_complex BEFORE peps_set_fermion) with
  * conj(psi_ex / psi) (square_spin_onehalf_xxz_obc.h:72-104), holes and O* = conj(hole / psi), sum O*, sum conj(E_loc) O*
- * (mc_energy_grad_evaluator.h:245-272), measurement, the SR store / matvec / natural gradient. Real-only: variational
- * compression and the structure-factor measurement. Conventions of a complex context:
+ * (mc_energy_grad_evaluator.h:245-272), measurement (structure factor included), the SR store / matvec / natural gradient,
+ * SVD and variational boundary compression. Conventions of a complex context:
  *   - peps_set_tps_c uploads the two planes of the packed state; peps_get_planar reads per-walker / state-shaped results as
  *     planes: what = 0 amplitudes [W], 1 local energies [W] (after peps_energy_and_holes), 2 holes [W][holes_stride] (the
  *     raw environment; O* = conj(hole / amplitude); fermion mode: the finished hole), 3 sum O*, 4 sum conj(E_loc) O*
  *     [tps_size], 5 the state [tps_size]. The real getters return the real planes.
  *   - the psi list of peps_energy_and_holes holds (rows+cols) entries of 2 W doubles (re[W] then im[W]);
  *   - every output array of peps_measure is planar: its real block followed by its imaginary block (twice the real size);
- *   - the accumulator device pointers address 2 * tps_size doubles (re plane, im plane). */
+ *   - the accumulator device pointers address 2 * tps_size doubles (re plane, im plane);
+ *   - the peps_probe_* calls return 2 W doubles (re[W], im[W]). */
 int peps_set_complex(peps_ctx *ctx);
 int peps_set_tps_c(peps_ctx *ctx, const double *re, const double *im, size_t n);
 int peps_get_planar(peps_ctx *ctx, int32_t what, double *re, double *im);

@@ -145,7 +145,8 @@ def _svd_trunc(theta, dmin, dmax, trunc_err):
 def multiply_mpo_variational(mps, mpo_sites, post, dmin, dmax, trunc_err, tol, max_iter, one_site=False):
     """BMPS::MultiplyMPO with VARIATION2Site / VARIATION1Site (bmps_impl.h:404-437 -> 864-995 / 997-1172).
     Init guess (:1176-1212): the MPS reduced to bond dimension <= 2, multiplied by the MPO with SVD compression.
-    lenv[k, e, a] / renv[c, g, j]: (result bond, MPO bond, MPS bond) / (MPS bond, MPO bond, result bond) (:703-729)."""
+    lenv[k, e, a] / renv[c, g, j]: (result bond, MPO bond, MPS bond) / (MPS bond, MPO bond, result bond) (:703-729).
+    The environments contract the CONJUGATE of the result tensors (the reference keeps `res_dag`, :885-947): complex states."""
     n = len(mps)
     if n == 2:
         return multiply_mpo(mps, mpo_sites, post, dmin, dmax, trunc_err)
@@ -163,7 +164,7 @@ def multiply_mpo_variational(mps, mpo_sites, post, dmin, dmax, trunc_err, tol, m
     renvs = [np.ones((1, 1, 1))]
     for i in range(n - 1, 1, -1):                            # GrowRightEnvironments_ (:731-743)
         r1 = es("bqc,cgj->bqgj", mps[i], renvs[-1])
-        renvs.append(es("fbuj,tuj->bft", es("bqgj,fqgu->fbuj", r1, m[i]), res[i]))
+        renvs.append(es("fbuj,tuj->bft", es("bqgj,fqgu->fbuj", r1, m[i]), np.conj(res[i])))   # res_dag (:885)
 
     def sweep_two_site(d0, d1):
         s_last = None
@@ -171,13 +172,13 @@ def multiply_mpo_variational(mps, mpo_sites, post, dmin, dmax, trunc_err, tol, m
             l2, r2, th = _two_site_theta(lenvs[-1], renvs[-1], mps[i], mps[i + 1], m[i], m[i + 1])
             u, s_last, vt = _svd_trunc(th, d0, d1, trunc_err)
             res[i] = u
-            lenvs.append(es("kofb,kot->tfb", l2, u))
+            lenvs.append(es("kofb,kot->tfb", l2, np.conj(u)))
             renvs.pop()
         for i in range(n - 2, 0, -1):                        # back: res[i+1] = Vt (:920-947)
             l2, r2, th = _two_site_theta(lenvs[-1], renvs[-1], mps[i], mps[i + 1], m[i], m[i + 1])
             u, s_last, vt = _svd_trunc(th, d0, d1, trunc_err)
             res[i + 1] = vt
-            renvs.append(es("fbuj,tuj->bft", r2, vt))
+            renvs.append(es("fbuj,tuj->bft", r2, np.conj(vt)))
             lenvs.pop()
         return s_last
 
@@ -202,7 +203,7 @@ def multiply_mpo_variational(mps, mpo_sites, post, dmin, dmax, trunc_err, tol, m
     u, s, vt = _svd_trunc(th, dmin, dmax, trunc_err)
     res[0] = u * s
     res[1] = vt
-    renvs.append(es("fbuj,tuj->bft", r2, vt))                # :1108-1110
+    renvs.append(es("fbuj,tuj->bft", r2, np.conj(vt)))       # :1108-1110
     last = 0.0
     for it in range(max_iter):
         for i in range(n - 1):                               # :1116-1131
@@ -211,7 +212,7 @@ def multiply_mpo_variational(mps, mpo_sites, post, dmin, dmax, trunc_err, tol, m
             k, o, t = a.shape
             q, _ = np.linalg.qr(a.reshape(k * o, t), mode="reduced")
             res[i] = q.reshape(k, o, q.shape[1])
-            lenvs.append(es("kofb,kot->tfb", l2, res[i]))
+            lenvs.append(es("kofb,kot->tfb", l2, np.conj(res[i])))
             renvs.pop()
         r_norm = 0.0
         for i in range(n - 1, 0, -1):                        # :1133-1151
@@ -220,7 +221,7 @@ def multiply_mpo_variational(mps, mpo_sites, post, dmin, dmax, trunc_err, tol, m
             u_, j_, k_ = a.shape
             q, r = np.linalg.qr(a.reshape(u_ * j_, k_), mode="reduced")
             res[i] = np.transpose(q.reshape(u_, j_, q.shape[1]), (2, 0, 1))
-            renvs.append(es("fbuj,tuj->bft", r2, res[i]))
+            renvs.append(es("fbuj,tuj->bft", r2, np.conj(res[i])))
             lenvs.pop()
             r_norm = float(np.linalg.norm(r))
         if it == 0 or abs(r_norm - last) / abs(r_norm) > tol:

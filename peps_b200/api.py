@@ -672,23 +672,30 @@ class WalkerBatch:
         return out
 
     # probes
+    def _probe_out(self):
+        return np.empty((2 if getattr(self, "is_complex", False) else 1, self.W))    # complex context: planar (re[W], im[W])
+
+    @staticmethod
+    def _probe_val(a):
+        return a[0] + 1j * a[1] if a.shape[0] == 2 else a[0]
+
     def probe_trace_row(self, row):
-        a = np.empty(self.W)
+        a = self._probe_out()
         self._ck(self.lib.peps_probe_trace_row(self.h, row, _dp(a)))
-        return a
+        return self._probe_val(a)
 
     def probe_tnn_trace(self, row, col, orient, cfg3):
         """ReplaceTNNSiteTrace for every walker: cfg3[w] = physical indices of the three consecutive sites."""
         c3 = np.ascontiguousarray(cfg3, dtype=np.int32).reshape(self.W, 3)
-        a = np.empty(self.W)
+        a = self._probe_out()
         self._ck(self.lib.peps_probe_tnn_trace(self.h, row, col, orient, _ip(c3), _dp(a)))
-        return a
+        return self._probe_val(a)
 
     def probe_plaquette_trace(self, kind, row, col, direction, orient):
         """kind 0: ReplaceNNNSiteTrace, 1: ReplaceSqrt5DistTwoSiteTrace, the two corner sites exchanging their spins."""
-        a = np.empty(self.W)
+        a = self._probe_out()
         self._ck(self.lib.peps_probe_plaquette_trace(self.h, kind, row, col, direction, orient, _dp(a)))
-        return a
+        return self._probe_val(a)
 
     def bmps_stack_size(self, pos):
         return self.lib.peps_bmps_stack_size(self.h, pos)

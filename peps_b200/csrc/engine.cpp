@@ -599,7 +599,29 @@ Engine::BMPSv Engine::absorb_svd(const BMPSv &mps, const std::vector<int> &sites
 BT Engine::truncated_right_vectors(const BT &theta, int rows, int cols, int dmin, int dmax, double terr) {
   const int tcap = std::min(dmax, std::min(rows, cols));
   BT B = alloc({tcap, cols});
-  if (rows >= cols && cols <= dmin) { be_set_identity(B.p, B.n, cols, cols, W_); return B; }
+  if (rows >= cols && cols <= dmin) {
+    be_set_identity(B.p, B.n, cols, cols, W_);
+    if (complex_) be_memset0(imag(B), sizeof(double) * (size_t)W_ * B.n);
+    return B;
+  }
+  if (complex_) {
+    // through the real embedding of theta (absorb_svd): singular values in exact pairs, the kept right singular subspace is
+    // J-invariant; B = rows of V^H (the CONJUGATES of the right singular vectors)
+    const int rows2 = 2 * rows, cols2 = 2 * cols;
+    const int brows2 = truncate_buffer_rows(rows2, cols2);
+    double *GM = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows2 * cols2);
+    if (brows2 > rows2) be_memset0(GM, sizeof(double) * (size_t)W_ * brows2 * cols2);
+    be_embed_complex(theta.p, imag(theta), theta.n, rows, cols, GM, (long)brows2 * cols2, W_);
+    const int dmax2 = (int)std::min<long>(2L * dmax, std::numeric_limits<int>::max()), dmin2 = (int)std::min<long>(2L * dmin, dmax2);
+    const int tcap2 = std::min(dmax2, std::min(rows2, cols2));
+    double *Bm = (double *)pool_.get(sizeof(double) * (size_t)W_ * tcap2 * cols2);
+    double *norms2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * rows2);
+    int32_t *order = (int32_t *)pool_.get(sizeof(int32_t) * (size_t)W_ * tcap2);
+    truncate_rows(la_, GM, (long)brows2 * cols2, rows2, cols2, dmin2, dmax2, terr, tcap2, Bm, (long)tcap2 * cols2, kept_, norms2, order);
+    be_complex_basis(Bm, (long)tcap2 * cols2, tcap2, cols, kept_, B.p, imag(B), (long)tcap * cols, tcap, kept_, W_);
+    for (void *q : {(void *)GM, (void *)Bm, (void *)norms2, (void *)order}) pool_.put(q);
+    return B;
+  }
   const int brows = truncate_buffer_rows(rows, cols);
   double *G = (double *)pool_.get(sizeof(double) * (size_t)W_ * brows * cols);
   if (brows > rows) be_memset0(G, sizeof(double) * (size_t)W_ * brows * cols);
@@ -615,8 +637,25 @@ Engine::BMPSv Engine::compress_mps(const BMPSv &mps, int dmin, int dmax, double 
   std::vector<BT> r((size_t)N);
   r[0] = alloc({1, 1});
   be_fill(r[0].p, 1.0, W_);
+  if (complex_) be_memset0(imag(r[0]), sizeof(double) * W_);
   for (int i = 0; i < N - 1; ++i) {
     const int k = r[(size_t)i].d[0], p = mps[(size_t)i].d[1], b = mps[(size_t)i].d[2], m = k * p, kk = std::min(m, b);
+    if (complex_) {
+      // R factor through the real embedding (absorb_svd): any real R with R^T R = M^T M gives r = (R1 - i R2) / sqrt2
+      BT A = einsum("ka,apb->kpb", ref(r[(size_t)i]), ref(mps[(size_t)i]));
+      const int m2 = 2 * m, b2 = 2 * b, kk2 = std::min(m2, b2);
+      QRLayout L2 = qr_layout(m2, b2);
+      const long wsM = (long)L2.m_pad * b2;
+      double *M = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsM);
+      if (L2.m_pad > m2) be_memset0(M, sizeof(double) * (size_t)W_ * wsM);
+      be_embed_complex(A.p, imag(A), A.n, m, b, M, wsM, W_);
+      release(A);
+      caqr(la_, M, wsM, m2, b2, L2);
+      r[(size_t)i + 1] = alloc({kk2, b});
+      be_split_r(M, wsM, kk2, b, r[(size_t)i + 1].p, imag(r[(size_t)i + 1]), (long)kk2 * b, W_);
+      pool_.put(M);
+      continue;
+    }
     QRLayout L = qr_layout(m, b);
     const long wsA = (long)L.m_pad * b;
     double *A = (double *)pool_.get(sizeof(double) * (size_t)W_ * wsA);
@@ -630,13 +669,14 @@ Engine::BMPSv Engine::compress_mps(const BMPSv &mps, int dmin, int dmax, double 
   BMPSv res((size_t)N);
   BT E = alloc({1, 1});
   be_fill(E.p, 1.0, W_);
+  if (complex_) be_memset0(imag(E), sizeof(double) * W_);
   for (int i = N - 1; i >= 1; --i) {
     BT X = einsum("apb,bj->apj", ref(mps[(size_t)i]), ref(E));
     BT Th = einsum("ka,apj->kpj", ref(r[(size_t)i]), ref(X));
     BT B2 = truncated_right_vectors(Th, Th.d[0], Th.d[1] * Th.d[2], dmin, dmax, terr);
     release(Th);
     BT B = B2; B.rank = 3; B.d[0] = B2.d[0]; B.d[1] = X.d[1]; B.d[2] = X.d[2];
-    BT En = einsum("apj,tpj->at", ref(X), ref(B));
+    BT En = einsum("apj,tpj->at", ref(X), ref(B), nullptr, /*conj_b=*/true);       // U S = Theta Vt^H
     release(X); release(E);
     E = En;
     res[(size_t)i] = B;
@@ -675,9 +715,23 @@ Engine::BMPSv Engine::absorb_variational(const BMPSv &mps, const std::vector<int
   };
   for (int i = N - 1; i > 1; --i) {                       // GrowRightEnvironments_ (:731-743)
     BT r2 = right2(i, renvs.back());
-    renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(res[(size_t)i])));
+    renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(res[(size_t)i]), nullptr, /*conj_b=*/true));   // res_dag (:885)
     release(r2);
   }
+  // per-row squared norms of a batched (rows x nc) matrix view, complex: |re|^2 + |im|^2
+  auto row_norms2 = [&](const BT &x, int rows, int nc, std::vector<double> &h) {
+    double *n2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * rows);
+    h.assign((size_t)W_ * rows, 0.0);
+    be_row_norms2(x.p, x.n, nc, rows, nc, n2, W_);
+    be_d2h(h.data(), n2, sizeof(double) * h.size());
+    if (complex_) {
+      std::vector<double> hi(h.size());
+      be_row_norms2(imag(x), x.n, nc, rows, nc, n2, W_);
+      be_d2h(hi.data(), n2, sizeof(double) * hi.size());
+      for (size_t q = 0; q < h.size(); ++q) h[q] += hi[q];
+    }
+    pool_.put(n2);
+  };
   // one two-site sweep; returns the batch maximum of sum |s - s_last| / s_0 over the last bond when `track`
   std::vector<double> s_last;                             // [W][t] singular values of the last bond of the previous sweep
   int s_last_t = -1;
@@ -687,7 +741,7 @@ Engine::BMPSv Engine::absorb_variational(const BMPSv &mps, const std::vector<int
       BT thT = einsum("kofb,fbuj->ujko", ref(l2), ref(r2));
       BT U = truncated_right_vectors(thT, thT.d[0] * thT.d[1], thT.d[2] * thT.d[3], d0, d1, terr_);
       BT Ut = U; Ut.rank = 3; Ut.d[0] = U.d[0]; Ut.d[1] = l2.d[0]; Ut.d[2] = l2.d[1];     // (t, k, o)
-      lenvs.push_back(einsum("kofb,tko->tfb", ref(l2), ref(Ut)));
+      lenvs.push_back(einsum("kofb,tko->tfb", ref(l2), ref(Ut), nullptr, /*conj_b=*/true));
       release(thT); release(l2); release(r2); release(U);
       release(renvs.back()); renvs.pop_back();
     }
@@ -698,13 +752,11 @@ Engine::BMPSv Engine::absorb_variational(const BMPSv &mps, const std::vector<int
       BT V = truncated_right_vectors(th, th.d[0] * th.d[1], th.d[2] * th.d[3], d0, d1, terr_);
       BT Vt = V; Vt.rank = 3; Vt.d[0] = V.d[0]; Vt.d[1] = r2.d[2]; Vt.d[2] = r2.d[3];      // (t, u, j)
       if (track && i == 1) {                              // singular values of this bond: column norms of theta V^T
-        BT us = einsum("kouj,tuj->tko", ref(th), ref(Vt));
+        BT us = einsum("kouj,tuj->tko", ref(th), ref(Vt), nullptr, /*conj_b=*/true);
         const int t = us.d[0], nc = us.d[1] * us.d[2];
-        double *n2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * t);
-        be_row_norms2(us.p, us.n, nc, t, nc, n2, W_);
-        std::vector<double> h((size_t)W_ * t);
-        be_d2h(h.data(), n2, sizeof(double) * h.size());
-        pool_.put(n2); release(us);
+        std::vector<double> h;
+        row_norms2(us, t, nc, h);
+        release(us);
         for (auto &x : h) x = std::sqrt(x);
         if (s_last_t == t) {
           for (int w = 0; w < W_; ++w) {
@@ -719,7 +771,7 @@ Engine::BMPSv Engine::absorb_variational(const BMPSv &mps, const std::vector<int
       }
       release(res[(size_t)i + 1]);
       res[(size_t)i + 1] = Vt;
-      renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Vt)));
+      renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Vt), nullptr, /*conj_b=*/true));
       release(th); release(l2); release(r2);
       release(lenvs.back()); lenvs.pop_back();
     }
@@ -731,9 +783,9 @@ Engine::BMPSv Engine::absorb_variational(const BMPSv &mps, const std::vector<int
     BT V = truncated_right_vectors(th, th.d[0] * th.d[1], th.d[2] * th.d[3], dmin_, dmax_, terr_);
     BT Vt = V; Vt.rank = 3; Vt.d[0] = V.d[0]; Vt.d[1] = r2.d[2]; Vt.d[2] = r2.d[3];
     release(res[0]); release(res[1]);
-    res[0] = einsum("kouj,tuj->kot", ref(th), ref(Vt));
+    res[0] = einsum("kouj,tuj->kot", ref(th), ref(Vt), nullptr, /*conj_b=*/true);      // U S = theta Vt^H
     res[1] = Vt;
-    if (keep_renv) renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Vt)));       // :1108-1110
+    if (keep_renv) renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Vt), nullptr, /*conj_b=*/true));       // :1108-1110
     release(th); release(l2); release(r2);
   };
   if (!one_site) {
@@ -753,7 +805,7 @@ Engine::BMPSv Engine::absorb_variational(const BMPSv &mps, const std::vector<int
         const int t = aT.d[0], nc = aT.d[1] * aT.d[2];
         BT Q = truncated_right_vectors(aT, t, nc, std::min(t, nc), std::min(t, nc), 0.0);
         BT Qt = Q; Qt.rank = 3; Qt.d[0] = Q.d[0]; Qt.d[1] = l2.d[0]; Qt.d[2] = l2.d[1];  // (t', k, o)
-        lenvs.push_back(einsum("kofb,tko->tfb", ref(l2), ref(Qt)));
+        lenvs.push_back(einsum("kofb,tko->tfb", ref(l2), ref(Qt), nullptr, /*conj_b=*/true));
         release(aT); release(l2); release(Q);
         release(renvs.back()); renvs.pop_back();
       }
@@ -763,18 +815,15 @@ Engine::BMPSv Engine::absorb_variational(const BMPSv &mps, const std::vector<int
         BT a = einsum("fbuj,kfb->kuj", ref(r2), ref(lenvs.back()));
         const int k = a.d[0], nc = a.d[1] * a.d[2];
         if (i == 1) {                                     // r.Get2Norm() of the last QR = |a|_F, batch maximum of the change
-          double *n2 = (double *)pool_.get(sizeof(double) * (size_t)W_ * k);
-          be_row_norms2(a.p, a.n, nc, k, nc, n2, W_);
-          std::vector<double> h((size_t)W_ * k);
-          be_d2h(h.data(), n2, sizeof(double) * h.size());
-          pool_.put(n2);
+          std::vector<double> h;
+          row_norms2(a, k, nc, h);
           for (int w = 0; w < W_; ++w) { double s2 = 0; for (int q = 0; q < k; ++q) s2 += h[(size_t)w * k + q]; r_norm = std::max(r_norm, std::sqrt(s2)); }
         }
         BT Q = truncated_right_vectors(a, k, nc, std::min(k, nc), std::min(k, nc), 0.0);
         BT Qt = Q; Qt.rank = 3; Qt.d[0] = Q.d[0]; Qt.d[1] = r2.d[2]; Qt.d[2] = r2.d[3];     // (t, u, j)
         release(res[(size_t)i]);
         res[(size_t)i] = Qt;
-        renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Qt)));
+        renvs.push_back(einsum("fbuj,tuj->bft", ref(r2), ref(Qt), nullptr, /*conj_b=*/true));
         release(a); release(r2);
         release(lenvs.back()); lenvs.pop_back();
       }
@@ -1021,7 +1070,7 @@ void Engine::probe_tnn_trace(int r, int c, int orient, const int32_t *cfg3_host,
     grow_full_bten(DOWN, c, r + 3, true);
   }
   tnn_trace_idx(r, c, orient, d, d + 1, d + 2, 3, psi_tmp_);
-  be_d2h(psi_host, psi_tmp_, sizeof(double) * W_);
+  be_d2h(psi_host, psi_tmp_, sizeof(double) * sw());
   pool_.put(d);
 }
 void Engine::one_site_trace(int r, int c, const int32_t *idx, int stride, double *psi_out) {     // trace.h:30-88
@@ -1207,7 +1256,7 @@ void Engine::probe_plaquette_trace(int kind, int row1, int col1, int dir, int or
     grow_full_bten2(DOWN, col1, row1 + span, true);
   }
   if (kind == 0) nnn_trace(row1, col1, dir, psi_tmp_, orient); else sqrt5_trace(row1, col1, dir, orient, psi_tmp_);
-  be_d2h(psi_host, psi_tmp_, sizeof(double) * W_);
+  be_d2h(psi_host, psi_tmp_, sizeof(double) * sw());
 }
 void Engine::punch_hole(int r, int c, int orient) {    // grow.h:150-183
   const BT *up, *down, *left, *right;
@@ -1892,8 +1941,8 @@ void Engine::bond_energy(int s1, int s2, const double *psi_ex, const double *psi
 }
 void Engine::set_complex() {
   if (complex_) return;
-  if (fermion_ || scheme_ != 0 || tps_loaded_)
-    throw std::logic_error("set_complex: call right after construction, before set_fermion / set_tps (SVD compression only)");
+  if (fermion_ || tps_loaded_)
+    throw std::logic_error("set_complex: call right after construction, before set_fermion / set_tps");
   be_sync();
   // per-walker scalar buffers allocated lazily so far are real-sized: drop them, they come back as planes
   be_free(psi_alt_); psi_alt_ = nullptr; psi_alt_slots_ = 0;
@@ -2526,7 +2575,7 @@ void Engine::probe_trace_row(int row, double *psi_host) {
   init_bten(LEFT);
   grow_full_bten(RIGHT, row, 2, true);
   nn_trace(row, 0, row, 1, HORIZONTAL, row * cols_, row * cols_ + 1, psi_tmp_);
-  be_d2h(psi_host, psi_tmp_, sizeof(double) * W_);
+  be_d2h(psi_host, psi_tmp_, sizeof(double) * sw());
 }
 
 }  // namespace peps

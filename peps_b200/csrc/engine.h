@@ -63,7 +63,6 @@ class Engine {
   // compression, 1 = two-site, 2 = one-site variational; the batch iterates until EVERY walker meets convergence_tol
   void set_compress_scheme(int scheme, double tol, int max_iter) {
     if (scheme < 0 || scheme > 2 || max_iter < 1) throw std::invalid_argument("set_compress_scheme: scheme in {0,1,2}, max_iter >= 1");
-    if (scheme != 0) require_real("variational compression");
     scheme_ = scheme; var_tol_ = tol; var_iter_ = max_iter; touch_all();
   }
   void set_jacobi(double tol, int inner, int max_sweeps) {

@@ -36,8 +36,6 @@ def test_complex_mode_guards(lib):
     from peps_b200.api import BMPSTruncateParams, WalkerBatch, PepsError, TableModel, FermionSplitIndexTPS
     b = WalkerBatch(3, 3, 2, 2, 1, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
     b.set_complex()
-    with pytest.raises(PepsError):                       # still real-only: variational compression
-        b.set_truncation(BMPSTruncateParams.Variational2Site(4, 4, 0.0, 1e-9, 5))
     b.close()
     b = WalkerBatch(3, 3, 2, 2, 1, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
     b.set_tps(np.zeros(b.tps_size))
@@ -120,3 +118,11 @@ def test_complex_measure_parity_hostsim(lib, j2):
 def test_complex_structure_factor_hostsim(lib):
     from parity_common import run_structure_factor_parity
     run_structure_factor_parity(lib, complex_=True)
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_complex_variational_compression_hostsim(lib, scheme):
+    """VARIATION2Site / VARIATION1Site on a complex state: the environments contract the conjugate of the result tensors
+    (res_dag, bmps_impl.h:885-947); amplitudes against the oracle restatement with the same number of sweeps."""
+    from parity_common import run_variational_parity
+    run_variational_parity(lib, scheme, complex_=True)

@@ -71,3 +71,9 @@ def test_cpp_wrapper_complex_on_cuda_library(lib):
 def test_complex_structure_factor_gpu(lib):
     from parity_common import run_structure_factor_parity
     run_structure_factor_parity(lib, complex_=True)
+
+
+@pytest.mark.parametrize("scheme", [1, 2])
+def test_complex_variational_compression_gpu(lib, scheme):
+    from parity_common import run_variational_parity
+    run_variational_parity(lib, scheme, complex_=True)
