@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <functional>
 #include <limits>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -297,6 +298,27 @@ class WalkerBatch {
     osum.resize(tps_size()); eosum.resize(tps_size());
     ck(peps_get_accumulators(h_, osum.data(), eosum.data(), osum.size()));
   }
+  // ---- stochastic reconfiguration: the O* samples of the walker loop stay in HBM (peps_sr_*; the reference keeps
+  // Ostar_samples as vector<SplitIndexTPS> on the host, mc_energy_grad_evaluator.h:273-277)
+  void SrReserve(size_t max_walker_samples) { ck(peps_sr_reserve(h_, (int64_t)max_walker_samples)); }
+  void SrCollect(bool on) { ck(peps_sr_collect(h_, on ? 1 : 0)); }
+  void SrClear() { ck(peps_sr_clear(h_)); }
+  size_t SrCount() { return (size_t)peps_sr_count(h_); }
+  // local, unnormalised sum_i (O*_i . v - mean_dot_v) O*_i  (SRSMatrix::operator*, stochastic_reconfiguration_smatrix.h:60-65)
+  std::vector<double> SrMatvec(const std::vector<double> &v, double mean_dot_v) {
+    std::vector<double> out(v.size());
+    ck(peps_sr_matvec(h_, v.data(), mean_dot_v, out.data(), v.size()));
+    return out;
+  }
+  // MeasureStructureFactor (structure_factor_measurement_mixin.h:89-228): raw S+S- overlaps [W][pairs], pairs in the
+  // reference's order (y1, x1, y2 > y1, x2)
+  std::vector<double> MeasureStructureFactor() {
+    std::vector<double> out((size_t)walkers_ * (size_t)peps_structure_factor_pairs(h_));
+    ck(peps_measure_structure_factor(h_, out.data()));
+    return out;
+  }
+  int rows() const { return rows_; }
+  int cols() const { return cols_; }
   peps_ctx *handle() { return h_; }
 
  private:
@@ -312,6 +334,15 @@ struct EvaluateResult {               // MCEnergyGradEvaluator::Result (mc_energ
   std::vector<double> gradient;       // packed like the TPS
   std::vector<double> accept_rates_avg;
   std::vector<double> energy_samples; // [walkers][samples_per_walker]
+  std::vector<double> Ostar_mean;     // with collect_sr_buffers: mean O* (packed), and the global sample count
+  size_t total_samples = 0;
+};
+
+struct ConjugateGradientParams {      // optimizer/optimizer_params.h:50-57
+  int max_iter = 100;
+  double relative_tolerance = 1e-4, absolute_tolerance = 0.0;
+  int residual_recompute_interval = 20;
+  double orthogonality_threshold = 0.5;
 };
 
 struct EvaluateResultComplex {        // the same for TenElemT = QLTEN_Complex
@@ -373,13 +404,19 @@ class MCEnergyGradEvaluator {
     for (int w = 0; w < walkers; ++w) seeds[(size_t)w] = seed + (uint32_t)w;
     batch_.SeedRNG(seeds);
   }
-  // Evaluate(state): state fan-out, RefreshWavefunctionComponent, the walker loop, energy binning, gradient
-  EvaluateResult Evaluate(const std::vector<double> &packed_tps) {
+  // Evaluate(state): state fan-out, RefreshWavefunctionComponent, the walker loop, energy binning, gradient.
+  // collect_sr_buffers (mc_energy_grad_evaluator.h:181-183, 273-277): keep the O* samples in HBM for CalculateNaturalGradient
+  EvaluateResult Evaluate(const std::vector<double> &packed_tps, bool collect_sr_buffers = false) {
     batch_.SetTPS(packed_tps);
     batch_.InitWalkers();
     const size_t W = (size_t)batch_.walkers();
     const size_t n = std::max<size_t>(1, (mc_.num_samples + W - 1) / W);
     batch_.ZeroAccumulators();
+    if (collect_sr_buffers) {
+      if (sr_cap_ < n * W) { batch_.SrReserve(n * W); sr_cap_ = n * W; }
+      batch_.SrClear();
+    }
+    batch_.SrCollect(collect_sr_buffers);
     EvaluateResult r;
     r.energy_samples.assign(W * n, 0.0);
     double acc = 0;
@@ -398,7 +435,31 @@ class MCEnergyGradEvaluator {
       r.gradient_norm += r.gradient[i] * r.gradient[i];
     }
     r.accept_rates_avg = {acc / (double)(n * W)};
+    batch_.SrCollect(false);
+    if (collect_sr_buffers) {
+      r.Ostar_mean.resize(osum.size());
+      for (size_t i = 0; i < osum.size(); ++i) r.Ostar_mean[i] = osum[i] / (double)(n * W);
+      r.total_samples = n * W;
+    }
     return r;
+  }
+  // Optimizer::CalculateNaturalGradient (optimizer/optimizer_impl.h:1031-1089) on the samples of the last
+  // Evaluate(state, true): solves (S + diag_shift) x = gradient with the reference's CG loop on the device
+  // (peps_sr_natural_gradient; single GPU here -- pass an all-reduce callback through the C ABI for several).
+  // Returns {natural gradient (packed), CG iterations, residual norm}; throws on an indefinite matrix / breakdown.
+  std::tuple<std::vector<double>, int, double> CalculateNaturalGradient(const EvaluateResult &r, double diag_shift,
+                                                                          const ConjugateGradientParams &cg = ConjugateGradientParams(),
+                                                                          const std::vector<double> *init_guess = nullptr) {
+    if (r.total_samples == 0) throw std::runtime_error("CalculateNaturalGradient: Evaluate(state, collect_sr_buffers = true) first");
+    peps_cg_params p{cg.max_iter, cg.relative_tolerance, cg.absolute_tolerance, cg.residual_recompute_interval, cg.orthogonality_threshold};
+    std::vector<double> x(r.gradient.size());
+    int32_t it = 0, reason = 0;
+    double resid = 0.0;
+    if (peps_sr_natural_gradient(batch_.handle(), r.gradient.data(), r.Ostar_mean.data(), (int64_t)r.total_samples, diag_shift, &p,
+                                 init_guess ? init_guess->data() : nullptr, nullptr, nullptr, x.data(), &it, &resid, &reason) != 0)
+      throw std::runtime_error(peps_last_error(batch_.handle()));
+    if (reason == 3 || reason == 4) throw std::runtime_error("CG solver terminated: indefinite matrix / numerical breakdown");
+    return std::make_tuple(x, (int)it, resid);
   }
   // EvaluateEnergyOnly (mc_energy_grad_evaluator.h:331-392): the step-selector trial -- StepSweep + CalEnergy per sample, no
   // holes / O* / gradient. Returns {energy, energy_error, mean acceptance rate}.
@@ -453,6 +514,59 @@ class MCEnergyGradEvaluator {
  private:
   MonteCarloParams mc_;
   WalkerBatch batch_;
+  size_t sr_cap_ = 0;
+};
+
+// MCPEPSMeasurer (algorithm/vmc_update/monte_carlo_peps_measurer_impl.h:172-257) on a prepared WalkerBatch (state, model,
+// updater, configurations and seeds set by the caller): warm up, then per sample `sweeps_between_samples` sweeps +
+// EvaluateObservables; a walker plays the role of a rank: per-walker sample means, then mean and standard error across the
+// walkers (GatherStatisticListOfData, monte_carlo_tools/statistics.h:288-339). Keys: energy, bond_energy_h / _v / _dr / _ur,
+// row_corr (the SmSp_row / SpSm_row channel of each walker), and SpSm_cross_raw with enable_structure_factor.
+class MCPEPSMeasurer {
+ public:
+  using Stats = std::map<std::string, std::pair<std::vector<double>, std::vector<double>>>;   // key -> (mean, stderr)
+  MCPEPSMeasurer(WalkerBatch &batch, const MonteCarloParams &mc, bool enable_structure_factor = false)
+      : b_(batch), mc_(mc), sf_(enable_structure_factor) {}
+  Stats Execute() {
+    const size_t W = (size_t)b_.walkers();
+    if (!mc_.is_warmed_up && mc_.num_warmup_sweeps > 0) b_.StepSweep((int)mc_.num_warmup_sweeps);
+    const size_t nper = std::max<size_t>(1, (mc_.num_samples + W - 1) / W);
+    std::map<std::string, std::vector<double>> sums;
+    auto add = [&](const std::string &k, const std::vector<double> &v) {
+      auto &s = sums[k];
+      if (s.empty()) s.assign(v.size(), 0.0);
+      for (size_t i = 0; i < v.size(); ++i) s[i] += v[i];
+    };
+    for (size_t s = 0; s < nper; ++s) {
+      b_.StepSweep((int)mc_.sweeps_between_samples);
+      WalkerBatch::Observables o = b_.Measure();
+      add("energy", o.energy); add("bond_energy_h", o.bond_energy_h); add("bond_energy_v", o.bond_energy_v);
+      add("bond_energy_dr", o.bond_energy_dr); add("bond_energy_ur", o.bond_energy_ur); add("row_corr", o.row_corr);
+      if (sf_) add("SpSm_cross_raw", b_.MeasureStructureFactor());
+    }
+    Stats out;
+    for (auto &kv : sums) {
+      const size_t per = kv.second.size() / W;
+      std::vector<double> mean(per, 0.0), err(per, std::numeric_limits<double>::infinity());
+      for (size_t w = 0; w < W; ++w) for (size_t i = 0; i < per; ++i) mean[i] += kv.second[w * per + i] / (double)nper / (double)W;
+      if (W > 1)
+        for (size_t i = 0; i < per; ++i) {
+          double v = 0.0;
+          for (size_t w = 0; w < W; ++w) { const double d = kv.second[w * per + i] / (double)nper - mean[i]; v += d * d; }
+          err[i] = std::sqrt(v / ((double)W * ((double)W - 1.0)));
+        }
+      out[kv.first] = {mean, err};
+    }
+    samples_per_walker_ = nper;
+    return out;
+  }
+  size_t samples_per_walker() const { return samples_per_walker_; }
+
+ private:
+  WalkerBatch &b_;
+  MonteCarloParams mc_;
+  bool sf_;
+  size_t samples_per_walker_ = 0;
 };
 
 // Seam B1: adapts the evaluator to `std::function<std::tuple<T, SITPS, double>(const SITPS&)>`

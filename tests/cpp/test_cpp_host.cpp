@@ -48,6 +48,27 @@ int main() {
                                          peps_b200::XXZModel{1.0, 1.0, 0.0}, seed);
     auto eo = ev2.EvaluateEnergyOnly(tps);
     std::printf("%.17g %.17g\n", std::get<0>(eo), std::get<2>(eo));
+    // SR through the wrapper: Evaluate with collect_sr_buffers, then CalculateNaturalGradient on the device-resident samples
+    peps_b200::MCEnergyGradEvaluator ev3(mc, peps_b200::BMPSTruncateParams::SVD(chi, chi, 0.0), rows, cols, phys, D, walkers,
+                                         peps_b200::XXZModel{1.0, 1.0, 0.0}, seed);
+    auto r3 = ev3.Evaluate(tps, true);
+    peps_b200::ConjugateGradientParams cg;
+    cg.max_iter = 200; cg.relative_tolerance = 1e-10;
+    auto ng = ev3.CalculateNaturalGradient(r3, 1e-3, cg);
+    double ng2 = 0.0;
+    for (double x : std::get<0>(ng)) ng2 += x * x;
+    std::printf("%.17g %d %zu\n", ng2, std::get<1>(ng), ev3.batch().SrCount());
+    // MCPEPSMeasurer on a fresh batch of the same chains
+    peps_b200::MCEnergyGradEvaluator ev4(mc, peps_b200::BMPSTruncateParams::SVD(chi, chi, 0.0), rows, cols, phys, D, walkers,
+                                         peps_b200::XXZModel{1.0, 1.0, 0.0}, seed);
+    ev4.batch().SetTPS(tps);
+    ev4.batch().InitWalkers();
+    peps_b200::MonteCarloParams mmc = mc;
+    mmc.is_warmed_up = true;
+    peps_b200::MCPEPSMeasurer meas(ev4.batch(), mmc, true);
+    auto st = meas.Execute();
+    std::printf("%.17g %.17g %.17g %zu\n", st["energy"].first[0], st["energy"].second[0], st["bond_energy_h"].first[0],
+                st["SpSm_cross_raw"].first.size());
   } catch (const std::exception &e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -28,7 +28,8 @@ def run_cpp_wrapper_case(lib, libdir, libfile, extra_link=()):
         inp = f"3 3 2 2 {W} {chi} {ns} {seed}\n{flat.size}\n" + " ".join(repr(float(x)) for x in flat) + "\n" + \
               " ".join(str(int(c)) for c in cfg.ravel()) + "\n"
         out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
-    e_cpp, err_cpp, gn_cpp, acc_cpp, e2, e_meas, e_bonds, d_table, n_rescued, e_only, acc_only = map(float, out)
+    (e_cpp, err_cpp, gn_cpp, acc_cpp, e2, e_meas, e_bonds, d_table, n_rescued, e_only, acc_only, ng2, ng_it, sr_n,
+     m_e, m_err, m_bh0, m_npairs) = map(float, out)
     assert abs(e_only - e_cpp) < 1e-12 and abs(acc_only - acc_cpp) < 1e-12     # EvaluateEnergyOnly: same chains, no holes
     assert d_table < 1e-13 and n_rescued == 0
     assert abs(e_meas - e_bonds) < 1e-10 * max(1.0, abs(e_meas))
@@ -43,6 +44,19 @@ def run_cpp_wrapper_case(lib, libdir, libfile, extra_link=()):
     assert abs(acc_cpp - res.accept_rates_avg[0]) < 1e-12
     ev2 = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(chi, chi, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
                                 MCUpdateSquareNNExchange(seed), walkers=W, lib=lib)
+    # SR and the measurer through the C++ wrapper against the Python mirror on the same chains
+    from peps_b200 import sr
+    from peps_b200.api import MCPEPSMeasurer
+    ev3 = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(chi, chi, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                                MCUpdateSquareNNExchange(seed), walkers=W, lib=lib)
+    r3 = ev3.Evaluate(collect_sr_buffers=True)
+    nat, iters, _ = ev3.CalculateNaturalGradient(r3, 1e-3, sr.ConjugateGradientParams(max_iter=200, relative_tolerance=1e-10))
+    assert int(ng_it) == iters and int(sr_n) == ev3.batch.sr_count()
+    assert abs(ng2 - nat.NormSquare()) < 1e-9 * nat.NormSquare()
+    pm = MCPEPSMeasurer(mc, BMPSTruncateParams.SVD(chi, chi, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
+                        MCUpdateSquareNNExchange(seed), W, lib=lib, enable_structure_factor=True).Execute()
+    assert abs(m_e - pm["energy"][0]) < 1e-12 and abs(m_err - pm["energy"][1]) < 1e-12
+    assert abs(m_bh0 - pm["bond_energy_h"][0][0, 0]) < 1e-12 and int(m_npairs) == pm["SpSm_cross"][0].size
     e_py, err_py, acc_py = ev2.EvaluateEnergyOnly()
     assert abs(e_py - res.energy) < 1e-12 and abs(err_py - res.energy_error) < 1e-12 and abs(acc_py[0] - res.accept_rates_avg[0]) < 1e-12
 
