@@ -98,6 +98,7 @@ Engine::~Engine() {
                   (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_, (void *)jastrow_v_, (void *)jr_, (void *)dens_d_, (void *)sr_desc2_, (void *)fs_target_d_, (void *)fs_coef_d_})
     be_free(p);
   for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); }
+  be_free(pin_.diag); be_free(pin_.target); be_free(pin_.coef);
   pool_.release_all();
   planner_.release_all();
   be_ctx_destroy(bectx_);
