@@ -545,7 +545,8 @@ from peps_b200.api import (BMPSTruncateParams, SplitIndexTPS, MCEnergyGradEvalua
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-tps = SplitIndexTPS(vmc.random_tps(4, 4, 2, 3, seed=4))
+from parity_common import complex_tps
+tps = SplitIndexTPS(complex_tps(4, 4, 3, 4) if {cx!r} else vmc.random_tps(4, 4, 2, 3, seed=4))
 W = 3
 cfgs = np.stack([vmc.shuffled_half_filled_config(4, 4, 50 + rank * W + w) for w in range(W)])
 mc = MonteCarloParams(num_samples=4 * W * world, num_warmup_sweeps=0, sweeps_between_samples=1, is_warmed_up=True)
@@ -559,10 +560,12 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_rank_nccl_evaluator_and_sr(lib):
+@pytest.mark.parametrize("cx", [False, True])
+def test_two_rank_nccl_evaluator_and_sr(lib, cx):
     """MCEnergyGradEvaluator + SR natural gradient over two GPUs (mc_energy_grad_evaluator.h:205-310): accumulators
     all-reduced by NCCL on peps_ostar_sum_device() pointers, the CG matvec output all-reduced on its device pointer.
-    Equals one GPU holding all six walkers. Skipped below two GPUs."""
+    Equals one GPU holding all six walkers. cx: a complex state (both planes of an accumulator / CG vector in one
+    all-reduce). Skipped below two GPUs."""
     import os, pickle, subprocess, sys, tempfile
     import torch
     if torch.cuda.device_count() < 2:
@@ -574,13 +577,14 @@ def test_two_rank_nccl_evaluator_and_sr(lib):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     with tempfile.TemporaryDirectory() as td:
         out, script = os.path.join(td, "res.pkl"), os.path.join(td, "worker.py")
-        open(script, "w").write(NCCL_WORKER.format(root=root, out=out))
-        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29711", WORLD_SIZE="2")
+        open(script, "w").write(NCCL_WORKER.format(root=root, out=out, cx=cx))
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29712" if cx else "29711", WORLD_SIZE="2")
         procs = [subprocess.Popen([sys.executable, script], env=dict(env, RANK=str(r))) for r in range(2)]
         for p in procs:
             assert p.wait(timeout=600) == 0
         two = pickle.load(open(out, "rb"))
-    tps = SplitIndexTPS(vmc.random_tps(4, 4, 2, 3, seed=4))
+    from parity_common import complex_tps
+    tps = SplitIndexTPS(complex_tps(4, 4, 3, 4) if cx else vmc.random_tps(4, 4, 2, 3, seed=4))
     cfgs = np.stack([vmc.shuffled_half_filled_config(4, 4, 50 + w) for w in range(6)])
     mc = MonteCarloParams(num_samples=24, num_warmup_sweeps=0, sweeps_between_samples=1, is_warmed_up=True)
     ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(6, 6, 0.0), tps, SquareSpinOneHalfXXZModelOBC(1, 1, 0),
