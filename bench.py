@@ -680,6 +680,10 @@ def main():
                 "frac": achieved / fp64_peak,
                 "peak_source": "cuBLAS DGEMM 4096^3 through torch.matmul, measured in this run (MEASURED_PEAKS.json carries no FP64 figure)",
                 "traffic": traffic,
+                "traffic_note": "not measured in-run; ncu --set full on six consecutive full-batch launches of this kernel inside a real "
+                                "148-walker sample (profiles/r2_ncu_final_apply_cols_kernel.txt): 1.1-1.25 ms launches (3256-4884 CTAs) "
+                                "read 1.5-1.7 GB and write 1.3-1.5 GB of DRAM -- the trailing matrix streams through once (read ~ "
+                                "write, no re-reads) -- with the DMMA pipe 59-63 % active and 31-33 % of the DRAM bandwidth in use",
                 "measured_on": f"one extra sample of the same workload with all {W} walkers in one lane (full-batch launches, the kernel alone "
                                "on the GPU), every launch bracketed by a CUDA-event pair on its stream; `per_lane` holds the same "
                                f"measurement on the timed loop's own lanes ({Ws} walkers each, one lane at a time)",
