@@ -86,6 +86,20 @@ class Configuration:
     def __eq__(self, other):
         return np.array_equal(self.data, other.data)
 
+    def Random(self, occupancy, seed=None):
+        """Configuration::Random(occupancy_num) (vmc_basic/configuration.h:127-164): occupancy[s] sites in state s, shuffled.
+        The reference draws from std::random_device (not reproducible); here an optional seed makes the draw repeatable."""
+        occ = [int(x) for x in occupancy]
+        if sum(occ) != self.data.size:
+            raise ValueError("Configuration.Random: the occupancy numbers must add up to the number of sites")
+        flat = np.concatenate([np.full(n, s_, dtype=np.int32) for s_, n in enumerate(occ)])
+        np.random.default_rng(seed).shuffle(flat)
+        self.data = flat.reshape(self.data.shape)
+        return self
+
+    def Sum(self):
+        return int(self.data.sum())
+
 
 @dataclass
 class PsiConsistencyWarningParams:
