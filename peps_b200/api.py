@@ -596,8 +596,11 @@ class WalkerBatch:
         e, eh, ev, edr, eur, corr = [(a[0] + 1j * a[1]) if npl == 2 else a[0] for a in (e, eh, ev, edr, eur, corr)]
         cfg = self.get_configs()
         if getattr(self, "phys_par", None) is not None:        # fermion models: requires_density_measurement (charge)
-            return {"energy": e, "charge": np.asarray(self.phys_par, dtype=float)[cfg], "bond_energy_h": eh,
-                    "bond_energy_v": ev, "bond_energy_dr": edr, "bond_energy_ur": eur}
+            out = {"energy": e, "charge": np.asarray(self.phys_par, dtype=float)[cfg], "bond_energy_h": eh,
+                   "bond_energy_v": ev, "bond_energy_dr": edr, "bond_energy_ur": eur}
+            if self.phys_par == (1, 1, 0):                     # t-J: CalSpinSzImpl (square_tJ_model.h:233-236): up, down, empty
+                out["spin_z"] = np.array([0.5, -0.5, 0.0])[cfg]
+            return out
         sz = cfg.astype(float) - 0.5
         first_down = (cfg[:, r // 2, c // 4] == 0)[:, None]          # EvaluateOffDiagOrderInRow channel split (:281-287)
         flat = sz.reshape(W, -1)
