@@ -310,3 +310,51 @@ def test_fermion_full_space_and_three_site_updaters_hostsim(lib, updater, model,
     """The multi-state updaters on fZ2 tensors ("work for both fermion and boson", square_nn_updater.h:251): chains
     bit-identical to the oracle's restatement, E_loc / O* after every sweep."""
     run_fermion_pipeline_parity(lib, 3, 4, 2, 3, (4, 4, 0.0), model=model, nsweeps=2, updater=updater, complex_=complex_)
+
+
+def test_evaluator_sr_and_measurer_on_complex_fermion_state(lib):
+    """MCEnergyGradEvaluator (+ SR natural gradient, MCPEPSMeasurer) on a complex FermionSplitIndexTPS: energy and gradient
+    = sum conj(E_loc) O* / N - conj(E) sum O* / N of the oracle chain."""
+    from oracle import fermion as F
+    from parity_common import fermion_configs
+    from peps_b200 import sr
+    from peps_b200.api import combine_energy_bins, MCPEPSMeasurer
+    rows, cols, D, W, n = 3, 4, 2, 2, 3
+    trunc = (4, 4, 0.0)
+    f = F.FermionTPS.random(rows, cols, D, 21, complex_=True)
+    ftps = FermionSplitIndexTPS(f.T, f.par, f.phys_par)
+    cfgs = fermion_configs(rows, cols, W, 2)
+    model = TableModel.spinless_fermion(1.0, 0.5, 0.2)
+    ev = MCEnergyGradEvaluator(MonteCarloParams(n * W, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(*trunc), ftps,
+                               model, MCUpdateSquareNNExchange(seed=77), W, configs=cfgs, lib=lib)
+    res = ev.Evaluate(ftps, collect_sr_buffers=True)
+    omodel = F.SpinlessFermionModel(1.0, 0.5, 0.2)
+    es = []
+    osum = [[[np.zeros_like(x) for x in site] for site in row] for row in f.T]
+    eosum = [[[np.zeros_like(x) for x in site] for site in row] for row in f.T]
+    for w in range(W):
+        wk = F.FermionWalker(f, cfgs[w], trunc)
+        up = F.FermionNNExchangeUpdater(77 + w)
+        for _ in range(n):
+            up.sweep(wk)
+            e, ost, _ = omodel.energy_and_holes(wk, True)
+            es.append(e)
+            for r in range(rows):
+                for c in range(cols):
+                    s = int(wk.config[r, c])
+                    osum[r][c][s] += ost[r][c]
+                    eosum[r][c][s] += np.conj(e) * ost[r][c]
+    N = n * W
+    es = np.array(es).reshape(W, n)
+    emean = complex(combine_energy_bins(es.real)[0], combine_energy_bins(es.imag)[0])
+    assert abs(res.energy - emean) < 1e-10
+    grad = np.concatenate([(eosum[r][c][s] / N - np.conj(emean) * osum[r][c][s] / N).ravel()
+                           for r in range(rows) for c in range(cols) for s in range(2)])
+    got = res.gradient.pack()
+    assert np.iscomplexobj(got) and np.max(np.abs(got - grad)) <= 1e-9 * max(1.0, np.max(np.abs(grad)))
+    assert isinstance(res.gradient, FermionSplitIndexTPS)
+    nat, iters, resid = ev.CalculateNaturalGradient(res, 1e-3, sr.ConjugateGradientParams(max_iter=200, relative_tolerance=1e-8))
+    assert iters > 0 and np.iscomplexobj(nat.pack())
+    obs = MCPEPSMeasurer(MonteCarloParams(4, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(*trunc), ftps, model,
+                         MCUpdateSquareNNExchange(seed=5), 2, lib=lib).Execute()
+    assert np.iscomplexobj(obs["bond_energy_h"][0]) and obs["charge"][0].shape == (rows, cols)
