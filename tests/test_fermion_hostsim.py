@@ -358,3 +358,51 @@ def test_evaluator_sr_and_measurer_on_complex_fermion_state(lib):
     obs = MCPEPSMeasurer(MonteCarloParams(4, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(*trunc), ftps, model,
                          MCUpdateSquareNNExchange(seed=5), 2, lib=lib).Execute()
     assert np.iscomplexobj(obs["bond_energy_h"][0]) and obs["charge"][0].shape == (rows, cols)
+
+
+def run_cpp_tj_pairing_case(lib, libdir, libfile, extra_link=()):
+    """tests/cpp/test_cpp_tj_pairing.cpp: SetBondPin / MeasureBondTerm with the probe-built tJSingletPairTerm tables of the C++
+    wrapper against the Python mirror (TableModel.SetSingletPairPinningField / measure_bond_observable) on the same library."""
+    import subprocess
+    import tempfile
+    from oracle import fermion as F
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rows, cols, D, W, chi, delta = 3, 3, 2, 3, 4, 0.07
+    f = F.FermionTPS.random(rows, cols, D, 23, phys_par=(1, 1, 0))
+    ftps = FermionSplitIndexTPS(f.T, f.par, (1, 1, 0))
+    rng = np.random.default_rng(8)
+    cfgs = []
+    while len(cfgs) < W:
+        c = rng.integers(0, 3, size=(rows, cols))
+        if f.parities(c).sum() % 2 == 0:
+            cfgs.append(c)
+    cfgs = np.stack(cfgs)
+    flat, lp = ftps.pack(), ftps.leg_par_flat()
+    pin = ((1, 0), (1, 1))
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "cpp_tj")
+        subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(root, "tests", "cpp", "test_cpp_tj_pairing.cpp"), "-o", exe,
+                               "-L" + libdir, "-l:" + libfile, "-Wl,-rpath," + libdir] + list(extra_link))
+        inp = (f"{rows} {cols} {D} {W} {chi} 1.0 0.3 0.2 {delta} {pin[0][0] * cols + pin[0][1]} {pin[1][0] * cols + pin[1][1]}\n"
+               + f"{lp.size} " + " ".join(map(str, lp)) + f"\n{flat.size} " + " ".join(repr(float(x)) for x in flat) + "\n"
+               + " ".join(str(int(c)) for c in cfgs.ravel()) + "\n")
+        out = np.array(subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split(), dtype=float)
+    b = WalkerBatch(rows, cols, 3, D, W, BMPSTruncateParams.SVD(chi, chi, 0.0), lib=lib)
+    b.set_fermion(ftps); b.set_tps(ftps); b.set_configs(cfgs); b.init_walkers()
+    b.set_model(TableModel.tj(1.0, 0.3, mu=0.2))
+    e0 = b.energy_and_holes(False)
+    b.set_model(TableModel.tj(1.0, 0.3, mu=0.2).SetSingletPairPinningField(pin[1], pin[0], delta))
+    e1 = b.energy_and_holes(False)
+    dd, d = TableModel.tj_singlet_pair_tables()
+    parts = [e0, e1]
+    for H in (dd, d):
+        h, v = b.measure_bond_observable(H)
+        parts += [h.ravel(), v.ravel()]
+    ref = np.concatenate(parts)
+    assert out.shape == ref.shape and np.max(np.abs(out - ref)) < 1e-12 * max(1.0, np.max(np.abs(ref)))
+    assert np.max(np.abs(e1 - e0)) > 0 or np.max(np.abs(ref[2 * W:])) > 0
+    b.close()
+
+
+def test_cpp_wrapper_tj_pairing(lib):
+    run_cpp_tj_pairing_case(lib, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"), "libpeps_hostsim.so")
