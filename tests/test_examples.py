@@ -1,0 +1,51 @@
+"""The example drivers run end to end on the host simulation (host logic only; the GPU twin runs the CUDA library)."""
+import os
+import sys
+
+import numpy as np
+
+import hostsim_lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "examples"))
+
+
+def run_tfim_example(lib):
+    """examples/tfim_vmc_optimize.py (the reference's transverse_field_ising_vmc_optimize.cpp flow: Evaluate -> natural gradient
+    -> update) on a 3x3 lattice: the SR iterations lower the energy towards the exact ground state."""
+    import tfim_vmc_optimize as ex
+    energies, state = ex.optimize(rows=3, cols=3, D=2, chi=4, h=0.5, walkers=8, samples=160, iters=8, step=0.15, lib=lib,
+                                  log=lambda *_: None)
+    # exact ground-state energy of H = -sum zz - h sum x on the 3x3 open lattice by dense diagonalisation
+    n = 9
+    H = np.zeros((2 ** n, 2 ** n))
+    idx = np.arange(2 ** n)
+    bits = (idx[:, None] >> np.arange(n)[None, :]) & 1
+    sz = 1.0 - 2.0 * bits
+    for r in range(3):
+        for c in range(3):
+            s = r * 3 + c
+            if c + 1 < 3:
+                H[idx, idx] += -sz[:, s] * sz[:, s + 1]
+            if r + 1 < 3:
+                H[idx, idx] += -sz[:, s] * sz[:, s + 3]
+            H[idx, idx ^ (1 << s)] += -0.5
+    e0 = np.linalg.eigvalsh(H)[0]
+    assert energies[-1] < energies[0] - 0.5, energies           # the optimisation works ...
+    assert energies[-1] > e0 - 0.3, (energies[-1], e0)          # ... and stays variational within the statistical error
+    return energies, e0
+
+
+def test_tfim_vmc_optimize_example_hostsim():
+    run_tfim_example(hostsim_lib.load())
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_tfim_vmc_optimize_example_gpu():
+    from peps_b200 import _lib
+    lib = _lib.load()
+    assert lib.peps_backend_name() == b"cuda-sm_100a"
+    run_tfim_example(lib)
