@@ -204,6 +204,11 @@ int peps_measure(peps_ctx *ctx, double *energy, double *e_h, double *e_v, double
  * creation / annihilation, parity-preserving targets); complex contexts return planar arrays. The model and its state are
  * untouched. */
 int peps_measure_bond_term(peps_ctx *ctx, int32_t T, const double *diag, const int32_t *target, const double *coef, double *out_h, double *out_v);
+/* The one-site analogue (table layout of kind 2 of peps_set_model_term): out[W][rows][cols] = sum_p' <p|O|p'> conj(psi(p') / psi),
+ * e.g. sigma_x of TransverseFieldIsingSquareOBC::EvaluateObservables (model_solvers/transverse_field_ising_square_obc.h:95-100,
+ * sigma_x(site) = -ex_term / h = conj(psi_flip / psi)) with the table {0 -> 1: 1, 1 -> 0: 1}. Bosonic contexts; planar output in a
+ * complex context. */
+int peps_measure_site_term(peps_ctx *ctx, int32_t T, const double *diag, const int32_t *target, const double *coef, double *out);
 /* StructureFactorMeasurementMixin::MeasureStructureFactor (model_solvers/base/structure_factor_measurement_mixin.h:89-228,
  * registry key SpSm_cross): all-pairs S+(y1,x1) S-(y2,x2) overlaps with y2 > y1 by "excited state propagation" -- the UP
  * boundary is forked at row y1 (BMPSContractor::BMPSWalker, bmps/impl/bmps_walker.h), absorbs the row with S+ applied and

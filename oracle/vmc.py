@@ -274,13 +274,26 @@ class TFIMModel:
                 e += -1 if config[row, col] == config[row + 1, col] else 1
         return e
 
-    def energy_and_holes(self, tps, w, calc_holes=True):
+    def measure(self, tps, w):
+        """EvaluateObservables (transverse_field_ising_square_obc.h:60-137): energy, spin_z = config - 1/2, sigma_x(site) =
+        -ex_term / h = conj(psi_flip / psi), SzSz_row along the middle row from (ly/2, lx/4)."""
+        rec = {}
+        e, _, _ = self.energy_and_holes(tps, w, False, rec=rec)
+        rows, cols = w.rows, w.cols
+        sz = w.config.astype(float) - 0.5
+        row, c1 = rows // 2, cols // 4
+        return {"energy": e, "spin_z": sz, "sigma_x": rec["sigma_x"],
+                "SzSz_row": np.array([sz[row, c1] * sz[row, c1 + i] for i in range(1, cols // 2 + 1)])}
+
+    def energy_and_holes(self, tps, w, calc_holes=True, rec=None):
         """CalEnergyAndHolesImplParsed (:208-247). Returns (E_loc, holes or None, psi_list)."""
         tn, c = w.tn, w.contractor
         rows, cols = w.rows, w.cols
         holes = [[None] * cols for _ in range(rows)] if calc_holes else None
         psi_list = []
         energy = 0.0
+        if rec is not None:
+            rec["sigma_x"] = np.zeros((rows, cols), dtype=np.result_type(tps[0][0][0].dtype, np.float64))
         c.set_truncate_params(*w.trunc)
         c.generate_bmps_approach(tn, UP)
         for row in range(rows):
@@ -295,6 +308,8 @@ class TFIMModel:
                 cfg = int(w.config[row, col])
                 psi_ex = c.replace_one_site_trace(tn, (row, col), tps[row][col][1 - cfg], HORIZONTAL)   # :191-204
                 energy = energy + (-self.h) * np.conj(psi_ex * inv_psi)
+                if rec is not None:
+                    rec["sigma_x"][row, col] = np.conj(psi_ex * inv_psi)
                 if col < cols - 1:
                     c.shift_bten_window(tn, RIGHT)
             if row < rows - 1:

@@ -50,6 +50,7 @@ SIGNATURES = {
     "peps_clear_model_terms": (C.c_int, [_P]),
     "peps_set_bond_pin": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _D, _I, _D]),
     "peps_measure_bond_term": (C.c_int, [_P, C.c_int32, _D, _I, _D, _D, _D]),
+    "peps_measure_site_term": (C.c_int, [_P, C.c_int32, _D, _I, _D, _D]),
     "peps_set_fermion": (C.c_int, [_P, _I, _I, C.c_size_t]),
     "peps_set_jastrow": (C.c_int, [_P, _D, _I]),
     "peps_set_complex": (C.c_int, [_P]),

@@ -620,6 +620,25 @@ class WalkerBatch:
         self._ck(self.lib.peps_measure_bond_term(self.h, T, _dp(diag), _ip(target), _dp(coef), _dp(oh), _dp(ov)))
         return (oh[0] + 1j * oh[1], ov[0] + 1j * ov[1]) if npl == 2 else (oh[0], ov[0])
 
+    def measure_site_observable(self, H1):
+        """A one-site operator as a (d, d) table on every site (peps_measure_site_term): [W][rows][cols] of
+        sum_p' H1[p, p'] conj(psi(p') / psi)."""
+        npl = 2 if getattr(self, "is_complex", False) else 1
+        T, diag, target, coef = TableModel.tables(H1)
+        out = np.empty((npl, self.W, self.rows, self.cols))
+        self._ck(self.lib.peps_measure_site_term(self.h, T, _dp(diag), _ip(target), _dp(coef), _dp(out)))
+        return out[0] + 1j * out[1] if npl == 2 else out[0]
+
+    def measure_tfim(self):
+        """TransverseFieldIsingSquareOBC::EvaluateObservables (transverse_field_ising_square_obc.h:60-146): energy, spin_z,
+        sigma_x (per site) and SzSz_row along the middle row."""
+        cfg = self.get_configs()
+        sz = cfg.astype(float) - 0.5
+        row, c1 = self.rows // 2, self.cols // 4
+        return {"energy": self.energy_and_holes(False), "spin_z": sz,
+                "sigma_x": self.measure_site_observable(np.array([[0.0, 1.0], [1.0, 0.0]])),
+                "SzSz_row": np.stack([sz[:, row, c1] * sz[:, row, c1 + i] for i in range(1, self.cols // 2 + 1)], axis=1)}
+
     def measure_sc_bond_singlet(self):
         """SC_bond_singlet_h / _v of the t-J measurement solvers (base/square_nnn_model_measurement_solver.h:116-131):
         (conj(delta_dag) + delta) / 2 per bond."""
@@ -786,7 +805,7 @@ class MCPEPSMeasurer:
         sums = None
         for _ in range(nper):
             b.sweep(self.mc.sweeps_between_samples)
-            obs = b.measure()
+            obs = b.measure_tfim() if isinstance(self.model, TransverseFieldIsingSquareOBC) else b.measure()
             if getattr(self.model, "enable_sc_measurement", False):  # t-J solvers: ModelType::enable_sc_measurement
                 obs["SC_bond_singlet_h"], obs["SC_bond_singlet_v"] = b.measure_sc_bond_singlet()
             if self.enable_structure_factor:                         # registry key SpSm_cross: overlap / amplitude

@@ -141,6 +141,9 @@ int64_t peps_structure_factor_pairs(peps_ctx *ctx) { return ctx->eng->structure_
 int peps_measure_bond_term(peps_ctx *ctx, int32_t T, const double *diag, const int32_t *target, const double *coef, double *out_h, double *out_v) {
   GUARD(ctx, ctx->eng->measure_bond_term(T, diag, target, coef, out_h, out_v))
 }
+int peps_measure_site_term(peps_ctx *ctx, int32_t T, const double *diag, const int32_t *target, const double *coef, double *out) {
+  GUARD(ctx, ctx->eng->measure_site_term(T, diag, target, coef, out))
+}
 int peps_set_bond_pin(peps_ctx *ctx, int32_t site1, int32_t site2, int32_t T, const double *diag, const int32_t *target, const double *coef) {
   GUARD(ctx, ctx->eng->set_bond_pin(site1, site2, T, diag, target, coef))
 }

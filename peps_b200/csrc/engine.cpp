@@ -95,7 +95,7 @@ Engine::~Engine() {
                   (void *)psi_row_, (void *)kept_, (void *)holes_, (void *)la_.offmax, (void *)la_.done, (void *)sr_ostar_,
                   (void *)sr_cfgs_, (void *)sr_delta_, (void *)psi_list_d_, (void *)term_ia_, (void *)term_ib_, (void *)term_cw_, (void *)idx_const_, (void *)idx_flip_, (void *)psi_alt_, (void *)bond_rec_, (void *)idx_perm_,
                   (void *)(fermion_ ? gtps_ : nullptr), (void *)gtps_off_d_, (void *)gidx_[0], (void *)gidx_[1], (void *)jw_[0],
-                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_, (void *)jastrow_v_, (void *)jr_, (void *)dens_d_, (void *)sr_desc2_, (void *)fs_target_d_, (void *)fs_coef_d_})
+                  (void *)jw_[1], (void *)phys_par_d_, (void *)fsign_, (void *)psi_loc_, (void *)jastrow_v_, (void *)jr_, (void *)dens_d_, (void *)sr_desc2_, (void *)fs_target_d_, (void *)fs_coef_d_, (void *)site_rec_})
     be_free(p);
   for (auto &t : term_) { be_free(t.diag); be_free(t.target); be_free(t.coef); }
   be_free(pin_.diag); be_free(pin_.target); be_free(pin_.coef);
@@ -1848,6 +1848,40 @@ void Engine::measure_bond_term(int T, const double *diag, const int32_t *target,
   } catch (...) { restore(); throw; }
   restore();
 }
+void Engine::measure_site_term(int T, const double *diag, const int32_t *target, const double *coef, double *out) {
+  require_boson("measure_site_term");
+  if (T < 0 || !diag || !out || (T > 0 && (!target || !coef))) throw std::invalid_argument("measure_site_term: null table");
+  be_sync();
+  TermTable saved[3] = {term_[0], term_[1], term_[2]}, saved_pin = pin_;
+  const bool s_on = tables_on_, s_ex = tables_exchange_only_, s_j = jastrow_on_;
+  for (auto &t : term_) t = TermTable();
+  pin_ = TermTable();
+  const size_t S = sw();
+  auto restore = [&]() {
+    be_sync();
+    free_table(term_[2]);
+    for (int k = 0; k < 3; ++k) term_[k] = saved[k];
+    pin_ = saved_pin;
+    tables_on_ = s_on; tables_exchange_only_ = s_ex; jastrow_on_ = s_j;
+    rec_sites_ = false;
+  };
+  try {
+    set_model_term(2, T, diag, target, coef);
+    jastrow_on_ = false;
+    if (!site_rec_) site_rec_ = (double *)be_malloc(sizeof(double) * (size_t)nsites_ * S);
+    be_memset0(site_rec_, sizeof(double) * (size_t)nsites_ * S);
+    rec_sites_ = true;
+    energy_and_holes_tables(false, nullptr, nullptr);
+    std::vector<double> rec((size_t)nsites_ * S);
+    be_d2h(rec.data(), site_rec_, sizeof(double) * rec.size());
+    const int np = complex_ ? 2 : 1;                    // complex context: planar output (real block, imaginary block)
+    for (int pl = 0; pl < np; ++pl)
+      for (int w = 0; w < W_; ++w)
+        for (int s = 0; s < nsites_; ++s)
+          out[(size_t)pl * W_ * nsites_ + (size_t)w * nsites_ + s] = rec[(size_t)s * S + (size_t)pl * W_ + w];
+  } catch (...) { restore(); throw; }
+  restore();
+}
 void Engine::clear_model_terms() {
   be_sync();
   for (auto &t : term_) free_table(t);
@@ -1890,7 +1924,8 @@ void Engine::energy_and_holes_tables(bool calc_holes, double *eloc_host, double 
     for (int col = 0; col < cols_; ++col) {
       if (calc_holes) punch_hole(row, col, HORIZONTAL);
       const int s1 = row * cols_ + col;
-      if (on.set) term(on, s1, -1, eloc_, [&](const int32_t *ia, const int32_t *, double *out) { one_site_trace(row, col, ia, 1, out); });
+      if (on.set) term(on, s1, -1, rec_sites_ ? site_rec_ + (size_t)s1 * sw() : eloc_,
+                       [&](const int32_t *ia, const int32_t *, double *out) { one_site_trace(row, col, ia, 1, out); });
       if (col < cols_ - 1) {
         nn_terms(s1, s1 + 1, bond_target(0, row, col), [&](const int32_t *ia, const int32_t *ib, double *out) {
           nn_trace_idx(row, col, row, col + 1, HORIZONTAL, ia, ib, 1, out);
@@ -1949,6 +1984,7 @@ void Engine::set_complex() {
   be_free(psi_alt_); psi_alt_ = nullptr; psi_alt_slots_ = 0;
   be_free(psi_list_d_); psi_list_d_ = nullptr;
   be_free(bond_rec_); bond_rec_ = nullptr;
+  be_free(site_rec_); site_rec_ = nullptr;
   if (sr_cap_ > 0) sr_reserve(0);
   auto grow = [&](double *&p, size_t n) { be_free(p); p = (double *)be_malloc(sizeof(double) * 2 * n); be_memset0(p, sizeof(double) * 2 * n); };
   grow(tps_, (size_t)tps_total_); gtps_ = tps_;

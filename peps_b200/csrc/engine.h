@@ -153,6 +153,10 @@ class Engine {
   // (base/square_nnn_model_measurement_solver.h:116-131; t-J: delta_dag / delta of square_tJ_model.h:546-602 as two
   // tables). Runs the measurement traversal with the operator in place of the model (Jastrow dressing off).
   void measure_bond_term(int T, const double *diag, const int32_t *target, const double *coef, double *out_h, double *out_v);
+  // The one-site analogue: out[W][rows][cols] = sum_p' <p|O|p'> conj(psi(p') / psi) for a one-site operator given by its table
+  // (layout of kind 2 of set_model_term), e.g. sigma_x of the transverse-field Ising measurement solver
+  // (transverse_field_ising_square_obc.h:95-100: sigma_x(site) = -ex_term / h). Bosonic contexts.
+  void measure_site_term(int T, const double *diag, const int32_t *target, const double *coef, double *out);
   // An extra table term on ONE NN bond (s1 = left / upper site, s2 = s1 + 1 or s1 + cols), added to the energy: the
   // singlet-pair pinning field of the t-J models (square_tJ_model.h:86-137, 256-289) as data. T = 0 clears it.
   void set_bond_pin(int s1, int s2, int T, const double *diag, const int32_t *target, const double *coef);
@@ -305,6 +309,8 @@ class Engine {
   double *psi_loc_ = nullptr;             // [W] psi of the current bond / plaquette along the same contraction path
   struct TermTable { bool set = false; int T = 0; double *diag = nullptr; int32_t *target = nullptr; double *coef = nullptr; };
   TermTable term_[3];
+  double *site_rec_ = nullptr;            // [nsites][W] (planes in a complex context): per-site records of measure_site_term
+  bool rec_sites_ = false;
   TermTable pin_;                         // extra term on the NN bond (pin_s1_, pin_s2_)
   int pin_s1_ = -1, pin_s2_ = -1;
   void upload_table(TermTable &t, int np, int T, const double *diag, const int32_t *target, const double *coef);

@@ -733,3 +733,33 @@ def run_boson_bond_observable_parity(lib):
     for k in ("energy", "bond_energy_h", "bond_energy_v", "bond_energy_dr", "bond_energy_ur"):
         assert np.allclose(obs_t[k], obs_b[k], rtol=1e-12, atol=1e-13), k
     b.close()
+
+
+def run_tfim_measure_parity(lib, complex_=False):
+    """TransverseFieldIsingSquareOBC::EvaluateObservables through peps_measure_site_term: sigma_x per site, energy, spin_z and
+    SzSz_row against the oracle; the model state is untouched."""
+    from peps_b200.api import TransverseFieldIsingSquareOBC, MCPEPSMeasurer, MCUpdateSquareNNFullSpaceUpdate
+    from peps_b200.api import MonteCarloParams, Configuration
+    rows, cols, D, W = 3, 4, 2, 3
+    tps = complex_tps(rows, cols, D, 31) if complex_ else vmc.random_tps(rows, cols, 2, D, seed=31)
+    cfgs = np.stack([vmc.shuffled_half_filled_config(rows, cols, 70 + w) for w in range(W)])
+    b = WalkerBatch(rows, cols, 2, D, W, BMPSTruncateParams.SVD(4, 4, 0.0), lib=lib)
+    if complex_:
+        b.set_complex()
+    b.set_tps(SplitIndexTPS(tps)); b.set_configs(cfgs); b.init_walkers()
+    b.set_model(TransverseFieldIsingSquareOBC(0.7))
+    e0 = b.energy_and_holes(False)
+    obs = b.measure_tfim()
+    model = vmc.TFIMModel(0.7)
+    for w in range(W):
+        ref = model.measure(tps, vmc.Walker(tps, cfgs[w], (4, 4, 0.0)))
+        for k, v in ref.items():
+            assert np.allclose(obs[k][w], v, rtol=1e-10, atol=1e-12), (k, w)
+    assert np.array_equal(b.energy_and_holes(False), e0)
+    # E = diagonal part - h sum sigma_x (transverse_field_ising_square_obc.h:95-122)
+    diag = np.array([model.diag_energy(cfgs[w]) for w in range(W)])
+    assert np.allclose(obs["energy"], diag - 0.7 * obs["sigma_x"].sum(axis=(1, 2)), rtol=1e-11)
+    b.close()
+    out = MCPEPSMeasurer(MonteCarloParams(6, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(4, 4, 0.0), SplitIndexTPS(tps),
+                         TransverseFieldIsingSquareOBC(0.7), MCUpdateSquareNNFullSpaceUpdate(seed=3), 3, lib=lib).Execute()
+    assert set(out) == {"energy", "spin_z", "sigma_x", "SzSz_row"} and out["sigma_x"][0].shape == (rows, cols)

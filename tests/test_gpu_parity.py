@@ -624,3 +624,10 @@ def test_variational_compression_gpu(lib, scheme):
     """VARIATION2Site / VARIATION1Site boundary compression (bmps_impl.h:864-1172) on the GPU vs the oracle."""
     from parity_common import run_variational_parity
     print("variational scheme", scheme, "worst rel err", run_variational_parity(lib, scheme))
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+def test_tfim_measurement_parity_gpu(lib, complex_):
+    """sigma_x per site (peps_measure_site_term), energy, spin_z, SzSz_row of the TFIM measurement solver on the CUDA path."""
+    from parity_common import run_tfim_measure_parity
+    run_tfim_measure_parity(lib, complex_)

@@ -428,3 +428,9 @@ def test_structure_factor_hostsim_and_brute_force():
 def test_variational_compression_hostsim(scheme):
     from parity_common import run_variational_parity
     print(run_variational_parity(hostsim_lib.load(), scheme))
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+def test_tfim_measurement_parity_hostsim(lib, complex_):
+    from parity_common import run_tfim_measure_parity
+    run_tfim_measure_parity(lib, complex_)
