@@ -49,3 +49,20 @@ def test_tfim_vmc_optimize_example_gpu():
     lib = _lib.load()
     assert lib.peps_backend_name() == b"cuda-sm_100a"
     run_tfim_example(lib)
+
+
+def test_tfim_mc_measure_example_hostsim(tmp_path):
+    """examples/tfim_mc_measure.py (the reference's transverse_field_ising_mc_measure.cpp flow): the optimised state of the
+    VMC example measures an energy consistent with its last optimisation energies, E = diag - h sum sigma_x holds for the
+    means, and DumpData writes the reference's stats layout."""
+    import tfim_vmc_optimize as ex
+    import tfim_mc_measure as mm
+    lib = hostsim_lib.load()
+    energies, state = ex.optimize(rows=3, cols=3, D=2, chi=4, h=0.5, walkers=8, samples=160, iters=6, step=0.15, lib=lib,
+                                  log=lambda *_: None)
+    r = mm.measure(state=state, rows=3, cols=3, D=2, chi=4, h=0.5, walkers=8, samples=240, out=str(tmp_path / "m"), lib=lib)
+    assert set(r) == {"energy", "spin_z", "sigma_x", "SzSz_row"}
+    assert abs(r["energy"][0] - energies[-1]) < 2.0 and r["energy"][0] < energies[0]
+    assert np.all(r["sigma_x"][0] > 0)                                     # a positive state: <sigma_x> > 0 on every site
+    for f in ("energy.csv", "sigma_x_mean.csv", "sigma_x_stderr.csv", "spin_z_mean.csv"):
+        assert os.path.exists(tmp_path / "m" / "stats" / f), f
