@@ -110,10 +110,10 @@ def read_qlten_fz2(path, dtype=None):
     buf = open(path, "rb").read()
     legs, coords, pos = _fz2_header(path, buf)
     rank = len(legs)
-    if dtype is None:
+    if dtype is None:                           # the element count is known: the stream ends with up to two newlines
         nel = sum(int(np.prod([legs[k][0][c[k]][1] for k in range(rank)])) for c in coords)
-        payload = len(buf) - pos - (1 if buf[-1:] == b"\n" and (len(buf) - pos) % 8 == 1 else 0)
-        dtype = np.complex128 if nel and payload == 16 * nel else np.float64
+        extra = len(buf) - pos - 16 * nel
+        dtype = np.complex128 if nel and 0 <= extra <= 2 and buf[len(buf) - extra:] == b"\n" * extra else np.float64
     out = np.zeros([l[2] for l in legs], dtype=dtype)
     offs = [np.concatenate([[0], np.cumsum([dg for _, dg in l[0]])]) for l in legs]
     item = np.dtype(dtype).itemsize
@@ -125,7 +125,7 @@ def read_qlten_fz2(path, dtype=None):
         out[tuple(slice(offs[k][c[k]], offs[k][c[k] + 1]) for k in range(rank))] = \
             np.frombuffer(buf[pos:pos + n * item], dtype=dtype).reshape(shp)
         pos += n * item
-    if len(buf) - pos > 1:
+    if len(buf) - pos > 2 or buf[pos:].strip(b"\n"):
         raise ValueError(f"{path}: {len(buf) - pos} trailing bytes (wrong element type?)")
     par = [np.concatenate([np.full(dg, qn % 2, dtype=np.int32) for qn, dg in l[0]]) for l in legs]
     return out, par, [l[1] for l in legs]

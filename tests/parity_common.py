@@ -278,13 +278,17 @@ def fermion_configs(rows, cols, W, phys, seed=10):
 
 
 def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", nsweeps=2, seed=3, tol=1e-10, seeds0=200,
-                                t2=0.6, check_holes=True, jastrow=False, complex_=False, updater="exchange"):
+                                t2=0.6, check_holes=True, jastrow=False, complex_=False, updater="exchange", state=None):
     """Sweeps + E_loc + O* of W walkers through the C ABI in fermion mode vs oracle/fermion.py, walker by walker:
     configurations and acceptance counts bit-identical, |amplitudes|, E_loc, O* to `tol` (relative)."""
     from oracle import fermion as F
     from peps_b200.api import FermionSplitIndexTPS, TableModel
     phys_par = (1, 0) if model == "spinless" else (1, 1, 0)
-    f = F.FermionTPS.random(rows, cols, D, seed, phys_par=phys_par, complex_=complex_)
+    if state is not None:                       # (oracle FermionTPS, configurations): a given physical state
+        f, given_cfgs = state
+        assert tuple(f.phys_par) == phys_par
+    else:
+        f = F.FermionTPS.random(rows, cols, D, seed, phys_par=phys_par, complex_=complex_)
     ftps = FermionSplitIndexTPS(f.T, f.par, phys_par)
     if model == "spinless":
         omodel = F.SpinlessFermionModel(1.0, t2, 0.3)
@@ -292,7 +296,7 @@ def run_fermion_pipeline_parity(lib, rows, cols, D, W, trunc, model="spinless", 
     else:
         omodel = F.tJModel(1.0, 0.3, mu=0.2, V=0.075, t2=t2 if model == "tj_nnn" else 0.0)
         tmodel = TableModel.tj(1.0, 0.3, V=0.075, mu=0.2, t2=t2 if model == "tj_nnn" else 0.0)
-    cfgs = fermion_configs(rows, cols, W, len(phys_par))
+    cfgs = given_cfgs if state is not None else fermion_configs(rows, cols, W, len(phys_par))
     tr = BMPSTruncateParams.SVD(*trunc)
     b = WalkerBatch(rows, cols, len(phys_par), D, W, tr, lib=lib)
     if complex_:
@@ -763,3 +767,51 @@ def run_tfim_measure_parity(lib, complex_=False):
     out = MCPEPSMeasurer(MonteCarloParams(6, 0, 1, Configuration(cfgs[0]), True), BMPSTruncateParams.SVD(4, 4, 0.0), SplitIndexTPS(tps),
                          TransverseFieldIsingSquareOBC(0.7), MCUpdateSquareNNFullSpaceUpdate(seed=3), 3, lib=lib).Execute()
     assert set(out) == {"energy", "spin_z", "sigma_x", "SzSz_row"} and out["sigma_x"][0].shape == (rows, cols)
+
+
+def ipeps_tj_state(rows, cols):
+    """An OBC t-J state tiled from the reference's iPEPS unit cell (tests/golden/ipeps_tj_ab.npz, re-packed from
+    tests/test_data/ipeps_tJ_t{a,b}_doping0.125.qlten): tensor a / b on the two sublattices, boundary legs reduced to dimension 1
+    by the dominant singular vector, NormalizeAllSite, times 3 -- the construction of ProjectedtJTensorNetwork
+    (tests/test_2d_tn/test_bmps_contractor.cpp:762-847) except that the boundary vector is taken from the EVEN sector of the
+    leg (the reference keeps the overall dominant one, which is odd for a's R and b's L leg; boundary legs are even here).
+    Returns an oracle FermionTPS with phys = (up, down, empty)."""
+    import os
+    from oracle import fermion as F
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ipeps_tj_ab.npz"))
+    bp = z["leg_par"][0].astype(np.int32)
+    assert all((z["leg_par"][k] == bp).all() for k in range(4)) and list(bp) == [0, 0, 1, 1] and list(z["phys_par"]) == [1, 1, 0]
+    one = np.zeros(1, dtype=np.int32)
+
+    def project(t, axis):
+        m = np.moveaxis(t, axis, 0).reshape(t.shape[axis], -1)
+        _, _, vt = np.linalg.svd(m[bp == 0], full_matrices=False)
+        return np.moveaxis(vt[0].reshape((1,) + tuple(np.delete(t.shape, axis))), 0, axis)
+
+    T = [[None] * cols for _ in range(rows)]
+    P = [[None] * cols for _ in range(rows)]
+    for r in range(rows):
+        for c in range(cols):
+            t = np.array(z["ta"] if (r + c) % 2 == 0 else z["tb"])
+            pars = [bp, bp, bp, bp]
+            if r == 0:
+                t, pars[3] = project(t, 3), one
+            elif r == rows - 1:
+                t, pars[1] = project(t, 1), one
+            if c == 0:
+                t, pars[0] = project(t, 0), one
+            elif c == cols - 1:
+                t, pars[2] = project(t, 2), one
+            mx = np.max(np.abs(t))
+            T[r][c] = [np.ascontiguousarray(t[..., s_]) * (3.0 / mx) for s_ in range(3)]
+            P[r][c] = pars
+    return F.FermionTPS(T, P, (1, 1, 0))
+
+
+def doped_tj_configs(rows, cols, W, seed=0):
+    """1/8 hole doping, equal numbers of up and down spins (even electron number), one shuffle per walker."""
+    n = rows * cols
+    holes = n // 8 + ((n - n // 8) % 2)
+    ne = n - holes
+    base = np.array([0] * (ne // 2) + [1] * (ne - ne // 2) + [2] * holes)
+    return np.stack([np.random.default_rng(seed + w).permutation(base).reshape(rows, cols) for w in range(W)])

@@ -201,3 +201,34 @@ def test_fermion_full_space_and_three_site_updaters_keep_amplitude_consistent(up
     assert f.parities(w.config).sum() % 2 == 0
     if updater == "three_site":
         assert sorted(w.config.ravel()) == sorted(cfg.ravel())              # permutations only
+
+
+def test_closures_agree_on_the_physical_tj_ipeps_state():
+    """The reference's fermionic closure check (ProjectedtJTensorNetwork::TestTrace, tests/test_2d_tn/test_bmps_contractor.cpp:
+    849-865: all amplitudes of one configuration agree to 1e-7 at D_b = 16..50) on a 10 x 12 OBC tiling of its physical t-J
+    iPEPS tensors: row closures of the horizontal machinery and column closures of the vertical machinery (times the
+    row-major / column-major permutation sign), NN- and three-site-replacement traces included."""
+    from parity_common import ipeps_tj_state, doped_tj_configs
+    from oracle.bmps import LEFT, RIGHT, UP, DOWN
+    rows, cols = 10, 12
+    f = ipeps_tj_state(rows, cols)
+    cfg = doped_tj_configs(rows, cols, 1, seed=5)[0]
+    assert f.parities(cfg).sum() % 2 == 0
+    w = F.FermionWalker(f, cfg, (16, 50, 1e-15))
+    c = w.contractor
+    vals = [w.amplitude]
+    for row in (2, rows // 2, rows - 1):
+        c.grow_bmps_for_row(w.tn_h, row); c.init_bten(w.tn_h, LEFT, row); c.grow_full_bten(w.tn_h, RIGHT, row, 2, True)
+        vals.append(c.trace(w.tn_h, (row, 0), HORIZONTAL))
+        c.init_bten(w.tn_h, LEFT, row); c.grow_full_bten(w.tn_h, RIGHT, row, 3, True)
+        vals.append(c.replace_tnn_site_trace(w.tn_h, (row, 0), HORIZONTAL, w.tn_h[row][0], w.tn_h[row][1], w.tn_h[row][2]))
+    sign = F.colmajor_sign(f, cfg)
+    for col in (1, cols // 2, cols - 1):
+        c.grow_bmps_for_col(w.tn_v, col); c.init_bten(w.tn_v, UP, col); c.grow_full_bten(w.tn_v, DOWN, col, 2, True)
+        vals.append(sign * c.trace(w.tn_v, (0, col), VERTICAL))
+        c.init_bten(w.tn_v, UP, col); c.grow_full_bten(w.tn_v, DOWN, col, 3, True)
+        vals.append(sign * c.replace_tnn_site_trace(w.tn_v, (0, col), VERTICAL, w.tn_v[0][col], w.tn_v[1][col], w.tn_v[2][col]))
+    vals = np.array(vals)
+    # same sign everywhere (the fermionic conventions of the two machineries agree) and equal up to the chi = 50 truncation
+    # (3e-6 here; the reference's 1e-7 is for its own boundary vectors at 20 x 24)
+    assert np.max(np.abs(vals / vals[0] - 1)) < 1e-5, vals / vals[0] - 1
