@@ -83,3 +83,27 @@ def test_exchange_updaters_conserve_sz(lib, updater):
     after = b.get_configs().sum(axis=(1, 2))
     assert moved > 0 and np.array_equal(before, after)
     b.close()
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+def test_split_index_tps_vector_space(complex_):
+    """SplitIndexTPS as the gradient / O* / CG vector type (two_dim_tn/tps/split_index_tps.h:171-177, 370-377): + - * scalar,
+    operator*(a, b) = sum conj(a) b, NormSquare, pack / unpack round trip (tests/test_2d_tn/test_split_index_tps.cpp)."""
+    rng = np.random.default_rng(1)
+
+    def rnd():
+        t = vmc.random_tps(3, 4, 2, 3, seed=int(rng.integers(1 << 30)))
+        if complex_:
+            t = [[[x + 1j * rng.standard_normal(x.shape) for x in site] for site in row] for row in t]
+        return SplitIndexTPS(t)
+    a, b = rnd(), rnd()
+    fa, fb = a.pack(), b.pack()
+    assert np.iscomplexobj(fa) == complex_
+    assert np.allclose((a + b).pack(), fa + fb) and np.allclose((a - b).pack(), fa - fb)
+    s = (0.3 - 0.2j) if complex_ else 0.3
+    assert np.allclose((a * s).pack(), fa * s) and np.allclose((s * a).pack(), fa * s)
+    assert abs((a * b) - np.vdot(fa, fb)) < 1e-12 * abs(np.vdot(fa, fb))          # conjugates the LEFT operand
+    assert abs(a.NormSquare() - np.vdot(fa, fa).real) < 1e-12 * a.NormSquare()
+    back = SplitIndexTPS.unpack(fa, a)
+    assert all(np.array_equal(x, y) for ra, rb in zip(a.t, back.t) for sa, sb in zip(ra, rb) for x, y in zip(sa, sb))
+    assert a.rows() == 3 and a.cols() == 4 and a.PhysicalDim() == 2 and a.bond_dim() == 3
