@@ -66,3 +66,20 @@ def test_tfim_mc_measure_example_hostsim(tmp_path):
     assert np.all(r["sigma_x"][0] > 0)                                     # a positive state: <sigma_x> > 0 on every site
     for f in ("energy.csv", "sigma_x_mean.csv", "sigma_x_stderr.csv", "spin_z_mean.csv"):
         assert os.path.exists(tmp_path / "m" / "stats" / f), f
+
+
+def test_heisenberg_vmc_optimize_example_hostsim():
+    """examples/heisenberg_vmc_optimize.py (the flow of the reference's integration test test_square_heisenberg_obc.cpp: SR
+    optimisation, then measurement) on the 2x2 simple-update fixture of K4: a few SR steps move the energy from -1.9952 towards
+    the exact -2, and the measured energy of the optimised state lies between them."""
+    import heisenberg_vmc_optimize as ex
+    from helpers import load_golden_tps
+    from peps_b200.api import SplitIndexTPS, Configuration
+    lib = hostsim_lib.load()
+    tps, z = load_golden_tps("heis2x2_double_su")
+    e_start = float(z["exp_energy"])                                       # -1.99521278793
+    energies, state = ex.optimize(SplitIndexTPS(tps), 2, 2, chi=16, walkers=16, samples=1600, iters=6, step=0.3, lib=lib,
+                                  log=lambda *_: None, init=Configuration(np.array([[0, 1], [1, 0]])))
+    obs = ex.measure(state, 2, 2, chi=16, walkers=16, samples=3200, lib=lib)
+    e_final, err = float(obs["energy"][0]), float(obs["energy"][1])
+    assert -2.0 - 4 * err - 1e-9 <= e_final < e_start - 1e-3, (e_start, energies, e_final, err)
