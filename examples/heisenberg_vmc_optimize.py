@@ -18,8 +18,10 @@ from peps_b200.api import (BMPSTruncateParams, Configuration, MCEnergyGradEvalua
 E_ED_3x4 = -6.691680193514947           # tests/integration_tests/test_square_heisenberg_obc.cpp:38
 
 
-def optimize(state, rows, cols, chi, walkers, samples, iters, step, diag_shift=1e-3, seed=1, lib=None, log=print, init=None):
-    model = SquareSpinOneHalfXXZModelOBC(1.0, 1.0, 0.0)
+def optimize(state, rows, cols, chi, walkers, samples, iters, step, diag_shift=1e-3, seed=1, lib=None, log=print, init=None,
+             model=None):
+    """`model`: any model of peps_b200.api (default Heisenberg); a FermionSplitIndexTPS state runs in fermion mode."""
+    model = model if model is not None else SquareSpinOneHalfXXZModelOBC(1.0, 1.0, 0.0)
     init = init if init is not None else Configuration(rows, cols).Random([rows * cols // 2, rows * cols - rows * cols // 2], seed=seed)
     mc = MonteCarloParams(num_samples=samples, num_warmup_sweeps=20, sweeps_between_samples=1, initial_config=init)
     ev = MCEnergyGradEvaluator(mc, BMPSTruncateParams.SVD(chi, 2 * chi, 1e-15), state, model, MCUpdateSquareNNExchange(seed=seed),
@@ -38,11 +40,12 @@ def optimize(state, rows, cols, chi, walkers, samples, iters, step, diag_shift=1
     return energies, state
 
 
-def measure(state, rows, cols, chi, walkers, samples, seed=7, lib=None):
-    init = Configuration(rows, cols).Random([rows * cols // 2, rows * cols - rows * cols // 2], seed=seed)
+def measure(state, rows, cols, chi, walkers, samples, seed=7, lib=None, init=None, model=None):
+    model = model if model is not None else SquareSpinOneHalfXXZModelOBC(1.0, 1.0, 0.0)
+    init = init if init is not None else Configuration(rows, cols).Random([rows * cols // 2, rows * cols - rows * cols // 2], seed=seed)
     mc = MonteCarloParams(num_samples=samples, num_warmup_sweeps=50, sweeps_between_samples=1, initial_config=init)
-    return MCPEPSMeasurer(mc, BMPSTruncateParams.SVD(chi, 2 * chi, 1e-15), state, SquareSpinOneHalfXXZModelOBC(1.0, 1.0, 0.0),
-                          MCUpdateSquareNNExchange(seed=seed), walkers, lib=lib).Execute()
+    return MCPEPSMeasurer(mc, BMPSTruncateParams.SVD(chi, 2 * chi, 1e-15), state, model, MCUpdateSquareNNExchange(seed=seed),
+                          walkers, lib=lib).Execute()
 
 
 if __name__ == "__main__":

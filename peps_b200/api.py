@@ -135,7 +135,7 @@ def compute_psi_consistency_summary_aligned(psi_list):
     ref = psi[int(np.argmax(np.abs(psi)))]
     aligned = psi.copy()
     if abs(ref) > 1e-14:
-        aligned = np.where(np.real(psi * np.conj(ref)) < 0.0, -psi, psi)
+        aligned = np.where(np.real(psi * np.conj(ref / abs(ref))) < 0.0, -psi, psi)    # unit phase of ref: no overflow for huge amplitudes
     mean = np.sum(aligned) / psi.size
     denom = max(abs(mean), np.finfo(np.float64).eps)
     return mean, float(np.max(np.abs(aligned - mean)) / denom)
@@ -190,9 +190,13 @@ class SplitIndexTPS:
             out.append(orow)
         return SplitIndexTPS(out)
 
+    def _like(self, tensors):
+        """A vector with this one's index structure (subclasses keep their extra structure, e.g. the fermion parities)."""
+        return SplitIndexTPS(tensors)
+
     def _zip(self, other, fn):
-        return SplitIndexTPS([[[fn(a, b) for a, b in zip(sa, sb)] for sa, sb in zip(ra, rb)]
-                              for ra, rb in zip(self.t, other.t)])
+        return self._like([[[fn(a, b) for a, b in zip(sa, sb)] for sa, sb in zip(ra, rb)]
+                           for ra, rb in zip(self.t, other.t)])
 
     def __add__(self, o):
         return self._zip(o, lambda a, b: a + b)
@@ -203,7 +207,7 @@ class SplitIndexTPS:
     def __mul__(self, s):
         if isinstance(s, SplitIndexTPS):           # operator*(SITPS, SITPS) = sum conj(a) b  (split_index_tps.h:370-377)
             return sum(np.vdot(a, b) for ra, rb in zip(self.t, s.t) for sa, sb in zip(ra, rb) for a, b in zip(sa, sb))
-        return SplitIndexTPS([[[x * s for x in site] for site in row] for row in self.t])
+        return self._like([[[x * s for x in site] for site in row] for row in self.t])
 
     __rmul__ = __mul__
 
@@ -220,6 +224,9 @@ class FermionSplitIndexTPS(SplitIndexTPS):
         super().__init__(tensors)
         self.par = par
         self.phys_par = tuple(int(x) for x in phys_par)
+
+    def _like(self, tensors):
+        return FermionSplitIndexTPS(tensors, self.par, self.phys_par)
 
     def leg_par_flat(self):
         return np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.int32).ravel()

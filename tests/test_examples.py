@@ -83,3 +83,29 @@ def test_heisenberg_vmc_optimize_example_hostsim():
     obs = ex.measure(state, 2, 2, chi=16, walkers=16, samples=3200, lib=lib)
     e_final, err = float(obs["energy"][0]), float(obs["energy"][1])
     assert -2.0 - 4 * err - 1e-9 <= e_final < e_start - 1e-3, (e_start, energies, e_final, err)
+
+
+@pytest.mark.parametrize("name,exact", [("sf2x2_t2_+0.0_double_su", -2.0), ("tj2x2_double_su", -2.9431635706137875)])
+def test_fermion_vmc_optimisation_reaches_the_exact_ground_energy_hostsim(name, exact):
+    """End to end in fermion mode (the flow of the reference's integration tests test_square_nn_spinless_free_fermion.cpp /
+    test_square_tj_model.cpp): SR from the reference's 2x2 simple-update fZ2 states (K8 energies -1.98218 / -2.78008) descends to
+    the exact ground energies (-2 and -2.94316, the `lowest` fixtures of K8) -- the fermionic O* / gradient and the device CG
+    point the right way, and the optimised FermionSplitIndexTPS measures that energy."""
+    import heisenberg_vmc_optimize as ex
+    from test_fermion_oracle import load_golden
+    from peps_b200.api import FermionSplitIndexTPS, Configuration, TableModel
+    lib = hostsim_lib.load()
+    f, z = load_golden(name)
+    ftps = FermionSplitIndexTPS(f.T, f.par, f.phys_par)
+    if name.startswith("sf"):
+        model, init = TableModel.spinless_fermion(1.0, 0.0, 0.0), [[0, 1], [1, 0]]
+    else:
+        model, init = TableModel.tj(1.0, 0.3, V=0.075), [[0, 2], [2, 1]]                  # SquaretJVModel(t, 0, J, J/4, mu = 0)
+    init = Configuration(np.array(init))
+    energies, state = ex.optimize(ftps, 2, 2, chi=8, walkers=16, samples=1600, iters=8, step=0.3, lib=lib, log=lambda *_: None,
+                                  init=init, model=model)
+    assert isinstance(state, FermionSplitIndexTPS)
+    obs = ex.measure(state, 2, 2, chi=8, walkers=16, samples=3200, lib=lib, init=init, model=model)
+    e, err = float(obs["energy"][0]), float(obs["energy"][1])
+    start = float(z["exp_energy"])
+    assert exact - 5 * err - 1e-6 <= e < start - 0.9 * (start - exact) + 5 * err, (start, energies, e, err, exact)
