@@ -854,7 +854,10 @@ class _CudaView:
 
 
 def _csv(x):
-    """ToCsvString (monte_carlo_peps_measurer_impl.h:24-29): scientific, max_digits10 = 17 significant digits."""
+    """ToCsvString (monte_carlo_peps_measurer_impl.h:24-36): scientific, max_digits10 = 17 significant digits; complex values
+    as the stream form of std::complex, (re,im)."""
+    if isinstance(x, (complex, np.complexfloating)):
+        return "(%.16e,%.16e)" % (x.real, x.imag)
     return "%.16e" % float(x)
 
 
@@ -868,7 +871,8 @@ def dump_measurement_stats(results, path, meta=None):
     stats = base + "stats/"
     os.makedirs(stats, exist_ok=True)
     for key, (mean, err) in results.items():
-        mean, err = np.asarray(mean, dtype=float), np.asarray(err, dtype=float)
+        mean = np.asarray(mean, dtype=complex if np.iscomplexobj(mean) else float)      # QLTEN_Complex runs keep complex means
+        err = np.asarray(err, dtype=float)
         if mean.ndim == 2:
             for suffix, arr in (("_mean.csv", mean), ("_stderr.csv", err)):
                 with open(stats + key + suffix, "w") as f:

@@ -117,3 +117,15 @@ def test_fermion_tps_writer_reproduces_reference_files(tmp_path, name):
     bad = type(f)([[[x + 1.0 for x in site] for site in row] for row in f.t], f.par, f.phys_par)   # parity-violating entries
     with pytest.raises(ValueError):
         pio.dump_fermion_tps(bad, str(tmp_path / "bad"), d)
+
+
+def test_measurement_stats_dump_complex_values(tmp_path):
+    """QLTEN_Complex measurement runs: ToCsvString(std::complex<double>) streams (re,im) (monte_carlo_peps_measurer_impl.h:31-36)."""
+    from peps_b200.api import dump_measurement_stats
+    res = {"bond_energy_h": (np.array([[0.5 + 0.25j, -1.0j]]), np.array([[0.1, 0.2]])), "energy": (np.array(-2.0 + 1e-3j), np.array(1e-4))}
+    dump_measurement_stats(res, str(tmp_path / "out"))
+    row = open(tmp_path / "out" / "stats" / "bond_energy_h_mean.csv").read().splitlines()[0]
+    assert row == "(5.0000000000000000e-01,2.5000000000000000e-01),(-0.0000000000000000e+00,-1.0000000000000000e+00)" or \
+        row == "(5.0000000000000000e-01,2.5000000000000000e-01),(0.0000000000000000e+00,-1.0000000000000000e+00)"
+    flat = open(tmp_path / "out" / "stats" / "energy.csv").read().splitlines()
+    assert flat[1].startswith("0,(-2.0000000000000000e+00,1.0000000000000000e-03),")
